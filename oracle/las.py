@@ -1,0 +1,326 @@
+"""Oracle: Listen-Attend-Spell forward pass (numpy restatement; test infrastructure only).
+
+Follows the reference graph code and restates the TensorFlow 1.15.2 ops it calls
+(tensorflow is not vendored/installable here -> parity UNPINNED, see oracle/__init__.py):
+
+* las/ops.py:10-20    lstm_cell        -> tf.nn.rnn_cell.LSTMCell  (gate order i,j,f,o; forget_bias=1)
+* las/ops.py:23-46    bilstm           -> tf.nn.bidirectional_dynamic_rnn / dynamic_rnn
+* las/ops.py:49-65    pyramidal_stack
+* las/ops.py:68-87    pyramidal_bilstm
+* las/model.py:104-142 listener
+* las/model.py:145-202 attend          -> tf.contrib.seq2seq.{Luong,Bahdanau,LuongMonotonic}Attention,
+                                          AttentionWrapper
+* las/model.py:205-349 speller         -> BasicDecoder + GreedyEmbeddingHelper / TrainingHelper +
+                                          dynamic_decode
+* utils/training_helper.py:122-153 DenseBinfDecoder (the output projection)
+
+Precision contract.  ``precision='fp32'`` computes everything in float32 like the reference.
+``precision='bf16'`` emulates the CUDA path's storage points (DESIGN.md "precision contract"):
+weights, layer inputs, stored gate pre-activations, recurrent h, attention keys/values and the
+attention vector are rounded to bfloat16 (round-to-nearest-even); accumulation, gates, cell
+state, softmax and logits stay float32.
+"""
+import numpy as np
+
+F32 = np.float32
+
+
+def round_bf16(x):
+    """float32 -> nearest-even bfloat16 -> float32."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32)
+    rounded = (u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)
+    out = rounded.view(np.float32)
+    return np.where(np.isfinite(x), out, x).astype(np.float32)
+
+
+def _q(precision):
+    if precision == "fp32":
+        return lambda a: np.asarray(a, dtype=F32)
+    if precision == "bf16":
+        return round_bf16
+    raise ValueError(precision)
+
+
+def sigmoid(x):
+    x = np.asarray(x, dtype=F32)
+    return (F32(1) / (F32(1) + np.exp(-x))).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# LSTMCell / dynamic_rnn
+# --------------------------------------------------------------------------------------
+def lstm_cell_step(z, c_prev):
+    """Gate math of tf LSTMCell given pre-activations z=[B,4U] (order i,j,f,o; forget_bias 1.0)."""
+    U = z.shape[1] // 4
+    i, j, f, o = z[:, :U], z[:, U:2 * U], z[:, 2 * U:3 * U], z[:, 3 * U:]
+    c = sigmoid(f + F32(1.0)) * c_prev + sigmoid(i) * np.tanh(j).astype(F32)
+    h = sigmoid(o) * np.tanh(c).astype(F32)
+    return c.astype(F32), h.astype(F32)
+
+
+def dynamic_rnn(x, lengths, kernel, bias, precision="fp32", reverse=False):
+    """tf.nn.dynamic_rnn over one LSTMCell with sequence_length semantics.
+
+    x [B,T,din] f32, lengths [B]; kernel [din+U,4U]; bias [4U].
+    Outputs are 0 for t >= len, state is frozen past len; ``reverse`` applies
+    reverse_sequence (within each length) on input and output (the bw direction of
+    bidirectional_dynamic_rnn).  Returns out [B,T,U], (c,h) final.
+    """
+    q = _q(precision)
+    B, T, din = x.shape
+    U = kernel.shape[1] // 4
+    wx, wh = q(kernel[:din]), q(kernel[din:])
+    xin = q(x)
+    # time-parallel input projection (mathematically what TF does per step inside [x,h]@kernel)
+    xproj = q(xin.reshape(B * T, din) @ wx + bias.astype(F32)).reshape(B, T, 4 * U)
+    c = np.zeros((B, U), F32)
+    h = np.zeros((B, U), F32)
+    out = np.zeros((B, T, U), F32)
+    lengths = np.asarray(lengths)
+    for s in range(T):
+        active = s < lengths
+        if not active.any():
+            break
+        t_idx = np.where(active, (lengths - 1 - s) if reverse else s, 0)
+        z = xproj[np.arange(B), t_idx] + h @ wh
+        c_new, h_new = lstm_cell_step(z.astype(F32), c)
+        h_new = q(h_new)
+        c = np.where(active[:, None], c_new, c)
+        h = np.where(active[:, None], h_new, h)
+        rows = np.nonzero(active)[0]
+        out[rows, t_idx[rows]] = h_new[rows]
+    return out, (c, h)
+
+
+def bilstm(x, lengths, params, scope, precision="fp32", unidirectional=False):
+    """las/ops.py:23-46.  ``params`` maps TF variable names to arrays."""
+    if unidirectional:
+        k = params[scope + "/rnn/lstm_cell/kernel"]
+        b = params[scope + "/rnn/lstm_cell/bias"]
+        return dynamic_rnn(x, lengths, k, b, precision)
+    outs, states = [], []
+    for d, rev in (("fw", False), ("bw", True)):
+        k = params[f"{scope}/bidirectional_rnn/{d}/lstm_cell/kernel"]
+        b = params[f"{scope}/bidirectional_rnn/{d}/lstm_cell/bias"]
+        o, st = dynamic_rnn(x, lengths, k, b, precision, reverse=rev)
+        outs.append(o)
+        states.append(st)
+    return tuple(outs), tuple(states)
+
+
+def pyramidal_stack(outputs, lengths):
+    """las/ops.py:49-65."""
+    B, T, D = outputs.shape
+    if T % 2:
+        outputs = np.concatenate([outputs, np.zeros((B, 1, D), outputs.dtype)], axis=1)
+    outputs = outputs.reshape(B, -1, 2 * D)
+    lengths = np.asarray(lengths)
+    return outputs, lengths // 2 + lengths % 2
+
+
+def pyramidal_bilstm(x, lengths, params, num_layers, precision="fp32", unidirectional=False,
+                     scope="listener"):
+    """las/ops.py:68-87."""
+    outputs = x
+    state = None
+    for layer in range(num_layers):
+        o, state = bilstm(outputs, lengths, params, f"{scope}/bilstm_{layer}", precision, unidirectional)
+        outputs = o if unidirectional else np.concatenate(o, -1)
+        if layer != 0:
+            outputs, lengths = pyramidal_stack(outputs, lengths)
+    return (outputs, np.asarray(lengths)), state
+
+
+def listener(encoder_inputs, source_sequence_length, params, hp, precision="fp32"):
+    """las/model.py:104-142 (pyramidal branch + non-pyramidal bidirectional MultiRNNCell branch)."""
+    if hp["use_pyramidal"]:
+        return pyramidal_bilstm(encoder_inputs, source_sequence_length, params, hp["encoder_layers"],
+                                precision, hp.get("unidirectional", False))
+    # stacked MultiRNNCell: each direction is an independent L-layer stack over the raw input
+    q = _q(precision)
+    B, T, _ = encoder_inputs.shape
+    lengths = np.asarray(source_sequence_length)
+    outs, states = [], []
+    dirs = (("fw", False),) if hp.get("unidirectional", False) else (("fw", False), ("bw", True))
+    for d, rev in dirs:
+        xin = encoder_inputs
+        st_d = []
+        for l in range(hp["encoder_layers"]):
+            base = ("listener/rnn" if hp.get("unidirectional", False)
+                    else f"listener/bidirectional_rnn/{d}")
+            k = params[f"{base}/multi_rnn_cell/cell_{l}/lstm_cell/kernel"]
+            b = params[f"{base}/multi_rnn_cell/cell_{l}/lstm_cell/bias"]
+            # NOTE: a MultiRNNCell steps all layers per time step; for a stack of LSTMs with
+            # length masking this equals running the layers one after another on the (already
+            # direction-reversed) sequence.  We run each layer in the direction's own time order.
+            xin, st = dynamic_rnn(xin, lengths, k, b, precision, reverse=rev)
+            st_d.append(st)
+        outs.append(xin)
+        states.append(tuple(st_d))
+    out = outs[0] if len(outs) == 1 else np.concatenate(outs, -1)
+    return (out, lengths), tuple(states)
+
+
+# --------------------------------------------------------------------------------------
+# attention mechanisms (tf.contrib.seq2seq)
+# --------------------------------------------------------------------------------------
+def _safe_cumprod_exclusive(x):
+    tiny = np.finfo(np.float32).tiny
+    logx = np.log(np.clip(x, tiny, 1.0)).astype(F32)
+    cs = np.cumsum(logx, axis=1, dtype=F32)
+    cs = np.concatenate([np.zeros_like(cs[:, :1]), cs[:, :-1]], axis=1)
+    return np.exp(cs).astype(F32)
+
+
+class Attention:
+    """values/keys setup of _BaseAttentionMechanism + score/probability fns."""
+
+    def __init__(self, attention_type, memory, memory_len, params, scope, precision="fp32"):
+        q = self.q = _q(precision)
+        self.type = attention_type
+        B, Tm, D = memory.shape
+        self.mask = (np.arange(Tm)[None, :] < np.asarray(memory_len)[:, None])
+        self.values = q(memory * self.mask[:, :, None].astype(F32))
+        wm = q(params[f"{scope}/memory_layer/kernel"])
+        self.keys = q((self.values.reshape(B * Tm, D) @ wm).reshape(B, Tm, -1))
+        pre = f"{scope}/decoder/attention_wrapper"
+        if attention_type == "bahdanau":
+            self.wq = q(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
+            self.v = params[f"{pre}/bahdanau_attention/attention_v"].astype(F32)
+        elif attention_type == "luong_monotonic":
+            self.score_bias = F32(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
+        elif attention_type != "luong":
+            raise NotImplementedError(attention_type)
+
+    def initial_alignments(self):
+        B, Tm = self.mask.shape
+        a = np.zeros((B, Tm), F32)
+        if self.type == "luong_monotonic":
+            a[:, 0] = 1.0
+        return a
+
+    def __call__(self, query, prev_alignments):
+        """query [B,Ud] (already quantised cell output) -> alignments [B,Tm] f32."""
+        if self.type == "bahdanau":
+            pq = (query @ self.wq).astype(F32)
+            score = np.einsum("btu,u->bt", np.tanh(self.keys + pq[:, None, :]).astype(F32), self.v,
+                              dtype=F32)
+        else:
+            score = np.einsum("btu,bu->bt", self.keys, query, dtype=F32)
+        if self.type == "luong_monotonic":
+            score = score + self.score_bias
+            with np.errstate(over="ignore"):
+                p = np.where(self.mask, sigmoid(score), F32(0)).astype(F32)
+            cp = _safe_cumprod_exclusive(F32(1) - p)
+            return (p * cp * np.cumsum(prev_alignments / np.clip(cp, 1e-10, 1.0), axis=1, dtype=F32)).astype(F32)
+        score = np.where(self.mask, score, -np.inf).astype(F32)
+        m = score.max(axis=1, keepdims=True)
+        e = np.exp(score - m).astype(F32)
+        return (e / e.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# AttentionWrapper(MultiRNNCell) + BasicDecoder + helpers + dynamic_decode
+# --------------------------------------------------------------------------------------
+class Speller:
+    """Default wiring of las/model.py:195-200 (bottom_only=False, attention_layer_size=None)."""
+
+    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller"):
+        self.q = _q(precision)
+        self.hp = hp
+        self.scope = scope
+        self.att = Attention(hp["attention_type"], enc_out, enc_len, params, scope, precision)
+        self.B, self.Tm, self.D = enc_out.shape
+        self.Ud = hp["decoder_units"]
+        self.V = hp["target_vocab_size"]
+        pre = f"{scope}/decoder/attention_wrapper/multi_rnn_cell"
+        self.cells = []
+        for k in range(hp["decoder_layers"]):
+            self.cells.append((self.q(params[f"{pre}/cell_{k}/lstm_cell/kernel"]),
+                               params[f"{pre}/cell_{k}/lstm_cell/bias"].astype(F32)))
+        self.wp = self.q(params[f"{scope}/decoder/projection_layer/kernel"])
+        self.bp = params[f"{scope}/decoder/projection_layer/bias"].astype(F32)
+        self.enc_len = np.asarray(enc_len)
+
+    def zero_state(self):
+        cs = [(np.zeros((self.B, self.Ud), F32), np.zeros((self.B, self.Ud), F32)) for _ in self.cells]
+        return dict(cells=cs, attention=np.zeros((self.B, self.D), F32),
+                    alignments=self.att.initial_alignments())
+
+    def step(self, x, state):
+        """AttentionWrapper.call + output projection.  x [B,V] (one-hot or teacher input)."""
+        q = self.q
+        inp = np.concatenate([x, state["attention"]], axis=1).astype(F32)
+        new_cells = []
+        for (k, b), (c, h) in zip(self.cells, state["cells"]):
+            z = (np.concatenate([inp, h], axis=1) @ k + b).astype(F32)
+            c2, h2 = lstm_cell_step(z, c)
+            h2 = q(h2)
+            new_cells.append((c2, h2))
+            inp = h2
+        align = self.att(inp, state["alignments"])
+        context = np.einsum("bt,btd->bd", align, self.att.values, dtype=F32)
+        attention = q(context)
+        logits = (attention @ self.wp + self.bp).astype(F32)
+        return logits, dict(cells=new_cells, attention=attention, alignments=align)
+
+    def one_hot(self, ids):
+        return np.eye(self.V, dtype=F32)[ids]
+
+    def greedy(self):
+        """GreedyEmbeddingHelper + dynamic_decode(impute_finished=False) (las/model.py:270-274,337-347)."""
+        hp = self.hp
+        max_iter = int(np.rint(F32(self.enc_len.max()) * F32(hp.get("decoding_length_factor", 1.0))))
+        state = self.zero_state()
+        ids = np.full((self.B,), hp["sos_id"], np.int64)
+        finished = np.zeros((self.B,), bool) | (0 >= max_iter)
+        seq_len = np.zeros((self.B,), np.int32)
+        logits_all, ids_all, align_all = [], [], []
+        time = 0
+        while not finished.all():
+            logits, state = self.step(self.one_hot(ids), state)
+            ids = logits.argmax(axis=1)
+            step_fin = ids == hp["eos_id"]
+            next_fin = step_fin | finished
+            seq_len = np.where(~finished, time + 1, seq_len).astype(np.int32)
+            next_fin |= (time + 1 >= max_iter)
+            logits_all.append(logits)
+            ids_all.append(ids.astype(np.int32))
+            align_all.append(state["alignments"])
+            finished = next_fin
+            time += 1
+        if not logits_all:
+            return (np.zeros((self.B, 0, self.V), F32), np.zeros((self.B, 0), np.int32),
+                    np.zeros((self.B, 0, self.Tm), F32), seq_len, state)
+        return (np.stack(logits_all, 1), np.stack(ids_all, 1), np.stack(align_all, 1), seq_len, state)
+
+    def teacher_forced(self, targets_inputs, target_len):
+        """TrainingHelper + dynamic_decode (las/model.py:276-296 with sampling_probability=0)."""
+        target_len = np.asarray(target_len)
+        steps = int(target_len.max())
+        if self.hp.get("max_symbols", -1) > 0:
+            steps = min(steps, self.hp["max_symbols"])
+        state = self.zero_state()
+        logits_all = []
+        for t in range(steps):
+            logits, state = self.step(self.one_hot(targets_inputs[:, t]), state)
+            logits_all.append(logits)
+        return np.stack(logits_all, 1), state
+
+
+# --------------------------------------------------------------------------------------
+# whole-path helpers
+# --------------------------------------------------------------------------------------
+def predict(features, lengths, params, hp, precision="fp32"):
+    """model_helper.py:165-297 PREDICT predictions dict (greedy, beam_width=0)."""
+    (enc_out, enc_len), enc_state = listener(features, lengths, params, hp, precision)
+    sp = Speller(enc_out, enc_len, params, hp, precision)
+    logits, ids, align, seq_len, _ = sp.greedy()
+    emb_c = np.concatenate([s[0] for s in enc_state], axis=1)
+    emb_h = np.concatenate([s[1] for s in enc_state], axis=1)
+    e = np.exp(logits - logits.max(-1, keepdims=True)) if logits.size else logits
+    probs = e / e.sum(-1, keepdims=True) if logits.size else logits
+    return dict(encoder_out=enc_out, source_length=enc_len, embedding=np.stack([emb_c, emb_h], 1),
+                sample_ids=ids, alignment=align, probs=probs, logits=logits,
+                final_sequence_length=seq_len)

@@ -1,0 +1,172 @@
+"""Oracle self-consistency: LSTM / listener / attention / losses against independent torch CPU ops."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import las as ol
+from oracle import losses as olo
+from phones_las_b200 import synth, weights
+from phones_las_b200.hparams import create_hparams
+
+
+def _torch_lstm_from_tf(kernel, bias, din):
+    U = kernel.shape[1] // 4
+    lstm = torch.nn.LSTM(din, U, batch_first=True)
+    def reorder(w):  # TF i,j,f,o -> torch i,f,g,o
+        i, j, f, o = np.split(w, 4, axis=-1)
+        return np.concatenate([i, f, j, o], axis=-1)
+    b = bias.copy()
+    b[2 * U:3 * U] += 1.0  # forget_bias folded in
+    with torch.no_grad():
+        lstm.weight_ih_l0.copy_(torch.from_numpy(reorder(kernel[:din]).T.copy()))
+        lstm.weight_hh_l0.copy_(torch.from_numpy(reorder(kernel[din:]).T.copy()))
+        lstm.bias_ih_l0.copy_(torch.from_numpy(reorder(b)))
+        lstm.bias_hh_l0.zero_()
+    return lstm
+
+
+def test_round_bf16_matches_torch():
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 3
+    ref = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    np.testing.assert_array_equal(ol.round_bf16(x), ref)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_dynamic_rnn_vs_torch_lstm(reverse):
+    rng = np.random.default_rng(3)
+    B, T, din, U = 4, 11, 6, 8
+    x = rng.standard_normal((B, T, din)).astype(np.float32)
+    lens = np.array([11, 7, 1, 4])
+    kernel = rng.uniform(-0.3, 0.3, (din + U, 4 * U)).astype(np.float32)
+    bias = rng.uniform(-0.1, 0.1, 4 * U).astype(np.float32)
+    out, (c, h) = ol.dynamic_rnn(x, lens, kernel, bias, reverse=reverse)
+    lstm = _torch_lstm_from_tf(kernel, bias, din)
+    for b in range(B):
+        xb = x[b, :lens[b]]
+        if reverse:
+            xb = xb[::-1].copy()
+        o, (hn, cn) = lstm(torch.from_numpy(xb)[None])
+        o = o[0].detach().numpy()
+        if reverse:
+            o = o[::-1]
+        np.testing.assert_allclose(out[b, :lens[b]], o, rtol=1e-5, atol=1e-6)
+        assert (out[b, lens[b]:] == 0).all()
+        np.testing.assert_allclose(h[b], hn[0, 0].detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(c[b], cn[0, 0].detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_pyramidal_shapes_and_lengths():
+    hp = create_hparams(target_vocab_size=16, encoder_layers=3, encoder_units=8, decoder_units=8,
+                        decoder_layers=1, num_channels=5)
+    params = weights.init_params(hp)
+    x, lens = synth.synth_features(3, 13, 5, var_len=True)
+    (out, olen), state = ol.pyramidal_bilstm(x, lens, params, 3)
+    assert out.shape == (3, 4, 32)  # T: 13 -> 13 -> 7 -> 4 ; depth 4U
+    np.testing.assert_array_equal(olen, [(-(-int(l) // 2) + 1) // 2 for l in lens])
+    for b in range(3):
+        assert (out[b, olen[b]:] == 0).all()
+    assert weights.encoder_output_depth(hp) == 32
+
+
+def test_pyramidal_stack_matches_even_odd_concat():
+    x = np.arange(2 * 5 * 3, dtype=np.float32).reshape(2, 5, 3)
+    y, l = ol.pyramidal_stack(x, np.array([5, 2]))
+    xp = np.concatenate([x, np.zeros((2, 1, 3), np.float32)], 1)
+    np.testing.assert_array_equal(y, np.concatenate([xp[:, ::2], xp[:, 1::2]], -1))
+    np.testing.assert_array_equal(l, [3, 1])
+
+
+@pytest.mark.parametrize("att", ["luong", "bahdanau", "luong_monotonic"])
+def test_greedy_decode_properties(att):
+    hp = create_hparams(target_vocab_size=12, encoder_layers=2, encoder_units=8, decoder_units=16,
+                        decoder_layers=2, num_channels=5, attention_type=att)
+    params = weights.init_params(hp, projection_scale=8.0)
+    x, lens = synth.synth_features(3, 12, 5, var_len=True)
+    pred = ol.predict(x, lens, params, hp)
+    T_dec = pred["sample_ids"].shape[1]
+    assert 1 <= T_dec <= int(round(pred["source_length"].max()))
+    a = pred["alignment"]
+    assert a.shape == (3, T_dec, pred["encoder_out"].shape[1])
+    for b in range(3):
+        assert (a[b, :, pred["source_length"][b]:] == 0).all()
+    if att != "luong_monotonic":
+        np.testing.assert_allclose(a.sum(-1), 1.0, rtol=1e-5)
+    np.testing.assert_array_equal(pred["sample_ids"], pred["logits"].argmax(-1))
+    # teacher forcing with the greedy ids reproduces the greedy logits
+    (enc, elen), _ = ol.listener(x, lens, params, hp)
+    sp = ol.Speller(enc, elen, params, hp)
+    tin = np.concatenate([np.full((3, 1), hp["sos_id"]), pred["sample_ids"][:, :-1]], 1)
+    tf_logits, _ = sp.teacher_forced(tin, np.full((3,), T_dec))
+    np.testing.assert_allclose(tf_logits, pred["logits"], rtol=1e-5, atol=1e-6)
+
+
+def test_bf16_mode_close_to_fp32():
+    hp = create_hparams(target_vocab_size=12, encoder_layers=3, encoder_units=16, decoder_units=16,
+                        decoder_layers=1, num_channels=5)
+    params = weights.init_params(hp)
+    x, lens = synth.synth_features(2, 16, 5)
+    (o32, _), _ = ol.listener(x, lens, params, hp, "fp32")
+    (o16, _), _ = ol.listener(x, lens, params, hp, "bf16")
+    rel = np.linalg.norm(o32 - o16) / np.linalg.norm(o32)
+    assert 0 < rel < 2e-2
+    np.testing.assert_array_equal(o16, ol.round_bf16(o16))
+
+
+def test_ctc_vs_torch():
+    rng = np.random.default_rng(5)
+    B, T, V, L = 4, 20, 9, 6
+    logits = rng.standard_normal((B, T, V + 1)).astype(np.float32)
+    labels = rng.integers(1, V + 1, (B, L))
+    labels[1, 2] = labels[1, 1]  # a repeat
+    lab_len = np.array([6, 5, 1, 3])
+    log_len = np.array([20, 15, 4, 9])
+    mine = olo.ctc_loss(logits, labels, lab_len, log_len, blank=0)
+    lp = torch.log_softmax(torch.from_numpy(logits), -1).transpose(0, 1)
+    ref = torch.nn.functional.ctc_loss(lp, torch.from_numpy(labels), torch.from_numpy(log_len),
+                                       torch.from_numpy(lab_len), blank=0, reduction="none")
+    np.testing.assert_allclose(mine, ref.numpy(), rtol=1e-5)
+
+
+def test_sequence_loss_vs_torch():
+    rng = np.random.default_rng(6)
+    logits = rng.standard_normal((3, 7, 10)).astype(np.float32)
+    tg = rng.integers(0, 10, (3, 7))
+    lens = np.array([7, 3, 5])
+    mine = olo.compute_loss(logits, tg, None, lens, "train", 2)
+    ce = torch.nn.functional.cross_entropy(torch.from_numpy(logits).reshape(-1, 10),
+                                           torch.from_numpy(tg).reshape(-1), reduction="none").reshape(3, 7)
+    w = torch.from_numpy(olo.sequence_mask(lens, 7))
+    np.testing.assert_allclose(mine, float((ce * w).sum() / w.sum()), rtol=1e-6)
+    # eval variant pads targets with eos / logits with zeros to max(len)
+    ev = olo.compute_loss(logits[:, :5], tg, np.array([5, 2, 5]), lens, "eval", 2)
+    assert np.isfinite(ev)
+
+
+def test_sigmoid_loss_and_binf_transform():
+    rng = np.random.default_rng(7)
+    logits = rng.standard_normal((2, 5, 6)).astype(np.float32)
+    tg = rng.integers(0, 2, (2, 5, 6)).astype(np.float32)
+    mine = olo.compute_loss_sigmoid_train(logits, tg, np.array([5, 3]))
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(torch.from_numpy(logits), torch.from_numpy(tg),
+                                                               reduction="none").mean(-1)
+    w = torch.from_numpy(olo.sequence_mask(np.array([5, 3]), 5))
+    np.testing.assert_allclose(mine, float((ref * w).sum() / w.sum()), rtol=1e-6)
+    M = rng.integers(0, 2, (3, 4)).astype(np.float32)
+    out = olo.transform_binf_to_phones(logits, M)
+    assert out.shape == (2, 5, 4)
+
+
+def test_clip_adam_edit_distance():
+    g = np.ones(16, np.float32)
+    np.testing.assert_allclose(np.linalg.norm(olo.clip_by_norm(g, 2.0)), 2.0, rtol=1e-6)
+    np.testing.assert_array_equal(olo.clip_by_norm(g * 0.1, 2.0), g * 0.1)
+    p = torch.nn.Parameter(torch.ones(4))
+    opt = torch.optim.Adam([p], lr=1e-3, eps=1e-8)
+    pn, m, v = np.ones(4), np.zeros(4), np.zeros(4)
+    for step in (1, 2, 3):
+        p.grad = torch.full((4,), 0.5)
+        opt.step()
+        pn, m, v = olo.adam_step(pn, np.full(4, 0.5), m, v, step, 1e-3)
+    np.testing.assert_allclose(pn, p.detach().numpy(), rtol=1e-5)
+    assert olo.edit_distance_merge([3, 3, 4, 2, 9], [3, 4, 4, 5, 2], 2) == pytest.approx(1 / 3)
+    assert olo.ctc_greedy_decode(np.eye(4)[None, [0, 0, 3, 1, 1, 3, 1]], [7]) == [[0, 1, 1]]
