@@ -1,0 +1,167 @@
+/* plas.h -- C ABI of libplas.so: the B200-native (sm_100a) phones-las hot path.
+ *
+ * The reference (sciforce/phones-las) is pure Python/TensorFlow and has no FFI of its own;
+ * each entry point below names the reference call it replaces (file:line in the reference
+ * tree).  Conventions:
+ *   - every function returns 0 on success or a negative PLAS_E* code; the message is
+ *     available from plas_last_error() (thread-local);
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *     buffer including workspaces (sizes from the *_workspace_bytes queries); nothing is
+ *     allocated or cached behind the caller's back;
+ *   - `stream` is a cudaStream_t (passed as void*); all work is enqueued on it, no call
+ *     synchronises the device;
+ *   - tensors are row-major, batch-major ([B,T,C]) like the reference's TF tensors;
+ *   - dtype codes: PLAS_F32 = 0, PLAS_BF16 = 1.
+ */
+#ifndef PLAS_H_
+#define PLAS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLAS_F32 0
+#define PLAS_BF16 1
+
+#define PLAS_ATT_LUONG 0
+#define PLAS_ATT_BAHDANAU 1
+#define PLAS_ATT_LUONG_MONOTONIC 2
+
+typedef void* plas_stream_t;
+
+const char* plas_last_error(void);
+int plas_version(void);
+int plas_num_sms(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  acoustic front-end.  Replaces calculate_acoustic_features (preprocess_all.py:69-130)
+ * -> speechpy.feature.{mfe,mfcc,extract_derivative_feature} / librosa.feature.{melspectrogram,
+ * mfcc,rms,delta} + amplitude_to_db, and the per-channel normalisation of
+ * utils/dataset_utils.py:213-220, batched over utterances.
+ * ---------------------------------------------------------------------------------- */
+typedef struct plas_frontend_desc {
+  int32_t backend;          /* 0 = speechpy, 1 = librosa (preprocess_all.py:204-205)            */
+  int32_t feature_type;     /* 0 = mfe, 1 = mfcc        (preprocess_all.py:202-203)            */
+  int32_t n_fft;            /* int(window * 16)         (preprocess_all.py:70)                 */
+  int32_t hop;              /* int(step * 16)           (preprocess_all.py:71)                 */
+  int32_t n_mels;
+  int32_t n_mfcc;
+  int32_t energy;           /* --energy                                                        */
+  int32_t deltas;           /* --deltas                                                        */
+  int32_t sp_delta_literal; /* speechpy derivative_extraction reading              */
+  int32_t n_fac;            /* radix factorisation of n_fft/2 (radices in {2,3,4,5,8})         */
+  int32_t fac[8];
+  int32_t fb_total;         /* number of non-zero filterbank weights                           */
+  int32_t _pad;
+  const float* window;      /* [n_fft] analysis window (ones / periodic Hann)                  */
+  const float* tw;          /* [n_fft/2][2]   exp(-2*pi*i*k/(n_fft/2))                         */
+  const float* tw_unpack;   /* [n_fft/2+1][2] exp(-2*pi*i*k/n_fft)                             */
+  const int32_t* fb_start;  /* [n_mels] first FFT bin of each mel filter                       */
+  const int32_t* fb_len;    /* [n_mels] number of bins                                         */
+  const int32_t* fb_off;    /* [n_mels] offset into fb_w                                       */
+  const float* fb_w;        /* [fb_total] filter weights                                       */
+  const float* dct;         /* [n_mfcc][n_mels] orthonormal DCT-II rows (mfcc) or NULL         */
+  const float* mean;        /* [C] or NULL  (utils/dataset_utils.py:213-220)                   */
+  const float* stdv;        /* [C] or NULL                                                     */
+} plas_frontend_desc;
+
+size_t plas_frontend_workspace_bytes(const plas_frontend_desc* d, int32_t B, int32_t T_max);
+
+/* wave [B][wave_stride] f32, n_samples [B]; feats [B][T_max][C] f32 (zero past each utterance's
+ * frame count), n_frames [B] written by the kernel. */
+int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave, const int32_t* n_samples,
+                      int32_t B, int64_t wave_stride, float* feats, int32_t* n_frames,
+                      int32_t T_max, int32_t C, void* workspace, size_t workspace_bytes,
+                      plas_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  time-parallel projections.  Replace the x-part of `concat([x,h]) @ kernel + bias`
+ * inside tf.nn.rnn_cell.LSTMCell (las/ops.py:11-12,35-40) hoisted out of the time loop, the
+ * pyramidal frame concat (las/ops.py:49-65, a free view here) and the attention
+ * memory_layer Dense (las/model.py:168-169).
+ *   C[M][ldc] = A[M][K] * Wt[N][K]^T + bias[N]
+ * bf16: tcgen05/TMEM/TMA kernel (N % 128 == 0, lda/ldw multiples of 8, 16-byte aligned bases).
+ * f32 : exact-fp32 SIMT kernel (reference-precision mode).
+ * ---------------------------------------------------------------------------------- */
+int plas_gemm_bf16(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
+                   int64_t ldw, const float* bias, void* C, int64_t ldc, plas_stream_t stream);
+int plas_gemm_f32(const float* A, int64_t M, int32_t K, int64_t lda, const float* Wt, int32_t N,
+                  int64_t ldw, const float* bias, float* C, int64_t ldc, plas_stream_t stream);
+/* f32 [rows][ld_in] -> bf16 [rows][ld_out], columns >= cols zero-filled. */
+int plas_cast_pad_bf16(const float* x, int64_t rows, int32_t cols, int64_t ld_in, void* y,
+                       int64_t ld_out, plas_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  persistent (bi)directional LSTM recurrence.  Replaces tf.nn.bidirectional_dynamic_rnn /
+ * tf.nn.dynamic_rnn over LSTMCell (las/ops.py:23-46) given the hoisted projections.
+ * Gate order inside a unit is TF's (i, j, f, o); forget_bias 1.0 is applied at run time.
+ * ---------------------------------------------------------------------------------- */
+typedef struct plas_rec_desc {
+  int32_t dtype;            /* PLAS_F32 / PLAS_BF16: type of xproj, whh, out                   */
+  int32_t B, T, U, ndir;    /* T = time extent of xproj/out; ndir 1 (fw) or 2 (fw,bw)          */
+  int32_t _pad;
+  const void* xproj;        /* [B][T][ndir*4U], column = dir*4U + 4*unit + gate                */
+  const void* whh;          /* packed recurrent weights, see plas_rec_pack_whh                  */
+  const int32_t* lengths;   /* [B]                                                             */
+  void* out;                /* [B][T_out][ndir*U], zero for t >= len (caller pre-zeroes)       */
+  int64_t out_batch_stride; /* elements between utterances in `out` (>= T*ndir*U)              */
+  float* c_final;           /* [ndir][B][U]                                                    */
+  float* h_final;           /* [ndir][B][U]                                                    */
+} plas_rec_desc;
+
+/* Layout contract for whh (host side packs once per checkpoint load):
+ *   f32 : [ndir][U/upc][U(k)][4*upc]  with column = 4*unit_local + gate
+ *   bf16: [ndir][U/32][8 warps][U/16 ksteps][32 lanes][8 bf16] mma.m16n8k16 B-fragments
+ * plas_rec_units_per_cta reports upc for (dtype,U). */
+int32_t plas_rec_units_per_cta(int32_t dtype, int32_t U);
+size_t plas_rec_workspace_bytes(const plas_rec_desc* d);
+int plas_bilstm_rec_fwd(const plas_rec_desc* d, void* workspace, size_t workspace_bytes,
+                        plas_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  attention decoder.  Replaces AttentionWrapper(MultiRNNCell) + BasicDecoder +
+ * GreedyEmbeddingHelper / TrainingHelper + dynamic_decode (las/model.py:145-202, 205-349) and the
+ * DenseBinfDecoder projection (utils/training_helper.py:122-153), all steps on the device.
+ * ---------------------------------------------------------------------------------- */
+typedef struct plas_dec_desc {
+  int32_t dtype;            /* PLAS_F32 / PLAS_BF16: type of keys, values, packed weights      */
+  int32_t B, Tm, D, Ud, V, n_layers, attention_type;
+  int32_t sos_id, eos_id;
+  int32_t max_steps;        /* capacity of the output buffers along the step axis              */
+  int32_t teacher_forced;   /* 0 = greedy, 1 = feed forced_ids, run exactly max_steps          */
+  float decoding_length_factor; /* greedy: stop at rint(max(mem_len) * factor)                 */
+  float score_bias;         /* luong_monotonic attention_score_bias                            */
+  const void* keys;         /* [B][Tm][Ud]  memory_layer(values)                               */
+  const void* values;       /* [B][Tm][D]   length-masked encoder outputs                      */
+  const int32_t* mem_len;   /* [B]                                                             */
+  const void* w_cell[4];    /* packed LSTM kernels (non-embedding rows), plas_dec_* layout     */
+  const void* w_emb;        /* [V][4Ud] cell-0 kernel rows of the one-hot input, col = 4u+g    */
+  const float* b_cell[4];   /* [4Ud] biases, col = 4*unit + gate                               */
+  const void* w_query;      /* [Ud][Ud] bahdanau query_layer kernel (row-major k,u) or NULL    */
+  const float* v_att;       /* [Ud] bahdanau attention_v or NULL                               */
+  const void* w_proj;       /* [D][V] projection kernel                                        */
+  const float* b_proj;      /* [V]                                                             */
+  const int32_t* forced_ids;/* [B][max_steps] teacher-forced inputs or NULL                    */
+  float* logits;            /* [B][max_steps][V]                                               */
+  int32_t* sample_ids;      /* [B][max_steps]                                                  */
+  float* alignment;         /* [B][max_steps][Tm] or NULL                                      */
+  int32_t* seq_len;         /* [B] final_sequence_length                                       */
+  int32_t* n_steps;         /* [1] number of decode iterations executed                        */
+} plas_dec_desc;
+
+size_t plas_decoder_workspace_bytes(const plas_dec_desc* d);
+int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t workspace_bytes,
+                     plas_stream_t stream);
+
+/* mask values past each length: y[b][t][:] = t < len[b] ? x[b][t][:] : 0  (attention `values`,
+ * tf.contrib.seq2seq _prepare_memory; las/model.py:168-169). dtype-generic, in place allowed. */
+int plas_mask_time(int32_t dtype, const void* x, void* y, const int32_t* len, int32_t B, int32_t T,
+                   int32_t D, plas_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAS_H_ */

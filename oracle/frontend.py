@@ -248,7 +248,7 @@ def lr_delta_explicit(data, order, width=9):
 # --------------------------------------------------------------------------------------
 def default_args(**kw):
     """argparse defaults of preprocess_all.py:202-211."""
-    d = dict(feature_type="mfcc", backend="speechpy", n_mfcc=13, n_mels=40, energy=False,
+    d = dict(feature_type="mfcc", backend="librosa", n_mfcc=13, n_mels=40, energy=False,
              window=20, step=10, deltas=False)
     d.update(kw)
     return SimpleNamespace(**d)

@@ -1,0 +1,125 @@
+"""ctypes binding of libplas.so (include/plas.h).  No fallback: a missing library raises."""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libplas.so")
+
+PLAS_F32, PLAS_BF16 = 0, 1
+ATT_CODES = {"luong": 0, "bahdanau": 1, "luong_monotonic": 2}
+
+
+class PlasError(RuntimeError):
+    pass
+
+
+class FrontendDesc(C.Structure):
+    _fields_ = [("backend", C.c_int32), ("feature_type", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32),
+                ("n_mels", C.c_int32), ("n_mfcc", C.c_int32), ("energy", C.c_int32), ("deltas", C.c_int32),
+                ("sp_delta_literal", C.c_int32), ("n_fac", C.c_int32), ("fac", C.c_int32 * 8),
+                ("fb_total", C.c_int32), ("_pad", C.c_int32),
+                ("window", C.c_void_p), ("tw", C.c_void_p), ("tw_unpack", C.c_void_p),
+                ("fb_start", C.c_void_p), ("fb_len", C.c_void_p), ("fb_off", C.c_void_p), ("fb_w", C.c_void_p),
+                ("dct", C.c_void_p), ("mean", C.c_void_p), ("stdv", C.c_void_p)]
+
+
+class RecDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("U", C.c_int32), ("ndir", C.c_int32),
+                ("_pad", C.c_int32),
+                ("xproj", C.c_void_p), ("whh", C.c_void_p), ("lengths", C.c_void_p), ("out", C.c_void_p),
+                ("out_batch_stride", C.c_int64), ("c_final", C.c_void_p), ("h_final", C.c_void_p)]
+
+
+class DecDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("Tm", C.c_int32), ("D", C.c_int32), ("Ud", C.c_int32),
+                ("V", C.c_int32), ("n_layers", C.c_int32), ("attention_type", C.c_int32),
+                ("sos_id", C.c_int32), ("eos_id", C.c_int32), ("max_steps", C.c_int32),
+                ("teacher_forced", C.c_int32), ("decoding_length_factor", C.c_float), ("score_bias", C.c_float),
+                ("keys", C.c_void_p), ("values", C.c_void_p), ("mem_len", C.c_void_p),
+                ("w_cell", C.c_void_p * 4), ("w_emb", C.c_void_p), ("b_cell", C.c_void_p * 4),
+                ("w_query", C.c_void_p), ("v_att", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p),
+                ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
+                ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p)]
+
+
+EXPORTS = {
+    "plas_last_error": (C.c_char_p, []),
+    "plas_version": (C.c_int, []),
+    "plas_num_sms": (C.c_int, []),
+    "plas_frontend_workspace_bytes": (C.c_size_t, [C.POINTER(FrontendDesc), C.c_int32, C.c_int32]),
+    "plas_frontend_fwd": (C.c_int, [C.POINTER(FrontendDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
+    "plas_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "plas_gemm_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "plas_cast_pad_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_void_p]),
+    "plas_rec_units_per_cta": (C.c_int32, [C.c_int32, C.c_int32]),
+    "plas_rec_workspace_bytes": (C.c_size_t, [C.POINTER(RecDesc)]),
+    "plas_bilstm_rec_fwd": (C.c_int, [C.POINTER(RecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_decoder_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
+    "plas_decoder_fwd": (C.c_int, [C.POINTER(DecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_mask_time": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libplas.so once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlasError(f"{LIB_PATH} not found: run `python -m phones_las_b200.build` "
+                            "(there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PlasError(f"libplas error {rc}: {lib().plas_last_error().decode()}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensor required"
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise PlasError("phones_las_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib()
+
+
+def dtype_code(precision):
+    return {"fp32": PLAS_F32, "bf16": PLAS_BF16}[precision]
+
+
+def torch_dtype(precision):
+    return {"fp32": torch.float32, "bf16": torch.bfloat16}[precision]
+
+
+# launch accounting for bench.py's gpu_launches (our kernels only)
+launch_count = 0
+
+
+def count_launches(n):
+    global launch_count
+    launch_count += n

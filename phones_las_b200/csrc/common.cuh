@@ -1,0 +1,89 @@
+// Shared helpers for the phones-las B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace plas {
+
+// ---- error plumbing (thread-local message behind plas_last_error) -------------------
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+
+#define PLAS_OK 0
+#define PLAS_EINVAL (-1)
+#define PLAS_ECUDA (-2)
+#define PLAS_EUNSUPPORTED (-3)
+
+#define PLAS_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return plas::set_err(PLAS_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,         \
+                           cudaGetErrorString(_e));                                         \
+  } while (0)
+
+#define PLAS_REQUIRE(cond, ...)                                                             \
+  do {                                                                                      \
+    if (!(cond)) return plas::set_err(PLAS_EINVAL, __VA_ARGS__);                            \
+  } while (0)
+
+int num_sms();
+
+// ---- device math ---------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// LSTM gate math of tf.nn.rnn_cell.LSTMCell (forget_bias = 1.0 added at run time).
+__device__ __forceinline__ void lstm_gates(float zi, float zj, float zf, float zo, float c_prev,
+                                           float& c, float& h) {
+  c = sigmoidf_acc(zf + 1.0f) * c_prev + sigmoidf_acc(zi) * tanhf(zj);
+  h = sigmoidf_acc(zo) * tanhf(c);
+}
+
+__device__ __forceinline__ float bf16_round(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// order-preserving float <-> uint mapping (for atomicMax on floats); 0 sorts below everything.
+__device__ __forceinline__ unsigned float_to_ordered(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---- inter-CTA signalling through L2 --------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+}  // namespace plas

@@ -32,7 +32,7 @@ def get_default_hparams():
 
 def get_default_feature_args():
     """preprocess_all.py:202-211 argparse defaults."""
-    return dict(feature_type="mfcc", backend="speechpy", n_mfcc=13, n_mels=40, energy=False,
+    return dict(feature_type="mfcc", backend="librosa", n_mfcc=13, n_mels=40, energy=False,
                 window=20, step=10, deltas=False)
 
 
@@ -129,21 +129,21 @@ def baseline_config(name):
     if name == "c1":  # TIMIT-shaped, fp32
         hp = create_hparams(target_vocab_size=64, encoder_layers=3, encoder_units=256, decoder_layers=1,
                             decoder_units=256, attention_type="luong", num_channels=39)
-        fa = feature_args(feature_type="mfcc", backend="speechpy", n_mfcc=13, n_mels=40, window=25,
-                          step=10, deltas=True)
+        fa = feature_args(feature_type="mfcc", backend="librosa", n_mfcc=12, n_mels=40, energy=True,
+                          window=25, step=10, deltas=True)
         return dict(hp=hp, fa=fa, batch=8, seconds=3.0, precision="fp32")
     if name in ("c2", "c4"):  # Librispeech-shaped, bf16
         hp = create_hparams(target_vocab_size=64, encoder_layers=4, encoder_units=512, decoder_layers=2,
-                            decoder_units=512, num_channels=81,
+                            decoder_units=512, num_channels=80,
                             attention_type="bahdanau" if name == "c2" else "luong_monotonic")
-        fa = feature_args(feature_type="mfe", backend="speechpy", n_mels=80, energy=True, window=25, step=10)
+        fa = feature_args(feature_type="mfe", backend="librosa", n_mels=80, window=25, step=10)
         return dict(hp=hp, fa=fa, batch=64 if name == "c2" else 128,
                     seconds=15.0 if name == "c2" else 30.0, precision="bf16")
     if name == "c3":  # multitask training shape
         hp = create_hparams(target_vocab_size=64, encoder_layers=3, encoder_units=256, decoder_layers=1,
                             decoder_units=256, attention_type="luong", num_channels=39, ctc_weight=0.3,
                             binf_count=60, multitask=True, binary_outputs=True)
-        fa = feature_args(feature_type="mfcc", backend="speechpy", n_mfcc=13, n_mels=40, window=25,
-                          step=10, deltas=True)
+        fa = feature_args(feature_type="mfcc", backend="librosa", n_mfcc=12, n_mels=40, energy=True,
+                          window=25, step=10, deltas=True)
         return dict(hp=hp, fa=fa, batch=32, seconds=3.0, precision="fp32")
     raise KeyError(name)

@@ -1,0 +1,175 @@
+"""Speller operator: attention decoder (greedy / teacher-forced) on the GPU.
+
+Mirrors ``las.model.speller`` (reference las/model.py:205-349) for the default wiring
+(bottom_only=False, attention_layer_size=None, embedding_size=0, beam_width=0):
+``speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_length,
+target_sequence_length, mode, hparams)`` -> ``(BasicDecoderOutput(rnn_output, sample_id),
+final_state, final_sequence_length)``.  The attention memory is prepared once per batch
+(length masking + memory_layer GEMM, las/model.py:168-169) and the whole decode loop runs inside
+one persistent kernel (plas_decoder_fwd).
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _lib, packing
+
+BasicDecoderOutput = namedtuple("BasicDecoderOutput", ["rnn_output", "sample_id"])
+SpellerState = namedtuple("SpellerState", ["alignment_history", "n_steps"])
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class SpellerWeights:
+    """Device-resident, kernel-layout copy of the ``speller/`` variables."""
+
+    def __init__(self, params, hp, enc_depth, precision="fp32", device="cuda", scope="speller"):
+        _lib.require_cuda()
+        for flag in ("bottom_only", "pass_hidden_state", "binf_projection"):
+            if hp.get(flag):
+                raise NotImplementedError(f"--{flag} decoder wiring is not built yet")
+        if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
+            raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
+        self.precision = precision
+        self.att = hp["attention_type"]
+        if self.att not in _lib.ATT_CODES:
+            raise NotImplementedError(f"attention_type={self.att}")
+        dt = _lib.torch_dtype(precision)
+        self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
+        D, Ud, V = self.D, self.Ud, self.V
+        up = lambda a, t=dt: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device=device, dtype=t).contiguous()
+        wm = np.asarray(params[f"{scope}/memory_layer/kernel"], np.float32)  # [D, Ud]
+        n_pad = _round_up(Ud, 128) if precision == "bf16" else Ud
+        wmt = np.zeros((n_pad, D), np.float32)
+        wmt[:Ud] = wm.T
+        self.w_mem_t = up(wmt)
+        pre = f"{scope}/decoder/attention_wrapper"
+        self.w_cell, self.b_cell = [], []
+        for k in range(self.L):
+            kern = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], np.float32)
+            bias = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], np.float32)
+            if k == 0:
+                assert kern.shape == (V + D + Ud, 4 * Ud), kern.shape
+                self.w_emb = up(packing.pack_unit_major(kern[:V], Ud))
+                rows = kern[V:]
+            else:
+                assert kern.shape == (2 * Ud, 4 * Ud), kern.shape
+                rows = kern
+            packed = packing.pack_cell_bf16(rows, Ud) if precision == "bf16" else packing.pack_cell_f32(rows, Ud)
+            self.w_cell.append(up(packed))
+            self.b_cell.append(up(packing.pack_unit_major(bias, Ud), torch.float32))
+        self.w_query = self.v_att = None
+        self.score_bias = 0.0
+        if self.att == "bahdanau":
+            self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
+            self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"], torch.float32)
+        elif self.att == "luong_monotonic":
+            self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
+        self.w_proj_t = up(np.asarray(params[f"{scope}/decoder/projection_layer/kernel"], np.float32).T)  # [V, D]
+        self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"], torch.float32)
+
+
+def prepare_memory(encoder_outputs, source_sequence_length, w):
+    """values = length-masked memory; keys = memory_layer(values) (tf.contrib.seq2seq
+    _BaseAttentionMechanism; reference las/model.py:168-169)."""
+    L = _lib.lib()
+    B, Tm, D = encoder_outputs.shape
+    enc = encoder_outputs.contiguous()
+    values = torch.empty_like(enc)
+    _lib.check(L.plas_mask_time(_lib.dtype_code(w.precision), _lib.ptr(enc), _lib.ptr(values),
+                                _lib.ptr(source_sequence_length), B, Tm, D, _lib.stream_ptr()))
+    n_pad = w.w_mem_t.shape[0]
+    keys = torch.empty((B * Tm, n_pad), dtype=enc.dtype, device=enc.device)
+    fn = L.plas_gemm_bf16 if w.precision == "bf16" else L.plas_gemm_f32
+    _lib.check(fn(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_mem_t), n_pad, D, None, _lib.ptr(keys), n_pad,
+                  _lib.stream_ptr()))
+    _lib.count_launches(2)
+    if n_pad != w.Ud:
+        keys = keys[:, :w.Ud].contiguous()
+    return keys.view(B, Tm, w.Ud), values
+
+
+def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_steps=None,
+           want_alignment=True, trim=True):
+    """Run the decoder kernel.  Greedy when ``forced_ids`` is None (max_steps defaults to
+    rint(Tm * decoding_length_factor), las/model.py:270-274); teacher-forced otherwise."""
+    L = _lib.lib()
+    dev = encoder_outputs.device
+    B, Tm, D = encoder_outputs.shape
+    assert D == w.D
+    mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).contiguous()
+    keys, values = prepare_memory(encoder_outputs, mem_len, w)
+    factor = float(hp.get("decoding_length_factor", 1.0))
+    if forced_ids is not None:
+        forced_ids = forced_ids.to(device=dev, dtype=torch.int32).contiguous()
+        steps = forced_ids.shape[1] if max_steps is None else min(max_steps, forced_ids.shape[1])
+        if forced_ids.shape[1] != steps:
+            forced_ids = forced_ids[:, :steps].contiguous()
+    else:
+        steps = int(np.rint(np.float32(Tm) * np.float32(factor))) if max_steps is None else max_steps
+    steps = max(int(steps), 0)
+    cap = max(steps, 1)
+    logits = torch.zeros((B, cap, w.V), dtype=torch.float32, device=dev)
+    ids = torch.zeros((B, cap), dtype=torch.int32, device=dev)
+    align = torch.zeros((B, cap, Tm), dtype=torch.float32, device=dev) if want_alignment else None
+    seq_len = torch.zeros((B,), dtype=torch.int32, device=dev)
+    n_steps = torch.zeros((1,), dtype=torch.int32, device=dev)
+    d = _lib.DecDesc()
+    d.dtype = _lib.dtype_code(w.precision)
+    d.B, d.Tm, d.D, d.Ud, d.V, d.n_layers = B, Tm, D, w.Ud, w.V, w.L
+    d.attention_type = _lib.ATT_CODES[w.att]
+    d.sos_id, d.eos_id = hp["sos_id"], hp["eos_id"]
+    d.max_steps = cap if steps > 0 else 0
+    d.teacher_forced = 1 if forced_ids is not None else 0
+    d.decoding_length_factor = factor
+    d.score_bias = w.score_bias
+    d.keys, d.values, d.mem_len = keys.data_ptr(), values.data_ptr(), mem_len.data_ptr()
+    for k in range(w.L):
+        d.w_cell[k] = w.w_cell[k].data_ptr()
+        d.b_cell[k] = w.b_cell[k].data_ptr()
+    d.w_emb = w.w_emb.data_ptr()
+    d.w_query = w.w_query.data_ptr() if w.w_query is not None else None
+    d.v_att = w.v_att.data_ptr() if w.v_att is not None else None
+    d.w_proj, d.b_proj = w.w_proj_t.data_ptr(), w.b_proj.data_ptr()
+    d.forced_ids = forced_ids.data_ptr() if forced_ids is not None else None
+    d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()
+    d.alignment = align.data_ptr() if align is not None else None
+    d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
+    need = L.plas_decoder_workspace_bytes(C.byref(d))
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    _lib.check(L.plas_decoder_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    _lib.count_launches(1)
+    if trim:
+        n = int(n_steps.item()) if steps > 0 else 0  # device->host read of the step count
+        logits, ids = logits[:, :n], ids[:, :n]
+        if align is not None:
+            align = align[:, :n]
+    return logits, ids, align, seq_len, n_steps
+
+
+def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_length, target_sequence_length,
+            mode, hparams, weights, binary_outputs=False, binf_embedding=None, transparent_projection=False):
+    """las/model.py:205-349.  mode 'train'/'eval' with ``decoder_inputs`` (targets_inputs ids [B,L])
+    runs teacher forcing (TrainingHelper, sampling_probability must be 0); otherwise greedy."""
+    if binary_outputs or binf_embedding is not None or transparent_projection:
+        raise NotImplementedError("binary-feature decoder variants are not built yet")
+    if mode == "train":
+        if float(hparams.get("sampling_probability", 0.0)) > 0.0:
+            raise NotImplementedError("scheduled sampling (las/model.py:279-288) is not built yet; "
+                                      "set sampling_probability=0")
+        steps = None
+        if target_sequence_length is not None:
+            steps = int(target_sequence_length.max().item())
+            if hparams.get("max_symbols", -1) and hparams.get("max_symbols", -1) > 0:
+                steps = min(steps, hparams["max_symbols"])
+        logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams,
+                                                      forced_ids=decoder_inputs, max_steps=steps,
+                                                      want_alignment=False)
+        seq_len = target_sequence_length
+    else:
+        logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams)
+    return BasicDecoderOutput(logits, ids), SpellerState(align, n_steps), seq_len

@@ -1,0 +1,74 @@
+"""K2+K3 parity: pyramidal BiLSTM listener (through the C-ABI) vs the oracle restatement of
+las/ops.py:23-87.  fp32: 1e-5 of tensor scale; bf16: see tests/util.assert_parity."""
+import numpy as np
+import pytest
+
+from oracle import las as ol
+from phones_las_b200 import synth, weights
+from phones_las_b200.hparams import create_hparams
+from tests.util import gpu, to_np, assert_parity
+
+CONFIGS = [
+    # (precision, B, T, C, U, L, var_len)
+    ("fp32", 3, 13, 5, 32, 3, True),
+    ("fp32", 8, 40, 39, 256, 3, True),
+    ("fp32", 20, 21, 7, 64, 2, True),
+    ("fp32", 2, 9, 4, 512, 1, False),
+    ("bf16", 3, 13, 5, 64, 3, True),
+    ("bf16", 16, 37, 80, 128, 4, True),
+    ("bf16", 33, 50, 81, 512, 2, True),
+]
+
+
+def _run(precision, B, T, C, U, L, var_len, unidirectional=False):
+    import torch
+    from phones_las_b200.listener import ListenerWeights, listener
+    hp = create_hparams(target_vocab_size=16, encoder_layers=L, encoder_units=U, decoder_units=32,
+                        decoder_layers=1, num_channels=C, unidirectional=unidirectional)
+    params = weights.init_params(hp, seed=U + L, bias_scale=0.1)
+    x, lens = synth.synth_features(B, T, C, seed=B + T, var_len=var_len)
+    (ref_out, ref_len), ref_state = ol.listener(x, lens, params, hp, precision)
+    w = ListenerWeights(params, hp, C, precision)
+    (out, olen), state = listener(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), "infer", hp, w)
+    torch.cuda.synchronize()
+    return (to_np(out), olen.cpu().numpy(), state), (ref_out, ref_len, ref_state)
+
+
+@gpu
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"{c[0]}-B{c[1]}-T{c[2]}-C{c[3]}-U{c[4]}-L{c[5]}")
+def test_listener_parity(cfg):
+    precision = cfg[0]
+    (out, olen, state), (ref_out, ref_len, ref_state) = _run(*cfg)
+    np.testing.assert_array_equal(olen, ref_len)
+    assert out.shape == ref_out.shape
+    assert_parity(out, ref_out, precision, "encoder_out")
+    for b in range(out.shape[0]):
+        assert (out[b, olen[b]:] == 0).all(), "outputs past the reduced length must be zero"
+    for d in range(2):
+        assert_parity(state[d][0], ref_state[d][0], precision, f"final c dir{d}")
+        assert_parity(state[d][1], ref_state[d][1], precision, f"final h dir{d}")
+
+
+@gpu
+def test_listener_unidirectional():
+    (out, olen, state), (ref_out, ref_len, ref_state) = _run("fp32", 4, 11, 6, 32, 2, True, unidirectional=True)
+    np.testing.assert_array_equal(olen, ref_len)
+    assert_parity(out, ref_out, "fp32", "encoder_out (unidirectional)")
+    assert_parity(state[0], ref_state[0], "fp32", "final c")
+
+
+@gpu
+def test_listener_batch_independence_full_width():
+    """c2-width layer stack (U=512, bf16) on a short sequence: an utterance's encoding must not depend
+    on its batch neighbours (batch groups are independent recurrences) -- bit-exact."""
+    import torch
+    from phones_las_b200.listener import ListenerWeights, listener
+    hp = create_hparams(target_vocab_size=16, encoder_layers=4, encoder_units=512, decoder_units=32,
+                        decoder_layers=1, num_channels=80)
+    params = weights.init_params(hp, seed=1)
+    x, lens = synth.synth_features(64, 64, 80, seed=2, var_len=True)
+    w = ListenerWeights(params, hp, 80, "bf16")
+    xt, lt = torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda()
+    (full, flen), _ = listener(xt, lt, "infer", hp, w)
+    (sub, slen), _ = listener(xt[40:45].contiguous(), lt[40:45].contiguous(), "infer", hp, w)
+    assert torch.equal(full[40:45], sub) and torch.equal(flen[40:45], slen)

@@ -1,0 +1,112 @@
+"""K4 parity: attention decoder (through the C-ABI) vs the oracle restatement of
+las/model.py:145-349 (AttentionWrapper + BasicDecoder + Greedy/Training helpers + dynamic_decode).
+Greedy ids must be bit-exact whenever the oracle's top-2 logit margin exceeds the numeric noise."""
+import numpy as np
+import pytest
+
+from oracle import las as ol
+from phones_las_b200 import synth, weights
+from phones_las_b200.hparams import create_hparams
+from tests.util import gpu, to_np, assert_parity, top2_margin
+
+CONFIGS = [
+    # precision, att, B, Tm, D(enc units*4 -> U), Ud, Ld, V
+    ("fp32", "luong", 3, 9, 16, 32, 1, 12),
+    ("fp32", "bahdanau", 5, 14, 16, 32, 2, 20),
+    ("fp32", "luong_monotonic", 4, 11, 16, 16, 2, 12),
+    ("fp32", "luong", 8, 30, 64, 256, 1, 64),
+    ("bf16", "luong", 3, 9, 16, 32, 1, 12),
+    ("bf16", "bahdanau", 16, 24, 32, 128, 2, 64),
+    ("bf16", "luong_monotonic", 7, 17, 16, 64, 2, 30),
+    ("bf16", "bahdanau", 70, 12, 16, 64, 2, 16),
+]
+
+
+def _setup(precision, att, B, Tm, U, Ud, Ld, V, seed=0):
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud,
+                        decoder_layers=Ld, num_channels=4, attention_type=att)
+    params = weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1)
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(seed + B)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    lens[0] = Tm
+    if precision == "bf16":
+        enc = ol.round_bf16(enc)
+    return hp, params, enc, lens, D
+
+
+def _device_speller(hp, params, D, precision):
+    from phones_las_b200.speller import SpellerWeights
+    return SpellerWeights(params, hp, D, precision)
+
+
+@gpu
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"{c[0]}-{c[1]}-B{c[2]}-Tm{c[3]}-Ud{c[5]}-L{c[6]}")
+def test_greedy_parity(cfg):
+    import torch
+    from phones_las_b200.speller import speller
+    precision = cfg[0]
+    hp, params, enc, lens, D = _setup(*cfg)
+    sp = ol.Speller(enc, lens, params, hp, precision)
+    ref_logits, ref_ids, ref_align, ref_len, _ = sp.greedy()
+    w = _device_speller(hp, params, D, precision)
+    enc_t = torch.from_numpy(enc).cuda().to(torch.bfloat16 if precision == "bf16" else torch.float32)
+    out, state, seq_len = speller(enc_t, None, None, torch.from_numpy(lens).cuda(), None, "infer", hp, w)
+    torch.cuda.synchronize()
+    ids, logits, align = out.sample_id.cpu().numpy(), to_np(out.rnn_output), to_np(state.alignment_history)
+    margin = top2_margin(ref_logits)
+    noise = 1e-4 if precision == "fp32" else 5e-2
+    if margin > noise:
+        assert ids.shape == ref_ids.shape, (ids.shape, ref_ids.shape)
+        np.testing.assert_array_equal(ids, ref_ids)
+        np.testing.assert_array_equal(seq_len.cpu().numpy(), ref_len)
+        assert_parity(logits, ref_logits, precision, "logits")
+        assert_parity(align, ref_align, precision, "alignment")
+    else:  # near-tie somewhere: compare the common prefix before the first disagreement only
+        n = min(ids.shape[1], ref_ids.shape[1])
+        agree = (ids[:, :n] == ref_ids[:, :n]).all(axis=0)
+        first_bad = n if agree.all() else int(np.argmin(agree))
+        assert first_bad >= 1
+        assert_parity(logits[:, :first_bad], ref_logits[:, :first_bad], precision, "logits prefix")
+
+
+@gpu
+@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("fp32", "bahdanau"), ("bf16", "luong_monotonic")])
+def test_teacher_forced_parity(precision, att):
+    import torch
+    from phones_las_b200.speller import speller
+    hp, params, enc, lens, D = _setup(precision, att, 6, 15, 16, 64, 2, 18, seed=3)
+    hp["sampling_probability"] = 0.0
+    tin, tout, tlen = synth.synth_labels(6, 9, 18, seed=4)
+    tlen[2] = 5
+    sp = ol.Speller(enc, lens, params, hp, precision)
+    ref_logits, _ = sp.teacher_forced(tin, tlen)
+    w = _device_speller(hp, params, D, precision)
+    enc_t = torch.from_numpy(enc).cuda().to(torch.bfloat16 if precision == "bf16" else torch.float32)
+    out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(),
+                        torch.from_numpy(tlen).cuda(), "train", hp, w)
+    torch.cuda.synchronize()
+    assert_parity(out.rnn_output, ref_logits, precision, "teacher-forced logits")
+
+
+@gpu
+def test_greedy_stops_at_eos_and_length_factor():
+    """All-EOS projection bias: every sequence finishes at step 1; decoding_length_factor caps steps."""
+    import torch
+    from phones_las_b200.speller import speller
+    hp, params, enc, lens, D = _setup("fp32", "luong", 4, 10, 16, 32, 1, 12)
+    p2 = dict(params)
+    b = np.zeros(12, np.float32)
+    b[hp["eos_id"]] = 100.0
+    p2["speller/decoder/projection_layer/bias"] = b
+    w = _device_speller(hp, p2, D, "fp32")
+    enc_t = torch.from_numpy(enc).cuda()
+    out, state, seq_len = speller(enc_t, None, None, torch.from_numpy(lens).cuda(), None, "infer", hp, w)
+    assert out.sample_id.shape[1] == 1 and (out.sample_id.cpu().numpy() == hp["eos_id"]).all()
+    assert (seq_len.cpu().numpy() == 1).all()
+    hp2 = dict(hp, decoding_length_factor=0.5)
+    w2 = _device_speller(hp2, params, D, "fp32")
+    out2, _, _ = speller(enc_t, None, None, torch.from_numpy(lens).cuda(), None, "infer", hp2, w2)
+    ref = ol.Speller(enc, lens, params, hp2, "fp32").greedy()
+    assert out2.sample_id.shape[1] == ref[1].shape[1] <= 5
