@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the phones-las hot path (front-end -> pyramidal BiLSTM listener ->
+greedy attention decode) on B200, in audio-seconds per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+One "step" = one pass of the whole hot path over one batch of synthetic audio of the workload's
+shape (default c2 = BASELINE.json configs[1]: 80-mel MFE, 4-layer pBLSTM 512, 2-layer decoder 512,
+bahdanau, batch 64 x 15 s, bf16).  Utterance batches shard across GPUs by batch (no data-path
+collective; "weak" scaling: every rank runs a full batch).  Rank 0 prints ONE JSON line.
+
+  value     device-resident throughput: waveforms already in HBM when the timed region starts.
+  e2e       same metric through the public host API (LASModel.transcribe_host): pinned host
+            waveform -> H2D -> kernels -> D2H of the decoded ids, all inside the timed region.
+  roofline  the dominant kernel of the step (by measured device time), algorithmic bytes/flops per
+            launch / its CUDA-event duration vs MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference
+            the CPU oracle (numpy restatement of the reference path; the reference itself needs
+            TF 1.15 + librosa + speechpy, none installable here) timed on the host cores on a
+            bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "audio-sec/sec (feats+pBLSTM+attn decode)"
+UNIT = "audio-sec/sec"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+# ----------------------------------------------------------------------------------------------
+# workload description and algorithmic work (DESIGN.md section 5 / SURVEY.md 8d)
+# ----------------------------------------------------------------------------------------------
+def workload(name):
+    from phones_las_b200.hparams import baseline_config, num_feature_channels, num_frames, SAMPLE_RATE
+    cfg = baseline_config(name)
+    hp, fa = cfg["hp"], cfg["fa"]
+    n_samples = int(round(cfg["seconds"] * SAMPLE_RATE))
+    T = num_frames(fa, n_samples)
+    cfg.update(name=name, n_samples=n_samples, T=T, C=num_feature_channels(fa))
+    return cfg
+
+
+def algorithmic_work(cfg, B, n_dec_steps):
+    """Per-step algorithmic bytes / flops of each kernel family for batch B."""
+    hp = cfg["hp"]
+    e = 2 if cfg["precision"] == "bf16" else 4
+    U, L, Ud, Ld, V = hp["encoder_units"], hp["encoder_layers"], hp["decoder_units"], hp["decoder_layers"], hp["target_vocab_size"]
+    T, C, N = cfg["T"], cfg["C"], cfg["n_samples"]
+    work = {"frontend": {"bytes": B * (4 * N + 4 * T * C), "launches": 1}}
+    gemm_flops, rec_bytes, rec_flops = 0.0, 0.0, 0.0
+    t, din = T, C
+    for l in range(L):
+        gemm_flops += 2.0 * B * t * din * 8 * U
+        rec_bytes += B * t * (8 * U * e + 2 * U * e)
+        rec_flops += 2.0 * B * t * U * 4 * U * 2
+        din = 2 * U if l == 0 else 4 * U
+        if l != 0:
+            t = (t + 1) // 2
+    D, Tm = din, t
+    work["inproj_gemm"] = {"flops": gemm_flops, "launches": L}
+    work["rec"] = {"bytes": rec_bytes, "flops": rec_flops, "launches": L}
+    work["memory_gemm"] = {"flops": 2.0 * B * Tm * D * Ud, "launches": 1}
+    w_bytes = ((D + Ud) * 4 * Ud + (Ld - 1) * 2 * Ud * 4 * Ud + D * V + (Ud * Ud if hp["attention_type"] == "bahdanau" else 0)) * e
+    work["decoder"] = {"bytes": float(n_dec_steps) * (B * Tm * (Ud + D) * e + w_bytes), "launches": 1}
+    work["_shape"] = {"Tm": Tm, "D": D}
+    return work
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ----------------------------------------------------------------------------------------------
+def oracle_step(cfg, params, wave):
+    """One pass of the reference path restated on the CPU (oracle/): features -> listener -> greedy."""
+    from oracle import frontend as ofe, las as ol
+    fa, hp = cfg["fa"], cfg["hp"]
+    feats = np.stack([ofe.calculate_acoustic_features(fa, wave[b]) for b in range(wave.shape[0])]).astype(np.float32)
+    nf = np.full((wave.shape[0],), feats.shape[1], np.int32)
+    pred = ol.predict(feats, nf, params, hp, "fp32")
+    return pred["sample_ids"]
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_cpu_sample(cfg, batch, steps, warmup):
+    from phones_las_b200 import synth, weights
+    params = weights.init_params(cfg["hp"], cfg["C"], seed=4321)
+    wave, _ = synth.synth_audio(batch, cfg["seconds"], seed=1234)
+    for _ in range(warmup):
+        oracle_step(cfg, params, wave)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(cfg, params, wave)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch * cfg["seconds"] / dt, dt
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path.  TF 1.15 / librosa / speechpy
+    cannot be installed in this image, so this is the oracle port, numpy with all
+    host BLAS threads, on a bounded sample (few utterances of the workload's shape per step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args.workload)
+    batch = args.ref_batch
+    # calibrate so that the whole run stays within a few minutes
+    v, dt = run_cpu_sample(cfg, 1, 1, 0)
+    budget = 150.0
+    while batch > 1 and dt * batch * (args.steps + args.warmup) > budget:
+        batch //= 2
+    value, dt = run_cpu_sample(cfg, batch, args.steps, args.warmup)
+    sample = f"{batch} utterances x {cfg['seconds']:.0f} s of workload {cfg['name']} per step, fp32 numpy oracle"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(cfg, batch, note="CPU oracle port of the reference path (TF1.15/librosa/speechpy not installable)"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(cfg, batch, **extra):
+    hp, fa = cfg["hp"], cfg["fa"]
+    d = {"workload": f"{cfg['name']}: {fa.n_mels}-mel {fa.feature_type.upper()} ({fa.backend}, window {fa.window} ms / step {fa.step} ms) "
+                     f"-> {hp['encoder_layers']}-layer pBLSTM {hp['encoder_units']} -> {hp['decoder_layers']}-layer decoder "
+                     f"{hp['decoder_units']} {hp['attention_type']} greedy, {cfg['seconds']:.0f} s utterances",
+         "batch_per_gpu": batch, "utterance_seconds": cfg["seconds"], "frames": cfg["T"], "channels": cfg["C"],
+         "vocab": hp["target_vocab_size"], "parallelism": "batch-sharded, no collective"}
+    d.update(extra)
+    return d
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from phones_las_b200 import _lib, synth, weights
+    from phones_las_b200.model import LASModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_cuda()
+
+    cfg = workload(args.workload)
+    hp, fa = cfg["hp"], cfg["fa"]
+    B = args.batch or cfg["batch"]
+    params = weights.init_params(hp, cfg["C"], seed=4321)
+    model = LASModel(params, hp, fa, precision=cfg["precision"], device=dev)
+
+    # inputs: NBUF distinct batches rotated between steps so no step finds its waveforms in L2
+    # (NBUF x B x N x 4 bytes > 126 MB L2); the per-step intermediates (~2 GB of gate pre-activations)
+    # exceed L2 on their own.
+    nbuf = max(2, int(np.ceil(2 * 126e6 / (B * cfg["n_samples"] * 4))))
+    host_waves, dev_waves = [], []
+    for i in range(nbuf):
+        w, _ = synth.synth_audio(B, cfg["seconds"], seed=1234 + rank * 100 + i)
+        hw = torch.from_numpy(w).pin_memory()
+        host_waves.append(hw)
+        dev_waves.append(hw.to(dev))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # ---- device-resident throughput ----------------------------------------------------------
+    n_dec = 0
+    for i in range(args.warmup):
+        pred = model.transcribe(dev_waves[i % nbuf])
+        n_dec = int(pred["sample_ids"].shape[1])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        pred = model.transcribe(dev_waves[i % nbuf])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count - l0
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    n_dec = int(pred["sample_ids"].shape[1])
+    audio_s = B * cfg["seconds"]
+    value = world * audio_s / (ms * 1e-3)
+
+    # ---- end to end through the host API -----------------------------------------------------
+    for i in range(min(args.warmup, 3)):
+        model.transcribe_host(host_waves[i % nbuf])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ids, slen = model.transcribe_host(host_waves[i % nbuf])
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    barrier()
+    e2e = {"value": world * audio_s / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(B * cfg["n_samples"] * 4),
+           "d2h_bytes_per_step": int(ids.numel() * 4 + slen.numel() * 4 + 4)}
+
+    # ---- per-kernel timeline for the roofline (separate pass, same stream, CUDA events) -------
+    stage_ms = {}
+    reps = max(3, min(args.steps, 10))
+    for i in range(reps):
+        _lib.timeline_start()
+        model.transcribe(dev_waves[i % nbuf])
+        for k, v in _lib.timeline_stop().items():
+            stage_ms.setdefault(k, []).append(sum(v))
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    work = algorithmic_work(cfg, B, n_dec)
+    stages = {}
+    for name, t_ms in stage_ms.items():
+        w = work.get(name, {})
+        ent = {"ms_per_step": t_ms, "launches_per_step": w.get("launches", 1)}
+        if name in ("inproj_gemm", "memory_gemm"):
+            ent.update(bound="tensor", achieved=w["flops"] / (t_ms * 1e-3) / 1e12, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s")
+        elif "bytes" in w:
+            ent.update(bound="hbm", achieved=w["bytes"] / (t_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+        if "achieved" in ent:
+            ent["frac"] = ent["achieved"] / ent["peak"]
+        stages[name] = ent
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    dw = stages[dom]
+    roofline = {"kernel": dom, "bound": dw.get("bound"), "achieved": dw.get("achieved"), "peak": dw.get("peak"),
+                "unit": dw.get("unit"), "frac": dw.get("frac"), "traffic": None,
+                "peak_source": peaks["_source"] + " (sustained figure: kernel timed inside a long step)",
+                "share_of_step": stage_ms[dom] / sum(stage_ms.values()),
+                "ms_per_launch": stage_ms[dom] / dw["launches_per_step"]}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get(dom)
+        except Exception:
+            pass
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": cfg["precision"], "data": "synthetic",
+            "config": config_dict(cfg, B, decode_steps=n_dec,
+                                  l2="inputs rotate over %d distinct batches (%.0f MB > 126 MB L2)" % (nbuf, nbuf * B * cfg["n_samples"] * 4 / 1e6),
+                                  weights="random init, seed 4321, TF variable layout"),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "stages": stages}
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = run_cpu_sample(cfg, args.cpu_batch, 1, 0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+                                "sample": f"{args.cpu_batch} utterances x {cfg['seconds']:.0f} s of workload {cfg['name']}, one pass "
+                                          f"({dt:.1f} s), fp32 numpy oracle (reference needs TF1.15/librosa/speechpy: not installable)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (default: the workload's)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="utterances in the cpu_baseline sample")
+    ap.add_argument("--ref-batch", type=int, default=8, help="utterances per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

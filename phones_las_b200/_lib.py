@@ -123,3 +123,44 @@ launch_count = 0
 def count_launches(n):
     global launch_count
     launch_count += n
+
+
+# optional per-stage device timeline (bench.py's roofline leg): a list of (stage, start, stop)
+# CUDA events recorded on torch's current stream -- the stream every kernel is launched on.
+_timeline = None
+
+
+def timeline_start():
+    global _timeline
+    _timeline = []
+
+
+def timeline_stop():
+    """-> {stage: [ms per launch, ...]} (synchronises)."""
+    global _timeline
+    tl, _timeline = _timeline, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in tl or []:
+        out.setdefault(name, []).append(a.elapsed_time(b))
+    return out
+
+
+class stage:
+    """``with _lib.stage("rec"):`` brackets one C-ABI call with CUDA events when a timeline is active."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _timeline is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timeline is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _timeline.append((self.name, self.a, b))
+        return False

@@ -190,9 +190,10 @@ class FrontendPlan:
         need = L.plas_frontend_workspace_bytes(C.byref(self.desc), B, T_max)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=wave.device)
-        _lib.check(L.plas_frontend_fwd(C.byref(self.desc), _lib.ptr(wave), _lib.ptr(n_samples), B, wave.stride(0),
-                                       _lib.ptr(feats), _lib.ptr(n_frames), T_max, self.C, _lib.ptr(self._ws),
-                                       self._ws.numel(), _lib.stream_ptr()))
+        with _lib.stage("frontend"):
+            _lib.check(L.plas_frontend_fwd(C.byref(self.desc), _lib.ptr(wave), _lib.ptr(n_samples), B, wave.stride(0),
+                                           _lib.ptr(feats), _lib.ptr(n_frames), T_max, self.C, _lib.ptr(self._ws),
+                                           self._ws.numel(), _lib.stream_ptr()))
         _lib.count_launches(self.launches())
         return feats, n_frames
 

@@ -63,8 +63,10 @@ def _gemm(precision, a2d, M, K, lda, wt, bias, out2d):
     L = _lib.lib()
     N = wt.shape[0]
     fn = L.plas_gemm_bf16 if precision == "bf16" else L.plas_gemm_f32
-    _lib.check(fn(_lib.ptr(a2d), M, K, lda, _lib.ptr(wt), N, wt.stride(0), _lib.ptr(bias) if bias is not None else None,
-                  _lib.ptr(out2d), out2d.stride(0), _lib.stream_ptr()))
+    with _lib.stage("inproj_gemm"):
+        _lib.check(fn(_lib.ptr(a2d), M, K, lda, _lib.ptr(wt), N, wt.stride(0),
+                      _lib.ptr(bias) if bias is not None else None, _lib.ptr(out2d), out2d.stride(0),
+                      _lib.stream_ptr()))
     _lib.count_launches(1)
 
 
@@ -85,7 +87,8 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out):
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
     need = L.plas_rec_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
-    _lib.check(L.plas_bilstm_rec_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    with _lib.stage("rec"):
+        _lib.check(L.plas_bilstm_rec_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1)
     return out, (c_fin, h_fin)
 
@@ -103,7 +106,8 @@ def pyramidal_bilstm(inputs, sequence_length, mode, hparams, weights):
         k_pad = w.layers[0]["k_pad"]
         x = torch.empty((B, T, k_pad), dtype=torch.bfloat16, device=inputs.device)
         src = inputs.contiguous()
-        _lib.check(L.plas_cast_pad_bf16(_lib.ptr(src), B * T, Cin, Cin, _lib.ptr(x), k_pad, _lib.stream_ptr()))
+        with _lib.stage("cast"):
+            _lib.check(L.plas_cast_pad_bf16(_lib.ptr(src), B * T, Cin, Cin, _lib.ptr(x), k_pad, _lib.stream_ptr()))
         _lib.count_launches(1)
     else:
         x = inputs.to(torch.float32).contiguous()

@@ -80,13 +80,15 @@ def prepare_memory(encoder_outputs, source_sequence_length, w):
     B, Tm, D = encoder_outputs.shape
     enc = encoder_outputs.contiguous()
     values = torch.empty_like(enc)
-    _lib.check(L.plas_mask_time(_lib.dtype_code(w.precision), _lib.ptr(enc), _lib.ptr(values),
-                                _lib.ptr(source_sequence_length), B, Tm, D, _lib.stream_ptr()))
+    with _lib.stage("mask"):
+        _lib.check(L.plas_mask_time(_lib.dtype_code(w.precision), _lib.ptr(enc), _lib.ptr(values),
+                                    _lib.ptr(source_sequence_length), B, Tm, D, _lib.stream_ptr()))
     n_pad = w.w_mem_t.shape[0]
     keys = torch.empty((B * Tm, n_pad), dtype=enc.dtype, device=enc.device)
     fn = L.plas_gemm_bf16 if w.precision == "bf16" else L.plas_gemm_f32
-    _lib.check(fn(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_mem_t), n_pad, D, None, _lib.ptr(keys), n_pad,
-                  _lib.stream_ptr()))
+    with _lib.stage("memory_gemm"):
+        _lib.check(fn(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_mem_t), n_pad, D, None, _lib.ptr(keys), n_pad,
+                      _lib.stream_ptr()))
     _lib.count_launches(2)
     if n_pad != w.Ud:
         keys = keys[:, :w.Ud].contiguous()
@@ -141,7 +143,8 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
     need = L.plas_decoder_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
-    _lib.check(L.plas_decoder_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    with _lib.stage("decoder"):
+        _lib.check(L.plas_decoder_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1)
     if trim:
         n = int(n_steps.item()) if steps > 0 else 0  # device->host read of the step count

@@ -41,7 +41,8 @@ def test_listener_parity(cfg):
     (out, olen, state), (ref_out, ref_len, ref_state) = _run(*cfg)
     np.testing.assert_array_equal(olen, ref_len)
     assert out.shape == ref_out.shape
-    assert_parity(out, ref_out, precision, "encoder_out")
+    L = cfg[5]
+    assert_parity(out, ref_out, precision, "encoder_out", bf16_fro=1e-3 if L <= 3 else 2e-3)
     for b in range(out.shape[0]):
         assert (out[b, olen[b]:] == 0).all(), "outputs past the reduced length must be zero"
     for d in range(2):
