@@ -88,6 +88,9 @@ int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave, const int3
  * ---------------------------------------------------------------------------------- */
 int plas_gemm_bf16(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
                    int64_t ldw, const float* bias, void* C, int64_t ldc, plas_stream_t stream);
+/* same product with an f32 result (used for PV = values x projection kernel, las/model.py:251-257) */
+int plas_gemm_bf16_f32out(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
+                          int64_t ldw, const float* bias, float* C, int64_t ldc, plas_stream_t stream);
 int plas_gemm_f32(const float* A, int64_t M, int32_t K, int64_t lda, const float* Wt, int32_t N,
                   int64_t ldw, const float* bias, float* C, int64_t ldc, plas_stream_t stream);
 /* f32 [rows][ld_in] -> bf16 [rows][ld_out], columns >= cols zero-filled. */
@@ -125,6 +128,9 @@ int plas_bilstm_rec_fwd(const plas_rec_desc* d, void* workspace, size_t workspac
  * K4  attention decoder.  Replaces AttentionWrapper(MultiRNNCell) + BasicDecoder +
  * GreedyEmbeddingHelper / TrainingHelper + dynamic_decode (las/model.py:145-202, 205-349) and the
  * DenseBinfDecoder projection (utils/training_helper.py:122-153), all steps on the device.
+ * Two kernels sit behind plas_decoder_fwd: a SIMT/mma.sync kernel (any shape, f32 or bf16) and a
+ * weight-stationary TMA + tcgen05 kernel (bf16, B <= 128, D and Ud multiples of 64) chosen when the
+ * *_tc weight layouts and pv are supplied.
  * ---------------------------------------------------------------------------------- */
 typedef struct plas_dec_desc {
   int32_t dtype;            /* PLAS_F32 / PLAS_BF16: type of keys, values, packed weights      */
@@ -150,6 +156,12 @@ typedef struct plas_dec_desc {
   float* alignment;         /* [B][max_steps][Tm] or NULL                                      */
   int32_t* seq_len;         /* [B] final_sequence_length                                       */
   int32_t* n_steps;         /* [1] number of decode iterations executed                        */
+  /* tensor-core path (bf16; optional -- NULL selects the SIMT kernel).  Layouts: plas_dec_pack notes */
+  const void* w_cell_tc[4]; /* [Ud/4][K_l/64][16 x 64 bf16, 128B-swizzled] UMMA B tiles per layer      */
+  const void* w_query_tc;   /* [Ud/16][Ud/64][16 x 64 bf16, 128B-swizzled] bahdanau query_layer        */
+  const float* pv;          /* [B][Tm][pv_ld] values x projection kernel (f32), logits = a.pv + b_proj */
+  int32_t pv_ld;
+  int32_t _pad2;
 } plas_dec_desc;
 
 size_t plas_decoder_workspace_bytes(const plas_dec_desc* d);

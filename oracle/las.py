@@ -17,8 +17,9 @@ Follows the reference graph code and restates the TensorFlow 1.15.2 ops it calls
 Precision contract.  ``precision='fp32'`` computes everything in float32 like the reference.
 ``precision='bf16'`` emulates the CUDA path's storage points (DESIGN.md "precision contract"):
 weights, layer inputs, stored gate pre-activations, recurrent h, attention keys/values and the
-attention vector are rounded to bfloat16 (round-to-nearest-even); accumulation, gates, cell
-state, softmax and logits stay float32.
+attention vector fed back to the decoder cell are rounded to bfloat16 (round-to-nearest-even);
+accumulation, gates, cell state, softmax, the context entering the output projection and the
+logits stay float32.
 """
 import numpy as np
 
@@ -261,8 +262,10 @@ class Speller:
             inp = h2
         align = self.att(inp, state["alignments"])
         context = np.einsum("bt,btd->bd", align, self.att.values, dtype=F32)
-        attention = q(context)
-        logits = (attention @ self.wp + self.bp).astype(F32)
+        attention = q(context)  # the recurrent feedback copy of the attention vector is rounded ...
+        # ... while the projection consumes the f32 context (fp32 mode: q is the identity, so this is
+        # exactly DenseBinfDecoder(attention); bf16 mode: one rounding point fewer)
+        logits = (context.astype(F32) @ self.wp + self.bp).astype(F32)
         return logits, dict(cells=new_cells, attention=attention, alignments=align)
 
     def one_hot(self, ids):

@@ -41,7 +41,9 @@ class DecDesc(C.Structure):
                 ("w_cell", C.c_void_p * 4), ("w_emb", C.c_void_p), ("b_cell", C.c_void_p * 4),
                 ("w_query", C.c_void_p), ("v_att", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p),
                 ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
-                ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p)]
+                ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p),
+                ("w_cell_tc", C.c_void_p * 4), ("w_query_tc", C.c_void_p), ("pv", C.c_void_p),
+                ("pv_ld", C.c_int32), ("_pad2", C.c_int32)]
 
 
 EXPORTS = {
@@ -54,6 +56,8 @@ EXPORTS = {
                                     C.c_void_p]),
     "plas_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "plas_gemm_bf16_f32out": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "plas_gemm_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "plas_cast_pad_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,

@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decoder_kernel(DecArgs p) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const AT qv = from_f32<AT>(acc[i]);
-            att_out[ch * 8 + i] = qv;
-            s_att[ch * 8 + i] = to_f32<AT>(qv);
+            att_out[ch * 8 + i] = qv;   // fed back to the cell in the storage dtype ...
+            s_att[ch * 8 + i] = acc[i];  // ... the projection consumes the f32 context
           }
         }
         __syncthreads();
@@ -430,6 +430,9 @@ static void dec_ws_layout(const plas_dec_desc& d, size_t* offs, size_t* total) {
   *total = off;
 }
 
+size_t dec_tc_workspace_bytes(const plas_dec_desc& d);
+int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace plas
 
 using namespace plas;
@@ -437,7 +440,8 @@ using namespace plas;
 extern "C" size_t plas_decoder_workspace_bytes(const plas_dec_desc* d) {
   size_t offs[10], total;
   dec_ws_layout(*d, offs, &total);
-  return total;
+  const size_t tc = dec_tc_workspace_bytes(*d);
+  return tc > total ? tc : total;
 }
 
 extern "C" int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t workspace_bytes,
@@ -454,6 +458,10 @@ extern "C" int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t 
   PLAS_REQUIRE(d->attention_type != PLAS_ATT_BAHDANAU || (d->w_query && d->v_att), "decoder: bahdanau needs query_layer/attention_v");
   PLAS_REQUIRE(!d->teacher_forced || d->forced_ids, "decoder: teacher forcing needs forced_ids");
   for (int l = 0; l < d->n_layers; ++l) PLAS_REQUIRE(d->w_cell[l] && d->b_cell[l], "decoder: layer %d weights missing", l);
+  {
+    const int rc = dec_tc_launch(*d, workspace, workspace_bytes, stream);
+    if (rc != 1) return rc;  // 1 = shape not eligible for the tensor-core kernel
+  }
   size_t offs[10], total;
   dec_ws_layout(*d, offs, &total);
   PLAS_REQUIRE(workspace_bytes >= total, "decoder: workspace %zu < %zu", workspace_bytes, total);

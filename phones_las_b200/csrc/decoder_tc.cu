@@ -1,0 +1,645 @@
+// K4 (tensor-core path, bf16) -- weight-stationary attention decoder for sm_100a.
+//
+// Same contract as decoder.cu (AttentionWrapper(MultiRNNCell) + BasicDecoder + Greedy/Training
+// helper + dynamic_decode, reference las/model.py:145-349; projection utils/training_helper.py:122-153)
+// but organised around what bounds a decode step on B200 -- bytes into each SM:
+//
+//  * LSTM layers (phase A): CTA s owns 16 gate columns (4 hidden units x i,j,f,o) of EVERY layer and
+//    keeps those weight slices resident in shared memory for the whole decode, laid out as
+//    K-major SWIZZLE_128B UMMA B tiles.  Per step only the activations X_l [B x K_l] stream in:
+//    TMA (cp.async.bulk.tensor, 128 x 64 boxes, rows >= B zero-filled) -> 16 KB ring stages ->
+//    tcgen05.mma (M=128, N=16, K=16; accumulator = 16 TMEM columns).  Epilogue thread r owns batch
+//    row r: it reads its 16 pre-activations with tcgen05.ld, adds bias and the one-hot embedding
+//    row, applies the TF gate math and keeps the cell state of its 4 units in registers.
+//  * query layer (bahdanau): the same machinery with 16 output columns per CTA on CTAs 0..Ud/16-1.
+//  * attention (phase B): work item = (utterance, half of the context channels).  A producer thread
+//    streams keys[b] and values[b][:, half] through the same ring with cp.async.bulk; 8 consumer
+//    warps compute scores -> masked softmax / monotonic scan -> context.  logits come from
+//    PV = values x W_proj (one tcgen05 GEMM per utterance batch, fp32): logits = a . PV + b.
+//  * greedy argmax / finished / sequence-length logic is replicated per CTA (deterministic), so
+//    no extra grid barrier is needed for sampling; CTA 0 writes the outputs.
+// Phases are separated by a grid barrier (L2 atomics); a step is L + 1 (+1 for bahdanau) barriers.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include "../../include/plas.h"
+
+namespace plas {
+
+constexpr int DT_THREADS = 288;   // warps 0..7 compute, warp 8 = TMA / bulk-copy producer
+constexpr int DT_STAGE = 16384;   // ring stage: one 128 x 64 bf16 TMA box
+constexpr int DT_MAX_STAGES = 8;
+
+struct alignas(64) DecTcArgs {
+  CUtensorMap tmX[4][2];  // per layer, per parity: X_l [B][K_l] bf16
+  CUtensorMap tmQ[2];     // per parity: top-layer h [B][Ud] (strided view into xbuf[L-1])
+  plas_dec_desc d;
+  const unsigned char* w_tc[4];  // [Ud/4][K_l/64][2048 B] swizzled UMMA B tiles
+  const unsigned char* wq_tc;    // [Ud/16][Ud/64][2048 B]
+  unsigned char* xbuf[4];        // [2][B][K_l] bf16
+  float* qbuf;                   // [B][Ud]
+  float* align_state;            // [B][Tm]
+  unsigned* bar;
+  int n_stages;
+  int off_w[4], off_wq, off_ring, off_misc;  // byte offsets from the 1024-aligned smem base
+  int tm_pad;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void dt_grid_barrier(unsigned* bar, unsigned& epoch) {
+  fence_proxy_async();  // generic-proxy global/shared writes of this phase vs TMA / bulk copies of the next
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    __threadfence();
+    red_release_add_u32(bar, 1u);
+    const unsigned target = epoch * gridDim.x;
+    unsigned spins = 0;
+    while (ld_acquire_u32(bar) < target) {
+      if (++spins > (1u << 28)) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  fence_proxy_async();
+}
+
+__device__ __forceinline__ float tanh_acc(float x) {  // 1 - 2/(e^{2x}+1): abs err ~1e-7, saturates cleanly
+  return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
+}
+
+struct RingState {
+  int stage;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int n) {
+    if (++stage == n) { stage = 0; phase ^= 1u; }
+  }
+};
+
+__global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_constant__ DecTcArgs p) {
+  extern __shared__ unsigned char dt_smem_raw[];
+  const plas_dec_desc& d = p.d;
+  const int B = d.B, Tm = d.Tm, D = d.D, Ud = d.Ud, V = d.V, L = d.n_layers;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NST = p.n_stages;
+  const uint32_t raw = smem_u32(dt_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* smem = dt_smem_raw + (base - raw);
+  const uint32_t ring = base + (uint32_t)p.off_ring;
+  unsigned char* ring_ptr = smem + p.off_ring;
+
+  // misc region: barriers, TMEM slot, small arrays
+  unsigned char* misc = smem + p.off_misc;
+  const uint32_t misc_u = base + (uint32_t)p.off_misc;
+  auto fullA = [&](int s) { return misc_u + 8u * s; };
+  auto emptyA = [&](int s) { return misc_u + 8u * (DT_MAX_STAGES + s); };
+  auto fullB = [&](int s) { return misc_u + 8u * (2 * DT_MAX_STAGES + s); };
+  auto emptyB = [&](int s) { return misc_u + 8u * (3 * DT_MAX_STAGES + s); };
+  const uint32_t tfull = misc_u + 8u * (4 * DT_MAX_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (4 * DT_MAX_STAGES + 1));
+  float* s_bias = reinterpret_cast<float*>(misc + 512);          // [4][16]
+  float* s_red = s_bias + 64;                                    // [64]
+  float* s_lp = s_red + 64;                                      // [8][32]
+  float* s_q = s_lp + 256;                                       // [Ud]
+  float* s_v = s_q + Ud;                                         // [Ud]
+  float* s_score = s_v + Ud;                                     // [tm_pad]
+  float* s_scan = s_score + p.tm_pad;                            // [2][tm_pad]
+  float* s_comb = s_scan + 2 * p.tm_pad;                         // [D/2]
+
+  const int nsl = Ud / 4;
+  const int nq = Ud / 16;
+  const bool bahdanau = d.attention_type == PLAS_ATT_BAHDANAU;
+  const bool monotonic = d.attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  const int slice = blockIdx.x;
+  const bool cell_cta = slice < nsl;
+  const bool q_cta = bahdanau && slice < nq;
+  int Kl[4];
+  for (int l = 0; l < 4; ++l) Kl[l] = (l == 0) ? (D + Ud) : 2 * Ud;
+
+  // ---- one-time setup: resident weight slices, barriers, TMEM ------------------------------
+  if (cell_cta) {
+    for (int l = 0; l < L; ++l) {
+      const size_t bytes = (size_t)(Kl[l] / 64) * 2048;
+      const uint4* src = reinterpret_cast<const uint4*>(p.w_tc[l] + (size_t)slice * bytes);
+      uint4* dst = reinterpret_cast<uint4*>(smem + p.off_w[l]);
+      for (int i = tid; i < (int)(bytes / 16); i += DT_THREADS) dst[i] = __ldg(src + i);
+      if (tid < 16) s_bias[l * 16 + tid] = d.b_cell[l][slice * 16 + tid];
+    }
+  }
+  if (q_cta) {
+    const size_t bytes = (size_t)(Ud / 64) * 2048;
+    const uint4* src = reinterpret_cast<const uint4*>(p.wq_tc + (size_t)slice * bytes);
+    uint4* dst = reinterpret_cast<uint4*>(smem + p.off_wq);
+    for (int i = tid; i < (int)(bytes / 16); i += DT_THREADS) dst[i] = __ldg(src + i);
+  }
+  if (bahdanau)
+    for (int u = tid; u < Ud; u += DT_THREADS) s_v[u] = d.v_att[u];
+  if (tid == 0) {
+    for (int s = 0; s < DT_MAX_STAGES; ++s) {
+      mbar_init(fullA(s), 1);
+      mbar_init(emptyA(s), 1);
+      mbar_init(fullB(s), 1);
+      mbar_init(emptyB(s), 8);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int l = 0; l < L; ++l)
+      for (int q2 = 0; q2 < 2; ++q2) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX[l][q2]) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();  // the resident weights were written with generic stores, UMMA reads them via the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- replicated decode state ----------------------------------------------------------------
+  const int row = tid - 128;                      // epilogue threads (warps 4..7) own batch row `row`
+  const bool row_thread = tid >= 128 && tid < 256;
+  const bool row_valid = row_thread && row < B;
+  float c_state[4][4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c_state[l][u] = 0.f;
+  int cur_id = d.sos_id;
+  int finished = 0;
+
+  int max_iter = d.max_steps;
+  if (!d.teacher_forced) {
+    int ml = 0;
+    for (int b = 0; b < B; ++b) ml = max(ml, d.mem_len[b]);
+    max_iter = min(max_iter, (int)rintf((float)ml * d.decoding_length_factor));
+  }
+
+  RingState prodA = {0, 0}, consA = {0, 0}, prodB = {0, 0}, consB = {0, 0};
+  uint32_t acc_parity = 0;
+  unsigned epoch = 0;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, 16);
+
+  // one [128 x K] x [K x 16] product: TMA producer (warp 8), MMA issuer (warp 0), result in TMEM cols 0..15
+  auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int nkb) {
+    if (warp == 8) {
+      if (lane == 0) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(emptyA(prodA.stage), prodA.phase ^ 1u);
+          mbar_expect_tx(fullA(prodA.stage), DT_STAGE);
+          tma_load_2d(ring + prodA.stage * DT_STAGE, tm, kb * 64, 0, fullA(prodA.stage));
+          prodA.advance(NST);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 0) {
+      if (lane == 0) {
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(fullA(consA.stage), consA.phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc(ring + consA.stage * DT_STAGE);
+          const uint64_t bdesc = umma_smem_desc(w_smem + kb * 2048);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(emptyA(consA.stage));
+          consA.advance(NST);
+        }
+        umma_commit(tfull);
+      }
+      __syncwarp();
+    }
+  };
+
+  int t = 0;
+  while (true) {
+    // ---- result of step t-1: argmax, finished / sequence-length logic (replicated), outputs (CTA 0)
+    if (t > 0 && row_valid) {
+      const float* lrow = d.logits + ((size_t)row * d.max_steps + (t - 1)) * V;
+      float best = -INFINITY;
+      int bi = 0;
+      for (int v = 0; v < V; ++v) {
+        const float x = __ldcg(lrow + v);
+        if (x > best) { best = x; bi = v; }
+      }
+      if (blockIdx.x == 0) d.sample_ids[(size_t)row * d.max_steps + (t - 1)] = bi;
+      if (!d.teacher_forced) {
+        if (!finished && blockIdx.x == 0) d.seq_len[row] = t;
+        finished = finished || (bi == d.eos_id) || (t >= max_iter);
+        cur_id = bi;
+      }
+    }
+    if (t >= max_iter) break;
+    {
+      const int all_done = __syncthreads_and(row_valid ? finished : 1);
+      if (!d.teacher_forced && t > 0 && all_done) break;
+    }
+    if (d.teacher_forced && row_valid) cur_id = d.forced_ids[(size_t)row * d.max_steps + t];
+    const int par = t & 1;
+
+    // ---------------- phase A: LSTM layers ----------------
+    for (int l = 0; l < L; ++l) {
+      if (cell_cta) {
+        const int K = Kl[l];
+        gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], K / 64);
+        if (row_thread) {
+          mbar_wait(tfull, acc_parity);
+          tc_fence_after();
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16), r);
+          tmem_ld_wait();
+          if (row_valid) {
+            float z[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(r[j]) + s_bias[l * 16 + j];
+            if (l == 0) {
+              const int id = max(0, min(cur_id, V - 1));
+              const uint4* er = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.w_emb) +
+                                                               (size_t)id * 4 * Ud + slice * 16);
+              const uint4 e0 = __ldg(er), e1 = __ldg(er + 1);
+              const unsigned ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                z[2 * j] += __uint_as_float(ew[j] << 16);
+                z[2 * j + 1] += __uint_as_float(ew[j] & 0xffff0000u);
+              }
+            }
+            __nv_bfloat16 hq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float cn, hn;
+              lstm_gates(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3], c_state[l][u], cn, hn);
+              c_state[l][u] = cn;
+              hq[u] = __float2bfloat16_rn(hn);
+            }
+            const uint2 pk = *reinterpret_cast<const uint2*>(hq);
+            __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(p.xbuf[l]) + (size_t)(par ^ 1) * B * K +
+                                (size_t)row * K + (K - Ud) + slice * 4;
+            *reinterpret_cast<uint2*>(xs) = pk;
+            if (l + 1 < L) {
+              __nv_bfloat16* xu = reinterpret_cast<__nv_bfloat16*>(p.xbuf[l + 1]) + (size_t)par * B * (2 * Ud) +
+                                  (size_t)row * (2 * Ud) + slice * 4;
+              *reinterpret_cast<uint2*>(xu) = pk;
+            }
+          }
+          tc_fence_before();
+        }
+        acc_parity ^= 1u;
+      }
+      dt_grid_barrier(p.bar, epoch);
+    }
+    // ---------------- query layer (bahdanau): q = h_top . W_q ----------------
+    if (bahdanau) {
+      if (q_cta) {
+        gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, Ud / 64);
+        if (row_thread) {
+          mbar_wait(tfull, acc_parity);
+          tc_fence_after();
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16), r);
+          tmem_ld_wait();
+          if (row_valid) {
+            float4* qd = reinterpret_cast<float4*>(p.qbuf + (size_t)row * Ud + slice * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              qd[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                  __uint_as_float(r[4 * j + 3]));
+          }
+          tc_fence_before();
+        }
+        acc_parity ^= 1u;
+      }
+      dt_grid_barrier(p.bar, epoch);
+    }
+    // ---------------- phase B: attention + context + logits ----------------
+    {
+      const int Dh = D / 2;
+      const int RK = DT_STAGE / (Ud * 2);   // key rows per stage
+      const int RV = DT_STAGE / (Dh * 2);   // value half-rows per stage
+      const int Ktop = Kl[L - 1];
+      const __nv_bfloat16* Htop = reinterpret_cast<const __nv_bfloat16*>(p.xbuf[L - 1]) + (size_t)(par ^ 1) * B * Ktop + (Ktop - Ud);
+      const int Vh = (V + 1) / 2;
+      for (int item = blockIdx.x; item < 2 * B; item += gridDim.x) {
+        const int b = item >> 1, half = item & 1;
+        const int len = min(d.mem_len[b], Tm);
+        const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud;
+        const __nv_bfloat16* vals = reinterpret_cast<const __nv_bfloat16*>(d.values) + (size_t)b * Tm * D + (size_t)half * Dh;
+        if (warp == 8) {
+          if (lane == 0) {
+            for (int r0 = 0; r0 < len; r0 += RK) {
+              const int n = min(RK, len - r0);
+              mbar_wait(emptyB(prodB.stage), prodB.phase ^ 1u);
+              mbar_expect_tx(fullB(prodB.stage), (uint32_t)(n * Ud * 2));
+              bulk_g2s(ring + prodB.stage * DT_STAGE, keys + (size_t)r0 * Ud, (uint32_t)(n * Ud * 2), fullB(prodB.stage));
+              prodB.advance(NST);
+            }
+            for (int r0 = 0; r0 < len; r0 += RV) {
+              const int n = min(RV, len - r0);
+              mbar_wait(emptyB(prodB.stage), prodB.phase ^ 1u);
+              mbar_expect_tx(fullB(prodB.stage), (uint32_t)(n * Dh * 2));
+              for (int i = 0; i < n; ++i)
+                bulk_g2s(ring + prodB.stage * DT_STAGE + (uint32_t)(i * Dh * 2), vals + (size_t)(r0 + i) * D,
+                         (uint32_t)(Dh * 2), fullB(prodB.stage));
+              prodB.advance(NST);
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        // ---- consumers: warps 0..7 ----
+        for (int u = tid; u < Ud; u += 256)
+          s_q[u] = bahdanau ? __ldcg(p.qbuf + (size_t)b * Ud + u) : __bfloat162float(Htop[(size_t)b * Ktop + u]);
+        consumer_sync();
+        for (int r0 = 0; r0 < len; r0 += RK) {
+          const int n = min(RK, len - r0);
+          mbar_wait(fullB(consB.stage), consB.phase);
+          const unsigned char* st = ring_ptr + consB.stage * DT_STAGE;
+          for (int r = warp; r < n; r += 8) {
+            const uint4* kr = reinterpret_cast<const uint4*>(st + (size_t)r * Ud * 2);
+            float acc = 0.f;
+            for (int c8 = lane; c8 < Ud / 8; c8 += 32) {
+              const uint4 kk = kr[c8];
+              const unsigned kw[4] = {kk.x, kk.y, kk.z, kk.w};
+              const int u0 = c8 * 8;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
+                if (bahdanau) {
+                  acc = fmaf(s_v[u0 + 2 * j], tanh_acc(k0 + s_q[u0 + 2 * j]), acc);
+                  acc = fmaf(s_v[u0 + 2 * j + 1], tanh_acc(k1 + s_q[u0 + 2 * j + 1]), acc);
+                } else {
+                  acc = fmaf(k0, s_q[u0 + 2 * j], acc);
+                  acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
+                }
+              }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) s_score[r0 + r] = acc;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(emptyB(consB.stage));
+          consB.advance(NST);
+        }
+        consumer_sync();
+        if (monotonic) {
+          // tf.contrib.seq2seq.monotonic_attention(mode='parallel'): two prefix sums along memory time
+          float* sa = s_scan;
+          float* sb = s_scan + p.tm_pad;
+          const float tiny = 1.17549435e-38f;
+          const float* prev = p.align_state + (size_t)b * Tm;
+          for (int tm = tid; tm < Tm; tm += 256) {
+            const float pc = (tm < len) ? sigmoidf_acc(s_score[tm] + d.score_bias) : 0.f;
+            s_score[tm] = pc;
+            sa[tm] = logf(fminf(fmaxf(1.f - pc, tiny), 1.f));
+          }
+          consumer_sync();
+          for (int off = 1; off < Tm; off <<= 1) {  // inclusive Hillis-Steele scan of the logs
+            for (int tm = tid; tm < Tm; tm += 256) sb[tm] = sa[tm] + (tm >= off ? sa[tm - off] : 0.f);
+            consumer_sync();
+            float* tmp = sa; sa = sb; sb = tmp;
+          }
+          for (int tm = tid; tm < Tm; tm += 256) {
+            const float cpv = expf(tm > 0 ? sa[tm - 1] : 0.f);  // exclusive cumulative product of (1 - p)
+            const float pv = (t == 0) ? (tm == 0 ? 1.f : 0.f) : __ldcg(prev + tm);
+            sb[tm] = pv / fminf(fmaxf(cpv, 1e-10f), 1.f);
+            s_score[tm] = s_score[tm] * cpv;  // p * cp
+          }
+          consumer_sync();
+          float* ra = sb;
+          float* rb = sa;
+          for (int off = 1; off < Tm; off <<= 1) {
+            for (int tm = tid; tm < Tm; tm += 256) rb[tm] = ra[tm] + (tm >= off ? ra[tm - off] : 0.f);
+            consumer_sync();
+            float* tmp = ra; ra = rb; rb = tmp;
+          }
+          for (int tm = tid; tm < Tm; tm += 256) s_score[tm] = s_score[tm] * ra[tm];
+          consumer_sync();
+          if (half == 0)
+            for (int tm = tid; tm < Tm; tm += 256) __stcg(p.align_state + (size_t)b * Tm + tm, s_score[tm]);
+        } else {
+          float m = -INFINITY;
+          for (int tm = tid; tm < len; tm += 256) m = fmaxf(m, s_score[tm]);
+          m = warp_max(m);
+          if (lane == 0) s_red[warp] = m;
+          consumer_sync();
+          m = s_red[0];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+          float sum = 0.f;
+          for (int tm = tid; tm < Tm; tm += 256) {
+            const float e = (tm < len) ? expf(s_score[tm] - m) : 0.f;
+            s_score[tm] = e;
+            sum += e;
+          }
+          sum = warp_sum(sum);
+          if (lane == 0) s_red[8 + warp] = sum;
+          consumer_sync();
+          sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += s_red[8 + w];
+          for (int tm = tid; tm < Tm; tm += 256) s_score[tm] = s_score[tm] / sum;
+          consumer_sync();
+        }
+        if (d.alignment && half == 0) {
+          float* ar = d.alignment + ((size_t)b * d.max_steps + t) * Tm;
+          for (int tm = tid; tm < Tm; tm += 256) ar[tm] = s_score[tm];
+        }
+        // context over this item's channel half: thread = (8-channel group, row parity)
+        {
+          const int cg = tid & 127, pr = tid >> 7;
+          const bool has = cg < Dh / 8;
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int r0 = 0; r0 < len; r0 += RV) {
+            const int n = min(RV, len - r0);
+            mbar_wait(fullB(consB.stage), consB.phase);
+            const unsigned char* st = ring_ptr + consB.stage * DT_STAGE;
+            if (has) {
+              for (int r = pr; r < n; r += 2) {
+                const float a = s_score[r0 + r];
+                const uint4 raw4 = *reinterpret_cast<const uint4*>(st + (size_t)r * Dh * 2 + cg * 16);
+                const unsigned w4[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  acc[2 * i] = fmaf(a, __uint_as_float(w4[i] << 16), acc[2 * i]);
+                  acc[2 * i + 1] = fmaf(a, __uint_as_float(w4[i] & 0xffff0000u), acc[2 * i + 1]);
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyB(consB.stage));
+            consB.advance(NST);
+          }
+          if (has && pr == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_comb[cg * 8 + i] = acc[i];
+          }
+          consumer_sync();
+          if (has && pr == 0) {
+            __nv_bfloat16 o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float2bfloat16_rn(acc[i] + s_comb[cg * 8 + i]);
+            __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(p.xbuf[0]) + (size_t)(par ^ 1) * B * (D + Ud) +
+                                 (size_t)b * (D + Ud) + (size_t)half * Dh + cg * 8;
+            *reinterpret_cast<uint4*>(att) = *reinterpret_cast<const uint4*>(o);
+          }
+        }
+        // logits of this item's vocabulary half: a . PV[b] + bias
+        {
+          const int v_lo = half ? Vh : 0, v_hi = half ? V : Vh;
+          const int vi = tid & 31, g = tid >> 5;
+          const float* pvb = d.pv + (size_t)b * Tm * d.pv_ld;
+          for (int vb = v_lo; vb < v_hi; vb += 32) {
+            const int v = vb + vi;
+            float acc = 0.f;
+            if (v < v_hi)
+              for (int tm = g; tm < len; tm += 8) acc = fmaf(s_score[tm], __ldg(pvb + (size_t)tm * d.pv_ld + v), acc);
+            s_lp[g * 32 + vi] = acc;
+            consumer_sync();
+            if (tid < 32 && vb + tid < v_hi) {
+              float s = d.b_proj[vb + tid];
+#pragma unroll
+              for (int w = 0; w < 8; ++w) s += s_lp[w * 32 + tid];
+              d.logits[((size_t)b * d.max_steps + t) * V + vb + tid] = s;
+            }
+            consumer_sync();
+          }
+        }
+      }
+      dt_grid_barrier(p.bar, epoch);
+    }
+    ++t;
+  }
+  if (blockIdx.x == 0 && tid == 0) *d.n_steps = t;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DecTcPlan {
+  bool ok;
+  int n_stages, tm_pad;
+  int off_w[4], off_wq, off_ring, off_misc;
+  size_t smem;
+  size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_bar, ws_total;
+};
+
+static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
+  DecTcPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  const bool shape_ok = d.dtype == PLAS_BF16 && d.w_cell_tc[0] && d.pv && d.B <= 128 && d.Ud % 64 == 0 &&
+                        d.D % 64 == 0 && d.D <= 2048 && d.Ud <= 2048 && (d.Ud / 4) <= num_sms() && d.Tm <= 4096 &&
+                        (d.attention_type != PLAS_ATT_BAHDANAU || d.w_query_tc);
+  if (!shape_ok) return pl;
+  int off = 0;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const int K = (l == 0) ? d.D + d.Ud : 2 * d.Ud;
+    pl.off_w[l] = off;
+    off += (K / 64) * 2048;
+  }
+  pl.off_wq = off;
+  if (d.attention_type == PLAS_ATT_BAHDANAU) off += (d.Ud / 64) * 2048;
+  pl.off_ring = off;  // multiples of 2048 -> 1024-aligned
+  pl.tm_pad = (d.Tm + 3) & ~3;
+  const int misc = 512 + 4 * (64 + 64 + 256 + 2 * d.Ud + 3 * pl.tm_pad + d.D / 2) + 64;
+  const int avail = 227 * 1024 - 1024 - off - misc;
+  int ns = avail / DT_STAGE;
+  if (ns > DT_MAX_STAGES) ns = DT_MAX_STAGES;
+  if (ns < 2) return pl;
+  pl.n_stages = ns;
+  pl.off_misc = off + ns * DT_STAGE;
+  pl.smem = (size_t)pl.off_misc + misc + 1024;
+  size_t w = 0;
+  auto take = [&](size_t bytes) { size_t o = w; w += (bytes + 255) & ~size_t(255); return o; };
+  for (int l = 0; l < 4; ++l) {
+    const size_t K = (l == 0) ? (size_t)d.D + d.Ud : (size_t)2 * d.Ud;
+    pl.ws_off_x[l] = take(l < d.n_layers ? 2 * (size_t)d.B * K * 2 : 0);
+  }
+  pl.ws_off_q = take((size_t)d.B * d.Ud * 4);
+  pl.ws_off_align = take((size_t)d.B * d.Tm * 4);
+  pl.ws_off_bar = take(4);
+  pl.ws_total = w;
+  pl.ok = true;
+  return pl;
+}
+
+size_t dec_tc_workspace_bytes(const plas_dec_desc& d) {
+  const DecTcPlan pl = dec_tc_plan(d);
+  return pl.ok ? pl.ws_total : 0;
+}
+
+// Returns PLAS_OK after a launch, 1 when the shape is not eligible (caller falls back), <0 on error.
+int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const char* force = getenv("PLAS_DEC_IMPL");
+  if (force && strcmp(force, "simt") == 0) return 1;
+  const DecTcPlan pl = dec_tc_plan(d);
+  if (!pl.ok) return 1;
+  PLAS_REQUIRE(workspace_bytes >= pl.ws_total, "decoder(tc): workspace %zu < %zu", workspace_bytes, pl.ws_total);
+  PLAS_CUDA(cudaMemsetAsync(workspace, 0, pl.ws_total, stream));
+  PLAS_CUDA(cudaMemsetAsync(d.seq_len, 0, (size_t)d.B * 4, stream));
+  PLAS_CUDA(cudaMemsetAsync(d.n_steps, 0, 4, stream));
+  if (d.max_steps == 0) return PLAS_OK;
+
+  DecTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d;
+  unsigned char* ws = (unsigned char*)workspace;
+  for (int l = 0; l < 4; ++l) {
+    a.xbuf[l] = ws + pl.ws_off_x[l];
+    a.w_tc[l] = (const unsigned char*)d.w_cell_tc[l];
+    a.off_w[l] = pl.off_w[l];
+  }
+  a.wq_tc = (const unsigned char*)d.w_query_tc;
+  a.qbuf = (float*)(ws + pl.ws_off_q);
+  a.align_state = (float*)(ws + pl.ws_off_align);
+  a.bar = (unsigned*)(ws + pl.ws_off_bar);
+  a.n_stages = pl.n_stages;
+  a.off_wq = pl.off_wq;
+  a.off_ring = pl.off_ring;
+  a.off_misc = pl.off_misc;
+  a.tm_pad = pl.tm_pad;
+  for (int l = 0; l < d.n_layers; ++l) {
+    const long long K = (l == 0) ? (long long)d.D + d.Ud : 2LL * d.Ud;
+    for (int par = 0; par < 2; ++par) {
+      int rc = make_map_bf16(&a.tmX[l][par], a.xbuf[l] + (size_t)par * d.B * K * 2, d.B, (int)K, K, 128);
+      if (rc) return rc;
+    }
+  }
+  {
+    const int l = d.n_layers - 1;
+    const long long K = (l == 0) ? (long long)d.D + d.Ud : 2LL * d.Ud;
+    for (int par = 0; par < 2; ++par) {
+      int rc = make_map_bf16(&a.tmQ[par], a.xbuf[l] + ((size_t)par * d.B * K + (size_t)(K - d.Ud)) * 2, d.B, d.Ud, K, 128);
+      if (rc) return rc;
+    }
+  }
+  PLAS_CUDA(cudaFuncSetAttribute(decoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int per_sm = 0;
+  PLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decoder_tc_kernel, DT_THREADS, pl.smem));
+  PLAS_REQUIRE(per_sm >= 1, "decoder(tc): kernel does not fit on an SM (%zu bytes of shared memory)", pl.smem);
+  int grid = num_sms();
+  const int want = (d.Ud / 4 > 2 * d.B) ? d.Ud / 4 : 2 * d.B;
+  if (grid > want) grid = want;
+  if (getenv("PLAS_DEBUG"))
+    fprintf(stderr, "[plas] decoder tc path: grid=%d stages=%d smem=%zu\n", grid, pl.n_stages, pl.smem);
+  void* args[] = {(void*)&a};
+  PLAS_CUDA(cudaLaunchCooperativeKernel((const void*)decoder_tc_kernel, dim3(grid), dim3(DT_THREADS), args, pl.smem, stream));
+  return PLAS_OK;
+}
+
+}  // namespace plas

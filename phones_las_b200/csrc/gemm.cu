@@ -11,11 +11,10 @@
 // out-of-bounds zero fill; N must be a multiple of 128.
 //
 // f32 path (plas_gemm_f32): exact-fp32 SIMT kernel, used only by the reference-precision mode.
-#include <cuda.h>
-
 #include <mutex>
 
 #include "common.cuh"
+#include "tcgen05.cuh"
 #include "../../include/plas.h"
 
 namespace plas {
@@ -23,78 +22,6 @@ namespace plas {
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();  // a protocol bug must fail loudly, not hang the GPU
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B; 8-row
-// swizzle atoms 1024 B apart).  Matches what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-  return d;
-}
-
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
 
@@ -111,10 +38,10 @@ struct GemmCfg {
                                     ((uint32_t)(G_BM >> 4) << 24);
 };
 
-template <int BN>
+template <int BN, bool OUT_F32>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, long long M, int N,
+                         const float* __restrict__ bias, void* __restrict__ Cv, long long M, int N,
                          int K, long long ldc) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ unsigned char gemm_smem_raw[];
@@ -217,14 +144,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       const long long row = (long long)m_blk * G_BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-      __nv_bfloat16* crow = C + row * ldc + (long long)n_blk * BN;
+      __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(Cv) + row * ldc + (long long)n_blk * BN;
+      float* crow32 = reinterpret_cast<float*>(Cv) + row * ldc + (long long)n_blk * BN;
       const float* brow = bias ? bias + (long long)n_blk * BN : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (row < M) {
+        if (row < M && OUT_F32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = __uint_as_float(r[j]) + (brow ? __ldg(brow + c0 + j) : 0.f);
+            v.y = __uint_as_float(r[j + 1]) + (brow ? __ldg(brow + c0 + j + 1) : 0.f);
+            v.z = __uint_as_float(r[j + 2]) + (brow ? __ldg(brow + c0 + j + 2) : 0.f);
+            v.w = __uint_as_float(r[j + 3]) + (brow ? __ldg(brow + c0 + j + 3) : 0.f);
+            *reinterpret_cast<float4*>(crow32 + c0 + j) = v;
+          }
+        } else if (row < M) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t pk[4];
@@ -315,38 +253,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  });
-  return fn;
-}
-
-static int make_map_bf16(CUtensorMap* map, const void* ptr, long long rows, int cols, long long ld, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return set_err(PLAS_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(PLAS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return PLAS_OK;
-}
-
-template <int BN>
+template <int BN, bool OUT_F32>
 static int launch_gemm_bf16(const void* A, long long M, int K, long long lda, const void* Wt, int N, long long ldw,
                             const float* bias, void* C, long long ldc, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -358,14 +265,14 @@ static int launch_gemm_bf16(const void* A, long long M, int K, long long lda, co
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, OUT_F32>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   PLAS_CUDA(attr_err);
   const long long tiles = ((M + G_BM - 1) / G_BM) * (N / BN);
   const int sms = num_sms() > 0 ? num_sms() : 148;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, bias, (__nv_bfloat16*)C, M, N, K, ldc);
+  gemm_bf16_tcgen05_kernel<BN, OUT_F32><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, bias, C, M, N, K, ldc);
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;
 }
@@ -374,18 +281,34 @@ static int launch_gemm_bf16(const void* A, long long M, int K, long long lda, co
 
 using namespace plas;
 
-extern "C" int plas_gemm_bf16(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
-                              int64_t ldw, const float* bias, void* C, int64_t ldc, plas_stream_t stream) {
+static int gemm_bf16_dispatch(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
+                              int64_t ldw, const float* bias, void* C, int64_t ldc, bool out_f32, plas_stream_t stream) {
   PLAS_REQUIRE(A && Wt && C, "gemm_bf16: null pointer");
   PLAS_REQUIRE(M > 0 && K > 0 && N > 0, "gemm_bf16: M=%lld K=%d N=%d", (long long)M, K, N);
   PLAS_REQUIRE(N % 128 == 0, "gemm_bf16: N=%d must be a multiple of 128 (pad the packed weights)", N);
   PLAS_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm_bf16: lda/ldw/ldc must be multiples of 8");
+  (void)out_f32;
   PLAS_REQUIRE(lda >= K && ldw >= K && ldc >= N, "gemm_bf16: leading dimension too small");
   PLAS_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)Wt % 16) == 0 && ((uintptr_t)C % 16) == 0,
                "gemm_bf16: pointers must be 16-byte aligned");
+  if (out_f32) {
+    if (N % 256 == 0)
+      return launch_gemm_bf16<256, true>(A, M, K, lda, Wt, N, ldw, bias, C, ldc, (cudaStream_t)stream);
+    return launch_gemm_bf16<128, true>(A, M, K, lda, Wt, N, ldw, bias, C, ldc, (cudaStream_t)stream);
+  }
   if (N % 256 == 0)
-    return launch_gemm_bf16<256>(A, M, K, lda, Wt, N, ldw, bias, C, ldc, (cudaStream_t)stream);
-  return launch_gemm_bf16<128>(A, M, K, lda, Wt, N, ldw, bias, C, ldc, (cudaStream_t)stream);
+    return launch_gemm_bf16<256, false>(A, M, K, lda, Wt, N, ldw, bias, C, ldc, (cudaStream_t)stream);
+  return launch_gemm_bf16<128, false>(A, M, K, lda, Wt, N, ldw, bias, C, ldc, (cudaStream_t)stream);
+}
+
+extern "C" int plas_gemm_bf16(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
+                              int64_t ldw, const float* bias, void* C, int64_t ldc, plas_stream_t stream) {
+  return gemm_bf16_dispatch(A, M, K, lda, Wt, N, ldw, bias, C, ldc, false, stream);
+}
+
+extern "C" int plas_gemm_bf16_f32out(const void* A, int64_t M, int32_t K, int64_t lda, const void* Wt, int32_t N,
+                                     int64_t ldw, const float* bias, float* C, int64_t ldc, plas_stream_t stream) {
+  return gemm_bf16_dispatch(A, M, K, lda, Wt, N, ldw, bias, C, ldc, true, stream);
 }
 
 extern "C" int plas_gemm_f32(const float* A, int64_t M, int32_t K, int64_t lda, const float* Wt, int32_t N,

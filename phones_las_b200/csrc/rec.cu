@@ -16,6 +16,9 @@
 //      (state frozen and output 0 for t >= len; the bw direction walks len-1-s),
 //   5. publishes its h slice (exchange buffer + the [B,T,ndir*U] output) and bumps the counter.
 // Only the CTAs of one (direction, group) ever synchronise with each other.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/plas.h"
 
@@ -205,6 +208,230 @@ __global__ void __launch_bounds__(REC_THREADS, 1) rec_bf16_kernel(RecArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 cluster variant (the fast path): the G CTAs of one (direction, group) form ONE thread-block
+// cluster (G <= 8 portable, 16 non-portable) and a group is R = 16*MT utterances.  h_t never
+// leaves the chip: every CTA pushes its R x 32 slice of h_t into the shared memory of all G CTAs
+// with st.async (DSMEM store that completes transaction bytes on the RECEIVER's mbarrier), so a
+// step is closed by each CTA's own mbarrier seeing G*R*64 bytes -- no cluster barrier, no L2 round
+// trip, no atomics, no fence.  Buffer reuse is safe without extra sync: a peer can only send h_s
+// after it has received my h_{s-1}, which I send after my last read of the buffer h_s lands in.
+// The next step's gate pre-activations are prefetched into registers a full step ahead, and the K
+// loop runs on independent accumulator sets so the mma.sync dependency chain stays short.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, const uint4& v, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int MT>
+__global__ void __launch_bounds__(REC_THREADS, 1) rec_bf16_cluster_kernel(RecArgs p) {
+  constexpr int R = 16 * MT;           // utterances per group
+  constexpr int KSPLIT = 4;            // independent accumulator sets along K
+  constexpr int MC = MT >= 2 ? 2 : 1;  // m-tiles per tensor-core pass
+  extern __shared__ __align__(16) unsigned char rec_smem[];
+  const plas_rec_desc& d = p.d;
+  const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
+  const int KS = U / 16;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  int bid = blockIdx.x;
+  const int ci = bid % p.G; bid /= p.G;  // == rank inside the cluster (1-D clusters of G consecutive CTAs)
+  const int gi = bid % p.n_groups;
+  const int dir = bid / p.n_groups;
+  const int row0 = gi * R;
+
+  uint4* s_w = reinterpret_cast<uint4*>(rec_smem);                                   // [8][KS][32] uint4
+  const int hstride = U + 8;                                                         // bf16 elements
+  __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(rec_smem + (size_t)U * 256); // [2][R][U+8]
+  __nv_bfloat16* s_stage = s_h + 2 * R * hstride;                                    // [R][32]
+  __shared__ int s_len[R];
+  __shared__ int s_tmax;
+  __shared__ __align__(8) unsigned long long s_bar[2];
+
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(d.whh) + ((size_t)dir * p.G + ci) * (size_t)(8 * KS * 32);
+    for (int i = tid; i < 8 * KS * 32; i += REC_THREADS) s_w[i] = src[i];
+  }
+  if (tid < R) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int r = 0; r < R; ++r) m = max(m, s_len[r]);
+    s_tmax = m;
+  }
+  __syncthreads();
+  const int Tg = s_tmax;
+  const uint32_t bar_addr[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
+  const uint32_t step_bytes = (uint32_t)(p.G * R * 64);  // bytes every CTA receives per step
+  if (tid == 0) {
+    mbar_init(bar_addr[0], 1);
+    mbar_init(bar_addr[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (Tg >= 2) mbar_expect_tx(bar_addr[0], step_bytes);  // h_0
+    if (Tg >= 3) mbar_expect_tx(bar_addr[1], step_bytes);  // h_1
+  }
+
+  const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  const int unit = ci * 32 + warp * 4 + q;
+  const int NX = ndir * 4 * U;
+  int len_r[MT][2];
+  const __nv_bfloat16* xrow[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int r = m * 16 + g + 8 * e;
+      len_r[m][e] = s_len[r];
+      xrow[m][e] = xproj + ((size_t)min(row0 + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
+    }
+  const uint32_t s_h_addr = smem_u32(s_h);
+  const int chunks_per_rank = R * 4;  // 16-byte chunks of one R x 32 slice
+  const int n_chunks = p.G * chunks_per_rank;
+
+  float c_state[MT][2], h_state[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) c_state[m][0] = c_state[m][1] = h_state[m][0] = h_state[m][1] = 0.f;
+
+  auto load_xp = [&](int s, uint2 (*xp)[2]) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        xp[m][e] = make_uint2(0u, 0u);
+        if (s < len_r[m][e]) {
+          const int t = dir ? (len_r[m][e] - 1 - s) : s;
+          xp[m][e] = __ldg(reinterpret_cast<const uint2*>(xrow[m][e] + (size_t)t * NX));
+        }
+      }
+  };
+
+  uint2 xp_next[MT][2];
+  load_xp(0, xp_next);
+  // every CTA of the cluster must be running, with its mbarriers initialised, before anyone pushes
+  cluster_sync_all();
+
+  for (int s = 0; s < Tg; ++s) {
+    uint2 xp[MT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { xp[m][0] = xp_next[m][0]; xp[m][1] = xp_next[m][1]; }
+    if (s + 1 < Tg) load_xp(s + 1, xp_next);
+    const bool have_h = s > 0;
+    const int bsel = (s - 1) & 1;
+    if (have_h) {
+      mbar_wait(bar_addr[bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
+      if (tid == 0 && s + 1 <= Tg - 2) mbar_expect_tx(bar_addr[bsel], step_bytes);  // re-arm for h_{s+1}
+    }
+    const __nv_bfloat16* hb = s_h + (size_t)(bsel & 1) * R * hstride;
+    const __nv_bfloat16* arow = hb + (lane & 15) * hstride + (lane >> 4) * 8;
+    const uint4* wf = s_w + (size_t)warp * KS * 32 + lane;
+    // m-tiles go through the tensor cores MC at a time; the accumulation order (four K-interleaved
+    // partial sums, added 0+1+2+3) is the same for every MT, so results do not depend on the group size
+#pragma unroll
+    for (int m0 = 0; m0 < MT; m0 += MC) {
+      float acc[KSPLIT][MC][2][4];
+#pragma unroll
+      for (int a = 0; a < KSPLIT; ++a)
+#pragma unroll
+        for (int m = 0; m < MC; ++m)
+#pragma unroll
+          for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[a][m][n][i] = 0.f;
+      if (have_h) {
+#pragma unroll 2
+        for (int ks = 0; ks < KS; ks += KSPLIT) {
+#pragma unroll
+          for (int a = 0; a < KSPLIT; ++a) {
+            const uint4 w = wf[(size_t)(ks + a) * 32];
+#pragma unroll
+            for (int m = 0; m < MC; ++m) {
+              uint32_t a0, a1, a2, a3;
+              ldmatrix_x4(a0, a1, a2, a3, arow + (size_t)(m0 + m) * 16 * hstride + (ks + a) * 16);
+              mma_bf16_16816(acc[a][m][0], a0, a1, a2, a3, w.x, w.y);
+              mma_bf16_16816(acc[a][m][1], a0, a1, a2, a3, w.z, w.w);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int mm = 0; mm < MC; ++mm)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int m = m0 + mm;
+          float z[2][2];  // [n-tile][pair element]: (i, j) and (f, o)
+#pragma unroll
+          for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              float v = acc[0][mm][n][2 * e + i];
+#pragma unroll
+              for (int a = 1; a < KSPLIT; ++a) v += acc[a][mm][n][2 * e + i];
+              z[n][i] = v;
+            }
+          const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[m][e].x);
+          const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[m][e].y);
+          const float zi = z[0][0] + __low2float(x01), zj = z[0][1] + __high2float(x01);
+          const float zf = z[1][0] + __low2float(x23), zo = z[1][1] + __high2float(x23);
+          // accurate expf/tanhf: a 1e-7 absolute error on a small tanh is ~1e-5 relative, which flips
+          // bf16 roundings of h and measurably widens the drift against the oracle
+          float cn, hn;
+          lstm_gates(zi, zj, zf, zo, c_state[m][e], cn, hn);
+          if (s < len_r[m][e]) {
+            c_state[m][e] = cn;
+            h_state[m][e] = bf16_round(hn);
+          }
+          s_stage[(m * 16 + g + 8 * e) * 32 + warp * 4 + q] = __float2bfloat16_rn(h_state[m][e]);
+        }
+    }
+    __syncthreads();
+    // publish the staged R x 32 slice: (a) to every CTA of the cluster through DSMEM (not needed
+    // after the last step), (b) for active rows to the [B,T,ndir*U] layer output in HBM
+    if (s + 1 < Tg) {
+      const uint32_t dst_buf = s_h_addr + (uint32_t)((s & 1) * R * hstride * 2);
+      for (int idx = tid; idx < n_chunks; idx += REC_THREADS) {
+        const int rank = idx / chunks_per_rank, chunk = idx - rank * chunks_per_rank;
+        const int r = chunk >> 2, ch = chunk & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+        const uint32_t local = dst_buf + (uint32_t)((r * hstride + ci * 32 + ch * 8) * 2);
+        st_async_v4(mapa_u32(local, (uint32_t)rank), v, mapa_u32(bar_addr[s & 1], (uint32_t)rank));
+      }
+    }
+    if (tid < chunks_per_rank) {
+      const int r = tid >> 2, ch = tid & 3;
+      const int b = row0 + r;
+      const int len = s_len[r];
+      if (b < B && s < len) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+        const int t = dir ? (len - 1 - s) : s;
+        __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
+        *reinterpret_cast<uint4*>(odst) = v;
+      }
+    }
+    __syncthreads();  // s_stage is rewritten by the next step's gate stage
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int b = row0 + m * 16 + g + 8 * e;
+      if (b < B) {
+        d.c_final[((size_t)dir * B + b) * U + unit] = c_state[m][e];
+        d.h_final[((size_t)dir * B + b) * U + unit] = h_state[m][e];
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // exact-fp32 SIMT variant (reference-precision mode).  upc units per CTA, thread = (unit, row group).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(REC_THREADS, 1) rec_f32_kernel(RecArgs p) {
@@ -344,6 +571,73 @@ static size_t rec_smem_bytes(int dtype, int U, int upc) {
   return (size_t)U * 4 * upc * 4 + (size_t)REC_ROWS * U * 4;
 }
 
+static bool rec_force_legacy() {
+  const char* e = getenv("PLAS_REC_IMPL");
+  return e && strcmp(e, "l2") == 0;
+}
+
+template <int MT>
+static int rec_try_cluster(RecArgs a, cudaStream_t stream, bool must_fit_one_wave, bool* launched) {
+  const plas_rec_desc& d = a.d;
+  constexpr int R = 16 * MT;
+  *launched = false;
+  const size_t smem_c = (size_t)d.U * 256 + (size_t)2 * R * (d.U + 8) * 2 + (size_t)R * 32 * 2;
+  if (smem_c > 227 * 1024) return PLAS_OK;
+  auto fn = rec_bf16_cluster_kernel<MT>;
+  PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  if (a.G > 8) PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  a.n_groups = (d.B + R - 1) / R;
+  const int clusters = d.ndir * a.n_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * a.G));
+  cfg.blockDim = dim3(REC_THREADS);
+  cfg.dynamicSmemBytes = smem_c;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg);
+  if (getenv("PLAS_DEBUG"))
+    fprintf(stderr, "[plas] rec cluster path: MT=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", MT,
+            a.G, clusters, max_clusters, cudaGetErrorString(qe), smem_c);
+  if (qe != cudaSuccess || max_clusters < 1) {
+    (void)cudaGetLastError();
+    return PLAS_OK;
+  }
+  if (must_fit_one_wave && clusters > max_clusters) return PLAS_OK;
+  a.group_offset = 0;
+  a.groups_here = a.n_groups;
+  PLAS_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+  *launched = true;
+  return PLAS_OK;
+}
+
+// Picks the smallest group size (16 / 32 / 64 utterances) whose clusters are all co-resident, so the
+// recurrence runs as one wave; falls back to the largest group size in several waves.
+// Returns PLAS_OK after a launch, 1 when no cluster shape can be scheduled, <0 on error.
+static int rec_launch_cluster(const RecArgs& a, cudaStream_t stream) {
+  bool launched = false;
+  const char* force = getenv("PLAS_REC_MT");
+  const int fmt = force ? atoi(force) : 0;
+  int rc;
+  if (fmt == 0 || fmt == 1) {
+    rc = rec_try_cluster<1>(a, stream, fmt == 0, &launched);
+    if (rc || launched) return rc;
+  }
+  if (fmt == 0 || fmt == 2) {
+    rc = rec_try_cluster<2>(a, stream, fmt == 0, &launched);
+    if (rc || launched) return rc;
+  }
+  rc = rec_try_cluster<4>(a, stream, false, &launched);
+  if (rc || launched) return rc;
+  return 1;
+}
+
 static void rec_ws_layout(const plas_rec_desc& d, size_t* o_ctr, size_t* o_hx, size_t* total) {
   const int n_groups = (d.B + REC_ROWS - 1) / REC_ROWS;
   const size_t esz = d.dtype == PLAS_BF16 ? 2 : 4;
@@ -392,8 +686,14 @@ extern "C" int plas_bilstm_rec_fwd(const plas_rec_desc* d, void* workspace, size
   a.upc = upc;
   a.G = d->U / upc;
   a.Bpad = a.n_groups * REC_ROWS;
-  PLAS_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)d->ndir * a.n_groups * 4, stream));
 
+  // fast path: one thread-block cluster per (direction, group), h exchanged through DSMEM
+  if (d->dtype == PLAS_BF16 && a.G <= 16 && !rec_force_legacy()) {
+    int rc = rec_launch_cluster(a, stream);
+    if (rc != 1) return rc;  // 1 = cluster shape not schedulable on this device: use the L2-exchange kernel
+  }
+
+  PLAS_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)d->ndir * a.n_groups * 4, stream));
   const size_t smem = rec_smem_bytes(d->dtype, d->U, upc);
   PLAS_REQUIRE(smem <= 227 * 1024, "rec: needs %zu bytes of shared memory", smem);
   const void* fn = d->dtype == PLAS_BF16 ? (const void*)rec_bf16_kernel : (const void*)rec_f32_kernel;

@@ -106,6 +106,39 @@ def pack_cell_bf16(w_rows, Ud):
     return out
 
 
+def swizzle128_tiles(w_nk):
+    """UMMA/TMA K-major SWIZZLE_128B image of a [16, K] operand: per 64-wide k block a 16 x 128-byte
+    tile whose 16-byte chunk c of row r is stored at chunk position c ^ (r % 8).  Returns [K/64][1024]."""
+    n, K = w_nk.shape
+    assert n == 16 and K % 64 == 0
+    t = np.asarray(w_nk, np.float32).reshape(16, K // 64, 8, 8)  # [row][k block][chunk][element]
+    out = np.empty((K // 64, 16, 8, 8), np.float32)
+    for r in range(16):
+        for c in range(8):
+            out[:, r, c ^ (r % 8), :] = t[r, :, c, :]
+    return out.reshape(K // 64, 1024)
+
+
+def pack_cell_tc(w_rows, Ud):
+    """Decoder LSTM rows for decoder_tc_kernel: [Ud/4][K/64][1024]; tile row = 4*unit_local + gate."""
+    K = w_rows.shape[0]
+    nsl = Ud // 4
+    out = np.zeros((nsl, K // 64, 1024), np.float32)
+    for s in range(nsl):
+        units = 4 * s + np.arange(4)
+        cols = (np.arange(GATES)[None, :] * Ud + units[:, None]).reshape(-1)
+        out[s] = swizzle128_tiles(np.asarray(w_rows, np.float32)[:, cols].T)
+    return out
+
+
+def pack_query_tc(wq, Ud):
+    """bahdanau query_layer kernel [Ud(k), Ud(out)] for decoder_tc_kernel: [Ud/16][Ud/64][1024]."""
+    out = np.zeros((Ud // 16, Ud // 64, 1024), np.float32)
+    for s in range(Ud // 16):
+        out[s] = swizzle128_tiles(np.asarray(wq, np.float32)[:, 16 * s:16 * s + 16].T)
+    return out
+
+
 def pack_unit_major(mat_or_vec, U):
     """Permute the last axis from TF gate-block order to (unit, gate) order."""
     return np.asarray(mat_or_vec, np.float32)[..., unit_major_cols(U)]

@@ -48,7 +48,10 @@ class SpellerWeights:
         wmt[:Ud] = wm.T
         self.w_mem_t = up(wmt)
         pre = f"{scope}/decoder/attention_wrapper"
-        self.w_cell, self.b_cell = [], []
+        self.w_cell, self.b_cell, self.w_cell_tc = [], [], []
+        # tensor-core decoder (decoder_tc.cu): bf16, D and Ud multiples of 64 (plas.h)
+        self.tc = precision == "bf16" and D % 64 == 0 and Ud % 64 == 0 and D <= 2048 and Ud <= 2048
+        self.w_query_tc = self.w_proj_pad = None
         for k in range(self.L):
             kern = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], np.float32)
             bias = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], np.float32)
@@ -61,16 +64,24 @@ class SpellerWeights:
                 rows = kern
             packed = packing.pack_cell_bf16(rows, Ud) if precision == "bf16" else packing.pack_cell_f32(rows, Ud)
             self.w_cell.append(up(packed))
+            if self.tc:
+                self.w_cell_tc.append(up(packing.pack_cell_tc(rows, Ud)))
             self.b_cell.append(up(packing.pack_unit_major(bias, Ud), torch.float32))
         self.w_query = self.v_att = None
         self.score_bias = 0.0
         if self.att == "bahdanau":
             self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
             self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"], torch.float32)
+            if self.tc:
+                self.w_query_tc = up(packing.pack_query_tc(params[f"{pre}/bahdanau_attention/query_layer/kernel"], Ud))
         elif self.att == "luong_monotonic":
             self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
         self.w_proj_t = up(np.asarray(params[f"{scope}/decoder/projection_layer/kernel"], np.float32).T)  # [V, D]
         self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"], torch.float32)
+        if self.tc:
+            wp = np.zeros((_round_up(V, 128), D), np.float32)
+            wp[:V] = np.asarray(params[f"{scope}/decoder/projection_layer/kernel"], np.float32).T
+            self.w_proj_pad = up(wp)
 
 
 def prepare_memory(encoder_outputs, source_sequence_length, w):
@@ -92,7 +103,16 @@ def prepare_memory(encoder_outputs, source_sequence_length, w):
     _lib.count_launches(2)
     if n_pad != w.Ud:
         keys = keys[:, :w.Ud].contiguous()
-    return keys.view(B, Tm, w.Ud), values
+    pv = None
+    if w.tc and B <= 128:
+        # PV = values x projection kernel (f32): the decoder forms logits as alignments . PV + bias
+        vp = w.w_proj_pad.shape[0]
+        pv = torch.empty((B * Tm, vp), dtype=torch.float32, device=enc.device)
+        with _lib.stage("memory_gemm"):
+            _lib.check(L.plas_gemm_bf16_f32out(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_proj_pad), vp, D, None,
+                                               _lib.ptr(pv), vp, _lib.stream_ptr()))
+        _lib.count_launches(1)
+    return keys.view(B, Tm, w.Ud), values, pv
 
 
 def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_steps=None,
@@ -104,7 +124,7 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     B, Tm, D = encoder_outputs.shape
     assert D == w.D
     mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).contiguous()
-    keys, values = prepare_memory(encoder_outputs, mem_len, w)
+    keys, values, pv = prepare_memory(encoder_outputs, mem_len, w)
     factor = float(hp.get("decoding_length_factor", 1.0))
     if forced_ids is not None:
         forced_ids = forced_ids.to(device=dev, dtype=torch.int32).contiguous()
@@ -141,6 +161,11 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()
     d.alignment = align.data_ptr() if align is not None else None
     d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
+    if pv is not None:
+        for k in range(w.L):
+            d.w_cell_tc[k] = w.w_cell_tc[k].data_ptr()
+        d.w_query_tc = w.w_query_tc.data_ptr() if w.w_query_tc is not None else None
+        d.pv, d.pv_ld = pv.data_ptr(), pv.shape[1]
     need = L.plas_decoder_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     with _lib.stage("decoder"):

@@ -41,13 +41,13 @@ def test_listener_parity(cfg):
     (out, olen, state), (ref_out, ref_len, ref_state) = _run(*cfg)
     np.testing.assert_array_equal(olen, ref_len)
     assert out.shape == ref_out.shape
-    L = cfg[5]
-    assert_parity(out, ref_out, precision, "encoder_out", bf16_fro=1e-3 if L <= 3 else 2e-3)
+    fro = 1e-3 if cfg[5] <= 3 else 2e-3  # deep bf16 stacks: see tests/util.assert_parity
+    assert_parity(out, ref_out, precision, "encoder_out", bf16_fro=fro)
     for b in range(out.shape[0]):
         assert (out[b, olen[b]:] == 0).all(), "outputs past the reduced length must be zero"
     for d in range(2):
-        assert_parity(state[d][0], ref_state[d][0], precision, f"final c dir{d}")
-        assert_parity(state[d][1], ref_state[d][1], precision, f"final h dir{d}")
+        assert_parity(state[d][0], ref_state[d][0], precision, f"final c dir{d}", bf16_fro=fro)
+        assert_parity(state[d][1], ref_state[d][1], precision, f"final h dir{d}", bf16_fro=fro)
 
 
 @gpu

