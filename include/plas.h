@@ -113,12 +113,17 @@ typedef struct plas_rec_desc {
   int64_t out_batch_stride; /* elements between utterances in `out` (>= T*ndir*U)              */
   float* c_final;           /* [ndir][B][U]                                                    */
   float* h_final;           /* [ndir][B][U]                                                    */
+  const void* whh_tc;       /* bf16, optional: [ndir][U/32][128][U] rows m = 4*unit_local + gate, the
+                               TMEM-resident operand of the tcgen05 recurrence (NULL: mma.sync kernels)  */
 } plas_rec_desc;
 
 /* Layout contract for whh (host side packs once per checkpoint load):
  *   f32 : [ndir][U/upc][U(k)][4*upc]  with column = 4*unit_local + gate
  *   bf16: [ndir][U/32][8 warps][U/16 ksteps][32 lanes][8 bf16] mma.m16n8k16 B-fragments
- * plas_rec_units_per_cta reports upc for (dtype,U). */
+ * plas_rec_units_per_cta reports upc for (dtype,U).
+ * Three kernels sit behind plas_bilstm_rec_fwd: tcgen05 with W_hh resident in tensor memory (bf16,
+ * U in {64,128,256,512}, needs whh_tc), an mma.sync thread-block-cluster kernel with W_hh resident in
+ * registers (bf16, same widths) and an L2-exchange cooperative kernel (any width, f32 or bf16). */
 int32_t plas_rec_units_per_cta(int32_t dtype, int32_t U);
 size_t plas_rec_workspace_bytes(const plas_rec_desc* d);
 int plas_bilstm_rec_fwd(const plas_rec_desc* d, void* workspace, size_t workspace_bytes,

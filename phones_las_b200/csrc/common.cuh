@@ -41,6 +41,27 @@ __device__ __forceinline__ void lstm_gates(float zi, float zj, float zf, float z
   h = sigmoidf_acc(zo) * tanhf(c);
 }
 
+// Cheaper gate math for the bf16 kernels, still ~2e-7 relative: sigmoid through ex2.approx/rcp.approx
+// (no cancellation: 1 + e^-x >= 1) and tanh as the Cephes odd polynomial below 0.625 (where
+// 1 - 2/(e^2x + 1) would lose relative accuracy to cancellation) and the exponential form above.
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_fast(float x) {
+  const float ax = fabsf(x);
+  const float x2 = x * x;
+  float p = fmaf(x2, -5.70498872745e-3f, 2.06390887954e-2f);
+  p = fmaf(p, x2, -5.37397155531e-2f);
+  p = fmaf(p, x2, 1.33314422036e-1f);
+  p = fmaf(p, x2, -3.33332819422e-1f);
+  const float small = fmaf(x * x2, p, x);
+  const float big = copysignf(1.0f - __fdividef(2.0f, __expf(2.0f * ax) + 1.0f), x);
+  return ax < 0.625f ? small : big;
+}
+__device__ __forceinline__ void lstm_gates_fast(float zi, float zj, float zf, float zo, float c_prev, float& c,
+                                                float& h) {
+  c = sigmoidf_fast(zf + 1.0f) * c_prev + sigmoidf_fast(zi) * tanhf_fast(zj);
+  h = sigmoidf_fast(zo) * tanhf_fast(c);
+}
+
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
@@ -84,6 +105,14 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one elected lane of a fully converged warp (lets the compiler keep descriptor operands in uniform
+// registers instead of emitting a per-thread uniformisation loop around tcgen05 / TMA instructions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- shared-memory addresses and mbarriers ---------------------------------------------

@@ -30,7 +30,7 @@ namespace plas {
 
 constexpr int DT_THREADS = 288;   // warps 0..7 compute, warp 8 = TMA / bulk-copy producer
 constexpr int DT_STAGE = 16384;   // ring stage: one 128 x 64 bf16 TMA box
-constexpr int DT_MAX_STAGES = 8;
+constexpr int DT_MAX_STAGES = 16;
 
 struct alignas(64) DecTcArgs {
   CUtensorMap tmX[4][2];  // per layer, per parity: X_l [B][K_l] bf16
@@ -42,7 +42,10 @@ struct alignas(64) DecTcArgs {
   float* qbuf;                   // [B][Ud]
   float* align_state;            // [B][Tm]
   unsigned* bar;
-  int n_stages;
+  unsigned long long* dbg;       // optional [8] phase timers (ns, summed over steps) written by CTA 0
+  int n_stages;                  // 16 KB stages of the attention ring
+  int n_stages_a;                // stages of the LSTM-phase ring (8 KB when B <= 64, else 16 KB)
+  int stage_a;                   // bytes per LSTM-phase stage (= TMA box bytes)
   int off_w[4], off_wq, off_ring, off_misc;  // byte offsets from the 1024-aligned smem base
   int tm_pad;
 };
@@ -73,8 +76,12 @@ __device__ __forceinline__ void dt_grid_barrier(unsigned* bar, unsigned& epoch) 
   fence_proxy_async();
 }
 
-__device__ __forceinline__ float tanh_acc(float x) {  // 1 - 2/(e^{2x}+1): abs err ~1e-7, saturates cleanly
-  return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
+// bahdanau scores need B*Tm*Ud tanh per decode step (6.2 M at c2): one MUFU op each.  tanh.approx.f32
+// has a relative error of 2^-11, an eighth of the bf16 quantisation of the keys it is applied to.
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 struct RingState {
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   const plas_dec_desc& d = p.d;
   const int B = d.B, Tm = d.Tm, D = d.D, Ud = d.Ud, V = d.V, L = d.n_layers;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NST = p.n_stages;
+  const int NST = p.n_stages, NSTA = p.n_stages_a, STA = p.stage_a;
   const uint32_t raw = smem_u32(dt_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* smem = dt_smem_raw + (base - raw);
@@ -106,7 +113,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   auto emptyB = [&](int s) { return misc_u + 8u * (3 * DT_MAX_STAGES + s); };
   const uint32_t tfull = misc_u + 8u * (4 * DT_MAX_STAGES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (4 * DT_MAX_STAGES + 1));
-  float* s_bias = reinterpret_cast<float*>(misc + 512);          // [4][16]
+  int* s_ids = reinterpret_cast<int*>(misc + 576);               // [128]  (barriers + TMEM slot end at 528)
+  float* s_bias = reinterpret_cast<float*>(misc + 1536);         // [4][16]
   float* s_red = s_bias + 64;                                    // [64]
   float* s_lp = s_red + 64;                                      // [8][32]
   float* s_q = s_lp + 256;                                       // [Ud]
@@ -190,30 +198,35 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   constexpr uint32_t IDESC = umma_idesc_bf16(128, 16);
 
   // one [128 x K] x [K x 16] product: TMA producer (warp 8), MMA issuer (warp 0), result in TMEM cols 0..15
+  // Every CTA reads the SAME activation matrix; walking the k blocks from a per-CTA offset keeps the
+  // 128+ CTAs from hammering the same few L2 lines in lock step.
   auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int nkb) {
+    const int kb0 = (int)(((long long)blockIdx.x * nkb) / gridDim.x);
     if (warp == 8) {
-      if (lane == 0) {
-        for (int kb = 0; kb < nkb; ++kb) {
+      if (elect_one()) {
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = (kb0 + i) % nkb;
           mbar_wait(emptyA(prodA.stage), prodA.phase ^ 1u);
-          mbar_expect_tx(fullA(prodA.stage), DT_STAGE);
-          tma_load_2d(ring + prodA.stage * DT_STAGE, tm, kb * 64, 0, fullA(prodA.stage));
-          prodA.advance(NST);
+          mbar_expect_tx(fullA(prodA.stage), (uint32_t)STA);
+          tma_load_2d(ring + prodA.stage * STA, tm, kb * 64, 0, fullA(prodA.stage));
+          prodA.advance(NSTA);
         }
       }
       __syncwarp();
     } else if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = (kb0 + i) % nkb;
           mbar_wait(fullA(consA.stage), consA.phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc(ring + consA.stage * DT_STAGE);
+          const uint64_t adesc = umma_smem_desc(ring + consA.stage * STA);
           const uint64_t bdesc = umma_smem_desc(w_smem + kb * 2048);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (i | k) != 0 ? 1u : 0u);
           umma_commit(emptyA(consA.stage));
-          consA.advance(NST);
+          consA.advance(NSTA);
         }
         umma_commit(tfull);
       }
@@ -221,22 +234,52 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     }
   };
 
+  // optional phase timers (PLAS_DEBUG): 0 prologue, 1..4 LSTM layers (incl. barrier), 5 query, 6 attention
+  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long tlast = 0;
+  const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  auto stamp = [&](int slot) {
+    if (timing) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      tacc[slot] += now - tlast;
+      tlast = now;
+    }
+  };
+  if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
+
   int t = 0;
   while (true) {
     // ---- result of step t-1: argmax, finished / sequence-length logic (replicated), outputs (CTA 0)
-    if (t > 0 && row_valid) {
-      const float* lrow = d.logits + ((size_t)row * d.max_steps + (t - 1)) * V;
-      float best = -INFINITY;
-      int bi = 0;
-      for (int v = 0; v < V; ++v) {
-        const float x = __ldcg(lrow + v);
-        if (x > best) { best = x; bi = v; }
+    if (t > 0) {
+      // warp w takes rows w, w+8, ...: coalesced logits read, shuffle argmax (lowest index wins ties)
+      if (warp < 8) {
+        for (int rr = warp; rr < B; rr += 8) {
+          const float* lrow = d.logits + ((size_t)rr * d.max_steps + (t - 1)) * V;
+          float best = -INFINITY;
+          int bi = 0x7fffffff;
+          for (int v = lane; v < V; v += 32) {
+            const float x = __ldcg(lrow + v);
+            if (x > best) { best = x; bi = v; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+          }
+          if (lane == 0) s_ids[rr] = (bi == 0x7fffffff) ? 0 : bi;
+        }
       }
-      if (blockIdx.x == 0) d.sample_ids[(size_t)row * d.max_steps + (t - 1)] = bi;
-      if (!d.teacher_forced) {
-        if (!finished && blockIdx.x == 0) d.seq_len[row] = t;
-        finished = finished || (bi == d.eos_id) || (t >= max_iter);
-        cur_id = bi;
+      __syncthreads();
+      if (row_valid) {
+        const int bi = s_ids[row];
+        if (blockIdx.x == 0) d.sample_ids[(size_t)row * d.max_steps + (t - 1)] = bi;
+        if (!d.teacher_forced) {
+          if (!finished && blockIdx.x == 0) d.seq_len[row] = t;
+          finished = finished || (bi == d.eos_id) || (t >= max_iter);
+          cur_id = bi;
+        }
       }
     }
     if (t >= max_iter) break;
@@ -246,6 +289,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     }
     if (d.teacher_forced && row_valid) cur_id = d.forced_ids[(size_t)row * d.max_steps + t];
     const int par = t & 1;
+    stamp(0);
 
     // ---------------- phase A: LSTM layers ----------------
     for (int l = 0; l < L; ++l) {
@@ -297,6 +341,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         acc_parity ^= 1u;
       }
       dt_grid_barrier(p.bar, epoch);
+      stamp(1 + l);
     }
     // ---------------- query layer (bahdanau): q = h_top . W_q ----------------
     if (bahdanau) {
@@ -320,6 +365,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         acc_parity ^= 1u;
       }
       dt_grid_barrier(p.bar, epoch);
+      stamp(5);
     }
     // ---------------- phase B: attention + context + logits ----------------
     {
@@ -335,7 +381,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud;
         const __nv_bfloat16* vals = reinterpret_cast<const __nv_bfloat16*>(d.values) + (size_t)b * Tm * D + (size_t)half * Dh;
         if (warp == 8) {
-          if (lane == 0) {
+          if (elect_one()) {
             for (int r0 = 0; r0 < len; r0 += RK) {
               const int n = min(RK, len - r0);
               mbar_wait(emptyB(prodB.stage), prodB.phase ^ 1u);
@@ -360,6 +406,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         for (int u = tid; u < Ud; u += 256)
           s_q[u] = bahdanau ? __ldcg(p.qbuf + (size_t)b * Ud + u) : __bfloat162float(Htop[(size_t)b * Ktop + u]);
         consumer_sync();
+        // scores: warp per memory position; lane owns the 8-element chunks c8 = lane, lane+32 of the
+        // depth (conflict-free 16-byte LDS of the staged keys); its slice of the query (and of
+        // attention_v) lives in registers for the whole item when Ud <= 512
+        const int n_c8 = Ud / 8;
+        const bool reg_path = n_c8 <= 64;
+        float qreg[16], vreg[16];
+        if (reg_path) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c8 = lane + 32 * cc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              qreg[cc * 8 + j] = (c8 < n_c8) ? s_q[c8 * 8 + j] : 0.f;
+              vreg[cc * 8 + j] = (c8 < n_c8 && bahdanau) ? s_v[c8 * 8 + j] : 0.f;
+            }
+          }
+        }
         for (int r0 = 0; r0 < len; r0 += RK) {
           const int n = min(RK, len - r0);
           mbar_wait(fullB(consB.stage), consB.phase);
@@ -367,19 +430,41 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
           for (int r = warp; r < n; r += 8) {
             const uint4* kr = reinterpret_cast<const uint4*>(st + (size_t)r * Ud * 2);
             float acc = 0.f;
-            for (int c8 = lane; c8 < Ud / 8; c8 += 32) {
-              const uint4 kk = kr[c8];
-              const unsigned kw[4] = {kk.x, kk.y, kk.z, kk.w};
-              const int u0 = c8 * 8;
+            if (reg_path) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
-                if (bahdanau) {
-                  acc = fmaf(s_v[u0 + 2 * j], tanh_acc(k0 + s_q[u0 + 2 * j]), acc);
-                  acc = fmaf(s_v[u0 + 2 * j + 1], tanh_acc(k1 + s_q[u0 + 2 * j + 1]), acc);
-                } else {
-                  acc = fmaf(k0, s_q[u0 + 2 * j], acc);
-                  acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
+              for (int cc = 0; cc < 2; ++cc) {
+                const int c8 = lane + 32 * cc;
+                if (c8 < n_c8) {
+                  const uint4 kk = kr[c8];
+                  const unsigned kw[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
+                    if (bahdanau) {
+                      acc = fmaf(vreg[cc * 8 + 2 * j], tanh_mufu(k0 + qreg[cc * 8 + 2 * j]), acc);
+                      acc = fmaf(vreg[cc * 8 + 2 * j + 1], tanh_mufu(k1 + qreg[cc * 8 + 2 * j + 1]), acc);
+                    } else {
+                      acc = fmaf(k0, qreg[cc * 8 + 2 * j], acc);
+                      acc = fmaf(k1, qreg[cc * 8 + 2 * j + 1], acc);
+                    }
+                  }
+                }
+              }
+            } else {
+              for (int c8 = lane; c8 < n_c8; c8 += 32) {
+                const uint4 kk = kr[c8];
+                const unsigned kw[4] = {kk.x, kk.y, kk.z, kk.w};
+                const int u0 = c8 * 8;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
+                  if (bahdanau) {
+                    acc = fmaf(s_v[u0 + 2 * j], tanh_mufu(k0 + s_q[u0 + 2 * j]), acc);
+                    acc = fmaf(s_v[u0 + 2 * j + 1], tanh_mufu(k1 + s_q[u0 + 2 * j + 1]), acc);
+                  } else {
+                    acc = fmaf(k0, s_q[u0 + 2 * j], acc);
+                    acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
+                  }
                 }
               }
             }
@@ -515,10 +600,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
           }
         }
       }
+      stamp(7);  // own attention work done, before the barrier
       dt_grid_barrier(p.bar, epoch);
+      stamp(6);
     }
     ++t;
   }
+  if (timing)
+    for (int i = 0; i < 8; ++i) p.dbg[i] = tacc[i];
   if (blockIdx.x == 0 && tid == 0) *d.n_steps = t;
   tc_fence_before();
   __syncthreads();
@@ -533,10 +622,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 struct DecTcPlan {
   bool ok;
-  int n_stages, tm_pad;
+  int n_stages, n_stages_a, stage_a, tm_pad;
   int off_w[4], off_wq, off_ring, off_misc;
   size_t smem;
-  size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_bar, ws_total;
+  size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_bar, ws_off_dbg, ws_total;
 };
 
 static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
@@ -556,12 +645,17 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   if (d.attention_type == PLAS_ATT_BAHDANAU) off += (d.Ud / 64) * 2048;
   pl.off_ring = off;  // multiples of 2048 -> 1024-aligned
   pl.tm_pad = (d.Tm + 3) & ~3;
-  const int misc = 512 + 4 * (64 + 64 + 256 + 2 * d.Ud + 3 * pl.tm_pad + d.D / 2) + 64;
+  const int misc = 1536 + 4 * (64 + 64 + 256 + 2 * d.Ud + 3 * pl.tm_pad + d.D / 2) + 64;
   const int avail = 227 * 1024 - 1024 - off - misc;
   int ns = avail / DT_STAGE;
   if (ns > DT_MAX_STAGES) ns = DT_MAX_STAGES;
   if (ns < 2) return pl;
   pl.n_stages = ns;
+  // LSTM phases: the TMA box holds min(B,128) rounded to 64 rows; with 64-row boxes the stage is 8 KB and
+  // the M=128 MMA reads 8 KB past it (rows 64..127 = don't-care TMEM lanes), hence one stage of slack
+  pl.stage_a = d.B <= 64 ? 8192 : 16384;
+  pl.n_stages_a = d.B <= 64 ? 2 * ns - 1 : ns;
+  if (pl.n_stages_a > DT_MAX_STAGES) pl.n_stages_a = DT_MAX_STAGES;
   pl.off_misc = off + ns * DT_STAGE;
   pl.smem = (size_t)pl.off_misc + misc + 1024;
   size_t w = 0;
@@ -573,6 +667,7 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   pl.ws_off_q = take((size_t)d.B * d.Ud * 4);
   pl.ws_off_align = take((size_t)d.B * d.Tm * 4);
   pl.ws_off_bar = take(4);
+  pl.ws_off_dbg = take(64);
   pl.ws_total = w;
   pl.ok = true;
   return pl;
@@ -608,7 +703,10 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   a.qbuf = (float*)(ws + pl.ws_off_q);
   a.align_state = (float*)(ws + pl.ws_off_align);
   a.bar = (unsigned*)(ws + pl.ws_off_bar);
+  a.dbg = getenv("PLAS_DEBUG") ? (unsigned long long*)(ws + pl.ws_off_dbg) : nullptr;
   a.n_stages = pl.n_stages;
+  a.n_stages_a = pl.n_stages_a;
+  a.stage_a = pl.stage_a;
   a.off_wq = pl.off_wq;
   a.off_ring = pl.off_ring;
   a.off_misc = pl.off_misc;
@@ -616,7 +714,7 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   for (int l = 0; l < d.n_layers; ++l) {
     const long long K = (l == 0) ? (long long)d.D + d.Ud : 2LL * d.Ud;
     for (int par = 0; par < 2; ++par) {
-      int rc = make_map_bf16(&a.tmX[l][par], a.xbuf[l] + (size_t)par * d.B * K * 2, d.B, (int)K, K, 128);
+      int rc = make_map_bf16(&a.tmX[l][par], a.xbuf[l] + (size_t)par * d.B * K * 2, d.B, (int)K, K, pl.stage_a / 128);
       if (rc) return rc;
     }
   }
@@ -624,7 +722,8 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
     const int l = d.n_layers - 1;
     const long long K = (l == 0) ? (long long)d.D + d.Ud : 2LL * d.Ud;
     for (int par = 0; par < 2; ++par) {
-      int rc = make_map_bf16(&a.tmQ[par], a.xbuf[l] + ((size_t)par * d.B * K + (size_t)(K - d.Ud)) * 2, d.B, d.Ud, K, 128);
+      int rc = make_map_bf16(&a.tmQ[par], a.xbuf[l] + ((size_t)par * d.B * K + (size_t)(K - d.Ud)) * 2, d.B, d.Ud, K,
+                             pl.stage_a / 128);
       if (rc) return rc;
     }
   }
@@ -636,9 +735,17 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   const int want = (d.Ud / 4 > 2 * d.B) ? d.Ud / 4 : 2 * d.B;
   if (grid > want) grid = want;
   if (getenv("PLAS_DEBUG"))
-    fprintf(stderr, "[plas] decoder tc path: grid=%d stages=%d smem=%zu\n", grid, pl.n_stages, pl.smem);
+    fprintf(stderr, "[plas] decoder tc path: grid=%d stages=%d (lstm ring %d x %d B) smem=%zu\n", grid, pl.n_stages,
+            pl.n_stages_a, pl.stage_a, pl.smem);
   void* args[] = {(void*)&a};
   PLAS_CUDA(cudaLaunchCooperativeKernel((const void*)decoder_tc_kernel, dim3(grid), dim3(DT_THREADS), args, pl.smem, stream));
+  if (a.dbg) {  // debug only: synchronises
+    unsigned long long h[8];
+    PLAS_CUDA(cudaStreamSynchronize(stream));
+    PLAS_CUDA(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[plas] decoder tc phase time (us, CTA 0): prologue %.1f  lstm %.1f %.1f %.1f %.1f  query %.1f  attention %.1f (own work %.1f)\n",
+            h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, (h[6] + h[7]) / 1e3, h[7] / 1e3);
+  }
   return PLAS_OK;
 }
 

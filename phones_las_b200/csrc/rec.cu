@@ -208,15 +208,25 @@ __global__ void __launch_bounds__(REC_THREADS, 1) rec_bf16_kernel(RecArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// bf16 cluster variant (the fast path): the G CTAs of one (direction, group) form ONE thread-block
-// cluster (G <= 8 portable, 16 non-portable) and a group is R = 16*MT utterances.  h_t never
-// leaves the chip: every CTA pushes its R x 32 slice of h_t into the shared memory of all G CTAs
-// with st.async (DSMEM store that completes transaction bytes on the RECEIVER's mbarrier), so a
-// step is closed by each CTA's own mbarrier seeing G*R*64 bytes -- no cluster barrier, no L2 round
-// trip, no atomics, no fence.  Buffer reuse is safe without extra sync: a peer can only send h_s
-// after it has received my h_{s-1}, which I send after my last read of the buffer h_s lands in.
-// The next step's gate pre-activations are prefetched into registers a full step ahead, and the K
-// loop runs on independent accumulator sets so the mma.sync dependency chain stays short.
+// bf16 cluster variant (the fast path).
+//
+// * The G = U/32 CTAs that share one recurrence form ONE thread-block cluster (G <= 8 portable,
+//   16 non-portable; U = 512 -> 16).
+// * W_hh is weight-stationary in REGISTERS: thread (warp, lane) keeps the mma.m16n8k16 B fragments
+//   of its warp's 16 gate columns for all U/16 k-steps (KS uint4 = 128 registers at U = 512), so the
+//   only shared-memory traffic of a step is the h tile itself.
+// * h_t never leaves the chip: every CTA pushes its 16 x 32 slice of h_t into the shared memory of
+//   all G CTAs with st.async (a DSMEM store that completes transaction bytes on the RECEIVER's
+//   mbarrier); a step is closed by each CTA's own mbarrier seeing G*1 KB -- no cluster barrier, no
+//   L2 round trip, no atomics, no fence.  Buffer reuse needs no extra sync: a peer can only send
+//   h_s after it received my h_{s-1}, which I send after my last read of the buffer h_s lands in.
+// * NG = 2 interleaves two independent 16-utterance groups of the same direction in one cluster:
+//   while group A's h is in flight the tensor cores work on group B, which hides the exchange
+//   latency and lets 2*ndir*ceil(B/32) clusters cover the batch (only 7 clusters of 16 CTAs are
+//   co-resident on a B200).
+// * Gate pre-activations are prefetched into registers a full item ahead; the K loop runs on four
+//   interleaved accumulator sets (summed 0+1+2+3) so the mma.sync dependency chain is U/64 deep and
+//   the result does not depend on NG.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, uint32_t rank) {
   uint32_t r;
@@ -232,201 +242,192 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int MT>
+template <int KS, int NG>
 __global__ void __launch_bounds__(REC_THREADS, 1) rec_bf16_cluster_kernel(RecArgs p) {
-  constexpr int R = 16 * MT;           // utterances per group
-  constexpr int KSPLIT = 4;            // independent accumulator sets along K
-  constexpr int MC = MT >= 2 ? 2 : 1;  // m-tiles per tensor-core pass
+  constexpr int U = KS * 16;
+  constexpr int G = U / 32;            // CTAs per cluster
+  constexpr int R = REC_ROWS;          // utterances per group
+  constexpr int HS = U + 8;            // padded row stride of the h tile (bf16 elements)
   extern __shared__ __align__(16) unsigned char rec_smem[];
   const plas_rec_desc& d = p.d;
-  const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
-  const int KS = U / 16;
+  const int B = d.B, T = d.T, ndir = d.ndir;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  int bid = blockIdx.x;
-  const int ci = bid % p.G; bid /= p.G;  // == rank inside the cluster (1-D clusters of G consecutive CTAs)
-  const int gi = bid % p.n_groups;
-  const int dir = bid / p.n_groups;
-  const int row0 = gi * R;
+  const int ci = blockIdx.x % G;       // rank inside the cluster (1-D clusters of G consecutive CTAs)
+  const int cl = blockIdx.x / G;
+  const int cpd = (p.n_groups + NG - 1) / NG;  // clusters per direction
+  const int dir = cl / cpd;
+  const int grp0 = (cl % cpd) * NG;    // first group of this cluster
 
-  uint4* s_w = reinterpret_cast<uint4*>(rec_smem);                                   // [8][KS][32] uint4
-  const int hstride = U + 8;                                                         // bf16 elements
-  __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(rec_smem + (size_t)U * 256); // [2][R][U+8]
-  __nv_bfloat16* s_stage = s_h + 2 * R * hstride;                                    // [R][32]
-  __shared__ int s_len[R];
-  __shared__ int s_tmax;
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(rec_smem);            // [NG][2][R][HS]
+  __nv_bfloat16* s_stage = s_h + (size_t)NG * 2 * R * HS;                     // [R][32]
+  __shared__ int s_len[NG][R];
+  __shared__ int s_tmax[NG];
+  __shared__ __align__(8) unsigned long long s_bar[NG][2];
 
+  // weight-stationary fragments: [dir][G][8 warps][KS][32 lanes] uint4 in global memory
+  uint4 wreg[KS];
   {
-    const uint4* src = reinterpret_cast<const uint4*>(d.whh) + ((size_t)dir * p.G + ci) * (size_t)(8 * KS * 32);
-    for (int i = tid; i < 8 * KS * 32; i += REC_THREADS) s_w[i] = src[i];
+    const uint4* src = reinterpret_cast<const uint4*>(d.whh) + (((size_t)dir * G + ci) * 8 + warp) * (size_t)(KS * 32) + lane;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) wreg[ks] = __ldg(src + (size_t)ks * 32);
   }
-  if (tid < R) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
+  if (tid < NG * R) {
+    const int gg = tid / R, r = tid % R;
+    const int b = (grp0 + gg) * R + r;
+    s_len[gg][r] = (grp0 + gg < p.n_groups && b < B) ? min(d.lengths[b], T) : 0;
+  }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < NG) {
     int m = 0;
-    for (int r = 0; r < R; ++r) m = max(m, s_len[r]);
-    s_tmax = m;
+    for (int r = 0; r < R; ++r) m = max(m, s_len[tid][r]);
+    s_tmax[tid] = m;
   }
   __syncthreads();
-  const int Tg = s_tmax;
-  const uint32_t bar_addr[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
-  const uint32_t step_bytes = (uint32_t)(p.G * R * 64);  // bytes every CTA receives per step
+  int Tg[NG];
+  int Tmax = 0;
+#pragma unroll
+  for (int gg = 0; gg < NG; ++gg) { Tg[gg] = s_tmax[gg]; Tmax = max(Tmax, Tg[gg]); }
+
+  const uint32_t step_bytes = (uint32_t)(G * R * 64);  // bytes every CTA receives per group step
+  uint32_t bar_addr[NG][2];
+#pragma unroll
+  for (int gg = 0; gg < NG; ++gg) { bar_addr[gg][0] = smem_u32(&s_bar[gg][0]); bar_addr[gg][1] = smem_u32(&s_bar[gg][1]); }
   if (tid == 0) {
-    mbar_init(bar_addr[0], 1);
-    mbar_init(bar_addr[1], 1);
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) {
+      mbar_init(bar_addr[gg][0], 1);
+      mbar_init(bar_addr[gg][1], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (Tg >= 2) mbar_expect_tx(bar_addr[0], step_bytes);  // h_0
-    if (Tg >= 3) mbar_expect_tx(bar_addr[1], step_bytes);  // h_1
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) {
+      if (Tg[gg] >= 2) mbar_expect_tx(bar_addr[gg][0], step_bytes);  // h_0
+      if (Tg[gg] >= 3) mbar_expect_tx(bar_addr[gg][1], step_bytes);  // h_1
+    }
   }
 
   const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
   const int unit = ci * 32 + warp * 4 + q;
   const int NX = ndir * 4 * U;
-  int len_r[MT][2];
-  const __nv_bfloat16* xrow[MT][2];
+  int len_r[NG][2];
+  const __nv_bfloat16* xrow[NG][2];
+  float c_state[NG][2], h_state[NG][2];
+  uint2 xp[NG][2];
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
+  for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int r = m * 16 + g + 8 * e;
-      len_r[m][e] = s_len[r];
-      xrow[m][e] = xproj + ((size_t)min(row0 + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
+      const int r = g + 8 * e;
+      len_r[gg][e] = s_len[gg][r];
+      xrow[gg][e] = xproj + ((size_t)min((grp0 + gg) * R + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
+      c_state[gg][e] = 0.f;
+      h_state[gg][e] = 0.f;
+      xp[gg][e] = make_uint2(0u, 0u);
+      if (0 < len_r[gg][e]) {
+        const int t = dir ? (len_r[gg][e] - 1) : 0;
+        xp[gg][e] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][e] + (size_t)t * NX));
+      }
     }
   const uint32_t s_h_addr = smem_u32(s_h);
-  const int chunks_per_rank = R * 4;  // 16-byte chunks of one R x 32 slice
-  const int n_chunks = p.G * chunks_per_rank;
-
-  float c_state[MT][2], h_state[MT][2];
-#pragma unroll
-  for (int m = 0; m < MT; ++m) c_state[m][0] = c_state[m][1] = h_state[m][0] = h_state[m][1] = 0.f;
-
-  auto load_xp = [&](int s, uint2 (*xp)[2]) {
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        xp[m][e] = make_uint2(0u, 0u);
-        if (s < len_r[m][e]) {
-          const int t = dir ? (len_r[m][e] - 1 - s) : s;
-          xp[m][e] = __ldg(reinterpret_cast<const uint2*>(xrow[m][e] + (size_t)t * NX));
-        }
-      }
-  };
-
-  uint2 xp_next[MT][2];
-  load_xp(0, xp_next);
   // every CTA of the cluster must be running, with its mbarriers initialised, before anyone pushes
   cluster_sync_all();
 
-  for (int s = 0; s < Tg; ++s) {
-    uint2 xp[MT][2];
+  for (int s = 0; s < Tmax; ++s) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m) { xp[m][0] = xp_next[m][0]; xp[m][1] = xp_next[m][1]; }
-    if (s + 1 < Tg) load_xp(s + 1, xp_next);
-    const bool have_h = s > 0;
-    const int bsel = (s - 1) & 1;
-    if (have_h) {
-      mbar_wait(bar_addr[bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
-      if (tid == 0 && s + 1 <= Tg - 2) mbar_expect_tx(bar_addr[bsel], step_bytes);  // re-arm for h_{s+1}
-    }
-    const __nv_bfloat16* hb = s_h + (size_t)(bsel & 1) * R * hstride;
-    const __nv_bfloat16* arow = hb + (lane & 15) * hstride + (lane >> 4) * 8;
-    const uint4* wf = s_w + (size_t)warp * KS * 32 + lane;
-    // m-tiles go through the tensor cores MC at a time; the accumulation order (four K-interleaved
-    // partial sums, added 0+1+2+3) is the same for every MT, so results do not depend on the group size
+    for (int gg = 0; gg < NG; ++gg) {
+      if (s >= Tg[gg]) continue;  // uniform over the cluster
+      const int bsel = (s - 1) & 1;
+      float acc[4][2][4];
 #pragma unroll
-    for (int m0 = 0; m0 < MT; m0 += MC) {
-      float acc[KSPLIT][MC][2][4];
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int a = 0; a < KSPLIT; ++a)
+        for (int n = 0; n < 2; ++n)
 #pragma unroll
-        for (int m = 0; m < MC; ++m)
+          for (int i = 0; i < 4; ++i) acc[a][n][i] = 0.f;
+      if (s > 0) {
+        mbar_wait(bar_addr[gg][bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
+        if (tid == 0 && s + 1 <= Tg[gg] - 2) mbar_expect_tx(bar_addr[gg][bsel], step_bytes);  // re-arm for h_{s+1}
+        const __nv_bfloat16* hb = s_h + (size_t)(gg * 2 + bsel) * R * HS;
+        const __nv_bfloat16* arow = hb + (lane & 15) * HS + (lane >> 4) * 8;
 #pragma unroll
-          for (int n = 0; n < 2; ++n)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[a][m][n][i] = 0.f;
-      if (have_h) {
-#pragma unroll 2
-        for (int ks = 0; ks < KS; ks += KSPLIT) {
-#pragma unroll
-          for (int a = 0; a < KSPLIT; ++a) {
-            const uint4 w = wf[(size_t)(ks + a) * 32];
-#pragma unroll
-            for (int m = 0; m < MC; ++m) {
-              uint32_t a0, a1, a2, a3;
-              ldmatrix_x4(a0, a1, a2, a3, arow + (size_t)(m0 + m) * 16 * hstride + (ks + a) * 16);
-              mma_bf16_16816(acc[a][m][0], a0, a1, a2, a3, w.x, w.y);
-              mma_bf16_16816(acc[a][m][1], a0, a1, a2, a3, w.z, w.w);
-            }
-          }
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(a0, a1, a2, a3, arow + ks * 16);
+          mma_bf16_16816(acc[ks & 3][0], a0, a1, a2, a3, wreg[ks].x, wreg[ks].y);
+          mma_bf16_16816(acc[ks & 3][1], a0, a1, a2, a3, wreg[ks].z, wreg[ks].w);
         }
       }
 #pragma unroll
-      for (int mm = 0; mm < MC; ++mm)
+      for (int e = 0; e < 2; ++e) {
+        float z[2][2];  // [n-tile][pair element]: (i, j) and (f, o)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int m = m0 + mm;
-          float z[2][2];  // [n-tile][pair element]: (i, j) and (f, o)
+        for (int n = 0; n < 2; ++n)
 #pragma unroll
-          for (int n = 0; n < 2; ++n)
+          for (int i = 0; i < 2; ++i) {
+            float v = acc[0][n][2 * e + i];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              float v = acc[0][mm][n][2 * e + i];
-#pragma unroll
-              for (int a = 1; a < KSPLIT; ++a) v += acc[a][mm][n][2 * e + i];
-              z[n][i] = v;
-            }
-          const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[m][e].x);
-          const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[m][e].y);
-          const float zi = z[0][0] + __low2float(x01), zj = z[0][1] + __high2float(x01);
-          const float zf = z[1][0] + __low2float(x23), zo = z[1][1] + __high2float(x23);
-          // accurate expf/tanhf: a 1e-7 absolute error on a small tanh is ~1e-5 relative, which flips
-          // bf16 roundings of h and measurably widens the drift against the oracle
-          float cn, hn;
-          lstm_gates(zi, zj, zf, zo, c_state[m][e], cn, hn);
-          if (s < len_r[m][e]) {
-            c_state[m][e] = cn;
-            h_state[m][e] = bf16_round(hn);
+            for (int a = 1; a < 4; ++a) v += acc[a][n][2 * e + i];
+            z[n][i] = v;
           }
-          s_stage[(m * 16 + g + 8 * e) * 32 + warp * 4 + q] = __float2bfloat16_rn(h_state[m][e]);
+        const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][e].x);
+        const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][e].y);
+        const float zi = z[0][0] + __low2float(x01), zj = z[0][1] + __high2float(x01);
+        const float zf = z[1][0] + __low2float(x23), zo = z[1][1] + __high2float(x23);
+        float cn, hn;
+        lstm_gates_fast(zi, zj, zf, zo, c_state[gg][e], cn, hn);
+        if (s < len_r[gg][e]) {
+          c_state[gg][e] = cn;
+          h_state[gg][e] = bf16_round(hn);
         }
-    }
-    __syncthreads();
-    // publish the staged R x 32 slice: (a) to every CTA of the cluster through DSMEM (not needed
-    // after the last step), (b) for active rows to the [B,T,ndir*U] layer output in HBM
-    if (s + 1 < Tg) {
-      const uint32_t dst_buf = s_h_addr + (uint32_t)((s & 1) * R * hstride * 2);
-      for (int idx = tid; idx < n_chunks; idx += REC_THREADS) {
-        const int rank = idx / chunks_per_rank, chunk = idx - rank * chunks_per_rank;
-        const int r = chunk >> 2, ch = chunk & 3;
-        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
-        const uint32_t local = dst_buf + (uint32_t)((r * hstride + ci * 32 + ch * 8) * 2);
-        st_async_v4(mapa_u32(local, (uint32_t)rank), v, mapa_u32(bar_addr[s & 1], (uint32_t)rank));
+        s_stage[(g + 8 * e) * 32 + warp * 4 + q] = __float2bfloat16_rn(h_state[gg][e]);
+        // prefetch this group's next gate pre-activations (consumed one full item later)
+        xp[gg][e] = make_uint2(0u, 0u);
+        if (s + 1 < len_r[gg][e]) {
+          const int t = dir ? (len_r[gg][e] - 2 - s) : (s + 1);
+          xp[gg][e] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][e] + (size_t)t * NX));
+        }
       }
-    }
-    if (tid < chunks_per_rank) {
-      const int r = tid >> 2, ch = tid & 3;
-      const int b = row0 + r;
-      const int len = s_len[r];
-      if (b < B && s < len) {
-        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
-        const int t = dir ? (len - 1 - s) : s;
-        __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
-        *reinterpret_cast<uint4*>(odst) = v;
+      __syncthreads();
+      // publish the staged 16 x 32 slice: (a) to every CTA of the cluster through DSMEM (not needed
+      // after the group's last step), (b) for active rows to the [B,T,ndir*U] layer output in HBM
+      if (s + 1 < Tg[gg]) {
+        const uint32_t dst_buf = s_h_addr + (uint32_t)(((gg * 2 + (s & 1)) * R * HS) * 2);
+#pragma unroll
+        for (int j = 0; j < (G * 64 + REC_THREADS - 1) / REC_THREADS; ++j) {
+          const int idx = tid + j * REC_THREADS;
+          if (idx < G * 64) {
+            const int rank = idx >> 6, chunk = idx & 63;
+            const int r = chunk >> 2, ch = chunk & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+            const uint32_t local = dst_buf + (uint32_t)((r * HS + ci * 32 + ch * 8) * 2);
+            st_async_v4(mapa_u32(local, (uint32_t)rank), v, mapa_u32(bar_addr[gg][s & 1], (uint32_t)rank));
+          }
+        }
       }
+      if (tid < 64) {
+        const int r = tid >> 2, ch = tid & 3;
+        const int b = (grp0 + gg) * R + r;
+        const int len = s_len[gg][r];
+        if (b < B && s < len) {
+          const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+          const int t = dir ? (len - 1 - s) : s;
+          __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
+          *reinterpret_cast<uint4*>(odst) = v;
+        }
+      }
+      __syncthreads();  // s_stage is rewritten by the next item's gate stage
     }
-    __syncthreads();  // s_stage is rewritten by the next step's gate stage
   }
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
+  for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int b = row0 + m * 16 + g + 8 * e;
-      if (b < B) {
-        d.c_final[((size_t)dir * B + b) * U + unit] = c_state[m][e];
-        d.h_final[((size_t)dir * B + b) * U + unit] = h_state[m][e];
+      const int b = (grp0 + gg) * R + g + 8 * e;
+      if (grp0 + gg < p.n_groups && b < B) {
+        d.c_final[((size_t)dir * B + b) * U + unit] = c_state[gg][e];
+        d.h_final[((size_t)dir * B + b) * U + unit] = h_state[gg][e];
       }
     }
 }
@@ -571,31 +572,33 @@ static size_t rec_smem_bytes(int dtype, int U, int upc) {
   return (size_t)U * 4 * upc * 4 + (size_t)REC_ROWS * U * 4;
 }
 
+int rec_tc_launch(const plas_rec_desc& d, cudaStream_t stream);
+
 static bool rec_force_legacy() {
   const char* e = getenv("PLAS_REC_IMPL");
   return e && strcmp(e, "l2") == 0;
 }
 
-template <int MT>
+template <int KS, int NG>
 static int rec_try_cluster(RecArgs a, cudaStream_t stream, bool must_fit_one_wave, bool* launched) {
   const plas_rec_desc& d = a.d;
-  constexpr int R = 16 * MT;
+  constexpr int U = KS * 16, G = U / 32;
   *launched = false;
-  const size_t smem_c = (size_t)d.U * 256 + (size_t)2 * R * (d.U + 8) * 2 + (size_t)R * 32 * 2;
-  if (smem_c > 227 * 1024) return PLAS_OK;
-  auto fn = rec_bf16_cluster_kernel<MT>;
+  const size_t smem_c = (size_t)NG * 2 * REC_ROWS * (U + 8) * 2 + (size_t)REC_ROWS * 32 * 2;
+  auto fn = rec_bf16_cluster_kernel<KS, NG>;
   PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-  if (a.G > 8) PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  a.n_groups = (d.B + R - 1) / R;
-  const int clusters = d.ndir * a.n_groups;
+  if (G > 8) PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  a.n_groups = (d.B + REC_ROWS - 1) / REC_ROWS;
+  a.G = G;
+  const int clusters = d.ndir * ((a.n_groups + NG - 1) / NG);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * a.G));
+  cfg.gridDim = dim3((unsigned)(clusters * G));
   cfg.blockDim = dim3(REC_THREADS);
   cfg.dynamicSmemBytes = smem_c;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)a.G;
+  attr[0].val.clusterDim.x = (unsigned)G;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -603,8 +606,8 @@ static int rec_try_cluster(RecArgs a, cudaStream_t stream, bool must_fit_one_wav
   int max_clusters = 0;
   cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg);
   if (getenv("PLAS_DEBUG"))
-    fprintf(stderr, "[plas] rec cluster path: MT=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", MT,
-            a.G, clusters, max_clusters, cudaGetErrorString(qe), smem_c);
+    fprintf(stderr, "[plas] rec cluster path: U=%d NG=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", U,
+            NG, G, clusters, max_clusters, cudaGetErrorString(qe), smem_c);
   if (qe != cudaSuccess || max_clusters < 1) {
     (void)cudaGetLastError();
     return PLAS_OK;
@@ -617,25 +620,32 @@ static int rec_try_cluster(RecArgs a, cudaStream_t stream, bool must_fit_one_wav
   return PLAS_OK;
 }
 
-// Picks the smallest group size (16 / 32 / 64 utterances) whose clusters are all co-resident, so the
-// recurrence runs as one wave; falls back to the largest group size in several waves.
+// One group per cluster when all clusters are co-resident (lowest latency); otherwise two
+// interleaved groups per cluster (half as many clusters, exchange latency hidden).
 // Returns PLAS_OK after a launch, 1 when no cluster shape can be scheduled, <0 on error.
-static int rec_launch_cluster(const RecArgs& a, cudaStream_t stream) {
+template <int KS>
+static int rec_launch_cluster_ks(const RecArgs& a, cudaStream_t stream) {
   bool launched = false;
-  const char* force = getenv("PLAS_REC_MT");
-  const int fmt = force ? atoi(force) : 0;
+  const char* force = getenv("PLAS_REC_NG");
+  const int fng = force ? atoi(force) : 0;
   int rc;
-  if (fmt == 0 || fmt == 1) {
-    rc = rec_try_cluster<1>(a, stream, fmt == 0, &launched);
+  if (fng == 0 || fng == 1) {
+    rc = rec_try_cluster<KS, 1>(a, stream, fng == 0, &launched);
     if (rc || launched) return rc;
   }
-  if (fmt == 0 || fmt == 2) {
-    rc = rec_try_cluster<2>(a, stream, fmt == 0, &launched);
-    if (rc || launched) return rc;
-  }
-  rc = rec_try_cluster<4>(a, stream, false, &launched);
+  rc = rec_try_cluster<KS, 2>(a, stream, false, &launched);
   if (rc || launched) return rc;
   return 1;
+}
+
+static int rec_launch_cluster(const RecArgs& a, cudaStream_t stream) {
+  switch (a.d.U) {
+    case 64: return rec_launch_cluster_ks<4>(a, stream);
+    case 128: return rec_launch_cluster_ks<8>(a, stream);
+    case 256: return rec_launch_cluster_ks<16>(a, stream);
+    case 512: return rec_launch_cluster_ks<32>(a, stream);
+    default: return 1;  // other widths use the L2-exchange kernel
+  }
 }
 
 static void rec_ws_layout(const plas_rec_desc& d, size_t* o_ctr, size_t* o_hx, size_t* total) {
@@ -687,7 +697,12 @@ extern "C" int plas_bilstm_rec_fwd(const plas_rec_desc* d, void* workspace, size
   a.G = d->U / upc;
   a.Bpad = a.n_groups * REC_ROWS;
 
-  // fast path: one thread-block cluster per (direction, group), h exchanged through DSMEM
+  // fastest path: tcgen05 with W_hh resident in tensor memory (rec_tc.cu)
+  {
+    const int rc = rec_tc_launch(*d, stream);
+    if (rc != 1) return rc;  // 1 = not eligible / not schedulable
+  }
+  // next: one thread-block cluster per (direction, group), mma.sync with W_hh resident in registers
   if (d->dtype == PLAS_BF16 && a.G <= 16 && !rec_force_legacy()) {
     int rc = rec_launch_cluster(a, stream);
     if (rc != 1) return rc;  // 1 = cluster shape not schedulable on this device: use the L2-exchange kernel

@@ -1,0 +1,405 @@
+// K3 (tensor-core path, bf16) -- BiLSTM recurrence with W_hh stationary in TENSOR MEMORY.
+//
+// Same contract as rec.cu (tf.nn.bidirectional_dynamic_rnn over LSTMCell, reference
+// las/ops.py:23-46, input projections hoisted into K2).  The step product is formulated transposed,
+//     Z^T [128 gate columns x NR utterances] = W_slice [128 x U] . h_{s-1}^T [U x NR],
+// so that one CTA's slice of W_hh (all four gates of 32 hidden units) is the M = 128 operand of
+// tcgen05.mma and can live in TMEM for the whole sequence (A-from-TMEM "TS" form: 128 lanes x U/2
+// packed-bf16 columns = 128 KB at U = 512), while the small, changing operand h_{s-1} (NR x U bf16,
+// K-major SWIZZLE_128B) sits in shared memory.  A step costs U/16 MMAs of max(M,128)*NR/256 cycles
+// (256 cycles at U = 512, NR = 16) instead of ~1100 cycles of mma.sync.
+//
+// The G = U/32 CTAs of one (direction, group of NR utterances) form a thread-block cluster; every
+// CTA pushes its NR x 32 slice of h_s straight into the (swizzled) operand tile of all G CTAs with
+// st.async, completing transaction bytes on each receiver's mbarrier -- h never leaves the chip and
+// there is no cluster barrier, no atomics and no fence on the step path (protocol as in rec.cu).
+//
+// Epilogue: thread (warp w, lane l) owns TMEM lane 32*(w%4)+l = gate column 4*unit+gate and half
+// of the utterances; a per-warp shared-memory transpose regroups (i,j,f,o) per (unit, utterance),
+// then the TF gate math (forget_bias 1.0, length masking, bw direction walking len-1-s) runs with
+// the cell state in registers.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+#include "../../include/plas.h"
+
+namespace plas {
+
+constexpr int RT_THREADS = 256;
+constexpr int RT_NACC = 4;    // independent accumulators (k-steps interleaved): back-to-back tcgen05.mma on ONE
+                              // accumulator serialise on its ~50-cycle latency, which dominates at N = 16..64
+
+struct RecTcArgs {
+  plas_rec_desc d;
+  const void* whh_tc;  // [ndir][G][128][U] bf16, row m = 4*unit_local + gate
+  int n_groups;
+  int dbg;  // timing experiments only (PLAS_REC_DBG): 1 = no exchange (wrong results), 2 = no gate math
+  int ss;   // 1: W slice resident in SHARED memory (SS form), 0: resident in TENSOR memory (TS form)
+};
+
+__device__ __forceinline__ uint32_t rt_mapa(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void rt_st_async_v4(uint32_t raddr, const uint4& v, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void rt_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <int KS, int NR>
+__global__ void __launch_bounds__(RT_THREADS, 1) rec_tc_kernel(RecTcArgs p) {
+  constexpr int U = KS * 16;
+  constexpr int G = U / 32;          // CTAs per cluster
+  constexpr int KB = U / 64;         // 64-wide k blocks of the h operand
+  constexpr int HR = NR / 2;         // utterances per warp half
+  constexpr int PP = NR / 8;         // (unit, utterance) pairs per thread
+  constexpr int TILE = NR * 128;     // bytes of one k block of the h operand
+  constexpr int HBUF = KB * TILE;    // bytes of one h operand buffer
+  constexpr int RT_ACOL0 = RT_NACC * NR;  // first TMEM column of the resident W slice (TS form)
+  constexpr uint32_t TMEM_COLS = (RT_ACOL0 + 8 * KS) <= 128 ? 128u : ((RT_ACOL0 + 8 * KS) <= 256 ? 256u : 512u);
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, NR);
+  extern __shared__ unsigned char rt_smem_raw[];
+  const plas_rec_desc& d = p.d;
+  const int B = d.B, T = d.T, ndir = d.ndir;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ci = blockIdx.x % G;     // rank inside the cluster
+  const int cl = blockIdx.x / G;
+  const int dir = cl / p.n_groups;
+  const int gi = cl % p.n_groups;
+  const int row0 = gi * NR;
+
+  const uint32_t raw = smem_u32(rt_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* smem = rt_smem_raw + (base - raw);
+  // [2][HBUF] h operand (UMMA K-major SWIZZLE_128B) | [8 warps][HR][33] f32 transpose | [NR][32] bf16 stage
+  // SS form: + [KB][128 rows x 128 B] W slice (UMMA K-major SWIZZLE_128B A operand) at the end
+  const uint32_t hbuf_u = base;
+  float* s_z = reinterpret_cast<float*>(smem + 2 * HBUF);
+  __nv_bfloat16* s_stage = reinterpret_cast<__nv_bfloat16*>(smem + 2 * HBUF + 8 * HR * 36 * 4);
+  constexpr int W_OFF = ((2 * HBUF + 8 * HR * 36 * 4 + NR * 32 * 2 + 1023) / 1024) * 1024;
+  const uint32_t wsm_u = base + W_OFF;
+  __shared__ int s_len[NR];
+  __shared__ int s_tmax;
+  __shared__ __align__(8) unsigned long long s_bar[3];  // h buffers 0/1, MMA completion
+  __shared__ uint32_t s_tmem;
+
+  if (tid < NR) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
+  __syncthreads();
+  if (tid == 0) {
+    int m = 0;
+    for (int r = 0; r < NR; ++r) m = max(m, s_len[r]);
+    s_tmax = m;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int Tg = s_tmax;
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t hbar[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
+  const uint32_t mbar = smem_u32(&s_bar[2]);
+  const uint32_t step_bytes = (uint32_t)(G * NR * 64);  // bytes every CTA receives per step
+  if (tid == 0) {
+    mbar_init(hbar[0], 1);
+    mbar_init(hbar[1], 1);
+    mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (Tg >= 2) mbar_expect_tx(hbar[0], step_bytes);  // h_0
+    if (Tg >= 3) mbar_expect_tx(hbar[1], step_bytes);  // h_1
+  }
+
+  // ---- resident W slice -> TMEM (lane m = gate column, 8*KS packed-bf16 columns) ---------------
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  if (warp < 4 && p.ss) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.whh_tc) +
+                                                       (((size_t)dir * G + ci) * 128 + tid) * U);
+    unsigned char* wdst = smem + W_OFF + (tid >> 3) * 1024 + (tid & 7) * 128;
+    for (int c = 0; c < U / 8; ++c)  // 16-byte chunk c of row tid -> k block c/8, swizzled chunk position
+      *reinterpret_cast<uint4*>(wdst + (size_t)(c >> 3) * 16384 + (((c & 7) ^ (tid & 7)) << 4)) = __ldg(wrow + c);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  } else if (warp < 4) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.whh_tc) +
+                                                       (((size_t)dir * G + ci) * 128 + tid) * U);
+#pragma unroll 4
+    for (int c0 = 0; c0 < 8 * KS; c0 += 8) {  // 8 columns = 16 bf16 = two uint4
+      const uint4 a = __ldg(wrow + c0 / 4), b = __ldg(wrow + c0 / 4 + 1);
+      const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      tmem_st8(tmem_base + lane_base + (uint32_t)(RT_ACOL0 + c0), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+
+  // ---- per-thread (unit, utterance) pairs ---------------------------------------------------------
+  // gate-math mapping: lane -> unit u8 = lane/4 of this warp's 8 units, utterances j, j+4, ... of the
+  // warp half (w/4)
+  const int u8 = lane >> 2, jq = lane & 3;
+  const int unit = ci * 32 + (warp & 3) * 8 + u8;
+  const int half0 = (warp >> 2) * HR;
+  const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+  const int NX = ndir * 4 * U;
+  int len_p[PP];
+  const __nv_bfloat16* xrow[PP];
+  float c_state[PP], h_state[PP];
+  uint2 xp[PP];
+#pragma unroll
+  for (int i = 0; i < PP; ++i) {
+    const int r = half0 + jq + 4 * i;
+    len_p[i] = s_len[r];
+    xrow[i] = xproj + ((size_t)min(row0 + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
+    c_state[i] = 0.f;
+    h_state[i] = 0.f;
+    xp[i] = make_uint2(0u, 0u);
+    if (0 < len_p[i]) {
+      const int t = dir ? (len_p[i] - 1) : 0;
+      xp[i] = __ldg(reinterpret_cast<const uint2*>(xrow[i] + (size_t)t * NX));
+    }
+  }
+  float* zt = s_z + (size_t)warp * HR * 36;  // this warp's transpose tile [HR][36] (32 columns + pad)
+
+  tc_fence_before();
+  __syncthreads();
+  // every CTA of the cluster must be running, with its mbarriers initialised, before anyone pushes
+  rt_cluster_sync();
+  tc_fence_after();
+
+  uint32_t mma_parity = 0;
+  for (int s = 0; s < Tg; ++s) {
+    const int bsel = (s - 1) & 1;
+    if (s > 0) {
+      if (!(p.dbg & 1)) mbar_wait(hbar[bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
+      if (warp == 0) {
+        if (elect_one()) {
+          if (s + 1 <= Tg - 2 && !(p.dbg & 1)) mbar_expect_tx(hbar[bsel], step_bytes);  // re-arm for h_{s+1}
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.async data -> tensor-core reads
+          tc_fence_after();
+          const uint32_t hb = hbuf_u + (uint32_t)(bsel * HBUF);
+          if (p.ss) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint64_t bdesc = umma_smem_desc(hb + (uint32_t)((ks >> 2) * TILE)) + (uint64_t)(2 * (ks & 3));
+              const uint64_t adesc = umma_smem_desc(wsm_u + (uint32_t)((ks >> 2) * 16384)) + (uint64_t)(2 * (ks & 3));
+              umma_bf16(tmem_base + (uint32_t)((ks % RT_NACC) * NR), adesc, bdesc, IDESC, ks >= RT_NACC ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint64_t bdesc = umma_smem_desc(hb + (uint32_t)((ks >> 2) * TILE)) + (uint64_t)(2 * (ks & 3));
+              umma_bf16_ts(tmem_base + (uint32_t)((ks % RT_NACC) * NR), tmem_base + (uint32_t)(RT_ACOL0 + 8 * ks), bdesc,
+                           IDESC, ks >= RT_NACC ? 1u : 0u);
+            }
+          }
+          umma_commit(mbar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(mbar, mma_parity);
+      mma_parity ^= 1u;
+      tc_fence_after();
+      // accumulator: lane = gate column, column = utterance; this warp half reads HR columns
+#pragma unroll
+      for (int c0 = 0; c0 < HR; c0 += 8) {
+        uint32_t r[RT_NACC][8];
+#pragma unroll
+        for (int a = 0; a < RT_NACC; ++a) tmem_ld8(tmem_base + lane_base + (uint32_t)(a * NR + half0 + c0), r[a]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          zt[(c0 + j) * 36 + lane] = (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) +
+                                     (__uint_as_float(r[2][j]) + __uint_as_float(r[3][j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+      const int rl = jq + 4 * i;  // utterance inside the warp half
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s > 0) z = *reinterpret_cast<const float4*>(zt + rl * 36 + 4 * u8);
+      const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[i].x);
+      const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[i].y);
+      float cn, hn;
+      if (p.dbg & 2) {
+        cn = z.x + __low2float(x01) + z.z + __low2float(x23);
+        hn = z.y + __high2float(x01) + z.w + __high2float(x23);
+      } else {
+        lstm_gates_fast(z.x + __low2float(x01), z.y + __high2float(x01), z.z + __low2float(x23),
+                        z.w + __high2float(x23), c_state[i], cn, hn);
+      }
+      if (s < len_p[i]) {
+        c_state[i] = cn;
+        h_state[i] = bf16_round(hn);
+      }
+      s_stage[(half0 + rl) * 32 + (warp & 3) * 8 + u8] = __float2bfloat16_rn(h_state[i]);
+      // prefetch the next gate pre-activations (consumed one full step later)
+      xp[i] = make_uint2(0u, 0u);
+      if (s + 1 < len_p[i]) {
+        const int t = dir ? (len_p[i] - 2 - s) : (s + 1);
+        xp[i] = __ldg(reinterpret_cast<const uint2*>(xrow[i] + (size_t)t * NX));
+      }
+    }
+    __syncthreads();
+    // publish the staged NR x 32 slice: (a) into the swizzled h operand of every CTA of the cluster
+    // (not needed after the last step), (b) for active rows to the [B,T,ndir*U] layer output in HBM
+    if (s + 1 < Tg && !(p.dbg & 1)) {
+      const uint32_t dst_buf = hbuf_u + (uint32_t)((s & 1) * HBUF) + (uint32_t)((ci >> 1) * TILE);
+      const uint32_t bar_l = hbar[s & 1];
+#pragma unroll
+      for (int j = 0; j < (G * NR * 4 + RT_THREADS - 1) / RT_THREADS; ++j) {
+        const int idx = tid + j * RT_THREADS;
+        if (idx < G * NR * 4) {
+          const int rank = idx / (NR * 4), chunk = idx % (NR * 4);
+          const int r = chunk >> 2, ch = chunk & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+          const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
+          const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+          rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
+        }
+      }
+    }
+    if (tid < NR * 4) {
+      const int r = tid >> 2, ch = tid & 3;
+      const int b = row0 + r;
+      const int len = s_len[r];
+      if (b < B && s < len) {
+        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+        const int t = dir ? (len - 1 - s) : s;
+        __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
+        *reinterpret_cast<uint4*>(odst) = v;
+      }
+    }
+    __syncthreads();  // s_stage / the transpose tiles are rewritten by the next step
+  }
+#pragma unroll
+  for (int i = 0; i < PP; ++i) {
+    const int b = row0 + half0 + jq + 4 * i;
+    if (b < B) {
+      d.c_final[((size_t)dir * B + b) * U + unit] = c_state[i];
+      d.h_final[((size_t)dir * B + b) * U + unit] = h_state[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int KS, int NR>
+static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, bool* launched) {
+  const plas_rec_desc& d = a.d;
+  constexpr int U = KS * 16, G = U / 32;
+  *launched = false;
+  // > 114 KB of shared memory: at most one CTA per SM, so the TMEM allocation can never contend
+  size_t smem = 1024 + (size_t)2 * (U / 64) * NR * 128 + (size_t)8 * (NR / 2) * 36 * 4 + (size_t)NR * 32 * 2;
+  if (a.ss) smem = ((smem + 1023) / 1024) * 1024 + (size_t)(U / 64) * 16384;
+  if (smem > 227 * 1024) return PLAS_OK;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  auto fn = rec_tc_kernel<KS, NR>;
+  PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (G > 8) PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  a.n_groups = (d.B + NR - 1) / NR;
+  const int clusters = d.ndir * a.n_groups;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * G));
+  cfg.blockDim = dim3(RT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg);
+  if (getenv("PLAS_DEBUG"))
+    fprintf(stderr, "[plas] rec tc path: U=%d NR=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", U, NR, G,
+            clusters, max_clusters, cudaGetErrorString(qe), smem);
+  if (qe != cudaSuccess || max_clusters < 1) {
+    (void)cudaGetLastError();
+    return PLAS_OK;
+  }
+  if (must_fit_one_wave && clusters > max_clusters) return PLAS_OK;
+  PLAS_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+  *launched = true;
+  return PLAS_OK;
+}
+
+template <int KS>
+static int rec_tc_launch_ks(const RecTcArgs& a, cudaStream_t stream) {
+  bool launched = false;
+  const char* force = getenv("PLAS_REC_NR");
+  const int fnr = force ? atoi(force) : 0;
+  int rc;
+  if (fnr == 0 || fnr == 16) {
+    rc = rec_tc_try<KS, 16>(a, stream, fnr == 0, &launched);
+    if (rc || launched) return rc;
+  }
+  if (fnr == 0 || fnr == 32) {
+    rc = rec_tc_try<KS, 32>(a, stream, fnr == 0, &launched);
+    if (rc || launched) return rc;
+  }
+  rc = rec_tc_try<KS, 64>(a, stream, false, &launched);
+  if (rc || launched) return rc;
+  return 1;
+}
+
+// Returns PLAS_OK after a launch, 1 when the shape is not eligible (caller falls back), <0 on error.
+int rec_tc_launch(const plas_rec_desc& d, cudaStream_t stream) {
+  const char* force = getenv("PLAS_REC_IMPL");
+  if (force && strcmp(force, "tc") != 0) return 1;
+  if (d.dtype != PLAS_BF16 || !d.whh_tc) return 1;
+  RecTcArgs a;
+  a.d = d;
+  a.whh_tc = d.whh_tc;
+  a.n_groups = 0;
+  a.dbg = getenv("PLAS_REC_DBG") ? atoi(getenv("PLAS_REC_DBG")) : 0;
+  a.ss = getenv("PLAS_REC_SS") ? atoi(getenv("PLAS_REC_SS")) : 0;
+  switch (d.U) {
+    case 64: return rec_tc_launch_ks<4>(a, stream);
+    case 128: return rec_tc_launch_ks<8>(a, stream);
+    case 256: return rec_tc_launch_ks<16>(a, stream);
+    case 512: return rec_tc_launch_ks<32>(a, stream);
+    default: return 1;
+  }
+}
+
+}  // namespace plas

@@ -50,8 +50,11 @@ class ListenerWeights:
                 whh = packing.pack_rec_bf16(kernels, din, U)
             else:
                 whh = packing.pack_rec_f32(kernels, din, U, self.upc)
+            whh_tc = None
+            if precision == "bf16" and U in (64, 128, 256, 512):
+                whh_tc = torch.from_numpy(packing.pack_rec_tc(kernels, din, U)).to(device=device, dtype=dt).contiguous()
             self.layers.append(dict(
-                din=din, k_pad=k_pad,
+                din=din, k_pad=k_pad, whh_tc=whh_tc,
                 wt=torch.from_numpy(wt).to(device=device, dtype=dt).contiguous(),
                 bias=torch.from_numpy(bs).to(device),
                 whh=torch.from_numpy(whh).to(device=device, dtype=dt).contiguous()))
@@ -85,6 +88,7 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out):
     d.xproj, d.whh, d.lengths, d.out = xproj.data_ptr(), lw["whh"].data_ptr(), lengths.data_ptr(), out.data_ptr()
     d.out_batch_stride = out.stride(0)
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
+    d.whh_tc = lw["whh_tc"].data_ptr() if lw.get("whh_tc") is not None else None
     need = L.plas_rec_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
     with _lib.stage("rec"):

@@ -83,6 +83,17 @@ def pack_rec_bf16(kernels, din, U):
     return out
 
 
+def pack_rec_tc(kernels, din, U):
+    """Recurrent weights for rec_tc_kernel (TMEM-resident A operand): [ndir][U/32][128][U], row
+    m = 4*unit_local + gate of CTA ci holds W_h[:, gate*U + ci*32 + unit_local] (K-major)."""
+    cols = unit_major_cols(U)
+    out = np.zeros((len(kernels), U // 32, 128, U), np.float32)
+    for d, k in enumerate(kernels):
+        wh = np.asarray(k[din:], np.float32)  # [U, 4U]
+        out[d] = wh[:, cols].T.reshape(U // 32, 128, U)
+    return out
+
+
 def pack_cell_f32(w_rows, Ud):
     """Decoder LSTM rows (non-embedding part) for decoder_kernel<float>: [Ud/4][K][16], col = 4*ul+gate."""
     K = w_rows.shape[0]

@@ -23,9 +23,18 @@ def probe(B, U, T, impl):
     print(f"B={B:4d} U={U:4d} T={T:5d} impl={impl:8s} rec {ms:8.3f} ms  -> {ms*1e3/T:6.2f} us/step", flush=True)
 
 if __name__ == "__main__":
-    os.environ["PLAS_DEBUG"] = "1"
-    for impl, mt in (("cluster", "0"), ("cluster", "1"), ("cluster", "2"), ("cluster", "4"), ("l2", "0")):
-        os.environ["PLAS_REC_MT"] = mt
-        for (B, U, T) in [(16, 512, 400), (64, 512, 400), (128, 512, 400), (64, 256, 400), (64, 128, 400)]:
-            print("MT", mt, end=" ")
-            probe(B, U, T, impl)
+    for ss in ("0", "1"):
+        os.environ["PLAS_REC_SS"] = ss
+        for dbg in ("0", "3"):
+            os.environ["PLAS_REC_DBG"] = dbg
+            for nr in ("16", "32"):
+                os.environ["PLAS_REC_NR"] = nr
+                for (B, U, T) in [(int(nr), 512, 400), (int(nr), 128, 400)]:
+                    print("ss", ss, "dbg", dbg, "NR", nr, end=" ")
+                    probe(B, U, T, "tc")
+    os.environ["PLAS_REC_DBG"] = "0"
+    os.environ["PLAS_REC_NR"] = "0"
+    for ss in ("0", "1"):
+        os.environ["PLAS_REC_SS"] = ss
+        print("ss", ss, end=" ")
+        probe(64, 512, 400, "tc")

@@ -41,7 +41,7 @@ def test_listener_parity(cfg):
     (out, olen, state), (ref_out, ref_len, ref_state) = _run(*cfg)
     np.testing.assert_array_equal(olen, ref_len)
     assert out.shape == ref_out.shape
-    fro = 1e-3 if cfg[5] <= 3 else 2e-3  # deep bf16 stacks: see tests/util.assert_parity
+    fro = 2e-3  # bf16 recurrent stacks: half a bf16 epsilon, see tests/util.assert_parity
     assert_parity(out, ref_out, precision, "encoder_out", bf16_fro=fro)
     for b in range(out.shape[0]):
         assert (out[b, olen[b]:] == 0).all(), "outputs past the reduced length must be zero"
