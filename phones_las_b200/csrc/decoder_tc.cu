@@ -46,6 +46,7 @@ struct alignas(64) DecTcArgs {
   int n_stages;                  // 16 KB stages of the attention ring
   int n_stages_a;                // stages of the LSTM-phase ring (8 KB when B <= 64, else 16 KB)
   int stage_a;                   // bytes per LSTM-phase stage (= TMA box bytes)
+  int cluster;                   // CTAs per cluster sharing the activation stream by TMA multicast (1, 2 or 4)
   int off_w[4], off_wq, off_ring, off_misc;  // byte offsets from the 1024-aligned smem base
   int tm_pad;
 };
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < DT_MAX_STAGES; ++s) {
       mbar_init(fullA(s), 1);
-      mbar_init(emptyA(s), 1);
+      mbar_init(emptyA(s), (uint32_t)p.cluster);  // every CTA of the cluster must have consumed the stage
       mbar_init(fullB(s), 1);
       mbar_init(emptyB(s), 8);
     }
@@ -170,8 +171,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   fence_proxy_async();  // the resident weights were written with generic stores, UMMA reads them via the async proxy
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1)  // peers' mbarriers must be initialised before anyone multicasts into / signals them
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int CL = p.cluster;
+  const int crank = blockIdx.x % CL;
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   // ---- replicated decode state ----------------------------------------------------------------
   const int row = tid - 128;                      // epilogue threads (warps 4..7) own batch row `row`
@@ -197,18 +203,44 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   unsigned epoch = 0;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, 16);
 
+  // optional phase timers (PLAS_DEBUG): 0 prologue, 1..4 LSTM layers (incl. barrier), 5 query, 6 attention
+  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  __shared__ unsigned long long s_tphase;          // start of the current phase (thread 0's last stamp)
+  unsigned long long tfine[4] = {0, 0, 0, 0};      // layer-0 detail: first box landed, MMAs issued, accumulator ready, epilogue done
+  const bool fine = p.dbg != nullptr && blockIdx.x == 0;
+  auto fine_stamp = [&](int slot) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    tfine[slot] += now - *(volatile unsigned long long*)&s_tphase;
+  };
+  unsigned long long tlast = 0;
+  const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  auto stamp = [&](int slot) {
+    if (timing) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      tacc[slot] += now - tlast;
+      tlast = now;
+      *(volatile unsigned long long*)&s_tphase = now;
+    }
+  };
+  if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
+
   // one [128 x K] x [K x 16] product: TMA producer (warp 8), MMA issuer (warp 0), result in TMEM cols 0..15
   // Every CTA reads the SAME activation matrix; walking the k blocks from a per-CTA offset keeps the
   // 128+ CTAs from hammering the same few L2 lines in lock step.
-  auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int nkb) {
-    const int kb0 = (int)(((long long)blockIdx.x * nkb) / gridDim.x);
+  auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int nkb, bool detail) {
+    const int kb0 = (int)(((long long)(blockIdx.x / CL) * CL * nkb) / gridDim.x);  // same order inside a cluster
     if (warp == 8) {
       if (elect_one()) {
         for (int i = 0; i < nkb; ++i) {
           const int kb = (kb0 + i) % nkb;
           mbar_wait(emptyA(prodA.stage), prodA.phase ^ 1u);
           mbar_expect_tx(fullA(prodA.stage), (uint32_t)STA);
-          tma_load_2d(ring + prodA.stage * STA, tm, kb * 64, 0, fullA(prodA.stage));
+          if (CL == 1)
+            tma_load_2d(ring + prodA.stage * STA, tm, kb * 64, 0, fullA(prodA.stage));
+          else if (i % CL == crank)  // one L2 read feeds all CL CTAs
+            tma_load_2d_mc(ring + prodA.stage * STA, tm, kb * 64, 0, fullA(prodA.stage), cmask);
           prodA.advance(NSTA);
         }
       }
@@ -219,34 +251,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         for (int i = 0; i < nkb; ++i) {
           const int kb = (kb0 + i) % nkb;
           mbar_wait(fullA(consA.stage), consA.phase);
+          if (detail && i == 0) fine_stamp(0);
           tc_fence_after();
           const uint64_t adesc = umma_smem_desc(ring + consA.stage * STA);
           const uint64_t bdesc = umma_smem_desc(w_smem + kb * 2048);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (i | k) != 0 ? 1u : 0u);
-          umma_commit(emptyA(consA.stage));
+          if (CL == 1) umma_commit(emptyA(consA.stage));
+          else umma_commit_mc(emptyA(consA.stage), cmask);
           consA.advance(NSTA);
         }
         umma_commit(tfull);
+        if (detail) fine_stamp(1);
       }
       __syncwarp();
     }
   };
-
-  // optional phase timers (PLAS_DEBUG): 0 prologue, 1..4 LSTM layers (incl. barrier), 5 query, 6 attention
-  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  unsigned long long tlast = 0;
-  const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-  auto stamp = [&](int slot) {
-    if (timing) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      tacc[slot] += now - tlast;
-      tlast = now;
-    }
-  };
-  if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
 
   int t = 0;
   while (true) {
@@ -295,9 +316,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     for (int l = 0; l < L; ++l) {
       if (cell_cta) {
         const int K = Kl[l];
-        gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], K / 64);
+        gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], K / 64, fine && l == 0);
         if (row_thread) {
           mbar_wait(tfull, acc_parity);
+          if (fine && l == 0 && tid == 128) fine_stamp(2);
           tc_fence_after();
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16), r);
@@ -337,6 +359,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
             }
           }
           tc_fence_before();
+          if (fine && l == 0 && tid == 128) fine_stamp(3);
         }
         acc_parity ^= 1u;
       }
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     // ---------------- query layer (bahdanau): q = h_top . W_q ----------------
     if (bahdanau) {
       if (q_cta) {
-        gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, Ud / 64);
+        gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, Ud / 64, false);
         if (row_thread) {
           mbar_wait(tfull, acc_parity);
           tc_fence_after();
@@ -608,6 +631,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   }
   if (timing)
     for (int i = 0; i < 8; ++i) p.dbg[i] = tacc[i];
+  if (fine) {  // written by the role threads that took the stamps (others hold zeros)
+    if (warp == 0 && tfine[0]) { p.dbg[8] = tfine[0]; p.dbg[9] = tfine[1]; }
+    if (tid == 128) { p.dbg[10] = tfine[2]; p.dbg[11] = tfine[3]; }
+  }
   if (blockIdx.x == 0 && tid == 0) *d.n_steps = t;
   tc_fence_before();
   __syncthreads();
@@ -622,7 +649,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 struct DecTcPlan {
   bool ok;
-  int n_stages, n_stages_a, stage_a, tm_pad;
+  int n_stages, n_stages_a, stage_a, tm_pad, cluster;
   int off_w[4], off_wq, off_ring, off_misc;
   size_t smem;
   size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_bar, ws_off_dbg, ws_total;
@@ -667,7 +694,7 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   pl.ws_off_q = take((size_t)d.B * d.Ud * 4);
   pl.ws_off_align = take((size_t)d.B * d.Tm * 4);
   pl.ws_off_bar = take(4);
-  pl.ws_off_dbg = take(64);
+  pl.ws_off_dbg = take(128);
   pl.ws_total = w;
   pl.ok = true;
   return pl;
@@ -707,6 +734,7 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   a.n_stages = pl.n_stages;
   a.n_stages_a = pl.n_stages_a;
   a.stage_a = pl.stage_a;
+  a.cluster = 1;
   a.off_wq = pl.off_wq;
   a.off_ring = pl.off_ring;
   a.off_misc = pl.off_misc;
@@ -734,17 +762,53 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   int grid = num_sms();
   const int want = (d.Ud / 4 > 2 * d.B) ? d.Ud / 4 : 2 * d.B;
   if (grid > want) grid = want;
-  if (getenv("PLAS_DEBUG"))
-    fprintf(stderr, "[plas] decoder tc path: grid=%d stages=%d (lstm ring %d x %d B) smem=%zu\n", grid, pl.n_stages,
-            pl.n_stages_a, pl.stage_a, pl.smem);
-  void* args[] = {(void*)&a};
-  PLAS_CUDA(cudaLaunchCooperativeKernel((const void*)decoder_tc_kernel, dim3(grid), dim3(DT_THREADS), args, pl.smem, stream));
+  // TMA multicast: clusters of 4 (or 2) consecutive CTAs share every activation box.  All CTAs of a cluster
+  // must take part in the LSTM phases, so the grid is trimmed to the slice count.
+  int cl = 4;
+  if (const char* e = getenv("PLAS_DEC_CL")) cl = atoi(e);
+  const int nsl = d.Ud / 4, nq = d.Ud / 16;
+  while (cl > 1 && (nsl % cl != 0 || nq % cl != 0 || nsl > num_sms())) cl >>= 1;
+  cudaError_t le = cudaErrorUnknown;
+  if (cl > 1) {
+    a.cluster = cl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nsl);
+    cfg.blockDim = dim3(DT_THREADS);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    int max_clusters = 0;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, decoder_tc_kernel, &cfg);
+    if (qe == cudaSuccess && max_clusters * cl >= nsl) le = cudaLaunchKernelEx(&cfg, decoder_tc_kernel, a);
+    if (getenv("PLAS_DEBUG"))
+      fprintf(stderr, "[plas] decoder tc path: cluster=%d grid=%d max_active_clusters=%d (%s) launch: %s\n", cl, nsl,
+              max_clusters, cudaGetErrorString(qe), cudaGetErrorString(le));
+    if (le != cudaSuccess) (void)cudaGetLastError();
+  }
+  if (le != cudaSuccess) {
+    a.cluster = 1;
+    if (getenv("PLAS_DEBUG"))
+      fprintf(stderr, "[plas] decoder tc path: grid=%d stages=%d (lstm ring %d x %d B) smem=%zu\n", grid, pl.n_stages,
+              pl.n_stages_a, pl.stage_a, pl.smem);
+    void* args[] = {(void*)&a};
+    PLAS_CUDA(cudaLaunchCooperativeKernel((const void*)decoder_tc_kernel, dim3(grid), dim3(DT_THREADS), args, pl.smem, stream));
+  }
   if (a.dbg) {  // debug only: synchronises
-    unsigned long long h[8];
+    unsigned long long h[16];
     PLAS_CUDA(cudaStreamSynchronize(stream));
     PLAS_CUDA(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
     fprintf(stderr, "[plas] decoder tc phase time (us, CTA 0): prologue %.1f  lstm %.1f %.1f %.1f %.1f  query %.1f  attention %.1f (own work %.1f)\n",
             h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, (h[6] + h[7]) / 1e3, h[7] / 1e3);
+    fprintf(stderr, "[plas]   layer 0 detail (us after phase start, summed): first box %.1f  MMAs issued %.1f  accumulator ready %.1f  epilogue done %.1f\n",
+            h[8] / 1e3, h[9] / 1e3, h[10] / 1e3, h[11] / 1e3);
   }
   return PLAS_OK;
 }

@@ -103,3 +103,42 @@ def test_pack_cell_layouts():
                 np.testing.assert_allclose(part[:, col], ref[:, g * Ud + u], rtol=1e-4, atol=1e-5)
     pu = packing.pack_unit_major(rows, Ud)
     np.testing.assert_array_equal(pu[:, 4 * 5 + 3], rows[:, 3 * Ud + 5])
+
+
+def test_swizzle128_tiles_roundtrip():
+    """Element (row r, k) of a [16, K] operand must sit at byte kb*2048 + r*128 + ((c ^ (r & 7)) << 4) + (k & 7)*2."""
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((16, 192)).astype(np.float32)
+    t = packing.swizzle128_tiles(w)  # [3][1024]
+    for r in range(16):
+        for k in range(192):
+            kb, c, e = k // 64, (k % 64) // 8, k % 8
+            pos = r * 64 + ((c ^ (r & 7)) * 8) + e
+            assert t[kb, pos] == w[r, k]
+
+
+def test_pack_cell_tc_and_query_tc():
+    rng = np.random.default_rng(1)
+    Ud, K = 64, 128
+    rows = rng.standard_normal((K, 4 * Ud)).astype(np.float32)
+    t = packing.pack_cell_tc(rows, Ud)
+    assert t.shape == (Ud // 4, K // 64, 1024)
+    s, ul, gate, k = 5, 2, 3, 77   # tile row 4*ul+gate of slice s holds TF column gate*Ud + 4*s+ul
+    r = 4 * ul + gate
+    kb, c, e = k // 64, (k % 64) // 8, k % 8
+    assert t[s, kb, r * 64 + ((c ^ (r & 7)) * 8) + e] == rows[k, gate * Ud + 4 * s + ul]
+    wq = rng.standard_normal((Ud, Ud)).astype(np.float32)
+    tq = packing.pack_query_tc(wq, Ud)
+    s, r, k = 2, 9, 40
+    kb, c, e = k // 64, (k % 64) // 8, k % 8
+    assert tq[s, kb, r * 64 + ((c ^ (r & 7)) * 8) + e] == wq[k, 16 * s + r]
+
+
+def test_pack_rec_tc_rows():
+    rng = np.random.default_rng(2)
+    U, din = 64, 5
+    kernels = [rng.standard_normal((din + U, 4 * U)).astype(np.float32) for _ in range(2)]
+    t = packing.pack_rec_tc(kernels, din, U)
+    assert t.shape == (2, U // 32, 128, U)
+    d, ci, ul, gate, k = 1, 1, 7, 2, 33
+    assert t[d, ci, 4 * ul + gate, k] == kernels[d][din + k, gate * U + ci * 32 + ul]
