@@ -336,7 +336,9 @@ def ours(args):
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                roofline["traffic"] = json.load(f).get(dom)
+                tj = json.load(f)
+            roofline["traffic"] = tj.get(dom)
+            roofline["traffic_note"] = tj.get("_note")
         except Exception:
             pass
 

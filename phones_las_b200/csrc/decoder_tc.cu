@@ -762,9 +762,11 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   int grid = num_sms();
   const int want = (d.Ud / 4 > 2 * d.B) ? d.Ud / 4 : 2 * d.B;
   if (grid > want) grid = want;
-  // TMA multicast: clusters of 4 (or 2) consecutive CTAs share every activation box.  All CTAs of a cluster
-  // must take part in the LSTM phases, so the grid is trimmed to the slice count.
-  int cl = 4;
+  // Optional TMA multicast (PLAS_DEC_CL=2|4): clusters of consecutive CTAs share every activation box, which
+  // cuts the L2 reads of the LSTM phases by the cluster size.  Measured at c2: no gain (15.5 us -> 17.8 us for
+  // layer 0) -- the phases are bound by bytes DELIVERED to each SM (~3.4 TB/s aggregate), not by L2 reads --
+  // and ncu cannot replay cooperative cluster launches, so it is off by default.
+  int cl = 1;
   if (const char* e = getenv("PLAS_DEC_CL")) cl = atoi(e);
   const int nsl = d.Ud / 4, nq = d.Ud / 16;
   while (cl > 1 && (nsl % cl != 0 || nq % cl != 0 || nsl > num_sms())) cl >>= 1;

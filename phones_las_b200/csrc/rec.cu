@@ -564,6 +564,7 @@ static int rec_upc(int dtype, int U) {
   if (dtype == PLAS_BF16) return 32;
   int upc = 32;
   while (upc > 8 && (size_t)U * 4 * upc * 4 > 160 * 1024) upc >>= 1;
+  while (upc > 4 && U % upc != 0) upc >>= 1;  // narrow layers: U = 16, 24, ...
   return upc;
 }
 

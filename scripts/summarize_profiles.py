@@ -1,0 +1,56 @@
+"""Turn gpurun_out/{launches.csv, prof_*.ncu-rep} into the tracked summaries under profiles/ (run on the CPU box)."""
+import collections, csv, io, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles"); SRC = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(OUT, exist_ok=True)
+
+# launch list -> per-kernel totals and shares
+lines = [l for l in open(os.path.join(SRC, "launches.csv")) if not l.startswith("==")]
+agg = collections.OrderedDict()
+for row in csv.DictReader(lines):
+    try: v = float(row["Metric Value"])
+    except ValueError: continue
+    a = agg.setdefault(row["Kernel Name"], [0, 0.0, row["Grid Size"], row["Block Size"]]); a[0] += 1; a[1] += v
+tot = sum(a[1] for a in agg.values())
+with open(os.path.join(OUT, f"{tag}_launches_summary.txt"), "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none over `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n")
+    f.write("# (5 passes of the hot path; per-launch times are cold-cache and serialised: compare SHARES)\n")
+    f.write(f"{'kernel':80s} {'launches':>8s} {'total_ms':>10s} {'share':>7s}  grid block\n")
+    for k, (n, t, g, b) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        f.write(f"{k[:80]:80s} {n:8d} {t/1e6:10.3f} {t/tot:7.3f}  {g} {b}\n")
+import shutil
+shutil.copy(os.path.join(SRC, "launches.csv"), os.path.join(OUT, f"{tag}_launches.csv"))
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__cluster_size" , "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic"]
+traffic = {}
+fam = {"rec_tc_kernel": "rec", "decoder_tc_kernel": "decoder", "gemm_bf16_tcgen05_kernel": "inproj_gemm", "fe_spectral_kernel": "frontend"}
+for k, name in fam.items():
+    rep = os.path.join(SRC, f"prof_{k}.ncu-rep")
+    if not os.path.exists(rep): continue
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    r = list(csv.reader(io.StringIO(raw)))
+    hdr, units, row = r[0], r[1], r[2]
+    vals = {h: (v, u) for h, u, v in zip(hdr, units, row)}
+    with open(os.path.join(OUT, f"{tag}_ncu_{k}.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{k} -s 4 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
+        f.write(f"# kernel: {vals.get('Kernel Name', ('?',))[0]}\n")
+        for key in KEYS:
+            for h in hdr:
+                if h == key or h.endswith(key):
+                    f.write(f"{h:90s} {vals[h][0]:>16s} {vals[h][1]}\n")
+        stalls = sorted(((float(v[0]), h) for h, v in vals.items() if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and v[0] not in ("", "n/a")), reverse=True)[:8]
+        f.write("# top warp-stall reasons (per issue-active):\n")
+        for v, h in stalls: f.write(f"{h:90s} {v:16.3f}\n")
+    def num(key):
+        v, u = vals.get(key, ("nan", ""))
+        x = float(v.replace(",", ""))
+        return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+    traffic[name] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+print(open(os.path.join(OUT, f"{tag}_launches_summary.txt")).read()[:3000]); print(traffic)
