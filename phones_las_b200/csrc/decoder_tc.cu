@@ -46,7 +46,8 @@ struct alignas(64) DecTcArgs {
   int n_stages;                  // 16 KB stages of the attention ring
   int n_stages_a;                // stages of the LSTM-phase ring (8 KB when B <= 64, else 16 KB)
   int stage_a;                   // bytes per LSTM-phase stage (= TMA box bytes)
-  int cluster;                   // CTAs per cluster sharing the activation stream by TMA multicast (1, 2 or 4)
+  int ksplit;                    // 1, or 4: clusters of 4 CTAs split K of the LSTM products (DSMEM reduction)
+  int off_part;                  // ksplit: [4 senders][128 rows][16] f32 partial sums (inside the ring's tail)
   int off_w[4], off_wq, off_ring, off_misc;  // byte offsets from the 1024-aligned smem base
   int tm_pad;
 };
@@ -54,6 +55,16 @@ struct alignas(64) DecTcArgs {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cl(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4_cl(uint32_t raddr, const uint4 v, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -113,6 +124,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   auto fullB = [&](int s) { return misc_u + 8u * (2 * DT_MAX_STAGES + s); };
   auto emptyB = [&](int s) { return misc_u + 8u * (3 * DT_MAX_STAGES + s); };
   const uint32_t tfull = misc_u + 8u * (4 * DT_MAX_STAGES);
+  const uint32_t pbar = misc_u + 8u * (4 * DT_MAX_STAGES) + 16u;  // K-split partial sums landed (tx bytes)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (4 * DT_MAX_STAGES + 1));
   int* s_ids = reinterpret_cast<int*>(misc + 576);               // [128]  (barriers + TMEM slot end at 528)
   float* s_bias = reinterpret_cast<float*>(misc + 1536);         // [4][16]
@@ -135,12 +147,26 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   for (int l = 0; l < 4; ++l) Kl[l] = (l == 0) ? (D + Ud) : 2 * Ud;
 
   // ---- one-time setup: resident weight slices, barriers, TMEM ------------------------------
+  const int KSP = p.ksplit;
+  const int crank = blockIdx.x % KSP;         // rank inside the K-split cluster
+  const int cbase = blockIdx.x - crank;       // first slice of the cluster
   if (cell_cta) {
     for (int l = 0; l < L; ++l) {
-      const size_t bytes = (size_t)(Kl[l] / 64) * 2048;
-      const uint4* src = reinterpret_cast<const uint4*>(p.w_tc[l] + (size_t)slice * bytes);
+      const int nkb = Kl[l] / 64;
       uint4* dst = reinterpret_cast<uint4*>(smem + p.off_w[l]);
-      for (int i = tid; i < (int)(bytes / 16); i += DT_THREADS) dst[i] = __ldg(src + i);
+      if (KSP == 1) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.w_tc[l] + (size_t)slice * nkb * 2048);
+        for (int i = tid; i < nkb * 128; i += DT_THREADS) dst[i] = __ldg(src + i);
+      } else {
+        // K quarter `crank` of the 4 slices of this cluster: per local k block a 64-row UMMA B tile, which in the
+        // 128B-swizzled K-major layout is just the four 16-row slice tiles back to back
+        const int nloc = nkb / KSP;
+        for (int i = tid; i < nloc * KSP * 128; i += DT_THREADS) {
+          const int w16 = i & 127, j = (i >> 7) % KSP, lkb = i / (128 * KSP);
+          const uint4* src = reinterpret_cast<const uint4*>(p.w_tc[l] + ((size_t)(cbase + j) * nkb + crank * nloc + lkb) * 2048);
+          dst[i] = __ldg(src + w16);
+        }
+      }
       if (tid < 16) s_bias[l * 16 + tid] = d.b_cell[l][slice * 16 + tid];
     }
   }
@@ -155,29 +181,27 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < DT_MAX_STAGES; ++s) {
       mbar_init(fullA(s), 1);
-      mbar_init(emptyA(s), (uint32_t)p.cluster);  // every CTA of the cluster must have consumed the stage
+      mbar_init(emptyA(s), 1);
       mbar_init(fullB(s), 1);
       mbar_init(emptyB(s), 8);
     }
     mbar_init(tfull, 1);
+    mbar_init(pbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int l = 0; l < L; ++l)
       for (int q2 = 0; q2 < 2; ++q2) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX[l][q2]) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_proxy_async();  // the resident weights were written with generic stores, UMMA reads them via the async proxy
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1)  // peers' mbarriers must be initialised before anyone multicasts into / signals them
+  if (KSP > 1)  // peers' mbarriers must be initialised before anyone signals them
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int CL = p.cluster;
-  const int crank = blockIdx.x % CL;
-  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   // ---- replicated decode state ----------------------------------------------------------------
   const int row = tid - 128;                      // epilogue threads (warps 4..7) own batch row `row`
@@ -227,20 +251,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
 
   // one [128 x K] x [K x 16] product: TMA producer (warp 8), MMA issuer (warp 0), result in TMEM cols 0..15
-  // Every CTA reads the SAME activation matrix; walking the k blocks from a per-CTA offset keeps the
-  // 128+ CTAs from hammering the same few L2 lines in lock step.
-  auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int nkb, bool detail) {
-    const int kb0 = (int)(((long long)(blockIdx.x / CL) * CL * nkb) / gridDim.x);  // same order inside a cluster
+  // one [128 x (nloc*64)] x [(nloc*64) x NC] product over the k blocks kb_lo .. kb_lo+nloc-1: TMA producer (warp 8),
+  // MMA issuer (warp 0), result in TMEM columns 0..NC-1.  Many CTAs read the SAME activation blocks; walking them
+  // from a per-CTA offset keeps the CTAs from hammering the same few L2 lines in lock step.
+  auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int kb_lo, int nloc, int ncols, uint32_t idesc, bool detail) {
+    const int rot = (int)(((long long)(blockIdx.x / KSP) * nloc * KSP) / gridDim.x) % nloc;
     if (warp == 8) {
       if (elect_one()) {
-        for (int i = 0; i < nkb; ++i) {
-          const int kb = (kb0 + i) % nkb;
+        for (int i = 0; i < nloc; ++i) {
+          const int lkb = (rot + i) % nloc;
           mbar_wait(emptyA(prodA.stage), prodA.phase ^ 1u);
           mbar_expect_tx(fullA(prodA.stage), (uint32_t)STA);
-          if (CL == 1)
-            tma_load_2d(ring + prodA.stage * STA, tm, kb * 64, 0, fullA(prodA.stage));
-          else if (i % CL == crank)  // one L2 read feeds all CL CTAs
-            tma_load_2d_mc(ring + prodA.stage * STA, tm, kb * 64, 0, fullA(prodA.stage), cmask);
+          tma_load_2d(ring + prodA.stage * STA, tm, (kb_lo + lkb) * 64, 0, fullA(prodA.stage));
           prodA.advance(NSTA);
         }
       }
@@ -248,18 +270,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     } else if (warp == 0) {
       if (elect_one()) {
         tc_fence_after();
-        for (int i = 0; i < nkb; ++i) {
-          const int kb = (kb0 + i) % nkb;
+        for (int i = 0; i < nloc; ++i) {
+          const int lkb = (rot + i) % nloc;
           mbar_wait(fullA(consA.stage), consA.phase);
           if (detail && i == 0) fine_stamp(0);
           tc_fence_after();
           const uint64_t adesc = umma_smem_desc(ring + consA.stage * STA);
-          const uint64_t bdesc = umma_smem_desc(w_smem + kb * 2048);
+          const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(lkb * ncols * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (i | k) != 0 ? 1u : 0u);
-          if (CL == 1) umma_commit(emptyA(consA.stage));
-          else umma_commit_mc(emptyA(consA.stage), cmask);
+            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit(emptyA(consA.stage));
           consA.advance(NSTA);
         }
         umma_commit(tfull);
@@ -268,6 +289,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
       __syncwarp();
     }
   };
+  constexpr uint32_t IDESC64 = umma_idesc_bf16(128, 64);
+  uint32_t pparity = 0;
+  float* s_part = reinterpret_cast<float*>(smem + p.off_part);
+  const uint32_t s_part_u = base + (uint32_t)p.off_part;
+  const uint32_t part_bytes = (uint32_t)((KSP - 1) * min(B, 128) * 64);
 
   int t = 0;
   while (true) {
@@ -316,14 +342,60 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     for (int l = 0; l < L; ++l) {
       if (cell_cta) {
         const int K = Kl[l];
-        gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], K / 64, fine && l == 0);
+        if (KSP == 1) gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], 0, K / 64, 16, IDESC, fine && l == 0);
+        else gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], crank * (K / 64 / KSP), K / 64 / KSP, 64, IDESC64, fine && l == 0);
         if (row_thread) {
+          if (KSP > 1 && tid == 128) mbar_expect_tx(pbar, part_bytes);  // partial sums of the 3 peers for my 16 columns
           mbar_wait(tfull, acc_parity);
           if (fine && l == 0 && tid == 128) fine_stamp(2);
           tc_fence_after();
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16), r);
-          tmem_ld_wait();
+          const uint32_t trow = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
+          if (KSP == 1) {
+            tmem_ld16(trow, r);
+            tmem_ld_wait();
+          } else {
+            // columns 16j..16j+15 of my K-partial belong to CTA j of the cluster: keep mine, push the rest (DSMEM)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t rj[16];
+              tmem_ld16(trow + (uint32_t)(16 * j), rj);
+              tmem_ld_wait();
+              if (j == crank) {
+#pragma unroll
+                for (int q4 = 0; q4 < 16; ++q4) r[q4] = rj[q4];
+              } else if (row_valid) {
+                const uint32_t dst = mapa_cl(s_part_u + (uint32_t)((crank * 128 + row) * 64), (uint32_t)j);
+                const uint32_t rb = mapa_cl(pbar, (uint32_t)j);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                  st_async_v4_cl(dst + 16 * q4, make_uint4(rj[4 * q4], rj[4 * q4 + 1], rj[4 * q4 + 2], rj[4 * q4 + 3]), rb);
+              }
+            }
+            mbar_wait(pbar, pparity);
+            pparity ^= 1u;
+            if (row_valid) {  // fixed summation order (sender 0,1,2,3) so every CTA adds the same way
+              float acc[16];
+#pragma unroll
+              for (int q4 = 0; q4 < 16; ++q4) acc[q4] = 0.f;
+#pragma unroll
+              for (int sr = 0; sr < 4; ++sr) {
+                if (sr == crank) {
+#pragma unroll
+                  for (int q4 = 0; q4 < 16; ++q4) acc[q4] += __uint_as_float(r[q4]);
+                } else {
+                  const float4* pr = reinterpret_cast<const float4*>(s_part + (size_t)(sr * 128 + row) * 16);
+#pragma unroll
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 v = pr[q4];
+                    acc[4 * q4] += v.x; acc[4 * q4 + 1] += v.y; acc[4 * q4 + 2] += v.z; acc[4 * q4 + 3] += v.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int q4 = 0; q4 < 16; ++q4) r[q4] = __float_as_uint(acc[q4]);
+            }
+          }
           if (row_valid) {
             float z[16];
 #pragma unroll
@@ -369,7 +441,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     // ---------------- query layer (bahdanau): q = h_top . W_q ----------------
     if (bahdanau) {
       if (q_cta) {
-        gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, Ud / 64, false);
+        gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, 0, Ud / 64, 16, IDESC, false);
         if (row_thread) {
           mbar_wait(tfull, acc_parity);
           tc_fence_after();
@@ -640,7 +712,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -649,7 +721,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------
 struct DecTcPlan {
   bool ok;
-  int n_stages, n_stages_a, stage_a, tm_pad, cluster;
+  int n_stages, n_stages_a, stage_a, tm_pad, ksplit, off_part;
   int off_w[4], off_wq, off_ring, off_misc;
   size_t smem;
   size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_bar, ws_off_dbg, ws_total;
@@ -683,6 +755,23 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   pl.stage_a = d.B <= 64 ? 8192 : 16384;
   pl.n_stages_a = d.B <= 64 ? 2 * ns - 1 : ns;
   if (pl.n_stages_a > DT_MAX_STAGES) pl.n_stages_a = DT_MAX_STAGES;
+  // K-split mode (clusters of 4): the last 32 KB of the ring hold the peers' partial sums during the LSTM phases
+  pl.ksplit = 1;
+  pl.off_part = off + ns * DT_STAGE - 32768;
+  {
+    bool ok = (d.Ud / 4) % 4 == 0 && ns * DT_STAGE - 32768 - (d.B <= 64 ? 8192 : 0) >= 2 * pl.stage_a;
+    for (int l = 0; l < d.n_layers; ++l) {
+      const int K = (l == 0) ? d.D + d.Ud : 2 * d.Ud;
+      ok = ok && (K / 64) % 4 == 0;
+    }
+    const char* e = getenv("PLAS_DEC_KSPLIT");
+    if (e && atoi(e) == 1) ok = false;
+    if (ok) {
+      pl.ksplit = 4;
+      pl.n_stages_a = (ns * DT_STAGE - 32768 - (d.B <= 64 ? 8192 : 0)) / pl.stage_a;
+      if (pl.n_stages_a > DT_MAX_STAGES) pl.n_stages_a = DT_MAX_STAGES;
+    }
+  }
   pl.off_misc = off + ns * DT_STAGE;
   pl.smem = (size_t)pl.off_misc + misc + 1024;
   size_t w = 0;
@@ -734,7 +823,8 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   a.n_stages = pl.n_stages;
   a.n_stages_a = pl.n_stages_a;
   a.stage_a = pl.stage_a;
-  a.cluster = 1;
+  a.ksplit = pl.ksplit;
+  a.off_part = pl.off_part;
   a.off_wq = pl.off_wq;
   a.off_ring = pl.off_ring;
   a.off_misc = pl.off_misc;
@@ -762,44 +852,45 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   int grid = num_sms();
   const int want = (d.Ud / 4 > 2 * d.B) ? d.Ud / 4 : 2 * d.B;
   if (grid > want) grid = want;
-  // Optional TMA multicast (PLAS_DEC_CL=2|4): clusters of consecutive CTAs share every activation box, which
-  // cuts the L2 reads of the LSTM phases by the cluster size.  Measured at c2: no gain (15.5 us -> 17.8 us for
-  // layer 0) -- the phases are bound by bytes DELIVERED to each SM (~3.4 TB/s aggregate), not by L2 reads --
-  // and ncu cannot replay cooperative cluster launches, so it is off by default.
-  int cl = 1;
-  if (const char* e = getenv("PLAS_DEC_CL")) cl = atoi(e);
-  const int nsl = d.Ud / 4, nq = d.Ud / 16;
-  while (cl > 1 && (nsl % cl != 0 || nq % cl != 0 || nsl > num_sms())) cl >>= 1;
+  // K-split mode: clusters of 4 consecutive CTAs (plain cluster launch -- all clusters must be co-resident for the
+  // grid barrier, which the occupancy query checks; ncu cannot replay a cooperative cluster launch).  TMA multicast
+  // of the activation boxes was tried instead and gave nothing: the phases are bound by the bytes DELIVERED to
+  // each SM (~3.4 TB/s aggregate L2->SM), not by L2 reads, so only splitting K reduces them.
+  const int nsl = d.Ud / 4;
   cudaError_t le = cudaErrorUnknown;
-  if (cl > 1) {
-    a.cluster = cl;
+  if (a.ksplit > 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)nsl);
     cfg.blockDim = dim3(DT_THREADS);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.x = (unsigned)a.ksplit;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeCooperative;
-    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 2;
+    cfg.numAttrs = 1;
     int max_clusters = 0;
     cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, decoder_tc_kernel, &cfg);
-    if (qe == cudaSuccess && max_clusters * cl >= nsl) le = cudaLaunchKernelEx(&cfg, decoder_tc_kernel, a);
+    if (qe == cudaSuccess && max_clusters * a.ksplit >= nsl) le = cudaLaunchKernelEx(&cfg, decoder_tc_kernel, a);
     if (getenv("PLAS_DEBUG"))
-      fprintf(stderr, "[plas] decoder tc path: cluster=%d grid=%d max_active_clusters=%d (%s) launch: %s\n", cl, nsl,
-              max_clusters, cudaGetErrorString(qe), cudaGetErrorString(le));
+      fprintf(stderr, "[plas] decoder tc path: ksplit=%d grid=%d stages=%d (lstm ring %d x %d B) max_active_clusters=%d (%s) launch: %s\n",
+              a.ksplit, nsl, pl.n_stages, pl.n_stages_a, pl.stage_a, max_clusters, cudaGetErrorString(qe), cudaGetErrorString(le));
     if (le != cudaSuccess) (void)cudaGetLastError();
   }
   if (le != cudaSuccess) {
-    a.cluster = 1;
+    if (a.ksplit > 1) {  // fall back to the single-CTA K loop: needs the stage count of that mode
+      a.ksplit = 1;
+      a.n_stages_a = d.B <= 64 ? 2 * pl.n_stages - 1 : pl.n_stages;
+      if (a.n_stages_a > DT_MAX_STAGES) a.n_stages_a = DT_MAX_STAGES;
+    }
+    int grid = num_sms();
+    const int want = (d.Ud / 4 > 2 * d.B) ? d.Ud / 4 : 2 * d.B;
+    if (grid > want) grid = want;
     if (getenv("PLAS_DEBUG"))
       fprintf(stderr, "[plas] decoder tc path: grid=%d stages=%d (lstm ring %d x %d B) smem=%zu\n", grid, pl.n_stages,
-              pl.n_stages_a, pl.stage_a, pl.smem);
+              a.n_stages_a, pl.stage_a, pl.smem);
     void* args[] = {(void*)&a};
     PLAS_CUDA(cudaLaunchCooperativeKernel((const void*)decoder_tc_kernel, dim3(grid), dim3(DT_THREADS), args, pl.smem, stream));
   }

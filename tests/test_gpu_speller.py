@@ -25,6 +25,9 @@ CONFIGS = [
     ("bf16", "luong_monotonic", 9, 37, 48, 64, 2, 30),
     ("bf16", "bahdanau", 128, 21, 32, 192, 3, 70),
     ("bf16", "luong", 64, 75, 256, 256, 1, 64),
+    # K-split cluster mode of the tensor-core decoder (every K_l a multiple of 256)
+    ("bf16", "bahdanau", 40, 30, 64, 256, 2, 40),
+    ("bf16", "luong_monotonic", 100, 22, 64, 256, 2, 33),
 ]
 
 
