@@ -41,6 +41,7 @@ struct alignas(64) DecTcArgs {
   unsigned char* xbuf[4];        // [2][B][K_l] bf16
   float* qbuf;                   // [B][Ud]
   float* align_state;            // [B][Tm]
+  int* next_ids;                 // [B] argmax of the step just decoded
   unsigned* bar;
   unsigned long long* dbg;       // optional [8] phase timers (ns, summed over steps) written by CTA 0
   int n_stages;                  // 16 KB stages of the attention ring
@@ -72,17 +73,15 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 
 __device__ __forceinline__ void dt_grid_barrier(unsigned* bar, unsigned& epoch) {
   fence_proxy_async();  // generic-proxy global/shared writes of this phase vs TMA / bulk copies of the next
-  __syncthreads();
+  __syncthreads();      // every thread's writes happen-before thread 0's release (cumulative at gpu scope)
   if (threadIdx.x == 0) {
     epoch += 1;
-    __threadfence();
     red_release_add_u32(bar, 1u);
     const unsigned target = epoch * gridDim.x;
     unsigned spins = 0;
     while (ld_acquire_u32(bar) < target) {
       if (++spins > (1u << 28)) __trap();
     }
-    __threadfence();
   }
   __syncthreads();
   fence_proxy_async();
@@ -232,6 +231,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   __shared__ unsigned long long s_tphase;          // start of the current phase (thread 0's last stamp)
   unsigned long long tfine[4] = {0, 0, 0, 0};      // layer-0 detail: first box landed, MMAs issued, accumulator ready, epilogue done
   const bool fine = p.dbg != nullptr && blockIdx.x == 0;
+  unsigned long long tfineB[4] = {0, 0, 0, 0};     // attention detail: scores, softmax, context, logits done
+  auto fineB = [&](int slot) {
+    if (fine && tid == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      tfineB[slot] += now - *(volatile unsigned long long*)&s_tphase;
+    }
+  };
   auto fine_stamp = [&](int slot) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -298,35 +305,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   int t = 0;
   while (true) {
     // ---- result of step t-1: argmax, finished / sequence-length logic (replicated), outputs (CTA 0)
-    if (t > 0) {
-      // warp w takes rows w, w+8, ...: coalesced logits read, shuffle argmax (lowest index wins ties)
-      if (warp < 8) {
-        for (int rr = warp; rr < B; rr += 8) {
-          const float* lrow = d.logits + ((size_t)rr * d.max_steps + (t - 1)) * V;
-          float best = -INFINITY;
-          int bi = 0x7fffffff;
-          for (int v = lane; v < V; v += 32) {
-            const float x = __ldcg(lrow + v);
-            if (x > best) { best = x; bi = v; }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-          }
-          if (lane == 0) s_ids[rr] = (bi == 0x7fffffff) ? 0 : bi;
-        }
-      }
-      __syncthreads();
-      if (row_valid) {
-        const int bi = s_ids[row];
-        if (blockIdx.x == 0) d.sample_ids[(size_t)row * d.max_steps + (t - 1)] = bi;
-        if (!d.teacher_forced) {
-          if (!finished && blockIdx.x == 0) d.seq_len[row] = t;
-          finished = finished || (bi == d.eos_id) || (t >= max_iter);
-          cur_id = bi;
-        }
+    if (t > 0 && row_valid) {
+      const int bi = __ldcg(p.next_ids + row);  // argmax of step t-1, written by the utterance's attention CTA
+      if (blockIdx.x == 0) d.sample_ids[(size_t)row * d.max_steps + (t - 1)] = bi;
+      if (!d.teacher_forced) {
+        if (!finished && blockIdx.x == 0) d.seq_len[row] = t;
+        finished = finished || (bi == d.eos_id) || (t >= max_iter);
+        cur_id = bi;
       }
     }
     if (t >= max_iter) break;
@@ -475,28 +460,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         const int len = min(d.mem_len[b], Tm);
         const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud;
         const __nv_bfloat16* vals = reinterpret_cast<const __nv_bfloat16*>(d.values) + (size_t)b * Tm * D + (size_t)half * Dh;
-        if (warp == 8) {
-          if (elect_one()) {
-            for (int r0 = 0; r0 < len; r0 += RK) {
-              const int n = min(RK, len - r0);
-              mbar_wait(emptyB(prodB.stage), prodB.phase ^ 1u);
-              mbar_expect_tx(fullB(prodB.stage), (uint32_t)(n * Ud * 2));
-              bulk_g2s(ring + prodB.stage * DT_STAGE, keys + (size_t)r0 * Ud, (uint32_t)(n * Ud * 2), fullB(prodB.stage));
-              prodB.advance(NST);
-            }
-            for (int r0 = 0; r0 < len; r0 += RV) {
-              const int n = min(RV, len - r0);
-              mbar_wait(emptyB(prodB.stage), prodB.phase ^ 1u);
-              mbar_expect_tx(fullB(prodB.stage), (uint32_t)(n * Dh * 2));
-              for (int i = 0; i < n; ++i)
-                bulk_g2s(ring + prodB.stage * DT_STAGE + (uint32_t)(i * Dh * 2), vals + (size_t)(r0 + i) * D,
-                         (uint32_t)(Dh * 2), fullB(prodB.stage));
-              prodB.advance(NST);
-            }
-          }
-          __syncwarp();
-          continue;
-        }
+        if (warp == 8) continue;  // the TMA producer warp has no role in this phase
         // ---- consumers: warps 0..7 ----
         for (int u = tid; u < Ud; u += 256)
           s_q[u] = bahdanau ? __ldcg(p.qbuf + (size_t)b * Ud + u) : __bfloat162float(Htop[(size_t)b * Ktop + u]);
@@ -518,37 +482,47 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
             }
           }
         }
-        for (int r0 = 0; r0 < len; r0 += RK) {
-          const int n = min(RK, len - r0);
-          mbar_wait(fullB(consB.stage), consB.phase);
-          const unsigned char* st = ring_ptr + consB.stage * DT_STAGE;
-          for (int r = warp; r < n; r += 8) {
-            const uint4* kr = reinterpret_cast<const uint4*>(st + (size_t)r * Ud * 2);
+        // keys stream straight from L2 into registers (a cp.async.bulk ring was measured at ~1.7 us per stage of
+        // latency; 4 rows x 2 chunks of 16 bytes in flight per lane does better): warp w takes rows w, w+8, ...
+        auto load_keys = [&](int r0, uint4 (*kk)[2]) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 8 * i;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c8 = lane + 32 * cc;
+              kk[i][cc] = make_uint4(0u, 0u, 0u, 0u);
+              if (reg_path && r < len && c8 < n_c8) kk[i][cc] = __ldg(reinterpret_cast<const uint4*>(keys + (size_t)r * Ud) + c8);
+            }
+          }
+        };
+        auto score_rows = [&](int r0, uint4 (*kk)[2]) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 8 * i;
+            if (r >= len) break;
             float acc = 0.f;
             if (reg_path) {
 #pragma unroll
               for (int cc = 0; cc < 2; ++cc) {
-                const int c8 = lane + 32 * cc;
-                if (c8 < n_c8) {
-                  const uint4 kk = kr[c8];
-                  const unsigned kw[4] = {kk.x, kk.y, kk.z, kk.w};
+                const unsigned kw[4] = {kk[i][cc].x, kk[i][cc].y, kk[i][cc].z, kk[i][cc].w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
-                    if (bahdanau) {
-                      acc = fmaf(vreg[cc * 8 + 2 * j], tanh_mufu(k0 + qreg[cc * 8 + 2 * j]), acc);
-                      acc = fmaf(vreg[cc * 8 + 2 * j + 1], tanh_mufu(k1 + qreg[cc * 8 + 2 * j + 1]), acc);
-                    } else {
-                      acc = fmaf(k0, qreg[cc * 8 + 2 * j], acc);
-                      acc = fmaf(k1, qreg[cc * 8 + 2 * j + 1], acc);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                  const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
+                  if (bahdanau) {
+                    acc = fmaf(vreg[cc * 8 + 2 * j], tanh_mufu(k0 + qreg[cc * 8 + 2 * j]), acc);
+                    acc = fmaf(vreg[cc * 8 + 2 * j + 1], tanh_mufu(k1 + qreg[cc * 8 + 2 * j + 1]), acc);
+                  } else {
+                    acc = fmaf(k0, qreg[cc * 8 + 2 * j], acc);
+                    acc = fmaf(k1, qreg[cc * 8 + 2 * j + 1], acc);
                   }
                 }
               }
             } else {
+              const uint4* kr = reinterpret_cast<const uint4*>(keys + (size_t)r * Ud);
               for (int c8 = lane; c8 < n_c8; c8 += 32) {
-                const uint4 kk = kr[c8];
-                const unsigned kw[4] = {kk.x, kk.y, kk.z, kk.w};
+                const uint4 k4 = __ldg(kr + c8);
+                const unsigned kw[4] = {k4.x, k4.y, k4.z, k4.w};
                 const int u0 = c8 * 8;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -564,13 +538,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
               }
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_score[r0 + r] = acc;
+            if (lane == 0) s_score[r] = acc;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(emptyB(consB.stage));
-          consB.advance(NST);
+        };
+        // keys stream straight from L2 into registers, software-pipelined: while the warp scores 4 rows the next
+        // 4 rows (2 x 16 bytes per lane each) are already in flight.  Warp w takes rows w, w+8, ...
+        {
+          uint4 ka[4][2], kb2[4][2];
+          load_keys(warp, ka);
+          for (int r0 = warp; r0 < len; r0 += 64) {
+            load_keys(r0 + 32, kb2);
+            score_rows(r0, ka);
+            load_keys(r0 + 64, ka);
+            score_rows(r0 + 32, kb2);
+          }
         }
         consumer_sync();
+        fineB(0);
         if (monotonic) {
           // tf.contrib.seq2seq.monotonic_attention(mode='parallel'): two prefix sums along memory time
           float* sa = s_scan;
@@ -630,6 +614,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
           for (int tm = tid; tm < Tm; tm += 256) s_score[tm] = s_score[tm] / sum;
           consumer_sync();
         }
+        fineB(1);
         if (d.alignment && half == 0) {
           float* ar = d.alignment + ((size_t)b * d.max_steps + t) * Tm;
           for (int tm = tid; tm < Tm; tm += 256) ar[tm] = s_score[tm];
@@ -639,25 +624,39 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
           const int cg = tid & 127, pr = tid >> 7;
           const bool has = cg < Dh / 8;
           float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int r0 = 0; r0 < len; r0 += RV) {
-            const int n = min(RV, len - r0);
-            mbar_wait(fullB(consB.stage), consB.phase);
-            const unsigned char* st = ring_ptr + consB.stage * DT_STAGE;
-            if (has) {
-              for (int r = pr; r < n; r += 2) {
-                const float a = s_score[r0 + r];
-                const uint4 raw4 = *reinterpret_cast<const uint4*>(st + (size_t)r * Dh * 2 + cg * 16);
-                const unsigned w4[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+          if (has) {
+            const uint4* vp = reinterpret_cast<const uint4*>(vals) + cg;  // row stride D/8 uint4
+            const size_t vstride = (size_t)(D / 8);
+            auto load_vals = [&](int r0, uint4* vv) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  acc[2 * i] = fmaf(a, __uint_as_float(w4[i] << 16), acc[2 * i]);
-                  acc[2 * i + 1] = fmaf(a, __uint_as_float(w4[i] & 0xffff0000u), acc[2 * i + 1]);
+              for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 2 * i;
+                vv[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (r < len) vv[i] = __ldg(vp + (size_t)r * vstride);
+              }
+            };
+            auto accum = [&](int r0, const uint4* vv) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 2 * i;
+                const float a = (r < len) ? s_score[r] : 0.f;
+                const unsigned w4[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  acc[2 * e] = fmaf(a, __uint_as_float(w4[e] << 16), acc[2 * e]);
+                  acc[2 * e + 1] = fmaf(a, __uint_as_float(w4[e] & 0xffff0000u), acc[2 * e + 1]);
                 }
               }
+            };
+            // rows pr, pr+2, ...: 8 x 16 bytes in flight per thread while the previous 8 rows are accumulated
+            uint4 va[8], vb2[8];
+            load_vals(pr, va);
+            for (int r0 = pr; r0 < len; r0 += 32) {
+              load_vals(r0 + 16, vb2);
+              accum(r0, va);
+              load_vals(r0 + 32, va);
+              accum(r0 + 16, vb2);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(emptyB(consB.stage));
-            consB.advance(NST);
           }
           if (has && pr == 1) {
 #pragma unroll
@@ -673,28 +672,49 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
             *reinterpret_cast<uint4*>(att) = *reinterpret_cast<const uint4*>(o);
           }
         }
-        // logits of this item's vocabulary half: a . PV[b] + bias
-        {
-          const int v_lo = half ? Vh : 0, v_hi = half ? V : Vh;
-          const int vi = tid & 31, g = tid >> 5;
+        fineB(2);
+        // logits = a . PV[b] + bias and their argmax (lowest index wins ties), by the half-0 item of the utterance
+        if (half == 0) {
+          const int vi = tid & 63, g = tid >> 6;
           const float* pvb = d.pv + (size_t)b * Tm * d.pv_ld;
-          for (int vb = v_lo; vb < v_hi; vb += 32) {
+          float best = -INFINITY;
+          int bi = 0x7fffffff;
+          for (int vb = 0; vb < V; vb += 64) {
             const int v = vb + vi;
             float acc = 0.f;
-            if (v < v_hi)
-              for (int tm = g; tm < len; tm += 8) acc = fmaf(s_score[tm], __ldg(pvb + (size_t)tm * d.pv_ld + v), acc);
-            s_lp[g * 32 + vi] = acc;
+            if (v < V) {
+              const float* pc = pvb + v;
+#pragma unroll 16
+              for (int tm = g; tm < len; tm += 4) acc = fmaf(s_score[tm], __ldg(pc + (size_t)tm * d.pv_ld), acc);
+            }
+            s_lp[g * 64 + vi] = acc;
             consumer_sync();
-            if (tid < 32 && vb + tid < v_hi) {
-              float s = d.b_proj[vb + tid];
-#pragma unroll
-              for (int w = 0; w < 8; ++w) s += s_lp[w * 32 + tid];
-              d.logits[((size_t)b * d.max_steps + t) * V + vb + tid] = s;
+            if (tid < 64 && vb + tid < V) {
+              const float sv = d.b_proj[vb + tid] + ((s_lp[tid] + s_lp[64 + tid]) + (s_lp[128 + tid] + s_lp[192 + tid]));
+              d.logits[((size_t)b * d.max_steps + t) * V + vb + tid] = sv;
+              if (sv > best) { best = sv; bi = vb + tid; }
             }
             consumer_sync();
           }
+          if (tid < 64) {  // two warps: shuffle argmax inside each, then combine through shared memory
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (lane == 0) { s_red[16 + 2 * warp] = best; s_red[17 + 2 * warp] = __int_as_float(bi); }
+          }
+          consumer_sync();
+          if (tid == 0) {
+            float b0 = s_red[16], b1 = s_red[18];
+            int i0 = __float_as_int(s_red[17]), i1 = __float_as_int(s_red[19]);
+            if (b1 > b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+            __stcg(p.next_ids + b, i0 == 0x7fffffff ? 0 : i0);
+          }
         }
       }
+      fineB(3);
       stamp(7);  // own attention work done, before the barrier
       dt_grid_barrier(p.bar, epoch);
       stamp(6);
@@ -706,6 +726,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   if (fine) {  // written by the role threads that took the stamps (others hold zeros)
     if (warp == 0 && tfine[0]) { p.dbg[8] = tfine[0]; p.dbg[9] = tfine[1]; }
     if (tid == 128) { p.dbg[10] = tfine[2]; p.dbg[11] = tfine[3]; }
+    if (tid == 0) for (int i = 0; i < 4; ++i) p.dbg[12 + i] = tfineB[i];
   }
   if (blockIdx.x == 0 && tid == 0) *d.n_steps = t;
   tc_fence_before();
@@ -724,7 +745,7 @@ struct DecTcPlan {
   int n_stages, n_stages_a, stage_a, tm_pad, ksplit, off_part;
   int off_w[4], off_wq, off_ring, off_misc;
   size_t smem;
-  size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_bar, ws_off_dbg, ws_total;
+  size_t ws_off_x[4], ws_off_q, ws_off_align, ws_off_ids, ws_off_bar, ws_off_dbg, ws_total;
 };
 
 static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
@@ -782,6 +803,7 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   }
   pl.ws_off_q = take((size_t)d.B * d.Ud * 4);
   pl.ws_off_align = take((size_t)d.B * d.Tm * 4);
+  pl.ws_off_ids = take((size_t)d.B * 4);
   pl.ws_off_bar = take(4);
   pl.ws_off_dbg = take(128);
   pl.ws_total = w;
@@ -818,6 +840,7 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   a.wq_tc = (const unsigned char*)d.w_query_tc;
   a.qbuf = (float*)(ws + pl.ws_off_q);
   a.align_state = (float*)(ws + pl.ws_off_align);
+  a.next_ids = (int*)(ws + pl.ws_off_ids);
   a.bar = (unsigned*)(ws + pl.ws_off_bar);
   a.dbg = getenv("PLAS_DEBUG") ? (unsigned long long*)(ws + pl.ws_off_dbg) : nullptr;
   a.n_stages = pl.n_stages;
@@ -902,6 +925,8 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
             h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, (h[6] + h[7]) / 1e3, h[7] / 1e3);
     fprintf(stderr, "[plas]   layer 0 detail (us after phase start, summed): first box %.1f  MMAs issued %.1f  accumulator ready %.1f  epilogue done %.1f\n",
             h[8] / 1e3, h[9] / 1e3, h[10] / 1e3, h[11] / 1e3);
+    fprintf(stderr, "[plas]   attention detail (us after phase start, summed): scores %.1f  softmax %.1f  context %.1f  logits %.1f\n",
+            h[12] / 1e3, h[13] / 1e3, h[14] / 1e3, h[15] / 1e3);
   }
   return PLAS_OK;
 }
