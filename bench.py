@@ -333,7 +333,7 @@ def ours(args):
                 "share_of_step": stage_ms[dom] / sum(stage_ms.values()),
                 "ms_per_launch": stage_ms[dom] / dw["launches_per_step"]}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and cfg["name"] == "c2" and B == cfg["batch"]:  # the captures are of this workload
         try:
             with open(prof) as f:
                 tj = json.load(f)

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   auto emptyB = [&](int s) { return misc_u + 8u * (3 * DT_MAX_STAGES + s); };
   const uint32_t tfull = misc_u + 8u * (4 * DT_MAX_STAGES);
   const uint32_t pbar = misc_u + 8u * (4 * DT_MAX_STAGES) + 16u;  // K-split partial sums landed (tx bytes)
+  const uint32_t sbar = misc_u + 8u * (4 * DT_MAX_STAGES) + 24u;  // the pair partner's partial scores landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (4 * DT_MAX_STAGES + 1));
   int* s_ids = reinterpret_cast<int*>(misc + 576);               // [128]  (barriers + TMEM slot end at 528)
   float* s_bias = reinterpret_cast<float*>(misc + 1536);         // [4][16]
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   float* s_score = s_v + Ud;                                     // [tm_pad]
   float* s_scan = s_score + p.tm_pad;                            // [2][tm_pad]
   float* s_comb = s_scan + 2 * p.tm_pad;                         // [D/2]
+  float* s_peer = s_comb + D / 2;                                // [2][tm_pad] partner's partial scores
 
   const int nsl = Ud / 4;
   const int nq = Ud / 16;
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     }
     mbar_init(tfull, 1);
     mbar_init(pbar, 1);
+    mbar_init(sbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int l = 0; l < L; ++l)
       for (int q2 = 0; q2 < 2; ++q2) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX[l][q2]) : "memory");
@@ -297,7 +300,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     }
   };
   constexpr uint32_t IDESC64 = umma_idesc_bf16(128, 64);
-  uint32_t pparity = 0;
+  uint32_t pparity = 0, sparity = 0;
+  int items_done = 0;
   float* s_part = reinterpret_cast<float*>(smem + p.off_part);
   const uint32_t s_part_u = base + (uint32_t)p.off_part;
   const uint32_t part_bytes = (uint32_t)((KSP - 1) * min(B, 128) * 64);
@@ -468,19 +472,37 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         // scores: warp per memory position; lane owns the 8-element chunks c8 = lane, lane+32 of the
         // depth (conflict-free 16-byte LDS of the staged keys); its slice of the query (and of
         // attention_v) lives in registers for the whole item when Ud <= 512
+        // In cluster mode the two CTAs of an utterance (consecutive ranks of one cluster) split the depth of the
+        // score reduction: each reads half of every key row and evaluates half of the tanh, then they swap partial
+        // scores through DSMEM.  Otherwise every CTA scores the full depth.
+        const bool pair_split = KSP > 1;
         const int n_c8 = Ud / 8;
-        const bool reg_path = n_c8 <= 64;
+        const int c8_lo = pair_split ? half * (n_c8 / 2) : 0;
+        const int c8_hi = pair_split ? c8_lo + n_c8 / 2 : n_c8;
+        const bool reg_path = (c8_hi - c8_lo) <= 64;
         float qreg[16], vreg[16];
         if (reg_path) {
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
-            const int c8 = lane + 32 * cc;
+            const int c8 = c8_lo + lane + 32 * cc;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              qreg[cc * 8 + j] = (c8 < n_c8) ? s_q[c8 * 8 + j] : 0.f;
-              vreg[cc * 8 + j] = (c8 < n_c8 && bahdanau) ? s_v[c8 * 8 + j] : 0.f;
+              qreg[cc * 8 + j] = (c8 < c8_hi) ? s_q[c8 * 8 + j] : 0.f;
+              vreg[cc * 8 + j] = (c8 < c8_hi && bahdanau) ? s_v[c8 * 8 + j] : 0.f;
             }
           }
+        }
+        // PV[b] (f32 [len][V]) is prefetched into the idle TMA ring with cp.async while scores and context run
+        const bool pv_smem = half == 0 && (V % 4 == 0) && (size_t)Tm * V * 4 <= (size_t)NST * DT_STAGE;
+        if (pv_smem) {
+          const float* pvb = d.pv + (size_t)b * Tm * d.pv_ld;
+          const int v4 = V / 4;
+          for (int i = tid; i < len * v4; i += 256) {
+            const int row = i / v4, c = i - row * v4;
+            const uint32_t dst = ring + (uint32_t)((row * V + 4 * c) * 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(pvb + (size_t)row * d.pv_ld + 4 * c) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
         }
         // keys stream straight from L2 into registers (a cp.async.bulk ring was measured at ~1.7 us per stage of
         // latency; 4 rows x 2 chunks of 16 bytes in flight per lane does better): warp w takes rows w, w+8, ...
@@ -490,50 +512,77 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
             const int r = r0 + 8 * i;
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
-              const int c8 = lane + 32 * cc;
+              const int c8 = c8_lo + lane + 32 * cc;
               kk[i][cc] = make_uint4(0u, 0u, 0u, 0u);
-              if (reg_path && r < len && c8 < n_c8) kk[i][cc] = __ldg(reinterpret_cast<const uint4*>(keys + (size_t)r * Ud) + c8);
+              if (reg_path && r < len && c8 < c8_hi) kk[i][cc] = __ldg(reinterpret_cast<const uint4*>(keys + (size_t)r * Ud) + c8);
             }
           }
         };
         auto score_rows = [&](int r0, uint4 (*kk)[2]) {
+          if (reg_path) {
+            // four rows at a time with independent accumulators: the MUFU.TANH -> FFMA chains of different rows
+            // overlap (one row alone is latency-bound on the special-function unit)
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              if (c8_lo + 32 * cc >= c8_hi) break;  // warp-uniform: this half-depth has one chunk per lane
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float k0[4], k1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const unsigned kw = j == 0 ? kk[i][cc].x : (j == 1 ? kk[i][cc].y : (j == 2 ? kk[i][cc].z : kk[i][cc].w));
+                  k0[i] = __uint_as_float(kw << 16);
+                  k1[i] = __uint_as_float(kw & 0xffff0000u);
+                }
+                if (bahdanau) {
+                  float t0[4], t1[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    t0[i] = tanh_mufu(k0[i] + qreg[cc * 8 + 2 * j]);
+                    t1[i] = tanh_mufu(k1[i] + qreg[cc * 8 + 2 * j + 1]);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    acc[i] = fmaf(vreg[cc * 8 + 2 * j], t0[i], acc[i]);
+                    acc[i] = fmaf(vreg[cc * 8 + 2 * j + 1], t1[i], acc[i]);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    acc[i] = fmaf(k0[i], qreg[cc * 8 + 2 * j], acc[i]);
+                    acc[i] = fmaf(k1[i], qreg[cc * 8 + 2 * j + 1], acc[i]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r0 + 8 * i;
+              const float sacc = warp_sum(acc[i]);
+              if (lane == 0 && r < len) s_score[r] = sacc;
+            }
+            return;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = r0 + 8 * i;
             if (r >= len) break;
             float acc = 0.f;
-            if (reg_path) {
+            const uint4* kr = reinterpret_cast<const uint4*>(keys + (size_t)r * Ud);
+            for (int c8 = c8_lo + lane; c8 < c8_hi; c8 += 32) {
+              const uint4 k4 = __ldg(kr + c8);
+              const unsigned kw[4] = {k4.x, k4.y, k4.z, k4.w};
+              const int u0 = c8 * 8;
 #pragma unroll
-              for (int cc = 0; cc < 2; ++cc) {
-                const unsigned kw[4] = {kk[i][cc].x, kk[i][cc].y, kk[i][cc].z, kk[i][cc].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
-                  if (bahdanau) {
-                    acc = fmaf(vreg[cc * 8 + 2 * j], tanh_mufu(k0 + qreg[cc * 8 + 2 * j]), acc);
-                    acc = fmaf(vreg[cc * 8 + 2 * j + 1], tanh_mufu(k1 + qreg[cc * 8 + 2 * j + 1]), acc);
-                  } else {
-                    acc = fmaf(k0, qreg[cc * 8 + 2 * j], acc);
-                    acc = fmaf(k1, qreg[cc * 8 + 2 * j + 1], acc);
-                  }
-                }
-              }
-            } else {
-              const uint4* kr = reinterpret_cast<const uint4*>(keys + (size_t)r * Ud);
-              for (int c8 = lane; c8 < n_c8; c8 += 32) {
-                const uint4 k4 = __ldg(kr + c8);
-                const unsigned kw[4] = {k4.x, k4.y, k4.z, k4.w};
-                const int u0 = c8 * 8;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
-                  if (bahdanau) {
-                    acc = fmaf(s_v[u0 + 2 * j], tanh_mufu(k0 + s_q[u0 + 2 * j]), acc);
-                    acc = fmaf(s_v[u0 + 2 * j + 1], tanh_mufu(k1 + s_q[u0 + 2 * j + 1]), acc);
-                  } else {
-                    acc = fmaf(k0, s_q[u0 + 2 * j], acc);
-                    acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
-                  }
+              for (int j = 0; j < 4; ++j) {
+                const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
+                if (bahdanau) {
+                  acc = fmaf(s_v[u0 + 2 * j], tanh_mufu(k0 + s_q[u0 + 2 * j]), acc);
+                  acc = fmaf(s_v[u0 + 2 * j + 1], tanh_mufu(k1 + s_q[u0 + 2 * j + 1]), acc);
+                } else {
+                  acc = fmaf(k0, s_q[u0 + 2 * j], acc);
+                  acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
                 }
               }
             }
@@ -554,6 +603,24 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
           }
         }
         consumer_sync();
+        if (pair_split) {
+          float* peer_buf = s_peer + (size_t)(items_done & 1) * p.tm_pad;
+          const uint32_t dst0 = mapa_cl(smem_u32(peer_buf), (uint32_t)(crank ^ 1));
+          const uint32_t rb = mapa_cl(sbar, (uint32_t)(crank ^ 1));
+          if (tid == 0) mbar_expect_tx(sbar, (uint32_t)(p.tm_pad * 4));
+          for (int i = tid; i < p.tm_pad / 4; i += 256) {
+            const float4 v = *reinterpret_cast<const float4*>(s_score + 4 * i);
+            st_async_v4_cl(dst0 + 16 * i, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)), rb);
+          }
+          mbar_wait(sbar, sparity);
+          sparity ^= 1u;
+          for (int tm = tid; tm < len; tm += 256) {  // same order in both CTAs: (depth half 0) + (depth half 1)
+            const float own = s_score[tm], oth = peer_buf[tm];
+            s_score[tm] = half == 0 ? own + oth : oth + own;
+          }
+          ++items_done;
+          consumer_sync();
+        }
         fineB(0);
         if (monotonic) {
           // tf.contrib.seq2seq.monotonic_attention(mode='parallel'): two prefix sums along memory time
@@ -677,15 +744,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         if (half == 0) {
           const int vi = tid & 63, g = tid >> 6;
           const float* pvb = d.pv + (size_t)b * Tm * d.pv_ld;
+          const float* pvs = reinterpret_cast<const float*>(ring_ptr);
+          if (pv_smem) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            consumer_sync();
+          }
           float best = -INFINITY;
           int bi = 0x7fffffff;
           for (int vb = 0; vb < V; vb += 64) {
             const int v = vb + vi;
             float acc = 0.f;
             if (v < V) {
-              const float* pc = pvb + v;
+              if (pv_smem) {
+#pragma unroll 8
+                for (int tm = g; tm < len; tm += 4) acc = fmaf(s_score[tm], pvs[tm * V + v], acc);
+              } else {
+                const float* pc = pvb + v;
 #pragma unroll 16
-              for (int tm = g; tm < len; tm += 4) acc = fmaf(s_score[tm], __ldg(pc + (size_t)tm * d.pv_ld), acc);
+                for (int tm = g; tm < len; tm += 4) acc = fmaf(s_score[tm], __ldg(pc + (size_t)tm * d.pv_ld), acc);
+              }
             }
             s_lp[g * 64 + vi] = acc;
             consumer_sync();
@@ -765,7 +842,7 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   if (d.attention_type == PLAS_ATT_BAHDANAU) off += (d.Ud / 64) * 2048;
   pl.off_ring = off;  // multiples of 2048 -> 1024-aligned
   pl.tm_pad = (d.Tm + 3) & ~3;
-  const int misc = 1536 + 4 * (64 + 64 + 256 + 2 * d.Ud + 3 * pl.tm_pad + d.D / 2) + 64;
+  const int misc = 1536 + 4 * (64 + 64 + 256 + 2 * d.Ud + 5 * pl.tm_pad + d.D / 2) + 64;
   const int avail = 227 * 1024 - 1024 - off - misc;
   int ns = avail / DT_STAGE;
   if (ns > DT_MAX_STAGES) ns = DT_MAX_STAGES;
