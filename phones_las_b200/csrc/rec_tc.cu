@@ -28,6 +28,7 @@
 namespace plas {
 
 constexpr int RT_THREADS = 256;
+constexpr int RT_THREADS2 = 288;  // 8 epilogue warps + 1 MMA-issuer warp
 constexpr int RT_NACC = 4;    // independent accumulators (k-steps interleaved): back-to-back tcgen05.mma on ONE
                               // accumulator serialise on its ~50-cycle latency, which dominates at N = 16..64
 
@@ -49,6 +50,7 @@ __device__ __forceinline__ void rt_st_async_v4(uint32_t raddr, const uint4& v, u
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
                : "memory");
 }
+__device__ __forceinline__ void rt_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void rt_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -74,17 +76,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
-template <int KS, int NR>
-__global__ void __launch_bounds__(RT_THREADS, 1) rec_tc_kernel(RecTcArgs p) {
+// NG independent 16-utterance groups of one direction share a cluster (and the TMEM-resident weights) and are
+// software-pipelined against each other: warp 8 waits for a group's h_{s-1} to land and issues its U/16 MMAs
+// (asynchronous, own accumulator columns), while the 8 epilogue warps run the gate math / exchange of the other
+// group(s).  The exchange latency (~0.5 us) and the MMA time of one group hide behind the epilogue of the others.
+template <int KS, int NG>
+__global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
   constexpr int U = KS * 16;
   constexpr int G = U / 32;          // CTAs per cluster
   constexpr int KB = U / 64;         // 64-wide k blocks of the h operand
+  constexpr int NR = 16;             // utterances per group
   constexpr int HR = NR / 2;         // utterances per warp half
-  constexpr int PP = NR / 8;         // (unit, utterance) pairs per thread
+  constexpr int PP = NR / 8;         // (unit, utterance) pairs per thread and group
   constexpr int TILE = NR * 128;     // bytes of one k block of the h operand
   constexpr int HBUF = KB * TILE;    // bytes of one h operand buffer
-  constexpr int RT_ACOL0 = RT_NACC * NR;  // first TMEM column of the resident W slice (TS form)
-  constexpr uint32_t TMEM_COLS = (RT_ACOL0 + 8 * KS) <= 128 ? 128u : ((RT_ACOL0 + 8 * KS) <= 256 ? 256u : 512u);
+  constexpr int ACOL0 = 64;          // first TMEM column of the resident W slice; accumulator of group g: 16g..16g+15
+  constexpr uint32_t TMEM_COLS = (ACOL0 + 8 * KS) <= 128 ? 128u : ((ACOL0 + 8 * KS) <= 256 ? 256u : 512u);
   constexpr uint32_t IDESC = umma_idesc_bf16(128, NR);
   extern __shared__ unsigned char rt_smem_raw[];
   const plas_rec_desc& d = p.d;
@@ -92,31 +99,32 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_tc_kernel(RecTcArgs p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ci = blockIdx.x % G;     // rank inside the cluster
   const int cl = blockIdx.x / G;
-  const int dir = cl / p.n_groups;
-  const int gi = cl % p.n_groups;
-  const int row0 = gi * NR;
+  const int cpd = (p.n_groups + NG - 1) / NG;  // clusters per direction
+  const int dir = cl / cpd;
+  const int grp0 = (cl % cpd) * NG;  // first 16-utterance group of this cluster
 
   const uint32_t raw = smem_u32(rt_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* smem = rt_smem_raw + (base - raw);
-  // [2][HBUF] h operand (UMMA K-major SWIZZLE_128B) | [8 warps][HR][33] f32 transpose | [NR][32] bf16 stage
-  // SS form: + [KB][128 rows x 128 B] W slice (UMMA K-major SWIZZLE_128B A operand) at the end
+  // [NG][2][HBUF] h operands (UMMA K-major SWIZZLE_128B) | [8 warps][HR][36] f32 transpose | [NR][32] bf16 stage
   const uint32_t hbuf_u = base;
-  float* s_z = reinterpret_cast<float*>(smem + 2 * HBUF);
-  __nv_bfloat16* s_stage = reinterpret_cast<__nv_bfloat16*>(smem + 2 * HBUF + 8 * HR * 36 * 4);
-  constexpr int W_OFF = ((2 * HBUF + 8 * HR * 36 * 4 + NR * 32 * 2 + 1023) / 1024) * 1024;
-  const uint32_t wsm_u = base + W_OFF;
-  __shared__ int s_len[NR];
-  __shared__ int s_tmax;
-  __shared__ __align__(8) unsigned long long s_bar[3];  // h buffers 0/1, MMA completion
+  float* s_z = reinterpret_cast<float*>(smem + NG * 2 * HBUF);
+  __nv_bfloat16* s_stage = reinterpret_cast<__nv_bfloat16*>(smem + NG * 2 * HBUF + 8 * HR * 36 * 4);
+  __shared__ int s_len[NG][NR];
+  __shared__ int s_tmax[NG];
+  __shared__ __align__(8) unsigned long long s_bar[NG][3];  // h buffers 0/1, MMA completion
   __shared__ uint32_t s_tmem;
 
-  if (tid < NR) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
+  if (tid < NG * NR) {
+    const int gg = tid / NR, r = tid % NR;
+    const int b = (grp0 + gg) * NR + r;
+    s_len[gg][r] = (grp0 + gg < p.n_groups && b < B) ? min(d.lengths[b], T) : 0;
+  }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < NG) {
     int m = 0;
-    for (int r = 0; r < NR; ++r) m = max(m, s_len[r]);
-    s_tmax = m;
+    for (int r = 0; r < NR; ++r) m = max(m, s_len[tid][r]);
+    s_tmax[tid] = m;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TMEM_COLS)
@@ -126,189 +134,194 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_tc_kernel(RecTcArgs p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const int Tg = s_tmax;
+  int Tg[NG];
+  int Tmax = 0;
+#pragma unroll
+  for (int gg = 0; gg < NG; ++gg) { Tg[gg] = s_tmax[gg]; Tmax = max(Tmax, Tg[gg]); }
   const uint32_t tmem_base = s_tmem;
-  const uint32_t hbar[2] = {smem_u32(&s_bar[0]), smem_u32(&s_bar[1])};
-  const uint32_t mbar = smem_u32(&s_bar[2]);
-  const uint32_t step_bytes = (uint32_t)(G * NR * 64);  // bytes every CTA receives per step
+  uint32_t hbar[NG][2], mbar[NG];
+#pragma unroll
+  for (int gg = 0; gg < NG; ++gg) {
+    hbar[gg][0] = smem_u32(&s_bar[gg][0]);
+    hbar[gg][1] = smem_u32(&s_bar[gg][1]);
+    mbar[gg] = smem_u32(&s_bar[gg][2]);
+  }
+  const uint32_t step_bytes = (uint32_t)(G * NR * 64);  // bytes every CTA receives per group step
   if (tid == 0) {
-    mbar_init(hbar[0], 1);
-    mbar_init(hbar[1], 1);
-    mbar_init(mbar, 1);
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) {
+      mbar_init(hbar[gg][0], 1);
+      mbar_init(hbar[gg][1], 1);
+      mbar_init(mbar[gg], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (Tg >= 2) mbar_expect_tx(hbar[0], step_bytes);  // h_0
-    if (Tg >= 3) mbar_expect_tx(hbar[1], step_bytes);  // h_1
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) {
+      if (Tg[gg] >= 2) mbar_expect_tx(hbar[gg][0], step_bytes);  // h_0
+      if (Tg[gg] >= 3) mbar_expect_tx(hbar[gg][1], step_bytes);  // h_1
+    }
   }
 
   // ---- resident W slice -> TMEM (lane m = gate column, 8*KS packed-bf16 columns) ---------------
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  if (warp < 4 && p.ss) {
-    const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.whh_tc) +
-                                                       (((size_t)dir * G + ci) * 128 + tid) * U);
-    unsigned char* wdst = smem + W_OFF + (tid >> 3) * 1024 + (tid & 7) * 128;
-    for (int c = 0; c < U / 8; ++c)  // 16-byte chunk c of row tid -> k block c/8, swizzled chunk position
-      *reinterpret_cast<uint4*>(wdst + (size_t)(c >> 3) * 16384 + (((c & 7) ^ (tid & 7)) << 4)) = __ldg(wrow + c);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  } else if (warp < 4) {
+  if (warp < 4) {
     const uint4* wrow = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.whh_tc) +
                                                        (((size_t)dir * G + ci) * 128 + tid) * U);
 #pragma unroll 4
     for (int c0 = 0; c0 < 8 * KS; c0 += 8) {  // 8 columns = 16 bf16 = two uint4
       const uint4 a = __ldg(wrow + c0 / 4), b = __ldg(wrow + c0 / 4 + 1);
       const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      tmem_st8(tmem_base + lane_base + (uint32_t)(RT_ACOL0 + c0), r);
+      tmem_st8(tmem_base + lane_base + (uint32_t)(ACOL0 + c0), r);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-
-  // ---- per-thread (unit, utterance) pairs ---------------------------------------------------------
-  // gate-math mapping: lane -> unit u8 = lane/4 of this warp's 8 units, utterances j, j+4, ... of the
-  // warp half (w/4)
-  const int u8 = lane >> 2, jq = lane & 3;
-  const int unit = ci * 32 + (warp & 3) * 8 + u8;
-  const int half0 = (warp >> 2) * HR;
-  const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
-  const int NX = ndir * 4 * U;
-  int len_p[PP];
-  const __nv_bfloat16* xrow[PP];
-  float c_state[PP], h_state[PP];
-  uint2 xp[PP];
-#pragma unroll
-  for (int i = 0; i < PP; ++i) {
-    const int r = half0 + jq + 4 * i;
-    len_p[i] = s_len[r];
-    xrow[i] = xproj + ((size_t)min(row0 + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
-    c_state[i] = 0.f;
-    h_state[i] = 0.f;
-    xp[i] = make_uint2(0u, 0u);
-    if (0 < len_p[i]) {
-      const int t = dir ? (len_p[i] - 1) : 0;
-      xp[i] = __ldg(reinterpret_cast<const uint2*>(xrow[i] + (size_t)t * NX));
-    }
-  }
-  float* zt = s_z + (size_t)warp * HR * 36;  // this warp's transpose tile [HR][36] (32 columns + pad)
-
   tc_fence_before();
   __syncthreads();
   // every CTA of the cluster must be running, with its mbarriers initialised, before anyone pushes
   rt_cluster_sync();
   tc_fence_after();
 
-  uint32_t mma_parity = 0;
-  for (int s = 0; s < Tg; ++s) {
-    const int bsel = (s - 1) & 1;
-    if (s > 0) {
-      if (!(p.dbg & 1)) mbar_wait(hbar[bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
-      if (warp == 0) {
-        if (elect_one()) {
-          if (s + 1 <= Tg - 2 && !(p.dbg & 1)) mbar_expect_tx(hbar[bsel], step_bytes);  // re-arm for h_{s+1}
+  if (warp == 8) {
+    // ===== MMA issuer: per (step, group) wait for h_{s-1}, re-arm the buffer's barrier, issue, commit =====
+    if (elect_one()) {
+      for (int s = 1; s < Tmax; ++s) {
+        const int bsel = (s - 1) & 1;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) {
+          if (s >= Tg[gg]) continue;
+          mbar_wait(hbar[gg][bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
+          if (s + 1 <= Tg[gg] - 2) mbar_expect_tx(hbar[gg][bsel], step_bytes);  // re-arm for h_{s+1}
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.async data -> tensor-core reads
           tc_fence_after();
-          const uint32_t hb = hbuf_u + (uint32_t)(bsel * HBUF);
-          if (p.ss) {
+          const uint32_t hb = hbuf_u + (uint32_t)((gg * 2 + bsel) * HBUF);
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint64_t bdesc = umma_smem_desc(hb + (uint32_t)((ks >> 2) * TILE)) + (uint64_t)(2 * (ks & 3));
-              const uint64_t adesc = umma_smem_desc(wsm_u + (uint32_t)((ks >> 2) * 16384)) + (uint64_t)(2 * (ks & 3));
-              umma_bf16(tmem_base + (uint32_t)((ks % RT_NACC) * NR), adesc, bdesc, IDESC, ks >= RT_NACC ? 1u : 0u);
-            }
-          } else {
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t bdesc = umma_smem_desc(hb + (uint32_t)((ks >> 2) * TILE)) + (uint64_t)(2 * (ks & 3));
+            umma_bf16_ts(tmem_base + (uint32_t)(gg * NR), tmem_base + (uint32_t)(ACOL0 + 8 * ks), bdesc, IDESC,
+                         ks != 0 ? 1u : 0u);
+          }
+          umma_commit(mbar[gg]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 0..7 =====
+    // gate-math mapping: lane -> unit u8 = lane/4 of this warp's 8 units, utterances jq, jq+4 of the warp half (w/4)
+    const int u8 = lane >> 2, jq = lane & 3;
+    const int unit = ci * 32 + (warp & 3) * 8 + u8;
+    const int half0 = (warp >> 2) * HR;
+    const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+    const int NX = ndir * 4 * U;
+    int len_p[NG][PP];
+    const __nv_bfloat16* xrow[NG][PP];
+    float c_state[NG][PP], h_state[NG][PP];
+    uint2 xp[NG][PP];
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint64_t bdesc = umma_smem_desc(hb + (uint32_t)((ks >> 2) * TILE)) + (uint64_t)(2 * (ks & 3));
-              umma_bf16_ts(tmem_base + (uint32_t)((ks % RT_NACC) * NR), tmem_base + (uint32_t)(RT_ACOL0 + 8 * ks), bdesc,
-                           IDESC, ks >= RT_NACC ? 1u : 0u);
+    for (int gg = 0; gg < NG; ++gg)
+#pragma unroll
+      for (int i = 0; i < PP; ++i) {
+        const int r = half0 + jq + 4 * i;
+        len_p[gg][i] = s_len[gg][r];
+        xrow[gg][i] = xproj + ((size_t)min((grp0 + gg) * NR + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
+        c_state[gg][i] = 0.f;
+        h_state[gg][i] = 0.f;
+        xp[gg][i] = make_uint2(0u, 0u);
+        if (0 < len_p[gg][i]) {
+          const int t = dir ? (len_p[gg][i] - 1) : 0;
+          xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][i] + (size_t)t * NX));
+        }
+      }
+    float* zt = s_z + (size_t)warp * HR * 36;  // this warp's transpose tile [HR][36] (32 columns + pad)
+    uint32_t mma_parity[NG];
+#pragma unroll
+    for (int gg = 0; gg < NG; ++gg) mma_parity[gg] = 0;
+
+    for (int s = 0; s < Tmax; ++s) {
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) {
+        if (s >= Tg[gg]) continue;  // uniform over the cluster
+        if (s > 0) {
+          mbar_wait(mbar[gg], mma_parity[gg]);
+          mma_parity[gg] ^= 1u;
+          tc_fence_after();
+          // accumulator: lane = gate column, column = utterance; this warp half reads HR columns
+          uint32_t r[HR];
+          tmem_ld8(tmem_base + lane_base + (uint32_t)(gg * NR + half0), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < HR; ++j) zt[j * 36 + lane] = __uint_as_float(r[j]);
+          tc_fence_before();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+          const int rl = jq + 4 * i;  // utterance inside the warp half
+          float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (s > 0) z = *reinterpret_cast<const float4*>(zt + rl * 36 + 4 * u8);
+          const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][i].x);
+          const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][i].y);
+          float cn, hn;
+          lstm_gates_fast(z.x + __low2float(x01), z.y + __high2float(x01), z.z + __low2float(x23), z.w + __high2float(x23),
+                          c_state[gg][i], cn, hn);
+          if (s < len_p[gg][i]) {
+            c_state[gg][i] = cn;
+            h_state[gg][i] = bf16_round(hn);
+          }
+          s_stage[(half0 + rl) * 32 + (warp & 3) * 8 + u8] = __float2bfloat16_rn(h_state[gg][i]);
+          // prefetch this group's next gate pre-activations (consumed one full round later)
+          xp[gg][i] = make_uint2(0u, 0u);
+          if (s + 1 < len_p[gg][i]) {
+            const int t = dir ? (len_p[gg][i] - 2 - s) : (s + 1);
+            xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][i] + (size_t)t * NX));
+          }
+        }
+        rt_epi_sync();
+        // publish the staged 16 x 32 slice: (a) into the swizzled h operand of every CTA of the cluster (not needed
+        // after the group's last step) -- thread = (destination, row, 16-byte chunk) so that the four chunks of a row
+        // leave as one contiguous 64-byte DSMEM segment (a per-warp publish without this barrier was measured 30%
+        // slower: scattered 16-byte remote stores) --, (b) for active rows to the [B,T,ndir*U] layer output in HBM
+        if (s + 1 < Tg[gg]) {
+          const uint32_t dst_buf = hbuf_u + (uint32_t)((gg * 2 + (s & 1)) * HBUF) + (uint32_t)((ci >> 1) * TILE);
+          const uint32_t bar_l = hbar[gg][s & 1];
+#pragma unroll
+          for (int j = 0; j < (G * NR * 4 + 255) / 256; ++j) {
+            const int idx = tid + j * 256;
+            if (idx < G * NR * 4) {
+              const int rank = idx / (NR * 4), chunk = idx % (NR * 4);
+              const int r = chunk >> 2, ch = chunk & 3;
+              const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+              const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
+              const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+              rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
             }
           }
-          umma_commit(mbar);
         }
-        __syncwarp();
-      }
-      mbar_wait(mbar, mma_parity);
-      mma_parity ^= 1u;
-      tc_fence_after();
-      // accumulator: lane = gate column, column = utterance; this warp half reads HR columns
-#pragma unroll
-      for (int c0 = 0; c0 < HR; c0 += 8) {
-        uint32_t r[RT_NACC][8];
-#pragma unroll
-        for (int a = 0; a < RT_NACC; ++a) tmem_ld8(tmem_base + lane_base + (uint32_t)(a * NR + half0 + c0), r[a]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          zt[(c0 + j) * 36 + lane] = (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) +
-                                     (__uint_as_float(r[2][j]) + __uint_as_float(r[3][j]));
-      }
-      tc_fence_before();
-      __syncwarp();
-    }
-#pragma unroll
-    for (int i = 0; i < PP; ++i) {
-      const int rl = jq + 4 * i;  // utterance inside the warp half
-      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (s > 0) z = *reinterpret_cast<const float4*>(zt + rl * 36 + 4 * u8);
-      const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[i].x);
-      const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[i].y);
-      float cn, hn;
-      if (p.dbg & 2) {
-        cn = z.x + __low2float(x01) + z.z + __low2float(x23);
-        hn = z.y + __high2float(x01) + z.w + __high2float(x23);
-      } else {
-        lstm_gates_fast(z.x + __low2float(x01), z.y + __high2float(x01), z.z + __low2float(x23),
-                        z.w + __high2float(x23), c_state[i], cn, hn);
-      }
-      if (s < len_p[i]) {
-        c_state[i] = cn;
-        h_state[i] = bf16_round(hn);
-      }
-      s_stage[(half0 + rl) * 32 + (warp & 3) * 8 + u8] = __float2bfloat16_rn(h_state[i]);
-      // prefetch the next gate pre-activations (consumed one full step later)
-      xp[i] = make_uint2(0u, 0u);
-      if (s + 1 < len_p[i]) {
-        const int t = dir ? (len_p[i] - 2 - s) : (s + 1);
-        xp[i] = __ldg(reinterpret_cast<const uint2*>(xrow[i] + (size_t)t * NX));
+        if (tid < NR * 4) {
+          const int r = tid >> 2, ch = tid & 3;
+          const int b = (grp0 + gg) * NR + r;
+          const int len = s_len[gg][r];
+          if (b < B && s < len) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
+            const int t = dir ? (len - 1 - s) : s;
+            __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
+            *reinterpret_cast<uint4*>(odst) = v;
+          }
+        }
+        rt_epi_sync();  // s_stage / the transpose tiles are rewritten by the next item
       }
     }
-    __syncthreads();
-    // publish the staged NR x 32 slice: (a) into the swizzled h operand of every CTA of the cluster
-    // (not needed after the last step), (b) for active rows to the [B,T,ndir*U] layer output in HBM
-    if (s + 1 < Tg && !(p.dbg & 1)) {
-      const uint32_t dst_buf = hbuf_u + (uint32_t)((s & 1) * HBUF) + (uint32_t)((ci >> 1) * TILE);
-      const uint32_t bar_l = hbar[s & 1];
 #pragma unroll
-      for (int j = 0; j < (G * NR * 4 + RT_THREADS - 1) / RT_THREADS; ++j) {
-        const int idx = tid + j * RT_THREADS;
-        if (idx < G * NR * 4) {
-          const int rank = idx / (NR * 4), chunk = idx % (NR * 4);
-          const int r = chunk >> 2, ch = chunk & 3;
-          const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
-          const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
-          const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-          rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
+    for (int gg = 0; gg < NG; ++gg)
+#pragma unroll
+      for (int i = 0; i < PP; ++i) {
+        const int b = (grp0 + gg) * NR + half0 + jq + 4 * i;
+        if (grp0 + gg < p.n_groups && b < B) {
+          d.c_final[((size_t)dir * B + b) * U + unit] = c_state[gg][i];
+          d.h_final[((size_t)dir * B + b) * U + unit] = h_state[gg][i];
         }
       }
-    }
-    if (tid < NR * 4) {
-      const int r = tid >> 2, ch = tid & 3;
-      const int b = row0 + r;
-      const int len = s_len[r];
-      if (b < B && s < len) {
-        const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
-        const int t = dir ? (len - 1 - s) : s;
-        __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
-        *reinterpret_cast<uint4*>(odst) = v;
-      }
-    }
-    __syncthreads();  // s_stage / the transpose tiles are rewritten by the next step
-  }
-#pragma unroll
-  for (int i = 0; i < PP; ++i) {
-    const int b = row0 + half0 + jq + 4 * i;
-    if (b < B) {
-      d.c_final[((size_t)dir * B + b) * U + unit] = c_state[i];
-      d.h_final[((size_t)dir * B + b) * U + unit] = h_state[i];
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -321,24 +334,23 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_tc_kernel(RecTcArgs p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int KS, int NR>
+template <int KS, int NG>
 static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, bool* launched) {
   const plas_rec_desc& d = a.d;
-  constexpr int U = KS * 16, G = U / 32;
+  constexpr int U = KS * 16, G = U / 32, NR = 16;
   *launched = false;
   // > 114 KB of shared memory: at most one CTA per SM, so the TMEM allocation can never contend
-  size_t smem = 1024 + (size_t)2 * (U / 64) * NR * 128 + (size_t)8 * (NR / 2) * 36 * 4 + (size_t)NR * 32 * 2;
-  if (a.ss) smem = ((smem + 1023) / 1024) * 1024 + (size_t)(U / 64) * 16384;
+  size_t smem = 1024 + (size_t)NG * 2 * (U / 64) * NR * 128 + (size_t)8 * (NR / 2) * 36 * 4 + (size_t)NR * 32 * 2;
   if (smem > 227 * 1024) return PLAS_OK;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  auto fn = rec_tc_kernel<KS, NR>;
+  auto fn = rec_tc_kernel<KS, NG>;
   PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (G > 8) PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   a.n_groups = (d.B + NR - 1) / NR;
-  const int clusters = d.ndir * a.n_groups;
+  const int clusters = d.ndir * ((a.n_groups + NG - 1) / NG);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * G));
-  cfg.blockDim = dim3(RT_THREADS);
+  cfg.blockDim = dim3(RT_THREADS2);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -351,7 +363,7 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   int max_clusters = 0;
   cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg);
   if (getenv("PLAS_DEBUG"))
-    fprintf(stderr, "[plas] rec tc path: U=%d NR=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", U, NR, G,
+    fprintf(stderr, "[plas] rec tc path: U=%d NG=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", U, NG, G,
             clusters, max_clusters, cudaGetErrorString(qe), smem);
   if (qe != cudaSuccess || max_clusters < 1) {
     (void)cudaGetLastError();
@@ -363,21 +375,22 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   return PLAS_OK;
 }
 
+// Fewest groups per cluster such that all clusters are co-resident (a B200 schedules 7 clusters of 16 CTAs).
 template <int KS>
 static int rec_tc_launch_ks(const RecTcArgs& a, cudaStream_t stream) {
   bool launched = false;
-  const char* force = getenv("PLAS_REC_NR");
-  const int fnr = force ? atoi(force) : 0;
+  const char* force = getenv("PLAS_REC_NG");
+  const int fng = force ? atoi(force) : 0;
   int rc;
-  if (fnr == 0 || fnr == 16) {
-    rc = rec_tc_try<KS, 16>(a, stream, fnr == 0, &launched);
+  if (fng == 0 || fng == 1) {
+    rc = rec_tc_try<KS, 1>(a, stream, fng == 0, &launched);
     if (rc || launched) return rc;
   }
-  if (fnr == 0 || fnr == 32) {
-    rc = rec_tc_try<KS, 32>(a, stream, fnr == 0, &launched);
+  if (fng == 0 || fng == 2) {
+    rc = rec_tc_try<KS, 2>(a, stream, fng == 0, &launched);
     if (rc || launched) return rc;
   }
-  rc = rec_tc_try<KS, 64>(a, stream, false, &launched);
+  rc = rec_tc_try<KS, 4>(a, stream, false, &launched);
   if (rc || launched) return rc;
   return 1;
 }
@@ -391,8 +404,8 @@ int rec_tc_launch(const plas_rec_desc& d, cudaStream_t stream) {
   a.d = d;
   a.whh_tc = d.whh_tc;
   a.n_groups = 0;
-  a.dbg = getenv("PLAS_REC_DBG") ? atoi(getenv("PLAS_REC_DBG")) : 0;
-  a.ss = getenv("PLAS_REC_SS") ? atoi(getenv("PLAS_REC_SS")) : 0;
+  a.dbg = 0;
+  a.ss = 0;
   switch (d.U) {
     case 64: return rec_tc_launch_ks<4>(a, stream);
     case 128: return rec_tc_launch_ks<8>(a, stream);

@@ -23,18 +23,9 @@ def probe(B, U, T, impl):
     print(f"B={B:4d} U={U:4d} T={T:5d} impl={impl:8s} rec {ms:8.3f} ms  -> {ms*1e3/T:6.2f} us/step", flush=True)
 
 if __name__ == "__main__":
-    for ss in ("0", "1"):
-        os.environ["PLAS_REC_SS"] = ss
-        for dbg in ("0", "3"):
-            os.environ["PLAS_REC_DBG"] = dbg
-            for nr in ("16", "32"):
-                os.environ["PLAS_REC_NR"] = nr
-                for (B, U, T) in [(int(nr), 512, 400), (int(nr), 128, 400)]:
-                    print("ss", ss, "dbg", dbg, "NR", nr, end=" ")
-                    probe(B, U, T, "tc")
-    os.environ["PLAS_REC_DBG"] = "0"
-    os.environ["PLAS_REC_NR"] = "0"
-    for ss in ("0", "1"):
-        os.environ["PLAS_REC_SS"] = ss
-        print("ss", ss, end=" ")
-        probe(64, 512, 400, "tc")
+    os.environ["PLAS_DEBUG"] = "1"
+    for ng in ("0", "1", "2", "4"):
+        os.environ["PLAS_REC_NG"] = ng
+        for (B, U, T) in [(16, 512, 400), (32, 512, 400), (64, 512, 400), (128, 512, 400), (64, 256, 400), (64, 128, 400)]:
+            print("NG", ng, end=" ")
+            probe(B, U, T, "tc")
