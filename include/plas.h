@@ -173,6 +173,23 @@ size_t plas_decoder_workspace_bytes(const plas_dec_desc* d);
 int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t workspace_bytes,
                      plas_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * K5  loss forward passes of las_model_fn (model_helper.py:20-130, 347-358).  f32 in, f32 out; sums are
+ * reduced in a fixed order (deterministic).  out3 = {sum(ce*w)/(sum(w)+1e-12), sum(ce*w), sum(w)}.
+ * ---------------------------------------------------------------------------------- */
+/* tf.contrib.seq2seq.sequence_loss (model_helper.py:30,75): logits [n_tokens][V], targets [n_tokens],
+ * weights [n_tokens] (NULL = all ones); ce_tokens [n_tokens] receives the per-token cross-entropy. */
+int plas_seq_ce_fwd(const float* logits, const int32_t* targets, const float* weights, int64_t n_tokens,
+                    int32_t V, float* ce_tokens, float* out3, plas_stream_t stream);
+/* sequence_loss_sigmoid (model_helper.py:81-95): per token the mean over n_feat of
+ * tf.nn.sigmoid_cross_entropy_with_logits, then the weighted mean over tokens. */
+int plas_sigmoid_ce_fwd(const float* logits, const float* labels, const float* weights, int64_t n_tokens,
+                        int32_t n_feat, float* ce_tokens, float* out3, plas_stream_t stream);
+/* tf.nn.ctc_loss_v2, dense labels, batch-major logits [B][T][C] (model_helper.py:355-356; blank = 0 there):
+ * loss[b] = -log p(labels[b,:label_len[b]] | logits[b,:logit_len[b]]). */
+int plas_ctc_fwd(const float* logits, const int32_t* labels, const int32_t* label_len, const int32_t* logit_len,
+                 int32_t B, int32_t T, int32_t C, int32_t Lmax, int32_t blank, float* loss, plas_stream_t stream);
+
 /* mask values past each length: y[b][t][:] = t < len[b] ? x[b][t][:] : 0  (attention `values`,
  * tf.contrib.seq2seq _prepare_memory; las/model.py:168-169). dtype-generic, in place allowed. */
 int plas_mask_time(int32_t dtype, const void* x, void* y, const int32_t* len, int32_t B, int32_t T,

@@ -68,6 +68,12 @@ EXPORTS = {
     "plas_bilstm_rec_fwd": (C.c_int, [C.POINTER(RecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_decoder_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
     "plas_decoder_fwd": (C.c_int, [C.POINTER(DecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_seq_ce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "plas_sigmoid_ce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "plas_ctc_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "plas_mask_time": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p]),
 }
