@@ -25,8 +25,7 @@ class ListenerWeights:
 
     def __init__(self, params, hp, num_channels, precision="fp32", device="cuda"):
         _lib.require_cuda()
-        if not hp["use_pyramidal"]:
-            raise NotImplementedError("non-pyramidal listener (las/model.py:111-142) is not built yet")
+        self.pyramidal = bool(hp["use_pyramidal"])
         self.precision = precision
         self.U = U = hp["encoder_units"]
         self.L = hp["encoder_layers"]
@@ -37,7 +36,10 @@ class ListenerWeights:
         self.layers = []
         din = num_channels
         for l in range(self.L):
-            if self.ndir == 2:
+            if not self.pyramidal:  # stacked MultiRNNCell per direction (las/model.py:111-142)
+                dirs = ["bidirectional_rnn/fw", "bidirectional_rnn/bw"] if self.ndir == 2 else ["rnn"]
+                names = [f"listener/{d}/multi_rnn_cell/cell_{l}/lstm_cell" for d in dirs]
+            elif self.ndir == 2:
                 names = [f"listener/bilstm_{l}/bidirectional_rnn/{d}/lstm_cell" for d in ("fw", "bw")]
             else:
                 names = [f"listener/bilstm_{l}/rnn/lstm_cell"]
@@ -46,6 +48,8 @@ class ListenerWeights:
             assert kernels[0].shape == (din + U, 4 * U), (kernels[0].shape, din, U)
             k_pad = _round_up(din, 64) if precision == "bf16" else din
             wt, bs = packing.pack_inproj(kernels, biases, din, U, k_pad)
+            # non-pyramidal layers >= 1: direction d reads only its own previous output, so the projection is one
+            # GEMM per direction (rows d*4U.. of wt are that direction's weights over its U inputs)
             if precision == "bf16":
                 whh = packing.pack_rec_bf16(kernels, din, U)
             else:
@@ -58,8 +62,8 @@ class ListenerWeights:
                 wt=torch.from_numpy(wt).to(device=device, dtype=dt).contiguous(),
                 bias=torch.from_numpy(bs).to(device),
                 whh=torch.from_numpy(whh).to(device=device, dtype=dt).contiguous()))
-            din = self.ndir * U * (1 if l == 0 else 2)
-        self.out_depth = din if self.L > 1 else self.ndir * U
+            din = (self.ndir * U * (1 if l == 0 else 2)) if self.pyramidal else U
+        self.out_depth = (self.ndir * U * (2 if self.L > 1 else 1)) if self.pyramidal else self.ndir * U
 
 
 def _gemm(precision, a2d, M, K, lda, wt, bias, out2d):
@@ -73,13 +77,32 @@ def _gemm(precision, a2d, M, K, lda, wt, bias, out2d):
     _lib.count_launches(1)
 
 
-def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out):
-    """One (bi)LSTM layer: x [B,T,K] (compute dtype, K == lw['k_pad']) -> out [B,t_alloc_out,ndir*U]."""
+def _gemm_view(precision, a, a_col0, M, K, lda, wt, w_row0, N, bias, out2d, out_col0):
+    """C[:, out_col0:out_col0+N] = A[:, a_col0:a_col0+K] @ wt[w_row0:w_row0+N, :K]^T + bias[w_row0:...] on strided
+    views of contiguous tensors (pointer arithmetic; every offset keeps the 16-byte alignment the kernels need)."""
+    L = _lib.lib()
+    esz = a.element_size()
+    fn = L.plas_gemm_bf16 if precision == "bf16" else L.plas_gemm_f32
+    with _lib.stage("inproj_gemm"):
+        _lib.check(fn(C.c_void_p(a.data_ptr() + a_col0 * esz), M, K, lda,
+                      C.c_void_p(wt.data_ptr() + w_row0 * wt.stride(0) * wt.element_size()), N, wt.stride(0),
+                      C.c_void_p(bias.data_ptr() + w_row0 * 4), C.c_void_p(out2d.data_ptr() + out_col0 * out2d.element_size()),
+                      out2d.stride(0), _lib.stream_ptr()))
+    _lib.count_launches(1)
+
+
+def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_input=False):
+    """One (bi)LSTM layer: x [B,T,K] (compute dtype, K == lw['k_pad']) -> out [B,t_alloc_out,ndir*U].
+    ``per_direction_input``: x is [B,T,ndir*U] and direction d reads only x[..., d*U:(d+1)*U] (stacked MultiRNNCell)."""
     L = _lib.lib()
     B, T, K = x.shape
     dt = x.dtype
     xproj = torch.empty((B * T, ndir * 4 * U), dtype=dt, device=x.device)
-    _gemm(precision, x.reshape(B * T, K), B * T, K, K, lw["wt"], lw["bias"], xproj)
+    if per_direction_input:
+        for dd in range(ndir):
+            _gemm_view(precision, x, dd * U, B * T, U, K, lw["wt"], dd * 4 * U, 4 * U, lw["bias"], xproj, dd * 4 * U)
+    else:
+        _gemm(precision, x.reshape(B * T, K), B * T, K, K, lw["wt"], lw["bias"], xproj)
     out = torch.zeros((B, t_alloc_out, ndir * U), dtype=dt, device=x.device)
     c_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
     h_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
@@ -132,9 +155,38 @@ def pyramidal_bilstm(inputs, sequence_length, mode, hparams, weights):
     return (x, lengths), enc_state
 
 
+def stacked_bilstm(inputs, sequence_length, mode, hparams, weights):
+    """Non-pyramidal branch of las/model.py:111-142: one MultiRNNCell stack per direction, no time reduction.
+    Layer 0 projects the shared input for both directions in one GEMM; deeper layers project each direction's own
+    previous output.  Returns outputs [B,T,ndir*U], the unchanged lengths and per-direction tuples of (c,h)."""
+    w = weights
+    precision = w.precision
+    B, T, Cin = inputs.shape
+    assert Cin == w.C, f"features have {Cin} channels, weights expect {w.C}"
+    lengths = sequence_length.to(device=inputs.device, dtype=torch.int32).contiguous()
+    L = _lib.lib()
+    if precision == "bf16":
+        k_pad = w.layers[0]["k_pad"]
+        x = torch.empty((B, T, k_pad), dtype=torch.bfloat16, device=inputs.device)
+        src = inputs.contiguous()
+        with _lib.stage("cast"):
+            _lib.check(L.plas_cast_pad_bf16(_lib.ptr(src), B * T, Cin, Cin, _lib.ptr(x), k_pad, _lib.stream_ptr()))
+        _lib.count_launches(1)
+    else:
+        x = inputs.to(torch.float32).contiguous()
+    states = []
+    for l, lw in enumerate(w.layers):
+        x, st = bilstm_layer(x, lengths, lw, w.U, w.ndir, precision, T, per_direction_input=(l > 0))
+        states.append(st)
+    per_dir = tuple(tuple((c[dd], h[dd]) for (c, h) in states) for dd in range(w.ndir))
+    return (x, lengths), (per_dir if w.ndir == 2 else per_dir[0])
+
+
 def listener(encoder_inputs, source_sequence_length, mode, hparams, weights):
     """las/model.py:104-142.  ``hparams`` is the flat dict (or the encoder view); ``weights`` a
     :class:`ListenerWeights`.  mode: 'train' | 'eval' | 'infer' (dropout must be 0 in 'train')."""
     if mode == "train" and float(hparams.get("dropout", 0.0)) > 0.0:
         raise NotImplementedError("input dropout in TRAIN mode (las/ops.py:14-18) is not built yet")
+    if not weights.pyramidal:
+        return stacked_bilstm(encoder_inputs, source_sequence_length, mode, hparams, weights)
     return pyramidal_bilstm(encoder_inputs, source_sequence_length, mode, hparams, weights)

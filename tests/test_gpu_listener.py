@@ -73,3 +73,25 @@ def test_listener_batch_independence_full_width():
     (full, flen), _ = listener(xt, lt, "infer", hp, w)
     (sub, slen), _ = listener(xt[40:45].contiguous(), lt[40:45].contiguous(), "infer", hp, w)
     assert torch.equal(full[40:45], sub) and torch.equal(flen[40:45], slen)
+
+
+@gpu
+@pytest.mark.parametrize("precision,B,T,C,U,L,uni", [("fp32", 5, 17, 9, 32, 3, False), ("bf16", 20, 33, 40, 64, 2, False),
+                                                     ("fp32", 3, 12, 6, 32, 2, True), ("bf16", 9, 21, 80, 128, 3, False)])
+def test_non_pyramidal_listener(precision, B, T, C, U, L, uni):
+    """las/model.py:111-142: stacked MultiRNNCell per direction, no time reduction, output depth ndir*U."""
+    import torch
+    from phones_las_b200.listener import ListenerWeights, listener
+    hp = create_hparams(target_vocab_size=16, encoder_layers=L, encoder_units=U, decoder_units=32, decoder_layers=1,
+                        num_channels=C, use_pyramidal=False, unidirectional=uni)
+    params = weights.init_params(hp, seed=U + L, bias_scale=0.1)
+    x, lens = synth.synth_features(B, T, C, seed=B + T, var_len=True)
+    (ref_out, ref_len), ref_state = ol.listener(x, lens, params, hp, precision)
+    w = ListenerWeights(params, hp, C, precision)
+    (out, olen), state = listener(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), "infer", hp, w)
+    np.testing.assert_array_equal(olen.cpu().numpy(), ref_len)
+    assert to_np(out).shape == ref_out.shape == (B, T, (1 if uni else 2) * U)
+    assert_parity(out, ref_out, precision, "encoder_out (stacked)", bf16_fro=2e-3)
+    top = state[L - 1] if uni else state[0][L - 1]
+    ref_top = ref_state[0][L - 1]
+    assert_parity(top[0], ref_top[0], precision, "final c (fw, top layer)", bf16_fro=2e-3)

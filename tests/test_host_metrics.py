@@ -1,0 +1,25 @@
+import numpy as np
+
+from oracle import losses as olo
+from phones_las_b200 import metrics
+
+
+def test_edit_distance_matches_oracle_and_quirks():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        B, L = 4, 12
+        hyp = rng.integers(2, 7, (B, L))
+        tru = rng.integers(2, 7, (B, L))
+        tru[:, 0] = 5  # non-empty truth
+        got = metrics.edit_distance(hyp, tru, eos_id=2)
+        for b in range(B):
+            ref = olo.edit_distance_merge(hyp[b].tolist(), tru[b].tolist(), eos_id=2)
+            assert abs(got[b] - ref) < 1e-12
+    # repeats are merged in BOTH sequences; everything after the first EOS is ignored
+    assert metrics.edit_distance([[3, 3, 4, 2, 9, 9]], [[3, 4, 4, 2, 1, 1]], eos_id=2)[0] == 0.0
+    assert metrics.edit_distance([[3, 5, 2]], [[3, 4, 2]], eos_id=2)[0] == 0.5
+    assert metrics.edit_distance([[2, 3]], [[2, 4]], eos_id=2)[0] == 0.0
+    assert np.isinf(metrics.edit_distance([[3, 2]], [[2, 4]], eos_id=2)[0])
+    # optional id mapping (metrics_utils.py:33-36)
+    mapping = np.array([0, 1, 2, 7, 7, 5])
+    assert metrics.edit_distance([[3, 2]], [[4, 2]], eos_id=2, mapping=mapping)[0] == 0.0
