@@ -113,6 +113,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Rows before this call belong to the warm-up (the sampler is started early so that nvidia-smi's own
+        start-up, which can hold the driver for a moment on a fresh box, does not land in the timed region)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -124,7 +129,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        first = getattr(self, "first", 0)
+        rows = self.rows[first:] if len(self.rows) > first else self.rows
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -262,13 +269,19 @@ def ours(args):
 
     # ---- device-resident throughput ----------------------------------------------------------
     n_dec = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         pred = model.transcribe(dev_waves[i % nbuf])
         n_dec = int(pred["sample_ids"].shape[1])
-    sampler = ClockSampler(local)
     barrier()
     if rank == 0:
-        sampler.start()
+        deadline = time.time() + 3.0  # let nvidia-smi deliver its first sample before the timed region starts
+        while not sampler.rows and sampler.proc is not None and time.time() < deadline:
+            time.sleep(0.05)
+        sampler.mark()
+    barrier()
     l0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

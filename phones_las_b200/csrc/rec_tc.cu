@@ -28,7 +28,8 @@
 namespace plas {
 
 constexpr int RT_THREADS = 256;
-constexpr int RT_THREADS2 = 288;  // 8 epilogue warps + 1 MMA-issuer warp
+constexpr int RT_THREADS2 = 416;  // 8 gate-math warps + 1 MMA-issuer warp + 4 publisher warps
+constexpr int RT_NPUB = 128;      // publisher threads
 constexpr int RT_NACC = 4;    // independent accumulators (k-steps interleaved): back-to-back tcgen05.mma on ONE
                               // accumulator serialise on its ~50-cycle latency, which dominates at N = 16..64
 
@@ -36,6 +37,7 @@ struct RecTcArgs {
   plas_rec_desc d;
   const void* whh_tc;  // [ndir][G][128][U] bf16, row m = 4*unit_local + gate
   int n_groups;
+  unsigned long long* tdbg;  // optional [8] ns counters written by CTA 0 (PLAS_DEBUG)
   int dbg;  // timing experiments only (PLAS_REC_DBG): 1 = no exchange (wrong results), 2 = no gate math
   int ss;   // 1: W slice resident in SHARED memory (SS form), 0: resident in TENSOR memory (TS form)
 };
@@ -50,7 +52,10 @@ __device__ __forceinline__ void rt_st_async_v4(uint32_t raddr, const uint4& v, u
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
                : "memory");
 }
-__device__ __forceinline__ void rt_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// named barriers between the 256 gate-math threads and the 128 publisher threads (double-buffered stage tile):
+// ids 2,3 = "stage tile b is full", ids 4,5 = "stage tile b has been published"
+__device__ __forceinline__ void rt_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void rt_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void rt_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -67,6 +72,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16 TMEM lanes x 8 columns in the mma-C-fragment distribution: thread t gets lane t/4 (r0,r1) and lane t/4+8
+// (r2,r3), columns 2*(t%4) and 2*(t%4)+1
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
@@ -184,12 +197,16 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
   if (warp == 8) {
     // ===== MMA issuer: per (step, group) wait for h_{s-1}, re-arm the buffer's barrier, issue, commit =====
     if (elect_one()) {
+      unsigned long long t_wait = 0, t_issue = 0, t0 = 0, t1 = 0;
+      const bool tm = p.tdbg != nullptr && blockIdx.x == 0;
       for (int s = 1; s < Tmax; ++s) {
         const int bsel = (s - 1) & 1;
 #pragma unroll
         for (int gg = 0; gg < NG; ++gg) {
           if (s >= Tg[gg]) continue;
+          if (tm) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
           mbar_wait(hbar[gg][bsel], (uint32_t)(((s - 1) >> 1) & 1));  // h_{s-1} of the whole group has landed
+          if (tm) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); t_wait += t1 - t0; }
           if (s + 1 <= Tg[gg] - 2) mbar_expect_tx(hbar[gg][bsel], step_bytes);  // re-arm for h_{s+1}
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.async data -> tensor-core reads
           tc_fence_after();
@@ -201,18 +218,67 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
                          ks != 0 ? 1u : 0u);
           }
           umma_commit(mbar[gg]);
+          if (tm) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0)); t_issue += t0 - t1; }
         }
       }
+      if (tm) { p.tdbg[0] = t_wait; p.tdbg[1] = t_issue; }
     }
     __syncwarp();
+  } else if (warp >= 9) {
+    // ===== publisher warps 9..12: push every staged 16 x 32 slice (a) into the swizzled h operand of every CTA of
+    // the cluster -- thread = (destination, row, 16-byte chunk), so the four chunks of a row leave as one contiguous
+    // 64-byte DSMEM segment (scattered 16-byte remote stores were measured 30% slower) -- and (b) for active rows to
+    // the [B,T,ndir*U] layer output in HBM.  An SM sends only ~20 bytes/clk over the SM-to-SM network, so the
+    // 16 KB of a group step keep the store unit busy for ~0.4 us: on their own warps these stores overlap the gate
+    // math of the next group instead of stalling it. =====
+    const int ptid = tid - 9 * 32;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
+    int n_item = 0;
+    for (int s = 0; s < Tmax; ++s) {
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) {
+        if (s >= Tg[gg]) continue;
+        const int sb = n_item & 1;
+        ++n_item;
+        const __nv_bfloat16* stg = s_stage + sb * (NR * 32);
+        rt_bar_sync(2 + sb, 256 + RT_NPUB);  // wait until the gate-math warps have filled the tile
+        if (s + 1 < Tg[gg]) {
+          const uint32_t dst_buf = hbuf_u + (uint32_t)((gg * 2 + (s & 1)) * HBUF) + (uint32_t)((ci >> 1) * TILE);
+          const uint32_t bar_l = hbar[gg][s & 1];
+#pragma unroll
+          for (int j = 0; j < (G * NR * 4 + RT_NPUB - 1) / RT_NPUB; ++j) {
+            const int idx = ptid + j * RT_NPUB;
+            if (idx < G * NR * 4) {
+              const int rank = idx / (NR * 4), chunk = idx % (NR * 4);
+              const int r = chunk >> 2, ch = chunk & 3;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 32 + ch * 8);
+              const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
+              const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+              rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
+            }
+          }
+        }
+        if (ptid < NR * 4) {
+          const int r = ptid >> 2, ch = ptid & 3;
+          const int b = (grp0 + gg) * NR + r;
+          const int len = s_len[gg][r];
+          if (b < B && s < len) {
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 32 + ch * 8);
+            const int t = dir ? (len - 1 - s) : s;
+            __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
+            *reinterpret_cast<uint4*>(odst) = v;
+          }
+        }
+        rt_bar_arrive(4 + sb, 256 + RT_NPUB);  // tile published: the gate-math warps may overwrite it
+      }
+    }
   } else {
-    // ===== epilogue warps 0..7 =====
-    // gate-math mapping: lane -> unit u8 = lane/4 of this warp's 8 units, utterances jq, jq+4 of the warp half (w/4)
+    // ===== gate-math warps 0..7 =====
+    // gate-math mapping: lane -> unit u8 = lane/4 of this warp's 8 units, utterances 2*jq, 2*jq+1 of the warp half (w/4)
     const int u8 = lane >> 2, jq = lane & 3;
     const int unit = ci * 32 + (warp & 3) * 8 + u8;
     const int half0 = (warp >> 2) * HR;
     const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
     const int NX = ndir * 4 * U;
     int len_p[NG][PP];
     const __nv_bfloat16* xrow[NG][PP];
@@ -222,7 +288,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
       for (int i = 0; i < PP; ++i) {
-        const int r = half0 + jq + 4 * i;
+        const int r = half0 + 2 * jq + i;
         len_p[gg][i] = s_len[gg][r];
         xrow[gg][i] = xproj + ((size_t)min((grp0 + gg) * NR + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
         c_state[gg][i] = 0.f;
@@ -233,33 +299,42 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
           xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][i] + (size_t)t * NX));
         }
       }
-    float* zt = s_z + (size_t)warp * HR * 36;  // this warp's transpose tile [HR][36] (32 columns + pad)
     uint32_t mma_parity[NG];
 #pragma unroll
     for (int gg = 0; gg < NG; ++gg) mma_parity[gg] = 0;
 
+    int n_item = 0;
+    unsigned long long e_wait = 0, e_gate = 0, e_push = 0, e0 = 0, e1 = 0;
+    const bool tme = p.tdbg != nullptr && blockIdx.x == 0 && tid == 0;
     for (int s = 0; s < Tmax; ++s) {
 #pragma unroll
       for (int gg = 0; gg < NG; ++gg) {
         if (s >= Tg[gg]) continue;  // uniform over the cluster
+        if (tme) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e0));
+        const int sb = n_item & 1;
+        __nv_bfloat16* stg = s_stage + sb * (NR * 32);
+        if (n_item >= 2) rt_bar_sync(4 + sb, 256 + RT_NPUB);  // the publishers are done with this tile's previous content
+        ++n_item;
+        uint32_t zr[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // [i,j | gates 0,1 of rows 0,1] then [f,o]: see below
         if (s > 0) {
           mbar_wait(mbar[gg], mma_parity[gg]);
+          if (tme) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e1)); e_wait += e1 - e0; e0 = e1; }
           mma_parity[gg] ^= 1u;
           tc_fence_after();
-          // accumulator: lane = gate column, column = utterance; this warp half reads HR columns
-          uint32_t r[HR];
-          tmem_ld8(tmem_base + lane_base + (uint32_t)(gg * NR + half0), r);
+          // accumulator: TMEM lane = gate column (8*gate + unit inside the warp's 32-lane quadrant), column =
+          // utterance.  Two 16x256b loads hand thread t all four gates of unit t/4 for utterances 2*(t%4), +1 of
+          // this warp half -- no shared-memory transpose.
+          tmem_ld_16x256b(tmem_base + lane_base + (uint32_t)(gg * NR + half0), zr);
+          tmem_ld_16x256b(tmem_base + lane_base + (16u << 16) + (uint32_t)(gg * NR + half0), zr + 4);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < HR; ++j) zt[j * 36 + lane] = __uint_as_float(r[j]);
           tc_fence_before();
-          __syncwarp();
         }
 #pragma unroll
         for (int i = 0; i < PP; ++i) {
-          const int rl = jq + 4 * i;  // utterance inside the warp half
-          float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (s > 0) z = *reinterpret_cast<const float4*>(zt + rl * 36 + 4 * u8);
+          const int rl = 2 * jq + i;  // utterance inside the warp half
+          // zr[0..1] = gate i (lane u8) rows 0,1; zr[2..3] = gate j (lane u8+8); zr[4..5] = gate f; zr[6..7] = gate o
+          const float4 z = make_float4(__uint_as_float(zr[i]), __uint_as_float(zr[2 + i]), __uint_as_float(zr[4 + i]),
+                                       __uint_as_float(zr[6 + i]));
           const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][i].x);
           const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][i].y);
           float cn, hn;
@@ -269,7 +344,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
             c_state[gg][i] = cn;
             h_state[gg][i] = bf16_round(hn);
           }
-          s_stage[(half0 + rl) * 32 + (warp & 3) * 8 + u8] = __float2bfloat16_rn(h_state[gg][i]);
+          stg[(half0 + rl) * 32 + (warp & 3) * 8 + u8] = __float2bfloat16_rn(h_state[gg][i]);
           // prefetch this group's next gate pre-activations (consumed one full round later)
           xp[gg][i] = make_uint2(0u, 0u);
           if (s + 1 < len_p[gg][i]) {
@@ -277,46 +352,18 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
             xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][i] + (size_t)t * NX));
           }
         }
-        rt_epi_sync();
-        // publish the staged 16 x 32 slice: (a) into the swizzled h operand of every CTA of the cluster (not needed
-        // after the group's last step) -- thread = (destination, row, 16-byte chunk) so that the four chunks of a row
-        // leave as one contiguous 64-byte DSMEM segment (a per-warp publish without this barrier was measured 30%
-        // slower: scattered 16-byte remote stores) --, (b) for active rows to the [B,T,ndir*U] layer output in HBM
-        if (s + 1 < Tg[gg]) {
-          const uint32_t dst_buf = hbuf_u + (uint32_t)((gg * 2 + (s & 1)) * HBUF) + (uint32_t)((ci >> 1) * TILE);
-          const uint32_t bar_l = hbar[gg][s & 1];
-#pragma unroll
-          for (int j = 0; j < (G * NR * 4 + 255) / 256; ++j) {
-            const int idx = tid + j * 256;
-            if (idx < G * NR * 4) {
-              const int rank = idx / (NR * 4), chunk = idx % (NR * 4);
-              const int r = chunk >> 2, ch = chunk & 3;
-              const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
-              const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
-              const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-              rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
-            }
-          }
-        }
-        if (tid < NR * 4) {
-          const int r = tid >> 2, ch = tid & 3;
-          const int b = (grp0 + gg) * NR + r;
-          const int len = s_len[gg][r];
-          if (b < B && s < len) {
-            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + r * 32 + ch * 8);
-            const int t = dir ? (len - 1 - s) : s;
-            __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
-            *reinterpret_cast<uint4*>(odst) = v;
-          }
-        }
-        rt_epi_sync();  // s_stage / the transpose tiles are rewritten by the next item
+        __threadfence_block();
+        rt_bar_arrive(2 + sb, 256 + RT_NPUB);  // stage tile sb is full: the publisher warps take it from here
+        if (tme) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e1)); e_gate += e1 - e0; e0 = e1; }
+        if (tme) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e1)); e_push += e1 - e0; }
       }
     }
+    if (tme) { p.tdbg[2] = e_wait; p.tdbg[3] = e_gate; p.tdbg[4] = e_push; }
 #pragma unroll
     for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
       for (int i = 0; i < PP; ++i) {
-        const int b = (grp0 + gg) * NR + half0 + jq + 4 * i;
+        const int b = (grp0 + gg) * NR + half0 + 2 * jq + i;
         if (grp0 + gg < p.n_groups && b < B) {
           d.c_final[((size_t)dir * B + b) * U + unit] = c_state[gg][i];
           d.h_final[((size_t)dir * B + b) * U + unit] = h_state[gg][i];
@@ -340,7 +387,7 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   constexpr int U = KS * 16, G = U / 32, NR = 16;
   *launched = false;
   // > 114 KB of shared memory: at most one CTA per SM, so the TMEM allocation can never contend
-  size_t smem = 1024 + (size_t)NG * 2 * (U / 64) * NR * 128 + (size_t)8 * (NR / 2) * 36 * 4 + (size_t)NR * 32 * 2;
+  size_t smem = 1024 + (size_t)NG * 2 * (U / 64) * NR * 128 + (size_t)8 * (NR / 2) * 36 * 4 + (size_t)2 * NR * 32 * 2;
   if (smem > 227 * 1024) return PLAS_OK;
   if (smem < 120 * 1024) smem = 120 * 1024;
   auto fn = rec_tc_kernel<KS, NG>;
@@ -370,7 +417,21 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
     return PLAS_OK;
   }
   if (must_fit_one_wave && clusters > max_clusters) return PLAS_OK;
+  unsigned long long* dbgbuf = nullptr;
+  if (getenv("PLAS_DEBUG")) {
+    PLAS_CUDA(cudaMalloc(&dbgbuf, 64));
+    PLAS_CUDA(cudaMemset(dbgbuf, 0, 64));
+  }
+  a.tdbg = dbgbuf;
   PLAS_CUDA(cudaLaunchKernelEx(&cfg, fn, a));
+  if (dbgbuf) {  // debug only: synchronises
+    unsigned long long h[8];
+    PLAS_CUDA(cudaStreamSynchronize(stream));
+    PLAS_CUDA(cudaMemcpy(h, dbgbuf, 64, cudaMemcpyDeviceToHost));
+    cudaFree(dbgbuf);
+    fprintf(stderr, "[plas]   rec tc CTA 0 (us): issuer wait-h %.1f issue %.1f | epilogue wait-mma %.1f ld+gates %.1f publish %.1f  (T=%d)\n",
+            h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, d.T);
+  }
   *launched = true;
   return PLAS_OK;
 }
@@ -406,6 +467,7 @@ int rec_tc_launch(const plas_rec_desc& d, cudaStream_t stream) {
   a.n_groups = 0;
   a.dbg = 0;
   a.ss = 0;
+  a.tdbg = nullptr;
   switch (d.U) {
     case 64: return rec_tc_launch_ks<4>(a, stream);
     case 128: return rec_tc_launch_ks<8>(a, stream);

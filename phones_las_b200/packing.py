@@ -84,13 +84,18 @@ def pack_rec_bf16(kernels, din, U):
 
 
 def pack_rec_tc(kernels, din, U):
-    """Recurrent weights for rec_tc_kernel (TMEM-resident A operand): [ndir][U/32][128][U], row
-    m = 4*unit_local + gate of CTA ci holds W_h[:, gate*U + ci*32 + unit_local] (K-major)."""
-    cols = unit_major_cols(U)
+    """Recurrent weights for rec_tc_kernel (TMEM-resident A operand): [ndir][U/32][128][U] (K-major).  Row (TMEM
+    lane) m = 32*q + 8*gate + u8 of CTA ci holds W_h[:, gate*U + ci*32 + 8*q + u8]: inside every 32-lane quadrant
+    the four gates of a unit sit 8 lanes apart, which is what the 16x256b TMEM load hands to one thread."""
     out = np.zeros((len(kernels), U // 32, 128, U), np.float32)
+    q, gate, u8 = np.meshgrid(np.arange(4), np.arange(4), np.arange(8), indexing="ij")
+    m = (32 * q + 8 * gate + u8).reshape(-1)
+    ul = (8 * q + u8).reshape(-1)
+    g = gate.reshape(-1)
     for d, k in enumerate(kernels):
         wh = np.asarray(k[din:], np.float32)  # [U, 4U]
-        out[d] = wh[:, cols].T.reshape(U // 32, 128, U)
+        for ci in range(U // 32):
+            out[d, ci, m] = wh[:, g * U + ci * 32 + ul].T
     return out
 
 

@@ -24,8 +24,8 @@ def probe(B, U, T, impl):
 
 if __name__ == "__main__":
     os.environ["PLAS_DEBUG"] = "1"
-    for ng in ("0", "1", "2", "4"):
+    for ng in ("1", "2"):
         os.environ["PLAS_REC_NG"] = ng
-        for (B, U, T) in [(16, 512, 400), (32, 512, 400), (64, 512, 400), (128, 512, 400), (64, 256, 400), (64, 128, 400)]:
+        for (B, U, T) in [(16 * int(ng), 512, 400), (64, 512, 400)]:
             print("NG", ng, end=" ")
             probe(B, U, T, "tc")

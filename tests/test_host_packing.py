@@ -140,5 +140,5 @@ def test_pack_rec_tc_rows():
     kernels = [rng.standard_normal((din + U, 4 * U)).astype(np.float32) for _ in range(2)]
     t = packing.pack_rec_tc(kernels, din, U)
     assert t.shape == (2, U // 32, 128, U)
-    d, ci, ul, gate, k = 1, 1, 7, 2, 33
-    assert t[d, ci, 4 * ul + gate, k] == kernels[d][din + k, gate * U + ci * 32 + ul]
+    d, ci, ul, gate, k = 1, 1, 13, 2, 33  # unit 13 of the CTA: quadrant 1, u8 = 5
+    assert t[d, ci, 32 * (ul // 8) + 8 * gate + ul % 8, k] == kernels[d][din + k, gate * U + ci * 32 + ul]
