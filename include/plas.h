@@ -105,11 +105,11 @@ int plas_cast_pad_bf16(const float* x, int64_t rows, int32_t cols, int64_t ld_in
 typedef struct plas_rec_desc {
   int32_t dtype;            /* PLAS_F32 / PLAS_BF16: type of xproj, whh, out                   */
   int32_t B, T, U, ndir;    /* T = time extent of xproj/out; ndir 1 (fw) or 2 (fw,bw)          */
-  int32_t _pad;
+  int32_t out_zeroed;       /* 1: the caller already zeroed `out`; 0: the call must leave out[b][t >= len] = 0 */
   const void* xproj;        /* [B][T][ndir*4U], column = dir*4U + 4*unit + gate                */
   const void* whh;          /* packed recurrent weights, see plas_rec_pack_whh                  */
   const int32_t* lengths;   /* [B]                                                             */
-  void* out;                /* [B][T_out][ndir*U], zero for t >= len (caller pre-zeroes)       */
+  void* out;                /* [B][T_out][ndir*U], zero for t >= len (see out_zeroed)          */
   int64_t out_batch_stride; /* elements between utterances in `out` (>= T*ndir*U)              */
   float* c_final;           /* [ndir][B][U]                                                    */
   float* h_final;           /* [ndir][B][U]                                                    */

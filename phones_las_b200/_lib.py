@@ -27,7 +27,7 @@ class FrontendDesc(C.Structure):
 
 class RecDesc(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("T", C.c_int32), ("U", C.c_int32), ("ndir", C.c_int32),
-                ("_pad", C.c_int32),
+                ("out_zeroed", C.c_int32),
                 ("xproj", C.c_void_p), ("whh", C.c_void_p), ("lengths", C.c_void_p), ("out", C.c_void_p),
                 ("out_batch_stride", C.c_int64), ("c_final", C.c_void_p), ("h_final", C.c_void_p),
                 ("whh_tc", C.c_void_p)]

@@ -698,11 +698,13 @@ extern "C" int plas_bilstm_rec_fwd(const plas_rec_desc* d, void* workspace, size
   a.G = d->U / upc;
   a.Bpad = a.n_groups * REC_ROWS;
 
-  // fastest path: tcgen05 with W_hh resident in tensor memory (rec_tc.cu)
+  // fastest path: tcgen05 with W_hh resident in tensor memory (rec_tc.cu); writes the zero padding itself
   {
     const int rc = rec_tc_launch(*d, stream);
     if (rc != 1) return rc;  // 1 = not eligible / not schedulable
   }
+  if (!d->out_zeroed)  // the other kernels only write active positions
+    PLAS_CUDA(cudaMemsetAsync(d->out, 0, (size_t)d->B * d->out_batch_stride * (d->dtype == PLAS_BF16 ? 2 : 4), stream));
   // next: one thread-block cluster per (direction, group), mma.sync with W_hh resident in registers
   if (d->dtype == PLAS_BF16 && a.G <= 16 && !rec_force_legacy()) {
     int rc = rec_launch_cluster(a, stream);

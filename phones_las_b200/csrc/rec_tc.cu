@@ -262,14 +262,37 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
           const int r = ptid >> 2, ch = ptid & 3;
           const int b = (grp0 + gg) * NR + r;
           const int len = s_len[gg][r];
-          if (b < B && s < len) {
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 32 + ch * 8);
-            const int t = dir ? (len - 1 - s) : s;
-            __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
-            *reinterpret_cast<uint4*>(odst) = v;
+          if (b < B) {
+            // active step: h at its own time index (bw walks len-1-s); past the length: the zero padding of frame s
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            int t = s;
+            if (s < len) {
+              v = *reinterpret_cast<const uint4*>(stg + r * 32 + ch * 8);
+              t = dir ? (len - 1 - s) : s;
+            }
+            if (s < len || !d.out_zeroed) {
+              __nv_bfloat16* odst = out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8;
+              *reinterpret_cast<uint4*>(odst) = v;
+            }
           }
         }
         rt_bar_arrive(4 + sb, 256 + RT_NPUB);  // tile published: the gate-math warps may overwrite it
+      }
+    }
+    if (!d.out_zeroed) {
+      // frames beyond the longest utterance of a group (and the even-length pad frame) are zero as well
+      const int t_alloc = (int)(d.out_batch_stride / (ndir * U));
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) {
+        if (grp0 + gg >= p.n_groups) continue;
+        const int n_t = t_alloc - Tg[gg];
+        for (int i = ptid; i < n_t * NR * 4; i += RT_NPUB) {
+          const int t = Tg[gg] + i / (NR * 4), r = (i / 4) % NR, ch = i & 3;
+          const int b = (grp0 + gg) * NR + r;
+          if (b < B)
+            *reinterpret_cast<uint4*>(out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8) =
+                make_uint4(0u, 0u, 0u, 0u);
+        }
       }
     }
   } else {

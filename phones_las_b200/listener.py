@@ -103,11 +103,12 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
             _gemm_view(precision, x, dd * U, B * T, U, K, lw["wt"], dd * 4 * U, 4 * U, lw["bias"], xproj, dd * 4 * U)
     else:
         _gemm(precision, x.reshape(B * T, K), B * T, K, K, lw["wt"], lw["bias"], xproj)
-    out = torch.zeros((B, t_alloc_out, ndir * U), dtype=dt, device=x.device)
+    out = torch.empty((B, t_alloc_out, ndir * U), dtype=dt, device=x.device)  # the kernel zero-fills t >= len
     c_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
     h_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
     d = _lib.RecDesc()
     d.dtype, d.B, d.T, d.U, d.ndir = _lib.dtype_code(precision), B, T, U, ndir
+    d.out_zeroed = 0
     d.xproj, d.whh, d.lengths, d.out = xproj.data_ptr(), lw["whh"].data_ptr(), lengths.data_ptr(), out.data_ptr()
     d.out_batch_stride = out.stride(0)
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()

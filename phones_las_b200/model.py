@@ -24,16 +24,22 @@ class DeviceWeights:
         self.speller = SpellerWeights(params, hp, wts.encoder_output_depth(hp), precision, device)
 
 
-def las_predict(features, hp, weights, want_alignment=True):
-    """model_helper.py:165-297 in PREDICT mode with beam_width == 0."""
+def las_predict(features, hp, weights, want_alignment=True, trim=True, want_probs=True):
+    """model_helper.py:165-297 in PREDICT mode with beam_width == 0.  ``trim=False`` keeps the step axis at its
+    static capacity and leaves the executed step count on the device (``n_steps``), so the call enqueues without a
+    host synchronisation (serving loop)."""
     x = features["encoder_inputs"]
     lens = features["source_sequence_length"]
     (enc_out, enc_len), enc_state = listener(x, lens, "infer", hp, weights.listener)
-    out, state, final_len = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller)
+    # the listener already zeroes its outputs past each (reduced) length: no separate masking pass
+    out, state, final_len = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller,
+                                    memory_is_masked=True, want_alignment=want_alignment, trim=trim)
     logits = out.rnn_output
     pred = {"encoder_out": enc_out, "source_length": enc_len, "sample_ids": out.sample_id,
             "logits": logits, "final_sequence_length": final_len, "alignment": state.alignment_history,
-            "probs": torch.softmax(logits, dim=-1)}
+            "n_steps": state.n_steps}
+    if want_probs:
+        pred["probs"] = torch.softmax(logits, dim=-1)
     if isinstance(enc_state[0], tuple):
         emb_c = torch.cat([s[0] for s in enc_state], dim=1)
         emb_h = torch.cat([s[1] for s in enc_state], dim=1)
@@ -55,13 +61,13 @@ class LASModel:
     def features(self, wave, n_samples=None):
         return self.plan(wave, n_samples)
 
-    def predict_from_features(self, feats, n_frames):
-        return las_predict({"encoder_inputs": feats, "source_sequence_length": n_frames}, self.hp, self.weights)
+    def predict_from_features(self, feats, n_frames, **kw):
+        return las_predict({"encoder_inputs": feats, "source_sequence_length": n_frames}, self.hp, self.weights, **kw)
 
-    def transcribe(self, wave, n_samples=None):
+    def transcribe(self, wave, n_samples=None, **kw):
         """wave [B,N] float32 on the device -> predictions dict (transcribe_audio_file.py:97-101)."""
         feats, n_frames = self.plan(wave, n_samples)
-        return self.predict_from_features(feats, n_frames)
+        return self.predict_from_features(feats, n_frames, **kw)
 
     def transcribe_host(self, wave_host, n_samples_host=None):
         """Host entry point: pinned host waveform in, host numpy ids out (H2D + D2H inside)."""
@@ -69,3 +75,68 @@ class LASModel:
         ns = n_samples_host.to("cuda", non_blocking=True) if n_samples_host is not None else None
         pred = self.transcribe(wave, ns)
         return pred["sample_ids"].cpu(), pred["final_sequence_length"].cpu()
+
+    def transcribe_stream(self, host_batches):
+        """Serving loop over pinned host waveform batches ([B,N] float32 each), fully pipelined: the host->device copy
+        of batch i+1 runs on a copy stream into one of two preallocated device buffers while the kernels of batch i
+        execute, nothing in a step synchronises the host (the decode step count stays on the device), and the ids of
+        batch i are read back (pinned, asynchronous) while batch i+1 is already enqueued.  Yields
+        (sample_ids [B,steps], final_sequence_length [B]) host tensors per batch, in order."""
+        dev = self.plan.device
+        # staging state lives on the model: cudaMalloc / cudaHostAlloc are slow and synchronise the device, so the
+        # copy stream, the two device input buffers and the pinned result buffers are created once and reused
+        st = self.__dict__.setdefault("_stream_state", {"copy_stream": torch.cuda.Stream(device=dev),
+                                                        "bufs": [None, None], "pinned": [None, None]})
+        copy_stream, bufs, pinned = st["copy_stream"], st["bufs"], st["pinned"]
+        consumed = [None, None]  # "kernels are done with the staging buffer" events of this call
+        torch.cuda.current_stream().synchronize()  # buffers may still be in use by an earlier call
+
+        def stage(hw, slot):
+            if bufs[slot] is None or bufs[slot].shape != hw.shape:
+                bufs[slot] = torch.empty(hw.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copy_stream):
+                if consumed[slot] is not None:
+                    copy_stream.wait_event(consumed[slot])  # do not overwrite a batch that is still being read
+                bufs[slot].copy_(hw, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return bufs[slot], ev
+
+        def finish(job):
+            (ids_h, len_h, n_h), ev = job
+            ev.synchronize()
+            n = int(n_h[0])
+            return ids_h[:, :n].clone(), len_h.clone()
+
+        it = iter(host_batches)
+        first = next(it, None)
+        if first is None:
+            return
+        slot = 0
+        cur = stage(first, slot)
+        pending = None
+        while cur is not None:
+            nxt = next(it, None)
+            staged = stage(nxt, slot ^ 1) if nxt is not None else None
+            dw, ev = cur
+            main = torch.cuda.current_stream()
+            main.wait_event(ev)
+            pred = self.transcribe(dw, want_alignment=False, trim=False, want_probs=False)
+            done = torch.cuda.Event()
+            done.record(main)
+            consumed[slot] = done
+            ids_d, len_d, n_d = pred["sample_ids"], pred["final_sequence_length"], pred["n_steps"]
+            if pinned[slot] is None or pinned[slot][0].shape != ids_d.shape:
+                pinned[slot] = (torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory(),
+                                torch.empty(len_d.shape, dtype=len_d.dtype).pin_memory(),
+                                torch.empty(n_d.shape, dtype=n_d.dtype).pin_memory())
+            for h_t, d_t in zip(pinned[slot], (ids_d, len_d, n_d)):
+                h_t.copy_(d_t, non_blocking=True)
+            rd = torch.cuda.Event()
+            rd.record(main)
+            if pending is not None:
+                yield finish(pending)  # batch i-1 is read while batch i runs
+            pending = (pinned[slot], rd)
+            cur, slot = staged, slot ^ 1
+        if pending is not None:
+            yield finish(pending)

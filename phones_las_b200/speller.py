@@ -84,23 +84,27 @@ class SpellerWeights:
             self.w_proj_pad = up(wp)
 
 
-def prepare_memory(encoder_outputs, source_sequence_length, w):
+def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=False):
     """values = length-masked memory; keys = memory_layer(values) (tf.contrib.seq2seq
     _BaseAttentionMechanism; reference las/model.py:168-169)."""
     L = _lib.lib()
     B, Tm, D = encoder_outputs.shape
     enc = encoder_outputs.contiguous()
-    values = torch.empty_like(enc)
-    with _lib.stage("mask"):
-        _lib.check(L.plas_mask_time(_lib.dtype_code(w.precision), _lib.ptr(enc), _lib.ptr(values),
-                                    _lib.ptr(source_sequence_length), B, Tm, D, _lib.stream_ptr()))
+    if memory_is_masked:
+        values = enc  # already zero for t >= length (our listener guarantees it)
+    else:
+        values = torch.empty_like(enc)
+        with _lib.stage("mask"):
+            _lib.check(L.plas_mask_time(_lib.dtype_code(w.precision), _lib.ptr(enc), _lib.ptr(values),
+                                        _lib.ptr(source_sequence_length), B, Tm, D, _lib.stream_ptr()))
+        _lib.count_launches(1)
     n_pad = w.w_mem_t.shape[0]
     keys = torch.empty((B * Tm, n_pad), dtype=enc.dtype, device=enc.device)
     fn = L.plas_gemm_bf16 if w.precision == "bf16" else L.plas_gemm_f32
     with _lib.stage("memory_gemm"):
         _lib.check(fn(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_mem_t), n_pad, D, None, _lib.ptr(keys), n_pad,
                       _lib.stream_ptr()))
-    _lib.count_launches(2)
+    _lib.count_launches(1)
     if n_pad != w.Ud:
         keys = keys[:, :w.Ud].contiguous()
     pv = None
@@ -116,7 +120,7 @@ def prepare_memory(encoder_outputs, source_sequence_length, w):
 
 
 def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_steps=None,
-           want_alignment=True, trim=True):
+           want_alignment=True, trim=True, memory_is_masked=False):
     """Run the decoder kernel.  Greedy when ``forced_ids`` is None (max_steps defaults to
     rint(Tm * decoding_length_factor), las/model.py:270-274); teacher-forced otherwise."""
     L = _lib.lib()
@@ -124,7 +128,7 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     B, Tm, D = encoder_outputs.shape
     assert D == w.D
     mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).contiguous()
-    keys, values, pv = prepare_memory(encoder_outputs, mem_len, w)
+    keys, values, pv = prepare_memory(encoder_outputs, mem_len, w, memory_is_masked)
     factor = float(hp.get("decoding_length_factor", 1.0))
     if forced_ids is not None:
         forced_ids = forced_ids.to(device=dev, dtype=torch.int32).contiguous()
@@ -180,7 +184,8 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
 
 
 def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_length, target_sequence_length,
-            mode, hparams, weights, binary_outputs=False, binf_embedding=None, transparent_projection=False):
+            mode, hparams, weights, binary_outputs=False, binf_embedding=None, transparent_projection=False,
+            memory_is_masked=False, want_alignment=True, trim=True):
     """las/model.py:205-349.  mode 'train'/'eval' with ``decoder_inputs`` (targets_inputs ids [B,L])
     runs teacher forcing (TrainingHelper, sampling_probability must be 0); otherwise greedy."""
     if binary_outputs or binf_embedding is not None or transparent_projection:
@@ -196,8 +201,10 @@ def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_leng
                 steps = min(steps, hparams["max_symbols"])
         logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams,
                                                       forced_ids=decoder_inputs, max_steps=steps,
-                                                      want_alignment=False)
+                                                      want_alignment=False, memory_is_masked=memory_is_masked)
         seq_len = target_sequence_length
     else:
-        logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams)
+        logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams,
+                                                      memory_is_masked=memory_is_masked, want_alignment=want_alignment,
+                                                      trim=trim)
     return BasicDecoderOutput(logits, ids), SpellerState(align, n_steps), seq_len

@@ -1,0 +1,52 @@
+"""End-to-end host API: waveform -> features -> listener -> speller (model.LASModel) vs the oracle, and the
+streaming serving loop (H2D of batch i+1 overlapping batch i) vs the synchronous call."""
+import numpy as np
+
+from oracle import frontend as ofe, las as ol
+from phones_las_b200 import synth, weights
+from phones_las_b200.hparams import create_hparams, feature_args, num_feature_channels
+from tests.util import gpu, assert_parity
+
+
+def _model(precision="fp32"):
+    from phones_las_b200.model import LASModel
+    fa = feature_args(feature_type="mfcc", backend="librosa", n_mfcc=12, n_mels=40, energy=True, window=25, step=10, deltas=True)
+    C = num_feature_channels(fa)
+    hp = create_hparams(target_vocab_size=24, encoder_layers=3, encoder_units=64, decoder_layers=1, decoder_units=64,
+                        attention_type="luong", num_channels=C)
+    params = weights.init_params(hp, C, seed=5, projection_scale=8.0, bias_scale=0.1)
+    return LASModel(params, hp, fa, precision=precision), hp, fa, params
+
+
+@gpu
+def test_transcribe_matches_oracle_fp32():
+    import torch
+    model, hp, fa, params = _model("fp32")
+    wave, lens = synth.synth_audio(3, 0.9, seed=2, var_len=True)
+    pred = model.transcribe(torch.from_numpy(wave).cuda(), torch.from_numpy(lens).cuda())
+    feats = [ofe.calculate_acoustic_features(fa, wave[b, :lens[b]]) for b in range(3)]
+    T = max(f.shape[0] for f in feats)
+    x = np.zeros((3, T, feats[0].shape[1]), np.float32)
+    for b, f in enumerate(feats):
+        x[b, :f.shape[0]] = f
+    nf = np.array([f.shape[0] for f in feats], np.int32)
+    ref = ol.predict(x, nf, params, hp, "fp32")
+    np.testing.assert_array_equal(pred["source_length"].cpu().numpy(), ref["source_length"])
+    # features differ by up to 1e-4 relative between the CUDA front-end and the oracle, so the encoder is compared
+    # at that level, not at 1e-5
+    enc = pred["encoder_out"].float().cpu().numpy()
+    assert np.abs(enc - ref["encoder_out"]).max() <= 2e-3 * np.abs(ref["encoder_out"]).max()
+    assert pred["embedding"].shape == (3, 2, 128) and pred["probs"].shape == pred["logits"].shape
+
+
+@gpu
+def test_transcribe_stream_equals_synchronous_calls():
+    import torch
+    model, hp, fa, params = _model("bf16")
+    batches = [torch.from_numpy(synth.synth_audio(4, 0.7, seed=10 + i)[0]).pin_memory() for i in range(4)]
+    sync = [model.transcribe_host(b) for b in batches]
+    streamed = list(model.transcribe_stream(batches))
+    assert len(streamed) == len(sync)
+    for (ids_a, len_a), (ids_b, len_b) in zip(sync, streamed):
+        assert torch.equal(ids_a, ids_b) and torch.equal(len_a, len_b)
+    assert list(model.transcribe_stream([])) == []
