@@ -113,8 +113,9 @@ typedef struct plas_rec_desc {
   int64_t out_batch_stride; /* elements between utterances in `out` (>= T*ndir*U)              */
   float* c_final;           /* [ndir][B][U]                                                    */
   float* h_final;           /* [ndir][B][U]                                                    */
-  const void* whh_tc;       /* bf16, optional: [ndir][U/32][128][U] rows m = 4*unit_local + gate, the
-                               TMEM-resident operand of the tcgen05 recurrence (NULL: mma.sync kernels)  */
+  const void* whh_tc;       /* bf16, optional: [ndir][U/32][128][U], row (TMEM lane) 32*q + 8*gate + u8 holds
+                               W_h[:, gate*U + 32*cta + 8*q + u8]; the TMEM-resident operand of the tcgen05
+                               recurrence (NULL: mma.sync kernels)                                         */
 } plas_rec_desc;
 
 /* Layout contract for whh (host side packs once per checkpoint load):

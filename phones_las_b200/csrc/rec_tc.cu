@@ -14,10 +14,9 @@
 // st.async, completing transaction bytes on each receiver's mbarrier -- h never leaves the chip and
 // there is no cluster barrier, no atomics and no fence on the step path (protocol as in rec.cu).
 //
-// Epilogue: thread (warp w, lane l) owns TMEM lane 32*(w%4)+l = gate column 4*unit+gate and half
-// of the utterances; a per-warp shared-memory transpose regroups (i,j,f,o) per (unit, utterance),
-// then the TF gate math (forget_bias 1.0, length masking, bw direction walking len-1-s) runs with
-// the cell state in registers.
+// Epilogue: the TMEM lanes of a warp quadrant are ordered 8*gate + unit, so two tcgen05.ld.16x256b hand
+// thread t all four gates of unit t/4 for two utterances -- no transpose --, then the TF gate math
+// (forget_bias 1.0, length masking, bw direction walking len-1-s) runs with the cell state in registers.
 #include <stdlib.h>
 #include <string.h>
 
@@ -35,7 +34,7 @@ constexpr int RT_NACC = 4;    // independent accumulators (k-steps interleaved):
 
 struct RecTcArgs {
   plas_rec_desc d;
-  const void* whh_tc;  // [ndir][G][128][U] bf16, row m = 4*unit_local + gate
+  const void* whh_tc;  // [ndir][G][128][U] bf16, row (TMEM lane) m = 32*q + 8*gate + u8 for unit 8*q + u8
   int n_groups;
   unsigned long long* tdbg;  // optional [8] ns counters written by CTA 0 (PLAS_DEBUG)
   int dbg;  // timing experiments only (PLAS_REC_DBG): 1 = no exchange (wrong results), 2 = no gate math
