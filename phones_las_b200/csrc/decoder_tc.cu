@@ -53,11 +53,6 @@ struct alignas(64) DecTcArgs {
   int tm_pad;
 };
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ uint32_t mapa_cl(uint32_t local_saddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
@@ -120,13 +115,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   const uint32_t misc_u = base + (uint32_t)p.off_misc;
   auto fullA = [&](int s) { return misc_u + 8u * s; };
   auto emptyA = [&](int s) { return misc_u + 8u * (DT_MAX_STAGES + s); };
-  auto fullB = [&](int s) { return misc_u + 8u * (2 * DT_MAX_STAGES + s); };
-  auto emptyB = [&](int s) { return misc_u + 8u * (3 * DT_MAX_STAGES + s); };
   const uint32_t tfull = misc_u + 8u * (4 * DT_MAX_STAGES);
   const uint32_t pbar = misc_u + 8u * (4 * DT_MAX_STAGES) + 16u;  // K-split partial sums landed (tx bytes)
   const uint32_t sbar = misc_u + 8u * (4 * DT_MAX_STAGES) + 24u;  // the pair partner's partial scores landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (4 * DT_MAX_STAGES + 1));
-  int* s_ids = reinterpret_cast<int*>(misc + 576);               // [128]  (barriers + TMEM slot end at 528)
   float* s_bias = reinterpret_cast<float*>(misc + 1536);         // [4][16]
   float* s_red = s_bias + 64;                                    // [64]
   float* s_lp = s_red + 64;                                      // [8][32]
@@ -183,8 +175,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     for (int s = 0; s < DT_MAX_STAGES; ++s) {
       mbar_init(fullA(s), 1);
       mbar_init(emptyA(s), 1);
-      mbar_init(fullB(s), 1);
-      mbar_init(emptyB(s), 8);
     }
     mbar_init(tfull, 1);
     mbar_init(pbar, 1);
@@ -224,7 +214,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     max_iter = min(max_iter, (int)rintf((float)ml * d.decoding_length_factor));
   }
 
-  RingState prodA = {0, 0}, consA = {0, 0}, prodB = {0, 0}, consB = {0, 0};
+  RingState prodA = {0, 0}, consA = {0, 0};
   uint32_t acc_parity = 0;
   unsigned epoch = 0;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, 16);
@@ -454,11 +444,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     // ---------------- phase B: attention + context + logits ----------------
     {
       const int Dh = D / 2;
-      const int RK = DT_STAGE / (Ud * 2);   // key rows per stage
-      const int RV = DT_STAGE / (Dh * 2);   // value half-rows per stage
       const int Ktop = Kl[L - 1];
       const __nv_bfloat16* Htop = reinterpret_cast<const __nv_bfloat16*>(p.xbuf[L - 1]) + (size_t)(par ^ 1) * B * Ktop + (Ktop - Ud);
-      const int Vh = (V + 1) / 2;
       for (int item = blockIdx.x; item < 2 * B; item += gridDim.x) {
         const int b = item >> 1, half = item & 1;
         const int len = min(d.mem_len[b], Tm);

@@ -26,19 +26,14 @@
 
 namespace plas {
 
-constexpr int RT_THREADS = 256;
 constexpr int RT_THREADS2 = 416;  // 8 gate-math warps + 1 MMA-issuer warp + 4 publisher warps
 constexpr int RT_NPUB = 128;      // publisher threads
-constexpr int RT_NACC = 4;    // independent accumulators (k-steps interleaved): back-to-back tcgen05.mma on ONE
-                              // accumulator serialise on its ~50-cycle latency, which dominates at N = 16..64
 
 struct RecTcArgs {
   plas_rec_desc d;
   const void* whh_tc;  // [ndir][G][128][U] bf16, row (TMEM lane) m = 32*q + 8*gate + u8 for unit 8*q + u8
   int n_groups;
   unsigned long long* tdbg;  // optional [8] ns counters written by CTA 0 (PLAS_DEBUG)
-  int dbg;  // timing experiments only (PLAS_REC_DBG): 1 = no exchange (wrong results), 2 = no gate math
-  int ss;   // 1: W slice resident in SHARED memory (SS form), 0: resident in TENSOR memory (TS form)
 };
 
 __device__ __forceinline__ uint32_t rt_mapa(uint32_t local_saddr, uint32_t rank) {
@@ -81,13 +76,6 @@ __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-
 // NG independent 16-utterance groups of one direction share a cluster (and the TMEM-resident weights) and are
 // software-pipelined against each other: warp 8 waits for a group's h_{s-1} to land and issues its U/16 MMAs
 // (asynchronous, own accumulator columns), while the 8 epilogue warps run the gate math / exchange of the other
@@ -118,10 +106,9 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
   const uint32_t raw = smem_u32(rt_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* smem = rt_smem_raw + (base - raw);
-  // [NG][2][HBUF] h operands (UMMA K-major SWIZZLE_128B) | [8 warps][HR][36] f32 transpose | [NR][32] bf16 stage
+  // [NG][2][HBUF] h operands (UMMA K-major SWIZZLE_128B) | [2][NR][32] bf16 stage tiles
   const uint32_t hbuf_u = base;
-  float* s_z = reinterpret_cast<float*>(smem + NG * 2 * HBUF);
-  __nv_bfloat16* s_stage = reinterpret_cast<__nv_bfloat16*>(smem + NG * 2 * HBUF + 8 * HR * 36 * 4);
+  __nv_bfloat16* s_stage = reinterpret_cast<__nv_bfloat16*>(smem + NG * 2 * HBUF);
   __shared__ int s_len[NG][NR];
   __shared__ int s_tmax[NG];
   __shared__ __align__(8) unsigned long long s_bar[NG][3];  // h buffers 0/1, MMA completion
@@ -409,7 +396,7 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   constexpr int U = KS * 16, G = U / 32, NR = 16;
   *launched = false;
   // > 114 KB of shared memory: at most one CTA per SM, so the TMEM allocation can never contend
-  size_t smem = 1024 + (size_t)NG * 2 * (U / 64) * NR * 128 + (size_t)8 * (NR / 2) * 36 * 4 + (size_t)2 * NR * 32 * 2;
+  size_t smem = 1024 + (size_t)NG * 2 * (U / 64) * NR * 128 + (size_t)2 * NR * 32 * 2;
   if (smem > 227 * 1024) return PLAS_OK;
   if (smem < 120 * 1024) smem = 120 * 1024;
   auto fn = rec_tc_kernel<KS, NG>;
@@ -487,8 +474,6 @@ int rec_tc_launch(const plas_rec_desc& d, cudaStream_t stream) {
   a.d = d;
   a.whh_tc = d.whh_tc;
   a.n_groups = 0;
-  a.dbg = 0;
-  a.ss = 0;
   a.tdbg = nullptr;
   switch (d.U) {
     case 64: return rec_tc_launch_ks<4>(a, stream);
