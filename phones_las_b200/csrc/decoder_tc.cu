@@ -48,6 +48,7 @@ struct alignas(64) DecTcArgs {
   int n_stages_a;                // stages of the LSTM-phase ring (8 KB when B <= 64, else 16 KB)
   int stage_a;                   // bytes per LSTM-phase stage (= TMA box bytes)
   int ksplit;                    // 1, or 4: clusters of 4 CTAs split K of the LSTM products (DSMEM reduction)
+  int no_pair_split;             // debugging: every attention CTA scores the full depth
   int off_part;                  // ksplit: [4 senders][128 rows][16] f32 partial sums (inside the ring's tail)
   int off_w[4], off_wq, off_ring, off_misc;  // byte offsets from the 1024-aligned smem base
   int tm_pad;
@@ -163,11 +164,21 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
       if (tid < 16) s_bias[l * 16 + tid] = d.b_cell[l][slice * 16 + tid];
     }
   }
+  const bool q_ksplit = KSP > 1 && (Ud / 64) % KSP == 0;
   if (q_cta) {
-    const size_t bytes = (size_t)(Ud / 64) * 2048;
-    const uint4* src = reinterpret_cast<const uint4*>(p.wq_tc + (size_t)slice * bytes);
+    const int nkb = Ud / 64;
     uint4* dst = reinterpret_cast<uint4*>(smem + p.off_wq);
-    for (int i = tid; i < (int)(bytes / 16); i += DT_THREADS) dst[i] = __ldg(src + i);
+    if (!q_ksplit) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.wq_tc + (size_t)slice * nkb * 2048);
+      for (int i = tid; i < nkb * 128; i += DT_THREADS) dst[i] = __ldg(src + i);
+    } else {  // same K-quarter x 4-slice layout as the cell weights
+      const int nloc = nkb / KSP;
+      for (int i = tid; i < nloc * KSP * 128; i += DT_THREADS) {
+        const int w16 = i & 127, j = (i >> 7) % KSP, lkb = i / (128 * KSP);
+        const uint4* src = reinterpret_cast<const uint4*>(p.wq_tc + ((size_t)(cbase + j) * nkb + crank * nloc + lkb) * 2048);
+        dst[i] = __ldg(src + w16);
+      }
+    }
   }
   if (bahdanau)
     for (int u = tid; u < Ud; u += DT_THREADS) s_v[u] = d.v_att[u];
@@ -182,6 +193,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int l = 0; l < L; ++l)
       for (int q2 = 0; q2 < 2; ++q2) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmX[l][q2]) : "memory");
+    for (int q2 = 0; q2 < 2; ++q2) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmQ[q2]) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -295,6 +307,58 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
   float* s_part = reinterpret_cast<float*>(smem + p.off_part);
   const uint32_t s_part_u = base + (uint32_t)p.off_part;
   const uint32_t part_bytes = (uint32_t)((KSP - 1) * min(B, 128) * 64);
+  const int PR = B <= 64 ? 64 : 128;  // rows of one sender's block in s_part
+
+  // the 16 pre-activation columns of this CTA for batch row `row` (TMEM lane of the thread), after the accumulator
+  // barrier: directly, or -- K-split -- own partial + the three peers' partials (DSMEM), summed in a fixed order
+  auto fetch_acc16 = [&](uint32_t* r, bool ksplit) {
+    const uint32_t trow = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
+    if (!ksplit) {
+      tmem_ld16(trow, r);
+      tmem_ld_wait();
+      return;
+    }
+    // columns 16j..16j+15 of my K-partial belong to CTA j of the cluster: keep mine, push the rest (DSMEM)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t rj[16];
+      tmem_ld16(trow + (uint32_t)(16 * j), rj);
+      tmem_ld_wait();
+      if (j == crank) {
+#pragma unroll
+        for (int q4 = 0; q4 < 16; ++q4) r[q4] = rj[q4];
+      } else if (row_valid) {
+        const uint32_t dst = mapa_cl(s_part_u + (uint32_t)((crank * PR + row) * 64), (uint32_t)j);
+        const uint32_t rb = mapa_cl(pbar, (uint32_t)j);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          st_async_v4_cl(dst + 16 * q4, make_uint4(rj[4 * q4], rj[4 * q4 + 1], rj[4 * q4 + 2], rj[4 * q4 + 3]), rb);
+      }
+    }
+    mbar_wait(pbar, pparity);
+    pparity ^= 1u;
+    if (row_valid) {  // fixed summation order (sender 0,1,2,3) so every CTA adds the same way
+      float acc[16];
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) acc[q4] = 0.f;
+#pragma unroll
+      for (int sr = 0; sr < 4; ++sr) {
+        if (sr == crank) {
+#pragma unroll
+          for (int q4 = 0; q4 < 16; ++q4) acc[q4] += __uint_as_float(r[q4]);
+        } else {
+          const float4* pr = reinterpret_cast<const float4*>(s_part + (size_t)(sr * PR + row) * 16);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 v = pr[q4];
+            acc[4 * q4] += v.x; acc[4 * q4 + 1] += v.y; acc[4 * q4 + 2] += v.z; acc[4 * q4 + 3] += v.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) r[q4] = __float_as_uint(acc[q4]);
+    }
+  };
 
   int t = 0;
   while (true) {
@@ -325,65 +389,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         else gemm_phase(&p.tmX[l][par], base + (uint32_t)p.off_w[l], crank * (K / 64 / KSP), K / 64 / KSP, 64, IDESC64, fine && l == 0);
         if (row_thread) {
           if (KSP > 1 && tid == 128) mbar_expect_tx(pbar, part_bytes);  // partial sums of the 3 peers for my 16 columns
+          // the one-hot input is a row lookup in the cell-0 kernel: fetch it while the MMAs run
+          uint4 e0 = make_uint4(0u, 0u, 0u, 0u), e1 = e0;
+          if (l == 0 && row_valid) {
+            const int id = max(0, min(cur_id, V - 1));
+            const uint4* er = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.w_emb) +
+                                                             (size_t)id * 4 * Ud + slice * 16);
+            e0 = __ldg(er);
+            e1 = __ldg(er + 1);
+          }
           mbar_wait(tfull, acc_parity);
           if (fine && l == 0 && tid == 128) fine_stamp(2);
           tc_fence_after();
           uint32_t r[16];
-          const uint32_t trow = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
-          if (KSP == 1) {
-            tmem_ld16(trow, r);
-            tmem_ld_wait();
-          } else {
-            // columns 16j..16j+15 of my K-partial belong to CTA j of the cluster: keep mine, push the rest (DSMEM)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t rj[16];
-              tmem_ld16(trow + (uint32_t)(16 * j), rj);
-              tmem_ld_wait();
-              if (j == crank) {
-#pragma unroll
-                for (int q4 = 0; q4 < 16; ++q4) r[q4] = rj[q4];
-              } else if (row_valid) {
-                const uint32_t dst = mapa_cl(s_part_u + (uint32_t)((crank * 128 + row) * 64), (uint32_t)j);
-                const uint32_t rb = mapa_cl(pbar, (uint32_t)j);
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                  st_async_v4_cl(dst + 16 * q4, make_uint4(rj[4 * q4], rj[4 * q4 + 1], rj[4 * q4 + 2], rj[4 * q4 + 3]), rb);
-              }
-            }
-            mbar_wait(pbar, pparity);
-            pparity ^= 1u;
-            if (row_valid) {  // fixed summation order (sender 0,1,2,3) so every CTA adds the same way
-              float acc[16];
-#pragma unroll
-              for (int q4 = 0; q4 < 16; ++q4) acc[q4] = 0.f;
-#pragma unroll
-              for (int sr = 0; sr < 4; ++sr) {
-                if (sr == crank) {
-#pragma unroll
-                  for (int q4 = 0; q4 < 16; ++q4) acc[q4] += __uint_as_float(r[q4]);
-                } else {
-                  const float4* pr = reinterpret_cast<const float4*>(s_part + (size_t)(sr * 128 + row) * 16);
-#pragma unroll
-                  for (int q4 = 0; q4 < 4; ++q4) {
-                    const float4 v = pr[q4];
-                    acc[4 * q4] += v.x; acc[4 * q4 + 1] += v.y; acc[4 * q4 + 2] += v.z; acc[4 * q4 + 3] += v.w;
-                  }
-                }
-              }
-#pragma unroll
-              for (int q4 = 0; q4 < 16; ++q4) r[q4] = __float_as_uint(acc[q4]);
-            }
-          }
+          fetch_acc16(r, KSP > 1);
           if (row_valid) {
             float z[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(r[j]) + s_bias[l * 16 + j];
             if (l == 0) {
-              const int id = max(0, min(cur_id, V - 1));
-              const uint4* er = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.w_emb) +
-                                                               (size_t)id * 4 * Ud + slice * 16);
-              const uint4 e0 = __ldg(er), e1 = __ldg(er + 1);
               const unsigned ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -420,13 +444,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
     // ---------------- query layer (bahdanau): q = h_top . W_q ----------------
     if (bahdanau) {
       if (q_cta) {
-        gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, 0, Ud / 64, 16, IDESC, false);
+        if (!q_ksplit) gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, 0, Ud / 64, 16, IDESC, false);
+        else gemm_phase(&p.tmQ[par ^ 1], base + (uint32_t)p.off_wq, crank * (Ud / 64 / KSP), Ud / 64 / KSP, 64, IDESC64, false);
         if (row_thread) {
+          if (q_ksplit && tid == 128) mbar_expect_tx(pbar, part_bytes);
           mbar_wait(tfull, acc_parity);
           tc_fence_after();
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)((warp - 4) * 32) << 16), r);
-          tmem_ld_wait();
+          fetch_acc16(r, q_ksplit);
           if (row_valid) {
             float4* qd = reinterpret_cast<float4*>(p.qbuf + (size_t)row * Ud + slice * 16);
 #pragma unroll
@@ -462,7 +487,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
         // In cluster mode the two CTAs of an utterance (consecutive ranks of one cluster) split the depth of the
         // score reduction: each reads half of every key row and evaluates half of the tanh, then they swap partial
         // scores through DSMEM.  Otherwise every CTA scores the full depth.
-        const bool pair_split = KSP > 1;
+        const bool pair_split = KSP > 1 && !p.no_pair_split;
         const int n_c8 = Ud / 8;
         const int c8_lo = pair_split ? half * (n_c8 / 2) : 0;
         const int c8_hi = pair_split ? c8_lo + n_c8 / 2 : n_c8;
@@ -599,6 +624,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decoder_tc_kernel(const __grid_
             const float4 v = *reinterpret_cast<const float4*>(s_score + 4 * i);
             st_async_v4_cl(dst0 + 16 * i, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)), rb);
           }
+          consumer_sync();  // every thread has read its chunk of the partial scores before they are overwritten below
           mbar_wait(sbar, sparity);
           sparity ^= 1u;
           for (int tm = tid; tm < len; tm += 256) {  // same order in both CTAs: (depth half 0) + (depth half 1)
@@ -840,11 +866,13 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
   pl.stage_a = d.B <= 64 ? 8192 : 16384;
   pl.n_stages_a = d.B <= 64 ? 2 * ns - 1 : ns;
   if (pl.n_stages_a > DT_MAX_STAGES) pl.n_stages_a = DT_MAX_STAGES;
-  // K-split mode (clusters of 4): the last 32 KB of the ring hold the peers' partial sums during the LSTM phases
+  // K-split mode (clusters of 4): the tail of the ring holds the peers' partial sums during the LSTM phases
+  // ([4 senders][64 or 128 rows][16] f32)
+  const int part_bytes = d.B <= 64 ? 16384 : 32768;
   pl.ksplit = 1;
-  pl.off_part = off + ns * DT_STAGE - 32768;
+  pl.off_part = off + ns * DT_STAGE - part_bytes;
   {
-    bool ok = (d.Ud / 4) % 4 == 0 && ns * DT_STAGE - 32768 - (d.B <= 64 ? 8192 : 0) >= 2 * pl.stage_a;
+    bool ok = (d.Ud / 4) % 4 == 0 && ns * DT_STAGE - part_bytes - (d.B <= 64 ? 8192 : 0) >= 2 * pl.stage_a;
     for (int l = 0; l < d.n_layers; ++l) {
       const int K = (l == 0) ? d.D + d.Ud : 2 * d.Ud;
       ok = ok && (K / 64) % 4 == 0;
@@ -853,7 +881,7 @@ static DecTcPlan dec_tc_plan(const plas_dec_desc& d) {
     if (e && atoi(e) == 1) ok = false;
     if (ok) {
       pl.ksplit = 4;
-      pl.n_stages_a = (ns * DT_STAGE - 32768 - (d.B <= 64 ? 8192 : 0)) / pl.stage_a;
+      pl.n_stages_a = (ns * DT_STAGE - part_bytes - (d.B <= 64 ? 8192 : 0)) / pl.stage_a;
       if (pl.n_stages_a > DT_MAX_STAGES) pl.n_stages_a = DT_MAX_STAGES;
     }
   }
@@ -911,6 +939,7 @@ int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_byte
   a.n_stages_a = pl.n_stages_a;
   a.stage_a = pl.stage_a;
   a.ksplit = pl.ksplit;
+  a.no_pair_split = getenv("PLAS_DEC_NOPAIR") ? 1 : 0;
   a.off_part = pl.off_part;
   a.off_wq = pl.off_wq;
   a.off_ring = pl.off_ring;
