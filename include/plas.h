@@ -196,6 +196,112 @@ int plas_ctc_fwd(const float* logits, const int32_t* labels, const int32_t* labe
 int plas_mask_time(int32_t dtype, const void* x, void* y, const int32_t* len, int32_t B, int32_t T,
                    int32_t D, plas_stream_t stream);
 
+/* ====================================================================================
+ * TRAINING PATH (exact fp32, TF checkpoint layouts).  Replaces the TRAIN graph of las_model_fn
+ * (model_helper.py:165-227, 319-358, 403-417): listener and speller forward with saved activations, their
+ * gradients (optimizer.compute_gradients, model_helper.py:415), the loss heads' gradients, L2 regularisation,
+ * per-tensor clip_by_norm and Adam.  Every weight and every weight gradient is in the layout of the TF variable
+ * (LSTMCell kernel [din+U][4U] with gate column blocks i|j|f|o, Dense kernels [in][out]).
+ * ==================================================================================== */
+
+/* C[z] = alpha * A(m,k) B(k,n) + beta * C + bias[n] with arbitrary element strides:
+ *   A(m,k) = A[z*batch_a + m*sam + k*sak],  B(k,n) = B[z*batch_b + k*sbk + n*sbn],  C[z*batch_c + m*ldc + n].
+ * Serves x @ W, dZ @ W^T and X^T @ dZ on the TF layouts without transposed copies. */
+typedef struct plas_gemm_ex_desc {
+  int64_t M;
+  int32_t N, K;
+  const float* A;
+  int64_t sam, sak;
+  const float* B;
+  int64_t sbk, sbn;
+  float* C;
+  int64_t ldc;
+  const float* bias;        /* [N] or NULL */
+  float alpha, beta;
+  int32_t batch;            /* >= 1 independent problems (grid.z) */
+  int32_t _pad;
+  int64_t batch_a, batch_b, batch_c;
+} plas_gemm_ex_desc;
+int plas_gemm_f32_ex(const plas_gemm_ex_desc* d, plas_stream_t stream);
+/* out[n] (+)= sum_m X[m][n]: bias gradients. */
+int plas_colsum_f32(const float* X, int64_t M, int32_t N, int64_t ld, float* out, int32_t accumulate,
+                    plas_stream_t stream);
+
+/* (bi)directional LSTM recurrence of one listener layer, forward-with-save and BPTT (las/ops.py:23-46 and its
+ * gradient).  `z` [B][T][ndir][4U] holds x W_x + b on entry of the forward call, the activated gates
+ * (sigmoid i, tanh j, sigmoid(f+1), sigmoid o) on exit, and dL/dz (zero for t >= len) after the backward call. */
+typedef struct plas_rec_train_desc {
+  int32_t B, T, U, ndir, din;
+  int32_t _pad;
+  float* z;
+  const float* kernel[2];   /* TF LSTMCell kernel [din+U][4U] of the fw / bw cell; rows din.. are W_hh          */
+  const int32_t* lengths;   /* [B]                                                                            */
+  float* out;               /* fwd: [B][T_out][ndir*U], caller-zeroed (stays 0 for t >= len)                  */
+  int64_t out_batch_stride;
+  float* c_save;            /* [B][T][ndir*U] cell states (fwd out, bwd in)                                   */
+  float* h_prev;            /* [B][T][ndir*U] h_{s-1} stored at the time index of step s (fwd out), caller-zeroed */
+  const float* dout;        /* bwd: dL/dout, strides of `out`                                                 */
+} plas_rec_train_desc;
+size_t plas_rec_train_workspace_bytes(const plas_rec_train_desc* d);
+int plas_bilstm_rec_train_fwd(const plas_rec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
+int plas_bilstm_rec_train_bwd(const plas_rec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
+
+/* Teacher-forced speller, forward and backward (las/model.py:205-296 TRAIN branch with TrainingHelper /
+ * TrainingSigmoidHelper, sampling_probability = 0; attention luong or bahdanau, default wiring).  x_in is the
+ * embedded decoder input of every step: one-hot ids (embedding_fn, las/model.py:245-246) or the binary-feature
+ * vectors of the binary_outputs speller (las/model.py:237-241).  The workspace carries the saved activations from
+ * the forward to the backward call. */
+typedef struct plas_dec_train_desc {
+  int32_t B, S, Tm, D, Ud, E, n_out, n_layers, attention_type;
+  int32_t dmemory_accumulate; /* 1: dmemory += ..., 0: dmemory = ...                                           */
+  const float* kernel[4];   /* cell_k/lstm_cell/kernel [(k == 0 ? E + D : Ud) + Ud][4Ud]                       */
+  const float* bias[4];     /* [4Ud]                                                                          */
+  const float* w_mem;       /* memory_layer/kernel [D][Ud]                                                    */
+  const float* w_query;     /* bahdanau query_layer/kernel [Ud][Ud] or NULL                                   */
+  const float* v_att;       /* bahdanau attention_v [Ud] or NULL                                              */
+  const float* w_proj;      /* projection_layer/kernel [D][n_out]                                             */
+  const float* b_proj;      /* [n_out]                                                                        */
+  const float* memory;      /* [B][Tm][D] encoder outputs, zero for t >= mem_len                              */
+  const int32_t* mem_len;   /* [B]                                                                            */
+  const float* x_in;        /* [B][S][E]                                                                      */
+  float* logits;            /* fwd out: [B][S][n_out]                                                         */
+  const float* dlogits;     /* bwd in : [B][S][n_out]                                                         */
+  float* dkernel[4];        /* bwd out, layouts of the parameters                                             */
+  float* dbias[4];
+  float* dw_mem;
+  float* dw_query;
+  float* dv_att;
+  float* dw_proj;
+  float* db_proj;
+  float* dmemory;           /* bwd out: [B][Tm][D] gradient wrt the encoder outputs                           */
+} plas_dec_train_desc;
+size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
+int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
+int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
+
+/* Loss heads with gradients.  dlogits = gscale * d(loss)/d(logits); out3 as in the forward-only calls. */
+int plas_seq_ce_grad(const float* logits, const int32_t* targets, const float* weights, int64_t n_tokens, int32_t V,
+                     float gscale, float* ce_tokens, float* out3, float* dlogits, plas_stream_t stream);
+int plas_sigmoid_ce_grad(const float* logits, const float* labels, const float* weights, int64_t n_tokens,
+                         int32_t n_feat, float gscale, float* ce_tokens, float* out3, float* dlogits,
+                         plas_stream_t stream);
+/* per-utterance CTC loss [B] and dlogits [B][T][C] = gscale * d(loss[b])/d(logits[b]) (zero for t >= logit_len) */
+size_t plas_ctc_grad_workspace_bytes(int32_t B, int32_t T, int32_t Lmax);
+int plas_ctc_grad(const float* logits, const int32_t* labels, const int32_t* label_len, const int32_t* logit_len,
+                  int32_t B, int32_t T, int32_t C, int32_t Lmax, int32_t blank, float gscale, float* loss,
+                  float* dlogits, void* workspace, size_t workspace_bytes, plas_stream_t stream);
+
+/* Optimiser (model_helper.py:404-417) on flat fp32 buffers; offsets [n_tensors+1] (device, int64) delimit the
+ * variables.  grad_l2_norm: g += l2_scale*w, norms[i] = ||g_i||, wsq[i] = ||w_i||^2 (optional, for the reported L2 term);  clip_scale: g_i *= clip/max(norms[i],clip) * post_scale
+ * (post_scale = 1/world_size before the data-parallel all-reduce);  adam_step: TF epsilon-hat form with
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller, gradients pre-multiplied by grad_scale. */
+int plas_grad_l2_norm(const float* params, float* grads, const int64_t* offsets, int32_t n_tensors, float l2_scale,
+                      float* norms, float* wsq, plas_stream_t stream);
+int plas_clip_scale(float* grads, const int64_t* offsets, int32_t n_tensors, const float* norms, float clip,
+                    float post_scale, plas_stream_t stream);
+int plas_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, float grad_scale, plas_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,206 @@
+"""Oracle: the TRAIN graph of las_model_fn as differentiable torch (CPU) code -- test infrastructure only.
+
+The numpy oracle (oracle/las.py, oracle/losses.py) restates forward values; this file restates the same
+functions with torch ops so that autograd yields the gradients the CUDA backward kernels are checked against
+(float64 by default: a reference for the floating-point backward pass).  It is
+cross-checked against the numpy oracle's forward values in tests/test_oracle_train.py.
+
+Follows (reference file:line):
+* las/ops.py:10-87             lstm_cell / bilstm / pyramidal_stack / pyramidal_bilstm
+* las/model.py:145-202         attend (luong, bahdanau; default wiring)
+* las/model.py:205-296,344-349 speller TRAIN branch: TrainingHelper / TrainingSigmoidHelper + BasicDecoder +
+                               dynamic_decode, DenseBinfDecoder projection (utils/training_helper.py:122-153)
+* model_helper.py:20-30        compute_loss TRAIN, :81-105 compute_loss_sigmoid TRAIN, :347-358 CTC head
+* model_helper.py:403-417      L2 regulariser, per-tensor clip_by_norm(2), Adam
+Parameters are a dict of TF variable names -> tensors in the TF checkpoint layout.
+"""
+import torch
+
+GRAD_NORM = 2.0  # model_helper.py:16
+
+
+def _cell(z, c_prev):
+    U = z.shape[1] // 4
+    i, j, f, o = z[:, :U], z[:, U:2 * U], z[:, 2 * U:3 * U], z[:, 3 * U:]
+    c = torch.sigmoid(f + 1.0) * c_prev + torch.sigmoid(i) * torch.tanh(j)
+    h = torch.sigmoid(o) * torch.tanh(c)
+    return c, h
+
+
+def dynamic_rnn(x, lengths, kernel, bias, reverse=False):
+    """tf.nn.dynamic_rnn with sequence_length (outputs 0 and state frozen past each length)."""
+    B, T, din = x.shape
+    U = kernel.shape[1] // 4
+    xproj = x.reshape(B * T, din) @ kernel[:din] + bias
+    xproj = xproj.reshape(B, T, 4 * U)
+    wh = kernel[din:]
+    c = x.new_zeros((B, U))
+    h = x.new_zeros((B, U))
+    ar = torch.arange(B)
+    steps = int(lengths.max())
+    rows_t = []
+    for s in range(steps):
+        active = (s < lengths)
+        t_idx = torch.where(active, (lengths - 1 - s) if reverse else torch.full_like(lengths, s),
+                            torch.zeros_like(lengths))
+        z = xproj[ar, t_idx] + h @ wh
+        c_new, h_new = _cell(z, c)
+        m = active[:, None].to(x.dtype)
+        c = m * c_new + (1 - m) * c
+        h = m * h_new + (1 - m) * h
+        rows_t.append((t_idx, active, h_new))
+    # scatter without in-place autograd trouble: build per-time outputs
+    pieces = x.new_zeros((B, T, U))
+    idx_b, idx_t, vals = [], [], []
+    for t_idx, active, h_new in rows_t:
+        rows = torch.nonzero(active)[:, 0]
+        idx_b.append(rows)
+        idx_t.append(t_idx[rows])
+        vals.append(h_new[rows])
+    if idx_b:
+        ib, it, vv = torch.cat(idx_b), torch.cat(idx_t), torch.cat(vals)
+        pieces = pieces.index_put((ib, it), vv)
+    return pieces, (c, h)
+
+
+def pyramidal_bilstm(x, lengths, params, num_layers, scope="listener"):
+    outputs = x
+    for layer in range(num_layers):
+        outs = []
+        for d, rev in (("fw", False), ("bw", True)):
+            k = params[f"{scope}/bilstm_{layer}/bidirectional_rnn/{d}/lstm_cell/kernel"]
+            b = params[f"{scope}/bilstm_{layer}/bidirectional_rnn/{d}/lstm_cell/bias"]
+            o, _ = dynamic_rnn(outputs, lengths, k, b, reverse=rev)
+            outs.append(o)
+        outputs = torch.cat(outs, -1)
+        if layer != 0:
+            B, T, D = outputs.shape
+            if T % 2:
+                outputs = torch.cat([outputs, outputs.new_zeros((B, 1, D))], 1)
+            outputs = outputs.reshape(B, -1, 2 * D)
+            lengths = lengths // 2 + lengths % 2
+    return outputs, lengths
+
+
+def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller"):
+    """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
+    binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns)."""
+    B, Tm, D = enc_out.shape
+    Ud = hp["decoder_units"]
+    att_type = hp["attention_type"]
+    mask = (torch.arange(Tm)[None, :] < enc_len[:, None])
+    values = enc_out * mask[:, :, None].to(enc_out.dtype)
+    keys = values @ params[f"{scope}/memory_layer/kernel"]
+    pre = f"{scope}/decoder/attention_wrapper"
+    cells = [(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"],
+              params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"]) for k in range(hp["decoder_layers"])]
+    wp = params[f"{scope}/decoder/projection_layer/kernel"]
+    bp = params[f"{scope}/decoder/projection_layer/bias"]
+    state = [(enc_out.new_zeros((B, Ud)), enc_out.new_zeros((B, Ud))) for _ in cells]
+    attention = enc_out.new_zeros((B, D))
+    logits = []
+    neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
+    for t in range(dec_inputs.shape[1]):
+        inp = torch.cat([dec_inputs[:, t], attention], 1)
+        new_state = []
+        for (k, b), (c, h) in zip(cells, state):
+            z = torch.cat([inp, h], 1) @ k + b
+            c2, h2 = _cell(z, c)
+            new_state.append((c2, h2))
+            inp = h2
+        state = new_state
+        if att_type == "bahdanau":
+            pq = inp @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
+            v = params[f"{pre}/bahdanau_attention/attention_v"]
+            score = (torch.tanh(keys + pq[:, None, :]) * v).sum(-1)
+        elif att_type == "luong":
+            score = torch.einsum("btu,bu->bt", keys, inp)
+        else:
+            raise NotImplementedError(att_type)
+        score = torch.where(mask, score, neg_inf)
+        align = torch.softmax(score, dim=1)
+        attention = torch.einsum("bt,btd->bd", align, values)
+        logits.append(attention @ wp + bp)
+    return torch.stack(logits, 1)
+
+
+def sequence_loss(logits, targets, weights):
+    lp = torch.log_softmax(logits, -1)
+    ce = -lp.gather(-1, targets[..., None].long())[..., 0]
+    return (ce * weights).sum() / (weights.sum() + 1e-12)
+
+
+def sequence_loss_sigmoid(logits, targets, weights):
+    x, z = logits, targets
+    ce = (torch.clamp(x, min=0) - x * z + torch.log1p(torch.exp(-x.abs()))).mean(-1)
+    return (ce * weights).sum() / (weights.sum() + 1e-12)
+
+
+def ctc_loss(logits, labels, label_length, logit_length, blank=0):
+    """Same recursion as oracle/losses.py:ctc_loss, differentiable.  Returns [B]."""
+    out = []
+    for b in range(logits.shape[0]):
+        T, L = int(logit_length[b]), int(label_length[b])
+        lp = torch.log_softmax(logits[b, :T], -1)
+        ext = torch.full((2 * L + 1,), blank, dtype=torch.long)
+        ext[1::2] = labels[b, :L].long()
+        S = 2 * L + 1
+        ninf = lp.new_full((1,), -1e30)  # finite stand-in for -inf: exp() underflows to 0, autograd stays NaN-free
+        can_skip = torch.zeros((S,), dtype=torch.bool)
+        can_skip[2:] = (ext[2:] != blank) & (ext[2:] != ext[:-2])
+        alpha = torch.cat([lp[0, ext[:2]], ninf.expand(max(S - 2, 0))])[:S]
+        for t in range(1, T):
+            a1 = torch.cat([ninf, alpha[:-1]])
+            a2 = torch.cat([ninf, ninf, alpha[:-2]])[:S]
+            a2 = torch.where(can_skip, a2, ninf.expand(S))
+            alpha = torch.logsumexp(torch.stack([alpha, a1, a2]), 0) + lp[t, ext]
+        tail = alpha[-1] if S == 1 else torch.logsumexp(alpha[-2:], 0)
+        out.append(-tail)
+    return torch.stack(out)
+
+
+def train_loss(params, features, lengths, labels, hp, binf=None):
+    """las_model_fn(mode=TRAIN) loss (model_helper.py:165-358, 411-413) with dropout = 0 and
+    sampling_probability = 0.  ``binf`` [n, V] enables the multitask binary-feature speller.
+    Returns (total loss incl. L2, dict of the parts)."""
+    dt = features.dtype
+    enc_out, enc_len = pyramidal_bilstm(features, lengths, params, hp["encoder_layers"])
+    tin, tout, tlen = labels["targets_inputs"], labels["targets_outputs"], labels["target_sequence_length"]
+    L = tin.shape[1]
+    w = (torch.arange(L)[None, :] < tlen[:, None]).to(dt)
+    parts = {}
+    loss = 0.0
+    V = hp["target_vocab_size"]
+    if not hp.get("binary_outputs") or hp.get("multitask"):
+        logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp)
+        parts["ce"] = sequence_loss(logits, tout, w)
+        parts["logits"] = logits
+        loss = loss + parts["ce"]
+    if hp.get("binary_outputs"):
+        bt = torch.as_tensor(binf, dtype=dt).t()  # [V, n]
+        logits_b = speller_train(enc_out, enc_len, bt[tin.long()], params, hp, scope="speller_binf")
+        parts["ce_binf"] = sequence_loss_sigmoid(logits_b, bt[tout.long()], w)
+        parts["logits_binf"] = logits_b
+        loss = loss + parts["ce_binf"]
+    if hp.get("ctc_weight", -1.0) > 0:
+        cl = enc_out @ params["ctc_logits/kernel"] + params["ctc_logits/bias"]
+        parts["ctc"] = ctc_loss(cl, tout, tlen, enc_len).mean()
+        loss = loss + parts["ctc"] * hp["ctc_weight"]
+    parts["audio_loss"] = loss
+    reg = sum((p * p).sum() for p in params.values()) * (0.5 * hp.get("l2_reg_scale", 0.0))
+    parts["encoder_out"] = enc_out
+    return loss + reg, parts
+
+
+def clip_and_adam(params, grads, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """model_helper.py:416-417: per-tensor tf.clip_by_norm(g, 2) then tf.train.AdamOptimizer (epsilon-hat form)."""
+    out_p, out_m, out_v = {}, {}, {}
+    lr_t = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+    for k, p in params.items():
+        g = grads[k]
+        n = g.pow(2).sum().sqrt()
+        g = g * (GRAD_NORM / torch.clamp(n, min=GRAD_NORM))
+        out_m[k] = b1 * m[k] + (1 - b1) * g
+        out_v[k] = b2 * v[k] + (1 - b2) * g * g
+        out_p[k] = p - lr_t * out_m[k] / (out_v[k].sqrt() + eps)
+    return out_p, out_m, out_v

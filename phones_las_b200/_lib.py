@@ -47,6 +47,32 @@ class DecDesc(C.Structure):
                 ("pv_ld", C.c_int32), ("_pad2", C.c_int32)]
 
 
+class GemmExDesc(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("A", C.c_void_p), ("sam", C.c_int64),
+                ("sak", C.c_int64), ("B", C.c_void_p), ("sbk", C.c_int64), ("sbn", C.c_int64), ("C", C.c_void_p),
+                ("ldc", C.c_int64), ("bias", C.c_void_p), ("alpha", C.c_float), ("beta", C.c_float),
+                ("batch", C.c_int32), ("_pad", C.c_int32), ("batch_a", C.c_int64), ("batch_b", C.c_int64),
+                ("batch_c", C.c_int64)]
+
+
+class RecTrainDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("U", C.c_int32), ("ndir", C.c_int32), ("din", C.c_int32),
+                ("_pad", C.c_int32), ("z", C.c_void_p), ("kernel", C.c_void_p * 2), ("lengths", C.c_void_p),
+                ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("c_save", C.c_void_p), ("h_prev", C.c_void_p),
+                ("dout", C.c_void_p)]
+
+
+class DecTrainDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("S", C.c_int32), ("Tm", C.c_int32), ("D", C.c_int32), ("Ud", C.c_int32),
+                ("E", C.c_int32), ("n_out", C.c_int32), ("n_layers", C.c_int32), ("attention_type", C.c_int32),
+                ("dmemory_accumulate", C.c_int32),
+                ("kernel", C.c_void_p * 4), ("bias", C.c_void_p * 4), ("w_mem", C.c_void_p), ("w_query", C.c_void_p),
+                ("v_att", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("memory", C.c_void_p),
+                ("mem_len", C.c_void_p), ("x_in", C.c_void_p), ("logits", C.c_void_p), ("dlogits", C.c_void_p),
+                ("dkernel", C.c_void_p * 4), ("dbias", C.c_void_p * 4), ("dw_mem", C.c_void_p), ("dw_query", C.c_void_p),
+                ("dv_att", C.c_void_p), ("dw_proj", C.c_void_p), ("db_proj", C.c_void_p), ("dmemory", C.c_void_p)]
+
+
 EXPORTS = {
     "plas_last_error": (C.c_char_p, []),
     "plas_version": (C.c_int, []),
@@ -76,6 +102,27 @@ EXPORTS = {
                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "plas_mask_time": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p]),
+    "plas_gemm_f32_ex": (C.c_int, [C.POINTER(GemmExDesc), C.c_void_p]),
+    "plas_colsum_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "plas_rec_train_workspace_bytes": (C.c_size_t, [C.POINTER(RecTrainDesc)]),
+    "plas_bilstm_rec_train_fwd": (C.c_int, [C.POINTER(RecTrainDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_bilstm_rec_train_bwd": (C.c_int, [C.POINTER(RecTrainDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_dec_train_workspace_bytes": (C.c_size_t, [C.POINTER(DecTrainDesc)]),
+    "plas_decoder_train_fwd": (C.c_int, [C.POINTER(DecTrainDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_decoder_train_bwd": (C.c_int, [C.POINTER(DecTrainDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_seq_ce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plas_sigmoid_ce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "plas_ctc_grad_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "plas_ctc_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                C.c_void_p]),
+    "plas_grad_l2_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "plas_clip_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
+    "plas_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),
 }
 
 _lib = None

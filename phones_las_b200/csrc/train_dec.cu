@@ -1,0 +1,624 @@
+// K4 (training) -- teacher-forced attention decoder, forward with saved activations and full backward (BPTT), exact
+// fp32, directly on the TF checkpoint layout.  Replaces speller(mode=TRAIN) (reference las/model.py:205-296,344-349:
+// attend -> AttentionWrapper(MultiRNNCell(LSTMCell)) + BasicDecoder + TrainingHelper / TrainingSigmoidHelper +
+// dynamic_decode, projection DenseBinfDecoder utils/training_helper.py:122-153) and its gradient
+// (optimizer.compute_gradients, model_helper.py:415).
+//
+// Structure.  Everything that does not depend on the previous step is hoisted into plas_gemm_f32_ex calls:
+//   forward : keys = memory W_mem;  Z_0 = x_in W_0[0:E] + b_0;  logits = Att W_proj + b_proj
+//   backward: dAtt(from logits) = dlogits W_proj^T;  all weight gradients (X^T dZ over the B*S saved rows);  per
+//             utterance dkeys = dScore^T H_top, dvalues = Align^T dAtt;  dmemory += dvalues + dkeys W_mem^T
+// and only the truly sequential part runs per step as small kernels (launched from the C++ loops below; the whole
+// training step is captured in a CUDA graph by the host):
+//   dec_cell_fwd   z = pre + [in1;h_{t-1}] W   (lane = batch row, CTA = a few units, warps split the reduction)
+//   dec_att_fwd    query -> scores over the memory -> masked softmax -> context      (CTA = utterance x D-slice)
+//   dec_att_bwd    dAtt_t -> dalign -> dscore -> dquery (luong) / dpq, dkeys, dv, dquery (bahdanau)
+//   dec_cell_bwd   gate derivatives, dz_t written IN PLACE over the saved gates
+//   dec_gemv_t     dinp = dz_t W^T   (gradient wrt [attention_{t-1}; h_{t-1}] that the next iteration consumes)
+// Saved tensors are batch-major [B][S][width] so the hoisted GEMMs see plain row-major matrices.
+#include "common.cuh"
+#include "../../include/plas.h"
+
+namespace plas {
+
+constexpr int DT_ROWS = 32;  // batch rows per CTA (lane = row)
+
+// ---------------------------------------------------------------------------------------------------------
+struct CellFwdArgs {
+  int B, Ud;
+  const float* pre; long long s_pre;    // [B][4Ud] pre-activations already holding x W + b (or NULL)
+  const float* bias;                    // [4Ud] added when pre == NULL
+  const float* in1; long long s1; int K1; const float* w1;  // rows of the TF kernel multiplying in1
+  const float* in2; long long s2; int K2; const float* w2;  // h_{t-1} and its rows
+  const float* c_prev; long long s_c;   // NULL at t == 0
+  float* z_out; long long s_z;          // activated gates (i, tanh j, f, o), gate-blocked [4][Ud]
+  float* c_out; float* h_out; long long s_h;
+  float* hprev_next;                    // slot t+1 of the h_{t-1} copy (NULL at the last step)
+};
+
+template <int UPC>
+__global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
+  __shared__ float s_red[8][4 * UPC][DT_ROWS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u0 = blockIdx.x * UPC;
+  const int b0 = blockIdx.y * DT_ROWS;
+  const int b = min(b0 + lane, p.B - 1);
+  const int Ud = p.Ud;
+  const int K4 = (p.K1 + p.K2) / 4;  // reduction length in float4 units
+  const int per = (K4 + 7) / 8;
+  const int q_lo = warp * per, q_hi = min(K4, q_lo + per);
+  float acc[4][UPC];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int u = 0; u < UPC; ++u) acc[g][u] = 0.f;
+  const int K1q = p.K1 / 4;
+  for (int q = q_lo; q < q_hi; ++q) {
+    float4 a;
+    const float* wrow;
+    if (q < K1q) {
+      a = *reinterpret_cast<const float4*>(p.in1 + (long long)b * p.s1 + 4 * q);
+      wrow = p.w1 + (size_t)(4 * q) * 4 * Ud;
+    } else {
+      a = *reinterpret_cast<const float4*>(p.in2 + (long long)b * p.s2 + 4 * (q - K1q));
+      wrow = p.w2 + (size_t)(4 * (q - K1q)) * 4 * Ud;
+    }
+    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float* wp = wrow + (size_t)kk * 4 * Ud + g * Ud + u0;
+        if (UPC == 4) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wp));
+          acc[g][0] = fmaf(av[kk], w.x, acc[g][0]);
+          acc[g][1] = fmaf(av[kk], w.y, acc[g][1]);
+          acc[g][2] = fmaf(av[kk], w.z, acc[g][2]);
+          acc[g][3] = fmaf(av[kk], w.w, acc[g][3]);
+        } else {
+          const float2 w = __ldg(reinterpret_cast<const float2*>(wp));
+          acc[g][0] = fmaf(av[kk], w.x, acc[g][0]);
+          acc[g][1] = fmaf(av[kk], w.y, acc[g][1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int u = 0; u < UPC; ++u) s_red[warp][g * UPC + u][lane] = acc[g][u];
+  __syncthreads();
+  if (threadIdx.x < DT_ROWS * UPC) {
+    const int r = threadIdx.x % DT_ROWS, u = threadIdx.x / DT_ROWS;
+    const int bb = b0 + r;
+    if (bb < p.B) {
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float s = p.pre ? p.pre[(long long)bb * p.s_pre + g * Ud + u0 + u] : p.bias[g * Ud + u0 + u];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_red[w][g * UPC + u][r];
+        z[g] = s;
+      }
+      const float cp = p.c_prev ? p.c_prev[(long long)bb * p.s_c + u0 + u] : 0.f;
+      const float gi = sigmoidf_acc(z[0]), gj = tanhf(z[1]), gf = sigmoidf_acc(z[2] + 1.0f), go = sigmoidf_acc(z[3]);
+      const float c = gf * cp + gi * gj;
+      const float h = go * tanhf(c);
+      float* zo = p.z_out + (long long)bb * p.s_z + u0 + u;
+      zo[0] = gi; zo[Ud] = gj; zo[2 * Ud] = gf; zo[3 * Ud] = go;
+      p.c_out[(long long)bb * p.s_h + u0 + u] = c;
+      p.h_out[(long long)bb * p.s_h + u0 + u] = h;
+      if (p.hprev_next) p.hprev_next[(long long)bb * p.s_h + u0 + u] = h;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct AttFwdArgs {
+  int B, Tm, D, Ud, type, dsplit;
+  const float* keys;     // [B][Tm][Ud]
+  const float* values;   // [B][Tm][D]
+  const int* mem_len;
+  const float* query; long long s_q;      // h_top of this step
+  const float* w_query; const float* v_att;  // bahdanau
+  float* pq; long long s_pq;              // bahdanau: saved processed query
+  float* align; long long s_al;           // [Tm] per row
+  float* att; long long s_att;            // context of this step
+  float* att_next;                        // slot t+1 of the attention_{t-1} copy (NULL at the last step)
+};
+
+__global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
+  extern __shared__ float att_smem[];
+  float* s_q = att_smem;          // [Ud] query (luong) or processed query (bahdanau)
+  float* s_sc = s_q + p.Ud;       // [Tm]
+  float* s_v = s_sc + p.Tm;       // [Ud] attention_v (bahdanau)
+  __shared__ float s_red[8];
+  __shared__ float s_bcast;
+  const int b = blockIdx.x, part = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Ud = p.Ud, Tm = p.Tm, D = p.D;
+  const int len = min(p.mem_len[b], Tm);
+  const float* q = p.query + (long long)b * p.s_q;
+  if (p.type == PLAS_ATT_BAHDANAU) {
+    for (int u = tid; u < Ud; u += 256) s_v[u] = q[u];  // raw query staged where attention_v goes afterwards
+    __syncthreads();
+    for (int u = tid; u < Ud; u += 256) {
+      float s = 0.f;
+      for (int k = 0; k < Ud; ++k) s = fmaf(s_v[k], __ldg(p.w_query + (size_t)k * Ud + u), s);
+      s_q[u] = s;
+      if (part == 0) p.pq[(long long)b * p.s_pq + u] = s;
+    }
+    __syncthreads();
+    for (int u = tid; u < Ud; u += 256) s_v[u] = p.v_att[u];
+  } else {
+    for (int u = tid; u < Ud; u += 256) s_q[u] = q[u];
+  }
+  __syncthreads();
+  const float* kb = p.keys + (size_t)b * Tm * Ud;
+  for (int t = warp; t < Tm; t += 8) {
+    float s = 0.f;
+    if (t < len) {
+      const float* kr = kb + (size_t)t * Ud;
+      if (p.type == PLAS_ATT_BAHDANAU)
+        for (int u = lane; u < Ud; u += 32) s = fmaf(s_v[u], tanhf(kr[u] + s_q[u]), s);
+      else
+        for (int u = lane; u < Ud; u += 32) s = fmaf(kr[u], s_q[u], s);
+      s = warp_sum(s);
+    }
+    if (lane == 0) s_sc[t] = t < len ? s : -INFINITY;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int t = tid; t < Tm; t += 256) m = fmaxf(m, s_sc[t]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float mm = s_red[0];
+    for (int w = 1; w < 8; ++w) mm = fmaxf(mm, s_red[w]);
+    s_bcast = mm;
+  }
+  __syncthreads();
+  m = s_bcast;
+  float e_sum = 0.f;
+  for (int t = tid; t < Tm; t += 256) {
+    const float e = t < len ? expf(s_sc[t] - m) : 0.f;
+    s_sc[t] = e;
+    e_sum += e;
+  }
+  e_sum = warp_sum(e_sum);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = e_sum;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    s_bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = s_bcast;
+  for (int t = tid; t < Tm; t += 256) {
+    const float a = s_sc[t] * inv;
+    s_sc[t] = a;
+    if (part == 0) p.align[(long long)b * p.s_al + t] = a;
+  }
+  __syncthreads();
+  const int dper = (D + p.dsplit - 1) / p.dsplit;
+  const int d_lo = part * dper, d_hi = min(D, d_lo + dper);
+  const float* vb = p.values + (size_t)b * Tm * D;
+  for (int d = d_lo + tid; d < d_hi; d += 256) {
+    float c = 0.f;
+    for (int t = 0; t < len; ++t) c = fmaf(s_sc[t], vb[(size_t)t * D + d], c);
+    p.att[(long long)b * p.s_att + d] = c;
+    if (p.att_next) p.att_next[(long long)b * p.s_att + d] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct AttBwdArgs {
+  int B, Tm, D, Ud, type;
+  const float* keys; const float* values; const int* mem_len;
+  const float* align; long long s_al;
+  float* dctx; long long s_dc;           // in: dlogits W_proj^T of this step; out: + recurrent part
+  const float* datt_next; long long s_dn;  // gradient wrt attention_{t} from step t+1's cell input (NULL at t = S-1)
+  float* dscore; long long s_ds;         // [Tm] saved for the hoisted dkeys GEMM (luong)
+  float* dq; long long s_dq;             // [Ud] gradient wrt the query (h_top)
+  // bahdanau
+  const float* pq; long long s_pq; const float* w_query; const float* v_att;
+  float* dpq; long long s_dpq; float* dkeys; float* dv_acc;
+};
+
+__global__ void __launch_bounds__(512) dec_att_bwd_kernel(AttBwdArgs p) {
+  extern __shared__ float attb_smem[];
+  float* s_dc = attb_smem;       // [D]
+  float* s_da = s_dc + p.D;      // [Tm] dalign -> dscore
+  float* s_dpq = s_da + p.Tm;    // [Ud]
+  __shared__ float s_red[16];
+  __shared__ float s_bcast;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Ud = p.Ud, Tm = p.Tm, D = p.D;
+  const int len = min(p.mem_len[b], Tm);
+  float* dctx = p.dctx + (long long)b * p.s_dc;
+  for (int d = tid; d < D; d += 512) {
+    float v = dctx[d];
+    if (p.datt_next) v += p.datt_next[(long long)b * p.s_dn + d];
+    s_dc[d] = v;
+    dctx[d] = v;
+  }
+  __syncthreads();
+  const float* vb = p.values + (size_t)b * Tm * D;
+  const float* al = p.align + (long long)b * p.s_al;
+  for (int t = warp; t < Tm; t += 16) {
+    float s = 0.f;
+    if (t < len) {
+      const float* vr = vb + (size_t)t * D;
+      for (int d = lane; d < D; d += 32) s = fmaf(s_dc[d], vr[d], s);
+      s = warp_sum(s);
+    }
+    if (lane == 0) s_da[t] = s;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = tid; t < Tm; t += 512) dot = fmaf(al[t], s_da[t], dot);
+  dot = warp_sum(dot);
+  if (lane == 0) s_red[warp] = dot;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 16; ++w) t += s_red[w];
+    s_bcast = t;
+  }
+  __syncthreads();
+  dot = s_bcast;
+  for (int t = tid; t < Tm; t += 512) {
+    const float ds = al[t] * (s_da[t] - dot);
+    s_da[t] = ds;
+    p.dscore[(long long)b * p.s_ds + t] = ds;
+  }
+  __syncthreads();
+  const float* kb = p.keys + (size_t)b * Tm * Ud;
+  if (p.type == PLAS_ATT_BAHDANAU) {
+    float* dkb = p.dkeys + (size_t)b * Tm * Ud;
+    for (int u = tid; u < Ud; u += 512) {
+      const float pqu = p.pq[(long long)b * p.s_pq + u];
+      const float vu = p.v_att[u];
+      float dpq = 0.f, dv = 0.f;
+      for (int t = 0; t < len; ++t) {
+        const float e = tanhf(kb[(size_t)t * Ud + u] + pqu);
+        const float dpre = s_da[t] * vu * (1.f - e * e);
+        dpq += dpre;
+        dkb[(size_t)t * Ud + u] += dpre;
+        dv = fmaf(s_da[t], e, dv);
+      }
+      s_dpq[u] = dpq;
+      p.dpq[(long long)b * p.s_dpq + u] = dpq;
+      p.dv_acc[(size_t)b * Ud + u] += dv;
+    }
+    __syncthreads();
+    for (int k = warp; k < Ud; k += 16) {  // dq[k] = sum_u dpq[u] W_query[k][u]
+      float s = 0.f;
+      const float* wr = p.w_query + (size_t)k * Ud;
+      for (int u = lane; u < Ud; u += 32) s = fmaf(s_dpq[u], __ldg(wr + u), s);
+      s = warp_sum(s);
+      if (lane == 0) p.dq[(long long)b * p.s_dq + k] = s;
+    }
+  } else {
+    for (int u = tid; u < Ud; u += 512) {
+      float s = 0.f;
+      for (int t = 0; t < len; ++t) s = fmaf(s_da[t], kb[(size_t)t * Ud + u], s);
+      p.dq[(long long)b * p.s_dq + u] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+struct CellBwdArgs {
+  int B, Ud;
+  float* z; long long s_z;               // saved gates of this step -> dz (in place)
+  const float* c_t; const float* c_prev; long long s_c;   // c_prev NULL at t == 0
+  float* dc_carry;                       // [B][Ud] in/out
+  int first;                             // 1 at t == S-1: the carry is zero
+  const float* dq; long long s_dq;       // top layer: gradient wrt the query (NULL otherwise)
+  const float* dh_next; long long s_dn;  // h-part of dinp of this layer from step t+1 (NULL at t == S-1)
+  const float* dh_above; long long s_da; // in1-part of dinp of the layer above, same step (NULL for the top layer)
+};
+
+__global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= p.B * p.Ud) return;
+  const int b = i / p.Ud, u = i % p.Ud;
+  const int Ud = p.Ud;
+  float dh = 0.f;
+  if (p.dq) dh += p.dq[(long long)b * p.s_dq + u];
+  if (p.dh_next) dh += p.dh_next[(long long)b * p.s_dn + u];
+  if (p.dh_above) dh += p.dh_above[(long long)b * p.s_da + u];
+  float* zp = p.z + (long long)b * p.s_z + u;
+  const float gi = zp[0], gj = zp[Ud], gf = zp[2 * Ud], go = zp[3 * Ud];
+  const float c = p.c_t[(long long)b * p.s_c + u];
+  const float cp = p.c_prev ? p.c_prev[(long long)b * p.s_c + u] : 0.f;
+  const float tc = tanhf(c);
+  const float carry = p.first ? 0.f : p.dc_carry[(size_t)b * Ud + u];
+  const float dc = carry + dh * go * (1.f - tc * tc);
+  zp[0] = dc * gj * gi * (1.f - gi);
+  zp[Ud] = dc * gi * (1.f - gj * gj);
+  zp[2 * Ud] = dc * cp * gf * (1.f - gf);
+  zp[3 * Ud] = dh * tc * go * (1.f - go);
+  p.dc_carry[(size_t)b * Ud + u] = dc * gf;
+}
+
+// dinp[b][k] = sum_n dz[b][n] W[k][n], k in [0, K): lane = batch row, CTA = 8 consecutive k, warps split n
+struct GemvTArgs {
+  int B, N, K;                           // N = 4Ud
+  const float* dz; long long s_z;
+  const float* w;                        // [K][N] rows of the TF kernel below the hoisted x rows
+  float* dinp; long long s_o;
+};
+
+__global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
+  __shared__ float s_red[8][8][DT_ROWS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * 8;
+  const int b0 = blockIdx.y * DT_ROWS;
+  const int b = min(b0 + lane, p.B - 1);
+  const int N4 = p.N / 4;
+  const int per = (N4 + 7) / 8;
+  const int q_lo = warp * per, q_hi = min(N4, q_lo + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float4* zrow = reinterpret_cast<const float4*>(p.dz + (long long)b * p.s_z);
+  for (int q = q_lo; q < q_hi; ++q) {
+    const float4 a = zrow[q];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = min(k0 + kk, p.K - 1);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * p.N) + q);
+      acc[kk] = fmaf(a.x, w.x, acc[kk]);
+      acc[kk] = fmaf(a.y, w.y, acc[kk]);
+      acc[kk] = fmaf(a.z, w.z, acc[kk]);
+      acc[kk] = fmaf(a.w, w.w, acc[kk]);
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) s_red[warp][kk][lane] = acc[kk];
+  __syncthreads();
+  {
+    const int r = threadIdx.x % DT_ROWS, kk = threadIdx.x / DT_ROWS;  // 256 threads = 32 rows x 8 k
+    const int bb = b0 + r, k = k0 + kk;
+    if (bb < p.B && k < p.K) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += s_red[w][kk][r];
+      p.dinp[(long long)bb * p.s_o + k] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------------
+struct DecTrainWs {
+  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx;
+  size_t z[4], c[4], h[4], hprev[4];
+  size_t total;
+};
+
+static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
+  DecTrainWs w;
+  size_t off = 0;
+  auto take = [&](size_t n_floats) {
+    const size_t o = off;
+    off += (n_floats * 4 + 255) & ~size_t(255);
+    return o;
+  };
+  const size_t B = d.B, S = d.S, Tm = d.Tm, D = d.D, Ud = d.Ud;
+  w.keys = take(B * Tm * Ud);
+  w.att = take(B * S * D);
+  w.att_prev = take(B * S * D);
+  w.align = take(B * S * Tm);
+  w.pq = take(B * S * Ud);
+  w.dscore = take(B * S * Tm);
+  w.dpq = take(B * S * Ud);
+  w.dq = take(B * Ud);
+  w.dkeys = take(B * Tm * Ud);
+  w.dv_acc = take(B * Ud);
+  w.dctx = take(B * S * D);
+  for (int l = 0; l < 4; ++l) {
+    w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = 0;
+    if (l >= d.n_layers) continue;
+    w.z[l] = take(B * S * 4 * Ud);
+    w.c[l] = take(B * S * Ud);
+    w.h[l] = take(B * S * Ud);
+    w.hprev[l] = take(B * S * Ud);
+    w.dinp[l] = take(B * ((l == 0 ? D : Ud) + Ud));
+    w.dc[l] = take(B * Ud);
+  }
+  w.total = off;
+  return w;
+}
+
+static int gemm(cudaStream_t st, long long M, int N, int K, const float* A, long long sam, long long sak, const float* Bm,
+                long long sbk, long long sbn, float* C, long long ldc, const float* bias = nullptr, float beta = 0.f,
+                int batch = 1, long long ba = 0, long long bb = 0, long long bc = 0) {
+  plas_gemm_ex_desc g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.sam = sam; g.sak = sak;
+  g.B = Bm; g.sbk = sbk; g.sbn = sbn;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.alpha = 1.f; g.beta = beta;
+  g.batch = batch; g.batch_a = ba; g.batch_b = bb; g.batch_c = bc;
+  return plas_gemm_f32_ex(&g, st);
+}
+
+static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_bytes) {
+  PLAS_REQUIRE(d && ws, "dec_train: null argument");
+  PLAS_REQUIRE(d->B > 0 && d->S > 0 && d->Tm > 0 && d->E > 0 && d->n_out > 0, "dec_train: bad shape");
+  PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_train: n_layers=%d", d->n_layers);
+  PLAS_REQUIRE(d->Ud % 8 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 8, D=%d of 4", d->Ud, d->D);
+  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU,
+               "dec_train: attention_type %d has no training path (luong, bahdanau)", d->attention_type);
+  PLAS_REQUIRE((size_t)(d->D + d->Tm + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
+  const DecTrainWs w = dec_train_ws(*d);
+  PLAS_REQUIRE(ws_bytes >= w.total, "dec_train: workspace %zu < %zu", ws_bytes, w.total);
+  return PLAS_OK;
+}
+
+}  // namespace plas
+
+using namespace plas;
+
+extern "C" size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d) { return dec_train_ws(*d).total; }
+
+extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes,
+                                      plas_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = dec_train_check(d, workspace, workspace_bytes);
+  if (rc) return rc;
+  PLAS_REQUIRE(d->memory && d->mem_len && d->x_in && d->logits && d->w_mem && d->w_proj && d->b_proj, "dec_train_fwd: null tensor");
+  const DecTrainWs w = dec_train_ws(*d);
+  unsigned char* base = (unsigned char*)workspace;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
+  const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
+  if (bah) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
+  // keys = memory_layer(values); the memory is already zero past each length (the listener guarantees it)
+  rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud);
+  if (rc) return rc;
+  // Z_0 = x_in W_0[0:E] + b_0 for every step at once
+  rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]);
+  if (rc) return rc;
+  PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
+  for (int l = 0; l < L; ++l) PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
+  const int upc = (Ud / 4 >= 100) ? 4 : 2;
+  const dim3 cgrid(Ud / upc, (B + DT_ROWS - 1) / DT_ROWS);
+  const int dsplit = D >= 512 ? 4 : 1;
+  const size_t att_smem = (size_t)(2 * Ud + Tm) * 4;
+  for (int t = 0; t < S; ++t) {
+    for (int l = 0; l < L; ++l) {
+      CellFwdArgs a;
+      a.B = B; a.Ud = Ud;
+      const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud;
+      if (l == 0) {
+        a.pre = F(w.z[0]) + (size_t)t * 4 * Ud; a.s_pre = sz; a.bias = nullptr;
+        a.in1 = F(w.att_prev) + (size_t)t * D; a.s1 = (long long)S * D; a.K1 = D;
+        a.w1 = d->kernel[0] + (size_t)E * 4 * Ud;
+        a.w2 = d->kernel[0] + (size_t)(E + D) * 4 * Ud;
+      } else {
+        a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
+        a.in1 = F(w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud;
+        a.w1 = d->kernel[l];
+        a.w2 = d->kernel[l] + (size_t)Ud * 4 * Ud;
+      }
+      a.in2 = F(w.hprev[l]) + (size_t)t * Ud; a.s2 = sh; a.K2 = Ud;
+      a.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; a.s_c = sh;
+      a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
+      a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
+      a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
+      if (upc == 4) dec_cell_fwd_kernel<4><<<cgrid, 256, 0, st>>>(a);
+      else dec_cell_fwd_kernel<2><<<cgrid, 256, 0, st>>>(a);
+    }
+    AttFwdArgs q;
+    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit;
+    q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
+    q.query = F(w.h[L - 1]) + (size_t)t * Ud; q.s_q = (long long)S * Ud;
+    q.w_query = d->w_query; q.v_att = d->v_att;
+    q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = (long long)S * Ud;
+    q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+    q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D;
+    q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
+    dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
+  }
+  PLAS_CUDA(cudaGetLastError());
+  // logits = DenseBinfDecoder(attention)
+  return gemm(st, (long long)B * S, d->n_out, D, F(w.att), D, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+}
+
+extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes,
+                                      plas_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = dec_train_check(d, workspace, workspace_bytes);
+  if (rc) return rc;
+  PLAS_REQUIRE(d->dlogits && d->dmemory && d->dw_mem && d->dw_proj && d->db_proj, "dec_train_bwd: null tensor");
+  const DecTrainWs w = dec_train_ws(*d);
+  unsigned char* base = (unsigned char*)workspace;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers, NO = d->n_out;
+  const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
+  const long long BS = (long long)B * S;
+  float* dctx = F(w.dctx);  // [B][S][D]
+  // projection layer: dAtt = dlogits W_proj^T, dW_proj = Att^T dlogits, db_proj = colsum(dlogits)
+  if ((rc = gemm(st, BS, D, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, dctx, D))) return rc;
+  if ((rc = gemm(st, D, NO, (int)BS, F(w.att), 1, D, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+  if ((rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
+  if (bah) {
+    PLAS_REQUIRE(d->dw_query && d->dv_att, "dec_train_bwd: bahdanau needs dw_query / dv_att");
+    PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
+    PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
+  }
+  const size_t attb_smem = (size_t)(D + Tm + Ud) * 4;
+  PLAS_CUDA(cudaFuncSetAttribute(dec_att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud;
+  for (int t = S - 1; t >= 0; --t) {
+    const bool last = t == S - 1;
+    AttBwdArgs q;
+    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type;
+    q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
+    q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+    q.dctx = dctx + (size_t)t * D; q.s_dc = (long long)S * D;
+    q.datt_next = last ? nullptr : F(w.dinp[0]); q.s_dn = D + Ud;
+    q.dscore = F(w.dscore) + (size_t)t * Tm; q.s_ds = (long long)S * Tm;
+    q.dq = F(w.dq); q.s_dq = Ud;
+    q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
+    q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
+    dec_att_bwd_kernel<<<B, 512, attb_smem, st>>>(q);
+    for (int l = L - 1; l >= 0; --l) {
+      const int Kin = (l == 0 ? D : Ud);
+      CellBwdArgs c;
+      c.B = B; c.Ud = Ud;
+      c.z = F(w.z[l]) + (size_t)t * 4 * Ud; c.s_z = sz;
+      c.c_t = F(w.c[l]) + (size_t)t * Ud; c.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; c.s_c = sh;
+      c.dc_carry = F(w.dc[l]); c.first = last ? 1 : 0;
+      c.dq = (l == L - 1) ? F(w.dq) : nullptr; c.s_dq = Ud;
+      c.dh_next = last ? nullptr : F(w.dinp[l]) + Kin; c.s_dn = Kin + Ud;
+      c.dh_above = (l < L - 1) ? F(w.dinp[l + 1]) : nullptr; c.s_da = 2 * Ud;
+      dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
+      GemvTArgs g;
+      g.B = B; g.N = 4 * Ud; g.K = Kin + Ud;
+      g.dz = c.z; g.s_z = sz;
+      g.w = d->kernel[l] + (size_t)(l == 0 ? E : 0) * 4 * Ud;
+      g.dinp = F(w.dinp[l]); g.s_o = Kin + Ud;
+      dec_gemv_t_kernel<<<dim3((g.K + 7) / 8, (B + DT_ROWS - 1) / DT_ROWS), 256, 0, st>>>(g);
+    }
+  }
+  PLAS_CUDA(cudaGetLastError());
+  // weight gradients over the B*S saved rows (z now holds dz)
+  for (int l = 0; l < L; ++l) {
+    PLAS_REQUIRE(d->dkernel[l] && d->dbias[l], "dec_train_bwd: null gradient tensor (layer %d)", l);
+    const float* dz = F(w.z[l]);
+    float* dk = d->dkernel[l];
+    if (l == 0) {
+      if ((rc = gemm(st, E, 4 * Ud, (int)BS, d->x_in, 1, E, dz, 4 * Ud, 1, dk, 4 * Ud))) return rc;
+      if ((rc = gemm(st, D, 4 * Ud, (int)BS, F(w.att_prev), 1, D, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + D) * 4 * Ud, 4 * Ud))) return rc;
+    } else {
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.h[l - 1]), 1, Ud, dz, 4 * Ud, 1, dk, 4 * Ud))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[l]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)Ud * 4 * Ud, 4 * Ud))) return rc;
+    }
+    if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;
+  }
+  const float* htop = F(w.h[L - 1]);
+  if (bah) {
+    if ((rc = gemm(st, Ud, Ud, (int)BS, htop, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
+    if ((rc = plas_colsum_f32(F(w.dv_acc), B, Ud, Ud, d->dv_att, 0, st))) return rc;
+  } else {
+    // dkeys[b] = dScore[b]^T H_top[b]
+    if ((rc = gemm(st, Tm, Ud, S, F(w.dscore), 1, Tm, htop, Ud, 1, F(w.dkeys), Ud, nullptr, 0.f, B, (long long)S * Tm,
+                   (long long)S * Ud, (long long)Tm * Ud)))
+      return rc;
+  }
+  // dvalues[b] = Align[b]^T dAtt[b]  (accumulated into the encoder-output gradient)
+  if ((rc = gemm(st, Tm, D, S, F(w.align), 1, Tm, dctx, D, 1, d->dmemory, D, nullptr, d->dmemory_accumulate ? 1.f : 0.f, B,
+                 (long long)S * Tm, (long long)S * D, (long long)Tm * D)))
+    return rc;
+  // memory_layer: dmemory += dkeys W_mem^T, dW_mem = memory^T dkeys
+  if ((rc = gemm(st, (long long)B * Tm, D, Ud, F(w.dkeys), Ud, 1, d->w_mem, 1, Ud, d->dmemory, D, nullptr, 1.f))) return rc;
+  return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud);
+}

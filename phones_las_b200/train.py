@@ -1,0 +1,406 @@
+"""Training step of the hot path on the GPU: ``las_model_fn(mode=TRAIN)`` without the Estimator glue.
+
+Mirrors model_helper.py:165-227 (listener + speller(s) in TRAIN mode), :319-358 (sequence / sigmoid / CTC losses,
+multitask sum), :403-417 (L2 regulariser, per-tensor ``clip_by_norm(grad, 2)``, Adam) and, for data-parallel runs,
+the CrossShardOptimizer order of :405-406 (clip locally, then average the gradients across ranks, then apply).
+Parity runs use ``dropout = 0`` and ``sampling_probability = 0`` (both are RNG-driven in TF).
+
+Every variable lives in ONE flat fp32 device buffer in the TF checkpoint layout; gradients and
+the Adam moments mirror it, so the data-parallel exchange is a single all-reduce of ``state.grads`` and a trained
+model exports to the reference's variable names unchanged.  All arithmetic runs in csrc/train_*.cu through the
+C-ABI; torch only owns memory, streams and the process group.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import variable_shapes
+
+GRAD_NORM = 2.0  # model_helper.py:16
+
+
+def _p(t, off_elems=0):
+    return t.data_ptr() + 4 * off_elems
+
+
+def gemm_ex(M, N, K, A, sam, sak, B, sbk, sbn, Cp, ldc, bias=None, beta=0.0, alpha=1.0, batch=1, ba=0, bb=0, bc=0):
+    """plas_gemm_f32_ex on raw device addresses (ints)."""
+    d = _lib.GemmExDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.sam, d.sak = A, sam, sak
+    d.B, d.sbk, d.sbn = B, sbk, sbn
+    d.C, d.ldc, d.bias = Cp, ldc, bias
+    d.alpha, d.beta = alpha, beta
+    d.batch, d.batch_a, d.batch_b, d.batch_c = batch, ba, bb, bc
+    _lib.check(_lib.lib().plas_gemm_f32_ex(C.byref(d), _lib.stream_ptr()))
+    _lib.count_launches(1)
+
+
+def colsum(X, M, N, ld, out, accumulate=False):
+    _lib.check(_lib.lib().plas_colsum_f32(C.c_void_p(X), M, N, ld, C.c_void_p(out), 1 if accumulate else 0, _lib.stream_ptr()))
+    _lib.count_launches(1)
+
+
+class TrainState:
+    """Flat parameter / gradient / Adam-moment buffers keyed by TF variable name."""
+
+    def __init__(self, params, device="cuda"):
+        _lib.require_cuda()
+        self.names = list(params.keys())
+        self.shapes = {k: tuple(np.shape(params[k])) for k in self.names}
+        sizes = [int(np.prod(self.shapes[k])) if self.shapes[k] else 1 for k in self.names]
+        # every tensor starts on a 16-byte boundary (vector loads in the kernels); padding stays zero
+        offs, off = [], 0
+        for n in sizes:
+            offs.append(off)
+            off += (n + 3) // 4 * 4
+        self.total = off
+        self.offsets_host = offs + [off]
+        self.sizes = sizes
+        flat = np.zeros((off,), np.float32)
+        for k, o, n in zip(self.names, offs, sizes):
+            flat[o:o + n] = np.asarray(params[k], np.float32).reshape(-1)
+        self.params = torch.from_numpy(flat).to(device)
+        self.grads = torch.zeros_like(self.params)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self.offsets = torch.tensor(self.offsets_host, dtype=torch.int64, device=device)
+        self.norms = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
+        self.wsq = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
+        self.index = {k: i for i, k in enumerate(self.names)}
+        self.step = 0
+
+    def has(self, name):
+        return name in self.index
+
+    def w(self, name, row=0):
+        """device address of variable ``name`` (+ ``row`` rows of its last dimension)."""
+        i = self.index[name]
+        cols = self.shapes[name][-1] if self.shapes[name] else 1
+        return _p(self.params, self.offsets_host[i] + row * cols)
+
+    def g(self, name, row=0):
+        i = self.index[name]
+        cols = self.shapes[name][-1] if self.shapes[name] else 1
+        return _p(self.grads, self.offsets_host[i] + row * cols)
+
+    def view(self, buf, name):
+        i = self.index[name]
+        o, n = self.offsets_host[i], self.sizes[i]
+        return buf[o:o + n].view(self.shapes[name])
+
+    def export_params(self):
+        """-> {tf_variable_name: float32 ndarray} (the exchange format of weights.py)."""
+        flat = self.params.cpu().numpy()
+        return {k: flat[o:o + n].reshape(self.shapes[k]).copy() for k, o, n in zip(self.names, self.offsets_host, self.sizes)}
+
+    def export_grads(self):
+        flat = self.grads.cpu().numpy()
+        return {k: flat[o:o + n].reshape(self.shapes[k]).copy() for k, o, n in zip(self.names, self.offsets_host, self.sizes)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# listener
+# --------------------------------------------------------------------------------------------------------------
+def _layer_names(l):
+    return [f"listener/bilstm_{l}/bidirectional_rnn/{d}/lstm_cell" for d in ("fw", "bw")]
+
+
+def _rec_desc(B, T, U, ndir, din, z, kernels, lengths, out, c_save, h_prev, dout=None):
+    d = _lib.RecTrainDesc()
+    d.B, d.T, d.U, d.ndir, d.din = B, T, U, ndir, din
+    d.z = z.data_ptr()
+    for i, k in enumerate(kernels):
+        d.kernel[i] = k
+    d.lengths = lengths.data_ptr()
+    d.out = out.data_ptr() if out is not None else None
+    d.out_batch_stride = (out if out is not None else dout).stride(0)
+    d.c_save, d.h_prev = c_save.data_ptr(), h_prev.data_ptr()
+    d.dout = dout.data_ptr() if dout is not None else None
+    return d
+
+
+def listener_train_fwd(x, lengths, st, hp):
+    """pyramidal_bilstm (las/ops.py:68-87) forward keeping what BPTT needs.  x [B,T,C] f32 -> (enc_out, enc_len, tape)."""
+    if not hp["use_pyramidal"] or hp["unidirectional"]:
+        raise NotImplementedError("the training path covers the pyramidal bidirectional listener")
+    L = _lib.lib()
+    U, ndir = hp["encoder_units"], 2
+    B = x.shape[0]
+    lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+    x = x.to(torch.float32).contiguous()
+    tape = []
+    for l in range(hp["encoder_layers"]):
+        T, din = x.shape[1], x.shape[2]
+        names = _layer_names(l)
+        z = torch.empty((B, T, ndir, 4 * U), dtype=torch.float32, device=x.device)
+        with _lib.stage("train_inproj"):
+            for dd, nm in enumerate(names):
+                gemm_ex(B * T, 4 * U, din, x.data_ptr(), din, 1, st.w(nm + "/kernel"), 4 * U, 1, _p(z, dd * 4 * U), ndir * 4 * U,
+                        bias=st.w(nm + "/bias"))
+        t_alloc = T if l == 0 else T + (T % 2)
+        out = torch.zeros((B, t_alloc, ndir * U), dtype=torch.float32, device=x.device)
+        c_save = torch.zeros((B, T, ndir * U), dtype=torch.float32, device=x.device)
+        h_prev = torch.zeros((B, T, ndir * U), dtype=torch.float32, device=x.device)
+        d = _rec_desc(B, T, U, ndir, din, z, [st.w(nm + "/kernel") for nm in names], lengths, out, c_save, h_prev)
+        need = L.plas_rec_train_workspace_bytes(C.byref(d))
+        ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
+        with _lib.stage("train_rec_fwd"):
+            _lib.check(L.plas_bilstm_rec_train_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+        _lib.count_launches(1)
+        tape.append(dict(x=x, z=z, c_save=c_save, h_prev=h_prev, lengths=lengths, T=T, din=din, t_alloc=t_alloc, ws=ws))
+        if l != 0:
+            out = out.view(B, t_alloc // 2, 2 * ndir * U)
+            lengths = torch.div(lengths, 2, rounding_mode="floor") + lengths % 2
+        x = out
+    return x, lengths, tape
+
+
+def listener_train_bwd(d_enc, tape, st, hp):
+    """Gradient of pyramidal_bilstm: per layer BPTT (plas_bilstm_rec_train_bwd) then dW = [x;h]^T dz, db, dx = dz W_x^T."""
+    L = _lib.lib()
+    U, ndir = hp["encoder_units"], 2
+    B = d_enc.shape[0]
+    dout = d_enc
+    for l in range(hp["encoder_layers"] - 1, -1, -1):
+        tp = tape[l]
+        T, din = tp["T"], tp["din"]
+        names = _layer_names(l)
+        dout = dout.reshape(B, tp["t_alloc"], ndir * U)
+        d = _rec_desc(B, T, U, ndir, din, tp["z"], [st.w(nm + "/kernel") for nm in names], tp["lengths"], None, tp["c_save"],
+                      tp["h_prev"], dout=dout)
+        need = tp["ws"].numel()
+        with _lib.stage("train_rec_bwd"):
+            _lib.check(L.plas_bilstm_rec_train_bwd(C.byref(d), _lib.ptr(tp["ws"]), need, _lib.stream_ptr()))
+        _lib.count_launches(1)
+        z, x, hp_ = tp["z"], tp["x"], tp["h_prev"]
+        M = B * T
+        dx = torch.empty((B, T, din), dtype=torch.float32, device=z.device) if l > 0 else None
+        with _lib.stage("train_wgrad"):
+            for dd, nm in enumerate(names):
+                zp = _p(z, dd * 4 * U)
+                gemm_ex(din, 4 * U, M, x.data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U)
+                gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U)
+                colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))
+        if l > 0:
+            with _lib.stage("train_dgrad"):
+                for dd, nm in enumerate(names):
+                    gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dx.data_ptr(), din,
+                            beta=0.0 if dd == 0 else 1.0)
+            dout = dx
+
+
+# --------------------------------------------------------------------------------------------------------------
+# speller
+# --------------------------------------------------------------------------------------------------------------
+class SpellerTrain:
+    """One teacher-forced speller (scope 'speller' or 'speller_binf') bound to a TrainState."""
+
+    def __init__(self, st, hp, scope, E, n_out):
+        self.st, self.hp, self.scope, self.E, self.n_out = st, hp, scope, E, n_out
+        if hp["attention_type"] not in ("luong", "bahdanau"):
+            raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
+        for flag in ("bottom_only", "pass_hidden_state", "binf_projection", "attention_layer_size", "embedding_size"):
+            if hp.get(flag):
+                raise NotImplementedError(f"training path: --{flag} is not built")
+
+    def _desc(self, memory, mem_len, x_in, logits, dlogits=None, dmemory=None):
+        st, hp, sc = self.st, self.hp, self.scope
+        B, Tm, D = memory.shape
+        d = _lib.DecTrainDesc()
+        d.B, d.S, d.Tm, d.D, d.Ud, d.E, d.n_out = B, x_in.shape[1], Tm, D, hp["decoder_units"], self.E, self.n_out
+        d.n_layers = hp["decoder_layers"]
+        d.attention_type = _lib.ATT_CODES[hp["attention_type"]]
+        d.dmemory_accumulate = 1
+        pre = f"{sc}/decoder/attention_wrapper"
+        for k in range(d.n_layers):
+            nm = f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell"
+            d.kernel[k], d.bias[k] = st.w(nm + "/kernel"), st.w(nm + "/bias")
+            d.dkernel[k], d.dbias[k] = st.g(nm + "/kernel"), st.g(nm + "/bias")
+        d.w_mem, d.dw_mem = st.w(f"{sc}/memory_layer/kernel"), st.g(f"{sc}/memory_layer/kernel")
+        if hp["attention_type"] == "bahdanau":
+            q, v = f"{pre}/bahdanau_attention/query_layer/kernel", f"{pre}/bahdanau_attention/attention_v"
+            d.w_query, d.v_att, d.dw_query, d.dv_att = st.w(q), st.w(v), st.g(q), st.g(v)
+        pk, pb = f"{sc}/decoder/projection_layer/kernel", f"{sc}/decoder/projection_layer/bias"
+        d.w_proj, d.b_proj, d.dw_proj, d.db_proj = st.w(pk), st.w(pb), st.g(pk), st.g(pb)
+        d.memory, d.mem_len, d.x_in = memory.data_ptr(), mem_len.data_ptr(), x_in.data_ptr()
+        d.logits = logits.data_ptr()
+        d.dlogits = dlogits.data_ptr() if dlogits is not None else None
+        d.dmemory = dmemory.data_ptr() if dmemory is not None else None
+        return d
+
+    def forward(self, memory, mem_len, x_in):
+        """memory [B,Tm,D] (zero past mem_len), x_in [B,S,E] -> logits [B,S,n_out]; keeps the tape on self."""
+        L = _lib.lib()
+        B, S = x_in.shape[0], x_in.shape[1]
+        self.memory, self.mem_len, self.x_in = memory.contiguous(), mem_len, x_in.contiguous()
+        self.logits = torch.empty((B, S, self.n_out), dtype=torch.float32, device=memory.device)
+        d = self._desc(self.memory, self.mem_len, self.x_in, self.logits)
+        need = L.plas_dec_train_workspace_bytes(C.byref(d))
+        self.ws = torch.empty((need,), dtype=torch.uint8, device=memory.device)
+        with _lib.stage("train_dec_fwd"):
+            _lib.check(L.plas_decoder_train_fwd(C.byref(d), _lib.ptr(self.ws), need, _lib.stream_ptr()))
+        _lib.count_launches(3 + S * (self.hp["decoder_layers"] + 1))
+        return self.logits
+
+    def backward(self, dlogits, d_enc):
+        """Accumulates into d_enc [B,Tm,D] and writes this speller's weight gradients into the TrainState."""
+        L = _lib.lib()
+        d = self._desc(self.memory, self.mem_len, self.x_in, self.logits, dlogits.contiguous(), d_enc)
+        with _lib.stage("train_dec_bwd"):
+            _lib.check(L.plas_decoder_train_bwd(C.byref(d), _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr()))
+        _lib.count_launches(12 + self.x_in.shape[1] * (1 + 2 * self.hp["decoder_layers"]))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# losses with gradients
+# --------------------------------------------------------------------------------------------------------------
+def _seq_mask(lengths, maxlen):
+    ar = torch.arange(maxlen, device=lengths.device)
+    return (ar[None, :] < lengths[:, None].to(ar.dtype)).to(torch.float32).contiguous()
+
+
+def seq_ce_grad(logits, targets, weights, gscale=1.0):
+    B, S, V = logits.shape
+    ce = torch.empty((B * S,), dtype=torch.float32, device=logits.device)
+    out3 = torch.empty((3,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits)
+    _lib.check(_lib.lib().plas_seq_ce_grad(_lib.ptr(logits), _lib.ptr(targets), _lib.ptr(weights), B * S, V, gscale, _lib.ptr(ce),
+                                           _lib.ptr(out3), _lib.ptr(dl), _lib.stream_ptr()))
+    _lib.count_launches(3)
+    return out3[0], dl
+
+
+def sigmoid_ce_grad(logits, labels, weights, gscale=1.0):
+    B, S, n = logits.shape
+    ce = torch.empty((B * S,), dtype=torch.float32, device=logits.device)
+    out3 = torch.empty((3,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits)
+    _lib.check(_lib.lib().plas_sigmoid_ce_grad(_lib.ptr(logits), _lib.ptr(labels), _lib.ptr(weights), B * S, n, gscale, _lib.ptr(ce),
+                                               _lib.ptr(out3), _lib.ptr(dl), _lib.stream_ptr()))
+    _lib.count_launches(3)
+    return out3[0], dl
+
+
+def ctc_grad(logits, labels, label_length, logit_length, gscale=1.0, blank=0):
+    L = _lib.lib()
+    B, T, Cn = logits.shape
+    Lmax = labels.shape[1]
+    loss = torch.empty((B,), dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits)
+    need = L.plas_ctc_grad_workspace_bytes(B, T, Lmax)
+    ws = torch.empty((max(need, 4),), dtype=torch.uint8, device=logits.device)
+    _lib.check(L.plas_ctc_grad(_lib.ptr(logits), _lib.ptr(labels), _lib.ptr(label_length), _lib.ptr(logit_length), B, T, Cn, Lmax,
+                               blank, gscale, _lib.ptr(loss), _lib.ptr(dl), _lib.ptr(ws), need, _lib.stream_ptr()))
+    _lib.count_launches(1)
+    return loss, dl
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the step
+# --------------------------------------------------------------------------------------------------------------
+def forward_backward(features, labels, st, hp, binf=None):
+    """Forward + backward of las_model_fn(TRAIN): fills ``st.grads`` (raw, before L2 / clipping) and returns the loss
+    parts as device scalars {ce, ce_binf, ctc, audio_loss}.  ``binf`` [n, V] float tensor (binf2phone, model_helper.py:179-186)
+    enables the multitask binary-feature speller when hp['binary_outputs']."""
+    if float(hp.get("dropout", 0.0)) > 0.0 or float(hp.get("sampling_probability", 0.0)) > 0.0:
+        raise NotImplementedError("training path: dropout / scheduled sampling are RNG-driven in TF and not built; set both to 0")
+    x, lens = features["encoder_inputs"], features["source_sequence_length"]
+    dev = x.device
+    tin = labels["targets_inputs"].to(device=dev, dtype=torch.int64)
+    tout = labels["targets_outputs"].to(device=dev, dtype=torch.int32).contiguous()
+    tlen = labels["target_sequence_length"].to(device=dev, dtype=torch.int32).contiguous()
+    V = hp["target_vocab_size"]
+    S = tin.shape[1]
+    st.grads.zero_()
+    enc_out, enc_len, tape = listener_train_fwd(x, lens, st, hp)
+    enc_out = enc_out.contiguous()
+    B, Tm, D = enc_out.shape
+    w = _seq_mask(tlen, S)
+    d_enc = torch.zeros_like(enc_out)
+    parts = {}
+    total = None
+    spellers = []
+    if not hp.get("binary_outputs") or hp.get("multitask"):
+        sp = SpellerTrain(st, hp, "speller", V, V)
+        logits = sp.forward(enc_out, enc_len, torch.nn.functional.one_hot(tin, V).to(torch.float32))
+        parts["ce"], dl = seq_ce_grad(logits, tout, w)
+        parts["logits"] = logits
+        spellers.append((sp, dl))
+        total = parts["ce"]
+    if hp.get("binary_outputs"):
+        bt = binf.to(device=dev, dtype=torch.float32).t().contiguous()  # [V, n]
+        n = bt.shape[1]
+        sp = SpellerTrain(st, hp, "speller_binf", n, n)
+        logits_b = sp.forward(enc_out, enc_len, bt[tin])
+        parts["ce_binf"], dlb = sigmoid_ce_grad(logits_b, bt[tout.long()].contiguous(), w)
+        parts["logits_binf"] = logits_b
+        spellers.append((sp, dlb))
+        total = parts["ce_binf"] if total is None else total + parts["ce_binf"]
+    if hp.get("ctc_weight", -1.0) > 0:  # model_helper.py:347-358
+        cw = float(hp["ctc_weight"])
+        Cn = V + 1
+        cl = torch.empty((B, Tm, Cn), dtype=torch.float32, device=dev)
+        gemm_ex(B * Tm, Cn, D, enc_out.data_ptr(), D, 1, st.w("ctc_logits/kernel"), Cn, 1, cl.data_ptr(), Cn, bias=st.w("ctc_logits/bias"))
+        per_utt, dcl = ctc_grad(cl, tout, tlen, enc_len, gscale=cw / B)
+        parts["ctc"] = per_utt.mean()
+        total = parts["ctc"] * cw if total is None else total + parts["ctc"] * cw
+        gemm_ex(D, Cn, B * Tm, enc_out.data_ptr(), 1, D, dcl.data_ptr(), Cn, 1, st.g("ctc_logits/kernel"), Cn)
+        colsum(dcl.data_ptr(), B * Tm, Cn, Cn, st.g("ctc_logits/bias"))
+        gemm_ex(B * Tm, D, Cn, dcl.data_ptr(), Cn, 1, st.w("ctc_logits/kernel"), 1, Cn, d_enc.data_ptr(), D, beta=1.0)
+    for sp, dl in spellers:
+        sp.backward(dl, d_enc)
+    listener_train_bwd(d_enc, tape, st, hp)
+    parts["audio_loss"] = total
+    parts["encoder_out"] = enc_out
+    return parts
+
+
+def apply_gradients(st, hp, world_size=1, allreduce=None):
+    """model_helper.py:404-417: g += l2*w; per-tensor clip_by_norm(2); [mean over ranks]; Adam."""
+    L = _lib.lib()
+    n = len(st.names)
+    _lib.check(L.plas_grad_l2_norm(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.offsets), n, float(hp.get("l2_reg_scale", 0.0)),
+                                   _lib.ptr(st.norms), _lib.ptr(st.wsq), _lib.stream_ptr()))
+    _lib.check(L.plas_clip_scale(_lib.ptr(st.grads), _lib.ptr(st.offsets), n, _lib.ptr(st.norms), GRAD_NORM, 1.0 / world_size,
+                                 _lib.stream_ptr()))
+    if allreduce is not None:
+        allreduce(st.grads)  # sum of (clipped / world_size) = CrossShardOptimizer's mean
+    st.step += 1
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    lr_t = float(hp["learning_rate"]) * (1.0 - b2 ** st.step) ** 0.5 / (1.0 - b1 ** st.step)
+    _lib.check(L.plas_adam_step(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.m), _lib.ptr(st.v), st.total, lr_t, b1, b2, eps,
+                                1.0, _lib.stream_ptr()))
+    _lib.count_launches(3)
+
+
+def train_step(features, labels, st, hp, binf=None, world_size=1, allreduce=None):
+    """One optimiser step.  Returns {'loss': audio_loss + L2 term, parts...} as device scalars."""
+    parts = forward_backward(features, labels, st, hp, binf)
+    apply_gradients(st, hp, world_size, allreduce)
+    reg = st.wsq.sum() * (0.5 * float(hp.get("l2_reg_scale", 0.0)))  # L2 term of the PRE-update weights
+    parts["loss"] = parts["audio_loss"] + reg
+    return parts
+
+
+def train_variable_shapes(hp, num_channels=None, binf_count=0):
+    """variable_shapes + the 'speller_binf/' twin of the multitask configuration (model_helper.py:221)."""
+    shapes = dict(variable_shapes(hp, num_channels))
+    if hp.get("binary_outputs"):
+        V = hp["target_vocab_size"]
+        for k, s in list(shapes.items()):
+            if not k.startswith("speller/"):
+                continue
+            nk = "speller_binf/" + k[len("speller/"):]
+            if k.endswith("cell_0/lstm_cell/kernel"):
+                s = (s[0] - V + binf_count, s[1])
+            elif k.endswith("projection_layer/kernel"):
+                s = (s[0], binf_count)
+            elif k.endswith("projection_layer/bias"):
+                s = (binf_count,)
+            shapes[nk] = s
+        if not hp.get("multitask"):
+            shapes = {k: s for k, s in shapes.items() if not k.startswith("speller/")}
+    return shapes

@@ -63,13 +63,13 @@ def variable_shapes(hp, num_channels=None):
     return shapes
 
 
-def init_params(hp, num_channels=None, seed=4321, projection_scale=1.0, bias_scale=0.0):
+def init_params(hp, num_channels=None, seed=4321, projection_scale=1.0, bias_scale=0.0, shapes=None):
     """Synthetic weights: LSTM kernels and the projection U(-0.075, 0.075)
     (las/ops.py:12, las/model.py:257), LSTM biases 0 (or U(-bias_scale, bias_scale) to exercise the
     bias path), Dense kernels / attention_v Glorot-uniform, attention_score_bias 0."""
     rng = np.random.default_rng(seed)
     params = {}
-    for name, shape in variable_shapes(hp, num_channels).items():
+    for name, shape in (shapes or variable_shapes(hp, num_channels)).items():
         if name.endswith("lstm_cell/kernel") or name.endswith("projection_layer/kernel"):
             w = rng.uniform(-0.075, 0.075, size=shape)
             if name.endswith("projection_layer/kernel"):

@@ -1,0 +1,219 @@
+"""Training-path parity (through the C-ABI): forward values and gradients of the CUDA TRAIN step vs the float64
+autograd restatement oracle/las_torch.py (model_helper.py:165-227, 319-358, 403-417), component by component and
+for whole multitask steps.  Bar (fp32 arithmetic): 2e-4 of each tensor's scale for gradients, 1e-4 for losses
+(north_star), parameters after Adam steps within 2e-5 absolute (lr 1e-3)."""
+import numpy as np
+import pytest
+
+from oracle import las_torch as lt
+from phones_las_b200 import synth, weights
+from phones_las_b200.hparams import create_hparams
+from tests.util import gpu, to_np, scaled_err
+
+GRAD_TOL = 2e-4
+
+
+def _tp(params, grad=True):
+    import torch
+    return {k: torch.tensor(v, dtype=torch.float64, requires_grad=grad) for k, v in params.items()}
+
+
+@gpu
+@pytest.mark.parametrize("M,N,K", [(70, 50, 33), (200, 130, 257), (5, 300, 1000)])
+def test_gemm_ex_all_layouts(M, N, K):
+    import torch
+    from phones_las_b200.train import gemm_ex, colsum
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn((M, K), generator=g).cuda()
+    B = torch.randn((K, N), generator=g).cuda()
+    bias = torch.randn((N,), generator=g).cuda()
+    ref = (A.double() @ B.double()).float()
+    C = torch.empty((M, N), device="cuda")
+    gemm_ex(M, N, K, A.data_ptr(), K, 1, B.data_ptr(), N, 1, C.data_ptr(), N, bias=bias.data_ptr())
+    assert scaled_err(C, ref + bias) < 1e-5
+    At, Bt = A.t().contiguous(), B.t().contiguous()  # the same product from transposed storage
+    C2 = torch.full((M, N), 1.0, device="cuda")
+    gemm_ex(M, N, K, At.data_ptr(), 1, M, Bt.data_ptr(), 1, K, C2.data_ptr(), N, beta=2.0, alpha=0.5)
+    assert scaled_err(C2, 0.5 * ref + 2.0) < 1e-5
+    # batched (grid.z)
+    Ab = torch.randn((3, M, 8), generator=g).cuda()
+    Bb = torch.randn((3, 8, N), generator=g).cuda()
+    Cb = torch.empty((3, M, N), device="cuda")
+    gemm_ex(M, N, 8, Ab.data_ptr(), 8, 1, Bb.data_ptr(), N, 1, Cb.data_ptr(), N, batch=3, ba=M * 8, bb=8 * N, bc=M * N)
+    assert scaled_err(Cb, torch.bmm(Ab, Bb)) < 1e-5
+    out = torch.empty((N,), device="cuda")
+    colsum(B.data_ptr(), K, N, N, out.data_ptr())
+    assert scaled_err(out, B.double().sum(0)) < 1e-5
+
+
+LISTENER_CFGS = [(3, 13, 5, 8, 2), (5, 21, 7, 16, 3), (20, 30, 39, 64, 3), (33, 40, 13, 256, 2)]
+
+
+@gpu
+@pytest.mark.parametrize("B,T,C,U,L", LISTENER_CFGS, ids=lambda v: str(v))
+def test_listener_forward_backward(B, T, C, U, L):
+    import torch
+    from phones_las_b200.train import TrainState, listener_train_fwd, listener_train_bwd
+    hp = create_hparams(target_vocab_size=12, encoder_layers=L, encoder_units=U, decoder_units=16, decoder_layers=1,
+                        num_channels=C, dropout=0.0, sampling_probability=0.0)
+    params = {k: v for k, v in weights.init_params(hp, seed=U + L, bias_scale=0.1).items() if k.startswith("listener/")}
+    x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
+    tp = _tp(params)
+    ref, ref_len = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, L)
+    g = torch.Generator().manual_seed(1)
+    dref = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * dref).sum().backward()
+    st = TrainState(params)
+    out, out_len, tape = listener_train_fwd(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), st, hp)
+    assert np.array_equal(to_np(out_len), ref_len.numpy())
+    assert scaled_err(out, ref.detach()) < 1e-5
+    listener_train_bwd(dref.float().cuda().contiguous(), tape, st, hp)
+    grads = st.export_grads()
+    for k in params:
+        e = scaled_err(grads[k], tp[k].grad)
+        assert e < GRAD_TOL, f"{k}: {e:.3e}"
+
+
+SPELLER_CFGS = [("luong", 3, 9, 16, 32, 1, 12, 5), ("bahdanau", 5, 14, 16, 32, 2, 20, 7), ("luong", 33, 30, 64, 256, 1, 64, 11),
+                ("bahdanau", 8, 20, 32, 64, 3, 30, 6), ("luong", 40, 12, 16, 128, 2, 16, 9)]
+
+
+@gpu
+@pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,S", SPELLER_CFGS, ids=lambda v: str(v))
+def test_speller_forward_backward(att, B, Tm, U, Ud, Ld, V, S):
+    import torch
+    from phones_las_b200.train import TrainState, SpellerTrain
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=4, attention_type=att, dropout=0.0, sampling_probability=0.0)
+    params = {k: v for k, v in weights.init_params(hp, seed=Ud, projection_scale=4.0, bias_scale=0.1).items()
+              if k.startswith("speller/")}
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(B)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    lens[0] = Tm
+    enc *= (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    ids = rng.integers(0, V, (B, S))
+    tp = _tp(params)
+    enc_t = torch.tensor(enc, dtype=torch.float64, requires_grad=True)
+    x64 = torch.nn.functional.one_hot(torch.tensor(ids), V).to(torch.float64)
+    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp)
+    dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+    (ref * dref).sum().backward()
+    st = TrainState(params)
+    sp = SpellerTrain(st, hp, "speller", V, V)
+    logits = sp.forward(torch.from_numpy(enc).cuda(), torch.from_numpy(lens).cuda(), x64.float().cuda())
+    assert scaled_err(logits, ref.detach()) < 1e-5
+    d_enc = torch.zeros((B, Tm, D), device="cuda")
+    sp.backward(dref.float().cuda(), d_enc)
+    mask = (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    assert scaled_err(to_np(d_enc) * mask, enc_t.grad.numpy() * mask) < GRAD_TOL  # positions past the length feed nothing
+    grads = st.export_grads()
+    for k in params:
+        e = scaled_err(grads[k], tp[k].grad)
+        assert e < GRAD_TOL, f"{k}: {e:.3e}"
+
+
+@gpu
+def test_loss_heads_with_gradients():
+    import torch
+    from phones_las_b200 import train as tr
+    rng = np.random.default_rng(4)
+    B, S, V, n = 6, 9, 21, 13
+    logits = rng.normal(size=(B, S, V)).astype(np.float32) * 2
+    targets = rng.integers(0, V, (B, S)).astype(np.int32)
+    tlen = np.array([9, 3, 5, 1, 8, 9])
+    w = (np.arange(S)[None, :] < tlen[:, None]).astype(np.float32)
+    x = torch.tensor(logits, dtype=torch.float64, requires_grad=True)
+    ref = lt.sequence_loss(x, torch.tensor(targets), torch.tensor(w, dtype=torch.float64))
+    ref.backward()
+    loss, dl = tr.seq_ce_grad(torch.from_numpy(logits).cuda(), torch.from_numpy(targets).cuda(), torch.from_numpy(w).cuda())
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert scaled_err(dl, x.grad) < 1e-5
+    lb = rng.normal(size=(B, S, n)).astype(np.float32) * 3
+    zb = (rng.uniform(size=(B, S, n)) < 0.3).astype(np.float32)
+    x = torch.tensor(lb, dtype=torch.float64, requires_grad=True)
+    ref = lt.sequence_loss_sigmoid(x, torch.tensor(zb, dtype=torch.float64), torch.tensor(w, dtype=torch.float64))
+    ref.backward()
+    loss, dl = tr.sigmoid_ce_grad(torch.from_numpy(lb).cuda(), torch.from_numpy(zb).cuda(), torch.from_numpy(w).cuda(), gscale=0.5)
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert scaled_err(dl, 0.5 * x.grad) < 1e-5
+    T, C = 25, 17
+    cl = rng.normal(size=(B, T, C)).astype(np.float32) * 2
+    labels = rng.integers(1, C, (B, 7)).astype(np.int32)
+    labels[1, 1] = labels[1, 0]
+    ll = np.array([7, 3, 4, 1, 0, 7], np.int32)
+    tl = np.array([25, 9, 20, 4, 6, 15], np.int32)
+    x = torch.tensor(cl, dtype=torch.float64, requires_grad=True)
+    ref = lt.ctc_loss(x, torch.tensor(labels), ll, tl)
+    ref.sum().backward()
+    loss, dl = tr.ctc_grad(torch.from_numpy(cl).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(ll).cuda(),
+                           torch.from_numpy(tl).cuda())
+    assert np.abs(to_np(loss) - ref.detach().numpy()).max() < 1e-4
+    assert scaled_err(dl, x.grad) < 2e-5
+
+
+def _full_setup(att, B, T, C, U, L, Ud, Ld, V, n_binf, S, multitask, ctc):
+    from phones_las_b200.train import train_variable_shapes
+    hp = create_hparams(target_vocab_size=V, encoder_layers=L, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=C, attention_type=att, dropout=0.0, sampling_probability=0.0,
+                        binary_outputs=multitask, multitask=multitask, binf_count=n_binf, ctc_weight=0.3 if ctc else -1.0,
+                        l2_reg_scale=1e-4, learning_rate=1e-3)
+    shapes = train_variable_shapes(hp, C, binf_count=n_binf)
+    params = weights.init_params(hp, seed=U + Ud, shapes=shapes, bias_scale=0.05)
+    x, lens = synth.synth_features(B, T, C, seed=B + 1, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    rng = np.random.default_rng(0)
+    tlen = np.maximum(2, (rng.uniform(0.5, 1.0, B) * S).astype(np.int32))
+    tlen[0] = S
+    binf = (rng.uniform(size=(n_binf, V)) < 0.4).astype(np.float32) if multitask else None
+    return hp, params, x, lens, tin, tout, tlen, binf
+
+
+FULL_CFGS = [("luong", 5, 37, 9, 16, 3, 32, 1, 14, 6, 7, True, True),
+             ("bahdanau", 4, 24, 5, 8, 2, 16, 2, 11, 0, 6, False, False),
+             ("luong", 18, 60, 39, 64, 3, 64, 1, 64, 62, 12, True, True)]
+
+
+@gpu
+@pytest.mark.parametrize("cfg", FULL_CFGS, ids=lambda c: f"{c[0]}-B{c[1]}-T{c[2]}-U{c[4]}-mt{int(c[11])}")
+def test_train_steps_match_autograd_adam(cfg):
+    """Two optimiser steps: losses, raw gradients of step 1 and the parameters after each step."""
+    import torch
+    from phones_las_b200 import train as tr
+    hp, params, x, lens, tin, tout, tlen, binf = _full_setup(*cfg)
+    st = tr.TrainState(params)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    binf_d = torch.from_numpy(binf).cuda() if binf is not None else None
+    ref_p = {k: torch.tensor(v, dtype=torch.float64) for k, v in params.items()}
+    ref_m = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    ref_v = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    for step in (1, 2):
+        tp = {k: v.clone().requires_grad_(True) for k, v in ref_p.items()}
+        ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, binf)
+        ref_loss.backward()
+        if step == 1:  # raw gradients before L2 / clipping
+            parts = tr.forward_backward(feats, labels, st, hp, binf_d)
+            raw = st.export_grads()
+            for k in params:
+                ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+                e = scaled_err(raw[k], ref_g)
+                assert e < GRAD_TOL, f"step1 grad {k}: {e:.3e}"
+            tr.apply_gradients(st, hp)
+            got_loss = (parts["audio_loss"] + st.wsq.sum() * 0.5 * hp["l2_reg_scale"]).item()
+        else:
+            parts = tr.train_step(feats, labels, st, hp, binf_d)
+            got_loss = parts["loss"].item()
+        assert abs(got_loss - ref_loss.item()) < 1e-4 * max(1.0, abs(ref_loss.item())), (step, got_loss, ref_loss.item())
+        for name in ("ce", "ce_binf", "ctc"):
+            if name in ref_parts:
+                assert abs(parts[name].item() - ref_parts[name].item()) < 1e-4 * max(1.0, abs(ref_parts[name].item())), name
+        ref_p, ref_m, ref_v = lt.clip_and_adam({k: v.detach() for k, v in tp.items()}, {k: v.grad for k, v in tp.items()},
+                                               ref_m, ref_v, step, hp["learning_rate"])
+        got = st.export_params()
+        for k in params:
+            d = np.abs(got[k] - ref_p[k].numpy()).max()
+            assert d < 2e-5, f"step {step} param {k}: {d:.3e}"

@@ -1,0 +1,106 @@
+"""The differentiable torch restatement (oracle/las_torch.py) must reproduce the numpy oracle's forward values
+before its autograd gradients are trusted as the reference for the CUDA backward pass."""
+import numpy as np
+import torch
+
+from oracle import las as ol, las_torch as lt, losses as olo
+from phones_las_b200 import synth, weights
+from phones_las_b200.hparams import create_hparams
+from phones_las_b200.train import train_variable_shapes
+
+
+def _tp(params, dtype=torch.float64):
+    return {k: torch.tensor(v, dtype=dtype) for k, v in params.items()}
+
+
+def test_listener_matches_numpy_oracle():
+    hp = create_hparams(target_vocab_size=12, encoder_layers=3, encoder_units=8, decoder_units=16, decoder_layers=1,
+                        num_channels=5)
+    params = weights.init_params(hp, seed=3, bias_scale=0.1)
+    x, lens = synth.synth_features(4, 13, 5, var_len=True)
+    (ref, ref_len), _ = ol.pyramidal_bilstm(x, lens, params, 3)
+    out, out_len = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), _tp(params), 3)
+    assert np.array_equal(out_len.numpy(), ref_len)
+    assert np.abs(out.numpy() - ref).max() < 2e-6
+
+
+def test_teacher_forced_matches_numpy_oracle():
+    for att, Ld in (("luong", 1), ("bahdanau", 2)):
+        hp = create_hparams(target_vocab_size=11, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=Ld,
+                            num_channels=4, attention_type=att)
+        params = weights.init_params(hp, seed=5, bias_scale=0.1)
+        D = weights.encoder_output_depth(hp)
+        rng = np.random.default_rng(0)
+        enc = rng.uniform(-1, 1, (3, 7, D)).astype(np.float32)
+        lens = np.array([7, 4, 5], np.int32)
+        enc *= (np.arange(7)[None, :, None] < lens[:, None, None])
+        tin, tout, tlen = synth.synth_labels(3, 5, 11)
+        ref, _ = ol.Speller(enc, lens, params, hp).teacher_forced(tin, tlen)
+        x = torch.nn.functional.one_hot(torch.tensor(tin, dtype=torch.int64), 11).to(torch.float64)
+        out = lt.speller_train(torch.tensor(enc, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), x, _tp(params), hp)
+        assert np.abs(out.numpy() - ref).max() < 5e-6, att
+
+
+def test_losses_match_numpy_oracle():
+    rng = np.random.default_rng(1)
+    B, S, V, n = 4, 6, 9, 7
+    logits = rng.normal(size=(B, S, V))
+    targets = rng.integers(0, V, (B, S))
+    tlen = np.array([6, 3, 5, 1])
+    w = olo.sequence_mask(tlen, S)
+    a = lt.sequence_loss(torch.tensor(logits), torch.tensor(targets), torch.tensor(w)).item()
+    assert abs(a - olo.sequence_loss(logits, targets, w)) < 1e-12
+    lb = rng.normal(size=(B, S, n))
+    zb = (rng.uniform(size=(B, S, n)) < 0.3).astype(np.float64)
+    a = lt.sequence_loss_sigmoid(torch.tensor(lb), torch.tensor(zb), torch.tensor(w)).item()
+    assert abs(a - olo.sequence_loss_sigmoid(lb, zb, w)) < 1e-12
+    T, C = 12, 8
+    cl = rng.normal(size=(B, T, C))
+    labels = rng.integers(1, C, (B, 5))
+    labels[1, 1] = labels[1, 0]  # a repeated label needs the blank between
+    ll = np.array([5, 3, 4, 1])
+    tl = np.array([12, 9, 10, 4])
+    a = lt.ctc_loss(torch.tensor(cl), torch.tensor(labels), ll, tl).numpy()
+    assert np.abs(a - olo.ctc_loss(cl, labels, ll, tl)).max() < 1e-9
+    # gradient of the differentiable restatement vs torch's own CTC
+    x = torch.tensor(cl, requires_grad=True)
+    lt.ctc_loss(x, torch.tensor(labels), ll, tl).sum().backward()
+    y = torch.tensor(cl, requires_grad=True)
+    torch.nn.functional.ctc_loss(torch.log_softmax(y, -1).transpose(0, 1), torch.tensor(labels), torch.tensor(tl), torch.tensor(ll),
+                                 blank=0, reduction="sum").backward()
+    assert (x.grad - y.grad).abs().max() < 1e-9
+
+
+def test_clip_and_adam_match_numpy_oracle():
+    rng = np.random.default_rng(2)
+    p = {"a": rng.normal(size=(5, 3)), "b": rng.normal(size=(4,)) * 10}
+    g = {"a": rng.normal(size=(5, 3)) * 3, "b": rng.normal(size=(4,)) * 0.1}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in p.items()}
+    tp = {k: torch.tensor(x) for k, x in p.items()}
+    np_, nm, nv = lt.clip_and_adam(tp, {k: torch.tensor(x) for k, x in g.items()}, {k: torch.tensor(x) for k, x in m.items()},
+                                   {k: torch.tensor(x) for k, x in v.items()}, 1, 1e-3)
+    for k in p:
+        ref, rm, rv = olo.adam_step(p[k], olo.clip_by_norm(g[k], 2.0), m[k], v[k], 1, 1e-3)
+        assert np.abs(np_[k].numpy() - ref).max() < 1e-12
+
+
+def test_train_loss_multitask_runs_and_has_all_gradients():
+    hp = create_hparams(target_vocab_size=10, encoder_layers=2, encoder_units=4, decoder_units=8, decoder_layers=1,
+                        num_channels=3, binary_outputs=True, multitask=True, ctc_weight=0.3, binf_count=6)
+    shapes = train_variable_shapes(hp, 3, binf_count=6)
+    params = weights.init_params(hp, seed=1, shapes=shapes, bias_scale=0.05)
+    assert any(k.startswith("speller_binf/") for k in params) and "ctc_logits/kernel" in params
+    assert params["speller_binf/decoder/attention_wrapper/multi_rnn_cell/cell_0/lstm_cell/kernel"].shape == (6 + 16 + 8, 32)
+    x, lens = synth.synth_features(3, 9, 3, var_len=True)
+    tin, tout, tlen = synth.synth_labels(3, 3, 10)
+    binf = (np.random.default_rng(0).uniform(size=(6, 10)) < 0.4).astype(np.float32)
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in params.items()}
+    labels = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout),
+                  target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    loss, parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), labels, hp, binf)
+    loss.backward()
+    assert np.isfinite(loss.item())
+    for k, t in tp.items():
+        assert t.grad is not None and torch.isfinite(t.grad).all(), k
+        assert t.grad.abs().max() > 0, k
