@@ -2,7 +2,10 @@
 """bench.py -- throughput of the phones-las hot path (front-end -> pyramidal BiLSTM listener ->
 greedy attention decode) on B200, in audio-seconds per second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4|c3]
+
+``--workload c3`` times the multitask TRAINING step (BASELINE.json configs[2]) instead: forward + backward + L2 + per-tensor clip
++ Adam on 32 utterances per GPU, one NCCL all-reduce of the flat gradient buffer per step when N > 1 (ours_train below).
 
 One "step" = one pass of the whole hot path over one batch of synthetic audio of the workload's
 shape (default c2 = BASELINE.json configs[1]: 80-mel MFE, 4-layer pBLSTM 512, 2-layer decoder 512,
@@ -377,6 +380,210 @@ def ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# training workload (c3 = BASELINE.json configs[2]: multitask step, batch 32 per GPU, gradient all-reduce)
+# ----------------------------------------------------------------------------------------------
+TRAIN_METRIC = "audio-sec/sec (multitask training step: listener + 2 spellers + CTC, fwd+bwd+Adam)"
+N_BINF = 62  # misc/binf_map_arpabet_extended.csv: 60 features + SOS/EOS rows (utils/ipa_utils.py:313-328)
+N_LABELS = 40
+
+
+def train_problem(cfg, B, seed):
+    from phones_las_b200 import synth
+    hp = dict(cfg["hp"])
+    hp.update(dropout=0.0, sampling_probability=0.0, binf_count=N_BINF)  # both are RNG-driven in TF: off
+    feats, lens = synth.synth_features(B, cfg["T"], cfg["C"], seed=seed)
+    tin, tout, tlen = synth.synth_labels(B, N_LABELS, hp["target_vocab_size"], seed=seed + 1)
+    binf = (np.random.default_rng(5).uniform(size=(N_BINF, hp["target_vocab_size"])) < 0.3).astype(np.float32)
+    return hp, feats, lens, tin, tout, tlen, binf
+
+
+def train_cpu_sample(cfg, batch):
+    """One forward + backward + clip + Adam of the differentiable CPU oracle (torch fp32, all host threads)."""
+    import torch
+    from oracle import las_torch as lt
+    from phones_las_b200 import weights
+    from phones_las_b200.train import train_variable_shapes
+    hp, feats, lens, tin, tout, tlen, binf = train_problem(cfg, batch, 1234)
+    params = weights.init_params(hp, cfg["C"], seed=4321, shapes=train_variable_shapes(hp, cfg["C"], N_BINF))
+    torch.set_num_threads(cpu_cores())
+    tp = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+    labels = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout),
+                  target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    t0 = time.perf_counter()
+    loss, _ = lt.train_loss(tp, torch.tensor(feats), torch.tensor(lens.astype(np.int64)), labels, hp, binf)
+    loss.backward()
+    zeros = {k: torch.zeros_like(v) for k, v in tp.items()}
+    lt.clip_and_adam({k: v.detach() for k, v in tp.items()}, {k: v.grad for k, v in tp.items()}, zeros, zeros, 1, hp["learning_rate"])
+    dt = time.perf_counter() - t0
+    return batch * cfg["seconds"] / dt, dt
+
+
+def train_config_dict(cfg, hp, B, world, **extra):
+    d = {"workload": f"c3: multitask training step, {cfg['C']}-dim features, {hp['encoder_layers']}-layer pBLSTM {hp['encoder_units']}, "
+                     f"phone speller + binary-feature speller ({N_BINF} features), 1-layer decoder {hp['decoder_units']} luong, "
+                     f"ctc_weight {hp['ctc_weight']}, {N_LABELS}+1 target tokens, {cfg['seconds']:.0f} s utterances, fp32, Adam + per-tensor clip + L2",
+         "batch_per_gpu": B, "utterance_seconds": cfg["seconds"], "frames": cfg["T"], "channels": cfg["C"],
+         "vocab": hp["target_vocab_size"],
+         "parallelism": f"dp{world}: batch-sharded replicas, one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1
+                        else "single GPU (no collective)",
+         "dropout": "0 and sampling_probability 0 (RNG-driven in TF; parity configuration)"}
+    d.update(extra)
+    return d
+
+
+def ours_train(args):
+    import torch
+    import torch.distributed as dist
+    from phones_las_b200 import _lib, parallel, weights, train as tr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_cuda()
+    cfg = workload("c3")
+    B = args.batch or cfg["batch"]
+    nbuf = 4
+    batches, host_batches = [], []
+    for i in range(nbuf):
+        hp, feats, lens, tin, tout, tlen, binf = train_problem(cfg, B, 1234 + 100 * rank + i)
+        hb = [torch.from_numpy(a).pin_memory() for a in (feats, lens, tin, tout, tlen)]
+        host_batches.append(hb)
+        batches.append([t.to(dev) for t in hb])
+    params = weights.init_params(hp, cfg["C"], seed=4321, shapes=tr.train_variable_shapes(hp, cfg["C"], N_BINF))
+    st = tr.TrainState(params, device=dev)
+    parallel.broadcast_parameters(st.params)
+    binf_d = torch.from_numpy(binf).to(dev)
+    allreduce = parallel.allreduce_gradients if world > 1 else None
+
+    def step(bt):
+        f = {"encoder_inputs": bt[0], "source_sequence_length": bt[1]}
+        lb = {"targets_inputs": bt[2], "targets_outputs": bt[3], "target_sequence_length": bt[4]}
+        return tr.train_step(f, lb, st, hp, binf_d, world_size=world, allreduce=allreduce)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        parts = step(batches[i % nbuf])
+    barrier()
+    if rank == 0:
+        deadline = time.time() + 3.0
+        while not sampler.rows and sampler.proc is not None and time.time() < deadline:
+            time.sleep(0.05)
+        sampler.mark()
+    barrier()
+    l0 = _lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        parts = step(batches[i % nbuf])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count - l0
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    audio_s = B * cfg["seconds"]
+    value = world * audio_s / (ms * 1e-3)
+    loss_last = float(parts["loss"].item())
+
+    # end to end: pinned host features + labels -> H2D -> step -> loss read back, every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        bt = [t.to(dev, non_blocking=True) for t in host_batches[i % nbuf]]
+        loss_host = float(step(bt)["loss"].item())
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    barrier()
+    h2d = int(sum(t.numel() * t.element_size() for t in host_batches[0]))
+    e2e = {"value": world * audio_s / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4}
+
+    stage_ms = {}
+    for i in range(3):
+        _lib.timeline_start()
+        step(batches[i % nbuf])
+        for k, v in _lib.timeline_stop().items():
+            stage_ms.setdefault(k, []).append(sum(v))
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    # dominant family: the fp32 GEMMs (projections, input and weight gradients); algorithmic flops of the listener part
+    U, L, T, C = hp["encoder_units"], hp["encoder_layers"], cfg["T"], cfg["C"]
+    fl, t, din = 0.0, T, C
+    for l in range(L):
+        fl += 2.0 * B * t * din * 8 * U * (2 if l == 0 else 3) + 2.0 * B * t * U * 8 * U  # fwd + dW (+ dX for l > 0) + dW_hh
+        din = 2 * U if l == 0 else 4 * U
+        if l != 0:
+            t = (t + 1) // 2
+    gemm_ms = sum(stage_ms.get(k, 0.0) for k in ("train_inproj", "train_wgrad", "train_dgrad"))
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA lanes x 2 flop x boost clock: the bound of an exact-fp32 GEMM
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    roofline = {"kernel": "gemm_f32_ex_kernel (train_inproj + train_wgrad + train_dgrad)", "bound": "fp32-pipe",
+                "achieved": fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": (fl / (gemm_ms * 1e-3) / 1e12) / fp32_peak if gemm_ms else None, "traffic": None,
+                "peak_source": "148 SMs x 128 FFMA/clk x 2 x 1.965 GHz (exact-fp32 SIMT path; the reference trains in fp32)",
+                "share_of_step": gemm_ms / sum(stage_ms.values()), "largest_stage": dom}
+    line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": train_config_dict(cfg, hp, B, world, weights="random init, seed 4321, TF variable layout",
+                                                             l2="4 distinct batches rotate; the step's activations (~0.5 GB) exceed the 126 MB L2"),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "stages": {k: {"ms_per_step": v} for k, v in stage_ms.items()}, "loss": loss_last, "loss_e2e": loss_host,
+            "trainable_parameters": int(sum(st.sizes))}
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt = train_cpu_sample(cfg, args.cpu_batch)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+                                "sample": f"{args.cpu_batch} utterances x {cfg['seconds']:.0f} s, one training step ({dt:.1f} s), torch-CPU fp32 "
+                                          f"restatement of the TRAIN graph (oracle/las_torch.py; TF 1.15 not installable)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm_train(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cfg = workload("c3")
+    batch = args.ref_batch
+    train_cpu_sample(cfg, 1)
+    ts = []
+    for _ in range(max(args.steps, 1)):
+        v, dt = train_cpu_sample(cfg, batch)
+        ts.append(dt)
+    dt = float(np.mean(ts))
+    value = batch * cfg["seconds"] / dt
+    hp = train_problem(cfg, 1, 0)[0]
+    sample = f"{batch} utterances x {cfg['seconds']:.0f} s per step, torch-CPU fp32 restatement of the TRAIN graph"
+    print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": train_config_dict(cfg, hp, batch, 1),
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,7 +597,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "c3":
+        reference_arm_train(args) if args.impl == "reference" else ours_train(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         ours(args)

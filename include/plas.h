@@ -221,6 +221,9 @@ typedef struct plas_gemm_ex_desc {
   int32_t batch;            /* >= 1 independent problems (grid.z) */
   int32_t _pad;
   int64_t batch_a, batch_b, batch_c;
+  float* split_ws;          /* optional scratch: long reductions over few output tiles (weight gradients) are cut
+                               into K slices whose partial products are summed in a fixed order (deterministic) */
+  size_t split_ws_bytes;
 } plas_gemm_ex_desc;
 int plas_gemm_f32_ex(const plas_gemm_ex_desc* d, plas_stream_t stream);
 /* out[n] (+)= sum_m X[m][n]: bias gradients. */

@@ -52,7 +52,7 @@ class GemmExDesc(C.Structure):
                 ("sak", C.c_int64), ("B", C.c_void_p), ("sbk", C.c_int64), ("sbn", C.c_int64), ("C", C.c_void_p),
                 ("ldc", C.c_int64), ("bias", C.c_void_p), ("alpha", C.c_float), ("beta", C.c_float),
                 ("batch", C.c_int32), ("_pad", C.c_int32), ("batch_a", C.c_int64), ("batch_b", C.c_int64),
-                ("batch_c", C.c_int64)]
+                ("batch_c", C.c_int64), ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_size_t)]
 
 
 class RecTrainDesc(C.Structure):
@@ -135,6 +135,10 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise PlasError(f"{LIB_PATH} not found: run `python -m phones_las_b200.build` "
                             "(there is no CPU fallback)")
+        from . import build as _build
+        stamp = os.path.join(HERE, "csrc", ".libplas.stamp")
+        if os.path.exists(stamp) and open(stamp).read() != _build._digest():
+            raise PlasError(f"{LIB_PATH} is older than its sources: run `python -m phones_las_b200.build`")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)

@@ -28,65 +28,70 @@ struct CellFwdArgs {
   int B, Ud;
   const float* pre; long long s_pre;    // [B][4Ud] pre-activations already holding x W + b (or NULL)
   const float* bias;                    // [4Ud] added when pre == NULL
-  const float* in1; long long s1; int K1; const float* w1;  // rows of the TF kernel multiplying in1
-  const float* in2; long long s2; int K2; const float* w2;  // h_{t-1} and its rows
+  const float* in1; long long s1; int K1;   // attention_{t-1} (layer 0) or h of the layer below
+  const float* in2; long long s2; int K2;   // h_{t-1} of this layer
+  const float* w;                       // rows of the TF kernel multiplying [in1; in2]: [K1+K2][4Ud]
   const float* c_prev; long long s_c;   // NULL at t == 0
   float* z_out; long long s_z;          // activated gates (i, tanh j, f, o), gate-blocked [4][Ud]
   float* c_out; float* h_out; long long s_h;
   float* hprev_next;                    // slot t+1 of the h_{t-1} copy (NULL at the last step)
 };
 
+// CTA = UPC units (4*UPC gate columns) x 32 batch rows.  The CTA's weight slice [K][4*UPC] is staged in shared
+// memory with one wave of independent vector loads; lane = batch row, the 8 warps split the reduction over K.
 template <int UPC>
 __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
-  __shared__ float s_red[8][4 * UPC][DT_ROWS + 1];
+  extern __shared__ __align__(16) float cf_smem[];
+  constexpr int NC = 4 * UPC;
+  float* s_w = cf_smem;  // [K][NC], column = g*UPC + u
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int u0 = blockIdx.x * UPC;
   const int b0 = blockIdx.y * DT_ROWS;
   const int b = min(b0 + lane, p.B - 1);
   const int Ud = p.Ud;
-  const int K4 = (p.K1 + p.K2) / 4;  // reduction length in float4 units
+  const int K = p.K1 + p.K2;
+  if (UPC == 4) {
+    for (int i = threadIdx.x; i < K * 4; i += 256) {
+      const int k = i >> 2, g = i & 3;
+      reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * 4 * Ud + g * Ud + u0));
+    }
+  } else {
+    for (int i = threadIdx.x; i < K * 4; i += 256) {
+      const int k = i >> 2, g = i & 3;
+      reinterpret_cast<float2*>(s_w)[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)k * 4 * Ud + g * Ud + u0));
+    }
+  }
+  const int K4 = K / 4;
   const int per = (K4 + 7) / 8;
   const int q_lo = warp * per, q_hi = min(K4, q_lo + per);
-  float acc[4][UPC];
-#pragma unroll
-  for (int g = 0; g < 4; ++g)
-#pragma unroll
-    for (int u = 0; u < UPC; ++u) acc[g][u] = 0.f;
   const int K1q = p.K1 / 4;
+  const float4* a1 = reinterpret_cast<const float4*>(p.in1 + (long long)b * p.s1);
+  const float4* a2 = reinterpret_cast<const float4*>(p.in2 + (long long)b * p.s2) - K1q;
+  float acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+  __syncthreads();
+#pragma unroll 4
   for (int q = q_lo; q < q_hi; ++q) {
-    float4 a;
-    const float* wrow;
-    if (q < K1q) {
-      a = *reinterpret_cast<const float4*>(p.in1 + (long long)b * p.s1 + 4 * q);
-      wrow = p.w1 + (size_t)(4 * q) * 4 * Ud;
-    } else {
-      a = *reinterpret_cast<const float4*>(p.in2 + (long long)b * p.s2 + 4 * (q - K1q));
-      wrow = p.w2 + (size_t)(4 * (q - K1q)) * 4 * Ud;
-    }
+    const float4 a = q < K1q ? a1[q] : a2[q];
     const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w + (size_t)(4 * q + kk) * NC);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float* wp = wrow + (size_t)kk * 4 * Ud + g * Ud + u0;
-        if (UPC == 4) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(wp));
-          acc[g][0] = fmaf(av[kk], w.x, acc[g][0]);
-          acc[g][1] = fmaf(av[kk], w.y, acc[g][1]);
-          acc[g][2] = fmaf(av[kk], w.z, acc[g][2]);
-          acc[g][3] = fmaf(av[kk], w.w, acc[g][3]);
-        } else {
-          const float2 w = __ldg(reinterpret_cast<const float2*>(wp));
-          acc[g][0] = fmaf(av[kk], w.x, acc[g][0]);
-          acc[g][1] = fmaf(av[kk], w.y, acc[g][1]);
-        }
+      for (int c4 = 0; c4 < NC / 4; ++c4) {
+        const float4 w = wr[c4];
+        acc[4 * c4 + 0] = fmaf(av[kk], w.x, acc[4 * c4 + 0]);
+        acc[4 * c4 + 1] = fmaf(av[kk], w.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(av[kk], w.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(av[kk], w.w, acc[4 * c4 + 3]);
       }
     }
   }
+  __syncthreads();  // everyone is done with s_w: reuse it for the cross-warp reduction
+  float* s_red = cf_smem;  // [8][NC][33]
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-#pragma unroll
-    for (int u = 0; u < UPC; ++u) s_red[warp][g * UPC + u][lane] = acc[g][u];
+  for (int c = 0; c < NC; ++c) s_red[(warp * NC + c) * (DT_ROWS + 1) + lane] = acc[c];
   __syncthreads();
   if (threadIdx.x < DT_ROWS * UPC) {
     const int r = threadIdx.x % DT_ROWS, u = threadIdx.x / DT_ROWS;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
       for (int g = 0; g < 4; ++g) {
         float s = p.pre ? p.pre[(long long)bb * p.s_pre + g * Ud + u0 + u] : p.bias[g * Ud + u0 + u];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += s_red[w][g * UPC + u][r];
+        for (int w = 0; w < 8; ++w) s += s_red[(w * NC + g * UPC + u) * (DT_ROWS + 1) + r];
         z[g] = s;
       }
       const float cp = p.c_prev ? p.c_prev[(long long)bb * p.s_c + u0 + u] : 0.f;
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
   const float* vb = p.values + (size_t)b * Tm * D;
   for (int d = d_lo + tid; d < d_hi; d += 256) {
     float c = 0.f;
+#pragma unroll 8
     for (int t = 0; t < len; ++t) c = fmaf(s_sc[t], vb[(size_t)t * D + d], c);
     p.att[(long long)b * p.s_att + d] = c;
     if (p.att_next) p.att_next[(long long)b * p.s_att + d] = c;
@@ -306,6 +312,7 @@ __global__ void __launch_bounds__(512) dec_att_bwd_kernel(AttBwdArgs p) {
   } else {
     for (int u = tid; u < Ud; u += 512) {
       float s = 0.f;
+#pragma unroll 8
       for (int t = 0; t < len; ++t) s = fmaf(s_da[t], kb[(size_t)t * Ud + u], s);
       p.dq[(long long)b * p.s_dq + u] = s;
     }
@@ -356,30 +363,39 @@ struct GemvTArgs {
 };
 
 __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
-  __shared__ float s_red[8][8][DT_ROWS + 1];
+  extern __shared__ __align__(16) float gv_smem[];
+  float4* s_w = reinterpret_cast<float4*>(gv_smem);  // [8][N/4] the CTA's 8 weight rows
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k0 = blockIdx.x * 8;
   const int b0 = blockIdx.y * DT_ROWS;
   const int b = min(b0 + lane, p.B - 1);
   const int N4 = p.N / 4;
+  for (int i = threadIdx.x; i < 8 * N4; i += 256) {
+    const int kk = i / N4, q = i - kk * N4;
+    const int k = min(k0 + kk, p.K - 1);
+    s_w[i] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * p.N) + q);
+  }
   const int per = (N4 + 7) / 8;
   const int q_lo = warp * per, q_hi = min(N4, q_lo + per);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float4* zrow = reinterpret_cast<const float4*>(p.dz + (long long)b * p.s_z);
+  __syncthreads();
+#pragma unroll 8
   for (int q = q_lo; q < q_hi; ++q) {
     const float4 a = zrow[q];
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
-      const int k = min(k0 + kk, p.K - 1);
-      const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * p.N) + q);
+      const float4 w = s_w[kk * N4 + q];
       acc[kk] = fmaf(a.x, w.x, acc[kk]);
       acc[kk] = fmaf(a.y, w.y, acc[kk]);
       acc[kk] = fmaf(a.z, w.z, acc[kk]);
       acc[kk] = fmaf(a.w, w.w, acc[kk]);
     }
   }
+  __syncthreads();
+  float* s_red = gv_smem;  // [8 warps][8][33]
 #pragma unroll
-  for (int kk = 0; kk < 8; ++kk) s_red[warp][kk][lane] = acc[kk];
+  for (int kk = 0; kk < 8; ++kk) s_red[(warp * 8 + kk) * (DT_ROWS + 1) + lane] = acc[kk];
   __syncthreads();
   {
     const int r = threadIdx.x % DT_ROWS, kk = threadIdx.x / DT_ROWS;  // 256 threads = 32 rows x 8 k
@@ -387,7 +403,7 @@ __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
     if (bb < p.B && k < p.K) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += s_red[w][kk][r];
+      for (int w = 0; w < 8; ++w) s += s_red[(w * 8 + kk) * (DT_ROWS + 1) + r];
       p.dinp[(long long)bb * p.s_o + k] = s;
     }
   }
@@ -399,6 +415,7 @@ __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
 struct DecTrainWs {
   size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx;
   size_t z[4], c[4], h[4], hprev[4];
+  size_t splitk, splitk_bytes;
   size_t total;
 };
 
@@ -432,14 +449,18 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
     w.dinp[l] = take(B * ((l == 0 ? D : Ud) + Ud));
     w.dc[l] = take(B * Ud);
   }
+  w.splitk_bytes = (size_t)4 * (d.E + D + Ud) * 4 * Ud * 4;  // up to 4 K-slices of the largest weight gradient
+  w.splitk = take(w.splitk_bytes / 4);
   w.total = off;
   return w;
 }
 
 static int gemm(cudaStream_t st, long long M, int N, int K, const float* A, long long sam, long long sak, const float* Bm,
                 long long sbk, long long sbn, float* C, long long ldc, const float* bias = nullptr, float beta = 0.f,
-                int batch = 1, long long ba = 0, long long bb = 0, long long bc = 0) {
+                int batch = 1, long long ba = 0, long long bb = 0, long long bc = 0, float* split_ws = nullptr,
+                size_t split_bytes = 0) {
   plas_gemm_ex_desc g;
+  g.split_ws = split_ws; g.split_ws_bytes = split_bytes;
   g.M = M; g.N = N; g.K = K;
   g.A = A; g.sam = sam; g.sak = sak;
   g.B = Bm; g.sbk = sbk; g.sbn = sbn;
@@ -488,6 +509,9 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
   for (int l = 0; l < L; ++l) PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
   const int upc = (Ud / 4 >= 100) ? 4 : 2;
+  PLAS_REQUIRE((size_t)(D + Ud) * 16 * upc <= 200 * 1024, "dec_train_fwd: D + Ud = %d too large for the staged weight slice", D + Ud);
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const dim3 cgrid(Ud / upc, (B + DT_ROWS - 1) / DT_ROWS);
   const int dsplit = D >= 512 ? 4 : 1;
   const size_t att_smem = (size_t)(2 * Ud + Tm) * 4;
@@ -499,21 +523,21 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       if (l == 0) {
         a.pre = F(w.z[0]) + (size_t)t * 4 * Ud; a.s_pre = sz; a.bias = nullptr;
         a.in1 = F(w.att_prev) + (size_t)t * D; a.s1 = (long long)S * D; a.K1 = D;
-        a.w1 = d->kernel[0] + (size_t)E * 4 * Ud;
-        a.w2 = d->kernel[0] + (size_t)(E + D) * 4 * Ud;
+        a.w = d->kernel[0] + (size_t)E * 4 * Ud;
       } else {
         a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
         a.in1 = F(w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud;
-        a.w1 = d->kernel[l];
-        a.w2 = d->kernel[l] + (size_t)Ud * 4 * Ud;
+        a.w = d->kernel[l];
       }
       a.in2 = F(w.hprev[l]) + (size_t)t * Ud; a.s2 = sh; a.K2 = Ud;
       a.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; a.s_c = sh;
       a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
       a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
-      if (upc == 4) dec_cell_fwd_kernel<4><<<cgrid, 256, 0, st>>>(a);
-      else dec_cell_fwd_kernel<2><<<cgrid, 256, 0, st>>>(a);
+      const size_t need = (size_t)(a.K1 + a.K2) * 4 * upc * 4, red = (size_t)8 * 4 * upc * (DT_ROWS + 1) * 4;
+      const size_t smem = need > red ? need : red;
+      if (upc == 4) dec_cell_fwd_kernel<4><<<cgrid, 256, smem, st>>>(a);
+      else dec_cell_fwd_kernel<2><<<cgrid, 256, smem, st>>>(a);
     }
     AttFwdArgs q;
     q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit;
@@ -555,6 +579,10 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   }
   const size_t attb_smem = (size_t)(D + Tm + Ud) * 4;
   PLAS_CUDA(cudaFuncSetAttribute(dec_att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PLAS_CUDA(cudaFuncSetAttribute(dec_gemv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  PLAS_REQUIRE((size_t)32 * Ud * 4 <= 200 * 1024, "dec_train_bwd: Ud = %d too large", Ud);
+  float* sk = F(w.splitk);
+  const size_t skb = w.splitk_bytes;
   const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud;
   for (int t = S - 1; t >= 0; --t) {
     const bool last = t == S - 1;
@@ -585,7 +613,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       g.dz = c.z; g.s_z = sz;
       g.w = d->kernel[l] + (size_t)(l == 0 ? E : 0) * 4 * Ud;
       g.dinp = F(w.dinp[l]); g.s_o = Kin + Ud;
-      dec_gemv_t_kernel<<<dim3((g.K + 7) / 8, (B + DT_ROWS - 1) / DT_ROWS), 256, 0, st>>>(g);
+      const size_t gsm = (size_t)8 * g.N * 4 > (size_t)64 * (DT_ROWS + 1) * 4 ? (size_t)8 * g.N * 4 : (size_t)64 * (DT_ROWS + 1) * 4;
+      dec_gemv_t_kernel<<<dim3((g.K + 7) / 8, (B + DT_ROWS - 1) / DT_ROWS), 256, gsm, st>>>(g);
     }
   }
   PLAS_CUDA(cudaGetLastError());
@@ -595,12 +624,12 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     const float* dz = F(w.z[l]);
     float* dk = d->dkernel[l];
     if (l == 0) {
-      if ((rc = gemm(st, E, 4 * Ud, (int)BS, d->x_in, 1, E, dz, 4 * Ud, 1, dk, 4 * Ud))) return rc;
-      if ((rc = gemm(st, D, 4 * Ud, (int)BS, F(w.att_prev), 1, D, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud))) return rc;
-      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + D) * 4 * Ud, 4 * Ud))) return rc;
+      if ((rc = gemm(st, E, 4 * Ud, (int)BS, d->x_in, 1, E, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      if ((rc = gemm(st, D, 4 * Ud, (int)BS, F(w.att_prev), 1, D, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + D) * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
     } else {
-      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.h[l - 1]), 1, Ud, dz, 4 * Ud, 1, dk, 4 * Ud))) return rc;
-      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[l]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)Ud * 4 * Ud, 4 * Ud))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.h[l - 1]), 1, Ud, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[l]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)Ud * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
     }
     if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;
   }

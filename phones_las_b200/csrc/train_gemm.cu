@@ -25,6 +25,9 @@ struct GemmExArgs {
   const float* bias;
   float alpha, beta;
   long long batch_a, batch_b, batch_c;
+  int split_k;       // > 1: blockIdx.z is a K slice, partial products go to split_ws[z][M][N]
+  int k_chunk;       // K elements per slice (multiple of TG_BK)
+  float* split_ws;
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
@@ -33,9 +36,12 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
   const int tid = threadIdx.x;
   const long long m0 = (long long)blockIdx.y * TG_BM;
   const int n0 = blockIdx.x * TG_BN;
-  const float* __restrict__ A = p.A + (long long)blockIdx.z * p.batch_a;
-  const float* __restrict__ B = p.B + (long long)blockIdx.z * p.batch_b;
-  float* __restrict__ C = p.C + (long long)blockIdx.z * p.batch_c;
+  const bool split = p.split_k > 1;
+  const float* __restrict__ A = p.A + (split ? 0 : (long long)blockIdx.z * p.batch_a);
+  const float* __restrict__ B = p.B + (split ? 0 : (long long)blockIdx.z * p.batch_b);
+  float* __restrict__ C = split ? p.split_ws + (long long)blockIdx.z * p.M * p.N : p.C + (long long)blockIdx.z * p.batch_c;
+  const int k_begin = split ? blockIdx.z * p.k_chunk : 0;
+  const int k_end = split ? min(p.K, k_begin + p.k_chunk) : p.K;
   const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads; thread tile = rows ty*8.., cols tx*4..
   const bool a_kfast = p.sak == 1;         // consecutive threads walk k (A row-major) or m (A^T view)
   const bool b_nfast = p.sbn == 1;
@@ -50,7 +56,7 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
       if (a_kfast) { r = i / TG_BK; c = i % TG_BK; } else { c = i / TG_BM; r = i % TG_BM; }
       const long long gm = m0 + r;
       const int gk = k0 + c;
-      ra[j] = (gm < p.M && gk < p.K) ? A[gm * p.sam + gk * p.sak] : 0.f;
+      ra[j] = (gm < p.M && gk < k_end) ? A[gm * p.sam + gk * p.sak] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -59,7 +65,7 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
       if (b_nfast) { c = i / TG_BN; r = i % TG_BN; } else { r = i / TG_BK; c = i % TG_BK; }
       const int gn = n0 + r;
       const int gk = k0 + c;
-      rb[j] = (gn < p.N && gk < p.K) ? B[gk * p.sbk + gn * p.sbn] : 0.f;
+      rb[j] = (gn < p.N && gk < k_end) ? B[gk * p.sbk + gn * p.sbn] : 0.f;
     }
   };
   auto store_tile = [&](int buf) {
@@ -79,13 +85,13 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
     }
   };
 
-  const int n_tiles = (p.K + TG_BK - 1) / TG_BK;
-  load_tile(0);
+  const int n_tiles = (k_end - k_begin + TG_BK - 1) / TG_BK;
+  load_tile(k_begin);
   store_tile(0);
   __syncthreads();
   for (int kt = 0; kt < n_tiles; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < n_tiles) load_tile((kt + 1) * TG_BK);  // global loads in flight during the FMAs
+    if (kt + 1 < n_tiles) load_tile(k_begin + (kt + 1) * TG_BK);  // global loads in flight during the FMAs
 #pragma unroll
     for (int k = 0; k < TG_BK; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8]);
@@ -109,11 +115,30 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= p.N) continue;
+      if (split) {
+        C[gm * p.N + gn] = acc[i][j];
+        continue;
+      }
       float v = p.alpha * acc[i][j];
       if (p.bias) v += p.bias[gn];
       if (p.beta != 0.f) v += p.beta * C[gm * p.ldc + gn];
       C[gm * p.ldc + gn] = v;
     }
+  }
+}
+
+// C = alpha * sum_z ws[z] + beta * C + bias  (fixed summation order: deterministic split-K)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmExArgs p) {
+  const long long total = p.M * p.N;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long m = i / p.N;
+    const int n = (int)(i - m * p.N);
+    float s = 0.f;
+    for (int z = 0; z < p.split_k; ++z) s += p.split_ws[(long long)z * total + i];
+    float v = p.alpha * s;
+    if (p.bias) v += p.bias[n];
+    if (p.beta != 0.f) v += p.beta * p.C[m * p.ldc + n];
+    p.C[m * p.ldc + n] = v;
   }
 }
 
@@ -153,8 +178,32 @@ extern "C" int plas_gemm_f32_ex(const plas_gemm_ex_desc* d, plas_stream_t stream
   a.batch_a = d->batch_a; a.batch_b = d->batch_b; a.batch_c = d->batch_c;
   const long long gy = (d->M + TG_BM - 1) / TG_BM;
   PLAS_REQUIRE(gy <= 65535 && d->batch <= 65535, "gemm_ex: M or batch too large");
-  dim3 grid((unsigned)((d->N + TG_BN - 1) / TG_BN), (unsigned)gy, (unsigned)d->batch);
+  const long long gx = (d->N + TG_BN - 1) / TG_BN;
+  // deterministic split-K for long reductions over few output tiles (weight gradients: K = B*T rows)
+  int split = 1;
+  if (d->split_ws && d->batch == 1 && d->K >= 512) {
+    const long long tiles = gx * gy;
+    const long long want = (2LL * num_sms() + tiles - 1) / tiles;
+    const long long by_ws = (long long)(d->split_ws_bytes / ((size_t)d->M * d->N * 4));
+    long long sp = want < d->K / 256 ? want : d->K / 256;
+    if (sp > by_ws) sp = by_ws;
+    if (sp > 64) sp = 64;
+    if (sp > 1) split = (int)sp;
+  }
+  a.split_k = split;
+  a.k_chunk = d->K;
+  a.split_ws = d->split_ws;
+  if (split > 1) {
+    a.k_chunk = ((d->K + split - 1) / split + TG_BK - 1) / TG_BK * TG_BK;
+    a.split_k = (d->K + a.k_chunk - 1) / a.k_chunk;
+  }
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)(a.split_k > 1 ? a.split_k : d->batch));
   gemm_f32_ex_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  if (a.split_k > 1) {
+    const long long total = d->M * d->N;
+    const int blocks = (int)((total + 255) / 256 < 4LL * num_sms() ? (total + 255) / 256 : 4LL * num_sms());
+    splitk_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  }
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;
 }

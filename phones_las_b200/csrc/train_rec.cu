@@ -3,29 +3,30 @@
 // tf.nn.rnn_cell.LSTMCell (reference las/ops.py:23-46; gate order i|j|f|o in column blocks, forget_bias 1.0) for
 // the TRAIN graph of model_helper.py:403-417.
 //
-// Same decomposition as the inference kernel (rec.cu): a (direction, 16-utterance group) is an independent
-// recurrence owned by G = U/upc co-resident CTAs that exchange the per-step vector through an L2-resident
-// ping-pong buffer with acquire/release counters; W_hh stays in shared memory for the whole sequence.
+// Decomposition (as in the inference kernel rec.cu): a (direction, group of R utterances) is an independent
+// recurrence owned by G = U/UPC co-resident CTAs (cooperative launch) that exchange the per-step vector through an
+// L2-resident ping-pong buffer with acquire/release counters; the CTA's slice of W_hh stays in shared memory for
+// the whole sequence.  256 threads = UPC units x R rows x KS slices of the reduction (partials summed in a fixed
+// order through shared memory).
 //   forward : z[b,t] (x-projections + bias, K2) is overwritten IN PLACE by the activated gates (i, tanh j, f, o);
-//             c_t and h_{s-1} are saved for the backward pass, h_t goes to the layer output.
-//   backward: walks the steps in reverse;  dh_s = dout[t] + dz_{s+1} W_hh^T  (the CTA holds the rows of W_hh of its
-//             own units, so the exchanged vector is dz, 4U wide);  gate derivatives from the saved activations;
-//             dz_s overwrites the saved gates IN PLACE and is what the weight / input gradient GEMMs consume
-//             (dW = [x;h_{s-1}]^T dz, dx = dz W_x^T: plas_gemm_f32_ex).  Positions t >= len are zeroed.
+//             c_t and h_{s-1} are saved for the backward pass, h_t goes to the layer output.  Exchanged: h (U wide).
+//   backward: walks the steps in reverse;  dh_s = dout[t] + dz_{s+1} W_hh^T  (the CTA holds the ROWS of W_hh of its
+//             own units, so the exchanged vector is dz, 4U wide -- hence small row groups, R = 8);  gate derivatives
+//             from the saved activations;  dz_s overwrites the saved gates IN PLACE and is what the weight / input
+//             gradient GEMMs consume (dW = [x;h_{s-1}]^T dz, dx = dz W_x^T: plas_gemm_f32_ex).  t >= len is zeroed.
+// The (R, UPC) shape is picked per call so that every group's CTAs are co-resident in as few launches as possible.
 #include "common.cuh"
 #include "../../include/plas.h"
 
 namespace plas {
 
 constexpr int RT_THREADS = 256;
-constexpr int RT_ROWS = 16;
-constexpr int RT_MAXR = 2;
 
 struct RecTrainArgs {
   plas_rec_train_desc d;
   float* xbuf;         // [2][ndir][Bpad][W] exchange (W = U forward, 4U backward)
   unsigned* counters;  // [ndir][n_groups]
-  int n_groups, group_offset, groups_here, upc, G, Bpad;
+  int n_groups, group_offset, groups_here, G, Bpad;
 };
 
 __device__ __forceinline__ void rt_wait(const unsigned* ctr, unsigned target) {
@@ -34,34 +35,39 @@ __device__ __forceinline__ void rt_wait(const unsigned* ctr, unsigned target) {
     if (++spins > (1u << 28)) __trap();
 }
 
+template <int R, int UPC>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainArgs p) {
+  constexpr int KS = RT_THREADS / (R * UPC);
+  static_assert(KS >= 1 && KS * R * UPC == RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const plas_rec_train_desc& d = p.d;
-  const int U = d.U, B = d.B, T = d.T, ndir = d.ndir, upc = p.upc;
+  const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
   const int tid = threadIdx.x;
   int bid = blockIdx.x;
   const int ci = bid % p.G; bid /= p.G;
   const int gi = p.group_offset + bid % p.groups_here;
   const int dir = bid / p.groups_here;
-  const int row0 = gi * RT_ROWS;
+  const int row0 = gi * R;
+  const int HS = U + 4;  // padded row stride of the staged h tile
 
-  float4* s_w = reinterpret_cast<float4*>(rt_smem);               // [U (k)][upc] : (i,j,f,o) columns of a unit
-  float* s_h = reinterpret_cast<float*>(s_w + (size_t)U * upc);  // [16][U]
-  __shared__ int s_len[RT_ROWS];
+  float4* s_w = reinterpret_cast<float4*>(rt_smem);               // [U (k)][UPC] : (i,j,f,o) columns of a unit
+  float* s_h = reinterpret_cast<float*>(s_w + (size_t)U * UPC);  // [R][HS]
+  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)R * HS);  // [KS][R][UPC]
+  __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
     const float* kern = d.kernel[dir] + (size_t)d.din * 4 * U;  // W_hh rows of the TF kernel
-    for (int i = tid; i < U * upc; i += RT_THREADS) {
-      const int k = i / upc, ul = i % upc;
-      const float* row = kern + (size_t)k * 4 * U + ci * upc + ul;
+    for (int i = tid; i < U * UPC; i += RT_THREADS) {
+      const int k = i / UPC, ul = i % UPC;
+      const float* row = kern + (size_t)k * 4 * U + ci * UPC + ul;
       s_w[i] = make_float4(row[0], row[U], row[2 * U], row[3 * U]);
     }
   }
-  if (tid < RT_ROWS) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
+  if (tid < R) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
   __syncthreads();
   if (tid == 0) {
     int m = 0;
-    for (int r = 0; r < RT_ROWS; ++r) m = max(m, s_len[r]);
+    for (int r = 0; r < R; ++r) m = max(m, s_len[r]);
     s_tmax = m;
   }
   __syncthreads();
@@ -69,74 +75,72 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
 
   float* hx = p.xbuf;
   unsigned* ctr = p.counters + dir * p.n_groups + gi;
-  const int ul = tid % upc, rg = tid / upc, nrg = RT_THREADS / upc;
-  const int unit = ci * upc + ul;
-  const size_t zrow = (size_t)ndir * 4 * U;  // floats per (b,t) in z
-  const size_t srow = (size_t)ndir * U;      // floats per (b,t) in c_save / h_prev
-  float c_state[RT_MAXR] = {0.f, 0.f}, h_state[RT_MAXR] = {0.f, 0.f};
+  const int ul = tid % UPC, r = (tid / UPC) % R, kh = tid / (UPC * R);
+  const int unit = ci * UPC + ul;
+  const int b = row0 + r;
+  const int len = s_len[r];
+  const size_t zrow = (size_t)ndir * 4 * U;
+  const size_t srow = (size_t)ndir * U;
+  const int kper = U / KS;  // host guarantees U % (4*KS) == 0
+  float c_state = 0.f, h_state = 0.f;
 
   for (int s = 0; s < Tg; ++s) {
-    float4 acc[RT_MAXR];
-    bool act[RT_MAXR];
-    int t_idx[RT_MAXR];
-#pragma unroll
-    for (int e = 0; e < RT_MAXR; ++e) {
-      const int r = rg + e * nrg;
-      act[e] = false;
-      acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      t_idx[e] = 0;
-      if (r < RT_ROWS) {
-        const int len = s_len[r];
-        act[e] = s < len;
-        t_idx[e] = dir ? (len - 1 - s) : s;
-        if (act[e]) {
-          const float* zp = d.z + ((size_t)(row0 + r) * T + t_idx[e]) * zrow + (size_t)dir * 4 * U + unit;
-          acc[e] = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
-        }
-      }
+    const bool act = s < len;
+    const int t_idx = dir ? (len - 1 - s) : s;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act && kh == 0) {
+      const float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
+      acc = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
     }
     if (s > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * s));
       __syncthreads();
       const float4* hsrc = reinterpret_cast<const float4*>(hx + (((size_t)((s - 1) & 1) * ndir + dir) * p.Bpad + row0) * U);
-      float4* hdst = reinterpret_cast<float4*>(s_h);
-      for (int i = tid; i < RT_ROWS * U / 4; i += RT_THREADS) hdst[i] = __ldcg(hsrc + i);
+      const int U4 = U / 4;
+      for (int i = tid; i < R * U4; i += RT_THREADS) {
+        const int rr = i / U4, c4 = i - rr * U4;
+        *reinterpret_cast<float4*>(s_h + rr * HS + 4 * c4) = __ldcg(hsrc + i);
+      }
       __syncthreads();
-      for (int k = 0; k < U; ++k) {
-        const float4 w = s_w[(size_t)k * upc + ul];
+      const float* hrow = s_h + r * HS + kh * kper;
+      const float4* wcol = s_w + (size_t)(kh * kper) * UPC + ul;
+#pragma unroll 2
+      for (int k = 0; k < kper; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
+        const float4 w0 = wcol[(size_t)(k + 0) * UPC], w1 = wcol[(size_t)(k + 1) * UPC];
+        const float4 w2 = wcol[(size_t)(k + 2) * UPC], w3 = wcol[(size_t)(k + 3) * UPC];
+        acc.x = fmaf(hv.x, w0.x, acc.x); acc.y = fmaf(hv.x, w0.y, acc.y); acc.z = fmaf(hv.x, w0.z, acc.z); acc.w = fmaf(hv.x, w0.w, acc.w);
+        acc.x = fmaf(hv.y, w1.x, acc.x); acc.y = fmaf(hv.y, w1.y, acc.y); acc.z = fmaf(hv.y, w1.z, acc.z); acc.w = fmaf(hv.y, w1.w, acc.w);
+        acc.x = fmaf(hv.z, w2.x, acc.x); acc.y = fmaf(hv.z, w2.y, acc.y); acc.z = fmaf(hv.z, w2.z, acc.z); acc.w = fmaf(hv.z, w2.w, acc.w);
+        acc.x = fmaf(hv.w, w3.x, acc.x); acc.y = fmaf(hv.w, w3.y, acc.y); acc.z = fmaf(hv.w, w3.z, acc.z); acc.w = fmaf(hv.w, w3.w, acc.w);
+      }
+      if (KS > 1) {
+        if (kh > 0) s_part[((kh - 1) * R + r) * UPC + ul] = acc;
+        __syncthreads();
+        if (kh == 0) {
 #pragma unroll
-        for (int e = 0; e < RT_MAXR; ++e) {
-          const int r = rg + e * nrg;
-          if (r < RT_ROWS) {
-            const float hv = s_h[r * U + k];
-            acc[e].x = fmaf(hv, w.x, acc[e].x);
-            acc[e].y = fmaf(hv, w.y, acc[e].y);
-            acc[e].z = fmaf(hv, w.z, acc[e].z);
-            acc[e].w = fmaf(hv, w.w, acc[e].w);
+          for (int q = 0; q < KS - 1; ++q) {
+            const float4 o = s_part[(q * R + r) * UPC + ul];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
           }
         }
       }
     }
-#pragma unroll
-    for (int e = 0; e < RT_MAXR; ++e) {
-      const int r = rg + e * nrg;
-      if (r >= RT_ROWS) continue;
-      const int b = row0 + r;
-      if (act[e]) {
-        const float gi_ = sigmoidf_acc(acc[e].x), gj = tanhf(acc[e].y), gf = sigmoidf_acc(acc[e].z + 1.0f),
-                    go = sigmoidf_acc(acc[e].w);
-        const float cn = gf * c_state[e] + gi_ * gj;
+    if (kh == 0) {
+      if (act) {
+        const float gi_ = sigmoidf_acc(acc.x), gj = tanhf(acc.y), gf = sigmoidf_acc(acc.z + 1.0f), go = sigmoidf_acc(acc.w);
+        const float cn = gf * c_state + gi_ * gj;
         const float hn = go * tanhf(cn);
-        const size_t bt = (size_t)b * T + t_idx[e];
+        const size_t bt = (size_t)b * T + t_idx;
         float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
         zp[0] = gi_; zp[U] = gj; zp[2 * U] = gf; zp[3 * U] = go;
         d.c_save[bt * srow + dir * U + unit] = cn;
-        d.h_prev[bt * srow + dir * U + unit] = h_state[e];
-        d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx[e] * srow + dir * U + unit] = hn;
-        c_state[e] = cn;
-        h_state[e] = hn;
+        d.h_prev[bt * srow + dir * U + unit] = h_state;
+        d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit] = hn;
+        c_state = cn;
+        h_state = hn;
       }
-      if (b < p.Bpad) hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state[e];
+      hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state;
     }
     __syncthreads();
     if (tid == 0) {
@@ -146,33 +150,38 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
   }
 }
 
+template <int R, int UPC>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainArgs p) {
+  constexpr int KS = RT_THREADS / (R * UPC);
+  static_assert(KS >= 1 && KS * R * UPC == RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const plas_rec_train_desc& d = p.d;
-  const int U = d.U, B = d.B, T = d.T, ndir = d.ndir, upc = p.upc;
+  const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
   const int tid = threadIdx.x;
   int bid = blockIdx.x;
   const int ci = bid % p.G; bid /= p.G;
   const int gi = p.group_offset + bid % p.groups_here;
   const int dir = bid / p.groups_here;
-  const int row0 = gi * RT_ROWS;
+  const int row0 = gi * R;
+  const int ZS = U + 1;  // padded row stride (float4 units) of the staged dz tile
 
-  float4* s_w = reinterpret_cast<float4*>(rt_smem);                  // [U (n4)][upc]: W_hh[unit][4*n4 .. 4*n4+3]
-  float4* s_dz = s_w + (size_t)U * upc;                              // [16][U] float4 = [16][4U]
-  __shared__ int s_len[RT_ROWS];
+  float4* s_w = reinterpret_cast<float4*>(rt_smem);  // [U (n4)][UPC]: W_hh[unit][4*n4 .. 4*n4+3]
+  float4* s_dz = s_w + (size_t)U * UPC;              // [R][ZS] float4 = [R][4U]
+  float* s_part = reinterpret_cast<float*>(s_dz + (size_t)R * ZS);  // [KS][R][UPC]
+  __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
     const float4* kern = reinterpret_cast<const float4*>(d.kernel[dir] + (size_t)d.din * 4 * U);
-    for (int i = tid; i < U * upc; i += RT_THREADS) {
+    for (int i = tid; i < U * UPC; i += RT_THREADS) {
       const int ul = i / U, n4 = i % U;
-      s_w[(size_t)n4 * upc + ul] = kern[(size_t)(ci * upc + ul) * U + n4];
+      s_w[(size_t)n4 * UPC + ul] = kern[(size_t)(ci * UPC + ul) * U + n4];
     }
   }
-  if (tid < RT_ROWS) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
+  if (tid < R) s_len[tid] = (row0 + tid < B) ? min(d.lengths[row0 + tid], T) : 0;
   __syncthreads();
   if (tid == 0) {
     int m = 0;
-    for (int r = 0; r < RT_ROWS; ++r) m = max(m, s_len[r]);
+    for (int r = 0; r < R; ++r) m = max(m, s_len[r]);
     s_tmax = m;
   }
   __syncthreads();
@@ -180,102 +189,88 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
 
   float* dzx = p.xbuf;
   unsigned* ctr = p.counters + dir * p.n_groups + gi;
-  const int ul = tid % upc, rg = tid / upc, nrg = RT_THREADS / upc;
-  const int unit = ci * upc + ul;
+  const int ul = tid % UPC, r = (tid / UPC) % R, kh = tid / (UPC * R);
+  const int unit = ci * UPC + ul;
+  const int b = row0 + r;
+  const int len = s_len[r];
   const size_t zrow = (size_t)ndir * 4 * U;
   const size_t srow = (size_t)ndir * U;
   const int W4 = 4 * U;
+  const int nper = U / KS;  // float4 chunks of the reduction per slice
 
   // the gradient GEMMs run over every (b,t) row: zero dz past each utterance's length
-#pragma unroll
-  for (int e = 0; e < RT_MAXR; ++e) {
-    const int r = rg + e * nrg;
-    if (r >= RT_ROWS || row0 + r >= B) continue;
-    for (int t = s_len[r]; t < T; ++t) {
-      float* zp = d.z + ((size_t)(row0 + r) * T + t) * zrow + (size_t)dir * 4 * U + unit;
+  if (kh == 0 && b < B) {
+    for (int t = len; t < T; ++t) {
+      float* zp = d.z + ((size_t)b * T + t) * zrow + (size_t)dir * 4 * U + unit;
       zp[0] = 0.f; zp[U] = 0.f; zp[2 * U] = 0.f; zp[3 * U] = 0.f;
     }
   }
 
-  float dc_carry[RT_MAXR] = {0.f, 0.f};
+  float dc_carry = 0.f;
   for (int j = 0; j < Tg; ++j) {
     const int s = Tg - 1 - j;
-    bool act[RT_MAXR];
-    int t_idx[RT_MAXR];
-    float4 g[RT_MAXR];
-    float c_t[RT_MAXR], c_prev[RT_MAXR], dh[RT_MAXR];
-#pragma unroll
-    for (int e = 0; e < RT_MAXR; ++e) {
-      const int r = rg + e * nrg;
-      act[e] = false;
-      t_idx[e] = 0;
-      dh[e] = 0.f;
-      c_t[e] = c_prev[e] = 0.f;
-      g[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < RT_ROWS) {
-        const int len = s_len[r];
-        act[e] = s < len;
-        t_idx[e] = dir ? (len - 1 - s) : s;
-        if (act[e]) {
-          const int b = row0 + r;
-          const size_t bt = (size_t)b * T + t_idx[e];
-          const float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
-          g[e] = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
-          c_t[e] = d.c_save[bt * srow + dir * U + unit];
-          if (s > 0) {
-            const size_t btp = (size_t)b * T + (dir ? t_idx[e] + 1 : t_idx[e] - 1);
-            c_prev[e] = d.c_save[btp * srow + dir * U + unit];
-          }
-          dh[e] = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx[e] * srow + dir * U + unit];
-        }
+    const bool act = s < len;
+    const int t_idx = dir ? (len - 1 - s) : s;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float c_t = 0.f, c_prev = 0.f, dh = 0.f;
+    if (act && kh == 0) {
+      const size_t bt = (size_t)b * T + t_idx;
+      const float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
+      g = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
+      c_t = d.c_save[bt * srow + dir * U + unit];
+      if (s > 0) {
+        const size_t btp = (size_t)b * T + (dir ? t_idx + 1 : t_idx - 1);
+        c_prev = d.c_save[btp * srow + dir * U + unit];
       }
+      dh = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit];
     }
     if (j > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * j));
       __syncthreads();
       const float4* src = reinterpret_cast<const float4*>(dzx + (((size_t)((j - 1) & 1) * ndir + dir) * p.Bpad + row0) * W4);
-      for (int i = tid; i < RT_ROWS * U; i += RT_THREADS) s_dz[i] = __ldcg(src + i);
+      for (int i = tid; i < R * U; i += RT_THREADS) {
+        const int rr = i / U, c4 = i - rr * U;
+        s_dz[rr * ZS + c4] = __ldcg(src + i);
+      }
       __syncthreads();
-      float racc[RT_MAXR] = {0.f, 0.f};
-      for (int n4 = 0; n4 < U; ++n4) {
-        const float4 w = s_w[(size_t)n4 * upc + ul];
+      float racc = 0.f;
+      const float4* zr = s_dz + r * ZS + kh * nper;
+      const float4* wc = s_w + (size_t)(kh * nper) * UPC + ul;
+#pragma unroll 4
+      for (int n4 = 0; n4 < nper; ++n4) {
+        const float4 v = zr[n4];
+        const float4 w = wc[(size_t)n4 * UPC];
+        racc = fmaf(v.x, w.x, racc);
+        racc = fmaf(v.y, w.y, racc);
+        racc = fmaf(v.z, w.z, racc);
+        racc = fmaf(v.w, w.w, racc);
+      }
+      if (KS > 1) {
+        if (kh > 0) s_part[((kh - 1) * R + r) * UPC + ul] = racc;
+        __syncthreads();
+        if (kh == 0) {
 #pragma unroll
-        for (int e = 0; e < RT_MAXR; ++e) {
-          const int r = rg + e * nrg;
-          if (r < RT_ROWS) {
-            const float4 v = s_dz[r * U + n4];
-            racc[e] = fmaf(v.x, w.x, racc[e]);
-            racc[e] = fmaf(v.y, w.y, racc[e]);
-            racc[e] = fmaf(v.z, w.z, racc[e]);
-            racc[e] = fmaf(v.w, w.w, racc[e]);
-          }
+          for (int q = 0; q < KS - 1; ++q) racc += s_part[(q * R + r) * UPC + ul];
         }
       }
-#pragma unroll
-      for (int e = 0; e < RT_MAXR; ++e) dh[e] += racc[e];
+      dh += racc;
     }
-#pragma unroll
-    for (int e = 0; e < RT_MAXR; ++e) {
-      const int r = rg + e * nrg;
-      if (r >= RT_ROWS) continue;
-      const int b = row0 + r;
+    if (kh == 0) {
       float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
-      if (act[e]) {
-        const float gi_ = g[e].x, gj = g[e].y, gf = g[e].z, go = g[e].w;
-        const float tc = tanhf(c_t[e]);
-        const float dc = dc_carry[e] + dh[e] * go * (1.f - tc * tc);
-        dzo = dh[e] * tc * go * (1.f - go);
+      if (act) {
+        const float gi_ = g.x, gj = g.y, gf = g.z, go = g.w;
+        const float tc = tanhf(c_t);
+        const float dc = dc_carry + dh * go * (1.f - tc * tc);
+        dzo = dh * tc * go * (1.f - go);
         dzi = dc * gj * gi_ * (1.f - gi_);
         dzj = dc * gi_ * (1.f - gj * gj);
-        dzf = dc * c_prev[e] * gf * (1.f - gf);
-        dc_carry[e] = dc * gf;
-        float* zp = d.z + ((size_t)b * T + t_idx[e]) * zrow + (size_t)dir * 4 * U + unit;
+        dzf = dc * c_prev * gf * (1.f - gf);
+        dc_carry = dc * gf;
+        float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
         zp[0] = dzi; zp[U] = dzj; zp[2 * U] = dzf; zp[3 * U] = dzo;
       }
-      if (b < p.Bpad) {
-        float* xp = dzx + (((size_t)(j & 1) * ndir + dir) * p.Bpad + b) * W4 + unit;
-        xp[0] = dzi; xp[U] = dzj; xp[2 * U] = dzf; xp[3 * U] = dzo;
-      }
+      float* xp = dzx + (((size_t)(j & 1) * ndir + dir) * p.Bpad + b) * W4 + unit;
+      xp[0] = dzi; xp[U] = dzj; xp[2 * U] = dzf; xp[3 * U] = dzo;
     }
     __syncthreads();
     if (tid == 0) {
@@ -285,20 +280,35 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
   }
 }
 
-static int rt_upc(int U) {
-  int upc = 32;
-  while (upc > 4 && ((size_t)U * 16 * upc > 128 * 1024 || U / upc < 8)) upc >>= 1;  // >= 8 CTAs per group when possible
-  while (upc > 4 && U % upc != 0) upc >>= 1;
-  return upc;
+// ---- host side ---------------------------------------------------------------------------------------------
+struct RtShape {
+  int R, UPC;
+  const void* fn;
+};
+#define RT_FWD(R, UPC) {R, UPC, (const void*)rec_train_fwd_kernel<R, UPC>}
+#define RT_BWD(R, UPC) {R, UPC, (const void*)rec_train_bwd_kernel<R, UPC>}
+static const RtShape rt_fwd_shapes[] = {RT_FWD(32, 4), RT_FWD(32, 8), RT_FWD(16, 8), RT_FWD(16, 16), RT_FWD(16, 4), RT_FWD(8, 32)};
+static const RtShape rt_bwd_shapes[] = {RT_BWD(8, 16), RT_BWD(8, 32), RT_BWD(16, 16), RT_BWD(8, 8), RT_BWD(8, 4), RT_BWD(16, 4)};
+
+static size_t rt_smem_bytes(const RtShape& sh, int U, bool backward) {
+  const int KS = RT_THREADS / (sh.R * sh.UPC);
+  if (backward) return (size_t)U * sh.UPC * 16 + (size_t)sh.R * (U + 1) * 16 + (size_t)KS * sh.R * sh.UPC * 4;
+  return (size_t)U * sh.UPC * 16 + (size_t)sh.R * (U + 4) * 4 + (size_t)KS * sh.R * sh.UPC * 16;
+}
+
+static bool rt_shape_ok(const RtShape& sh, int U, bool backward) {
+  const int KS = RT_THREADS / (sh.R * sh.UPC);
+  // forward slices k in float4 steps, backward slices the U float4 chunks of a W_hh row
+  return U % sh.UPC == 0 && U % (backward ? KS : 4 * KS) == 0 && rt_smem_bytes(sh, U, backward) <= 200 * 1024;
 }
 
 static void rt_ws_layout(const plas_rec_train_desc& d, size_t* o_ctr, size_t* o_x, size_t* total) {
-  const int n_groups = (d.B + RT_ROWS - 1) / RT_ROWS;
+  const size_t bpad = ((size_t)d.B + 31) / 32 * 32;  // covers every row-group size
   size_t off = 0;
   *o_ctr = off;
-  off += ((size_t)d.ndir * n_groups * 4 + 255) & ~size_t(255);
+  off += ((size_t)d.ndir * ((d.B + 7) / 8) * 4 + 255) & ~size_t(255);
   *o_x = off;
-  off += ((size_t)2 * d.ndir * n_groups * RT_ROWS * 4 * d.U * 4 + 255) & ~size_t(255);
+  off += ((size_t)2 * d.ndir * bpad * 4 * d.U * 4 + 255) & ~size_t(255);
   *total = off;
 }
 
@@ -308,38 +318,49 @@ static int rt_launch(const plas_rec_train_desc* d, void* workspace, size_t works
   PLAS_REQUIRE(d->B > 0 && d->T > 0 && d->U > 0 && (d->ndir == 1 || d->ndir == 2) && d->din > 0, "rec_train: bad shape");
   PLAS_REQUIRE(d->z && d->kernel[0] && (d->ndir == 1 || d->kernel[1]) && d->lengths && d->c_save, "rec_train: null tensor");
   PLAS_REQUIRE(backward ? d->dout != nullptr : (d->out != nullptr && d->h_prev != nullptr), "rec_train: null tensor");
-  PLAS_REQUIRE(d->U % 4 == 0 && d->U <= 1024, "rec_train: U=%d unsupported", d->U);
-  const int upc = rt_upc(d->U);
-  PLAS_REQUIRE(d->U % upc == 0 && RT_THREADS % upc == 0 && RT_THREADS / upc * RT_MAXR >= RT_ROWS,
-               "rec_train: U=%d unsupported (upc=%d)", d->U, upc);
+  PLAS_REQUIRE(d->U % 4 == 0 && d->U <= 1024, "rec_train: U=%d unsupported (multiple of 4, <= 1024)", d->U);
   PLAS_REQUIRE(d->out_batch_stride >= (int64_t)d->T * d->ndir * d->U, "rec_train: out_batch_stride too small");
   size_t o_ctr, o_x, total;
   rt_ws_layout(*d, &o_ctr, &o_x, &total);
   PLAS_REQUIRE(workspace_bytes >= total, "rec_train: workspace %zu < %zu", workspace_bytes, total);
+
+  // pick the shape with the fewest launches (all CTAs of a group must be co-resident), then the most CTAs
+  const RtShape* shapes = backward ? rt_bwd_shapes : rt_fwd_shapes;
+  const int n_shapes = 6;
+  const RtShape* best = nullptr;
+  int best_launches = 1 << 30, best_gpl = 0;
+  size_t best_smem = 0;
+  for (int i = 0; i < n_shapes; ++i) {
+    const RtShape& sh = shapes[i];
+    if (!rt_shape_ok(sh, d->U, backward)) continue;
+    const size_t smem = rt_smem_bytes(sh, d->U, backward);
+    PLAS_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sh.fn, RT_THREADS, smem));
+    const int resident = per_sm * num_sms();
+    const int ctas_per_group = d->ndir * (d->U / sh.UPC);
+    const int gpl = resident / ctas_per_group;
+    if (gpl < 1) continue;
+    const int n_groups = (d->B + sh.R - 1) / sh.R;
+    const int launches = (n_groups + gpl - 1) / gpl;
+    if (launches < best_launches) {
+      best = &sh; best_launches = launches; best_gpl = gpl; best_smem = smem;
+    }
+  }
+  PLAS_REQUIRE(best != nullptr, "rec_train: no kernel shape fits U=%d", d->U);
   RecTrainArgs a;
   a.d = *d;
   a.counters = (unsigned*)((unsigned char*)workspace + o_ctr);
   a.xbuf = (float*)((unsigned char*)workspace + o_x);
-  a.n_groups = (d->B + RT_ROWS - 1) / RT_ROWS;
-  a.upc = upc;
-  a.G = d->U / upc;
-  a.Bpad = a.n_groups * RT_ROWS;
+  a.n_groups = (d->B + best->R - 1) / best->R;
+  a.G = d->U / best->UPC;
+  a.Bpad = a.n_groups * best->R;
   PLAS_CUDA(cudaMemsetAsync(a.counters, 0, (size_t)d->ndir * a.n_groups * 4, stream));
-  const size_t smem = (size_t)d->U * upc * 16 + (size_t)RT_ROWS * d->U * 4 * (backward ? 4 : 1);
-  PLAS_REQUIRE(smem <= 227 * 1024, "rec_train: needs %zu bytes of shared memory", smem);
-  const void* fn = backward ? (const void*)rec_train_bwd_kernel : (const void*)rec_train_fwd_kernel;
-  PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  PLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RT_THREADS, smem));
-  const int resident = per_sm * num_sms();
-  const int ctas_per_group = d->ndir * a.G;
-  const int gpl = resident / ctas_per_group;
-  PLAS_REQUIRE(gpl >= 1, "rec_train: %d CTAs per group cannot be co-resident (%d slots)", ctas_per_group, resident);
-  for (int g0 = 0; g0 < a.n_groups; g0 += gpl) {
+  for (int g0 = 0; g0 < a.n_groups; g0 += best_gpl) {
     a.group_offset = g0;
-    a.groups_here = (a.n_groups - g0 < gpl) ? (a.n_groups - g0) : gpl;
+    a.groups_here = (a.n_groups - g0 < best_gpl) ? (a.n_groups - g0) : best_gpl;
     void* args[] = {&a};
-    PLAS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas_per_group * a.groups_here), dim3(RT_THREADS), args, smem, stream));
+    PLAS_CUDA(cudaLaunchCooperativeKernel(best->fn, dim3(d->ndir * a.G * a.groups_here), dim3(RT_THREADS), args, best_smem, stream));
   }
   return PLAS_OK;
 }

@@ -46,3 +46,22 @@ def gather_ids(sample_ids, seq_len, n_global, pad_id=0):
     out_len = torch.cat([lbufs[r][:int(shapes[r][0])] for r in range(world)], dim=0)
     assert ids.shape[0] == n_global, (ids.shape, n_global)
     return ids, out_len
+
+
+def allreduce_gradients(flat_grads):
+    """The one exchange step of the training path: sum the flat fp32 gradient buffer over the
+    ranks (NCCL over NVLink/NVSwitch on the GPU box).  ``train.apply_gradients`` has already clipped every tensor
+    locally and divided by the world size, so the sum is the mean of the clipped shard gradients -- the order
+    tf.tpu.CrossShardOptimizer gives the reference (clip at model_helper.py:416, cross-shard mean inside
+    apply_gradients, model_helper.py:405-406,417).  All ranks then apply identical Adam updates to identical
+    replicas of the parameters and optimiser state."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+    return flat_grads
+
+
+def broadcast_parameters(flat_params, src=0):
+    """Make every replica start from rank ``src``'s parameters."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat_params, src=src)
+    return flat_params

@@ -25,7 +25,7 @@ def _p(t, off_elems=0):
     return t.data_ptr() + 4 * off_elems
 
 
-def gemm_ex(M, N, K, A, sam, sak, B, sbk, sbn, Cp, ldc, bias=None, beta=0.0, alpha=1.0, batch=1, ba=0, bb=0, bc=0):
+def gemm_ex(M, N, K, A, sam, sak, B, sbk, sbn, Cp, ldc, bias=None, beta=0.0, alpha=1.0, batch=1, ba=0, bb=0, bc=0, split_ws=None):
     """plas_gemm_f32_ex on raw device addresses (ints)."""
     d = _lib.GemmExDesc()
     d.M, d.N, d.K = M, N, K
@@ -34,6 +34,8 @@ def gemm_ex(M, N, K, A, sam, sak, B, sbk, sbn, Cp, ldc, bias=None, beta=0.0, alp
     d.C, d.ldc, d.bias = Cp, ldc, bias
     d.alpha, d.beta = alpha, beta
     d.batch, d.batch_a, d.batch_b, d.batch_c = batch, ba, bb, bc
+    if split_ws is not None:  # deterministic split-K scratch (weight gradients)
+        d.split_ws, d.split_ws_bytes = split_ws.data_ptr(), split_ws.numel() * split_ws.element_size()
     _lib.check(_lib.lib().plas_gemm_f32_ex(C.byref(d), _lib.stream_ptr()))
     _lib.count_launches(1)
 
@@ -70,6 +72,7 @@ class TrainState:
         self.norms = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
         self.wsq = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
         self.index = {k: i for i, k in enumerate(self.names)}
+        self.split_ws = torch.empty((32 << 20,), dtype=torch.uint8, device=device)  # split-K scratch of the dW GEMMs
         self.step = 0
 
     def has(self, name):
@@ -181,8 +184,8 @@ def listener_train_bwd(d_enc, tape, st, hp):
         with _lib.stage("train_wgrad"):
             for dd, nm in enumerate(names):
                 zp = _p(z, dd * 4 * U)
-                gemm_ex(din, 4 * U, M, x.data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U)
-                gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U)
+                gemm_ex(din, 4 * U, M, x.data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
+                gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U, split_ws=st.split_ws)
                 colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))
         if l > 0:
             with _lib.stage("train_dgrad"):
@@ -347,7 +350,7 @@ def forward_backward(features, labels, st, hp, binf=None):
         per_utt, dcl = ctc_grad(cl, tout, tlen, enc_len, gscale=cw / B)
         parts["ctc"] = per_utt.mean()
         total = parts["ctc"] * cw if total is None else total + parts["ctc"] * cw
-        gemm_ex(D, Cn, B * Tm, enc_out.data_ptr(), 1, D, dcl.data_ptr(), Cn, 1, st.g("ctc_logits/kernel"), Cn)
+        gemm_ex(D, Cn, B * Tm, enc_out.data_ptr(), 1, D, dcl.data_ptr(), Cn, 1, st.g("ctc_logits/kernel"), Cn, split_ws=st.split_ws)
         colsum(dcl.data_ptr(), B * Tm, Cn, Cn, st.g("ctc_logits/bias"))
         gemm_ex(B * Tm, D, Cn, dcl.data_ptr(), Cn, 1, st.w("ctc_logits/kernel"), 1, Cn, d_enc.data_ptr(), D, beta=1.0)
     for sp, dl in spellers:

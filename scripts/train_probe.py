@@ -18,6 +18,10 @@ binf = torch.from_numpy((np.random.default_rng(0).uniform(size=(n, V)) < 0.3).as
 feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
 labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
           "target_sequence_length": torch.from_numpy(tlen).cuda()}
+if "--one" in sys.argv:  # a single step, for ncu launch lists
+    tr.train_step(feats, labels, st, hp, binf)
+    torch.cuda.synchronize()
+    sys.exit(0)
 for _ in range(3):
     p = tr.train_step(feats, labels, st, hp, binf)
 torch.cuda.synchronize()
