@@ -302,6 +302,8 @@ int plas_grad_l2_norm(const float* params, float* grads, const int64_t* offsets,
                       float* norms, float* wsq, plas_stream_t stream);
 int plas_clip_scale(float* grads, const int64_t* offsets, int32_t n_tensors, const float* norms, float clip,
                     float post_scale, plas_stream_t stream);
+/* y += alpha * x: sums the encoder-output gradients of the heads (the spellers run on separate streams). */
+int plas_axpy_f32(float* y, const float* x, int64_t n, float alpha, plas_stream_t stream);
 int plas_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1,
                    float beta2, float eps, float grad_scale, plas_stream_t stream);
 

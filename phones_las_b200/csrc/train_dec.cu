@@ -16,6 +16,8 @@
 //   dec_cell_bwd   gate derivatives, dz_t written IN PLACE over the saved gates
 //   dec_gemv_t     dinp = dz_t W^T   (gradient wrt [attention_{t-1}; h_{t-1}] that the next iteration consumes)
 // Saved tensors are batch-major [B][S][width] so the hoisted GEMMs see plain row-major matrices.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "../../include/plas.h"
 
@@ -37,58 +39,81 @@ struct CellFwdArgs {
   float* hprev_next;                    // slot t+1 of the h_{t-1} copy (NULL at the last step)
 };
 
-// CTA = UPC units (4*UPC gate columns) x 32 batch rows.  The CTA's weight slice [K][4*UPC] is staged in shared
-// memory with one wave of independent vector loads; lane = batch row, the 8 warps split the reduction over K.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int CF_KC = 1280;  // reduction chunk staged per pass (activations 32 x KC + weights KC x 4*UPC in smem)
+
+// CTA = UPC units (4*UPC gate columns) x 32 batch rows.  Per pass the CTA stages a KC-wide chunk of the 32
+// activation rows and of its weight slice in shared memory with one wave of independent 16-byte cp.async copies
+// (the whole point: the step is latency-bound, so every byte must be in flight at once); lane = batch row, the 8
+// warps split the chunk's reduction, partials meet in shared memory.
 template <int UPC>
 __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
   extern __shared__ __align__(16) float cf_smem[];
   constexpr int NC = 4 * UPC;
-  float* s_w = cf_smem;  // [K][NC], column = g*UPC + u
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int u0 = blockIdx.x * UPC;
   const int b0 = blockIdx.y * DT_ROWS;
-  const int b = min(b0 + lane, p.B - 1);
   const int Ud = p.Ud;
   const int K = p.K1 + p.K2;
-  if (UPC == 4) {
-    for (int i = threadIdx.x; i < K * 4; i += 256) {
-      const int k = i >> 2, g = i & 3;
-      reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * 4 * Ud + g * Ud + u0));
-    }
-  } else {
-    for (int i = threadIdx.x; i < K * 4; i += 256) {
-      const int k = i >> 2, g = i & 3;
-      reinterpret_cast<float2*>(s_w)[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)k * 4 * Ud + g * Ud + u0));
-    }
-  }
-  const int K4 = K / 4;
-  const int per = (K4 + 7) / 8;
-  const int q_lo = warp * per, q_hi = min(K4, q_lo + per);
-  const int K1q = p.K1 / 4;
-  const float4* a1 = reinterpret_cast<const float4*>(p.in1 + (long long)b * p.s1);
-  const float4* a2 = reinterpret_cast<const float4*>(p.in2 + (long long)b * p.s2) - K1q;
+  const int kc_max = min(K, CF_KC);
+  const int AS = kc_max + 4;                 // padded activation row stride (floats): conflict-free float4 reads
+  float* s_a = cf_smem;                      // [32][AS]
+  float* s_w = s_a + (size_t)DT_ROWS * AS;   // [kc][NC], column = g*UPC + u
   float acc[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) acc[c] = 0.f;
-  __syncthreads();
-#pragma unroll 4
-  for (int q = q_lo; q < q_hi; ++q) {
-    const float4 a = q < K1q ? a1[q] : a2[q];
-    const float av[4] = {a.x, a.y, a.z, a.w};
+  for (int kc0 = 0; kc0 < K; kc0 += CF_KC) {
+    const int kc = min(CF_KC, K - kc0);
+    const int kq = kc / 4;
+    if (kc0 > 0) __syncthreads();
+    for (int i = threadIdx.x; i < DT_ROWS * kq; i += 256) {
+      const int r = i / kq, q = i - r * kq;
+      const int b = min(b0 + r, p.B - 1);
+      const int k = kc0 + 4 * q;
+      const float* src = k < p.K1 ? p.in1 + (long long)b * p.s1 + k : p.in2 + (long long)b * p.s2 + (k - p.K1);
+      cp_async16(s_a + (size_t)r * AS + 4 * q, src);
+    }
+    if (UPC == 4) {
+      for (int i = threadIdx.x; i < kc * 4; i += 256) {
+        const int k = i >> 2, g = i & 3;
+        cp_async16(s_w + (size_t)i * 4, p.w + (size_t)(kc0 + k) * 4 * Ud + g * Ud + u0);
+      }
+    } else {
+      for (int i = threadIdx.x; i < kc * 4; i += 256) {
+        const int k = i >> 2, g = i & 3;
+        reinterpret_cast<float2*>(s_w)[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)(kc0 + k) * 4 * Ud + g * Ud + u0));
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int per = (kq + 7) / 8;
+    const int q_lo = warp * per, q_hi = min(kq, q_lo + per);
+    const float* arow = s_a + (size_t)lane * AS;
+#pragma unroll 2
+    for (int q = q_lo; q < q_hi; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(arow + 4 * q);
+      const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const float4* wr = reinterpret_cast<const float4*>(s_w + (size_t)(4 * q + kk) * NC);
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (size_t)(4 * q + kk) * NC);
 #pragma unroll
-      for (int c4 = 0; c4 < NC / 4; ++c4) {
-        const float4 w = wr[c4];
-        acc[4 * c4 + 0] = fmaf(av[kk], w.x, acc[4 * c4 + 0]);
-        acc[4 * c4 + 1] = fmaf(av[kk], w.y, acc[4 * c4 + 1]);
-        acc[4 * c4 + 2] = fmaf(av[kk], w.z, acc[4 * c4 + 2]);
-        acc[4 * c4 + 3] = fmaf(av[kk], w.w, acc[4 * c4 + 3]);
+        for (int c4 = 0; c4 < NC / 4; ++c4) {
+          const float4 w = wr[c4];
+          acc[4 * c4 + 0] = fmaf(av[kk], w.x, acc[4 * c4 + 0]);
+          acc[4 * c4 + 1] = fmaf(av[kk], w.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(av[kk], w.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(av[kk], w.w, acc[4 * c4 + 3]);
+        }
       }
     }
   }
-  __syncthreads();  // everyone is done with s_w: reuse it for the cross-warp reduction
+  __syncthreads();  // everyone is done with the staged tiles: reuse them for the cross-warp reduction
   float* s_red = cf_smem;  // [8][NC][33]
 #pragma unroll
   for (int c = 0; c < NC; ++c) s_red[(warp * NC + c) * (DT_ROWS + 1) + lane] = acc[c];
@@ -120,7 +145,7 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
 
 // ---------------------------------------------------------------------------------------------------------
 struct AttFwdArgs {
-  int B, Tm, D, Ud, type, dsplit;
+  int B, Tm, D, Ud, type, dsplit, staged;
   const float* keys;     // [B][Tm][Ud]
   const float* values;   // [B][Tm][D]
   const int* mem_len;
@@ -132,24 +157,52 @@ struct AttFwdArgs {
   float* att_next;                        // slot t+1 of the attention_{t-1} copy (NULL at the last step)
 };
 
+// CTA = (utterance, D-slice).  The utterance's keys and the CTA's slice of the values are staged in shared memory
+// with one wave of cp.async copies when they fit (staged != 0), so the step is one L2 round trip deep instead of
+// one per memory row; otherwise rows stream from L2.
 __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
-  extern __shared__ float att_smem[];
+  extern __shared__ __align__(16) float att_smem[];
+  const int Ud = p.Ud, Tm = p.Tm, D = p.D;
   float* s_q = att_smem;          // [Ud] query (luong) or processed query (bahdanau)
-  float* s_sc = s_q + p.Ud;       // [Tm]
-  float* s_v = s_sc + p.Tm;       // [Ud] attention_v (bahdanau)
+  float* s_v = s_q + Ud;          // [Ud] attention_v (bahdanau)
+  float* s_sc = s_v + Ud;         // [Tm rounded to 4]
+  float* s_keys = s_sc + ((Tm + 3) & ~3);  // staged: [len][Ud]
   __shared__ float s_red[8];
   __shared__ float s_bcast;
   const int b = blockIdx.x, part = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Ud = p.Ud, Tm = p.Tm, D = p.D;
   const int len = min(p.mem_len[b], Tm);
+  const int dper = (D + p.dsplit - 1) / p.dsplit;
+  const int d_lo = part * dper, d_hi = min(D, d_lo + dper);
+  const int dw = d_hi - d_lo;
+  float* s_vals = s_keys + (size_t)Tm * Ud;  // staged: [len][dper]
+  const float* kb = p.keys + (size_t)b * Tm * Ud;
+  const float* vb = p.values + (size_t)b * Tm * D;
+  if (p.staged) {
+    const int kq = len * Ud / 4;
+    for (int i = tid; i < kq; i += 256) cp_async16(s_keys + 4 * i, kb + 4 * i);
+    const int dq = dw / 4;
+    for (int i = tid; i < len * dq; i += 256) {
+      const int t = i / dq, q = i - t * dq;
+      cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   const float* q = p.query + (long long)b * p.s_q;
   if (p.type == PLAS_ATT_BAHDANAU) {
     for (int u = tid; u < Ud; u += 256) s_v[u] = q[u];  // raw query staged where attention_v goes afterwards
     __syncthreads();
     for (int u = tid; u < Ud; u += 256) {
-      float s = 0.f;
-      for (int k = 0; k < Ud; ++k) s = fmaf(s_v[k], __ldg(p.w_query + (size_t)k * Ud + u), s);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int k = 0;
+      for (; k + 4 <= Ud; k += 4) {
+        s0 = fmaf(s_v[k], __ldg(p.w_query + (size_t)k * Ud + u), s0);
+        s1 = fmaf(s_v[k + 1], __ldg(p.w_query + (size_t)(k + 1) * Ud + u), s1);
+        s2 = fmaf(s_v[k + 2], __ldg(p.w_query + (size_t)(k + 2) * Ud + u), s2);
+        s3 = fmaf(s_v[k + 3], __ldg(p.w_query + (size_t)(k + 3) * Ud + u), s3);
+      }
+      for (; k < Ud; ++k) s0 = fmaf(s_v[k], __ldg(p.w_query + (size_t)k * Ud + u), s0);
+      const float s = (s0 + s1) + (s2 + s3);
       s_q[u] = s;
       if (part == 0) p.pq[(long long)b * p.s_pq + u] = s;
     }
@@ -158,12 +211,13 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
   } else {
     for (int u = tid; u < Ud; u += 256) s_q[u] = q[u];
   }
+  if (p.staged) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const float* kb = p.keys + (size_t)b * Tm * Ud;
+  const float* kbase = p.staged ? s_keys : kb;
   for (int t = warp; t < Tm; t += 8) {
     float s = 0.f;
     if (t < len) {
-      const float* kr = kb + (size_t)t * Ud;
+      const float* kr = kbase + (size_t)t * Ud;
       if (p.type == PLAS_ATT_BAHDANAU)
         for (int u = lane; u < Ud; u += 32) s = fmaf(s_v[u], tanhf(kr[u] + s_q[u]), s);
       else
@@ -208,13 +262,21 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     if (part == 0) p.align[(long long)b * p.s_al + t] = a;
   }
   __syncthreads();
-  const int dper = (D + p.dsplit - 1) / p.dsplit;
-  const int d_lo = part * dper, d_hi = min(D, d_lo + dper);
-  const float* vb = p.values + (size_t)b * Tm * D;
   for (int d = d_lo + tid; d < d_hi; d += 256) {
-    float c = 0.f;
+    float c0 = 0.f, c1 = 0.f;
+    if (p.staged) {
+      const float* vs = s_vals + (d - d_lo);
+      int t = 0;
+      for (; t + 2 <= len; t += 2) {
+        c0 = fmaf(s_sc[t], vs[(size_t)t * dper], c0);
+        c1 = fmaf(s_sc[t + 1], vs[(size_t)(t + 1) * dper], c1);
+      }
+      if (t < len) c0 = fmaf(s_sc[t], vs[(size_t)t * dper], c0);
+    } else {
 #pragma unroll 8
-    for (int t = 0; t < len; ++t) c = fmaf(s_sc[t], vb[(size_t)t * D + d], c);
+      for (int t = 0; t < len; ++t) c0 = fmaf(s_sc[t], vb[(size_t)t * D + d], c0);
+    }
+    const float c = c0 + c1;
     p.att[(long long)b * p.s_att + d] = c;
     if (p.att_next) p.att_next[(long long)b * p.s_att + d] = c;
   }
@@ -222,7 +284,7 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
 
 // ---------------------------------------------------------------------------------------------------------
 struct AttBwdArgs {
-  int B, Tm, D, Ud, type;
+  int B, Tm, D, Ud, type, nsplit, staged;
   const float* keys; const float* values; const int* mem_len;
   const float* align; long long s_al;
   float* dctx; long long s_dc;           // in: dlogits W_proj^T of this step; out: + recurrent part
@@ -234,75 +296,118 @@ struct AttBwdArgs {
   float* dpq; long long s_dpq; float* dkeys; float* dv_acc;
 };
 
-__global__ void __launch_bounds__(512) dec_att_bwd_kernel(AttBwdArgs p) {
-  extern __shared__ float attb_smem[];
-  float* s_dc = attb_smem;       // [D]
-  float* s_da = s_dc + p.D;      // [Tm] dalign -> dscore
-  float* s_dpq = s_da + p.Tm;    // [Ud]
-  __shared__ float s_red[16];
-  __shared__ float s_bcast;
-  const int b = blockIdx.x;
+// Cluster of NS CTAs per utterance (grid (B, NS), cluster (1, NS, 1)).  CTA `part` owns a D-slice of the context
+// gradient / values and a Ud-slice of the query gradient / keys, staged in shared memory with one wave of cp.async
+// copies when they fit.  dalign needs the whole depth: the partial dot products are exchanged through distributed
+// shared memory and summed in a fixed order by every CTA (likewise dpq for the bahdanau query layer).
+__global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float attb_smem[];
+  const int Ud = p.Ud, Tm = p.Tm, D = p.D, NS = p.nsplit;
+  const int Tp = (Tm + 3) & ~3;
+  const int b = blockIdx.x, part = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Ud = p.Ud, Tm = p.Tm, D = p.D;
+  const int dper = D / NS, uper = Ud / NS;
+  const int d_lo = part * dper, u_lo = part * uper;
+  float* s_dc = attb_smem;               // [dper]
+  float* s_part = s_dc + dper;           // [NS][Tp] partial dalign of every CTA of the cluster
+  float* s_da = s_part + (size_t)NS * Tp;  // [Tp] dalign -> dscore
+  float* s_dpq = s_da + Tp;              // [Ud] (bahdanau)
+  float* s_vals = s_dpq + Ud;            // staged [len][dper]
+  float* s_keys = s_vals + (size_t)Tm * dper;  // staged [len][uper]
+  __shared__ float s_red[8];
+  __shared__ float s_bcast;
   const int len = min(p.mem_len[b], Tm);
-  float* dctx = p.dctx + (long long)b * p.s_dc;
-  for (int d = tid; d < D; d += 512) {
+  const float* vb = p.values + (size_t)b * Tm * D;
+  const float* kb = p.keys + (size_t)b * Tm * Ud;
+  if (p.staged) {
+    const int dq = dper / 4, uq = uper / 4;
+    for (int i = tid; i < len * dq; i += 256) {
+      const int t = i / dq, q = i - t * dq;
+      cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+    }
+    for (int i = tid; i < len * uq; i += 256) {
+      const int t = i / uq, q = i - t * uq;
+      cp_async16(s_keys + (size_t)t * uper + 4 * q, kb + (size_t)t * Ud + u_lo + 4 * q);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (NS > 1) cluster.barrier_arrive();  // every CTA of the cluster must be running before its shared memory is written remotely
+  float* dctx = p.dctx + (long long)b * p.s_dc + d_lo;
+  for (int d = tid; d < dper; d += 256) {
     float v = dctx[d];
-    if (p.datt_next) v += p.datt_next[(long long)b * p.s_dn + d];
+    if (p.datt_next) v += p.datt_next[(long long)b * p.s_dn + d_lo + d];
     s_dc[d] = v;
     dctx[d] = v;
   }
+  if (p.staged) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const float* vb = p.values + (size_t)b * Tm * D;
+  if (NS > 1) cluster.barrier_wait();
   const float* al = p.align + (long long)b * p.s_al;
-  for (int t = warp; t < Tm; t += 16) {
+  for (int t = warp; t < Tm; t += 8) {
     float s = 0.f;
     if (t < len) {
-      const float* vr = vb + (size_t)t * D;
-      for (int d = lane; d < D; d += 32) s = fmaf(s_dc[d], vr[d], s);
+      const float* vr = p.staged ? s_vals + (size_t)t * dper : vb + (size_t)t * D + d_lo;
+      for (int d = lane; d < dper; d += 32) s = fmaf(s_dc[d], vr[d], s);
       s = warp_sum(s);
     }
-    if (lane == 0) s_da[t] = s;
+    if (lane == 0) {
+      for (int r = 0; r < NS; ++r) {
+        float* remote = NS > 1 ? cluster.map_shared_rank(s_part, r) : s_part;
+        remote[part * Tp + t] = s;
+      }
+    }
   }
-  __syncthreads();
+  if (NS > 1) cluster.sync(); else __syncthreads();
   float dot = 0.f;
-  for (int t = tid; t < Tm; t += 512) dot = fmaf(al[t], s_da[t], dot);
+  for (int t = tid; t < Tm; t += 256) {
+    float v = 0.f;
+    for (int r = 0; r < NS; ++r) v += s_part[r * Tp + t];
+    s_da[t] = v;
+    dot = fmaf(al[t], v, dot);
+  }
   dot = warp_sum(dot);
   if (lane == 0) s_red[warp] = dot;
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
-    for (int w = 0; w < 16; ++w) t += s_red[w];
+    for (int w = 0; w < 8; ++w) t += s_red[w];
     s_bcast = t;
   }
   __syncthreads();
   dot = s_bcast;
-  for (int t = tid; t < Tm; t += 512) {
+  for (int t = tid; t < Tm; t += 256) {
     const float ds = al[t] * (s_da[t] - dot);
     s_da[t] = ds;
-    p.dscore[(long long)b * p.s_ds + t] = ds;
+    if (part == 0) p.dscore[(long long)b * p.s_ds + t] = ds;
   }
   __syncthreads();
-  const float* kb = p.keys + (size_t)b * Tm * Ud;
   if (p.type == PLAS_ATT_BAHDANAU) {
     float* dkb = p.dkeys + (size_t)b * Tm * Ud;
-    for (int u = tid; u < Ud; u += 512) {
+    for (int uu = tid; uu < uper; uu += 256) {
+      const int u = u_lo + uu;
       const float pqu = p.pq[(long long)b * p.s_pq + u];
       const float vu = p.v_att[u];
       float dpq = 0.f, dv = 0.f;
       for (int t = 0; t < len; ++t) {
-        const float e = tanhf(kb[(size_t)t * Ud + u] + pqu);
+        const float kv = p.staged ? s_keys[(size_t)t * uper + uu] : kb[(size_t)t * Ud + u];
+        const float e = tanhf(kv + pqu);
         const float dpre = s_da[t] * vu * (1.f - e * e);
         dpq += dpre;
         dkb[(size_t)t * Ud + u] += dpre;
         dv = fmaf(s_da[t], e, dv);
       }
-      s_dpq[u] = dpq;
       p.dpq[(long long)b * p.s_dpq + u] = dpq;
       p.dv_acc[(size_t)b * Ud + u] += dv;
+      for (int r = 0; r < NS; ++r) {
+        float* remote = NS > 1 ? cluster.map_shared_rank(s_dpq, r) : s_dpq;
+        remote[u] = dpq;
+      }
     }
-    __syncthreads();
-    for (int k = warp; k < Ud; k += 16) {  // dq[k] = sum_u dpq[u] W_query[k][u]
+    if (NS > 1) cluster.sync(); else __syncthreads();
+    for (int kk = warp; kk < uper; kk += 8) {  // dq[k] = sum_u dpq[u] W_query[k][u]
+      const int k = u_lo + kk;
       float s = 0.f;
       const float* wr = p.w_query + (size_t)k * Ud;
       for (int u = lane; u < Ud; u += 32) s = fmaf(s_dpq[u], __ldg(wr + u), s);
@@ -310,11 +415,20 @@ __global__ void __launch_bounds__(512) dec_att_bwd_kernel(AttBwdArgs p) {
       if (lane == 0) p.dq[(long long)b * p.s_dq + k] = s;
     }
   } else {
-    for (int u = tid; u < Ud; u += 512) {
-      float s = 0.f;
+    for (int uu = tid; uu < uper; uu += 256) {
+      float s0 = 0.f, s1 = 0.f;
+      if (p.staged) {
+        int t = 0;
+        for (; t + 2 <= len; t += 2) {
+          s0 = fmaf(s_da[t], s_keys[(size_t)t * uper + uu], s0);
+          s1 = fmaf(s_da[t + 1], s_keys[(size_t)(t + 1) * uper + uu], s1);
+        }
+        if (t < len) s0 = fmaf(s_da[t], s_keys[(size_t)t * uper + uu], s0);
+      } else {
 #pragma unroll 8
-      for (int t = 0; t < len; ++t) s = fmaf(s_da[t], kb[(size_t)t * Ud + u], s);
-      p.dq[(long long)b * p.s_dq + u] = s;
+        for (int t = 0; t < len; ++t) s0 = fmaf(s_da[t], kb[(size_t)t * Ud + u_lo + uu], s0);
+      }
+      p.dq[(long long)b * p.s_dq + u_lo + uu] = s0 + s1;
     }
   }
 }
@@ -362,34 +476,48 @@ struct GemvTArgs {
   float* dinp; long long s_o;
 };
 
+constexpr int GV_NC = 1024;  // reduction chunk staged per pass
+
 __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
   extern __shared__ __align__(16) float gv_smem[];
-  float4* s_w = reinterpret_cast<float4*>(gv_smem);  // [8][N/4] the CTA's 8 weight rows
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k0 = blockIdx.x * 8;
   const int b0 = blockIdx.y * DT_ROWS;
-  const int b = min(b0 + lane, p.B - 1);
-  const int N4 = p.N / 4;
-  for (int i = threadIdx.x; i < 8 * N4; i += 256) {
-    const int kk = i / N4, q = i - kk * N4;
-    const int k = min(k0 + kk, p.K - 1);
-    s_w[i] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)k * p.N) + q);
-  }
-  const int per = (N4 + 7) / 8;
-  const int q_lo = warp * per, q_hi = min(N4, q_lo + per);
+  const int nc_max = min(p.N, GV_NC);
+  const int AS = nc_max + 4;
+  float* s_a = gv_smem;                      // [32][AS] dz rows
+  float* s_w = s_a + (size_t)DT_ROWS * AS;   // [8][nc] the CTA's 8 weight rows
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float4* zrow = reinterpret_cast<const float4*>(p.dz + (long long)b * p.s_z);
-  __syncthreads();
-#pragma unroll 8
-  for (int q = q_lo; q < q_hi; ++q) {
-    const float4 a = zrow[q];
+  for (int n0 = 0; n0 < p.N; n0 += GV_NC) {
+    const int nc = min(GV_NC, p.N - n0);
+    const int nq = nc / 4;
+    if (n0 > 0) __syncthreads();
+    for (int i = threadIdx.x; i < DT_ROWS * nq; i += 256) {
+      const int r = i / nq, q = i - r * nq;
+      const int b = min(b0 + r, p.B - 1);
+      cp_async16(s_a + (size_t)r * AS + 4 * q, p.dz + (long long)b * p.s_z + n0 + 4 * q);
+    }
+    for (int i = threadIdx.x; i < 8 * nq; i += 256) {
+      const int kk = i / nq, q = i - kk * nq;
+      const int k = min(k0 + kk, p.K - 1);
+      cp_async16(s_w + (size_t)kk * nc + 4 * q, p.w + (size_t)k * p.N + n0 + 4 * q);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int per = (nq + 7) / 8;
+    const int q_lo = warp * per, q_hi = min(nq, q_lo + per);
+    const float* arow = s_a + (size_t)lane * AS;
+#pragma unroll 4
+    for (int q = q_lo; q < q_hi; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(arow + 4 * q);
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const float4 w = s_w[kk * N4 + q];
-      acc[kk] = fmaf(a.x, w.x, acc[kk]);
-      acc[kk] = fmaf(a.y, w.y, acc[kk]);
-      acc[kk] = fmaf(a.z, w.z, acc[kk]);
-      acc[kk] = fmaf(a.w, w.w, acc[kk]);
+      for (int kk = 0; kk < 8; ++kk) {
+        const float4 w = *reinterpret_cast<const float4*>(s_w + (size_t)kk * nc + 4 * q);
+        acc[kk] = fmaf(a.x, w.x, acc[kk]);
+        acc[kk] = fmaf(a.y, w.y, acc[kk]);
+        acc[kk] = fmaf(a.z, w.z, acc[kk]);
+        acc[kk] = fmaf(a.w, w.w, acc[kk]);
+      }
     }
   }
   __syncthreads();
@@ -476,7 +604,7 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   PLAS_REQUIRE(d->Ud % 8 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 8, D=%d of 4", d->Ud, d->D);
   PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU,
                "dec_train: attention_type %d has no training path (luong, bahdanau)", d->attention_type);
-  PLAS_REQUIRE((size_t)(d->D + d->Tm + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
+  PLAS_REQUIRE((size_t)(d->D + 5 * (d->Tm + 4) + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
   const DecTrainWs w = dec_train_ws(*d);
   PLAS_REQUIRE(ws_bytes >= w.total, "dec_train: workspace %zu < %zu", ws_bytes, w.total);
   return PLAS_OK;
@@ -508,13 +636,16 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   if (rc) return rc;
   PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
   for (int l = 0; l < L; ++l) PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
-  const int upc = (Ud / 4 >= 100) ? 4 : 2;
-  PLAS_REQUIRE((size_t)(D + Ud) * 16 * upc <= 200 * 1024, "dec_train_fwd: D + Ud = %d too large for the staged weight slice", D + Ud);
-  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int upc = 2;  // 32 rows x (1280 + 4) activations + 1280 x 8 weights = 205 KB of shared memory
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   const dim3 cgrid(Ud / upc, (B + DT_ROWS - 1) / DT_ROWS);
-  const int dsplit = D >= 512 ? 4 : 1;
-  const size_t att_smem = (size_t)(2 * Ud + Tm) * 4;
+  const int dsplit = (D >= 512 && D % 16 == 0) ? 4 : 1;
+  size_t att_smem = (size_t)(2 * Ud + ((Tm + 3) & ~3)) * 4;
+  const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
+  const int att_staged = (Ud % 4 == 0 && (D / dsplit) % 4 == 0 && att_smem + att_stage <= 220 * 1024) ? 1 : 0;
+  if (att_staged) att_smem += att_stage;
+  PLAS_CUDA(cudaFuncSetAttribute(dec_att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   for (int t = 0; t < S; ++t) {
     for (int l = 0; l < L; ++l) {
       CellFwdArgs a;
@@ -534,13 +665,14 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
       a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
-      const size_t need = (size_t)(a.K1 + a.K2) * 4 * upc * 4, red = (size_t)8 * 4 * upc * (DT_ROWS + 1) * 4;
+      const int kcm = (a.K1 + a.K2) < CF_KC ? (a.K1 + a.K2) : CF_KC;
+      const size_t need = (size_t)DT_ROWS * (kcm + 4) * 4 + (size_t)kcm * 4 * upc * 4, red = (size_t)8 * 4 * upc * (DT_ROWS + 1) * 4;
       const size_t smem = need > red ? need : red;
       if (upc == 4) dec_cell_fwd_kernel<4><<<cgrid, 256, smem, st>>>(a);
       else dec_cell_fwd_kernel<2><<<cgrid, 256, smem, st>>>(a);
     }
     AttFwdArgs q;
-    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit;
+    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit; q.staged = att_staged;
     q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
     q.query = F(w.h[L - 1]) + (size_t)t * Ud; q.s_q = (long long)S * Ud;
     q.w_query = d->w_query; q.v_att = d->v_att;
@@ -577,17 +709,21 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
     PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
   }
-  const size_t attb_smem = (size_t)(D + Tm + Ud) * 4;
-  PLAS_CUDA(cudaFuncSetAttribute(dec_att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const int ns = (D % 16 == 0 && Ud % 16 == 0 && D >= 256) ? 4 : 1;
+  const int Tp = (Tm + 3) & ~3;
+  size_t attb_smem = (size_t)(D / ns + (ns + 1) * Tp + Ud) * 4;
+  const size_t attb_stage = (size_t)Tm * (D / ns + Ud / ns) * 4;
+  const int attb_staged = ((D / ns) % 4 == 0 && (Ud / ns) % 4 == 0 && attb_smem + attb_stage <= 220 * 1024) ? 1 : 0;
+  if (attb_staged) attb_smem += attb_stage;
+  PLAS_CUDA(cudaFuncSetAttribute(dec_att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   PLAS_CUDA(cudaFuncSetAttribute(dec_gemv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  PLAS_REQUIRE((size_t)32 * Ud * 4 <= 200 * 1024, "dec_train_bwd: Ud = %d too large", Ud);
   float* sk = F(w.splitk);
   const size_t skb = w.splitk_bytes;
   const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud;
   for (int t = S - 1; t >= 0; --t) {
     const bool last = t == S - 1;
     AttBwdArgs q;
-    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type;
+    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.nsplit = ns; q.staged = attb_staged;
     q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
     q.dctx = dctx + (size_t)t * D; q.s_dc = (long long)S * D;
@@ -596,7 +732,21 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     q.dq = F(w.dq); q.s_dq = Ud;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
     q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
-    dec_att_bwd_kernel<<<B, 512, attb_smem, st>>>(q);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(B, ns);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = attb_smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = (unsigned)ns;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_att_bwd_kernel, q));
+    }
     for (int l = L - 1; l >= 0; --l) {
       const int Kin = (l == 0 ? D : Ud);
       CellBwdArgs c;
@@ -613,7 +763,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       g.dz = c.z; g.s_z = sz;
       g.w = d->kernel[l] + (size_t)(l == 0 ? E : 0) * 4 * Ud;
       g.dinp = F(w.dinp[l]); g.s_o = Kin + Ud;
-      const size_t gsm = (size_t)8 * g.N * 4 > (size_t)64 * (DT_ROWS + 1) * 4 ? (size_t)8 * g.N * 4 : (size_t)64 * (DT_ROWS + 1) * 4;
+      const int ncm = g.N < GV_NC ? g.N : GV_NC;
+      const size_t gsm = (size_t)DT_ROWS * (ncm + 4) * 4 + (size_t)8 * ncm * 4;
       dec_gemv_t_kernel<<<dim3((g.K + 7) / 8, (B + DT_ROWS - 1) / DT_ROWS), 256, gsm, st>>>(g);
     }
   }

@@ -5,13 +5,14 @@
 //                      transposed copies of the weights exist on the training path;  grid.z batches independent
 //                      problems (per-utterance dkeys / dvalues of the attention backward).
 //   plas_colsum_f32    bias gradients (column sums, fixed order).
-// 128x64x16 tiles, 256 threads, 8x4 register micro-tile, tile loads walk whichever operand dimension is contiguous.
+// 128x128x16 (or 128x64x16) tiles, 256 threads, 8x8 (8x4) register micro-tile, double-buffered shared memory; operand
+// tiles are fetched with 16-byte loads along whichever dimension is contiguous (scalar fallback for odd shapes).
 #include "common.cuh"
 #include "../../include/plas.h"
 
 namespace plas {
 
-constexpr int TG_BM = 128, TG_BN = 64, TG_BK = 16;
+constexpr int TG_BM = 128, TG_BK = 16;
 
 struct GemmExArgs {
   long long M;
@@ -28,60 +29,116 @@ struct GemmExArgs {
   int split_k;       // > 1: blockIdx.z is a K slice, partial products go to split_ws[z][M][N]
   int k_chunk;       // K elements per slice (multiple of TG_BK)
   float* split_ws;
+  int a_vec, b_vec;  // operand tiles can be fetched with aligned 16-byte loads along their contiguous dimension
 };
 
-__global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
+// BN = 128: 8x8 register micro-tile (64 FMA per 4 LDS.128);  BN = 64: 8x4 (narrow outputs: vocabulary, features).
+template <int BN, bool VEC>
+__global__ void __launch_bounds__(256, 2) gemm_f32_ex_kernel(GemmExArgs p) {
+  constexpr int TN = BN / 16;  // columns per thread (8 or 4), as TN/4 groups of 4 that are 64 columns apart
   __shared__ __align__(16) float sA[2][TG_BK][TG_BM + 4];
-  __shared__ __align__(16) float sB[2][TG_BK][TG_BN + 4];
+  __shared__ __align__(16) float sB[2][TG_BK][BN + 4];
   const int tid = threadIdx.x;
   const long long m0 = (long long)blockIdx.y * TG_BM;
-  const int n0 = blockIdx.x * TG_BN;
+  const int n0 = blockIdx.x * BN;
   const bool split = p.split_k > 1;
   const float* __restrict__ A = p.A + (split ? 0 : (long long)blockIdx.z * p.batch_a);
   const float* __restrict__ B = p.B + (split ? 0 : (long long)blockIdx.z * p.batch_b);
   float* __restrict__ C = split ? p.split_ws + (long long)blockIdx.z * p.M * p.N : p.C + (long long)blockIdx.z * p.batch_c;
   const int k_begin = split ? blockIdx.z * p.k_chunk : 0;
   const int k_end = split ? min(p.K, k_begin + p.k_chunk) : p.K;
-  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads; thread tile = rows ty*8.., cols tx*4..
+  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads; thread tile = rows ty*8.., cols tx*4 (+64)
   const bool a_kfast = p.sak == 1;         // consecutive threads walk k (A row-major) or m (A^T view)
   const bool b_nfast = p.sbn == 1;
-  float acc[8][4] = {};
-  float ra[8], rb[4];
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float4 ra[VEC ? 2 : 1], rb[VEC ? BN / 64 : 1];
+  float sa_[VEC ? 1 : 8], sb_[VEC ? 1 : BN / 16];  // scalar staging (unaligned / odd-sized operands)
 
   auto load_tile = [&](int k0) {
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = tid + j * 256;
-      int r, c;
-      if (a_kfast) { r = i / TG_BK; c = i % TG_BK; } else { c = i / TG_BM; r = i % TG_BM; }
-      const long long gm = m0 + r;
-      const int gk = k0 + c;
-      ra[j] = (gm < p.M && gk < k_end) ? A[gm * p.sam + gk * p.sak] : 0.f;
+      for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * 256;
+        long long gm; int gk;
+        if (a_kfast) { gm = m0 + (i >> 2); gk = k0 + 4 * (i & 3); } else { gk = k0 + (i >> 5); gm = m0 + 4 * (i & 31); }
+        ra[j] = (gm < p.M && gk < k_end) ? *reinterpret_cast<const float4*>(A + gm * p.sam + gk * p.sak) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = tid + j * 256;
+        int r, c;
+        if (a_kfast) { r = i / TG_BK; c = i % TG_BK; } else { c = i / TG_BM; r = i % TG_BM; }
+        const long long gm = m0 + r;
+        const int gk = k0 + c;
+        sa_[j] = (gm < p.M && gk < k_end) ? A[gm * p.sam + gk * p.sak] : 0.f;
+      }
     }
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = tid + j * 256;
-      int r, c;  // r = n index, c = k index
-      if (b_nfast) { c = i / TG_BN; r = i % TG_BN; } else { r = i / TG_BK; c = i % TG_BK; }
-      const int gn = n0 + r;
-      const int gk = k0 + c;
-      rb[j] = (gn < p.N && gk < k_end) ? B[gk * p.sbk + gn * p.sbn] : 0.f;
+      for (int j = 0; j < BN / 64; ++j) {
+        const int i = tid + j * 256;
+        int gn, gk;
+        if (b_nfast) { gk = k0 + i / (BN / 4); gn = n0 + 4 * (i % (BN / 4)); } else { gn = n0 + (i >> 2); gk = k0 + 4 * (i & 3); }
+        rb[j] = (gn < p.N && gk < k_end) ? *reinterpret_cast<const float4*>(B + (long long)gk * p.sbk + (long long)gn * p.sbn)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        const int i = tid + j * 256;
+        int r, c;  // r = n index, c = k index
+        if (b_nfast) { c = i / BN; r = i % BN; } else { r = i / TG_BK; c = i % TG_BK; }
+        const int gn = n0 + r;
+        const int gk = k0 + c;
+        sb_[j] = (gn < p.N && gk < k_end) ? B[(long long)gk * p.sbk + (long long)gn * p.sbn] : 0.f;
+      }
     }
   };
   auto store_tile = [&](int buf) {
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = tid + j * 256;
-      int r, c;
-      if (a_kfast) { r = i / TG_BK; c = i % TG_BK; } else { c = i / TG_BM; r = i % TG_BM; }
-      sA[buf][c][r] = ra[j];
+      for (int j = 0; j < 2; ++j) {
+        const int i = tid + j * 256;
+        if (a_kfast) {
+          const int r = i >> 2, c = 4 * (i & 3);
+          sA[buf][c][r] = ra[j].x; sA[buf][c + 1][r] = ra[j].y; sA[buf][c + 2][r] = ra[j].z; sA[buf][c + 3][r] = ra[j].w;
+        } else {
+          *reinterpret_cast<float4*>(&sA[buf][i >> 5][4 * (i & 31)]) = ra[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = tid + j * 256;
+        int r, c;
+        if (a_kfast) { r = i / TG_BK; c = i % TG_BK; } else { c = i / TG_BM; r = i % TG_BM; }
+        sA[buf][c][r] = sa_[j];
+      }
     }
+    if (VEC) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = tid + j * 256;
-      int r, c;
-      if (b_nfast) { c = i / TG_BN; r = i % TG_BN; } else { r = i / TG_BK; c = i % TG_BK; }
-      sB[buf][c][r] = rb[j];
+      for (int j = 0; j < BN / 64; ++j) {
+        const int i = tid + j * 256;
+        if (b_nfast) {
+          *reinterpret_cast<float4*>(&sB[buf][i / (BN / 4)][4 * (i % (BN / 4))]) = rb[j];
+        } else {
+          const int r = i >> 2, c = 4 * (i & 3);
+          sB[buf][c][r] = rb[j].x; sB[buf][c + 1][r] = rb[j].y; sB[buf][c + 2][r] = rb[j].z; sB[buf][c + 3][r] = rb[j].w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        const int i = tid + j * 256;
+        int r, c;
+        if (b_nfast) { c = i / BN; r = i % BN; } else { r = i / TG_BK; c = i % TG_BK; }
+        sB[buf][c][r] = sb_[j];
+      }
     }
   };
 
@@ -96,13 +153,17 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
     for (int k = 0; k < TG_BK; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8]);
       const float4 a1 = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 8 + 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 4]);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+      float b[TN];
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        const float4 bv = *reinterpret_cast<const float4*>(&sB[buf][k][tx * 4 + 64 * g]);
+        b[4 * g] = bv.x; b[4 * g + 1] = bv.y; b[4 * g + 2] = bv.z; b[4 * g + 3] = bv.w;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     if (kt + 1 < n_tiles) store_tile(buf ^ 1);
     __syncthreads();
@@ -112,8 +173,8 @@ __global__ void __launch_bounds__(256) gemm_f32_ex_kernel(GemmExArgs p) {
     const long long gm = m0 + ty * 8 + i;
     if (gm >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * 4 + 64 * (j / 4) + (j % 4);
       if (gn >= p.N) continue;
       if (split) {
         C[gm * p.N + gn] = acc[i][j];
@@ -178,7 +239,19 @@ extern "C" int plas_gemm_f32_ex(const plas_gemm_ex_desc* d, plas_stream_t stream
   a.batch_a = d->batch_a; a.batch_b = d->batch_b; a.batch_c = d->batch_c;
   const long long gy = (d->M + TG_BM - 1) / TG_BM;
   PLAS_REQUIRE(gy <= 65535 && d->batch <= 65535, "gemm_ex: M or batch too large");
-  const long long gx = (d->N + TG_BN - 1) / TG_BN;
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+  // 16-byte operand fetches: contiguous dimension with a multiple-of-4 extent, every row / batch start aligned
+  if (d->sak == 1) a.a_vec = d->K % 4 == 0 && d->sam % 4 == 0;
+  else if (d->sam == 1) a.a_vec = d->M % 4 == 0 && d->sak % 4 == 0;
+  else a.a_vec = 0;
+  a.a_vec = a.a_vec && al16(d->A) && d->batch_a % 4 == 0;
+  if (d->sbn == 1) a.b_vec = d->N % 4 == 0 && d->sbk % 4 == 0;
+  else if (d->sbk == 1) a.b_vec = d->K % 4 == 0 && d->sbn % 4 == 0;
+  else a.b_vec = 0;
+  a.b_vec = a.b_vec && al16(d->B) && d->batch_b % 4 == 0;
+  const bool vec = a.a_vec && a.b_vec;
+  const int BN = (vec && d->N > 64) ? 128 : 64;
+  const long long gx = (d->N + BN - 1) / BN;
   // deterministic split-K for long reductions over few output tiles (weight gradients: K = B*T rows)
   int split = 1;
   if (d->split_ws && d->batch == 1 && d->K >= 512) {
@@ -198,7 +271,9 @@ extern "C" int plas_gemm_f32_ex(const plas_gemm_ex_desc* d, plas_stream_t stream
     a.split_k = (d->K + a.k_chunk - 1) / a.k_chunk;
   }
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)(a.split_k > 1 ? a.split_k : d->batch));
-  gemm_f32_ex_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  if (BN == 128) gemm_f32_ex_kernel<128, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else if (vec) gemm_f32_ex_kernel<64, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else gemm_f32_ex_kernel<64, false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   if (a.split_k > 1) {
     const long long total = d->M * d->N;
     const int blocks = (int)((total + 255) / 256 < 4LL * num_sms() ? (total + 255) / 256 : 4LL * num_sms());

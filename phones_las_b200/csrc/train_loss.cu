@@ -268,9 +268,22 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long long n, float alpha) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(alpha, x[i], y[i]);
+}
+
 }  // namespace plas
 
 using namespace plas;
+
+extern "C" int plas_axpy_f32(float* y, const float* x, int64_t n, float alpha, plas_stream_t stream_) {
+  PLAS_REQUIRE(y && x && n > 0, "axpy: bad argument");
+  const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
+  axpy_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(y, x, n, alpha);
+  PLAS_CUDA(cudaGetLastError());
+  return PLAS_OK;
+}
 
 extern "C" int plas_seq_ce_grad(const float* logits, const int32_t* targets, const float* weights, int64_t n_tokens,
                                 int32_t V, float gscale, float* ce_tokens, float* out3, float* dlogits, plas_stream_t stream_) {

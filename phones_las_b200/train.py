@@ -74,6 +74,12 @@ class TrainState:
         self.index = {k: i for i, k in enumerate(self.names)}
         self.split_ws = torch.empty((32 << 20,), dtype=torch.uint8, device=device)  # split-K scratch of the dW GEMMs
         self.step = 0
+        self._streams = []
+
+    def side_streams(self, n):
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.params.device))
+        return self._streams[:n]
 
     def has(self, name):
         return name in self.index
@@ -324,24 +330,36 @@ def forward_backward(features, labels, st, hp, binf=None):
     w = _seq_mask(tlen, S)
     d_enc = torch.zeros_like(enc_out)
     parts = {}
-    total = None
-    spellers = []
+    # the heads only share the encoder outputs: each speller (forward, loss, backward) runs on its own stream while the
+    # CTC head runs on the caller's, each accumulating into its own encoder-output gradient buffer
+    jobs = []
     if not hp.get("binary_outputs") or hp.get("multitask"):
-        sp = SpellerTrain(st, hp, "speller", V, V)
-        logits = sp.forward(enc_out, enc_len, torch.nn.functional.one_hot(tin, V).to(torch.float32))
-        parts["ce"], dl = seq_ce_grad(logits, tout, w)
-        parts["logits"] = logits
-        spellers.append((sp, dl))
-        total = parts["ce"]
+        jobs.append(("speller", "ce", V, torch.nn.functional.one_hot(tin, V).to(torch.float32), None))
     if hp.get("binary_outputs"):
         bt = binf.to(device=dev, dtype=torch.float32).t().contiguous()  # [V, n]
-        n = bt.shape[1]
-        sp = SpellerTrain(st, hp, "speller_binf", n, n)
-        logits_b = sp.forward(enc_out, enc_len, bt[tin])
-        parts["ce_binf"], dlb = sigmoid_ce_grad(logits_b, bt[tout.long()].contiguous(), w)
-        parts["logits_binf"] = logits_b
-        spellers.append((sp, dlb))
-        total = parts["ce_binf"] if total is None else total + parts["ce_binf"]
+        jobs.append(("speller_binf", "ce_binf", bt.shape[1], bt[tin], bt[tout.long()].contiguous()))
+    main = torch.cuda.current_stream()
+    d_enc_heads = [torch.zeros_like(enc_out) for _ in jobs]  # zero-filled on the caller's stream BEFORE the fork event
+    ready = torch.cuda.Event()
+    ready.record(main)
+    side = st.side_streams(len(jobs))
+    pending = []
+    for (scope, key, n_out, x_in, lab), stream, d_enc_j in zip(jobs, side, d_enc_heads):
+        with torch.cuda.stream(stream):
+            stream.wait_event(ready)
+            sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out)
+            logits = sp.forward(enc_out, enc_len, x_in)
+            if lab is None:
+                parts[key], dl = seq_ce_grad(logits, tout, w)
+                parts["logits"] = logits
+            else:
+                parts[key], dl = sigmoid_ce_grad(logits, lab, w)
+                parts["logits_binf"] = logits
+            sp.backward(dl, d_enc_j)
+            done = torch.cuda.Event()
+            done.record(stream)
+        pending.append((d_enc_j, done, sp))
+    total = None
     if hp.get("ctc_weight", -1.0) > 0:  # model_helper.py:347-358
         cw = float(hp["ctc_weight"])
         Cn = V + 1
@@ -349,26 +367,37 @@ def forward_backward(features, labels, st, hp, binf=None):
         gemm_ex(B * Tm, Cn, D, enc_out.data_ptr(), D, 1, st.w("ctc_logits/kernel"), Cn, 1, cl.data_ptr(), Cn, bias=st.w("ctc_logits/bias"))
         per_utt, dcl = ctc_grad(cl, tout, tlen, enc_len, gscale=cw / B)
         parts["ctc"] = per_utt.mean()
-        total = parts["ctc"] * cw if total is None else total + parts["ctc"] * cw
+        total = parts["ctc"] * cw
         gemm_ex(D, Cn, B * Tm, enc_out.data_ptr(), 1, D, dcl.data_ptr(), Cn, 1, st.g("ctc_logits/kernel"), Cn, split_ws=st.split_ws)
         colsum(dcl.data_ptr(), B * Tm, Cn, Cn, st.g("ctc_logits/bias"))
         gemm_ex(B * Tm, D, Cn, dcl.data_ptr(), Cn, 1, st.w("ctc_logits/kernel"), 1, Cn, d_enc.data_ptr(), D, beta=1.0)
-    for sp, dl in spellers:
-        sp.backward(dl, d_enc)
+    for (d_enc_j, done, _), (_, key, _, _, _) in zip(pending, jobs):
+        main.wait_event(done)
+        _lib.check(_lib.lib().plas_axpy_f32(_lib.ptr(d_enc), _lib.ptr(d_enc_j), d_enc.numel(), 1.0, _lib.stream_ptr()))
+        _lib.count_launches(1)
+        total = parts[key] if total is None else total + parts[key]
     listener_train_bwd(d_enc, tape, st, hp)
     parts["audio_loss"] = total
     parts["encoder_out"] = enc_out
     return parts
 
 
-def apply_gradients(st, hp, world_size=1, allreduce=None):
-    """model_helper.py:404-417: g += l2*w; per-tensor clip_by_norm(2); [mean over ranks]; Adam."""
+def regularise_and_clip(st, hp, world_size=1):
+    """g += l2*w (model_helper.py:411-413); per-tensor clip_by_norm(g, 2) (:416); pre-scale by 1/world for the cross-rank mean."""
     L = _lib.lib()
     n = len(st.names)
     _lib.check(L.plas_grad_l2_norm(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.offsets), n, float(hp.get("l2_reg_scale", 0.0)),
                                    _lib.ptr(st.norms), _lib.ptr(st.wsq), _lib.stream_ptr()))
     _lib.check(L.plas_clip_scale(_lib.ptr(st.grads), _lib.ptr(st.offsets), n, _lib.ptr(st.norms), GRAD_NORM, 1.0 / world_size,
                                  _lib.stream_ptr()))
+    _lib.count_launches(2)
+
+
+def apply_gradients(st, hp, world_size=1, allreduce=None, clipped=False):
+    """model_helper.py:404-417: g += l2*w; per-tensor clip_by_norm(2); [mean over ranks]; Adam."""
+    L = _lib.lib()
+    if not clipped:
+        regularise_and_clip(st, hp, world_size)
     if allreduce is not None:
         allreduce(st.grads)  # sum of (clipped / world_size) = CrossShardOptimizer's mean
     st.step += 1
@@ -376,7 +405,7 @@ def apply_gradients(st, hp, world_size=1, allreduce=None):
     lr_t = float(hp["learning_rate"]) * (1.0 - b2 ** st.step) ** 0.5 / (1.0 - b1 ** st.step)
     _lib.check(L.plas_adam_step(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.m), _lib.ptr(st.v), st.total, lr_t, b1, b2, eps,
                                 1.0, _lib.stream_ptr()))
-    _lib.count_launches(3)
+    _lib.count_launches(1)
 
 
 def train_step(features, labels, st, hp, binf=None, world_size=1, allreduce=None):
@@ -386,6 +415,44 @@ def train_step(features, labels, st, hp, binf=None, world_size=1, allreduce=None
     reg = st.wsq.sum() * (0.5 * float(hp.get("l2_reg_scale", 0.0)))  # L2 term of the PRE-update weights
     parts["loss"] = parts["audio_loss"] + reg
     return parts
+
+
+class GraphedTrainStep:
+    """The training step captured once in a CUDA graph (the ~500 small launches of a step -- per-step decoder kernels on
+    two streams, GEMMs, persistent recurrences -- replay without host involvement).  Shapes (B, T, S) are those of the
+    example batch; lengths and values may change freely between replays.  Adam's step-dependent learning rate and the
+    data-parallel all-reduce stay outside the graph."""
+
+    def __init__(self, features, labels, st, hp, binf=None, world_size=1, allreduce=None):
+        self.st, self.hp, self.world, self.allreduce = st, hp, world_size, allreduce
+        self.f = {k: v.clone() for k, v in features.items()}
+        self.l = {k: v.clone() for k, v in labels.items()}
+        self.binf = binf
+        warm = torch.cuda.Stream(device=st.params.device)
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):  # one eager pass: function attributes set, allocator primed, side streams created
+            forward_backward(self.f, self.l, st, hp, binf)
+            regularise_and_clip(st, hp, world_size)
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count
+        with torch.cuda.graph(self.graph):
+            self.parts = forward_backward(self.f, self.l, st, hp, binf)
+            regularise_and_clip(st, hp, world_size)
+        self.launches_per_replay = _lib.launch_count - n0
+
+    def __call__(self, features, labels):
+        for k, v in features.items():
+            self.f[k].copy_(v, non_blocking=True)
+        for k, v in labels.items():
+            self.l[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        _lib.count_launches(self.launches_per_replay)
+        apply_gradients(self.st, self.hp, self.world, self.allreduce, clipped=True)
+        parts = dict(self.parts)
+        parts["loss"] = parts["audio_loss"] + self.st.wsq.sum() * (0.5 * float(self.hp.get("l2_reg_scale", 0.0)))
+        return parts
 
 
 def train_variable_shapes(hp, num_channels=None, binf_count=0):

@@ -31,6 +31,15 @@ for _ in range(5):
     tr.train_step(feats, labels, st, hp, binf)
 torch.cuda.synchronize()
 print("eager ms/step", (time.perf_counter() - t0) / 5 * 1e3)
+g = tr.GraphedTrainStep(feats, labels, st, hp, binf)
+for _ in range(3):
+    g(feats, labels)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(10):
+    g(feats, labels)
+torch.cuda.synchronize()
+print("graphed ms/step", (time.perf_counter() - t0) / 10 * 1e3, "launches/replay", g.launches_per_replay)
 _lib.timeline_start()
 tr.train_step(feats, labels, st, hp, binf)
 tl = _lib.timeline_stop()

@@ -226,3 +226,32 @@ def test_train_steps_match_autograd_adam(cfg):
         for k in params:
             diff = np.abs(got[k] - ref_p[k].numpy())
             assert diff.max() < 1e-4 and diff.mean() < 1e-6, f"step {step} param {k}: max {diff.max():.3e} mean {diff.mean():.3e}"
+
+
+@gpu
+def test_graphed_step_equals_eager_step():
+    """The CUDA-graph replay of the step must leave bit-identical parameters to the eager step (same kernels, same order)."""
+    import torch
+    from phones_las_b200 import train as tr
+    hp, params, x, lens, tin, tout, tlen, binf = _full_setup(*FULL_CFGS[2])
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    binf_d = torch.from_numpy(binf).cuda()
+    st_e, st_g = tr.TrainState(params), tr.TrainState(params)
+    graphed = tr.GraphedTrainStep(feats, labels, st_g, hp, binf_d)
+    st_g.grads.zero_()
+    for _ in range(3):
+        pe = tr.train_step(feats, labels, st_e, hp, binf_d)
+        pg = graphed(feats, labels)
+    torch.cuda.synchronize()
+    assert pe["loss"].item() == pg["loss"].item()
+    assert torch.equal(st_e.params, st_g.params)
+    # a different batch of the same shape through the same graph
+    x2 = torch.from_numpy(x[::-1].copy()).cuda()
+    l2 = torch.from_numpy(lens[::-1].copy()).cuda()
+    f2 = {"encoder_inputs": x2, "source_sequence_length": l2}
+    pe = tr.train_step(f2, labels, st_e, hp, binf_d)
+    pg = graphed(f2, labels)
+    torch.cuda.synchronize()
+    assert pe["loss"].item() == pg["loss"].item() and torch.equal(st_e.params, st_g.params)
