@@ -46,7 +46,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr int CF_KC = 1280;  // reduction chunk staged per pass (activations 32 x KC + weights KC x 4*UPC in smem)
+constexpr int CF_KC = 640;   // reduction chunk staged per pass (activations 32 x KC + weights KC x 4*UPC in smem)
 
 // CTA = UPC units (4*UPC gate columns) x 32 batch rows.  Per pass the CTA stages a KC-wide chunk of the 32
 // activation rows and of its weight slice in shared memory with one wave of independent 16-byte cp.async copies
@@ -476,7 +476,7 @@ struct GemvTArgs {
   float* dinp; long long s_o;
 };
 
-constexpr int GV_NC = 1024;  // reduction chunk staged per pass
+constexpr int GV_NC = 512;   // reduction chunk staged per pass
 
 __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
   extern __shared__ __align__(16) float gv_smem[];

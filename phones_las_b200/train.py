@@ -173,6 +173,7 @@ def listener_train_bwd(d_enc, tape, st, hp):
     U, ndir = hp["encoder_units"], 2
     B = d_enc.shape[0]
     dout = d_enc
+    side = st.side_streams(3)[2]
     for l in range(hp["encoder_layers"] - 1, -1, -1):
         tp = tape[l]
         T, din = tp["T"], tp["din"]
@@ -186,19 +187,29 @@ def listener_train_bwd(d_enc, tape, st, hp):
         _lib.count_launches(1)
         z, x, hp_ = tp["z"], tp["x"], tp["h_prev"]
         M = B * T
-        dx = torch.empty((B, T, din), dtype=torch.float32, device=z.device) if l > 0 else None
-        with _lib.stage("train_wgrad"):
-            for dd, nm in enumerate(names):
-                zp = _p(z, dd * 4 * U)
-                gemm_ex(din, 4 * U, M, x.data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
-                gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U, split_ws=st.split_ws)
-                colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))
-        if l > 0:
+        main = torch.cuda.current_stream()
+        if l > 0:  # input gradient first: the next recurrence depends on it
+            dx = torch.empty((B, T, din), dtype=torch.float32, device=z.device)
             with _lib.stage("train_dgrad"):
                 for dd, nm in enumerate(names):
                     gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dx.data_ptr(), din,
                             beta=0.0 if dd == 0 else 1.0)
             dout = dx
+        # weight gradients on a side stream: they only need dz, and overlap the (latency-bound) recurrence of the layer below
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            with _lib.stage("train_wgrad"):
+                for dd, nm in enumerate(names):
+                    zp = _p(z, dd * 4 * U)
+                    gemm_ex(din, 4 * U, M, x.data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
+                    gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U,
+                            split_ws=st.split_ws)
+                    colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))
+    done = torch.cuda.Event()
+    done.record(side)
+    torch.cuda.current_stream().wait_event(done)
 
 
 # --------------------------------------------------------------------------------------------------------------
