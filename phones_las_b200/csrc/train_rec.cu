@@ -35,10 +35,13 @@ __device__ __forceinline__ void rt_wait(const unsigned* ctr, unsigned target) {
     if (++spins > (1u << 28)) __trap();
 }
 
-template <int R, int UPC>
+// Thread = (unit ul, block of RB rows, k-slice kh): one weight vector fetched from shared memory feeds RB rows from
+// registers, so the W_hh slice is read R/RB times per step instead of R times (with RB = 1 the step is bound by those
+// shared-memory reads: ncu short_scoreboard + barrier stalls, FMA pipe 13 % active).
+template <int R, int UPC, int RB>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainArgs p) {
-  constexpr int KS = RT_THREADS / (R * UPC);
-  static_assert(KS >= 1 && KS * R * UPC == RT_THREADS, "bad shape");
+  constexpr int NRB = R / RB, TPS = UPC * NRB, KS = RT_THREADS / TPS;
+  static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const plas_rec_train_desc& d = p.d;
   const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
 
   float4* s_w = reinterpret_cast<float4*>(rt_smem);               // [U (k)][UPC] : (i,j,f,o) columns of a unit
   float* s_h = reinterpret_cast<float*>(s_w + (size_t)U * UPC);  // [R][HS]
-  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)R * HS);  // [KS][R][UPC]
+  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)R * HS);  // [KS-1][R][UPC]
   __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
@@ -75,22 +78,26 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
 
   float* hx = p.xbuf;
   unsigned* ctr = p.counters + dir * p.n_groups + gi;
-  const int ul = tid % UPC, r = (tid / UPC) % R, kh = tid / (UPC * R);
+  const int ul = tid % UPC, r0 = ((tid / UPC) % NRB) * RB, kh = tid / TPS;
   const int unit = ci * UPC + ul;
-  const int b = row0 + r;
-  const int len = s_len[r];
   const size_t zrow = (size_t)ndir * 4 * U;
   const size_t srow = (size_t)ndir * U;
-  const int kper = U / KS;  // host guarantees U % (4*KS) == 0
-  float c_state = 0.f, h_state = 0.f;
+  const int kper = U / KS;  // host guarantees (U / KS) % 4 == 0
+  float c_state[RB], h_state[RB];
+#pragma unroll
+  for (int i = 0; i < RB; ++i) c_state[i] = h_state[i] = 0.f;
 
   for (int s = 0; s < Tg; ++s) {
-    const bool act = s < len;
-    const int t_idx = dir ? (len - 1 - s) : s;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act && kh == 0) {
-      const float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
-      acc = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
+    float4 acc[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int len = s_len[r0 + i];
+      if (kh == 0 && s < len) {
+        const int t_idx = dir ? (len - 1 - s) : s;
+        const float* zp = d.z + ((size_t)(row0 + r0 + i) * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
+        acc[i] = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
+      }
     }
     if (s > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * s));
@@ -102,45 +109,61 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
         *reinterpret_cast<float4*>(s_h + rr * HS + 4 * c4) = __ldcg(hsrc + i);
       }
       __syncthreads();
-      const float* hrow = s_h + r * HS + kh * kper;
+      const float* hrow = s_h + r0 * HS + kh * kper;
       const float4* wcol = s_w + (size_t)(kh * kper) * UPC + ul;
 #pragma unroll 2
       for (int k = 0; k < kper; k += 4) {
-        const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
         const float4 w0 = wcol[(size_t)(k + 0) * UPC], w1 = wcol[(size_t)(k + 1) * UPC];
         const float4 w2 = wcol[(size_t)(k + 2) * UPC], w3 = wcol[(size_t)(k + 3) * UPC];
-        acc.x = fmaf(hv.x, w0.x, acc.x); acc.y = fmaf(hv.x, w0.y, acc.y); acc.z = fmaf(hv.x, w0.z, acc.z); acc.w = fmaf(hv.x, w0.w, acc.w);
-        acc.x = fmaf(hv.y, w1.x, acc.x); acc.y = fmaf(hv.y, w1.y, acc.y); acc.z = fmaf(hv.y, w1.z, acc.z); acc.w = fmaf(hv.y, w1.w, acc.w);
-        acc.x = fmaf(hv.z, w2.x, acc.x); acc.y = fmaf(hv.z, w2.y, acc.y); acc.z = fmaf(hv.z, w2.z, acc.z); acc.w = fmaf(hv.z, w2.w, acc.w);
-        acc.x = fmaf(hv.w, w3.x, acc.x); acc.y = fmaf(hv.w, w3.y, acc.y); acc.z = fmaf(hv.w, w3.z, acc.z); acc.w = fmaf(hv.w, w3.w, acc.w);
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const float4 hv = *reinterpret_cast<const float4*>(hrow + i * HS + k);
+          float4& a = acc[i];
+          a.x = fmaf(hv.x, w0.x, a.x); a.y = fmaf(hv.x, w0.y, a.y); a.z = fmaf(hv.x, w0.z, a.z); a.w = fmaf(hv.x, w0.w, a.w);
+          a.x = fmaf(hv.y, w1.x, a.x); a.y = fmaf(hv.y, w1.y, a.y); a.z = fmaf(hv.y, w1.z, a.z); a.w = fmaf(hv.y, w1.w, a.w);
+          a.x = fmaf(hv.z, w2.x, a.x); a.y = fmaf(hv.z, w2.y, a.y); a.z = fmaf(hv.z, w2.z, a.z); a.w = fmaf(hv.z, w2.w, a.w);
+          a.x = fmaf(hv.w, w3.x, a.x); a.y = fmaf(hv.w, w3.y, a.y); a.z = fmaf(hv.w, w3.z, a.z); a.w = fmaf(hv.w, w3.w, a.w);
+        }
       }
       if (KS > 1) {
-        if (kh > 0) s_part[((kh - 1) * R + r) * UPC + ul] = acc;
+        if (kh > 0) {
+#pragma unroll
+          for (int i = 0; i < RB; ++i) s_part[((kh - 1) * R + r0 + i) * UPC + ul] = acc[i];
+        }
         __syncthreads();
         if (kh == 0) {
 #pragma unroll
           for (int q = 0; q < KS - 1; ++q) {
-            const float4 o = s_part[(q * R + r) * UPC + ul];
-            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+              const float4 o = s_part[(q * R + r0 + i) * UPC + ul];
+              acc[i].x += o.x; acc[i].y += o.y; acc[i].z += o.z; acc[i].w += o.w;
+            }
           }
         }
       }
     }
     if (kh == 0) {
-      if (act) {
-        const float gi_ = sigmoidf_acc(acc.x), gj = tanhf(acc.y), gf = sigmoidf_acc(acc.z + 1.0f), go = sigmoidf_acc(acc.w);
-        const float cn = gf * c_state + gi_ * gj;
-        const float hn = go * tanhf(cn);
-        const size_t bt = (size_t)b * T + t_idx;
-        float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
-        zp[0] = gi_; zp[U] = gj; zp[2 * U] = gf; zp[3 * U] = go;
-        d.c_save[bt * srow + dir * U + unit] = cn;
-        d.h_prev[bt * srow + dir * U + unit] = h_state;
-        d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit] = hn;
-        c_state = cn;
-        h_state = hn;
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int b = row0 + r0 + i;
+        const int len = s_len[r0 + i];
+        if (s < len) {
+          const int t_idx = dir ? (len - 1 - s) : s;
+          const float gi_ = sigmoidf_acc(acc[i].x), gj = tanhf(acc[i].y), gf = sigmoidf_acc(acc[i].z + 1.0f), go = sigmoidf_acc(acc[i].w);
+          const float cn = gf * c_state[i] + gi_ * gj;
+          const float hn = go * tanhf(cn);
+          const size_t bt = (size_t)b * T + t_idx;
+          float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
+          zp[0] = gi_; zp[U] = gj; zp[2 * U] = gf; zp[3 * U] = go;
+          d.c_save[bt * srow + dir * U + unit] = cn;
+          d.h_prev[bt * srow + dir * U + unit] = h_state[i];
+          d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit] = hn;
+          c_state[i] = cn;
+          h_state[i] = hn;
+        }
+        hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state[i];
       }
-      hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state;
     }
     __syncthreads();
     if (tid == 0) {
@@ -150,10 +173,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
   }
 }
 
-template <int R, int UPC>
+template <int R, int UPC, int RB>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainArgs p) {
-  constexpr int KS = RT_THREADS / (R * UPC);
-  static_assert(KS >= 1 && KS * R * UPC == RT_THREADS, "bad shape");
+  constexpr int NRB = R / RB, TPS = UPC * NRB, KS = RT_THREADS / TPS;
+  static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const plas_rec_train_desc& d = p.d;
   const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
@@ -167,7 +190,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
 
   float4* s_w = reinterpret_cast<float4*>(rt_smem);  // [U (n4)][UPC]: W_hh[unit][4*n4 .. 4*n4+3]
   float4* s_dz = s_w + (size_t)U * UPC;              // [R][ZS] float4 = [R][4U]
-  float* s_part = reinterpret_cast<float*>(s_dz + (size_t)R * ZS);  // [KS][R][UPC]
+  float* s_part = reinterpret_cast<float*>(s_dz + (size_t)R * ZS);  // [KS-1][R][UPC]
   __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
@@ -189,40 +212,51 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
 
   float* dzx = p.xbuf;
   unsigned* ctr = p.counters + dir * p.n_groups + gi;
-  const int ul = tid % UPC, r = (tid / UPC) % R, kh = tid / (UPC * R);
+  const int ul = tid % UPC, r0 = ((tid / UPC) % NRB) * RB, kh = tid / TPS;
   const int unit = ci * UPC + ul;
-  const int b = row0 + r;
-  const int len = s_len[r];
   const size_t zrow = (size_t)ndir * 4 * U;
   const size_t srow = (size_t)ndir * U;
   const int W4 = 4 * U;
   const int nper = U / KS;  // float4 chunks of the reduction per slice
 
   // the gradient GEMMs run over every (b,t) row: zero dz past each utterance's length
-  if (kh == 0 && b < B) {
-    for (int t = len; t < T; ++t) {
-      float* zp = d.z + ((size_t)b * T + t) * zrow + (size_t)dir * 4 * U + unit;
-      zp[0] = 0.f; zp[U] = 0.f; zp[2 * U] = 0.f; zp[3 * U] = 0.f;
+  if (kh == 0) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int b = row0 + r0 + i;
+      if (b >= B) continue;
+      for (int t = s_len[r0 + i]; t < T; ++t) {
+        float* zp = d.z + ((size_t)b * T + t) * zrow + (size_t)dir * 4 * U + unit;
+        zp[0] = 0.f; zp[U] = 0.f; zp[2 * U] = 0.f; zp[3 * U] = 0.f;
+      }
     }
   }
 
-  float dc_carry = 0.f;
+  float dc_carry[RB];
+#pragma unroll
+  for (int i = 0; i < RB; ++i) dc_carry[i] = 0.f;
   for (int j = 0; j < Tg; ++j) {
     const int s = Tg - 1 - j;
-    const bool act = s < len;
-    const int t_idx = dir ? (len - 1 - s) : s;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    float c_t = 0.f, c_prev = 0.f, dh = 0.f;
-    if (act && kh == 0) {
-      const size_t bt = (size_t)b * T + t_idx;
-      const float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
-      g = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
-      c_t = d.c_save[bt * srow + dir * U + unit];
-      if (s > 0) {
-        const size_t btp = (size_t)b * T + (dir ? t_idx + 1 : t_idx - 1);
-        c_prev = d.c_save[btp * srow + dir * U + unit];
+    float4 g[RB];
+    float c_t[RB], c_prev[RB], dh[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      c_t[i] = c_prev[i] = dh[i] = 0.f;
+      const int len = s_len[r0 + i];
+      if (kh == 0 && s < len) {
+        const int b = row0 + r0 + i;
+        const int t_idx = dir ? (len - 1 - s) : s;
+        const size_t bt = (size_t)b * T + t_idx;
+        const float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
+        g[i] = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
+        c_t[i] = d.c_save[bt * srow + dir * U + unit];
+        if (s > 0) {
+          const size_t btp = (size_t)b * T + (dir ? t_idx + 1 : t_idx - 1);
+          c_prev[i] = d.c_save[btp * srow + dir * U + unit];
+        }
+        dh[i] = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit];
       }
-      dh = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit];
     }
     if (j > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * j));
@@ -233,44 +267,61 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
         s_dz[rr * ZS + c4] = __ldcg(src + i);
       }
       __syncthreads();
-      float racc = 0.f;
-      const float4* zr = s_dz + r * ZS + kh * nper;
+      float racc[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) racc[i] = 0.f;
+      const float4* zr = s_dz + r0 * ZS + kh * nper;
       const float4* wc = s_w + (size_t)(kh * nper) * UPC + ul;
 #pragma unroll 4
       for (int n4 = 0; n4 < nper; ++n4) {
-        const float4 v = zr[n4];
         const float4 w = wc[(size_t)n4 * UPC];
-        racc = fmaf(v.x, w.x, racc);
-        racc = fmaf(v.y, w.y, racc);
-        racc = fmaf(v.z, w.z, racc);
-        racc = fmaf(v.w, w.w, racc);
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+          const float4 v = zr[i * ZS + n4];
+          racc[i] = fmaf(v.x, w.x, racc[i]);
+          racc[i] = fmaf(v.y, w.y, racc[i]);
+          racc[i] = fmaf(v.z, w.z, racc[i]);
+          racc[i] = fmaf(v.w, w.w, racc[i]);
+        }
       }
       if (KS > 1) {
-        if (kh > 0) s_part[((kh - 1) * R + r) * UPC + ul] = racc;
+        if (kh > 0) {
+#pragma unroll
+          for (int i = 0; i < RB; ++i) s_part[((kh - 1) * R + r0 + i) * UPC + ul] = racc[i];
+        }
         __syncthreads();
         if (kh == 0) {
 #pragma unroll
-          for (int q = 0; q < KS - 1; ++q) racc += s_part[(q * R + r) * UPC + ul];
+          for (int q = 0; q < KS - 1; ++q)
+#pragma unroll
+            for (int i = 0; i < RB; ++i) racc[i] += s_part[(q * R + r0 + i) * UPC + ul];
         }
       }
-      dh += racc;
+#pragma unroll
+      for (int i = 0; i < RB; ++i) dh[i] += racc[i];
     }
     if (kh == 0) {
-      float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
-      if (act) {
-        const float gi_ = g.x, gj = g.y, gf = g.z, go = g.w;
-        const float tc = tanhf(c_t);
-        const float dc = dc_carry + dh * go * (1.f - tc * tc);
-        dzo = dh * tc * go * (1.f - go);
-        dzi = dc * gj * gi_ * (1.f - gi_);
-        dzj = dc * gi_ * (1.f - gj * gj);
-        dzf = dc * c_prev * gf * (1.f - gf);
-        dc_carry = dc * gf;
-        float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
-        zp[0] = dzi; zp[U] = dzj; zp[2 * U] = dzf; zp[3 * U] = dzo;
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int b = row0 + r0 + i;
+        const int len = s_len[r0 + i];
+        float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+        if (s < len) {
+          const int t_idx = dir ? (len - 1 - s) : s;
+          const float gi_ = g[i].x, gj = g[i].y, gf = g[i].z, go = g[i].w;
+          const float tc = tanhf(c_t[i]);
+          const float dc = dc_carry[i] + dh[i] * go * (1.f - tc * tc);
+          dzo = dh[i] * tc * go * (1.f - go);
+          dzi = dc * gj * gi_ * (1.f - gi_);
+          dzj = dc * gi_ * (1.f - gj * gj);
+          dzf = dc * c_prev[i] * gf * (1.f - gf);
+          dc_carry[i] = dc * gf;
+          float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
+          zp[0] = dzi; zp[U] = dzj; zp[2 * U] = dzf; zp[3 * U] = dzo;
+        }
+        float* xp = dzx + (((size_t)(j & 1) * ndir + dir) * p.Bpad + b) * W4 + unit;
+        xp[0] = dzi; xp[U] = dzj; xp[2 * U] = dzf; xp[3 * U] = dzo;
       }
-      float* xp = dzx + (((size_t)(j & 1) * ndir + dir) * p.Bpad + b) * W4 + unit;
-      xp[0] = dzi; xp[U] = dzj; xp[2 * U] = dzf; xp[3 * U] = dzo;
     }
     __syncthreads();
     if (tid == 0) {
@@ -282,26 +333,25 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
 
 // ---- host side ---------------------------------------------------------------------------------------------
 struct RtShape {
-  int R, UPC;
+  int R, UPC, RB;
   const void* fn;
 };
-#define RT_FWD(R, UPC) {R, UPC, (const void*)rec_train_fwd_kernel<R, UPC>}
-#define RT_BWD(R, UPC) {R, UPC, (const void*)rec_train_bwd_kernel<R, UPC>}
-// order = preference among shapes needing the same number of launches (measured at U = 256, B = 32: (16,8) 3.8 ms,
-// (16,4) 3.9, (32,4) 4.2, (8,32) 5.4, (16,16) 5.5, (32,8) 5.8 for the three layers of c3)
-static const RtShape rt_fwd_shapes[] = {RT_FWD(16, 8), RT_FWD(16, 4), RT_FWD(32, 4), RT_FWD(32, 8), RT_FWD(16, 16), RT_FWD(8, 32)};
-static const RtShape rt_bwd_shapes[] = {RT_BWD(8, 16), RT_BWD(8, 32), RT_BWD(16, 16), RT_BWD(8, 8), RT_BWD(8, 4), RT_BWD(16, 4)};
+#define RT_FWD(R, UPC, RB) {R, UPC, RB, (const void*)rec_train_fwd_kernel<R, UPC, RB>}
+#define RT_BWD(R, UPC, RB) {R, UPC, RB, (const void*)rec_train_bwd_kernel<R, UPC, RB>}
+// order = preference among shapes needing the same number of launches; the RB = 1 shapes serve narrow layers
+static const RtShape rt_fwd_shapes[] = {RT_FWD(16, 8, 4), RT_FWD(32, 4, 4), RT_FWD(16, 8, 1), RT_FWD(16, 4, 1), RT_FWD(32, 4, 1), RT_FWD(8, 32, 1)};
+static const RtShape rt_bwd_shapes[] = {RT_BWD(8, 16, 4), RT_BWD(8, 16, 1), RT_BWD(8, 32, 1), RT_BWD(8, 8, 1), RT_BWD(8, 4, 1), RT_BWD(16, 4, 1)};
 
 static size_t rt_smem_bytes(const RtShape& sh, int U, bool backward) {
-  const int KS = RT_THREADS / (sh.R * sh.UPC);
+  const int KS = RT_THREADS / (sh.R / sh.RB * sh.UPC);
   if (backward) return (size_t)U * sh.UPC * 16 + (size_t)sh.R * (U + 1) * 16 + (size_t)KS * sh.R * sh.UPC * 4;
   return (size_t)U * sh.UPC * 16 + (size_t)sh.R * (U + 4) * 4 + (size_t)KS * sh.R * sh.UPC * 16;
 }
 
 static bool rt_shape_ok(const RtShape& sh, int U, bool backward) {
-  const int KS = RT_THREADS / (sh.R * sh.UPC);
+  const int KS = RT_THREADS / (sh.R / sh.RB * sh.UPC);
   // forward slices k in float4 steps, backward slices the U float4 chunks of a W_hh row
-  return U % sh.UPC == 0 && U % (backward ? KS : 4 * KS) == 0 && rt_smem_bytes(sh, U, backward) <= 200 * 1024;
+  return U % sh.UPC == 0 && U % (backward ? KS : 4 * KS) == 0 && KS <= 16 && rt_smem_bytes(sh, U, backward) <= 200 * 1024;
 }
 
 static void rt_ws_layout(const plas_rec_train_desc& d, size_t* o_ctr, size_t* o_x, size_t* total) {
