@@ -41,7 +41,7 @@ __device__ __forceinline__ void rt_wait(const unsigned* ctr, unsigned target) {
 template <int R, int UPC, int RB>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainArgs p) {
   constexpr int NRB = R / RB, TPS = UPC * NRB, KS = RT_THREADS / TPS;
-  static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS, "bad shape");
+  static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS && R * UPC <= RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const plas_rec_train_desc& d = p.d;
   const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
 
   float4* s_w = reinterpret_cast<float4*>(rt_smem);               // [U (k)][UPC] : (i,j,f,o) columns of a unit
   float* s_h = reinterpret_cast<float*>(s_w + (size_t)U * UPC);  // [R][HS]
-  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)R * HS);  // [KS-1][R][UPC]
+  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)R * HS);  // [KS][R][UPC] partial pre-activations
   __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
@@ -78,26 +78,26 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
 
   float* hx = p.xbuf;
   unsigned* ctr = p.counters + dir * p.n_groups + gi;
+  // compute role: (unit ul, row block r0.., k-slice kh);  finalise role (tid < R*UPC): one (row fr, unit ful) pair --
+  // the gate math is spread over R*UPC threads instead of the few kh == 0 threads
   const int ul = tid % UPC, r0 = ((tid / UPC) % NRB) * RB, kh = tid / TPS;
-  const int unit = ci * UPC + ul;
+  const bool fin = tid < R * UPC;
+  const int fr = fin ? tid / UPC : 0, ful = tid % UPC;
+  const int unit = ci * UPC + ful;
+  const int b = row0 + fr;
+  const int len = s_len[fr];
   const size_t zrow = (size_t)ndir * 4 * U;
   const size_t srow = (size_t)ndir * U;
   const int kper = U / KS;  // host guarantees (U / KS) % 4 == 0
-  float c_state[RB], h_state[RB];
-#pragma unroll
-  for (int i = 0; i < RB; ++i) c_state[i] = h_state[i] = 0.f;
+  float c_state = 0.f, h_state = 0.f;
 
   for (int s = 0; s < Tg; ++s) {
-    float4 acc[RB];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int len = s_len[r0 + i];
-      if (kh == 0 && s < len) {
-        const int t_idx = dir ? (len - 1 - s) : s;
-        const float* zp = d.z + ((size_t)(row0 + r0 + i) * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
-        acc[i] = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
-      }
+    const bool act = fin && s < len;
+    const int t_idx = dir ? (len - 1 - s) : s;
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {  // prefetch this step's pre-activations; they are consumed after the exchange
+      const float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
+      z = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
     }
     if (s > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * s));
@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
         *reinterpret_cast<float4*>(s_h + rr * HS + 4 * c4) = __ldcg(hsrc + i);
       }
       __syncthreads();
+      float4 acc[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* hrow = s_h + r0 * HS + kh * kper;
       const float4* wcol = s_w + (size_t)(kh * kper) * UPC + ul;
 #pragma unroll 2
@@ -125,45 +128,32 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
           a.x = fmaf(hv.w, w3.x, a.x); a.y = fmaf(hv.w, w3.y, a.y); a.z = fmaf(hv.w, w3.z, a.z); a.w = fmaf(hv.w, w3.w, a.w);
         }
       }
-      if (KS > 1) {
-        if (kh > 0) {
 #pragma unroll
-          for (int i = 0; i < RB; ++i) s_part[((kh - 1) * R + r0 + i) * UPC + ul] = acc[i];
-        }
-        __syncthreads();
-        if (kh == 0) {
+      for (int i = 0; i < RB; ++i) s_part[(kh * R + r0 + i) * UPC + ul] = acc[i];
+      __syncthreads();
+      if (fin) {
 #pragma unroll
-          for (int q = 0; q < KS - 1; ++q) {
-#pragma unroll
-            for (int i = 0; i < RB; ++i) {
-              const float4 o = s_part[(q * R + r0 + i) * UPC + ul];
-              acc[i].x += o.x; acc[i].y += o.y; acc[i].z += o.z; acc[i].w += o.w;
-            }
-          }
+        for (int q = 0; q < KS; ++q) {  // fixed order: deterministic
+          const float4 o = s_part[(q * R + fr) * UPC + ful];
+          z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w;
         }
       }
     }
-    if (kh == 0) {
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const int b = row0 + r0 + i;
-        const int len = s_len[r0 + i];
-        if (s < len) {
-          const int t_idx = dir ? (len - 1 - s) : s;
-          const float gi_ = sigmoidf_acc(acc[i].x), gj = tanhf(acc[i].y), gf = sigmoidf_acc(acc[i].z + 1.0f), go = sigmoidf_acc(acc[i].w);
-          const float cn = gf * c_state[i] + gi_ * gj;
-          const float hn = go * tanhf(cn);
-          const size_t bt = (size_t)b * T + t_idx;
-          float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
-          zp[0] = gi_; zp[U] = gj; zp[2 * U] = gf; zp[3 * U] = go;
-          d.c_save[bt * srow + dir * U + unit] = cn;
-          d.h_prev[bt * srow + dir * U + unit] = h_state[i];
-          d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit] = hn;
-          c_state[i] = cn;
-          h_state[i] = hn;
-        }
-        hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state[i];
+    if (fin) {
+      if (act) {
+        const float gi_ = sigmoidf_acc(z.x), gj = tanhf(z.y), gf = sigmoidf_acc(z.z + 1.0f), go = sigmoidf_acc(z.w);
+        const float cn = gf * c_state + gi_ * gj;
+        const float hn = go * tanhf(cn);
+        const size_t bt = (size_t)b * T + t_idx;
+        float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
+        zp[0] = gi_; zp[U] = gj; zp[2 * U] = gf; zp[3 * U] = go;
+        d.c_save[bt * srow + dir * U + unit] = cn;
+        d.h_prev[bt * srow + dir * U + unit] = h_state;
+        d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit] = hn;
+        c_state = cn;
+        h_state = hn;
       }
+      hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state;
     }
     __syncthreads();
     if (tid == 0) {
@@ -176,7 +166,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
 template <int R, int UPC, int RB>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainArgs p) {
   constexpr int NRB = R / RB, TPS = UPC * NRB, KS = RT_THREADS / TPS;
-  static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS, "bad shape");
+  static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS && R * UPC <= RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
   const plas_rec_train_desc& d = p.d;
   const int U = d.U, B = d.B, T = d.T, ndir = d.ndir;
@@ -190,7 +180,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
 
   float4* s_w = reinterpret_cast<float4*>(rt_smem);  // [U (n4)][UPC]: W_hh[unit][4*n4 .. 4*n4+3]
   float4* s_dz = s_w + (size_t)U * UPC;              // [R][ZS] float4 = [R][4U]
-  float* s_part = reinterpret_cast<float*>(s_dz + (size_t)R * ZS);  // [KS-1][R][UPC]
+  float* s_part = reinterpret_cast<float*>(s_dz + (size_t)R * ZS);  // [KS][R][UPC] partial dh
   __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
@@ -212,51 +202,42 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
 
   float* dzx = p.xbuf;
   unsigned* ctr = p.counters + dir * p.n_groups + gi;
-  const int ul = tid % UPC, r0 = ((tid / UPC) % NRB) * RB, kh = tid / TPS;
-  const int unit = ci * UPC + ul;
+  const int ul = tid % UPC, r0 = ((tid / UPC) % NRB) * RB, kh = tid / TPS;  // compute role
+  const bool fin = tid < R * UPC;                                            // finalise role: one (row, unit) pair
+  const int fr = fin ? tid / UPC : 0, ful = tid % UPC;
+  const int unit = ci * UPC + ful;
+  const int b = row0 + fr;
+  const int len = s_len[fr];
   const size_t zrow = (size_t)ndir * 4 * U;
   const size_t srow = (size_t)ndir * U;
   const int W4 = 4 * U;
   const int nper = U / KS;  // float4 chunks of the reduction per slice
 
   // the gradient GEMMs run over every (b,t) row: zero dz past each utterance's length
-  if (kh == 0) {
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int b = row0 + r0 + i;
-      if (b >= B) continue;
-      for (int t = s_len[r0 + i]; t < T; ++t) {
-        float* zp = d.z + ((size_t)b * T + t) * zrow + (size_t)dir * 4 * U + unit;
-        zp[0] = 0.f; zp[U] = 0.f; zp[2 * U] = 0.f; zp[3 * U] = 0.f;
-      }
+  if (fin && b < B) {
+    for (int t = len; t < T; ++t) {
+      float* zp = d.z + ((size_t)b * T + t) * zrow + (size_t)dir * 4 * U + unit;
+      zp[0] = 0.f; zp[U] = 0.f; zp[2 * U] = 0.f; zp[3 * U] = 0.f;
     }
   }
 
-  float dc_carry[RB];
-#pragma unroll
-  for (int i = 0; i < RB; ++i) dc_carry[i] = 0.f;
+  float dc_carry = 0.f;
   for (int j = 0; j < Tg; ++j) {
     const int s = Tg - 1 - j;
-    float4 g[RB];
-    float c_t[RB], c_prev[RB], dh[RB];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      c_t[i] = c_prev[i] = dh[i] = 0.f;
-      const int len = s_len[r0 + i];
-      if (kh == 0 && s < len) {
-        const int b = row0 + r0 + i;
-        const int t_idx = dir ? (len - 1 - s) : s;
-        const size_t bt = (size_t)b * T + t_idx;
-        const float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
-        g[i] = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
-        c_t[i] = d.c_save[bt * srow + dir * U + unit];
-        if (s > 0) {
-          const size_t btp = (size_t)b * T + (dir ? t_idx + 1 : t_idx - 1);
-          c_prev[i] = d.c_save[btp * srow + dir * U + unit];
-        }
-        dh[i] = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit];
+    const bool act = fin && s < len;
+    const int t_idx = dir ? (len - 1 - s) : s;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float c_t = 0.f, c_prev = 0.f, dh = 0.f;
+    if (act) {
+      const size_t bt = (size_t)b * T + t_idx;
+      const float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
+      g = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
+      c_t = d.c_save[bt * srow + dir * U + unit];
+      if (s > 0) {
+        const size_t btp = (size_t)b * T + (dir ? t_idx + 1 : t_idx - 1);
+        c_prev = d.c_save[btp * srow + dir * U + unit];
       }
+      dh = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit];
     }
     if (j > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * j));
@@ -284,44 +265,30 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
           racc[i] = fmaf(v.w, w.w, racc[i]);
         }
       }
-      if (KS > 1) {
-        if (kh > 0) {
 #pragma unroll
-          for (int i = 0; i < RB; ++i) s_part[((kh - 1) * R + r0 + i) * UPC + ul] = racc[i];
-        }
-        __syncthreads();
-        if (kh == 0) {
+      for (int i = 0; i < RB; ++i) s_part[(kh * R + r0 + i) * UPC + ul] = racc[i];
+      __syncthreads();
+      if (fin) {
 #pragma unroll
-          for (int q = 0; q < KS - 1; ++q)
-#pragma unroll
-            for (int i = 0; i < RB; ++i) racc[i] += s_part[(q * R + r0 + i) * UPC + ul];
-        }
+        for (int q = 0; q < KS; ++q) dh += s_part[(q * R + fr) * UPC + ful];  // fixed order: deterministic
       }
-#pragma unroll
-      for (int i = 0; i < RB; ++i) dh[i] += racc[i];
     }
-    if (kh == 0) {
-#pragma unroll
-      for (int i = 0; i < RB; ++i) {
-        const int b = row0 + r0 + i;
-        const int len = s_len[r0 + i];
-        float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
-        if (s < len) {
-          const int t_idx = dir ? (len - 1 - s) : s;
-          const float gi_ = g[i].x, gj = g[i].y, gf = g[i].z, go = g[i].w;
-          const float tc = tanhf(c_t[i]);
-          const float dc = dc_carry[i] + dh[i] * go * (1.f - tc * tc);
-          dzo = dh[i] * tc * go * (1.f - go);
-          dzi = dc * gj * gi_ * (1.f - gi_);
-          dzj = dc * gi_ * (1.f - gj * gj);
-          dzf = dc * c_prev[i] * gf * (1.f - gf);
-          dc_carry[i] = dc * gf;
-          float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
-          zp[0] = dzi; zp[U] = dzj; zp[2 * U] = dzf; zp[3 * U] = dzo;
-        }
-        float* xp = dzx + (((size_t)(j & 1) * ndir + dir) * p.Bpad + b) * W4 + unit;
-        xp[0] = dzi; xp[U] = dzj; xp[2 * U] = dzf; xp[3 * U] = dzo;
+    if (fin) {
+      float dzi = 0.f, dzj = 0.f, dzf = 0.f, dzo = 0.f;
+      if (act) {
+        const float gi_ = g.x, gj = g.y, gf = g.z, go = g.w;
+        const float tc = tanhf(c_t);
+        const float dc = dc_carry + dh * go * (1.f - tc * tc);
+        dzo = dh * tc * go * (1.f - go);
+        dzi = dc * gj * gi_ * (1.f - gi_);
+        dzj = dc * gi_ * (1.f - gj * gj);
+        dzf = dc * c_prev * gf * (1.f - gf);
+        dc_carry = dc * gf;
+        float* zp = d.z + ((size_t)b * T + t_idx) * zrow + (size_t)dir * 4 * U + unit;
+        zp[0] = dzi; zp[U] = dzj; zp[2 * U] = dzf; zp[3 * U] = dzo;
       }
+      float* xp = dzx + (((size_t)(j & 1) * ndir + dir) * p.Bpad + b) * W4 + unit;
+      xp[0] = dzi; xp[U] = dzj; xp[2 * U] = dzf; xp[3 * U] = dzo;
     }
     __syncthreads();
     if (tid == 0) {
