@@ -391,7 +391,9 @@ N_LABELS = 40
 def train_problem(cfg, B, seed):
     from phones_las_b200 import synth
     hp = dict(cfg["hp"])
-    hp.update(dropout=0.0, sampling_probability=0.0, binf_count=N_BINF)  # both are RNG-driven in TF: off
+    # dropout 0.2 as in the reference's defaults (utils/params_utils.py:36; counter-based masks);
+    # scheduled sampling is not built: sampling_probability 0
+    hp.update(dropout=0.2, sampling_probability=0.0, binf_count=N_BINF)
     feats, lens = synth.synth_features(B, cfg["T"], cfg["C"], seed=seed)
     tin, tout, tlen = synth.synth_labels(B, N_LABELS, hp["target_vocab_size"], seed=seed + 1)
     binf = (np.random.default_rng(5).uniform(size=(N_BINF, hp["target_vocab_size"])) < 0.3).astype(np.float32)
@@ -410,8 +412,11 @@ def train_cpu_sample(cfg, batch):
     tp = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
     labels = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout),
                   target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    from phones_las_b200.train import reference_masks
+    rm = reference_masks(hp, 1, batch, cfg["T"], cfg["C"], N_LABELS + 1, binf_count=N_BINF)
     t0 = time.perf_counter()
-    loss, _ = lt.train_loss(tp, torch.tensor(feats), torch.tensor(lens.astype(np.int64)), labels, hp, binf)
+    masks = {sc: {k: torch.tensor(v) for k, v in m.items()} for sc, m in rm.items()}
+    loss, _ = lt.train_loss(tp, torch.tensor(feats), torch.tensor(lens.astype(np.int64)), labels, hp, binf, masks=masks)
     loss.backward()
     zeros = {k: torch.zeros_like(v) for k, v in tp.items()}
     lt.clip_and_adam({k: v.detach() for k, v in tp.items()}, {k: v.grad for k, v in tp.items()}, zeros, zeros, 1, hp["learning_rate"])
@@ -427,7 +432,7 @@ def train_config_dict(cfg, hp, B, world, **extra):
          "vocab": hp["target_vocab_size"],
          "parallelism": f"dp{world}: batch-sharded replicas, one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1
                         else "single GPU (no collective)",
-         "dropout": "0 and sampling_probability 0 (RNG-driven in TF; parity configuration)"}
+         "dropout": "0.2 on every LSTM cell input (counter-based masks), sampling_probability 0 (scheduled sampling not built)"}
     d.update(extra)
     return d
 

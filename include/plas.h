@@ -257,6 +257,9 @@ int plas_bilstm_rec_train_bwd(const plas_rec_train_desc* d, void* workspace, siz
 typedef struct plas_dec_train_desc {
   int32_t B, S, Tm, D, Ud, E, n_out, n_layers, attention_type;
   int32_t dmemory_accumulate; /* 1: dmemory += ..., 0: dmemory = ...                                           */
+  float keep_prob;          /* 1 - dropout of the decoder cells' inputs (1.0 = off).  x_in must already be dropped out by
+                               the caller (plas_dropout_f32); the kernels drop attention_{t-1} and the inter-layer h     */
+  uint32_t drop_seed;       /* masks: attention uses drop_seed, layer l's output uses drop_seed + 1 + l                  */
   const float* kernel[4];   /* cell_k/lstm_cell/kernel [(k == 0 ? E + D : Ud) + Ud][4Ud]                       */
   const float* bias[4];     /* [4Ud]                                                                          */
   const float* w_mem;       /* memory_layer/kernel [D][Ud]                                                    */
@@ -277,6 +280,7 @@ typedef struct plas_dec_train_desc {
   float* dw_proj;
   float* db_proj;
   float* dmemory;           /* bwd out: [B][Tm][D] gradient wrt the encoder outputs                           */
+  const uint32_t* drop_step; /* device optimiser-step counter added to the dropout seeds (NULL = 0)             */
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
@@ -302,6 +306,12 @@ int plas_grad_l2_norm(const float* params, float* grads, const int64_t* offsets,
                       float* norms, float* wsq, plas_stream_t stream);
 int plas_clip_scale(float* grads, const int64_t* offsets, int32_t n_tensors, const float* norms, float clip,
                     float post_scale, plas_stream_t stream);
+/* Input dropout of the TRAIN graph (DropoutWrapper(input_keep_prob = 1 - dropout), las/ops.py:14-18): y = x * m / keep_prob
+ * with a counter-based mask m(seed + *step * 0x85EBCA77, element index) -- `step` (device, may be NULL = 0) is the optimiser step,
+ * read on the device so that a captured CUDA graph draws fresh masks on every replay; the same call on a gradient tensor is the
+ * backward pass.  In place allowed. */
+int plas_dropout_f32(const float* x, float* y, int64_t n, uint32_t seed, const uint32_t* step, float keep_prob,
+                     plas_stream_t stream);
 /* y += alpha * x: sums the encoder-output gradients of the heads (the spellers run on separate streams). */
 int plas_axpy_f32(float* y, const float* x, int64_t n, float alpha, plas_stream_t stream);
 int plas_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1,

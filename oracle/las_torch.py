@@ -63,14 +63,17 @@ def dynamic_rnn(x, lengths, kernel, bias, reverse=False):
     return pieces, (c, h)
 
 
-def pyramidal_bilstm(x, lengths, params, num_layers, scope="listener"):
+def pyramidal_bilstm(x, lengths, params, num_layers, scope="listener", masks=None):
+    """``masks[(layer, dir)]`` [B,T,din]: input-dropout multipliers (1/keep or 0) of each cell's DropoutWrapper
+    (las/ops.py:14-18), supplied by the caller so that the stochastic op is checked on identical masks."""
     outputs = x
     for layer in range(num_layers):
         outs = []
-        for d, rev in (("fw", False), ("bw", True)):
+        for di, (d, rev) in enumerate((("fw", False), ("bw", True))):
             k = params[f"{scope}/bilstm_{layer}/bidirectional_rnn/{d}/lstm_cell/kernel"]
             b = params[f"{scope}/bilstm_{layer}/bidirectional_rnn/{d}/lstm_cell/bias"]
-            o, _ = dynamic_rnn(outputs, lengths, k, b, reverse=rev)
+            xin = outputs if masks is None else outputs * masks[(layer, di)]
+            o, _ = dynamic_rnn(xin, lengths, k, b, reverse=rev)
             outs.append(o)
         outputs = torch.cat(outs, -1)
         if layer != 0:
@@ -82,9 +85,11 @@ def pyramidal_bilstm(x, lengths, params, num_layers, scope="listener"):
     return outputs, lengths
 
 
-def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller"):
+def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
-    binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns)."""
+    binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
+    ``masks``: input-dropout multipliers of the decoder cells: 'x' [B,L,E] and 'att' [B,L,D] (slot t multiplies
+    attention_{t-1}) for cell 0's input [x_t; attention_{t-1}], ('h', l) [B,L,Ud] for the output of layer l feeding l+1."""
     B, Tm, D = enc_out.shape
     Ud = hp["decoder_units"]
     att_type = hp["attention_type"]
@@ -101,13 +106,18 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller"):
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
     for t in range(dec_inputs.shape[1]):
-        inp = torch.cat([dec_inputs[:, t], attention], 1)
+        if masks is None:
+            inp = torch.cat([dec_inputs[:, t], attention], 1)
+        else:
+            inp = torch.cat([dec_inputs[:, t] * masks["x"][:, t], attention * masks["att"][:, t]], 1)
         new_state = []
-        for (k, b), (c, h) in zip(cells, state):
+        for li, ((k, b), (c, h)) in enumerate(zip(cells, state)):
             z = torch.cat([inp, h], 1) @ k + b
             c2, h2 = _cell(z, c)
             new_state.append((c2, h2))
             inp = h2
+            if masks is not None and li + 1 < len(cells):
+                inp = h2 * masks[("h", li)][:, t]
         state = new_state
         if att_type == "bahdanau":
             pq = inp @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
@@ -159,12 +169,13 @@ def ctc_loss(logits, labels, label_length, logit_length, blank=0):
     return torch.stack(out)
 
 
-def train_loss(params, features, lengths, labels, hp, binf=None):
+def train_loss(params, features, lengths, labels, hp, binf=None, masks=None):
     """las_model_fn(mode=TRAIN) loss (model_helper.py:165-358, 411-413) with dropout = 0 and
     sampling_probability = 0.  ``binf`` [n, V] enables the multitask binary-feature speller.
     Returns (total loss incl. L2, dict of the parts)."""
     dt = features.dtype
-    enc_out, enc_len = pyramidal_bilstm(features, lengths, params, hp["encoder_layers"])
+    masks = masks or {}
+    enc_out, enc_len = pyramidal_bilstm(features, lengths, params, hp["encoder_layers"], masks=masks.get("listener"))
     tin, tout, tlen = labels["targets_inputs"], labels["targets_outputs"], labels["target_sequence_length"]
     L = tin.shape[1]
     w = (torch.arange(L)[None, :] < tlen[:, None]).to(dt)
@@ -172,13 +183,15 @@ def train_loss(params, features, lengths, labels, hp, binf=None):
     loss = 0.0
     V = hp["target_vocab_size"]
     if not hp.get("binary_outputs") or hp.get("multitask"):
-        logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp)
+        logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp,
+                               masks=masks.get("speller"))
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits
         loss = loss + parts["ce"]
     if hp.get("binary_outputs"):
         bt = torch.as_tensor(binf, dtype=dt).t()  # [V, n]
-        logits_b = speller_train(enc_out, enc_len, bt[tin.long()], params, hp, scope="speller_binf")
+        logits_b = speller_train(enc_out, enc_len, bt[tin.long()], params, hp, scope="speller_binf",
+                                 masks=masks.get("speller_binf"))
         parts["ce_binf"] = sequence_loss_sigmoid(logits_b, bt[tout.long()], w)
         parts["logits_binf"] = logits_b
         loss = loss + parts["ce_binf"]

@@ -65,12 +65,13 @@ class RecTrainDesc(C.Structure):
 class DecTrainDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("S", C.c_int32), ("Tm", C.c_int32), ("D", C.c_int32), ("Ud", C.c_int32),
                 ("E", C.c_int32), ("n_out", C.c_int32), ("n_layers", C.c_int32), ("attention_type", C.c_int32),
-                ("dmemory_accumulate", C.c_int32),
+                ("dmemory_accumulate", C.c_int32), ("keep_prob", C.c_float), ("drop_seed", C.c_uint32),
                 ("kernel", C.c_void_p * 4), ("bias", C.c_void_p * 4), ("w_mem", C.c_void_p), ("w_query", C.c_void_p),
                 ("v_att", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("memory", C.c_void_p),
                 ("mem_len", C.c_void_p), ("x_in", C.c_void_p), ("logits", C.c_void_p), ("dlogits", C.c_void_p),
                 ("dkernel", C.c_void_p * 4), ("dbias", C.c_void_p * 4), ("dw_mem", C.c_void_p), ("dw_query", C.c_void_p),
-                ("dv_att", C.c_void_p), ("dw_proj", C.c_void_p), ("db_proj", C.c_void_p), ("dmemory", C.c_void_p)]
+                ("dv_att", C.c_void_p), ("dw_proj", C.c_void_p), ("db_proj", C.c_void_p), ("dmemory", C.c_void_p),
+                ("drop_step", C.c_void_p)]
 
 
 EXPORTS = {
@@ -121,6 +122,7 @@ EXPORTS = {
     "plas_grad_l2_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
     "plas_clip_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
+    "plas_dropout_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_float, C.c_void_p]),
     "plas_axpy_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "plas_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_void_p]),

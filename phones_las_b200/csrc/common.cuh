@@ -77,6 +77,24 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
   return __float2bfloat16_rn(v);
 }
 
+// Counter-based dropout mask (training; tf.nn.rnn_cell.DropoutWrapper(input_keep_prob), las/ops.py:14-18): element `idx` of
+// the tensor identified by `seed` is kept when the top 24 bits of a murmur3-finalised hash fall below keep_prob.  No mask
+// is stored: the backward pass regenerates it from the same (seed, idx).  Mirrored in numpy by train.dropout_mask.
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t idx, uint32_t seed) {
+  uint32_t x = (uint32_t)idx * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x85EBCA77u + seed;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  x += seed * 0x27D4EB2Fu;
+  x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+  return x;
+}
+// seed of a tensor at optimiser step s = seed(step 0) + s * DROP_STEP_MUL: the kernels read s from device memory, so a
+// captured CUDA graph draws fresh masks on every replay
+constexpr uint32_t DROP_STEP_MUL = 0x85EBCA77u;
+// multiplier applied to a dropped-out input: 1/keep when kept, 0 otherwise (thresh = keep_prob * 2^24)
+__device__ __forceinline__ float drop_scale(uint64_t idx, uint32_t seed, uint32_t thresh, float inv_keep) {
+  return (drop_hash(idx, seed) >> 8) < thresh ? inv_keep : 0.f;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -37,6 +37,8 @@ struct CellFwdArgs {
   float* z_out; long long s_z;          // activated gates (i, tanh j, f, o), gate-blocked [4][Ud]
   float* c_out; float* h_out; long long s_h;
   float* hprev_next;                    // slot t+1 of the h_{t-1} copy (NULL at the last step)
+  float* hdrop_out;                     // dropped-out copy of h feeding the layer above (NULL: no dropout / top layer)
+  long long idx_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index of (b,u) = b*s_h + idx_base + u
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -139,6 +141,9 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
       p.c_out[(long long)bb * p.s_h + u0 + u] = c;
       p.h_out[(long long)bb * p.s_h + u0 + u] = h;
       if (p.hprev_next) p.hprev_next[(long long)bb * p.s_h + u0 + u] = h;
+      if (p.hdrop_out)
+        p.hdrop_out[(long long)bb * p.s_h + u0 + u] =
+            h * drop_scale((uint64_t)((long long)bb * p.s_h + p.idx_base + u0 + u), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
     }
   }
 }
@@ -155,6 +160,7 @@ struct AttFwdArgs {
   float* align; long long s_al;           // [Tm] per row
   float* att; long long s_att;            // context of this step
   float* att_next;                        // slot t+1 of the attention_{t-1} copy (NULL at the last step)
+  long long next_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index b*s_att + next_base + d
 };
 
 // CTA = (utterance, D-slice).  The utterance's keys and the CTA's slice of the values are staged in shared memory
@@ -278,7 +284,9 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     }
     const float c = c0 + c1;
     p.att[(long long)b * p.s_att + d] = c;
-    if (p.att_next) p.att_next[(long long)b * p.s_att + d] = c;
+    if (p.att_next)
+      p.att_next[(long long)b * p.s_att + d] =
+          p.inv_keep == 1.f ? c : c * drop_scale((uint64_t)((long long)b * p.s_att + p.next_base + d), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
   }
 }
 
@@ -294,6 +302,7 @@ struct AttBwdArgs {
   // bahdanau
   const float* pq; long long s_pq; const float* w_query; const float* v_att;
   float* dpq; long long s_dpq; float* dkeys; float* dv_acc;
+  long long next_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask of attention_t as step t+1's input
 };
 
 // Cluster of NS CTAs per utterance (grid (B, NS), cluster (1, NS, 1)).  CTA `part` owns a D-slice of the context
@@ -337,7 +346,11 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
   float* dctx = p.dctx + (long long)b * p.s_dc + d_lo;
   for (int d = tid; d < dper; d += 256) {
     float v = dctx[d];
-    if (p.datt_next) v += p.datt_next[(long long)b * p.s_dn + d_lo + d];
+    if (p.datt_next) {
+      float gnext = p.datt_next[(long long)b * p.s_dn + d_lo + d];
+      if (p.inv_keep != 1.f) gnext *= drop_scale((uint64_t)((long long)b * p.s_dc + p.next_base + d_lo + d), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
+      v += gnext;
+    }
     s_dc[d] = v;
     dctx[d] = v;
   }
@@ -443,6 +456,7 @@ struct CellBwdArgs {
   const float* dq; long long s_dq;       // top layer: gradient wrt the query (NULL otherwise)
   const float* dh_next; long long s_dn;  // h-part of dinp of this layer from step t+1 (NULL at t == S-1)
   const float* dh_above; long long s_da; // in1-part of dinp of the layer above, same step (NULL for the top layer)
+  long long idx_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask of this layer's h feeding the layer above
 };
 
 __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
@@ -453,7 +467,11 @@ __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
   float dh = 0.f;
   if (p.dq) dh += p.dq[(long long)b * p.s_dq + u];
   if (p.dh_next) dh += p.dh_next[(long long)b * p.s_dn + u];
-  if (p.dh_above) dh += p.dh_above[(long long)b * p.s_da + u];
+  if (p.dh_above) {
+    float ga = p.dh_above[(long long)b * p.s_da + u];
+    if (p.inv_keep != 1.f) ga *= drop_scale((uint64_t)((long long)b * p.s_c + p.idx_base + u), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
+    dh += ga;
+  }
   float* zp = p.z + (long long)b * p.s_z + u;
   const float gi = zp[0], gj = zp[Ud], gf = zp[2 * Ud], go = zp[3 * Ud];
   const float c = p.c_t[(long long)b * p.s_c + u];
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
   size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx;
-  size_t z[4], c[4], h[4], hprev[4];
+  size_t z[4], c[4], h[4], hprev[4], hdrop[4];
   size_t splitk, splitk_bytes;
   size_t total;
 };
@@ -568,12 +586,13 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
   w.dv_acc = take(B * Ud);
   w.dctx = take(B * S * D);
   for (int l = 0; l < 4; ++l) {
-    w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = 0;
+    w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = w.hdrop[l] = 0;
     if (l >= d.n_layers) continue;
     w.z[l] = take(B * S * 4 * Ud);
     w.c[l] = take(B * S * Ud);
     w.h[l] = take(B * S * Ud);
     w.hprev[l] = take(B * S * Ud);
+    if (l + 1 < d.n_layers) w.hdrop[l] = take(B * S * Ud);
     w.dinp[l] = take(B * ((l == 0 ? D : Ud) + Ud));
     w.dc[l] = take(B * Ud);
   }
@@ -601,6 +620,7 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   PLAS_REQUIRE(d && ws, "dec_train: null argument");
   PLAS_REQUIRE(d->B > 0 && d->S > 0 && d->Tm > 0 && d->E > 0 && d->n_out > 0, "dec_train: bad shape");
   PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_train: n_layers=%d", d->n_layers);
+  PLAS_REQUIRE(d->keep_prob > 0.f && d->keep_prob <= 1.f, "dec_train: keep_prob=%f", d->keep_prob);
   PLAS_REQUIRE(d->Ud % 8 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 8, D=%d of 4", d->Ud, d->D);
   PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU,
                "dec_train: attention_type %d has no training path (luong, bahdanau)", d->attention_type);
@@ -636,6 +656,9 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   if (rc) return rc;
   PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
   for (int l = 0; l < L; ++l) PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
+  const bool drop = d->keep_prob < 1.f;
+  const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
+  const float inv_keep = 1.0f / d->keep_prob;
   const int upc = 2;  // 32 rows x (1280 + 4) activations + 1280 x 8 weights = 205 KB of shared memory
   PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -657,7 +680,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
         a.w = d->kernel[0] + (size_t)E * 4 * Ud;
       } else {
         a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
-        a.in1 = F(w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud;
+        a.in1 = F(drop ? w.hdrop[l - 1] : w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud;
         a.w = d->kernel[l];
       }
       a.in2 = F(w.hprev[l]) + (size_t)t * Ud; a.s2 = sh; a.K2 = Ud;
@@ -665,6 +688,8 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
       a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
+      a.hdrop_out = (drop && l + 1 < L) ? F(w.hdrop[l]) + (size_t)t * Ud : nullptr;
+      a.idx_base = (long long)t * Ud; a.seed = d->drop_seed + 1 + l; a.thresh = thresh; a.inv_keep = inv_keep; a.step_ptr = d->drop_step;
       const int kcm = (a.K1 + a.K2) < CF_KC ? (a.K1 + a.K2) : CF_KC;
       const size_t need = (size_t)DT_ROWS * (kcm + 4) * 4 + (size_t)kcm * 4 * upc * 4, red = (size_t)8 * 4 * upc * (DT_ROWS + 1) * 4;
       const size_t smem = need > red ? need : red;
@@ -680,6 +705,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
     q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D;
     q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
+    q.next_base = (long long)(t + 1) * D; q.seed = d->drop_seed; q.thresh = thresh; q.inv_keep = inv_keep; q.step_ptr = d->drop_step;
     dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
   }
   PLAS_CUDA(cudaGetLastError());
@@ -720,6 +746,9 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   float* sk = F(w.splitk);
   const size_t skb = w.splitk_bytes;
   const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud;
+  const bool drop = d->keep_prob < 1.f;
+  const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
+  const float inv_keep = 1.0f / d->keep_prob;
   for (int t = S - 1; t >= 0; --t) {
     const bool last = t == S - 1;
     AttBwdArgs q;
@@ -732,6 +761,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     q.dq = F(w.dq); q.s_dq = Ud;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
     q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
+    q.next_base = (long long)(t + 1) * D; q.seed = d->drop_seed; q.thresh = thresh; q.inv_keep = inv_keep; q.step_ptr = d->drop_step;
     {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(B, ns);
@@ -757,6 +787,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       c.dq = (l == L - 1) ? F(w.dq) : nullptr; c.s_dq = Ud;
       c.dh_next = last ? nullptr : F(w.dinp[l]) + Kin; c.s_dn = Kin + Ud;
       c.dh_above = (l < L - 1) ? F(w.dinp[l + 1]) : nullptr; c.s_da = 2 * Ud;
+      c.idx_base = (long long)t * Ud; c.seed = d->drop_seed + 1 + l; c.thresh = thresh; c.inv_keep = inv_keep; c.step_ptr = d->drop_step;
       dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
       GemvTArgs g;
       g.B = B; g.N = 4 * Ud; g.K = Kin + Ud;
@@ -779,7 +810,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       if ((rc = gemm(st, D, 4 * Ud, (int)BS, F(w.att_prev), 1, D, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
       if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + D) * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
     } else {
-      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.h[l - 1]), 1, Ud, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(drop ? w.hdrop[l - 1] : w.h[l - 1]), 1, Ud, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
       if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[l]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)Ud * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
     }
     if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;

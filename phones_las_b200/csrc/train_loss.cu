@@ -268,6 +268,14 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// y[i] = x[i] * mask(seed, i) / keep  (forward on activations, backward on their gradients: same op, same seed)
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, unsigned seed0,
+                               const unsigned* __restrict__ step_ptr, unsigned thresh, float inv_keep) {
+  const unsigned seed = seed0 + (step_ptr ? *step_ptr : 0u) * DROP_STEP_MUL;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * drop_scale((uint64_t)i, seed, thresh, inv_keep);
+}
+
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long long n, float alpha) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, x[i], y[i]);
@@ -276,6 +284,15 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 }  // namespace plas
 
 using namespace plas;
+
+extern "C" int plas_dropout_f32(const float* x, float* y, int64_t n, uint32_t seed, const uint32_t* step, float keep_prob,
+                                plas_stream_t stream_) {
+  PLAS_REQUIRE(x && y && n > 0 && keep_prob > 0.f && keep_prob <= 1.f, "dropout: bad argument");
+  const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
+  dropout_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(x, y, n, seed, step, (unsigned)(keep_prob * 16777216.0f), 1.0f / keep_prob);
+  PLAS_CUDA(cudaGetLastError());
+  return PLAS_OK;
+}
 
 extern "C" int plas_axpy_f32(float* y, const float* x, int64_t n, float alpha, plas_stream_t stream_) {
   PLAS_REQUIRE(y && x && n > 0, "axpy: bad argument");

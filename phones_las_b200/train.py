@@ -3,7 +3,8 @@
 Mirrors model_helper.py:165-227 (listener + speller(s) in TRAIN mode), :319-358 (sequence / sigmoid / CTC losses,
 multitask sum), :403-417 (L2 regulariser, per-tensor ``clip_by_norm(grad, 2)``, Adam) and, for data-parallel runs,
 the CrossShardOptimizer order of :405-406 (clip locally, then average the gradients across ranks, then apply).
-Parity runs use ``dropout = 0`` and ``sampling_probability = 0`` (both are RNG-driven in TF).
+Input dropout uses a counter-based mask (TF's RNG stream cannot be reproduced: parity is checked against the oracle on
+identical masks); scheduled sampling is not built (``sampling_probability`` must be 0).
 
 Every variable lives in ONE flat fp32 device buffer in the TF checkpoint layout; gradients and
 the Adam moments mirror it, so the data-parallel exchange is a single all-reduce of ``state.grads`` and a trained
@@ -45,6 +46,70 @@ def colsum(X, M, N, ld, out, accumulate=False):
     _lib.count_launches(1)
 
 
+# --------------------------------------------------------------------------------------------------------------
+# input dropout (DropoutWrapper(input_keep_prob = 1 - dropout) around every LSTMCell in TRAIN, las/ops.py:14-18)
+# --------------------------------------------------------------------------------------------------------------
+def _u32(x):
+    return np.uint32(x & 0xFFFFFFFF)
+
+
+def drop_seed(base, step, tensor_id):
+    """32-bit seed of one dropped-out tensor at one optimiser step."""
+    return int((int(base) * 0x9E3779B1 + int(step) * 0x85EBCA77 + int(tensor_id) * 0xC2B2AE3D + 0x165667B1) & 0xFFFFFFFF)
+
+
+def dropout_mask(n, seed, keep_prob):
+    """numpy mirror of drop_scale() in csrc/common.cuh: multipliers (1/keep or 0) of elements 0..n-1 of the tensor `seed`."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64)
+        sd = np.uint32(seed)
+        x = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32) * np.uint32(0x9E3779B1) + (idx >> np.uint64(32)).astype(np.uint32) * np.uint32(0x85EBCA77) + sd
+        x ^= x >> np.uint32(16); x *= np.uint32(0x85EBCA6B); x ^= x >> np.uint32(13); x *= np.uint32(0xC2B2AE35); x ^= x >> np.uint32(16)
+        x += sd * np.uint32(0x27D4EB2F)
+        x ^= x >> np.uint32(15); x *= np.uint32(0x2C1B3C6D); x ^= x >> np.uint32(12); x *= np.uint32(0x297A2D39); x ^= x >> np.uint32(15)
+    thresh = np.uint32(np.float32(keep_prob) * np.float32(16777216.0))
+    return np.where((x >> np.uint32(8)) < thresh, np.float32(1.0) / np.float32(keep_prob), np.float32(0.0)).astype(np.float32)
+
+
+def dropout_(x, y, seed, keep_prob, step_dev=None):
+    """y = x * mask(seed + step * 0x85EBCA77) / keep_prob on the device (plas_dropout_f32; ``step_dev`` = the TrainState's device
+    step counter, None = 0); the same call on a gradient is the backward pass."""
+    _lib.check(_lib.lib().plas_dropout_f32(_lib.ptr(x), _lib.ptr(y), x.numel(), seed, _lib.ptr(step_dev), keep_prob, _lib.stream_ptr()))
+    _lib.count_launches(1)
+    return y
+
+
+LISTENER_TID = 1      # + 2*layer + direction
+SPELLER_TID = 100     # + 10*speller index: +0 decoder inputs, +1 attention_{t-1}, +2+l output of decoder layer l
+
+
+def reference_masks(hp, step, B, T, C, S, binf_count=0):
+    """The multipliers the device path applies at optimiser step ``step``, as numpy arrays keyed like oracle/las_torch.py's
+    ``masks`` argument (test support: lets the CPU oracle replay the stochastic op on identical masks)."""
+    keep = 1.0 - float(hp.get("dropout", 0.0))
+    base = int(hp.get("dropout_seed", 0))
+    U, V, Ud = hp["encoder_units"], hp["target_vocab_size"], hp["decoder_units"]
+    out = {"listener": {}}
+    t, din = T, C
+    for l in range(hp["encoder_layers"]):
+        for dd in range(2):
+            out["listener"][(l, dd)] = dropout_mask(B * t * din, drop_seed(base, step, LISTENER_TID + 2 * l + dd), keep).reshape(B, t, din)
+        din = 2 * U if l == 0 else 4 * U
+        if l != 0:
+            t = (t + 1) // 2
+    D = din
+    for si, (scope, E) in enumerate((("speller", V), ("speller_binf", binf_count))):
+        if E <= 0:
+            continue
+        tid = SPELLER_TID + 10 * si
+        m = {"x": dropout_mask(B * S * E, drop_seed(base, step, tid), keep).reshape(B, S, E),
+             "att": dropout_mask(B * S * D, drop_seed(base, step, tid + 1), keep).reshape(B, S, D)}
+        for l in range(hp["decoder_layers"] - 1):
+            m[("h", l)] = dropout_mask(B * S * Ud, (drop_seed(base, step, tid + 1) + 1 + l) & 0xFFFFFFFF, keep).reshape(B, S, Ud)
+        out[scope] = m
+    return out
+
+
 class TrainState:
     """Flat parameter / gradient / Adam-moment buffers keyed by TF variable name."""
 
@@ -73,8 +138,19 @@ class TrainState:
         self.wsq = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
         self.index = {k: i for i, k in enumerate(self.names)}
         self.split_ws = torch.empty((32 << 20,), dtype=torch.uint8, device=device)  # split-K scratch of the dW GEMMs
-        self.step = 0
+        self.step_dev = torch.zeros((1,), dtype=torch.int32, device=device)  # read by the dropout kernels (graph-safe seeds)
+        self._step = 0
         self._streams = []
+
+    @property
+    def step(self):
+        """Number of optimiser steps applied so far (mirrored on the device for the dropout seeds)."""
+        return self._step
+
+    @step.setter
+    def step(self, n):
+        self._step = int(n)
+        self.step_dev.fill_(int(n))
 
     def side_streams(self, n):
         while len(self._streams) < n:
@@ -132,7 +208,8 @@ def _rec_desc(B, T, U, ndir, din, z, kernels, lengths, out, c_save, h_prev, dout
 
 
 def listener_train_fwd(x, lengths, st, hp):
-    """pyramidal_bilstm (las/ops.py:68-87) forward keeping what BPTT needs.  x [B,T,C] f32 -> (enc_out, enc_len, tape)."""
+    """pyramidal_bilstm (las/ops.py:68-87) forward keeping what BPTT needs.  x [B,T,C] f32 -> (enc_out, enc_len, tape).
+    With hp['dropout'] > 0 every cell sees its own dropped-out copy of the layer input (one DropoutWrapper per cell)."""
     if not hp["use_pyramidal"] or hp["unidirectional"]:
         raise NotImplementedError("the training path covers the pyramidal bidirectional listener")
     L = _lib.lib()
@@ -140,14 +217,18 @@ def listener_train_fwd(x, lengths, st, hp):
     B = x.shape[0]
     lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
     x = x.to(torch.float32).contiguous()
+    keep = 1.0 - float(hp.get("dropout", 0.0))
+    base = int(hp.get("dropout_seed", 0))
     tape = []
     for l in range(hp["encoder_layers"]):
         T, din = x.shape[1], x.shape[2]
         names = _layer_names(l)
         z = torch.empty((B, T, ndir, 4 * U), dtype=torch.float32, device=x.device)
+        seeds = [drop_seed(base, 0, LISTENER_TID + 2 * l + dd) for dd in range(ndir)]  # + step * DROP_STEP_MUL on the device
+        xs = [dropout_(x, torch.empty_like(x), seeds[dd], keep, st.step_dev) for dd in range(ndir)] if keep < 1.0 else [x, x]
         with _lib.stage("train_inproj"):
             for dd, nm in enumerate(names):
-                gemm_ex(B * T, 4 * U, din, x.data_ptr(), din, 1, st.w(nm + "/kernel"), 4 * U, 1, _p(z, dd * 4 * U), ndir * 4 * U,
+                gemm_ex(B * T, 4 * U, din, xs[dd].data_ptr(), din, 1, st.w(nm + "/kernel"), 4 * U, 1, _p(z, dd * 4 * U), ndir * 4 * U,
                         bias=st.w(nm + "/bias"))
         t_alloc = T if l == 0 else T + (T % 2)
         out = torch.zeros((B, t_alloc, ndir * U), dtype=torch.float32, device=x.device)
@@ -159,7 +240,8 @@ def listener_train_fwd(x, lengths, st, hp):
         with _lib.stage("train_rec_fwd"):
             _lib.check(L.plas_bilstm_rec_train_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
         _lib.count_launches(1)
-        tape.append(dict(x=x, z=z, c_save=c_save, h_prev=h_prev, lengths=lengths, T=T, din=din, t_alloc=t_alloc, ws=ws))
+        tape.append(dict(xs=xs, seeds=seeds, keep=keep, z=z, c_save=c_save, h_prev=h_prev, lengths=lengths, T=T, din=din,
+                         t_alloc=t_alloc, ws=ws))
         if l != 0:
             out = out.view(B, t_alloc // 2, 2 * ndir * U)
             lengths = torch.div(lengths, 2, rounding_mode="floor") + lengths % 2
@@ -185,15 +267,23 @@ def listener_train_bwd(d_enc, tape, st, hp):
         with _lib.stage("train_rec_bwd"):
             _lib.check(L.plas_bilstm_rec_train_bwd(C.byref(d), _lib.ptr(tp["ws"]), need, _lib.stream_ptr()))
         _lib.count_launches(1)
-        z, x, hp_ = tp["z"], tp["x"], tp["h_prev"]
+        z, xs, hp_, keep = tp["z"], tp["xs"], tp["h_prev"], tp["keep"]
         M = B * T
         main = torch.cuda.current_stream()
         if l > 0:  # input gradient first: the next recurrence depends on it
             dx = torch.empty((B, T, din), dtype=torch.float32, device=z.device)
             with _lib.stage("train_dgrad"):
                 for dd, nm in enumerate(names):
-                    gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dx.data_ptr(), din,
-                            beta=0.0 if dd == 0 else 1.0)
+                    if keep < 1.0:  # each direction saw its own mask: dx = sum_d mask_d * (dz_d W_d^T)
+                        dxd = dx if dd == 0 else torch.empty_like(dx)
+                        gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dxd.data_ptr(), din)
+                        dropout_(dxd, dxd, tp["seeds"][dd], keep, st.step_dev)
+                        if dd > 0:
+                            _lib.check(L.plas_axpy_f32(_lib.ptr(dx), _lib.ptr(dxd), dx.numel(), 1.0, _lib.stream_ptr()))
+                            _lib.count_launches(1)
+                    else:
+                        gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dx.data_ptr(), din,
+                                beta=0.0 if dd == 0 else 1.0)
             dout = dx
         # weight gradients on a side stream: they only need dz, and overlap the (latency-bound) recurrence of the layer below
         ev = torch.cuda.Event()
@@ -203,7 +293,7 @@ def listener_train_bwd(d_enc, tape, st, hp):
             with _lib.stage("train_wgrad"):
                 for dd, nm in enumerate(names):
                     zp = _p(z, dd * 4 * U)
-                    gemm_ex(din, 4 * U, M, x.data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
+                    gemm_ex(din, 4 * U, M, xs[dd].data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
                     gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U,
                             split_ws=st.split_ws)
                     colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))
@@ -218,8 +308,11 @@ def listener_train_bwd(d_enc, tape, st, hp):
 class SpellerTrain:
     """One teacher-forced speller (scope 'speller' or 'speller_binf') bound to a TrainState."""
 
-    def __init__(self, st, hp, scope, E, n_out):
+    def __init__(self, st, hp, scope, E, n_out, index=0):
         self.st, self.hp, self.scope, self.E, self.n_out = st, hp, scope, E, n_out
+        self.keep = 1.0 - float(hp.get("dropout", 0.0))
+        self.tid = SPELLER_TID + 10 * index
+        self.base = int(hp.get("dropout_seed", 0))
         if hp["attention_type"] not in ("luong", "bahdanau"):
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
         for flag in ("bottom_only", "pass_hidden_state", "binf_projection", "attention_layer_size", "embedding_size"):
@@ -234,6 +327,9 @@ class SpellerTrain:
         d.n_layers = hp["decoder_layers"]
         d.attention_type = _lib.ATT_CODES[hp["attention_type"]]
         d.dmemory_accumulate = 1
+        d.keep_prob = self.keep
+        d.drop_seed = drop_seed(self.base, 0, self.tid + 1)  # + step * DROP_STEP_MUL on the device
+        d.drop_step = st.step_dev.data_ptr()
         pre = f"{sc}/decoder/attention_wrapper"
         for k in range(d.n_layers):
             nm = f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell"
@@ -255,7 +351,10 @@ class SpellerTrain:
         """memory [B,Tm,D] (zero past mem_len), x_in [B,S,E] -> logits [B,S,n_out]; keeps the tape on self."""
         L = _lib.lib()
         B, S = x_in.shape[0], x_in.shape[1]
-        self.memory, self.mem_len, self.x_in = memory.contiguous(), mem_len, x_in.contiguous()
+        x_in = x_in.contiguous()
+        if self.keep < 1.0:  # the cell input [x_t; attention_{t-1}] is dropped out; x_t here, attention inside the kernels
+            x_in = dropout_(x_in, torch.empty_like(x_in), drop_seed(self.base, 0, self.tid), self.keep, self.st.step_dev)
+        self.memory, self.mem_len, self.x_in = memory.contiguous(), mem_len, x_in
         self.logits = torch.empty((B, S, self.n_out), dtype=torch.float32, device=memory.device)
         d = self._desc(self.memory, self.mem_len, self.x_in, self.logits)
         need = L.plas_dec_train_workspace_bytes(C.byref(d))
@@ -325,8 +424,8 @@ def forward_backward(features, labels, st, hp, binf=None):
     """Forward + backward of las_model_fn(TRAIN): fills ``st.grads`` (raw, before L2 / clipping) and returns the loss
     parts as device scalars {ce, ce_binf, ctc, audio_loss}.  ``binf`` [n, V] float tensor (binf2phone, model_helper.py:179-186)
     enables the multitask binary-feature speller when hp['binary_outputs']."""
-    if float(hp.get("dropout", 0.0)) > 0.0 or float(hp.get("sampling_probability", 0.0)) > 0.0:
-        raise NotImplementedError("training path: dropout / scheduled sampling are RNG-driven in TF and not built; set both to 0")
+    if float(hp.get("sampling_probability", 0.0)) > 0.0:
+        raise NotImplementedError("training path: scheduled sampling (las/model.py:279-288) is not built; set sampling_probability=0")
     x, lens = features["encoder_inputs"], features["source_sequence_length"]
     dev = x.device
     tin = labels["targets_inputs"].to(device=dev, dtype=torch.int64)
@@ -358,7 +457,7 @@ def forward_backward(features, labels, st, hp, binf=None):
     for (scope, key, n_out, x_in, lab), stream, d_enc_j in zip(jobs, side, d_enc_heads):
         with torch.cuda.stream(stream):
             stream.wait_event(ready)
-            sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out)
+            sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out, index=0 if scope == "speller" else 1)
             logits = sp.forward(enc_out, enc_len, x_in)
             if lab is None:
                 parts[key], dl = seq_ce_grad(logits, tout, w)
@@ -411,7 +510,8 @@ def apply_gradients(st, hp, world_size=1, allreduce=None, clipped=False):
         regularise_and_clip(st, hp, world_size)
     if allreduce is not None:
         allreduce(st.grads)  # sum of (clipped / world_size) = CrossShardOptimizer's mean
-    st.step += 1
+    st._step += 1
+    st.step_dev.add_(1)
     b1, b2, eps = 0.9, 0.999, 1e-8
     lr_t = float(hp["learning_rate"]) * (1.0 - b2 ** st.step) ** 0.5 / (1.0 - b1 ** st.step)
     _lib.check(L.plas_adam_step(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.m), _lib.ptr(st.v), st.total, lr_t, b1, b2, eps,

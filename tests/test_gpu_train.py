@@ -229,11 +229,14 @@ def test_train_steps_match_autograd_adam(cfg):
 
 
 @gpu
-def test_graphed_step_equals_eager_step():
-    """The CUDA-graph replay of the step must leave bit-identical parameters to the eager step (same kernels, same order)."""
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_graphed_step_equals_eager_step(dropout):
+    """The CUDA-graph replay of the step must leave bit-identical parameters to the eager step (same kernels, same order);
+    with dropout the replays must draw the same fresh masks as the eager steps (seeds read from the device step counter)."""
     import torch
     from phones_las_b200 import train as tr
     hp, params, x, lens, tin, tout, tlen, binf = _full_setup(*FULL_CFGS[2])
+    hp["dropout"] = dropout
     feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
     labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
               "target_sequence_length": torch.from_numpy(tlen).cuda()}
@@ -255,3 +258,107 @@ def test_graphed_step_equals_eager_step():
     pg = graphed(f2, labels)
     torch.cuda.synchronize()
     assert pe["loss"].item() == pg["loss"].item() and torch.equal(st_e.params, st_g.params)
+
+
+# ---- input dropout (DropoutWrapper(input_keep_prob), las/ops.py:14-18): checked against the oracle on identical masks ----
+@gpu
+def test_dropout_kernel_matches_numpy_mirror():
+    import torch
+    from phones_las_b200 import train as tr
+    x = torch.randn((3, 1237), generator=torch.Generator().manual_seed(0)).cuda()
+    for keep, seed in ((0.8, tr.drop_seed(0, 1, 5)), (0.5, tr.drop_seed(7, 123456, 111)), (1.0, 3)):
+        y = tr.dropout_(x, torch.empty_like(x), seed, keep)
+        ref = x.cpu().numpy() * tr.dropout_mask(x.numel(), seed, keep).reshape(x.shape)
+        assert np.array_equal(to_np(y), ref.astype(np.float32))
+
+
+@gpu
+def test_listener_with_dropout():
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, U, L = 6, 26, 7, 16, 3
+    hp = create_hparams(target_vocab_size=12, encoder_layers=L, encoder_units=U, decoder_units=16, decoder_layers=1,
+                        num_channels=C, dropout=0.3, sampling_probability=0.0)
+    params = {k: v for k, v in weights.init_params(hp, seed=4, bias_scale=0.1).items() if k.startswith("listener/")}
+    x, lens = synth.synth_features(B, T, C, seed=1, var_len=True)
+    st = tr.TrainState(params)
+    st.step = 5
+    masks = {k: torch.tensor(v, dtype=torch.float64) for k, v in tr.reference_masks(hp, 5, B, T, C, 4)["listener"].items()}
+    tp = _tp(params)
+    ref, _ = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, L, masks=masks)
+    dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    (ref * dref).sum().backward()
+    out, _, tape = tr.listener_train_fwd(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), st, hp)
+    assert scaled_err(out, ref.detach()) < 1e-5
+    tr.listener_train_bwd(dref.float().cuda().contiguous(), tape, st, hp)
+    grads = st.export_grads()
+    for k in params:
+        assert grad_err(grads[k], tp[k].grad) < GRAD_TOL, k
+
+
+@gpu
+@pytest.mark.parametrize("att,Ld", [("luong", 1), ("bahdanau", 3)])
+def test_speller_with_dropout(att, Ld):
+    import torch
+    from phones_las_b200 import train as tr
+    B, Tm, U, Ud, V, S = 7, 15, 16, 32, 13, 6
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=4, attention_type=att, dropout=0.25, sampling_probability=0.0)
+    params = {k: v for k, v in weights.init_params(hp, seed=9, projection_scale=4.0, bias_scale=0.1).items() if k.startswith("speller/")}
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(3)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    enc *= (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    ids = rng.integers(0, V, (B, S))
+    st = tr.TrainState(params)
+    st.step = 2
+    rm = tr.reference_masks(hp, 2, B, 4 * Tm, 4, S)["speller"]
+    assert rm["att"].shape == (B, S, D)
+    masks = {k: torch.tensor(v, dtype=torch.float64) for k, v in rm.items()}
+    tp = _tp(params)
+    enc_t = torch.tensor(enc, dtype=torch.float64, requires_grad=True)
+    x64 = torch.nn.functional.one_hot(torch.tensor(ids), V).to(torch.float64)
+    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp, masks=masks)
+    dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+    (ref * dref).sum().backward()
+    sp = tr.SpellerTrain(st, hp, "speller", V, V)
+    logits = sp.forward(torch.from_numpy(enc).cuda(), torch.from_numpy(lens).cuda(), x64.float().cuda())
+    assert scaled_err(logits, ref.detach()) < 1e-5
+    d_enc = torch.zeros((B, Tm, D), device="cuda")
+    sp.backward(dref.float().cuda(), d_enc)
+    mask = (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    assert scaled_err(to_np(d_enc) * mask, enc_t.grad.numpy() * mask) < GRAD_TOL
+    grads = st.export_grads()
+    for k in params:
+        assert grad_err(grads[k], tp[k].grad) < GRAD_TOL, k
+
+
+@gpu
+def test_train_step_with_dropout_matches_oracle_on_same_masks():
+    import torch
+    from phones_las_b200 import train as tr
+    cfg = ("luong", 6, 90, 9, 16, 3, 32, 2, 14, 6, 7, True, True)
+    hp, params, x, lens, tin, tout, tlen, binf = _full_setup(*cfg)
+    hp["dropout"] = 0.2
+    hp["dropout_seed"] = 11
+    st = tr.TrainState(params)
+    st.step = 3
+    B, T, C = x.shape
+    S = tin.shape[1]
+    rm = tr.reference_masks(hp, 3, B, T, C, S, binf_count=binf.shape[0])
+    masks = {sc: {k: torch.tensor(v, dtype=torch.float64) for k, v in m.items()} for sc, m in rm.items()}
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, binf, masks=masks)
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp, torch.from_numpy(binf).cuda())
+    for name in ("ce", "ce_binf", "ctc"):
+        assert abs(parts[name].item() - ref_parts[name].item()) < 1e-4 * max(1.0, abs(ref_parts[name].item())), name
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k

@@ -104,3 +104,30 @@ def test_train_loss_multitask_runs_and_has_all_gradients():
     for k, t in tp.items():
         assert t.grad is not None and torch.isfinite(t.grad).all(), k
         assert t.grad.abs().max() > 0, k
+
+
+def test_dropout_mask_mirror_statistics_and_oracle_masks():
+    """Host mirror of the device dropout hash: keep rate, independence across steps/tensors, 1/keep scaling, and the
+    oracle's masked forward differs from the unmasked one only through the masks."""
+    from phones_las_b200.train import dropout_mask, drop_seed, reference_masks
+    m1 = dropout_mask(200000, drop_seed(0, 3, 7), 0.8)
+    m2 = dropout_mask(200000, drop_seed(0, 4, 7), 0.8)
+    m3 = dropout_mask(200000, drop_seed(0, 3, 8), 0.8)
+    assert set(np.unique(m1)) == {np.float32(0.0), np.float32(1.25)}
+    assert abs((m1 > 0).mean() - 0.8) < 5e-3
+    for other in (m2, m3):  # independent masks agree on 0.8^2 + 0.2^2 = 0.68 of the elements
+        assert abs(((m1 > 0) == (other > 0)).mean() - 0.68) < 1e-2
+    assert np.array_equal(dropout_mask(1000, 5, 1.0), np.ones(1000, np.float32))
+    hp = create_hparams(target_vocab_size=10, encoder_layers=2, encoder_units=4, decoder_units=8, decoder_layers=2,
+                        num_channels=3, dropout=0.5)
+    rm = reference_masks(hp, 1, 3, 9, 3, 4)
+    assert rm["listener"][(1, 0)].shape == (3, 9, 8) and rm["speller"]["att"].shape == (3, 4, 16) and ("h", 0) in rm["speller"]
+    params = weights.init_params(hp, seed=1)
+    x, lens = synth.synth_features(3, 9, 3)
+    tp = _tp(params)
+    masks = {k: torch.tensor(v, dtype=torch.float64) for k, v in rm["listener"].items()}
+    a, _ = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, 2, masks=masks)
+    ones = {k: torch.ones_like(v) for k, v in masks.items()}
+    b, _ = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, 2, masks=ones)
+    c, _ = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, 2)
+    assert torch.equal(b, c) and not torch.allclose(a, c)
