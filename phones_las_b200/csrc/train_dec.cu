@@ -48,102 +48,97 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr int CF_KC = 640;   // reduction chunk staged per pass (activations 32 x KC + weights KC x 4*UPC in smem)
+constexpr int CF_KS = 8;    // K-slices = CTAs per cluster
+constexpr int CF_UG = 16;   // units per column group (64 gate columns)
 
-// CTA = UPC units (4*UPC gate columns) x 32 batch rows.  Per pass the CTA stages a KC-wide chunk of the 32
-// activation rows and of its weight slice in shared memory with one wave of independent 16-byte cp.async copies
-// (the whole point: the step is latency-bound, so every byte must be in flight at once); lane = batch row, the 8
-// warps split the chunk's reduction, partials meet in shared memory.
-template <int UPC>
+// z = pre + [in1; in2] W for one step, as a [32 rows] x [K] x [4Ud] product cut in BOTH directions: grid = (8 K-slices) x
+// (Ud/16 column groups) x (row chunks), the 8 K-slices of a column group forming one thread-block cluster.  A CTA stages
+// only its K-slice of the activations (32 x K/8) and of the weights (K/8 x 64) -- the activations cross L2->SM once per
+// column group instead of once per 2 units -- multiplies (lane = batch row, warp = 2 units x 4 gates), and sends each
+// warp's partial sums to the CTA that owns those 2 units through distributed shared memory; after one cluster barrier
+// every CTA sums the 8 partials of its units in a fixed order and applies the gate math.
 __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float cf_smem[];
-  constexpr int NC = 4 * UPC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int u0 = blockIdx.x * UPC;
-  const int b0 = blockIdx.y * DT_ROWS;
+  const int ks = blockIdx.x;                  // K-slice = rank in the cluster
+  const int u0 = blockIdx.y * CF_UG;
+  const int b0 = blockIdx.z * DT_ROWS;
   const int Ud = p.Ud;
-  const int K = p.K1 + p.K2;
-  const int kc_max = min(K, CF_KC);
-  const int AS = kc_max + 4;                 // padded activation row stride (floats): conflict-free float4 reads
-  float* s_a = cf_smem;                      // [32][AS]
-  float* s_w = s_a + (size_t)DT_ROWS * AS;   // [kc][NC], column = g*UPC + u
-  float acc[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
-  for (int kc0 = 0; kc0 < K; kc0 += CF_KC) {
-    const int kc = min(CF_KC, K - kc0);
-    const int kq = kc / 4;
-    if (kc0 > 0) __syncthreads();
-    for (int i = threadIdx.x; i < DT_ROWS * kq; i += 256) {
-      const int r = i / kq, q = i - r * kq;
-      const int b = min(b0 + r, p.B - 1);
-      const int k = kc0 + 4 * q;
-      const float* src = k < p.K1 ? p.in1 + (long long)b * p.s1 + k : p.in2 + (long long)b * p.s2 + (k - p.K1);
-      cp_async16(s_a + (size_t)r * AS + 4 * q, src);
-    }
-    if (UPC == 4) {
-      for (int i = threadIdx.x; i < kc * 4; i += 256) {
-        const int k = i >> 2, g = i & 3;
-        cp_async16(s_w + (size_t)i * 4, p.w + (size_t)(kc0 + k) * 4 * Ud + g * Ud + u0);
-      }
-    } else {
-      for (int i = threadIdx.x; i < kc * 4; i += 256) {
-        const int k = i >> 2, g = i & 3;
-        reinterpret_cast<float2*>(s_w)[i] = __ldg(reinterpret_cast<const float2*>(p.w + (size_t)(kc0 + k) * 4 * Ud + g * Ud + u0));
-      }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    const int per = (kq + 7) / 8;
-    const int q_lo = warp * per, q_hi = min(kq, q_lo + per);
-    const float* arow = s_a + (size_t)lane * AS;
+  const int K = p.K1 + p.K2, K4 = K / 4;
+  const int per = (K4 + CF_KS - 1) / CF_KS;   // float4 chunks of the reduction per slice
+  const int q_lo = ks * per, nq = max(0, min(K4, q_lo + per) - q_lo);
+  const int AS = 4 * per + 4;                 // padded activation row stride
+  float* s_a = cf_smem;                                   // [32][AS]
+  float* s_w = s_a + (size_t)DT_ROWS * AS;                // [4*per][64], column = unit_local*4 + gate
+  float* s_red = s_w + (size_t)4 * per * 4 * CF_UG;       // [8 src][32 rows][8] partial sums of my 2 units
+  cluster.barrier_arrive();  // every CTA of the cluster must be running before its shared memory is written remotely
+  for (int i = threadIdx.x; i < DT_ROWS * nq; i += 256) {
+    const int r = i / nq, q = i - r * nq;
+    const int b = min(b0 + r, p.B - 1);
+    const int k = 4 * (q_lo + q);
+    const float* src = k < p.K1 ? p.in1 + (long long)b * p.s1 + k : p.in2 + (long long)b * p.s2 + (k - p.K1);
+    cp_async16(s_a + (size_t)r * AS + 4 * q, src);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = threadIdx.x; i < 4 * nq * 16; i += 256) {  // 16 float4 per weight row: 4 gates x 4 groups of 4 units
+    const int kk = i >> 4, g = (i >> 2) & 3, j = i & 3;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(4 * q_lo + kk) * 4 * Ud + g * Ud + u0 + 4 * j));
+    float* dst = s_w + (size_t)kk * 64 + (4 * j) * 4 + g;
+    dst[0] = w.x; dst[4] = w.y; dst[8] = w.z; dst[12] = w.w;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* arow = s_a + (size_t)lane * AS;
+  const float* wbase = s_w + 8 * warp;
 #pragma unroll 2
-    for (int q = q_lo; q < q_hi; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(arow + 4 * q);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+  for (int q = 0; q < nq; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(arow + 4 * q);
+    const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float4* wr = reinterpret_cast<const float4*>(s_w + (size_t)(4 * q + kk) * NC);
-#pragma unroll
-        for (int c4 = 0; c4 < NC / 4; ++c4) {
-          const float4 w = wr[c4];
-          acc[4 * c4 + 0] = fmaf(av[kk], w.x, acc[4 * c4 + 0]);
-          acc[4 * c4 + 1] = fmaf(av[kk], w.y, acc[4 * c4 + 1]);
-          acc[4 * c4 + 2] = fmaf(av[kk], w.z, acc[4 * c4 + 2]);
-          acc[4 * c4 + 3] = fmaf(av[kk], w.w, acc[4 * c4 + 3]);
-        }
-      }
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wbase + (size_t)(4 * q + kk) * 64);
+      const float4 w1 = *reinterpret_cast<const float4*>(wbase + (size_t)(4 * q + kk) * 64 + 4);
+      acc[0] = fmaf(av[kk], w0.x, acc[0]); acc[1] = fmaf(av[kk], w0.y, acc[1]);
+      acc[2] = fmaf(av[kk], w0.z, acc[2]); acc[3] = fmaf(av[kk], w0.w, acc[3]);
+      acc[4] = fmaf(av[kk], w1.x, acc[4]); acc[5] = fmaf(av[kk], w1.y, acc[5]);
+      acc[6] = fmaf(av[kk], w1.z, acc[6]); acc[7] = fmaf(av[kk], w1.w, acc[7]);
     }
   }
-  __syncthreads();  // everyone is done with the staged tiles: reuse them for the cross-warp reduction
-  float* s_red = cf_smem;  // [8][NC][33]
-#pragma unroll
-  for (int c = 0; c < NC; ++c) s_red[(warp * NC + c) * (DT_ROWS + 1) + lane] = acc[c];
-  __syncthreads();
-  if (threadIdx.x < DT_ROWS * UPC) {
-    const int r = threadIdx.x % DT_ROWS, u = threadIdx.x / DT_ROWS;
-    const int bb = b0 + r;
+  cluster.barrier_wait();
+  {
+    float* remote = cluster.map_shared_rank(s_red, warp) + ((size_t)ks * DT_ROWS + lane) * 8;  // warp w's units belong to rank w
+    *reinterpret_cast<float4*>(remote) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(remote + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  cluster.sync();
+  if (threadIdx.x < DT_ROWS * 2) {
+    const int r = threadIdx.x % DT_ROWS, uu = threadIdx.x / DT_ROWS;
+    const int bb = b0 + r, u = u0 + 2 * ks + uu;
     if (bb < p.B) {
       float z[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float s = p.pre ? p.pre[(long long)bb * p.s_pre + g * Ud + u0 + u] : p.bias[g * Ud + u0 + u];
+      for (int g = 0; g < 4; ++g) z[g] = p.pre ? p.pre[(long long)bb * p.s_pre + g * Ud + u] : p.bias[g * Ud + u];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += s_red[(w * NC + g * UPC + u) * (DT_ROWS + 1) + r];
-        z[g] = s;
+      for (int src = 0; src < CF_KS; ++src) {  // fixed order: deterministic
+        const float4 v = *reinterpret_cast<const float4*>(s_red + ((size_t)src * DT_ROWS + r) * 8 + 4 * uu);
+        z[0] += v.x; z[1] += v.y; z[2] += v.z; z[3] += v.w;
       }
-      const float cp = p.c_prev ? p.c_prev[(long long)bb * p.s_c + u0 + u] : 0.f;
+      const float cp = p.c_prev ? p.c_prev[(long long)bb * p.s_c + u] : 0.f;
       const float gi = sigmoidf_acc(z[0]), gj = tanhf(z[1]), gf = sigmoidf_acc(z[2] + 1.0f), go = sigmoidf_acc(z[3]);
       const float c = gf * cp + gi * gj;
       const float h = go * tanhf(c);
-      float* zo = p.z_out + (long long)bb * p.s_z + u0 + u;
+      float* zo = p.z_out + (long long)bb * p.s_z + u;
       zo[0] = gi; zo[Ud] = gj; zo[2 * Ud] = gf; zo[3 * Ud] = go;
-      p.c_out[(long long)bb * p.s_h + u0 + u] = c;
-      p.h_out[(long long)bb * p.s_h + u0 + u] = h;
-      if (p.hprev_next) p.hprev_next[(long long)bb * p.s_h + u0 + u] = h;
+      p.c_out[(long long)bb * p.s_h + u] = c;
+      p.h_out[(long long)bb * p.s_h + u] = h;
+      if (p.hprev_next) p.hprev_next[(long long)bb * p.s_h + u] = h;
       if (p.hdrop_out)
-        p.hdrop_out[(long long)bb * p.s_h + u0 + u] =
-            h * drop_scale((uint64_t)((long long)bb * p.s_h + p.idx_base + u0 + u), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
+        p.hdrop_out[(long long)bb * p.s_h + u] =
+            h * drop_scale((uint64_t)((long long)bb * p.s_h + p.idx_base + u), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL,
+                           p.thresh, p.inv_keep);
     }
   }
 }
@@ -494,63 +489,70 @@ struct GemvTArgs {
   float* dinp; long long s_o;
 };
 
-constexpr int GV_NC = 512;   // reduction chunk staged per pass
+constexpr int GV_NS = 8;    // N-slices = CTAs per cluster
+constexpr int GV_KG = 64;   // outputs per CTA group
 
+// dinp[b][k] = sum_n dz[b][n] W[k][n]: grid = (8 N-slices) x (K/64 output groups) x (row chunks), the 8 slices of a group in
+// one cluster.  Same scheme as dec_cell_fwd_kernel: stage the slice (32 x N/8 of dz, 64 x N/8 of W), multiply (lane = batch
+// row, warp = 8 outputs), send the partials to the owning CTA through distributed shared memory, sum in a fixed order.
 __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float gv_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k0 = blockIdx.x * 8;
-  const int b0 = blockIdx.y * DT_ROWS;
-  const int nc_max = min(p.N, GV_NC);
-  const int AS = nc_max + 4;
-  float* s_a = gv_smem;                      // [32][AS] dz rows
-  float* s_w = s_a + (size_t)DT_ROWS * AS;   // [8][nc] the CTA's 8 weight rows
+  const int ns = blockIdx.x;
+  const int k0 = blockIdx.y * GV_KG;
+  const int b0 = blockIdx.z * DT_ROWS;
+  const int N4 = p.N / 4;
+  const int per = (N4 + GV_NS - 1) / GV_NS;
+  const int q_lo = ns * per, nq = max(0, min(N4, q_lo + per) - q_lo);
+  const int AS = 4 * per + 4;
+  float* s_a = gv_smem;                                 // [32][AS] slice of the dz rows
+  float* s_w = s_a + (size_t)DT_ROWS * AS;              // [64][4*per] slice of the CTA group's weight rows
+  float* s_red = s_w + (size_t)GV_KG * 4 * per;         // [8 src][32 rows][8] partial sums of my 8 outputs
+  cluster.barrier_arrive();
+  for (int i = threadIdx.x; i < DT_ROWS * nq; i += 256) {
+    const int r = i / nq, q = i - r * nq;
+    const int b = min(b0 + r, p.B - 1);
+    cp_async16(s_a + (size_t)r * AS + 4 * q, p.dz + (long long)b * p.s_z + 4 * (q_lo + q));
+  }
+  for (int i = threadIdx.x; i < GV_KG * nq; i += 256) {
+    const int kk = i / nq, q = i - kk * nq;
+    const int k = min(k0 + kk, p.K - 1);
+    cp_async16(s_w + (size_t)kk * 4 * per + 4 * q, p.w + (size_t)k * p.N + 4 * (q_lo + q));
+  }
+  cp_async_wait_all();
+  __syncthreads();
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int n0 = 0; n0 < p.N; n0 += GV_NC) {
-    const int nc = min(GV_NC, p.N - n0);
-    const int nq = nc / 4;
-    if (n0 > 0) __syncthreads();
-    for (int i = threadIdx.x; i < DT_ROWS * nq; i += 256) {
-      const int r = i / nq, q = i - r * nq;
-      const int b = min(b0 + r, p.B - 1);
-      cp_async16(s_a + (size_t)r * AS + 4 * q, p.dz + (long long)b * p.s_z + n0 + 4 * q);
-    }
-    for (int i = threadIdx.x; i < 8 * nq; i += 256) {
-      const int kk = i / nq, q = i - kk * nq;
-      const int k = min(k0 + kk, p.K - 1);
-      cp_async16(s_w + (size_t)kk * nc + 4 * q, p.w + (size_t)k * p.N + n0 + 4 * q);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    const int per = (nq + 7) / 8;
-    const int q_lo = warp * per, q_hi = min(nq, q_lo + per);
-    const float* arow = s_a + (size_t)lane * AS;
-#pragma unroll 4
-    for (int q = q_lo; q < q_hi; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(arow + 4 * q);
+  const float* arow = s_a + (size_t)lane * AS;
+  const float* wbase = s_w + (size_t)(8 * warp) * 4 * per;
+#pragma unroll 2
+  for (int q = 0; q < nq; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(arow + 4 * q);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const float4 w = *reinterpret_cast<const float4*>(s_w + (size_t)kk * nc + 4 * q);
-        acc[kk] = fmaf(a.x, w.x, acc[kk]);
-        acc[kk] = fmaf(a.y, w.y, acc[kk]);
-        acc[kk] = fmaf(a.z, w.z, acc[kk]);
-        acc[kk] = fmaf(a.w, w.w, acc[kk]);
-      }
+    for (int kk = 0; kk < 8; ++kk) {
+      const float4 w = *reinterpret_cast<const float4*>(wbase + (size_t)kk * 4 * per + 4 * q);
+      acc[kk] = fmaf(a.x, w.x, acc[kk]);
+      acc[kk] = fmaf(a.y, w.y, acc[kk]);
+      acc[kk] = fmaf(a.z, w.z, acc[kk]);
+      acc[kk] = fmaf(a.w, w.w, acc[kk]);
     }
   }
-  __syncthreads();
-  float* s_red = gv_smem;  // [8 warps][8][33]
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) s_red[(warp * 8 + kk) * (DT_ROWS + 1) + lane] = acc[kk];
-  __syncthreads();
+  cluster.barrier_wait();
   {
-    const int r = threadIdx.x % DT_ROWS, kk = threadIdx.x / DT_ROWS;  // 256 threads = 32 rows x 8 k
-    const int bb = b0 + r, k = k0 + kk;
+    float* remote = cluster.map_shared_rank(s_red, warp) + ((size_t)ns * DT_ROWS + lane) * 8;  // warp w's outputs belong to rank w
+    *reinterpret_cast<float4*>(remote) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(remote + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  cluster.sync();
+  {
+    const int r = threadIdx.x % DT_ROWS, j = threadIdx.x / DT_ROWS;  // 256 threads = 32 rows x my 8 outputs
+    const int bb = b0 + r, k = k0 + 8 * ns + j;
     if (bb < p.B && k < p.K) {
-      float s = 0.f;
+      float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += s_red[(w * 8 + kk) * (DT_ROWS + 1) + r];
-      p.dinp[(long long)bb * p.s_o + k] = s;
+      for (int src = 0; src < GV_NS; ++src) sum += s_red[((size_t)src * DT_ROWS + r) * 8 + j];  // fixed order
+      p.dinp[(long long)bb * p.s_o + k] = sum;
     }
   }
 }
@@ -621,7 +623,7 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   PLAS_REQUIRE(d->B > 0 && d->S > 0 && d->Tm > 0 && d->E > 0 && d->n_out > 0, "dec_train: bad shape");
   PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_train: n_layers=%d", d->n_layers);
   PLAS_REQUIRE(d->keep_prob > 0.f && d->keep_prob <= 1.f, "dec_train: keep_prob=%f", d->keep_prob);
-  PLAS_REQUIRE(d->Ud % 8 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 8, D=%d of 4", d->Ud, d->D);
+  PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
   PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU,
                "dec_train: attention_type %d has no training path (luong, bahdanau)", d->attention_type);
   PLAS_REQUIRE((size_t)(d->D + 5 * (d->Tm + 4) + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
@@ -659,10 +661,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   const bool drop = d->keep_prob < 1.f;
   const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
   const float inv_keep = 1.0f / d->keep_prob;
-  const int upc = 2;  // 32 rows x (1280 + 4) activations + 1280 x 8 weights = 205 KB of shared memory
-  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  const dim3 cgrid(Ud / upc, (B + DT_ROWS - 1) / DT_ROWS);
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   const int dsplit = (D >= 512 && D % 16 == 0) ? 4 : 1;
   size_t att_smem = (size_t)(2 * Ud + ((Tm + 3) & ~3)) * 4;
   const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
@@ -690,11 +689,24 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
       a.hdrop_out = (drop && l + 1 < L) ? F(w.hdrop[l]) + (size_t)t * Ud : nullptr;
       a.idx_base = (long long)t * Ud; a.seed = d->drop_seed + 1 + l; a.thresh = thresh; a.inv_keep = inv_keep; a.step_ptr = d->drop_step;
-      const int kcm = (a.K1 + a.K2) < CF_KC ? (a.K1 + a.K2) : CF_KC;
-      const size_t need = (size_t)DT_ROWS * (kcm + 4) * 4 + (size_t)kcm * 4 * upc * 4, red = (size_t)8 * 4 * upc * (DT_ROWS + 1) * 4;
-      const size_t smem = need > red ? need : red;
-      if (upc == 4) dec_cell_fwd_kernel<4><<<cgrid, 256, smem, st>>>(a);
-      else dec_cell_fwd_kernel<2><<<cgrid, 256, smem, st>>>(a);
+      {
+        const int per = ((a.K1 + a.K2) / 4 + CF_KS - 1) / CF_KS;
+        const size_t smem = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)4 * per * 4 * CF_UG + (size_t)CF_KS * DT_ROWS * 8) * 4;
+        PLAS_REQUIRE(smem <= 220 * 1024, "dec_train_fwd: cell input depth %d too large", a.K1 + a.K2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CF_KS, Ud / CF_UG, (B + DT_ROWS - 1) / DT_ROWS);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CF_KS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_cell_fwd_kernel, a));
+      }
     }
     AttFwdArgs q;
     q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit; q.staged = att_staged;
@@ -794,9 +806,24 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       g.dz = c.z; g.s_z = sz;
       g.w = d->kernel[l] + (size_t)(l == 0 ? E : 0) * 4 * Ud;
       g.dinp = F(w.dinp[l]); g.s_o = Kin + Ud;
-      const int ncm = g.N < GV_NC ? g.N : GV_NC;
-      const size_t gsm = (size_t)DT_ROWS * (ncm + 4) * 4 + (size_t)8 * ncm * 4;
-      dec_gemv_t_kernel<<<dim3((g.K + 7) / 8, (B + DT_ROWS - 1) / DT_ROWS), 256, gsm, st>>>(g);
+      {
+        const int per = (g.N / 4 + GV_NS - 1) / GV_NS;
+        const size_t gsm = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)GV_KG * 4 * per + (size_t)GV_NS * DT_ROWS * 8) * 4;
+        PLAS_REQUIRE(gsm <= 220 * 1024, "dec_train_bwd: Ud = %d too large", Ud);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(GV_NS, (g.K + GV_KG - 1) / GV_KG, (B + DT_ROWS - 1) / DT_ROWS);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = gsm;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = GV_NS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_gemv_t_kernel, g));
+      }
     }
   }
   PLAS_CUDA(cudaGetLastError());
