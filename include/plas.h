@@ -302,8 +302,9 @@ int plas_ctc_grad(const float* logits, const int32_t* labels, const int32_t* lab
  * variables.  grad_l2_norm: g += l2_scale*w, norms[i] = ||g_i||, wsq[i] = ||w_i||^2 (optional, for the reported L2 term);  clip_scale: g_i *= clip/max(norms[i],clip) * post_scale
  * (post_scale = 1/world_size before the data-parallel all-reduce);  adam_step: TF epsilon-hat form with
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller, gradients pre-multiplied by grad_scale. */
+size_t plas_grad_l2_norm_scratch_bytes(int32_t n_tensors);
 int plas_grad_l2_norm(const float* params, float* grads, const int64_t* offsets, int32_t n_tensors, float l2_scale,
-                      float* norms, float* wsq, plas_stream_t stream);
+                      float* norms, float* wsq, void* scratch, size_t scratch_bytes, plas_stream_t stream);
 int plas_clip_scale(float* grads, const int64_t* offsets, int32_t n_tensors, const float* norms, float clip,
                     float post_scale, plas_stream_t stream);
 /* Input dropout of the TRAIN graph (DropoutWrapper(input_keep_prob = 1 - dropout), las/ops.py:14-18): y = x * m / keep_prob

@@ -218,12 +218,18 @@ __global__ void ctc_grad_kernel(const float* __restrict__ logits, const int* __r
 }
 
 // ---- optimiser ------------------------------------------------------------------------------------------
+constexpr int L2_SPLIT = 16;  // slices per tensor (stage 1), summed in a fixed order by stage 2
+
+// stage 1: CTA (slice j, tensor i): g += l2*w over its slice, partial sums of g^2 and w^2 -> part[i][j][2]
 __global__ void __launch_bounds__(1024) grad_l2_norm_kernel(const float* __restrict__ params, float* __restrict__ grads,
                                                             const long long* __restrict__ offsets, float l2,
-                                                            float* __restrict__ norms, float* __restrict__ wsq) {
+                                                            double* __restrict__ part) {
   __shared__ double s[1024];
   __shared__ double s2[1024];
-  const long long lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+  const long long t_lo = offsets[blockIdx.y], t_hi = offsets[blockIdx.y + 1];
+  const long long per = (t_hi - t_lo + L2_SPLIT - 1) / L2_SPLIT;
+  const long long lo = t_lo + (long long)blockIdx.x * per;
+  const long long hi = lo + per < t_hi ? lo + per : t_hi;
   double a = 0.0, w2 = 0.0;
   for (long long i = lo + threadIdx.x; i < hi; i += 1024) {
     const float w = params[i];
@@ -243,9 +249,22 @@ __global__ void __launch_bounds__(1024) grad_l2_norm_kernel(const float* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    norms[blockIdx.x] = (float)sqrt(s[0]);
-    if (wsq) wsq[blockIdx.x] = (float)s2[0];
+    part[((size_t)blockIdx.y * L2_SPLIT + blockIdx.x) * 2] = s[0];
+    part[((size_t)blockIdx.y * L2_SPLIT + blockIdx.x) * 2 + 1] = s2[0];
   }
+}
+
+// stage 2: one thread per tensor, fixed order
+__global__ void grad_l2_norm_finish_kernel(const double* __restrict__ part, int n, float* __restrict__ norms, float* __restrict__ wsq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0, w2 = 0.0;
+  for (int j = 0; j < L2_SPLIT; ++j) {
+    a += part[((size_t)i * L2_SPLIT + j) * 2];
+    w2 += part[((size_t)i * L2_SPLIT + j) * 2 + 1];
+  }
+  norms[i] = (float)sqrt(a);
+  if (wsq) wsq[i] = (float)w2;
 }
 
 __global__ void clip_scale_kernel(float* __restrict__ grads, const long long* __restrict__ offsets,
@@ -348,10 +367,15 @@ extern "C" int plas_ctc_grad(const float* logits, const int32_t* labels, const i
   return PLAS_OK;
 }
 
+extern "C" size_t plas_grad_l2_norm_scratch_bytes(int32_t n_tensors) { return (size_t)n_tensors * L2_SPLIT * 2 * sizeof(double); }
+
 extern "C" int plas_grad_l2_norm(const float* params, float* grads, const int64_t* offsets, int32_t n_tensors, float l2_scale,
-                                 float* norms, float* wsq, plas_stream_t stream_) {
-  PLAS_REQUIRE(params && grads && offsets && norms && n_tensors > 0, "grad_l2_norm: bad argument");
-  grad_l2_norm_kernel<<<n_tensors, 1024, 0, (cudaStream_t)stream_>>>(params, grads, (const long long*)offsets, l2_scale, norms, wsq);
+                                 float* norms, float* wsq, void* scratch, size_t scratch_bytes, plas_stream_t stream_) {
+  PLAS_REQUIRE(params && grads && offsets && norms && scratch && n_tensors > 0, "grad_l2_norm: bad argument");
+  PLAS_REQUIRE(scratch_bytes >= plas_grad_l2_norm_scratch_bytes(n_tensors), "grad_l2_norm: scratch too small");
+  grad_l2_norm_kernel<<<dim3(L2_SPLIT, n_tensors), 1024, 0, (cudaStream_t)stream_>>>(params, grads, (const long long*)offsets, l2_scale,
+                                                                                     (double*)scratch);
+  grad_l2_norm_finish_kernel<<<(n_tensors + 127) / 128, 128, 0, (cudaStream_t)stream_>>>((const double*)scratch, n_tensors, norms, wsq);
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;
 }

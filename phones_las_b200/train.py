@@ -136,6 +136,7 @@ class TrainState:
         self.offsets = torch.tensor(self.offsets_host, dtype=torch.int64, device=device)
         self.norms = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
         self.wsq = torch.zeros((len(self.names),), dtype=torch.float32, device=device)
+        self.l2_scratch = torch.empty((_lib.lib().plas_grad_l2_norm_scratch_bytes(len(self.names)),), dtype=torch.uint8, device=device)
         self.index = {k: i for i, k in enumerate(self.names)}
         self.split_ws = torch.empty((32 << 20,), dtype=torch.uint8, device=device)  # split-K scratch of the dW GEMMs
         self.step_dev = torch.zeros((1,), dtype=torch.int32, device=device)  # read by the dropout kernels (graph-safe seeds)
@@ -497,10 +498,10 @@ def regularise_and_clip(st, hp, world_size=1):
     L = _lib.lib()
     n = len(st.names)
     _lib.check(L.plas_grad_l2_norm(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.offsets), n, float(hp.get("l2_reg_scale", 0.0)),
-                                   _lib.ptr(st.norms), _lib.ptr(st.wsq), _lib.stream_ptr()))
+                                   _lib.ptr(st.norms), _lib.ptr(st.wsq), _lib.ptr(st.l2_scratch), st.l2_scratch.numel(), _lib.stream_ptr()))
     _lib.check(L.plas_clip_scale(_lib.ptr(st.grads), _lib.ptr(st.offsets), n, _lib.ptr(st.norms), GRAD_NORM, 1.0 / world_size,
                                  _lib.stream_ptr()))
-    _lib.count_launches(2)
+    _lib.count_launches(3)
 
 
 def apply_gradients(st, hp, world_size=1, allreduce=None, clipped=False):
