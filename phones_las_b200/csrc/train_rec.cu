@@ -14,7 +14,12 @@
 //             own units, so the exchanged vector is dz, 4U wide -- hence small row groups, R = 8);  gate derivatives
 //             from the saved activations;  dz_s overwrites the saved gates IN PLACE and is what the weight / input
 //             gradient GEMMs consume (dW = [x;h_{s-1}]^T dz, dx = dz W_x^T: plas_gemm_f32_ex).  t >= len is zeroed.
-// The (R, UPC) shape is picked per call so that every group's CTAs are co-resident in as few launches as possible.
+// The (R, UPC, RB) shape is picked per call so that every group's CTAs are co-resident in as few launches as possible.
+// Forward only, when U/32 <= 8 and every (direction, group) fits in one wave: the CTAs of a group form a thread-block
+// cluster and exchange h through distributed shared memory with one cluster barrier per step (2.57 ms vs 2.86 ms at c3).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/plas.h"
 
@@ -38,8 +43,12 @@ __device__ __forceinline__ void rt_wait(const unsigned* ctr, unsigned target) {
 // Thread = (unit ul, block of RB rows, k-slice kh): one weight vector fetched from shared memory feeds RB rows from
 // registers, so the W_hh slice is read R/RB times per step instead of R times (with RB = 1 the step is bound by those
 // shared-memory reads: ncu short_scoreboard + barrier stalls, FMA pipe 13 % active).
-template <int R, int UPC, int RB>
+// CL: the G <= 8 CTAs of a (direction, group) form one thread-block cluster; h_s is pushed in 16-byte pieces into the
+// double-buffered tile of every CTA through distributed shared memory and ONE cluster barrier per step replaces the three
+// L2 round trips of the counter protocol (poll, tile load, fence + atomic).
+template <int R, int UPC, int RB, bool CL>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainArgs p) {
+  namespace cg = cooperative_groups;
   constexpr int NRB = R / RB, TPS = UPC * NRB, KS = RT_THREADS / TPS;
   static_assert(R % RB == 0 && KS >= 1 && KS * TPS == RT_THREADS && R * UPC <= RT_THREADS, "bad shape");
   extern __shared__ __align__(16) unsigned char rt_smem[];
@@ -54,8 +63,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
   const int HS = U + 4;  // padded row stride of the staged h tile
 
   float4* s_w = reinterpret_cast<float4*>(rt_smem);               // [U (k)][UPC] : (i,j,f,o) columns of a unit
-  float* s_h = reinterpret_cast<float*>(s_w + (size_t)U * UPC);  // [R][HS]
-  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)R * HS);  // [KS][R][UPC] partial pre-activations
+  float* s_h = reinterpret_cast<float*>(s_w + (size_t)U * UPC);  // [2 if CL][R][HS]
+  float4* s_part = reinterpret_cast<float4*>(s_h + (size_t)(CL ? 2 : 1) * R * HS);  // [KS][R][UPC] partial pre-activations
+  float* s_stage = reinterpret_cast<float*>(s_part + (size_t)KS * R * UPC);          // CL: [R][UPC] slice to push
   __shared__ int s_len[R];
   __shared__ int s_tmax;
   {
@@ -90,6 +100,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
   const size_t srow = (size_t)ndir * U;
   const int kper = U / KS;  // host guarantees (U / KS) % 4 == 0
   float c_state = 0.f, h_state = 0.f;
+  if (CL) cg::this_cluster().sync();  // every CTA of the cluster is running before its shared memory is written remotely
 
   for (int s = 0; s < Tg; ++s) {
     const bool act = fin && s < len;
@@ -100,19 +111,21 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
       z = make_float4(zp[0], zp[U], zp[2 * U], zp[3 * U]);
     }
     if (s > 0) {
-      if (tid == 0) rt_wait(ctr, (unsigned)(p.G * s));
-      __syncthreads();
-      const float4* hsrc = reinterpret_cast<const float4*>(hx + (((size_t)((s - 1) & 1) * ndir + dir) * p.Bpad + row0) * U);
-      const int U4 = U / 4;
-      for (int i = tid; i < R * U4; i += RT_THREADS) {
-        const int rr = i / U4, c4 = i - rr * U4;
-        *reinterpret_cast<float4*>(s_h + rr * HS + 4 * c4) = __ldcg(hsrc + i);
+      if (!CL) {
+        if (tid == 0) rt_wait(ctr, (unsigned)(p.G * s));
+        __syncthreads();
+        const float4* hsrc = reinterpret_cast<const float4*>(hx + (((size_t)((s - 1) & 1) * ndir + dir) * p.Bpad + row0) * U);
+        const int U4 = U / 4;
+        for (int i = tid; i < R * U4; i += RT_THREADS) {
+          const int rr = i / U4, c4 = i - rr * U4;
+          *reinterpret_cast<float4*>(s_h + rr * HS + 4 * c4) = __ldcg(hsrc + i);
+        }
+        __syncthreads();
       }
-      __syncthreads();
       float4 acc[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* hrow = s_h + r0 * HS + kh * kper;
+      const float* hrow = s_h + (CL ? (size_t)((s - 1) & 1) * R * HS : 0) + r0 * HS + kh * kper;
       const float4* wcol = s_w + (size_t)(kh * kper) * UPC + ul;
 #pragma unroll 2
       for (int k = 0; k < kper; k += 4) {
@@ -153,16 +166,29 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
         c_state = cn;
         h_state = hn;
       }
-      hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state;
+      if (CL) s_stage[fr * UPC + ful] = h_state;
+      else hx[(((size_t)(s & 1) * ndir + dir) * p.Bpad + b) * U + unit] = h_state;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (CL) {
+      constexpr int Q = UPC / 4;  // 16-byte pieces per row of the CTA's slice
+      float* tile = s_h + (size_t)(s & 1) * R * HS + ci * UPC;
+      for (int i = tid; i < R * Q * p.G; i += RT_THREADS) {
+        const int c = i / (R * Q), e = i - c * (R * Q);
+        const int rr = e / Q, q = e - rr * Q;
+        const float4 v = reinterpret_cast<const float4*>(s_stage)[rr * Q + q];
+        *reinterpret_cast<float4*>(cg::this_cluster().map_shared_rank(tile + rr * HS + 4 * q, c)) = v;
+      }
+      cg::this_cluster().sync();  // h_s has landed everywhere; everyone is done reading h_{s-1}
+    } else if (tid == 0) {
       __threadfence();
       red_release_add_u32(ctr, 1u);
     }
   }
 }
 
+// (A cluster/DSMEM exchange was measured for the backward pass too: 4.06 ms vs 3.53 ms for the three layers of c3 -- dz is
+// four times wider than h, 32 KB land in every CTA per step -- so the backward recurrence keeps the L2 exchange.)
 template <int R, int UPC, int RB>
 __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainArgs p) {
   constexpr int NRB = R / RB, TPS = UPC * NRB, KS = RT_THREADS / TPS;
@@ -303,8 +329,10 @@ struct RtShape {
   int R, UPC, RB;
   const void* fn;
 };
-#define RT_FWD(R, UPC, RB) {R, UPC, RB, (const void*)rec_train_fwd_kernel<R, UPC, RB>}
+#define RT_FWD(R, UPC, RB) {R, UPC, RB, (const void*)rec_train_fwd_kernel<R, UPC, RB, false>}
 #define RT_BWD(R, UPC, RB) {R, UPC, RB, (const void*)rec_train_bwd_kernel<R, UPC, RB>}
+// thread-block-cluster variant of the forward recurrence: 8 utterances per group, 32 units per CTA (G = U/32 <= 8), 4 rows per thread (KS = 4)
+constexpr int RT_CL_R = 8, RT_CL_UPC = 32, RT_CL_RB = 4, RT_CL_KS = RT_THREADS / (RT_CL_UPC * RT_CL_R / RT_CL_RB);
 // order = preference among shapes needing the same number of launches; the RB = 1 shapes serve narrow layers
 static const RtShape rt_fwd_shapes[] = {RT_FWD(16, 8, 4), RT_FWD(32, 4, 4), RT_FWD(16, 8, 1), RT_FWD(16, 4, 1), RT_FWD(32, 4, 1), RT_FWD(8, 32, 1)};
 static const RtShape rt_bwd_shapes[] = {RT_BWD(8, 16, 4), RT_BWD(8, 16, 1), RT_BWD(8, 32, 1), RT_BWD(8, 8, 1), RT_BWD(8, 4, 1), RT_BWD(16, 4, 1)};
@@ -343,7 +371,50 @@ static int rt_launch(const plas_rec_train_desc* d, void* workspace, size_t works
   rt_ws_layout(*d, &o_ctr, &o_x, &total);
   PLAS_REQUIRE(workspace_bytes >= total, "rec_train: workspace %zu < %zu", workspace_bytes, total);
 
-  // pick the shape with the fewest launches (all CTAs of a group must be co-resident), then the most CTAs
+  // preferred: one portable-size cluster (<= 8 CTAs) per (direction, group), exchange through distributed shared memory
+  const char* mode = getenv("PLAS_RT_EXCHANGE");  // "l2" forces the counter protocol (tuning aid)
+  if (!backward && d->U % RT_CL_UPC == 0 && d->U / RT_CL_UPC <= 8 && d->U % (4 * RT_CL_KS) == 0 && !(mode && mode[0] == 'l')) {
+    const int G = d->U / RT_CL_UPC;
+    const size_t smem = (size_t)d->U * RT_CL_UPC * 16 + (size_t)2 * RT_CL_R * (d->U + 4) * 4 +
+                        (size_t)RT_CL_KS * RT_CL_R * RT_CL_UPC * 16 + (size_t)RT_CL_R * RT_CL_UPC * 4;
+    if (smem <= 220 * 1024) {
+      const void* fn = (const void*)rec_train_fwd_kernel<RT_CL_R, RT_CL_UPC, RT_CL_RB, true>;
+      PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RecTrainArgs a;
+      a.d = *d;
+      a.counters = nullptr;
+      a.xbuf = nullptr;
+      a.n_groups = (d->B + RT_CL_R - 1) / RT_CL_R;
+      a.G = G;
+      a.Bpad = a.n_groups * RT_CL_R;
+      a.group_offset = 0;
+      a.groups_here = a.n_groups;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(d->ndir * a.n_groups * G));
+      cfg.blockDim = dim3(RT_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)G;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      // only when every cluster is co-resident (one wave): with more groups than that the L2 variants, which spread a
+      // group over more CTAs, finish sooner (measured at B = 64: 5.1 ms vs 3.5 ms)
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        max_clusters = 0;
+      }
+      if (d->ndir * a.n_groups <= max_clusters) {
+        PLAS_CUDA(cudaLaunchKernelEx(&cfg, rec_train_fwd_kernel<RT_CL_R, RT_CL_UPC, RT_CL_RB, true>, a));
+        return PLAS_OK;
+      }
+    }
+  }
+  // otherwise L2 exchange: pick the shape with the fewest launches (all CTAs of a group must be co-resident), then the most CTAs
   const RtShape* shapes = backward ? rt_bwd_shapes : rt_fwd_shapes;
   const int n_shapes = 6;
   const RtShape* best = nullptr;
