@@ -52,7 +52,9 @@ def test_gemm_ex_all_layouts(M, N, K):
     assert scaled_err(out, B.double().sum(0)) < 1e-5
 
 
-LISTENER_CFGS = [(3, 13, 5, 8, 2), (5, 21, 7, 16, 3), (20, 30, 39, 64, 3), (33, 40, 13, 256, 2)]
+LISTENER_CFGS = [(3, 13, 5, 8, 2), (5, 21, 7, 16, 3), (20, 30, 39, 64, 3), (33, 40, 13, 256, 2),
+                 (70, 12, 9, 256, 2),   # more groups than fit one wave of clusters: L2-exchange forward
+                 (3, 14, 16, 512, 2)]   # c2 width: 16 CTAs per group, no cluster variant
 
 
 @gpu
@@ -81,7 +83,9 @@ def test_listener_forward_backward(B, T, C, U, L):
 
 
 SPELLER_CFGS = [("luong", 3, 9, 16, 32, 1, 12, 5), ("bahdanau", 5, 14, 16, 32, 2, 20, 7), ("luong", 33, 30, 64, 256, 1, 64, 11),
-                ("bahdanau", 8, 20, 32, 64, 3, 30, 6), ("luong", 40, 12, 16, 128, 2, 16, 9)]
+                ("bahdanau", 8, 20, 32, 64, 3, 30, 6), ("luong", 40, 12, 16, 128, 2, 16, 9),
+                # c2 shapes (D = 2048, Ud = 512) with a memory too long to stage in shared memory: streaming attention paths
+                ("luong", 3, 200, 512, 512, 1, 20, 3), ("bahdanau", 2, 190, 512, 512, 2, 12, 3)]
 
 
 @gpu
