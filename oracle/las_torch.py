@@ -85,6 +85,36 @@ def pyramidal_bilstm(x, lengths, params, num_layers, scope="listener", masks=Non
     return outputs, lengths
 
 
+def listener(x, lengths, params, hp, masks=None):
+    """las/model.py:104-142: pyramidal (las/ops.py:68-87) or stacked MultiRNNCell listener, bi- or unidirectional.
+    ``masks[(layer, dir)]``: input-dropout multipliers over the WHOLE layer input; a stacked cell (layer >= 1) reads the
+    column slice of its own direction."""
+    uni = bool(hp.get("unidirectional", False))
+    L, U = hp["encoder_layers"], hp["encoder_units"]
+    dirs = (("rnn", False),) if uni else (("bidirectional_rnn/fw", False), ("bidirectional_rnn/bw", True))
+    outputs = x
+    for layer in range(L):
+        outs = []
+        for di, (d, rev) in enumerate(dirs):
+            if hp["use_pyramidal"]:
+                name = f"listener/bilstm_{layer}/{d}/lstm_cell"
+            else:
+                name = f"listener/{d}/multi_rnn_cell/cell_{layer}/lstm_cell"
+            xin = outputs if masks is None else outputs * masks[(layer, di)]
+            if not hp["use_pyramidal"] and layer > 0:
+                xin = xin[..., di * U:(di + 1) * U]
+            o, _ = dynamic_rnn(xin, lengths, params[name + "/kernel"], params[name + "/bias"], reverse=rev)
+            outs.append(o)
+        outputs = torch.cat(outs, -1)
+        if hp["use_pyramidal"] and layer != 0:
+            B, T, D = outputs.shape
+            if T % 2:
+                outputs = torch.cat([outputs, outputs.new_zeros((B, 1, D))], 1)
+            outputs = outputs.reshape(B, -1, 2 * D)
+            lengths = lengths // 2 + lengths % 2
+    return outputs, lengths
+
+
 def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
     binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
@@ -175,7 +205,7 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None):
     Returns (total loss incl. L2, dict of the parts)."""
     dt = features.dtype
     masks = masks or {}
-    enc_out, enc_len = pyramidal_bilstm(features, lengths, params, hp["encoder_layers"], masks=masks.get("listener"))
+    enc_out, enc_len = listener(features, lengths, params, hp, masks=masks.get("listener"))
     tin, tout, tlen = labels["targets_inputs"], labels["targets_outputs"], labels["target_sequence_length"]
     L = tin.shape[1]
     w = (torch.arange(L)[None, :] < tlen[:, None]).to(dt)

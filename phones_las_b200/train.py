@@ -90,13 +90,17 @@ def reference_masks(hp, step, B, T, C, S, binf_count=0):
     base = int(hp.get("dropout_seed", 0))
     U, V, Ud = hp["encoder_units"], hp["target_vocab_size"], hp["decoder_units"]
     out = {"listener": {}}
+    ndir, pyr = (1 if hp.get("unidirectional") else 2), bool(hp.get("use_pyramidal", True))
     t, din = T, C
     for l in range(hp["encoder_layers"]):
-        for dd in range(2):
+        for dd in range(ndir):  # the mask covers the whole layer input; a stacked cell reads its own column slice of it
             out["listener"][(l, dd)] = dropout_mask(B * t * din, drop_seed(base, step, LISTENER_TID + 2 * l + dd), keep).reshape(B, t, din)
-        din = 2 * U if l == 0 else 4 * U
-        if l != 0:
-            t = (t + 1) // 2
+        if pyr:
+            din = ndir * U if l == 0 else 2 * ndir * U
+            if l != 0:
+                t = (t + 1) // 2
+        else:
+            din = ndir * U
     D = din
     for si, (scope, E) in enumerate((("speller", V), ("speller_binf", binf_count))):
         if E <= 0:
@@ -190,8 +194,14 @@ class TrainState:
 # --------------------------------------------------------------------------------------------------------------
 # listener
 # --------------------------------------------------------------------------------------------------------------
-def _layer_names(l):
-    return [f"listener/bilstm_{l}/bidirectional_rnn/{d}/lstm_cell" for d in ("fw", "bw")]
+def _layer_names(l, hp):
+    """TF variable scopes of the cells of listener layer l, one per direction (las/ops.py:23-46, las/model.py:111-142)."""
+    uni = bool(hp["unidirectional"])
+    if hp["use_pyramidal"]:
+        dirs = ["rnn"] if uni else ["bidirectional_rnn/fw", "bidirectional_rnn/bw"]
+        return [f"listener/bilstm_{l}/{d}/lstm_cell" for d in dirs]
+    dirs = ["rnn"] if uni else ["bidirectional_rnn/fw", "bidirectional_rnn/bw"]
+    return [f"listener/{d}/multi_rnn_cell/cell_{l}/lstm_cell" for d in dirs]
 
 
 def _rec_desc(B, T, U, ndir, din, z, kernels, lengths, out, c_save, h_prev, dout=None):
@@ -209,12 +219,13 @@ def _rec_desc(B, T, U, ndir, din, z, kernels, lengths, out, c_save, h_prev, dout
 
 
 def listener_train_fwd(x, lengths, st, hp):
-    """pyramidal_bilstm (las/ops.py:68-87) forward keeping what BPTT needs.  x [B,T,C] f32 -> (enc_out, enc_len, tape).
-    With hp['dropout'] > 0 every cell sees its own dropped-out copy of the layer input (one DropoutWrapper per cell)."""
-    if not hp["use_pyramidal"] or hp["unidirectional"]:
-        raise NotImplementedError("the training path covers the pyramidal bidirectional listener")
+    """listener (las/model.py:104-142) forward keeping what BPTT needs: pyramidal_bilstm (las/ops.py:68-87) or the stacked
+    MultiRNNCell listener, bidirectional or unidirectional.  x [B,T,C] f32 -> (enc_out, enc_len, tape).
+    With hp['dropout'] > 0 every cell sees its own dropped-out copy of its input (one DropoutWrapper per cell).
+    In the stacked (non-pyramidal) listener each direction is its own stack: from layer 1 on, direction d reads only the U
+    columns of its own previous output -- a strided view for the GEMMs, no copy."""
     L = _lib.lib()
-    U, ndir = hp["encoder_units"], 2
+    U, ndir, pyr = hp["encoder_units"], (1 if hp["unidirectional"] else 2), bool(hp["use_pyramidal"])
     B = x.shape[0]
     lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
     x = x.to(torch.float32).contiguous()
@@ -222,16 +233,19 @@ def listener_train_fwd(x, lengths, st, hp):
     base = int(hp.get("dropout_seed", 0))
     tape = []
     for l in range(hp["encoder_layers"]):
-        T, din = x.shape[1], x.shape[2]
-        names = _layer_names(l)
+        T, width = x.shape[1], x.shape[2]
+        own = (not pyr) and l > 0           # direction d reads columns [d*U, (d+1)*U) of x
+        din = U if own else width           # input depth of one cell
+        names = _layer_names(l, hp)
         z = torch.empty((B, T, ndir, 4 * U), dtype=torch.float32, device=x.device)
         seeds = [drop_seed(base, 0, LISTENER_TID + 2 * l + dd) for dd in range(ndir)]  # + step * DROP_STEP_MUL on the device
-        xs = [dropout_(x, torch.empty_like(x), seeds[dd], keep, st.step_dev) for dd in range(ndir)] if keep < 1.0 else [x, x]
+        xs = [dropout_(x, torch.empty_like(x), seeds[dd], keep, st.step_dev) for dd in range(ndir)] if keep < 1.0 else [x] * ndir
         with _lib.stage("train_inproj"):
             for dd, nm in enumerate(names):
-                gemm_ex(B * T, 4 * U, din, xs[dd].data_ptr(), din, 1, st.w(nm + "/kernel"), 4 * U, 1, _p(z, dd * 4 * U), ndir * 4 * U,
-                        bias=st.w(nm + "/bias"))
-        t_alloc = T if l == 0 else T + (T % 2)
+                gemm_ex(B * T, 4 * U, din, _p(xs[dd], dd * U if own else 0), width, 1, st.w(nm + "/kernel"), 4 * U, 1,
+                        _p(z, dd * 4 * U), ndir * 4 * U, bias=st.w(nm + "/bias"))
+        stack = pyr and l != 0
+        t_alloc = T + (T % 2) if stack else T
         out = torch.zeros((B, t_alloc, ndir * U), dtype=torch.float32, device=x.device)
         c_save = torch.zeros((B, T, ndir * U), dtype=torch.float32, device=x.device)
         h_prev = torch.zeros((B, T, ndir * U), dtype=torch.float32, device=x.device)
@@ -242,8 +256,8 @@ def listener_train_fwd(x, lengths, st, hp):
             _lib.check(L.plas_bilstm_rec_train_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
         _lib.count_launches(1)
         tape.append(dict(xs=xs, seeds=seeds, keep=keep, z=z, c_save=c_save, h_prev=h_prev, lengths=lengths, T=T, din=din,
-                         t_alloc=t_alloc, ws=ws))
-        if l != 0:
+                         width=width, own=own, t_alloc=t_alloc, ws=ws))
+        if stack:  # pyramidal_stack: free view + ceil-halved lengths (las/ops.py:49-65)
             out = out.view(B, t_alloc // 2, 2 * ndir * U)
             lengths = torch.div(lengths, 2, rounding_mode="floor") + lengths % 2
         x = out
@@ -251,16 +265,16 @@ def listener_train_fwd(x, lengths, st, hp):
 
 
 def listener_train_bwd(d_enc, tape, st, hp):
-    """Gradient of pyramidal_bilstm: per layer BPTT (plas_bilstm_rec_train_bwd) then dW = [x;h]^T dz, db, dx = dz W_x^T."""
+    """Gradient of the listener: per layer BPTT (plas_bilstm_rec_train_bwd) then dW = [x;h]^T dz, db, dx = dz W_x^T."""
     L = _lib.lib()
-    U, ndir = hp["encoder_units"], 2
+    U, ndir = hp["encoder_units"], (1 if hp["unidirectional"] else 2)
     B = d_enc.shape[0]
     dout = d_enc
     side = st.side_streams(3)[2]
     for l in range(hp["encoder_layers"] - 1, -1, -1):
         tp = tape[l]
-        T, din = tp["T"], tp["din"]
-        names = _layer_names(l)
+        T, din, width, own = tp["T"], tp["din"], tp["width"], tp["own"]
+        names = _layer_names(l, hp)
         dout = dout.reshape(B, tp["t_alloc"], ndir * U)
         d = _rec_desc(B, T, U, ndir, din, tp["z"], [st.w(nm + "/kernel") for nm in names], tp["lengths"], None, tp["c_save"],
                       tp["h_prev"], dout=dout)
@@ -272,19 +286,23 @@ def listener_train_bwd(d_enc, tape, st, hp):
         M = B * T
         main = torch.cuda.current_stream()
         if l > 0:  # input gradient first: the next recurrence depends on it
-            dx = torch.empty((B, T, din), dtype=torch.float32, device=z.device)
+            dx = torch.empty((B, T, width), dtype=torch.float32, device=z.device)
             with _lib.stage("train_dgrad"):
                 for dd, nm in enumerate(names):
-                    if keep < 1.0:  # each direction saw its own mask: dx = sum_d mask_d * (dz_d W_d^T)
+                    zp, wk = _p(z, dd * 4 * U), st.w(nm + "/kernel")
+                    if keep < 1.0:  # each cell saw its own mask: dx = sum_d mask_d * (dz_d W_d^T)
                         dxd = dx if dd == 0 else torch.empty_like(dx)
-                        gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dxd.data_ptr(), din)
+                        if own:
+                            dxd.zero_()
+                        gemm_ex(M, din, 4 * U, zp, ndir * 4 * U, 1, wk, 1, 4 * U, _p(dxd, dd * U if own else 0), width)
                         dropout_(dxd, dxd, tp["seeds"][dd], keep, st.step_dev)
                         if dd > 0:
                             _lib.check(L.plas_axpy_f32(_lib.ptr(dx), _lib.ptr(dxd), dx.numel(), 1.0, _lib.stream_ptr()))
                             _lib.count_launches(1)
+                    elif own:  # the directions' inputs are disjoint column slices
+                        gemm_ex(M, din, 4 * U, zp, ndir * 4 * U, 1, wk, 1, 4 * U, _p(dx, dd * U), width)
                     else:
-                        gemm_ex(M, din, 4 * U, _p(z, dd * 4 * U), ndir * 4 * U, 1, st.w(nm + "/kernel"), 1, 4 * U, dx.data_ptr(), din,
-                                beta=0.0 if dd == 0 else 1.0)
+                        gemm_ex(M, din, 4 * U, zp, ndir * 4 * U, 1, wk, 1, 4 * U, dx.data_ptr(), width, beta=0.0 if dd == 0 else 1.0)
             dout = dx
         # weight gradients on a side stream: they only need dz, and overlap the (latency-bound) recurrence of the layer below
         ev = torch.cuda.Event()
@@ -294,7 +312,8 @@ def listener_train_bwd(d_enc, tape, st, hp):
             with _lib.stage("train_wgrad"):
                 for dd, nm in enumerate(names):
                     zp = _p(z, dd * 4 * U)
-                    gemm_ex(din, 4 * U, M, xs[dd].data_ptr(), 1, din, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
+                    gemm_ex(din, 4 * U, M, _p(xs[dd], dd * U if own else 0), 1, width, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U,
+                            split_ws=st.split_ws)
                     gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U,
                             split_ws=st.split_ws)
                     colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))

@@ -366,3 +366,32 @@ def test_train_step_with_dropout_matches_oracle_on_same_masks():
     for k in params:
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+
+
+@gpu
+@pytest.mark.parametrize("pyr,uni,dropout", [(False, False, 0.0), (True, True, 0.0), (False, True, 0.0), (False, False, 0.3), (True, True, 0.3)])
+def test_stacked_and_unidirectional_listener_training(pyr, uni, dropout):
+    """las/model.py:111-142 (stacked MultiRNNCell listener) and the unidirectional variants, forward + backward."""
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, U, L = 6, 22, 7, 16, 3
+    hp = create_hparams(target_vocab_size=12, encoder_layers=L, encoder_units=U, decoder_units=16, decoder_layers=1,
+                        num_channels=C, use_pyramidal=pyr, unidirectional=uni, dropout=dropout, sampling_probability=0.0)
+    params = {k: v for k, v in weights.init_params(hp, seed=6, bias_scale=0.1).items() if k.startswith("listener/")}
+    x, lens = synth.synth_features(B, T, C, seed=2, var_len=True)
+    st = tr.TrainState(params)
+    st.step = 4
+    masks = None
+    if dropout > 0:
+        masks = {k: torch.tensor(v, dtype=torch.float64) for k, v in tr.reference_masks(hp, 4, B, T, C, 4)["listener"].items()}
+    tp = _tp(params)
+    ref, ref_len = lt.listener(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, hp, masks=masks)
+    dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    (ref * dref).sum().backward()
+    out, out_len, tape = tr.listener_train_fwd(torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda(), st, hp)
+    assert out.shape == ref.shape and np.array_equal(to_np(out_len), ref_len.numpy())
+    assert scaled_err(out, ref.detach()) < 1e-5
+    tr.listener_train_bwd(dref.float().cuda().contiguous(), tape, st, hp)
+    grads = st.export_grads()
+    for k in params:
+        assert grad_err(grads[k], tp[k].grad) < GRAD_TOL, k

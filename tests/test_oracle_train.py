@@ -131,3 +131,16 @@ def test_dropout_mask_mirror_statistics_and_oracle_masks():
     b, _ = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, 2, masks=ones)
     c, _ = lt.pyramidal_bilstm(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, 2)
     assert torch.equal(b, c) and not torch.allclose(a, c)
+
+
+def test_general_listener_matches_numpy_oracle():
+    """Stacked (non-pyramidal) and unidirectional listeners of the differentiable restatement vs the numpy oracle."""
+    for pyr, uni in ((False, False), (True, True), (False, True)):
+        hp = create_hparams(target_vocab_size=12, encoder_layers=3, encoder_units=8, decoder_units=16, decoder_layers=1,
+                            num_channels=5, use_pyramidal=pyr, unidirectional=uni)
+        params = weights.init_params(hp, seed=3, bias_scale=0.1)
+        x, lens = synth.synth_features(4, 13, 5, var_len=True)
+        (ref, ref_len), _ = ol.listener(x, lens, params, hp)
+        out, out_len = lt.listener(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), _tp(params), hp)
+        assert np.array_equal(out_len.numpy(), ref_len), (pyr, uni)
+        assert np.abs(out.numpy() - ref).max() < 2e-6, (pyr, uni)
