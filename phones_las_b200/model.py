@@ -49,6 +49,21 @@ def las_predict(features, hp, weights, want_alignment=True, trim=True, want_prob
     return pred
 
 
+def las_eval(features, labels, hp, weights):
+    """model_helper.py:165-345 in EVAL mode (beam_width == 0, no binary-feature speller): greedy decode, the EVAL branch of
+    ``compute_loss`` (logits cut at max(final_sequence_length), targets padded with eos, mask = elementwise max of the
+    lengths; model_helper.py:54-76) and the ``edit_distance`` metric with repeat merging and EOS trimming
+    (utils/metrics_utils.py:8-41, host side).  Returns {'loss', 'edit_distance' [B] (numpy), 'sample_ids', ...}."""
+    from . import losses, metrics
+    pred = las_predict(features, hp, weights, want_alignment=False, want_probs=False)
+    targets = labels["targets_outputs"].to(pred["logits"].device)
+    tlen = labels["target_sequence_length"].to(pred["logits"].device)
+    loss = losses.compute_loss(pred["logits"], targets, pred["final_sequence_length"], tlen, "eval", hp["eos_id"])
+    ed = metrics.edit_distance(pred["sample_ids"].cpu().numpy(), targets.cpu().numpy(), hp["eos_id"], hp.get("mapping"))
+    return {"loss": loss, "edit_distance": ed, "sample_ids": pred["sample_ids"], "logits": pred["logits"],
+            "final_sequence_length": pred["final_sequence_length"]}
+
+
 class LASModel:
     """Front-end + listener + speller with device-resident weights."""
 

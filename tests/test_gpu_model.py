@@ -50,3 +50,25 @@ def test_transcribe_stream_equals_synchronous_calls():
     for (ids_a, len_a), (ids_b, len_b) in zip(sync, streamed):
         assert torch.equal(ids_a, ids_b) and torch.equal(len_a, len_b)
     assert list(model.transcribe_stream([])) == []
+
+
+@gpu
+def test_eval_mode_loss_and_edit_distance_match_oracle():
+    """las_model_fn(mode=EVAL): greedy decode + EVAL-branch sequence loss + edit distance vs the oracle."""
+    import torch
+    from oracle import losses as olo
+    from phones_las_b200.model import DeviceWeights, las_eval
+    hp = create_hparams(target_vocab_size=20, encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=32,
+                        attention_type="luong", num_channels=6)
+    params = weights.init_params(hp, 6, seed=9, projection_scale=8.0, bias_scale=0.1)
+    x, lens = synth.synth_features(5, 30, 6, seed=4, var_len=True)
+    tin, tout, tlen = synth.synth_labels(5, 6, 20, seed=8)
+    tlen = np.array([7, 4, 6, 2, 7], np.int32)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_outputs": torch.from_numpy(tout), "target_sequence_length": torch.from_numpy(tlen)}
+    out = las_eval(feats, labels, hp, DeviceWeights(params, hp, 6, "fp32"))
+    ref = ol.predict(x, lens, params, hp, "fp32")
+    ref_loss = olo.compute_loss(ref["logits"], tout, ref["final_sequence_length"], tlen, "eval", hp["eos_id"])
+    assert abs(out["loss"].item() - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    ref_ed = [olo.edit_distance_merge(list(ref["sample_ids"][b]), list(tout[b]), hp["eos_id"]) for b in range(5)]
+    np.testing.assert_allclose(out["edit_distance"], ref_ed, rtol=0, atol=1e-12)
