@@ -6,7 +6,6 @@ out (``encoder_out, source_length, embedding, sample_ids, alignment, probs``).  
 bundles a front-end plan with the device weights and follows the call order of
 ``transcribe_audio_file.py:97-101``.
 """
-import numpy as np
 import torch
 
 from . import _lib, weights as wts

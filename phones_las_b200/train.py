@@ -49,10 +49,6 @@ def colsum(X, M, N, ld, out, accumulate=False):
 # --------------------------------------------------------------------------------------------------------------
 # input dropout (DropoutWrapper(input_keep_prob = 1 - dropout) around every LSTMCell in TRAIN, las/ops.py:14-18)
 # --------------------------------------------------------------------------------------------------------------
-def _u32(x):
-    return np.uint32(x & 0xFFFFFFFF)
-
-
 def drop_seed(base, step, tensor_id):
     """32-bit seed of one dropped-out tensor at one optimiser step."""
     return int((int(base) * 0x9E3779B1 + int(step) * 0x85EBCA77 + int(tensor_id) * 0xC2B2AE3D + 0x165667B1) & 0xFFFFFFFF)
@@ -162,9 +158,6 @@ class TrainState:
             self._streams.append(torch.cuda.Stream(device=self.params.device))
         return self._streams[:n]
 
-    def has(self, name):
-        return name in self.index
-
     def w(self, name, row=0):
         """device address of variable ``name`` (+ ``row`` rows of its last dimension)."""
         i = self.index[name]
@@ -175,11 +168,6 @@ class TrainState:
         i = self.index[name]
         cols = self.shapes[name][-1] if self.shapes[name] else 1
         return _p(self.grads, self.offsets_host[i] + row * cols)
-
-    def view(self, buf, name):
-        i = self.index[name]
-        o, n = self.offsets_host[i], self.sizes[i]
-        return buf[o:o + n].view(self.shapes[name])
 
     def export_params(self):
         """-> {tf_variable_name: float32 ndarray} (the exchange format of weights.py)."""

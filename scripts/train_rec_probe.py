@@ -1,4 +1,4 @@
-"""Listener-only timing of the training recurrences at c3 shapes for every kernel shape (PLAS_RT_*_SHAPE)."""
+"""Listener-only timing of the training recurrences at c3 shapes: cluster (default) vs L2 exchange, B = 32 and 64."""
 import os, subprocess, sys
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np, torch
@@ -18,10 +18,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         out, ol, tape = tr.listener_train_fwd(xd, ld, st, hp)
         tr.listener_train_bwd(torch.ones_like(out), tape, st, hp)
     tl = _lib.timeline_stop()
-    print(os.environ.get("PLAS_RT_FWD_SHAPE"), os.environ.get("PLAS_RT_BWD_SHAPE"),
-          {k: round(sum(v), 3) for k, v in tl.items() if "rec" in k}, flush=True)
+    print("B", B, "exchange", os.environ.get("PLAS_RT_EXCHANGE", "cluster"), {k: round(sum(v), 3) for k, v in tl.items() if "rec" in k}, flush=True)
 else:
-    for i in range(6):
-        env = dict(os.environ, PLAS_RT_FWD_SHAPE=str(i), PLAS_RT_BWD_SHAPE=str(i))
-        r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
-        print(r.stdout.strip() or r.stderr.strip()[-300:], flush=True)
+    for pb in ("32", "64"):
+        for mode in (None, "l2"):
+            env = dict(os.environ, PB=pb)
+            if mode:
+                env["PLAS_RT_EXCHANGE"] = mode
+            r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
+            print(r.stdout.strip() or r.stderr.strip()[-300:], flush=True)
