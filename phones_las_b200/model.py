@@ -72,6 +72,15 @@ class LASModel:
         self.plan = FrontendPlan(feature_flags, means, stds, device)
         self.weights = DeviceWeights(params, hp, num_feature_channels(feature_flags), precision, device)
 
+    @classmethod
+    def from_model_dir(cls, model_dir, feature_flags, precision="fp32", means=None, stds=None, device="cuda"):
+        """Build the model from a reference ``model_dir`` as train.py leaves it: ``hparams.json`` (utils/params_utils.py:28-30)
+        and the latest TF checkpoint (tf_checkpoint.py), variables under their TF names."""
+        from . import hparams as hps, tf_checkpoint
+        hp = hps.create_hparams(model_dir=model_dir)
+        params = tf_checkpoint.load_model_variables(model_dir)
+        return cls(params, hp, feature_flags, precision=precision, means=means, stds=stds, device=device)
+
     def features(self, wave, n_samples=None):
         return self.plan(wave, n_samples)
 

@@ -174,6 +174,38 @@ class TrainState:
         flat = self.params.cpu().numpy()
         return {k: flat[o:o + n].reshape(self.shapes[k]).copy() for k, o, n in zip(self.names, self.offsets_host, self.sizes)}
 
+    # -- TF checkpoint interchange (tf_checkpoint.py): variables under their TF names plus the slots tf.train.AdamOptimizer keeps
+    def save_checkpoint(self, prefix):
+        """Write model.ckpt-style files the reference's Estimator could warm-start from: every variable, its Adam moments as
+        ``<name>/Adam`` and ``<name>/Adam_1``, ``beta1_power`` / ``beta2_power`` (= beta^(t+1) after t steps, as TF keeps them)
+        and ``global_step``."""
+        from . import tf_checkpoint
+        out = self.export_params()
+        m, v = self.m.cpu().numpy(), self.v.cpu().numpy()
+        for k, o, n in zip(self.names, self.offsets_host, self.sizes):
+            out[k + "/Adam"] = m[o:o + n].reshape(self.shapes[k]).copy()
+            out[k + "/Adam_1"] = v[o:o + n].reshape(self.shapes[k]).copy()
+        out["beta1_power"] = np.array(0.9 ** (self.step + 1), np.float32)
+        out["beta2_power"] = np.array(0.999 ** (self.step + 1), np.float32)
+        out["global_step"] = np.array(self.step, np.int64)
+        tf_checkpoint.write_checkpoint(prefix, out)
+
+    @classmethod
+    def from_checkpoint(cls, prefix, names, device="cuda"):
+        """Restore a TrainState for the variables ``names`` (ordered) from a TF bundle; missing Adam slots start at zero."""
+        from . import tf_checkpoint
+        ck = tf_checkpoint.read_checkpoint(prefix)
+        st = cls({k: ck[k] for k in names}, device=device)
+        m, v = np.zeros((st.total,), np.float32), np.zeros((st.total,), np.float32)
+        for k, o, n in zip(st.names, st.offsets_host, st.sizes):
+            if k + "/Adam" in ck:
+                m[o:o + n] = ck[k + "/Adam"].reshape(-1)
+                v[o:o + n] = ck[k + "/Adam_1"].reshape(-1)
+        st.m.copy_(torch.from_numpy(m))
+        st.v.copy_(torch.from_numpy(v))
+        st.step = int(ck["global_step"]) if "global_step" in ck else 0
+        return st
+
     def export_grads(self):
         flat = self.grads.cpu().numpy()
         return {k: flat[o:o + n].reshape(self.shapes[k]).copy() for k, o, n in zip(self.names, self.offsets_host, self.sizes)}

@@ -395,3 +395,33 @@ def test_stacked_and_unidirectional_listener_training(pyr, uni, dropout):
     grads = st.export_grads()
     for k in params:
         assert grad_err(grads[k], tp[k].grad) < GRAD_TOL, k
+
+
+@gpu
+def test_checkpoint_save_restore_resumes_training_identically(tmp_path):
+    """TrainState <-> TF bundle (variables + Adam slots + global_step): a restored state continues bit-identically, and the
+    saved model_dir serves LASModel.from_model_dir (hparams.json + checkpoint, the reference's layout)."""
+    import torch
+    from phones_las_b200 import train as tr, tf_checkpoint
+    from phones_las_b200.hparams import save_hparams, feature_args
+    hp, params, x, lens, tin, tout, tlen, binf = _full_setup(*FULL_CFGS[1])
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    st = tr.TrainState(params)
+    for _ in range(2):
+        tr.train_step(feats, labels, st, hp)
+    prefix = str(tmp_path / "model.ckpt-2")
+    st.save_checkpoint(prefix)
+    st2 = tr.TrainState.from_checkpoint(tf_checkpoint.latest_checkpoint(str(tmp_path)), list(params))
+    assert st2.step == 2 and torch.equal(st.params, st2.params) and torch.equal(st.m, st2.m) and torch.equal(st.v, st2.v)
+    a = tr.train_step(feats, labels, st, hp)["loss"].item()
+    b = tr.train_step(feats, labels, st2, hp)["loss"].item()
+    assert a == b and torch.equal(st.params, st2.params)
+    # inference from the same directory
+    from phones_las_b200.model import LASModel
+    save_hparams(hp, str(tmp_path))
+    fa = feature_args(feature_type="mfe", backend="speechpy", n_mels=4, energy=True, window=25, step=10)  # 4 mels + energy = 5 channels
+    model = LASModel.from_model_dir(str(tmp_path), fa, precision="fp32")
+    pred = model.predict_from_features(feats["encoder_inputs"], feats["source_sequence_length"])
+    assert pred["sample_ids"].shape[0] == x.shape[0]
