@@ -241,9 +241,11 @@ typedef struct plas_rec_train_desc {
   const int32_t* lengths;   /* [B]                                                                            */
   float* out;               /* fwd: [B][T_out][ndir*U], caller-zeroed (stays 0 for t >= len)                  */
   int64_t out_batch_stride;
-  float* c_save;            /* [B][T][ndir*U] cell states (fwd out, bwd in)                                   */
-  float* h_prev;            /* [B][T][ndir*U] h_{s-1} stored at the time index of step s (fwd out), caller-zeroed */
+  float* c_save;            /* [B][T][ndir*U] cell states (fwd out, bwd in); NULL in a forward-only (inference) call */
+  float* h_prev;            /* [B][T][ndir*U] h_{s-1} stored at the time index of step s (fwd out), caller-zeroed; may be NULL */
   const float* dout;        /* bwd: dL/dout, strides of `out`                                                 */
+  float* c_final;           /* fwd, optional: [ndir][B][U] final cell / hidden states (encoder_state, las/ops.py:35-46) */
+  float* h_final;
 } plas_rec_train_desc;
 size_t plas_rec_train_workspace_bytes(const plas_rec_train_desc* d);
 int plas_bilstm_rec_train_fwd(const plas_rec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
@@ -285,6 +287,34 @@ typedef struct plas_dec_train_desc {
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
 int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
+
+/* fp32 inference decoder (reference-precision mode) built from the same step kernels, on the TF checkpoint layout: greedy
+ * (GreedyEmbeddingHelper + dynamic_decode, las/model.py:337-347) or teacher-forced, luong / bahdanau attention, default
+ * wiring.  A host loop of small launches over a 2-slot state ring; launches after every utterance has finished are no-ops.
+ * keys = memory_layer(values) is computed by the caller (plas_gemm_f32 / plas_gemm_f32_ex). */
+typedef struct plas_dec_infer_desc {
+  int32_t B, Tm, D, Ud, V, n_layers, attention_type, sos_id, eos_id;
+  int32_t max_steps;        /* capacity of the outputs along the step axis                                     */
+  int32_t teacher_forced;   /* 0 = greedy, 1 = feed forced_ids and run exactly max_steps                        */
+  float decoding_length_factor; /* greedy: stop at rint(max(mem_len) * factor)                                 */
+  const float* kernel[4];   /* cell_k/lstm_cell/kernel, TF layout [(k == 0 ? V + D : Ud) + Ud][4Ud]             */
+  const float* bias[4];     /* [4Ud], gate blocks i|j|f|o                                                      */
+  const float* w_query;     /* bahdanau query_layer/kernel [Ud][Ud] or NULL                                    */
+  const float* v_att;       /* bahdanau attention_v [Ud] or NULL                                               */
+  const float* w_proj;      /* projection_layer/kernel [D][V]                                                  */
+  const float* b_proj;      /* [V]                                                                             */
+  const float* keys;        /* [B][Tm][Ud]                                                                     */
+  const float* values;      /* [B][Tm][D], zero for t >= mem_len                                               */
+  const int32_t* mem_len;   /* [B]                                                                             */
+  const int32_t* forced_ids;/* [B][max_steps] or NULL                                                          */
+  float* logits;            /* [B][max_steps][V], caller-zeroed (steps that are not executed stay 0)           */
+  int32_t* sample_ids;      /* [B][max_steps], caller-zeroed                                                   */
+  float* alignment;         /* [B][max_steps][Tm] or NULL                                                      */
+  int32_t* seq_len;         /* [B] final_sequence_length                                                       */
+  int32_t* n_steps;         /* [1] number of decode iterations executed                                        */
+} plas_dec_infer_desc;
+size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d);
+int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
 
 /* Loss heads with gradients.  dlogits = gscale * d(loss)/d(logits); out3 as in the forward-only calls. */
 int plas_seq_ce_grad(const float* logits, const int32_t* targets, const float* weights, int64_t n_tokens, int32_t V,

@@ -59,7 +59,7 @@ class RecTrainDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("U", C.c_int32), ("ndir", C.c_int32), ("din", C.c_int32),
                 ("_pad", C.c_int32), ("z", C.c_void_p), ("kernel", C.c_void_p * 2), ("lengths", C.c_void_p),
                 ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("c_save", C.c_void_p), ("h_prev", C.c_void_p),
-                ("dout", C.c_void_p)]
+                ("dout", C.c_void_p), ("c_final", C.c_void_p), ("h_final", C.c_void_p)]
 
 
 class DecTrainDesc(C.Structure):
@@ -72,6 +72,16 @@ class DecTrainDesc(C.Structure):
                 ("dkernel", C.c_void_p * 4), ("dbias", C.c_void_p * 4), ("dw_mem", C.c_void_p), ("dw_query", C.c_void_p),
                 ("dv_att", C.c_void_p), ("dw_proj", C.c_void_p), ("db_proj", C.c_void_p), ("dmemory", C.c_void_p),
                 ("drop_step", C.c_void_p)]
+
+
+class DecInferDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("Tm", C.c_int32), ("D", C.c_int32), ("Ud", C.c_int32), ("V", C.c_int32),
+                ("n_layers", C.c_int32), ("attention_type", C.c_int32), ("sos_id", C.c_int32), ("eos_id", C.c_int32),
+                ("max_steps", C.c_int32), ("teacher_forced", C.c_int32), ("decoding_length_factor", C.c_float),
+                ("kernel", C.c_void_p * 4), ("bias", C.c_void_p * 4), ("w_query", C.c_void_p), ("v_att", C.c_void_p),
+                ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("keys", C.c_void_p), ("values", C.c_void_p),
+                ("mem_len", C.c_void_p), ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
+                ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p)]
 
 
 EXPORTS = {
@@ -111,6 +121,8 @@ EXPORTS = {
     "plas_dec_train_workspace_bytes": (C.c_size_t, [C.POINTER(DecTrainDesc)]),
     "plas_decoder_train_fwd": (C.c_int, [C.POINTER(DecTrainDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_decoder_train_bwd": (C.c_int, [C.POINTER(DecTrainDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_decoder_infer_f32_workspace_bytes": (C.c_size_t, [C.POINTER(DecInferDesc)]),
+    "plas_decoder_infer_f32": (C.c_int, [C.POINTER(DecInferDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_seq_ce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "plas_sigmoid_ce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p,

@@ -37,6 +37,7 @@ struct CellFwdArgs {
   float* z_out; long long s_z;          // activated gates (i, tanh j, f, o), gate-blocked [4][Ud]
   float* c_out; float* h_out; long long s_h;
   float* hprev_next;                    // slot t+1 of the h_{t-1} copy (NULL at the last step)
+  const int* skip;                      // inference loop: *skip != 0 -> every utterance has finished, the launch is a no-op
   float* hdrop_out;                     // dropped-out copy of h feeding the layer above (NULL: no dropout / top layer)
   long long idx_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index of (b,u) = b*s_h + idx_base + u
 };
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float cf_smem[];
+  if (p.skip && *p.skip) return;              // uniform over the grid: taken before any cluster barrier
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ks = blockIdx.x;                  // K-slice = rank in the cluster
   const int u0 = blockIdx.y * CF_UG;
@@ -155,6 +157,7 @@ struct AttFwdArgs {
   float* align; long long s_al;           // [Tm] per row
   float* att; long long s_att;            // context of this step
   float* att_next;                        // slot t+1 of the attention_{t-1} copy (NULL at the last step)
+  const int* skip;                        // inference loop: *skip != 0 -> no-op
   long long next_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index b*s_att + next_base + d
 };
 
@@ -163,6 +166,7 @@ struct AttFwdArgs {
 // one per memory row; otherwise rows stream from L2.
 __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
   extern __shared__ __align__(16) float att_smem[];
+  if (p.skip && *p.skip) return;
   const int Ud = p.Ud, Tm = p.Tm, D = p.D;
   float* s_q = att_smem;          // [Ud] query (luong) or processed query (bahdanau)
   float* s_v = s_q + Ud;          // [Ud] attention_v (bahdanau)
@@ -558,6 +562,109 @@ __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// fp32 inference (reference-precision mode) built from the same step kernels: greedy (GreedyEmbeddingHelper +
+// dynamic_decode, las/model.py:337-347) or teacher-forced decoding as a host loop of small launches over a 2-slot state
+// ring, replacing the persistent SIMT kernel of decoder.cu for luong / bahdanau attention (240 us -> ~45 us per step at c1).
+// ---------------------------------------------------------------------------------------------------------
+struct InferState {
+  int* cur_ids;    // [B] input ids of the next step
+  int* finished;   // [B]
+  int* done;       // [1] every utterance has finished (or max_iter reached)
+  int* max_iter;   // [1]
+};
+
+__global__ void dec_infer_init_kernel(InferState st, const int* __restrict__ mem_len, int B, int max_steps, int teacher_forced,
+                                      float factor, int sos_id, int* __restrict__ seq_len, int* __restrict__ n_steps) {
+  __shared__ int s_max;
+  if (threadIdx.x == 0) {
+    int mi = max_steps;
+    if (!teacher_forced) {  // greedy stop: rint(max(mem_len) * factor)  (las/model.py:270-274)
+      int ml = 0;
+      for (int b = 0; b < B; ++b) ml = max(ml, mem_len[b]);
+      mi = min(mi, (int)rintf((float)ml * factor));
+    }
+    s_max = mi;
+    *st.max_iter = mi;
+    *st.done = mi <= 0 ? 1 : 0;
+    *n_steps = 0;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    st.cur_ids[b] = sos_id;
+    st.finished[b] = s_max <= 0 ? 1 : 0;
+    seq_len[b] = 0;
+  }
+}
+
+// pre[b][:] = W_0[id_b][:] + b_0: the one-hot input picks a row of the cell-0 kernel (embedding_fn, las/model.py:245-246)
+__global__ void dec_infer_embed_kernel(InferState st, const int* __restrict__ forced, long long s_forced, const float* __restrict__ w0,
+                                       const float* __restrict__ b0, int B, int N, int V, float* __restrict__ pre, long long s_pre) {
+  if (*st.done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N, n = i - b * N;
+  int id = forced ? forced[(long long)b * s_forced] : st.cur_ids[b];
+  id = max(0, min(id, V - 1));
+  pre[(long long)b * s_pre + n] = w0[(size_t)id * N + n] + b0[n];
+}
+
+// logits = context W_proj + b (DenseBinfDecoder), greedy argmax (lowest index wins ties); one CTA per utterance
+__global__ void __launch_bounds__(256) dec_infer_sample_kernel(InferState st, const float* __restrict__ att, long long s_att, int D, int V,
+                                                               const float* __restrict__ w_proj, const float* __restrict__ b_proj,
+                                                               float* __restrict__ logits, long long s_logits,
+                                                               int* __restrict__ sample_ids, long long s_ids) {
+  extern __shared__ float sm_smem[];
+  if (*st.done) return;
+  float* s_a = sm_smem;       // [D]
+  float* s_part = s_a + D;    // [4][V]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int d = tid; d < D; d += 256) s_a[d] = att[(long long)b * s_att + d];
+  __syncthreads();
+  const int slices = 4;
+  for (int i = tid; i < slices * V; i += 256) {
+    const int sl = i / V, v = i - sl * V;
+    const int dper = (D + slices - 1) / slices;
+    const int d_hi = min(D, (sl + 1) * dper);
+    float acc = 0.f;
+    for (int d = sl * dper; d < d_hi; ++d) acc = fmaf(s_a[d], __ldg(w_proj + (size_t)d * V + v), acc);
+    s_part[i] = acc;
+  }
+  __syncthreads();
+  float* s_logit = s_a;  // reuse
+  for (int v = tid; v < V; v += 256) {
+    const float lg = ((s_part[v] + s_part[V + v]) + (s_part[2 * V + v] + s_part[3 * V + v])) + b_proj[v];
+    s_logit[v] = lg;
+    logits[(long long)b * s_logits + v] = lg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0;
+    float bv = s_logit[0];
+    for (int v = 1; v < V; ++v)
+      if (s_logit[v] > bv) { bv = s_logit[v]; best = v; }
+    sample_ids[(long long)b * s_ids] = best;
+    st.cur_ids[b] = best;
+  }
+}
+
+// finished / sequence-length bookkeeping of dynamic_decode (one thread: B is small and the order must be fixed)
+__global__ void dec_infer_finish_kernel(InferState st, int B, int t, int eos_id, int teacher_forced, int* __restrict__ seq_len,
+                                        int* __restrict__ n_steps) {
+  if (threadIdx.x != 0 || *st.done) return;
+  const int max_iter = *st.max_iter;
+  int all = 1;
+  for (int b = 0; b < B; ++b) {
+    const int was = st.finished[b];
+    if (!was) seq_len[b] = t + 1;
+    const int now = was || (st.cur_ids[b] == eos_id) || (t + 1 >= max_iter);
+    st.finished[b] = now;
+    all &= now;
+  }
+  *n_steps = t + 1;
+  if ((all && !teacher_forced) || t + 1 >= max_iter) *st.done = 1;  // teacher forcing runs exactly max_steps
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
@@ -632,6 +739,135 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   return PLAS_OK;
 }
 
+// ---- fp32 inference loop ----------------------------------------------------------------------------------------------
+struct DecInferWs {
+  size_t z[4], c[4], h[4], att, pq, align, ints, total;
+};
+
+static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
+  DecInferWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  };
+  const size_t B = d.B, Ud = d.Ud, D = d.D, Tm = d.Tm;
+  for (int l = 0; l < 4; ++l) {
+    w.z[l] = w.c[l] = w.h[l] = 0;
+    if (l >= d.n_layers) continue;
+    w.z[l] = take(B * 2 * 4 * Ud * 4);
+    w.c[l] = take(B * 2 * Ud * 4);
+    w.h[l] = take(B * 2 * Ud * 4);
+  }
+  w.att = take(B * 2 * D * 4);
+  w.pq = take(B * Ud * 4);
+  w.align = take(B * Tm * 4);
+  w.ints = take((2 * B + 8) * 4);
+  w.total = off;
+  return w;
+}
+
+}  // namespace plas
+
+using namespace plas;
+
+extern "C" size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d) { return dec_infer_ws(*d).total; }
+
+extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  PLAS_REQUIRE(d && workspace, "dec_infer: null argument");
+  PLAS_REQUIRE(d->B > 0 && d->Tm > 0 && d->V > 0 && d->max_steps >= 0, "dec_infer: bad shape");
+  PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_infer: n_layers=%d", d->n_layers);
+  PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_infer: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
+  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU, "dec_infer: attention_type %d", d->attention_type);
+  PLAS_REQUIRE(d->keys && d->values && d->mem_len && d->w_proj && d->b_proj && d->logits && d->sample_ids && d->seq_len && d->n_steps,
+               "dec_infer: null tensor");
+  if (d->attention_type == PLAS_ATT_BAHDANAU) PLAS_REQUIRE(d->w_query && d->v_att, "dec_infer: bahdanau needs query_layer / attention_v");
+  if (d->teacher_forced) PLAS_REQUIRE(d->forced_ids != nullptr, "dec_infer: teacher forcing needs forced_ids");
+  const DecInferWs w = dec_infer_ws(*d);
+  PLAS_REQUIRE(workspace_bytes >= w.total, "dec_infer: workspace %zu < %zu", workspace_bytes, w.total);
+  unsigned char* base = (unsigned char*)workspace;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int B = d->B, Tm = d->Tm, D = d->D, Ud = d->Ud, V = d->V, L = d->n_layers, S = d->max_steps;
+  InferState is;
+  int* ints = reinterpret_cast<int*>(base + w.ints);
+  is.cur_ids = ints; is.finished = ints + B; is.done = ints + 2 * B; is.max_iter = ints + 2 * B + 1;
+  for (int l = 0; l < L; ++l) {
+    PLAS_REQUIRE(d->kernel[l] && d->bias[l], "dec_infer: null weights (layer %d)", l);
+    PLAS_CUDA(cudaMemsetAsync(F(w.h[l]), 0, (size_t)B * 2 * Ud * 4, st));
+  }
+  PLAS_CUDA(cudaMemsetAsync(F(w.att), 0, (size_t)B * 2 * D * 4, st));
+  dec_infer_init_kernel<<<1, 128, 0, st>>>(is, d->mem_len, B, S, d->teacher_forced, d->decoding_length_factor, d->sos_id, d->seq_len, d->n_steps);
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  PLAS_CUDA(cudaFuncSetAttribute(dec_att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  const int dsplit = (D >= 512 && D % 16 == 0) ? 4 : 1;
+  size_t att_smem = (size_t)(2 * Ud + ((Tm + 3) & ~3)) * 4;
+  const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
+  const int att_staged = (Ud % 4 == 0 && (D / dsplit) % 4 == 0 && att_smem + att_stage <= 220 * 1024) ? 1 : 0;
+  if (att_staged) att_smem += att_stage;
+  const size_t smp_smem = (size_t)(D + 4 * V) * 4;
+  PLAS_REQUIRE(smp_smem <= 200 * 1024, "dec_infer: D/V too large");
+  if (smp_smem > 48 * 1024) PLAS_CUDA(cudaFuncSetAttribute(dec_infer_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp_smem));
+  for (int t = 0; t < S; ++t) {
+    const int slot = t & 1, prev = slot ^ 1;
+    dec_infer_embed_kernel<<<(B * 4 * Ud + 255) / 256, 256, 0, st>>>(is, d->forced_ids ? d->forced_ids + t : nullptr, S, d->kernel[0], d->bias[0], B,
+                                                                     4 * Ud, V, F(w.z[0]) + (size_t)slot * 4 * Ud, 2LL * 4 * Ud);
+    for (int l = 0; l < L; ++l) {
+      CellFwdArgs a;
+      a.B = B; a.Ud = Ud; a.skip = is.done;
+      if (l == 0) {
+        a.pre = F(w.z[0]) + (size_t)slot * 4 * Ud; a.s_pre = 2LL * 4 * Ud; a.bias = nullptr;
+        a.in1 = F(w.att) + (size_t)prev * D; a.s1 = 2LL * D; a.K1 = D;
+        a.w = d->kernel[0] + (size_t)V * 4 * Ud;
+      } else {
+        a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
+        a.in1 = F(w.h[l - 1]) + (size_t)slot * Ud; a.s1 = 2LL * Ud; a.K1 = Ud;
+        a.w = d->kernel[l];
+      }
+      a.in2 = F(w.h[l]) + (size_t)prev * Ud; a.s2 = 2LL * Ud; a.K2 = Ud;
+      a.c_prev = t > 0 ? F(w.c[l]) + (size_t)prev * Ud : nullptr; a.s_c = 2LL * Ud;
+      a.z_out = F(w.z[l]) + (size_t)slot * 4 * Ud; a.s_z = 2LL * 4 * Ud;
+      a.c_out = F(w.c[l]) + (size_t)slot * Ud; a.h_out = F(w.h[l]) + (size_t)slot * Ud; a.s_h = 2LL * Ud;
+      a.hprev_next = nullptr; a.hdrop_out = nullptr;
+      a.idx_base = 0; a.seed = 0; a.thresh = 0; a.inv_keep = 1.f; a.step_ptr = nullptr;
+      const int per = ((a.K1 + a.K2) / 4 + CF_KS - 1) / CF_KS;
+      const size_t smem = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)4 * per * 4 * CF_UG + (size_t)CF_KS * DT_ROWS * 8) * 4;
+      PLAS_REQUIRE(smem <= 220 * 1024, "dec_infer: cell input depth %d too large", a.K1 + a.K2);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CF_KS, Ud / CF_UG, (B + DT_ROWS - 1) / DT_ROWS);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = CF_KS;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_cell_fwd_kernel, a));
+    }
+    AttFwdArgs q;
+    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit; q.staged = att_staged; q.skip = is.done;
+    q.keys = d->keys; q.values = d->values; q.mem_len = d->mem_len;
+    q.query = F(w.h[L - 1]) + (size_t)slot * Ud; q.s_q = 2LL * Ud;
+    q.w_query = d->w_query; q.v_att = d->v_att;
+    q.pq = F(w.pq); q.s_pq = Ud;
+    if (d->alignment) { q.align = d->alignment + (size_t)t * Tm; q.s_al = (long long)S * Tm; }
+    else { q.align = F(w.align); q.s_al = Tm; }
+    q.att = F(w.att) + (size_t)slot * D; q.s_att = 2LL * D;
+    q.att_next = nullptr; q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
+    dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
+    dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, F(w.att) + (size_t)slot * D, 2LL * D, D, V, d->w_proj, d->b_proj,
+                                                      d->logits + (size_t)t * V, (long long)S * V, d->sample_ids + t, S);
+    dec_infer_finish_kernel<<<1, 32, 0, st>>>(is, B, t, d->eos_id, d->teacher_forced, d->seq_len, d->n_steps);
+  }
+  PLAS_CUDA(cudaGetLastError());
+  return PLAS_OK;
+}
+
+namespace plas {
 }  // namespace plas
 
 using namespace plas;
@@ -686,6 +922,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       a.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; a.s_c = sh;
       a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
       a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
+      a.skip = nullptr;
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
       a.hdrop_out = (drop && l + 1 < L) ? F(w.hdrop[l]) + (size_t)t * Ud : nullptr;
       a.idx_base = (long long)t * Ud; a.seed = d->drop_seed + 1 + l; a.thresh = thresh; a.inv_keep = inv_keep; a.step_ptr = d->drop_step;
@@ -716,6 +953,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = (long long)S * Ud;
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
     q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D;
+    q.skip = nullptr;
     q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
     q.next_base = (long long)(t + 1) * D; q.seed = d->drop_seed; q.thresh = thresh; q.inv_keep = inv_keep; q.step_ptr = d->drop_step;
     dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);

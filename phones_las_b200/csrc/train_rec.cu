@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
         const size_t bt = (size_t)b * T + t_idx;
         float* zp = d.z + bt * zrow + (size_t)dir * 4 * U + unit;
         zp[0] = gi_; zp[U] = gj; zp[2 * U] = gf; zp[3 * U] = go;
-        d.c_save[bt * srow + dir * U + unit] = cn;
-        d.h_prev[bt * srow + dir * U + unit] = h_state;
+        if (d.c_save) d.c_save[bt * srow + dir * U + unit] = cn;   // saved only for a later backward call
+        if (d.h_prev) d.h_prev[bt * srow + dir * U + unit] = h_state;
         d.out[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit] = hn;
         c_state = cn;
         h_state = hn;
@@ -184,6 +184,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_fwd_kernel(RecTrainAr
       __threadfence();
       red_release_add_u32(ctr, 1u);
     }
+  }
+  if (fin && b < B && d.c_final) {  // final (c, h) of every utterance: the state is frozen past its length
+    d.c_final[((size_t)dir * B + b) * U + unit] = c_state;
+    d.h_final[((size_t)dir * B + b) * U + unit] = h_state;
   }
 }
 
@@ -363,8 +367,8 @@ static int rt_launch(const plas_rec_train_desc* d, void* workspace, size_t works
                      bool backward) {
   PLAS_REQUIRE(d && workspace, "rec_train: null argument");
   PLAS_REQUIRE(d->B > 0 && d->T > 0 && d->U > 0 && (d->ndir == 1 || d->ndir == 2) && d->din > 0, "rec_train: bad shape");
-  PLAS_REQUIRE(d->z && d->kernel[0] && (d->ndir == 1 || d->kernel[1]) && d->lengths && d->c_save, "rec_train: null tensor");
-  PLAS_REQUIRE(backward ? d->dout != nullptr : (d->out != nullptr && d->h_prev != nullptr), "rec_train: null tensor");
+  PLAS_REQUIRE(d->z && d->kernel[0] && (d->ndir == 1 || d->kernel[1]) && d->lengths, "rec_train: null tensor");
+  PLAS_REQUIRE(backward ? (d->dout != nullptr && d->c_save != nullptr) : d->out != nullptr, "rec_train: null tensor");
   PLAS_REQUIRE(d->U % 4 == 0 && d->U <= 1024, "rec_train: U=%d unsupported (multiple of 4, <= 1024)", d->U);
   PLAS_REQUIRE(d->out_batch_stride >= (int64_t)d->T * d->ndir * d->U, "rec_train: out_batch_stride too small");
   size_t o_ctr, o_x, total;

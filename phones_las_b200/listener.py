@@ -9,6 +9,7 @@ and the pyramidal frame concat (las/ops.py:49-65) is a free view: layer outputs 
 an even, zero-padded time extent so ``[B,T,2U] -> [B,T/2,4U]`` is a reshape of the same bytes.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -57,8 +58,11 @@ class ListenerWeights:
             whh_tc = None
             if precision == "bf16" and U in (64, 128, 256, 512):
                 whh_tc = torch.from_numpy(packing.pack_rec_tc(kernels, din, U)).to(device=device, dtype=dt).contiguous()
+            # fp32: the row-blocked recurrence of csrc/train_rec.cu (forward-only call) reads the TF layout directly
+            tf_kernel = [torch.from_numpy(k).to(device) for k in kernels] if precision == "fp32" and U % 4 == 0 else None
+            tf_bias = [torch.from_numpy(b).to(device) for b in biases] if tf_kernel is not None else None
             self.layers.append(dict(
-                din=din, k_pad=k_pad, whh_tc=whh_tc,
+                din=din, k_pad=k_pad, whh_tc=whh_tc, tf_kernel=tf_kernel, tf_bias=tf_bias,
                 wt=torch.from_numpy(wt).to(device=device, dtype=dt).contiguous(),
                 bias=torch.from_numpy(bs).to(device),
                 whh=torch.from_numpy(whh).to(device=device, dtype=dt).contiguous()))
@@ -97,6 +101,8 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
     L = _lib.lib()
     B, T, K = x.shape
     dt = x.dtype
+    if lw.get("tf_kernel") is not None and os.environ.get("PLAS_REC_IMPL") != "l2":
+        return _bilstm_layer_f32(x, lengths, lw, U, ndir, t_alloc_out, per_direction_input)
     xproj = torch.empty((B * T, ndir * 4 * U), dtype=dt, device=x.device)
     if per_direction_input:
         for dd in range(ndir):
@@ -117,6 +123,36 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
     with _lib.stage("rec"):
         _lib.check(L.plas_bilstm_rec_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    _lib.count_launches(1)
+    return out, (c_fin, h_fin)
+
+
+def _bilstm_layer_f32(x, lengths, lw, U, ndir, t_alloc_out, per_direction_input):
+    """fp32 (reference-precision) layer on the TF weight layout: strided fp32 GEMM per direction (plas_gemm_f32_ex) + the
+    row-blocked persistent recurrence (plas_bilstm_rec_train_fwd called forward-only: nothing saved, final states returned)."""
+    from .train import gemm_ex
+    L = _lib.lib()
+    B, T, K = x.shape
+    din = U if per_direction_input else K
+    z = torch.empty((B, T, ndir, 4 * U), dtype=torch.float32, device=x.device)
+    with _lib.stage("inproj_gemm"):
+        for dd in range(ndir):
+            gemm_ex(B * T, 4 * U, din, x.data_ptr() + (4 * dd * U if per_direction_input else 0), K, 1, lw["tf_kernel"][dd].data_ptr(),
+                    4 * U, 1, z.data_ptr() + 4 * dd * 4 * U, ndir * 4 * U, bias=lw["tf_bias"][dd].data_ptr())
+    out = torch.zeros((B, t_alloc_out, ndir * U), dtype=torch.float32, device=x.device)
+    c_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
+    h_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
+    d = _lib.RecTrainDesc()
+    d.B, d.T, d.U, d.ndir, d.din = B, T, U, ndir, din
+    d.z = z.data_ptr()
+    for dd in range(ndir):
+        d.kernel[dd] = lw["tf_kernel"][dd].data_ptr()
+    d.lengths, d.out, d.out_batch_stride = lengths.data_ptr(), out.data_ptr(), out.stride(0)
+    d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
+    need = L.plas_rec_train_workspace_bytes(C.byref(d))
+    ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
+    with _lib.stage("rec"):
+        _lib.check(L.plas_bilstm_rec_train_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1)
     return out, (c_fin, h_fin)
 

@@ -9,6 +9,7 @@ final_state, final_sequence_length)``.  The attention memory is prepared once pe
 one persistent kernel (plas_decoder_fwd).
 """
 import ctypes as C
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -78,6 +79,13 @@ class SpellerWeights:
             self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
         self.w_proj_t = up(np.asarray(params[f"{scope}/decoder/projection_layer/kernel"], np.float32).T)  # [V, D]
         self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"], torch.float32)
+        # fp32: the step-kernel decoder (csrc/train_dec.cu, plas_decoder_infer_f32) reads the TF layout directly
+        self.tf = None
+        if precision == "fp32" and self.att in ("luong", "bahdanau") and Ud % 16 == 0 and D % 4 == 0:
+            self.tf = dict(
+                kernel=[up(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], torch.float32) for k in range(self.L)],
+                bias=[up(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], torch.float32) for k in range(self.L)],
+                w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"], torch.float32))
         if self.tc:
             wp = np.zeros((_round_up(V, 128), D), np.float32)
             wp[:V] = np.asarray(params[f"{scope}/decoder/projection_layer/kernel"], np.float32).T
@@ -144,6 +152,9 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     align = torch.zeros((B, cap, Tm), dtype=torch.float32, device=dev) if want_alignment else None
     seq_len = torch.zeros((B,), dtype=torch.int32, device=dev)
     n_steps = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if w.tf is not None and os.environ.get("PLAS_DEC_IMPL") != "simt":
+        return _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, factor, logits, ids, align, seq_len,
+                                 n_steps, trim)
     d = _lib.DecDesc()
     d.dtype = _lib.dtype_code(w.precision)
     d.B, d.Tm, d.D, d.Ud, d.V, d.n_layers = B, Tm, D, w.Ud, w.V, w.L
@@ -177,6 +188,39 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     _lib.count_launches(1)
     if trim:
         n = int(n_steps.item()) if steps > 0 else 0  # device->host read of the step count
+        logits, ids = logits[:, :n], ids[:, :n]
+        if align is not None:
+            align = align[:, :n]
+    return logits, ids, align, seq_len, n_steps
+
+
+def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, factor, logits, ids, align, seq_len, n_steps, trim):
+    """fp32 (reference-precision) decode through plas_decoder_infer_f32: a loop of step kernels on the TF weight layout."""
+    B, Tm, D = values.shape
+    d = _lib.DecInferDesc()
+    d.B, d.Tm, d.D, d.Ud, d.V, d.n_layers = B, Tm, D, w.Ud, w.V, w.L
+    d.attention_type = _lib.ATT_CODES[w.att]
+    d.sos_id, d.eos_id = hp["sos_id"], hp["eos_id"]
+    d.max_steps = cap if steps > 0 else 0
+    d.teacher_forced = 1 if forced_ids is not None else 0
+    d.decoding_length_factor = factor
+    for k in range(w.L):
+        d.kernel[k], d.bias[k] = w.tf["kernel"][k].data_ptr(), w.tf["bias"][k].data_ptr()
+    d.w_query = w.w_query.data_ptr() if w.w_query is not None else None
+    d.v_att = w.v_att.data_ptr() if w.v_att is not None else None
+    d.w_proj, d.b_proj = w.tf["w_proj"].data_ptr(), w.b_proj.data_ptr()
+    d.keys, d.values, d.mem_len = keys.data_ptr(), values.data_ptr(), mem_len.data_ptr()
+    d.forced_ids = forced_ids.data_ptr() if forced_ids is not None else None
+    d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()
+    d.alignment = align.data_ptr() if align is not None else None
+    d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
+    need = L.plas_decoder_infer_f32_workspace_bytes(C.byref(d))
+    ws = torch.empty((need,), dtype=torch.uint8, device=values.device)
+    with _lib.stage("decoder"):
+        _lib.check(L.plas_decoder_infer_f32(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    _lib.count_launches(1 + d.max_steps * (4 + w.L))
+    if trim:
+        n = int(n_steps.item()) if steps > 0 else 0
         logits, ids = logits[:, :n], ids[:, :n]
         if align is not None:
             align = align[:, :n]
