@@ -312,6 +312,12 @@ typedef struct plas_dec_infer_desc {
   float* alignment;         /* [B][max_steps][Tm] or NULL                                                      */
   int32_t* seq_len;         /* [B] final_sequence_length                                                       */
   int32_t* n_steps;         /* [1] number of decode iterations executed                                        */
+  int32_t bottom_only;      /* AttentionMultiCell wiring (las/model.py:20-69,185-193): attention wraps cell 0 only; cell l >= 1 reads
+                               [output below (the NEW attention for l = 1); OLD attention; h_{t-1}], kernel [(D or Ud) + D + Ud][4Ud];
+                               the projection reads the top cell's h ([Ud][V]) when n_layers > 1                  */
+  int32_t _pad;
+  const float* c_init[4];   /* pass_hidden_state (las/model.py:259-267): initial cell / hidden state of layer l [B][Ud] or NULL */
+  const float* h_init[4];
 } plas_dec_infer_desc;
 size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d);
 int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

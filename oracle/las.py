@@ -177,7 +177,7 @@ def _safe_cumprod_exclusive(x):
 class Attention:
     """values/keys setup of _BaseAttentionMechanism + score/probability fns."""
 
-    def __init__(self, attention_type, memory, memory_len, params, scope, precision="fp32"):
+    def __init__(self, attention_type, memory, memory_len, params, scope, precision="fp32", prefix=None):
         q = self.q = _q(precision)
         self.type = attention_type
         B, Tm, D = memory.shape
@@ -185,7 +185,7 @@ class Attention:
         self.values = q(memory * self.mask[:, :, None].astype(F32))
         wm = q(params[f"{scope}/memory_layer/kernel"])
         self.keys = q((self.values.reshape(B * Tm, D) @ wm).reshape(B, Tm, -1))
-        pre = f"{scope}/decoder/attention_wrapper"
+        pre = prefix or f"{scope}/decoder/attention_wrapper"
         if attention_type == "bahdanau":
             self.wq = q(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
             self.v = params[f"{pre}/bahdanau_attention/attention_v"].astype(F32)
@@ -225,33 +225,51 @@ class Attention:
 # AttentionWrapper(MultiRNNCell) + BasicDecoder + helpers + dynamic_decode
 # --------------------------------------------------------------------------------------
 class Speller:
-    """Default wiring of las/model.py:195-200 (bottom_only=False, attention_layer_size=None)."""
+    """las/model.py:185-200 with attention_layer_size=None: the default wiring (AttentionWrapper around the MultiRNNCell) or
+    ``bottom_only`` (GNMT-style AttentionMultiCell, las/model.py:20-69: attention wraps cell 0 only; cell 0's output is the
+    NEW attention, every upper cell reads [previous output; OLD attention]; the decoder output is the top cell's h), with
+    ``pass_hidden_state`` (las/model.py:259-267: cell l starts from the listener's final state l = fw, bw)."""
 
-    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller"):
+    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller", encoder_state=None):
         self.q = _q(precision)
         self.hp = hp
         self.scope = scope
-        self.att = Attention(hp["attention_type"], enc_out, enc_len, params, scope, precision)
+        self.att = Attention(hp["attention_type"], enc_out, enc_len, params, scope, precision,
+                             prefix=(f"{scope}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper"
+                                     if hp.get("bottom_only") else None))
         self.B, self.Tm, self.D = enc_out.shape
         self.Ud = hp["decoder_units"]
         self.V = hp["target_vocab_size"]
-        pre = f"{scope}/decoder/attention_wrapper/multi_rnn_cell"
+        self.bottom_only = bool(hp.get("bottom_only", False))
+        self.init_state = None
+        if hp.get("pass_hidden_state") and self.bottom_only:
+            # zip(decoder zero_state, encoder_state): cell l <- final (c, h) of the last listener layer, l = 0 fw, 1 bw
+            self.init_state = [(np.asarray(c, F32), np.asarray(h, F32)) for (c, h) in encoder_state]
         self.cells = []
         for k in range(hp["decoder_layers"]):
-            self.cells.append((self.q(params[f"{pre}/cell_{k}/lstm_cell/kernel"]),
-                               params[f"{pre}/cell_{k}/lstm_cell/bias"].astype(F32)))
+            if self.bottom_only:
+                name = (f"{scope}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper/lstm_cell" if k == 0
+                        else f"{scope}/decoder/multi_rnn_cell/cell_{k}/lstm_cell")
+            else:
+                name = f"{scope}/decoder/attention_wrapper/multi_rnn_cell/cell_{k}/lstm_cell"
+            self.cells.append((self.q(params[name + "/kernel"]), params[name + "/bias"].astype(F32)))
         self.wp = self.q(params[f"{scope}/decoder/projection_layer/kernel"])
         self.bp = params[f"{scope}/decoder/projection_layer/bias"].astype(F32)
         self.enc_len = np.asarray(enc_len)
 
     def zero_state(self):
         cs = [(np.zeros((self.B, self.Ud), F32), np.zeros((self.B, self.Ud), F32)) for _ in self.cells]
+        if self.init_state is not None:
+            for l, st in enumerate(self.init_state[:len(cs)]):
+                cs[l] = st
         return dict(cells=cs, attention=np.zeros((self.B, self.D), F32),
                     alignments=self.att.initial_alignments())
 
     def step(self, x, state):
         """AttentionWrapper.call + output projection.  x [B,V] (one-hot or teacher input)."""
         q = self.q
+        if self.bottom_only:
+            return self._step_bottom_only(x, state)
         inp = np.concatenate([x, state["attention"]], axis=1).astype(F32)
         new_cells = []
         for (k, b), (c, h) in zip(self.cells, state["cells"]):
@@ -267,6 +285,28 @@ class Speller:
         # exactly DenseBinfDecoder(attention); bf16 mode: one rounding point fewer)
         logits = (context.astype(F32) @ self.wp + self.bp).astype(F32)
         return logits, dict(cells=new_cells, attention=attention, alignments=align)
+
+    def _step_bottom_only(self, x, state):
+        """AttentionMultiCell.__call__ (las/model.py:34-69, use_new_attention=False) + projection of the top cell's output."""
+        q = self.q
+        old_att = state["attention"]
+        (k0, b0), (c, h) = self.cells[0], state["cells"][0]
+        z = (np.concatenate([x, old_att, h], axis=1) @ k0 + b0).astype(F32)
+        c2, h2 = lstm_cell_step(z, c)
+        h2 = q(h2)
+        new_cells = [(c2, h2)]
+        align = self.att(h2, state["alignments"])
+        context = np.einsum("bt,btd->bd", align, self.att.values, dtype=F32)
+        cur = q(context)  # AttentionWrapper(output_attention=True) returns the attention as cell 0's output
+        for (k, b), (c, h) in zip(self.cells[1:], state["cells"][1:]):
+            z = (np.concatenate([cur, old_att, h], axis=1) @ k + b).astype(F32)
+            c2, h2 = lstm_cell_step(z, c)
+            h2 = q(h2)
+            new_cells.append((c2, h2))
+            cur = h2
+        out = context.astype(F32) if len(self.cells) == 1 else cur
+        logits = (out @ self.wp + self.bp).astype(F32)
+        return logits, dict(cells=new_cells, attention=q(context), alignments=align)
 
     def one_hot(self, ids):
         return np.eye(self.V, dtype=F32)[ids]
@@ -318,7 +358,7 @@ class Speller:
 def predict(features, lengths, params, hp, precision="fp32"):
     """model_helper.py:165-297 PREDICT predictions dict (greedy, beam_width=0)."""
     (enc_out, enc_len), enc_state = listener(features, lengths, params, hp, precision)
-    sp = Speller(enc_out, enc_len, params, hp, precision)
+    sp = Speller(enc_out, enc_len, params, hp, precision, encoder_state=enc_state)
     logits, ids, align, seq_len, _ = sp.greedy()
     emb_c = np.concatenate([s[0] for s in enc_state], axis=1)
     emb_h = np.concatenate([s[1] for s in enc_state], axis=1)

@@ -31,7 +31,8 @@ struct CellFwdArgs {
   const float* pre; long long s_pre;    // [B][4Ud] pre-activations already holding x W + b (or NULL)
   const float* bias;                    // [4Ud] added when pre == NULL
   const float* in1; long long s1; int K1;   // attention_{t-1} (layer 0) or h of the layer below
-  const float* in2; long long s2; int K2;   // h_{t-1} of this layer
+  const float* in2; long long s2; int K2;   // h_{t-1} of this layer (default wiring) / old attention (bottom_only upper cells)
+  const float* in3; long long s3; int K3;   // bottom_only upper cells: h_{t-1} of this layer; K3 = 0 otherwise
   const float* w;                       // rows of the TF kernel multiplying [in1; in2]: [K1+K2][4Ud]
   const float* c_prev; long long s_c;   // NULL at t == 0
   float* z_out; long long s_z;          // activated gates (i, tanh j, f, o), gate-blocked [4][Ud]
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
   const int u0 = blockIdx.y * CF_UG;
   const int b0 = blockIdx.z * DT_ROWS;
   const int Ud = p.Ud;
-  const int K = p.K1 + p.K2, K4 = K / 4;
+  const int K = p.K1 + p.K2 + p.K3, K4 = K / 4;
   const int per = (K4 + CF_KS - 1) / CF_KS;   // float4 chunks of the reduction per slice
   const int q_lo = ks * per, nq = max(0, min(K4, q_lo + per) - q_lo);
   const int AS = 4 * per + 4;                 // padded activation row stride
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
     const int r = i / nq, q = i - r * nq;
     const int b = min(b0 + r, p.B - 1);
     const int k = 4 * (q_lo + q);
-    const float* src = k < p.K1 ? p.in1 + (long long)b * p.s1 + k : p.in2 + (long long)b * p.s2 + (k - p.K1);
+    const float* src = k < p.K1 ? p.in1 + (long long)b * p.s1 + k
+                       : (k < p.K1 + p.K2 ? p.in2 + (long long)b * p.s2 + (k - p.K1) : p.in3 + (long long)b * p.s3 + (k - p.K1 - p.K2));
     cp_async16(s_a + (size_t)r * AS + 4 * q, src);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -806,52 +808,69 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
   const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
   const int att_staged = (Ud % 4 == 0 && (D / dsplit) % 4 == 0 && att_smem + att_stage <= 220 * 1024) ? 1 : 0;
   if (att_staged) att_smem += att_stage;
-  const size_t smp_smem = (size_t)(D + 4 * V) * 4;
+  const size_t smp_smem = (size_t)((D > Ud ? D : Ud) + 4 * V) * 4;  // D >= Ud is not assumed: sized below for the larger of the two
+  int rc = PLAS_OK;
   PLAS_REQUIRE(smp_smem <= 200 * 1024, "dec_infer: D/V too large");
   if (smp_smem > 48 * 1024) PLAS_CUDA(cudaFuncSetAttribute(dec_infer_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp_smem));
-  for (int t = 0; t < S; ++t) {
+  const bool bottom = d->bottom_only != 0;
+  const int Dout = (bottom && L > 1) ? Ud : D;  // what the projection reads: the top cell's h (AttentionMultiCell) or the attention
+  auto launch_cell = [&](int t, int l) -> int {
     const int slot = t & 1, prev = slot ^ 1;
-    dec_infer_embed_kernel<<<(B * 4 * Ud + 255) / 256, 256, 0, st>>>(is, d->forced_ids ? d->forced_ids + t : nullptr, S, d->kernel[0], d->bias[0], B,
-                                                                     4 * Ud, V, F(w.z[0]) + (size_t)slot * 4 * Ud, 2LL * 4 * Ud);
-    for (int l = 0; l < L; ++l) {
-      CellFwdArgs a;
-      a.B = B; a.Ud = Ud; a.skip = is.done;
-      if (l == 0) {
-        a.pre = F(w.z[0]) + (size_t)slot * 4 * Ud; a.s_pre = 2LL * 4 * Ud; a.bias = nullptr;
-        a.in1 = F(w.att) + (size_t)prev * D; a.s1 = 2LL * D; a.K1 = D;
-        a.w = d->kernel[0] + (size_t)V * 4 * Ud;
-      } else {
-        a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
-        a.in1 = F(w.h[l - 1]) + (size_t)slot * Ud; a.s1 = 2LL * Ud; a.K1 = Ud;
-        a.w = d->kernel[l];
-      }
-      a.in2 = F(w.h[l]) + (size_t)prev * Ud; a.s2 = 2LL * Ud; a.K2 = Ud;
-      a.c_prev = t > 0 ? F(w.c[l]) + (size_t)prev * Ud : nullptr; a.s_c = 2LL * Ud;
-      a.z_out = F(w.z[l]) + (size_t)slot * 4 * Ud; a.s_z = 2LL * 4 * Ud;
-      a.c_out = F(w.c[l]) + (size_t)slot * Ud; a.h_out = F(w.h[l]) + (size_t)slot * Ud; a.s_h = 2LL * Ud;
-      a.hprev_next = nullptr; a.hdrop_out = nullptr;
-      a.idx_base = 0; a.seed = 0; a.thresh = 0; a.inv_keep = 1.f; a.step_ptr = nullptr;
-      const int per = ((a.K1 + a.K2) / 4 + CF_KS - 1) / CF_KS;
-      const size_t smem = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)4 * per * 4 * CF_UG + (size_t)CF_KS * DT_ROWS * 8) * 4;
-      PLAS_REQUIRE(smem <= 220 * 1024, "dec_infer: cell input depth %d too large", a.K1 + a.K2);
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(CF_KS, Ud / CF_UG, (B + DT_ROWS - 1) / DT_ROWS);
-      cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = CF_KS;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_cell_fwd_kernel, a));
+    CellFwdArgs a;
+    a.B = B; a.Ud = Ud; a.skip = is.done;
+    // h_{t-1} / c_{t-1} of this layer: the state ring, or the caller's initial state at t = 0 (pass_hidden_state)
+    const float* hprev = (t == 0 && d->h_init[l]) ? d->h_init[l] : F(w.h[l]) + (size_t)prev * Ud;
+    const long long s_hprev = (t == 0 && d->h_init[l]) ? Ud : 2LL * Ud;
+    const float* att_old = F(w.att) + (size_t)prev * D;
+    a.in3 = nullptr; a.s3 = 0; a.K3 = 0;
+    if (l == 0) {  // [x_t; attention_{t-1}; h_{t-1}]: the x rows are the gathered `pre`
+      a.pre = F(w.z[0]) + (size_t)slot * 4 * Ud; a.s_pre = 2LL * 4 * Ud; a.bias = nullptr;
+      a.in1 = att_old; a.s1 = 2LL * D; a.K1 = D;
+      a.in2 = hprev; a.s2 = s_hprev; a.K2 = Ud;
+      a.w = d->kernel[0] + (size_t)V * 4 * Ud;
+    } else if (!bottom) {  // MultiRNNCell inside the AttentionWrapper: [h of the layer below; h_{t-1}]
+      a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
+      a.in1 = F(w.h[l - 1]) + (size_t)slot * Ud; a.s1 = 2LL * Ud; a.K1 = Ud;
+      a.in2 = hprev; a.s2 = s_hprev; a.K2 = Ud;
+      a.w = d->kernel[l];
+    } else {  // AttentionMultiCell: [output of the cell below (cell 0's output is the NEW attention); OLD attention; h_{t-1}]
+      a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
+      if (l == 1) { a.in1 = F(w.att) + (size_t)slot * D; a.s1 = 2LL * D; a.K1 = D; }
+      else { a.in1 = F(w.h[l - 1]) + (size_t)slot * Ud; a.s1 = 2LL * Ud; a.K1 = Ud; }
+      a.in2 = att_old; a.s2 = 2LL * D; a.K2 = D;
+      a.in3 = hprev; a.s3 = s_hprev; a.K3 = Ud;
+      a.w = d->kernel[l];
     }
+    a.c_prev = t > 0 ? F(w.c[l]) + (size_t)prev * Ud : d->c_init[l];
+    a.s_c = (t == 0) ? Ud : 2LL * Ud;
+    a.z_out = F(w.z[l]) + (size_t)slot * 4 * Ud; a.s_z = 2LL * 4 * Ud;
+    a.c_out = F(w.c[l]) + (size_t)slot * Ud; a.h_out = F(w.h[l]) + (size_t)slot * Ud; a.s_h = 2LL * Ud;
+    a.hprev_next = nullptr; a.hdrop_out = nullptr;
+    a.idx_base = 0; a.seed = 0; a.thresh = 0; a.inv_keep = 1.f; a.step_ptr = nullptr;
+    const int per = ((a.K1 + a.K2 + a.K3) / 4 + CF_KS - 1) / CF_KS;
+    const size_t smem = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)4 * per * 4 * CF_UG + (size_t)CF_KS * DT_ROWS * 8) * 4;
+    PLAS_REQUIRE(smem <= 220 * 1024, "dec_infer: cell input depth %d too large", a.K1 + a.K2 + a.K3);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CF_KS, Ud / CF_UG, (B + DT_ROWS - 1) / DT_ROWS);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CF_KS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_cell_fwd_kernel, a));
+    return PLAS_OK;
+  };
+  auto launch_attention = [&](int t, int query_layer) {
+    const int slot = t & 1;
     AttFwdArgs q;
     q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit; q.staged = att_staged; q.skip = is.done;
     q.keys = d->keys; q.values = d->values; q.mem_len = d->mem_len;
-    q.query = F(w.h[L - 1]) + (size_t)slot * Ud; q.s_q = 2LL * Ud;
+    q.query = F(w.h[query_layer]) + (size_t)slot * Ud; q.s_q = 2LL * Ud;
     q.w_query = d->w_query; q.v_att = d->v_att;
     q.pq = F(w.pq); q.s_pq = Ud;
     if (d->alignment) { q.align = d->alignment + (size_t)t * Tm; q.s_al = (long long)S * Tm; }
@@ -859,7 +878,23 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     q.att = F(w.att) + (size_t)slot * D; q.s_att = 2LL * D;
     q.att_next = nullptr; q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
     dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
-    dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, F(w.att) + (size_t)slot * D, 2LL * D, D, V, d->w_proj, d->b_proj,
+  };
+  for (int t = 0; t < S; ++t) {
+    const int slot = t & 1;
+    dec_infer_embed_kernel<<<(B * 4 * Ud + 255) / 256, 256, 0, st>>>(is, d->forced_ids ? d->forced_ids + t : nullptr, S, d->kernel[0], d->bias[0], B,
+                                                                     4 * Ud, V, F(w.z[0]) + (size_t)slot * 4 * Ud, 2LL * 4 * Ud);
+    if (bottom) {  // attention right after cell 0 (its query), upper cells afterwards
+      if ((rc = launch_cell(t, 0))) return rc;
+      launch_attention(t, 0);
+      for (int l = 1; l < L; ++l)
+        if ((rc = launch_cell(t, l))) return rc;
+    } else {
+      for (int l = 0; l < L; ++l)
+        if ((rc = launch_cell(t, l))) return rc;
+      launch_attention(t, L - 1);
+    }
+    const float* out = (bottom && L > 1) ? F(w.h[L - 1]) + (size_t)slot * Ud : F(w.att) + (size_t)slot * D;
+    dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, out, (bottom && L > 1) ? 2LL * Ud : 2LL * D, Dout, V, d->w_proj, d->b_proj,
                                                       d->logits + (size_t)t * V, (long long)S * V, d->sample_ids + t, S);
     dec_infer_finish_kernel<<<1, 32, 0, st>>>(is, B, t, d->eos_id, d->teacher_forced, d->seq_len, d->n_steps);
   }
@@ -919,6 +954,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
         a.w = d->kernel[l];
       }
       a.in2 = F(w.hprev[l]) + (size_t)t * Ud; a.s2 = sh; a.K2 = Ud;
+      a.in3 = nullptr; a.s3 = 0; a.K3 = 0;
       a.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; a.s_c = sh;
       a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
       a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;

@@ -30,9 +30,13 @@ class SpellerWeights:
 
     def __init__(self, params, hp, enc_depth, precision="fp32", device="cuda", scope="speller"):
         _lib.require_cuda()
-        for flag in ("bottom_only", "pass_hidden_state", "binf_projection"):
-            if hp.get(flag):
-                raise NotImplementedError(f"--{flag} decoder wiring is not built yet")
+        if hp.get("binf_projection"):
+            raise NotImplementedError("--binf_projection decoder wiring is not built yet")
+        self.bottom_only = bool(hp.get("bottom_only"))
+        self.pass_hidden_state = bool(hp.get("pass_hidden_state")) and self.bottom_only  # las/model.py:260 needs both
+        if self.bottom_only:
+            self._init_bottom_only(params, hp, enc_depth, precision, device, scope)
+            return
         if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
             raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
         self.precision = precision
@@ -92,6 +96,42 @@ class SpellerWeights:
             self.w_proj_pad = up(wp)
 
 
+def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
+    """GNMT-style AttentionMultiCell wiring (las/model.py:20-69, 185-193): fp32 step-kernel decoder only."""
+    if precision != "fp32":
+        raise NotImplementedError("--bottom_only is built for the fp32 step-kernel decoder (precision='fp32')")
+    if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
+        raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
+    self.precision, self.att = precision, hp["attention_type"]
+    if self.att not in ("luong", "bahdanau"):
+        raise NotImplementedError(f"--bottom_only with attention_type={self.att}")
+    self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
+    D, Ud, V = self.D, self.Ud, self.V
+    if Ud % 16 or D % 4:
+        raise NotImplementedError("--bottom_only needs decoder_units % 16 == 0 and encoder depth % 4 == 0")
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device).contiguous()
+    wm = np.asarray(params[f"{scope}/memory_layer/kernel"], np.float32)
+    self.w_mem_t = up(wm.T)
+    pre = f"{scope}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper"
+    names = [f"{pre}/lstm_cell"] + [f"{scope}/decoder/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(1, self.L)]
+    kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
+    for k, kern in enumerate(kernels):
+        din = (V + D) if k == 0 else ((D if k == 1 else Ud) + D)
+        assert kern.shape == (din + Ud, 4 * Ud), (k, kern.shape)
+    self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names],
+                   w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]))
+    self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"])
+    self.w_query = self.v_att = None
+    self.score_bias = 0.0
+    if self.att == "bahdanau":
+        self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
+        self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"])
+    self.tc = False
+
+
+SpellerWeights._init_bottom_only = _init_bottom_only
+
+
 def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=False):
     """values = length-masked memory; keys = memory_layer(values) (tf.contrib.seq2seq
     _BaseAttentionMechanism; reference las/model.py:168-169)."""
@@ -128,7 +168,7 @@ def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=
 
 
 def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_steps=None,
-           want_alignment=True, trim=True, memory_is_masked=False):
+           want_alignment=True, trim=True, memory_is_masked=False, initial_state=None):
     """Run the decoder kernel.  Greedy when ``forced_ids`` is None (max_steps defaults to
     rint(Tm * decoding_length_factor), las/model.py:270-274); teacher-forced otherwise."""
     L = _lib.lib()
@@ -154,7 +194,7 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     n_steps = torch.zeros((1,), dtype=torch.int32, device=dev)
     if w.tf is not None and os.environ.get("PLAS_DEC_IMPL") != "simt":
         return _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, factor, logits, ids, align, seq_len,
-                                 n_steps, trim)
+                                 n_steps, trim, initial_state)
     d = _lib.DecDesc()
     d.dtype = _lib.dtype_code(w.precision)
     d.B, d.Tm, d.D, d.Ud, d.V, d.n_layers = B, Tm, D, w.Ud, w.V, w.L
@@ -194,7 +234,8 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     return logits, ids, align, seq_len, n_steps
 
 
-def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, factor, logits, ids, align, seq_len, n_steps, trim):
+def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, factor, logits, ids, align, seq_len, n_steps, trim,
+                      initial_state=None):
     """fp32 (reference-precision) decode through plas_decoder_infer_f32: a loop of step kernels on the TF weight layout."""
     B, Tm, D = values.shape
     d = _lib.DecInferDesc()
@@ -214,6 +255,14 @@ def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, f
     d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()
     d.alignment = align.data_ptr() if align is not None else None
     d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
+    d.bottom_only = 1 if getattr(w, "bottom_only", False) else 0
+    keep_alive = []
+    if initial_state is not None:  # pass_hidden_state: cell l starts from (c, h) number l of the listener's final state
+        for l, (c0, h0) in enumerate(initial_state[:w.L]):
+            c0, h0 = c0.to(torch.float32).contiguous(), h0.to(torch.float32).contiguous()
+            assert c0.shape == (B, w.Ud), "pass_hidden_state needs encoder_units == decoder_units"
+            keep_alive += [c0, h0]
+            d.c_init[l], d.h_init[l] = c0.data_ptr(), h0.data_ptr()
     need = L.plas_decoder_infer_f32_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=values.device)
     with _lib.stage("decoder"):
@@ -234,6 +283,9 @@ def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_leng
     runs teacher forcing (TrainingHelper, sampling_probability must be 0); otherwise greedy."""
     if binary_outputs or binf_embedding is not None or transparent_projection:
         raise NotImplementedError("binary-feature decoder variants are not built yet")
+    init = None
+    if getattr(weights, "pass_hidden_state", False):  # las/model.py:259-267
+        init = encoder_state if isinstance(encoder_state[0], (tuple, list)) else (encoder_state,)
     if mode == "train":
         if float(hparams.get("sampling_probability", 0.0)) > 0.0:
             raise NotImplementedError("scheduled sampling (las/model.py:279-288) is not built yet; "
@@ -245,10 +297,11 @@ def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_leng
                 steps = min(steps, hparams["max_symbols"])
         logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams,
                                                       forced_ids=decoder_inputs, max_steps=steps,
-                                                      want_alignment=False, memory_is_masked=memory_is_masked)
+                                                      want_alignment=False, memory_is_masked=memory_is_masked,
+                                                      initial_state=init)
         seq_len = target_sequence_length
     else:
         logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams,
                                                       memory_is_masked=memory_is_masked, want_alignment=want_alignment,
-                                                      trim=trim)
+                                                      trim=trim, initial_state=init)
     return BasicDecoderOutput(logits, ids), SpellerState(align, n_steps), seq_len

@@ -44,17 +44,25 @@ def variable_shapes(hp, num_channels=None):
     D = encoder_output_depth(hp)
     A = D  # attention_layer_size=None -> attention = context (depth D)
     shapes["speller/memory_layer/kernel"] = (D, Ud)
-    pre = "speller/decoder/attention_wrapper"
+    bottom = bool(hp.get("bottom_only"))
+    pre = "speller/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper" if bottom else "speller/decoder/attention_wrapper"
     for k in range(Ld):
-        din = (V + A) if k == 0 else Ud
-        shapes[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"] = (din + Ud, 4 * Ud)
-        shapes[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"] = (4 * Ud,)
+        if bottom:  # AttentionMultiCell (las/model.py:20-69): cell 0 under the attention wrapper, upper cells read [prev; old attention]
+            name = f"{pre}/lstm_cell" if k == 0 else f"speller/decoder/multi_rnn_cell/cell_{k}/lstm_cell"
+            din = (V + A) if k == 0 else ((A if k == 1 else Ud) + A)
+        else:
+            name = f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell"
+            din = (V + A) if k == 0 else Ud
+        shapes[name + "/kernel"] = (din + Ud, 4 * Ud)
+        shapes[name + "/bias"] = (4 * Ud,)
     at = hp["attention_type"]
     if at == "bahdanau":
         shapes[f"{pre}/bahdanau_attention/query_layer/kernel"] = (Ud, Ud)
         shapes[f"{pre}/bahdanau_attention/attention_v"] = (Ud,)
     elif at == "luong_monotonic":
         shapes[f"{pre}/luong_monotonic_attention/attention_score_bias"] = ()
+    if bottom and Ld > 1:
+        A = Ud  # the projection reads the top cell's output
     shapes["speller/decoder/projection_layer/kernel"] = (A, V)
     shapes["speller/decoder/projection_layer/bias"] = (V,)
     if hp.get("ctc_weight", -1) > 0:

@@ -72,3 +72,24 @@ def test_eval_mode_loss_and_edit_distance_match_oracle():
     assert abs(out["loss"].item() - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
     ref_ed = [olo.edit_distance_merge(list(ref["sample_ids"][b]), list(tout[b]), hp["eos_id"]) for b in range(5)]
     np.testing.assert_allclose(out["edit_distance"], ref_ed, rtol=0, atol=1e-12)
+
+
+@gpu
+def test_true_las_configuration_end_to_end():
+    """README's "true LAS" flags (--use_pyramidal --pass_hidden_state --bottom_only): the listener's final (c, h) of the
+    last layer seed the two decoder cells; predictions vs the oracle (fp32)."""
+    import torch
+    from phones_las_b200.model import DeviceWeights, las_predict
+    hp = create_hparams(target_vocab_size=18, encoder_layers=3, encoder_units=32, decoder_layers=2, decoder_units=32,
+                        attention_type="luong", num_channels=6, use_pyramidal=True, pass_hidden_state=True, bottom_only=True)
+    params = weights.init_params(hp, 6, seed=3, projection_scale=8.0, bias_scale=0.1)
+    x, lens = synth.synth_features(5, 40, 6, seed=6, var_len=True)
+    ref = ol.predict(x, lens, params, hp, "fp32")
+    pred = las_predict({"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()},
+                       hp, DeviceWeights(params, hp, 6, "fp32"))
+    assert_parity(pred["embedding"], ref["embedding"], "fp32", "encoder final states")
+    assert_parity(pred["logits"][:, :1], ref["logits"][:, :1], "fp32", "logits step 0")
+    s = np.sort(ref["logits"], -1)
+    if float((s[..., -1] - s[..., -2]).min()) > 1e-4:
+        np.testing.assert_array_equal(pred["sample_ids"].cpu().numpy(), ref["sample_ids"])
+        assert_parity(pred["logits"], ref["logits"], "fp32", "logits")

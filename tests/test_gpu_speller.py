@@ -162,3 +162,47 @@ def test_decoder_full_width_deterministic_and_first_steps(att, Tm):
         ids = ref_logits.argmax(axis=1)
         if not (ids == runs[0][0][:, t].cpu().numpy()).all():
             break  # a near-tie flipped an id: later steps follow different inputs
+
+
+# ---- GNMT-style AttentionMultiCell wiring (las/model.py:20-69, 185-193) and pass_hidden_state (las/model.py:259-267) ----
+def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0):
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=pass_state)
+    params = weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1)
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(seed + B)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    lens[0] = Tm
+    enc *= (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    state = tuple((rng.uniform(-1, 1, (B, U)).astype(np.float32), rng.uniform(-1, 1, (B, U)).astype(np.float32)) for _ in range(2))
+    return hp, params, enc, lens, D, state
+
+
+@gpu
+@pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,pass_state", [("luong", 4, 11, 16, 32, 1, 12, False), ("luong", 5, 13, 16, 32, 2, 14, False),
+                                                           ("bahdanau", 6, 17, 16, 48, 3, 20, False), ("luong", 5, 12, 32, 32, 2, 16, True),
+                                                           ("bahdanau", 35, 21, 16, 16, 2, 18, True)])
+def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, pass_state):
+    import torch
+    from phones_las_b200.speller import speller
+    hp, params, enc, lens, D, state = _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state)
+    w = _device_speller(hp, params, D, "fp32")
+    enc_t = torch.from_numpy(enc).cuda()
+    state_t = tuple((torch.from_numpy(c).cuda(), torch.from_numpy(h).cuda()) for c, h in state)
+    sp = ol.Speller(enc, lens, params, hp, "fp32", encoder_state=state)
+    ref_logits, ref_ids, ref_align, ref_len, _ = sp.greedy()
+    out, st, seq_len = speller(enc_t, state_t, None, torch.from_numpy(lens).cuda(), None, "infer", hp, w)
+    logits, ids, align = to_np(out.rnn_output), out.sample_id.cpu().numpy(), to_np(st.alignment_history)
+    assert_parity(logits[:, :1], ref_logits[:, :1], "fp32", "logits step 0")
+    if top2_margin(ref_logits) > 1e-4:
+        np.testing.assert_array_equal(ids, ref_ids)
+        np.testing.assert_array_equal(seq_len.cpu().numpy(), ref_len)
+        assert_parity(logits, ref_logits, "fp32", "logits")
+        assert_parity(align, ref_align, "fp32", "alignment")
+    tin, tout, tlen = synth.synth_labels(B, 5, V, seed=4)
+    hp["sampling_probability"] = 0.0
+    ref_tf, _ = ol.Speller(enc, lens, params, hp, "fp32", encoder_state=state).teacher_forced(tin, tlen)
+    out, _, _ = speller(enc_t, state_t, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(),
+                        "train", hp, w)
+    assert_parity(out.rnn_output, ref_tf, "fp32", "teacher-forced logits")

@@ -170,3 +170,27 @@ def test_clip_adam_edit_distance():
     np.testing.assert_allclose(pn, p.detach().numpy(), rtol=1e-5)
     assert olo.edit_distance_merge([3, 3, 4, 2, 9], [3, 4, 4, 5, 2], 2) == pytest.approx(1 / 3)
     assert olo.ctc_greedy_decode(np.eye(4)[None, [0, 0, 3, 1, 1, 3, 1]], [7]) == [[0, 1, 1]]
+
+
+def test_bottom_only_variable_layout_and_oracle_wiring():
+    """AttentionMultiCell (las/model.py:20-69): variable names / shapes of the bottom_only decoder and the oracle's wiring
+    (cell 1 reads [new attention; old attention; h], the projection reads the top cell)."""
+    from phones_las_b200 import weights as W
+    from phones_las_b200.hparams import create_hparams as ch
+    hp = ch(target_vocab_size=12, encoder_layers=2, encoder_units=8, decoder_units=8, decoder_layers=3, num_channels=5,
+            bottom_only=True, pass_hidden_state=True)
+    sh = W.variable_shapes(hp)
+    D = 32
+    assert sh["speller/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper/lstm_cell/kernel"] == (12 + D + 8, 32)
+    assert sh["speller/decoder/multi_rnn_cell/cell_1/lstm_cell/kernel"] == (D + D + 8, 32)
+    assert sh["speller/decoder/multi_rnn_cell/cell_2/lstm_cell/kernel"] == (8 + D + 8, 32)
+    assert sh["speller/decoder/projection_layer/kernel"] == (8, 12)
+    params = W.init_params(hp, seed=2, projection_scale=8.0)
+    from phones_las_b200 import synth as S
+    x, lens = S.synth_features(3, 10, 5, var_len=True)
+    (enc, enc_len), enc_state = ol.listener(x, lens, params, hp)
+    a = ol.Speller(enc, enc_len, params, hp, encoder_state=enc_state)
+    b = ol.Speller(enc, enc_len, params, dict(hp, pass_hidden_state=False))
+    la, _ = a.teacher_forced(np.full((3, 2), 3), np.array([2, 2, 2]))
+    lb, _ = b.teacher_forced(np.full((3, 2), 3), np.array([2, 2, 2]))
+    assert la.shape == (3, 2, 12) and not np.allclose(la, lb)  # the encoder state really seeds the cells
