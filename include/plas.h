@@ -246,6 +246,8 @@ typedef struct plas_rec_train_desc {
   const float* dout;        /* bwd: dL/dout, strides of `out`                                                 */
   float* c_final;           /* fwd, optional: [ndir][B][U] final cell / hidden states (encoder_state, las/ops.py:35-46) */
   float* h_final;
+  const float* dc_final;    /* bwd, optional: gradients wrt the final states [ndir][B][U] (decoder cells seeded from them, */
+  const float* dh_final;    /*                pass_hidden_state, las/model.py:259-267)                                      */
 } plas_rec_train_desc;
 size_t plas_rec_train_workspace_bytes(const plas_rec_train_desc* d);
 int plas_bilstm_rec_train_fwd(const plas_rec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
@@ -262,6 +264,9 @@ typedef struct plas_dec_train_desc {
   float keep_prob;          /* 1 - dropout of the decoder cells' inputs (1.0 = off).  x_in must already be dropped out by
                                the caller (plas_dropout_f32); the kernels drop attention_{t-1} and the inter-layer h     */
   uint32_t drop_seed;       /* masks: attention uses drop_seed, layer l's output uses drop_seed + 1 + l                  */
+  int32_t bottom_only;      /* AttentionMultiCell wiring (las/model.py:20-69,185-193): cell l >= 1 kernels are
+                               [(l == 1 ? D : Ud) + D + Ud][4Ud], w_proj is [Ud][n_out] when n_layers > 1; keep_prob must be 1 */
+  int32_t _pad;
   const float* kernel[4];   /* cell_k/lstm_cell/kernel [(k == 0 ? E + D : Ud) + Ud][4Ud]                       */
   const float* bias[4];     /* [4Ud]                                                                          */
   const float* w_mem;       /* memory_layer/kernel [D][Ud]                                                    */
@@ -283,6 +288,10 @@ typedef struct plas_dec_train_desc {
   float* db_proj;
   float* dmemory;           /* bwd out: [B][Tm][D] gradient wrt the encoder outputs                           */
   const uint32_t* drop_step; /* device optimiser-step counter added to the dropout seeds (NULL = 0)             */
+  const float* c_init[4];   /* bottom_only + pass_hidden_state: initial (c, h) of cell l [B][Ud] or NULL (zeros)  */
+  const float* h_init[4];
+  float* dc_init[4];        /* bwd out, optional: gradients wrt the initial states                                */
+  float* dh_init[4];
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

@@ -85,7 +85,7 @@ def pyramidal_bilstm(x, lengths, params, num_layers, scope="listener", masks=Non
     return outputs, lengths
 
 
-def listener(x, lengths, params, hp, masks=None):
+def listener(x, lengths, params, hp, masks=None, return_state=False):
     """las/model.py:104-142: pyramidal (las/ops.py:68-87) or stacked MultiRNNCell listener, bi- or unidirectional.
     ``masks[(layer, dir)]``: input-dropout multipliers over the WHOLE layer input; a stacked cell (layer >= 1) reads the
     column slice of its own direction."""
@@ -93,8 +93,9 @@ def listener(x, lengths, params, hp, masks=None):
     L, U = hp["encoder_layers"], hp["encoder_units"]
     dirs = (("rnn", False),) if uni else (("bidirectional_rnn/fw", False), ("bidirectional_rnn/bw", True))
     outputs = x
+    states = []
     for layer in range(L):
-        outs = []
+        outs, states = [], []
         for di, (d, rev) in enumerate(dirs):
             if hp["use_pyramidal"]:
                 name = f"listener/bilstm_{layer}/{d}/lstm_cell"
@@ -103,8 +104,9 @@ def listener(x, lengths, params, hp, masks=None):
             xin = outputs if masks is None else outputs * masks[(layer, di)]
             if not hp["use_pyramidal"] and layer > 0:
                 xin = xin[..., di * U:(di + 1) * U]
-            o, _ = dynamic_rnn(xin, lengths, params[name + "/kernel"], params[name + "/bias"], reverse=rev)
+            o, st = dynamic_rnn(xin, lengths, params[name + "/kernel"], params[name + "/bias"], reverse=rev)
             outs.append(o)
+            states.append(st)
         outputs = torch.cat(outs, -1)
         if hp["use_pyramidal"] and layer != 0:
             B, T, D = outputs.shape
@@ -112,10 +114,12 @@ def listener(x, lengths, params, hp, masks=None):
                 outputs = torch.cat([outputs, outputs.new_zeros((B, 1, D))], 1)
             outputs = outputs.reshape(B, -1, 2 * D)
             lengths = lengths // 2 + lengths % 2
+    if return_state:  # final (c, h) of the last layer, one per direction (encoder_state of las/ops.py:68-87)
+        return outputs, lengths, tuple(states)
     return outputs, lengths
 
 
-def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None):
+def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
     binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
     ``masks``: input-dropout multipliers of the decoder cells: 'x' [B,L,E] and 'att' [B,L,D] (slot t multiplies
@@ -126,16 +130,47 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
     mask = (torch.arange(Tm)[None, :] < enc_len[:, None])
     values = enc_out * mask[:, :, None].to(enc_out.dtype)
     keys = values @ params[f"{scope}/memory_layer/kernel"]
-    pre = f"{scope}/decoder/attention_wrapper"
-    cells = [(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"],
-              params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"]) for k in range(hp["decoder_layers"])]
+    bottom = bool(hp.get("bottom_only", False))
+    if bottom:  # AttentionMultiCell (las/model.py:20-69)
+        pre = f"{scope}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper"
+        names = [f"{pre}/lstm_cell"] + [f"{scope}/decoder/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(1, hp["decoder_layers"])]
+        cells = [(params[n + "/kernel"], params[n + "/bias"]) for n in names]
+    else:
+        pre = f"{scope}/decoder/attention_wrapper"
+        cells = [(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"],
+                  params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"]) for k in range(hp["decoder_layers"])]
     wp = params[f"{scope}/decoder/projection_layer/kernel"]
     bp = params[f"{scope}/decoder/projection_layer/bias"]
     state = [(enc_out.new_zeros((B, Ud)), enc_out.new_zeros((B, Ud))) for _ in cells]
+    if bottom and hp.get("pass_hidden_state") and encoder_state is not None:  # las/model.py:259-267
+        for l, st in enumerate(encoder_state[:len(state)]):
+            state[l] = st
     attention = enc_out.new_zeros((B, D))
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
     for t in range(dec_inputs.shape[1]):
+        if bottom:
+            if masks is not None:
+                raise NotImplementedError("dropout masks with bottom_only")
+            old = attention
+            (k0, b0), (c, h) = cells[0], state[0]
+            c0, h0 = _cell(torch.cat([dec_inputs[:, t], old, h], 1) @ k0 + b0, c)
+            new_state = [(c0, h0)]
+            if att_type == "bahdanau":
+                pq = h0 @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
+                score = (torch.tanh(keys + pq[:, None, :]) * params[f"{pre}/bahdanau_attention/attention_v"]).sum(-1)
+            else:
+                score = torch.einsum("btu,bu->bt", keys, h0)
+            align = torch.softmax(torch.where(mask, score, neg_inf), dim=1)
+            attention = torch.einsum("bt,btd->bd", align, values)
+            cur = attention
+            for (k, b), (c, h) in zip(cells[1:], state[1:]):
+                c2, h2 = _cell(torch.cat([cur, old, h], 1) @ k + b, c)
+                new_state.append((c2, h2))
+                cur = h2
+            state = new_state
+            logits.append(cur @ wp + bp)
+            continue
         if masks is None:
             inp = torch.cat([dec_inputs[:, t], attention], 1)
         else:
@@ -205,7 +240,7 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None):
     Returns (total loss incl. L2, dict of the parts)."""
     dt = features.dtype
     masks = masks or {}
-    enc_out, enc_len = listener(features, lengths, params, hp, masks=masks.get("listener"))
+    enc_out, enc_len, enc_state = listener(features, lengths, params, hp, masks=masks.get("listener"), return_state=True)
     tin, tout, tlen = labels["targets_inputs"], labels["targets_outputs"], labels["target_sequence_length"]
     L = tin.shape[1]
     w = (torch.arange(L)[None, :] < tlen[:, None]).to(dt)
@@ -214,14 +249,14 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None):
     V = hp["target_vocab_size"]
     if not hp.get("binary_outputs") or hp.get("multitask"):
         logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp,
-                               masks=masks.get("speller"))
+                               masks=masks.get("speller"), encoder_state=enc_state)
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits
         loss = loss + parts["ce"]
     if hp.get("binary_outputs"):
         bt = torch.as_tensor(binf, dtype=dt).t()  # [V, n]
         logits_b = speller_train(enc_out, enc_len, bt[tin.long()], params, hp, scope="speller_binf",
-                                 masks=masks.get("speller_binf"))
+                                 masks=masks.get("speller_binf"), encoder_state=enc_state)
         parts["ce_binf"] = sequence_loss_sigmoid(logits_b, bt[tout.long()], w)
         parts["logits_binf"] = logits_b
         loss = loss + parts["ce_binf"]

@@ -59,19 +59,21 @@ class RecTrainDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("U", C.c_int32), ("ndir", C.c_int32), ("din", C.c_int32),
                 ("_pad", C.c_int32), ("z", C.c_void_p), ("kernel", C.c_void_p * 2), ("lengths", C.c_void_p),
                 ("out", C.c_void_p), ("out_batch_stride", C.c_int64), ("c_save", C.c_void_p), ("h_prev", C.c_void_p),
-                ("dout", C.c_void_p), ("c_final", C.c_void_p), ("h_final", C.c_void_p)]
+                ("dout", C.c_void_p), ("c_final", C.c_void_p), ("h_final", C.c_void_p), ("dc_final", C.c_void_p), ("dh_final", C.c_void_p)]
 
 
 class DecTrainDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("S", C.c_int32), ("Tm", C.c_int32), ("D", C.c_int32), ("Ud", C.c_int32),
                 ("E", C.c_int32), ("n_out", C.c_int32), ("n_layers", C.c_int32), ("attention_type", C.c_int32),
                 ("dmemory_accumulate", C.c_int32), ("keep_prob", C.c_float), ("drop_seed", C.c_uint32),
+                ("bottom_only", C.c_int32), ("_pad", C.c_int32),
                 ("kernel", C.c_void_p * 4), ("bias", C.c_void_p * 4), ("w_mem", C.c_void_p), ("w_query", C.c_void_p),
                 ("v_att", C.c_void_p), ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("memory", C.c_void_p),
                 ("mem_len", C.c_void_p), ("x_in", C.c_void_p), ("logits", C.c_void_p), ("dlogits", C.c_void_p),
                 ("dkernel", C.c_void_p * 4), ("dbias", C.c_void_p * 4), ("dw_mem", C.c_void_p), ("dw_query", C.c_void_p),
                 ("dv_att", C.c_void_p), ("dw_proj", C.c_void_p), ("db_proj", C.c_void_p), ("dmemory", C.c_void_p),
-                ("drop_step", C.c_void_p)]
+                ("drop_step", C.c_void_p), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4),
+                ("dc_init", C.c_void_p * 4), ("dh_init", C.c_void_p * 4)]
 
 
 class DecInferDesc(C.Structure):

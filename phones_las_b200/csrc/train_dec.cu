@@ -298,6 +298,7 @@ struct AttBwdArgs {
   const float* align; long long s_al;
   float* dctx; long long s_dc;           // in: dlogits W_proj^T of this step; out: + recurrent part
   const float* datt_next; long long s_dn;  // gradient wrt attention_{t} from step t+1's cell input (NULL at t = S-1)
+  const float* extra[4]; long long s_extra[4];  // bottom_only: further sources of the attention gradient (NULL = absent)
   float* dscore; long long s_ds;         // [Tm] saved for the hoisted dkeys GEMM (luong)
   float* dq; long long s_dq;             // [Ud] gradient wrt the query (h_top)
   // bahdanau
@@ -352,6 +353,9 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
       if (p.inv_keep != 1.f) gnext *= drop_scale((uint64_t)((long long)b * p.s_dc + p.next_base + d_lo + d), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
       v += gnext;
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (p.extra[e]) v += p.extra[e][(long long)b * p.s_extra[e] + d_lo + d];
     s_dc[d] = v;
     dctx[d] = v;
   }
@@ -451,7 +455,8 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
 struct CellBwdArgs {
   int B, Ud;
   float* z; long long s_z;               // saved gates of this step -> dz (in place)
-  const float* c_t; const float* c_prev; long long s_c;   // c_prev NULL at t == 0
+  const float* c_t; const float* c_prev; long long s_c;   // c_prev NULL at t == 0 (or the initial state)
+  long long s_cp;                        // row stride of c_prev
   float* dc_carry;                       // [B][Ud] in/out
   int first;                             // 1 at t == S-1: the carry is zero
   const float* dq; long long s_dq;       // top layer: gradient wrt the query (NULL otherwise)
@@ -476,7 +481,7 @@ __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
   float* zp = p.z + (long long)b * p.s_z + u;
   const float gi = zp[0], gj = zp[Ud], gf = zp[2 * Ud], go = zp[3 * Ud];
   const float c = p.c_t[(long long)b * p.s_c + u];
-  const float cp = p.c_prev ? p.c_prev[(long long)b * p.s_c + u] : 0.f;
+  const float cp = p.c_prev ? p.c_prev[(long long)b * p.s_cp + u] : 0.f;
   const float tc = tanhf(c);
   const float carry = p.first ? 0.f : p.dc_carry[(size_t)b * Ud + u];
   const float dc = carry + dh * go * (1.f - tc * tc);
@@ -670,7 +675,7 @@ __global__ void dec_infer_finish_kernel(InferState st, int B, int t, int eos_id,
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
-  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx;
+  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh;
   size_t z[4], c[4], h[4], hprev[4], hdrop[4];
   size_t splitk, splitk_bytes;
   size_t total;
@@ -696,6 +701,7 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
   w.dkeys = take(B * Tm * Ud);
   w.dv_acc = take(B * Ud);
   w.dctx = take(B * S * D);
+  w.gh = take(B * S * Ud);  // bottom_only: dlogits W_proj^T when the projection reads the top cell
   for (int l = 0; l < 4; ++l) {
     w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = w.hdrop[l] = 0;
     if (l >= d.n_layers) continue;
@@ -704,7 +710,7 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
     w.h[l] = take(B * S * Ud);
     w.hprev[l] = take(B * S * Ud);
     if (l + 1 < d.n_layers) w.hdrop[l] = take(B * S * Ud);
-    w.dinp[l] = take(B * ((l == 0 ? D : Ud) + Ud));
+    w.dinp[l] = take(2 * B * (2 * D + Ud));  // 2 slots (bottom_only keeps step t+1's while step t's is written), widest layout
     w.dc[l] = take(B * Ud);
   }
   w.splitk_bytes = (size_t)4 * (d.E + D + Ud) * 4 * Ud * 4;  // up to 4 K-slices of the largest weight gradient
@@ -903,6 +909,264 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
 }
 
 namespace plas {
+// ---------------------------------------------------------------------------------------------------------
+// bottom_only training (GNMT-style AttentionMultiCell, las/model.py:20-69, 185-193; README's "true LAS" with pass_hidden_state):
+// attention wraps cell 0 only.  Per step: cell 0 ([x_t; attention_{t-1}; h0_{t-1}]) -> attention (query h0_t) -> cells
+// l >= 1 ([output below -- the NEW attention for l = 1 --; attention_{t-1}; h_{l,t-1}]) ; logits = h_top W_proj (L > 1).
+// Same kernels and saved tensors as the default wiring; only the orchestration differs.
+// ---------------------------------------------------------------------------------------------------------
+static int launch_cell_fwd(cudaStream_t st, const CellFwdArgs& a, int B, int Ud) {
+  const int per = ((a.K1 + a.K2 + a.K3) / 4 + CF_KS - 1) / CF_KS;
+  const size_t smem = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)4 * per * 4 * CF_UG + (size_t)CF_KS * DT_ROWS * 8) * 4;
+  PLAS_REQUIRE(smem <= 220 * 1024, "decoder cell: input depth %d too large", a.K1 + a.K2 + a.K3);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CF_KS, Ud / CF_UG, (B + DT_ROWS - 1) / DT_ROWS);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CF_KS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_cell_fwd_kernel, a));
+  return PLAS_OK;
+}
+
+static int launch_gemv_t(cudaStream_t st, const GemvTArgs& g, int B) {
+  const int per = (g.N / 4 + GV_NS - 1) / GV_NS;
+  const size_t gsm = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)GV_KG * 4 * per + (size_t)GV_NS * DT_ROWS * 8) * 4;
+  PLAS_REQUIRE(gsm <= 220 * 1024, "decoder gemv_t: N = %d too large", g.N);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(GV_NS, (g.K + GV_KG - 1) / GV_KG, (B + DT_ROWS - 1) / DT_ROWS);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = gsm;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GV_NS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_gemv_t_kernel, g));
+  return PLAS_OK;
+}
+
+static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, cudaStream_t st) {
+  const DecTrainWs w = dec_train_ws(*d);
+  unsigned char* base = (unsigned char*)workspace;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
+  PLAS_REQUIRE(d->keep_prob == 1.f, "dec_train: dropout with bottom_only is not built");
+  if (d->attention_type == PLAS_ATT_BAHDANAU) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
+  int rc;
+  if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud))) return rc;
+  if ((rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]))) return rc;
+  PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
+  for (int l = 0; l < L; ++l) {  // h_{-1}: zeros or the listener's final state (pass_hidden_state, las/model.py:259-267)
+    if (d->h_init[l]) PLAS_CUDA(cudaMemcpy2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, d->h_init[l], (size_t)Ud * 4, (size_t)Ud * 4, B, cudaMemcpyDeviceToDevice, st));
+    else PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
+  }
+  PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  PLAS_CUDA(cudaFuncSetAttribute(dec_att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  const int dsplit = (D >= 512 && D % 16 == 0) ? 4 : 1;
+  size_t att_smem = (size_t)(2 * Ud + ((Tm + 3) & ~3)) * 4;
+  const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
+  const int att_staged = (Ud % 4 == 0 && (D / dsplit) % 4 == 0 && att_smem + att_stage <= 220 * 1024) ? 1 : 0;
+  if (att_staged) att_smem += att_stage;
+  const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud, sd = (long long)S * D;
+  for (int t = 0; t < S; ++t) {
+    for (int l = 0; l < L; ++l) {
+      CellFwdArgs a;
+      a.B = B; a.Ud = Ud; a.skip = nullptr;
+      a.in3 = nullptr; a.s3 = 0; a.K3 = 0;
+      if (l == 0) {
+        a.pre = F(w.z[0]) + (size_t)t * 4 * Ud; a.s_pre = sz; a.bias = nullptr;
+        a.in1 = F(w.att_prev) + (size_t)t * D; a.s1 = sd; a.K1 = D;
+        a.in2 = F(w.hprev[0]) + (size_t)t * Ud; a.s2 = sh; a.K2 = Ud;
+        a.w = d->kernel[0] + (size_t)E * 4 * Ud;
+      } else {
+        a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
+        if (l == 1) { a.in1 = F(w.att) + (size_t)t * D; a.s1 = sd; a.K1 = D; }
+        else { a.in1 = F(w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud; }
+        a.in2 = F(w.att_prev) + (size_t)t * D; a.s2 = sd; a.K2 = D;
+        a.in3 = F(w.hprev[l]) + (size_t)t * Ud; a.s3 = sh; a.K3 = Ud;
+        a.w = d->kernel[l];
+      }
+      if (t > 0) { a.c_prev = F(w.c[l]) + (size_t)(t - 1) * Ud; a.s_c = sh; }
+      else { a.c_prev = d->c_init[l]; a.s_c = Ud; }
+      a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
+      a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
+      a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
+      a.hdrop_out = nullptr; a.idx_base = 0; a.seed = 0; a.thresh = 0; a.inv_keep = 1.f; a.step_ptr = nullptr;
+      if ((rc = launch_cell_fwd(st, a, B, Ud))) return rc;
+      if (l == 0) {  // the attention follows cell 0 (its query) and feeds cell 1 of the same step
+        AttFwdArgs q;
+        q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.dsplit = dsplit; q.staged = att_staged; q.skip = nullptr;
+        q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
+        q.query = F(w.h[0]) + (size_t)t * Ud; q.s_q = sh;
+        q.w_query = d->w_query; q.v_att = d->v_att;
+        q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh;
+        q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+        q.att = F(w.att) + (size_t)t * D; q.s_att = sd;
+        q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
+        q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
+        dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
+      }
+    }
+  }
+  PLAS_CUDA(cudaGetLastError());
+  if (L > 1) return gemm(st, (long long)B * S, d->n_out, Ud, F(w.h[L - 1]), Ud, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+  return gemm(st, (long long)B * S, d->n_out, D, F(w.att), D, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+}
+
+static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, cudaStream_t st) {
+  const DecTrainWs w = dec_train_ws(*d);
+  unsigned char* base = (unsigned char*)workspace;
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers, NO = d->n_out;
+  const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
+  const long long BS = (long long)B * S;
+  const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud, sd = (long long)S * D;
+  float* dctx = F(w.dctx);
+  float* sk = F(w.splitk);
+  const size_t skb = w.splitk_bytes;
+  int rc;
+  // projection: reads the top cell's h (L > 1) or the attention (L == 1)
+  if (L > 1) {
+    if ((rc = gemm(st, BS, Ud, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, F(w.gh), Ud))) return rc;
+    if ((rc = gemm(st, Ud, NO, (int)BS, F(w.h[L - 1]), 1, Ud, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+    PLAS_CUDA(cudaMemsetAsync(dctx, 0, (size_t)BS * D * 4, st));
+  } else {
+    if ((rc = gemm(st, BS, D, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, dctx, D))) return rc;
+    if ((rc = gemm(st, D, NO, (int)BS, F(w.att), 1, D, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+  }
+  if ((rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
+  if (bah) {
+    PLAS_REQUIRE(d->dw_query && d->dv_att, "dec_train_bwd: bahdanau needs dw_query / dv_att");
+    PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
+    PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
+  }
+  const int ns = (D % 16 == 0 && Ud % 16 == 0 && D >= 256) ? 4 : 1;
+  const int Tp = (Tm + 3) & ~3;
+  size_t attb_smem = (size_t)(D / ns + (ns + 1) * Tp + Ud) * 4;
+  const size_t attb_stage = (size_t)Tm * (D / ns + Ud / ns) * 4;
+  const int attb_staged = ((D / ns) % 4 == 0 && (Ud / ns) % 4 == 0 && attb_smem + attb_stage <= 220 * 1024) ? 1 : 0;
+  if (attb_staged) attb_smem += attb_stage;
+  PLAS_CUDA(cudaFuncSetAttribute(dec_att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  PLAS_CUDA(cudaFuncSetAttribute(dec_gemv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  // dinp_l = dz_l W_l^T lives in two slots (parity of t): step t reads step t+1's while it writes its own
+  auto Kin = [&](int l) { return l == 0 ? D : ((l == 1 ? D : Ud) + D); };        // input columns before the h part
+  auto dinp = [&](int l, int t) { return F(w.dinp[l]) + (size_t)(t & 1) * B * (2 * D + Ud); };
+  for (int t = S - 1; t >= 0; --t) {
+    const bool last = t == S - 1;
+    auto cell_and_gemv = [&](int l) -> int {
+      CellBwdArgs c;
+      c.B = B; c.Ud = Ud;
+      c.z = F(w.z[l]) + (size_t)t * 4 * Ud; c.s_z = sz;
+      c.c_t = F(w.c[l]) + (size_t)t * Ud; c.s_c = sh;
+      if (t > 0) { c.c_prev = F(w.c[l]) + (size_t)(t - 1) * Ud; c.s_cp = sh; }
+      else { c.c_prev = d->c_init[l]; c.s_cp = Ud; }
+      c.dc_carry = F(w.dc[l]); c.first = last ? 1 : 0;
+      if (l == 0) { c.dq = F(w.dq); c.s_dq = Ud; }                                          // gradient wrt the query h0_t
+      else if (l == L - 1) { c.dq = F(w.gh) + (size_t)t * Ud; c.s_dq = sh; }                // the projection reads the top cell
+      else { c.dq = nullptr; c.s_dq = 0; }
+      c.dh_next = last ? nullptr : dinp(l, t + 1) + Kin(l); c.s_dn = Kin(l) + Ud;
+      // the layer above reads this layer's h as its first input segment -- except above cell 0, whose output is the attention
+      c.dh_above = (l >= 1 && l < L - 1) ? dinp(l + 1, t) : nullptr; c.s_da = Kin(l + 1 < L ? l + 1 : l) + Ud;
+      c.idx_base = 0; c.seed = 0; c.thresh = 0; c.inv_keep = 1.f; c.step_ptr = nullptr;
+      dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
+      GemvTArgs g;
+      g.B = B; g.N = 4 * Ud; g.K = Kin(l) + Ud;
+      g.dz = c.z; g.s_z = sz;
+      g.w = d->kernel[l] + (size_t)(l == 0 ? E : 0) * 4 * Ud;
+      g.dinp = dinp(l, t); g.s_o = g.K;
+      return launch_gemv_t(st, g, B);
+    };
+    for (int l = L - 1; l >= 1; --l)
+      if ((rc = cell_and_gemv(l))) return rc;
+    AttBwdArgs q;
+    q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.nsplit = ns; q.staged = attb_staged;
+    q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
+    q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+    q.dctx = dctx + (size_t)t * D; q.s_dc = sd;
+    q.datt_next = last ? nullptr : dinp(0, t + 1); q.s_dn = D + Ud;      // attention_t was cell 0's input at step t+1
+    for (int e = 0; e < 4; ++e) { q.extra[e] = nullptr; q.s_extra[e] = 0; }
+    int ne = 0;
+    if (L > 1) { q.extra[ne] = dinp(1, t); q.s_extra[ne] = Kin(1) + Ud; ++ne; }   // ... cell 1's first input at this step
+    if (!last)
+      for (int l = 1; l < L && ne < 4; ++l) {                                      // ... and every upper cell's OLD attention at step t+1
+        q.extra[ne] = dinp(l, t + 1) + (l == 1 ? D : Ud); q.s_extra[ne] = Kin(l) + Ud; ++ne;
+      }
+    q.dscore = F(w.dscore) + (size_t)t * Tm; q.s_ds = (long long)S * Tm;
+    q.dq = F(w.dq); q.s_dq = Ud;
+    q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
+    q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
+    q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(B, ns);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = attb_smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = (unsigned)ns;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_att_bwd_kernel, q));
+    }
+    if ((rc = cell_and_gemv(0))) return rc;
+  }
+  PLAS_CUDA(cudaGetLastError());
+  // gradients wrt the initial states (flow into the listener's final states with pass_hidden_state)
+  for (int l = 0; l < L; ++l) {
+    if (d->dh_init[l])
+      PLAS_CUDA(cudaMemcpy2DAsync(d->dh_init[l], (size_t)Ud * 4, dinp(l, 0) + Kin(l), (size_t)(Kin(l) + Ud) * 4, (size_t)Ud * 4, B,
+                                  cudaMemcpyDeviceToDevice, st));
+    if (d->dc_init[l]) PLAS_CUDA(cudaMemcpyAsync(d->dc_init[l], F(w.dc[l]), (size_t)B * Ud * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  // weight gradients over the B*S saved rows (z now holds dz)
+  for (int l = 0; l < L; ++l) {
+    PLAS_REQUIRE(d->dkernel[l] && d->dbias[l], "dec_train_bwd: null gradient tensor (layer %d)", l);
+    const float* dz = F(w.z[l]);
+    float* dk = d->dkernel[l];
+    auto wg = [&](const float* a, int rows, size_t row0) {
+      return gemm(st, rows, 4 * Ud, (int)BS, a, 1, rows, dz, 4 * Ud, 1, dk + row0 * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb);
+    };
+    if (l == 0) {
+      if ((rc = wg(d->x_in, E, 0))) return rc;
+      if ((rc = wg(F(w.att_prev), D, E))) return rc;
+      if ((rc = wg(F(w.hprev[0]), Ud, (size_t)E + D))) return rc;
+    } else {
+      const int k1 = l == 1 ? D : Ud;
+      if ((rc = wg(l == 1 ? F(w.att) : F(w.h[l - 1]), k1, 0))) return rc;
+      if ((rc = wg(F(w.att_prev), D, k1))) return rc;
+      if ((rc = wg(F(w.hprev[l]), Ud, (size_t)k1 + D))) return rc;
+    }
+    if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;
+  }
+  const float* h0 = F(w.h[0]);  // the query is cell 0's output
+  if (bah) {
+    if ((rc = gemm(st, Ud, Ud, (int)BS, h0, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
+    if ((rc = plas_colsum_f32(F(w.dv_acc), B, Ud, Ud, d->dv_att, 0, st))) return rc;
+  } else {
+    if ((rc = gemm(st, Tm, Ud, S, F(w.dscore), 1, Tm, h0, Ud, 1, F(w.dkeys), Ud, nullptr, 0.f, B, (long long)S * Tm, (long long)S * Ud,
+                   (long long)Tm * Ud)))
+      return rc;
+  }
+  if ((rc = gemm(st, Tm, D, S, F(w.align), 1, Tm, dctx, D, 1, d->dmemory, D, nullptr, d->dmemory_accumulate ? 1.f : 0.f, B, (long long)S * Tm,
+                 (long long)S * D, (long long)Tm * D)))
+    return rc;
+  if ((rc = gemm(st, (long long)B * Tm, D, Ud, F(w.dkeys), Ud, 1, d->w_mem, 1, Ud, d->dmemory, D, nullptr, 1.f))) return rc;
+  return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud);
+}
+
 }  // namespace plas
 
 using namespace plas;
@@ -915,6 +1179,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   int rc = dec_train_check(d, workspace, workspace_bytes);
   if (rc) return rc;
   PLAS_REQUIRE(d->memory && d->mem_len && d->x_in && d->logits && d->w_mem && d->w_proj && d->b_proj, "dec_train_fwd: null tensor");
+  if (d->bottom_only) return dec_train_fwd_bottom(d, workspace, st);
   const DecTrainWs w = dec_train_ws(*d);
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
@@ -1005,6 +1270,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   int rc = dec_train_check(d, workspace, workspace_bytes);
   if (rc) return rc;
   PLAS_REQUIRE(d->dlogits && d->dmemory && d->dw_mem && d->dw_proj && d->db_proj, "dec_train_bwd: null tensor");
+  if (d->bottom_only) return dec_train_bwd_bottom(d, workspace, st);
   const DecTrainWs w = dec_train_ws(*d);
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
@@ -1047,6 +1313,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     q.dq = F(w.dq); q.s_dq = Ud;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
     q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
+    for (int e = 0; e < 4; ++e) { q.extra[e] = nullptr; q.s_extra[e] = 0; }
     q.next_base = (long long)(t + 1) * D; q.seed = d->drop_seed; q.thresh = thresh; q.inv_keep = inv_keep; q.step_ptr = d->drop_step;
     {
       cudaLaunchConfig_t cfg = {};
@@ -1068,7 +1335,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       CellBwdArgs c;
       c.B = B; c.Ud = Ud;
       c.z = F(w.z[l]) + (size_t)t * 4 * Ud; c.s_z = sz;
-      c.c_t = F(w.c[l]) + (size_t)t * Ud; c.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; c.s_c = sh;
+      c.c_t = F(w.c[l]) + (size_t)t * Ud; c.c_prev = t > 0 ? F(w.c[l]) + (size_t)(t - 1) * Ud : nullptr; c.s_c = sh; c.s_cp = sh;
       c.dc_carry = F(w.dc[l]); c.first = last ? 1 : 0;
       c.dq = (l == L - 1) ? F(w.dq) : nullptr; c.s_dq = Ud;
       c.dh_next = last ? nullptr : F(w.dinp[l]) + Kin; c.s_dn = Kin + Ud;

@@ -268,6 +268,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
         c_prev = d.c_save[btp * srow + dir * U + unit];
       }
       dh = d.dout[(size_t)b * d.out_batch_stride + (size_t)t_idx * srow + dir * U + unit];
+      if (s == len - 1 && d.dh_final) {  // the final state IS the state after the last active step (pass_hidden_state)
+        dh += d.dh_final[((size_t)dir * B + b) * U + unit];
+        dc_carry += d.dc_final[((size_t)dir * B + b) * U + unit];
+      }
     }
     if (j > 0) {
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * j));

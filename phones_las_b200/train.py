@@ -270,13 +270,16 @@ def listener_train_fwd(x, lengths, st, hp):
         c_save = torch.zeros((B, T, ndir * U), dtype=torch.float32, device=x.device)
         h_prev = torch.zeros((B, T, ndir * U), dtype=torch.float32, device=x.device)
         d = _rec_desc(B, T, U, ndir, din, z, [st.w(nm + "/kernel") for nm in names], lengths, out, c_save, h_prev)
+        c_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)  # encoder_state of the layer (pass_hidden_state)
+        h_fin = torch.empty((ndir, B, U), dtype=torch.float32, device=x.device)
+        d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
         need = L.plas_rec_train_workspace_bytes(C.byref(d))
         ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
         with _lib.stage("train_rec_fwd"):
             _lib.check(L.plas_bilstm_rec_train_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
         _lib.count_launches(1)
         tape.append(dict(xs=xs, seeds=seeds, keep=keep, z=z, c_save=c_save, h_prev=h_prev, lengths=lengths, T=T, din=din,
-                         width=width, own=own, t_alloc=t_alloc, ws=ws))
+                         width=width, own=own, t_alloc=t_alloc, ws=ws, c_fin=c_fin, h_fin=h_fin))
         if stack:  # pyramidal_stack: free view + ceil-halved lengths (las/ops.py:49-65)
             out = out.view(B, t_alloc // 2, 2 * ndir * U)
             lengths = torch.div(lengths, 2, rounding_mode="floor") + lengths % 2
@@ -284,8 +287,9 @@ def listener_train_fwd(x, lengths, st, hp):
     return x, lengths, tape
 
 
-def listener_train_bwd(d_enc, tape, st, hp):
-    """Gradient of the listener: per layer BPTT (plas_bilstm_rec_train_bwd) then dW = [x;h]^T dz, db, dx = dz W_x^T."""
+def listener_train_bwd(d_enc, tape, st, hp, d_final=None):
+    """Gradient of the listener: per layer BPTT (plas_bilstm_rec_train_bwd) then dW = [x;h]^T dz, db, dx = dz W_x^T.
+    ``d_final`` = (dc [ndir,B,U], dh [ndir,B,U]): gradients wrt the LAST layer's final states (pass_hidden_state)."""
     L = _lib.lib()
     U, ndir = hp["encoder_units"], (1 if hp["unidirectional"] else 2)
     B = d_enc.shape[0]
@@ -298,6 +302,8 @@ def listener_train_bwd(d_enc, tape, st, hp):
         dout = dout.reshape(B, tp["t_alloc"], ndir * U)
         d = _rec_desc(B, T, U, ndir, din, tp["z"], [st.w(nm + "/kernel") for nm in names], tp["lengths"], None, tp["c_save"],
                       tp["h_prev"], dout=dout)
+        if d_final is not None and l == hp["encoder_layers"] - 1:
+            d.dc_final, d.dh_final = d_final[0].data_ptr(), d_final[1].data_ptr()
         need = tp["ws"].numel()
         with _lib.stage("train_rec_bwd"):
             _lib.check(L.plas_bilstm_rec_train_bwd(C.byref(d), _lib.ptr(tp["ws"]), need, _lib.stream_ptr()))
@@ -353,11 +359,16 @@ class SpellerTrain:
         self.keep = 1.0 - float(hp.get("dropout", 0.0))
         self.tid = SPELLER_TID + 10 * index
         self.base = int(hp.get("dropout_seed", 0))
+        self.init = self.d_init = None
         if hp["attention_type"] not in ("luong", "bahdanau"):
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
-        for flag in ("bottom_only", "pass_hidden_state", "binf_projection", "attention_layer_size", "embedding_size"):
+        for flag in ("binf_projection", "attention_layer_size", "embedding_size"):
             if hp.get(flag):
                 raise NotImplementedError(f"training path: --{flag} is not built")
+        self.bottom = bool(hp.get("bottom_only"))
+        self.pass_state = self.bottom and bool(hp.get("pass_hidden_state"))  # las/model.py:260 needs both flags
+        if self.bottom and float(hp.get("dropout", 0.0)) > 0.0:
+            raise NotImplementedError("training path: dropout with --bottom_only is not built")
 
     def _desc(self, memory, mem_len, x_in, logits, dlogits=None, dmemory=None):
         st, hp, sc = self.st, self.hp, self.scope
@@ -370,9 +381,13 @@ class SpellerTrain:
         d.keep_prob = self.keep
         d.drop_seed = drop_seed(self.base, 0, self.tid + 1)  # + step * DROP_STEP_MUL on the device
         d.drop_step = st.step_dev.data_ptr()
-        pre = f"{sc}/decoder/attention_wrapper"
+        d.bottom_only = 1 if self.bottom else 0
+        pre = f"{sc}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper" if self.bottom else f"{sc}/decoder/attention_wrapper"
         for k in range(d.n_layers):
-            nm = f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell"
+            if self.bottom:  # AttentionMultiCell scopes (las/model.py:43-54)
+                nm = f"{pre}/lstm_cell" if k == 0 else f"{sc}/decoder/multi_rnn_cell/cell_{k}/lstm_cell"
+            else:
+                nm = f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell"
             d.kernel[k], d.bias[k] = st.w(nm + "/kernel"), st.w(nm + "/bias")
             d.dkernel[k], d.dbias[k] = st.g(nm + "/kernel"), st.g(nm + "/bias")
         d.w_mem, d.dw_mem = st.w(f"{sc}/memory_layer/kernel"), st.g(f"{sc}/memory_layer/kernel")
@@ -385,11 +400,21 @@ class SpellerTrain:
         d.logits = logits.data_ptr()
         d.dlogits = dlogits.data_ptr() if dlogits is not None else None
         d.dmemory = dmemory.data_ptr() if dmemory is not None else None
+        if self.init is not None:
+            for l, (c0, h0) in enumerate(self.init):
+                d.c_init[l], d.h_init[l] = c0.data_ptr(), h0.data_ptr()
+                if self.d_init is not None:
+                    d.dc_init[l], d.dh_init[l] = self.d_init[l][0].data_ptr(), self.d_init[l][1].data_ptr()
         return d
 
-    def forward(self, memory, mem_len, x_in):
-        """memory [B,Tm,D] (zero past mem_len), x_in [B,S,E] -> logits [B,S,n_out]; keeps the tape on self."""
+    def forward(self, memory, mem_len, x_in, initial_state=None):
+        """memory [B,Tm,D] (zero past mem_len), x_in [B,S,E] -> logits [B,S,n_out]; keeps the tape on self.
+        ``initial_state``: [(c, h)] per decoder cell (pass_hidden_state: the listener's final fw / bw states)."""
         L = _lib.lib()
+        self.init, self.d_init = None, None
+        if self.pass_state and initial_state is not None:
+            self.init = [(c.contiguous(), h.contiguous()) for c, h in initial_state[:self.hp["decoder_layers"]]]
+            assert self.init[0][0].shape[1] == self.hp["decoder_units"], "pass_hidden_state needs encoder_units == decoder_units"
         B, S = x_in.shape[0], x_in.shape[1]
         x_in = x_in.contiguous()
         if self.keep < 1.0:  # the cell input [x_t; attention_{t-1}] is dropped out; x_t here, attention inside the kernels
@@ -405,8 +430,11 @@ class SpellerTrain:
         return self.logits
 
     def backward(self, dlogits, d_enc):
-        """Accumulates into d_enc [B,Tm,D] and writes this speller's weight gradients into the TrainState."""
+        """Accumulates into d_enc [B,Tm,D] and writes this speller's weight gradients into the TrainState; with
+        pass_hidden_state the gradients wrt the initial states land in ``self.d_init`` [(dc, dh)] per seeded cell."""
         L = _lib.lib()
+        if self.init is not None:
+            self.d_init = [(torch.empty_like(c), torch.empty_like(h)) for c, h in self.init]
         d = self._desc(self.memory, self.mem_len, self.x_in, self.logits, dlogits.contiguous(), d_enc)
         with _lib.stage("train_dec_bwd"):
             _lib.check(L.plas_decoder_train_bwd(C.byref(d), _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr()))
@@ -479,6 +507,9 @@ def forward_backward(features, labels, st, hp, binf=None):
     B, Tm, D = enc_out.shape
     w = _seq_mask(tlen, S)
     d_enc = torch.zeros_like(enc_out)
+    # encoder_state (las/ops.py:68-87): final (c, h) of the last listener layer per direction -- seeds the decoder cells with
+    # --pass_hidden_state --bottom_only (las/model.py:259-267)
+    enc_state = [(tape[-1]["c_fin"][dd], tape[-1]["h_fin"][dd]) for dd in range(tape[-1]["c_fin"].shape[0])]
     parts = {}
     # the heads only share the encoder outputs: each speller (forward, loss, backward) runs on its own stream while the
     # CTC head runs on the caller's, each accumulating into its own encoder-output gradient buffer
@@ -498,7 +529,7 @@ def forward_backward(features, labels, st, hp, binf=None):
         with torch.cuda.stream(stream):
             stream.wait_event(ready)
             sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out, index=0 if scope == "speller" else 1)
-            logits = sp.forward(enc_out, enc_len, x_in)
+            logits = sp.forward(enc_out, enc_len, x_in, initial_state=enc_state)
             if lab is None:
                 parts[key], dl = seq_ce_grad(logits, tout, w)
                 parts["logits"] = logits
@@ -526,7 +557,16 @@ def forward_backward(features, labels, st, hp, binf=None):
         _lib.check(_lib.lib().plas_axpy_f32(_lib.ptr(d_enc), _lib.ptr(d_enc_j), d_enc.numel(), 1.0, _lib.stream_ptr()))
         _lib.count_launches(1)
         total = parts[key] if total is None else total + parts[key]
-    listener_train_bwd(d_enc, tape, st, hp)
+    d_final = None
+    for _, _, sp in pending:  # gradients wrt the listener's final states from the seeded decoder cells
+        if sp.d_init is not None:
+            if d_final is None:
+                d_final = (torch.zeros_like(tape[-1]["c_fin"]), torch.zeros_like(tape[-1]["h_fin"]))
+            for l, (dc0, dh0) in enumerate(sp.d_init):
+                for buf, g in ((d_final[0][l], dc0), (d_final[1][l], dh0)):
+                    _lib.check(_lib.lib().plas_axpy_f32(_lib.ptr(buf), _lib.ptr(g), g.numel(), 1.0, _lib.stream_ptr()))
+                    _lib.count_launches(1)
+    listener_train_bwd(d_enc, tape, st, hp, d_final)
     parts["audio_loss"] = total
     parts["encoder_out"] = enc_out
     return parts
@@ -615,7 +655,7 @@ def train_variable_shapes(hp, num_channels=None, binf_count=0):
             if not k.startswith("speller/"):
                 continue
             nk = "speller_binf/" + k[len("speller/"):]
-            if k.endswith("cell_0/lstm_cell/kernel"):
+            if k.endswith(("cell_0/lstm_cell/kernel", "cell_0_attention/attention_wrapper/lstm_cell/kernel")):
                 s = (s[0] - V + binf_count, s[1])
             elif k.endswith("projection_layer/kernel"):
                 s = (s[0], binf_count)

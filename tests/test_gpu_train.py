@@ -425,3 +425,38 @@ def test_checkpoint_save_restore_resumes_training_identically(tmp_path):
     model = LASModel.from_model_dir(str(tmp_path), fa, precision="fp32")
     pred = model.predict_from_features(feats["encoder_inputs"], feats["source_sequence_length"])
     assert pred["sample_ids"].shape[0] == x.shape[0]
+
+
+# ---- README's "true LAS" flags in training: bottom_only (AttentionMultiCell) and pass_hidden_state ----
+@gpu
+@pytest.mark.parametrize("att,B,T,U,Ud,Ld,ps", [("luong", 5, 40, 16, 32, 1, False), ("luong", 6, 44, 16, 32, 2, False),
+                                                  ("bahdanau", 4, 36, 16, 48, 3, False), ("luong", 7, 40, 32, 32, 2, True),
+                                                  ("bahdanau", 34, 30, 16, 16, 2, True)])
+def test_train_step_bottom_only_and_pass_hidden_state(att, B, T, U, Ud, Ld, ps):
+    """Whole forward + backward with the AttentionMultiCell wiring; with pass_hidden_state the decoder cells start from the
+    listener's final states and their gradients flow back into the listener's BPTT."""
+    import torch
+    from phones_las_b200 import train as tr
+    C, V, S = 6, 13, 5
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
+                        attention_type=att, dropout=0.0, sampling_probability=0.0, bottom_only=True, pass_hidden_state=ps,
+                        l2_reg_scale=1e-4, ctc_weight=0.3)
+    params = weights.init_params(hp, seed=U + Ud + Ld, bias_scale=0.05)
+    x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp)
+    ref_loss.backward()
+    st = tr.TrainState(params)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp)
+    assert scaled_err(parts["logits"], ref_parts["logits"].detach()) < 1e-5
+    for name in ("ce", "ctc"):
+        assert abs(parts[name].item() - ref_parts[name].item()) < 1e-4 * max(1.0, abs(ref_parts[name].item())), name
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k

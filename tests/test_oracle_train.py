@@ -144,3 +144,20 @@ def test_general_listener_matches_numpy_oracle():
         out, out_len = lt.listener(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), _tp(params), hp)
         assert np.array_equal(out_len.numpy(), ref_len), (pyr, uni)
         assert np.abs(out.numpy() - ref).max() < 2e-6, (pyr, uni)
+
+
+def test_bottom_only_teacher_forced_matches_numpy_oracle():
+    """The differentiable restatement of the AttentionMultiCell wiring (+ pass_hidden_state) vs the numpy oracle."""
+    for att, Ld, ps in (("luong", 2, True), ("bahdanau", 3, False), ("luong", 1, False)):
+        hp = create_hparams(target_vocab_size=11, encoder_layers=2, encoder_units=8, decoder_units=8, decoder_layers=Ld,
+                            num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=ps)
+        params = weights.init_params(hp, seed=5, bias_scale=0.1)
+        x, lens = synth.synth_features(3, 12, 4, var_len=True)
+        (enc, enc_len), enc_state = ol.listener(x, lens, params, hp)
+        tin, tout, tlen = synth.synth_labels(3, 5, 11)
+        ref, _ = ol.Speller(enc, enc_len, params, hp, encoder_state=enc_state).teacher_forced(tin, tlen)
+        tp = _tp(params)
+        e, el, es = lt.listener(torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), tp, hp, return_state=True)
+        x64 = torch.nn.functional.one_hot(torch.tensor(tin, dtype=torch.int64), 11).to(torch.float64)
+        out = lt.speller_train(e, el, x64, tp, hp, encoder_state=es)
+        assert np.abs(out.numpy() - ref).max() < 5e-6, (att, Ld, ps)
