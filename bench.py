@@ -392,7 +392,7 @@ def train_problem(cfg, B, seed):
     from phones_las_b200 import synth
     hp = dict(cfg["hp"])
     # dropout 0.2 as in the reference's defaults (utils/params_utils.py:36; counter-based masks);
-    # scheduled sampling is not built: sampling_probability 0
+    # scheduled sampling exists for the phone speller only (the reference's binary-feature variant is ill-defined): 0 here
     hp.update(dropout=0.2, sampling_probability=0.0, binf_count=N_BINF)
     feats, lens = synth.synth_features(B, cfg["T"], cfg["C"], seed=seed)
     tin, tout, tlen = synth.synth_labels(B, N_LABELS, hp["target_vocab_size"], seed=seed + 1)
@@ -432,7 +432,7 @@ def train_config_dict(cfg, hp, B, world, **extra):
          "vocab": hp["target_vocab_size"],
          "parallelism": f"dp{world}: batch-sharded replicas, one NCCL all-reduce of the flat fp32 gradient buffer per step" if world > 1
                         else "single GPU (no collective)",
-         "dropout": "0.2 on every LSTM cell input (counter-based masks), sampling_probability 0 (scheduled sampling not built)"}
+         "dropout": "0.2 on every LSTM cell input (counter-based masks); sampling_probability 0 (multitask: the binary-feature speller has no scheduled sampling)"}
     d.update(extra)
     return d
 

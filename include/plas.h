@@ -292,6 +292,14 @@ typedef struct plas_dec_train_desc {
   const float* h_init[4];
   float* dc_init[4];        /* bwd out, optional: gradients wrt the initial states                                */
   float* dh_init[4];
+  /* scheduled sampling of the phone speller (las/model.py:279-288, utils/training_helper.py:48-87): with probability
+   * sample_prob per (utterance, step) the next input is the one-hot of an id drawn from Categorical(logits_t); the forward call
+   * rewrites x_in[b][t+1] through x_in_rw (= x_in) so that the backward call sees the inputs actually fed */
+  float sample_prob;        /* 0 = teacher forcing                                                              */
+  uint32_t sample_seed;     /* selection uses sample_seed, the categorical draw sample_seed + 1 (+ step, drop_step) */
+  uint32_t xdrop_seed;      /* dropout seed of x_in (a sampled input is dropped out like the one it replaces)    */
+  uint32_t _pad2;
+  float* x_in_rw;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

@@ -119,7 +119,8 @@ def listener(x, lengths, params, hp, masks=None, return_state=False):
     return outputs, lengths
 
 
-def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None):
+def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None, sampling=None,
+                  fed_inputs=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
     binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
     ``masks``: input-dropout multipliers of the decoder cells: 'x' [B,L,E] and 'att' [B,L,D] (slot t multiplies
@@ -148,13 +149,29 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
     attention = enc_out.new_zeros((B, D))
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
-    for t in range(dec_inputs.shape[1]):
+    # scheduled sampling (ScheduledEmbeddingTrainingHelper, las/model.py:279-288): ``sampling`` = (selected [B,S] bool, gumbel
+    # [B,S,V]); where selected[b,t], the input of step t+1 becomes one_hot(argmax(logits_t + gumbel_t)) -- a draw from
+    # Categorical(logits_t) by Gumbel-max, with the caller's noise so that the stochastic op is replayed exactly.  The inputs
+    # that were actually fed are appended to ``fed_inputs`` (a list) when given.
+    dec_inputs = [dec_inputs[:, t] for t in range(dec_inputs.shape[1])]
+
+    def maybe_sample(t, logits_t):
+        if sampling is None or t + 1 >= len(dec_inputs):
+            return
+        sel = torch.as_tensor(sampling[0][:, t])
+        ids = (logits_t.detach() + torch.as_tensor(sampling[1][:, t], dtype=logits_t.dtype)).argmax(-1)
+        drawn = torch.nn.functional.one_hot(ids, logits_t.shape[-1]).to(logits_t.dtype)
+        dec_inputs[t + 1] = torch.where(sel[:, None], drawn, dec_inputs[t + 1])
+
+    for t in range(len(dec_inputs)):
+        if fed_inputs is not None:
+            fed_inputs.append(dec_inputs[t])
         if bottom:
             if masks is not None:
                 raise NotImplementedError("dropout masks with bottom_only")
             old = attention
             (k0, b0), (c, h) = cells[0], state[0]
-            c0, h0 = _cell(torch.cat([dec_inputs[:, t], old, h], 1) @ k0 + b0, c)
+            c0, h0 = _cell(torch.cat([dec_inputs[t], old, h], 1) @ k0 + b0, c)
             new_state = [(c0, h0)]
             if att_type == "bahdanau":
                 pq = h0 @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
@@ -170,11 +187,12 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
                 cur = h2
             state = new_state
             logits.append(cur @ wp + bp)
+            maybe_sample(t, logits[-1])
             continue
         if masks is None:
-            inp = torch.cat([dec_inputs[:, t], attention], 1)
+            inp = torch.cat([dec_inputs[t], attention], 1)
         else:
-            inp = torch.cat([dec_inputs[:, t] * masks["x"][:, t], attention * masks["att"][:, t]], 1)
+            inp = torch.cat([dec_inputs[t] * masks["x"][:, t], attention * masks["att"][:, t]], 1)
         new_state = []
         for li, ((k, b), (c, h)) in enumerate(zip(cells, state)):
             z = torch.cat([inp, h], 1) @ k + b
@@ -196,6 +214,7 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
         align = torch.softmax(score, dim=1)
         attention = torch.einsum("bt,btd->bd", align, values)
         logits.append(attention @ wp + bp)
+        maybe_sample(t, logits[-1])
     return torch.stack(logits, 1)
 
 
@@ -234,7 +253,7 @@ def ctc_loss(logits, labels, label_length, logit_length, blank=0):
     return torch.stack(out)
 
 
-def train_loss(params, features, lengths, labels, hp, binf=None, masks=None):
+def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sampling=None):
     """las_model_fn(mode=TRAIN) loss (model_helper.py:165-358, 411-413) with dropout = 0 and
     sampling_probability = 0.  ``binf`` [n, V] enables the multitask binary-feature speller.
     Returns (total loss incl. L2, dict of the parts)."""
@@ -249,7 +268,7 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None):
     V = hp["target_vocab_size"]
     if not hp.get("binary_outputs") or hp.get("multitask"):
         logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp,
-                               masks=masks.get("speller"), encoder_state=enc_state)
+                               masks=masks.get("speller"), encoder_state=enc_state, sampling=sampling)
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits
         loss = loss + parts["ce"]

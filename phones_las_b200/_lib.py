@@ -73,7 +73,9 @@ class DecTrainDesc(C.Structure):
                 ("dkernel", C.c_void_p * 4), ("dbias", C.c_void_p * 4), ("dw_mem", C.c_void_p), ("dw_query", C.c_void_p),
                 ("dv_att", C.c_void_p), ("dw_proj", C.c_void_p), ("db_proj", C.c_void_p), ("dmemory", C.c_void_p),
                 ("drop_step", C.c_void_p), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4),
-                ("dc_init", C.c_void_p * 4), ("dh_init", C.c_void_p * 4)]
+                ("dc_init", C.c_void_p * 4), ("dh_init", C.c_void_p * 4),
+                ("sample_prob", C.c_float), ("sample_seed", C.c_uint32), ("xdrop_seed", C.c_uint32), ("_pad2", C.c_uint32),
+                ("x_in_rw", C.c_void_p)]
 
 
 class DecInferDesc(C.Structure):

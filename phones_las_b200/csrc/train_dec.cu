@@ -568,6 +568,67 @@ __global__ void __launch_bounds__(256) dec_gemv_t_kernel(GemvTArgs p) {
   }
 }
 
+// Scheduled sampling of the phone speller (ScheduledEmbeddingTrainingHelper / TPUScheduledEmbeddingTrainingHelper,
+// utils/training_helper.py:48-87, las/model.py:279-288): with probability p per (utterance, step) the NEXT step's input is
+// the one-hot of an id drawn from Categorical(logits_t) instead of the target.  One CTA per utterance: rows that are not
+// selected exit at once; a selected row computes its logits, draws by Gumbel-max, and rewrites x_in[b][t+1] and the hoisted
+// pre-activations Z_0[b][t+1] = W_0[id] + b_0.  Counter-based randomness (same hash as dropout): nothing differentiable
+// flows through the draw, so the backward pass is untouched -- it simply sees the inputs that were actually fed.
+struct SchedSampleArgs {
+  const float* out; long long s_out; int Dout, V;   // what the projection reads at step t
+  const float* w_proj; const float* b_proj;
+  float* x_next; long long s_x;                     // x_in[.][t+1][:], E == V
+  float* z_next; long long s_z; int N;              // Z_0[.][t+1][:], N = 4Ud
+  const float* w0; const float* b0;                 // cell-0 kernel rows of the one-hot input [V][N], bias [N]
+  long long idx_base; int S;                        // flat (b, t) index = b*S + t (idx_base = t)
+  unsigned seed_sel, seed_cat, p_thresh; const unsigned* step_ptr;
+  unsigned xdrop_seed, xdrop_thresh; float xdrop_inv_keep;  // input dropout of x_{t+1} (thresh 2^24 / inv_keep 1 = off)
+};
+
+__global__ void __launch_bounds__(256) dec_sched_sample_kernel(SchedSampleArgs p) {
+  extern __shared__ float ss_smem[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const unsigned stepv = (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL;
+  const uint64_t bt = (uint64_t)b * p.S + p.idx_base;
+  if ((drop_hash(bt, p.seed_sel + stepv) >> 8) >= p.p_thresh) return;  // this row keeps its teacher input
+  float* s_a = ss_smem;            // [Dout]
+  float* s_part = s_a + p.Dout;    // [4][V]
+  __shared__ int s_best;
+  const int V = p.V, D = p.Dout;
+  for (int d = tid; d < D; d += 256) s_a[d] = p.out[(long long)b * p.s_out + d];
+  __syncthreads();
+  for (int i = tid; i < 4 * V; i += 256) {
+    const int sl = i / V, v = i - sl * V;
+    const int dper = (D + 3) / 4;
+    const int d_hi = min(D, (sl + 1) * dper);
+    float acc = 0.f;
+    for (int d = sl * dper; d < d_hi; ++d) acc = fmaf(s_a[d], __ldg(p.w_proj + (size_t)d * V + v), acc);
+    s_part[i] = acc;
+  }
+  __syncthreads();
+  float* s_logit = s_a;
+  for (int v = tid; v < V; v += 256) {
+    const float lg = ((s_part[v] + s_part[V + v]) + (s_part[2 * V + v] + s_part[3 * V + v])) + p.b_proj[v];
+    const float u = ((float)(drop_hash(bt * V + v, p.seed_cat + stepv) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    s_logit[v] = lg - logf(-logf(u));  // Gumbel-max: argmax(logits + g) ~ Categorical(softmax(logits))
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0;
+    float bv = s_logit[0];
+    for (int v = 1; v < V; ++v)
+      if (s_logit[v] > bv) { bv = s_logit[v]; best = v; }
+    s_best = best;
+  }
+  __syncthreads();
+  const int best = s_best;
+  const float sc = p.xdrop_inv_keep == 1.f ? 1.f
+                                           : drop_scale((uint64_t)((long long)b * p.s_x + (p.idx_base + 1) * V + best), p.xdrop_seed + stepv,
+                                                        p.xdrop_thresh, p.xdrop_inv_keep);
+  for (int v = tid; v < V; v += 256) p.x_next[(long long)b * p.s_x + v] = v == best ? sc : 0.f;
+  for (int n = tid; n < p.N; n += 256) p.z_next[(long long)b * p.s_z + n] = fmaf(sc, p.w0[(size_t)best * p.N + n], p.b0[n]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // fp32 inference (reference-precision mode) built from the same step kernels: greedy (GreedyEmbeddingHelper +
 // dynamic_decode, las/model.py:337-347) or teacher-forced decoding as a host loop of small launches over a 2-slot state
@@ -738,6 +799,9 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   PLAS_REQUIRE(d->B > 0 && d->S > 0 && d->Tm > 0 && d->E > 0 && d->n_out > 0, "dec_train: bad shape");
   PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_train: n_layers=%d", d->n_layers);
   PLAS_REQUIRE(d->keep_prob > 0.f && d->keep_prob <= 1.f, "dec_train: keep_prob=%f", d->keep_prob);
+  PLAS_REQUIRE(d->sample_prob >= 0.f && d->sample_prob <= 1.f, "dec_train: sample_prob=%f", d->sample_prob);
+  if (d->sample_prob > 0.f)
+    PLAS_REQUIRE(d->x_in_rw != nullptr && d->E == d->n_out, "dec_train: scheduled sampling needs one-hot inputs (E == n_out) and a writable x_in");
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
   PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU,
                "dec_train: attention_type %d has no training path (luong, bahdanau)", d->attention_type);
@@ -955,6 +1019,27 @@ static int launch_gemv_t(cudaStream_t st, const GemvTArgs& g, int B) {
   return PLAS_OK;
 }
 
+// launched after the attention (default wiring) / the top cell (bottom_only) of step t when sampling_probability > 0
+static int launch_sched_sample(cudaStream_t st, const plas_dec_train_desc* d, const DecTrainWs& w, unsigned char* base, int t, const float* out,
+                               long long s_out, int Dout) {
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  const int B = d->B, S = d->S, Ud = d->Ud, E = d->E;
+  SchedSampleArgs a;
+  a.out = out; a.s_out = s_out; a.Dout = Dout; a.V = d->n_out;
+  a.w_proj = d->w_proj; a.b_proj = d->b_proj;
+  a.x_next = d->x_in_rw + (size_t)(t + 1) * E; a.s_x = (long long)S * E;
+  a.z_next = F(w.z[0]) + (size_t)(t + 1) * 4 * Ud; a.s_z = (long long)S * 4 * Ud; a.N = 4 * Ud;
+  a.w0 = d->kernel[0]; a.b0 = d->bias[0];
+  a.idx_base = t; a.S = S;
+  a.seed_sel = d->sample_seed; a.seed_cat = d->sample_seed + 1; a.p_thresh = (unsigned)(d->sample_prob * 16777216.0f); a.step_ptr = d->drop_step;
+  a.xdrop_seed = d->xdrop_seed; a.xdrop_thresh = (unsigned)(d->keep_prob * 16777216.0f); a.xdrop_inv_keep = 1.0f / d->keep_prob;
+  const size_t smem = (size_t)(Dout + 4 * d->n_out) * 4;
+  PLAS_REQUIRE(smem <= 200 * 1024, "scheduled sampling: projection too large");
+  if (smem > 48 * 1024) PLAS_CUDA(cudaFuncSetAttribute(dec_sched_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dec_sched_sample_kernel<<<B, 256, smem, st>>>(a);
+  return PLAS_OK;
+}
+
 static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, cudaStream_t st) {
   const DecTrainWs w = dec_train_ws(*d);
   unsigned char* base = (unsigned char*)workspace;
@@ -1016,6 +1101,11 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
         q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
         dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
       }
+    }
+    if (d->sample_prob > 0.f && t + 1 < S) {
+      if (L > 1) rc = launch_sched_sample(st, d, w, base, t, F(w.h[L - 1]) + (size_t)t * Ud, sh, Ud);
+      else rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * D, sd, D);
+      if (rc) return rc;
     }
   }
   PLAS_CUDA(cudaGetLastError());
@@ -1258,6 +1348,8 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
     q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
     q.next_base = (long long)(t + 1) * D; q.seed = d->drop_seed; q.thresh = thresh; q.inv_keep = inv_keep; q.step_ptr = d->drop_step;
     dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
+    if (d->sample_prob > 0.f && t + 1 < S)
+      if ((rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * D, (long long)S * D, D))) return rc;
   }
   PLAS_CUDA(cudaGetLastError());
   // logits = DenseBinfDecoder(attention)

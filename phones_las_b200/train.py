@@ -54,17 +54,33 @@ def drop_seed(base, step, tensor_id):
     return int((int(base) * 0x9E3779B1 + int(step) * 0x85EBCA77 + int(tensor_id) * 0xC2B2AE3D + 0x165667B1) & 0xFFFFFFFF)
 
 
-def dropout_mask(n, seed, keep_prob):
-    """numpy mirror of drop_scale() in csrc/common.cuh: multipliers (1/keep or 0) of elements 0..n-1 of the tensor `seed`."""
+def hash_u24(n, seed):
+    """numpy mirror of drop_hash() >> 8 in csrc/common.cuh for the indices 0..n-1: 24-bit uniform integers."""
     with np.errstate(over="ignore"):
         idx = np.arange(n, dtype=np.uint64)
-        sd = np.uint32(seed)
+        sd = np.uint32(seed & 0xFFFFFFFF)
         x = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32) * np.uint32(0x9E3779B1) + (idx >> np.uint64(32)).astype(np.uint32) * np.uint32(0x85EBCA77) + sd
         x ^= x >> np.uint32(16); x *= np.uint32(0x85EBCA6B); x ^= x >> np.uint32(13); x *= np.uint32(0xC2B2AE35); x ^= x >> np.uint32(16)
         x += sd * np.uint32(0x27D4EB2F)
         x ^= x >> np.uint32(15); x *= np.uint32(0x2C1B3C6D); x ^= x >> np.uint32(12); x *= np.uint32(0x297A2D39); x ^= x >> np.uint32(15)
+    return x >> np.uint32(8)
+
+
+def dropout_mask(n, seed, keep_prob):
+    """numpy mirror of drop_scale(): multipliers (1/keep or 0) of elements 0..n-1 of the tensor `seed`."""
     thresh = np.uint32(np.float32(keep_prob) * np.float32(16777216.0))
-    return np.where((x >> np.uint32(8)) < thresh, np.float32(1.0) / np.float32(keep_prob), np.float32(0.0)).astype(np.float32)
+    return np.where(hash_u24(n, seed) < thresh, np.float32(1.0) / np.float32(keep_prob), np.float32(0.0)).astype(np.float32)
+
+
+def reference_sampling(hp, step, B, S, V, speller_index=0):
+    """Scheduled-sampling randomness of the device path at optimiser step ``step`` (test support): ``selected`` [B,S] bool (row b
+    replaces its input of step t+1 by a sample drawn at step t) and the Gumbel noise [B,S,V] added to the logits of step t."""
+    base = int(hp.get("dropout_seed", 0))
+    seed = drop_seed(base, step, SPELLER_TID + 10 * speller_index + 9)
+    p = np.uint32(np.float32(hp["sampling_probability"]) * np.float32(16777216.0))
+    selected = (hash_u24(B * S, seed) < p).reshape(B, S)
+    u = (hash_u24(B * S * V, (seed + 1) & 0xFFFFFFFF).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    return selected, (-np.log(-np.log(u.astype(np.float64)))).reshape(B, S, V)
 
 
 def dropout_(x, y, seed, keep_prob, step_dev=None):
@@ -360,6 +376,11 @@ class SpellerTrain:
         self.tid = SPELLER_TID + 10 * index
         self.base = int(hp.get("dropout_seed", 0))
         self.init = self.d_init = None
+        # scheduled sampling (las/model.py:279-288): the phone speller draws ids from its own logits; the binary-feature
+        # speller's ScheduledSigmoidHelper path of the reference is shape-inconsistent and is not built
+        self.sample_prob = float(hp.get("sampling_probability", 0.0))
+        if self.sample_prob > 0.0 and (scope != "speller" or E != n_out):
+            raise NotImplementedError("training path: scheduled sampling is built for the phone speller only; set sampling_probability=0")
         if hp["attention_type"] not in ("luong", "bahdanau"):
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
         for flag in ("binf_projection", "attention_layer_size", "embedding_size"):
@@ -381,6 +402,10 @@ class SpellerTrain:
         d.keep_prob = self.keep
         d.drop_seed = drop_seed(self.base, 0, self.tid + 1)  # + step * DROP_STEP_MUL on the device
         d.drop_step = st.step_dev.data_ptr()
+        d.sample_prob = self.sample_prob
+        d.sample_seed = drop_seed(self.base, 0, self.tid + 9)
+        d.xdrop_seed = drop_seed(self.base, 0, self.tid)
+        d.x_in_rw = x_in.data_ptr()
         d.bottom_only = 1 if self.bottom else 0
         pre = f"{sc}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper" if self.bottom else f"{sc}/decoder/attention_wrapper"
         for k in range(d.n_layers):
@@ -492,8 +517,6 @@ def forward_backward(features, labels, st, hp, binf=None):
     """Forward + backward of las_model_fn(TRAIN): fills ``st.grads`` (raw, before L2 / clipping) and returns the loss
     parts as device scalars {ce, ce_binf, ctc, audio_loss}.  ``binf`` [n, V] float tensor (binf2phone, model_helper.py:179-186)
     enables the multitask binary-feature speller when hp['binary_outputs']."""
-    if float(hp.get("sampling_probability", 0.0)) > 0.0:
-        raise NotImplementedError("training path: scheduled sampling (las/model.py:279-288) is not built; set sampling_probability=0")
     x, lens = features["encoder_inputs"], features["source_sequence_length"]
     dev = x.device
     tin = labels["targets_inputs"].to(device=dev, dtype=torch.int64)

@@ -460,3 +460,73 @@ def test_train_step_bottom_only_and_pass_hidden_state(att, B, T, U, Ud, Ld, ps):
     for k in params:
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+
+
+# ---- scheduled sampling of the phone speller (las/model.py:279-288): replayed by the oracle on the same randomness ----
+@gpu
+@pytest.mark.parametrize("att,Ld,bottom,dropout", [("luong", 1, False, 0.0), ("bahdanau", 2, False, 0.0), ("luong", 2, True, 0.0),
+                                                    ("luong", 2, False, 0.25)])
+def test_scheduled_sampling_speller(att, Ld, bottom, dropout):
+    import torch
+    from phones_las_b200 import train as tr
+    B, Tm, U, Ud, V, S = 9, 14, 16, 32, 13, 8
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=4,
+                        attention_type=att, dropout=dropout, sampling_probability=0.5, bottom_only=bottom)
+    params = {k: v for k, v in weights.init_params(hp, seed=3, projection_scale=6.0, bias_scale=0.1).items() if k.startswith("speller/")}
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(5)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    enc *= (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    ids = rng.integers(0, V, (B, S))
+    st = tr.TrainState(params)
+    st.step = 7
+    sampling = tr.reference_sampling(hp, 7, B, S, V)
+    assert 0.2 < sampling[0].mean() < 0.8
+    masks = None
+    if dropout > 0:
+        masks = {k: torch.tensor(v, dtype=torch.float64) for k, v in tr.reference_masks(hp, 7, B, 4 * Tm, 4, S)["speller"].items()}
+    tp = _tp(params)
+    enc_t = torch.tensor(enc, dtype=torch.float64, requires_grad=True)
+    x64 = torch.nn.functional.one_hot(torch.tensor(ids), V).to(torch.float64)
+    fed = []
+    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp, masks=masks, sampling=sampling, fed_inputs=fed)
+    fed = torch.stack(fed, 1)
+    assert not torch.equal(fed, x64)  # some inputs really were replaced by samples
+    dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
+    (ref * dref).sum().backward()
+    sp = tr.SpellerTrain(st, hp, "speller", V, V)
+    logits = sp.forward(torch.from_numpy(enc).cuda(), torch.from_numpy(lens).cuda(), x64.float().cuda())
+    expect_x = fed if masks is None else fed * masks["x"]
+    np.testing.assert_allclose(to_np(sp.x_in), expect_x.numpy(), rtol=0, atol=1e-6)   # the same ids were drawn
+    assert scaled_err(logits, ref.detach()) < 1e-5
+    d_enc = torch.zeros((B, Tm, D), device="cuda")
+    sp.backward(dref.float().cuda(), d_enc)
+    grads = st.export_grads()
+    for k in params:
+        assert grad_err(grads[k], tp[k].grad) < GRAD_TOL, k
+
+
+@gpu
+def test_default_hparams_training_step_runs_with_dropout_and_sampling():
+    """The reference's default training flags (dropout 0.2, sampling_probability 0.1; utils/params_utils.py:36,59) on a plain
+    LAS: a few optimiser steps, eager and graph replay bit-identical, loss finite."""
+    import torch
+    from phones_las_b200 import train as tr
+    hp = create_hparams(target_vocab_size=20, encoder_layers=3, encoder_units=32, decoder_units=32, decoder_layers=2, num_channels=9,
+                        ctc_weight=0.3)
+    assert hp["dropout"] == 0.2 and hp["sampling_probability"] == 0.1
+    params = weights.init_params(hp, seed=1)
+    x, lens = synth.synth_features(10, 120, 9, seed=3, var_len=True)
+    tin, tout, tlen = synth.synth_labels(10, 9, 20, seed=4)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    st_e, st_g = tr.TrainState(params), tr.TrainState(params)
+    graphed = tr.GraphedTrainStep(feats, labels, st_g, hp)
+    for _ in range(3):
+        pe = tr.train_step(feats, labels, st_e, hp)
+        pg = graphed(feats, labels)
+    torch.cuda.synchronize()
+    assert np.isfinite(pe["loss"].item()) and pe["loss"].item() == pg["loss"].item()
+    assert torch.equal(st_e.params, st_g.params)
