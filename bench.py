@@ -603,6 +603,79 @@ def reference_arm_train(args):
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------
+# front-end sweep (c5 = BASELINE.json configs[4]): MFCC / MFE feature extraction alone, 16 kHz, window 25 ms / step 10 ms
+# ----------------------------------------------------------------------------------------------
+FE_METRIC = "audio-sec/sec (acoustic front-end alone: framing, FFT, mel, log, DCT, energy, deltas)"
+
+
+def ours_frontend(args):
+    import torch
+    import torch.distributed as dist
+    from phones_las_b200 import _lib
+    from phones_las_b200.frontend import FrontendPlan
+    from phones_las_b200.hparams import feature_args, num_feature_channels, SAMPLE_RATE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_cuda()
+    seconds, B = 3.0, args.batch or 16384
+    N = int(seconds * SAMPLE_RATE)
+    variants = {"mfcc39": feature_args(feature_type="mfcc", backend="librosa", n_mfcc=12, n_mels=40, energy=True, window=25, step=10, deltas=True),
+                "mfe80": feature_args(feature_type="mfe", backend="librosa", n_mels=80, window=25, step=10)}
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wave = (0.1 * torch.randn((B, N), generator=g, device=dev)).clamp_(-1, 1)  # B*N*4 bytes (3.1 GB at 16k utterances) >> L2
+    results = {}
+    for name, fa in variants.items():
+        plan = FrontendPlan(fa, device=dev)
+        C = num_feature_channels(fa)
+        out = torch.empty((B, plan.max_frames(N), C), dtype=torch.float32, device=dev)
+        for _ in range(args.warmup):
+            plan(wave, out=out)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            plan(wave, out=out)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        algo = B * (4 * N + 4 * out.shape[1] * C)  # 4N bytes in + 4TC bytes out per utterance
+        results[name] = {"ms_per_step": ms, "audio_s_per_s": world * B * seconds / (ms * 1e-3), "hbm_gbs": algo / (ms * 1e-3) / 1e9,
+                         "channels": C, "frames": int(out.shape[1])}
+        del out
+    if rank == 0:
+        peaks = load_peaks()
+        head = results["mfcc39"]
+        line = {"metric": FE_METRIC, "value": head["audio_s_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"c5: front-end alone, {B} utterances x {seconds:.0f} s per GPU, 16 kHz, window 25 ms / step 10 ms; "
+                                       "headline = librosa MFCC 12 + energy + deltas (39 channels)", "batch_per_gpu": B,
+                           "l2": f"one {B * N * 4 / 1e9:.1f} GB waveform batch per step (>> 126 MB L2)"},
+                "roofline": {"kernel": "fe_spectral_kernel (+ fe_librosa_post / fe_librosa_delta)", "bound": "hbm", "achieved": head["hbm_gbs"],
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["hbm_gbs"] / peaks["hbm_gbs"], "traffic": None,
+                             "peak_source": peaks["_source"],
+                             "note": "FP32-issue-bound mixed-radix FFT (DESIGN.md section 3, K1): the HBM fraction is reported as north_star asks"},
+                "variants": results, "gpu_launches": int(_lib.launch_count)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -616,7 +689,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "c3":
+    if args.workload == "c5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "c5 is a front-end-only sweep; the reference arm is defined for c1-c4"}), flush=True)
+        else:
+            ours_frontend(args)
+    elif args.workload == "c3":
         reference_arm_train(args) if args.impl == "reference" else ours_train(args)
     elif args.impl == "reference":
         reference_arm(args)

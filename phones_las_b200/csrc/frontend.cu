@@ -501,20 +501,37 @@ extern "C" int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave,
   const size_t smem = fe_spectral_smem(*d);
   PLAS_REQUIRE(smem <= 227 * 1024, "frontend: %zu bytes of shared memory needed", smem);
   PLAS_CUDA(cudaFuncSetAttribute(fe_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((T_max + FE_FRAMES - 1) / FE_FRAMES, B);
-  fe_spectral_kernel<<<grid, FE_THREADS, smem, stream>>>(a);
-  PLAS_CUDA(cudaGetLastError());
-  if (d->backend == 1) {
-    const size_t smem_b = (size_t)FE_WARPS * d->n_mels * 4;
-    fe_librosa_post_kernel<<<grid, FE_THREADS, smem_b, stream>>>(a);
+  // gridDim.y carries the utterance index (<= 65535): large batches (the 64 k-utterance sweep of BASELINE configs[4]) go in chunks
+  const int Dbase = nb + (d->energy ? 1 : 0);
+  constexpr int FE_MAX_B = 32768;
+  const FeArgs a0 = a;
+  for (int b0 = 0; b0 < B; b0 += FE_MAX_B) {
+    const int nb_here = B - b0 < FE_MAX_B ? B - b0 : FE_MAX_B;
+    a = a0;
+    a.B = nb_here;
+    a.wave = a0.wave + (size_t)b0 * wave_stride;
+    a.n_samples = a0.n_samples + b0;
+    a.feats = a0.feats + (size_t)b0 * T_max * C;
+    a.n_frames = a0.n_frames + b0;
+    if (d->backend == 1) {
+      a.umax = a0.umax + b0;
+      a.db = a0.db + (size_t)b0 * T_max * d->n_mels;
+      a.rms = a0.rms + (size_t)b0 * T_max;
+      if (a0.base) a.base = a0.base + (size_t)b0 * T_max * Dbase;
+    }
+    dim3 grid((T_max + FE_FRAMES - 1) / FE_FRAMES, nb_here);
+    fe_spectral_kernel<<<grid, FE_THREADS, smem, stream>>>(a);
     PLAS_CUDA(cudaGetLastError());
-    if (d->deltas) {
-      const int Dbase = nb + (d->energy ? 1 : 0);
-      const size_t total_el = (size_t)B * T_max * Dbase;
-      int blocks = (int)((total_el + 255) / 256);
-      if (blocks > 148 * 16) blocks = 148 * 16;
-      fe_librosa_delta_kernel<<<blocks, 256, 0, stream>>>(a);
+    if (d->backend == 1) {
+      const size_t smem_b = (size_t)FE_WARPS * d->n_mels * 4;
+      fe_librosa_post_kernel<<<grid, FE_THREADS, smem_b, stream>>>(a);
       PLAS_CUDA(cudaGetLastError());
+      if (d->deltas) {
+        const size_t total_el = (size_t)nb_here * T_max * Dbase;
+        int blocks = (int)((total_el + 255) / 256 < 148 * 16 ? (total_el + 255) / 256 : 148 * 16);
+        fe_librosa_delta_kernel<<<blocks, 256, 0, stream>>>(a);
+        PLAS_CUDA(cudaGetLastError());
+      }
     }
   }
   return PLAS_OK;

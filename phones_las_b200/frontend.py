@@ -194,7 +194,7 @@ class FrontendPlan:
             _lib.check(L.plas_frontend_fwd(C.byref(self.desc), _lib.ptr(wave), _lib.ptr(n_samples), B, wave.stride(0),
                                            _lib.ptr(feats), _lib.ptr(n_frames), T_max, self.C, _lib.ptr(self._ws),
                                            self._ws.numel(), _lib.stream_ptr()))
-        _lib.count_launches(self.launches())
+        _lib.count_launches(self.launches() * ((B + 32767) // 32768))  # the C side cuts batches above the grid limit into chunks
         return feats, n_frames
 
 

@@ -96,3 +96,26 @@ def test_frontend_full_size_property():
     assert float(spread.max()) <= 80.0 + 1e-3
     ref = ofe.calculate_acoustic_features(fa, wave[7])
     assert (np.abs(to_np(feats[7]) - ref) / np.maximum(1.0, np.abs(ref))).max() <= 1e-4
+
+
+@gpu
+@pytest.mark.parametrize("backend,deltas", [("librosa", True), ("speechpy", True)])
+def test_batches_beyond_the_grid_limit(backend, deltas):
+    """BASELINE configs[4] sweeps up to 64 k utterances: batches above gridDim.y's 65535 are cut into chunks inside the
+    C-ABI call; rows from every chunk must equal the same rows computed in a small batch."""
+    import torch
+    from phones_las_b200.frontend import FrontendPlan
+    from phones_las_b200.hparams import feature_args
+    fa = feature_args(feature_type="mfcc", backend=backend, n_mfcc=12, n_mels=40, energy=(backend == "librosa"), window=25, step=10,
+                      deltas=deltas)
+    B, N = 70001, 1200
+    g = torch.Generator(device="cuda").manual_seed(3)
+    wave = (0.2 * torch.randn((B, N), generator=g, device="cuda")).clamp_(-1, 1)
+    n = torch.randint(600, N + 1, (B,), generator=g, device="cuda", dtype=torch.int32)
+    plan = FrontendPlan(fa)
+    feats, nf = plan(wave, n)
+    rows = torch.tensor([0, 1, 32767, 32768, 40000, 65535, 65536, 70000], device="cuda")
+    ref, ref_nf = plan(wave[rows].contiguous(), n[rows].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(nf[rows], ref_nf)
+    assert torch.equal(feats[rows], ref)
