@@ -1,6 +1,7 @@
 """End-to-end host API: waveform -> features -> listener -> speller (model.LASModel) vs the oracle, and the
 streaming serving loop (H2D of batch i+1 overlapping batch i) vs the synchronous call."""
 import numpy as np
+import pytest
 
 from oracle import frontend as ofe, las as ol
 from phones_las_b200 import synth, weights
@@ -93,3 +94,27 @@ def test_true_las_configuration_end_to_end():
     if float((s[..., -1] - s[..., -2]).min()) > 1e-4:
         np.testing.assert_array_equal(pred["sample_ids"].cpu().numpy(), ref["sample_ids"])
         assert_parity(pred["logits"], ref["logits"], "fp32", "logits")
+
+
+@gpu
+@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("bf16", "bahdanau"), ("bf16", "luong_monotonic")])
+def test_empty_and_single_frame_utterances_do_not_disturb_the_batch(precision, att):
+    """Ragged edge cases: an empty waveform (librosa still emits its one reflect-padded frame) and a one-frame utterance in the
+    batch; the other utterances must decode exactly as they do without them."""
+    import torch
+    from phones_las_b200.model import LASModel
+    fa = feature_args(feature_type="mfe", backend="librosa", n_mels=40, window=25, step=10)
+    C = num_feature_channels(fa)
+    hp = create_hparams(target_vocab_size=32, encoder_layers=3, encoder_units=64, decoder_layers=2, decoder_units=64,
+                        attention_type=att, num_channels=C)
+    params = weights.init_params(hp, C, seed=7, projection_scale=8.0)
+    wave, lens = synth.synth_audio(5, 0.8, seed=3, var_len=True)
+    lens[2], lens[3] = 0, 450
+    model = LASModel(params, hp, fa, precision=precision)
+    full = model.transcribe(torch.from_numpy(wave).cuda(), torch.from_numpy(lens).cuda())
+    keep = [0, 1, 4]
+    sub = model.transcribe(torch.from_numpy(wave[keep]).cuda(), torch.from_numpy(lens[keep]).cuda())
+    assert full["source_length"].tolist()[2:4] == [1, 1]
+    n = min(full["sample_ids"].shape[1], sub["sample_ids"].shape[1])
+    assert torch.equal(full["sample_ids"][keep][:, :n], sub["sample_ids"][:, :n])
+    assert bool(torch.isfinite(full["logits"][keep]).all())
