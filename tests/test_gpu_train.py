@@ -530,3 +530,31 @@ def test_default_hparams_training_step_runs_with_dropout_and_sampling():
     torch.cuda.synchronize()
     assert np.isfinite(pe["loss"].item()) and pe["loss"].item() == pg["loss"].item()
     assert torch.equal(st_e.params, st_g.params)
+
+
+@gpu
+@pytest.mark.parametrize("B,T,S", [(1, 9, 2), (2, 5, 1), (3, 64, 3)])
+def test_tiny_batches_and_sequences_train(B, T, S):
+    """Degenerate sizes: one utterance, sequences that pyramid down to a single frame, a single target token."""
+    import torch
+    from phones_las_b200 import train as tr
+    C, V = 5, 9
+    hp = create_hparams(target_vocab_size=V, encoder_layers=3, encoder_units=16, decoder_units=16, decoder_layers=1, num_channels=C,
+                        dropout=0.0, sampling_probability=0.0, l2_reg_scale=1e-4)
+    params = weights.init_params(hp, seed=2, bias_scale=0.05)
+    x, lens = synth.synth_features(B, T, C, seed=1)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3) if S > 1 else (np.full((B, 1), 1, np.int32), np.full((B, 1), 2, np.int32), np.ones((B,), np.int32))
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, _ = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp)
+    ref_loss.backward()
+    st = tr.TrainState(params)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp)
+    assert abs(parts["ce"].item() + 0.0 - (ref_loss.item() - 0.5 * hp["l2_reg_scale"] * sum((v.detach() ** 2).sum().item() for v in tp.values()))) < 1e-4
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k
