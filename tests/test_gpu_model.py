@@ -118,3 +118,40 @@ def test_empty_and_single_frame_utterances_do_not_disturb_the_batch(precision, a
     n = min(full["sample_ids"].shape[1], sub["sample_ids"].shape[1])
     assert torch.equal(full["sample_ids"][keep][:, :n], sub["sample_ids"][:, :n])
     assert bool(torch.isfinite(full["logits"][keep]).all())
+
+
+@gpu
+def test_workflow_tfrecord_to_training_to_checkpoint_to_serving(tmp_path):
+    """The reference's workflow on its own file formats: TFRecords -> padded batches -> optimiser steps -> TF checkpoint +
+    hparams.json in a model_dir -> model restored from that directory for evaluation.  The loss must go down on the
+    training batch and the restored model must reproduce the trained parameters' predictions."""
+    import torch
+    from phones_las_b200 import tfrecord, tf_checkpoint, train as tr
+    from phones_las_b200.hparams import save_hparams
+    from phones_las_b200.model import DeviceWeights, las_eval, LASModel
+    vocab = ["<unk>", "<s>", "</s>"] + [f"p{i}" for i in range(9)]
+    C = 6
+    rng = np.random.default_rng(0)
+    examples = [(rng.normal(size=(int(rng.integers(20, 33)), C)).astype(np.float32),
+                 [vocab[i] for i in rng.integers(3, len(vocab), int(rng.integers(2, 6)))]) for _ in range(8)]
+    path = str(tmp_path / "train.tfr")
+    tfrecord.write_dataset(path, examples)
+    (f, l), = list(tfrecord.batches(tfrecord.read_dataset(path, C), vocab, batch_size=8))
+    hp = create_hparams(target_vocab_size=len(vocab), encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=16,
+                        attention_type="luong", num_channels=C, dropout=0.0, sampling_probability=0.0, learning_rate=5e-3)
+    params = weights.init_params(hp, C, seed=1)
+    st = tr.TrainState(params)
+    feats = {k: torch.from_numpy(v).cuda() for k, v in f.items()}
+    labels = {k: torch.from_numpy(v).cuda() for k, v in l.items()}
+    losses = [tr.train_step(feats, labels, st, hp)["loss"].item() for _ in range(12)]
+    assert losses[-1] < losses[0]
+    model_dir = str(tmp_path / "model_dir")
+    st.save_checkpoint(model_dir + "/model.ckpt-12")
+    save_hparams(hp, model_dir)
+    restored = tf_checkpoint.load_model_variables(model_dir)
+    trained = st.export_params()
+    assert set(restored) == set(trained) and all(np.array_equal(restored[k], trained[k]) for k in trained)
+    a = las_eval(feats, labels, hp, DeviceWeights(trained, hp, C, "fp32"))
+    fa = feature_args(feature_type="mfe", backend="speechpy", n_mels=C - 1, energy=True, window=25, step=10)
+    b = las_eval(feats, labels, hp, LASModel.from_model_dir(model_dir, fa, precision="fp32").weights)
+    assert a["loss"].item() == b["loss"].item() and np.array_equal(a["edit_distance"], b["edit_distance"])
