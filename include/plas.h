@@ -332,9 +332,11 @@ typedef struct plas_dec_infer_desc {
   int32_t bottom_only;      /* AttentionMultiCell wiring (las/model.py:20-69,185-193): attention wraps cell 0 only; cell l >= 1 reads
                                [output below (the NEW attention for l = 1); OLD attention; h_{t-1}], kernel [(D or Ud) + D + Ud][4Ud];
                                the projection reads the top cell's h ([Ud][V]) when n_layers > 1                  */
-  int32_t _pad;
+  int32_t att_layer;        /* attention_layer_size A (0 = none): attention = [cell output; context] W, W = w_att_layer [Ud + D][A]; the
+                               fed-back attention, cell 0's kernel ([V + A + Ud][4Ud]) and w_proj ([A][V]) then use A          */
   const float* c_init[4];   /* pass_hidden_state (las/model.py:259-267): initial cell / hidden state of layer l [B][Ud] or NULL */
   const float* h_init[4];
+  const float* w_att_layer; /* attention_wrapper/attention_layer/kernel or NULL                                 */
 } plas_dec_infer_desc;
 size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d);
 int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

@@ -253,6 +253,8 @@ class Speller:
             else:
                 name = f"{scope}/decoder/attention_wrapper/multi_rnn_cell/cell_{k}/lstm_cell"
             self.cells.append((self.q(params[name + "/kernel"]), params[name + "/bias"].astype(F32)))
+        al = f"{scope}/decoder/attention_wrapper/attention_layer/kernel"
+        self.wal = self.q(params[al]) if (hp.get("attention_layer_size") and not self.bottom_only) else None
         self.wp = self.q(params[f"{scope}/decoder/projection_layer/kernel"])
         self.bp = params[f"{scope}/decoder/projection_layer/bias"].astype(F32)
         self.enc_len = np.asarray(enc_len)
@@ -262,7 +264,7 @@ class Speller:
         if self.init_state is not None:
             for l, st in enumerate(self.init_state[:len(cs)]):
                 cs[l] = st
-        return dict(cells=cs, attention=np.zeros((self.B, self.D), F32),
+        return dict(cells=cs, attention=np.zeros((self.B, self.D if self.wal is None else self.wal.shape[1]), F32),
                     alignments=self.att.initial_alignments())
 
     def step(self, x, state):
@@ -280,6 +282,8 @@ class Speller:
             inp = h2
         align = self.att(inp, state["alignments"])
         context = np.einsum("bt,btd->bd", align, self.att.values, dtype=F32)
+        if self.wal is not None:  # attention_layer_size: attention = Dense([cell_output; context]), no bias
+            context = (np.concatenate([inp, context], axis=1) @ self.wal).astype(F32)
         attention = q(context)  # the recurrent feedback copy of the attention vector is rounded ...
         # ... while the projection consumes the f32 context (fp32 mode: q is the identity, so this is
         # exactly DenseBinfDecoder(attention); bf16 mode: one rounding point fewer)

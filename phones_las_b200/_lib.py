@@ -86,7 +86,8 @@ class DecInferDesc(C.Structure):
                 ("w_proj", C.c_void_p), ("b_proj", C.c_void_p), ("keys", C.c_void_p), ("values", C.c_void_p),
                 ("mem_len", C.c_void_p), ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
                 ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p),
-                ("bottom_only", C.c_int32), ("_pad", C.c_int32), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4)]
+                ("bottom_only", C.c_int32), ("att_layer", C.c_int32), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4),
+                ("w_att_layer", C.c_void_p)]
 
 
 EXPORTS = {

@@ -813,7 +813,7 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
 
 // ---- fp32 inference loop ----------------------------------------------------------------------------------------------
 struct DecInferWs {
-  size_t z[4], c[4], h[4], att, pq, align, ints, total;
+  size_t z[4], c[4], h[4], att, ctx, pq, align, ints, total;
 };
 
 static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
@@ -832,7 +832,9 @@ static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
     w.c[l] = take(B * 2 * Ud * 4);
     w.h[l] = take(B * 2 * Ud * 4);
   }
-  w.att = take(B * 2 * D * 4);
+  const size_t A = d.att_layer > 0 ? (size_t)d.att_layer : D;  // width of the attention vector fed back / projected
+  w.att = take(B * 2 * A * 4);
+  w.ctx = take(B * D * 4);
   w.pq = take(B * Ud * 4);
   w.align = take(B * Tm * 4);
   w.ints = take((2 * B + 8) * 4);
@@ -869,7 +871,10 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     PLAS_REQUIRE(d->kernel[l] && d->bias[l], "dec_infer: null weights (layer %d)", l);
     PLAS_CUDA(cudaMemsetAsync(F(w.h[l]), 0, (size_t)B * 2 * Ud * 4, st));
   }
-  PLAS_CUDA(cudaMemsetAsync(F(w.att), 0, (size_t)B * 2 * D * 4, st));
+  const int A = d->att_layer > 0 ? d->att_layer : D;
+  if (d->att_layer > 0)
+    PLAS_REQUIRE(d->w_att_layer && !d->bottom_only && A % 4 == 0, "dec_infer: attention_layer_size needs its kernel, the default wiring and A % 4 == 0");
+  PLAS_CUDA(cudaMemsetAsync(F(w.att), 0, (size_t)B * 2 * A * 4, st));
   dec_infer_init_kernel<<<1, 128, 0, st>>>(is, d->mem_len, B, S, d->teacher_forced, d->decoding_length_factor, d->sos_id, d->seq_len, d->n_steps);
   PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   PLAS_CUDA(cudaFuncSetAttribute(dec_att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -878,12 +883,12 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
   const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
   const int att_staged = (Ud % 4 == 0 && (D / dsplit) % 4 == 0 && att_smem + att_stage <= 220 * 1024) ? 1 : 0;
   if (att_staged) att_smem += att_stage;
-  const size_t smp_smem = (size_t)((D > Ud ? D : Ud) + 4 * V) * 4;  // D >= Ud is not assumed: sized below for the larger of the two
+  const size_t smp_smem = (size_t)((D > Ud ? (D > A ? D : A) : (Ud > A ? Ud : A)) + 4 * V) * 4;  // D >= Ud is not assumed: sized below for the larger of the two
   int rc = PLAS_OK;
   PLAS_REQUIRE(smp_smem <= 200 * 1024, "dec_infer: D/V too large");
   if (smp_smem > 48 * 1024) PLAS_CUDA(cudaFuncSetAttribute(dec_infer_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp_smem));
   const bool bottom = d->bottom_only != 0;
-  const int Dout = (bottom && L > 1) ? Ud : D;  // what the projection reads: the top cell's h (AttentionMultiCell) or the attention
+  const int Dout = (bottom && L > 1) ? Ud : A;  // what the projection reads: the top cell's h (AttentionMultiCell) or the attention
   auto launch_cell = [&](int t, int l) -> int {
     const int slot = t & 1, prev = slot ^ 1;
     CellFwdArgs a;
@@ -891,11 +896,11 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     // h_{t-1} / c_{t-1} of this layer: the state ring, or the caller's initial state at t = 0 (pass_hidden_state)
     const float* hprev = (t == 0 && d->h_init[l]) ? d->h_init[l] : F(w.h[l]) + (size_t)prev * Ud;
     const long long s_hprev = (t == 0 && d->h_init[l]) ? Ud : 2LL * Ud;
-    const float* att_old = F(w.att) + (size_t)prev * D;
+    const float* att_old = F(w.att) + (size_t)prev * A;
     a.in3 = nullptr; a.s3 = 0; a.K3 = 0;
     if (l == 0) {  // [x_t; attention_{t-1}; h_{t-1}]: the x rows are the gathered `pre`
       a.pre = F(w.z[0]) + (size_t)slot * 4 * Ud; a.s_pre = 2LL * 4 * Ud; a.bias = nullptr;
-      a.in1 = att_old; a.s1 = 2LL * D; a.K1 = D;
+      a.in1 = att_old; a.s1 = 2LL * A; a.K1 = A;
       a.in2 = hprev; a.s2 = s_hprev; a.K2 = Ud;
       a.w = d->kernel[0] + (size_t)V * 4 * Ud;
     } else if (!bottom) {  // MultiRNNCell inside the AttentionWrapper: [h of the layer below; h_{t-1}]
@@ -945,7 +950,8 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     q.pq = F(w.pq); q.s_pq = Ud;
     if (d->alignment) { q.align = d->alignment + (size_t)t * Tm; q.s_al = (long long)S * Tm; }
     else { q.align = F(w.align); q.s_al = Tm; }
-    q.att = F(w.att) + (size_t)slot * D; q.s_att = 2LL * D;
+    if (d->att_layer > 0) { q.att = F(w.ctx); q.s_att = D; }        // the context goes through the attention layer below
+    else { q.att = F(w.att) + (size_t)slot * D; q.s_att = 2LL * D; }
     q.att_next = nullptr; q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
     dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
   };
@@ -962,9 +968,14 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
       for (int l = 0; l < L; ++l)
         if ((rc = launch_cell(t, l))) return rc;
       launch_attention(t, L - 1);
+      if (d->att_layer > 0) {  // attention = Dense([cell output; context]), no bias (AttentionWrapper attention_layer_size)
+        float* att_t = F(w.att) + (size_t)slot * A;
+        if ((rc = gemm(st, B, A, Ud, F(w.h[L - 1]) + (size_t)slot * Ud, 2LL * Ud, 1, d->w_att_layer, A, 1, att_t, 2LL * A))) return rc;
+        if ((rc = gemm(st, B, A, D, F(w.ctx), D, 1, d->w_att_layer + (size_t)Ud * A, A, 1, att_t, 2LL * A, nullptr, 1.f))) return rc;
+      }
     }
-    const float* out = (bottom && L > 1) ? F(w.h[L - 1]) + (size_t)slot * Ud : F(w.att) + (size_t)slot * D;
-    dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, out, (bottom && L > 1) ? 2LL * Ud : 2LL * D, Dout, V, d->w_proj, d->b_proj,
+    const float* out = (bottom && L > 1) ? F(w.h[L - 1]) + (size_t)slot * Ud : F(w.att) + (size_t)slot * A;
+    dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, out, (bottom && L > 1) ? 2LL * Ud : 2LL * A, Dout, V, d->w_proj, d->b_proj,
                                                       d->logits + (size_t)t * V, (long long)S * V, d->sample_ids + t, S);
     dec_infer_finish_kernel<<<1, 32, 0, st>>>(is, B, t, d->eos_id, d->teacher_forced, d->seq_len, d->n_steps);
   }

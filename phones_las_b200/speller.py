@@ -37,8 +37,11 @@ class SpellerWeights:
         if self.bottom_only:
             self._init_bottom_only(params, hp, enc_depth, precision, device, scope)
             return
-        if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
-            raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
+        if hp.get("embedding_size") or hp.get("beam_width"):
+            raise NotImplementedError("embedding_size / beam_width != 0 are not built yet")
+        if hp.get("attention_layer_size"):
+            self._init_attention_layer(params, hp, enc_depth, precision, device, scope)
+            return
         self.precision = precision
         self.att = hp["attention_type"]
         if self.att not in _lib.ATT_CODES:
@@ -129,7 +132,39 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     self.tc = False
 
 
+def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope):
+    """attention_layer_size = A (las/model.py:180-200): AttentionWrapper's Dense over [cell output; context]; the attention fed
+    back to cell 0 and read by the projection is A wide.  fp32 step-kernel decoder only."""
+    if precision != "fp32" or hp["attention_type"] not in ("luong", "bahdanau"):
+        raise NotImplementedError("attention_layer_size is built for the fp32 step-kernel decoder with luong / bahdanau attention")
+    self.precision, self.att = precision, hp["attention_type"]
+    self.bottom_only = self.pass_hidden_state = False
+    self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
+    D, Ud, V, A = self.D, self.Ud, self.V, int(hp["attention_layer_size"])
+    if Ud % 16 or D % 4 or A % 4:
+        raise NotImplementedError("attention_layer_size needs decoder_units % 16 == 0, encoder depth % 4 == 0 and A % 4 == 0")
+    self.A = A
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device).contiguous()
+    self.w_mem_t = up(np.asarray(params[f"{scope}/memory_layer/kernel"], np.float32).T)
+    pre = f"{scope}/decoder/attention_wrapper"
+    names = [f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(self.L)]
+    kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
+    assert kernels[0].shape == (V + A + Ud, 4 * Ud), kernels[0].shape
+    self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names],
+                   w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]),
+                   w_att_layer=up(params[f"{pre}/attention_layer/kernel"]))
+    assert self.tf["w_att_layer"].shape == (Ud + D, A) and self.tf["w_proj"].shape == (A, V)
+    self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"])
+    self.w_query = self.v_att = None
+    self.score_bias = 0.0
+    if self.att == "bahdanau":
+        self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
+        self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"])
+    self.tc = False
+
+
 SpellerWeights._init_bottom_only = _init_bottom_only
+SpellerWeights._init_attention_layer = _init_attention_layer
 
 
 def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=False):
@@ -256,6 +291,8 @@ def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, f
     d.alignment = align.data_ptr() if align is not None else None
     d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
     d.bottom_only = 1 if getattr(w, "bottom_only", False) else 0
+    if "w_att_layer" in w.tf:
+        d.att_layer, d.w_att_layer = w.A, w.tf["w_att_layer"].data_ptr()
     keep_alive = []
     if initial_state is not None:  # pass_hidden_state: cell l starts from (c, h) number l of the listener's final state
         for l, (c0, h0) in enumerate(initial_state[:w.L]):

@@ -42,7 +42,7 @@ def variable_shapes(hp, num_channels=None):
                 shapes[f"listener/{d}/multi_rnn_cell/cell_{l}/lstm_cell/bias"] = (4 * U,)
                 din = U
     D = encoder_output_depth(hp)
-    A = D  # attention_layer_size=None -> attention = context (depth D)
+    A = hp.get("attention_layer_size") or D  # attention_layer_size=None -> attention = context (depth D)
     shapes["speller/memory_layer/kernel"] = (D, Ud)
     bottom = bool(hp.get("bottom_only"))
     pre = "speller/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper" if bottom else "speller/decoder/attention_wrapper"
@@ -61,6 +61,8 @@ def variable_shapes(hp, num_channels=None):
         shapes[f"{pre}/bahdanau_attention/attention_v"] = (Ud,)
     elif at == "luong_monotonic":
         shapes[f"{pre}/luong_monotonic_attention/attention_score_bias"] = ()
+    if hp.get("attention_layer_size"):  # AttentionWrapper's Dense over [cell output; context], no bias (las/model.py:180-200)
+        shapes[f"{pre}/attention_layer/kernel"] = (Ud + D, A)
     if bottom and Ld > 1:
         A = Ud  # the projection reads the top cell's output
     shapes["speller/decoder/projection_layer/kernel"] = (A, V)

@@ -206,3 +206,38 @@ def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm,
     out, _, _ = speller(enc_t, state_t, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(),
                         "train", hp, w)
     assert_parity(out.rnn_output, ref_tf, "fp32", "teacher-forced logits")
+
+
+@gpu
+@pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,A", [("luong", 4, 11, 16, 32, 1, 12, 24), ("bahdanau", 6, 17, 16, 48, 2, 20, 40),
+                                                   ("luong", 34, 9, 16, 16, 2, 14, 8)])
+def test_attention_layer_size_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, A):
+    """attention_layer_size = A (las/model.py:180-200): attention = Dense([cell output; context]); fed back and projected A wide."""
+    import torch
+    from phones_las_b200.speller import speller
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=4, attention_type=att, attention_layer_size=A)
+    params = weights.init_params(hp, seed=Ud + A, projection_scale=8.0, bias_scale=0.1)
+    D = weights.encoder_output_depth(hp)
+    assert params["speller/decoder/attention_wrapper/attention_layer/kernel"].shape == (Ud + D, A)
+    assert params["speller/decoder/projection_layer/kernel"].shape == (A, V)
+    rng = np.random.default_rng(B)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    lens[0] = Tm
+    enc *= (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    w = _device_speller(hp, params, D, "fp32")
+    enc_t = torch.from_numpy(enc).cuda()
+    ref_logits, ref_ids, ref_align, ref_len, _ = ol.Speller(enc, lens, params, hp, "fp32").greedy()
+    out, st, seq_len = speller(enc_t, None, None, torch.from_numpy(lens).cuda(), None, "infer", hp, w)
+    logits, ids = to_np(out.rnn_output), out.sample_id.cpu().numpy()
+    assert_parity(logits[:, :1], ref_logits[:, :1], "fp32", "logits step 0")
+    if top2_margin(ref_logits) > 1e-4:
+        np.testing.assert_array_equal(ids, ref_ids)
+        assert_parity(logits, ref_logits, "fp32", "logits")
+        assert_parity(to_np(st.alignment_history), ref_align, "fp32", "alignment")
+    tin, tout, tlen = synth.synth_labels(B, 5, V, seed=4)
+    hp["sampling_probability"] = 0.0
+    ref_tf, _ = ol.Speller(enc, lens, params, hp, "fp32").teacher_forced(tin, tlen)
+    out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(), "train", hp, w)
+    assert_parity(out.rnn_output, ref_tf, "fp32", "teacher-forced logits")
