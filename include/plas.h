@@ -300,6 +300,12 @@ typedef struct plas_dec_train_desc {
   uint32_t xdrop_seed;      /* dropout seed of x_in (a sampled input is dropped out like the one it replaces)    */
   uint32_t _pad2;
   float* x_in_rw;
+  /* attention_layer_size = att_layer (0 = none; default wiring, no dropout): attention = [h_top; context] W, W = w_att_layer
+   * [Ud + D][A]; cell 0's kernel is then [E + A + Ud][4Ud] and w_proj [A][n_out] */
+  const float* w_att_layer;
+  float* dw_att_layer;
+  int32_t att_layer;
+  int32_t _pad3;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

@@ -146,7 +146,8 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
     if bottom and hp.get("pass_hidden_state") and encoder_state is not None:  # las/model.py:259-267
         for l, st in enumerate(encoder_state[:len(state)]):
             state[l] = st
-    attention = enc_out.new_zeros((B, D))
+    w_al = params[f"{pre}/attention_layer/kernel"] if (hp.get("attention_layer_size") and not bottom) else None
+    attention = enc_out.new_zeros((B, D if w_al is None else w_al.shape[1]))
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
     # scheduled sampling (ScheduledEmbeddingTrainingHelper, las/model.py:279-288): ``sampling`` = (selected [B,S] bool, gumbel
@@ -213,6 +214,8 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
         score = torch.where(mask, score, neg_inf)
         align = torch.softmax(score, dim=1)
         attention = torch.einsum("bt,btd->bd", align, values)
+        if w_al is not None:  # attention_layer_size: attention = Dense([cell output; context]), no bias
+            attention = torch.cat([inp, attention], 1) @ w_al
         logits.append(attention @ wp + bp)
         maybe_sample(t, logits[-1])
     return torch.stack(logits, 1)

@@ -75,7 +75,8 @@ class DecTrainDesc(C.Structure):
                 ("drop_step", C.c_void_p), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4),
                 ("dc_init", C.c_void_p * 4), ("dh_init", C.c_void_p * 4),
                 ("sample_prob", C.c_float), ("sample_seed", C.c_uint32), ("xdrop_seed", C.c_uint32), ("_pad2", C.c_uint32),
-                ("x_in_rw", C.c_void_p)]
+                ("x_in_rw", C.c_void_p), ("w_att_layer", C.c_void_p), ("dw_att_layer", C.c_void_p), ("att_layer", C.c_int32),
+                ("_pad3", C.c_int32)]
 
 
 class DecInferDesc(C.Structure):

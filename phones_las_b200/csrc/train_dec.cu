@@ -492,6 +492,15 @@ __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
   p.dc_carry[(size_t)b * Ud + u] = dc * gf;
 }
 
+// dst[b][i] = a[b][i] + (c ? c[b][i] : 0) on strided rows (assembles the gradient wrt the attention vector)
+__global__ void dec_add_rows_kernel(float* __restrict__ dst, long long s_dst, const float* __restrict__ a, long long s_a,
+                                    const float* __restrict__ c, long long s_c, int B, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const int b = i / n, k = i - b * n;
+  dst[(long long)b * s_dst + k] = a[(long long)b * s_a + k] + (c ? c[(long long)b * s_c + k] : 0.f);
+}
+
 // dinp[b][k] = sum_n dz[b][n] W[k][n], k in [0, K): lane = batch row, CTA = 8 consecutive k, warps split n
 struct GemvTArgs {
   int B, N, K;                           // N = 4Ud
@@ -736,7 +745,7 @@ __global__ void dec_infer_finish_kernel(InferState st, int B, int t, int eos_id,
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
-  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh;
+  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh, ctx, datt, dqx;
   size_t z[4], c[4], h[4], hprev[4], hdrop[4];
   size_t splitk, splitk_bytes;
   size_t total;
@@ -752,8 +761,9 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
   };
   const size_t B = d.B, S = d.S, Tm = d.Tm, D = d.D, Ud = d.Ud;
   w.keys = take(B * Tm * Ud);
-  w.att = take(B * S * D);
-  w.att_prev = take(B * S * D);
+  const size_t Aw = d.att_layer > 0 ? (size_t)d.att_layer : D;  // width of the attention vector that is fed back and projected
+  w.att = take(B * S * Aw);
+  w.att_prev = take(B * S * Aw);
   w.align = take(B * S * Tm);
   w.pq = take(B * S * Ud);
   w.dscore = take(B * S * Tm);
@@ -763,6 +773,12 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
   w.dv_acc = take(B * Ud);
   w.dctx = take(B * S * D);
   w.gh = take(B * S * Ud);  // bottom_only: dlogits W_proj^T when the projection reads the top cell
+  w.ctx = w.datt = w.dqx = 0;
+  if (d.att_layer > 0) {    // attention_layer_size: the context and the gradient wrt the (A-wide) attention are kept separately
+    w.ctx = take(B * S * D);
+    w.datt = take(B * S * (size_t)d.att_layer);
+    w.dqx = take(B * Ud);
+  }
   for (int l = 0; l < 4; ++l) {
     w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = w.hdrop[l] = 0;
     if (l >= d.n_layers) continue;
@@ -771,10 +787,10 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
     w.h[l] = take(B * S * Ud);
     w.hprev[l] = take(B * S * Ud);
     if (l + 1 < d.n_layers) w.hdrop[l] = take(B * S * Ud);
-    w.dinp[l] = take(2 * B * (2 * D + Ud));  // 2 slots (bottom_only keeps step t+1's while step t's is written), widest layout
+    w.dinp[l] = take(2 * B * (2 * (D > Aw ? D : Aw) + Ud));  // 2 slots (bottom_only keeps step t+1's while step t's is written), widest layout
     w.dc[l] = take(B * Ud);
   }
-  w.splitk_bytes = (size_t)4 * (d.E + D + Ud) * 4 * Ud * 4;  // up to 4 K-slices of the largest weight gradient
+  w.splitk_bytes = (size_t)4 * (d.E + (D > Aw ? D : Aw) + Ud) * 4 * Ud * 4;  // up to 4 K-slices of the largest weight gradient
   w.splitk = take(w.splitk_bytes / 4);
   w.total = off;
   return w;
@@ -1057,6 +1073,7 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
   PLAS_REQUIRE(d->keep_prob == 1.f, "dec_train: dropout with bottom_only is not built");
+  PLAS_REQUIRE(d->att_layer == 0, "dec_train: attention_layer_size with bottom_only is not built");
   if (d->attention_type == PLAS_ATT_BAHDANAU) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
   int rc;
   if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud))) return rc;
@@ -1285,6 +1302,9 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
+  const int A = d->att_layer > 0 ? d->att_layer : D;  // width of the attention vector (attention_layer_size or the context depth)
+  if (d->att_layer > 0)
+    PLAS_REQUIRE(d->w_att_layer && A % 4 == 0 && d->keep_prob == 1.f, "dec_train: attention_layer_size needs its kernel, A %% 4 == 0 and no dropout");
   const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
   if (bah) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
   // keys = memory_layer(values); the memory is already zero past each length (the listener guarantees it)
@@ -1293,7 +1313,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   // Z_0 = x_in W_0[0:E] + b_0 for every step at once
   rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]);
   if (rc) return rc;
-  PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
+  PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * A * 4, 0, (size_t)A * 4, B, st));
   for (int l = 0; l < L; ++l) PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
   const bool drop = d->keep_prob < 1.f;
   const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
@@ -1312,8 +1332,8 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud;
       if (l == 0) {
         a.pre = F(w.z[0]) + (size_t)t * 4 * Ud; a.s_pre = sz; a.bias = nullptr;
-        a.in1 = F(w.att_prev) + (size_t)t * D; a.s1 = (long long)S * D; a.K1 = D;
-        a.w = d->kernel[0] + (size_t)E * 4 * Ud;
+        a.in1 = F(w.att_prev) + (size_t)t * A; a.s1 = (long long)S * A; a.K1 = A;
+        a.w = d->kernel[0] + (size_t)E * 4 * Ud;  // rows: [x (E, hoisted); attention (A); h (Ud)]
       } else {
         a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
         a.in1 = F(drop ? w.hdrop[l - 1] : w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud;
@@ -1354,17 +1374,28 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
     q.w_query = d->w_query; q.v_att = d->v_att;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = (long long)S * Ud;
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
-    q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D;
+    if (d->att_layer > 0) { q.att = F(w.ctx) + (size_t)t * D; q.s_att = (long long)S * D; }
+    else { q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D; }
     q.skip = nullptr;
-    q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
+    q.att_next = (t + 1 < S && d->att_layer == 0) ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
     q.next_base = (long long)(t + 1) * D; q.seed = d->drop_seed; q.thresh = thresh; q.inv_keep = inv_keep; q.step_ptr = d->drop_step;
     dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
+    if (d->att_layer > 0) {  // attention_t = [h_top_t; context_t] W_att (no bias), then the copy that step t+1 reads
+      float* att_t = F(w.att) + (size_t)t * A;
+      if ((rc = gemm(st, B, A, Ud, F(w.h[L - 1]) + (size_t)t * Ud, (long long)S * Ud, 1, d->w_att_layer, A, 1, att_t, (long long)S * A))) return rc;
+      if ((rc = gemm(st, B, A, D, F(w.ctx) + (size_t)t * D, (long long)S * D, 1, d->w_att_layer + (size_t)Ud * A, A, 1, att_t, (long long)S * A,
+                     nullptr, 1.f)))
+        return rc;
+      if (t + 1 < S)
+        PLAS_CUDA(cudaMemcpy2DAsync(F(w.att_prev) + (size_t)(t + 1) * A, (size_t)S * A * 4, att_t, (size_t)S * A * 4, (size_t)A * 4, B,
+                                    cudaMemcpyDeviceToDevice, st));
+    }
     if (d->sample_prob > 0.f && t + 1 < S)
-      if ((rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * D, (long long)S * D, D))) return rc;
+      if ((rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * A, (long long)S * A, A))) return rc;
   }
   PLAS_CUDA(cudaGetLastError());
   // logits = DenseBinfDecoder(attention)
-  return gemm(st, (long long)B * S, d->n_out, D, F(w.att), D, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+  return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
 }
 
 extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes,
@@ -1381,9 +1412,13 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
   const long long BS = (long long)B * S;
   float* dctx = F(w.dctx);  // [B][S][D]
+  const int AL = d->att_layer;                 // attention_layer_size (0 = none)
+  const int A = AL > 0 ? AL : D;               // width of the attention vector
+  float* datt = AL > 0 ? F(w.datt) : dctx;     // gradient wrt the attention vector ([B][S][A]); without the layer it IS dctx
+  if (AL > 0) PLAS_REQUIRE(d->w_att_layer && d->dw_att_layer, "dec_train_bwd: attention_layer_size needs w_att_layer / dw_att_layer");
   // projection layer: dAtt = dlogits W_proj^T, dW_proj = Att^T dlogits, db_proj = colsum(dlogits)
-  if ((rc = gemm(st, BS, D, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, dctx, D))) return rc;
-  if ((rc = gemm(st, D, NO, (int)BS, F(w.att), 1, D, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+  if ((rc = gemm(st, BS, A, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, datt, A))) return rc;
+  if ((rc = gemm(st, A, NO, (int)BS, F(w.att), 1, A, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
   if ((rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
   if (bah) {
     PLAS_REQUIRE(d->dw_query && d->dv_att, "dec_train_bwd: bahdanau needs dw_query / dv_att");
@@ -1406,12 +1441,18 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   const float inv_keep = 1.0f / d->keep_prob;
   for (int t = S - 1; t >= 0; --t) {
     const bool last = t == S - 1;
+    if (AL > 0) {  // datt_t = dlogits_t W_proj^T + (step t+1's cell-0 input gradient); back through attention = [h_top; ctx] W_att
+      float* da = datt + (size_t)t * A;
+      if (!last) dec_add_rows_kernel<<<(B * A + 255) / 256, 256, 0, st>>>(da, (long long)S * A, da, (long long)S * A, F(w.dinp[0]), A + Ud, B, A);
+      if ((rc = gemm(st, B, Ud, A, da, (long long)S * A, 1, d->w_att_layer, 1, A, F(w.dqx), Ud))) return rc;
+      if ((rc = gemm(st, B, D, A, da, (long long)S * A, 1, d->w_att_layer + (size_t)Ud * A, 1, A, dctx + (size_t)t * D, (long long)S * D))) return rc;
+    }
     AttBwdArgs q;
     q.B = B; q.Tm = Tm; q.D = D; q.Ud = Ud; q.type = d->attention_type; q.nsplit = ns; q.staged = attb_staged;
     q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
     q.dctx = dctx + (size_t)t * D; q.s_dc = (long long)S * D;
-    q.datt_next = last ? nullptr : F(w.dinp[0]); q.s_dn = D + Ud;
+    q.datt_next = (last || AL > 0) ? nullptr : F(w.dinp[0]); q.s_dn = D + Ud;  // with the attention layer it is added to datt below
     q.dscore = F(w.dscore) + (size_t)t * Tm; q.s_ds = (long long)S * Tm;
     q.dq = F(w.dq); q.s_dq = Ud;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
@@ -1434,7 +1475,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       PLAS_CUDA(cudaLaunchKernelEx(&cfg, dec_att_bwd_kernel, q));
     }
     for (int l = L - 1; l >= 0; --l) {
-      const int Kin = (l == 0 ? D : Ud);
+      const int Kin = (l == 0 ? A : Ud);
       CellBwdArgs c;
       c.B = B; c.Ud = Ud;
       c.z = F(w.z[l]) + (size_t)t * 4 * Ud; c.s_z = sz;
@@ -1442,7 +1483,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       c.dc_carry = F(w.dc[l]); c.first = last ? 1 : 0;
       c.dq = (l == L - 1) ? F(w.dq) : nullptr; c.s_dq = Ud;
       c.dh_next = last ? nullptr : F(w.dinp[l]) + Kin; c.s_dn = Kin + Ud;
-      c.dh_above = (l < L - 1) ? F(w.dinp[l + 1]) : nullptr; c.s_da = 2 * Ud;
+      c.dh_above = (l < L - 1) ? F(w.dinp[l + 1]) : (AL > 0 ? F(w.dqx) : nullptr);  // top layer: the attention layer's h part
+      c.s_da = (l < L - 1) ? 2 * Ud : Ud;
       c.idx_base = (long long)t * Ud; c.seed = d->drop_seed + 1 + l; c.thresh = thresh; c.inv_keep = inv_keep; c.step_ptr = d->drop_step;
       dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
       GemvTArgs g;
@@ -1478,8 +1520,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     float* dk = d->dkernel[l];
     if (l == 0) {
       if ((rc = gemm(st, E, 4 * Ud, (int)BS, d->x_in, 1, E, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
-      if ((rc = gemm(st, D, 4 * Ud, (int)BS, F(w.att_prev), 1, D, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
-      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + D) * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      if ((rc = gemm(st, A, 4 * Ud, (int)BS, F(w.att_prev), 1, A, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + A) * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
     } else {
       if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(drop ? w.hdrop[l - 1] : w.h[l - 1]), 1, Ud, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
       if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[l]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)Ud * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
@@ -1487,6 +1529,10 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;
   }
   const float* htop = F(w.h[L - 1]);
+  if (AL > 0) {  // dW_att = [H_top; Ctx]^T dAtt
+    if ((rc = gemm(st, Ud, A, (int)BS, htop, 1, Ud, datt, A, 1, d->dw_att_layer, A, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+    if ((rc = gemm(st, D, A, (int)BS, F(w.ctx), 1, D, datt, A, 1, d->dw_att_layer + (size_t)Ud * A, A, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+  }
   if (bah) {
     if ((rc = gemm(st, Ud, Ud, (int)BS, htop, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
     if ((rc = plas_colsum_f32(F(w.dv_acc), B, Ud, Ud, d->dv_att, 0, st))) return rc;

@@ -383,9 +383,12 @@ class SpellerTrain:
             raise NotImplementedError("training path: scheduled sampling is built for the phone speller only; set sampling_probability=0")
         if hp["attention_type"] not in ("luong", "bahdanau"):
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
-        for flag in ("binf_projection", "attention_layer_size", "embedding_size"):
+        for flag in ("binf_projection", "embedding_size"):
             if hp.get(flag):
                 raise NotImplementedError(f"training path: --{flag} is not built")
+        self.att_layer = int(hp.get("attention_layer_size") or 0)
+        if self.att_layer and (hp.get("bottom_only") or float(hp.get("dropout", 0.0)) > 0.0):
+            raise NotImplementedError("training path: attention_layer_size with --bottom_only or dropout is not built")
         self.bottom = bool(hp.get("bottom_only"))
         self.pass_state = self.bottom and bool(hp.get("pass_hidden_state"))  # las/model.py:260 needs both flags
         if self.bottom and float(hp.get("dropout", 0.0)) > 0.0:
@@ -416,6 +419,9 @@ class SpellerTrain:
             d.kernel[k], d.bias[k] = st.w(nm + "/kernel"), st.w(nm + "/bias")
             d.dkernel[k], d.dbias[k] = st.g(nm + "/kernel"), st.g(nm + "/bias")
         d.w_mem, d.dw_mem = st.w(f"{sc}/memory_layer/kernel"), st.g(f"{sc}/memory_layer/kernel")
+        if self.att_layer:  # AttentionWrapper's attention_layer (las/model.py:180-200)
+            al = f"{pre}/attention_layer/kernel"
+            d.att_layer, d.w_att_layer, d.dw_att_layer = self.att_layer, st.w(al), st.g(al)
         if hp["attention_type"] == "bahdanau":
             q, v = f"{pre}/bahdanau_attention/query_layer/kernel", f"{pre}/bahdanau_attention/attention_v"
             d.w_query, d.v_att, d.dw_query, d.dv_att = st.w(q), st.w(v), st.g(q), st.g(v)

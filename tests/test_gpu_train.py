@@ -558,3 +558,37 @@ def test_tiny_batches_and_sequences_train(B, T, S):
     for k in params:
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+
+
+@gpu
+@pytest.mark.parametrize("att,Ld,A,sampling", [("luong", 1, 24, 0.0), ("bahdanau", 2, 40, 0.0), ("luong", 2, 16, 0.4)])
+def test_train_step_attention_layer_size(att, Ld, A, sampling):
+    """attention_layer_size = A in training: attention = Dense([h_top; context]) fed back A wide; forward, gradients (including
+    the attention layer's kernel), optionally with scheduled sampling on top."""
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, U, Ud, V, S = 6, 40, 6, 16, 32, 13, 6
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
+                        attention_type=att, dropout=0.0, sampling_probability=sampling, attention_layer_size=A, l2_reg_scale=1e-4,
+                        ctc_weight=0.3)
+    params = weights.init_params(hp, seed=A, bias_scale=0.05, projection_scale=4.0)
+    assert "speller/decoder/attention_wrapper/attention_layer/kernel" in params
+    x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    st = tr.TrainState(params)
+    st.step = 2
+    sampling_rng = tr.reference_sampling(hp, 2, B, S, V) if sampling > 0 else None
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp,
+                                        sampling=sampling_rng)
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp)
+    assert scaled_err(parts["logits"], ref_parts["logits"].detach()) < 1e-5
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k
