@@ -306,6 +306,9 @@ typedef struct plas_dec_train_desc {
   float* dw_att_layer;
   int32_t att_layer;
   int32_t _pad3;
+  /* luong_monotonic (tf.contrib.seq2seq.LuongMonotonicAttention, las/model.py:157-158): attention_score_bias [1] and its gradient */
+  const float* score_bias;
+  float* dscore_bias;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
@@ -343,6 +346,7 @@ typedef struct plas_dec_infer_desc {
   const float* c_init[4];   /* pass_hidden_state (las/model.py:259-267): initial cell / hidden state of layer l [B][Ud] or NULL */
   const float* h_init[4];
   const float* w_att_layer; /* attention_wrapper/attention_layer/kernel or NULL                                 */
+  const float* score_bias;  /* luong_monotonic attention_score_bias [1] (device) or NULL                       */
 } plas_dec_infer_desc;
 size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d);
 int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

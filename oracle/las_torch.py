@@ -119,6 +119,16 @@ def listener(x, lengths, params, hp, masks=None, return_state=False):
     return outputs, lengths
 
 
+def monotonic_attention(p_choose, previous):
+    """tf.contrib.seq2seq.monotonic_attention(mode='parallel') as LuongMonotonicAttention uses it (las/model.py:157-158):
+    a = p * cumprod_excl(1 - p) * cumsum(previous / clip(cumprod_excl(1 - p), 1e-10, 1)), the cumprod in log space with the
+    argument clipped to [tiny, 1] (safe_cumprod)."""
+    tiny = torch.finfo(p_choose.dtype).tiny
+    logs = torch.log(torch.clamp(1 - p_choose, tiny, 1.0))
+    cp = torch.exp(torch.cumsum(logs, 1) - logs)  # exclusive
+    return p_choose * cp * torch.cumsum(previous / torch.clamp(cp, 1e-10, 1.0), 1)
+
+
 def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None, sampling=None,
                   fed_inputs=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
@@ -150,6 +160,11 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
     attention = enc_out.new_zeros((B, D if w_al is None else w_al.shape[1]))
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
+    mono = att_type == "luong_monotonic"
+    if mono:  # the alignments are a recurrent state, initialised to a dirac at frame 0 (_BaseMonotonicAttentionMechanism)
+        align = torch.zeros((B, Tm), dtype=enc_out.dtype)
+        align[:, 0] = 1.0
+        score_bias = params[f"{pre}/luong_monotonic_attention/attention_score_bias"]
     # scheduled sampling (ScheduledEmbeddingTrainingHelper, las/model.py:279-288): ``sampling`` = (selected [B,S] bool, gumbel
     # [B,S,V]); where selected[b,t], the input of step t+1 becomes one_hot(argmax(logits_t + gumbel_t)) -- a draw from
     # Categorical(logits_t) by Gumbel-max, with the caller's noise so that the stochastic op is replayed exactly.  The inputs
@@ -179,7 +194,10 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
                 score = (torch.tanh(keys + pq[:, None, :]) * params[f"{pre}/bahdanau_attention/attention_v"]).sum(-1)
             else:
                 score = torch.einsum("btu,bu->bt", keys, h0)
-            align = torch.softmax(torch.where(mask, score, neg_inf), dim=1)
+            if mono:
+                align = monotonic_attention(torch.where(mask, torch.sigmoid(score + score_bias), torch.zeros_like(score)), align)
+            else:
+                align = torch.softmax(torch.where(mask, score, neg_inf), dim=1)
             attention = torch.einsum("bt,btd->bd", align, values)
             cur = attention
             for (k, b), (c, h) in zip(cells[1:], state[1:]):
@@ -207,12 +225,14 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
             pq = inp @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
             v = params[f"{pre}/bahdanau_attention/attention_v"]
             score = (torch.tanh(keys + pq[:, None, :]) * v).sum(-1)
-        elif att_type == "luong":
+        elif att_type in ("luong", "luong_monotonic"):
             score = torch.einsum("btu,bu->bt", keys, inp)
         else:
             raise NotImplementedError(att_type)
-        score = torch.where(mask, score, neg_inf)
-        align = torch.softmax(score, dim=1)
+        if mono:
+            align = monotonic_attention(torch.where(mask, torch.sigmoid(score + score_bias), torch.zeros_like(score)), align)
+        else:
+            align = torch.softmax(torch.where(mask, score, neg_inf), dim=1)
         attention = torch.einsum("bt,btd->bd", align, values)
         if w_al is not None:  # attention_layer_size: attention = Dense([cell output; context]), no bias
             attention = torch.cat([inp, attention], 1) @ w_al

@@ -76,7 +76,7 @@ class DecTrainDesc(C.Structure):
                 ("dc_init", C.c_void_p * 4), ("dh_init", C.c_void_p * 4),
                 ("sample_prob", C.c_float), ("sample_seed", C.c_uint32), ("xdrop_seed", C.c_uint32), ("_pad2", C.c_uint32),
                 ("x_in_rw", C.c_void_p), ("w_att_layer", C.c_void_p), ("dw_att_layer", C.c_void_p), ("att_layer", C.c_int32),
-                ("_pad3", C.c_int32)]
+                ("_pad3", C.c_int32), ("score_bias", C.c_void_p), ("dscore_bias", C.c_void_p)]
 
 
 class DecInferDesc(C.Structure):
@@ -88,7 +88,7 @@ class DecInferDesc(C.Structure):
                 ("mem_len", C.c_void_p), ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
                 ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p),
                 ("bottom_only", C.c_int32), ("att_layer", C.c_int32), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4),
-                ("w_att_layer", C.c_void_p)]
+                ("w_att_layer", C.c_void_p), ("score_bias", C.c_void_p)]
 
 
 EXPORTS = {

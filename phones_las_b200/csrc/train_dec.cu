@@ -17,6 +17,7 @@
 //   dec_gemv_t     dinp = dz_t W^T   (gradient wrt [attention_{t-1}; h_{t-1}] that the next iteration consumes)
 // Saved tensors are batch-major [B][S][width] so the hoisted GEMMs see plain row-major matrices.
 #include <cooperative_groups.h>
+#include <float.h>
 
 #include "common.cuh"
 #include "../../include/plas.h"
@@ -160,6 +161,10 @@ struct AttFwdArgs {
   float* att; long long s_att;            // context of this step
   float* att_next;                        // slot t+1 of the attention_{t-1} copy (NULL at the last step)
   const int* skip;                        // inference loop: *skip != 0 -> no-op
+  // luong_monotonic (tf.contrib.seq2seq.LuongMonotonicAttention): p = sigmoid(score + bias), a = p * cumprod_excl(1-p) * cumsum(a_prev / cumprod)
+  const float* score_bias;                // [1] attention_score_bias
+  const float* align_prev; long long s_ap;  // alignments of step t-1 (NULL at t == 0: a dirac at frame 0)
+  float* p_save; long long s_ps;          // training: the choose probabilities of this step (NULL in inference)
   long long next_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index b*s_att + next_base + d
 };
 
@@ -234,6 +239,27 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     if (lane == 0) s_sc[t] = t < len ? s : -INFINITY;
   }
   __syncthreads();
+  if (p.type == PLAS_ATT_LUONG_MONOTONIC) {
+    // one thread walks the memory in order (the recurrences are sequential and short; same operation order as the oracle)
+    if (tid == 0) {
+      const float bias = *p.score_bias;
+      float cs = 0.f, run = 0.f;
+      for (int t = 0; t < Tm; ++t) {
+        const float pc = t < len ? sigmoidf_acc(s_sc[t] + bias) : 0.f;
+        const float cp = expf(cs);                                   // exclusive cumprod of (1 - p) in log space
+        const float prev = p.align_prev ? p.align_prev[(long long)b * p.s_ap + t] : (t == 0 ? 1.f : 0.f);
+        run += prev / fminf(fmaxf(cp, 1e-10f), 1.f);
+        const float a = pc * cp * run;
+        cs += logf(fminf(fmaxf(1.f - pc, FLT_MIN), 1.f));
+        s_sc[t] = a;
+        if (part == 0) {
+          p.align[(long long)b * p.s_al + t] = a;
+          if (p.p_save) p.p_save[(long long)b * p.s_ps + t] = pc;
+        }
+      }
+    }
+    __syncthreads();
+  } else {
   float m = -INFINITY;
   for (int t = tid; t < Tm; t += 256) m = fmaxf(m, s_sc[t]);
   m = warp_max(m);
@@ -269,6 +295,7 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     if (part == 0) p.align[(long long)b * p.s_al + t] = a;
   }
   __syncthreads();
+  }
   for (int d = d_lo + tid; d < d_hi; d += 256) {
     float c0 = 0.f, c1 = 0.f;
     if (p.staged) {
@@ -299,6 +326,10 @@ struct AttBwdArgs {
   float* dctx; long long s_dc;           // in: dlogits W_proj^T of this step; out: + recurrent part
   const float* datt_next; long long s_dn;  // gradient wrt attention_{t} from step t+1's cell input (NULL at t = S-1)
   const float* extra[4]; long long s_extra[4];  // bottom_only: further sources of the attention gradient (NULL = absent)
+  // luong_monotonic: saved choose probabilities, previous alignments, the gradient wrt the alignments of this step coming from
+  // step t+1 (the alignments are a recurrent state) and the one this step hands to step t-1; d(attention_score_bias) per utterance
+  const float* score_p; long long s_sp; const float* align_prev; long long s_ap;
+  const float* dalign_in; float* dalign_out; float* dbias_acc;
   float* dscore; long long s_ds;         // [Tm] saved for the hoisted dkeys GEMM (luong)
   float* dq; long long s_dq;             // [Ud] gradient wrt the query (h_top)
   // bahdanau
@@ -324,7 +355,8 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
   float* s_dc = attb_smem;               // [dper]
   float* s_part = s_dc + dper;           // [NS][Tp] partial dalign of every CTA of the cluster
   float* s_da = s_part + (size_t)NS * Tp;  // [Tp] dalign -> dscore
-  float* s_dpq = s_da + Tp;              // [Ud] (bahdanau)
+  float* s_mono = s_da + Tp;             // [2][Tp] (luong_monotonic: cumprod, running sum)
+  float* s_dpq = s_mono + 2 * Tp;        // [Ud] (bahdanau)
   float* s_vals = s_dpq + Ud;            // staged [len][dper]
   float* s_keys = s_vals + (size_t)Tm * dper;  // staged [len][uper]
   __shared__ float s_red[8];
@@ -395,10 +427,51 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
   }
   __syncthreads();
   dot = s_bcast;
-  for (int t = tid; t < Tm; t += 256) {
-    const float ds = al[t] * (s_da[t] - dot);
-    s_da[t] = ds;
-    if (part == 0) p.dscore[(long long)b * p.s_ds + t] = ds;
+  if (p.type == PLAS_ATT_LUONG_MONOTONIC) {
+    // a_i = p_i cp_i Q_i with cp = cumprod_excl(1 - p) (log space, clipped), Q_i = sum_{j<=i} a_prev_j / clip(cp_j): one thread,
+    // forward recompute, then two reverse running sums
+    if (tid == 0) {
+      float* s_cp = s_mono;
+      float* s_Q = s_mono + Tp;
+      float cs = 0.f, run = 0.f;
+      for (int t = 0; t < Tm; ++t) {
+        const float pc = p.score_p[(long long)b * p.s_sp + t];
+        const float cp = expf(cs);
+        const float prev = p.align_prev ? p.align_prev[(long long)b * p.s_ap + t] : (t == 0 ? 1.f : 0.f);
+        run += prev / fminf(fmaxf(cp, 1e-10f), 1.f);
+        s_cp[t] = cp;
+        s_Q[t] = run;
+        cs += logf(fminf(fmaxf(1.f - pc, FLT_MIN), 1.f));
+      }
+      float R = 0.f, E = 0.f, dbias = 0.f;
+      for (int t = Tm - 1; t >= 0; --t) {
+        const float pc = p.score_p[(long long)b * p.s_sp + t];
+        const float prev = p.align_prev ? p.align_prev[(long long)b * p.s_ap + t] : (t == 0 ? 1.f : 0.f);
+        const float da = s_da[t] + (p.dalign_in ? p.dalign_in[(size_t)b * Tm + t] : 0.f);
+        const float cp = s_cp[t], Q = s_Q[t];
+        const float c = fminf(fmaxf(cp, 1e-10f), 1.f);
+        R += da * pc * cp;                                    // dL/dQ_i summed over i >= t  = dL/dq_t
+        if (part == 0) p.dalign_out[(size_t)b * Tm + t] = R / c;  // gradient wrt the previous alignments
+        float dcp = da * pc * Q;
+        if (cp >= 1e-10f) dcp -= R * prev / (c * c);
+        float dp = da * cp * Q;
+        const float dlogx = E;                                // sum_{i > t} dcp_i cp_i
+        E += dcp * cp;
+        const float om = 1.f - pc;
+        if (om >= FLT_MIN) dp -= dlogx / om;
+        const float ds = t < len ? dp * pc * om : 0.f;
+        s_da[t] = ds;
+        dbias += ds;
+        if (part == 0) p.dscore[(long long)b * p.s_ds + t] = ds;
+      }
+      if (part == 0) p.dbias_acc[b] += dbias;
+    }
+  } else {
+    for (int t = tid; t < Tm; t += 256) {
+      const float ds = al[t] * (s_da[t] - dot);
+      s_da[t] = ds;
+      if (part == 0) p.dscore[(long long)b * p.s_ds + t] = ds;
+    }
   }
   __syncthreads();
   if (p.type == PLAS_ATT_BAHDANAU) {
@@ -745,7 +818,7 @@ __global__ void dec_infer_finish_kernel(InferState st, int B, int t, int eos_id,
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
-  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh, ctx, datt, dqx;
+  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh, ctx, datt, dqx, psave, dalign, dbias;
   size_t z[4], c[4], h[4], hprev[4], hdrop[4];
   size_t splitk, splitk_bytes;
   size_t total;
@@ -774,6 +847,10 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
   w.dctx = take(B * S * D);
   w.gh = take(B * S * Ud);  // bottom_only: dlogits W_proj^T when the projection reads the top cell
   w.ctx = w.datt = w.dqx = 0;
+  const bool mono = d.attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  w.psave = take(mono ? B * S * Tm : 0);   // choose probabilities of every step
+  w.dalign = take(mono ? 2 * B * Tm : 0);  // gradient wrt the alignment state, two slots (parity of t)
+  w.dbias = take(mono ? B : 0);            // d(attention_score_bias) per utterance
   if (d.att_layer > 0) {    // attention_layer_size: the context and the gradient wrt the (A-wide) attention are kept separately
     w.ctx = take(B * S * D);
     w.datt = take(B * S * (size_t)d.att_layer);
@@ -819,9 +896,10 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   if (d->sample_prob > 0.f)
     PLAS_REQUIRE(d->x_in_rw != nullptr && d->E == d->n_out, "dec_train: scheduled sampling needs one-hot inputs (E == n_out) and a writable x_in");
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
-  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU,
-               "dec_train: attention_type %d has no training path (luong, bahdanau)", d->attention_type);
-  PLAS_REQUIRE((size_t)(d->D + 5 * (d->Tm + 4) + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
+  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU || d->attention_type == PLAS_ATT_LUONG_MONOTONIC,
+               "dec_train: attention_type %d has no training path (luong, bahdanau, luong_monotonic)", d->attention_type);
+  if (d->attention_type == PLAS_ATT_LUONG_MONOTONIC) PLAS_REQUIRE(d->score_bias != nullptr, "dec_train: luong_monotonic needs attention_score_bias");
+  PLAS_REQUIRE((size_t)(d->D + 7 * (d->Tm + 4) + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
   const DecTrainWs w = dec_train_ws(*d);
   PLAS_REQUIRE(ws_bytes >= w.total, "dec_train: workspace %zu < %zu", ws_bytes, w.total);
   return PLAS_OK;
@@ -852,7 +930,7 @@ static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
   w.att = take(B * 2 * A * 4);
   w.ctx = take(B * D * 4);
   w.pq = take(B * Ud * 4);
-  w.align = take(B * Tm * 4);
+  w.align = take(2 * B * Tm * 4);  // two slots (parity of t): the monotonic scan reads step t-1's while it writes its own
   w.ints = take((2 * B + 8) * 4);
   w.total = off;
   return w;
@@ -870,7 +948,9 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
   PLAS_REQUIRE(d->B > 0 && d->Tm > 0 && d->V > 0 && d->max_steps >= 0, "dec_infer: bad shape");
   PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_infer: n_layers=%d", d->n_layers);
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_infer: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
-  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU, "dec_infer: attention_type %d", d->attention_type);
+  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU || d->attention_type == PLAS_ATT_LUONG_MONOTONIC,
+               "dec_infer: attention_type %d", d->attention_type);
+  if (d->attention_type == PLAS_ATT_LUONG_MONOTONIC) PLAS_REQUIRE(d->score_bias != nullptr, "dec_infer: luong_monotonic needs attention_score_bias");
   PLAS_REQUIRE(d->keys && d->values && d->mem_len && d->w_proj && d->b_proj && d->logits && d->sample_ids && d->seq_len && d->n_steps,
                "dec_infer: null tensor");
   if (d->attention_type == PLAS_ATT_BAHDANAU) PLAS_REQUIRE(d->w_query && d->v_att, "dec_infer: bahdanau needs query_layer / attention_v");
@@ -964,8 +1044,14 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     q.query = F(w.h[query_layer]) + (size_t)slot * Ud; q.s_q = 2LL * Ud;
     q.w_query = d->w_query; q.v_att = d->v_att;
     q.pq = F(w.pq); q.s_pq = Ud;
-    if (d->alignment) { q.align = d->alignment + (size_t)t * Tm; q.s_al = (long long)S * Tm; }
-    else { q.align = F(w.align); q.s_al = Tm; }
+    q.score_bias = d->score_bias; q.p_save = nullptr; q.s_ps = 0;
+    if (d->alignment) {
+      q.align = d->alignment + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+      q.align_prev = t > 0 ? d->alignment + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
+    } else {
+      q.align = F(w.align) + (size_t)slot * B * Tm; q.s_al = Tm;
+      q.align_prev = t > 0 ? F(w.align) + (size_t)(slot ^ 1) * B * Tm : nullptr; q.s_ap = Tm;
+    }
     if (d->att_layer > 0) { q.att = F(w.ctx); q.s_att = D; }        // the context goes through the attention layer below
     else { q.att = F(w.att) + (size_t)slot * D; q.s_att = 2LL * D; }
     q.att_next = nullptr; q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
@@ -1124,6 +1210,8 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
         q.w_query = d->w_query; q.v_att = d->v_att;
         q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh;
         q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+        q.score_bias = d->score_bias; q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
+        q.p_save = F(w.psave) + (size_t)t * Tm; q.s_ps = q.s_al;
         q.att = F(w.att) + (size_t)t * D; q.s_att = sd;
         q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
         q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
@@ -1168,9 +1256,14 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
     PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
   }
+  const bool mono = d->attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  if (mono) {
+    PLAS_REQUIRE(d->dscore_bias != nullptr, "dec_train_bwd: luong_monotonic needs dscore_bias");
+    PLAS_CUDA(cudaMemsetAsync(F(w.dbias), 0, (size_t)B * 4, st));
+  }
   const int ns = (D % 16 == 0 && Ud % 16 == 0 && D >= 256) ? 4 : 1;
   const int Tp = (Tm + 3) & ~3;
-  size_t attb_smem = (size_t)(D / ns + (ns + 1) * Tp + Ud) * 4;
+  size_t attb_smem = (size_t)(D / ns + (ns + 3) * Tp + Ud) * 4;
   const size_t attb_stage = (size_t)Tm * (D / ns + Ud / ns) * 4;
   const int attb_staged = ((D / ns) % 4 == 0 && (Ud / ns) % 4 == 0 && attb_smem + attb_stage <= 220 * 1024) ? 1 : 0;
   if (attb_staged) attb_smem += attb_stage;
@@ -1220,6 +1313,10 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
         q.extra[ne] = dinp(l, t + 1) + (l == 1 ? D : Ud); q.s_extra[ne] = Kin(l) + Ud; ++ne;
       }
     q.dscore = F(w.dscore) + (size_t)t * Tm; q.s_ds = (long long)S * Tm;
+    q.score_p = F(w.psave) + (size_t)t * Tm; q.s_sp = q.s_al;
+    q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
+    q.dalign_in = last ? nullptr : F(w.dalign) + (size_t)((t + 1) & 1) * B * Tm;
+    q.dalign_out = F(w.dalign) + (size_t)(t & 1) * B * Tm; q.dbias_acc = F(w.dbias);
     q.dq = F(w.dq); q.s_dq = Ud;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
     q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
@@ -1281,6 +1378,7 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   if ((rc = gemm(st, Tm, D, S, F(w.align), 1, Tm, dctx, D, 1, d->dmemory, D, nullptr, d->dmemory_accumulate ? 1.f : 0.f, B, (long long)S * Tm,
                  (long long)S * D, (long long)Tm * D)))
     return rc;
+  if (mono && (rc = plas_colsum_f32(F(w.dbias), B, 1, 1, d->dscore_bias, 0, st))) return rc;
   if ((rc = gemm(st, (long long)B * Tm, D, Ud, F(w.dkeys), Ud, 1, d->w_mem, 1, Ud, d->dmemory, D, nullptr, 1.f))) return rc;
   return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud);
 }
@@ -1374,6 +1472,8 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
     q.w_query = d->w_query; q.v_att = d->v_att;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = (long long)S * Ud;
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
+    q.score_bias = d->score_bias; q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
+    q.p_save = F(w.psave) + (size_t)t * Tm; q.s_ps = q.s_al;
     if (d->att_layer > 0) { q.att = F(w.ctx) + (size_t)t * D; q.s_att = (long long)S * D; }
     else { q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D; }
     q.skip = nullptr;
@@ -1425,9 +1525,14 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
     PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
   }
+  const bool mono = d->attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  if (mono) {
+    PLAS_REQUIRE(d->dscore_bias != nullptr, "dec_train_bwd: luong_monotonic needs dscore_bias");
+    PLAS_CUDA(cudaMemsetAsync(F(w.dbias), 0, (size_t)B * 4, st));
+  }
   const int ns = (D % 16 == 0 && Ud % 16 == 0 && D >= 256) ? 4 : 1;
   const int Tp = (Tm + 3) & ~3;
-  size_t attb_smem = (size_t)(D / ns + (ns + 1) * Tp + Ud) * 4;
+  size_t attb_smem = (size_t)(D / ns + (ns + 3) * Tp + Ud) * 4;
   const size_t attb_stage = (size_t)Tm * (D / ns + Ud / ns) * 4;
   const int attb_staged = ((D / ns) % 4 == 0 && (Ud / ns) % 4 == 0 && attb_smem + attb_stage <= 220 * 1024) ? 1 : 0;
   if (attb_staged) attb_smem += attb_stage;
@@ -1454,6 +1559,10 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     q.dctx = dctx + (size_t)t * D; q.s_dc = (long long)S * D;
     q.datt_next = (last || AL > 0) ? nullptr : F(w.dinp[0]); q.s_dn = D + Ud;  // with the attention layer it is added to datt below
     q.dscore = F(w.dscore) + (size_t)t * Tm; q.s_ds = (long long)S * Tm;
+    q.score_p = F(w.psave) + (size_t)t * Tm; q.s_sp = q.s_al;
+    q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
+    q.dalign_in = last ? nullptr : F(w.dalign) + (size_t)((t + 1) & 1) * B * Tm;
+    q.dalign_out = F(w.dalign) + (size_t)(t & 1) * B * Tm; q.dbias_acc = F(w.dbias);
     q.dq = F(w.dq); q.s_dq = Ud;
     q.pq = F(w.pq) + (size_t)t * Ud; q.s_pq = sh; q.w_query = d->w_query; q.v_att = d->v_att;
     q.dpq = F(w.dpq) + (size_t)t * Ud; q.s_dpq = sh; q.dkeys = F(w.dkeys); q.dv_acc = F(w.dv_acc);
@@ -1547,6 +1656,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
                  (long long)S * Tm, (long long)S * D, (long long)Tm * D)))
     return rc;
   // memory_layer: dmemory += dkeys W_mem^T, dW_mem = memory^T dkeys
+  if (mono && (rc = plas_colsum_f32(F(w.dbias), B, 1, 1, d->dscore_bias, 0, st))) return rc;
   if ((rc = gemm(st, (long long)B * Tm, D, Ud, F(w.dkeys), Ud, 1, d->w_mem, 1, Ud, d->dmemory, D, nullptr, 1.f))) return rc;
   return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud);
 }

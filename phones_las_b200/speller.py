@@ -84,11 +84,12 @@ class SpellerWeights:
                 self.w_query_tc = up(packing.pack_query_tc(params[f"{pre}/bahdanau_attention/query_layer/kernel"], Ud))
         elif self.att == "luong_monotonic":
             self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
+            self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
         self.w_proj_t = up(np.asarray(params[f"{scope}/decoder/projection_layer/kernel"], np.float32).T)  # [V, D]
         self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"], torch.float32)
         # fp32: the step-kernel decoder (csrc/train_dec.cu, plas_decoder_infer_f32) reads the TF layout directly
         self.tf = None
-        if precision == "fp32" and self.att in ("luong", "bahdanau") and Ud % 16 == 0 and D % 4 == 0:
+        if precision == "fp32" and self.att in ("luong", "bahdanau", "luong_monotonic") and Ud % 16 == 0 and D % 4 == 0:
             self.tf = dict(
                 kernel=[up(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], torch.float32) for k in range(self.L)],
                 bias=[up(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], torch.float32) for k in range(self.L)],
@@ -106,7 +107,7 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
         raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
     self.precision, self.att = precision, hp["attention_type"]
-    if self.att not in ("luong", "bahdanau"):
+    if self.att not in ("luong", "bahdanau", "luong_monotonic"):
         raise NotImplementedError(f"--bottom_only with attention_type={self.att}")
     self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
     D, Ud, V = self.D, self.Ud, self.V
@@ -129,14 +130,17 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     if self.att == "bahdanau":
         self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
         self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"])
+    elif self.att == "luong_monotonic":
+        self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
+        self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
     self.tc = False
 
 
 def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope):
     """attention_layer_size = A (las/model.py:180-200): AttentionWrapper's Dense over [cell output; context]; the attention fed
     back to cell 0 and read by the projection is A wide.  fp32 step-kernel decoder only."""
-    if precision != "fp32" or hp["attention_type"] not in ("luong", "bahdanau"):
-        raise NotImplementedError("attention_layer_size is built for the fp32 step-kernel decoder with luong / bahdanau attention")
+    if precision != "fp32" or hp["attention_type"] not in ("luong", "bahdanau", "luong_monotonic"):
+        raise NotImplementedError("attention_layer_size is built for the fp32 step-kernel decoder with luong / bahdanau / luong_monotonic attention")
     self.precision, self.att = precision, hp["attention_type"]
     self.bottom_only = self.pass_hidden_state = False
     self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
@@ -160,6 +164,9 @@ def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope)
     if self.att == "bahdanau":
         self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
         self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"])
+    elif self.att == "luong_monotonic":
+        self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
+        self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
     self.tc = False
 
 
@@ -285,6 +292,7 @@ def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, f
     d.w_query = w.w_query.data_ptr() if w.w_query is not None else None
     d.v_att = w.v_att.data_ptr() if w.v_att is not None else None
     d.w_proj, d.b_proj = w.tf["w_proj"].data_ptr(), w.b_proj.data_ptr()
+    d.score_bias = w.score_bias_dev.data_ptr() if w.att == "luong_monotonic" else None
     d.keys, d.values, d.mem_len = keys.data_ptr(), values.data_ptr(), mem_len.data_ptr()
     d.forced_ids = forced_ids.data_ptr() if forced_ids is not None else None
     d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()

@@ -381,7 +381,7 @@ class SpellerTrain:
         self.sample_prob = float(hp.get("sampling_probability", 0.0))
         if self.sample_prob > 0.0 and (scope != "speller" or E != n_out):
             raise NotImplementedError("training path: scheduled sampling is built for the phone speller only; set sampling_probability=0")
-        if hp["attention_type"] not in ("luong", "bahdanau"):
+        if hp["attention_type"] not in ("luong", "bahdanau", "luong_monotonic"):
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
         for flag in ("binf_projection", "embedding_size"):
             if hp.get(flag):
@@ -425,6 +425,9 @@ class SpellerTrain:
         if hp["attention_type"] == "bahdanau":
             q, v = f"{pre}/bahdanau_attention/query_layer/kernel", f"{pre}/bahdanau_attention/attention_v"
             d.w_query, d.v_att, d.dw_query, d.dv_att = st.w(q), st.w(v), st.g(q), st.g(v)
+        if hp["attention_type"] == "luong_monotonic":
+            sb = f"{pre}/luong_monotonic_attention/attention_score_bias"
+            d.score_bias, d.dscore_bias = st.w(sb), st.g(sb)
         pk, pb = f"{sc}/decoder/projection_layer/kernel", f"{sc}/decoder/projection_layer/bias"
         d.w_proj, d.b_proj, d.dw_proj, d.db_proj = st.w(pk), st.w(pb), st.g(pk), st.g(pb)
         d.memory, d.mem_len, d.x_in = memory.data_ptr(), mem_len.data_ptr(), x_in.data_ptr()

@@ -90,7 +90,7 @@ def test_greedy_parity(cfg):
 
 
 @gpu
-@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("fp32", "bahdanau"), ("bf16", "luong_monotonic")])
+@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("fp32", "bahdanau"), ("bf16", "luong_monotonic"), ("fp32", "luong_monotonic")])
 def test_teacher_forced_parity(precision, att):
     import torch
     from phones_las_b200.speller import speller
@@ -106,6 +106,10 @@ def test_teacher_forced_parity(precision, att):
                         torch.from_numpy(tlen).cuda(), "train", hp, w)
     torch.cuda.synchronize()
     assert_parity(out.rnn_output, ref_logits, precision, "teacher-forced logits")
+    # without the alignment history the alignment state lives in the decoder's own (ping-pong) workspace
+    out2, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(),
+                         torch.from_numpy(tlen).cuda(), "train", hp, w, want_alignment=False)
+    assert torch.equal(out2.rnn_output, out.rnn_output)
 
 
 @gpu
@@ -182,7 +186,8 @@ def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0):
 @gpu
 @pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,pass_state", [("luong", 4, 11, 16, 32, 1, 12, False), ("luong", 5, 13, 16, 32, 2, 14, False),
                                                            ("bahdanau", 6, 17, 16, 48, 3, 20, False), ("luong", 5, 12, 32, 32, 2, 16, True),
-                                                           ("bahdanau", 35, 21, 16, 16, 2, 18, True)])
+                                                           ("bahdanau", 35, 21, 16, 16, 2, 18, True),
+                                                           ("luong_monotonic", 5, 13, 16, 32, 2, 14, False)])
 def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, pass_state):
     import torch
     from phones_las_b200.speller import speller
@@ -210,7 +215,7 @@ def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm,
 
 @gpu
 @pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,A", [("luong", 4, 11, 16, 32, 1, 12, 24), ("bahdanau", 6, 17, 16, 48, 2, 20, 40),
-                                                   ("luong", 34, 9, 16, 16, 2, 14, 8)])
+                                                   ("luong", 34, 9, 16, 16, 2, 14, 8), ("luong_monotonic", 4, 11, 16, 32, 2, 12, 24)])
 def test_attention_layer_size_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, A):
     """attention_layer_size = A (las/model.py:180-200): attention = Dense([cell output; context]); fed back and projected A wide."""
     import torch

@@ -85,7 +85,17 @@ def test_listener_forward_backward(B, T, C, U, L):
 SPELLER_CFGS = [("luong", 3, 9, 16, 32, 1, 12, 5), ("bahdanau", 5, 14, 16, 32, 2, 20, 7), ("luong", 33, 30, 64, 256, 1, 64, 11),
                 ("bahdanau", 8, 20, 32, 64, 3, 30, 6), ("luong", 40, 12, 16, 128, 2, 16, 9),
                 # c2 shapes (D = 2048, Ud = 512) with a memory too long to stage in shared memory: streaming attention paths
-                ("luong", 3, 200, 512, 512, 1, 20, 3), ("bahdanau", 2, 190, 512, 512, 2, 12, 3)]
+                ("luong", 3, 200, 512, 512, 1, 20, 3), ("bahdanau", 2, 190, 512, 512, 2, 12, 3),
+                # luong_monotonic: the alignments are a recurrent state (small, 4-CTA cluster and streaming attention paths)
+                ("luong_monotonic", 5, 14, 16, 32, 2, 20, 7), ("luong_monotonic", 33, 30, 64, 256, 1, 64, 11),
+                ("luong_monotonic", 3, 200, 512, 512, 1, 20, 3)]
+
+
+def _set_score_bias(params, value=-0.6):
+    for k in params:
+        if k.endswith("attention_score_bias"):
+            params[k] = np.float32(value)
+    return params
 
 
 @gpu
@@ -95,8 +105,8 @@ def test_speller_forward_backward(att, B, Tm, U, Ud, Ld, V, S):
     from phones_las_b200.train import TrainState, SpellerTrain
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
                         num_channels=4, attention_type=att, dropout=0.0, sampling_probability=0.0)
-    params = {k: v for k, v in weights.init_params(hp, seed=Ud, projection_scale=4.0, bias_scale=0.1).items()
-              if k.startswith("speller/")}
+    params = _set_score_bias({k: v for k, v in weights.init_params(hp, seed=Ud, projection_scale=4.0, bias_scale=0.1).items()
+                              if k.startswith("speller/")})
     D = weights.encoder_output_depth(hp)
     rng = np.random.default_rng(B)
     enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
@@ -301,14 +311,14 @@ def test_listener_with_dropout():
 
 
 @gpu
-@pytest.mark.parametrize("att,Ld", [("luong", 1), ("bahdanau", 3)])
+@pytest.mark.parametrize("att,Ld", [("luong", 1), ("bahdanau", 3), ("luong_monotonic", 2)])
 def test_speller_with_dropout(att, Ld):
     import torch
     from phones_las_b200 import train as tr
     B, Tm, U, Ud, V, S = 7, 15, 16, 32, 13, 6
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
                         num_channels=4, attention_type=att, dropout=0.25, sampling_probability=0.0)
-    params = {k: v for k, v in weights.init_params(hp, seed=9, projection_scale=4.0, bias_scale=0.1).items() if k.startswith("speller/")}
+    params = _set_score_bias({k: v for k, v in weights.init_params(hp, seed=9, projection_scale=4.0, bias_scale=0.1).items() if k.startswith("speller/")})
     D = weights.encoder_output_depth(hp)
     rng = np.random.default_rng(3)
     enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
@@ -431,7 +441,7 @@ def test_checkpoint_save_restore_resumes_training_identically(tmp_path):
 @gpu
 @pytest.mark.parametrize("att,B,T,U,Ud,Ld,ps", [("luong", 5, 40, 16, 32, 1, False), ("luong", 6, 44, 16, 32, 2, False),
                                                   ("bahdanau", 4, 36, 16, 48, 3, False), ("luong", 7, 40, 32, 32, 2, True),
-                                                  ("bahdanau", 34, 30, 16, 16, 2, True)])
+                                                  ("bahdanau", 34, 30, 16, 16, 2, True), ("luong_monotonic", 6, 44, 32, 32, 2, True)])
 def test_train_step_bottom_only_and_pass_hidden_state(att, B, T, U, Ud, Ld, ps):
     """Whole forward + backward with the AttentionMultiCell wiring; with pass_hidden_state the decoder cells start from the
     listener's final states and their gradients flow back into the listener's BPTT."""
@@ -441,7 +451,7 @@ def test_train_step_bottom_only_and_pass_hidden_state(att, B, T, U, Ud, Ld, ps):
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
                         attention_type=att, dropout=0.0, sampling_probability=0.0, bottom_only=True, pass_hidden_state=ps,
                         l2_reg_scale=1e-4, ctc_weight=0.3)
-    params = weights.init_params(hp, seed=U + Ud + Ld, bias_scale=0.05)
+    params = _set_score_bias(weights.init_params(hp, seed=U + Ud + Ld, bias_scale=0.05), 0.3)
     x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
     tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
     tp = _tp(params)
@@ -561,7 +571,8 @@ def test_tiny_batches_and_sequences_train(B, T, S):
 
 
 @gpu
-@pytest.mark.parametrize("att,Ld,A,sampling", [("luong", 1, 24, 0.0), ("bahdanau", 2, 40, 0.0), ("luong", 2, 16, 0.4)])
+@pytest.mark.parametrize("att,Ld,A,sampling", [("luong", 1, 24, 0.0), ("bahdanau", 2, 40, 0.0), ("luong", 2, 16, 0.4),
+                                                 ("luong_monotonic", 2, 24, 0.3)])
 def test_train_step_attention_layer_size(att, Ld, A, sampling):
     """attention_layer_size = A in training: attention = Dense([h_top; context]) fed back A wide; forward, gradients (including
     the attention layer's kernel), optionally with scheduled sampling on top."""
@@ -571,7 +582,7 @@ def test_train_step_attention_layer_size(att, Ld, A, sampling):
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
                         attention_type=att, dropout=0.0, sampling_probability=sampling, attention_layer_size=A, l2_reg_scale=1e-4,
                         ctc_weight=0.3)
-    params = weights.init_params(hp, seed=A, bias_scale=0.05, projection_scale=4.0)
+    params = _set_score_bias(weights.init_params(hp, seed=A, bias_scale=0.05, projection_scale=4.0), -0.4)
     assert "speller/decoder/attention_wrapper/attention_layer/kernel" in params
     x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
     tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)

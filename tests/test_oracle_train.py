@@ -25,10 +25,12 @@ def test_listener_matches_numpy_oracle():
 
 
 def test_teacher_forced_matches_numpy_oracle():
-    for att, Ld in (("luong", 1), ("bahdanau", 2)):
+    for att, Ld in (("luong", 1), ("bahdanau", 2), ("luong_monotonic", 2)):
         hp = create_hparams(target_vocab_size=11, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=Ld,
                             num_channels=4, attention_type=att)
         params = weights.init_params(hp, seed=5, bias_scale=0.1)
+        if att == "luong_monotonic":
+            params["speller/decoder/attention_wrapper/luong_monotonic_attention/attention_score_bias"] = np.float32(-0.6)
         D = weights.encoder_output_depth(hp)
         rng = np.random.default_rng(0)
         enc = rng.uniform(-1, 1, (3, 7, D)).astype(np.float32)
@@ -148,10 +150,13 @@ def test_general_listener_matches_numpy_oracle():
 
 def test_bottom_only_teacher_forced_matches_numpy_oracle():
     """The differentiable restatement of the AttentionMultiCell wiring (+ pass_hidden_state) vs the numpy oracle."""
-    for att, Ld, ps in (("luong", 2, True), ("bahdanau", 3, False), ("luong", 1, False)):
+    for att, Ld, ps in (("luong", 2, True), ("bahdanau", 3, False), ("luong", 1, False), ("luong_monotonic", 2, False)):
         hp = create_hparams(target_vocab_size=11, encoder_layers=2, encoder_units=8, decoder_units=8, decoder_layers=Ld,
                             num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=ps)
         params = weights.init_params(hp, seed=5, bias_scale=0.1)
+        for k in params:
+            if k.endswith("attention_score_bias"):
+                params[k] = np.float32(0.4)
         x, lens = synth.synth_features(3, 12, 4, var_len=True)
         (enc, enc_len), enc_state = ol.listener(x, lens, params, hp)
         tin, tout, tlen = synth.synth_labels(3, 5, 11)
@@ -161,3 +166,17 @@ def test_bottom_only_teacher_forced_matches_numpy_oracle():
         x64 = torch.nn.functional.one_hot(torch.tensor(tin, dtype=torch.int64), 11).to(torch.float64)
         out = lt.speller_train(e, el, x64, tp, hp, encoder_state=es)
         assert np.abs(out.numpy() - ref).max() < 5e-6, (att, Ld, ps)
+
+
+def test_monotonic_attention_is_the_recursive_definition():
+    """The 'parallel' closed form used by LuongMonotonicAttention equals the recurrence it solves,
+    a_i = p_i ((1 - p_{i-1}) a_{i-1} / p_{i-1} + prev_i), and keeps the total mass <= 1."""
+    rng = np.random.default_rng(1)
+    p = torch.tensor(rng.uniform(0.05, 0.95, (3, 9)))
+    prev = torch.tensor(rng.dirichlet(np.ones(9), 3))
+    a = lt.monotonic_attention(p, prev)
+    q = torch.zeros(3)
+    for i in range(9):  # q_i = (1 - p_{i-1}) q_{i-1} + prev_i,  a_i = p_i q_i
+        q = (q * (1 - p[:, i - 1]) if i else q) + prev[:, i]
+        assert torch.allclose(a[:, i], p[:, i] * q, atol=1e-12)
+    assert (a.sum(1) <= 1 + 1e-9).all()
