@@ -29,6 +29,8 @@ extern "C" {
 #define PLAS_ATT_LUONG 0
 #define PLAS_ATT_BAHDANAU 1
 #define PLAS_ATT_LUONG_MONOTONIC 2
+#define PLAS_ATT_BAHDANAU_MONOTONIC 3 /* fp32 step kernels only (plas_decoder_infer_f32: mode 'hard'; plas_decoder_train_*: sigmoid noise) */
+#define PLAS_ATT_CUSTOM 4             /* fp32 step kernels only: CustomAttention, las/model.py:72-101 */
 
 typedef void* plas_stream_t;
 
@@ -309,6 +311,10 @@ typedef struct plas_dec_train_desc {
   /* luong_monotonic (tf.contrib.seq2seq.LuongMonotonicAttention, las/model.py:157-158): attention_score_bias [1] and its gradient */
   const float* score_bias;
   float* dscore_bias;
+  /* bahdanau_monotonic in TRAIN mode (las/model.py:159-162): sigmoid_noise * N(0,1) is added to the scores; the normal deviates
+   * come from the counter hash with seed noise_seed (+ drop_step), so the oracle can replay them (train.reference_noise) */
+  float sigmoid_noise;
+  uint32_t noise_seed;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
@@ -348,6 +354,9 @@ typedef struct plas_dec_infer_desc {
   const float* w_att_layer; /* attention_wrapper/attention_layer/kernel or NULL                                 */
   const float* score_bias;  /* luong_monotonic attention_score_bias [1] (device) or NULL                       */
 } plas_dec_infer_desc;
+/* x = max(x, 0) in place: CustomAttention's keys = relu(memory_layer(values)) (las/model.py:94), applied by the caller of
+ * plas_decoder_infer_f32 to the keys it passes. */
+int plas_relu_f32(float* x, int64_t n, plas_stream_t stream);
 size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d);
 int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
 

@@ -186,29 +186,41 @@ class Attention:
         wm = q(params[f"{scope}/memory_layer/kernel"])
         self.keys = q((self.values.reshape(B * Tm, D) @ wm).reshape(B, Tm, -1))
         pre = prefix or f"{scope}/decoder/attention_wrapper"
-        if attention_type == "bahdanau":
-            self.wq = q(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
-            self.v = params[f"{pre}/bahdanau_attention/attention_v"].astype(F32)
-        elif attention_type == "luong_monotonic":
-            self.score_bias = F32(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
-        elif attention_type != "luong":
+        if attention_type in ("bahdanau", "bahdanau_monotonic"):
+            self.wq = q(params[f"{pre}/{attention_type}_attention/query_layer/kernel"])
+            self.v = params[f"{pre}/{attention_type}_attention/attention_v"].astype(F32)
+        elif attention_type == "custom":  # CustomAttention, las/model.py:72-101: relu on the keys and on its own query layer
+            self.wq = q(params[f"{pre}/query_layer/kernel"])
+            self.keys = np.maximum(self.keys, F32(0))
+        elif attention_type not in ("luong", "luong_monotonic"):
             raise NotImplementedError(attention_type)
+        if attention_type.endswith("_monotonic"):
+            self.score_bias = F32(params[f"{pre}/{attention_type}_attention/attention_score_bias"])
 
     def initial_alignments(self):
         B, Tm = self.mask.shape
         a = np.zeros((B, Tm), F32)
-        if self.type == "luong_monotonic":
+        if self.type.endswith("_monotonic"):
             a[:, 0] = 1.0
         return a
 
     def __call__(self, query, prev_alignments):
         """query [B,Ud] (already quantised cell output) -> alignments [B,Tm] f32."""
-        if self.type == "bahdanau":
+        if self.type in ("bahdanau", "bahdanau_monotonic"):
             pq = (query @ self.wq).astype(F32)
             score = np.einsum("btu,u->bt", np.tanh(self.keys + pq[:, None, :]).astype(F32), self.v,
                               dtype=F32)
+        elif self.type == "custom":
+            score = np.einsum("btu,bu->bt", self.keys, np.maximum((query @ self.wq).astype(F32), F32(0)), dtype=F32)
         else:
             score = np.einsum("btu,bu->bt", self.keys, query, dtype=F32)
+        if self.type == "bahdanau_monotonic":
+            # outside TRAIN the reference asks for mode='hard' (las/model.py:161-164): p = [score > 0] * cumsum(prev),
+            # alignments = p * cumprod_exclusive(1 - p)  (tf.contrib.seq2seq.monotonic_attention)
+            p = np.where(self.mask & (score + self.score_bias > 0), F32(1), F32(0)) * np.cumsum(prev_alignments, axis=1, dtype=F32)
+            one_m = F32(1) - p
+            cp = np.concatenate([np.ones_like(p[:, :1]), np.cumprod(one_m, axis=1, dtype=F32)[:, :-1]], axis=1)
+            return (p * cp).astype(F32)
         if self.type == "luong_monotonic":
             score = score + self.score_bias
             with np.errstate(over="ignore"):

@@ -130,12 +130,17 @@ def monotonic_attention(p_choose, previous):
 
 
 def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None, sampling=None,
-                  fed_inputs=None):
+                  fed_inputs=None, score_noise=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
     binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
     ``masks``: input-dropout multipliers of the decoder cells: 'x' [B,L,E] and 'att' [B,L,D] (slot t multiplies
-    attention_{t-1}) for cell 0's input [x_t; attention_{t-1}], ('h', l) [B,L,Ud] for the output of layer l feeding l+1."""
+    attention_{t-1}) for cell 0's input [x_t; attention_{t-1}], ('h', l) [B,L,Ud] for the output of layer l feeding l+1.
+    ``score_noise`` [B,L,Tm]: bahdanau_monotonic in TRAIN mode adds sigmoid_noise * N(0,1) to the scores (las/model.py:161-162);
+    the caller passes the (already scaled) deviates -- or a callable (B, L, Tm) -> deviates -- so that the stochastic op is
+    replayed exactly (None = no noise)."""
     B, Tm, D = enc_out.shape
+    if callable(score_noise):
+        score_noise = score_noise(B, dec_inputs.shape[1], Tm)
     Ud = hp["decoder_units"]
     att_type = hp["attention_type"]
     mask = (torch.arange(Tm)[None, :] < enc_len[:, None])
@@ -160,11 +165,30 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
     attention = enc_out.new_zeros((B, D if w_al is None else w_al.shape[1]))
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
-    mono = att_type == "luong_monotonic"
+    mono = att_type.endswith("_monotonic")
     if mono:  # the alignments are a recurrent state, initialised to a dirac at frame 0 (_BaseMonotonicAttentionMechanism)
         align = torch.zeros((B, Tm), dtype=enc_out.dtype)
         align[:, 0] = 1.0
-        score_bias = params[f"{pre}/luong_monotonic_attention/attention_score_bias"]
+        score_bias = params[f"{pre}/{att_type}_attention/attention_score_bias"]
+    if att_type == "custom":  # CustomAttention (las/model.py:72-101)
+        keys = torch.relu(keys)
+
+    def attend(query, t, align):
+        if att_type in ("bahdanau", "bahdanau_monotonic"):
+            pq = query @ params[f"{pre}/{att_type}_attention/query_layer/kernel"]
+            score = (torch.tanh(keys + pq[:, None, :]) * params[f"{pre}/{att_type}_attention/attention_v"]).sum(-1)
+        elif att_type == "custom":
+            score = torch.einsum("btu,bu->bt", keys, torch.relu(query @ params[f"{pre}/query_layer/kernel"]))
+        elif att_type in ("luong", "luong_monotonic"):
+            score = torch.einsum("btu,bu->bt", keys, query)
+        else:
+            raise NotImplementedError(att_type)
+        if not mono:
+            return torch.softmax(torch.where(mask, score, neg_inf), dim=1)
+        score = score + score_bias
+        if score_noise is not None:
+            score = score + torch.as_tensor(score_noise[:, t], dtype=score.dtype)
+        return monotonic_attention(torch.where(mask, torch.sigmoid(score), torch.zeros_like(score)), align)
     # scheduled sampling (ScheduledEmbeddingTrainingHelper, las/model.py:279-288): ``sampling`` = (selected [B,S] bool, gumbel
     # [B,S,V]); where selected[b,t], the input of step t+1 becomes one_hot(argmax(logits_t + gumbel_t)) -- a draw from
     # Categorical(logits_t) by Gumbel-max, with the caller's noise so that the stochastic op is replayed exactly.  The inputs
@@ -189,15 +213,7 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
             (k0, b0), (c, h) = cells[0], state[0]
             c0, h0 = _cell(torch.cat([dec_inputs[t], old, h], 1) @ k0 + b0, c)
             new_state = [(c0, h0)]
-            if att_type == "bahdanau":
-                pq = h0 @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
-                score = (torch.tanh(keys + pq[:, None, :]) * params[f"{pre}/bahdanau_attention/attention_v"]).sum(-1)
-            else:
-                score = torch.einsum("btu,bu->bt", keys, h0)
-            if mono:
-                align = monotonic_attention(torch.where(mask, torch.sigmoid(score + score_bias), torch.zeros_like(score)), align)
-            else:
-                align = torch.softmax(torch.where(mask, score, neg_inf), dim=1)
+            align = attend(h0, t, align if mono else None)
             attention = torch.einsum("bt,btd->bd", align, values)
             cur = attention
             for (k, b), (c, h) in zip(cells[1:], state[1:]):
@@ -221,18 +237,7 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
             if masks is not None and li + 1 < len(cells):
                 inp = h2 * masks[("h", li)][:, t]
         state = new_state
-        if att_type == "bahdanau":
-            pq = inp @ params[f"{pre}/bahdanau_attention/query_layer/kernel"]
-            v = params[f"{pre}/bahdanau_attention/attention_v"]
-            score = (torch.tanh(keys + pq[:, None, :]) * v).sum(-1)
-        elif att_type in ("luong", "luong_monotonic"):
-            score = torch.einsum("btu,bu->bt", keys, inp)
-        else:
-            raise NotImplementedError(att_type)
-        if mono:
-            align = monotonic_attention(torch.where(mask, torch.sigmoid(score + score_bias), torch.zeros_like(score)), align)
-        else:
-            align = torch.softmax(torch.where(mask, score, neg_inf), dim=1)
+        align = attend(inp, t, align if mono else None)
         attention = torch.einsum("bt,btd->bd", align, values)
         if w_al is not None:  # attention_layer_size: attention = Dense([cell output; context]), no bias
             attention = torch.cat([inp, attention], 1) @ w_al
@@ -276,7 +281,7 @@ def ctc_loss(logits, labels, label_length, logit_length, blank=0):
     return torch.stack(out)
 
 
-def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sampling=None):
+def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sampling=None, score_noise=None):
     """las_model_fn(mode=TRAIN) loss (model_helper.py:165-358, 411-413) with dropout = 0 and
     sampling_probability = 0.  ``binf`` [n, V] enables the multitask binary-feature speller.
     Returns (total loss incl. L2, dict of the parts)."""
@@ -291,7 +296,7 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sam
     V = hp["target_vocab_size"]
     if not hp.get("binary_outputs") or hp.get("multitask"):
         logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp,
-                               masks=masks.get("speller"), encoder_state=enc_state, sampling=sampling)
+                               masks=masks.get("speller"), encoder_state=enc_state, sampling=sampling, score_noise=score_noise)
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits
         loss = loss + parts["ce"]

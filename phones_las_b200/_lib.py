@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libplas.so")
 
 PLAS_F32, PLAS_BF16 = 0, 1
-ATT_CODES = {"luong": 0, "bahdanau": 1, "luong_monotonic": 2}
+ATT_CODES = {"luong": 0, "bahdanau": 1, "luong_monotonic": 2, "bahdanau_monotonic": 3, "custom": 4}
 
 
 class PlasError(RuntimeError):
@@ -76,7 +76,8 @@ class DecTrainDesc(C.Structure):
                 ("dc_init", C.c_void_p * 4), ("dh_init", C.c_void_p * 4),
                 ("sample_prob", C.c_float), ("sample_seed", C.c_uint32), ("xdrop_seed", C.c_uint32), ("_pad2", C.c_uint32),
                 ("x_in_rw", C.c_void_p), ("w_att_layer", C.c_void_p), ("dw_att_layer", C.c_void_p), ("att_layer", C.c_int32),
-                ("_pad3", C.c_int32), ("score_bias", C.c_void_p), ("dscore_bias", C.c_void_p)]
+                ("_pad3", C.c_int32), ("score_bias", C.c_void_p), ("dscore_bias", C.c_void_p),
+                ("sigmoid_noise", C.c_float), ("noise_seed", C.c_uint32)]
 
 
 class DecInferDesc(C.Structure):
@@ -110,6 +111,7 @@ EXPORTS = {
     "plas_rec_units_per_cta": (C.c_int32, [C.c_int32, C.c_int32]),
     "plas_rec_workspace_bytes": (C.c_size_t, [C.POINTER(RecDesc)]),
     "plas_bilstm_rec_fwd": (C.c_int, [C.POINTER(RecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "plas_relu_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "plas_decoder_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
     "plas_decoder_fwd": (C.c_int, [C.POINTER(DecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_seq_ce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

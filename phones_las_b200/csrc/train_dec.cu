@@ -148,6 +148,23 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
   }
 }
 
+// CustomAttention: keys = relu(memory_layer(values)) and its backward (gradient passes where the output is positive)
+__global__ void dec_relu_kernel(float* x, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[i] = fmaxf(x[i], 0.f);
+}
+__global__ void dec_relu_grad_kernel(float* dx, const float* y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n && !(y[i] > 0.f)) dx[i] = 0.f;
+}
+
+// standard normal from the counter-based hash (Box-Muller on two 24-bit uniforms); numpy mirror: train.reference_noise
+__device__ __forceinline__ float hash_normal(uint64_t idx, uint32_t seed) {
+  const float u1 = ((float)(drop_hash(idx, seed) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(drop_hash(idx, seed + 1u) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 struct AttFwdArgs {
   int B, Tm, D, Ud, type, dsplit, staged;
@@ -165,6 +182,8 @@ struct AttFwdArgs {
   const float* score_bias;                // [1] attention_score_bias
   const float* align_prev; long long s_ap;  // alignments of step t-1 (NULL at t == 0: a dirac at frame 0)
   float* p_save; long long s_ps;          // training: the choose probabilities of this step (NULL in inference)
+  // bahdanau_monotonic (las/model.py:159-164): TRAIN adds noise_scale * N(0,1) to the scores (sigmoid_noise), otherwise mode 'hard'
+  int hard; float noise_scale; unsigned noise_seed; long long noise_base;  // noise index b*s_al + noise_base + t
   long long next_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index b*s_att + next_base + d
 };
 
@@ -201,7 +220,10 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   const float* q = p.query + (long long)b * p.s_q;
-  if (p.type == PLAS_ATT_BAHDANAU) {
+  const bool bah = p.type == PLAS_ATT_BAHDANAU || p.type == PLAS_ATT_BAHDANAU_MONOTONIC;
+  const bool mono = p.type == PLAS_ATT_LUONG_MONOTONIC || p.type == PLAS_ATT_BAHDANAU_MONOTONIC;
+  const bool custom = p.type == PLAS_ATT_CUSTOM;  // CustomAttention (las/model.py:72-101): query = relu(query_layer(h)), luong score
+  if (bah || custom) {
     for (int u = tid; u < Ud; u += 256) s_v[u] = q[u];  // raw query staged where attention_v goes afterwards
     __syncthreads();
     for (int u = tid; u < Ud; u += 256) {
@@ -214,12 +236,14 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
         s3 = fmaf(s_v[k + 3], __ldg(p.w_query + (size_t)(k + 3) * Ud + u), s3);
       }
       for (; k < Ud; ++k) s0 = fmaf(s_v[k], __ldg(p.w_query + (size_t)k * Ud + u), s0);
-      const float s = (s0 + s1) + (s2 + s3);
+      float s = (s0 + s1) + (s2 + s3);
+      if (custom) s = fmaxf(s, 0.f);
       s_q[u] = s;
       if (part == 0) p.pq[(long long)b * p.s_pq + u] = s;
     }
     __syncthreads();
-    for (int u = tid; u < Ud; u += 256) s_v[u] = p.v_att[u];
+    if (bah)
+      for (int u = tid; u < Ud; u += 256) s_v[u] = p.v_att[u];
   } else {
     for (int u = tid; u < Ud; u += 256) s_q[u] = q[u];
   }
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     float s = 0.f;
     if (t < len) {
       const float* kr = kbase + (size_t)t * Ud;
-      if (p.type == PLAS_ATT_BAHDANAU)
+      if (bah)
         for (int u = lane; u < Ud; u += 32) s = fmaf(s_v[u], tanhf(kr[u] + s_q[u]), s);
       else
         for (int u = lane; u < Ud; u += 32) s = fmaf(kr[u], s_q[u], s);
@@ -239,13 +263,31 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     if (lane == 0) s_sc[t] = t < len ? s : -INFINITY;
   }
   __syncthreads();
-  if (p.type == PLAS_ATT_LUONG_MONOTONIC) {
+  if (mono && p.hard) {
+    // monotonic_attention(mode='hard'): p = [score > 0] * cumsum(prev), a = p * cumprod_excl(1 - p)
+    if (tid == 0) {
+      const float bias = *p.score_bias;
+      float cum = 0.f, cp = 1.f;
+      for (int t = 0; t < Tm; ++t) {
+        cum += p.align_prev ? p.align_prev[(long long)b * p.s_ap + t] : (t == 0 ? 1.f : 0.f);
+        const float pc = (t < len && s_sc[t] + bias > 0.f) ? cum : 0.f;
+        const float a = pc * cp;
+        cp *= 1.f - pc;
+        s_sc[t] = a;
+        if (part == 0) p.align[(long long)b * p.s_al + t] = a;
+      }
+    }
+    __syncthreads();
+  } else if (mono) {
     // one thread walks the memory in order (the recurrences are sequential and short; same operation order as the oracle)
     if (tid == 0) {
       const float bias = *p.score_bias;
+      const unsigned nseed = p.noise_seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL;
       float cs = 0.f, run = 0.f;
       for (int t = 0; t < Tm; ++t) {
-        const float pc = t < len ? sigmoidf_acc(s_sc[t] + bias) : 0.f;
+        float sc = s_sc[t] + bias;
+        if (p.noise_scale != 0.f && t < len) sc += p.noise_scale * hash_normal((uint64_t)((long long)b * p.s_al + p.noise_base + t), nseed);
+        const float pc = t < len ? sigmoidf_acc(sc) : 0.f;
         const float cp = expf(cs);                                   // exclusive cumprod of (1 - p) in log space
         const float prev = p.align_prev ? p.align_prev[(long long)b * p.s_ap + t] : (t == 0 ? 1.f : 0.f);
         run += prev / fminf(fmaxf(cp, 1e-10f), 1.f);
@@ -427,7 +469,9 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
   }
   __syncthreads();
   dot = s_bcast;
-  if (p.type == PLAS_ATT_LUONG_MONOTONIC) {
+  const bool bah = p.type == PLAS_ATT_BAHDANAU || p.type == PLAS_ATT_BAHDANAU_MONOTONIC;
+  const bool custom = p.type == PLAS_ATT_CUSTOM;
+  if (p.type == PLAS_ATT_LUONG_MONOTONIC || p.type == PLAS_ATT_BAHDANAU_MONOTONIC) {
     // a_i = p_i cp_i Q_i with cp = cumprod_excl(1 - p) (log space, clipped), Q_i = sum_{j<=i} a_prev_j / clip(cp_j): one thread,
     // forward recompute, then two reverse running sums
     if (tid == 0) {
@@ -474,7 +518,7 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
     }
   }
   __syncthreads();
-  if (p.type == PLAS_ATT_BAHDANAU) {
+  if (bah) {
     float* dkb = p.dkeys + (size_t)b * Tm * Ud;
     for (int uu = tid; uu < uper; uu += 256) {
       const int u = u_lo + uu;
@@ -519,7 +563,28 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
 #pragma unroll 8
         for (int t = 0; t < len; ++t) s0 = fmaf(s_da[t], kb[(size_t)t * Ud + u_lo + uu], s0);
       }
-      p.dq[(long long)b * p.s_dq + u_lo + uu] = s0 + s1;
+      if (!custom) {
+        p.dq[(long long)b * p.s_dq + u_lo + uu] = s0 + s1;
+      } else {  // the score read relu(query_layer(h)): back through the relu, then (below) through the query layer
+        const int u = u_lo + uu;
+        const float dpq = p.pq[(long long)b * p.s_pq + u] > 0.f ? s0 + s1 : 0.f;
+        p.dpq[(long long)b * p.s_dpq + u] = dpq;
+        for (int r = 0; r < NS; ++r) {
+          float* remote = NS > 1 ? cluster.map_shared_rank(s_dpq, r) : s_dpq;
+          remote[u] = dpq;
+        }
+      }
+    }
+    if (custom) {
+      if (NS > 1) cluster.sync(); else __syncthreads();
+      for (int kk = warp; kk < uper; kk += 8) {  // dq[k] = sum_u dpq[u] W_query[k][u]
+        const int k = u_lo + kk;
+        float s = 0.f;
+        const float* wr = p.w_query + (size_t)k * Ud;
+        for (int u = lane; u < Ud; u += 32) s = fmaf(s_dpq[u], __ldg(wr + u), s);
+        s = warp_sum(s);
+        if (lane == 0) p.dq[(long long)b * p.s_dq + k] = s;
+      }
     }
   }
 }
@@ -847,7 +912,7 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
   w.dctx = take(B * S * D);
   w.gh = take(B * S * Ud);  // bottom_only: dlogits W_proj^T when the projection reads the top cell
   w.ctx = w.datt = w.dqx = 0;
-  const bool mono = d.attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  const bool mono = d.attention_type == PLAS_ATT_LUONG_MONOTONIC || d.attention_type == PLAS_ATT_BAHDANAU_MONOTONIC;
   w.psave = take(mono ? B * S * Tm : 0);   // choose probabilities of every step
   w.dalign = take(mono ? 2 * B * Tm : 0);  // gradient wrt the alignment state, two slots (parity of t)
   w.dbias = take(mono ? B : 0);            // d(attention_score_bias) per utterance
@@ -887,6 +952,9 @@ static int gemm(cudaStream_t st, long long M, int N, int K, const float* A, long
   return plas_gemm_f32_ex(&g, st);
 }
 
+static inline bool att_is_bah(int t) { return t == PLAS_ATT_BAHDANAU || t == PLAS_ATT_BAHDANAU_MONOTONIC; }
+static inline bool att_is_mono(int t) { return t == PLAS_ATT_LUONG_MONOTONIC || t == PLAS_ATT_BAHDANAU_MONOTONIC; }
+
 static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_bytes) {
   PLAS_REQUIRE(d && ws, "dec_train: null argument");
   PLAS_REQUIRE(d->B > 0 && d->S > 0 && d->Tm > 0 && d->E > 0 && d->n_out > 0, "dec_train: bad shape");
@@ -896,9 +964,10 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   if (d->sample_prob > 0.f)
     PLAS_REQUIRE(d->x_in_rw != nullptr && d->E == d->n_out, "dec_train: scheduled sampling needs one-hot inputs (E == n_out) and a writable x_in");
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
-  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU || d->attention_type == PLAS_ATT_LUONG_MONOTONIC,
-               "dec_train: attention_type %d has no training path (luong, bahdanau, luong_monotonic)", d->attention_type);
-  if (d->attention_type == PLAS_ATT_LUONG_MONOTONIC) PLAS_REQUIRE(d->score_bias != nullptr, "dec_train: luong_monotonic needs attention_score_bias");
+  PLAS_REQUIRE(d->attention_type >= PLAS_ATT_LUONG && d->attention_type <= PLAS_ATT_CUSTOM, "dec_train: attention_type %d", d->attention_type);
+  if (att_is_mono(d->attention_type)) PLAS_REQUIRE(d->score_bias != nullptr, "dec_train: monotonic attention needs attention_score_bias");
+  if (att_is_bah(d->attention_type)) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train: bahdanau needs query_layer / attention_v");
+  if (d->attention_type == PLAS_ATT_CUSTOM) PLAS_REQUIRE(d->w_query != nullptr, "dec_train: custom attention needs its query_layer");
   PLAS_REQUIRE((size_t)(d->D + 7 * (d->Tm + 4) + 2 * d->Ud) * 4 <= 200 * 1024, "dec_train: D/Tm/Ud too large for one CTA");
   const DecTrainWs w = dec_train_ws(*d);
   PLAS_REQUIRE(ws_bytes >= w.total, "dec_train: workspace %zu < %zu", ws_bytes, w.total);
@@ -940,6 +1009,13 @@ static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
 
 using namespace plas;
 
+extern "C" int plas_relu_f32(float* x, int64_t n, plas_stream_t stream_) {
+  PLAS_REQUIRE(x != nullptr && n >= 0, "relu: bad argument");
+  if (n) dec_relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, (size_t)n);
+  PLAS_CUDA(cudaGetLastError());
+  return PLAS_OK;
+}
+
 extern "C" size_t plas_decoder_infer_f32_workspace_bytes(const plas_dec_infer_desc* d) { return dec_infer_ws(*d).total; }
 
 extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream_) {
@@ -948,12 +1024,12 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
   PLAS_REQUIRE(d->B > 0 && d->Tm > 0 && d->V > 0 && d->max_steps >= 0, "dec_infer: bad shape");
   PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "dec_infer: n_layers=%d", d->n_layers);
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_infer: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
-  PLAS_REQUIRE(d->attention_type == PLAS_ATT_LUONG || d->attention_type == PLAS_ATT_BAHDANAU || d->attention_type == PLAS_ATT_LUONG_MONOTONIC,
-               "dec_infer: attention_type %d", d->attention_type);
-  if (d->attention_type == PLAS_ATT_LUONG_MONOTONIC) PLAS_REQUIRE(d->score_bias != nullptr, "dec_infer: luong_monotonic needs attention_score_bias");
+  PLAS_REQUIRE(d->attention_type >= PLAS_ATT_LUONG && d->attention_type <= PLAS_ATT_CUSTOM, "dec_infer: attention_type %d", d->attention_type);
+  if (att_is_mono(d->attention_type)) PLAS_REQUIRE(d->score_bias != nullptr, "dec_infer: monotonic attention needs attention_score_bias");
+  if (d->attention_type == PLAS_ATT_CUSTOM) PLAS_REQUIRE(d->w_query != nullptr, "dec_infer: custom attention needs its query_layer (and relu'd keys)");
   PLAS_REQUIRE(d->keys && d->values && d->mem_len && d->w_proj && d->b_proj && d->logits && d->sample_ids && d->seq_len && d->n_steps,
                "dec_infer: null tensor");
-  if (d->attention_type == PLAS_ATT_BAHDANAU) PLAS_REQUIRE(d->w_query && d->v_att, "dec_infer: bahdanau needs query_layer / attention_v");
+  if (att_is_bah(d->attention_type)) PLAS_REQUIRE(d->w_query && d->v_att, "dec_infer: bahdanau needs query_layer / attention_v");
   if (d->teacher_forced) PLAS_REQUIRE(d->forced_ids != nullptr, "dec_infer: teacher forcing needs forced_ids");
   const DecInferWs w = dec_infer_ws(*d);
   PLAS_REQUIRE(workspace_bytes >= w.total, "dec_infer: workspace %zu < %zu", workspace_bytes, w.total);
@@ -1045,6 +1121,7 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     q.w_query = d->w_query; q.v_att = d->v_att;
     q.pq = F(w.pq); q.s_pq = Ud;
     q.score_bias = d->score_bias; q.p_save = nullptr; q.s_ps = 0;
+    q.hard = d->attention_type == PLAS_ATT_BAHDANAU_MONOTONIC ? 1 : 0; q.noise_scale = 0.f; q.noise_seed = 0; q.noise_base = 0;
     if (d->alignment) {
       q.align = d->alignment + (size_t)t * Tm; q.s_al = (long long)S * Tm;
       q.align_prev = t > 0 ? d->alignment + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
@@ -1160,9 +1237,11 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
   PLAS_REQUIRE(d->keep_prob == 1.f, "dec_train: dropout with bottom_only is not built");
   PLAS_REQUIRE(d->att_layer == 0, "dec_train: attention_layer_size with bottom_only is not built");
-  if (d->attention_type == PLAS_ATT_BAHDANAU) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
+  const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
+
   int rc;
   if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud))) return rc;
+  if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
   if ((rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]))) return rc;
   PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
   for (int l = 0; l < L; ++l) {  // h_{-1}: zeros or the listener's final state (pass_hidden_state, las/model.py:259-267)
@@ -1212,9 +1291,11 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
         q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
         q.score_bias = d->score_bias; q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
         q.p_save = F(w.psave) + (size_t)t * Tm; q.s_ps = q.s_al;
+    q.hard = 0; q.noise_scale = d->attention_type == PLAS_ATT_BAHDANAU_MONOTONIC ? d->sigmoid_noise : 0.f;
+    q.noise_seed = d->noise_seed; q.noise_base = (long long)t * Tm;
         q.att = F(w.att) + (size_t)t * D; q.s_att = sd;
         q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
-        q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = nullptr;
+        q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = d->drop_step;  // (the noise seed follows the step)
         dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
       }
     }
@@ -1234,7 +1315,8 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers, NO = d->n_out;
-  const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
+  const bool bah = att_is_bah(d->attention_type);
+  const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
   const long long BS = (long long)B * S;
   const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud, sd = (long long)S * D;
   float* dctx = F(w.dctx);
@@ -1256,7 +1338,7 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
     PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
   }
-  const bool mono = d->attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  const bool mono = att_is_mono(d->attention_type);
   if (mono) {
     PLAS_REQUIRE(d->dscore_bias != nullptr, "dec_train_bwd: luong_monotonic needs dscore_bias");
     PLAS_CUDA(cudaMemsetAsync(F(w.dbias), 0, (size_t)B * 4, st));
@@ -1370,10 +1452,15 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   if (bah) {
     if ((rc = gemm(st, Ud, Ud, (int)BS, h0, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
     if ((rc = plas_colsum_f32(F(w.dv_acc), B, Ud, Ud, d->dv_att, 0, st))) return rc;
-  } else {
-    if ((rc = gemm(st, Tm, Ud, S, F(w.dscore), 1, Tm, h0, Ud, 1, F(w.dkeys), Ud, nullptr, 0.f, B, (long long)S * Tm, (long long)S * Ud,
-                   (long long)Tm * Ud)))
+  } else {  // dkeys[b] = dScore[b]^T Q[b], Q = the query the score read (custom: relu(query_layer(h)), saved in pq)
+    if ((rc = gemm(st, Tm, Ud, S, F(w.dscore), 1, Tm, custom ? F(w.pq) : h0, Ud, 1, F(w.dkeys), Ud, nullptr, 0.f, B, (long long)S * Tm,
+                   (long long)S * Ud, (long long)Tm * Ud)))
       return rc;
+    if (custom) {  // keys = relu(memory_layer(values)); dW_query = H^T dPQ
+      dec_relu_grad_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.dkeys), F(w.keys), (size_t)B * Tm * Ud);
+      PLAS_REQUIRE(d->dw_query != nullptr, "dec_train_bwd: custom attention needs dw_query");
+      if ((rc = gemm(st, Ud, Ud, (int)BS, h0, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
+    }
   }
   if ((rc = gemm(st, Tm, D, S, F(w.align), 1, Tm, dctx, D, 1, d->dmemory, D, nullptr, d->dmemory_accumulate ? 1.f : 0.f, B, (long long)S * Tm,
                  (long long)S * D, (long long)Tm * D)))
@@ -1403,11 +1490,14 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   const int A = d->att_layer > 0 ? d->att_layer : D;  // width of the attention vector (attention_layer_size or the context depth)
   if (d->att_layer > 0)
     PLAS_REQUIRE(d->w_att_layer && A % 4 == 0 && d->keep_prob == 1.f, "dec_train: attention_layer_size needs its kernel, A %% 4 == 0 and no dropout");
-  const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
+  const bool bah = att_is_bah(d->attention_type);
+  const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
   if (bah) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
   // keys = memory_layer(values); the memory is already zero past each length (the listener guarantees it)
   rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud);
   if (rc) return rc;
+  if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
+  if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
   // Z_0 = x_in W_0[0:E] + b_0 for every step at once
   rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]);
   if (rc) return rc;
@@ -1474,6 +1564,8 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
     q.score_bias = d->score_bias; q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
     q.p_save = F(w.psave) + (size_t)t * Tm; q.s_ps = q.s_al;
+    q.hard = 0; q.noise_scale = d->attention_type == PLAS_ATT_BAHDANAU_MONOTONIC ? d->sigmoid_noise : 0.f;
+    q.noise_seed = d->noise_seed; q.noise_base = (long long)t * Tm;
     if (d->att_layer > 0) { q.att = F(w.ctx) + (size_t)t * D; q.s_att = (long long)S * D; }
     else { q.att = F(w.att) + (size_t)t * D; q.s_att = (long long)S * D; }
     q.skip = nullptr;
@@ -1509,7 +1601,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers, NO = d->n_out;
-  const bool bah = d->attention_type == PLAS_ATT_BAHDANAU;
+  const bool bah = att_is_bah(d->attention_type);
+  const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
   const long long BS = (long long)B * S;
   float* dctx = F(w.dctx);  // [B][S][D]
   const int AL = d->att_layer;                 // attention_layer_size (0 = none)
@@ -1525,7 +1618,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
     PLAS_CUDA(cudaMemsetAsync(F(w.dv_acc), 0, (size_t)B * Ud * 4, st));
   }
-  const bool mono = d->attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  const bool mono = att_is_mono(d->attention_type);
   if (mono) {
     PLAS_REQUIRE(d->dscore_bias != nullptr, "dec_train_bwd: luong_monotonic needs dscore_bias");
     PLAS_CUDA(cudaMemsetAsync(F(w.dbias), 0, (size_t)B * 4, st));
@@ -1646,10 +1739,15 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     if ((rc = gemm(st, Ud, Ud, (int)BS, htop, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
     if ((rc = plas_colsum_f32(F(w.dv_acc), B, Ud, Ud, d->dv_att, 0, st))) return rc;
   } else {
-    // dkeys[b] = dScore[b]^T H_top[b]
-    if ((rc = gemm(st, Tm, Ud, S, F(w.dscore), 1, Tm, htop, Ud, 1, F(w.dkeys), Ud, nullptr, 0.f, B, (long long)S * Tm,
+    // dkeys[b] = dScore[b]^T Q[b], Q = the query the score read: H_top, or relu(query_layer(H_top)) (custom, saved in pq)
+    if ((rc = gemm(st, Tm, Ud, S, F(w.dscore), 1, Tm, custom ? F(w.pq) : htop, Ud, 1, F(w.dkeys), Ud, nullptr, 0.f, B, (long long)S * Tm,
                    (long long)S * Ud, (long long)Tm * Ud)))
       return rc;
+    if (custom) {  // keys = relu(memory_layer(values)); dW_query = H_top^T dPQ
+      dec_relu_grad_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.dkeys), F(w.keys), (size_t)B * Tm * Ud);
+      PLAS_REQUIRE(d->dw_query != nullptr, "dec_train_bwd: custom attention needs dw_query");
+      if ((rc = gemm(st, Ud, Ud, (int)BS, htop, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
+    }
   }
   // dvalues[b] = Align[b]^T dAtt[b]  (accumulated into the encoder-output gradient)
   if ((rc = gemm(st, Tm, D, S, F(w.align), 1, Tm, dctx, D, 1, d->dmemory, D, nullptr, d->dmemory_accumulate ? 1.f : 0.f, B,

@@ -39,13 +39,13 @@ class SpellerWeights:
             return
         if hp.get("embedding_size") or hp.get("beam_width"):
             raise NotImplementedError("embedding_size / beam_width != 0 are not built yet")
-        if hp.get("attention_layer_size"):
-            self._init_attention_layer(params, hp, enc_depth, precision, device, scope)
+        if hp["attention_type"] not in _lib.ATT_CODES:
+            raise NotImplementedError(f"attention_type={hp['attention_type']}")
+        if hp.get("attention_layer_size") or hp["attention_type"] in ("bahdanau_monotonic", "custom"):
+            self._init_attention_layer(params, hp, enc_depth, precision, device, scope)  # fp32 step-kernel decoder only
             return
         self.precision = precision
         self.att = hp["attention_type"]
-        if self.att not in _lib.ATT_CODES:
-            raise NotImplementedError(f"attention_type={self.att}")
         dt = _lib.torch_dtype(precision)
         self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
         D, Ud, V = self.D, self.Ud, self.V
@@ -75,7 +75,7 @@ class SpellerWeights:
             if self.tc:
                 self.w_cell_tc.append(up(packing.pack_cell_tc(rows, Ud)))
             self.b_cell.append(up(packing.pack_unit_major(bias, Ud), torch.float32))
-        self.w_query = self.v_att = None
+        self.w_query = self.v_att = self.score_bias_dev = None
         self.score_bias = 0.0
         if self.att == "bahdanau":
             self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
@@ -107,7 +107,7 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
         raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
     self.precision, self.att = precision, hp["attention_type"]
-    if self.att not in ("luong", "bahdanau", "luong_monotonic"):
+    if self.att not in _lib.ATT_CODES:
         raise NotImplementedError(f"--bottom_only with attention_type={self.att}")
     self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
     D, Ud, V = self.D, self.Ud, self.V
@@ -125,29 +125,42 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names],
                    w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]))
     self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"])
-    self.w_query = self.v_att = None
-    self.score_bias = 0.0
-    if self.att == "bahdanau":
-        self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
-        self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"])
-    elif self.att == "luong_monotonic":
-        self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
-        self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
+    _attention_params(self, params, pre, up, device)
     self.tc = False
 
 
+def _attention_params(self, params, pre, up, device):
+    """Attention-mechanism variables of the fp32 step-kernel decoder.  Scopes as tf.contrib.seq2seq names them under the
+    AttentionWrapper scope ``pre`` ([3P-recalled]): ``<type>_attention/{query_layer/kernel, attention_v,
+    attention_score_bias}``; CustomAttention (las/model.py:72-101) calls its own Dense 'query_layer' outside the luong scope."""
+    self.w_query = self.v_att = self.score_bias_dev = None
+    self.score_bias = 0.0
+    if self.att in ("bahdanau", "bahdanau_monotonic"):
+        self.w_query = up(params[f"{pre}/{self.att}_attention/query_layer/kernel"])
+        self.v_att = up(params[f"{pre}/{self.att}_attention/attention_v"])
+    elif self.att == "custom":
+        self.w_query = up(params[f"{pre}/query_layer/kernel"])
+    if self.att.endswith("_monotonic"):
+        self.score_bias = float(params[f"{pre}/{self.att}_attention/attention_score_bias"])
+        self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
+
+
 def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope):
-    """attention_layer_size = A (las/model.py:180-200): AttentionWrapper's Dense over [cell output; context]; the attention fed
-    back to cell 0 and read by the projection is A wide.  fp32 step-kernel decoder only."""
-    if precision != "fp32" or hp["attention_type"] not in ("luong", "bahdanau", "luong_monotonic"):
-        raise NotImplementedError("attention_layer_size is built for the fp32 step-kernel decoder with luong / bahdanau / luong_monotonic attention")
+    """The default wiring on the fp32 step-kernel decoder only: attention_layer_size = A (las/model.py:180-200: AttentionWrapper's
+    Dense over [cell output; context]; the attention fed back to cell 0 and read by the projection is A wide) and / or the
+    attention types the fused decoders do not carry (bahdanau_monotonic, custom)."""
+    if precision != "fp32":
+        raise NotImplementedError("attention_layer_size / bahdanau_monotonic / custom attention are built for the fp32 step-kernel decoder")
     self.precision, self.att = precision, hp["attention_type"]
     self.bottom_only = self.pass_hidden_state = False
     self.D, self.Ud, self.V, self.L = enc_depth, hp["decoder_units"], hp["target_vocab_size"], hp["decoder_layers"]
-    D, Ud, V, A = self.D, self.Ud, self.V, int(hp["attention_layer_size"])
+    has_layer = bool(hp.get("attention_layer_size"))
+    D, Ud, V = self.D, self.Ud, self.V
+    A = int(hp["attention_layer_size"]) if has_layer else D
     if Ud % 16 or D % 4 or A % 4:
-        raise NotImplementedError("attention_layer_size needs decoder_units % 16 == 0, encoder depth % 4 == 0 and A % 4 == 0")
-    self.A = A
+        raise NotImplementedError("the step-kernel decoder needs decoder_units % 16 == 0, encoder depth % 4 == 0 and A % 4 == 0")
+    if has_layer:
+        self.A = A
     up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device).contiguous()
     self.w_mem_t = up(np.asarray(params[f"{scope}/memory_layer/kernel"], np.float32).T)
     pre = f"{scope}/decoder/attention_wrapper"
@@ -155,18 +168,13 @@ def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope)
     kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
     assert kernels[0].shape == (V + A + Ud, 4 * Ud), kernels[0].shape
     self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names],
-                   w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]),
-                   w_att_layer=up(params[f"{pre}/attention_layer/kernel"]))
-    assert self.tf["w_att_layer"].shape == (Ud + D, A) and self.tf["w_proj"].shape == (A, V)
+                   w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]))
+    if has_layer:
+        self.tf["w_att_layer"] = up(params[f"{pre}/attention_layer/kernel"])
+        assert self.tf["w_att_layer"].shape == (Ud + D, A)
+    assert self.tf["w_proj"].shape == (A, V)
     self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"])
-    self.w_query = self.v_att = None
-    self.score_bias = 0.0
-    if self.att == "bahdanau":
-        self.w_query = up(params[f"{pre}/bahdanau_attention/query_layer/kernel"])
-        self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"])
-    elif self.att == "luong_monotonic":
-        self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
-        self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
+    _attention_params(self, params, pre, up, device)
     self.tc = False
 
 
@@ -197,6 +205,9 @@ def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=
     _lib.count_launches(1)
     if n_pad != w.Ud:
         keys = keys[:, :w.Ud].contiguous()
+    if w.att == "custom":  # CustomAttention: keys = relu(memory_layer(values)) (las/model.py:94)
+        _lib.check(L.plas_relu_f32(_lib.ptr(keys), keys.numel(), _lib.stream_ptr()))
+        _lib.count_launches(1)
     pv = None
     if w.tc and B <= 128:
         # PV = values x projection kernel (f32): the decoder forms logits as alignments . PV + bias
@@ -292,7 +303,7 @@ def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, f
     d.w_query = w.w_query.data_ptr() if w.w_query is not None else None
     d.v_att = w.v_att.data_ptr() if w.v_att is not None else None
     d.w_proj, d.b_proj = w.tf["w_proj"].data_ptr(), w.b_proj.data_ptr()
-    d.score_bias = w.score_bias_dev.data_ptr() if w.att == "luong_monotonic" else None
+    d.score_bias = w.score_bias_dev.data_ptr() if w.score_bias_dev is not None else None
     d.keys, d.values, d.mem_len = keys.data_ptr(), values.data_ptr(), mem_len.data_ptr()
     d.forced_ids = forced_ids.data_ptr() if forced_ids is not None else None
     d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()

@@ -83,6 +83,18 @@ def reference_sampling(hp, step, B, S, V, speller_index=0):
     return selected, (-np.log(-np.log(u.astype(np.float64)))).reshape(B, S, V)
 
 
+def reference_noise(hp, step, B, S, Tm, speller_index=0, scale=1.0):
+    """bahdanau_monotonic's TRAIN-mode score noise (las/model.py:161-162, sigmoid_noise = 1) as the device path draws it at
+    optimiser step ``step`` (test support): scale * N(0,1) [B,S,Tm], Box-Muller on two counter-hash uniforms (hash_normal in
+    csrc/train_dec.cu)."""
+    seed = drop_seed(int(hp.get("dropout_seed", 0)), step, SPELLER_TID + 10 * speller_index + 8)
+    n = B * S * Tm
+    u1 = (hash_u24(n, seed).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    u2 = (hash_u24(n, (seed + 1) & 0xFFFFFFFF).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    arg = (np.float32(6.283185307179586) * u2).astype(np.float64)
+    return (scale * np.sqrt(-2.0 * np.log(u1.astype(np.float64))) * np.cos(arg)).reshape(B, S, Tm)
+
+
 def dropout_(x, y, seed, keep_prob, step_dev=None):
     """y = x * mask(seed + step * 0x85EBCA77) / keep_prob on the device (plas_dropout_f32; ``step_dev`` = the TrainState's device
     step counter, None = 0); the same call on a gradient is the backward pass."""
@@ -381,8 +393,10 @@ class SpellerTrain:
         self.sample_prob = float(hp.get("sampling_probability", 0.0))
         if self.sample_prob > 0.0 and (scope != "speller" or E != n_out):
             raise NotImplementedError("training path: scheduled sampling is built for the phone speller only; set sampling_probability=0")
-        if hp["attention_type"] not in ("luong", "bahdanau", "luong_monotonic"):
+        if hp["attention_type"] not in _lib.ATT_CODES:
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
+        # bahdanau_monotonic in TRAIN mode: sigmoid_noise = 1.0 (las/model.py:161-162); tests may set 0 for a noise-free check
+        self.sigmoid_noise = 1.0 if hp["attention_type"] == "bahdanau_monotonic" else 0.0
         for flag in ("binf_projection", "embedding_size"):
             if hp.get(flag):
                 raise NotImplementedError(f"training path: --{flag} is not built")
@@ -422,12 +436,17 @@ class SpellerTrain:
         if self.att_layer:  # AttentionWrapper's attention_layer (las/model.py:180-200)
             al = f"{pre}/attention_layer/kernel"
             d.att_layer, d.w_att_layer, d.dw_att_layer = self.att_layer, st.w(al), st.g(al)
-        if hp["attention_type"] == "bahdanau":
-            q, v = f"{pre}/bahdanau_attention/query_layer/kernel", f"{pre}/bahdanau_attention/attention_v"
+        at = hp["attention_type"]
+        if at in ("bahdanau", "bahdanau_monotonic"):
+            q, v = f"{pre}/{at}_attention/query_layer/kernel", f"{pre}/{at}_attention/attention_v"
             d.w_query, d.v_att, d.dw_query, d.dv_att = st.w(q), st.w(v), st.g(q), st.g(v)
-        if hp["attention_type"] == "luong_monotonic":
-            sb = f"{pre}/luong_monotonic_attention/attention_score_bias"
+        elif at == "custom":  # CustomAttention's own query layer (las/model.py:92-93)
+            q = f"{pre}/query_layer/kernel"
+            d.w_query, d.dw_query = st.w(q), st.g(q)
+        if at.endswith("_monotonic"):
+            sb = f"{pre}/{at}_attention/attention_score_bias"
             d.score_bias, d.dscore_bias = st.w(sb), st.g(sb)
+            d.sigmoid_noise, d.noise_seed = self.sigmoid_noise, drop_seed(self.base, 0, self.tid + 8)
         pk, pb = f"{sc}/decoder/projection_layer/kernel", f"{sc}/decoder/projection_layer/bias"
         d.w_proj, d.b_proj, d.dw_proj, d.db_proj = st.w(pk), st.w(pb), st.g(pk), st.g(pb)
         d.memory, d.mem_len, d.x_in = memory.data_ptr(), mem_len.data_ptr(), x_in.data_ptr()

@@ -61,6 +61,12 @@ def variable_shapes(hp, num_channels=None):
         shapes[f"{pre}/bahdanau_attention/attention_v"] = (Ud,)
     elif at == "luong_monotonic":
         shapes[f"{pre}/luong_monotonic_attention/attention_score_bias"] = ()
+    elif at == "bahdanau_monotonic":  # scopes [3P-recalled] like the others
+        shapes[f"{pre}/bahdanau_monotonic_attention/query_layer/kernel"] = (Ud, Ud)
+        shapes[f"{pre}/bahdanau_monotonic_attention/attention_v"] = (Ud,)
+        shapes[f"{pre}/bahdanau_monotonic_attention/attention_score_bias"] = ()
+    elif at == "custom":              # CustomAttention's own Dense 'query_layer' (las/model.py:92-93)
+        shapes[f"{pre}/query_layer/kernel"] = (Ud, Ud)
     if hp.get("attention_layer_size"):  # AttentionWrapper's Dense over [cell output; context], no bias (las/model.py:180-200)
         shapes[f"{pre}/attention_layer/kernel"] = (Ud + D, A)
     if bottom and Ld > 1:
@@ -86,8 +92,8 @@ def init_params(hp, num_channels=None, seed=4321, projection_scale=1.0, bias_sca
                 w = w * projection_scale
         elif name.endswith("/bias"):
             w = rng.uniform(-bias_scale, bias_scale, size=shape) if bias_scale else np.zeros(shape)
-        elif name.endswith("attention_score_bias"):
-            w = np.zeros(shape)
+        elif name.endswith("attention_score_bias"):  # TF initialises it to 0; non-zero with bias_scale to exercise it
+            w = rng.uniform(-bias_scale, bias_scale, size=shape) if bias_scale else np.zeros(shape)
         elif name.endswith("attention_v"):
             lim = np.sqrt(6.0 / (shape[0] + 1))
             w = rng.uniform(-lim, lim, size=shape)

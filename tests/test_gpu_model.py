@@ -97,7 +97,8 @@ def test_true_las_configuration_end_to_end():
 
 
 @gpu
-@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("bf16", "bahdanau"), ("bf16", "luong_monotonic")])
+@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("bf16", "bahdanau"), ("bf16", "luong_monotonic"), ("fp32", "custom"),
+                                           ("fp32", "bahdanau_monotonic")])
 def test_empty_and_single_frame_utterances_do_not_disturb_the_batch(precision, att):
     """Ragged edge cases: an empty waveform (librosa still emits its one reflect-padded frame) and a one-frame utterance in the
     batch; the other utterances must decode exactly as they do without them."""

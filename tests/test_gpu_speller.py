@@ -15,6 +15,12 @@ CONFIGS = [
     ("fp32", "bahdanau", 5, 14, 16, 32, 2, 20),
     ("fp32", "luong_monotonic", 4, 11, 16, 16, 2, 12),
     ("fp32", "luong", 8, 30, 64, 256, 1, 64),
+    # attention types carried by the fp32 step-kernel decoder only: CustomAttention and bahdanau_monotonic,
+    # which the reference runs in mode='hard' outside TRAIN (las/model.py:159-164)
+    ("fp32", "custom", 5, 14, 16, 32, 2, 20),
+    ("fp32", "custom", 8, 30, 64, 256, 1, 64),
+    ("fp32", "bahdanau_monotonic", 5, 14, 16, 32, 2, 20),
+    ("fp32", "bahdanau_monotonic", 8, 30, 64, 256, 1, 64),
     ("bf16", "luong", 3, 9, 16, 32, 1, 12),
     ("bf16", "bahdanau", 16, 24, 32, 128, 2, 64),
     ("bf16", "luong_monotonic", 7, 17, 16, 64, 2, 30),
@@ -90,7 +96,8 @@ def test_greedy_parity(cfg):
 
 
 @gpu
-@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("fp32", "bahdanau"), ("bf16", "luong_monotonic"), ("fp32", "luong_monotonic")])
+@pytest.mark.parametrize("precision,att", [("fp32", "luong"), ("fp32", "bahdanau"), ("bf16", "luong_monotonic"), ("fp32", "luong_monotonic"),
+                                           ("fp32", "custom"), ("fp32", "bahdanau_monotonic")])
 def test_teacher_forced_parity(precision, att):
     import torch
     from phones_las_b200.speller import speller
@@ -187,7 +194,9 @@ def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0):
 @pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,pass_state", [("luong", 4, 11, 16, 32, 1, 12, False), ("luong", 5, 13, 16, 32, 2, 14, False),
                                                            ("bahdanau", 6, 17, 16, 48, 3, 20, False), ("luong", 5, 12, 32, 32, 2, 16, True),
                                                            ("bahdanau", 35, 21, 16, 16, 2, 18, True),
-                                                           ("luong_monotonic", 5, 13, 16, 32, 2, 14, False)])
+                                                           ("luong_monotonic", 5, 13, 16, 32, 2, 14, False),
+                                                           ("custom", 5, 13, 16, 32, 2, 14, False),
+                                                           ("bahdanau_monotonic", 6, 15, 32, 32, 3, 14, True)])
 def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, pass_state):
     import torch
     from phones_las_b200.speller import speller
@@ -215,7 +224,8 @@ def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm,
 
 @gpu
 @pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,A", [("luong", 4, 11, 16, 32, 1, 12, 24), ("bahdanau", 6, 17, 16, 48, 2, 20, 40),
-                                                   ("luong", 34, 9, 16, 16, 2, 14, 8), ("luong_monotonic", 4, 11, 16, 32, 2, 12, 24)])
+                                                   ("luong", 34, 9, 16, 16, 2, 14, 8), ("luong_monotonic", 4, 11, 16, 32, 2, 12, 24),
+                                                   ("custom", 4, 11, 16, 32, 2, 12, 24), ("bahdanau_monotonic", 5, 12, 16, 32, 1, 12, 16)])
 def test_attention_layer_size_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, A):
     """attention_layer_size = A (las/model.py:180-200): attention = Dense([cell output; context]); fed back and projected A wide."""
     import torch

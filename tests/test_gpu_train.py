@@ -88,7 +88,19 @@ SPELLER_CFGS = [("luong", 3, 9, 16, 32, 1, 12, 5), ("bahdanau", 5, 14, 16, 32, 2
                 ("luong", 3, 200, 512, 512, 1, 20, 3), ("bahdanau", 2, 190, 512, 512, 2, 12, 3),
                 # luong_monotonic: the alignments are a recurrent state (small, 4-CTA cluster and streaming attention paths)
                 ("luong_monotonic", 5, 14, 16, 32, 2, 20, 7), ("luong_monotonic", 33, 30, 64, 256, 1, 64, 11),
-                ("luong_monotonic", 3, 200, 512, 512, 1, 20, 3)]
+                ("luong_monotonic", 3, 200, 512, 512, 1, 20, 3),
+                # CustomAttention (relu keys + relu query layer) and bahdanau_monotonic (TRAIN: score noise, replayed by the oracle)
+                ("custom", 5, 14, 16, 32, 2, 20, 7), ("custom", 33, 30, 64, 256, 1, 64, 11), ("custom", 3, 200, 512, 512, 1, 20, 3),
+                ("bahdanau_monotonic", 5, 14, 16, 32, 2, 20, 7), ("bahdanau_monotonic", 8, 20, 64, 256, 1, 30, 6),
+                ("bahdanau_monotonic", 2, 190, 512, 512, 2, 12, 3)]
+
+
+def _score_noise(hp, step):
+    """bahdanau_monotonic adds N(0,1) to the scores in TRAIN mode: the oracle replays the device's deviates."""
+    if hp["attention_type"] != "bahdanau_monotonic":
+        return None
+    from phones_las_b200.train import reference_noise
+    return lambda B, S, Tm: reference_noise(hp, step, B, S, Tm)
 
 
 def _set_score_bias(params, value=-0.6):
@@ -117,10 +129,11 @@ def test_speller_forward_backward(att, B, Tm, U, Ud, Ld, V, S):
     tp = _tp(params)
     enc_t = torch.tensor(enc, dtype=torch.float64, requires_grad=True)
     x64 = torch.nn.functional.one_hot(torch.tensor(ids), V).to(torch.float64)
-    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp)
+    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp, score_noise=_score_noise(hp, 3))
     dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
     (ref * dref).sum().backward()
     st = TrainState(params)
+    st.step = 3
     sp = SpellerTrain(st, hp, "speller", V, V)
     logits = sp.forward(torch.from_numpy(enc).cuda(), torch.from_numpy(lens).cuda(), x64.float().cuda())
     assert scaled_err(logits, ref.detach()) < 1e-5
@@ -311,7 +324,7 @@ def test_listener_with_dropout():
 
 
 @gpu
-@pytest.mark.parametrize("att,Ld", [("luong", 1), ("bahdanau", 3), ("luong_monotonic", 2)])
+@pytest.mark.parametrize("att,Ld", [("luong", 1), ("bahdanau", 3), ("luong_monotonic", 2), ("custom", 2), ("bahdanau_monotonic", 1)])
 def test_speller_with_dropout(att, Ld):
     import torch
     from phones_las_b200 import train as tr
@@ -333,7 +346,7 @@ def test_speller_with_dropout(att, Ld):
     tp = _tp(params)
     enc_t = torch.tensor(enc, dtype=torch.float64, requires_grad=True)
     x64 = torch.nn.functional.one_hot(torch.tensor(ids), V).to(torch.float64)
-    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp, masks=masks)
+    ref = lt.speller_train(enc_t, torch.tensor(lens.astype(np.int64)), x64, tp, hp, masks=masks, score_noise=_score_noise(hp, 2))
     dref = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2), dtype=torch.float64)
     (ref * dref).sum().backward()
     sp = tr.SpellerTrain(st, hp, "speller", V, V)
@@ -441,7 +454,8 @@ def test_checkpoint_save_restore_resumes_training_identically(tmp_path):
 @gpu
 @pytest.mark.parametrize("att,B,T,U,Ud,Ld,ps", [("luong", 5, 40, 16, 32, 1, False), ("luong", 6, 44, 16, 32, 2, False),
                                                   ("bahdanau", 4, 36, 16, 48, 3, False), ("luong", 7, 40, 32, 32, 2, True),
-                                                  ("bahdanau", 34, 30, 16, 16, 2, True), ("luong_monotonic", 6, 44, 32, 32, 2, True)])
+                                                  ("bahdanau", 34, 30, 16, 16, 2, True), ("luong_monotonic", 6, 44, 32, 32, 2, True),
+                                                  ("custom", 6, 44, 16, 32, 2, False), ("bahdanau_monotonic", 5, 44, 32, 32, 2, True)])
 def test_train_step_bottom_only_and_pass_hidden_state(att, B, T, U, Ud, Ld, ps):
     """Whole forward + backward with the AttentionMultiCell wiring; with pass_hidden_state the decoder cells start from the
     listener's final states and their gradients flow back into the listener's BPTT."""
@@ -456,7 +470,8 @@ def test_train_step_bottom_only_and_pass_hidden_state(att, B, T, U, Ud, Ld, ps):
     tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
     tp = _tp(params)
     rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
-    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp)
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp,
+                                        score_noise=_score_noise(hp, 0))
     ref_loss.backward()
     st = tr.TrainState(params)
     feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
@@ -572,7 +587,7 @@ def test_tiny_batches_and_sequences_train(B, T, S):
 
 @gpu
 @pytest.mark.parametrize("att,Ld,A,sampling", [("luong", 1, 24, 0.0), ("bahdanau", 2, 40, 0.0), ("luong", 2, 16, 0.4),
-                                                 ("luong_monotonic", 2, 24, 0.3)])
+                                                 ("luong_monotonic", 2, 24, 0.3), ("custom", 2, 24, 0.0), ("bahdanau_monotonic", 1, 16, 0.3)])
 def test_train_step_attention_layer_size(att, Ld, A, sampling):
     """attention_layer_size = A in training: attention = Dense([h_top; context]) fed back A wide; forward, gradients (including
     the attention layer's kernel), optionally with scheduled sampling on top."""
@@ -592,7 +607,7 @@ def test_train_step_attention_layer_size(att, Ld, A, sampling):
     tp = _tp(params)
     rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
     ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp,
-                                        sampling=sampling_rng)
+                                        sampling=sampling_rng, score_noise=_score_noise(hp, 2))
     ref_loss.backward()
     feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
     labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),

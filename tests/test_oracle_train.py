@@ -25,7 +25,7 @@ def test_listener_matches_numpy_oracle():
 
 
 def test_teacher_forced_matches_numpy_oracle():
-    for att, Ld in (("luong", 1), ("bahdanau", 2), ("luong_monotonic", 2)):
+    for att, Ld in (("luong", 1), ("bahdanau", 2), ("luong_monotonic", 2), ("custom", 2)):
         hp = create_hparams(target_vocab_size=11, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=Ld,
                             num_channels=4, attention_type=att)
         params = weights.init_params(hp, seed=5, bias_scale=0.1)
@@ -150,7 +150,7 @@ def test_general_listener_matches_numpy_oracle():
 
 def test_bottom_only_teacher_forced_matches_numpy_oracle():
     """The differentiable restatement of the AttentionMultiCell wiring (+ pass_hidden_state) vs the numpy oracle."""
-    for att, Ld, ps in (("luong", 2, True), ("bahdanau", 3, False), ("luong", 1, False), ("luong_monotonic", 2, False)):
+    for att, Ld, ps in (("luong", 2, True), ("bahdanau", 3, False), ("luong", 1, False), ("luong_monotonic", 2, False), ("custom", 2, False)):
         hp = create_hparams(target_vocab_size=11, encoder_layers=2, encoder_units=8, decoder_units=8, decoder_layers=Ld,
                             num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=ps)
         params = weights.init_params(hp, seed=5, bias_scale=0.1)
@@ -180,3 +180,37 @@ def test_monotonic_attention_is_the_recursive_definition():
         q = (q * (1 - p[:, i - 1]) if i else q) + prev[:, i]
         assert torch.allclose(a[:, i], p[:, i] * q, atol=1e-12)
     assert (a.sum(1) <= 1 + 1e-9).all()
+
+
+def test_hard_monotonic_attention_is_first_active_frame_at_or_after_the_previous_one():
+    """bahdanau_monotonic outside TRAIN (mode='hard', las/model.py:163-164): the alignment is a one-hot at the first frame
+    >= the previously attended one whose biased score is positive (inside the utterance), or all zero when there is none."""
+    hp = create_hparams(target_vocab_size=9, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=1,
+                        num_channels=4, attention_type="bahdanau_monotonic")
+    params = weights.init_params(hp, seed=2, bias_scale=0.2)
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(5)
+    B, Tm = 6, 12
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.array([12, 7, 9, 12, 3, 10], np.int32)
+    att = ol.Attention("bahdanau_monotonic", enc, lens, params, "speller")
+    pre = "speller/decoder/attention_wrapper/bahdanau_monotonic_attention"
+    prev = att.initial_alignments()
+    assert (prev[:, 0] == 1).all() and prev.sum() == B
+    seen_move = False
+    for step in range(6):
+        q = rng.uniform(-2, 2, (B, 16)).astype(np.float32)
+        a = att(q, prev)
+        score = np.einsum("btu,u->bt", np.tanh(att.keys + (q @ params[pre + "/query_layer/kernel"])[:, None, :]),
+                          params[pre + "/attention_v"]) + params[pre + "/attention_score_bias"]
+        for b in range(B):
+            want = np.zeros(Tm, np.float32)
+            if prev[b].any():
+                k = int(prev[b].argmax())
+                hits = [i for i in range(k, int(lens[b])) if score[b, i] > 0]
+                if hits:
+                    want[hits[0]] = 1.0
+                    seen_move |= hits[0] > k
+            np.testing.assert_array_equal(a[b], want)
+        prev = a
+    assert seen_move
