@@ -92,8 +92,8 @@ def init_params(hp, num_channels=None, seed=4321, projection_scale=1.0, bias_sca
                 w = w * projection_scale
         elif name.endswith("/bias"):
             w = rng.uniform(-bias_scale, bias_scale, size=shape) if bias_scale else np.zeros(shape)
-        elif name.endswith("attention_score_bias"):  # TF initialises it to 0; non-zero with bias_scale to exercise it
-            w = rng.uniform(-bias_scale, bias_scale, size=shape) if bias_scale else np.zeros(shape)
+        elif name.endswith("attention_score_bias"):
+            w = np.zeros(shape)
         elif name.endswith("attention_v"):
             lim = np.sqrt(6.0 / (shape[0] + 1))
             w = rng.uniform(-lim, lim, size=shape)

@@ -37,10 +37,18 @@ CONFIGS = [
 ]
 
 
+def _score_bias(params, value=0.25):
+    """attention_score_bias is initialised to 0 (as TF does): give the monotonic mechanisms a non-zero one."""
+    for k in params:
+        if k.endswith("attention_score_bias"):
+            params[k] = np.float32(value)
+    return params
+
+
 def _setup(precision, att, B, Tm, U, Ud, Ld, V, seed=0):
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud,
                         decoder_layers=Ld, num_channels=4, attention_type=att)
-    params = weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1)
+    params = _score_bias(weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1))
     D = weights.encoder_output_depth(hp)
     rng = np.random.default_rng(seed + B)
     enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
@@ -179,7 +187,7 @@ def test_decoder_full_width_deterministic_and_first_steps(att, Tm):
 def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0):
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
                         num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=pass_state)
-    params = weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1)
+    params = _score_bias(weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1))
     D = weights.encoder_output_depth(hp)
     rng = np.random.default_rng(seed + B)
     enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
@@ -232,7 +240,7 @@ def test_attention_layer_size_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V
     from phones_las_b200.speller import speller
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
                         num_channels=4, attention_type=att, attention_layer_size=A)
-    params = weights.init_params(hp, seed=Ud + A, projection_scale=8.0, bias_scale=0.1)
+    params = _score_bias(weights.init_params(hp, seed=Ud + A, projection_scale=8.0, bias_scale=0.1))
     D = weights.encoder_output_depth(hp)
     assert params["speller/decoder/attention_wrapper/attention_layer/kernel"].shape == (Ud + D, A)
     assert params["speller/decoder/projection_layer/kernel"].shape == (A, V)

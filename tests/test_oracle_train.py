@@ -188,6 +188,7 @@ def test_hard_monotonic_attention_is_first_active_frame_at_or_after_the_previous
     hp = create_hparams(target_vocab_size=9, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=1,
                         num_channels=4, attention_type="bahdanau_monotonic")
     params = weights.init_params(hp, seed=2, bias_scale=0.2)
+    params["speller/decoder/attention_wrapper/bahdanau_monotonic_attention/attention_score_bias"] = np.float32(0.15)
     D = weights.encoder_output_depth(hp)
     rng = np.random.default_rng(5)
     B, Tm = 6, 12
