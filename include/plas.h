@@ -315,6 +315,12 @@ typedef struct plas_dec_train_desc {
    * come from the counter hash with seed noise_seed (+ drop_step), so the oracle can replay them (train.reference_noise) */
   float sigmoid_noise;
   uint32_t noise_seed;
+  /* --binf_projection (las/model.py:180-183,251-257; utils/training_helper.py:17-27,122-153): the projection is the constant
+   * [M; 1 - M] (w_proj; b_proj = zeros; dw_proj = db_proj = NULL) applied to the 2n-wide attention vectors; the regulariser
+   * compute_log_probs_loss reads those vectors (att_out, fwd out [B][S][A], optional) and its gradient enters through
+   * datt_extra (bwd in [B][S][A], optional).  Default wiring only. */
+  float* att_out;
+  const float* datt_extra;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);
@@ -367,6 +373,10 @@ int plas_sigmoid_ce_grad(const float* logits, const float* labels, const float* 
                          int32_t n_feat, float gscale, float* ce_tokens, float* out3, float* dlogits,
                          plas_stream_t stream);
 /* per-utterance CTC loss [B] and dlogits [B][T][C] = gscale * d(loss[b])/d(logits[b]) (zero for t >= logit_len) */
+/* compute_log_probs_loss (model_helper.py:132-146) and its gradient: att [n_rows][2 n_feat] = [log p1 | log p0];
+ * out3[0] = weight * mean(|p1 + p0 - 1| + relu(log p1) + relu(log p0)); datt = d(out3[0]) / d(att); reg_rows [n_rows] scratch. */
+int plas_log_probs_reg_grad(const float* att, int64_t n_rows, int32_t n_feat, float weight, float* reg_rows, float* out3,
+                            float* datt, plas_stream_t stream);
 size_t plas_ctc_grad_workspace_bytes(int32_t B, int32_t T, int32_t Lmax);
 int plas_ctc_grad(const float* logits, const int32_t* labels, const int32_t* label_len, const int32_t* logit_len,
                   int32_t B, int32_t T, int32_t C, int32_t Lmax, int32_t blank, float gscale, float* loss,

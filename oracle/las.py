@@ -242,7 +242,7 @@ class Speller:
     NEW attention, every upper cell reads [previous output; OLD attention]; the decoder output is the top cell's h), with
     ``pass_hidden_state`` (las/model.py:259-267: cell l starts from the listener's final state l = fw, bw)."""
 
-    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller", encoder_state=None):
+    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller", encoder_state=None, binf=None):
         self.q = _q(precision)
         self.hp = hp
         self.scope = scope
@@ -269,6 +269,13 @@ class Speller:
         self.wal = self.q(params[al]) if (hp.get("attention_layer_size") and not self.bottom_only) else None
         self.wp = self.q(params[f"{scope}/decoder/projection_layer/kernel"])
         self.bp = params[f"{scope}/decoder/projection_layer/bias"].astype(F32)
+        # --binf_projection (las/model.py:240-241,251-257): ``binf`` = binf2phone [n, V]; the decoder is fed the binary-feature
+        # column of the previous phone, the 2n-wide attention vector is read as [log p1 | log p0] and mapped to phone scores by
+        # transform_binf_to_phones (DenseBinfDecoder with inner_projection_layer=False: its Dense variables are never used)
+        self.binf = None if binf is None else np.asarray(binf, F32)
+        if self.binf is not None:
+            assert hp.get("binf_projection") and not self.bottom_only and self.wal is not None
+            assert self.wal.shape[1] == 2 * self.binf.shape[0], "attention_layer_size must be 2 * binf_count (las/model.py:180-183)"
         self.enc_len = np.asarray(enc_len)
 
     def zero_state(self):
@@ -299,7 +306,11 @@ class Speller:
         attention = q(context)  # the recurrent feedback copy of the attention vector is rounded ...
         # ... while the projection consumes the f32 context (fp32 mode: q is the identity, so this is
         # exactly DenseBinfDecoder(attention); bf16 mode: one rounding point fewer)
-        logits = (context.astype(F32) @ self.wp + self.bp).astype(F32)
+        if self.binf is not None:  # utils/training_helper.py:17-27
+            n = self.binf.shape[0]
+            logits = (context[:, :n] @ self.binf + context[:, n:2 * n] @ (F32(1) - self.binf)).astype(F32)
+        else:
+            logits = (context.astype(F32) @ self.wp + self.bp).astype(F32)
         return logits, dict(cells=new_cells, attention=attention, alignments=align)
 
     def _step_bottom_only(self, x, state):
@@ -325,6 +336,9 @@ class Speller:
         return logits, dict(cells=new_cells, attention=q(context), alignments=align)
 
     def one_hot(self, ids):
+        """embedding_fn (las/model.py:228-246): one-hot ids, or the phone's binary-feature column under --binf_projection."""
+        if self.binf is not None:
+            return np.ascontiguousarray(self.binf.T[ids])
         return np.eye(self.V, dtype=F32)[ids]
 
     def greedy(self):

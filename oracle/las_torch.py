@@ -130,14 +130,17 @@ def monotonic_attention(p_choose, previous):
 
 
 def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None, sampling=None,
-                  fed_inputs=None, score_noise=None):
+                  fed_inputs=None, score_noise=None, binf=None, attention_out=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
     binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
     ``masks``: input-dropout multipliers of the decoder cells: 'x' [B,L,E] and 'att' [B,L,D] (slot t multiplies
     attention_{t-1}) for cell 0's input [x_t; attention_{t-1}], ('h', l) [B,L,Ud] for the output of layer l feeding l+1.
     ``score_noise`` [B,L,Tm]: bahdanau_monotonic in TRAIN mode adds sigmoid_noise * N(0,1) to the scores (las/model.py:161-162);
     the caller passes the (already scaled) deviates -- or a callable (B, L, Tm) -> deviates -- so that the stochastic op is
-    replayed exactly (None = no noise)."""
+    replayed exactly (None = no noise).
+    ``binf`` [n, V] (--binf_projection, las/model.py:251-257): the projection is transform_binf_to_phones of the 2n-wide attention
+    vector instead of the Dense layer; the attention vectors [B,L,2n] are appended to the list ``attention_out`` (they feed
+    compute_log_probs_loss, model_helper.py:243-245,330-331)."""
     B, Tm, D = enc_out.shape
     if callable(score_noise):
         score_noise = score_noise(B, dec_inputs.shape[1], Tm)
@@ -241,7 +244,13 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
         attention = torch.einsum("bt,btd->bd", align, values)
         if w_al is not None:  # attention_layer_size: attention = Dense([cell output; context]), no bias
             attention = torch.cat([inp, attention], 1) @ w_al
-        logits.append(attention @ wp + bp)
+        if attention_out is not None:
+            attention_out.append(attention)
+        if binf is not None:  # utils/training_helper.py:17-27
+            nb = binf.shape[0]
+            logits.append(attention[:, :nb] @ binf + attention[:, nb:2 * nb] @ (1 - binf))
+        else:
+            logits.append(attention @ wp + bp)
         maybe_sample(t, logits[-1])
     return torch.stack(logits, 1)
 
@@ -256,6 +265,15 @@ def sequence_loss_sigmoid(logits, targets, weights):
     x, z = logits, targets
     ce = (torch.clamp(x, min=0) - x * z + torch.log1p(torch.exp(-x.abs()))).mean(-1)
     return (ce * weights).sum() / (weights.sum() + 1e-12)
+
+
+def compute_log_probs_loss(outputs):
+    """model_helper.py:132-146 (the normalisation constant carries no gradient: tf.stop_gradient)."""
+    n = outputs.shape[-1] // 2
+    l1, l0 = outputs[..., :n], outputs[..., n:2 * n]
+    c = (-(l1 + l0) / 2).detach()
+    loss = ((torch.exp(l1 + c) + torch.exp(l0 + c)) / torch.exp(c) - 1).abs() + torch.relu(l1) + torch.relu(l0)
+    return loss.mean()
 
 
 def ctc_loss(logits, labels, label_length, logit_length, blank=0):
@@ -300,7 +318,18 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sam
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits
         loss = loss + parts["ce"]
-    if hp.get("binary_outputs"):
+    if hp.get("binary_outputs") and hp.get("binf_projection"):
+        # model_helper.py:221-227 (phone ids in, embedded as binary-feature columns), :243-245 (raw attention split off),
+        # :326-331 (softmax CE on the transformed logits + the log-probability regulariser)
+        M = torch.as_tensor(binf, dtype=dt)
+        atts = []
+        logits_b = speller_train(enc_out, enc_len, M.t()[tin.long()], params, hp, scope="speller_binf",
+                                 masks=masks.get("speller_binf"), encoder_state=enc_state, binf=M, attention_out=atts)
+        parts["ce_binf"] = sequence_loss(logits_b, tout, w)
+        parts["log_probs_reg"] = compute_log_probs_loss(torch.stack(atts, 1))
+        parts["logits_binf"] = logits_b
+        loss = loss + parts["ce_binf"] + parts["log_probs_reg"] * hp.get("binf_projection_reg_weight", 1.0)
+    elif hp.get("binary_outputs"):
         bt = torch.as_tensor(binf, dtype=dt).t()  # [V, n]
         logits_b = speller_train(enc_out, enc_len, bt[tin.long()], params, hp, scope="speller_binf",
                                  masks=masks.get("speller_binf"), encoder_state=enc_state)

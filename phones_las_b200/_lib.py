@@ -77,7 +77,7 @@ class DecTrainDesc(C.Structure):
                 ("sample_prob", C.c_float), ("sample_seed", C.c_uint32), ("xdrop_seed", C.c_uint32), ("_pad2", C.c_uint32),
                 ("x_in_rw", C.c_void_p), ("w_att_layer", C.c_void_p), ("dw_att_layer", C.c_void_p), ("att_layer", C.c_int32),
                 ("_pad3", C.c_int32), ("score_bias", C.c_void_p), ("dscore_bias", C.c_void_p),
-                ("sigmoid_noise", C.c_float), ("noise_seed", C.c_uint32)]
+                ("sigmoid_noise", C.c_float), ("noise_seed", C.c_uint32), ("att_out", C.c_void_p), ("datt_extra", C.c_void_p)]
 
 
 class DecInferDesc(C.Structure):
@@ -112,6 +112,7 @@ EXPORTS = {
     "plas_rec_workspace_bytes": (C.c_size_t, [C.POINTER(RecDesc)]),
     "plas_bilstm_rec_fwd": (C.c_int, [C.POINTER(RecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_relu_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "plas_log_probs_reg_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "plas_decoder_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
     "plas_decoder_fwd": (C.c_int, [C.POINTER(DecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_seq_ce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

@@ -600,6 +600,7 @@ struct CellBwdArgs {
   const float* dq; long long s_dq;       // top layer: gradient wrt the query (NULL otherwise)
   const float* dh_next; long long s_dn;  // h-part of dinp of this layer from step t+1 (NULL at t == S-1)
   const float* dh_above; long long s_da; // in1-part of dinp of the layer above, same step (NULL for the top layer)
+  const float* dh_extra; long long s_dx; // a further, never dropped-out reader of h (the attention layer's h part) or NULL
   long long idx_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask of this layer's h feeding the layer above
 };
 
@@ -611,6 +612,7 @@ __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
   float dh = 0.f;
   if (p.dq) dh += p.dq[(long long)b * p.s_dq + u];
   if (p.dh_next) dh += p.dh_next[(long long)b * p.s_dn + u];
+  if (p.dh_extra) dh += p.dh_extra[(long long)b * p.s_dx + u];
   if (p.dh_above) {
     float ga = p.dh_above[(long long)b * p.s_da + u];
     if (p.inv_keep != 1.f) ga *= drop_scale((uint64_t)((long long)b * p.s_c + p.idx_base + u), p.seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL, p.thresh, p.inv_keep);
@@ -630,13 +632,22 @@ __global__ void __launch_bounds__(256) dec_cell_bwd_kernel(CellBwdArgs p) {
   p.dc_carry[(size_t)b * Ud + u] = dc * gf;
 }
 
-// dst[b][i] = a[b][i] + (c ? c[b][i] : 0) on strided rows (assembles the gradient wrt the attention vector)
+// dst[b][i] = (a ? a[b][i] : 0) + (c ? m[b][i] c[b][i] : 0) on strided rows; m = the input-dropout multiplier of element
+// b * s_mask + mask_base + i (1 when inv_keep == 1).  Assembles the gradient wrt the attention vector (a = datt_t, c = cell 0's
+// input gradient of step t+1) and, with a = NULL, writes the dropped-out copy of attention_t that step t+1 reads.
 __global__ void dec_add_rows_kernel(float* __restrict__ dst, long long s_dst, const float* __restrict__ a, long long s_a,
-                                    const float* __restrict__ c, long long s_c, int B, int n) {
+                                    const float* __restrict__ c, long long s_c, int B, int n, long long s_mask = 0, long long mask_base = 0,
+                                    unsigned seed = 0, unsigned thresh = 0, float inv_keep = 1.f, const unsigned* step_ptr = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n) return;
   const int b = i / n, k = i - b * n;
-  dst[(long long)b * s_dst + k] = a[(long long)b * s_a + k] + (c ? c[(long long)b * s_c + k] : 0.f);
+  float v = a ? a[(long long)b * s_a + k] : 0.f;
+  if (c) {
+    float g = c[(long long)b * s_c + k];
+    if (inv_keep != 1.f) g *= drop_scale((uint64_t)((long long)b * s_mask + mask_base + k), seed + (step_ptr ? *step_ptr : 0u) * DROP_STEP_MUL, thresh, inv_keep);
+    v += g;
+  }
+  dst[(long long)b * s_dst + k] = v;
 }
 
 // dinp[b][k] = sum_n dz[b][n] W[k][n], k in [0, K): lane = batch row, CTA = 8 consecutive k, warps split n
@@ -1370,6 +1381,7 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
       c.dh_next = last ? nullptr : dinp(l, t + 1) + Kin(l); c.s_dn = Kin(l) + Ud;
       // the layer above reads this layer's h as its first input segment -- except above cell 0, whose output is the attention
       c.dh_above = (l >= 1 && l < L - 1) ? dinp(l + 1, t) : nullptr; c.s_da = Kin(l + 1 < L ? l + 1 : l) + Ud;
+      c.dh_extra = nullptr; c.s_dx = 0;
       c.idx_base = 0; c.seed = 0; c.thresh = 0; c.inv_keep = 1.f; c.step_ptr = nullptr;
       dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
       GemvTArgs g;
@@ -1489,7 +1501,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
   const int A = d->att_layer > 0 ? d->att_layer : D;  // width of the attention vector (attention_layer_size or the context depth)
   if (d->att_layer > 0)
-    PLAS_REQUIRE(d->w_att_layer && A % 4 == 0 && d->keep_prob == 1.f, "dec_train: attention_layer_size needs its kernel, A %% 4 == 0 and no dropout");
+    PLAS_REQUIRE(d->w_att_layer && A % 4 == 0, "dec_train: attention_layer_size needs its kernel and A %% 4 == 0");
   const bool bah = att_is_bah(d->attention_type);
   const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
   if (bah) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
@@ -1578,14 +1590,16 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       if ((rc = gemm(st, B, A, D, F(w.ctx) + (size_t)t * D, (long long)S * D, 1, d->w_att_layer + (size_t)Ud * A, A, 1, att_t, (long long)S * A,
                      nullptr, 1.f)))
         return rc;
-      if (t + 1 < S)
-        PLAS_CUDA(cudaMemcpy2DAsync(F(w.att_prev) + (size_t)(t + 1) * A, (size_t)S * A * 4, att_t, (size_t)S * A * 4, (size_t)A * 4, B,
-                                    cudaMemcpyDeviceToDevice, st));
+      if (t + 1 < S)  // the (dropped-out) copy that cell 0 reads at step t+1: mask element [b][t+1][a] of the [B][S][A] tensor
+        dec_add_rows_kernel<<<(B * A + 255) / 256, 256, 0, st>>>(F(w.att_prev) + (size_t)(t + 1) * A, (long long)S * A, nullptr, 0, att_t,
+                                                                 (long long)S * A, B, A, (long long)S * A, (long long)(t + 1) * A, d->drop_seed,
+                                                                 thresh, inv_keep, d->drop_step);
     }
     if (d->sample_prob > 0.f && t + 1 < S)
       if ((rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * A, (long long)S * A, A))) return rc;
   }
   PLAS_CUDA(cudaGetLastError());
+  if (d->att_out) PLAS_CUDA(cudaMemcpyAsync(d->att_out, F(w.att), (size_t)B * S * A * 4, cudaMemcpyDeviceToDevice, st));
   // logits = DenseBinfDecoder(attention)
   return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
 }
@@ -1595,7 +1609,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   cudaStream_t st = (cudaStream_t)stream_;
   int rc = dec_train_check(d, workspace, workspace_bytes);
   if (rc) return rc;
-  PLAS_REQUIRE(d->dlogits && d->dmemory && d->dw_mem && d->dw_proj && d->db_proj, "dec_train_bwd: null tensor");
+  PLAS_REQUIRE(d->dlogits && d->dmemory && d->dw_mem, "dec_train_bwd: null tensor");
+  PLAS_REQUIRE(d->bottom_only == 0 || (d->dw_proj && d->db_proj && !d->datt_extra), "dec_train_bwd: bottom_only needs dw_proj / db_proj, no datt_extra");
   if (d->bottom_only) return dec_train_bwd_bottom(d, workspace, st);
   const DecTrainWs w = dec_train_ws(*d);
   unsigned char* base = (unsigned char*)workspace;
@@ -1610,9 +1625,12 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   float* datt = AL > 0 ? F(w.datt) : dctx;     // gradient wrt the attention vector ([B][S][A]); without the layer it IS dctx
   if (AL > 0) PLAS_REQUIRE(d->w_att_layer && d->dw_att_layer, "dec_train_bwd: attention_layer_size needs w_att_layer / dw_att_layer");
   // projection layer: dAtt = dlogits W_proj^T, dW_proj = Att^T dlogits, db_proj = colsum(dlogits)
-  if ((rc = gemm(st, BS, A, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, datt, A))) return rc;
-  if ((rc = gemm(st, A, NO, (int)BS, F(w.att), 1, A, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
-  if ((rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
+  // (+ datt_extra: a gradient that reaches the attention vectors directly, e.g. the --binf_projection regulariser)
+  if (d->datt_extra) PLAS_CUDA(cudaMemcpyAsync(datt, d->datt_extra, (size_t)BS * A * 4, cudaMemcpyDeviceToDevice, st));
+  if ((rc = gemm(st, BS, A, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, datt, A, nullptr, d->datt_extra ? 1.f : 0.f))) return rc;
+  // dw_proj / db_proj NULL: the projection is a constant (transform_binf_to_phones under --binf_projection)
+  if (d->dw_proj && (rc = gemm(st, A, NO, (int)BS, F(w.att), 1, A, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+  if (d->db_proj && (rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
   if (bah) {
     PLAS_REQUIRE(d->dw_query && d->dv_att, "dec_train_bwd: bahdanau needs dw_query / dv_att");
     PLAS_CUDA(cudaMemsetAsync(F(w.dkeys), 0, (size_t)B * Tm * Ud * 4, st));
@@ -1641,7 +1659,9 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     const bool last = t == S - 1;
     if (AL > 0) {  // datt_t = dlogits_t W_proj^T + (step t+1's cell-0 input gradient); back through attention = [h_top; ctx] W_att
       float* da = datt + (size_t)t * A;
-      if (!last) dec_add_rows_kernel<<<(B * A + 255) / 256, 256, 0, st>>>(da, (long long)S * A, da, (long long)S * A, F(w.dinp[0]), A + Ud, B, A);
+      if (!last)
+        dec_add_rows_kernel<<<(B * A + 255) / 256, 256, 0, st>>>(da, (long long)S * A, da, (long long)S * A, F(w.dinp[0]), A + Ud, B, A,
+                                                                 (long long)S * A, (long long)(t + 1) * A, d->drop_seed, thresh, inv_keep, d->drop_step);
       if ((rc = gemm(st, B, Ud, A, da, (long long)S * A, 1, d->w_att_layer, 1, A, F(w.dqx), Ud))) return rc;
       if ((rc = gemm(st, B, D, A, da, (long long)S * A, 1, d->w_att_layer + (size_t)Ud * A, 1, A, dctx + (size_t)t * D, (long long)S * D))) return rc;
     }
@@ -1685,8 +1705,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
       c.dc_carry = F(w.dc[l]); c.first = last ? 1 : 0;
       c.dq = (l == L - 1) ? F(w.dq) : nullptr; c.s_dq = Ud;
       c.dh_next = last ? nullptr : F(w.dinp[l]) + Kin; c.s_dn = Kin + Ud;
-      c.dh_above = (l < L - 1) ? F(w.dinp[l + 1]) : (AL > 0 ? F(w.dqx) : nullptr);  // top layer: the attention layer's h part
-      c.s_da = (l < L - 1) ? 2 * Ud : Ud;
+      c.dh_above = (l < L - 1) ? F(w.dinp[l + 1]) : nullptr; c.s_da = 2 * Ud;
+      c.dh_extra = (l == L - 1 && AL > 0) ? F(w.dqx) : nullptr; c.s_dx = Ud;  // top layer: the attention layer's h part
       c.idx_base = (long long)t * Ud; c.seed = d->drop_seed + 1 + l; c.thresh = thresh; c.inv_keep = inv_keep; c.step_ptr = d->drop_step;
       dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
       GemvTArgs g;

@@ -69,6 +69,33 @@ __global__ void sigmoid_ce_grad_kernel(const float* __restrict__ logits, const f
 }
 
 // out[0] = sum(ce*w) / (sum(w) + 1e-12), out[1] = sum(ce*w), out[2] = sum(w)
+// compute_log_probs_loss (model_helper.py:132-146) of the --binf_projection speller: the attention vector is read as
+// [log p(feature = 1) | log p(feature = 0)]; the regulariser |p1 + p0 - 1| + relu(log p1) + relu(log p0), averaged over every
+// element, pushes it towards normalised log-probabilities.  One warp per row; reg_tok[row] = weight * (row mean); the gradient
+// treats the stabilising constant c = -(l1 + l0) / 2 as a constant (tf.stop_gradient), like the reference.
+__global__ void log_probs_reg_grad_kernel(const float* __restrict__ att, long long n_tok, int n, float weight,
+                                          float* __restrict__ reg_tok, float* __restrict__ datt) {
+  const int lane = threadIdx.x & 31;
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= n_tok) return;
+  const float* row = att + tok * 2 * n;
+  float* drow = datt + tok * 2 * n;
+  const float coef = weight / ((float)n_tok * (float)n);
+  float s = 0.f;
+  for (int k = lane; k < n; k += 32) {
+    const float l1 = row[k], l0 = row[n + k];
+    const float c = -(l1 + l0) * 0.5f;
+    const float e1 = expf(l1 + c), e0 = expf(l0 + c), ec = expf(c);
+    const float dev = (e1 + e0) / ec - 1.f;
+    s += fabsf(dev) + fmaxf(l1, 0.f) + fmaxf(l0, 0.f);
+    const float sg = dev > 0.f ? 1.f : (dev < 0.f ? -1.f : 0.f);
+    drow[k] = coef * (sg * e1 / ec + (l1 > 0.f ? 1.f : 0.f));
+    drow[n + k] = coef * (sg * e0 / ec + (l0 > 0.f ? 1.f : 0.f));
+  }
+  s = warp_sum(s);
+  if (lane == 0) reg_tok[tok] = weight * s / (float)n;
+}
+
 __global__ void weighted_mean2_kernel(const float* __restrict__ ce, const float* __restrict__ w, long long n_tok,
                                       float* __restrict__ out) {
   __shared__ double s_num[256], s_den[256];
@@ -342,6 +369,16 @@ extern "C" int plas_sigmoid_ce_grad(const float* logits, const float* labels, co
   sigmoid_ce_grad_kernel<<<(unsigned)((n_tokens + 7) / 8), 256, 0, st>>>(logits, labels, weights, out3 + 2, n_tokens, n_feat,
                                                                          gscale, ce_tokens, dlogits);
   weighted_mean2_kernel<<<1, 256, 0, st>>>(ce_tokens, weights, n_tokens, out3);
+  PLAS_CUDA(cudaGetLastError());
+  return PLAS_OK;
+}
+
+extern "C" int plas_log_probs_reg_grad(const float* att, int64_t n_rows, int32_t n_feat, float weight, float* reg_rows, float* out3,
+                                       float* datt, plas_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  PLAS_REQUIRE(att && reg_rows && out3 && datt && n_rows > 0 && n_feat > 0, "log_probs_reg_grad: bad argument");
+  log_probs_reg_grad_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(att, n_rows, n_feat, weight, reg_rows, datt);
+  weighted_mean2_kernel<<<1, 256, 0, st>>>(reg_rows, nullptr, n_rows, out3);
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;
 }

@@ -85,6 +85,8 @@ def create_hparams(args=None, target_vocab_size=None, binf_count=None, sos_id=SO
             hp[k] = v
     if model_dir:
         save_hparams(hp, model_dir)
+    if hp.get("binf_projection") and not hp.get("binf_sampling") and hp.get("binf_count"):
+        hp["attention_layer_size"] = 2 * int(hp["binf_count"])  # las/model.py:180-183: [log p1 | log p0] per binary feature
     return hp
 
 

@@ -16,11 +16,21 @@ from .speller import SpellerWeights, speller
 
 
 class DeviceWeights:
-    def __init__(self, params, hp, num_channels=None, precision="fp32", device="cuda"):
+    def __init__(self, params, hp, num_channels=None, precision="fp32", device="cuda", binf=None):
+        """``binf`` (binf2phone [n, V]): with hp['binary_outputs'] and hp['binf_projection'] the 'speller_binf' scope is built
+        too (model_helper.py:219-227); the phone speller then exists only under --multitask (model_helper.py:212-217)."""
         C = num_channels or hp["num_channels"]
         self.precision = precision
         self.listener = ListenerWeights(params, hp, C, precision, device)
-        self.speller = SpellerWeights(params, hp, wts.encoder_output_depth(hp), precision, device)
+        D = wts.encoder_output_depth(hp)
+        self.speller = self.speller_binf = None
+        if not hp.get("binary_outputs") or hp.get("multitask"):
+            self.speller = SpellerWeights(params, hp, D, precision, device)
+        if hp.get("binary_outputs"):
+            if binf is None or not hp.get("binf_projection"):
+                raise NotImplementedError("binary_outputs at inference is built for --binf_projection (pass binf=binf2phone)")
+            self.speller_binf = SpellerWeights(params, hp, D, precision, device, scope="speller_binf", binf=binf)
+            self.binf = torch.as_tensor(binf, dtype=torch.float32, device=device)
 
 
 def las_predict(features, hp, weights, want_alignment=True, trim=True, want_probs=True):
@@ -31,12 +41,22 @@ def las_predict(features, hp, weights, want_alignment=True, trim=True, want_prob
     lens = features["source_sequence_length"]
     (enc_out, enc_len), enc_state = listener(x, lens, "infer", hp, weights.listener)
     # the listener already zeroes its outputs past each (reduced) length: no separate masking pass
-    out, state, final_len = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller,
-                                    memory_is_masked=True, want_alignment=want_alignment, trim=trim)
-    logits = out.rnn_output
-    pred = {"encoder_out": enc_out, "source_length": enc_len, "sample_ids": out.sample_id,
-            "logits": logits, "final_sequence_length": final_len, "alignment": state.alignment_history,
-            "n_steps": state.n_steps}
+    pred = {"encoder_out": enc_out, "source_length": enc_len}
+    logits = None
+    if weights.speller is not None:
+        out, state, final_len = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller,
+                                        memory_is_masked=True, want_alignment=want_alignment, trim=trim)
+        logits = out.rnn_output
+        pred.update({"sample_ids": out.sample_id, "logits": logits, "final_sequence_length": final_len,
+                     "alignment": state.alignment_history, "n_steps": state.n_steps})
+    if getattr(weights, "speller_binf", None) is not None:  # model_helper.py:219-227,241-251,272-275 (--binf_projection)
+        out_b, state_b, final_len_b = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller_binf,
+                                              binf_embedding=weights.binf, memory_is_masked=True, want_alignment=want_alignment, trim=trim)
+        pred.update({"logits_binf": out_b.rnn_output, "sample_ids_phones_binf": out_b.sample_id,
+                     "final_sequence_length_binf": final_len_b, "alignment_binf": state_b.alignment_history})
+        if logits is None:
+            logits = out_b.rnn_output  # probs = softmax(logits_binf) when there is no phone speller (model_helper.py:295-296)
+            pred["n_steps"] = state_b.n_steps
     if want_probs:
         pred["probs"] = torch.softmax(logits, dim=-1)
     if isinstance(enc_state[0], tuple):

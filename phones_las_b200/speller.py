@@ -28,10 +28,18 @@ def _round_up(x, m):
 class SpellerWeights:
     """Device-resident, kernel-layout copy of the ``speller/`` variables."""
 
-    def __init__(self, params, hp, enc_depth, precision="fp32", device="cuda", scope="speller"):
+    def __init__(self, params, hp, enc_depth, precision="fp32", device="cuda", scope="speller", binf=None):
+        """``binf`` (binf2phone [n, V], numpy): the --binf_projection wiring of the 'speller_binf' scope (las/model.py:240-241,
+        251-257): inputs are the previous phone's binary-feature column, the 2n-wide attention vector is mapped to phone scores
+        by transform_binf_to_phones.  Both are linear, so they fold into the weights the step kernels already read: the V
+        embedding rows of cell 0's kernel become M^T W_0[:n], the projection becomes the constant [M; 1 - M] with a zero bias."""
         _lib.require_cuda()
-        if hp.get("binf_projection"):
-            raise NotImplementedError("--binf_projection decoder wiring is not built yet")
+        self.binf_projection = binf is not None
+        if self.binf_projection:
+            if not hp.get("binf_projection") or hp.get("bottom_only"):
+                raise NotImplementedError("a binf2phone matrix needs --binf_projection and the default decoder wiring")
+            self._init_attention_layer(params, hp, enc_depth, precision, device, scope, binf=np.asarray(binf, np.float32))
+            return
         self.bottom_only = bool(hp.get("bottom_only"))
         self.pass_hidden_state = bool(hp.get("pass_hidden_state")) and self.bottom_only  # las/model.py:260 needs both
         if self.bottom_only:
@@ -145,7 +153,7 @@ def _attention_params(self, params, pre, up, device):
         self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
 
 
-def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope):
+def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope, binf=None):
     """The default wiring on the fp32 step-kernel decoder only: attention_layer_size = A (las/model.py:180-200: AttentionWrapper's
     Dense over [cell output; context]; the attention fed back to cell 0 and read by the projection is A wide) and / or the
     attention types the fused decoders do not carry (bahdanau_monotonic, custom)."""
@@ -166,14 +174,20 @@ def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope)
     pre = f"{scope}/decoder/attention_wrapper"
     names = [f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(self.L)]
     kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
+    if binf is not None:  # --binf_projection: fold embedding_fn and transform_binf_to_phones into the weights (see __init__)
+        n = binf.shape[0]
+        assert binf.shape[1] == V and A == 2 * n and kernels[0].shape == (n + A + Ud, 4 * Ud), (binf.shape, A, kernels[0].shape)
+        kernels[0] = np.concatenate([binf.T.astype(np.float64) @ kernels[0][:n].astype(np.float64), kernels[0][n:]], 0).astype(np.float32)
+        w_proj, b_proj = np.concatenate([binf, 1.0 - binf], 0), np.zeros((V,), np.float32)
+    else:
+        w_proj, b_proj = params[f"{scope}/decoder/projection_layer/kernel"], params[f"{scope}/decoder/projection_layer/bias"]
     assert kernels[0].shape == (V + A + Ud, 4 * Ud), kernels[0].shape
-    self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names],
-                   w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]))
+    self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names], w_proj=up(w_proj))
     if has_layer:
         self.tf["w_att_layer"] = up(params[f"{pre}/attention_layer/kernel"])
         assert self.tf["w_att_layer"].shape == (Ud + D, A)
     assert self.tf["w_proj"].shape == (A, V)
-    self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"])
+    self.b_proj = up(b_proj)
     _attention_params(self, params, pre, up, device)
     self.tc = False
 
@@ -337,8 +351,12 @@ def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_leng
             memory_is_masked=False, want_alignment=True, trim=True):
     """las/model.py:205-349.  mode 'train'/'eval' with ``decoder_inputs`` (targets_inputs ids [B,L])
     runs teacher forcing (TrainingHelper, sampling_probability must be 0); otherwise greedy."""
-    if binary_outputs or binf_embedding is not None or transparent_projection:
-        raise NotImplementedError("binary-feature decoder variants are not built yet")
+    if binf_embedding is not None and not getattr(weights, "binf_projection", False):
+        raise NotImplementedError("a binf2phone matrix is used by the --binf_projection wiring only: build the SpellerWeights with binf=")
+    if binary_outputs or transparent_projection:
+        # binary_outputs without --binf_projection: the reference's own non-TRAIN graph slices an n-wide output as [n:2n]
+        # (utils/training_helper.py:19-21) and cannot be built; with --binf_sampling it decodes through InferenceHelper
+        raise NotImplementedError("binary-feature decoding is built for --binf_projection only (DESIGN.md)")
     init = None
     if getattr(weights, "pass_hidden_state", False):  # las/model.py:259-267
         init = encoder_state if isinstance(encoder_state[0], (tuple, list)) else (encoder_state,)

@@ -125,7 +125,7 @@ def reference_masks(hp, step, B, T, C, S, binf_count=0):
                 t = (t + 1) // 2
         else:
             din = ndir * U
-    D = din
+    D = int(hp.get("attention_layer_size") or din)  # width of the attention vector that is fed back (las/model.py:180-200)
     for si, (scope, E) in enumerate((("speller", V), ("speller_binf", binf_count))):
         if E <= 0:
             continue
@@ -382,8 +382,19 @@ def listener_train_bwd(d_enc, tape, st, hp, d_final=None):
 class SpellerTrain:
     """One teacher-forced speller (scope 'speller' or 'speller_binf') bound to a TrainState."""
 
-    def __init__(self, st, hp, scope, E, n_out, index=0):
+    def __init__(self, st, hp, scope, E, n_out, index=0, binf=None):
+        """``binf`` (device tensor [n, V], binf2phone): --binf_projection wiring of this speller (las/model.py:251-257): the
+        projection is the constant transform_binf_to_phones map [M; 1 - M] on the 2n-wide attention vectors, which ``forward``
+        keeps in ``self.att_vec`` for the log-probability regulariser."""
         self.st, self.hp, self.scope, self.E, self.n_out = st, hp, scope, E, n_out
+        self.proj_const = self.att_vec = None
+        if binf is not None:
+            if hp.get("binf_trainable"):
+                raise NotImplementedError("training path: --binf_trainable (a trainable binf2phone matrix) is not built")
+            M = binf.to(torch.float32)
+            self.proj_const = torch.cat([M, 1.0 - M], 0).contiguous()  # [2n, V]
+            self.zero_bias = torch.zeros((M.shape[1],), dtype=torch.float32, device=M.device)
+            assert int(hp.get("attention_layer_size") or 0) == self.proj_const.shape[0] and n_out == M.shape[1]
         self.keep = 1.0 - float(hp.get("dropout", 0.0))
         self.tid = SPELLER_TID + 10 * index
         self.base = int(hp.get("dropout_seed", 0))
@@ -397,12 +408,11 @@ class SpellerTrain:
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
         # bahdanau_monotonic in TRAIN mode: sigmoid_noise = 1.0 (las/model.py:161-162); tests may set 0 for a noise-free check
         self.sigmoid_noise = 1.0 if hp["attention_type"] == "bahdanau_monotonic" else 0.0
-        for flag in ("binf_projection", "embedding_size"):
-            if hp.get(flag):
-                raise NotImplementedError(f"training path: --{flag} is not built")
+        if hp.get("embedding_size"):
+            raise NotImplementedError("training path: --embedding_size is not built")
         self.att_layer = int(hp.get("attention_layer_size") or 0)
-        if self.att_layer and (hp.get("bottom_only") or float(hp.get("dropout", 0.0)) > 0.0):
-            raise NotImplementedError("training path: attention_layer_size with --bottom_only or dropout is not built")
+        if self.att_layer and hp.get("bottom_only"):
+            raise NotImplementedError("training path: attention_layer_size with --bottom_only is not built")
         self.bottom = bool(hp.get("bottom_only"))
         self.pass_state = self.bottom and bool(hp.get("pass_hidden_state"))  # las/model.py:260 needs both flags
         if self.bottom and float(hp.get("dropout", 0.0)) > 0.0:
@@ -447,8 +457,13 @@ class SpellerTrain:
             sb = f"{pre}/{at}_attention/attention_score_bias"
             d.score_bias, d.dscore_bias = st.w(sb), st.g(sb)
             d.sigmoid_noise, d.noise_seed = self.sigmoid_noise, drop_seed(self.base, 0, self.tid + 8)
-        pk, pb = f"{sc}/decoder/projection_layer/kernel", f"{sc}/decoder/projection_layer/bias"
-        d.w_proj, d.b_proj, d.dw_proj, d.db_proj = st.w(pk), st.w(pb), st.g(pk), st.g(pb)
+        if self.proj_const is not None:  # constant projection: the Dense variables exist (checkpoint layout) but are never used
+            d.w_proj, d.b_proj, d.dw_proj, d.db_proj = self.proj_const.data_ptr(), self.zero_bias.data_ptr(), None, None
+            d.att_out = self.att_vec.data_ptr()
+            d.datt_extra = self.datt_extra.data_ptr() if self.datt_extra is not None else None
+        else:
+            pk, pb = f"{sc}/decoder/projection_layer/kernel", f"{sc}/decoder/projection_layer/bias"
+            d.w_proj, d.b_proj, d.dw_proj, d.db_proj = st.w(pk), st.w(pb), st.g(pk), st.g(pb)
         d.memory, d.mem_len, d.x_in = memory.data_ptr(), mem_len.data_ptr(), x_in.data_ptr()
         d.logits = logits.data_ptr()
         d.dlogits = dlogits.data_ptr() if dlogits is not None else None
@@ -474,6 +489,9 @@ class SpellerTrain:
             x_in = dropout_(x_in, torch.empty_like(x_in), drop_seed(self.base, 0, self.tid), self.keep, self.st.step_dev)
         self.memory, self.mem_len, self.x_in = memory.contiguous(), mem_len, x_in
         self.logits = torch.empty((B, S, self.n_out), dtype=torch.float32, device=memory.device)
+        self.datt_extra = None
+        if self.proj_const is not None:
+            self.att_vec = torch.empty((B, S, self.proj_const.shape[0]), dtype=torch.float32, device=memory.device)
         d = self._desc(self.memory, self.mem_len, self.x_in, self.logits)
         need = L.plas_dec_train_workspace_bytes(C.byref(d))
         self.ws = torch.empty((need,), dtype=torch.uint8, device=memory.device)
@@ -482,10 +500,12 @@ class SpellerTrain:
         _lib.count_launches(3 + S * (self.hp["decoder_layers"] + 1))
         return self.logits
 
-    def backward(self, dlogits, d_enc):
+    def backward(self, dlogits, d_enc, datt_extra=None):
         """Accumulates into d_enc [B,Tm,D] and writes this speller's weight gradients into the TrainState; with
-        pass_hidden_state the gradients wrt the initial states land in ``self.d_init`` [(dc, dh)] per seeded cell."""
+        pass_hidden_state the gradients wrt the initial states land in ``self.d_init`` [(dc, dh)] per seeded cell.
+        ``datt_extra`` [B,S,A] (--binf_projection): gradient that reaches the attention vectors besides the projection's."""
         L = _lib.lib()
+        self.datt_extra = None if datt_extra is None else datt_extra.contiguous()
         if self.init is not None:
             self.d_init = [(torch.empty_like(c), torch.empty_like(h)) for c, h in self.init]
         d = self._desc(self.memory, self.mem_len, self.x_in, self.logits, dlogits.contiguous(), d_enc)
@@ -511,6 +531,18 @@ def seq_ce_grad(logits, targets, weights, gscale=1.0):
                                            _lib.ptr(out3), _lib.ptr(dl), _lib.stream_ptr()))
     _lib.count_launches(3)
     return out3[0], dl
+
+
+def log_probs_reg_grad(att, weight=1.0):
+    """compute_log_probs_loss (model_helper.py:132-146) of the attention vectors [B,S,2n] -> (weight * loss, d/d att)."""
+    B, S, A = att.shape
+    rows = torch.empty((B * S,), dtype=torch.float32, device=att.device)
+    out3 = torch.empty((3,), dtype=torch.float32, device=att.device)
+    datt = torch.empty_like(att)
+    _lib.check(_lib.lib().plas_log_probs_reg_grad(_lib.ptr(att), B * S, A // 2, float(weight), _lib.ptr(rows), _lib.ptr(out3),
+                                                  _lib.ptr(datt), _lib.stream_ptr()))
+    _lib.count_launches(2)
+    return out3[0], datt
 
 
 def sigmoid_ce_grad(logits, labels, weights, gscale=1.0):
@@ -567,9 +599,13 @@ def forward_backward(features, labels, st, hp, binf=None):
     jobs = []
     if not hp.get("binary_outputs") or hp.get("multitask"):
         jobs.append(("speller", "ce", V, torch.nn.functional.one_hot(tin, V).to(torch.float32), None))
+    proj = bool(hp.get("binf_projection"))
     if hp.get("binary_outputs"):
         bt = binf.to(device=dev, dtype=torch.float32).t().contiguous()  # [V, n]
-        jobs.append(("speller_binf", "ce_binf", bt.shape[1], bt[tin], bt[tout.long()].contiguous()))
+        if proj:  # model_helper.py:221-227: phone ids in (embedded as binary-feature columns), phone logits out
+            jobs.append(("speller_binf", "ce_binf", V, bt[tin], None))
+        else:
+            jobs.append(("speller_binf", "ce_binf", bt.shape[1], bt[tin], bt[tout.long()].contiguous()))
     main = torch.cuda.current_stream()
     d_enc_heads = [torch.zeros_like(enc_out) for _ in jobs]  # zero-filled on the caller's stream BEFORE the fork event
     ready = torch.cuda.Event()
@@ -579,15 +615,20 @@ def forward_backward(features, labels, st, hp, binf=None):
     for (scope, key, n_out, x_in, lab), stream, d_enc_j in zip(jobs, side, d_enc_heads):
         with torch.cuda.stream(stream):
             stream.wait_event(ready)
-            sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out, index=0 if scope == "speller" else 1)
+            binf_proj = proj and scope == "speller_binf"
+            sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out, index=0 if scope == "speller" else 1,
+                              binf=binf.to(device=dev) if binf_proj else None)
             logits = sp.forward(enc_out, enc_len, x_in, initial_state=enc_state)
+            datt_extra = None
             if lab is None:
                 parts[key], dl = seq_ce_grad(logits, tout, w)
-                parts["logits"] = logits
+                parts["logits" if scope == "speller" else "logits_binf"] = logits
+                if binf_proj:  # + compute_log_probs_loss(raw attention) * binf_projection_reg_weight (model_helper.py:326-331)
+                    parts["log_probs_reg"], datt_extra = log_probs_reg_grad(sp.att_vec, float(hp.get("binf_projection_reg_weight", 1.0)))
             else:
                 parts[key], dl = sigmoid_ce_grad(logits, lab, w)
                 parts["logits_binf"] = logits
-            sp.backward(dl, d_enc_j)
+            sp.backward(dl, d_enc_j, datt_extra)
             done = torch.cuda.Event()
             done.record(stream)
         pending.append((d_enc_j, done, sp))
@@ -608,6 +649,8 @@ def forward_backward(features, labels, st, hp, binf=None):
         _lib.check(_lib.lib().plas_axpy_f32(_lib.ptr(d_enc), _lib.ptr(d_enc_j), d_enc.numel(), 1.0, _lib.stream_ptr()))
         _lib.count_launches(1)
         total = parts[key] if total is None else total + parts[key]
+    if "log_probs_reg" in parts:
+        total = total + parts["log_probs_reg"]
     d_final = None
     for _, _, sp in pending:  # gradients wrt the listener's final states from the seeded decoder cells
         if sp.d_init is not None:
@@ -708,6 +751,8 @@ def train_variable_shapes(hp, num_channels=None, binf_count=0):
             nk = "speller_binf/" + k[len("speller/"):]
             if k.endswith(("cell_0/lstm_cell/kernel", "cell_0_attention/attention_wrapper/lstm_cell/kernel")):
                 s = (s[0] - V + binf_count, s[1])
+            elif hp.get("binf_projection"):
+                pass  # Dense(V) is built on the 2n-wide attention but never used (inner_projection_layer=False, las/model.py:251-257)
             elif k.endswith("projection_layer/kernel"):
                 s = (s[0], binf_count)
             elif k.endswith("projection_layer/bias"):

@@ -156,3 +156,37 @@ def test_workflow_tfrecord_to_training_to_checkpoint_to_serving(tmp_path):
     fa = feature_args(feature_type="mfe", backend="speechpy", n_mels=C - 1, energy=True, window=25, step=10)
     b = las_eval(feats, labels, hp, LASModel.from_model_dir(model_dir, fa, precision="fp32").weights)
     assert a["loss"].item() == b["loss"].item() and np.array_equal(a["edit_distance"], b["edit_distance"])
+
+
+@gpu
+@pytest.mark.parametrize("multitask", [False, True])
+def test_predict_binf_projection(multitask):
+    """las_model_fn(PREDICT) with --binary_outputs --binf_projection (model_helper.py:219-227,241-251,272-296): the
+    'speller_binf' decoder is fed the previous phone's binary-feature column and emits phone logits through
+    transform_binf_to_phones; predictions carry logits_binf / sample_ids_phones_binf / alignment_binf."""
+    import torch
+    from phones_las_b200.model import DeviceWeights, las_predict
+    from phones_las_b200.train import train_variable_shapes
+    B, T, C, V, n = 5, 40, 6, 16, 8
+    hp = create_hparams(target_vocab_size=V, binf_count=n, encoder_layers=2, encoder_units=16, decoder_layers=2, decoder_units=32,
+                        attention_type="luong", num_channels=C, binary_outputs=True, binf_projection=True, multitask=multitask)
+    params = weights.init_params(hp, C, seed=3, shapes=train_variable_shapes(hp, C, binf_count=n), bias_scale=0.1, projection_scale=8.0)
+    params["speller_binf/decoder/attention_wrapper/attention_layer/kernel"] = params["speller_binf/decoder/attention_wrapper/attention_layer/kernel"] * 8.0
+    binf = (np.random.default_rng(2).uniform(size=(n, V)) < 0.4).astype(np.float32)
+    x, lens = synth.synth_features(B, T, C, seed=4, var_len=True)
+    (enc, enc_len), enc_state = ol.listener(x, lens, params, hp)
+    ref_logits, ref_ids, ref_align, ref_len, _ = ol.Speller(enc, enc_len, params, hp, "fp32", scope="speller_binf", binf=binf).greedy()
+    w = DeviceWeights(params, hp, C, "fp32", binf=binf)
+    assert (w.speller is not None) == multitask
+    pred = las_predict({"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}, hp, w)
+    assert ("sample_ids" in pred) == multitask
+    logits = pred["logits_binf"].cpu().numpy()
+    assert_parity(logits[:, :1], ref_logits[:, :1], "fp32", "logits_binf step 0")
+    from tests.util import top2_margin
+    if top2_margin(ref_logits) > 1e-4:
+        np.testing.assert_array_equal(pred["sample_ids_phones_binf"].cpu().numpy(), ref_ids)
+        np.testing.assert_array_equal(pred["final_sequence_length_binf"].cpu().numpy(), ref_len)
+        assert_parity(logits, ref_logits, "fp32", "logits_binf")
+        assert_parity(pred["alignment_binf"].cpu().numpy(), ref_align, "fp32", "alignment_binf")
+    if not multitask:
+        assert torch.allclose(pred["probs"], torch.softmax(pred["logits_binf"], -1))

@@ -618,3 +618,82 @@ def test_train_step_attention_layer_size(att, Ld, A, sampling):
     for k in params:
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+
+
+# ---- --binf_projection: DenseBinfDecoder as transform_binf_to_phones + compute_log_probs_loss ----
+def _binf_projection_setup(multitask, dropout, att="luong", Ld=1):
+    B, T, C, U, Ud, V, n, S = 5, 60, 6, 16, 32, 14, 6, 6
+    hp = create_hparams(target_vocab_size=V, binf_count=n, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=C, attention_type=att, dropout=dropout, sampling_probability=0.0, binary_outputs=True,
+                        binf_projection=True, multitask=multitask, binf_projection_reg_weight=0.7, l2_reg_scale=1e-4, ctc_weight=0.2)
+    assert hp["attention_layer_size"] == 2 * n  # las/model.py:180-183
+    from phones_las_b200.train import train_variable_shapes
+    shapes = train_variable_shapes(hp, C, binf_count=n)
+    assert shapes["speller_binf/decoder/attention_wrapper/multi_rnn_cell/cell_0/lstm_cell/kernel"] == (n + 2 * n + Ud, 4 * Ud)
+    assert shapes["speller_binf/decoder/projection_layer/kernel"] == (2 * n, V)  # built by Dense but never used
+    assert ("speller/memory_layer/kernel" in shapes) == multitask
+    params = weights.init_params(hp, seed=11, shapes=shapes, bias_scale=0.05, projection_scale=4.0)
+    # attention vectors on both sides of 0, so that every branch of the regulariser (|p1 + p0 - 1|, the two relus) is exercised
+    params["speller_binf/decoder/attention_wrapper/attention_layer/kernel"] = params["speller_binf/decoder/attention_wrapper/attention_layer/kernel"] * 6.0
+    x, lens = synth.synth_features(B, T, C, seed=B + 2, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=5)
+    binf = (np.random.default_rng(1).uniform(size=(n, V)) < 0.4).astype(np.float32)
+    return hp, params, x, lens, tin, tout, tlen, binf, (B, T, C, S, n)
+
+
+@gpu
+@pytest.mark.parametrize("multitask,dropout,att,Ld", [(False, 0.0, "luong", 1), (True, 0.0, "bahdanau", 2), (True, 0.25, "luong", 2),
+                                                      (False, 0.3, "bahdanau", 1)])
+def test_train_step_binf_projection(multitask, dropout, att, Ld):
+    """The binary-feature speller in projection mode: fed the previous phone's feature column, its 2n-wide attention vector is
+    mapped to phone logits by the constant [M; 1 - M]; loss = softmax CE + reg_weight * compute_log_probs_loss(attention)."""
+    import torch
+    from phones_las_b200 import train as tr
+    hp, params, x, lens, tin, tout, tlen, binf, (B, T, C, S, n) = _binf_projection_setup(multitask, dropout, att, Ld)
+    st = tr.TrainState(params)
+    st.step = 4
+    masks = None
+    if dropout > 0:
+        masks = {sc: ({kk: torch.tensor(vv, dtype=torch.float64) for kk, vv in m.items()})
+                 for sc, m in tr.reference_masks(hp, 4, B, T, C, S, binf_count=n).items()}
+        assert masks["speller_binf"]["att"].shape == (B, S, 2 * n)
+        if not multitask:
+            masks.pop("speller")
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, binf, masks=masks)
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp, torch.from_numpy(binf).cuda())
+    assert scaled_err(parts["logits_binf"], ref_parts["logits_binf"].detach()) < 1e-5
+    assert ref_parts["log_probs_reg"].item() > 1e-3
+    for name, scale in (("ce_binf", 1.0), ("log_probs_reg", 0.7), ("ctc", 1.0)) + ((("ce", 1.0),) if multitask else ()):
+        want = ref_parts[name].item() * scale
+        assert abs(parts[name].item() - want) < 1e-4 * max(1.0, abs(want)), name
+    ref_audio = ref_parts["audio_loss"].item()
+    assert abs(parts["audio_loss"].item() - ref_audio) < 1e-4 * max(1.0, abs(ref_audio))
+    raw = st.export_grads()
+    for k in params:
+        g = tp[k].grad if tp[k].grad is not None else torch.zeros_like(tp[k])
+        ref_g = g - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+    unused = raw["speller_binf/decoder/projection_layer/kernel"]
+    assert not unused.any()  # the Dense variables of the projection layer receive no gradient from the decoder
+    tr.apply_gradients(st, hp)  # L2 + clip + Adam run over the whole flat buffer, unused variables included
+
+
+@gpu
+def test_log_probs_regulariser_matches_autograd():
+    import torch
+    from phones_las_b200 import train as tr
+    g = torch.Generator().manual_seed(0)
+    att = (torch.randn((7, 5, 24), generator=g) * 1.5)
+    att[0, 0, :3] = 0.0
+    ref_in = att.double().requires_grad_(True)
+    ref = lt.compute_log_probs_loss(ref_in) * 0.3
+    ref.backward()
+    val, datt = tr.log_probs_reg_grad(att.cuda(), 0.3)
+    assert abs(val.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert scaled_err(datt, ref_in.grad) < 1e-5

@@ -215,3 +215,34 @@ def test_hard_monotonic_attention_is_first_active_frame_at_or_after_the_previous
             np.testing.assert_array_equal(a[b], want)
         prev = a
     assert seen_move
+
+
+def test_binf_projection_oracles_agree():
+    """--binf_projection: the numpy decoder (embedding = binary-feature column, projection = transform_binf_to_phones) vs the
+    differentiable restatement, and the regulariser vs oracle/losses.py."""
+    n, V = 6, 11
+    hp = create_hparams(target_vocab_size=V, binf_count=n, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=2,
+                        num_channels=4, binary_outputs=True, binf_projection=True)
+    assert hp["attention_layer_size"] == 2 * n
+    shapes = train_variable_shapes(hp, 4, binf_count=n)
+    assert not any(k.startswith("speller/") for k in shapes)
+    params = weights.init_params(hp, seed=5, bias_scale=0.1, shapes=shapes)
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(0)
+    enc = rng.uniform(-1, 1, (3, 7, D)).astype(np.float32)
+    lens = np.array([7, 4, 5], np.int32)
+    enc *= (np.arange(7)[None, :, None] < lens[:, None, None])
+    binf = (rng.uniform(size=(n, V)) < 0.4).astype(np.float32)
+    tin, tout, tlen = synth.synth_labels(3, 5, V)
+    sp = ol.Speller(enc, lens, params, hp, scope="speller_binf", binf=binf)
+    ref, _ = sp.teacher_forced(tin, tlen)
+    assert ref.shape == (3, tin.shape[1], V)
+    atts = []
+    x = torch.tensor(binf.T[tin], dtype=torch.float64)
+    out = lt.speller_train(torch.tensor(enc, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), x, _tp(params), hp,
+                           scope="speller_binf", binf=torch.tensor(binf, dtype=torch.float64), attention_out=atts)
+    assert np.abs(out.numpy() - ref).max() < 5e-6
+    att = torch.stack(atts, 1) * 8.0
+    assert abs(lt.compute_log_probs_loss(att).item() - olo.compute_log_probs_loss(att.numpy())) < 1e-9
+    greedy = sp.greedy()
+    assert greedy[0].shape[2] == V and greedy[1].max() < V
