@@ -321,6 +321,8 @@ typedef struct plas_dec_train_desc {
    * datt_extra (bwd in [B][S][A], optional).  Default wiring only. */
   float* att_out;
   const float* datt_extra;
+  /* bwd out, optional: gradient wrt x_in [B][S][E] (embedding_size != 0, las/model.py:230-237: it flows into target_embedding) */
+  float* dx_in;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

@@ -273,6 +273,8 @@ class Speller:
         # column of the previous phone, the 2n-wide attention vector is read as [log p1 | log p0] and mapped to phone scores by
         # transform_binf_to_phones (DenseBinfDecoder with inner_projection_layer=False: its Dense variables are never used)
         self.binf = None if binf is None else np.asarray(binf, F32)
+        if hp.get("embedding_size"):
+            self.target_embedding = np.asarray(params[f"{scope}/target_embedding"], F32)
         if self.binf is not None:
             assert hp.get("binf_projection") and not self.bottom_only and self.wal is not None
             assert self.wal.shape[1] == 2 * self.binf.shape[0], "attention_layer_size must be 2 * binf_count (las/model.py:180-183)"
@@ -337,6 +339,8 @@ class Speller:
 
     def one_hot(self, ids):
         """embedding_fn (las/model.py:228-246): one-hot ids, or the phone's binary-feature column under --binf_projection."""
+        if self.hp.get("embedding_size"):  # las/model.py:230-237
+            return self.q(self.target_embedding[ids])
         if self.binf is not None:
             return np.ascontiguousarray(self.binf.T[ids])
         return np.eye(self.V, dtype=F32)[ids]

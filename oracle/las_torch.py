@@ -313,7 +313,11 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sam
     loss = 0.0
     V = hp["target_vocab_size"]
     if not hp.get("binary_outputs") or hp.get("multitask"):
-        logits = speller_train(enc_out, enc_len, torch.nn.functional.one_hot(tin.long(), V).to(dt), params, hp,
+        if hp.get("embedding_size"):  # las/model.py:230-237
+            dec_in = params["speller/target_embedding"][tin.long()]
+        else:
+            dec_in = torch.nn.functional.one_hot(tin.long(), V).to(dt)
+        logits = speller_train(enc_out, enc_len, dec_in, params, hp,
                                masks=masks.get("speller"), encoder_state=enc_state, sampling=sampling, score_noise=score_noise)
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits

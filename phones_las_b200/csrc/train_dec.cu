@@ -1450,6 +1450,7 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     };
     if (l == 0) {
       if ((rc = wg(d->x_in, E, 0))) return rc;
+      if (d->dx_in && (rc = gemm(st, BS, E, 4 * Ud, dz, 4 * Ud, 1, d->kernel[0], 1, 4 * Ud, d->dx_in, E))) return rc;  // dX = dZ_0 W_0[0:E]^T
       if ((rc = wg(F(w.att_prev), D, E))) return rc;
       if ((rc = wg(F(w.hprev[0]), Ud, (size_t)E + D))) return rc;
     } else {
@@ -1742,6 +1743,8 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
     float* dk = d->dkernel[l];
     if (l == 0) {
       if ((rc = gemm(st, E, 4 * Ud, (int)BS, d->x_in, 1, E, dz, 4 * Ud, 1, dk, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+      // gradient wrt the decoder inputs (embedding_size != 0: flows into target_embedding): dX = dZ_0 W_0[0:E]^T
+      if (d->dx_in && (rc = gemm(st, BS, E, 4 * Ud, dz, 4 * Ud, 1, d->kernel[0], 1, 4 * Ud, d->dx_in, E))) return rc;
       if ((rc = gemm(st, A, 4 * Ud, (int)BS, F(w.att_prev), 1, A, dz, 4 * Ud, 1, dk + (size_t)E * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
       if ((rc = gemm(st, Ud, 4 * Ud, (int)BS, F(w.hprev[0]), 1, Ud, dz, 4 * Ud, 1, dk + (size_t)(E + A) * 4 * Ud, 4 * Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
     } else {

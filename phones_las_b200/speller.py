@@ -25,6 +25,18 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def fold_embedding(params, hp, scope, kern0):
+    """embedding_size != 0 (las/model.py:230-237): the decoder input is a row of ``<scope>/target_embedding`` [V, E] instead of a
+    one-hot.  Cell 0's first E kernel rows only ever see such rows, so the lookup folds into the weights: the V 'one-hot' rows
+    the decoders read become target_embedding @ kernel[:E]."""
+    E = int(hp.get("embedding_size") or 0)
+    if not E:
+        return kern0
+    emb = np.asarray(params[f"{scope}/target_embedding"], np.float64)
+    assert emb.shape == (hp["target_vocab_size"], E), emb.shape
+    return np.concatenate([(emb @ kern0[:E].astype(np.float64)).astype(np.float32), kern0[E:]], 0)
+
+
 class SpellerWeights:
     """Device-resident, kernel-layout copy of the ``speller/`` variables."""
 
@@ -45,8 +57,8 @@ class SpellerWeights:
         if self.bottom_only:
             self._init_bottom_only(params, hp, enc_depth, precision, device, scope)
             return
-        if hp.get("embedding_size") or hp.get("beam_width"):
-            raise NotImplementedError("embedding_size / beam_width != 0 are not built yet")
+        if hp.get("beam_width"):
+            raise NotImplementedError("beam_width != 0 is not built (SURVEY section 2: out of scope)")
         if hp["attention_type"] not in _lib.ATT_CODES:
             raise NotImplementedError(f"attention_type={hp['attention_type']}")
         if hp.get("attention_layer_size") or hp["attention_type"] in ("bahdanau_monotonic", "custom"):
@@ -72,6 +84,7 @@ class SpellerWeights:
             kern = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], np.float32)
             bias = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], np.float32)
             if k == 0:
+                kern = fold_embedding(params, hp, scope, kern)
                 assert kern.shape == (V + D + Ud, 4 * Ud), kern.shape
                 self.w_emb = up(packing.pack_unit_major(kern[:V], Ud))
                 rows = kern[V:]
@@ -99,7 +112,8 @@ class SpellerWeights:
         self.tf = None
         if precision == "fp32" and self.att in ("luong", "bahdanau", "luong_monotonic") and Ud % 16 == 0 and D % 4 == 0:
             self.tf = dict(
-                kernel=[up(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], torch.float32) for k in range(self.L)],
+                kernel=[up(fold_embedding(params, hp, scope, np.asarray(params[f"{pre}/multi_rnn_cell/cell_0/lstm_cell/kernel"], np.float32)) if k == 0
+                           else params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], torch.float32) for k in range(self.L)],
                 bias=[up(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], torch.float32) for k in range(self.L)],
                 w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"], torch.float32))
         if self.tc:
@@ -112,8 +126,8 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     """GNMT-style AttentionMultiCell wiring (las/model.py:20-69, 185-193): fp32 step-kernel decoder only."""
     if precision != "fp32":
         raise NotImplementedError("--bottom_only is built for the fp32 step-kernel decoder (precision='fp32')")
-    if hp.get("attention_layer_size") or hp.get("embedding_size") or hp.get("beam_width"):
-        raise NotImplementedError("attention_layer_size / embedding_size / beam_width != 0 are not built yet")
+    if hp.get("attention_layer_size") or hp.get("beam_width"):
+        raise NotImplementedError("attention_layer_size / beam_width != 0 with --bottom_only are not built")
     self.precision, self.att = precision, hp["attention_type"]
     if self.att not in _lib.ATT_CODES:
         raise NotImplementedError(f"--bottom_only with attention_type={self.att}")
@@ -127,6 +141,7 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     pre = f"{scope}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper"
     names = [f"{pre}/lstm_cell"] + [f"{scope}/decoder/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(1, self.L)]
     kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
+    kernels[0] = fold_embedding(params, hp, scope, kernels[0])
     for k, kern in enumerate(kernels):
         din = (V + D) if k == 0 else ((D if k == 1 else Ud) + D)
         assert kern.shape == (din + Ud, 4 * Ud), (k, kern.shape)
@@ -174,6 +189,8 @@ def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope,
     pre = f"{scope}/decoder/attention_wrapper"
     names = [f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(self.L)]
     kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
+    if binf is None:
+        kernels[0] = fold_embedding(params, hp, scope, kernels[0])
     if binf is not None:  # --binf_projection: fold embedding_fn and transform_binf_to_phones into the weights (see __init__)
         n = binf.shape[0]
         assert binf.shape[1] == V and A == 2 * n and kernels[0].shape == (n + A + Ud, 4 * Ud), (binf.shape, A, kernels[0].shape)

@@ -126,7 +126,7 @@ def reference_masks(hp, step, B, T, C, S, binf_count=0):
         else:
             din = ndir * U
     D = int(hp.get("attention_layer_size") or din)  # width of the attention vector that is fed back (las/model.py:180-200)
-    for si, (scope, E) in enumerate((("speller", V), ("speller_binf", binf_count))):
+    for si, (scope, E) in enumerate((("speller", int(hp.get("embedding_size") or 0) or V), ("speller_binf", binf_count))):
         if E <= 0:
             continue
         tid = SPELLER_TID + 10 * si
@@ -191,6 +191,12 @@ class TrainState:
         i = self.index[name]
         cols = self.shapes[name][-1] if self.shapes[name] else 1
         return _p(self.params, self.offsets_host[i] + row * cols)
+
+    def view(self, name):
+        """the parameter ``name`` as a tensor view of the flat buffer (gather source for embedding lookups)."""
+        i = self.index[name]
+        o = self.offsets_host[i]
+        return self.params[o:o + int(np.prod(self.shapes[name]))].view(self.shapes[name])
 
     def g(self, name, row=0):
         i = self.index[name]
@@ -408,8 +414,10 @@ class SpellerTrain:
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
         # bahdanau_monotonic in TRAIN mode: sigmoid_noise = 1.0 (las/model.py:161-162); tests may set 0 for a noise-free check
         self.sigmoid_noise = 1.0 if hp["attention_type"] == "bahdanau_monotonic" else 0.0
-        if hp.get("embedding_size"):
-            raise NotImplementedError("training path: --embedding_size is not built")
+        if hp.get("embedding_size") and (hp.get("binary_outputs") or self.sample_prob > 0.0):
+            # the reference's embedding_fn looks float feature vectors up in target_embedding there (las/model.py:229-237): ill-formed
+            raise NotImplementedError("training path: --embedding_size with binary_outputs or scheduled sampling is not built")
+        self.dx_in = None
         self.att_layer = int(hp.get("attention_layer_size") or 0)
         if self.att_layer and hp.get("bottom_only"):
             raise NotImplementedError("training path: attention_layer_size with --bottom_only is not built")
@@ -467,6 +475,7 @@ class SpellerTrain:
         d.memory, d.mem_len, d.x_in = memory.data_ptr(), mem_len.data_ptr(), x_in.data_ptr()
         d.logits = logits.data_ptr()
         d.dlogits = dlogits.data_ptr() if dlogits is not None else None
+        d.dx_in = self.dx_in.data_ptr() if (self.dx_in is not None and dlogits is not None) else None
         d.dmemory = dmemory.data_ptr() if dmemory is not None else None
         if self.init is not None:
             for l, (c0, h0) in enumerate(self.init):
@@ -500,18 +509,22 @@ class SpellerTrain:
         _lib.count_launches(3 + S * (self.hp["decoder_layers"] + 1))
         return self.logits
 
-    def backward(self, dlogits, d_enc, datt_extra=None):
+    def backward(self, dlogits, d_enc, datt_extra=None, want_dx=False):
         """Accumulates into d_enc [B,Tm,D] and writes this speller's weight gradients into the TrainState; with
         pass_hidden_state the gradients wrt the initial states land in ``self.d_init`` [(dc, dh)] per seeded cell.
         ``datt_extra`` [B,S,A] (--binf_projection): gradient that reaches the attention vectors besides the projection's."""
         L = _lib.lib()
         self.datt_extra = None if datt_extra is None else datt_extra.contiguous()
+        # want_dx: also the gradient wrt the decoder inputs (through their dropout mask), left in self.dx_in [B,S,E]
+        self.dx_in = torch.empty_like(self.x_in) if want_dx else None
         if self.init is not None:
             self.d_init = [(torch.empty_like(c), torch.empty_like(h)) for c, h in self.init]
         d = self._desc(self.memory, self.mem_len, self.x_in, self.logits, dlogits.contiguous(), d_enc)
         with _lib.stage("train_dec_bwd"):
             _lib.check(L.plas_decoder_train_bwd(C.byref(d), _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr()))
         _lib.count_launches(12 + self.x_in.shape[1] * (1 + 2 * self.hp["decoder_layers"]))
+        if want_dx and self.keep < 1.0:
+            dropout_(self.dx_in, self.dx_in, drop_seed(self.base, 0, self.tid), self.keep, self.st.step_dev)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -597,8 +610,12 @@ def forward_backward(features, labels, st, hp, binf=None):
     # the heads only share the encoder outputs: each speller (forward, loss, backward) runs on its own stream while the
     # CTC head runs on the caller's, each accumulating into its own encoder-output gradient buffer
     jobs = []
+    emb = bool(hp.get("embedding_size"))
+    onehot = torch.nn.functional.one_hot(tin, V).to(torch.float32)
     if not hp.get("binary_outputs") or hp.get("multitask"):
-        jobs.append(("speller", "ce", V, torch.nn.functional.one_hot(tin, V).to(torch.float32), None))
+        # embedding_fn (las/model.py:228-246): one-hot ids, or rows of speller/target_embedding [V, E]
+        x_sp = st.view("speller/target_embedding")[tin].contiguous() if emb else onehot
+        jobs.append(("speller", "ce", V, x_sp, None))
     proj = bool(hp.get("binf_projection"))
     if hp.get("binary_outputs"):
         bt = binf.to(device=dev, dtype=torch.float32).t().contiguous()  # [V, n]
@@ -628,7 +645,11 @@ def forward_backward(features, labels, st, hp, binf=None):
             else:
                 parts[key], dl = sigmoid_ce_grad(logits, lab, w)
                 parts["logits_binf"] = logits
-            sp.backward(dl, d_enc_j, datt_extra)
+            want_dx = emb and scope == "speller"
+            sp.backward(dl, d_enc_j, datt_extra, want_dx=want_dx)
+            if want_dx:  # d(target_embedding)[v] = sum of dX over the positions that fed phone v: OneHot^T dX, fixed order
+                E = x_in.shape[2]
+                gemm_ex(V, E, B * S, onehot.data_ptr(), 1, V, sp.dx_in.data_ptr(), E, 1, st.g("speller/target_embedding"), E)
             done = torch.cuda.Event()
             done.record(stream)
         pending.append((d_enc_j, done, sp))

@@ -44,15 +44,18 @@ def variable_shapes(hp, num_channels=None):
     D = encoder_output_depth(hp)
     A = hp.get("attention_layer_size") or D  # attention_layer_size=None -> attention = context (depth D)
     shapes["speller/memory_layer/kernel"] = (D, Ud)
+    Ein = int(hp.get("embedding_size") or 0) or V  # width of the decoder inputs: embedding lookup or one-hot (las/model.py:228-246)
+    if hp.get("embedding_size"):
+        shapes["speller/target_embedding"] = (V, Ein)
     bottom = bool(hp.get("bottom_only"))
     pre = "speller/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper" if bottom else "speller/decoder/attention_wrapper"
     for k in range(Ld):
         if bottom:  # AttentionMultiCell (las/model.py:20-69): cell 0 under the attention wrapper, upper cells read [prev; old attention]
             name = f"{pre}/lstm_cell" if k == 0 else f"speller/decoder/multi_rnn_cell/cell_{k}/lstm_cell"
-            din = (V + A) if k == 0 else ((A if k == 1 else Ud) + A)
+            din = (Ein + A) if k == 0 else ((A if k == 1 else Ud) + A)
         else:
             name = f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell"
-            din = (V + A) if k == 0 else Ud
+            din = (Ein + A) if k == 0 else Ud
         shapes[name + "/kernel"] = (din + Ud, 4 * Ud)
         shapes[name + "/bias"] = (4 * Ud,)
     at = hp["attention_type"]

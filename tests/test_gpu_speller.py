@@ -264,3 +264,40 @@ def test_attention_layer_size_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V
     ref_tf, _ = ol.Speller(enc, lens, params, hp, "fp32").teacher_forced(tin, tlen)
     out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(), "train", hp, w)
     assert_parity(out.rnn_output, ref_tf, "fp32", "teacher-forced logits")
+
+
+# ---- embedding_size != 0 (las/model.py:230-237): the lookup folds into cell 0's kernel rows, for every decoder ----
+@gpu
+@pytest.mark.parametrize("precision,att,B,Tm,U,Ud,Ld,V,E,bottom", [("fp32", "luong", 4, 11, 16, 32, 1, 12, 8, False),
+                                                                  ("fp32", "bahdanau", 6, 17, 16, 48, 2, 20, 16, True),
+                                                                  ("bf16", "bahdanau", 9, 21, 32, 64, 2, 30, 24, False),
+                                                                  ("fp32", "luong_monotonic", 5, 10, 16, 32, 2, 14, 6, False)])
+def test_target_embedding_greedy_and_teacher_forced(precision, att, B, Tm, U, Ud, Ld, V, E, bottom):
+    import torch
+    from phones_las_b200.speller import speller
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
+                        num_channels=4, attention_type=att, embedding_size=E, bottom_only=bottom)
+    params = _score_bias(weights.init_params(hp, seed=Ud + E, projection_scale=8.0, bias_scale=0.1))
+    assert params["speller/target_embedding"].shape == (V, E)
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(B)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    lens[0] = Tm
+    enc *= (np.arange(Tm)[None, :, None] < lens[:, None, None])
+    if precision == "bf16":
+        enc = ol.round_bf16(enc)
+    w = _device_speller(hp, params, D, precision)
+    enc_t = torch.from_numpy(enc).cuda().to(torch.bfloat16 if precision == "bf16" else torch.float32)
+    ref_logits, ref_ids, ref_align, ref_len, _ = ol.Speller(enc, lens, params, hp, precision).greedy()
+    out, st, seq_len = speller(enc_t, None, None, torch.from_numpy(lens).cuda(), None, "infer", hp, w)
+    logits, ids = to_np(out.rnn_output), out.sample_id.cpu().numpy()
+    assert_parity(logits[:, :1], ref_logits[:, :1], precision, "logits step 0")
+    if top2_margin(ref_logits) > (1e-4 if precision == "fp32" else 5e-2):
+        np.testing.assert_array_equal(ids, ref_ids)
+        assert_parity(logits, ref_logits, precision, "logits")
+    tin, tout, tlen = synth.synth_labels(B, 5, V, seed=4)
+    hp["sampling_probability"] = 0.0
+    ref_tf, _ = ol.Speller(enc, lens, params, hp, precision).teacher_forced(tin, tlen)
+    out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(), "train", hp, w)
+    assert_parity(out.rnn_output, ref_tf, precision, "teacher-forced logits")

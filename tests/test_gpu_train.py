@@ -697,3 +697,39 @@ def test_log_probs_regulariser_matches_autograd():
     val, datt = tr.log_probs_reg_grad(att.cuda(), 0.3)
     assert abs(val.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
     assert scaled_err(datt, ref_in.grad) < 1e-5
+
+
+# ---- embedding_size != 0 (las/model.py:230-237): decoder inputs are rows of speller/target_embedding ----
+@gpu
+@pytest.mark.parametrize("att,Ld,bottom,dropout", [("luong", 1, False, 0.0), ("bahdanau", 2, False, 0.25), ("luong", 2, True, 0.0)])
+def test_train_step_target_embedding(att, Ld, bottom, dropout):
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, U, Ud, V, S, E = 6, 44, 6, 16, 32, 13, 6, 10
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
+                        attention_type=att, dropout=dropout, sampling_probability=0.0, embedding_size=E, bottom_only=bottom,
+                        l2_reg_scale=1e-4, ctc_weight=0.3)
+    params = weights.init_params(hp, seed=E + Ld, bias_scale=0.05, projection_scale=4.0)
+    x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    st = tr.TrainState(params)
+    st.step = 2
+    masks = None
+    if dropout > 0:
+        rm = tr.reference_masks(hp, 2, B, T, C, S)
+        assert rm["speller"]["x"].shape == (B, S, E)
+        masks = {sc: {kk: torch.tensor(vv, dtype=torch.float64) for kk, vv in m.items()} for sc, m in rm.items()}
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, masks=masks)
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp)
+    assert scaled_err(parts["logits"], ref_parts["logits"].detach()) < 1e-5
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+    assert np.abs(raw["speller/target_embedding"]).max() > 0

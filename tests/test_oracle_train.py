@@ -246,3 +246,25 @@ def test_binf_projection_oracles_agree():
     assert abs(lt.compute_log_probs_loss(att).item() - olo.compute_log_probs_loss(att.numpy())) < 1e-9
     greedy = sp.greedy()
     assert greedy[0].shape[2] == V and greedy[1].max() < V
+
+
+def test_embedding_size_oracles_agree():
+    """embedding_size != 0 (las/model.py:230-237): decoder inputs are rows of speller/target_embedding."""
+    V, E = 11, 6
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=4, decoder_units=16, decoder_layers=2, num_channels=4,
+                        embedding_size=E, l2_reg_scale=0.0)
+    params = weights.init_params(hp, seed=5, bias_scale=0.1)
+    assert params["speller/target_embedding"].shape == (V, E)
+    assert params["speller/decoder/attention_wrapper/multi_rnn_cell/cell_0/lstm_cell/kernel"].shape[0] == E + weights.encoder_output_depth(hp) + 16
+    x, lens = synth.synth_features(3, 12, 4, var_len=True)
+    (enc, enc_len), _ = ol.listener(x, lens, params, hp)
+    tin, tout, tlen = synth.synth_labels(3, 5, V)
+    ref, _ = ol.Speller(enc, enc_len, params, hp).teacher_forced(tin, tlen)
+    tp = {k: v.requires_grad_(True) for k, v in _tp(params).items()}
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    loss, parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp)
+    assert np.abs(parts["logits"].detach().numpy() - ref).max() < 5e-6
+    loss.backward()
+    g = tp["speller/target_embedding"].grad
+    used = np.unique(tin)
+    assert g[used].abs().sum() > 0 and g[[v for v in range(V) if v not in used]].abs().sum() == 0
