@@ -210,17 +210,22 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
         if fed_inputs is not None:
             fed_inputs.append(dec_inputs[t])
         if bottom:
-            if masks is not None:
-                raise NotImplementedError("dropout masks with bottom_only")
             old = attention
             (k0, b0), (c, h) = cells[0], state[0]
-            c0, h0 = _cell(torch.cat([dec_inputs[t], old, h], 1) @ k0 + b0, c)
+            if masks is None:
+                inp0 = torch.cat([dec_inputs[t], old, h], 1)
+            else:  # DropoutWrapper on every cell: cell 0 drops [x_t; attention_{t-1}], cell l >= 1 its [output below; old attention]
+                inp0 = torch.cat([dec_inputs[t] * masks["x"][:, t], old * masks["att"][:, t], h], 1)
+            c0, h0 = _cell(inp0 @ k0 + b0, c)
             new_state = [(c0, h0)]
             align = attend(h0, t, align if mono else None)
             attention = torch.einsum("bt,btd->bd", align, values)
             cur = attention
-            for (k, b), (c, h) in zip(cells[1:], state[1:]):
-                c2, h2 = _cell(torch.cat([cur, old, h], 1) @ k + b, c)
+            for li, ((k, b), (c, h)) in enumerate(zip(cells[1:], state[1:]), start=1):
+                xin = torch.cat([cur, old], 1)
+                if masks is not None:
+                    xin = xin * masks[("in", li)][:, t]
+                c2, h2 = _cell(torch.cat([xin, h], 1) @ k + b, c)
                 new_state.append((c2, h2))
                 cur = h2
             state = new_state

@@ -42,6 +42,10 @@ struct CellFwdArgs {
   const int* skip;                      // inference loop: *skip != 0 -> every utterance has finished, the launch is a no-op
   float* hdrop_out;                     // dropped-out copy of h feeding the layer above (NULL: no dropout / top layer)
   long long idx_base; unsigned seed, thresh; float inv_keep; const unsigned* step_ptr;  // mask index of (b,u) = b*s_h + idx_base + u
+  // bottom_only with dropout (DropoutWrapper around every cell of the AttentionMultiCell): the first Kdrop input columns are the
+  // cell's dropped-out input; the mask is applied as the row is staged (element b*dm_stride + dm_base + k of the cell's
+  // [B][S][Kdrop] mask, seed dm_seed) and the dropped row is kept in xdrop for the weight-gradient GEMM.  Kdrop = 0: none.
+  int Kdrop; long long dm_stride, dm_base; unsigned dm_seed; float* xdrop; long long s_xd;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -95,6 +99,20 @@ __global__ void __launch_bounds__(256) dec_cell_fwd_kernel(CellFwdArgs p) {
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (p.Kdrop > 0 && 4 * q_lo < p.Kdrop) {
+    const unsigned dseed = p.dm_seed + (p.step_ptr ? *p.step_ptr : 0u) * DROP_STEP_MUL;
+    for (int i = threadIdx.x; i < DT_ROWS * nq * 4; i += 256) {
+      const int r = i / (nq * 4), c = i - r * (nq * 4);
+      const int k = 4 * q_lo + c;
+      const int b = b0 + r;
+      if (k < p.Kdrop && b < p.B) {
+        const float v = s_a[(size_t)r * AS + c] * drop_scale((uint64_t)((long long)b * p.dm_stride + p.dm_base + k), dseed, p.thresh, p.inv_keep);
+        s_a[(size_t)r * AS + c] = v;
+        if (blockIdx.y == 0 && p.xdrop) p.xdrop[(long long)b * p.s_xd + k] = v;
+      }
+    }
+    __syncthreads();
+  }
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float* arow = s_a + (size_t)lane * AS;
   const float* wbase = s_w + 8 * warp;
@@ -894,7 +912,7 @@ __global__ void dec_infer_finish_kernel(InferState st, int B, int t, int eos_id,
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
-  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh, ctx, datt, dqx, psave, dalign, dbias;
+  size_t keys, att, att_prev, align, pq, dscore, dpq, dinp[4], dq, dc[4], dkeys, dv_acc, dctx, gh, ctx, datt, dqx, psave, dalign, dbias, xdrop[4];
   size_t z[4], c[4], h[4], hprev[4], hdrop[4];
   size_t splitk, splitk_bytes;
   size_t total;
@@ -933,8 +951,10 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
     w.dqx = take(B * Ud);
   }
   for (int l = 0; l < 4; ++l) {
-    w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = w.hdrop[l] = 0;
+    w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = w.hdrop[l] = w.xdrop[l] = 0;
     if (l >= d.n_layers) continue;
+    if (d.bottom_only && d.keep_prob < 1.f)  // dropped-out inputs of cell l: attention_{t-1} (l = 0) or [output below; old attention]
+      w.xdrop[l] = take(B * S * (l == 0 ? D : (l == 1 ? D : Ud) + D));
     w.z[l] = take(B * S * 4 * Ud);
     w.c[l] = take(B * S * Ud);
     w.h[l] = take(B * S * Ud);
@@ -1104,6 +1124,7 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     a.z_out = F(w.z[l]) + (size_t)slot * 4 * Ud; a.s_z = 2LL * 4 * Ud;
     a.c_out = F(w.c[l]) + (size_t)slot * Ud; a.h_out = F(w.h[l]) + (size_t)slot * Ud; a.s_h = 2LL * Ud;
     a.hprev_next = nullptr; a.hdrop_out = nullptr;
+    a.Kdrop = 0; a.dm_stride = a.dm_base = 0; a.dm_seed = 0; a.xdrop = nullptr; a.s_xd = 0;
     a.idx_base = 0; a.seed = 0; a.thresh = 0; a.inv_keep = 1.f; a.step_ptr = nullptr;
     const int per = ((a.K1 + a.K2 + a.K3) / 4 + CF_KS - 1) / CF_KS;
     const size_t smem = ((size_t)DT_ROWS * (4 * per + 4) + (size_t)4 * per * 4 * CF_UG + (size_t)CF_KS * DT_ROWS * 8) * 4;
@@ -1246,9 +1267,11 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
-  PLAS_REQUIRE(d->keep_prob == 1.f, "dec_train: dropout with bottom_only is not built");
   PLAS_REQUIRE(d->att_layer == 0, "dec_train: attention_layer_size with bottom_only is not built");
   const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
+  const bool drop = d->keep_prob < 1.f;
+  const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
+  const float inv_keep = 1.0f / d->keep_prob;
 
   int rc;
   if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud))) return rc;
@@ -1290,7 +1313,13 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
       a.z_out = F(w.z[l]) + (size_t)t * 4 * Ud; a.s_z = sz;
       a.c_out = F(w.c[l]) + (size_t)t * Ud; a.h_out = F(w.h[l]) + (size_t)t * Ud; a.s_h = sh;
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
-      a.hdrop_out = nullptr; a.idx_base = 0; a.seed = 0; a.thresh = 0; a.inv_keep = 1.f; a.step_ptr = nullptr;
+      a.hdrop_out = nullptr; a.idx_base = 0; a.seed = 0; a.thresh = thresh; a.inv_keep = inv_keep; a.step_ptr = d->drop_step;
+      a.Kdrop = 0; a.dm_stride = a.dm_base = 0; a.dm_seed = 0; a.xdrop = nullptr; a.s_xd = 0;
+      if (drop) {  // input dropout of cell l: seed drop_seed + l, mask tensor [B][S][Kdrop]
+        a.Kdrop = l == 0 ? D : a.K1 + a.K2;
+        a.dm_stride = (long long)S * a.Kdrop; a.dm_base = (long long)t * a.Kdrop; a.dm_seed = d->drop_seed + (unsigned)l;
+        a.xdrop = F(w.xdrop[l]) + (size_t)t * a.Kdrop; a.s_xd = a.dm_stride;
+      }
       if ((rc = launch_cell_fwd(st, a, B, Ud))) return rc;
       if (l == 0) {  // the attention follows cell 0 (its query) and feeds cell 1 of the same step
         AttFwdArgs q;
@@ -1333,6 +1362,9 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   float* dctx = F(w.dctx);
   float* sk = F(w.splitk);
   const size_t skb = w.splitk_bytes;
+  const bool drop = d->keep_prob < 1.f;
+  const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
+  const float inv_keep = 1.0f / d->keep_prob;
   int rc;
   // projection: reads the top cell's h (L > 1) or the attention (L == 1)
   if (L > 1) {
@@ -1389,7 +1421,11 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
       g.dz = c.z; g.s_z = sz;
       g.w = d->kernel[l] + (size_t)(l == 0 ? E : 0) * 4 * Ud;
       g.dinp = dinp(l, t); g.s_o = g.K;
-      return launch_gemv_t(st, g, B);
+      if ((rc = launch_gemv_t(st, g, B))) return rc;
+      if (drop)  // back through the cell's input dropout: every reader of dinp's input columns then sees the masked gradient
+        dec_add_rows_kernel<<<(B * Kin(l) + 255) / 256, 256, 0, st>>>(dinp(l, t), g.K, nullptr, 0, dinp(l, t), g.K, B, Kin(l), (long long)S * Kin(l),
+                                                                      (long long)t * Kin(l), d->drop_seed + (unsigned)l, thresh, inv_keep, d->drop_step);
+      return PLAS_OK;
     };
     for (int l = L - 1; l >= 1; --l)
       if ((rc = cell_and_gemv(l))) return rc;
@@ -1451,12 +1487,16 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     if (l == 0) {
       if ((rc = wg(d->x_in, E, 0))) return rc;
       if (d->dx_in && (rc = gemm(st, BS, E, 4 * Ud, dz, 4 * Ud, 1, d->kernel[0], 1, 4 * Ud, d->dx_in, E))) return rc;  // dX = dZ_0 W_0[0:E]^T
-      if ((rc = wg(F(w.att_prev), D, E))) return rc;
+      if ((rc = wg(drop ? F(w.xdrop[0]) : F(w.att_prev), D, E))) return rc;
       if ((rc = wg(F(w.hprev[0]), Ud, (size_t)E + D))) return rc;
     } else {
       const int k1 = l == 1 ? D : Ud;
-      if ((rc = wg(l == 1 ? F(w.att) : F(w.h[l - 1]), k1, 0))) return rc;
-      if ((rc = wg(F(w.att_prev), D, k1))) return rc;
+      if (drop) {  // the dropped-out [output below; old attention] rows the forward pass kept
+        if ((rc = wg(F(w.xdrop[l]), k1 + D, 0))) return rc;
+      } else {
+        if ((rc = wg(l == 1 ? F(w.att) : F(w.h[l - 1]), k1, 0))) return rc;
+        if ((rc = wg(F(w.att_prev), D, k1))) return rc;
+      }
       if ((rc = wg(F(w.hprev[l]), Ud, (size_t)k1 + D))) return rc;
     }
     if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;
@@ -1548,6 +1588,7 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
       a.skip = nullptr;
       a.hprev_next = t + 1 < S ? F(w.hprev[l]) + (size_t)(t + 1) * Ud : nullptr;
       a.hdrop_out = (drop && l + 1 < L) ? F(w.hdrop[l]) + (size_t)t * Ud : nullptr;
+      a.Kdrop = 0; a.dm_stride = a.dm_base = 0; a.dm_seed = 0; a.xdrop = nullptr; a.s_xd = 0;
       a.idx_base = (long long)t * Ud; a.seed = d->drop_seed + 1 + l; a.thresh = thresh; a.inv_keep = inv_keep; a.step_ptr = d->drop_step;
       {
         const int per = ((a.K1 + a.K2) / 4 + CF_KS - 1) / CF_KS;

@@ -134,6 +134,10 @@ def reference_masks(hp, step, B, T, C, S, binf_count=0):
              "att": dropout_mask(B * S * D, drop_seed(base, step, tid + 1), keep).reshape(B, S, D)}
         for l in range(hp["decoder_layers"] - 1):
             m[("h", l)] = dropout_mask(B * S * Ud, (drop_seed(base, step, tid + 1) + 1 + l) & 0xFFFFFFFF, keep).reshape(B, S, Ud)
+        if hp.get("bottom_only"):  # AttentionMultiCell: cell l >= 1 drops its whole input [output below; old attention]
+            for l in range(1, hp["decoder_layers"]):
+                K = (D if l == 1 else Ud) + D
+                m[("in", l)] = dropout_mask(B * S * K, (drop_seed(base, step, tid + 1) + l) & 0xFFFFFFFF, keep).reshape(B, S, K)
         out[scope] = m
     return out
 
@@ -423,8 +427,6 @@ class SpellerTrain:
             raise NotImplementedError("training path: attention_layer_size with --bottom_only is not built")
         self.bottom = bool(hp.get("bottom_only"))
         self.pass_state = self.bottom and bool(hp.get("pass_hidden_state"))  # las/model.py:260 needs both flags
-        if self.bottom and float(hp.get("dropout", 0.0)) > 0.0:
-            raise NotImplementedError("training path: dropout with --bottom_only is not built")
 
     def _desc(self, memory, mem_len, x_in, logits, dlogits=None, dmemory=None):
         st, hp, sc = self.st, self.hp, self.scope

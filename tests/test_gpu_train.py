@@ -733,3 +733,42 @@ def test_train_step_target_embedding(att, Ld, bottom, dropout):
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
     assert np.abs(raw["speller/target_embedding"]).max() > 0
+
+
+@gpu
+@pytest.mark.parametrize("att,Ld,U,Ud,ps,sampling", [("luong", 1, 16, 32, False, 0.0), ("bahdanau", 3, 16, 48, False, 0.0),
+                                                     ("luong", 2, 32, 32, True, 0.0), ("luong_monotonic", 2, 16, 32, False, 0.3)])
+def test_train_step_bottom_only_with_dropout(att, Ld, U, Ud, ps, sampling):
+    """The README's 'true LAS' flags with the default-style dropout: every cell of the AttentionMultiCell sits in a DropoutWrapper,
+    so cell 0 drops [x_t; attention_{t-1}] and cell l >= 1 its whole input [output below; old attention]."""
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, V, S = 6, 44, 6, 13, 6
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
+                        attention_type=att, dropout=0.25, sampling_probability=sampling, bottom_only=True, pass_hidden_state=ps,
+                        l2_reg_scale=1e-4, ctc_weight=0.3)
+    params = _set_score_bias(weights.init_params(hp, seed=U + Ud + Ld, bias_scale=0.05, projection_scale=4.0), 0.3)
+    x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    st = tr.TrainState(params)
+    st.step = 3
+    rm = tr.reference_masks(hp, 3, B, T, C, S)
+    D = weights.encoder_output_depth(hp)
+    for l in range(1, Ld):
+        assert rm["speller"][("in", l)].shape == (B, S, (D if l == 1 else Ud) + D)
+    masks = {sc: {kk: torch.tensor(vv, dtype=torch.float64) for kk, vv in m.items()} for sc, m in rm.items()}
+    sampling_rng = tr.reference_sampling(hp, 3, B, S, V) if sampling > 0 else None
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, masks=masks,
+                                        sampling=sampling_rng)
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp)
+    assert scaled_err(parts["logits"], ref_parts["logits"].detach()) < 1e-5
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k
