@@ -69,18 +69,31 @@ def las_predict(features, hp, weights, want_alignment=True, trim=True, want_prob
 
 
 def las_eval(features, labels, hp, weights):
-    """model_helper.py:165-345 in EVAL mode (beam_width == 0, no binary-feature speller): greedy decode, the EVAL branch of
+    """model_helper.py:165-345 in EVAL mode (beam_width == 0; phone speller and / or the --binf_projection speller): greedy decode, the EVAL branch of
     ``compute_loss`` (logits cut at max(final_sequence_length), targets padded with eos, mask = elementwise max of the
     lengths; model_helper.py:54-76) and the ``edit_distance`` metric with repeat merging and EOS trimming
     (utils/metrics_utils.py:8-41, host side).  Returns {'loss', 'edit_distance' [B] (numpy), 'sample_ids', ...}."""
     from . import losses, metrics
     pred = las_predict(features, hp, weights, want_alignment=False, want_probs=False)
-    targets = labels["targets_outputs"].to(pred["logits"].device)
-    tlen = labels["target_sequence_length"].to(pred["logits"].device)
-    loss = losses.compute_loss(pred["logits"], targets, pred["final_sequence_length"], tlen, "eval", hp["eos_id"])
-    ed = metrics.edit_distance(pred["sample_ids"].cpu().numpy(), targets.cpu().numpy(), hp["eos_id"], hp.get("mapping"))
-    return {"loss": loss, "edit_distance": ed, "sample_ids": pred["sample_ids"], "logits": pred["logits"],
-            "final_sequence_length": pred["final_sequence_length"]}
+    dev = pred["encoder_out"].device
+    targets = labels["targets_outputs"].to(dev)
+    tlen = labels["target_sequence_length"].to(dev)
+    out, loss = {}, None
+    if "logits" in pred:
+        loss = losses.compute_loss(pred["logits"], targets, pred["final_sequence_length"], tlen, "eval", hp["eos_id"])
+        out.update(edit_distance=metrics.edit_distance(pred["sample_ids"].cpu().numpy(), targets.cpu().numpy(), hp["eos_id"], hp.get("mapping")),
+                   sample_ids=pred["sample_ids"], logits=pred["logits"], final_sequence_length=pred["final_sequence_length"])
+    if "logits_binf" in pred:
+        # --binf_projection: the same softmax loss on the transformed logits (model_helper.py:326-329; the log-probability
+        # regulariser exists in TRAIN only, :243-245,330-331) and 'edit_distance_binf' (:304-306)
+        loss_b = losses.compute_loss(pred["logits_binf"], targets, pred["final_sequence_length_binf"], tlen, "eval", hp["eos_id"])
+        loss = loss_b if loss is None else loss + loss_b
+        out.update(loss_binf=loss_b, logits_binf=pred["logits_binf"], sample_ids_phones_binf=pred["sample_ids_phones_binf"],
+                   edit_distance_binf=metrics.edit_distance(pred["sample_ids_phones_binf"].cpu().numpy(), targets.cpu().numpy(),
+                                                            hp["eos_id"], hp.get("mapping")))
+        out.setdefault("edit_distance", out["edit_distance_binf"])  # model_helper.py:308
+    out["loss"] = loss
+    return out
 
 
 class LASModel:

@@ -86,3 +86,31 @@ def test_no_cuda_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(_lib.PlasError):
         _lib.require_cuda()
+
+
+def test_training_descriptor_layouts_match_c():
+    """Every field offset (and the size) of the training-path / fp32-inference descriptors: ctypes mirror vs gcc on plas.h."""
+    import subprocess
+    import tempfile
+    from phones_las_b200 import _lib
+    structs = {"plas_gemm_ex_desc": _lib.GemmExDesc, "plas_rec_train_desc": _lib.RecTrainDesc,
+               "plas_dec_train_desc": _lib.DecTrainDesc, "plas_dec_infer_desc": _lib.DecInferDesc}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("%zu\\n", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({cname}, {fname}));')
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "plas.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0;\n}\n"
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
+    i = 0
+    for cname, cls in structs.items():
+        assert out[i] == ctypes.sizeof(cls), cname
+        i += 1
+        for fname, *_ in cls._fields_:
+            assert out[i] == getattr(cls, fname).offset, f"{cname}.{fname}"
+            i += 1

@@ -190,3 +190,12 @@ def test_predict_binf_projection(multitask):
         assert_parity(pred["alignment_binf"].cpu().numpy(), ref_align, "fp32", "alignment_binf")
     if not multitask:
         assert torch.allclose(pred["probs"], torch.softmax(pred["logits_binf"], -1))
+    # EVAL mode: softmax loss of the projected logits against the phone targets (+ the phone speller's under --multitask)
+    from oracle import losses as olo
+    from phones_las_b200.model import las_eval
+    tin, tout, tlen = synth.synth_labels(B, 7, V, seed=6)
+    ev = las_eval({"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()},
+                  {"targets_outputs": torch.from_numpy(tout).cuda(), "target_sequence_length": torch.from_numpy(tlen).cuda()}, hp, w)
+    want = olo.compute_loss(ref_logits, tout, ref_len, tlen, "eval", hp["eos_id"])
+    assert abs(ev["loss_binf"].item() - want) < 1e-4 * max(1.0, abs(want))
+    assert ev["edit_distance_binf"].shape == (B,) and ("loss_binf" in ev) and (("logits" in ev) == multitask)
