@@ -265,8 +265,9 @@ class Speller:
             else:
                 name = f"{scope}/decoder/attention_wrapper/multi_rnn_cell/cell_{k}/lstm_cell"
             self.cells.append((self.q(params[name + "/kernel"]), params[name + "/bias"].astype(F32)))
-        al = f"{scope}/decoder/attention_wrapper/attention_layer/kernel"
-        self.wal = self.q(params[al]) if (hp.get("attention_layer_size") and not self.bottom_only) else None
+        al = (f"{scope}/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper/attention_layer/kernel" if self.bottom_only
+              else f"{scope}/decoder/attention_wrapper/attention_layer/kernel")
+        self.wal = self.q(params[al]) if hp.get("attention_layer_size") else None
         self.wp = self.q(params[f"{scope}/decoder/projection_layer/kernel"])
         self.bp = params[f"{scope}/decoder/projection_layer/bias"].astype(F32)
         # --binf_projection (las/model.py:240-241,251-257): ``binf`` = binf2phone [n, V]; the decoder is fed the binary-feature
@@ -276,7 +277,7 @@ class Speller:
         if hp.get("embedding_size"):
             self.target_embedding = np.asarray(params[f"{scope}/target_embedding"], F32)
         if self.binf is not None:
-            assert hp.get("binf_projection") and not self.bottom_only and self.wal is not None
+            assert hp.get("binf_projection") and not self.bottom_only and self.wal is not None  # bottom_only: not restated
             assert self.wal.shape[1] == 2 * self.binf.shape[0], "attention_layer_size must be 2 * binf_count (las/model.py:180-183)"
         self.enc_len = np.asarray(enc_len)
 
@@ -326,6 +327,8 @@ class Speller:
         new_cells = [(c2, h2)]
         align = self.att(h2, state["alignments"])
         context = np.einsum("bt,btd->bd", align, self.att.values, dtype=F32)
+        if self.wal is not None:  # attention_layer_size: attention = Dense([cell 0 output; context]), no bias
+            context = (np.concatenate([h2, context], axis=1) @ self.wal).astype(F32)
         cur = q(context)  # AttentionWrapper(output_attention=True) returns the attention as cell 0's output
         for (k, b), (c, h) in zip(self.cells[1:], state["cells"][1:]):
             z = (np.concatenate([cur, old_att, h], axis=1) @ k + b).astype(F32)

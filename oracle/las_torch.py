@@ -164,7 +164,7 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
     if bottom and hp.get("pass_hidden_state") and encoder_state is not None:  # las/model.py:259-267
         for l, st in enumerate(encoder_state[:len(state)]):
             state[l] = st
-    w_al = params[f"{pre}/attention_layer/kernel"] if (hp.get("attention_layer_size") and not bottom) else None
+    w_al = params[f"{pre}/attention_layer/kernel"] if hp.get("attention_layer_size") else None
     attention = enc_out.new_zeros((B, D if w_al is None else w_al.shape[1]))
     logits = []
     neg_inf = torch.tensor(float("-inf"), dtype=enc_out.dtype)
@@ -220,6 +220,8 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
             new_state = [(c0, h0)]
             align = attend(h0, t, align if mono else None)
             attention = torch.einsum("bt,btd->bd", align, values)
+            if w_al is not None:  # attention_layer_size: attention = Dense([cell 0 output; context]), no bias
+                attention = torch.cat([h0, attention], 1) @ w_al
             cur = attention
             for li, ((k, b), (c, h)) in enumerate(zip(cells[1:], state[1:]), start=1):
                 xin = torch.cat([cur, old], 1)

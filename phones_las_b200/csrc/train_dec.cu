@@ -954,7 +954,7 @@ static DecTrainWs dec_train_ws(const plas_dec_train_desc& d) {
     w.z[l] = w.c[l] = w.h[l] = w.hprev[l] = w.dinp[l] = w.dc[l] = w.hdrop[l] = w.xdrop[l] = 0;
     if (l >= d.n_layers) continue;
     if (d.bottom_only && d.keep_prob < 1.f)  // dropped-out inputs of cell l: attention_{t-1} (l = 0) or [output below; old attention]
-      w.xdrop[l] = take(B * S * (l == 0 ? D : (l == 1 ? D : Ud) + D));
+      w.xdrop[l] = take(B * S * (l == 0 ? Aw : (l == 1 ? Aw : Ud) + Aw));
     w.z[l] = take(B * S * 4 * Ud);
     w.c[l] = take(B * S * Ud);
     w.h[l] = take(B * S * Ud);
@@ -1076,7 +1076,7 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
   }
   const int A = d->att_layer > 0 ? d->att_layer : D;
   if (d->att_layer > 0)
-    PLAS_REQUIRE(d->w_att_layer && !d->bottom_only && A % 4 == 0, "dec_infer: attention_layer_size needs its kernel, the default wiring and A % 4 == 0");
+    PLAS_REQUIRE(d->w_att_layer && A % 4 == 0, "dec_infer: attention_layer_size needs its kernel and A %% 4 == 0");
   PLAS_CUDA(cudaMemsetAsync(F(w.att), 0, (size_t)B * 2 * A * 4, st));
   dec_infer_init_kernel<<<1, 128, 0, st>>>(is, d->mem_len, B, S, d->teacher_forced, d->decoding_length_factor, d->sos_id, d->seq_len, d->n_steps);
   PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
@@ -1113,9 +1113,9 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
       a.w = d->kernel[l];
     } else {  // AttentionMultiCell: [output of the cell below (cell 0's output is the NEW attention); OLD attention; h_{t-1}]
       a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
-      if (l == 1) { a.in1 = F(w.att) + (size_t)slot * D; a.s1 = 2LL * D; a.K1 = D; }
+      if (l == 1) { a.in1 = F(w.att) + (size_t)slot * A; a.s1 = 2LL * A; a.K1 = A; }
       else { a.in1 = F(w.h[l - 1]) + (size_t)slot * Ud; a.s1 = 2LL * Ud; a.K1 = Ud; }
-      a.in2 = att_old; a.s2 = 2LL * D; a.K2 = D;
+      a.in2 = att_old; a.s2 = 2LL * A; a.K2 = A;
       a.in3 = hprev; a.s3 = s_hprev; a.K3 = Ud;
       a.w = d->kernel[l];
     }
@@ -1173,6 +1173,11 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     if (bottom) {  // attention right after cell 0 (its query), upper cells afterwards
       if ((rc = launch_cell(t, 0))) return rc;
       launch_attention(t, 0);
+      if (d->att_layer > 0) {  // the wrapped cell 0 emits attention = Dense([h0; context]) (A wide)
+        float* att_t = F(w.att) + (size_t)slot * A;
+        if ((rc = gemm(st, B, A, Ud, F(w.h[0]) + (size_t)slot * Ud, 2LL * Ud, 1, d->w_att_layer, A, 1, att_t, 2LL * A))) return rc;
+        if ((rc = gemm(st, B, A, D, F(w.ctx), D, 1, d->w_att_layer + (size_t)Ud * A, A, 1, att_t, 2LL * A, nullptr, 1.f))) return rc;
+      }
       for (int l = 1; l < L; ++l)
         if ((rc = launch_cell(t, l))) return rc;
     } else {
@@ -1267,7 +1272,8 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   unsigned char* base = (unsigned char*)workspace;
   auto F = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
   const int B = d->B, S = d->S, Tm = d->Tm, D = d->D, Ud = d->Ud, E = d->E, L = d->n_layers;
-  PLAS_REQUIRE(d->att_layer == 0, "dec_train: attention_layer_size with bottom_only is not built");
+  const int AL = d->att_layer, A = AL > 0 ? AL : D;  // attention_layer_size: the wrapped cell 0 emits Dense([h0; context]), A wide
+  if (AL > 0) PLAS_REQUIRE(d->w_att_layer && A % 4 == 0, "dec_train: attention_layer_size needs its kernel and A %% 4 == 0");
   const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
   const bool drop = d->keep_prob < 1.f;
   const unsigned thresh = (unsigned)(d->keep_prob * 16777216.0f);
@@ -1277,7 +1283,7 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud))) return rc;
   if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
   if ((rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]))) return rc;
-  PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * D * 4, 0, (size_t)D * 4, B, st));
+  PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * A * 4, 0, (size_t)A * 4, B, st));
   for (int l = 0; l < L; ++l) {  // h_{-1}: zeros or the listener's final state (pass_hidden_state, las/model.py:259-267)
     if (d->h_init[l]) PLAS_CUDA(cudaMemcpy2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, d->h_init[l], (size_t)Ud * 4, (size_t)Ud * 4, B, cudaMemcpyDeviceToDevice, st));
     else PLAS_CUDA(cudaMemset2DAsync(F(w.hprev[l]), (size_t)S * Ud * 4, 0, (size_t)Ud * 4, B, st));
@@ -1289,7 +1295,7 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   const size_t att_stage = (size_t)Tm * Ud * 4 + (size_t)Tm * (D / dsplit) * 4;
   const int att_staged = (Ud % 4 == 0 && (D / dsplit) % 4 == 0 && att_smem + att_stage <= 220 * 1024) ? 1 : 0;
   if (att_staged) att_smem += att_stage;
-  const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud, sd = (long long)S * D;
+  const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud, sd = (long long)S * D, sa = (long long)S * A;
   for (int t = 0; t < S; ++t) {
     for (int l = 0; l < L; ++l) {
       CellFwdArgs a;
@@ -1297,14 +1303,14 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
       a.in3 = nullptr; a.s3 = 0; a.K3 = 0;
       if (l == 0) {
         a.pre = F(w.z[0]) + (size_t)t * 4 * Ud; a.s_pre = sz; a.bias = nullptr;
-        a.in1 = F(w.att_prev) + (size_t)t * D; a.s1 = sd; a.K1 = D;
+        a.in1 = F(w.att_prev) + (size_t)t * A; a.s1 = sa; a.K1 = A;
         a.in2 = F(w.hprev[0]) + (size_t)t * Ud; a.s2 = sh; a.K2 = Ud;
         a.w = d->kernel[0] + (size_t)E * 4 * Ud;
       } else {
         a.pre = nullptr; a.s_pre = 0; a.bias = d->bias[l];
-        if (l == 1) { a.in1 = F(w.att) + (size_t)t * D; a.s1 = sd; a.K1 = D; }
+        if (l == 1) { a.in1 = F(w.att) + (size_t)t * A; a.s1 = sa; a.K1 = A; }
         else { a.in1 = F(w.h[l - 1]) + (size_t)t * Ud; a.s1 = sh; a.K1 = Ud; }
-        a.in2 = F(w.att_prev) + (size_t)t * D; a.s2 = sd; a.K2 = D;
+        a.in2 = F(w.att_prev) + (size_t)t * A; a.s2 = sa; a.K2 = A;
         a.in3 = F(w.hprev[l]) + (size_t)t * Ud; a.s3 = sh; a.K3 = Ud;
         a.w = d->kernel[l];
       }
@@ -1316,7 +1322,7 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
       a.hdrop_out = nullptr; a.idx_base = 0; a.seed = 0; a.thresh = thresh; a.inv_keep = inv_keep; a.step_ptr = d->drop_step;
       a.Kdrop = 0; a.dm_stride = a.dm_base = 0; a.dm_seed = 0; a.xdrop = nullptr; a.s_xd = 0;
       if (drop) {  // input dropout of cell l: seed drop_seed + l, mask tensor [B][S][Kdrop]
-        a.Kdrop = l == 0 ? D : a.K1 + a.K2;
+        a.Kdrop = l == 0 ? A : a.K1 + a.K2;
         a.dm_stride = (long long)S * a.Kdrop; a.dm_base = (long long)t * a.Kdrop; a.dm_seed = d->drop_seed + (unsigned)l;
         a.xdrop = F(w.xdrop[l]) + (size_t)t * a.Kdrop; a.s_xd = a.dm_stride;
       }
@@ -1333,21 +1339,29 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
         q.p_save = F(w.psave) + (size_t)t * Tm; q.s_ps = q.s_al;
     q.hard = 0; q.noise_scale = d->attention_type == PLAS_ATT_BAHDANAU_MONOTONIC ? d->sigmoid_noise : 0.f;
     q.noise_seed = d->noise_seed; q.noise_base = (long long)t * Tm;
-        q.att = F(w.att) + (size_t)t * D; q.s_att = sd;
-        q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr;
+        if (AL > 0) { q.att = F(w.ctx) + (size_t)t * D; q.s_att = sd; q.att_next = nullptr; }  // the context goes through the attention layer
+        else { q.att = F(w.att) + (size_t)t * D; q.s_att = sd; q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr; }
         q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = d->drop_step;  // (the noise seed follows the step)
         dec_att_fwd_kernel<<<dim3(B, dsplit), 256, att_smem, st>>>(q);
+        if (AL > 0) {  // attention_t = [h0_t; context_t] W_att (no bias), and the copy every cell reads as OLD attention at step t+1
+          float* att_t = F(w.att) + (size_t)t * A;
+          if ((rc = gemm(st, B, A, Ud, F(w.h[0]) + (size_t)t * Ud, sh, 1, d->w_att_layer, A, 1, att_t, sa))) return rc;
+          if ((rc = gemm(st, B, A, D, F(w.ctx) + (size_t)t * D, sd, 1, d->w_att_layer + (size_t)Ud * A, A, 1, att_t, sa, nullptr, 1.f))) return rc;
+          if (t + 1 < S)
+            PLAS_CUDA(cudaMemcpy2DAsync(F(w.att_prev) + (size_t)(t + 1) * A, (size_t)sa * 4, att_t, (size_t)sa * 4, (size_t)A * 4, B,
+                                        cudaMemcpyDeviceToDevice, st));
+        }
       }
     }
     if (d->sample_prob > 0.f && t + 1 < S) {
       if (L > 1) rc = launch_sched_sample(st, d, w, base, t, F(w.h[L - 1]) + (size_t)t * Ud, sh, Ud);
-      else rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * D, sd, D);
+      else rc = launch_sched_sample(st, d, w, base, t, F(w.att) + (size_t)t * A, sa, A);
       if (rc) return rc;
     }
   }
   PLAS_CUDA(cudaGetLastError());
   if (L > 1) return gemm(st, (long long)B * S, d->n_out, Ud, F(w.h[L - 1]), Ud, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
-  return gemm(st, (long long)B * S, d->n_out, D, F(w.att), D, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+  return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
 }
 
 static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, cudaStream_t st) {
@@ -1360,6 +1374,10 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   const long long BS = (long long)B * S;
   const long long sz = (long long)S * 4 * Ud, sh = (long long)S * Ud, sd = (long long)S * D;
   float* dctx = F(w.dctx);
+  const int AL = d->att_layer, A = AL > 0 ? AL : D;
+  float* datt = AL > 0 ? F(w.datt) : dctx;     // gradient wrt the attention vectors [B][S][A]; without the layer it IS dctx
+  if (AL > 0) PLAS_REQUIRE(d->w_att_layer && d->dw_att_layer, "dec_train_bwd: attention_layer_size needs w_att_layer / dw_att_layer");
+  const long long sa = (long long)S * A;
   float* sk = F(w.splitk);
   const size_t skb = w.splitk_bytes;
   const bool drop = d->keep_prob < 1.f;
@@ -1370,10 +1388,10 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   if (L > 1) {
     if ((rc = gemm(st, BS, Ud, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, F(w.gh), Ud))) return rc;
     if ((rc = gemm(st, Ud, NO, (int)BS, F(w.h[L - 1]), 1, Ud, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
-    PLAS_CUDA(cudaMemsetAsync(dctx, 0, (size_t)BS * D * 4, st));
+    PLAS_CUDA(cudaMemsetAsync(datt, 0, (size_t)BS * A * 4, st));
   } else {
-    if ((rc = gemm(st, BS, D, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, dctx, D))) return rc;
-    if ((rc = gemm(st, D, NO, (int)BS, F(w.att), 1, D, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+    if ((rc = gemm(st, BS, A, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, datt, A))) return rc;
+    if ((rc = gemm(st, A, NO, (int)BS, F(w.att), 1, A, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
   }
   if ((rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
   if (bah) {
@@ -1395,8 +1413,8 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   PLAS_CUDA(cudaFuncSetAttribute(dec_att_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   PLAS_CUDA(cudaFuncSetAttribute(dec_gemv_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   // dinp_l = dz_l W_l^T lives in two slots (parity of t): step t reads step t+1's while it writes its own
-  auto Kin = [&](int l) { return l == 0 ? D : ((l == 1 ? D : Ud) + D); };        // input columns before the h part
-  auto dinp = [&](int l, int t) { return F(w.dinp[l]) + (size_t)(t & 1) * B * (2 * D + Ud); };
+  auto Kin = [&](int l) { return l == 0 ? A : ((l == 1 ? A : Ud) + A); };        // input columns before the h part
+  auto dinp = [&](int l, int t) { return F(w.dinp[l]) + (size_t)(t & 1) * B * (2 * (D > A ? D : A) + Ud); };
   for (int t = S - 1; t >= 0; --t) {
     const bool last = t == S - 1;
     auto cell_and_gemv = [&](int l) -> int {
@@ -1413,7 +1431,7 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
       c.dh_next = last ? nullptr : dinp(l, t + 1) + Kin(l); c.s_dn = Kin(l) + Ud;
       // the layer above reads this layer's h as its first input segment -- except above cell 0, whose output is the attention
       c.dh_above = (l >= 1 && l < L - 1) ? dinp(l + 1, t) : nullptr; c.s_da = Kin(l + 1 < L ? l + 1 : l) + Ud;
-      c.dh_extra = nullptr; c.s_dx = 0;
+      c.dh_extra = (l == 0 && AL > 0) ? F(w.dqx) : nullptr; c.s_dx = Ud;  // the attention layer also reads h0
       c.idx_base = 0; c.seed = 0; c.thresh = 0; c.inv_keep = 1.f; c.step_ptr = nullptr;
       dec_cell_bwd_kernel<<<(B * Ud + 255) / 256, 256, 0, st>>>(c);
       GemvTArgs g;
@@ -1434,14 +1452,30 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     q.keys = F(w.keys); q.values = d->memory; q.mem_len = d->mem_len;
     q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
     q.dctx = dctx + (size_t)t * D; q.s_dc = sd;
-    q.datt_next = last ? nullptr : dinp(0, t + 1); q.s_dn = D + Ud;      // attention_t was cell 0's input at step t+1
+    q.datt_next = nullptr; q.s_dn = 0;
     for (int e = 0; e < 4; ++e) { q.extra[e] = nullptr; q.s_extra[e] = 0; }
-    int ne = 0;
-    if (L > 1) { q.extra[ne] = dinp(1, t); q.s_extra[ne] = Kin(1) + Ud; ++ne; }   // ... cell 1's first input at this step
-    if (!last)
-      for (int l = 1; l < L && ne < 4; ++l) {                                      // ... and every upper cell's OLD attention at step t+1
-        q.extra[ne] = dinp(l, t + 1) + (l == 1 ? D : Ud); q.s_extra[ne] = Kin(l) + Ud; ++ne;
-      }
+    if (AL > 0) {
+      // gradient wrt attention_t (A wide): the projection (L == 1, already in datt) + cell 0's input at step t+1 + cell 1's first
+      // input at this step + every upper cell's OLD attention at step t+1; then back through attention = [h0; context] W_att
+      float* da = datt + (size_t)t * A;
+      auto add = [&](const float* src, long long stride) {
+        dec_add_rows_kernel<<<(B * A + 255) / 256, 256, 0, st>>>(da, sa, da, sa, src, stride, B, A);
+      };
+      if (!last) add(dinp(0, t + 1), Kin(0) + Ud);
+      if (L > 1) add(dinp(1, t), Kin(1) + Ud);
+      if (!last)
+        for (int l = 1; l < L; ++l) add(dinp(l, t + 1) + (l == 1 ? A : Ud), Kin(l) + Ud);
+      if ((rc = gemm(st, B, Ud, A, da, sa, 1, d->w_att_layer, 1, A, F(w.dqx), Ud))) return rc;
+      if ((rc = gemm(st, B, D, A, da, sa, 1, d->w_att_layer + (size_t)Ud * A, 1, A, dctx + (size_t)t * D, sd))) return rc;
+    } else {
+      q.datt_next = last ? nullptr : dinp(0, t + 1); q.s_dn = D + Ud;      // attention_t was cell 0's input at step t+1
+      int ne = 0;
+      if (L > 1) { q.extra[ne] = dinp(1, t); q.s_extra[ne] = Kin(1) + Ud; ++ne; }   // ... cell 1's first input at this step
+      if (!last)
+        for (int l = 1; l < L && ne < 4; ++l) {                                      // ... and every upper cell's OLD attention at step t+1
+          q.extra[ne] = dinp(l, t + 1) + (l == 1 ? D : Ud); q.s_extra[ne] = Kin(l) + Ud; ++ne;
+        }
+    }
     q.dscore = F(w.dscore) + (size_t)t * Tm; q.s_ds = (long long)S * Tm;
     q.score_p = F(w.psave) + (size_t)t * Tm; q.s_sp = q.s_al;
     q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
@@ -1487,21 +1521,25 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     if (l == 0) {
       if ((rc = wg(d->x_in, E, 0))) return rc;
       if (d->dx_in && (rc = gemm(st, BS, E, 4 * Ud, dz, 4 * Ud, 1, d->kernel[0], 1, 4 * Ud, d->dx_in, E))) return rc;  // dX = dZ_0 W_0[0:E]^T
-      if ((rc = wg(drop ? F(w.xdrop[0]) : F(w.att_prev), D, E))) return rc;
-      if ((rc = wg(F(w.hprev[0]), Ud, (size_t)E + D))) return rc;
+      if ((rc = wg(drop ? F(w.xdrop[0]) : F(w.att_prev), A, E))) return rc;
+      if ((rc = wg(F(w.hprev[0]), Ud, (size_t)E + A))) return rc;
     } else {
-      const int k1 = l == 1 ? D : Ud;
+      const int k1 = l == 1 ? A : Ud;
       if (drop) {  // the dropped-out [output below; old attention] rows the forward pass kept
-        if ((rc = wg(F(w.xdrop[l]), k1 + D, 0))) return rc;
+        if ((rc = wg(F(w.xdrop[l]), k1 + A, 0))) return rc;
       } else {
         if ((rc = wg(l == 1 ? F(w.att) : F(w.h[l - 1]), k1, 0))) return rc;
-        if ((rc = wg(F(w.att_prev), D, k1))) return rc;
+        if ((rc = wg(F(w.att_prev), A, k1))) return rc;
       }
-      if ((rc = wg(F(w.hprev[l]), Ud, (size_t)k1 + D))) return rc;
+      if ((rc = wg(F(w.hprev[l]), Ud, (size_t)k1 + A))) return rc;
     }
     if ((rc = plas_colsum_f32(dz, BS, 4 * Ud, 4 * Ud, d->dbias[l], 0, st))) return rc;
   }
   const float* h0 = F(w.h[0]);  // the query is cell 0's output
+  if (AL > 0) {  // dW_att = [H0; Ctx]^T dAtt
+    if ((rc = gemm(st, Ud, A, (int)BS, h0, 1, Ud, datt, A, 1, d->dw_att_layer, A, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+    if ((rc = gemm(st, D, A, (int)BS, F(w.ctx), 1, D, datt, A, 1, d->dw_att_layer + (size_t)Ud * A, A, nullptr, 0.f, 1, 0, 0, 0, sk, skb))) return rc;
+  }
   if (bah) {
     if ((rc = gemm(st, Ud, Ud, (int)BS, h0, 1, Ud, F(w.dpq), Ud, 1, d->dw_query, Ud))) return rc;
     if ((rc = plas_colsum_f32(F(w.dv_acc), B, Ud, Ud, d->dv_att, 0, st))) return rc;

@@ -126,8 +126,8 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     """GNMT-style AttentionMultiCell wiring (las/model.py:20-69, 185-193): fp32 step-kernel decoder only."""
     if precision != "fp32":
         raise NotImplementedError("--bottom_only is built for the fp32 step-kernel decoder (precision='fp32')")
-    if hp.get("attention_layer_size") or hp.get("beam_width"):
-        raise NotImplementedError("attention_layer_size / beam_width != 0 with --bottom_only are not built")
+    if hp.get("beam_width"):
+        raise NotImplementedError("beam_width != 0 is not built (SURVEY section 2: out of scope)")
     self.precision, self.att = precision, hp["attention_type"]
     if self.att not in _lib.ATT_CODES:
         raise NotImplementedError(f"--bottom_only with attention_type={self.att}")
@@ -142,11 +142,18 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     names = [f"{pre}/lstm_cell"] + [f"{scope}/decoder/multi_rnn_cell/cell_{k}/lstm_cell" for k in range(1, self.L)]
     kernels = [np.asarray(params[n + "/kernel"], np.float32) for n in names]
     kernels[0] = fold_embedding(params, hp, scope, kernels[0])
+    A = int(hp.get("attention_layer_size") or 0) or D  # the wrapped cell 0 emits Dense([h0; context]) when attention_layer_size is set
+    if A % 4:
+        raise NotImplementedError("attention_layer_size must be a multiple of 4")
     for k, kern in enumerate(kernels):
-        din = (V + D) if k == 0 else ((D if k == 1 else Ud) + D)
+        din = (V + A) if k == 0 else ((A if k == 1 else Ud) + A)
         assert kern.shape == (din + Ud, 4 * Ud), (k, kern.shape)
     self.tf = dict(kernel=[up(k) for k in kernels], bias=[up(params[n + "/bias"]) for n in names],
                    w_proj=up(params[f"{scope}/decoder/projection_layer/kernel"]))
+    if hp.get("attention_layer_size"):
+        self.A = A
+        self.tf["w_att_layer"] = up(params[f"{pre}/attention_layer/kernel"])
+        assert self.tf["w_att_layer"].shape == (Ud + D, A)
     self.b_proj = up(params[f"{scope}/decoder/projection_layer/bias"])
     _attention_params(self, params, pre, up, device)
     self.tc = False

@@ -423,8 +423,6 @@ class SpellerTrain:
             raise NotImplementedError("training path: --embedding_size with binary_outputs or scheduled sampling is not built")
         self.dx_in = None
         self.att_layer = int(hp.get("attention_layer_size") or 0)
-        if self.att_layer and hp.get("bottom_only"):
-            raise NotImplementedError("training path: attention_layer_size with --bottom_only is not built")
         self.bottom = bool(hp.get("bottom_only"))
         self.pass_state = self.bottom and bool(hp.get("pass_hidden_state"))  # las/model.py:260 needs both flags
 

@@ -184,9 +184,9 @@ def test_decoder_full_width_deterministic_and_first_steps(att, Tm):
 
 
 # ---- GNMT-style AttentionMultiCell wiring (las/model.py:20-69, 185-193) and pass_hidden_state (las/model.py:259-267) ----
-def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0):
+def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0, A=None):
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
-                        num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=pass_state)
+                        num_channels=4, attention_type=att, bottom_only=True, pass_hidden_state=pass_state, attention_layer_size=A)
     params = _score_bias(weights.init_params(hp, seed=seed + Ud, projection_scale=8.0, bias_scale=0.1))
     D = weights.encoder_output_depth(hp)
     rng = np.random.default_rng(seed + B)
@@ -198,17 +198,24 @@ def _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, seed=0):
     return hp, params, enc, lens, D, state
 
 
-@gpu
-@pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,pass_state", [("luong", 4, 11, 16, 32, 1, 12, False), ("luong", 5, 13, 16, 32, 2, 14, False),
+BOTTOM_CFGS = [("luong", 4, 11, 16, 32, 1, 12, False), ("luong", 5, 13, 16, 32, 2, 14, False),
                                                            ("bahdanau", 6, 17, 16, 48, 3, 20, False), ("luong", 5, 12, 32, 32, 2, 16, True),
                                                            ("bahdanau", 35, 21, 16, 16, 2, 18, True),
                                                            ("luong_monotonic", 5, 13, 16, 32, 2, 14, False),
                                                            ("custom", 5, 13, 16, 32, 2, 14, False),
-                                                           ("bahdanau_monotonic", 6, 15, 32, 32, 3, 14, True)])
-def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, pass_state):
+                                                           ("bahdanau_monotonic", 6, 15, 32, 32, 3, 14, True),
+                                                           # + attention_layer_size (the trailing 9th field): cell 0 emits Dense([h0; context])
+                                                           ("luong", 5, 13, 16, 32, 2, 14, False, 24), ("bahdanau", 6, 12, 32, 32, 3, 15, True, 40),
+                                                           ("luong_monotonic", 4, 11, 16, 32, 1, 12, False, 16)]
+BOTTOM_CFGS = [c if len(c) == 9 else c + (None,) for c in BOTTOM_CFGS]
+
+
+@gpu
+@pytest.mark.parametrize("att,B,Tm,U,Ud,Ld,V,pass_state,A", BOTTOM_CFGS, ids=lambda v: str(v))
+def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V, pass_state, A):
     import torch
     from phones_las_b200.speller import speller
-    hp, params, enc, lens, D, state = _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state)
+    hp, params, enc, lens, D, state = _setup_true_las(att, B, Tm, U, Ud, Ld, V, pass_state, A=A)
     w = _device_speller(hp, params, D, "fp32")
     enc_t = torch.from_numpy(enc).cuda()
     state_t = tuple((torch.from_numpy(c).cuda(), torch.from_numpy(h).cuda()) for c, h in state)

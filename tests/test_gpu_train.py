@@ -772,3 +772,41 @@ def test_train_step_bottom_only_with_dropout(att, Ld, U, Ud, ps, sampling):
     for k in params:
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+
+
+@gpu
+@pytest.mark.parametrize("att,Ld,U,Ud,ps,A,dropout", [("luong", 1, 16, 32, False, 24, 0.0), ("bahdanau", 3, 32, 32, True, 40, 0.0),
+                                                      ("luong", 2, 16, 32, False, 16, 0.25), ("custom", 2, 16, 48, False, 20, 0.0)])
+def test_train_step_bottom_only_attention_layer(att, Ld, U, Ud, ps, A, dropout):
+    """attention_layer_size inside the AttentionMultiCell: the wrapped cell 0 emits Dense([h0; context]) (A wide); cell 1 reads it
+    as its first input, every upper cell reads the previous step's as OLD attention."""
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, V, S = 6, 44, 6, 13, 6
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
+                        attention_type=att, dropout=dropout, sampling_probability=0.0, bottom_only=True, pass_hidden_state=ps,
+                        attention_layer_size=A, l2_reg_scale=1e-4, ctc_weight=0.3)
+    params = weights.init_params(hp, seed=A + Ld, bias_scale=0.05, projection_scale=4.0)
+    assert params["speller/decoder/multi_rnn_cell/cell_0_attention/attention_wrapper/attention_layer/kernel"].shape[1] == A
+    x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    st = tr.TrainState(params)
+    st.step = 3
+    masks = None
+    if dropout > 0:
+        masks = {sc: {kk: torch.tensor(vv, dtype=torch.float64) for kk, vv in m.items()}
+                 for sc, m in tr.reference_masks(hp, 3, B, T, C, S).items()}
+        assert masks["speller"]["att"].shape == (B, S, A)
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, masks=masks)
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp)
+    assert scaled_err(parts["logits"], ref_parts["logits"].detach()) < 1e-5
+    raw = st.export_grads()
+    for k in params:
+        ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
+        assert grad_err(raw[k], ref_g) < GRAD_TOL, k
