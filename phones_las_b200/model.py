@@ -99,20 +99,23 @@ def las_eval(features, labels, hp, weights):
 class LASModel:
     """Front-end + listener + speller with device-resident weights."""
 
-    def __init__(self, params, hp, feature_flags, precision="fp32", means=None, stds=None, device="cuda"):
+    def __init__(self, params, hp, feature_flags, precision="fp32", means=None, stds=None, device="cuda", binf=None):
+        """``binf``: binf2phone [n, V] (utils/ipa_utils.py:313-328) for --binary_outputs --binf_projection models."""
         _lib.require_cuda()
         self.hp, self.fa, self.precision = hp, feature_flags, precision
         self.plan = FrontendPlan(feature_flags, means, stds, device)
-        self.weights = DeviceWeights(params, hp, num_feature_channels(feature_flags), precision, device)
+        self.weights = DeviceWeights(params, hp, num_feature_channels(feature_flags), precision, device, binf=binf)
 
     @classmethod
-    def from_model_dir(cls, model_dir, feature_flags, precision="fp32", means=None, stds=None, device="cuda"):
+    def from_model_dir(cls, model_dir, feature_flags, precision="fp32", means=None, stds=None, device="cuda", binf=None):
         """Build the model from a reference ``model_dir`` as train.py leaves it: ``hparams.json`` (utils/params_utils.py:28-30)
         and the latest TF checkpoint (tf_checkpoint.py), variables under their TF names."""
         from . import hparams as hps, tf_checkpoint
         hp = hps.create_hparams(model_dir=model_dir)
         params = tf_checkpoint.load_model_variables(model_dir)
-        return cls(params, hp, feature_flags, precision=precision, means=means, stds=stds, device=device)
+        if binf is None and "binf2phone" in params:  # --binf_trainable keeps the matrix as a variable (model_helper.py:183)
+            binf = params["binf2phone"]
+        return cls(params, hp, feature_flags, precision=precision, means=means, stds=stds, device=device, binf=binf)
 
     def features(self, wave, n_samples=None):
         return self.plan(wave, n_samples)
@@ -130,7 +133,8 @@ class LASModel:
         wave = wave_host.to("cuda", non_blocking=True)
         ns = n_samples_host.to("cuda", non_blocking=True) if n_samples_host is not None else None
         pred = self.transcribe(wave, ns)
-        return pred["sample_ids"].cpu(), pred["final_sequence_length"].cpu()
+        key, klen = ("sample_ids", "final_sequence_length") if "sample_ids" in pred else ("sample_ids_phones_binf", "final_sequence_length_binf")
+        return pred[key].cpu(), pred[klen].cpu()
 
     def transcribe_stream(self, host_batches):
         """Serving loop over pinned host waveform batches ([B,N] float32 each), fully pipelined: the host->device copy

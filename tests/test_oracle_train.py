@@ -268,3 +268,23 @@ def test_embedding_size_oracles_agree():
     g = tp["speller/target_embedding"].grad
     used = np.unique(tin)
     assert g[used].abs().sum() > 0 and g[[v for v in range(V) if v not in used]].abs().sum() == 0
+
+
+def test_weight_folds_are_the_maps_they_replace():
+    """The inference path folds two linear input / output maps into the decoder weights; check the identities on the CPU:
+    embedding lookup (target_embedding[id] @ W0[:E] == folded row id) and transform_binf_to_phones (att @ [M; 1 - M])."""
+    from phones_las_b200.speller import fold_embedding
+    rng = np.random.default_rng(0)
+    V, E, rest, G = 9, 5, 7, 12
+    hp = dict(embedding_size=E, target_vocab_size=V)
+    kern = rng.normal(size=(E + rest, G)).astype(np.float32)
+    emb = rng.normal(size=(V, E)).astype(np.float32)
+    folded = fold_embedding({"speller/target_embedding": emb}, hp, "speller", kern)
+    assert folded.shape == (V + rest, G) and np.array_equal(folded[V:], kern[E:])
+    ids = np.array([3, 0, 8])
+    np.testing.assert_allclose(np.eye(V, dtype=np.float32)[ids] @ folded[:V], emb[ids] @ kern[:E], rtol=1e-5, atol=1e-6)
+    assert fold_embedding({}, dict(embedding_size=0, target_vocab_size=V), "speller", kern) is kern
+    n = 4
+    M = (rng.uniform(size=(n, V)) < 0.5).astype(np.float32)
+    att = rng.normal(size=(6, 2 * n)).astype(np.float32)
+    np.testing.assert_allclose(att @ np.concatenate([M, 1 - M], 0), olo.transform_binf_to_phones(att, M), rtol=1e-5, atol=1e-6)
