@@ -375,6 +375,9 @@ int plas_sigmoid_ce_grad(const float* logits, const float* labels, const float* 
                          int32_t n_feat, float gscale, float* ce_tokens, float* out3, float* dlogits,
                          plas_stream_t stream);
 /* per-utterance CTC loss [B] and dlogits [B][T][C] = gscale * d(loss[b])/d(logits[b]) (zero for t >= logit_len) */
+/* x[i] += mean + std * N(0,1): the periodic weight noise of model_helper.py:418-432 (NOISE_MEAN = 0, --noise_std) on one
+ * 'kernel' variable; deviates from the counter hash with seed + *step * 0x85EBCA77 (step: device counter or NULL). */
+int plas_add_normal_noise_f32(float* x, int64_t n, uint32_t seed, const uint32_t* step, float mean, float std, plas_stream_t stream);
 /* compute_log_probs_loss (model_helper.py:132-146) and its gradient: att [n_rows][2 n_feat] = [log p1 | log p0];
  * out3[0] = weight * mean(|p1 + p0 - 1| + relu(log p1) + relu(log p0)); datt = d(out3[0]) / d(att); reg_rows [n_rows] scratch. */
 int plas_log_probs_reg_grad(const float* att, int64_t n_rows, int32_t n_feat, float weight, float* reg_rows, float* out3,

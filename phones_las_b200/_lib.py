@@ -113,6 +113,7 @@ EXPORTS = {
     "plas_rec_workspace_bytes": (C.c_size_t, [C.POINTER(RecDesc)]),
     "plas_bilstm_rec_fwd": (C.c_int, [C.POINTER(RecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "plas_relu_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "plas_add_normal_noise_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "plas_log_probs_reg_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "plas_decoder_workspace_bytes": (C.c_size_t, [C.POINTER(DecDesc)]),
     "plas_decoder_fwd": (C.c_int, [C.POINTER(DecDesc), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -95,6 +95,14 @@ __device__ __forceinline__ float drop_scale(uint64_t idx, uint32_t seed, uint32_
   return (drop_hash(idx, seed) >> 8) < thresh ? inv_keep : 0.f;
 }
 
+// standard normal from the counter-based hash (Box-Muller on two 24-bit uniforms); numpy mirrors: train.reference_noise,
+// train.reference_weight_noise
+__device__ __forceinline__ float hash_normal(uint64_t idx, uint32_t seed) {
+  const float u1 = ((float)(drop_hash(idx, seed) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(drop_hash(idx, seed + 1u) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

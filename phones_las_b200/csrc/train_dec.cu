@@ -176,13 +176,6 @@ __global__ void dec_relu_grad_kernel(float* dx, const float* y, size_t n) {
   if (i < n && !(y[i] > 0.f)) dx[i] = 0.f;
 }
 
-// standard normal from the counter-based hash (Box-Muller on two 24-bit uniforms); numpy mirror: train.reference_noise
-__device__ __forceinline__ float hash_normal(uint64_t idx, uint32_t seed) {
-  const float u1 = ((float)(drop_hash(idx, seed) >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float u2 = ((float)(drop_hash(idx, seed + 1u) >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 struct AttFwdArgs {
   int B, Tm, D, Ud, type, dsplit, staged;

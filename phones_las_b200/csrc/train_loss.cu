@@ -322,6 +322,15 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
     y[i] = x[i] * drop_scale((uint64_t)i, seed, thresh, inv_keep);
 }
 
+// periodic Gaussian weight noise (model_helper.py:418-432): x += mean + std * N(0,1), deviates from the counter hash
+__global__ void add_normal_noise_kernel(float* __restrict__ x, long long n, unsigned seed0, const unsigned* __restrict__ step,
+                                        float mean, float std) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned seed = seed0 + (step ? *step : 0u) * DROP_STEP_MUL;
+  x[i] += mean + std * hash_normal((uint64_t)i, seed);
+}
+
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long long n, float alpha) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = fmaf(alpha, x[i], y[i]);
@@ -336,6 +345,14 @@ extern "C" int plas_dropout_f32(const float* x, float* y, int64_t n, uint32_t se
   PLAS_REQUIRE(x && y && n > 0 && keep_prob > 0.f && keep_prob <= 1.f, "dropout: bad argument");
   const int blocks = (int)((n + 1023) / 1024 < 148 * 8 ? (n + 1023) / 1024 : 148 * 8);
   dropout_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(x, y, n, seed, step, (unsigned)(keep_prob * 16777216.0f), 1.0f / keep_prob);
+  PLAS_CUDA(cudaGetLastError());
+  return PLAS_OK;
+}
+
+extern "C" int plas_add_normal_noise_f32(float* x, int64_t n, uint32_t seed, const uint32_t* step, float mean, float std,
+                                         plas_stream_t stream_) {
+  PLAS_REQUIRE(x != nullptr && n >= 0 && std >= 0.f, "add_normal_noise: bad argument");
+  if (n) add_normal_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, n, seed, step, mean, std);
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;
 }

@@ -712,6 +712,34 @@ def apply_gradients(st, hp, world_size=1, allreduce=None, clipped=False):
     _lib.check(L.plas_adam_step(_lib.ptr(st.params), _lib.ptr(st.grads), _lib.ptr(st.m), _lib.ptr(st.v), st.total, lr_t, b1, b2, eps,
                                 1.0, _lib.stream_ptr()))
     _lib.count_launches(1)
+    # --add_noise N (model_helper.py:418-432): when the global step (before this update) is a positive multiple of N, every
+    # variable named '.../kernel' also receives N(0, noise_std) noise
+    period, prev_step = int(hp.get("add_noise", 0) or 0), st.step - 1
+    if period > 0 and prev_step > 0 and prev_step % period == 0:
+        add_weight_noise(st, hp)
+
+
+WEIGHT_NOISE_TID = 900  # + index of the variable
+
+
+def add_weight_noise(st, hp):
+    std = float(hp.get("noise_std", 0.1))
+    for i, name in enumerate(st.names):
+        if name.endswith("kernel"):
+            n = int(np.prod(st.shapes[name]))
+            _lib.check(_lib.lib().plas_add_normal_noise_f32(st.w(name), n, drop_seed(int(hp.get("dropout_seed", 0)), 0, WEIGHT_NOISE_TID + i),
+                                                            _lib.ptr(st.step_dev), 0.0, std, _lib.stream_ptr()))
+            _lib.count_launches(1)
+
+
+def reference_weight_noise(st, hp, name, step):
+    """numpy mirror of the noise ``add_weight_noise`` adds to variable ``name`` when the device step counter reads ``step``."""
+    i, n = st.index[name], int(np.prod(st.shapes[name]))
+    seed = drop_seed(int(hp.get("dropout_seed", 0)), step, WEIGHT_NOISE_TID + i)
+    u1 = (hash_u24(n, seed).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    u2 = (hash_u24(n, (seed + 1) & 0xFFFFFFFF).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    z = np.sqrt(-2.0 * np.log(u1.astype(np.float64))) * np.cos((np.float32(6.283185307179586) * u2).astype(np.float64))
+    return (float(hp.get("noise_std", 0.1)) * z).reshape(st.shapes[name])
 
 
 def train_step(features, labels, st, hp, binf=None, world_size=1, allreduce=None):

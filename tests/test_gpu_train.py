@@ -810,3 +810,41 @@ def test_train_step_bottom_only_attention_layer(att, Ld, U, Ud, ps, A, dropout):
     for k in params:
         ref_g = tp[k].grad - hp["l2_reg_scale"] * tp[k].detach()
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
+
+
+@gpu
+def test_periodic_weight_noise():
+    """--add_noise N --noise_std s (model_helper.py:418-432): when the global step is a positive multiple of N, every '.../kernel'
+    variable receives N(0, s) noise on top of the Adam update; biases and the other steps are untouched."""
+    import torch
+    from phones_las_b200 import train as tr
+    B, T, C, V, S = 4, 30, 5, 11, 5
+    base = dict(target_vocab_size=V, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=1, num_channels=C,
+                attention_type="luong", dropout=0.0, sampling_probability=0.0, ctc_weight=0.2)
+    hp0, hp1 = create_hparams(**base), create_hparams(add_noise=2, noise_std=0.05, **base)
+    params = weights.init_params(hp0, seed=1, bias_scale=0.05)
+    x, lens = synth.synth_features(B, T, C, seed=2, var_len=True)
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=3)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    st0, st1 = tr.TrainState(params), tr.TrainState(params)
+    for step in (1, 2):  # global step 0 and 1 before the update: no noise
+        tr.train_step(feats, labels, st0, hp0)
+        tr.train_step(feats, labels, st1, hp1)
+        assert torch.equal(st0.params, st1.params)
+    tr.train_step(feats, labels, st0, hp0)
+    tr.train_step(feats, labels, st1, hp1)  # global step 2 before this update: noise
+    p0, p1 = st0.export_params(), st1.export_params()
+    n_kernels = 0
+    for k in params:
+        diff = p1[k].astype(np.float64) - p0[k]
+        if k.endswith("kernel"):
+            want = tr.reference_weight_noise(st1, hp1, k, 3)
+            assert np.abs(diff - want).max() < 1e-6, k
+            n_kernels += 1
+        else:
+            assert not diff.any(), k
+    assert n_kernels >= 6
+    z = np.concatenate([(p1[k].astype(np.float64) - p0[k]).ravel() for k in params if k.endswith("kernel")]) / 0.05
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1.0) < 0.05
