@@ -177,3 +177,21 @@ def edit_distance_merge(hyp, truth, eos_id):
             cur = min(d[j] + 1, d[j - 1] + 1, prev + (h[i - 1] != t[j - 1]))
             prev, d[j] = d[j], cur
     return d[len(t)] / max(len(t), 1)
+
+
+def ctc_greedy_decoder(logits, lengths):
+    """tf.nn.ctc_greedy_decoder(merge_repeated=True) + sparse.to_dense (model_helper.py:351-353): per-frame argmax over the
+    V + 1 classes, repeats merged, then the blank -- the LAST class for this op -- removed; rows padded with 0."""
+    blank = logits.shape[-1] - 1
+    rows = []
+    for b in range(logits.shape[0]):
+        path = logits[b, :int(lengths[b])].argmax(-1)
+        keep = np.ones(len(path), bool)
+        keep[1:] = path[1:] != path[:-1]
+        seq = path[keep]
+        rows.append(seq[seq != blank])
+    width = max((len(r) for r in rows), default=0)
+    out = np.zeros((len(rows), width), np.int32)
+    for b, r in enumerate(rows):
+        out[b, :len(r)] = r
+    return out

@@ -50,3 +50,22 @@ def edit_distance(hypothesis, truth, eos_id, mapping=None):
         else:
             out[i] = _levenshtein(h, t) / len(t)
     return out
+
+
+def ctc_greedy_decode(best_path, lengths, blank):
+    """tf.nn.ctc_greedy_decoder(merge_repeated=True) + tf.sparse.to_dense (model_helper.py:351-353): ``best_path`` [B, T] = the
+    per-frame argmax class; per utterance the first ``lengths[b]`` frames are collapsed (repeats merged, then ``blank`` removed;
+    the decoder's blank is the LAST class, num_classes - 1) and the rows are padded with 0 to the longest result."""
+    seqs = []
+    for row, n in zip(np.asarray(best_path), np.asarray(lengths)):
+        out, prev = [], None
+        for c in row[:int(n)].tolist():
+            if c != prev and c != blank:
+                out.append(int(c))
+            prev = c
+        seqs.append(out)
+    width = max((len(q) for q in seqs), default=0)
+    dense = np.zeros((len(seqs), width), np.int32)
+    for i, q in enumerate(seqs):
+        dense[i, :len(q)] = q
+    return dense

@@ -6,6 +6,7 @@ out (``encoder_out, source_length, embedding, sample_ids, alignment, probs``).  
 bundles a front-end plan with the device weights and follows the call order of
 ``transcribe_audio_file.py:97-101``.
 """
+import numpy as np
 import torch
 
 from . import _lib, weights as wts
@@ -31,6 +32,10 @@ class DeviceWeights:
                 raise NotImplementedError("binary_outputs at inference is built for --binf_projection (pass binf=binf2phone)")
             self.speller_binf = SpellerWeights(params, hp, D, precision, device, scope="speller_binf", binf=binf)
             self.binf = torch.as_tensor(binf, dtype=torch.float32, device=device)
+        self.ctc = None
+        if hp.get("ctc_weight", -1.0) > 0 and "ctc_logits/kernel" in params:  # the CTC head of EVAL mode (model_helper.py:347-363)
+            up = lambda a: torch.as_tensor(np.asarray(a, np.float32), device=device).contiguous()
+            self.ctc = (up(params["ctc_logits/kernel"]), up(params["ctc_logits/bias"]))
 
 
 def las_predict(features, hp, weights, want_alignment=True, trim=True, want_probs=True):
@@ -92,6 +97,14 @@ def las_eval(features, labels, hp, weights):
                    edit_distance_binf=metrics.edit_distance(pred["sample_ids_phones_binf"].cpu().numpy(), targets.cpu().numpy(),
                                                             hp["eos_id"], hp.get("mapping")))
         out.setdefault("edit_distance", out["edit_distance_binf"])  # model_helper.py:308
+    if getattr(weights, "ctc", None) is not None:
+        # CTC head (model_helper.py:347-363): loss += mean(ctc_loss) * ctc_weight; 'ctc_edit_distance' of the greedy CTC path
+        # (its blank is the last class, while the loss uses blank 0 -- the reference's own mismatch, kept)
+        ctc, ctc_logits = losses.ctc_head(pred["encoder_out"], pred["source_length"], targets, tlen, *weights.ctc)
+        loss = loss + ctc * float(hp["ctc_weight"])
+        best = ctc_logits.argmax(-1).cpu().numpy()
+        decoded = metrics.ctc_greedy_decode(best, pred["source_length"].cpu().numpy(), ctc_logits.shape[-1] - 1)
+        out.update(ctc_loss=ctc, ctc_edit_distance=metrics.edit_distance(decoded, targets.cpu().numpy(), hp["eos_id"], hp.get("mapping")))
     out["loss"] = loss
     return out
 

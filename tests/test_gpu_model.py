@@ -199,3 +199,34 @@ def test_predict_binf_projection(multitask):
     want = olo.compute_loss(ref_logits, tout, ref_len, tlen, "eval", hp["eos_id"])
     assert abs(ev["loss_binf"].item() - want) < 1e-4 * max(1.0, abs(want))
     assert ev["edit_distance_binf"].shape == (B,) and ("loss_binf" in ev) and (("logits" in ev) == multitask)
+
+
+@gpu
+def test_eval_mode_ctc_head_and_ctc_edit_distance():
+    """EVAL with ctc_weight > 0 (model_helper.py:347-363): the loss gains mean(ctc_loss) * ctc_weight and the metrics gain the
+    edit distance of the greedy CTC path."""
+    import torch
+    from oracle import losses as olo
+    from phones_las_b200.model import DeviceWeights, las_eval
+    V = 12
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=32,
+                        attention_type="luong", num_channels=6, ctc_weight=0.4)
+    params = weights.init_params(hp, 6, seed=9, projection_scale=8.0, bias_scale=0.1)
+    assert params["ctc_logits/kernel"].shape[1] == V + 1
+    params["ctc_logits/kernel"] = params["ctc_logits/kernel"] * 6.0
+    x, lens = synth.synth_features(5, 44, 6, seed=4, var_len=True)
+    tin, tout, tlen = synth.synth_labels(5, 6, V, seed=8)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_outputs": torch.from_numpy(tout), "target_sequence_length": torch.from_numpy(tlen)}
+    out = las_eval(feats, labels, hp, DeviceWeights(params, hp, 6, "fp32"))
+    ref = ol.predict(x, lens, params, hp, "fp32")
+    cl = ref["encoder_out"] @ params["ctc_logits/kernel"] + params["ctc_logits/bias"]
+    ref_ctc = olo.ctc_loss(cl, tout, tlen, ref["source_length"]).mean()
+    assert np.isfinite(ref_ctc) and abs(out["ctc_loss"].item() - ref_ctc) < 1e-4 * max(1.0, abs(ref_ctc))
+    ref_ce = olo.compute_loss(ref["logits"], tout, ref["final_sequence_length"], tlen, "eval", hp["eos_id"])
+    want = ref_ce + 0.4 * ref_ctc
+    assert abs(out["loss"].item() - want) < 1e-4 * max(1.0, abs(want))
+    decoded = olo.ctc_greedy_decoder(cl, ref["source_length"])
+    assert decoded.shape[1] > 0
+    ref_ed = [olo.edit_distance_merge(list(decoded[b]), list(tout[b]), hp["eos_id"]) for b in range(5)]
+    np.testing.assert_allclose(out["ctc_edit_distance"], ref_ed, rtol=0, atol=1e-12)

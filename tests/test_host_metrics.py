@@ -23,3 +23,16 @@ def test_edit_distance_matches_oracle_and_quirks():
     # optional id mapping (metrics_utils.py:33-36)
     mapping = np.array([0, 1, 2, 7, 7, 5])
     assert metrics.edit_distance([[3, 2]], [[4, 2]], eos_id=2, mapping=mapping)[0] == 0.0
+
+
+def test_ctc_greedy_decode_known_answer_and_oracle():
+    from oracle import losses as olo
+    from phones_las_b200 import metrics
+    blank = 4
+    path = np.array([[1, 1, 4, 1, 2, 2, 4, 4, 3], [4, 4, 0, 0, 4, 0, 3, 3, 3]])
+    got = metrics.ctc_greedy_decode(path, [9, 6], blank)
+    np.testing.assert_array_equal(got, [[1, 1, 2, 3], [0, 0, 0, 0]])  # second row: frames past its length are ignored; zero padding
+    rng = np.random.default_rng(0)
+    logits = rng.normal(size=(5, 17, 7)).astype(np.float32)
+    lens = np.array([17, 3, 9, 1, 12])
+    np.testing.assert_array_equal(metrics.ctc_greedy_decode(logits.argmax(-1), lens, 6), olo.ctc_greedy_decoder(logits, lens))
