@@ -27,11 +27,16 @@ class DeviceWeights:
         self.speller = self.speller_binf = None
         if not hp.get("binary_outputs") or hp.get("multitask"):
             self.speller = SpellerWeights(params, hp, D, precision, device)
-        if hp.get("binary_outputs"):
-            if binf is None or not hp.get("binf_projection"):
-                raise NotImplementedError("binary_outputs at inference is built for --binf_projection (pass binf=binf2phone)")
+        if hp.get("binary_outputs") and hp.get("binf_projection"):
+            if binf is None:
+                raise ValueError("--binf_projection needs the binf2phone matrix (binf=)")
             self.speller_binf = SpellerWeights(params, hp, D, precision, device, scope="speller_binf", binf=binf)
             self.binf = torch.as_tensor(binf, dtype=torch.float32, device=device)
+        elif hp.get("binary_outputs") and not hp.get("multitask"):
+            # without --binf_projection the reference's own non-TRAIN graph of the binary-feature speller cannot be built
+            # (transform_binf_to_phones slices [n:2n] out of an n-wide Dense output, utils/training_helper.py:19-21); under
+            # --multitask the phone speller is served and the binary-feature one (a TRAIN-time auxiliary task) is skipped
+            raise NotImplementedError("binary_outputs without --binf_projection has no inference graph (DESIGN.md section 8)")
         self.ctc = None
         if hp.get("ctc_weight", -1.0) > 0 and "ctc_logits/kernel" in params:  # the CTC head of EVAL mode (model_helper.py:347-363)
             up = lambda a: torch.as_tensor(np.asarray(a, np.float32), device=device).contiguous()

@@ -230,3 +230,25 @@ def test_eval_mode_ctc_head_and_ctc_edit_distance():
     assert decoded.shape[1] > 0
     ref_ed = [olo.edit_distance_merge(list(decoded[b]), list(tout[b]), hp["eos_id"]) for b in range(5)]
     np.testing.assert_allclose(out["ctc_edit_distance"], ref_ed, rtol=0, atol=1e-12)
+
+
+@gpu
+def test_multitask_model_serves_the_phone_speller():
+    """A model trained in the c3 configuration (multitask, binary-feature speller without --binf_projection) is served through
+    its phone speller; its binary-feature speller exists at TRAIN time only (the reference's non-TRAIN graph for it is ill-formed)."""
+    import torch
+    from phones_las_b200.model import DeviceWeights, las_predict
+    from phones_las_b200.train import train_variable_shapes
+    V, n, C = 14, 6, 6
+    hp = create_hparams(target_vocab_size=V, binf_count=n, encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=32,
+                        attention_type="luong", num_channels=C, binary_outputs=True, multitask=True, ctc_weight=0.3)
+    params = weights.init_params(hp, C, seed=3, shapes=train_variable_shapes(hp, C, binf_count=n), bias_scale=0.1, projection_scale=8.0)
+    assert any(k.startswith("speller_binf/") for k in params)
+    x, lens = synth.synth_features(4, 30, C, seed=4, var_len=True)
+    w = DeviceWeights(params, hp, C, "fp32")
+    assert w.speller is not None and w.speller_binf is None
+    pred = las_predict({"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}, hp, w)
+    ref = ol.predict(x, lens, params, hp, "fp32")
+    assert_parity(pred["logits"][:, :1].cpu().numpy(), ref["logits"][:, :1], "fp32", "logits step 0")
+    with pytest.raises(NotImplementedError):
+        DeviceWeights(params, dict(hp, multitask=False), C, "fp32")
