@@ -361,6 +361,16 @@ typedef struct plas_dec_infer_desc {
   const float* h_init[4];
   const float* w_att_layer; /* attention_wrapper/attention_layer/kernel or NULL                                 */
   const float* score_bias;  /* luong_monotonic attention_score_bias [1] (device) or NULL                       */
+  /* Beam search (PREDICT with beam_width > 0, las/model.py:219-226,298-319: tf.contrib.seq2seq.BeamSearchDecoder, length penalty
+   * 0, + gather_tree).  B, keys, values, mem_len, c_init / h_init are then the TILED batch (tile_batch: row b*W + w); logits,
+   * sample_ids and alignment are not written; seq_len [B] = dynamic_decode's per-hypothesis sequence lengths. */
+  int32_t beam_width;       /* W (0 = greedy / teacher forced), <= 32                                          */
+  int32_t _pad_beam;
+  int32_t* beam_predicted;  /* out [B / W][max_steps][W]: predicted_ids after gather_tree (eos past each end)  */
+  int32_t* beam_parent;     /* out [max_steps][B]: parent beam of every step                                   */
+  int32_t* beam_word;       /* out [max_steps][B]: word id of every step                                       */
+  float* beam_scores;       /* out [B] final log-probabilities, or NULL                                        */
+  int32_t* beam_lengths;    /* out [B] final BeamSearchDecoderState.lengths, or NULL                           */
 } plas_dec_infer_desc;
 /* x = max(x, 0) in place: CustomAttention's keys = relu(memory_layer(values)) (las/model.py:94), applied by the caller of
  * plas_decoder_infer_f32 to the keys it passes. */

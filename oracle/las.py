@@ -375,6 +375,85 @@ class Speller:
                     np.zeros((self.B, 0, self.Tm), F32), seq_len, state)
         return (np.stack(logits_all, 1), np.stack(ids_all, 1), np.stack(align_all, 1), seq_len, state)
 
+    def beam_search(self, beam_width):
+        """tf.contrib.seq2seq.BeamSearchDecoder (length_penalty_weight = 0) + dynamic_decode + gather_tree, as
+        las/model.py:219-226,298-319 builds it for PREDICT with beam_width > 0 (start tokens = sos; no partial targets).
+        ``self`` must have been built on the TILED memory (tile_batch: row b*W + w = utterance b, also for an encoder_state).
+        Returns (predicted_ids [B, T, W] after gather_tree, parent_ids [B, T, W], step word ids [B, T, W], final log-probs [B, W],
+        final state lengths [B, W], dynamic_decode's sequence lengths [B, W])."""
+        hp, W, V = self.hp, int(beam_width), self.V
+        assert self.B % W == 0
+        B = self.B // W
+        eos = hp["eos_id"]
+        max_iter = int(np.rint(F32(self.enc_len.max()) * F32(hp.get("decoding_length_factor", 1.0))))
+        state = self.zero_state()
+        ids = np.full((self.B,), hp["sos_id"], np.int64)
+        log_probs = np.full((B, W), -np.inf, F32)
+        log_probs[:, 0] = 0.0                               # initialize(): one_hot(0, W, on 0.0, off -inf)
+        finished = np.ones((B, W), bool)
+        finished[:, 0] = False                              # self._finished = one_hot(0, W, on False, off True)
+        lengths = np.zeros((B, W), np.int64)
+        seq_len = np.zeros((B, W), np.int32)
+        words, parents = [], []
+        time = 0
+        done = max_iter <= 0
+        while not done:
+            logits, state = self.step(self.one_hot(ids), state)
+            lg = logits.reshape(B, W, V).astype(F32)
+            m = lg.max(-1, keepdims=True)
+            lsm = (lg - m - np.log(np.exp(lg - m).sum(-1, keepdims=True, dtype=F32))).astype(F32)
+            fin_row = np.full((V,), np.finfo(np.float32).min, F32)
+            fin_row[eos] = 0.0                              # _mask_probs: a finished beam can only be continued by eos, at no cost
+            step_lp = np.where(finished[:, :, None], fin_row[None, None, :], lsm)
+            with np.errstate(over="ignore", invalid="ignore"):
+                total = (log_probs[:, :, None] + step_lp).astype(F32).reshape(B, W * V)
+            order = np.argsort(-total, axis=1, kind="stable")
+            idx = order[:, :W]                                           # top_k: ties -> the lower index first
+            top = np.take_along_axis(total, order[:, :W + 1], 1).astype(np.float64)
+            with np.errstate(invalid="ignore"):
+                gaps = top[:, :-1] - top[:, 1:]
+            gaps = gaps[np.isfinite(gaps)]
+            if gaps.size:                                                # how decisive the selections were (for parity tests)
+                self.beam_margin = min(getattr(self, "beam_margin", np.inf), float(gaps.min()))
+            new_lp = np.take_along_axis(total, idx, 1)
+            word, beam = (idx % V).astype(np.int32), (idx // V).astype(np.int32)
+            prev_fin = np.take_along_axis(finished, beam, 1)
+            next_fin = prev_fin | (word == eos)
+            lengths = np.take_along_axis(lengths, beam, 1) + (~prev_fin).astype(np.int64)
+            seq_len = np.where(~finished, time + 1, seq_len).astype(np.int32)   # dynamic_decode, on the slot's previous flag
+            flat = (np.arange(B)[:, None] * W + beam).reshape(-1)               # gather the cell state by parent beam
+            state = dict(cells=[(c[flat], h[flat]) for c, h in state["cells"]], attention=state["attention"][flat],
+                         alignments=state["alignments"][flat])
+            log_probs, finished = new_lp, next_fin
+            words.append(word)
+            parents.append(beam)
+            ids = word.reshape(-1).astype(np.int64)
+            time += 1
+            done = finished.all() or time >= max_iter
+        T = len(words)
+        if T == 0:
+            z = np.zeros((B, 0, W), np.int32)
+            return z, z, z, log_probs, lengths, seq_len
+        step_ids, parent_ids = np.stack(words, 1), np.stack(parents, 1)         # [B, T, W]
+        out = np.full((B, T, W), eos, np.int32)                                 # gather_tree (beam_search_ops.cc)
+        for b in range(B):
+            max_len = min(T, int(lengths[b].max()))
+            if max_len <= 0:
+                continue
+            for w in range(W):
+                out[b, max_len - 1, w] = step_ids[b, max_len - 1, w]
+                parent = parent_ids[b, max_len - 1, w]
+                for level in range(max_len - 2, -1, -1):
+                    out[b, level, w] = step_ids[b, level, parent]
+                    parent = parent_ids[b, level, parent]
+                fin = False
+                for t in range(max_len):
+                    if fin:
+                        out[b, t, w] = eos
+                    elif out[b, t, w] == eos:
+                        fin = True
+        return out, parent_ids, step_ids, log_probs, lengths, seq_len
+
     def teacher_forced(self, targets_inputs, target_len):
         """TrainingHelper + dynamic_decode (las/model.py:276-296 with sampling_probability=0)."""
         target_len = np.asarray(target_len)

@@ -90,7 +90,9 @@ class DecInferDesc(C.Structure):
                 ("mem_len", C.c_void_p), ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
                 ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p),
                 ("bottom_only", C.c_int32), ("att_layer", C.c_int32), ("c_init", C.c_void_p * 4), ("h_init", C.c_void_p * 4),
-                ("w_att_layer", C.c_void_p), ("score_bias", C.c_void_p)]
+                ("w_att_layer", C.c_void_p), ("score_bias", C.c_void_p), ("beam_width", C.c_int32), ("_pad_beam", C.c_int32),
+                ("beam_predicted", C.c_void_p), ("beam_parent", C.c_void_p), ("beam_word", C.c_void_p), ("beam_scores", C.c_void_p),
+                ("beam_lengths", C.c_void_p)]
 
 
 EXPORTS = {

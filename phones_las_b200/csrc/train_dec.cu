@@ -902,6 +902,156 @@ __global__ void dec_infer_finish_kernel(InferState st, int B, int t, int eos_id,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Beam search (tf.contrib.seq2seq.BeamSearchDecoder with length_penalty_weight = 0, las/model.py:219-226,298-319) on the same
+// step kernels: the batch is the tiled one (row b*W + w = beam w of utterance b).  Per step the logits of the W beams of an
+// utterance are turned into W*V candidate scores, the best W are kept (ties: the lower flat index, like tf.nn.top_k), and
+// every piece of decoder state is gathered by parent beam.
+// ---------------------------------------------------------------------------------------------------------
+struct BeamState {
+  float* logp;    // [B] total log-probability of each live hypothesis
+  int* fin;       // [B] (InferState.finished)
+  int* len;       // [B] BeamSearchDecoderState.lengths
+  int* parent;    // [S][B] parent beam of each step
+  int* word;      // [S][B] word id of each step
+};
+
+__global__ void dec_beam_init_kernel(InferState st, BeamState bs, int B, int W, int sos_id, int* __restrict__ seq_len) {
+  const int max_iter = *st.max_iter;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int w = i % W;
+    bs.logp[i] = w == 0 ? 0.f : -INFINITY;   // initialize(): one_hot(0, W, on_value 0, off_value -inf)
+    st.finished[i] = (w != 0 || max_iter <= 0) ? 1 : 0;  // BeamSearchDecoder._finished: one_hot(0, W, on False, off True)
+    bs.len[i] = 0;
+    st.cur_ids[i] = sos_id;
+    seq_len[i] = 0;
+  }
+}
+
+// one CTA per utterance: scores of the W*V continuations, W rounds of block arg-max, bookkeeping of _beam_search_step
+__global__ void __launch_bounds__(256) dec_beam_step_kernel(InferState st, BeamState bs, const float* __restrict__ logits, int B, int W, int V,
+                                                            int t, int eos_id, int* __restrict__ seq_len) {
+  extern __shared__ float bm_smem[];
+  if (*st.done) return;
+  float* s_tot = bm_smem;                       // [W][V]
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_chosen[32];
+  __shared__ float s_cval[32];
+  __shared__ float s_lse[32];
+  __shared__ int s_fin[32], s_len[32];
+  __shared__ float s_lp[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* lg = logits + (size_t)b * W * V;
+  if (tid < W) { s_fin[tid] = st.finished[b * W + tid]; s_len[tid] = bs.len[b * W + tid]; s_lp[tid] = bs.logp[b * W + tid]; }
+  for (int w = warp; w < W; w += 8) {           // log-sum-exp of each beam's logits
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, lg[(size_t)w * V + v]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(lg[(size_t)w * V + v] - m);
+    s = warp_sum(s);
+    if (lane == 0) s_lse[w] = m + logf(s);
+  }
+  __syncthreads();
+  for (int i = tid; i < W * V; i += 256) {
+    const int w = i / V, v = i - w * V;
+    // _mask_probs: a finished beam is continued by eos only, at no cost (every other word gets the most negative float)
+    const float step = s_fin[w] ? (v == eos_id ? 0.f : -FLT_MAX) : lg[i] - s_lse[w];
+    s_tot[i] = s_lp[w] + step;
+  }
+  __syncthreads();
+  for (int k = 0; k < W; ++k) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < W * V; i += 256) {
+      bool taken = false;
+      for (int j = 0; j < k; ++j) taken |= s_chosen[j] == i;
+      const float v = s_tot[i];
+      if (!taken && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w8 = 1; w8 < 8; ++w8)
+        if (s_val[w8] > bv || (s_val[w8] == bv && s_idx[w8] < bi)) { bv = s_val[w8]; bi = s_idx[w8]; }
+      s_chosen[k] = bi;
+      s_cval[k] = bv;
+    }
+    __syncthreads();
+  }
+  if (tid < W) {
+    const int i = b * W + tid;
+    const int idx = s_chosen[tid];
+    const int beam = idx / V, word = idx - beam * V;
+    const int prev_fin = s_fin[beam];
+    if (!s_fin[tid]) seq_len[i] = t + 1;        // dynamic_decode's sequence_lengths follow the slot's previous finished flag
+    bs.logp[i] = s_cval[tid];
+    st.finished[i] = prev_fin | (word == eos_id);
+    bs.len[i] = s_len[beam] + (prev_fin ? 0 : 1);
+    bs.parent[(size_t)t * B + i] = beam;
+    bs.word[(size_t)t * B + i] = word;
+    st.cur_ids[i] = word;
+  }
+}
+
+// dst[i][:] = src[(i / W) * W + parent[i]][:]: the cell state of every hypothesis follows its parent beam
+__global__ void dec_beam_gather_kernel(InferState st, float* __restrict__ dst, const float* __restrict__ src, long long s_src, int width,
+                                       const int* __restrict__ parent, int B, int W) {
+  if (*st.done) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * width) return;
+  const int r = (int)(i / width), c = (int)(i - (long long)r * width);
+  dst[i] = src[(long long)((r / W) * W + parent[r]) * s_src + c];
+}
+__global__ void dec_beam_scatter_kernel(InferState st, float* __restrict__ dst, long long s_dst, const float* __restrict__ src, int width, int B) {
+  if (*st.done) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * width) return;
+  const int r = (int)(i / width), c = (int)(i - (long long)r * width);
+  dst[(long long)r * s_dst + c] = src[i];
+}
+
+__global__ void dec_beam_finish_kernel(InferState st, int B, int t, int* __restrict__ n_steps) {
+  if (threadIdx.x != 0 || *st.done) return;
+  int all = 1;
+  for (int i = 0; i < B; ++i) all &= st.finished[i];
+  *n_steps = t + 1;
+  if (all || t + 1 >= *st.max_iter) *st.done = 1;
+}
+
+// beam_search_ops.cc gather_tree: back-trace every final hypothesis through its parents; after the first eos only eos
+__global__ void dec_beam_gather_tree_kernel(BeamState bs, const int* __restrict__ n_steps, int B, int W, int S, int eos_id,
+                                            int* __restrict__ predicted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const int b = i / W, w = i - b * W;
+  const int T = *n_steps;
+  int* out = predicted + (size_t)b * S * W + w;  // [b][t][w]
+  for (int t = 0; t < S; ++t) out[(size_t)t * W] = eos_id;
+  int max_len = 0;
+  for (int j = 0; j < W; ++j) max_len = max(max_len, bs.len[b * W + j]);
+  max_len = min(max_len, T);
+  if (max_len <= 0) return;
+  out[(size_t)(max_len - 1) * W] = bs.word[(size_t)(max_len - 1) * B + i];
+  int parent = bs.parent[(size_t)(max_len - 1) * B + i];
+  for (int level = max_len - 2; level >= 0; --level) {
+    out[(size_t)level * W] = bs.word[(size_t)level * B + b * W + parent];
+    parent = bs.parent[(size_t)level * B + b * W + parent];
+  }
+  bool fin = false;
+  for (int t = 0; t < max_len; ++t) {
+    if (fin) out[(size_t)t * W] = eos_id;
+    else if (out[(size_t)t * W] == eos_id) fin = true;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------------------
 struct DecTrainWs {
@@ -1001,6 +1151,7 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
 // ---- fp32 inference loop ----------------------------------------------------------------------------------------------
 struct DecInferWs {
   size_t z[4], c[4], h[4], att, ctx, pq, align, ints, total;
+  size_t b_logits, b_logp, b_len, b_ids, b_scratch;  // beam search
 };
 
 static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
@@ -1025,6 +1176,15 @@ static DecInferWs dec_infer_ws(const plas_dec_infer_desc& d) {
   w.pq = take(B * Ud * 4);
   w.align = take(2 * B * Tm * 4);  // two slots (parity of t): the monotonic scan reads step t-1's while it writes its own
   w.ints = take((2 * B + 8) * 4);
+  w.b_logits = w.b_logp = w.b_len = w.b_ids = w.b_scratch = 0;
+  if (d.beam_width > 0) {
+    const size_t mw = (Ud > A ? Ud : A) > Tm ? (Ud > A ? Ud : A) : Tm;
+    w.b_logits = take(B * (size_t)d.V * 4);
+    w.b_logp = take(B * 4);
+    w.b_len = take(B * 4);
+    w.b_ids = take(B * 4);
+    w.b_scratch = take(B * mw * 4);  // out-of-place target of the state gathers
+  }
   w.total = off;
   return w;
 }
@@ -1051,8 +1211,8 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
   PLAS_REQUIRE(d->attention_type >= PLAS_ATT_LUONG && d->attention_type <= PLAS_ATT_CUSTOM, "dec_infer: attention_type %d", d->attention_type);
   if (att_is_mono(d->attention_type)) PLAS_REQUIRE(d->score_bias != nullptr, "dec_infer: monotonic attention needs attention_score_bias");
   if (d->attention_type == PLAS_ATT_CUSTOM) PLAS_REQUIRE(d->w_query != nullptr, "dec_infer: custom attention needs its query_layer (and relu'd keys)");
-  PLAS_REQUIRE(d->keys && d->values && d->mem_len && d->w_proj && d->b_proj && d->logits && d->sample_ids && d->seq_len && d->n_steps,
-               "dec_infer: null tensor");
+  PLAS_REQUIRE(d->keys && d->values && d->mem_len && d->w_proj && d->b_proj && d->seq_len && d->n_steps, "dec_infer: null tensor");
+  PLAS_REQUIRE(d->beam_width > 0 || (d->logits && d->sample_ids), "dec_infer: null logits / sample_ids");
   if (att_is_bah(d->attention_type)) PLAS_REQUIRE(d->w_query && d->v_att, "dec_infer: bahdanau needs query_layer / attention_v");
   if (d->teacher_forced) PLAS_REQUIRE(d->forced_ids != nullptr, "dec_infer: teacher forcing needs forced_ids");
   const DecInferWs w = dec_infer_ws(*d);
@@ -1072,6 +1232,18 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
     PLAS_REQUIRE(d->w_att_layer && A % 4 == 0, "dec_infer: attention_layer_size needs its kernel and A %% 4 == 0");
   PLAS_CUDA(cudaMemsetAsync(F(w.att), 0, (size_t)B * 2 * A * 4, st));
   dec_infer_init_kernel<<<1, 128, 0, st>>>(is, d->mem_len, B, S, d->teacher_forced, d->decoding_length_factor, d->sos_id, d->seq_len, d->n_steps);
+  const int W = d->beam_width;
+  BeamState bs = {};
+  if (W > 0) {
+    PLAS_REQUIRE(W <= 32 && B % W == 0 && !d->teacher_forced && !d->alignment, "dec_infer: beam search needs beam_width <= 32, a tiled batch, no forcing / alignment output");
+    PLAS_REQUIRE(d->beam_predicted && d->beam_parent && d->beam_word, "dec_infer: beam search needs beam_predicted / beam_parent / beam_word");
+    PLAS_REQUIRE((size_t)W * V * 4 <= 200 * 1024, "dec_infer: beam_width * V too large");
+    bs.logp = F(w.b_logp); bs.fin = is.finished; bs.len = reinterpret_cast<int*>(base + w.b_len);
+    bs.parent = d->beam_parent; bs.word = d->beam_word;
+    dec_beam_init_kernel<<<1, 128, 0, st>>>(is, bs, B, W, d->sos_id, d->seq_len);
+    if ((size_t)W * V * 4 > 48 * 1024)
+      PLAS_CUDA(cudaFuncSetAttribute(dec_beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)W * V * 4)));
+  }
   PLAS_CUDA(cudaFuncSetAttribute(dec_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   PLAS_CUDA(cudaFuncSetAttribute(dec_att_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   const int dsplit = (D >= 512 && D % 16 == 0) ? 4 : 1;
@@ -1184,9 +1356,33 @@ extern "C" int plas_decoder_infer_f32(const plas_dec_infer_desc* d, void* worksp
       }
     }
     const float* out = (bottom && L > 1) ? F(w.h[L - 1]) + (size_t)slot * Ud : F(w.att) + (size_t)slot * A;
+    if (W > 0) {  // beam search: logits of every hypothesis, then the W best continuations per utterance and the state gathers
+      dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, out, (bottom && L > 1) ? 2LL * Ud : 2LL * A, Dout, V, d->w_proj, d->b_proj,
+                                                        F(w.b_logits), V, reinterpret_cast<int*>(base + w.b_ids), 1);
+      dec_beam_step_kernel<<<B / W, 256, (size_t)W * V * 4, st>>>(is, bs, F(w.b_logits), B, W, V, t, d->eos_id, d->seq_len);
+      const int* parent = d->beam_parent + (size_t)t * B;
+      auto regather = [&](float* buf, long long stride, int width) {
+        const unsigned blocks = (unsigned)(((size_t)B * width + 255) / 256);
+        dec_beam_gather_kernel<<<blocks, 256, 0, st>>>(is, F(w.b_scratch), buf, stride, width, parent, B, W);
+        dec_beam_scatter_kernel<<<blocks, 256, 0, st>>>(is, buf, stride, F(w.b_scratch), width, B);
+      };
+      for (int l = 0; l < L; ++l) {
+        regather(F(w.c[l]) + (size_t)slot * Ud, 2LL * Ud, Ud);
+        regather(F(w.h[l]) + (size_t)slot * Ud, 2LL * Ud, Ud);
+      }
+      regather(F(w.att) + (size_t)slot * A, 2LL * A, A);
+      if (att_is_mono(d->attention_type)) regather(F(w.align) + (size_t)slot * B * Tm, Tm, Tm);
+      dec_beam_finish_kernel<<<1, 32, 0, st>>>(is, B, t, d->n_steps);
+      continue;
+    }
     dec_infer_sample_kernel<<<B, 256, smp_smem, st>>>(is, out, (bottom && L > 1) ? 2LL * Ud : 2LL * A, Dout, V, d->w_proj, d->b_proj,
                                                       d->logits + (size_t)t * V, (long long)S * V, d->sample_ids + t, S);
     dec_infer_finish_kernel<<<1, 32, 0, st>>>(is, B, t, d->eos_id, d->teacher_forced, d->seq_len, d->n_steps);
+  }
+  if (W > 0) {
+    dec_beam_gather_tree_kernel<<<(B + 127) / 128, 128, 0, st>>>(bs, d->n_steps, B, W, S, d->eos_id, d->beam_predicted);
+    if (d->beam_scores) PLAS_CUDA(cudaMemcpyAsync(d->beam_scores, bs.logp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    if (d->beam_lengths) PLAS_CUDA(cudaMemcpyAsync(d->beam_lengths, bs.len, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
   }
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;

@@ -53,13 +53,22 @@ def las_predict(features, hp, weights, want_alignment=True, trim=True, want_prob
     # the listener already zeroes its outputs past each (reduced) length: no separate masking pass
     pred = {"encoder_out": enc_out, "source_length": enc_len}
     logits = None
-    if weights.speller is not None:
+    if int(hp.get("beam_width", 0) or 0) > 0:
+        # PREDICT with beam search (model_helper.py:231-237): sample_ids = predicted_ids [B, T, W] (beam 0 is the best hypothesis);
+        # there are no logits / probs / alignment in this mode
+        sp = weights.speller if weights.speller is not None else weights.speller_binf
+        out, state, final_len = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, sp,
+                                        binf_embedding=getattr(weights, "binf", None) if sp is weights.speller_binf else None, memory_is_masked=True)
+        key = "sample_ids" if weights.speller is not None else "sample_ids_phones_binf"
+        pred.update({key: out.predicted_ids, "final_sequence_length": final_len, "n_steps": state.n_steps})
+        want_probs = False
+    elif weights.speller is not None:
         out, state, final_len = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller,
                                         memory_is_masked=True, want_alignment=want_alignment, trim=trim)
         logits = out.rnn_output
         pred.update({"sample_ids": out.sample_id, "logits": logits, "final_sequence_length": final_len,
                      "alignment": state.alignment_history, "n_steps": state.n_steps})
-    if getattr(weights, "speller_binf", None) is not None:  # model_helper.py:219-227,241-251,272-275 (--binf_projection)
+    if getattr(weights, "speller_binf", None) is not None and not int(hp.get("beam_width", 0) or 0):  # model_helper.py:219-227,241-251,272-275
         out_b, state_b, final_len_b = speller(enc_out, enc_state, None, enc_len, None, "infer", hp, weights.speller_binf,
                                               binf_embedding=weights.binf, memory_is_masked=True, want_alignment=want_alignment, trim=trim)
         pred.update({"logits_binf": out_b.rnn_output, "sample_ids_phones_binf": out_b.sample_id,

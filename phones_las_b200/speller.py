@@ -57,8 +57,6 @@ class SpellerWeights:
         if self.bottom_only:
             self._init_bottom_only(params, hp, enc_depth, precision, device, scope)
             return
-        if hp.get("beam_width"):
-            raise NotImplementedError("beam_width != 0 is not built (SURVEY section 2: out of scope)")
         if hp["attention_type"] not in _lib.ATT_CODES:
             raise NotImplementedError(f"attention_type={hp['attention_type']}")
         if hp.get("attention_layer_size") or hp["attention_type"] in ("bahdanau_monotonic", "custom"):
@@ -126,8 +124,6 @@ def _init_bottom_only(self, params, hp, enc_depth, precision, device, scope):
     """GNMT-style AttentionMultiCell wiring (las/model.py:20-69, 185-193): fp32 step-kernel decoder only."""
     if precision != "fp32":
         raise NotImplementedError("--bottom_only is built for the fp32 step-kernel decoder (precision='fp32')")
-    if hp.get("beam_width"):
-        raise NotImplementedError("beam_width != 0 is not built (SURVEY section 2: out of scope)")
     self.precision, self.att = precision, hp["attention_type"]
     if self.att not in _lib.ATT_CODES:
         raise NotImplementedError(f"--bottom_only with attention_type={self.att}")
@@ -326,7 +322,7 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
 
 
 def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, factor, logits, ids, align, seq_len, n_steps, trim,
-                      initial_state=None):
+                      initial_state=None, beam=None):
     """fp32 (reference-precision) decode through plas_decoder_infer_f32: a loop of step kernels on the TF weight layout."""
     B, Tm, D = values.shape
     d = _lib.DecInferDesc()
@@ -344,8 +340,13 @@ def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, f
     d.score_bias = w.score_bias_dev.data_ptr() if w.score_bias_dev is not None else None
     d.keys, d.values, d.mem_len = keys.data_ptr(), values.data_ptr(), mem_len.data_ptr()
     d.forced_ids = forced_ids.data_ptr() if forced_ids is not None else None
-    d.logits, d.sample_ids = logits.data_ptr(), ids.data_ptr()
+    d.logits = logits.data_ptr() if logits is not None else None
+    d.sample_ids = ids.data_ptr() if ids is not None else None
     d.alignment = align.data_ptr() if align is not None else None
+    if beam is not None:  # BeamSearchDecoder on the tiled batch
+        d.beam_width = beam["width"]
+        d.beam_predicted, d.beam_parent, d.beam_word = beam["predicted"].data_ptr(), beam["parent"].data_ptr(), beam["word"].data_ptr()
+        d.beam_scores, d.beam_lengths = beam["scores"].data_ptr(), beam["lengths"].data_ptr()
     d.seq_len, d.n_steps = seq_len.data_ptr(), n_steps.data_ptr()
     d.bottom_only = 1 if getattr(w, "bottom_only", False) else 0
     if "w_att_layer" in w.tf:
@@ -362,12 +363,51 @@ def _decode_f32_steps(L, w, hp, keys, values, mem_len, forced_ids, steps, cap, f
     with _lib.stage("decoder"):
         _lib.check(L.plas_decoder_infer_f32(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1 + d.max_steps * (4 + w.L))
+    if beam is not None:
+        return None
     if trim:
         n = int(n_steps.item()) if steps > 0 else 0
         logits, ids = logits[:, :n], ids[:, :n]
         if align is not None:
             align = align[:, :n]
     return logits, ids, align, seq_len, n_steps
+
+
+FinalBeamSearchDecoderOutput = namedtuple("FinalBeamSearchDecoderOutput", ["predicted_ids", "beam_search_decoder_output"])
+BeamSearchDecoderOutput = namedtuple("BeamSearchDecoderOutput", ["scores", "predicted_ids", "parent_ids"])
+
+
+def decode_beam(encoder_outputs, source_sequence_length, w, hp, beam_width, memory_is_masked=False, initial_state=None):
+    """PREDICT with beam_width > 0 (las/model.py:215-226,298-319): tile_batch of the memory (and of the initial state),
+    tf.contrib.seq2seq.BeamSearchDecoder from the sos token with length penalty 0, dynamic_decode, gather_tree.  fp32 step-kernel
+    decoder.  Returns (FinalBeamSearchDecoderOutput(predicted_ids [B, T, W], ...), final log-probs [B, W], lengths [B, W],
+    sequence lengths [B, W], n_steps)."""
+    if w.tf is None:
+        raise NotImplementedError("beam search is built on the fp32 step-kernel decoder (precision='fp32')")
+    L = _lib.lib()
+    W = int(beam_width)
+    dev = encoder_outputs.device
+    Bb, Tm, D = encoder_outputs.shape
+    enc = encoder_outputs.repeat_interleave(W, dim=0).contiguous()  # tile_batch: row b*W + w
+    mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).repeat_interleave(W).contiguous()
+    if initial_state is not None:
+        initial_state = [(c.repeat_interleave(W, dim=0), h.repeat_interleave(W, dim=0)) for c, h in initial_state]
+    keys, values, _ = prepare_memory(enc, mem_len, w, memory_is_masked)
+    factor = float(hp.get("decoding_length_factor", 1.0))
+    steps = max(int(np.rint(np.float32(Tm) * np.float32(factor))), 0)
+    cap = max(steps, 1)
+    B = Bb * W
+    beam = dict(width=W, predicted=torch.full((Bb, cap, W), int(hp["eos_id"]), dtype=torch.int32, device=dev),
+                parent=torch.zeros((cap, B), dtype=torch.int32, device=dev), word=torch.zeros((cap, B), dtype=torch.int32, device=dev),
+                scores=torch.zeros((B,), dtype=torch.float32, device=dev), lengths=torch.zeros((B,), dtype=torch.int32, device=dev))
+    seq_len = torch.zeros((B,), dtype=torch.int32, device=dev)
+    n_steps = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _decode_f32_steps(L, w, hp, keys, values, mem_len, None, steps, cap, factor, None, None, None, seq_len, n_steps, False,
+                      initial_state, beam=beam)
+    n = int(n_steps.item()) if steps > 0 else 0
+    step_out = BeamSearchDecoderOutput(None, beam["word"][:n].view(n, Bb, W).permute(1, 0, 2), beam["parent"][:n].view(n, Bb, W).permute(1, 0, 2))
+    out = FinalBeamSearchDecoderOutput(beam["predicted"][:, :n], step_out)
+    return out, beam["scores"].view(Bb, W), beam["lengths"].view(Bb, W), seq_len.view(Bb, W), n_steps
 
 
 def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_length, target_sequence_length,
@@ -398,6 +438,10 @@ def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_leng
                                                       want_alignment=False, memory_is_masked=memory_is_masked,
                                                       initial_state=init)
         seq_len = target_sequence_length
+    elif mode == "infer" and int(hparams.get("beam_width", 0) or 0) > 0:  # las/model.py:215-226,298-319 (PREDICT only)
+        out, scores, lengths, seq_len, n_steps = decode_beam(encoder_outputs, source_sequence_length, weights, hparams,
+                                                             int(hparams["beam_width"]), memory_is_masked, init)
+        return out, SpellerState(None, n_steps), seq_len
     else:
         logits, ids, align, seq_len, n_steps = decode(encoder_outputs, source_sequence_length, weights, hparams,
                                                       memory_is_masked=memory_is_masked, want_alignment=want_alignment,

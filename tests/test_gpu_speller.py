@@ -308,3 +308,62 @@ def test_target_embedding_greedy_and_teacher_forced(precision, att, B, Tm, U, Ud
     ref_tf, _ = ol.Speller(enc, lens, params, hp, precision).teacher_forced(tin, tlen)
     out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(), "train", hp, w)
     assert_parity(out.rnn_output, ref_tf, precision, "teacher-forced logits")
+
+
+# ---- beam search (PREDICT with beam_width > 0, las/model.py:215-226,298-319) ----
+# (attention, decoder layers, beam width, seed, bottom_only + pass_hidden_state, attention_layer_size, eos bias): seeds chosen with the
+# oracle so that the selections are decisive (smallest gap between adjacent candidates > 2e-3) and hypotheses end at different steps
+BEAM_CFGS = [("luong", 1, 3, 0, False, None, 0.15), ("luong_monotonic", 2, 2, 5, False, None, 0.3), ("luong_monotonic", 2, 2, 7, False, None, 0.3),
+             ("luong", 2, 3, 5, True, None, 0.15), ("luong", 2, 5, 3, False, 12, 0.15), ("custom", 1, 3, 7, False, None, 0.3),
+             ("bahdanau", 2, 4, 0, False, None, 0.3), ("luong", 1, 1, 5, False, None, 0.0)]
+
+
+@gpu
+@pytest.mark.parametrize("att,Ld,W,seed,bottom,A,eos_bias", BEAM_CFGS, ids=lambda v: str(v))
+def test_beam_search_matches_oracle(att, Ld, W, seed, bottom, A, eos_bias):
+    """tf.contrib.seq2seq.BeamSearchDecoder + gather_tree restated by the oracle vs the device loop: step word / parent ids,
+    the back-traced predicted_ids, final log-probabilities, state lengths and dynamic_decode's sequence lengths."""
+    import torch
+    from phones_las_b200.speller import decode_beam, speller
+    B, T, C, V, U, Ud = 4, 24, 4, 10, 16, 16
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
+                        attention_type=att, bottom_only=bottom, pass_hidden_state=bottom, attention_layer_size=A, beam_width=W)
+    params = _score_bias(weights.init_params(hp, seed=seed, bias_scale=0.1, projection_scale=10.0))
+    k0 = [k for k in params if k.endswith("lstm_cell/kernel") and ("cell_0/" in k or "cell_0_attention" in k) and k.startswith("speller")][0]
+    kern = params[k0].copy()
+    kern[:V] *= 30.0  # the next token depends on the previous one and the attention is peaked: hypotheses really differ
+    params[k0] = kern
+    params["speller/memory_layer/kernel"] = params["speller/memory_layer/kernel"] * 30.0
+    pb = params["speller/decoder/projection_layer/bias"].copy()
+    pb[hp["eos_id"]] += eos_bias
+    params["speller/decoder/projection_layer/bias"] = pb
+    x, lens = synth.synth_features(B, T, C, seed=seed, var_len=True)
+    (enc, enc_len), enc_state = ol.listener(x, lens, params, hp)
+    est = tuple((np.repeat(c, W, 0), np.repeat(h, W, 0)) for c, h in enc_state) if bottom else None
+    sp = ol.Speller(np.repeat(enc, W, 0), np.repeat(enc_len, W, 0), params, hp, "fp32", encoder_state=est)
+    ref_pred, ref_parent, ref_word, ref_lp, ref_len, ref_seq = sp.beam_search(W)
+    D = weights.encoder_output_depth(hp)
+    w = _device_speller(hp, params, D, "fp32")
+    state_t = tuple((torch.from_numpy(c).cuda(), torch.from_numpy(h).cuda()) for c, h in enc_state)
+    enc_t, len_t = torch.from_numpy(enc).cuda(), torch.from_numpy(enc_len.astype(np.int32)).cuda()
+    out, st, seq_len = speller(enc_t, state_t, None, len_t, None, "infer", hp, w)
+    n = int(st.n_steps.item())
+    assert n == ref_pred.shape[1] and out.predicted_ids.shape == (B, n, W)
+    decisive = getattr(sp, "beam_margin", np.inf) > 1e-3
+    assert decisive or att == "bahdanau" or W == 1
+    if decisive:
+        np.testing.assert_array_equal(out.beam_search_decoder_output.predicted_ids.cpu().numpy(), ref_word)
+        np.testing.assert_array_equal(out.beam_search_decoder_output.parent_ids.cpu().numpy(), ref_parent)
+        np.testing.assert_array_equal(out.predicted_ids.cpu().numpy(), ref_pred)
+        np.testing.assert_array_equal(seq_len.cpu().numpy(), ref_seq)
+        init = [(c, h) for c, h in state_t] if bottom else None
+        _, scores, lengths, _, _ = decode_beam(enc_t, len_t, w, hp, W, initial_state=init)
+        np.testing.assert_array_equal(lengths.cpu().numpy(), ref_len)
+        np.testing.assert_allclose(scores.cpu().numpy(), ref_lp, rtol=1e-4, atol=1e-4)
+    if W == 1:  # a single beam is the greedy search (until its eos; afterwards predicted_ids stay eos)
+        g_ids = ol.Speller(enc, enc_len, params, hp, "fp32", encoder_state=enc_state if bottom else None).greedy()[1]
+        for b in range(B):
+            row, ref_row = out.predicted_ids[b, :, 0].cpu().numpy(), g_ids[b]
+            stop = np.nonzero(ref_row == hp["eos_id"])[0]
+            upto = (stop[0] + 1) if len(stop) else len(ref_row)
+            np.testing.assert_array_equal(row[:min(upto, n)], ref_row[:min(upto, n)])

@@ -194,3 +194,33 @@ def test_bottom_only_variable_layout_and_oracle_wiring():
     la, _ = a.teacher_forced(np.full((3, 2), 3), np.array([2, 2, 2]))
     lb, _ = b.teacher_forced(np.full((3, 2), 3), np.array([2, 2, 2]))
     assert la.shape == (3, 2, 12) and not np.allclose(la, lb)  # the encoder state really seeds the cells
+
+
+def test_beam_search_width_one_is_greedy_and_wider_beams_score_at_least_as_well():
+    """BeamSearchDecoder restatement: with one beam it is the greedy search (ids up to and including the first eos, then eos);
+    the best hypothesis of a wider beam never has a lower log-probability than the greedy one."""
+    from phones_las_b200 import synth
+    hp = create_hparams(target_vocab_size=10, encoder_layers=2, encoder_units=16, decoder_units=16, decoder_layers=1, num_channels=4,
+                        attention_type="luong")
+    params = weights.init_params(hp, seed=0, bias_scale=0.1, projection_scale=10.0)
+    k0 = "speller/decoder/attention_wrapper/multi_rnn_cell/cell_0/lstm_cell/kernel"
+    kern = params[k0].copy()
+    kern[:10] *= 30.0
+    params[k0] = kern
+    params["speller/memory_layer/kernel"] = params["speller/memory_layer/kernel"] * 30.0
+    pb = params["speller/decoder/projection_layer/bias"].copy()
+    pb[hp["eos_id"]] += 0.15
+    params["speller/decoder/projection_layer/bias"] = pb
+    x, lens = synth.synth_features(4, 24, 4, seed=0, var_len=True)
+    (enc, enc_len), _ = ol.listener(x, lens, params, hp)
+    g_logits, g_ids, _, g_len, _ = ol.Speller(enc, enc_len, params, hp).greedy()
+    one = ol.Speller(enc, enc_len, params, hp).beam_search(1)
+    eos = hp["eos_id"]
+    for b in range(4):
+        stop = np.nonzero(g_ids[b] == eos)[0]
+        upto = min((stop[0] + 1) if len(stop) else g_ids.shape[1], one[0].shape[1])
+        np.testing.assert_array_equal(one[0][b, :upto, 0], g_ids[b, :upto])
+        assert (one[0][b, upto:, 0] == eos).all()
+    wide = ol.Speller(np.repeat(enc, 3, 0), np.repeat(enc_len, 3, 0), params, hp).beam_search(3)
+    assert (wide[3][:, 0] >= one[3][:, 0] - 1e-5).all() and (np.diff(wide[3], axis=1) <= 1e-6).all()
+    assert len(np.unique(wide[4])) >= 3  # hypotheses of different lengths: finished beams are carried along at no cost
