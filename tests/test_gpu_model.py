@@ -252,3 +252,22 @@ def test_multitask_model_serves_the_phone_speller():
     assert_parity(pred["logits"][:, :1].cpu().numpy(), ref["logits"][:, :1], "fp32", "logits step 0")
     with pytest.raises(NotImplementedError):
         DeviceWeights(params, dict(hp, multitask=False), C, "fp32")
+
+
+@gpu
+def test_predict_with_beam_search_returns_predicted_ids():
+    """las_model_fn(PREDICT) with beam_width > 0 (model_helper.py:231-237): sample_ids = predicted_ids [B, T, W]; no logits / probs."""
+    import torch
+    from phones_las_b200.model import DeviceWeights, las_predict
+    hp = create_hparams(target_vocab_size=12, encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=32,
+                        attention_type="luong", num_channels=6, beam_width=3)
+    params = weights.init_params(hp, 6, seed=2, projection_scale=8.0, bias_scale=0.1)
+    x, lens = synth.synth_features(3, 30, 6, seed=4, var_len=True)
+    pred = las_predict({"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}, hp,
+                       DeviceWeights(params, hp, 6, "fp32"))
+    n = int(pred["n_steps"].item())
+    assert pred["sample_ids"].shape == (3, n, 3) and "logits" not in pred and "probs" not in pred
+    (enc, enc_len), _ = ol.listener(x, lens, params, hp)
+    ref = ol.Speller(np.repeat(enc, 3, 0), np.repeat(enc_len, 3, 0), params, hp, "fp32").beam_search(3)
+    assert ref[0].shape[1] == n
+    np.testing.assert_array_equal(pred["sample_ids"][:, :, 0].cpu().numpy(), ref[0][:, :, 0])  # the best hypothesis
