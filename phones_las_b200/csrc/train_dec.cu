@@ -16,6 +16,13 @@
 //   dec_cell_bwd   gate derivatives, dz_t written IN PLACE over the saved gates
 //   dec_gemv_t     dinp = dz_t W^T   (gradient wrt [attention_{t-1}; h_{t-1}] that the next iteration consumes)
 // Saved tensors are batch-major [B][S][width] so the hoisted GEMMs see plain row-major matrices.
+//
+// Variants carried by the same kernels, selected by descriptor fields (plas.h): the five attention mechanisms of
+// las/model.py:153-166 (luong, bahdanau, luong_monotonic, bahdanau_monotonic with TRAIN-mode score noise / hard mode outside
+// TRAIN, custom), the AttentionMultiCell wiring (bottom_only) with pass_hidden_state, attention_layer_size, input dropout,
+// scheduled sampling, a constant projection + extra attention gradient (--binf_projection), the input gradient
+// (embedding_size).  This file also holds the fp32 inference loop built from the same step kernels
+// (plas_decoder_infer_f32: greedy, teacher-forced, beam search).
 #include <cooperative_groups.h>
 #include <float.h>
 
@@ -1526,8 +1533,8 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
         q.align = F(w.align) + (size_t)t * Tm; q.s_al = (long long)S * Tm;
         q.score_bias = d->score_bias; q.align_prev = t > 0 ? F(w.align) + (size_t)(t - 1) * Tm : nullptr; q.s_ap = q.s_al;
         q.p_save = F(w.psave) + (size_t)t * Tm; q.s_ps = q.s_al;
-    q.hard = 0; q.noise_scale = d->attention_type == PLAS_ATT_BAHDANAU_MONOTONIC ? d->sigmoid_noise : 0.f;
-    q.noise_seed = d->noise_seed; q.noise_base = (long long)t * Tm;
+        q.hard = 0; q.noise_scale = d->attention_type == PLAS_ATT_BAHDANAU_MONOTONIC ? d->sigmoid_noise : 0.f;
+        q.noise_seed = d->noise_seed; q.noise_base = (long long)t * Tm;
         if (AL > 0) { q.att = F(w.ctx) + (size_t)t * D; q.s_att = sd; q.att_next = nullptr; }  // the context goes through the attention layer
         else { q.att = F(w.att) + (size_t)t * D; q.s_att = sd; q.att_next = t + 1 < S ? F(w.att_prev) + (size_t)(t + 1) * D : nullptr; }
         q.next_base = 0; q.seed = 0; q.thresh = 0; q.inv_keep = 1.f; q.step_ptr = d->drop_step;  // (the noise seed follows the step)
