@@ -332,7 +332,8 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sam
     if hp.get("binary_outputs") and hp.get("binf_projection"):
         # model_helper.py:221-227 (phone ids in, embedded as binary-feature columns), :243-245 (raw attention split off),
         # :326-331 (softmax CE on the transformed logits + the log-probability regulariser)
-        M = torch.as_tensor(binf, dtype=dt)
+        # --binf_trainable: the map is the variable 'binf2phone' (model_helper.py:181-186), read by the embedding and the projection
+        M = params["binf2phone"] if hp.get("binf_trainable") else torch.as_tensor(binf, dtype=dt)
         atts = []
         logits_b = speller_train(enc_out, enc_len, M.t()[tin.long()], params, hp, scope="speller_binf",
                                  masks=masks.get("speller_binf"), encoder_state=enc_state, binf=M, attention_out=atts)

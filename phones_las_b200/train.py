@@ -397,11 +397,11 @@ class SpellerTrain:
         projection is the constant transform_binf_to_phones map [M; 1 - M] on the 2n-wide attention vectors, which ``forward``
         keeps in ``self.att_vec`` for the log-probability regulariser."""
         self.st, self.hp, self.scope, self.E, self.n_out = st, hp, scope, E, n_out
-        self.proj_const = self.att_vec = None
+        self.proj_const = self.att_vec = self.dproj = None
         if binf is not None:
-            if hp.get("binf_trainable"):
-                raise NotImplementedError("training path: --binf_trainable (a trainable binf2phone matrix) is not built")
             M = binf.to(torch.float32)
+            if hp.get("binf_trainable"):  # the matrix is the variable 'binf2phone' (model_helper.py:183): keep d([M; 1 - M])
+                self.dproj = torch.empty((2 * M.shape[0], M.shape[1]), dtype=torch.float32, device=M.device)
             self.proj_const = torch.cat([M, 1.0 - M], 0).contiguous()  # [2n, V]
             self.zero_bias = torch.zeros((M.shape[1],), dtype=torch.float32, device=M.device)
             assert int(hp.get("attention_layer_size") or 0) == self.proj_const.shape[0] and n_out == M.shape[1]
@@ -466,7 +466,8 @@ class SpellerTrain:
             d.score_bias, d.dscore_bias = st.w(sb), st.g(sb)
             d.sigmoid_noise, d.noise_seed = self.sigmoid_noise, drop_seed(self.base, 0, self.tid + 8)
         if self.proj_const is not None:  # constant projection: the Dense variables exist (checkpoint layout) but are never used
-            d.w_proj, d.b_proj, d.dw_proj, d.db_proj = self.proj_const.data_ptr(), self.zero_bias.data_ptr(), None, None
+            d.w_proj, d.b_proj, d.db_proj = self.proj_const.data_ptr(), self.zero_bias.data_ptr(), None
+            d.dw_proj = self.dproj.data_ptr() if self.dproj is not None else None
             d.att_out = self.att_vec.data_ptr()
             d.datt_extra = self.datt_extra.data_ptr() if self.datt_extra is not None else None
         else:
@@ -617,6 +618,9 @@ def forward_backward(features, labels, st, hp, binf=None):
         x_sp = st.view("speller/target_embedding")[tin].contiguous() if emb else onehot
         jobs.append(("speller", "ce", V, x_sp, None))
     proj = bool(hp.get("binf_projection"))
+    trainable_binf = proj and bool(hp.get("binf_trainable"))
+    if trainable_binf:  # binf2phone is a variable (model_helper.py:181-186): the live parameter replaces the constant
+        binf = st.view("binf2phone")
     if hp.get("binary_outputs"):
         bt = binf.to(device=dev, dtype=torch.float32).t().contiguous()  # [V, n]
         if proj:  # model_helper.py:221-227: phone ids in (embedded as binary-feature columns), phone logits out
@@ -645,9 +649,19 @@ def forward_backward(features, labels, st, hp, binf=None):
             else:
                 parts[key], dl = sigmoid_ce_grad(logits, lab, w)
                 parts["logits_binf"] = logits
-            want_dx = emb and scope == "speller"
+            want_dx = (emb and scope == "speller") or (binf_proj and trainable_binf)
             sp.backward(dl, d_enc_j, datt_extra, want_dx=want_dx)
-            if want_dx:  # d(target_embedding)[v] = sum of dX over the positions that fed phone v: OneHot^T dX, fixed order
+            if binf_proj and trainable_binf:
+                # d(binf2phone) = dW[:n] - dW[n:] (projection [M; 1 - M]) + (OneHot^T dX)^T (the inputs are columns of M)
+                n_b, gM = bt.shape[1], st.g("binf2phone")
+                for rows, sign in ((sp.dproj[:n_b], 1.0), (sp.dproj[n_b:], -1.0)):
+                    _lib.check(_lib.lib().plas_axpy_f32(C.c_void_p(gM), _lib.ptr(rows), rows.numel(), sign, _lib.stream_ptr()))
+                    _lib.count_launches(1)
+                gemm_ex(n_b, V, B * S, sp.dx_in.data_ptr(), 1, n_b, onehot.data_ptr(), V, 1, gM, V, beta=1.0)
+                continue_embedding = False
+            else:
+                continue_embedding = True
+            if want_dx and continue_embedding:  # d(target_embedding)[v] = sum of dX over the positions that fed phone v: OneHot^T dX
                 E = x_in.shape[2]
                 gemm_ex(V, E, B * S, onehot.data_ptr(), 1, V, sp.dx_in.data_ptr(), E, 1, st.g("speller/target_embedding"), E)
             done = torch.cuda.Event()
@@ -792,6 +806,8 @@ class GraphedTrainStep:
 def train_variable_shapes(hp, num_channels=None, binf_count=0):
     """variable_shapes + the 'speller_binf/' twin of the multitask configuration (model_helper.py:221)."""
     shapes = dict(variable_shapes(hp, num_channels))
+    if hp.get("binary_outputs") and hp.get("binf_trainable") and hp.get("binf_projection"):
+        shapes["binf2phone"] = (binf_count, hp["target_vocab_size"])  # model_helper.py:183 (initialised from the constant map)
     if hp.get("binary_outputs"):
         V = hp["target_vocab_size"]
         for k, s in list(shapes.items()):

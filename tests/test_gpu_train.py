@@ -621,11 +621,12 @@ def test_train_step_attention_layer_size(att, Ld, A, sampling):
 
 
 # ---- --binf_projection: DenseBinfDecoder as transform_binf_to_phones + compute_log_probs_loss ----
-def _binf_projection_setup(multitask, dropout, att="luong", Ld=1):
+def _binf_projection_setup(multitask, dropout, att="luong", Ld=1, trainable=False):
     B, T, C, U, Ud, V, n, S = 5, 60, 6, 16, 32, 14, 6, 6
     hp = create_hparams(target_vocab_size=V, binf_count=n, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld,
                         num_channels=C, attention_type=att, dropout=dropout, sampling_probability=0.0, binary_outputs=True,
-                        binf_projection=True, multitask=multitask, binf_projection_reg_weight=0.7, l2_reg_scale=1e-4, ctc_weight=0.2)
+                        binf_projection=True, multitask=multitask, binf_projection_reg_weight=0.7, l2_reg_scale=1e-4, ctc_weight=0.2,
+                        binf_trainable=trainable)
     assert hp["attention_layer_size"] == 2 * n  # las/model.py:180-183
     from phones_las_b200.train import train_variable_shapes
     shapes = train_variable_shapes(hp, C, binf_count=n)
@@ -638,18 +639,22 @@ def _binf_projection_setup(multitask, dropout, att="luong", Ld=1):
     x, lens = synth.synth_features(B, T, C, seed=B + 2, var_len=True)
     tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=5)
     binf = (np.random.default_rng(1).uniform(size=(n, V)) < 0.4).astype(np.float32)
+    assert ("binf2phone" in shapes) == trainable
+    if trainable:  # --binf_trainable: the map is a variable initialised from the constant (model_helper.py:183)
+        params["binf2phone"] = binf.copy()
     return hp, params, x, lens, tin, tout, tlen, binf, (B, T, C, S, n)
 
 
 @gpu
-@pytest.mark.parametrize("multitask,dropout,att,Ld", [(False, 0.0, "luong", 1), (True, 0.0, "bahdanau", 2), (True, 0.25, "luong", 2),
-                                                      (False, 0.3, "bahdanau", 1)])
-def test_train_step_binf_projection(multitask, dropout, att, Ld):
+@pytest.mark.parametrize("multitask,dropout,att,Ld,trainable", [(False, 0.0, "luong", 1, False), (True, 0.0, "bahdanau", 2, False),
+                                                                (True, 0.25, "luong", 2, False), (False, 0.3, "bahdanau", 1, False),
+                                                                (False, 0.0, "luong", 2, True), (True, 0.25, "luong", 1, True)])
+def test_train_step_binf_projection(multitask, dropout, att, Ld, trainable):
     """The binary-feature speller in projection mode: fed the previous phone's feature column, its 2n-wide attention vector is
     mapped to phone logits by the constant [M; 1 - M]; loss = softmax CE + reg_weight * compute_log_probs_loss(attention)."""
     import torch
     from phones_las_b200 import train as tr
-    hp, params, x, lens, tin, tout, tlen, binf, (B, T, C, S, n) = _binf_projection_setup(multitask, dropout, att, Ld)
+    hp, params, x, lens, tin, tout, tlen, binf, (B, T, C, S, n) = _binf_projection_setup(multitask, dropout, att, Ld, trainable)
     st = tr.TrainState(params)
     st.step = 4
     masks = None
@@ -681,6 +686,8 @@ def test_train_step_binf_projection(multitask, dropout, att, Ld):
         assert grad_err(raw[k], ref_g) < GRAD_TOL, k
     unused = raw["speller_binf/decoder/projection_layer/kernel"]
     assert not unused.any()  # the Dense variables of the projection layer receive no gradient from the decoder
+    if trainable:
+        assert np.abs(raw["binf2phone"]).max() > 0
     tr.apply_gradients(st, hp)  # L2 + clip + Adam run over the whole flat buffer, unused variables included
 
 
