@@ -323,6 +323,10 @@ typedef struct plas_dec_train_desc {
   const float* datt_extra;
   /* bwd out, optional: gradient wrt x_in [B][S][E] (embedding_size != 0, las/model.py:230-237: it flows into target_embedding) */
   float* dx_in;
+  /* scheduled sampling when the decoder inputs are not one-hot (embedding_size != 0, --binf_projection): the sampled id feeds
+   * row id of sample_table [n_out][E]; sample_fed_ids [B][S] (caller pre-fills it with targets_inputs) receives the ids fed */
+  const float* sample_table;
+  int32_t* sample_fed_ids;
 } plas_dec_train_desc;
 size_t plas_dec_train_workspace_bytes(const plas_dec_train_desc* d);
 int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes, plas_stream_t stream);

@@ -130,7 +130,7 @@ def monotonic_attention(p_choose, previous):
 
 
 def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", masks=None, encoder_state=None, sampling=None,
-                  fed_inputs=None, score_noise=None, binf=None, attention_out=None):
+                  fed_inputs=None, score_noise=None, binf=None, attention_out=None, table=None):
     """Teacher-forced decode.  dec_inputs [B,L,E] float (one-hot ids, or binary-feature vectors for the
     binary_outputs speller).  Returns logits [B,L,n_out] (n_out = projection kernel columns).
     ``masks``: input-dropout multipliers of the decoder cells: 'x' [B,L,E] and 'att' [B,L,D] (slot t multiplies
@@ -203,7 +203,10 @@ def speller_train(enc_out, enc_len, dec_inputs, params, hp, scope="speller", mas
             return
         sel = torch.as_tensor(sampling[0][:, t])
         ids = (logits_t.detach() + torch.as_tensor(sampling[1][:, t], dtype=logits_t.dtype)).argmax(-1)
-        drawn = torch.nn.functional.one_hot(ids, logits_t.shape[-1]).to(logits_t.dtype)
+        if table is not None:  # embedding_fn other than one-hot: the sampled id feeds its embedding row (differentiable wrt the table)
+            drawn = table[ids]
+        else:
+            drawn = torch.nn.functional.one_hot(ids, logits_t.shape[-1]).to(logits_t.dtype)
         dec_inputs[t + 1] = torch.where(sel[:, None], drawn, dec_inputs[t + 1])
 
     for t in range(len(dec_inputs)):
@@ -306,7 +309,7 @@ def ctc_loss(logits, labels, label_length, logit_length, blank=0):
     return torch.stack(out)
 
 
-def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sampling=None, score_noise=None):
+def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sampling=None, score_noise=None, sampling_binf=None):
     """las_model_fn(mode=TRAIN) loss (model_helper.py:165-358, 411-413) with dropout = 0 and
     sampling_probability = 0.  ``binf`` [n, V] enables the multitask binary-feature speller.
     Returns (total loss incl. L2, dict of the parts)."""
@@ -324,7 +327,7 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sam
             dec_in = params["speller/target_embedding"][tin.long()]
         else:
             dec_in = torch.nn.functional.one_hot(tin.long(), V).to(dt)
-        logits = speller_train(enc_out, enc_len, dec_in, params, hp,
+        logits = speller_train(enc_out, enc_len, dec_in, params, hp, table=params["speller/target_embedding"] if hp.get("embedding_size") else None,
                                masks=masks.get("speller"), encoder_state=enc_state, sampling=sampling, score_noise=score_noise)
         parts["ce"] = sequence_loss(logits, tout, w)
         parts["logits"] = logits
@@ -336,7 +339,8 @@ def train_loss(params, features, lengths, labels, hp, binf=None, masks=None, sam
         M = params["binf2phone"] if hp.get("binf_trainable") else torch.as_tensor(binf, dtype=dt)
         atts = []
         logits_b = speller_train(enc_out, enc_len, M.t()[tin.long()], params, hp, scope="speller_binf",
-                                 masks=masks.get("speller_binf"), encoder_state=enc_state, binf=M, attention_out=atts)
+                                 masks=masks.get("speller_binf"), encoder_state=enc_state, binf=M, attention_out=atts,
+                                 sampling=sampling_binf, table=M.t())
         parts["ce_binf"] = sequence_loss(logits_b, tout, w)
         parts["log_probs_reg"] = compute_log_probs_loss(torch.stack(atts, 1))
         parts["logits_binf"] = logits_b

@@ -78,7 +78,7 @@ class DecTrainDesc(C.Structure):
                 ("x_in_rw", C.c_void_p), ("w_att_layer", C.c_void_p), ("dw_att_layer", C.c_void_p), ("att_layer", C.c_int32),
                 ("_pad3", C.c_int32), ("score_bias", C.c_void_p), ("dscore_bias", C.c_void_p),
                 ("sigmoid_noise", C.c_float), ("noise_seed", C.c_uint32), ("att_out", C.c_void_p), ("datt_extra", C.c_void_p),
-                ("dx_in", C.c_void_p)]
+                ("dx_in", C.c_void_p), ("sample_table", C.c_void_p), ("sample_fed_ids", C.c_void_p)]
 
 
 class DecInferDesc(C.Structure):

@@ -759,6 +759,9 @@ struct SchedSampleArgs {
   long long idx_base; int S;                        // flat (b, t) index = b*S + t (idx_base = t)
   unsigned seed_sel, seed_cat, p_thresh; const unsigned* step_ptr;
   unsigned xdrop_seed, xdrop_thresh; float xdrop_inv_keep;  // input dropout of x_{t+1} (thresh 2^24 / inv_keep 1 = off)
+  // embedding_fn other than one-hot (target_embedding, or the binary-feature columns of --binf_projection): the sampled id feeds
+  // row `id` of table [V][E]; fed_ids[b][t+1] records it for the input-side gradient.  table == NULL: one-hot, E == V.
+  const float* table; int E; int* fed_ids;
 };
 
 __global__ void __launch_bounds__(256) dec_sched_sample_kernel(SchedSampleArgs p) {
@@ -798,6 +801,26 @@ __global__ void __launch_bounds__(256) dec_sched_sample_kernel(SchedSampleArgs p
   }
   __syncthreads();
   const int best = s_best;
+  if (p.fed_ids && tid == 0) p.fed_ids[(long long)b * p.S + p.idx_base + 1] = best;
+  if (p.table) {  // dense input row: x_{t+1} = table[best] (through its dropout mask), Z_0 = x W_0[0:E] + b_0
+    float* s_x = ss_smem;  // [E] (the projection scratch is free now)
+    __syncthreads();
+    for (int e = tid; e < p.E; e += 256) {
+      const float sc = p.xdrop_inv_keep == 1.f ? 1.f
+                                               : drop_scale((uint64_t)((long long)b * p.s_x + (long long)(p.idx_base + 1) * p.E + e),
+                                                            p.xdrop_seed + stepv, p.xdrop_thresh, p.xdrop_inv_keep);
+      const float xv = p.table[(size_t)best * p.E + e] * sc;
+      s_x[e] = xv;
+      p.x_next[(long long)b * p.s_x + e] = xv;
+    }
+    __syncthreads();
+    for (int n = tid; n < p.N; n += 256) {
+      float acc = p.b0[n];
+      for (int e = 0; e < p.E; ++e) acc = fmaf(s_x[e], p.w0[(size_t)e * p.N + n], acc);
+      p.z_next[(long long)b * p.s_z + n] = acc;
+    }
+    return;
+  }
   const float sc = p.xdrop_inv_keep == 1.f ? 1.f
                                            : drop_scale((uint64_t)((long long)b * p.s_x + (p.idx_base + 1) * V + best), p.xdrop_seed + stepv,
                                                         p.xdrop_thresh, p.xdrop_inv_keep);
@@ -1143,7 +1166,8 @@ static int dec_train_check(const plas_dec_train_desc* d, void* ws, size_t ws_byt
   PLAS_REQUIRE(d->keep_prob > 0.f && d->keep_prob <= 1.f, "dec_train: keep_prob=%f", d->keep_prob);
   PLAS_REQUIRE(d->sample_prob >= 0.f && d->sample_prob <= 1.f, "dec_train: sample_prob=%f", d->sample_prob);
   if (d->sample_prob > 0.f)
-    PLAS_REQUIRE(d->x_in_rw != nullptr && d->E == d->n_out, "dec_train: scheduled sampling needs one-hot inputs (E == n_out) and a writable x_in");
+    PLAS_REQUIRE(d->x_in_rw != nullptr && (d->E == d->n_out || d->sample_table != nullptr),
+                 "dec_train: scheduled sampling needs a writable x_in and one-hot inputs (E == n_out) or the embedding table");
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 4 == 0, "dec_train: Ud=%d must be a multiple of 16, D=%d of 4", d->Ud, d->D);
   PLAS_REQUIRE(d->attention_type >= PLAS_ATT_LUONG && d->attention_type <= PLAS_ATT_CUSTOM, "dec_train: attention_type %d", d->attention_type);
   if (att_is_mono(d->attention_type)) PLAS_REQUIRE(d->score_bias != nullptr, "dec_train: monotonic attention needs attention_score_bias");
@@ -1456,7 +1480,8 @@ static int launch_sched_sample(cudaStream_t st, const plas_dec_train_desc* d, co
   a.idx_base = t; a.S = S;
   a.seed_sel = d->sample_seed; a.seed_cat = d->sample_seed + 1; a.p_thresh = (unsigned)(d->sample_prob * 16777216.0f); a.step_ptr = d->drop_step;
   a.xdrop_seed = d->xdrop_seed; a.xdrop_thresh = (unsigned)(d->keep_prob * 16777216.0f); a.xdrop_inv_keep = 1.0f / d->keep_prob;
-  const size_t smem = (size_t)(Dout + 4 * d->n_out) * 4;
+  a.table = d->sample_table; a.E = E; a.fed_ids = d->sample_fed_ids;
+  const size_t smem = (size_t)((Dout > E ? Dout : E) + 4 * d->n_out) * 4;
   PLAS_REQUIRE(smem <= 200 * 1024, "scheduled sampling: projection too large");
   if (smem > 48 * 1024) PLAS_CUDA(cudaFuncSetAttribute(dec_sched_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dec_sched_sample_kernel<<<B, 256, smem, st>>>(a);

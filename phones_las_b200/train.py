@@ -392,7 +392,7 @@ def listener_train_bwd(d_enc, tape, st, hp, d_final=None):
 class SpellerTrain:
     """One teacher-forced speller (scope 'speller' or 'speller_binf') bound to a TrainState."""
 
-    def __init__(self, st, hp, scope, E, n_out, index=0, binf=None):
+    def __init__(self, st, hp, scope, E, n_out, index=0, binf=None, table=None):
         """``binf`` (device tensor [n, V], binf2phone): --binf_projection wiring of this speller (las/model.py:251-257): the
         projection is the constant transform_binf_to_phones map [M; 1 - M] on the 2n-wide attention vectors, which ``forward``
         keeps in ``self.att_vec`` for the log-probability regulariser."""
@@ -411,16 +411,20 @@ class SpellerTrain:
         self.init = self.d_init = None
         # scheduled sampling (las/model.py:279-288): the phone speller draws ids from its own logits; the binary-feature
         # speller's ScheduledSigmoidHelper path of the reference is shape-inconsistent and is not built
+        # ``table`` [n_out, E]: embedding_fn when the inputs are not one-hot (target_embedding, or the binary-feature columns of
+        # --binf_projection) -- a sampled id then feeds its row, and ``self.fed_ids`` records the ids actually fed
         self.sample_prob = float(hp.get("sampling_probability", 0.0))
-        if self.sample_prob > 0.0 and (scope != "speller" or E != n_out):
-            raise NotImplementedError("training path: scheduled sampling is built for the phone speller only; set sampling_probability=0")
+        self.table, self.fed_ids = table, None
+        if self.sample_prob > 0.0 and E != n_out and table is None:
+            raise NotImplementedError("training path: scheduled sampling of the binary-feature speller (ScheduledSigmoidHelper) is not built; "
+                                      "set sampling_probability=0")
         if hp["attention_type"] not in _lib.ATT_CODES:
             raise NotImplementedError(f"training path: attention_type={hp['attention_type']}")
         # bahdanau_monotonic in TRAIN mode: sigmoid_noise = 1.0 (las/model.py:161-162); tests may set 0 for a noise-free check
         self.sigmoid_noise = 1.0 if hp["attention_type"] == "bahdanau_monotonic" else 0.0
-        if hp.get("embedding_size") and (hp.get("binary_outputs") or self.sample_prob > 0.0):
+        if hp.get("embedding_size") and hp.get("binary_outputs"):
             # the reference's embedding_fn looks float feature vectors up in target_embedding there (las/model.py:229-237): ill-formed
-            raise NotImplementedError("training path: --embedding_size with binary_outputs or scheduled sampling is not built")
+            raise NotImplementedError("training path: --embedding_size with binary_outputs is not built")
         self.dx_in = None
         self.att_layer = int(hp.get("attention_layer_size") or 0)
         self.bottom = bool(hp.get("bottom_only"))
@@ -438,6 +442,8 @@ class SpellerTrain:
         d.drop_seed = drop_seed(self.base, 0, self.tid + 1)  # + step * DROP_STEP_MUL on the device
         d.drop_step = st.step_dev.data_ptr()
         d.sample_prob = self.sample_prob
+        if self.sample_prob > 0.0 and self.table is not None:
+            d.sample_table, d.sample_fed_ids = self.table.data_ptr(), self.fed_ids.data_ptr()
         d.sample_seed = drop_seed(self.base, 0, self.tid + 9)
         d.xdrop_seed = drop_seed(self.base, 0, self.tid)
         d.x_in_rw = x_in.data_ptr()
@@ -485,10 +491,14 @@ class SpellerTrain:
                     d.dc_init[l], d.dh_init[l] = self.d_init[l][0].data_ptr(), self.d_init[l][1].data_ptr()
         return d
 
-    def forward(self, memory, mem_len, x_in, initial_state=None):
+    def forward(self, memory, mem_len, x_in, initial_state=None, ids=None):
         """memory [B,Tm,D] (zero past mem_len), x_in [B,S,E] -> logits [B,S,n_out]; keeps the tape on self.
-        ``initial_state``: [(c, h)] per decoder cell (pass_hidden_state: the listener's final fw / bw states)."""
+        ``initial_state``: [(c, h)] per decoder cell (pass_hidden_state: the listener's final fw / bw states).
+        ``ids`` [B,S]: the teacher ids behind ``x_in`` (needed with scheduled sampling through an embedding ``table``)."""
         L = _lib.lib()
+        if self.sample_prob > 0.0 and self.table is not None:
+            self.table = self.table.to(torch.float32).contiguous()
+            self.fed_ids = ids.to(torch.int32).contiguous().clone()
         self.init, self.d_init = None, None
         if self.pass_state and initial_state is not None:
             self.init = [(c.contiguous(), h.contiguous()) for c, h in initial_state[:self.hp["decoder_layers"]]]
@@ -637,9 +647,12 @@ def forward_backward(features, labels, st, hp, binf=None):
         with torch.cuda.stream(stream):
             stream.wait_event(ready)
             binf_proj = proj and scope == "speller_binf"
+            table = st.view("speller/target_embedding") if (emb and scope == "speller") else (bt if binf_proj else None)
             sp = SpellerTrain(st, hp, scope, x_in.shape[2], n_out, index=0 if scope == "speller" else 1,
-                              binf=binf.to(device=dev) if binf_proj else None)
-            logits = sp.forward(enc_out, enc_len, x_in, initial_state=enc_state)
+                              binf=binf.to(device=dev) if binf_proj else None, table=table)
+            logits = sp.forward(enc_out, enc_len, x_in, initial_state=enc_state, ids=tin)
+            # the ids that were actually fed (scheduled sampling replaces some): the input-side gradients scatter by them
+            fed_onehot = onehot if sp.fed_ids is None else torch.nn.functional.one_hot(sp.fed_ids.long(), V).to(torch.float32)
             datt_extra = None
             if lab is None:
                 parts[key], dl = seq_ce_grad(logits, tout, w)
@@ -657,13 +670,13 @@ def forward_backward(features, labels, st, hp, binf=None):
                 for rows, sign in ((sp.dproj[:n_b], 1.0), (sp.dproj[n_b:], -1.0)):
                     _lib.check(_lib.lib().plas_axpy_f32(C.c_void_p(gM), _lib.ptr(rows), rows.numel(), sign, _lib.stream_ptr()))
                     _lib.count_launches(1)
-                gemm_ex(n_b, V, B * S, sp.dx_in.data_ptr(), 1, n_b, onehot.data_ptr(), V, 1, gM, V, beta=1.0)
+                gemm_ex(n_b, V, B * S, sp.dx_in.data_ptr(), 1, n_b, fed_onehot.data_ptr(), V, 1, gM, V, beta=1.0)
                 continue_embedding = False
             else:
                 continue_embedding = True
             if want_dx and continue_embedding:  # d(target_embedding)[v] = sum of dX over the positions that fed phone v: OneHot^T dX
                 E = x_in.shape[2]
-                gemm_ex(V, E, B * S, onehot.data_ptr(), 1, V, sp.dx_in.data_ptr(), E, 1, st.g("speller/target_embedding"), E)
+                gemm_ex(V, E, B * S, fed_onehot.data_ptr(), 1, V, sp.dx_in.data_ptr(), E, 1, st.g("speller/target_embedding"), E)
             done = torch.cuda.Event()
             done.record(stream)
         pending.append((d_enc_j, done, sp))

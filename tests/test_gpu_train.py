@@ -708,13 +708,15 @@ def test_log_probs_regulariser_matches_autograd():
 
 # ---- embedding_size != 0 (las/model.py:230-237): decoder inputs are rows of speller/target_embedding ----
 @gpu
-@pytest.mark.parametrize("att,Ld,bottom,dropout", [("luong", 1, False, 0.0), ("bahdanau", 2, False, 0.25), ("luong", 2, True, 0.0)])
-def test_train_step_target_embedding(att, Ld, bottom, dropout):
+@pytest.mark.parametrize("att,Ld,bottom,dropout,sampling", [("luong", 1, False, 0.0, 0.0), ("bahdanau", 2, False, 0.25, 0.0),
+                                                            ("luong", 2, True, 0.0, 0.0), ("luong", 1, False, 0.25, 0.4),
+                                                            ("bahdanau", 2, True, 0.0, 0.3)])
+def test_train_step_target_embedding(att, Ld, bottom, dropout, sampling):
     import torch
     from phones_las_b200 import train as tr
     B, T, C, U, Ud, V, S, E = 6, 44, 6, 16, 32, 13, 6, 10
     hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=U, decoder_units=Ud, decoder_layers=Ld, num_channels=C,
-                        attention_type=att, dropout=dropout, sampling_probability=0.0, embedding_size=E, bottom_only=bottom,
+                        attention_type=att, dropout=dropout, sampling_probability=sampling, embedding_size=E, bottom_only=bottom,
                         l2_reg_scale=1e-4, ctc_weight=0.3)
     params = weights.init_params(hp, seed=E + Ld, bias_scale=0.05, projection_scale=4.0)
     x, lens = synth.synth_features(B, T, C, seed=B, var_len=True)
@@ -726,9 +728,12 @@ def test_train_step_target_embedding(att, Ld, bottom, dropout):
         rm = tr.reference_masks(hp, 2, B, T, C, S)
         assert rm["speller"]["x"].shape == (B, S, E)
         masks = {sc: {kk: torch.tensor(vv, dtype=torch.float64) for kk, vv in m.items()} for sc, m in rm.items()}
+    # scheduled sampling: a sampled id feeds its embedding row, and the embedding gradient scatters by the ids actually fed
+    sampling_rng = tr.reference_sampling(hp, 2, B, S, V) if sampling > 0 else None
     tp = _tp(params)
     rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
-    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, masks=masks)
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, masks=masks,
+                                        sampling=sampling_rng)
     ref_loss.backward()
     feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
     labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
@@ -855,3 +860,36 @@ def test_periodic_weight_noise():
     assert n_kernels >= 6
     z = np.concatenate([(p1[k].astype(np.float64) - p0[k]).ravel() for k in params if k.endswith("kernel")]) / 0.05
     assert abs(z.mean()) < 0.05 and abs(z.std() - 1.0) < 0.05
+
+
+@gpu
+@pytest.mark.parametrize("multitask,dropout", [(False, 0.0), (True, 0.25)])
+def test_train_step_binf_projection_with_scheduled_sampling(multitask, dropout):
+    """The reference's default sampling_probability is 0.1: in projection mode the sampled phone feeds its binary-feature column
+    (TPUScheduledEmbeddingTrainingHelper with outputs_count = V, las/model.py:284-288)."""
+    import torch
+    from phones_las_b200 import train as tr
+    hp, params, x, lens, tin, tout, tlen, binf, (B, T, C, S, n) = _binf_projection_setup(multitask, dropout, "luong", 2, trainable=True)
+    hp["sampling_probability"] = 0.4
+    V = hp["target_vocab_size"]
+    st = tr.TrainState(params)
+    st.step = 4
+    masks = None
+    if dropout > 0:
+        masks = {sc: ({kk: torch.tensor(vv, dtype=torch.float64) for kk, vv in m.items()})
+                 for sc, m in tr.reference_masks(hp, 4, B, T, C, S, binf_count=n).items()}
+    tp = _tp(params)
+    rl = dict(targets_inputs=torch.tensor(tin), targets_outputs=torch.tensor(tout), target_sequence_length=torch.tensor(tlen.astype(np.int64)))
+    ref_loss, ref_parts = lt.train_loss(tp, torch.tensor(x, dtype=torch.float64), torch.tensor(lens.astype(np.int64)), rl, hp, binf, masks=masks,
+                                        sampling=tr.reference_sampling(hp, 4, B, S, V, 0) if multitask else None,
+                                        sampling_binf=tr.reference_sampling(hp, 4, B, S, V, 1))
+    ref_loss.backward()
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    labels = {"targets_inputs": torch.from_numpy(tin).cuda(), "targets_outputs": torch.from_numpy(tout).cuda(),
+              "target_sequence_length": torch.from_numpy(tlen).cuda()}
+    parts = tr.forward_backward(feats, labels, st, hp, torch.from_numpy(binf).cuda())
+    assert scaled_err(parts["logits_binf"], ref_parts["logits_binf"].detach()) < 1e-5
+    raw = st.export_grads()
+    for k in params:
+        g = tp[k].grad if tp[k].grad is not None else torch.zeros_like(tp[k])
+        assert grad_err(raw[k], g - hp["l2_reg_scale"] * tp[k].detach()) < GRAD_TOL, k
