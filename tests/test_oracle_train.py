@@ -288,3 +288,20 @@ def test_weight_folds_are_the_maps_they_replace():
     M = (rng.uniform(size=(n, V)) < 0.5).astype(np.float32)
     att = rng.normal(size=(6, 2 * n)).astype(np.float32)
     np.testing.assert_allclose(att @ np.concatenate([M, 1 - M], 0), olo.transform_binf_to_phones(att, M), rtol=1e-5, atol=1e-6)
+
+
+def test_reference_noise_and_bottom_only_masks_mirrors():
+    """Host mirrors of the device randomness used by the parity tests: the bahdanau_monotonic score noise is standard normal,
+    deterministic, and changes with the optimiser step; the AttentionMultiCell input masks have the cell-input widths."""
+    from phones_las_b200 import train as tr
+    hp = create_hparams(target_vocab_size=9, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=3, num_channels=4,
+                        attention_type="bahdanau_monotonic", bottom_only=True, dropout=0.25)
+    a, b, c = tr.reference_noise(hp, 1, 32, 10, 40), tr.reference_noise(hp, 1, 32, 10, 40), tr.reference_noise(hp, 2, 32, 10, 40)
+    assert a.shape == (32, 10, 40) and np.array_equal(a, b) and not np.array_equal(a, c)
+    assert abs(a.mean()) < 0.03 and abs(a.std() - 1.0) < 0.03 and np.abs(a).max() < 6.0
+    assert abs(np.corrcoef(a.ravel(), c.ravel())[0, 1]) < 0.03
+    rm = tr.reference_masks(hp, 1, 4, 20, 4, 6)["speller"]
+    D = weights.encoder_output_depth(hp)
+    assert rm["att"].shape == (4, 6, D) and rm[("in", 1)].shape == (4, 6, 2 * D) and rm[("in", 2)].shape == (4, 6, 16 + D)
+    keep = np.mean(rm[("in", 1)] > 0)
+    assert abs(keep - 0.75) < 0.03 and set(np.unique(rm[("in", 1)])) == {0.0, np.float32(1.0) / np.float32(0.75)}
