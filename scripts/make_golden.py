@@ -36,6 +36,38 @@ LAS_CASES = {
 }
 
 
+# decoder variants added after the first fixtures: oracle-regression pins only (their CUDA parity tests compare with the live
+# oracle on seeded inputs, tests/test_gpu_speller.py); name: hyper-parameter overrides, beam width
+VARIANT_CASES = {
+    "las_variant_custom": (dict(attention_type="custom"), 0),
+    "las_variant_bahdanau_monotonic_hard": (dict(attention_type="bahdanau_monotonic"), 0),
+    "las_variant_true_las_attention_layer": (dict(attention_type="luong", bottom_only=True, pass_hidden_state=True, attention_layer_size=24), 0),
+    "las_variant_embedding": (dict(attention_type="bahdanau", embedding_size=12), 0),
+    "las_variant_beam3": (dict(attention_type="luong"), 3),
+}
+
+
+def variant_case(spec):
+    over, beam = spec
+    B, T, C, V = 3, 22, 6, 14
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=16, decoder_units=16, decoder_layers=2, num_channels=C,
+                        **over)
+    params = weights.init_params(hp, C, seed=13, projection_scale=8.0, bias_scale=0.1)
+    for k in params:
+        if k.endswith("attention_score_bias"):
+            params[k] = np.float32(0.2)
+    x, lens = synth.synth_features(B, T, C, seed=6, var_len=True)
+    (enc, enc_len), enc_state = ol.listener(x, lens, params, hp)
+    if beam:
+        sp = ol.Speller(np.repeat(enc, beam, 0), np.repeat(enc_len, beam, 0), params, hp, "fp32")
+        pred, parent, word, lp, length, seq = sp.beam_search(beam)
+        return dict(x=x, lens=lens, predicted_ids=pred, parent_ids=parent, word_ids=word, log_probs=lp.astype(np.float32),
+                    lengths=length.astype(np.int32), sequence_lengths=seq)
+    logits, ids, align, seq_len, _ = ol.Speller(enc, enc_len, params, hp, "fp32", encoder_state=enc_state).greedy()
+    return dict(x=x, lens=lens, sample_ids=ids, logits=logits.astype(np.float32), alignment=align.astype(np.float32),
+                final_sequence_length=seq_len)
+
+
 def frontend_case(kw):
     fa = feature_args(**kw)
     wave, lens = synth.synth_audio(2, 0.6, seed=17, var_len=True, silence=True)
@@ -61,6 +93,8 @@ def build_all():
         out[name] = frontend_case(kw)
     for name, spec in LAS_CASES.items():
         out[name] = las_case(spec)
+    for name, spec in VARIANT_CASES.items():
+        out[name] = variant_case(spec)
     return out
 
 
