@@ -224,3 +224,49 @@ def test_beam_search_width_one_is_greedy_and_wider_beams_score_at_least_as_well(
     wide = ol.Speller(np.repeat(enc, 3, 0), np.repeat(enc_len, 3, 0), params, hp).beam_search(3)
     assert (wide[3][:, 0] >= one[3][:, 0] - 1e-5).all() and (np.diff(wide[3], axis=1) <= 1e-6).all()
     assert len(np.unique(wide[4])) >= 3  # hypotheses of different lengths: finished beams are carried along at no cost
+
+
+def test_beam_search_with_a_full_beam_finds_the_exhaustive_optimum():
+    """Independent check of the BeamSearchDecoder restatement: with a beam wide enough never to prune (V = 4, 3 steps, W = 16) its
+    best hypothesis and score equal those of an exhaustive search over every sequence (a hypothesis stops at its first eos)."""
+    from itertools import product
+    from phones_las_b200 import synth
+    V, W, steps = 4, 16, 3
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=1, num_channels=4,
+                        attention_type="luong", decoding_length_factor=0.5)
+    params = weights.init_params(hp, seed=3, bias_scale=0.1, projection_scale=20.0)
+    k0 = "speller/decoder/attention_wrapper/multi_rnn_cell/cell_0/lstm_cell/kernel"
+    kern = params[k0].copy()
+    kern[:V] *= 30.0
+    params[k0] = kern
+    x, lens = synth.synth_features(2, 12, 4, seed=1)           # T' = 6 -> max_iter = rint(6 * 0.5) = 3
+    (enc, enc_len), _ = ol.listener(x, lens, params, hp)
+    assert int(np.rint(enc_len.max() * 0.5)) == steps
+    eos, sos = hp["eos_id"], hp["sos_id"]
+    out = ol.Speller(np.repeat(enc, W, 0), np.repeat(enc_len, W, 0), params, hp).beam_search(W)
+    sp1 = ol.Speller(enc, enc_len, params, hp)
+
+    def score(b, seq):  # log-probability of emitting seq (stopping after its first eos) for utterance b
+        state = sp1.zero_state()
+        ids = np.full((sp1.B,), sos, np.int64)
+        total = 0.0
+        for tok in seq:
+            logits, state = sp1.step(sp1.one_hot(ids), state)
+            lg = logits[b].astype(np.float64)
+            total += lg[tok] - (lg.max() + np.log(np.exp(lg - lg.max()).sum()))
+            if tok == eos:
+                break
+            ids = np.full((sp1.B,), tok, np.int64)
+        return total
+
+    for b in range(2):
+        best, best_seq = -np.inf, None
+        for seq in product(range(V), repeat=steps):
+            cut = seq[:seq.index(eos) + 1] if eos in seq else seq
+            if len(cut) < steps and seq[len(cut):] != (eos,) * (steps - len(cut)):
+                continue  # enumerate each stopped hypothesis once (padded with eos)
+            sc = score(b, cut)
+            if sc > best:
+                best, best_seq = sc, seq
+        assert abs(out[3][b, 0] - best) < 1e-4, (out[3][b], best)
+        np.testing.assert_array_equal(out[0][b, :, 0], np.array(best_seq))
