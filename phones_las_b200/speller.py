@@ -1,12 +1,18 @@
-"""Speller operator: attention decoder (greedy / teacher-forced) on the GPU.
+"""Speller operator: attention decoder (greedy / teacher-forced / beam search) on the GPU.
 
-Mirrors ``las.model.speller`` (reference las/model.py:205-349) for the default wiring
-(bottom_only=False, attention_layer_size=None, embedding_size=0, beam_width=0):
+Mirrors ``las.model.speller`` (reference las/model.py:205-349):
 ``speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_length,
 target_sequence_length, mode, hparams)`` -> ``(BasicDecoderOutput(rnn_output, sample_id),
-final_state, final_sequence_length)``.  The attention memory is prepared once per batch
-(length masking + memory_layer GEMM, las/model.py:168-169) and the whole decode loop runs inside
-one persistent kernel (plas_decoder_fwd).
+final_state, final_sequence_length)`` (``FinalBeamSearchDecoderOutput`` with ``beam_width > 0``).  The attention memory is
+prepared once per batch (length masking + memory_layer GEMM, las/model.py:168-169).  Two decoder families sit underneath:
+
+* the fused decoders (``plas_decoder_fwd``: the whole decode loop inside one persistent kernel; bf16 tensor-core or SIMT) for the
+  default wiring with luong / bahdanau / luong_monotonic attention -- the BASELINE configurations;
+* the fp32 step-kernel decoder (``plas_decoder_infer_f32``, a host loop over the training path's step kernels on the TF weight
+  layout) for reference precision and for every other variant: bahdanau_monotonic (mode 'hard'), custom attention, the
+  AttentionMultiCell wiring (bottom_only, pass_hidden_state), attention_layer_size, --binf_projection, beam search.
+
+``embedding_size`` folds into the weights of both (``fold_embedding``).  DESIGN.md section 8 lists what is not built.
 """
 import ctypes as C
 import os

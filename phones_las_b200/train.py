@@ -3,8 +3,10 @@
 Mirrors model_helper.py:165-227 (listener + speller(s) in TRAIN mode), :319-358 (sequence / sigmoid / CTC losses,
 multitask sum), :403-417 (L2 regulariser, per-tensor ``clip_by_norm(grad, 2)``, Adam) and, for data-parallel runs,
 the CrossShardOptimizer order of :405-406 (clip locally, then average the gradients across ranks, then apply).
-Input dropout uses a counter-based mask (TF's RNG stream cannot be reproduced: parity is checked against the oracle on
-identical masks); scheduled sampling is not built (``sampling_probability`` must be 0).
+Every stochastic op -- input dropout, scheduled sampling, bahdanau_monotonic's score noise, the periodic weight noise -- draws
+from a counter-based hash keyed by (tensor, optimiser step): TF's RNG stream cannot be reproduced, so parity is checked against
+the oracle replaying the same draws through the numpy mirrors below (``reference_masks``, ``reference_sampling``,
+``reference_noise``, ``reference_weight_noise``).  Decoder variants: DESIGN.md section 8.
 
 Every variable lives in ONE flat fp32 device buffer in the TF checkpoint layout; gradients and
 the Adam moments mirror it, so the data-parallel exchange is a single all-reduce of ``state.grads`` and a trained
