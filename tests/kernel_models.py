@@ -113,3 +113,36 @@ def pack_bfrag_cols(w_kn, ntile_cols_a, ntile_cols_b):
                 out[ks, lane, 4 * ti + 2] = w_kn[k0 + 8, col]
                 out[ks, lane, 4 * ti + 3] = w_kn[k0 + 9, col]
     return out
+
+
+def monotonic_attention_backward(p, prev, da, length):
+    """Mirrors the luong_monotonic / bahdanau_monotonic branch of dec_att_bwd_kernel (csrc/train_dec.cu) for one utterance:
+    forward recompute of cp = cumprod_excl(1 - p) (log space, clipped) and Q = cumsum(prev / clip(cp)), then two reverse running
+    sums.  p [T] saved choose probabilities, prev [T] previous alignments, da [T] gradient wrt the alignments a = p cp Q.
+    Returns (dscore [T] = gradient wrt the pre-sigmoid scores, dprev [T])."""
+    T = len(p)
+    tiny = np.finfo(np.float32).tiny
+    cp, Q = np.zeros(T), np.zeros(T)
+    cs = run = 0.0
+    for t in range(T):
+        cp[t] = np.exp(cs)
+        run += prev[t] / min(max(cp[t], 1e-10), 1.0)
+        Q[t] = run
+        cs += np.log(min(max(1.0 - p[t], tiny), 1.0))
+    ds, dprev = np.zeros(T), np.zeros(T)
+    R = E = 0.0
+    for t in range(T - 1, -1, -1):
+        c = min(max(cp[t], 1e-10), 1.0)
+        R += da[t] * p[t] * cp[t]
+        dprev[t] = R / c
+        dcp = da[t] * p[t] * Q[t]
+        if cp[t] >= 1e-10:
+            dcp -= R * prev[t] / (c * c)
+        dp = da[t] * cp[t] * Q[t]
+        dlogx = E
+        E += dcp * cp[t]
+        om = 1.0 - p[t]
+        if om >= tiny:
+            dp -= dlogx / om
+        ds[t] = dp * p[t] * om if t < length else 0.0
+    return ds, dprev

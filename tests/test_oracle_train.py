@@ -305,3 +305,21 @@ def test_reference_noise_and_bottom_only_masks_mirrors():
     assert rm["att"].shape == (4, 6, D) and rm[("in", 1)].shape == (4, 6, 2 * D) and rm[("in", 2)].shape == (4, 6, 16 + D)
     keep = np.mean(rm[("in", 1)] > 0)
     assert abs(keep - 0.75) < 0.03 and set(np.unique(rm[("in", 1)])) == {0.0, np.float32(1.0) / np.float32(0.75)}
+
+
+def test_monotonic_attention_backward_kernel_model_matches_autograd():
+    """The reverse-scan formulas of the monotonic branch of dec_att_bwd_kernel (numpy model in tests/kernel_models.py) against
+    autograd through the 'parallel' closed form, including a padded tail and a saturated choose probability."""
+    from tests import kernel_models as km
+    rng = np.random.default_rng(2)
+    for T, length in ((9, 9), (12, 8), (6, 1)):
+        score = torch.tensor(rng.normal(size=T) * 2.0, requires_grad=True)
+        prev = torch.tensor(rng.dirichlet(np.ones(T)) * 0.9, requires_grad=True)
+        mask = torch.arange(T) < length
+        p = torch.where(mask, torch.sigmoid(score), torch.zeros(T, dtype=torch.float64))
+        a = lt.monotonic_attention(p[None], prev[None])[0]
+        da = torch.tensor(rng.normal(size=T))
+        (a * da).sum().backward()
+        ds, dprev = km.monotonic_attention_backward(p.detach().numpy(), prev.detach().numpy(), da.numpy(), length)
+        np.testing.assert_allclose(ds, score.grad.numpy(), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(dprev, prev.grad.numpy(), rtol=1e-9, atol=1e-12)
