@@ -160,7 +160,8 @@ def listener(encoder_inputs, source_sequence_length, params, hp, precision="fp32
         outs.append(xin)
         states.append(tuple(st_d))
     out = outs[0] if len(outs) == 1 else np.concatenate(outs, -1)
-    return (out, lengths), tuple(states)
+    # bidirectional_dynamic_rnn returns (fw MultiRNNCell state, bw state); dynamic_rnn the single stack's state
+    return (out, lengths), (tuple(states) if len(states) == 2 else states[0])
 
 
 # --------------------------------------------------------------------------------------
@@ -476,10 +477,27 @@ def predict(features, lengths, params, hp, precision="fp32"):
     (enc_out, enc_len), enc_state = listener(features, lengths, params, hp, precision)
     sp = Speller(enc_out, enc_len, params, hp, precision, encoder_state=enc_state)
     logits, ids, align, seq_len, _ = sp.greedy()
-    emb_c = np.concatenate([s[0] for s in enc_state], axis=1)
-    emb_h = np.concatenate([s[1] for s in enc_state], axis=1)
     e = np.exp(logits - logits.max(-1, keepdims=True)) if logits.size else logits
     probs = e / e.sum(-1, keepdims=True) if logits.size else logits
-    return dict(encoder_out=enc_out, source_length=enc_len, embedding=np.stack([emb_c, emb_h], 1),
-                sample_ids=ids, alignment=align, probs=probs, logits=logits,
-                final_sequence_length=seq_len)
+    out = dict(encoder_out=enc_out, source_length=enc_len, sample_ids=ids, alignment=align, probs=probs, logits=logits,
+               final_sequence_length=seq_len)
+    emb = encoder_embedding(enc_state)
+    if emb is not None:
+        out["embedding"] = emb
+    return out
+
+
+def encoder_embedding(enc_state):
+    """model_helper.py:258-268: ``tf.concat([x.c for x in encoder_state])`` works when the state is a sequence of LSTMStateTuples
+    (pyramidal bidirectional: (fw, bw); stacked unidirectional: one per layer); a single LSTMStateTuple (pyramidal
+    unidirectional) takes the ``encoder_state.c`` branch; the stacked bidirectional state (a tuple of per-direction tuples)
+    fails both and the prediction has no 'embedding'."""
+    is_pair = lambda s: isinstance(s, (tuple, list)) and len(s) == 2 and all(isinstance(t, np.ndarray) for t in s)
+    if is_pair(enc_state):
+        emb_c, emb_h = enc_state
+    elif isinstance(enc_state, (tuple, list)) and len(enc_state) and all(is_pair(s) for s in enc_state):
+        emb_c = np.concatenate([s[0] for s in enc_state], axis=1)
+        emb_h = np.concatenate([s[1] for s in enc_state], axis=1)
+    else:
+        return None
+    return np.stack([emb_c, emb_h], 1)

@@ -78,13 +78,26 @@ def las_predict(features, hp, weights, want_alignment=True, trim=True, want_prob
             pred["n_steps"] = state_b.n_steps
     if want_probs:
         pred["probs"] = torch.softmax(logits, dim=-1)
-    if isinstance(enc_state[0], tuple):
+    emb = encoder_embedding(enc_state)
+    if emb is not None:
+        pred["embedding"] = emb
+    return pred
+
+
+def encoder_embedding(enc_state):
+    """predictions['embedding'] (model_helper.py:258-268): stack(concat of the c's, concat of the h's) when ``encoder_state`` is a
+    sequence of (c, h) pairs -- the pyramidal bidirectional (fw, bw) pair or the unidirectional MultiRNNCell stack --, the pair
+    itself for the pyramidal unidirectional listener, and NO embedding for the stacked bidirectional listener, whose state is
+    (tuple of fw layer states, tuple of bw layer states): there ``x.c`` raises and the reference falls through to None."""
+    is_pair = lambda s: isinstance(s, (tuple, list)) and len(s) == 2 and all(torch.is_tensor(t) for t in s)
+    if is_pair(enc_state):
+        emb_c, emb_h = enc_state
+    elif isinstance(enc_state, (tuple, list)) and len(enc_state) and all(is_pair(s) for s in enc_state):
         emb_c = torch.cat([s[0] for s in enc_state], dim=1)
         emb_h = torch.cat([s[1] for s in enc_state], dim=1)
     else:
-        emb_c, emb_h = enc_state
-    pred["embedding"] = torch.stack([emb_c, emb_h], dim=1)
-    return pred
+        return None
+    return torch.stack([emb_c, emb_h], dim=1)
 
 
 def las_eval(features, labels, hp, weights):

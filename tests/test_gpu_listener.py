@@ -93,5 +93,5 @@ def test_non_pyramidal_listener(precision, B, T, C, U, L, uni):
     assert to_np(out).shape == ref_out.shape == (B, T, (1 if uni else 2) * U)
     assert_parity(out, ref_out, precision, "encoder_out (stacked)", bf16_fro=2e-3)
     top = state[L - 1] if uni else state[0][L - 1]
-    ref_top = ref_state[0][L - 1]
+    ref_top = ref_state[L - 1] if uni else ref_state[0][L - 1]
     assert_parity(top[0], ref_top[0], precision, "final c (fw, top layer)", bf16_fro=2e-3)

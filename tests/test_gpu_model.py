@@ -41,6 +41,33 @@ def test_transcribe_matches_oracle_fp32():
 
 
 @gpu
+@pytest.mark.parametrize("pyr,uni", [(False, False), (False, True), (True, True), (True, False)])
+def test_predict_and_eval_for_every_listener_kind(pyr, uni):
+    """The reference CLI default is the stacked bidirectional listener (--use_pyramidal is off): las_predict / las_eval must run
+    for it and follow model_helper.py:258-268 for 'embedding' -- present for (fw, bw) pairs and unidirectional stacks, the single
+    pair of the pyramidal unidirectional listener, absent for the stacked bidirectional state."""
+    import torch
+    from phones_las_b200.model import DeviceWeights, las_eval, las_predict
+    hp = create_hparams(target_vocab_size=20, encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=32,
+                        attention_type="luong", num_channels=6, use_pyramidal=pyr, unidirectional=uni)
+    params = weights.init_params(hp, 6, seed=9, projection_scale=8.0, bias_scale=0.1)
+    x, lens = synth.synth_features(5, 22, 6, seed=4, var_len=True)
+    tin, tout, tlen = synth.synth_labels(5, 6, 20, seed=8)
+    feats = {"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}
+    w = DeviceWeights(params, hp, 6, "fp32")
+    pred = las_predict(feats, hp, w)
+    ref = ol.predict(x, lens, params, hp, "fp32")
+    assert ("embedding" in pred) == ("embedding" in ref) == (not (uni is False and pyr is False))
+    if "embedding" in ref:
+        assert_parity(pred["embedding"], ref["embedding"], "fp32", "embedding")
+    assert_parity(pred["encoder_out"], ref["encoder_out"], "fp32", "encoder_out")
+    np.testing.assert_array_equal(pred["sample_ids"].cpu().numpy(), ref["sample_ids"])
+    labels = {"targets_outputs": torch.from_numpy(tout), "target_sequence_length": torch.from_numpy(tlen)}
+    out = las_eval(feats, labels, hp, w)
+    assert np.isfinite(out["loss"].item())
+
+
+@gpu
 def test_transcribe_stream_equals_synchronous_calls():
     import torch
     model, hp, fa, params = _model("bf16")

@@ -270,3 +270,26 @@ def test_beam_search_with_a_full_beam_finds_the_exhaustive_optimum():
                 best, best_seq = sc, seq
         assert abs(out[3][b, 0] - best) < 1e-4, (out[3][b], best)
         np.testing.assert_array_equal(out[0][b, :, 0], np.array(best_seq))
+
+
+def test_prediction_embedding_follows_the_reference_state_nesting():
+    """model_helper.py:258-268: 'embedding' exists for sequences of (c, h) pairs and for a single pair, not for the stacked
+    bidirectional state ((fw layers), (bw layers)) -- the reference CLI default; oracle and host mirror agree (CPU tensors)."""
+    import torch
+    from phones_las_b200.model import encoder_embedding
+    from phones_las_b200.hparams import create_hparams
+    from phones_las_b200 import synth, weights
+    for pyr, uni, has in ((True, False, True), (True, True, True), (False, True, True), (False, False, False)):
+        hp = create_hparams(target_vocab_size=12, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=1,
+                            num_channels=5, use_pyramidal=pyr, unidirectional=uni)
+        params = weights.init_params(hp, seed=3, bias_scale=0.1)
+        x, lens = synth.synth_features(3, 11, 5, var_len=True)
+        pred = ol.predict(x, lens, params, hp)
+        assert ("embedding" in pred) == has, (pyr, uni)
+        _, st = ol.listener(x, lens, params, hp)
+        to_t = lambda s: tuple(to_t(e) for e in s) if isinstance(s, tuple) else torch.from_numpy(s)
+        emb = encoder_embedding(to_t(st))
+        assert (emb is not None) == has
+        if has:
+            np.testing.assert_array_equal(emb.numpy(), pred["embedding"])
+            assert emb.shape == (3, 2, 8 * (1 if (pyr and uni) else 2))
