@@ -170,6 +170,13 @@ typedef struct plas_dec_desc {
   const float* pv;          /* [B][Tm][pv_ld] values x projection kernel (f32), logits = a.pv + b_proj */
   int32_t pv_ld;
   int32_t _pad2;
+  /* folded-context tensor-core path (decoder_fold.cu; bf16, optional).  The context fed back to cell 0
+   * (AttentionWrapper, las/model.py:195-200) is linear in the values, so vw = values x W0[V:V+D] lets the
+   * attention phase emit cell 0's pre-activation part sum_t a_t vw[t] directly; the cells then only
+   * contract over h (K = Ud).  Tile layout of w_x_tc / w_h_tc = w_cell_tc's with K = Ud.              */
+  const void* vw;           /* [B][Tm][4Ud] bf16, column = 4*unit + gate                                */
+  const void* w_x_tc[4];    /* l >= 1: rows 0..Ud-1 of cell l's kernel (its input = h of the cell below) */
+  const void* w_h_tc[4];    /* recurrent rows of cell l's kernel (l = 0: rows V+D.. ; l >= 1: rows Ud..) */
 } plas_dec_desc;
 
 size_t plas_decoder_workspace_bytes(const plas_dec_desc* d);

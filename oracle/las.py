@@ -19,7 +19,10 @@ Precision contract.  ``precision='fp32'`` computes everything in float32 like th
 weights, layer inputs, stored gate pre-activations, recurrent h, attention keys/values and the
 attention vector fed back to the decoder cell are rounded to bfloat16 (round-to-nearest-even);
 accumulation, gates, cell state, softmax, the context entering the output projection and the
-logits stay float32.
+logits stay float32.  Where the folded-context tensor-core decoder runs (``folded_context_decoder``: bf16,
+default wiring, decoder_units and encoder depth multiples of 64) the fed-back context is never formed:
+cell 0 adds ``alignments @ VW`` with ``VW = bf16(values @ W0[V:V+D])`` -- the rounding point moves from
+the context to VW.
 """
 import numpy as np
 
@@ -41,6 +44,15 @@ def _q(precision):
     if precision == "bf16":
         return round_bf16
     raise ValueError(precision)
+
+
+def folded_context_decoder(hp, B, D, precision):
+    """Shapes on which the CUDA path runs decoder_fold.cu (speller.SpellerWeights.tc + dec_fold_plan): its bf16 storage
+    points differ from the other decoders' (VW instead of the fed-back context), so the emulation must know."""
+    Ud = hp["decoder_units"]
+    return (precision == "bf16" and not hp.get("bottom_only") and not hp.get("attention_layer_size")
+            and not hp.get("binf_projection") and hp["attention_type"] in ("luong", "bahdanau", "luong_monotonic")
+            and D % 64 == 0 and Ud % 64 == 0 and D <= 2048 and Ud // 4 <= 148 and B <= 128)
 
 
 def sigmoid(x):
@@ -243,7 +255,8 @@ class Speller:
     NEW attention, every upper cell reads [previous output; OLD attention]; the decoder output is the top cell's h), with
     ``pass_hidden_state`` (las/model.py:259-267: cell l starts from the listener's final state l = fw, bw)."""
 
-    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller", encoder_state=None, binf=None):
+    def __init__(self, enc_out, enc_len, params, hp, precision="fp32", scope="speller", encoder_state=None, binf=None,
+                 fold_context=None):
         self.q = _q(precision)
         self.hp = hp
         self.scope = scope
@@ -281,14 +294,24 @@ class Speller:
             assert hp.get("binf_projection") and not self.bottom_only and self.wal is not None  # bottom_only: not restated
             assert self.wal.shape[1] == 2 * self.binf.shape[0], "attention_layer_size must be 2 * binf_count (las/model.py:180-183)"
         self.enc_len = np.asarray(enc_len)
+        # folded-context decoder: VW = bf16(values @ W0[V:V+D]) replaces the bf16 copy of the fed-back context
+        self.fold = (folded_context_decoder(hp, self.B, self.D, precision) and binf is None) if fold_context is None else bool(fold_context)
+        self.nx = int(hp.get("embedding_size") or 0) or self.V  # width of the decoder input (one-hot or target_embedding row)
+        if self.fold:
+            k0 = self.cells[0][0]
+            self.vw = self.q((self.att.values.reshape(self.B * self.Tm, self.D) @ k0[self.nx:self.nx + self.D]).astype(F32)
+                             ).reshape(self.B, self.Tm, 4 * self.Ud)
 
     def zero_state(self):
         cs = [(np.zeros((self.B, self.Ud), F32), np.zeros((self.B, self.Ud), F32)) for _ in self.cells]
         if self.init_state is not None:
             for l, st in enumerate(self.init_state[:len(cs)]):
                 cs[l] = st
-        return dict(cells=cs, attention=np.zeros((self.B, self.D if self.wal is None else self.wal.shape[1]), F32),
-                    alignments=self.att.initial_alignments())
+        st = dict(cells=cs, attention=np.zeros((self.B, self.D if self.wal is None else self.wal.shape[1]), F32),
+                  alignments=self.att.initial_alignments())
+        if self.fold:
+            st["zctx"] = np.zeros((self.B, 4 * self.Ud), F32)
+        return st
 
     def step(self, x, state):
         """AttentionWrapper.call + output projection.  x [B,V] (one-hot or teacher input)."""
@@ -297,8 +320,11 @@ class Speller:
             return self._step_bottom_only(x, state)
         inp = np.concatenate([x, state["attention"]], axis=1).astype(F32)
         new_cells = []
-        for (k, b), (c, h) in zip(self.cells, state["cells"]):
-            z = (np.concatenate([inp, h], axis=1) @ k + b).astype(F32)
+        for li, ((k, b), (c, h)) in enumerate(zip(self.cells, state["cells"])):
+            if self.fold and li == 0:  # context rows of cell 0 folded into VW: z = x W[:V] + a_{t-1} VW + h W[V+D:] + b
+                z = (x.astype(F32) @ k[:self.nx] + state["zctx"] + h @ k[self.nx + self.D:] + b).astype(F32)
+            else:
+                z = (np.concatenate([inp, h], axis=1) @ k + b).astype(F32)
             c2, h2 = lstm_cell_step(z, c)
             h2 = q(h2)
             new_cells.append((c2, h2))
@@ -315,7 +341,10 @@ class Speller:
             logits = (context[:, :n] @ self.binf + context[:, n:2 * n] @ (F32(1) - self.binf)).astype(F32)
         else:
             logits = (context.astype(F32) @ self.wp + self.bp).astype(F32)
-        return logits, dict(cells=new_cells, attention=attention, alignments=align)
+        new_state = dict(cells=new_cells, attention=attention, alignments=align)
+        if self.fold:
+            new_state["zctx"] = np.einsum("bt,btz->bz", align, self.vw, dtype=F32)
+        return logits, new_state
 
     def _step_bottom_only(self, x, state):
         """AttentionMultiCell.__call__ (las/model.py:34-69, use_new_attention=False) + projection of the top cell's output."""
@@ -423,7 +452,8 @@ class Speller:
             lengths = np.take_along_axis(lengths, beam, 1) + (~prev_fin).astype(np.int64)
             seq_len = np.where(~finished, time + 1, seq_len).astype(np.int32)   # dynamic_decode, on the slot's previous flag
             flat = (np.arange(B)[:, None] * W + beam).reshape(-1)               # gather the cell state by parent beam
-            state = dict(cells=[(c[flat], h[flat]) for c, h in state["cells"]], attention=state["attention"][flat],
+            state = dict({k: v[flat] for k, v in state.items() if k == "zctx"},
+                         cells=[(c[flat], h[flat]) for c, h in state["cells"]], attention=state["attention"][flat],
                          alignments=state["alignments"][flat])
             log_probs, finished = new_lp, next_fin
             words.append(word)

@@ -44,7 +44,8 @@ class DecDesc(C.Structure):
                 ("forced_ids", C.c_void_p), ("logits", C.c_void_p), ("sample_ids", C.c_void_p),
                 ("alignment", C.c_void_p), ("seq_len", C.c_void_p), ("n_steps", C.c_void_p),
                 ("w_cell_tc", C.c_void_p * 4), ("w_query_tc", C.c_void_p), ("pv", C.c_void_p),
-                ("pv_ld", C.c_int32), ("_pad2", C.c_int32)]
+                ("pv_ld", C.c_int32), ("_pad2", C.c_int32),
+                ("vw", C.c_void_p), ("w_x_tc", C.c_void_p * 4), ("w_h_tc", C.c_void_p * 4)]
 
 
 class GemmExDesc(C.Structure):

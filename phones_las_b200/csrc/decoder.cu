@@ -432,6 +432,8 @@ static void dec_ws_layout(const plas_dec_desc& d, size_t* offs, size_t* total) {
 
 size_t dec_tc_workspace_bytes(const plas_dec_desc& d);
 int dec_tc_launch(const plas_dec_desc& d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t dec_fold_workspace_bytes(const plas_dec_desc& d);
+int dec_fold_launch(const plas_dec_desc& d, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace plas
 
@@ -441,7 +443,9 @@ extern "C" size_t plas_decoder_workspace_bytes(const plas_dec_desc* d) {
   size_t offs[10], total;
   dec_ws_layout(*d, offs, &total);
   const size_t tc = dec_tc_workspace_bytes(*d);
-  return tc > total ? tc : total;
+  const size_t fold = dec_fold_workspace_bytes(*d);
+  if (tc > total) total = tc;
+  return fold > total ? fold : total;
 }
 
 extern "C" int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t workspace_bytes,
@@ -459,7 +463,9 @@ extern "C" int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t 
   PLAS_REQUIRE(!d->teacher_forced || d->forced_ids, "decoder: teacher forcing needs forced_ids");
   for (int l = 0; l < d->n_layers; ++l) PLAS_REQUIRE(d->w_cell[l] && d->b_cell[l], "decoder: layer %d weights missing", l);
   {
-    const int rc = dec_tc_launch(*d, workspace, workspace_bytes, stream);
+    int rc = dec_fold_launch(*d, workspace, workspace_bytes, stream);
+    if (rc != 1) return rc;  // 1 = shape not eligible for the folded-context tensor-core kernel
+    rc = dec_tc_launch(*d, workspace, workspace_bytes, stream);
     if (rc != 1) return rc;  // 1 = shape not eligible for the tensor-core kernel
   }
   size_t offs[10], total;

@@ -83,7 +83,8 @@ class SpellerWeights:
         self.w_cell, self.b_cell, self.w_cell_tc = [], [], []
         # tensor-core decoder (decoder_tc.cu): bf16, D and Ud multiples of 64 (plas.h)
         self.tc = precision == "bf16" and D % 64 == 0 and Ud % 64 == 0 and D <= 2048 and Ud <= 2048
-        self.w_query_tc = self.w_proj_pad = None
+        self.w_query_tc = self.w_proj_pad = self.w_vw_t = None
+        self.w_x_tc, self.w_h_tc = [None] * 4, [None] * 4
         for k in range(self.L):
             kern = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/kernel"], np.float32)
             bias = np.asarray(params[f"{pre}/multi_rnn_cell/cell_{k}/lstm_cell/bias"], np.float32)
@@ -99,6 +100,14 @@ class SpellerWeights:
             self.w_cell.append(up(packed))
             if self.tc:
                 self.w_cell_tc.append(up(packing.pack_cell_tc(rows, Ud)))
+                # folded-context decoder (decoder_fold.cu): every cell contracts over h only (K = Ud); the context rows of
+                # cell 0 move into VW = values . W0[V:V+D] (prepare_memory), 4Ud wide with unit-major columns
+                if k == 0:
+                    self.w_vw_t = up(np.ascontiguousarray(packing.pack_unit_major(rows[:D], Ud).T))  # [4Ud, D] K-major
+                    self.w_h_tc[0] = up(packing.pack_cell_tc(rows[D:], Ud))
+                else:
+                    self.w_x_tc[k] = up(packing.pack_cell_tc(rows[:Ud], Ud))
+                    self.w_h_tc[k] = up(packing.pack_cell_tc(rows[Ud:], Ud))
             self.b_cell.append(up(packing.pack_unit_major(bias, Ud), torch.float32))
         self.w_query = self.v_att = self.score_bias_dev = None
         self.score_bias = 0.0
@@ -248,7 +257,14 @@ def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=
     if w.att == "custom":  # CustomAttention: keys = relu(memory_layer(values)) (las/model.py:94)
         _lib.check(L.plas_relu_f32(_lib.ptr(keys), keys.numel(), _lib.stream_ptr()))
         _lib.count_launches(1)
-    pv = None
+    pv = vw = None
+    if w.tc and B <= 128 and w.w_vw_t is not None and (4 * w.Ud) % 128 == 0:
+        # VW = values x W0[V:V+D] (bf16): cell 0's share of the fed-back context, emitted by the attention phase as a . VW
+        vw = torch.empty((B * Tm, 4 * w.Ud), dtype=enc.dtype, device=enc.device)
+        with _lib.stage("memory_gemm"):
+            _lib.check(L.plas_gemm_bf16(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_vw_t), 4 * w.Ud, D, None, _lib.ptr(vw),
+                                        4 * w.Ud, _lib.stream_ptr()))
+        _lib.count_launches(1)
     if w.tc and B <= 128:
         # PV = values x projection kernel (f32): the decoder forms logits as alignments . PV + bias
         vp = w.w_proj_pad.shape[0]
@@ -257,7 +273,7 @@ def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=
             _lib.check(L.plas_gemm_bf16_f32out(_lib.ptr(values), B * Tm, D, D, _lib.ptr(w.w_proj_pad), vp, D, None,
                                                _lib.ptr(pv), vp, _lib.stream_ptr()))
         _lib.count_launches(1)
-    return keys.view(B, Tm, w.Ud), values, pv
+    return keys.view(B, Tm, w.Ud), values, pv, vw
 
 
 def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_steps=None,
@@ -269,7 +285,7 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
     B, Tm, D = encoder_outputs.shape
     assert D == w.D
     mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).contiguous()
-    keys, values, pv = prepare_memory(encoder_outputs, mem_len, w, memory_is_masked)
+    keys, values, pv, vw = prepare_memory(encoder_outputs, mem_len, w, memory_is_masked)
     factor = float(hp.get("decoding_length_factor", 1.0))
     if forced_ids is not None:
         forced_ids = forced_ids.to(device=dev, dtype=torch.int32).contiguous()
@@ -314,6 +330,12 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
             d.w_cell_tc[k] = w.w_cell_tc[k].data_ptr()
         d.w_query_tc = w.w_query_tc.data_ptr() if w.w_query_tc is not None else None
         d.pv, d.pv_ld = pv.data_ptr(), pv.shape[1]
+        if vw is not None:
+            d.vw = vw.data_ptr()
+            for k in range(w.L):
+                d.w_h_tc[k] = w.w_h_tc[k].data_ptr()
+                if k:
+                    d.w_x_tc[k] = w.w_x_tc[k].data_ptr()
     need = L.plas_decoder_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     with _lib.stage("decoder"):
@@ -398,7 +420,7 @@ def decode_beam(encoder_outputs, source_sequence_length, w, hp, beam_width, memo
     mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).repeat_interleave(W).contiguous()
     if initial_state is not None:
         initial_state = [(c.repeat_interleave(W, dim=0), h.repeat_interleave(W, dim=0)) for c, h in initial_state]
-    keys, values, _ = prepare_memory(enc, mem_len, w, memory_is_masked)
+    keys, values, _, _ = prepare_memory(enc, mem_len, w, memory_is_masked)
     factor = float(hp.get("decoding_length_factor", 1.0))
     steps = max(int(np.rint(np.float32(Tm) * np.float32(factor))), 0)
     cap = max(steps, 1)
