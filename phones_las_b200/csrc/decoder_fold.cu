@@ -34,18 +34,18 @@
 
 namespace plas {
 
-constexpr int DF_THREADS = 256;   // 8 warps (2 per scheduler: 255 registers each); GEMM phases: warp 0 MMA issuer, warp 1 TMA
+constexpr int DF_THREADS = 256;   // 8 warps (2 per scheduler: 255 registers each); GEMM phases: warp 0 MMA issuer, warp 1 copy
                                   // producer, warps 4..7 epilogue rows; attention phase: all 8 warps
 constexpr int DF_MAX_STAGES = 16;
 constexpr int DF_CL = 4;          // cluster size (always)
 
 struct alignas(64) DecFoldArgs {
-  CUtensorMap tmH[4][2];         // per layer, per parity: h_l [B][Ud] bf16
   plas_dec_desc d;
   const unsigned char* w_x[4];   // l >= 1: [Ud/4][Ud/64][2048 B] swizzled UMMA B tiles of the input rows of layer l
   const unsigned char* w_h[4];   // recurrent rows of layer l, same layout
   const unsigned char* w_q;      // [Ud/16][Ud/64][2048 B] bahdanau query layer
-  unsigned char* hbuf[4];        // [2][B][Ud] bf16
+  unsigned char* hbuf[4];        // [2 parities][Ud/64 k blocks][RT rows][64] bf16: K-major SWIZZLE_128B UMMA A tiles, written in
+                                 // place by the producers of h so that a k block is ONE contiguous bulk copy
   float* qbuf;                   // [B][Ud]
   float* zh0;                    // [B][4Ud]  h0_t . W0h (unit-major columns)
   float* c0;                     // [B][Ud]   cell-0 state
@@ -53,12 +53,11 @@ struct alignas(64) DecFoldArgs {
   int* next_ids;                 // [B] argmax of the step just decoded
   unsigned* bar;
   unsigned long long* dbg;       // optional phase timers (ns summed over steps), CTA 0
-  int ksp;                       // 1, or 4: the clusters split K of the GEMM phases
   int as;                        // CTAs per utterance in the attention phase (2 or 4)
   int keys_res;                  // this CTA's key slice is resident in shared memory
-  int n_stages_a, stage_a;       // TMA ring of the GEMM phases
+  int n_stages_a, stage_a;       // activation ring of the GEMM phases; stage_a = tile bytes = RT * 128
   int off_w[4];                  // per phase: resident weight tiles
-  int off_keys, off_ring, off_part, off_comb, off_pv, pv_cap, off_misc;
+  int off_keys, off_ring, off_comb, off_pv, pv_cap, off_att, off_misc;
   int tm_pad, v_pad;
 };
 
@@ -74,11 +73,16 @@ __device__ __forceinline__ void df_st_async_v4(uint32_t raddr, const uint4 v, ui
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
                : "memory");
 }
+__device__ __forceinline__ void df_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void df_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void df_consumer_sync() { __syncthreads(); }
+__device__ __forceinline__ void df_sync() { __syncthreads(); }
 
 __device__ __forceinline__ void df_grid_barrier(unsigned* bar, unsigned& epoch) {
-  df_fence_proxy_async();  // generic-proxy global/shared writes of this phase vs TMA reads of the next
+  df_fence_proxy_async();  // generic-proxy global/shared writes of this phase vs bulk copies of the next
   __syncthreads();         // every thread's writes happen-before thread 0's release (cumulative at gpu scope)
   if (threadIdx.x == 0) {
     epoch += 1;
@@ -101,13 +105,95 @@ __device__ __forceinline__ float df_tanh_mufu(float x) {
   return y;
 }
 
-struct DfRing {
-  int stage;
-  uint32_t phase;
-  __device__ __forceinline__ void advance(int n) {
-    if (++stage == n) { stage = 0; phase ^= 1u; }
+// byte offset of element (row r, unit u) inside an activation buffer of k-block tiles [Ud/64][RT][128 B] whose 16-byte chunks
+// are XOR-swizzled by the row (what TMA's SWIZZLE_128B would write and the UMMA descriptor expects)
+__device__ __forceinline__ size_t df_h_off(int r, int u, int tile_bytes) {
+  return (size_t)(u >> 6) * tile_bytes + (size_t)r * 128 + (size_t)((((u & 63) >> 3) ^ (r & 7)) << 4) + (size_t)((u & 7) << 1);
+}
+
+// scores of 4 memory rows (r0, r0+8, r0+16, r0+24) of one warp from the rows' 16-byte key chunks: lane owns chunks lane (and
+// lane+32 when NCC == 2) of this part's depth; q / v are zero where the lane has no chunk, so clamped loads are harmless
+template <int NCC, bool BAHDANAU>
+__device__ __forceinline__ void df_score4(const uint4 (*kk)[2], const float* qreg, const float* vreg, float* acc) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < NCC; ++cc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float k0[4], k1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned kw = j == 0 ? kk[i][cc].x : (j == 1 ? kk[i][cc].y : (j == 2 ? kk[i][cc].z : kk[i][cc].w));
+        k0[i] = __uint_as_float(kw << 16);
+        k1[i] = __uint_as_float(kw & 0xffff0000u);
+      }
+      if (BAHDANAU) {
+        // four rows with independent accumulators: the MUFU.TANH -> FFMA chains of different rows overlap
+        float t0[4], t1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          t0[i] = df_tanh_mufu(k0[i] + qreg[cc * 8 + 2 * j]);
+          t1[i] = df_tanh_mufu(k1[i] + qreg[cc * 8 + 2 * j + 1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i] = fmaf(vreg[cc * 8 + 2 * j], t0[i], acc[i]);
+          acc[i] = fmaf(vreg[cc * 8 + 2 * j + 1], t1[i], acc[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i] = fmaf(k0[i], qreg[cc * 8 + 2 * j], acc[i]);
+          acc[i] = fmaf(k1[i], qreg[cc * 8 + 2 * j + 1], acc[i]);
+        }
+      }
+    }
   }
-};
+}
+
+// all scores of one item: warp w takes rows w, w+8, ...; kb = this part's key slice (uint4 units, row stride kstride), in shared
+// memory (RES) or global memory.  Loads are unconditional (row and chunk indices clamped into the slice): no divergent
+// branches around them, the next group's loads are in flight while the current one is scored.
+template <int NCC, bool BAHDANAU, bool RES>
+__device__ __forceinline__ void df_scores(const uint4* kb, int kstride, int n_c8, int len, int warp, int lane,
+                                          const float* qreg, const float* vreg, float* s_score) {
+  int c8c[2];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) c8c[cc] = min(lane + 32 * cc, n_c8 - 1);
+  auto load4 = [&](int r0, uint4 (*kk)[2]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rc = min(r0 + 8 * i, len - 1);
+#pragma unroll
+      for (int cc = 0; cc < NCC; ++cc) {
+        const uint4* src = kb + (size_t)rc * kstride + c8c[cc];
+        kk[i][cc] = RES ? *src : __ldg(src);
+      }
+    }
+  };
+  auto finish4 = [&](int r0, float* acc) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 8 * i;
+      const float sacc = warp_sum(acc[i]);
+      if (lane == 0 && r < len) s_score[r] = sacc;
+    }
+  };
+  uint4 ka[4][2], kb2[4][2];
+  float acc[4];
+  load4(warp, ka);
+  for (int r0 = warp; r0 < len; r0 += 64) {
+    load4(r0 + 32, kb2);
+    df_score4<NCC, BAHDANAU>(ka, qreg, vreg, acc);
+    finish4(r0, acc);
+    load4(r0 + 64, ka);
+    if (r0 + 32 < len) {
+      df_score4<NCC, BAHDANAU>(kb2, qreg, vreg, acc);
+      finish4(r0 + 32, acc);
+    }
+  }
+}
 
 }  // namespace
 
@@ -128,39 +214,36 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   unsigned char* misc = smem + p.off_misc;
   const uint32_t misc_u = base + (uint32_t)p.off_misc;
   auto fullA = [&](int s) { return misc_u + 8u * s; };
-  auto emptyA = [&](int s) { return misc_u + 8u * (DF_MAX_STAGES + s); };
-  const uint32_t tfull = misc_u + 8u * (2 * DF_MAX_STAGES);
-  const uint32_t pbar = tfull + 8u;    // K-split partial sums landed (tx bytes)
-  const uint32_t sbar = tfull + 16u;   // the partners' partial scores landed
-  const uint32_t lbar = tfull + 24u;   // the partners' partial logits landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * DF_MAX_STAGES + 4));
-  float* s_bias = reinterpret_cast<float*>(misc + 512);          // [4][16] biases of layers 1..L-1 (this CTA's columns)
-  float* s_red = s_bias + 64;                                    // [64]
+  const uint32_t wave_done = misc_u + 8u * DF_MAX_STAGES;  // the MMAs that read the current wave of ring stages completed
+  const uint32_t tfull = wave_done + 8u;
+  const uint32_t sbar = tfull + 8u;    // the partners' partial scores landed (tx bytes)
+  const uint32_t lbar = tfull + 16u;   // the partners' partial logits landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (DF_MAX_STAGES + 6));
+  float* s_bias = reinterpret_cast<float*>(misc + 256);          // [4][16] biases of layers 1..L-1 (this CTA's columns)
+  float* s_v = s_bias + 64;                                      // [Ud] attention_v (lives for the whole decode)
+  // scratch of the attention phase: inside the region the GEMM phases use as their activation ring (the phases alternate)
+  float* s_comb = reinterpret_cast<float*>(smem + p.off_comb);   // [<= 2048] zctx partials of the row groups
+  float* s_pv = reinterpret_cast<float*>(smem + p.off_pv);       // PV rows of this part (prefetched per step)
+  float* s_red = reinterpret_cast<float*>(smem + p.off_att);     // [64]
   float* s_lp = s_red + 64;                                      // [4][64]
   float* s_lmine = s_lp + 256;                                   // [v_pad] my partial logits
   float* s_lpart = s_lmine + p.v_pad;                            // [4][v_pad] partial logits by part
   float* s_q = s_lpart + 4 * p.v_pad;                            // [Ud]
-  float* s_v = s_q + Ud;                                         // [Ud]
-  float* s_score = s_v + Ud;                                     // [tm_pad]
+  float* s_score = s_q + Ud;                                     // [tm_pad]
   float* s_scan = s_score + p.tm_pad;                            // [2][tm_pad]
   float* s_peer = s_scan + 2 * p.tm_pad;                         // [4][tm_pad] partial scores by part
-  float* s_comb = reinterpret_cast<float*>(smem + p.off_comb);   // [<= 2048] zctx partials of the row groups
-  float* s_pv = reinterpret_cast<float*>(smem + p.off_pv);       // PV rows of this part (prefetched per step)
 
   const int nkb = Ud / 64;
   const int nq = Ud / 16;
   const bool bahdanau = d.attention_type == PLAS_ATT_BAHDANAU;
   const bool monotonic = d.attention_type == PLAS_ATT_LUONG_MONOTONIC;
   const int slice = blockIdx.x;                   // this CTA owns gate columns 16*slice .. +15 of every layer
-  const bool q_cta = bahdanau && slice < nq;      // ... and query-layer columns 16*slice .. +15 (uniform per cluster)
-  const int KSP = p.ksp;
-  const int krank = blockIdx.x % KSP;             // rank inside the K-split group (0 when KSP == 1)
-  const int kbase = blockIdx.x - krank;
+  const bool q_cta = bahdanau && slice < nq;      // ... and query-layer columns 16*slice .. +15
   const int crank = blockIdx.x % DF_CL;           // rank inside the cluster
-  const int nloc = nkb / KSP;                     // k blocks of 64 this CTA multiplies per phase
   const int AS = p.as;
   const int part = crank % AS;                    // which part of its utterances this CTA handles
   const int pbase = crank - part;                 // cluster rank of part 0 of my attention group
+  const size_t hpar = (size_t)nkb * STA;          // bytes of one parity of an activation buffer
 
   // groups of a phase, in accumulator-column order: [x: input rows of layer ph+1] [h: recurrent rows of layer ph] [q]
   auto has_x = [&](int ph) { return ph < L - 1; };
@@ -172,50 +255,41 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   for (int ph = 0; ph < L; ++ph) {
     const int ng = n_groups(ph);
     uint4* dst = reinterpret_cast<uint4*>(smem + p.off_w[ph]);
-    // tile (lkb, g, j): 16 columns of CTA kbase + j, k block krank*nloc + lkb -- per local k block the groups' tiles
-    // stack into one (16*KSP*ng)-row K-major UMMA B tile (8-row swizzle atoms, 1024 B apart)
-    for (int i = tid; i < nloc * ng * KSP * 128; i += DF_THREADS) {
+    // per k block the groups' 16-row tiles stack into one (16*ng)-row K-major UMMA B tile (8-row swizzle atoms, 1024 B apart)
+    for (int i = tid; i < nkb * ng * 128; i += DF_THREADS) {
       const int w16 = i & 127;
-      int rest = i >> 7;
-      const int j = rest % KSP; rest /= KSP;
-      const int g = rest % ng;
-      const int lkb = rest / ng;
+      const int g = (i >> 7) % ng;
+      const int kb = (i >> 7) / ng;
       const unsigned char* src;
       if (has_x(ph) && g == 0) src = p.w_x[ph + 1];
       else if (g == (has_x(ph) ? 1 : 0)) src = p.w_h[ph];
       else src = p.w_q;
-      const uint4* s4 = reinterpret_cast<const uint4*>(src + ((size_t)(kbase + j) * nkb + krank * nloc + lkb) * 2048);
-      dst[i] = __ldg(s4 + w16);
+      dst[i] = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)slice * nkb + kb) * 2048) + w16);
     }
     if (ph >= 1 && tid < 16) s_bias[ph * 16 + tid] = d.b_cell[ph][slice * 16 + tid];
   }
   if (bahdanau)
     for (int u = tid; u < Ud; u += DF_THREADS) s_v[u] = d.v_att[u];
   const int Dk = Ud / AS;                          // key depth of a part
+  const int n_c8 = Dk / 8;                         // its 16-byte chunks per memory row
   if (p.keys_res) {                                // single item per CTA: its key slice stays on chip
     const int b = blockIdx.x / AS;
     if (b < B) {
-      const int cpr = Dk / 8;                      // 16-byte chunks per row
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud + part * Dk);
       uint4* dst = reinterpret_cast<uint4*>(smem + p.off_keys);
-      for (int i = tid; i < Tm * cpr; i += DF_THREADS) {
-        const int r = i / cpr, c = i - r * cpr;
+      for (int i = tid; i < Tm * n_c8; i += DF_THREADS) {
+        const int r = i / n_c8, c = i - r * n_c8;
         dst[i] = __ldg(src + (size_t)r * (Ud / 8) + c);
       }
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < DF_MAX_STAGES; ++s) {
-      mbar_init(fullA(s), 1);
-      mbar_init(emptyA(s), 1);
-    }
+    for (int s = 0; s < DF_MAX_STAGES; ++s) mbar_init(fullA(s), 1);
+    mbar_init(wave_done, 1);
     mbar_init(tfull, 1);
-    mbar_init(pbar, 1);
     mbar_init(sbar, 1);
     mbar_init(lbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int l = 0; l < L; ++l)
-      for (int q2 = 0; q2 < 2; ++q2) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmH[l][q2]) : "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -231,7 +305,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
 
   // ---- replicated decode state ---------------------------------------------------------------------------------
   const int row = tid - 128;                      // epilogue threads (warps 4..7) own batch row `row`
-  const bool row_thread = tid >= 128 && tid < 256;
+  const bool row_thread = tid >= 128;
   const bool row_valid = row_thread && row < B;
   float c_state[L][4];                            // cell states of layers 1..L-1 (index 0 unused)
   float carry[L][16];                             // h_{l,t-1} . W_lh for layers 1..L-1
@@ -251,183 +325,142 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
     max_iter = min(max_iter, (int)rintf((float)ml * d.decoding_length_factor));
   }
 
-  DfRing prodA = {0, 0}, consA = {0, 0};
+  uint32_t full_bits = 0, wave_parity = 0;  // mbarrier parities: ring stages (bit j, MMA issuer) / wave_done (producer)
   uint32_t acc_parity = 0;
   unsigned epoch = 0;
-  uint32_t pparity = 0, sparity = 0, lparity = 0;
-  float* s_part = reinterpret_cast<float*>(smem + p.off_part);
-  const uint32_t s_part_u = base + (uint32_t)p.off_part;
-  const int PR = B <= 64 ? 64 : 128;              // rows of one sender's block in s_part
+  uint32_t sparity = 0, lparity = 0;
 
-  // phase timers (PLAS_DEBUG): 0 bookkeeping, 1..4 GEMM phases (incl. barrier), 5 scores, 6 softmax+logits push,
-  // 7 context, 8 argmax + cell 0, 9 attention barrier wait
-  unsigned long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // phase timers (PLAS_DEBUG): 0 bookkeeping, 1..4 GEMM phases (incl. barrier), 5 query load, 6 score compute, 7 score exchange,
+  // 8 softmax + logits push, 9 context, 10 argmax + cell 0, 11 attention barrier wait; fine[] = GEMM phase 0 detail by the role
+  // threads (time since the phase started): 0 first tile landed, 1 MMAs issued, 2 accumulator ready, 3 accumulator read, 4 epilogue done
+  unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long tfine[5] = {0, 0, 0, 0, 0};
   unsigned long long tlast = 0;
+  __shared__ unsigned long long s_tphase;
   const bool timing = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool fine = p.dbg != nullptr && blockIdx.x == 0;
   auto stamp = [&](int slot) {
     if (timing) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       tacc[slot] += now - tlast;
       tlast = now;
+      *(volatile unsigned long long*)&s_tphase = now;
     }
+  };
+  auto fine_stamp = [&](int slot) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    tfine[slot] += now - *(volatile unsigned long long*)&s_tphase;
   };
   if (timing) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tlast));
 
-  // one [128 x (nloc*64)] x [(nloc*64) x ncols] product over this CTA's k blocks of h_l: TMA producer (warp 1), MMA issuer
-  // (warp 0), result in TMEM columns 0..ncols-1.  Many CTAs read the SAME activation blocks; walking them from a per-CTA
-  // offset keeps the CTAs from hammering the same few L2 lines in lock step.
-  auto gemm_phase = [&](const CUtensorMap* tm, uint32_t w_smem, int ncols) {
-    const int rot = (int)(((long long)(blockIdx.x / KSP) * nloc * KSP) / gridDim.x) % nloc;
+  // one [128 x Ud] x [Ud x ncols] product: copy producer (warp 1: one contiguous bulk copy per k-block tile of h), MMA issuer
+  // (warp 0), result in TMEM columns 0..ncols-1.  The tiles go through the ring in waves of NSTA: all copies of a wave are
+  // issued back to back (normally ONE wave: a stage per k block), a later wave waits until the MMAs of the previous one have
+  // read their stages.  All CTAs read the SAME tiles; walking them from a per-CTA offset keeps the CTAs from hammering the
+  // same few L2 lines in lock step.
+  auto gemm_phase = [&](const unsigned char* a_tiles, uint32_t w_smem, int ncols, bool detail) {
+    const int rot = (int)(((long long)blockIdx.x * nkb) / gridDim.x) % nkb;
     const uint32_t idesc = umma_idesc_bf16(128, ncols);
     if (warp == 1) {
       if (elect_one()) {
-        for (int i = 0; i < nloc; ++i) {
-          const int lkb = (rot + i) % nloc;
-          mbar_wait(emptyA(prodA.stage), prodA.phase ^ 1u);
-          mbar_expect_tx(fullA(prodA.stage), (uint32_t)STA);
-          tma_load_2d(ring + prodA.stage * STA, tm, (krank * nloc + lkb) * 64, 0, fullA(prodA.stage));
-          prodA.advance(NSTA);
+        for (int i0 = 0; i0 < nkb; i0 += NSTA) {
+          if (i0 > 0) {
+            mbar_wait(wave_done, wave_parity);
+            wave_parity ^= 1u;
+          }
+          const int n = min(NSTA, nkb - i0);
+          for (int j = 0; j < n; ++j) {
+            const int kb = (rot + i0 + j) % nkb;
+            mbar_expect_tx(fullA(j), (uint32_t)STA);
+            df_bulk_g2s(ring + j * STA, a_tiles + (size_t)kb * STA, (uint32_t)STA, fullA(j));
+          }
         }
       }
       __syncwarp();
     } else if (warp == 0) {
       if (elect_one()) {
         tc_fence_after();
-        for (int i = 0; i < nloc; ++i) {
-          const int lkb = (rot + i) % nloc;
-          mbar_wait(fullA(consA.stage), consA.phase);
-          tc_fence_after();
-          const uint64_t adesc = umma_smem_desc(ring + consA.stage * STA);
-          const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(lkb * ncols * 128));
+        for (int i0 = 0; i0 < nkb; i0 += NSTA) {
+          const int n = min(NSTA, nkb - i0);
+          for (int j = 0; j < n; ++j) {
+            const int kb = (rot + i0 + j) % nkb;
+            mbar_wait(fullA(j), (full_bits >> j) & 1u);
+            full_bits ^= 1u << j;
+            if (detail && i0 + j == 0) fine_stamp(0);
+            tc_fence_after();
+            const uint64_t adesc = umma_smem_desc(ring + j * STA);
+            const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(kb * ncols * 128));
+            // the four K=16 slices of a k block accumulate into four separate accumulators (TMEM columns 64*k ..): back-to-back
+            // MMAs into ONE accumulator serialise on its read-modify-write latency (~140 clk each at these tiny N), four
+            // interleaved chains overlap; the epilogue adds the four partial sums in a fixed order
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
-          umma_commit(emptyA(consA.stage));
-          consA.advance(NSTA);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + (uint32_t)(64 * k), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i0 | j) != 0 ? 1u : 0u);
+          }
+          if (i0 + n < nkb) umma_commit(wave_done);
         }
         umma_commit(tfull);
+        if (detail) fine_stamp(1);
       }
       __syncwarp();
     }
-  };
-
-  // epilogue of a GEMM phase (row threads): the 16 pre-activation columns of this CTA for batch row `row` of each of the
-  // phase's groups -- directly, or (K-split) own partial + the three peers' partials (DSMEM), summed in a fixed order
-  auto fetch_groups = [&](int ng, float (*acc)[16]) {
-    const uint32_t trow = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
-    if (KSP == 1) {
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        if (g < ng) {
-          uint32_t r[16];
-          tmem_ld16(trow + (uint32_t)(16 * g), r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q4 = 0; q4 < 16; ++q4) acc[g][q4] = __uint_as_float(r[q4]);
-        }
-      }
-      return;
-    }
-    // columns 16(4g + j) .. +15 of my K-partial belong to CTA j of the cluster: keep mine, push the rest (DSMEM)
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      if (g < ng) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t rj[16];
-          tmem_ld16(trow + (uint32_t)(16 * (4 * g + j)), rj);
-          tmem_ld_wait();
-          if (j == krank) {
-#pragma unroll
-            for (int q4 = 0; q4 < 16; ++q4) acc[g][q4] = __uint_as_float(rj[q4]);
-          } else if (row_valid) {
-            const int slot = krank < j ? krank : krank - 1;   // receiver j numbers its three senders 0..2 in rank order
-            const uint32_t dst = df_mapa(s_part_u + (uint32_t)(((g * 3 + slot) * PR + row) * 64), (uint32_t)j);
-            const uint32_t rb = df_mapa(pbar, (uint32_t)j);
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              df_st_async_v4(dst + 16 * q4, make_uint4(rj[4 * q4], rj[4 * q4 + 1], rj[4 * q4 + 2], rj[4 * q4 + 3]), rb);
-          }
-        }
-      }
-    }
-    mbar_wait(pbar, pparity);
-    pparity ^= 1u;
-    if (row_valid) {  // fixed summation order (sender 0,1,2,3) so every run adds the same way
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        if (g < ng) {
-          float sum[16];
-#pragma unroll
-          for (int q4 = 0; q4 < 16; ++q4) sum[q4] = 0.f;
-#pragma unroll
-          for (int sr = 0; sr < 4; ++sr) {
-            if (sr == krank) {
-#pragma unroll
-              for (int q4 = 0; q4 < 16; ++q4) sum[q4] += acc[g][q4];
-            } else {
-              const int slot = sr < krank ? sr : sr - 1;
-              const float4* pr = reinterpret_cast<const float4*>(s_part + (size_t)((g * 3 + slot) * PR + row) * 16);
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 v = pr[q4];
-                sum[4 * q4] += v.x; sum[4 * q4 + 1] += v.y; sum[4 * q4 + 2] += v.z; sum[4 * q4 + 3] += v.w;
-              }
-            }
-          }
-#pragma unroll
-          for (int q4 = 0; q4 < 16; ++q4) acc[g][q4] = sum[q4];
-        }
-      }
-    }
-  };
-
-  // ---- cell 0 for the 8 gate columns col0..col0+7 (two hidden units) of utterance b: z = zctx + h0.W0h + W_emb[id] + b0 ----
-  auto cell0 = [&](int b, int col0, const float* zctx, int id, int par_out) {
-    const float4* zh = reinterpret_cast<const float4*>(p.zh0 + (size_t)b * W4 + col0);
-    const float4 zh_a = __ldcg(zh), zh_b = __ldcg(zh + 1);
-    const float4* bb = reinterpret_cast<const float4*>(d.b_cell[0] + col0);
-    const float4 b_a = __ldg(bb), b_b = __ldg(bb + 1);
-    const int idc = max(0, min(id, V - 1));
-    const uint4 e = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.w_emb) + (size_t)idc * W4 + col0));
-    const unsigned ew[4] = {e.x, e.y, e.z, e.w};
-    float z[8] = {zh_a.x + b_a.x, zh_a.y + b_a.y, zh_a.z + b_a.z, zh_a.w + b_a.w,
-                  zh_b.x + b_b.x, zh_b.y + b_b.y, zh_b.z + b_b.z, zh_b.w + b_b.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      z[2 * j] += __uint_as_float(ew[j] << 16);
-      z[2 * j + 1] += __uint_as_float(ew[j] & 0xffff0000u);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] += zctx[j];
-    const int u0 = col0 >> 2;
-    float2* cp = reinterpret_cast<float2*>(p.c0 + (size_t)b * Ud + u0);
-    const float2 cprev = *cp;
-    float c_a, h_a, c_b, h_b;
-    lstm_gates(z[0], z[1], z[2], z[3], cprev.x, c_a, h_a);
-    lstm_gates(z[4], z[5], z[6], z[7], cprev.y, c_b, h_b);
-    *cp = make_float2(c_a, c_b);
-    __nv_bfloat162 hq = __floats2bfloat162_rn(h_a, h_b);
-    __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(p.hbuf[0]) + ((size_t)par_out * B + b) * Ud + u0;
-    *reinterpret_cast<__nv_bfloat162*>(hd) = hq;
   };
 
   const int n_items = AS * B;
   const int Wh = W4 / AS;                        // zctx columns of a part
   const int ncg = Wh / 8;                        // 8-column groups (16 bytes of VW) of a part
   const int NPR = 256 / ncg;                     // row groups that split the memory rows of the context sum
-  const int cgi = tid % ncg, pri = tid / ncg;    // consumer thread -> (column group, row group); pri >= NPR idles
-  const bool ctx_thread = tid < 256 && pri < NPR;
+  const int cgi = tid % ncg, pri = tid / ncg;    // thread -> (column group, row group); pri >= NPR idles
+  const bool ctx_thread = pri < NPR;
+  const bool cell_thread = ctx_thread && pri == 0;
+  const int col0 = part * Wh + cgi * 8;          // first of the 8 gate columns (two hidden units) a cell_thread owns
+
+  // ---- cell 0 for gate columns col0..col0+7 of utterance b: z = zctx + (h0 . W0h + b0 in zb) + W_emb[id] ----
+  auto cell0 = [&](int b, const float* zctx, const float* zb, float2 cprev, int id, int par_out) {
+    const int idc = max(0, min(id, V - 1));
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.w_emb) + (size_t)idc * W4 + col0));
+    const unsigned ew[4] = {e.x, e.y, e.z, e.w};
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      z[2 * j] = zctx[2 * j] + zb[2 * j] + __uint_as_float(ew[j] << 16);
+      z[2 * j + 1] = zctx[2 * j + 1] + zb[2 * j + 1] + __uint_as_float(ew[j] & 0xffff0000u);
+    }
+    const int u0 = col0 >> 2;
+    float c_a, h_a, c_b, h_b;
+    lstm_gates_fast(z[0], z[1], z[2], z[3], cprev.x, c_a, h_a);
+    lstm_gates_fast(z[4], z[5], z[6], z[7], cprev.y, c_b, h_b);
+    *reinterpret_cast<float2*>(p.c0 + (size_t)b * Ud + u0) = make_float2(c_a, c_b);
+    *reinterpret_cast<__nv_bfloat162*>(p.hbuf[0] + (size_t)par_out * hpar + df_h_off(b, u0, STA)) = __floats2bfloat162_rn(h_a, h_b);
+  };
+  // the operands of cell 0 that do not depend on the sampled id: h0 . W0h (ZH0) + b0, and the cell state
+  auto cell0_operands = [&](int b, float* zb, float2& cprev, bool first) {
+    const float4* bb = reinterpret_cast<const float4*>(d.b_cell[0] + col0);
+    const float4 b_a = __ldg(bb), b_b = __ldg(bb + 1);
+    float4 zh_a = make_float4(0.f, 0.f, 0.f, 0.f), zh_b = zh_a;
+    cprev = make_float2(0.f, 0.f);
+    if (!first) {
+      const float4* zh = reinterpret_cast<const float4*>(p.zh0 + (size_t)b * W4 + col0);
+      zh_a = __ldcg(zh); zh_b = __ldcg(zh + 1);
+      cprev = *reinterpret_cast<const float2*>(p.c0 + (size_t)b * Ud + (col0 >> 2));
+    }
+    zb[0] = zh_a.x + b_a.x; zb[1] = zh_a.y + b_a.y; zb[2] = zh_a.z + b_a.z; zb[3] = zh_a.w + b_a.w;
+    zb[4] = zh_b.x + b_b.x; zb[5] = zh_b.y + b_b.y; zb[6] = zh_b.z + b_b.z; zb[7] = zh_b.w + b_b.w;
+  };
 
   // ---- prologue: cell 0 of step 0 (no attention yet: zctx = 0, h0 = 0, c0 = 0; input = sos / the first forced id) ----
   if (max_iter > 0) {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / AS;
-      if (ctx_thread && pri == 0) {
+      if (cell_thread) {
         const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float zb[8];
+        float2 cprev;
+        cell0_operands(b, zb, cprev, true);
         const int id0 = d.teacher_forced ? d.forced_ids[(size_t)b * d.max_steps] : d.sos_id;
-        cell0(b, part * Wh + cgi * 8, zero, id0, 0);
+        cell0(b, zero, zb, cprev, id0, 0);
       }
     }
     df_grid_barrier(p.bar, epoch);
@@ -456,13 +489,31 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
 #pragma unroll
     for (int ph = 0; ph < L; ++ph) {
       const int ng = n_groups(ph);
-      gemm_phase(&p.tmH[ph][par], base + (uint32_t)p.off_w[ph], ng * KSP * 16);
+      gemm_phase(p.hbuf[ph] + (size_t)par * hpar, base + (uint32_t)p.off_w[ph], ng * 16, fine && ph == 0);
       if (row_thread) {
-        if (KSP > 1 && tid == 128) mbar_expect_tx(pbar, (uint32_t)(ng * 3 * B * 64));
-        mbar_wait(tfull, acc_parity);
+        // one lane per warp polls: 128 threads spinning on the mbarrier would queue ahead of the producer's and the copy
+        // engine's own barrier operations in the shared-memory atomic unit
+        if (lane == 0) mbar_wait(tfull, acc_parity);
+        __syncwarp();
+        if (fine && ph == 0 && tid == 128) fine_stamp(2);
         tc_fence_after();
-        float acc[3][16];
-        fetch_groups(ng, acc);
+        const uint32_t trow = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
+        uint32_t acc[3][16];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          if (g < ng) {  // (K slice 0 + 1) + (2 + 3), always in this order
+            uint32_t a0[16], a1[16], a2[16], a3[16];
+            tmem_ld16(trow + (uint32_t)(16 * g), a0);
+            tmem_ld16(trow + (uint32_t)(64 + 16 * g), a1);
+            tmem_ld16(trow + (uint32_t)(128 + 16 * g), a2);
+            tmem_ld16(trow + (uint32_t)(192 + 16 * g), a3);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q4 = 0; q4 < 16; ++q4)
+              acc[g][q4] = __float_as_uint((__uint_as_float(a0[q4]) + __uint_as_float(a1[q4])) + (__uint_as_float(a2[q4]) + __uint_as_float(a3[q4])));
+          }
+        }
+        if (fine && ph == 0 && tid == 128) fine_stamp(3);
         if (row_valid) {
           int g = 0;
           if (has_x(ph)) {  // layer ph+1: z = h_ph . W_x + (h_{ph+1,t-1} . W_h carried from the previous step) + b
@@ -471,53 +522,66 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float cn, hn;
-              lstm_gates(acc[0][4 * u] + carry[l1][4 * u] + s_bias[l1 * 16 + 4 * u],
-                         acc[0][4 * u + 1] + carry[l1][4 * u + 1] + s_bias[l1 * 16 + 4 * u + 1],
-                         acc[0][4 * u + 2] + carry[l1][4 * u + 2] + s_bias[l1 * 16 + 4 * u + 2],
-                         acc[0][4 * u + 3] + carry[l1][4 * u + 3] + s_bias[l1 * 16 + 4 * u + 3], c_state[l1][u], cn, hn);
+              lstm_gates_fast(__uint_as_float(acc[0][4 * u]) + carry[l1][4 * u] + s_bias[l1 * 16 + 4 * u],
+                              __uint_as_float(acc[0][4 * u + 1]) + carry[l1][4 * u + 1] + s_bias[l1 * 16 + 4 * u + 1],
+                              __uint_as_float(acc[0][4 * u + 2]) + carry[l1][4 * u + 2] + s_bias[l1 * 16 + 4 * u + 2],
+                              __uint_as_float(acc[0][4 * u + 3]) + carry[l1][4 * u + 3] + s_bias[l1 * 16 + 4 * u + 3],
+                              c_state[l1][u], cn, hn);
               c_state[l1][u] = cn;
               hq[u] = __float2bfloat16_rn(hn);
             }
-            __nv_bfloat16* hd = reinterpret_cast<__nv_bfloat16*>(p.hbuf[l1]) + ((size_t)par * B + row) * Ud + slice * 4;
-            *reinterpret_cast<uint2*>(hd) = *reinterpret_cast<const uint2*>(hq);
+            *reinterpret_cast<uint2*>(p.hbuf[l1] + (size_t)par * hpar + df_h_off(row, slice * 4, STA)) = *reinterpret_cast<const uint2*>(hq);
             g = 1;
           }
           if (ph == 0) {  // h0_t . W0h: read by the attention CTAs when they run cell 0 of step t+1
             float4* zd = reinterpret_cast<float4*>(p.zh0 + (size_t)row * W4 + slice * 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) zd[j] = make_float4(acc[g][4 * j], acc[g][4 * j + 1], acc[g][4 * j + 2], acc[g][4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              zd[j] = make_float4(__uint_as_float(acc[g][4 * j]), __uint_as_float(acc[g][4 * j + 1]), __uint_as_float(acc[g][4 * j + 2]),
+                                  __uint_as_float(acc[g][4 * j + 3]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) carry[ph][j] = acc[g][j];
+            for (int j = 0; j < 16; ++j) carry[ph][j] = __uint_as_float(acc[g][j]);
           }
           if (has_q(ph)) {
             float4* qd = reinterpret_cast<float4*>(p.qbuf + (size_t)row * Ud + slice * 16);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              qd[j] = make_float4(acc[g + 1][4 * j], acc[g + 1][4 * j + 1], acc[g + 1][4 * j + 2], acc[g + 1][4 * j + 3]);
+              qd[j] = make_float4(__uint_as_float(acc[g + 1][4 * j]), __uint_as_float(acc[g + 1][4 * j + 1]),
+                                  __uint_as_float(acc[g + 1][4 * j + 2]), __uint_as_float(acc[g + 1][4 * j + 3]));
           }
         }
         tc_fence_before();
+        if (fine && ph == 0 && tid == 128) fine_stamp(4);
       }
       acc_parity ^= 1u;
       // the barrier after the top phase is only needed when its result is read in this step (query layer) or by the
       // cell 0 that follows the attention (L == 1: ZH0)
-      if (ph < L - 1 || bahdanau || L == 1) df_grid_barrier(p.bar, epoch);
-      else __syncthreads();  // the attention phase reuses the ring / partial-sum region
+      if (ph < L - 1 || bahdanau || L == 1) {
+        df_grid_barrier(p.bar, epoch);
+      } else {
+        // the attention phase reuses the ring region, also for what the partner CTAs push into it: every CTA of the
+        // cluster must be done with its MMAs first
+        tc_fence_before();
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+      }
       stamp(1 + ph);
     }
 
     // ---------------- attention + logits + cell 0 of step t+1 ----------------
     {
-      const __nv_bfloat16* Htop = reinterpret_cast<const __nv_bfloat16*>(p.hbuf[L - 1]) + (size_t)par * B * Ud;
+      const unsigned char* Htop = p.hbuf[L - 1] + (size_t)par * hpar;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / AS;
         const int len = min(d.mem_len[b], Tm);
-        const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud + part * Dk;
         // ---- query ----
         for (int u = tid; u < Ud; u += 256)
           s_q[u] = bahdanau ? __ldcg(p.qbuf + (size_t)b * Ud + u)
-                            : __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short*>(Htop) + (size_t)b * Ud + u) << 16);
+                            : __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short*>(Htop + df_h_off(b, u, STA))) << 16);
+        // the id-independent operands of cell 0 (t+1): issued now, consumed after the argmax
+        float zb[8];
+        float2 cprev = make_float2(0.f, 0.f);
+        if (cell_thread) cell0_operands(b, zb, cprev, false);
         // PV rows of this part (f32 [rows][V]) are prefetched into the idle ring region with cp.async while scores run
         const int rchunk = (Tm + AS - 1) / AS;
         const int r_lo = min(part * rchunk, len), r_hi = min(r_lo + rchunk, len);
@@ -533,120 +597,63 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        df_consumer_sync();
-        // ---- scores: warp per memory position, lane owns 16-byte chunks lane, lane+32 of this part's key depth ----
-        const int n_c8 = Dk / 8;
-        const bool reg_path = n_c8 <= 64;
-        float qreg[16], vreg[16];
-        if (reg_path) {
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c8 = lane + 32 * cc;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              qreg[cc * 8 + j] = (c8 < n_c8) ? s_q[part * Dk + c8 * 8 + j] : 0.f;
-              vreg[cc * 8 + j] = (c8 < n_c8 && bahdanau) ? s_v[part * Dk + c8 * 8 + j] : 0.f;
-            }
-          }
-        }
-        const uint4* kres = reinterpret_cast<const uint4*>(smem + p.off_keys);
-        auto load_keys = [&](int r0, uint4 (*kk)[2]) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = r0 + 8 * i;
+        df_sync();
+        stamp(5);
+        // ---- scores over this part's key depth: warp per memory row, lane owns 16-byte chunks lane (, lane+32) ----
+        if (len > 0) {
+          if (n_c8 <= 64) {
+            float qreg[16], vreg[16];
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               const int c8 = lane + 32 * cc;
-              kk[i][cc] = make_uint4(0u, 0u, 0u, 0u);
-              if (reg_path && r < len && c8 < n_c8)
-                kk[i][cc] = p.keys_res ? kres[r * n_c8 + c8] : __ldg(reinterpret_cast<const uint4*>(keys + (size_t)r * Ud) + c8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                qreg[cc * 8 + j] = (c8 < n_c8) ? s_q[part * Dk + c8 * 8 + j] : 0.f;
+                vreg[cc * 8 + j] = (c8 < n_c8 && bahdanau) ? s_v[part * Dk + c8 * 8 + j] : 0.f;
+              }
             }
-          }
-        };
-        auto score_rows = [&](int r0, uint4 (*kk)[2]) {
-          if (reg_path) {
-            // four rows at a time with independent accumulators: the MUFU.TANH -> FFMA chains of different rows overlap
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint4* kres = reinterpret_cast<const uint4*>(smem + p.off_keys);
+            const uint4* kglb = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud + part * Dk);
+            const bool two = n_c8 > 32;
+            if (p.keys_res) {
+              if (bahdanau) { if (two) df_scores<2, true, true>(kres, n_c8, n_c8, len, warp, lane, qreg, vreg, s_score);
+                              else df_scores<1, true, true>(kres, n_c8, n_c8, len, warp, lane, qreg, vreg, s_score); }
+              else { if (two) df_scores<2, false, true>(kres, n_c8, n_c8, len, warp, lane, qreg, vreg, s_score);
+                     else df_scores<1, false, true>(kres, n_c8, n_c8, len, warp, lane, qreg, vreg, s_score); }
+            } else {
+              if (bahdanau) { if (two) df_scores<2, true, false>(kglb, Ud / 8, n_c8, len, warp, lane, qreg, vreg, s_score);
+                              else df_scores<1, true, false>(kglb, Ud / 8, n_c8, len, warp, lane, qreg, vreg, s_score); }
+              else { if (two) df_scores<2, false, false>(kglb, Ud / 8, n_c8, len, warp, lane, qreg, vreg, s_score);
+                     else df_scores<1, false, false>(kglb, Ud / 8, n_c8, len, warp, lane, qreg, vreg, s_score); }
+            }
+          } else {  // very wide decoders: chunks straight from memory
+            const __nv_bfloat16* keys = reinterpret_cast<const __nv_bfloat16*>(d.keys) + (size_t)b * Tm * Ud + part * Dk;
+            for (int r = warp; r < len; r += 8) {
+              float acc = 0.f;
+              const uint4* kr = reinterpret_cast<const uint4*>(keys + (size_t)r * Ud);
+              for (int c8 = lane; c8 < n_c8; c8 += 32) {
+                const uint4 k4 = __ldg(kr + c8);
+                const unsigned kw[4] = {k4.x, k4.y, k4.z, k4.w};
+                const int u0 = part * Dk + c8 * 8;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              if (32 * cc >= n_c8) break;  // warp-uniform
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float k0[4], k1[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const unsigned kw = j == 0 ? kk[i][cc].x : (j == 1 ? kk[i][cc].y : (j == 2 ? kk[i][cc].z : kk[i][cc].w));
-                  k0[i] = __uint_as_float(kw << 16);
-                  k1[i] = __uint_as_float(kw & 0xffff0000u);
-                }
-                if (bahdanau) {
-                  float t0[4], t1[4];
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    t0[i] = df_tanh_mufu(k0[i] + qreg[cc * 8 + 2 * j]);
-                    t1[i] = df_tanh_mufu(k1[i] + qreg[cc * 8 + 2 * j + 1]);
-                  }
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    acc[i] = fmaf(vreg[cc * 8 + 2 * j], t0[i], acc[i]);
-                    acc[i] = fmaf(vreg[cc * 8 + 2 * j + 1], t1[i], acc[i]);
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    acc[i] = fmaf(k0[i], qreg[cc * 8 + 2 * j], acc[i]);
-                    acc[i] = fmaf(k1[i], qreg[cc * 8 + 2 * j + 1], acc[i]);
+                for (int j = 0; j < 4; ++j) {
+                  const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
+                  if (bahdanau) {
+                    acc = fmaf(s_v[u0 + 2 * j], df_tanh_mufu(k0 + s_q[u0 + 2 * j]), acc);
+                    acc = fmaf(s_v[u0 + 2 * j + 1], df_tanh_mufu(k1 + s_q[u0 + 2 * j + 1]), acc);
+                  } else {
+                    acc = fmaf(k0, s_q[u0 + 2 * j], acc);
+                    acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
                   }
                 }
               }
+              acc = warp_sum(acc);
+              if (lane == 0) s_score[r] = acc;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = r0 + 8 * i;
-              const float sacc = warp_sum(acc[i]);
-              if (lane == 0 && r < len) s_score[r] = sacc;
-            }
-            return;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // very wide decoders: chunks from memory
-            const int r = r0 + 8 * i;
-            if (r >= len) break;
-            float acc = 0.f;
-            const uint4* kr = reinterpret_cast<const uint4*>(keys + (size_t)r * Ud);
-            for (int c8 = lane; c8 < n_c8; c8 += 32) {
-              const uint4 k4 = p.keys_res ? kres[r * n_c8 + c8] : __ldg(kr + c8);
-              const unsigned kw[4] = {k4.x, k4.y, k4.z, k4.w};
-              const int u0 = part * Dk + c8 * 8;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float k0 = __uint_as_float(kw[j] << 16), k1 = __uint_as_float(kw[j] & 0xffff0000u);
-                if (bahdanau) {
-                  acc = fmaf(s_v[u0 + 2 * j], df_tanh_mufu(k0 + s_q[u0 + 2 * j]), acc);
-                  acc = fmaf(s_v[u0 + 2 * j + 1], df_tanh_mufu(k1 + s_q[u0 + 2 * j + 1]), acc);
-                } else {
-                  acc = fmaf(k0, s_q[u0 + 2 * j], acc);
-                  acc = fmaf(k1, s_q[u0 + 2 * j + 1], acc);
-                }
-              }
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) s_score[r] = acc;
-          }
-        };
-        {
-          // software-pipelined: while the warp scores 4 rows the next 4 rows are already in flight (matters when the
-          // keys stream from L2).  Warp w takes rows w, w+8, ...
-          uint4 ka[4][2], kb2[4][2];
-          load_keys(warp, ka);
-          for (int r0 = warp; r0 < len; r0 += 64) {
-            load_keys(r0 + 32, kb2);
-            score_rows(r0, ka);
-            load_keys(r0 + 64, ka);
-            score_rows(r0 + 32, kb2);
           }
         }
-        df_consumer_sync();
+        df_sync();
+        stamp(6);
         // ---- swap partial scores with the other parts of the utterance (DSMEM) and add them in part order ----
         {
           if (tid == 0) mbar_expect_tx(sbar, (uint32_t)((AS - 1) * p.tm_pad * 4));
@@ -659,17 +666,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
               df_st_async_v4(dst0 + 16 * i, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)), rb);
             }
           }
-          df_consumer_sync();  // every thread has read its chunks of the partial scores before they are overwritten below
-          mbar_wait(sbar, sparity);
+          if (tid == 0) mbar_wait(sbar, sparity);
           sparity ^= 1u;
+          df_sync();  // the partners' scores are in, and every thread has read its chunks of the own ones before they are overwritten
           for (int tm = tid; tm < len; tm += 256) {
             float s = 0.f;
             for (int q = 0; q < AS; ++q) s += (q == part) ? s_score[tm] : s_peer[(size_t)q * p.tm_pad + tm];
             s_score[tm] = s;
           }
-          df_consumer_sync();
+          df_sync();
         }
-        stamp(5);
+        stamp(7);
         if (monotonic) {
           // tf.contrib.seq2seq.monotonic_attention(mode='parallel'): two prefix sums along memory time
           float* sa = s_scan;
@@ -681,10 +688,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             s_score[tm] = pc;
             sa[tm] = logf(fminf(fmaxf(1.f - pc, tiny), 1.f));
           }
-          df_consumer_sync();
+          df_sync();
           for (int off = 1; off < Tm; off <<= 1) {  // inclusive Hillis-Steele scan of the logs
             for (int tm = tid; tm < Tm; tm += 256) sb[tm] = sa[tm] + (tm >= off ? sa[tm - off] : 0.f);
-            df_consumer_sync();
+            df_sync();
             float* tmp = sa; sa = sb; sb = tmp;
           }
           for (int tm = tid; tm < Tm; tm += 256) {
@@ -693,22 +700,22 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             sb[tm] = pv / fminf(fmaxf(cpv, 1e-10f), 1.f);
             s_score[tm] = s_score[tm] * cpv;  // p * cp
           }
-          df_consumer_sync();
+          df_sync();
           float* ra = sb;
           float* rb = sa;
           for (int off = 1; off < Tm; off <<= 1) {
             for (int tm = tid; tm < Tm; tm += 256) rb[tm] = ra[tm] + (tm >= off ? ra[tm - off] : 0.f);
-            df_consumer_sync();
+            df_sync();
             float* tmp = ra; ra = rb; rb = tmp;
           }
           for (int tm = tid; tm < Tm; tm += 256) s_score[tm] = s_score[tm] * ra[tm];
-          df_consumer_sync();
+          df_sync();
         } else {
           float m = -INFINITY;
           for (int tm = tid; tm < len; tm += 256) m = fmaxf(m, s_score[tm]);
           m = warp_max(m);
           if (lane == 0) s_red[warp] = m;
-          df_consumer_sync();
+          df_sync();
           m = s_red[0];
 #pragma unroll
           for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
@@ -720,12 +727,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
           }
           sum = warp_sum(sum);
           if (lane == 0) s_red[8 + warp] = sum;
-          df_consumer_sync();
+          df_sync();
           sum = 0.f;
 #pragma unroll
           for (int w = 0; w < 8; ++w) sum += s_red[8 + w];
           for (int tm = tid; tm < Tm; tm += 256) s_score[tm] = s_score[tm] / sum;
-          df_consumer_sync();
+          df_sync();
         }
         if (part == 0) {
           if (monotonic)  // read by every part of the utterance in the next step
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
           const float* pvb = d.pv + (size_t)b * Tm * d.pv_ld;
           if (pv_smem) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            df_consumer_sync();
+            df_sync();
           }
           for (int vb = 0; vb < V; vb += 64) {
             const int v = vb + vi;
@@ -757,10 +764,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
               }
             }
             s_lp[g * 64 + vi] = acc;
-            df_consumer_sync();
+            df_sync();
             if (tid < 64 && vb + tid < p.v_pad)
               s_lmine[vb + tid] = (vb + tid < V) ? ((s_lp[tid] + s_lp[64 + tid]) + (s_lp[128 + tid] + s_lp[192 + tid])) : 0.f;
-            df_consumer_sync();
+            df_sync();
           }
           if (tid == 0) mbar_expect_tx(lbar, (uint32_t)((AS - 1) * p.v_pad * 4));
           for (int i = tid; i < p.v_pad / 4; i += 256) {
@@ -774,19 +781,15 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             }
           }
         }
-        stamp(6);
+        stamp(8);
         // ---- zctx over this part's columns: thread = (8-column group, row group); VW streams from L2 ----
         float zacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (ctx_thread) {
+        if (ctx_thread && len > 0) {
           const uint4* vp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.vw) + (size_t)b * Tm * W4 + part * Wh) + cgi;
           const size_t vstride = (size_t)(W4 / 8);
-          auto load_vals = [&](int r0, uint4* vv) {
+          auto load_vals = [&](int r0, uint4* vv) {  // unconditional (row clamped): rows >= len get weight 0 below
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = r0 + NPR * i;
-              vv[i] = make_uint4(0u, 0u, 0u, 0u);
-              if (r < len) vv[i] = __ldg(vp + (size_t)r * vstride);
-            }
+            for (int i = 0; i < 8; ++i) vv[i] = __ldg(vp + (size_t)min(r0 + NPR * i, len - 1) * vstride);
           };
           auto accum = [&](int r0, const uint4* vv) {
 #pragma unroll
@@ -815,21 +818,21 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             for (int i = 0; i < 8; ++i) s_comb[(size_t)(pri - 1) * Wh + cgi * 8 + i] = zacc[i];
           }
         }
-        df_consumer_sync();
-        if (ctx_thread && pri == 0) {
+        df_sync();
+        if (cell_thread) {
           for (int q = 1; q < NPR; ++q) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) zacc[i] += s_comb[(size_t)(q - 1) * Wh + cgi * 8 + i];
           }
         }
-        stamp(7);
+        stamp(9);
         // ---- logits = sum of the parts' partial logits (part order) + bias; argmax, lowest index wins ties ----
-        mbar_wait(lbar, lparity);
-        lparity ^= 1u;
         {
           float best = -INFINITY;
           int bi = 0x7fffffff;
           if (tid < 64) {
+            if (lane == 0) mbar_wait(lbar, lparity);
+            __syncwarp();
             for (int vb = 0; vb < V; vb += 64) {
               const int v = vb + tid;
               if (v < V) {
@@ -848,28 +851,33 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             }
             if (lane == 0) { s_red[16 + 2 * warp] = best; s_red[17 + 2 * warp] = __int_as_float(bi); }
           }
-          df_consumer_sync();
+          lparity ^= 1u;
+          df_sync();
           float b0 = s_red[16], b1 = s_red[18];
           int i0 = __float_as_int(s_red[17]), i1 = __float_as_int(s_red[19]);
           if (b1 > b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
           const int id_t = i0 == 0x7fffffff ? 0 : i0;
           if (part == 0 && tid == 0) __stcg(p.next_ids + b, id_t);
           // ---- cell 0 of step t+1 for this part's hidden units ----
-          if (t + 1 < max_iter && ctx_thread && pri == 0) {
+          if (t + 1 < max_iter && cell_thread) {
             const int id_in = d.teacher_forced ? d.forced_ids[(size_t)b * d.max_steps + t + 1] : id_t;
-            cell0(b, part * Wh + cgi * 8, zacc, id_in, par ^ 1);
+            cell0(b, zacc, zb, cprev, id_in, par ^ 1);
           }
-          df_consumer_sync();  // s_red / s_score / s_lpart are rewritten by the next item
+          df_sync();  // s_red / s_score / s_lpart are rewritten by the next item
         }
-        stamp(8);
+        stamp(10);
       }
       df_grid_barrier(p.bar, epoch);
-      stamp(9);
+      stamp(11);
     }
     ++t;
   }
   if (timing)
-    for (int i = 0; i < 10; ++i) p.dbg[i] = tacc[i];
+    for (int i = 0; i < 12; ++i) p.dbg[i] = tacc[i];
+  if (fine) {  // written by the role threads that took the stamps
+    if (warp == 0 && tfine[0]) { p.dbg[12] = tfine[0]; p.dbg[13] = tfine[1]; }
+    if (tid == 128) { p.dbg[14] = tfine[2]; p.dbg[15] = tfine[3]; p.dbg[16] = tfine[4]; }
+  }
   if (blockIdx.x == 0 && tid == 0) *d.n_steps = t;
   tc_fence_before();
   __syncthreads();
@@ -886,8 +894,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
 // ---------------------------------------------------------------------------------------------
 struct DecFoldPlan {
   bool ok;
-  int ksp, as, keys_res, n_stages_a, stage_a, tm_pad, v_pad;
-  int off_w[4], off_keys, off_ring, off_part, off_comb, off_pv, pv_cap, off_misc;
+  int as, keys_res, n_stages_a, stage_a, tm_pad, v_pad;
+  int off_w[4], off_keys, off_ring, off_comb, off_pv, pv_cap, off_att, off_misc;
   size_t smem;
   size_t ws_off_h[4], ws_off_q, ws_off_zh0, ws_off_c0, ws_off_align, ws_off_ids, ws_off_bar, ws_off_dbg, ws_total;
 };
@@ -904,74 +912,78 @@ static DecFoldPlan dec_fold_plan(const plas_dec_desc& d) {
   for (int l = 1; l < d.n_layers; ++l)
     if (!d.w_x_tc[l] || !d.w_h_tc[l]) return pl;
   const int L = d.n_layers, Ud = d.Ud, nkb = Ud / 64, grid = Ud / 4;
-  pl.ksp = (nkb % 4 == 0) ? 4 : 1;
-  {
-    const char* e = getenv("PLAS_DEC_KSPLIT");
-    if (e && atoi(e) == 1) pl.ksp = 1;
-  }
   pl.as = (4 * d.B <= grid) ? 4 : 2;
-  // zctx column groups of a part must fit the 256 consumer threads; key depth of a part in whole 16-byte chunks
+  // zctx column groups of a part must fit the 256 threads; key depth of a part in whole 16-byte chunks
   if ((4 * Ud / pl.as) % 8 != 0 || (4 * Ud / pl.as) / 8 > 256 || (Ud / pl.as) % 8 != 0) return pl;
   pl.tm_pad = (d.Tm + 3) & ~3;
   pl.v_pad = (d.V + 3) & ~3;
   int off = 0;
-  int ng_max = 1;
   for (int ph = 0; ph < L; ++ph) {
-    const int ng = (ph < L - 1 ? 1 : 0) + 1 + ((ph == L - 1 && bahdanau) ? 1 : 0);  // q group only on the first Ud/16 CTAs; sized for them
-    if (ng > ng_max) ng_max = ng;
+    const int ng = (ph < L - 1 ? 1 : 0) + 1 + ((ph == L - 1 && bahdanau) ? 1 : 0);  // the q group exists on the first Ud/16 CTAs only; sized for them
     pl.off_w[ph] = off;
-    off += ng * 32 * Ud;  // 16 columns x Ud x bf16 per group (the K-split layout holds 64 columns x Ud/4: same bytes)
+    off += ng * 32 * Ud;  // 16 columns x Ud x bf16 per group
   }
-  // region shared by the GEMM phases (TMA ring + K-split partial sums) and the attention phase (zctx partials + PV rows)
-  pl.off_ring = off;
-  pl.stage_a = d.B <= 64 ? 8192 : 16384;
-  const int nloc = nkb / pl.ksp;
-  pl.n_stages_a = nloc < DF_MAX_STAGES ? nloc : DF_MAX_STAGES;
-  if (pl.n_stages_a > 6) pl.n_stages_a = 6;
-  // 64-row boxes: the M=128 MMA reads 8 KB past a stage (rows 64..127 = don't-care TMEM lanes): one stage of slack
-  const int ring_bytes = pl.n_stages_a * pl.stage_a + (d.B <= 64 ? 8192 : 0);
-  const int part_bytes = pl.ksp > 1 ? ng_max * 3 * (d.B <= 64 ? 64 : 128) * 64 : 0;
-  pl.off_part = off + ring_bytes;
-  int region = ring_bytes + part_bytes;
-  if (region < 8192 + 4096) region = 8192 + 4096;
-  pl.off_comb = off;
-  pl.off_pv = off + 8192;
-  const int misc = 512 + 4 * (64 + 64 + 256 + 5 * pl.v_pad + 2 * Ud + 7 * pl.tm_pad) + 64;
-  // remaining shared memory: first a larger PV window, then the resident key slice
-  int avail = 227 * 1024 - 1024 - off - region - misc;
-  if (avail < 0) return pl;
+  pl.stage_a = d.B <= 64 ? 8192 : 16384;  // one k-block tile of h: 64 or 128 rows x 128 B
+  const int misc = 256 + 4 * (64 + Ud) + 64;  // barriers, TMEM slot, biases, attention_v
+  int avail = 227 * 1024 - 1024 - off - misc;
+  // the region the phases share: activation ring of the GEMM phases (ideally a stage per k block: one wave of copies) |
+  // attention phase: zctx partials (8 KB), the PV window of a part when it fits, scratch arrays
+  const int att_bytes = (4 * (64 + 256 + 5 * pl.v_pad + Ud + 7 * pl.tm_pad) + 1023) & ~1023;
   const int rchunk = (d.Tm + pl.as - 1) / pl.as;
-  const int pv_need = 8192 + rchunk * d.V * 4;
-  if (d.V % 4 == 0 && pv_need > region) {
-    const int grow = ((pv_need - region) + 1023) & ~1023;
-    if (grow <= avail) { region += grow; avail -= grow; }
-  }
-  pl.pv_cap = region - 8192;
-  off += region;
+  const int pv_bytes = (d.V % 4 == 0) ? ((rchunk * d.V * 4 + 1023) & ~1023) : 0;
+  int att_need = 8192 + att_bytes;
+  if (att_need > avail) return pl;
+  int pv_win = 0;
+  if (pv_bytes && att_need + pv_bytes <= avail) { pv_win = pv_bytes; att_need += pv_bytes; }
+  int ns = nkb < DF_MAX_STAGES ? nkb : DF_MAX_STAGES;
+  // the resident key slice (one attention item per CTA) comes before the last ring stages: give up stages (never below
+  // two, i.e. more waves) only if that is what lets the keys fit
   pl.keys_res = 0;
+  int key_bytes = 0;
   {
-    const int key_bytes = ((d.Tm * (Ud / pl.as) * 2) + 1023) & ~1023;
+    const int kb = ((d.Tm * (Ud / pl.as) * 2) + 1023) & ~1023;
     const bool single_item = pl.as * d.B <= grid;
     const char* e = getenv("PLAS_DEC_KEYS_RES");
-    if (single_item && key_bytes <= avail && !(e && atoi(e) == 0)) {
-      pl.keys_res = 1;
-      pl.off_keys = off;
-      off += key_bytes;
+    if (single_item && !(e && atoi(e) == 0)) {
+      int ns_k = ns;
+      while (ns_k > 2 && (ns_k * pl.stage_a > att_need ? ns_k * pl.stage_a : att_need) + kb > avail) --ns_k;
+      if ((ns_k * pl.stage_a > att_need ? ns_k * pl.stage_a : att_need) + kb <= avail && ns_k * 2 >= ns) {
+        pl.keys_res = 1;
+        key_bytes = kb;
+        ns = ns_k;
+      }
     }
+  }
+  while (ns > 1 && (ns * pl.stage_a > att_need ? ns * pl.stage_a : att_need) + key_bytes > avail) --ns;
+  const int region = ns * pl.stage_a > att_need ? ns * pl.stage_a : att_need;
+  if (region + key_bytes > avail) return pl;
+  pl.n_stages_a = ns;
+  pl.off_ring = off;
+  pl.off_comb = off;
+  pl.off_pv = off + 8192;
+  pl.pv_cap = pv_win;
+  pl.off_att = off + 8192 + pv_win;
+  off += region;
+  if (pl.keys_res) {
+    pl.off_keys = off;
+    off += key_bytes;
   }
   pl.off_misc = off;
   pl.smem = (size_t)off + misc + 1024;
+  // 64-row tiles: the M=128 MMA reads 8 KB past a stage (rows 64..127 feed TMEM lanes nobody reads); keep those bytes allocated
+  const size_t over = (size_t)pl.off_ring + (size_t)pl.n_stages_a * pl.stage_a + 8192 + 1024;
+  if (d.B <= 64 && pl.smem < over) pl.smem = over;
   if (pl.smem > 227 * 1024) return pl;
   size_t w = 0;
   auto take = [&](size_t bytes) { size_t o = w; w += (bytes + 255) & ~size_t(255); return o; };
-  for (int l = 0; l < 4; ++l) pl.ws_off_h[l] = take(l < L ? 2 * (size_t)d.B * Ud * 2 : 0);
+  for (int l = 0; l < 4; ++l) pl.ws_off_h[l] = take(l < L ? 2 * (size_t)nkb * pl.stage_a : 0);
   pl.ws_off_q = take((size_t)d.B * Ud * 4);
   pl.ws_off_zh0 = take((size_t)d.B * 4 * Ud * 4);
   pl.ws_off_c0 = take((size_t)d.B * Ud * 4);
   pl.ws_off_align = take(2 * (size_t)d.B * d.Tm * 4);
   pl.ws_off_ids = take((size_t)d.B * 4);
   pl.ws_off_bar = take(4);
-  pl.ws_off_dbg = take(128);
+  pl.ws_off_dbg = take(512);
   pl.ws_total = w;
   pl.ok = true;
   return pl;
@@ -1035,25 +1047,19 @@ int dec_fold_launch(const plas_dec_desc& d, void* workspace, size_t workspace_by
   a.next_ids = (int*)(ws + pl.ws_off_ids);
   a.bar = (unsigned*)(ws + pl.ws_off_bar);
   a.dbg = getenv("PLAS_DEBUG") ? (unsigned long long*)(ws + pl.ws_off_dbg) : nullptr;
-  a.ksp = pl.ksp;
   a.as = pl.as;
   a.keys_res = pl.keys_res;
   a.n_stages_a = pl.n_stages_a;
   a.stage_a = pl.stage_a;
   a.off_keys = pl.off_keys;
   a.off_ring = pl.off_ring;
-  a.off_part = pl.off_part;
   a.off_comb = pl.off_comb;
   a.off_pv = pl.off_pv;
   a.pv_cap = pl.pv_cap;
+  a.off_att = pl.off_att;
   a.off_misc = pl.off_misc;
   a.tm_pad = pl.tm_pad;
   a.v_pad = pl.v_pad;
-  for (int l = 0; l < d.n_layers; ++l)
-    for (int par = 0; par < 2; ++par) {
-      int rc = make_map_bf16(&a.tmH[l][par], a.hbuf[l] + (size_t)par * d.B * d.Ud * 2, d.B, d.Ud, d.Ud, pl.stage_a / 128);
-      if (rc) return rc;
-    }
   const int grid = d.Ud / 4;
   int max_clusters = 0;
   cudaError_t le;
@@ -1064,19 +1070,21 @@ int dec_fold_launch(const plas_dec_desc& d, void* workspace, size_t workspace_by
     default: le = dec_fold_launch_l<4>(a, grid, pl.smem, stream, &max_clusters); break;
   }
   if (getenv("PLAS_DEBUG"))
-    fprintf(stderr, "[plas] decoder fold path: L=%d ksplit=%d as=%d keys_res=%d grid=%d smem=%zu ring %d x %d B pv_cap=%d max_active_clusters=%d launch: %s\n",
-            d.n_layers, pl.ksp, pl.as, pl.keys_res, grid, pl.smem, pl.n_stages_a, pl.stage_a, pl.pv_cap, max_clusters, cudaGetErrorString(le));
+    fprintf(stderr, "[plas] decoder fold path: L=%d as=%d keys_res=%d grid=%d smem=%zu ring %d x %d B pv_cap=%d max_active_clusters=%d launch: %s\n",
+            d.n_layers, pl.as, pl.keys_res, grid, pl.smem, pl.n_stages_a, pl.stage_a, pl.pv_cap, max_clusters, cudaGetErrorString(le));
   if (le == cudaErrorCooperativeLaunchTooLarge) {
     (void)cudaGetLastError();
     return 1;  // not all clusters fit at once: the caller falls back
   }
   PLAS_CUDA(le);
   if (a.dbg) {  // debug only: synchronises
-    unsigned long long h[10];
+    unsigned long long h[17];
     PLAS_CUDA(cudaStreamSynchronize(stream));
     PLAS_CUDA(cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[plas] decoder fold phase time (us, CTA 0): bookkeeping %.1f  gemm %.1f %.1f %.1f %.1f  scores %.1f  softmax+logits %.1f  context %.1f  argmax+cell0 %.1f  barrier %.1f\n",
-            h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, h[6] / 1e3, h[7] / 1e3, h[8] / 1e3, h[9] / 1e3);
+    fprintf(stderr, "[plas] decoder fold phase time (us, CTA 0): bookkeeping %.1f  gemm %.1f %.1f %.1f %.1f  query load %.1f  scores %.1f  exchange %.1f  softmax+logits %.1f  context %.1f  argmax+cell0 %.1f  barrier %.1f\n",
+            h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, h[6] / 1e3, h[7] / 1e3, h[8] / 1e3, h[9] / 1e3, h[10] / 1e3, h[11] / 1e3);
+    fprintf(stderr, "[plas]   gemm phase 0 detail (us after phase start, summed): first tile %.1f  MMAs issued %.1f  accumulator ready %.1f  accumulator read %.1f  epilogue done %.1f\n",
+            h[12] / 1e3, h[13] / 1e3, h[14] / 1e3, h[15] / 1e3, h[16] / 1e3);
   }
   return PLAS_OK;
 }
