@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   df_fence_proxy_async();  // the resident weights were written with generic stores, UMMA reads them via the async proxy
@@ -304,9 +304,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   const uint32_t tmem_base = *tmem_slot;
 
   // ---- replicated decode state ---------------------------------------------------------------------------------
-  const int row = tid - 128;                      // epilogue threads (warps 4..7) own batch row `row`
+  // epilogue threads (warps 4..7) own batch row `row` = their TMEM lane's row of D.  B <= 64 runs the MMAs with M = 64 (an
+  // SS-mode MMA fetches its A rows from shared memory at about a row per clock whatever N is, so 64 rows cost half of 128):
+  // D row i then sits in lane 32*(i/16) + i%16 -- the first 16 lanes of every warp quadrant (scripts/micro/m64_probe.cu)
+  const bool m64 = B <= 64;
   const bool row_thread = tid >= 128;
-  const bool row_valid = row_thread && row < B;
+  const int row = m64 ? ((warp - 4) * 16 + lane) : (tid - 128);
+  const bool row_valid = row_thread && row < B && (!m64 || lane < 16);
   float c_state[L][4];                            // cell states of layers 1..L-1 (index 0 unused)
   float carry[L][16];                             // h_{l,t-1} . W_lh for layers 1..L-1
 #pragma unroll
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   // same few L2 lines in lock step.
   auto gemm_phase = [&](const unsigned char* a_tiles, uint32_t w_smem, int ncols, bool detail) {
     const int rot = (int)(((long long)blockIdx.x * nkb) / gridDim.x) % nkb;
-    const uint32_t idesc = umma_idesc_bf16(128, ncols);
+    const uint32_t idesc = umma_idesc_bf16(m64 ? 64 : 128, ncols);
     if (warp == 1) {
       if (elect_one()) {
         for (int i0 = 0; i0 < nkb; i0 += NSTA) {
@@ -392,12 +396,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             tc_fence_after();
             const uint64_t adesc = umma_smem_desc(ring + j * STA);
             const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(kb * ncols * 128));
-            // the four K=16 slices of a k block accumulate into four separate accumulators (TMEM columns 64*k ..): back-to-back
-            // MMAs into ONE accumulator serialise on its read-modify-write latency (~140 clk each at these tiny N), four
-            // interleaved chains overlap; the epilogue adds the four partial sums in a fixed order
+            // measured: an SS-mode MMA of this size costs ~60 ns whatever M (64 / 128), N (32 / 128) or the accumulator it
+            // targets (one chain or four interleaved ones) -- the 2 us of a phase's 32 MMAs are a fixed per-instruction
+            // operand-fetch cost; only the A-from-TMEM form (rec_tc.cu: ~6 ns per MMA) avoids it
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + (uint32_t)(64 * k), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i0 | j) != 0 ? 1u : 0u);
+              umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i0 | j | k) != 0 ? 1u : 0u);
           }
           if (i0 + n < nkb) umma_commit(wave_done);
         }
@@ -499,20 +503,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)((warp - 4) * 32) << 16);
         uint32_t acc[3][16];
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          if (g < ng) {  // (K slice 0 + 1) + (2 + 3), always in this order
-            uint32_t a0[16], a1[16], a2[16], a3[16];
-            tmem_ld16(trow + (uint32_t)(16 * g), a0);
-            tmem_ld16(trow + (uint32_t)(64 + 16 * g), a1);
-            tmem_ld16(trow + (uint32_t)(128 + 16 * g), a2);
-            tmem_ld16(trow + (uint32_t)(192 + 16 * g), a3);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q4 = 0; q4 < 16; ++q4)
-              acc[g][q4] = __float_as_uint((__uint_as_float(a0[q4]) + __uint_as_float(a1[q4])) + (__uint_as_float(a2[q4]) + __uint_as_float(a3[q4])));
-          }
-        }
+        tmem_ld16(trow, acc[0]);
+        if (ng > 1) tmem_ld16(trow + 16u, acc[1]);
+        if (ng > 2) tmem_ld16(trow + 32u, acc[2]);
+        tmem_ld_wait();
         if (fine && ph == 0 && tid == 128) fine_stamp(3);
         if (row_valid) {
           int g = 0;
@@ -885,7 +879,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
   }
 }
 

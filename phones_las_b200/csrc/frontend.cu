@@ -273,15 +273,42 @@ __global__ void __launch_bounds__(FE_THREADS) fe_spectral_kernel(FeArgs p) {
 
     if (!librosa) {
       float* out = p.feats + ((size_t)b * p.T_max + t) * p.C;
+      // speechpy extract_derivative_feature (preprocess_all.py:120-123): two passes of derivative_extraction along the
+      // FEATURE axis over the D base features in cep[0..D), then [f_k, d f_k, dd f_k] interleaved per base channel
+      auto sp_deltas_out = [&](float* cep, int D) {
+        for (int pass = 0; pass < 2; ++pass) {
+          const float* F = cep + pass * D;
+          float* G = cep + (pass + 1) * D;
+          for (int k = lane; k < D; k += 32) {
+            float acc = F[min(k + 1, D - 1)] + 2.f * F[min(k + 2, D - 1)];
+            if (!d.sp_delta_literal) acc -= F[max(k - 1, 0)] + F[max(k - 2, 0)];
+            G[k] = acc / 10.f;
+          }
+          __syncwarp();
+        }
+        for (int i = lane; i < 3 * D; i += 32) {
+          const int k = i / 3, which = i - 3 * k;
+          out[i] = norm_ch(p, cep[which * D + k], i);
+        }
+      };
       if (d.feature_type == 0) {  // speechpy mfe: log([mel, energy] + 1e-8)
+        float* cep = P;  // [3][n_mels + 1] with --deltas (the power spectrum is dead by now)
         for (int m = lane; m < n_mels; m += 32) {
           float v = mel[m];
           v = (v == 0.f) ? eps64 : v;
-          out[m] = norm_ch(p, logf(v + 1e-8f), m);
+          v = logf(v + 1e-8f);
+          if (d.deltas) cep[m] = v;
+          else out[m] = norm_ch(p, v, m);
         }
         if (lane == 0) {
-          const float v = (E == 0.f) ? eps64 : E;
-          out[n_mels] = norm_ch(p, logf(v + 1e-8f), n_mels);
+          float v = (E == 0.f) ? eps64 : E;
+          v = logf(v + 1e-8f);
+          if (d.deltas) cep[n_mels] = v;
+          else out[n_mels] = norm_ch(p, v, n_mels);
+        }
+        if (d.deltas) {
+          __syncwarp();
+          sp_deltas_out(cep, n_mels + 1);
         }
       } else {  // speechpy mfcc: DCT-II(log mel), c0 := log(energy), optional feature-axis deltas
         for (int m = lane; m < n_mels; m += 32) {
@@ -300,20 +327,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_spectral_kernel(FeArgs p) {
         }
         __syncwarp();
         if (d.deltas) {
-          for (int pass = 0; pass < 2; ++pass) {
-            const float* F = cep + pass * D;
-            float* G = cep + (pass + 1) * D;
-            for (int k = lane; k < D; k += 32) {
-              float acc = F[min(k + 1, D - 1)] + 2.f * F[min(k + 2, D - 1)];
-              if (!d.sp_delta_literal) acc -= F[max(k - 1, 0)] + F[max(k - 2, 0)];
-              G[k] = acc / 10.f;
-            }
-            __syncwarp();
-          }
-          for (int i = lane; i < 3 * D; i += 32) {
-            const int k = i / 3, which = i - 3 * k;
-            out[i] = norm_ch(p, cep[which * D + k], i);
-          }
+          sp_deltas_out(cep, D);
         } else {
           for (int k = lane; k < D; k += 32) out[k] = norm_ch(p, cep[k], k);
         }
@@ -475,12 +489,12 @@ extern "C" int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave,
   PLAS_REQUIRE(prod == d->n_fft / 2, "frontend: radices multiply to %d, need %d", prod, d->n_fft / 2);
   const int nb = (d->feature_type == 0 ? d->n_mels : d->n_mfcc);
   int C_expect;
-  if (d->backend == 0) C_expect = (d->feature_type == 0) ? d->n_mels + 1 : d->n_mfcc * (d->deltas ? 3 : 1);
+  if (d->backend == 0) C_expect = ((d->feature_type == 0) ? d->n_mels + 1 : d->n_mfcc) * (d->deltas ? 3 : 1);
   else C_expect = (nb + (d->energy ? 1 : 0)) * (d->deltas ? 3 : 1);
   PLAS_REQUIRE(C == C_expect, "frontend: C=%d but the flags produce %d channels", C, C_expect);
-  PLAS_REQUIRE(!(d->backend == 0 && d->feature_type == 0 && d->deltas), "frontend: speechpy mfe+deltas unsupported");
   PLAS_REQUIRE(d->feature_type == 0 || d->dct, "frontend: mfcc needs a DCT matrix");
-  PLAS_REQUIRE(3 * nb <= d->n_fft + 2 || d->backend == 1, "frontend: n_mfcc too large for the work buffer");
+  PLAS_REQUIRE(3 * (nb + (d->feature_type == 0 ? 1 : 0)) <= d->n_fft + 2 || d->backend == 1,
+               "frontend: too many base features for the per-warp work buffer");
 
   FeArgs a;
   a.d = *d;

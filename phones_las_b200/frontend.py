@@ -92,8 +92,6 @@ def frontend_tables(args):
     if backend == 0 and feature_type == 0 and not args.energy:
         # preprocess_all.py:77-79: the reference raises NameError on this flag combination
         raise NameError("name 'acoustic_features' is not defined (speechpy mfe requires --energy)")
-    if backend == 0 and feature_type == 0 and args.deltas:
-        raise NotImplementedError("speechpy mfe with --deltas")
     n = n_fft // 2
     fac = _factorize(n)
     if backend == 0:

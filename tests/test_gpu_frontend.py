@@ -14,6 +14,9 @@ CASES = [
     dict(feature_type="mfe", backend="speechpy", n_mels=40, energy=True, window=20),
     dict(feature_type="mfcc", backend="speechpy", n_mfcc=13, n_mels=40, window=25, deltas=True),
     dict(feature_type="mfcc", backend="speechpy", n_mfcc=13, n_mels=40, window=25),
+    # speechpy mfe followed by extract_derivative_feature along the feature axis (preprocess_all.py:72-79 then :120-123)
+    dict(feature_type="mfe", backend="speechpy", n_mels=80, energy=True, window=25, deltas=True),
+    dict(feature_type="mfe", backend="speechpy", n_mels=40, energy=True, window=20, deltas=True),
     dict(feature_type="mfe", backend="librosa", n_mels=80, window=25),
     dict(feature_type="mfe", backend="librosa", n_mels=40, window=20, energy=True, deltas=True),
     dict(feature_type="mfcc", backend="librosa", n_mfcc=12, n_mels=40, window=25, energy=True, deltas=True),
@@ -53,7 +56,7 @@ def test_frontend_parity(case):
 
 
 @gpu
-@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[4], CASES[6]], ids=["sp-mfe", "sp-mfcc-d", "lr-mfe", "lr-mfcc-d"])
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[4], CASES[6], CASES[8]], ids=["sp-mfe", "sp-mfcc-d", "sp-mfe-d", "lr-mfe", "lr-mfcc-d"])
 def test_frontend_silence_and_normalisation(case):
     fa = feature_args(**case)
     wave, lens = synth.synth_audio(3, 1.0, seed=5, var_len=True, silence=True)
