@@ -35,6 +35,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv[1:]:
+    # the CPU arm uses every core this process may run on: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers,
+    # which would throttle numpy's BLAS to one thread (round-1 SCALE records) -- set the pools before numpy is imported
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(cpu_cores())
+
 import numpy as np  # noqa: E402
 
 METRIC = "audio-sec/sec (feats+pBLSTM+attn decode)"
@@ -79,6 +93,25 @@ def algorithmic_work(cfg, B, n_dec_steps):
     work["decoder"] = {"bytes": float(n_dec_steps) * (B * Tm * (Ud + D) * e + w_bytes), "launches": 1}
     work["_shape"] = {"Tm": Tm, "D": D}
     return work
+
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA lanes x 2 flop x boost clock
+
+
+def frontend_flops_per_frame(fa):
+    """Algorithmic FLOPs of one frame of calculate_acoustic_features (preprocess_all.py:69-130) as K1 evaluates it: window,
+    real FFT as a half-size complex FFT (5 n log2 n) + unpack (10 per bin), power (3 per bin), the non-zero mel weights
+    (2 each), log / dB (1 per mel), DCT (2 n_mels n_mfcc), Savitzky-Golay deltas (2 x 9 taps x 2 per base channel)."""
+    from phones_las_b200.frontend import frontend_tables
+    tb = frontend_tables(fa)
+    n_fft = tb["n_fft"]
+    n = n_fft // 2
+    fl = n_fft + 5.0 * n * np.log2(n) + 13.0 * (n + 1) + 2.0 * len(tb["fb_w"]) + fa.n_mels
+    if fa.feature_type == "mfcc":
+        fl += 2.0 * fa.n_mels * fa.n_mfcc
+    if fa.deltas:
+        fl += 2 * 9 * 2 * (tb["C"] // 3)
+    return float(fl)
 
 
 def load_peaks():
@@ -164,11 +197,20 @@ def oracle_step(cfg, params, wave):
     return pred["sample_ids"]
 
 
-def cpu_cores():
+def set_cpu_threads():
+    """All host threads for BLAS / torch, whatever the launcher exported; returns the count actually configured."""
+    n = cpu_cores()
     try:
-        return len(os.sched_getaffinity(0))
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
     except Exception:
-        return os.cpu_count() or 1
+        pass
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return n
 
 
 def run_cpu_sample(cfg, batch, steps, warmup):
@@ -191,20 +233,30 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = set_cpu_threads()
     cfg = workload(args.workload)
-    batch = args.ref_batch
-    # calibrate so that the whole run stays within a few minutes
-    v, dt = run_cpu_sample(cfg, 1, 1, 0)
-    budget = 150.0
-    while batch > 1 and dt * batch * (args.steps + args.warmup) > budget:
-        batch //= 2
-    value, dt = run_cpu_sample(cfg, batch, args.steps, args.warmup)
-    sample = f"{batch} utterances x {cfg['seconds']:.0f} s of workload {cfg['name']} per step, fp32 numpy oracle"
+    # the GPU arm's own batch (per-step numpy matmuls are then [B x K] x [K x 4U] like the GPU's, not weight-bandwidth-bound
+    # GEMVs); one warm-up pass doubles as the calibration -- the batch is halved only if K steps would not fit the budget
+    batch = args.ref_batch or args.batch or cfg["batch"]
+    budget = float(os.environ.get("PLAS_REF_BUDGET_S", "330"))
+    warm_done = 0
+    while True:
+        _, dt = run_cpu_sample(cfg, batch, 1, 0)
+        warm_done += 1
+        if batch == 1 or dt * args.steps <= budget:
+            break
+        batch = max(1, batch // 2)
+    for _ in range(max(0, min(args.warmup, 1) - warm_done)):
+        run_cpu_sample(cfg, batch, 1, 0)
+    value, dt = run_cpu_sample(cfg, batch, args.steps, 0)
+    same = batch == (args.batch or cfg["batch"])
+    sample = (f"{batch} utterances x {cfg['seconds']:.0f} s of workload {cfg['name']} per step ({'the GPU arm\'s batch' if same else 'largest batch whose K steps fit %.0f s' % budget}), "
+              f"fp32 numpy oracle on {cores} threads; {warm_done} calibration/warm-up pass(es)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "same_config": bool(same),
             "config": config_dict(cfg, batch, note="CPU oracle port of the reference path (TF1.15/librosa/speechpy not installable)"),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -222,6 +274,35 @@ def config_dict(cfg, batch, **extra):
 
 
 # ----------------------------------------------------------------------------------------------
+# one process group for the whole run (the default invocation measures several workloads back to back)
+# ----------------------------------------------------------------------------------------------
+_CTX = {}
+
+
+def dist_ctx():
+    if not _CTX:
+        import torch
+        import torch.distributed as dist
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        _CTX.update(world=world, rank=rank, local=local, dev=dev)
+    return _CTX["world"], _CTX["rank"], _CTX["local"], _CTX["dev"]
+
+
+def dist_done():
+    if _CTX and _CTX["world"] > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
 def ours(args):
@@ -230,15 +311,7 @@ def ours(args):
     from phones_las_b200 import _lib, synth, weights
     from phones_las_b200.model import LASModel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = dist_ctx()
     _lib.require_cuda()
 
     cfg = workload(args.workload)
@@ -327,10 +400,10 @@ def ours(args):
             stage_ms.setdefault(k, []).append(sum(v))
     stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
 
+    del model, dev_waves, host_waves
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = load_peaks()
     work = algorithmic_work(cfg, B, n_dec)
@@ -344,6 +417,10 @@ def ours(args):
             ent.update(bound="hbm", achieved=w["bytes"] / (t_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
         if "achieved" in ent:
             ent["frac"] = ent["achieved"] / ent["peak"]
+        if name == "frontend":  # formally HBM-bound (north_star), in practice FP32-issue-bound: report both
+            fl = frontend_flops_per_frame(fa) * B * cfg["T"]
+            ent.update(fp32_tflops=fl / (t_ms * 1e-3) / 1e12, fp32_peak_tflops=FP32_PEAK_TFLOPS,
+                       fp32_pipe_frac=fl / (t_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, flops_per_frame=frontend_flops_per_frame(fa))
         stages[name] = ent
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     dw = stages[dom]
@@ -371,13 +448,12 @@ def ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "stages": stages}
     if world == 1 and not args.no_cpu_baseline:
+        cores = set_cpu_threads()
         v, dt = run_cpu_sample(cfg, args.cpu_batch, 1, 0)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_batch} utterances x {cfg['seconds']:.0f} s of workload {cfg['name']}, one pass "
                                           f"({dt:.1f} s), fp32 numpy oracle (reference needs TF1.15/librosa/speechpy: not installable)"}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # ----------------------------------------------------------------------------------------------
@@ -442,15 +518,7 @@ def ours_train(args):
     import torch.distributed as dist
     from phones_las_b200 import _lib, parallel, weights, train as tr
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = dist_ctx()
     _lib.require_cuda()
     cfg = workload("c3")
     B = args.batch or cfg["batch"]
@@ -471,6 +539,8 @@ def ours_train(args):
         f = {"encoder_inputs": bt[0], "source_sequence_length": bt[1]}
         lb = {"targets_inputs": bt[2], "targets_outputs": bt[3], "target_sequence_length": bt[4]}
         return tr.train_step(f, lb, st, hp, binf_d, world_size=world, allreduce=allreduce)
+
+    step.hp, step.binf = hp, binf_d
 
     def barrier():
         if world > 1:
@@ -544,10 +614,9 @@ def ours_train(args):
         for k, v in _lib.timeline_stop().items():
             stage_ms.setdefault(k, []).append(sum(v))
     stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    dp = dp_check(world, rank, dev, st, step, batches, parallel) if world > 1 else None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     peaks = load_peaks()
     # dominant family: the fp32 GEMMs (projections, input and weight gradients); algorithmic flops of the listener part
     U, L, T, C = hp["encoder_units"], hp["encoder_layers"], cfg["T"], cfg["C"]
@@ -558,7 +627,7 @@ def ours_train(args):
         if l != 0:
             t = (t + 1) // 2
     gemm_ms = sum(stage_ms.get(k, 0.0) for k in ("train_inproj", "train_wgrad", "train_dgrad"))
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # FFMA lanes x 2 flop x boost clock: the bound of an exact-fp32 GEMM
+    fp32_peak = FP32_PEAK_TFLOPS  # the bound of an exact-fp32 GEMM
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     roofline = {"kernel": "gemm_f32_ex_kernel (train_inproj + train_wgrad + train_dgrad)", "bound": "fp32-pipe",
                 "achieved": fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -572,14 +641,55 @@ def ours_train(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "stages": {k: {"ms_per_step": v} for k, v in stage_ms.items()}, "loss": loss_last, "loss_e2e": loss_host,
             "trainable_parameters": int(sum(st.sizes))}
+    if dp is not None:
+        line["dp_check"] = dp
     if world == 1 and not args.no_cpu_baseline:
         v, dt = train_cpu_sample(cfg, args.cpu_batch)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
                                 "sample": f"{args.cpu_batch} utterances x {cfg['seconds']:.0f} s, one training step ({dt:.1f} s), torch-CPU fp32 "
                                           f"restatement of the TRAIN graph (oracle/las_torch.py; TF 1.15 not installable)"}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def dp_check(world, rank, dev, st, step, batches, parallel):
+    """Data-parallel correctness on the real kernels (model_helper.py:405-406,416-417): 3 eager steps on rank-specific
+    batches, then (a) max |param_rank0 - param_rank_k| over all parameters and ranks (replicas must stay identical) and
+    (b) the NCCL-reduced gradient buffer against the sum of the all-gathered per-shard buffers (each already clipped per
+    tensor and divided by the world size = the mean of the clipped shard gradients), plus the time of one all-reduce."""
+    import torch
+    import torch.distributed as dist
+    errs, ar_ms = [], []
+
+    def checked_allreduce(flat):
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        want = torch.stack(gathered, 0).to(torch.float64).sum(0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        parallel.allreduce_gradients(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms.append(e0.elapsed_time(e1))
+        scale = float(want.abs().max().clamp_min(1e-30))
+        errs.append(float((flat.to(torch.float64) - want).abs().max()) / scale)
+        return flat
+
+    from phones_las_b200 import train as tr
+    for i in range(3):
+        bt = batches[i % len(batches)]
+        f = {"encoder_inputs": bt[0], "source_sequence_length": bt[1]}
+        lb = {"targets_inputs": bt[2], "targets_outputs": bt[3], "target_sequence_length": bt[4]}
+        tr.train_step(f, lb, st, step.hp, step.binf, world_size=world, allreduce=checked_allreduce)
+    ref = st.params.clone()
+    dist.broadcast(ref, src=0)
+    diff = (st.params - ref).abs().max().reshape(1)
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    e = torch.tensor([max(errs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    return {"steps": 3, "param_max_abs_diff_across_ranks": float(diff.item()),
+            "allreduce_vs_sum_of_gathered_shard_grads_max_rel": float(e.item()),
+            "allreduce_ms": float(np.median(ar_ms)), "allreduce_bytes": int(st.grads.numel() * 4),
+            "note": "shard gradients are clipped per tensor and scaled by 1/world before the sum: the reduced buffer is the mean of the clipped shard gradients"}
 
 
 def reference_arm_train(args):
@@ -616,18 +726,11 @@ def ours_frontend(args):
     from phones_las_b200.frontend import FrontendPlan
     from phones_las_b200.hparams import feature_args, num_feature_channels, SAMPLE_RATE
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = dist_ctx()
     _lib.require_cuda()
     seconds, B = 3.0, args.batch or 16384
     N = int(seconds * SAMPLE_RATE)
+    l0 = _lib.launch_count
     variants = {"mfcc39": feature_args(feature_type="mfcc", backend="librosa", n_mfcc=12, n_mels=40, energy=True, window=25, step=10, deltas=True),
                 "mfe80": feature_args(feature_type="mfe", backend="librosa", n_mels=80, window=25, step=10)}
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -654,7 +757,10 @@ def ours_frontend(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         algo = B * (4 * N + 4 * out.shape[1] * C)  # 4N bytes in + 4TC bytes out per utterance
+        fl = frontend_flops_per_frame(fa) * B * out.shape[1]
         results[name] = {"ms_per_step": ms, "audio_s_per_s": world * B * seconds / (ms * 1e-3), "hbm_gbs": algo / (ms * 1e-3) / 1e9,
+                         "hbm_frac": algo / (ms * 1e-3) / 1e9 / load_peaks()["hbm_gbs"],
+                         "fp32_tflops": fl / (ms * 1e-3) / 1e12, "fp32_pipe_frac": fl / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
                          "channels": C, "frames": int(out.shape[1])}
         del out
     if rank == 0:
@@ -670,10 +776,40 @@ def ours_frontend(args):
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["hbm_gbs"] / peaks["hbm_gbs"], "traffic": None,
                              "peak_source": peaks["_source"],
                              "note": "FP32-issue-bound mixed-radix FFT (DESIGN.md section 3, K1): the HBM fraction is reported as north_star asks"},
-                "variants": results, "gpu_launches": int(_lib.launch_count)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+                "variants": results, "gpu_launches": int(_lib.launch_count - l0)}
+        return line
+    return None
+
+
+def parity_quotes():
+    """Measured parity at the BASELINE shapes (tests/test_gpu_baseline_shapes.py, committed under profiles/): quoted here so the
+    bench line says what north_star's tolerances look like on this path instead of a widened test tolerance hiding it."""
+    out = {}
+    for c in ("c1", "c2", "c4"):
+        pth = os.path.join(ROOT, "profiles", f"r02_parity_shapes_{c}.json")
+        if not os.path.exists(pth):
+            continue
+        with open(pth) as f:
+            d = json.load(f)
+        ent = {"precision": d["precision"], "B": d["B"], "T": d["T"], "decode_steps": d["decode_steps"],
+               "encoder_out_rel_fro_vs_emulated_oracle": d["vs_emul"]["encoder_out_fro"],
+               "greedy_ids_identical_fraction_vs_emulated_oracle": d["vs_emul"]["ids"]["fraction_identical"],
+               "greedy_ids_identical_on_decisive_steps": d["vs_emul"]["ids"]["decisive_prefix_identical"] == d["vs_emul"]["ids"]["decisive_prefix_pairs"]}
+        if "vs_fp32" in d:
+            ent.update({"encoder_out_rel_fro_vs_fp32_oracle": d["vs_fp32"]["encoder_out_fro"],
+                        "emulated_bf16_oracle_vs_fp32_oracle": d["emul_vs_fp32"]["encoder_out_fro"],
+                        "greedy_ids_identical_fraction_vs_fp32_oracle": d["vs_fp32"]["ids"]["fraction_identical"],
+                        "north_star_1e-3_vs_fp32_met": bool(d["vs_fp32"]["encoder_out_fro"] <= 1e-3)})
+        out[c] = ent
+    if out:
+        out["_note"] = ("oracle = CPU restatement (parity unpinned against TF: no reference vectors exist); bf16 storage of h / gate "
+                        "pre-activations puts ANY bf16 implementation ~7e-3 from float32 after 4 layers x 1501 steps; the CUDA path sits on that floor")
+    return out
+
+
+def compact(line, keys=("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches",
+                        "roofline", "stages", "dp_check", "variants", "loss")):
+    return {k: line[k] for k in keys if k in line}
 
 
 def main():
@@ -685,21 +821,52 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (default: the workload's)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances in the cpu_baseline sample")
-    ap.add_argument("--ref-batch", type=int, default=8, help="utterances per step of the reference arm")
+    ap.add_argument("--ref-batch", type=int, default=0, help="utterances per step of the reference arm (default: the GPU arm's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="default c2 run only: skip the c3-training / c4 / c5 sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "c5":
-        if args.impl == "reference":
+    if args.impl == "reference":
+        if args.workload == "c5":
             print(json.dumps({"impl": "reference", "unavailable": "c5 is a front-end-only sweep; the reference arm is defined for c1-c4"}), flush=True)
+        elif args.workload == "c3":
+            reference_arm_train(args)
         else:
-            ours_frontend(args)
+            reference_arm(args)
+        return
+    world, rank, _, _ = dist_ctx()
+    if args.workload == "c5":
+        line = ours_frontend(args)
     elif args.workload == "c3":
-        reference_arm_train(args) if args.impl == "reference" else ours_train(args)
-    elif args.impl == "reference":
-        reference_arm(args)
+        line = ours_train(args)
     else:
-        ours(args)
+        line = ours(args)
+        if args.workload == "c2" and not args.batch and not args.no_sub_records:
+            # the other BASELINE configurations, measured in the same run on the same ranks (each with its own barrier + CUDA-event
+            # timing, max over ranks): c3 = the training step with its NCCL all-reduce and the data-parallel check, c4 = long-form
+            # inference with the global batch of 128 split over the ranks, c5 = the front-end alone
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.steps, sub_args.no_cpu_baseline = max(3, min(args.steps, 5)), True
+            subs = {}
+            for name, fn, over in (("train_c3", ours_train, dict(workload="c3")),
+                                   ("c4", ours, dict(workload="c4", batch=max(1, 128 // world))),
+                                   ("c5", ours_frontend, dict(workload="c5", batch=16384))):
+                a = argparse.Namespace(**vars(sub_args))
+                for k, v in over.items():
+                    setattr(a, k, v)
+                try:
+                    sub = fn(a)
+                    if sub is not None:
+                        subs[name] = compact(sub)
+                except Exception as e:  # a sub-record must never take the headline line down with it
+                    if rank == 0:
+                        subs[name] = {"error": f"{type(e).__name__}: {e}"}
+            if line is not None:
+                line["sub_records"] = subs
+                line["parity"] = parity_quotes()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    dist_done()
 
 
 if __name__ == "__main__":

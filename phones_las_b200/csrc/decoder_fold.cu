@@ -54,6 +54,7 @@ struct alignas(64) DecFoldArgs {
   unsigned* bar;
   unsigned long long* dbg;       // optional phase timers (ns summed over steps), CTA 0
   int as;                        // CTAs per utterance in the attention phase (2 or 4)
+  int m64;                       // B <= 64: MMAs with M = 64
   int keys_res;                  // this CTA's key slice is resident in shared memory
   int n_stages_a, stage_a;       // activation ring of the GEMM phases; stage_a = tile bytes = RT * 128
   int off_w[4];                  // per phase: resident weight tiles
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   // epilogue threads (warps 4..7) own batch row `row` = their TMEM lane's row of D.  B <= 64 runs the MMAs with M = 64 (an
   // SS-mode MMA fetches its A rows from shared memory at about a row per clock whatever N is, so 64 rows cost half of 128):
   // D row i then sits in lane 32*(i/16) + i%16 -- the first 16 lanes of every warp quadrant (scripts/micro/m64_probe.cu)
-  const bool m64 = B <= 64;
+  const bool m64 = p.m64 != 0;
   const bool row_thread = tid >= 128;
   const int row = m64 ? ((warp - 4) * 16 + lane) : (tid - 128);
   const bool row_valid = row_thread && row < B && (!m64 || lane < 16);
@@ -396,9 +397,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             tc_fence_after();
             const uint64_t adesc = umma_smem_desc(ring + j * STA);
             const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(kb * ncols * 128));
-            // measured: an SS-mode MMA of this size costs ~60 ns whatever M (64 / 128), N (32 / 128) or the accumulator it
-            // targets (one chain or four interleaved ones) -- the 2 us of a phase's 32 MMAs are a fixed per-instruction
-            // operand-fetch cost; only the A-from-TMEM form (rec_tc.cu: ~6 ns per MMA) avoids it
+            // measured (A/B in one run): an SS-mode MMA of this size costs ~60 ns whatever M (64 / 128), N (32 / 128) or the
+            // accumulator it targets (one chain or four interleaved ones) -- the 2 us of a phase's 32 MMAs are a fixed
+            // per-instruction operand-fetch cost; only the A-from-TMEM form (rec_tc.cu: ~6 ns per MMA) avoids it
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i0 | j | k) != 0 ? 1u : 0u);
@@ -1042,6 +1043,10 @@ int dec_fold_launch(const plas_dec_desc& d, void* workspace, size_t workspace_by
   a.bar = (unsigned*)(ws + pl.ws_off_bar);
   a.dbg = getenv("PLAS_DEBUG") ? (unsigned long long*)(ws + pl.ws_off_dbg) : nullptr;
   a.as = pl.as;
+  {
+    const char* e = getenv("PLAS_DEC_M64");
+    a.m64 = (d.B <= 64 && !(e && atoi(e) == 0)) ? 1 : 0;
+  }
   a.keys_res = pl.keys_res;
   a.n_stages_a = pl.n_stages_a;
   a.stage_a = pl.stage_a;
