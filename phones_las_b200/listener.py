@@ -26,6 +26,7 @@ class ListenerWeights:
 
     def __init__(self, params, hp, num_channels, precision="fp32", device="cuda"):
         _lib.require_cuda()
+        self._params, self._device, self._train_state = params, device, None  # TRAIN mode with dropout: train_state()
         self.pyramidal = bool(hp["use_pyramidal"])
         self.precision = precision
         self.U = U = hp["encoder_units"]
@@ -68,6 +69,17 @@ class ListenerWeights:
                 whh=torch.from_numpy(whh).to(device=device, dtype=dt).contiguous()))
             din = (self.ndir * U * (1 if l == 0 else 2)) if self.pyramidal else U
         self.out_depth = (self.ndir * U * (2 if self.L > 1 else 1)) if self.pyramidal else self.ndir * U
+
+
+def _train_state(self):
+    """The variables as a ``train.TrainState`` (flat fp32 buffer in the TF layout) for the TRAIN-mode kernels; built on first use."""
+    if self._train_state is None:
+        from . import train as tr
+        self._train_state = tr.TrainState({k: v for k, v in self._params.items() if not k.startswith("_")}, device=self._device)
+    return self._train_state
+
+
+ListenerWeights.train_state = _train_state
 
 
 def _gemm(precision, a2d, M, K, lda, wt, bias, out2d):
@@ -219,11 +231,31 @@ def stacked_bilstm(inputs, sequence_length, mode, hparams, weights):
     return (x, lengths), (per_dir if w.ndir == 2 else per_dir[0])
 
 
-def listener(encoder_inputs, source_sequence_length, mode, hparams, weights):
+def _listener_train_dropout(encoder_inputs, source_sequence_length, hparams, weights, step):
+    """TRAIN mode with input dropout (las/ops.py:14-18: DropoutWrapper(input_keep_prob = 1 - dropout) around every cell): the
+    forward pass of the training path's kernels (train.listener_train_fwd; fp32, counter-based masks keyed by
+    hparams['dropout_seed'] and the optimiser ``step``), returned in the operator's output format."""
+    from . import train as tr
+    if weights.precision != "fp32":
+        raise NotImplementedError("TRAIN-mode dropout runs on the fp32 training kernels: build the ListenerWeights with precision='fp32'")
+    st = weights.train_state()
+    if step is not None:
+        st.step = int(step)
+    out, lengths, tape = tr.listener_train_fwd(encoder_inputs, source_sequence_length, st, hparams)
+    ndir = tape[-1]["c_fin"].shape[0]
+    if weights.pyramidal:  # final state of the last layer: (fw, bw) or the single direction's (c, h)
+        per_dir = tuple((tape[-1]["c_fin"][dd], tape[-1]["h_fin"][dd]) for dd in range(ndir))
+        return (out, lengths), (per_dir if ndir == 2 else per_dir[0])
+    per_dir = tuple(tuple((t["c_fin"][dd], t["h_fin"][dd]) for t in tape) for dd in range(ndir))
+    return (out, lengths), (per_dir if ndir == 2 else per_dir[0])
+
+
+def listener(encoder_inputs, source_sequence_length, mode, hparams, weights, step=None):
     """las/model.py:104-142.  ``hparams`` is the flat dict (or the encoder view); ``weights`` a
-    :class:`ListenerWeights`.  mode: 'train' | 'eval' | 'infer' (dropout must be 0 in 'train')."""
+    :class:`ListenerWeights`.  mode: 'train' | 'eval' | 'infer'.  In 'train' with hparams['dropout'] > 0 every LSTM cell
+    input is dropped out (las/ops.py:14-18); ``step`` selects the mask stream (the optimiser step of train.train_step)."""
     if mode == "train" and float(hparams.get("dropout", 0.0)) > 0.0:
-        raise NotImplementedError("input dropout in TRAIN mode (las/ops.py:14-18) is not built yet")
+        return _listener_train_dropout(encoder_inputs, source_sequence_length, hparams, weights, step)
     if not weights.pyramidal:
         return stacked_bilstm(encoder_inputs, source_sequence_length, mode, hparams, weights)
     return pyramidal_bilstm(encoder_inputs, source_sequence_length, mode, hparams, weights)

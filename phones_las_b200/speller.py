@@ -52,6 +52,7 @@ class SpellerWeights:
         by transform_binf_to_phones.  Both are linear, so they fold into the weights the step kernels already read: the V
         embedding rows of cell 0's kernel become M^T W_0[:n], the projection becomes the constant [M; 1 - M] with a zero bias."""
         _lib.require_cuda()
+        self._params, self._device, self._train_state, self.scope = params, device, None, scope  # TRAIN mode: train_state()
         self.binf_projection = binf is not None
         if self.binf_projection:
             if not hp.get("binf_projection") or hp.get("bottom_only"):
@@ -227,6 +228,15 @@ def _init_attention_layer(self, params, hp, enc_depth, precision, device, scope,
     self.tc = False
 
 
+def _train_state(self):
+    """The variables as a ``train.TrainState`` (flat fp32 buffer in the TF layout) for the TRAIN-mode kernels; built on first use."""
+    if self._train_state is None:
+        from . import train as tr
+        self._train_state = tr.TrainState({k: v for k, v in self._params.items() if not k.startswith("_")}, device=self._device)
+    return self._train_state
+
+
+SpellerWeights.train_state = _train_state
 SpellerWeights._init_bottom_only = _init_bottom_only
 SpellerWeights._init_attention_layer = _init_attention_layer
 
@@ -438,11 +448,58 @@ def decode_beam(encoder_outputs, source_sequence_length, w, hp, beam_width, memo
     return out, beam["scores"].view(Bb, W), beam["lengths"].view(Bb, W), seq_len.view(Bb, W), n_steps
 
 
+def _speller_train_stochastic(encoder_outputs, decoder_inputs, source_sequence_length, target_sequence_length, hparams, weights, init,
+                              memory_is_masked, step):
+    """The TRAIN branch with its RNG-driven parts (las/model.py:276-296): scheduled sampling (sampling_probability > 0: after step
+    t a Bernoulli(p) draw decides per utterance whether step t+1 is fed a sample from Categorical(logits_t) instead of the teacher
+    id) and DropoutWrapper input dropout (las/ops.py:14-18).  Runs the forward pass of the training kernels (train.SpellerTrain;
+    fp32; counter-based RNG keyed by hparams['dropout_seed'] and the optimiser ``step``, mirrored in numpy by
+    train.reference_sampling / reference_masks).  sample_id follows the scheduled helpers: the id drawn at step t where the row
+    sampled, -1 otherwise (a draw that equals the teacher id cannot be told apart and reads -1)."""
+    from . import train as tr
+    if weights.precision != "fp32" or getattr(weights, "binf_projection", False):
+        raise NotImplementedError("TRAIN-mode dropout / scheduled sampling run on the fp32 training kernels of the phone speller")
+    L = _lib.lib()
+    st = weights.train_state()
+    if step is not None:
+        st.step = int(step)
+    dev = encoder_outputs.device
+    B, Tm, D = encoder_outputs.shape
+    V = hparams["target_vocab_size"]
+    steps = decoder_inputs.shape[1]
+    if target_sequence_length is not None:
+        steps = min(steps, int(target_sequence_length.max().item()))
+        if hparams.get("max_symbols", -1) and hparams.get("max_symbols", -1) > 0:
+            steps = min(steps, hparams["max_symbols"])
+    ids = decoder_inputs[:, :steps].to(device=dev, dtype=torch.int64).contiguous()
+    mem_len = source_sequence_length.to(device=dev, dtype=torch.int32).contiguous()
+    memory = encoder_outputs.to(torch.float32).contiguous()
+    if not memory_is_masked:
+        masked = torch.empty_like(memory)
+        _lib.check(L.plas_mask_time(_lib.dtype_code("fp32"), _lib.ptr(memory), _lib.ptr(masked), _lib.ptr(mem_len), B, Tm, D, _lib.stream_ptr()))
+        _lib.count_launches(1)
+        memory = masked
+    emb = bool(hparams.get("embedding_size"))
+    table = st.view(f"{weights.scope}/target_embedding") if emb else None
+    x_in = table[ids].contiguous() if emb else torch.nn.functional.one_hot(ids, V).to(torch.float32)
+    sp = tr.SpellerTrain(st, hparams, weights.scope, x_in.shape[2], V, index=0, table=table)
+    logits = sp.forward(memory, mem_len, x_in, initial_state=init, ids=ids)
+    sample_id = torch.full((B, steps), -1, dtype=torch.int32, device=dev)
+    if sp.fed_ids is not None and steps > 1:
+        fed, teach = sp.fed_ids[:, 1:steps].to(torch.int32), ids[:, 1:].to(torch.int32)
+        sample_id[:, :steps - 1] = torch.where(fed != teach, fed, torch.full_like(fed, -1))
+    elif float(hparams.get("sampling_probability", 0.0)) == 0.0:
+        sample_id = logits.argmax(-1).to(torch.int32)  # TrainingHelper
+    n_steps = torch.full((1,), steps, dtype=torch.int32, device=dev)
+    return BasicDecoderOutput(logits, sample_id), SpellerState(None, n_steps), target_sequence_length
+
+
 def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_length, target_sequence_length,
             mode, hparams, weights, binary_outputs=False, binf_embedding=None, transparent_projection=False,
-            memory_is_masked=False, want_alignment=True, trim=True):
-    """las/model.py:205-349.  mode 'train'/'eval' with ``decoder_inputs`` (targets_inputs ids [B,L])
-    runs teacher forcing (TrainingHelper, sampling_probability must be 0); otherwise greedy."""
+            memory_is_masked=False, want_alignment=True, trim=True, step=None):
+    """las/model.py:205-349.  mode 'train'/'eval' with ``decoder_inputs`` (targets_inputs ids [B,L]) runs teacher forcing
+    (TrainingHelper), in 'train' with scheduled sampling when hparams['sampling_probability'] > 0 and input dropout when
+    hparams['dropout'] > 0 (``step`` selects the RNG stream, as in train.train_step); otherwise greedy."""
     if binf_embedding is not None and not getattr(weights, "binf_projection", False):
         raise NotImplementedError("a binf2phone matrix is used by the --binf_projection wiring only: build the SpellerWeights with binf=")
     if binary_outputs or transparent_projection:
@@ -452,10 +509,10 @@ def speller(encoder_outputs, encoder_state, decoder_inputs, source_sequence_leng
     init = None
     if getattr(weights, "pass_hidden_state", False):  # las/model.py:259-267
         init = encoder_state if isinstance(encoder_state[0], (tuple, list)) else (encoder_state,)
+    if mode == "train" and (float(hparams.get("sampling_probability", 0.0)) > 0.0 or float(hparams.get("dropout", 0.0)) > 0.0):
+        return _speller_train_stochastic(encoder_outputs, decoder_inputs, source_sequence_length, target_sequence_length, hparams,
+                                         weights, init, memory_is_masked, step)
     if mode == "train":
-        if float(hparams.get("sampling_probability", 0.0)) > 0.0:
-            raise NotImplementedError("scheduled sampling (las/model.py:279-288) is not built yet; "
-                                      "set sampling_probability=0")
         steps = None
         if target_sequence_length is not None:
             steps = int(target_sequence_length.max().item())

@@ -444,8 +444,10 @@ class SpellerTrain:
         d.drop_seed = drop_seed(self.base, 0, self.tid + 1)  # + step * DROP_STEP_MUL on the device
         d.drop_step = st.step_dev.data_ptr()
         d.sample_prob = self.sample_prob
+        if self.sample_prob > 0.0 and self.fed_ids is not None:  # the ids actually fed (teacher or drawn), step by step
+            d.sample_fed_ids = self.fed_ids.data_ptr()
         if self.sample_prob > 0.0 and self.table is not None:
-            d.sample_table, d.sample_fed_ids = self.table.data_ptr(), self.fed_ids.data_ptr()
+            d.sample_table = self.table.data_ptr()
         d.sample_seed = drop_seed(self.base, 0, self.tid + 9)
         d.xdrop_seed = drop_seed(self.base, 0, self.tid)
         d.x_in_rw = x_in.data_ptr()
@@ -500,6 +502,7 @@ class SpellerTrain:
         L = _lib.lib()
         if self.sample_prob > 0.0 and self.table is not None:
             self.table = self.table.to(torch.float32).contiguous()
+        if self.sample_prob > 0.0 and (self.table is not None or ids is not None):
             self.fed_ids = ids.to(torch.int32).contiguous().clone()
         self.init, self.d_init = None, None
         if self.pass_state and initial_state is not None:

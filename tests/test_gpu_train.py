@@ -893,3 +893,116 @@ def test_train_step_binf_projection_with_scheduled_sampling(multitask, dropout):
     for k in params:
         g = tp[k].grad if tp[k].grad is not None else torch.zeros_like(tp[k])
         assert grad_err(raw[k], g - hp["l2_reg_scale"] * tp[k].detach()) < GRAD_TOL, k
+
+
+@gpu
+def test_data_parallel_replicas_on_real_kernels_match_cross_shard_mean():
+    """Data-parallel order on the REAL kernels (model_helper.py:405-406,416-417): two replicas each run forward + backward + L2 +
+    per-tensor clip on their shard with the 1/world scale, the exchange sums the two flat buffers (what the NCCL all-reduce of
+    bench.py's dp_check does across GPUs), both apply Adam.  The replicas must stay bit-identical and equal Adam on the MEAN of
+    the per-shard clipped gradients of the float64 autograd oracle (not the gradient of the concatenated batch: every shard
+    normalises its loss by its own token count)."""
+    import torch
+    from phones_las_b200 import train as tr
+    hp, params, x, lens, tin, tout, tlen, binf = _full_setup(*FULL_CFGS[0])
+    B = x.shape[0]
+    half = B // 2
+    shards = [(0, half), (half, B)]
+    reps = [tr.TrainState(params), tr.TrainState(params)]
+    binf_d = torch.from_numpy(binf).cuda() if binf is not None else None
+    ref_p = {k: torch.tensor(v, dtype=torch.float64) for k, v in params.items()}
+    ref_m = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    ref_v = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    for step in (1, 2):
+        ref_g = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+        for st, (lo, hi) in zip(reps, shards):
+            feats = {"encoder_inputs": torch.from_numpy(x[lo:hi]).cuda(), "source_sequence_length": torch.from_numpy(lens[lo:hi]).cuda()}
+            labels = {"targets_inputs": torch.from_numpy(tin[lo:hi]).cuda(), "targets_outputs": torch.from_numpy(tout[lo:hi]).cuda(),
+                      "target_sequence_length": torch.from_numpy(tlen[lo:hi]).cuda()}
+            tr.forward_backward(feats, labels, st, hp, binf_d)
+            tr.regularise_and_clip(st, hp, 2)  # g += l2 w; clip_by_norm(g, 2) per tensor; / world
+            tp = {k: v.clone().requires_grad_(True) for k, v in ref_p.items()}
+            rl = dict(targets_inputs=torch.tensor(tin[lo:hi]), targets_outputs=torch.tensor(tout[lo:hi]),
+                      target_sequence_length=torch.tensor(tlen[lo:hi].astype(np.int64)))
+            loss, _ = lt.train_loss(tp, torch.tensor(x[lo:hi], dtype=torch.float64), torch.tensor(lens[lo:hi].astype(np.int64)), rl, hp, binf)
+            loss.backward()
+            for k in ref_g:
+                g = tp[k].grad
+                ref_g[k] += 0.5 * g * (lt.GRAD_NORM / torch.clamp(g.pow(2).sum().sqrt(), min=lt.GRAD_NORM))
+        total = reps[0].grads + reps[1].grads  # the all-reduce (sum of the clipped / world buffers)
+        for st in reps:
+            st.grads.copy_(total)
+            tr.apply_gradients(st, hp, 2, None, clipped=True)
+        assert torch.equal(reps[0].params, reps[1].params), "replicas diverged"
+        # the mean of clipped gradients has per-tensor norm <= 2: the oracle's clip_and_adam leaves it unchanged
+        ref_p, ref_m, ref_v = lt.clip_and_adam(ref_p, ref_g, ref_m, ref_v, step, hp["learning_rate"])
+        got = reps[0].export_params()
+        for k in params:
+            diff = np.abs(got[k] - ref_p[k].numpy())
+            assert diff.max() < 1e-4 and diff.mean() < 1e-6, f"step {step} param {k}: max {diff.max():.3e} mean {diff.mean():.3e}"
+
+
+@gpu
+@pytest.mark.parametrize("pyr,uni", [(True, False), (False, False), (True, True)])
+def test_operator_level_train_mode_listener_dropout(pyr, uni):
+    """listener(..., mode='train') with dropout > 0 (las/ops.py:14-18) through the reference-named operator: same numbers as the
+    training path's forward (whose masks are checked against the oracle above), different from the dropout-free output, and a
+    different mask stream per optimiser step."""
+    import torch
+    from phones_las_b200 import train as tr
+    from phones_las_b200.listener import ListenerWeights, listener
+    C = 5
+    hp = create_hparams(target_vocab_size=12, encoder_layers=2, encoder_units=16, decoder_units=16, decoder_layers=1,
+                        num_channels=C, use_pyramidal=pyr, unidirectional=uni, dropout=0.3, sampling_probability=0.0)
+    params = weights.init_params(hp, seed=3, bias_scale=0.1)
+    x, lens = synth.synth_features(4, 13, C, var_len=True)
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lens).cuda()
+    w = ListenerWeights(params, hp, C, "fp32")
+    (out, olen), state = listener(xd, ld, "train", hp, w, step=2)
+    st = tr.TrainState(params)
+    st.step = 2
+    ref_out, ref_len, tape = tr.listener_train_fwd(xd, ld, st, hp)
+    assert torch.equal(out, ref_out) and torch.equal(olen, ref_len)
+    (out_eval, _), state_eval = listener(xd, ld, "eval", hp, w)
+    assert out_eval.shape == out.shape and not torch.allclose(out_eval.float(), out)
+    (out3, _), _ = listener(xd, ld, "train", hp, w, step=3)
+    assert not torch.equal(out3, out)
+    flat = lambda s: [t for e in s for t in (flat(e) if isinstance(e, tuple) else [e])]
+    assert [t.shape for t in flat(state)] == [t.shape for t in flat(state_eval)]  # same nesting as the inference operator
+
+
+@gpu
+def test_operator_level_train_mode_speller_scheduled_sampling_and_dropout():
+    """speller(..., mode='train') with sampling_probability > 0 and dropout > 0 (las/model.py:279-288, las/ops.py:14-18) runs the
+    training kernels' forward: identical logits to train.SpellerTrain on the same step, sampled ids reported where the fed id
+    differs from the teacher's."""
+    import torch
+    from phones_las_b200 import train as tr
+    from phones_las_b200.speller import SpellerWeights, speller
+    V, B, Tm, S = 14, 6, 11, 7
+    hp = create_hparams(target_vocab_size=V, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=2, num_channels=4,
+                        attention_type="bahdanau", dropout=0.2, sampling_probability=0.5)
+    params = weights.init_params(hp, seed=5, projection_scale=4.0, bias_scale=0.1)
+    D = weights.encoder_output_depth(hp)
+    rng = np.random.default_rng(1)
+    enc = rng.uniform(-1, 1, (B, Tm, D)).astype(np.float32)
+    lens = np.maximum(1, (rng.uniform(0.4, 1.0, B) * Tm).astype(np.int32))
+    tin, tout, tlen = synth.synth_labels(B, S - 1, V, seed=4)
+    w = SpellerWeights(params, hp, D, "fp32")
+    enc_d, len_d, tin_d, tlen_d = (torch.from_numpy(a).cuda() for a in (enc, lens, tin, tlen))
+    out, state, seq_len = speller(enc_d, None, tin_d, len_d, tlen_d, "train", hp, w, step=1)
+    st = tr.TrainState(params)
+    st.step = 1
+    mask = (torch.arange(Tm, device="cuda")[None, :] < len_d[:, None]).unsqueeze(-1)
+    sp = tr.SpellerTrain(st, hp, "speller", V, V)
+    ids = tin_d[:, :int(tlen.max())].long()
+    ref = sp.forward((enc_d * mask).contiguous(), len_d.int(), torch.nn.functional.one_hot(ids, V).float(), ids=ids)
+    assert torch.equal(out.rnn_output, ref)
+    sid = out.sample_id.cpu().numpy()
+    assert sid.shape == ids.shape and (sid[:, -1] == -1).all()
+    fed = sp.fed_ids.cpu().numpy()
+    drawn = fed[:, 1:] != tin[:, 1:fed.shape[1]]
+    assert drawn.any() and (sid[:, :-1][drawn] == fed[:, 1:][drawn]).all() and (sid[:, :-1][~drawn] == -1).all()
+    hp0 = dict(hp, sampling_probability=0.0, dropout=0.0)
+    out0, _, _ = speller(enc_d, None, tin_d, len_d, tlen_d, "train", hp0, w)
+    assert not torch.allclose(out0.rnn_output[:, :ref.shape[1]].float(), ref)
