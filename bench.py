@@ -469,7 +469,7 @@ def train_problem(cfg, B, seed):
     hp = dict(cfg["hp"])
     # dropout 0.2 as in the reference's defaults (utils/params_utils.py:36; counter-based masks);
     # scheduled sampling exists for the phone speller only (the reference's binary-feature variant is ill-defined): 0 here
-    hp.update(dropout=0.2, sampling_probability=0.0, binf_count=N_BINF)
+    hp.update(dropout=0.2, sampling_probability=0.0, binf_count=N_BINF, replica_id=int(os.environ.get("RANK", "0")))
     feats, lens = synth.synth_features(B, cfg["T"], cfg["C"], seed=seed)
     tin, tout, tlen = synth.synth_labels(B, N_LABELS, hp["target_vocab_size"], seed=seed + 1)
     binf = (np.random.default_rng(5).uniform(size=(N_BINF, hp["target_vocab_size"])) < 0.3).astype(np.float32)

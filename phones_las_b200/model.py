@@ -189,12 +189,16 @@ class LASModel:
                                                         "bufs": [None, None], "pinned": [None, None]})
         copy_stream, bufs, pinned = st["copy_stream"], st["bufs"], st["pinned"]
         consumed = [None, None]  # "kernels are done with the staging buffer" events of this call
-        torch.cuda.current_stream().synchronize()  # buffers may still be in use by an earlier call
+        main_stream = torch.cuda.current_stream()
+        main_stream.synchronize()  # buffers may still be in use by an earlier call
 
         def stage(hw, slot):
-            if bufs[slot] is None or bufs[slot].shape != hw.shape:
-                bufs[slot] = torch.empty(hw.shape, dtype=torch.float32, device=dev)
             with torch.cuda.stream(copy_stream):
+                if bufs[slot] is None or bufs[slot].shape != hw.shape:
+                    # allocated under the copy stream: a block the caching allocator hands out here is then ordered after its
+                    # previous owner's work on THIS stream, and main-stream kernels never saw it
+                    copy_stream.wait_stream(main_stream)
+                    bufs[slot] = torch.empty(hw.shape, dtype=torch.float32, device=dev)
                 if consumed[slot] is not None:
                     copy_stream.wait_event(consumed[slot])  # do not overwrite a batch that is still being read
                 bufs[slot].copy_(hw, non_blocking=True)
@@ -225,7 +229,11 @@ class LASModel:
             done = torch.cuda.Event()
             done.record(main)
             consumed[slot] = done
-            ids_d, len_d, n_d = pred["sample_ids"], pred["final_sequence_length"], pred["n_steps"]
+            if int(self.hp.get("beam_width", 0) or 0) > 0:
+                raise NotImplementedError("transcribe_stream serves greedy decoding (beam search returns [B, T, W] ids: use transcribe)")
+            key, klen = (("sample_ids", "final_sequence_length") if "sample_ids" in pred
+                         else ("sample_ids_phones_binf", "final_sequence_length_binf"))  # --binf_projection without --multitask
+            ids_d, len_d, n_d = pred[key], pred[klen], pred["n_steps"]
             if pinned[slot] is None or pinned[slot][0].shape != ids_d.shape:
                 pinned[slot] = (torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory(),
                                 torch.empty(len_d.shape, dtype=len_d.dtype).pin_memory(),

@@ -285,10 +285,11 @@ def _shape_from_proto(buf):
     return tuple(dims)
 
 
-def read_checkpoint(prefix, verify=True, names=None):
+def read_checkpoint(prefix, verify=True, names=None, skip_unsupported=False):
     """``prefix`` = path without the .index / .data-* suffix (e.g. model_dir/model.ckpt-1234).
     -> {variable_name: ndarray}; ``names`` (iterable or predicate) restricts what is loaded (optimizer slots are skipped with
-    ``names=lambda n: not n.endswith(('/Adam', '/Adam_1'))``)."""
+    ``names=lambda n: not n.endswith(('/Adam', '/Adam_1'))``).  ``skip_unsupported``: entries whose dtype is not numeric
+    (string / resource entries a TF saver adds) are ignored instead of raising."""
     table = read_table(prefix + ".index", verify)
     if not table or table[0][0] != b"":
         raise ValueError("bundle header missing")
@@ -307,6 +308,10 @@ def read_checkpoint(prefix, verify=True, names=None):
             raise ValueError(f"{name}: partitioned variables (slices) are not supported")
         dt = _DTYPES.get(e.get(1, [0])[0])
         if dt is None:
+            # non-numeric saver entries (DT_STRING such as _CHECKPOINTABLE_OBJECT_GRAPH, resource handles, ...) carry no model
+            # variable: skipped unless the caller asked for this very name
+            if skip_unsupported and not (names is not None and not callable(names) and name in set(names)):
+                continue
             raise ValueError(f"{name}: unsupported dtype code {e.get(1, [0])[0]}")
         shape = _shape_from_proto(e[2][0]) if 2 in e else ()
         shard, off, size = e.get(3, [0])[0], e.get(4, [0])[0], e.get(5, [0])[0]
@@ -365,5 +370,6 @@ def load_model_variables(model_dir):
     if prefix is None:
         raise FileNotFoundError(f"no checkpoint state file in {model_dir}")
     skip = ("/Adam", "/Adam_1")
-    v = read_checkpoint(prefix, names=lambda n: not n.endswith(skip) and n not in ("global_step", "beta1_power", "beta2_power"))
+    v = read_checkpoint(prefix, names=lambda n: not n.endswith(skip) and n not in ("global_step", "beta1_power", "beta2_power"),
+                        skip_unsupported=True)
     return {k: np.asarray(a, np.float32) for k, a in v.items() if a.dtype.kind == "f"}

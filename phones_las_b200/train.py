@@ -51,6 +51,13 @@ def colsum(X, M, N, ld, out, accumulate=False):
 # --------------------------------------------------------------------------------------------------------------
 # input dropout (DropoutWrapper(input_keep_prob = 1 - dropout) around every LSTMCell in TRAIN, las/ops.py:14-18)
 # --------------------------------------------------------------------------------------------------------------
+def seed_base(hp):
+    """Base seed of the dropout masks, scheduled-sampling draws and attention noise of THIS replica: data-parallel ranks set
+    hp['replica_id'] = rank so that their masks decorrelate, as independent workers' would.  The periodic weight noise
+    (--add_noise) keeps the plain hp['dropout_seed']: it must be identical on every rank or the replicas would diverge."""
+    return (int(hp.get("dropout_seed", 0)) + 1000003 * int(hp.get("replica_id", 0) or 0)) & 0xFFFFFFFF
+
+
 def drop_seed(base, step, tensor_id):
     """32-bit seed of one dropped-out tensor at one optimiser step."""
     return int((int(base) * 0x9E3779B1 + int(step) * 0x85EBCA77 + int(tensor_id) * 0xC2B2AE3D + 0x165667B1) & 0xFFFFFFFF)
@@ -77,7 +84,7 @@ def dropout_mask(n, seed, keep_prob):
 def reference_sampling(hp, step, B, S, V, speller_index=0):
     """Scheduled-sampling randomness of the device path at optimiser step ``step`` (test support): ``selected`` [B,S] bool (row b
     replaces its input of step t+1 by a sample drawn at step t) and the Gumbel noise [B,S,V] added to the logits of step t."""
-    base = int(hp.get("dropout_seed", 0))
+    base = seed_base(hp)
     seed = drop_seed(base, step, SPELLER_TID + 10 * speller_index + 9)
     p = np.uint32(np.float32(hp["sampling_probability"]) * np.float32(16777216.0))
     selected = (hash_u24(B * S, seed) < p).reshape(B, S)
@@ -89,7 +96,7 @@ def reference_noise(hp, step, B, S, Tm, speller_index=0, scale=1.0):
     """bahdanau_monotonic's TRAIN-mode score noise (las/model.py:161-162, sigmoid_noise = 1) as the device path draws it at
     optimiser step ``step`` (test support): scale * N(0,1) [B,S,Tm], Box-Muller on two counter-hash uniforms (hash_normal in
     csrc/train_dec.cu)."""
-    seed = drop_seed(int(hp.get("dropout_seed", 0)), step, SPELLER_TID + 10 * speller_index + 8)
+    seed = drop_seed(seed_base(hp), step, SPELLER_TID + 10 * speller_index + 8)
     n = B * S * Tm
     u1 = (hash_u24(n, seed).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
     u2 = (hash_u24(n, (seed + 1) & 0xFFFFFFFF).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
@@ -113,7 +120,7 @@ def reference_masks(hp, step, B, T, C, S, binf_count=0):
     """The multipliers the device path applies at optimiser step ``step``, as numpy arrays keyed like oracle/las_torch.py's
     ``masks`` argument (test support: lets the CPU oracle replay the stochastic op on identical masks)."""
     keep = 1.0 - float(hp.get("dropout", 0.0))
-    base = int(hp.get("dropout_seed", 0))
+    base = seed_base(hp)
     U, V, Ud = hp["encoder_units"], hp["target_vocab_size"], hp["decoder_units"]
     out = {"listener": {}}
     ndir, pyr = (1 if hp.get("unidirectional") else 2), bool(hp.get("use_pyramidal", True))
@@ -290,7 +297,7 @@ def listener_train_fwd(x, lengths, st, hp):
     lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
     x = x.to(torch.float32).contiguous()
     keep = 1.0 - float(hp.get("dropout", 0.0))
-    base = int(hp.get("dropout_seed", 0))
+    base = seed_base(hp)
     tape = []
     for l in range(hp["encoder_layers"]):
         T, width = x.shape[1], x.shape[2]
@@ -409,7 +416,7 @@ class SpellerTrain:
             assert int(hp.get("attention_layer_size") or 0) == self.proj_const.shape[0] and n_out == M.shape[1]
         self.keep = 1.0 - float(hp.get("dropout", 0.0))
         self.tid = SPELLER_TID + 10 * index
-        self.base = int(hp.get("dropout_seed", 0))
+        self.base = seed_base(hp)
         self.init = self.d_init = None
         # scheduled sampling (las/model.py:279-288): the phone speller draws ids from its own logits; the binary-feature
         # speller's ScheduledSigmoidHelper path of the reference is shape-inconsistent and is not built

@@ -298,3 +298,28 @@ def test_predict_with_beam_search_returns_predicted_ids():
     ref = ol.Speller(np.repeat(enc, 3, 0), np.repeat(enc_len, 3, 0), params, hp, "fp32").beam_search(3)
     assert ref[0].shape[1] == n
     np.testing.assert_array_equal(pred["sample_ids"][:, :, 0].cpu().numpy(), ref[0][:, :, 0])  # the best hypothesis
+
+
+@gpu
+def test_exported_model_serves_the_signature(tmp_path):
+    """export.py workflow: model_dir -> export_saved_model -> ServingModel.predict must return the serving signature's outputs
+    (sample_ids, alignment, probs) identical to las_predict on the original variables."""
+    import torch
+    from phones_las_b200 import export, tf_checkpoint as tc
+    from phones_las_b200.model import DeviceWeights, las_predict
+    model_dir = str(tmp_path / "model")
+    hp = create_hparams(target_vocab_size=20, encoder_layers=2, encoder_units=16, decoder_layers=1, decoder_units=32,
+                        attention_type="luong", num_channels=6, model_dir=model_dir)
+    params = weights.init_params(hp, 6, seed=9, projection_scale=8.0, bias_scale=0.1)
+    tc.write_checkpoint(f"{model_dir}/model.ckpt-1", params)
+    path = export.export_saved_model(model_dir, str(tmp_path / "export"), 6)
+    served = export.ServingModel(path, "fp32")
+    x, lens = synth.synth_features(4, 21, 6, seed=4, var_len=True)
+    got = served.predict({"encoder_inputs": x, "source_sequence_length": lens})
+    ref = las_predict({"encoder_inputs": torch.from_numpy(x).cuda(), "source_sequence_length": torch.from_numpy(lens).cuda()}, hp,
+                      DeviceWeights(params, hp, 6, "fp32"))
+    assert set(got) == {"sample_ids", "alignment", "probs"}
+    for k in got:
+        assert torch.equal(got[k], ref[k]), k
+    with pytest.raises(ValueError):
+        served.predict({"encoder_inputs": x[:, :, :5], "source_sequence_length": lens})

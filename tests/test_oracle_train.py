@@ -323,3 +323,18 @@ def test_monotonic_attention_backward_kernel_model_matches_autograd():
         ds, dprev = km.monotonic_attention_backward(p.detach().numpy(), prev.detach().numpy(), da.numpy(), length)
         np.testing.assert_allclose(ds, score.grad.numpy(), rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(dprev, prev.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_replica_id_decorrelates_dropout_but_not_weight_noise():
+    """Data-parallel ranks set hp['replica_id']: dropout / sampling masks differ per replica, the weight-noise seed (which has
+    to stay identical on every rank) does not depend on it."""
+    from phones_las_b200 import train as tr
+    hp0 = create_hparams(target_vocab_size=12, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=1, num_channels=5,
+                         dropout=0.3, sampling_probability=0.2)
+    hp0["dropout_seed"] = 11
+    hp1 = dict(hp0, replica_id=1)
+    m0, m1 = tr.reference_masks(hp0, 1, 3, 10, 5, 6), tr.reference_masks(hp1, 1, 3, 10, 5, 6)
+    k = sorted(m0["listener"])[0]
+    assert not np.array_equal(m0["listener"][k], m1["listener"][k])
+    assert tr.seed_base(hp0) != tr.seed_base(hp1) and tr.seed_base(hp0) == 11
+    assert tr.drop_seed(int(hp0["dropout_seed"]), 4, tr.WEIGHT_NOISE_TID) == tr.drop_seed(int(hp1["dropout_seed"]), 4, tr.WEIGHT_NOISE_TID)

@@ -67,3 +67,47 @@ def test_checkpoint_round_trip_under_reference_names(tmp_path):
     open(prefix + ".data-00000-of-00001", "wb").write(bytes(data))
     with pytest.raises(ValueError):
         tfc.read_checkpoint(prefix)
+
+
+def test_non_numeric_saver_entries_are_skipped_when_loading_model_variables(tmp_path):
+    """A TF saver adds DT_STRING entries (e.g. _CHECKPOINTABLE_OBJECT_GRAPH) next to the variables: load_model_variables must
+    ignore them; read_checkpoint without skip_unsupported still refuses what it cannot decode."""
+    import pytest
+    from phones_las_b200 import tf_checkpoint as tc
+    prefix = str(tmp_path / "model.ckpt-7")
+    tc.write_checkpoint(prefix, {"listener/w": np.arange(6, dtype=np.float32).reshape(2, 3), "global_step": np.int64(7)})
+    # append a DT_STRING (7) entry to the index by rewriting it through the module's own table writer
+    table = tc.read_table(prefix + ".index")
+    entry = tc._field(1, 0, tc._put_varint(7)) + tc._field(2, 2, b"") + tc._field(4, 0, tc._put_varint(0)) + tc._field(5, 0, tc._put_varint(0))
+    table = sorted(table + [(b"_CHECKPOINTABLE_OBJECT_GRAPH", entry)], key=lambda kv: kv[0])
+    tc.write_table(prefix + ".index", table)
+    with pytest.raises(ValueError):
+        tc.read_checkpoint(prefix)
+    got = tc.read_checkpoint(prefix, skip_unsupported=True)
+    assert set(got) == {"listener/w", "global_step"}
+    mv = tc.load_model_variables(str(tmp_path))
+    assert set(mv) == {"listener/w"} and np.array_equal(mv["listener/w"], np.arange(6, dtype=np.float32).reshape(2, 3))
+
+
+def test_export_saved_model_directory_layout_and_signature(tmp_path):
+    """export.py:57-79 on this runtime: model_dir (hparams.json + checkpoint) -> export_dir/<timestamp>/{variables/variables.*,
+    hparams.json, signature.json}; only listener/ and speller/ variables travel; the signature is export.py:39-65's."""
+    import json
+    from phones_las_b200 import export, tf_checkpoint as tc, weights
+    from phones_las_b200.hparams import create_hparams, load_hparams
+    model_dir = str(tmp_path / "model")
+    hp = create_hparams(target_vocab_size=12, encoder_layers=2, encoder_units=8, decoder_units=16, decoder_layers=1, num_channels=5,
+                        model_dir=model_dir)
+    params = weights.init_params(hp, 5, seed=1)
+    extra = {"ctc_logits/kernel": np.zeros((32, 13), np.float32), "global_step": np.int64(3)}
+    extra.update({k + "/Adam": np.zeros_like(v) for k, v in params.items()})
+    tc.write_checkpoint(os.path.join(model_dir, "model.ckpt-3"), dict(params, **extra))
+    out = export.export_saved_model(model_dir, str(tmp_path / "export"), 5, timestamp=1700000000)
+    assert out.endswith("1700000000") and os.path.exists(os.path.join(out, "variables", "variables.index"))
+    got = tc.read_checkpoint(os.path.join(out, "variables", "variables"))
+    assert set(got) == set(params) and all(np.array_equal(got[k], params[k]) for k in params)
+    sig = json.load(open(os.path.join(out, "signature.json")))["serving_default"]
+    assert sig["inputs"]["encoder_inputs"] == {"dtype": "float32", "shape": [None, None, 5]}
+    assert sig["inputs"]["source_sequence_length"] == {"dtype": "int32", "shape": [None]}
+    assert set(sig["outputs"]) == {"sample_ids", "alignment", "probs"} and sig["method_name"] == "tensorflow/serving/predict"
+    assert load_hparams(out)["decoder_units"] == 16
