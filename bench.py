@@ -617,6 +617,7 @@ def ours_train(args):
     dp = dp_check(world, rank, dev, st, step, batches, parallel) if world > 1 else None
     if rank != 0:
         return None
+    fam = train_gemm_family(cfg, hp, B, dev)
     peaks = load_peaks()
     # dominant family: the fp32 GEMMs (projections, input and weight gradients); algorithmic flops of the listener part
     U, L, T, C = hp["encoder_units"], hp["encoder_layers"], cfg["T"], cfg["C"]
@@ -626,14 +627,15 @@ def ours_train(args):
         din = 2 * U if l == 0 else 4 * U
         if l != 0:
             t = (t + 1) // 2
-    gemm_ms = sum(stage_ms.get(k, 0.0) for k in ("train_inproj", "train_wgrad", "train_dgrad"))
-    fp32_peak = FP32_PEAK_TFLOPS  # the bound of an exact-fp32 GEMM
     dom = max(stage_ms, key=lambda k: stage_ms[k])
-    roofline = {"kernel": "gemm_f32_ex_kernel (train_inproj + train_wgrad + train_dgrad)", "bound": "fp32-pipe",
-                "achieved": fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": (fl / (gemm_ms * 1e-3) / 1e12) / fp32_peak if gemm_ms else None, "traffic": None,
-                "peak_source": "148 SMs x 128 FFMA/clk x 2 x 1.965 GHz (exact-fp32 SIMT path; the reference trains in fp32)",
-                "share_of_step": gemm_ms / sum(stage_ms.values()), "largest_stage": dom}
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # kind::tf32 runs at half the bf16 rate; the 3x split is counted as work done
+    roofline = {"kernel": "gemm_tf32x3_tcgen05_kernel (+ split3 kernels): listener projections, input and weight gradients",
+                "bound": "tensor", "achieved": 3.0 * fam["flops"] / (fam["tf32x3_ms"] * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": 3.0 * fam["flops"] / (fam["tf32x3_ms"] * 1e-3) / 1e12 / tf32_peak, "traffic": None,
+                "peak_source": peaks["_source"] + " (sustained bf16 figure / 2 for tf32)",
+                "share_of_step": fam["tf32x3_ms"] / ms, "largest_stage": dom,
+                "note": "achieved = 3 x fp32-equivalent flops (the three TF32 products) / device time of the family incl. its split kernels; "
+                        "the step is bound by the latency of its recurrences and per-step decoder kernels, not by this family"}
     line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": train_config_dict(cfg, hp, B, world, weights="random init, seed 4321, TF variable layout",
@@ -641,6 +643,7 @@ def ours_train(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "stages": {k: {"ms_per_step": v} for k, v in stage_ms.items()}, "loss": loss_last, "loss_e2e": loss_host,
             "trainable_parameters": int(sum(st.sizes))}
+    line["gemm_family"] = fam
     if dp is not None:
         line["dp_check"] = dp
     if world == 1 and not args.no_cpu_baseline:
@@ -649,6 +652,76 @@ def ours_train(args):
                                 "sample": f"{args.cpu_batch} utterances x {cfg['seconds']:.0f} s, one training step ({dt:.1f} s), torch-CPU fp32 "
                                           f"restatement of the TRAIN graph (oracle/las_torch.py; TF 1.15 not installable)"}
     return line
+
+
+def train_gemm_family(cfg, hp, B, dev, reps=5):
+    """Device time of the listener's contraction family of ONE training step (x W + b, dZ W^T, X^T dZ and h^T dZ for every layer
+    and direction, the LSTMCell matmul of las/ops.py:11-12 and its gradients), each problem timed back to back with CUDA events:
+    the exact-fp32 SIMT kernel (plas_gemm_f32_ex) vs the 3xTF32 tensor-core path (operand splits + plas_gemm_tf32x3_tn)."""
+    import torch
+    from phones_las_b200 import train as tr
+    U, L, ndir = hp["encoder_units"], hp["encoder_layers"], (1 if hp["unidirectional"] else 2)
+    probs, t, din = [], cfg["T"], cfg["C"]
+    for l in range(L):
+        M = B * t
+        for _ in range(ndir):
+            probs.append(("fwd", M, 4 * U, din))
+            if l > 0:
+                probs.append(("dgrad", M, din, 4 * U))
+            probs.append(("wgrad", din, 4 * U, M))
+            probs.append(("wgrad", U, 4 * U, M))
+        din = 2 * U if l == 0 else 4 * U
+        if l != 0:
+            t = (t + 1) // 2
+    g = torch.Generator(device=dev).manual_seed(7)
+    rnd = lambda *sh: torch.randn(sh, generator=g, device=dev, dtype=torch.float32)
+    out = {"simt_ms": 0.0, "tf32x3_ms": 0.0, "flops": 0.0}
+    split_ws = torch.empty((64 << 20,), dtype=torch.uint8, device=dev)
+    for kind, M, N, K in probs:
+        if kind == "fwd":      # C[M][N] = A[M][K] W[K][N] + b
+            a, w, bias = rnd(M, K + (-K) % 4), rnd(K, N), rnd(N)
+            lda = a.shape[1]
+            simt = lambda: tr.gemm_ex(M, N, K, a.data_ptr(), lda, 1, w.data_ptr(), N, 1, c.data_ptr(), N, bias=bias.data_ptr())
+            def tc():
+                a3, seg = tr.split3(a.data_ptr(), M, K, lda, 0, False, dev)
+                b3, _ = tr.split3(w.data_ptr(), K, N, N, 1, True, dev)
+                tr.gemm_tc(a3, b3, M, N, seg, c.data_ptr(), N, bias=bias.data_ptr())
+        elif kind == "dgrad":  # C[M][N] = dZ[M][K] W[N][K]^T
+            a, w = rnd(M, K), rnd(N, K)
+            simt = lambda: tr.gemm_ex(M, N, K, a.data_ptr(), K, 1, w.data_ptr(), 1, K, c.data_ptr(), N)
+            def tc():
+                a3, seg = tr.split3(a.data_ptr(), M, K, K, 0, False, dev)
+                b3, _ = tr.split3(w.data_ptr(), N, K, K, 1, False, dev)
+                tr.gemm_tc(a3, b3, M, N, seg, c.data_ptr(), N)
+        else:                  # C[M][N] = X[K][M]^T dZ[K][N]
+            a, w = rnd(K, M + (-M) % 4), rnd(K, N)
+            lda = a.shape[1]
+            simt = lambda: tr.gemm_ex(M, N, K, a.data_ptr(), 1, lda, w.data_ptr(), N, 1, c.data_ptr(), N, split_ws=split_ws)
+            def tc():
+                b3, seg = tr.split3(w.data_ptr(), K, N, N, 1, True, dev)
+                a3, _ = tr.split3(a.data_ptr(), K, M, lda, 0, True, dev)
+                tr.gemm_tc(a3, b3, M, N, seg, c.data_ptr(), N)
+        c = torch.empty((M, N), dtype=torch.float32, device=dev)
+        for name, fn in (("simt_ms", simt), ("tf32x3_ms", tc)):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.graphs.graph(gr := torch.cuda.CUDAGraph()):  # graph replay: device time without host launch gaps
+                fn()
+            e0.record()
+            for _ in range(reps):
+                gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] += e0.elapsed_time(e1) / reps
+        out["flops"] += 2.0 * M * N * K
+        del a, w, c
+    out["speedup"] = out["simt_ms"] / out["tf32x3_ms"]
+    out["simt_tflops"] = out["flops"] / (out["simt_ms"] * 1e-3) / 1e12
+    out["tf32x3_tflops_fp32_equivalent"] = out["flops"] / (out["tf32x3_ms"] * 1e-3) / 1e12
+    out["problems"] = len(probs)
+    out["note"] = "tf32x3 time includes the operand split / transpose kernels; flops counted once (fp32-equivalent), the tensor pipe does 3x"
+    return out
 
 
 def dp_check(world, rank, dev, st, step, batches, parallel):
@@ -808,7 +881,7 @@ def parity_quotes():
 
 
 def compact(line, keys=("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "dtype", "config", "e2e", "gpu_launches",
-                        "roofline", "stages", "dp_check", "variants", "loss")):
+                        "roofline", "stages", "dp_check", "gemm_family", "variants", "loss")):
     return {k: line[k] for k in keys if k in line}
 
 

@@ -235,6 +235,21 @@ typedef struct plas_gemm_ex_desc {
   size_t split_ws_bytes;
 } plas_gemm_ex_desc;
 int plas_gemm_f32_ex(const plas_gemm_ex_desc* d, plas_stream_t stream);
+/* The same contractions on the tensor pipe with fp32-level accuracy (3xTF32, north_star item 2): every fp32 operand is split
+ * into hi = nearest TF32 and lo = x - hi, and  a.b ~= a_hi.b_hi + a_lo.b_hi + a_hi.b_lo  is ONE tcgen05 kind::tf32 GEMM over a
+ * concatenated contraction axis, [A_hi | A_lo | A_hi] . [B_hi | B_hi | B_lo]^T (gemm_tf32.cu).
+ * plas_split3_f32 writes such an operand: out[r][seg*seg_ld + c] for seg = 0..2 from X[r][c] (transpose = 0, seg_ld >= cols), or
+ * out[c][seg*seg_ld + r] (transpose = 1, seg_ld >= rows: turns X^T dZ / x W on the TF layouts into the TN form below); columns
+ * past the data are zero; pattern 0 = (hi, lo, hi) for the left operand, 1 = (hi, hi, lo) for the right one.
+ * plas_gemm_tf32x3_tn: C[M][N] (+)= A3[M][K3] . B3[N][K3]^T (+ bias[N]); K3 = 3*seg_ld; lda/ldb/ldc multiples of 4, 16-byte bases.
+ * Problems with few output tiles and a long contraction (weight gradients) are cut into K slices whose partial tiles go to the
+ * caller's scratch and are added in a fixed order (deterministic). */
+int plas_split3_f32(const float* X, int64_t rows, int32_t cols, int64_t ld, float* out, int64_t ld_out, int64_t seg_ld,
+                    int32_t pattern, int32_t transpose, plas_stream_t stream);
+size_t plas_gemm_tf32x3_scratch_bytes(int64_t M, int32_t N, int32_t K3); /* split-K scratch (few output tiles, long K); 0 = none */
+int plas_gemm_tf32x3_tn(const float* A3, int64_t M, int32_t K3, int64_t lda, const float* B3, int32_t N, int64_t ldb,
+                        const float* bias, float* C, int64_t ldc, int32_t accumulate, void* scratch, size_t scratch_bytes,
+                        plas_stream_t stream);
 /* out[n] (+)= sum_m X[m][n]: bias gradients. */
 int plas_colsum_f32(const float* X, int64_t M, int32_t N, int64_t ld, float* out, int32_t accumulate,
                     plas_stream_t stream);

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libplas.so")
-SOURCES = ["common.cu", "frontend.cu", "gemm.cu", "rec.cu", "decoder.cu", "decoder_tc.cu", "decoder_fold.cu", "rec_tc.cu", "losses.cu",
+SOURCES = ["common.cu", "frontend.cu", "gemm.cu", "gemm_tf32.cu", "rec.cu", "decoder.cu", "decoder_tc.cu", "decoder_fold.cu", "rec_tc.cu", "losses.cu",
            "train_gemm.cu", "train_rec.cu", "train_dec.cu", "train_loss.cu"]
 HEADERS = ["common.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "plas.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -147,6 +147,8 @@ def _bilstm_layer_f32(x, lengths, lw, U, ndir, t_alloc_out, per_direction_input)
     B, T, K = x.shape
     din = U if per_direction_input else K
     z = torch.empty((B, T, ndir, 4 * U), dtype=torch.float32, device=x.device)
+    # exact-fp32 SIMT GEMM on purpose: the 3xTF32 tensor-core GEMM of the training path (train.gemm_tc) is 2^-21-accurate per
+    # product, which after three recurrent layers measures 1.4e-5 on encoder_out -- above this mode's 1e-5 bar
     with _lib.stage("inproj_gemm"):
         for dd in range(ndir):
             gemm_ex(B * T, 4 * U, din, x.data_ptr() + (4 * dd * U if per_direction_input else 0), K, 1, lw["tf_kernel"][dd].data_ptr(),

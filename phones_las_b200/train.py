@@ -14,6 +14,7 @@ model exports to the reference's variable names unchanged.  All arithmetic runs 
 C-ABI; torch only owns memory, streams and the process group.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -41,6 +42,43 @@ def gemm_ex(M, N, K, A, sam, sak, B, sbk, sbn, Cp, ldc, bias=None, beta=0.0, alp
         d.split_ws, d.split_ws_bytes = split_ws.data_ptr(), split_ws.numel() * split_ws.element_size()
     _lib.check(_lib.lib().plas_gemm_f32_ex(C.byref(d), _lib.stream_ptr()))
     _lib.count_launches(1)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the big contractions of the listener on the tensor pipe: 3xTF32 (csrc/gemm_tf32.cu).  The operands are split (and, where
+# the TF layout asks for it, transposed) into [hi | lo | hi] / [hi | hi | lo] copies first, so every product is the same TN
+# tcgen05 GEMM over a 3x longer contraction axis.  Small or oddly aligned problems stay on the exact-fp32 SIMT kernel.
+# --------------------------------------------------------------------------------------------------------------
+TC_MIN_FLOPS = 1.0e8
+
+
+def use_tc(M, N, K, *ptrs_lds):
+    if os.environ.get("PLAS_TRAIN_GEMM") == "simt" or 2.0 * M * N * K < TC_MIN_FLOPS:
+        return False
+    return all(int(v) % 4 == 0 for v in ptrs_lds)  # 16-byte aligned bases (addresses are passed / 4) and leading dimensions
+
+
+def split3(X, rows, cols, ld, pattern, transpose, device):
+    """-> (tensor [rows or cols][3 * seg], seg): the [hi | lo | hi] (pattern 0) / [hi | hi | lo] (pattern 1) TF32 split of the
+    fp32 matrix at device address X, optionally transposed; seg = contraction length rounded up to a whole k block."""
+    inner = rows if transpose else cols
+    seg = (inner + 31) // 32 * 32
+    out = torch.empty((cols if transpose else rows, 3 * seg), dtype=torch.float32, device=device)
+    _lib.check(_lib.lib().plas_split3_f32(C.c_void_p(X), rows, cols, ld, _lib.ptr(out), 3 * seg, seg, pattern, 1 if transpose else 0,
+                                          _lib.stream_ptr()))
+    _lib.count_launches(1)
+    return out, seg
+
+
+def gemm_tc(A3, B3, M, N, seg, Cp, ldc, bias=None, accumulate=False):
+    """C[M][N] (+)= A3 . B3^T (+ bias) on pre-split operands."""
+    L = _lib.lib()
+    need = L.plas_gemm_tf32x3_scratch_bytes(M, N, 3 * seg)
+    ws = torch.empty((need,), dtype=torch.uint8, device=A3.device) if need else None
+    _lib.check(L.plas_gemm_tf32x3_tn(_lib.ptr(A3), M, 3 * seg, A3.shape[1], _lib.ptr(B3), N, B3.shape[1],
+                                     C.c_void_p(bias) if bias else None, C.c_void_p(Cp), ldc, 1 if accumulate else 0,
+                                     _lib.ptr(ws), need, _lib.stream_ptr()))
+    _lib.count_launches(2 if need else 1)
 
 
 def colsum(X, M, N, ld, out, accumulate=False):
@@ -309,8 +347,14 @@ def listener_train_fwd(x, lengths, st, hp):
         xs = [dropout_(x, torch.empty_like(x), seeds[dd], keep, st.step_dev) for dd in range(ndir)] if keep < 1.0 else [x] * ndir
         with _lib.stage("train_inproj"):
             for dd, nm in enumerate(names):
-                gemm_ex(B * T, 4 * U, din, _p(xs[dd], dd * U if own else 0), width, 1, st.w(nm + "/kernel"), 4 * U, 1,
-                        _p(z, dd * 4 * U), ndir * 4 * U, bias=st.w(nm + "/bias"))
+                xa = _p(xs[dd], dd * U if own else 0)
+                if use_tc(B * T, 4 * U, din, xa // 4, width, st.w(nm + "/bias") // 4):  # x W + b = [x split] . [W^T split]^T
+                    a3, seg = split3(xa, B * T, din, width, 0, False, x.device)
+                    b3, _ = split3(st.w(nm + "/kernel"), din, 4 * U, 4 * U, 1, True, x.device)
+                    gemm_tc(a3, b3, B * T, 4 * U, seg, _p(z, dd * 4 * U), ndir * 4 * U, bias=st.w(nm + "/bias"))
+                else:
+                    gemm_ex(B * T, 4 * U, din, xa, width, 1, st.w(nm + "/kernel"), 4 * U, 1,
+                            _p(z, dd * 4 * U), ndir * 4 * U, bias=st.w(nm + "/bias"))
         stack = pyr and l != 0
         t_alloc = T + (T % 2) if stack else T
         out = torch.zeros((B, t_alloc, ndir * U), dtype=torch.float32, device=x.device)
@@ -361,9 +405,24 @@ def listener_train_bwd(d_enc, tape, st, hp, d_final=None):
         if l > 0:  # input gradient first: the next recurrence depends on it
             dx = torch.empty((B, T, width), dtype=torch.float32, device=z.device)
             with _lib.stage("train_dgrad"):
+                tc_d = use_tc(M, din, 4 * U, width, U)
                 for dd, nm in enumerate(names):
                     zp, wk = _p(z, dd * 4 * U), st.w(nm + "/kernel")
-                    if keep < 1.0:  # each cell saw its own mask: dx = sum_d mask_d * (dz_d W_d^T)
+                    if tc_d:  # dz W^T = [dz split] . [W split]^T: W [din][4U] already has the contraction index contiguous
+                        dz3, segz = split3(zp, M, 4 * U, ndir * 4 * U, 0, False, z.device)
+                        w3, _ = split3(wk, din, 4 * U, 4 * U, 1, False, z.device)
+                    if keep < 1.0 and tc_d:
+                        dxd = dx if dd == 0 else torch.empty_like(dx)
+                        if own:
+                            dxd.zero_()
+                        gemm_tc(dz3, w3, M, din, segz, _p(dxd, dd * U if own else 0), width)
+                        dropout_(dxd, dxd, tp["seeds"][dd], keep, st.step_dev)
+                        if dd > 0:
+                            _lib.check(L.plas_axpy_f32(_lib.ptr(dx), _lib.ptr(dxd), dx.numel(), 1.0, _lib.stream_ptr()))
+                            _lib.count_launches(1)
+                    elif tc_d:
+                        gemm_tc(dz3, w3, M, din, segz, _p(dx, dd * U if own else 0), width, accumulate=(dd > 0 and not own))
+                    elif keep < 1.0:  # each cell saw its own mask: dx = sum_d mask_d * (dz_d W_d^T)
                         dxd = dx if dd == 0 else torch.empty_like(dx)
                         if own:
                             dxd.zero_()
@@ -385,10 +444,19 @@ def listener_train_bwd(d_enc, tape, st, hp, d_final=None):
             with _lib.stage("train_wgrad"):
                 for dd, nm in enumerate(names):
                     zp = _p(z, dd * 4 * U)
-                    gemm_ex(din, 4 * U, M, _p(xs[dd], dd * U if own else 0), 1, width, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U,
-                            split_ws=st.split_ws)
-                    gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U,
-                            split_ws=st.split_ws)
+                    xa = _p(xs[dd], dd * U if own else 0)
+                    if use_tc(din + U, 4 * U, M, xa // 4, width, st.g(nm + "/kernel") // 4):
+                        # X^T dZ = [X^T split] . [dZ^T split]^T: both operands transposed into the TN form; one CTA walks the whole
+                        # contraction of its output tile, so the sum order is fixed (deterministic without split-K scratch)
+                        dzt3, segm = split3(zp, M, 4 * U, ndir * 4 * U, 1, True, z.device)
+                        xt3, _ = split3(xa, M, din, width, 0, True, z.device)
+                        gemm_tc(xt3, dzt3, din, 4 * U, segm, st.g(nm + "/kernel"), 4 * U)
+                        ht3, _ = split3(_p(hp_, dd * U), M, U, ndir * U, 0, True, z.device)
+                        gemm_tc(ht3, dzt3, U, 4 * U, segm, st.g(nm + "/kernel", din), 4 * U)
+                    else:
+                        gemm_ex(din, 4 * U, M, xa, 1, width, zp, ndir * 4 * U, 1, st.g(nm + "/kernel"), 4 * U, split_ws=st.split_ws)
+                        gemm_ex(U, 4 * U, M, _p(hp_, dd * U), 1, ndir * U, zp, ndir * 4 * U, 1, st.g(nm + "/kernel", din), 4 * U,
+                                split_ws=st.split_ws)
                     colsum(zp, M, 4 * U, ndir * 4 * U, st.g(nm + "/bias"))
     done = torch.cuda.Event()
     done.record(side)
