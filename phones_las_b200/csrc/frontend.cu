@@ -14,6 +14,8 @@
 //   librosa back end  : top_db clips against the utterance-global max, so kernel A writes dB
 //                       values + an atomicMax per utterance, kernel B clips/DCTs, kernel C adds
 //                       the Savitzky-Golay deltas along time.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/plas.h"
 
@@ -37,6 +39,7 @@ struct FeArgs {
   float* rms;      // librosa: [B][T_max]
   unsigned* umax;  // librosa: [B]
   float* base;     // librosa + deltas: [B][T_max][Dbase]
+  int generic_fft; // debugging / A-B: run the generic Stockham passes even for n_fft = 400
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -133,6 +136,60 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
   }
 }
 
+// n_fft = 400 (window 25 ms, the BASELINE configurations): the 200-point complex FFT as radix 8, 5, 5 Stockham passes with
+// every stride, modulus and twiddle step a compile-time constant (the generic passes above spend most of their instructions on
+// runtime index arithmetic), 16-byte stores out of the radix-8 pass, and the window applied while the first pass loads its
+// samples straight from the staged span.  Result in bufA.
+__device__ __forceinline__ void fft200_windowed(const float* __restrict__ x, const float* __restrict__ win,
+                                                const float2* __restrict__ tw, float2* __restrict__ bufA,
+                                                float2* __restrict__ bufB, int lane) {
+  if (lane < 25) {  // pass 1: radix 8, Ns = 1: butterfly j reads elements j + 25 t, writes 8 j .. 8 j + 7
+    const float2* x2 = reinterpret_cast<const float2*>(x);
+    const float2* w2 = reinterpret_cast<const float2*>(win);
+    float2 v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float2 xv = x2[lane + 25 * t], wv = w2[lane + 25 * t];
+      v[t] = make_float2(xv.x * wv.x, xv.y * wv.y);
+    }
+    Bfly<8>::run(v);
+    float4* o = reinterpret_cast<float4*>(bufA + 8 * lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = make_float4(v[2 * u].x, v[2 * u].y, v[2 * u + 1].x, v[2 * u + 1].y);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {  // pass 2: radix 5, Ns = 8, twiddle step 5: 40 butterflies
+    const int j = lane + 32 * r;
+    if (j < 40) {
+      const int k = j & 7;
+      float2 v[5];
+      v[0] = bufA[j];
+#pragma unroll
+      for (int t = 1; t < 5; ++t) v[t] = cmul(bufA[j + 40 * t], tw[5 * k * t]);
+      Bfly<5>::run(v);
+      float2* o = bufB + (j - k) * 5 + k;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) o[8 * u] = v[u];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {  // pass 3: radix 5, Ns = 40, twiddle step 1
+    const int j = lane + 32 * r;
+    if (j < 40) {
+      float2 v[5];
+      v[0] = bufB[j];
+#pragma unroll
+      for (int t = 1; t < 5; ++t) v[t] = cmul(bufB[j + 40 * t], tw[j * t]);
+      Bfly<5>::run(v);
+#pragma unroll
+      for (int u = 0; u < 5; ++u) bufA[j + 40 * u] = v[u];
+    }
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ int frames_of(const plas_frontend_desc& d, int N) {
   if (d.backend == 1) return 1 + N / d.hop;
   return N >= d.n_fft ? (N - d.n_fft) / d.hop : 0;
@@ -143,7 +200,9 @@ __device__ __forceinline__ float norm_ch(const FeArgs& p, float v, int c) {
   return v;
 }
 
-__global__ void __launch_bounds__(FE_THREADS) fe_spectral_kernel(FeArgs p) {
+// 4 CTAs per SM (<= 64 registers, ~55 KB of shared memory each at n_fft = 400): the kernel is issue-bound, occupancy hides its
+// shared-memory latencies
+__global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   extern __shared__ __align__(16) unsigned char fe_smem[];
   const plas_frontend_desc& d = p.d;
   const int n_fft = d.n_fft, hop = d.hop, n = n_fft / 2, n_mels = d.n_mels;
@@ -171,7 +230,8 @@ __global__ void __launch_bounds__(FE_THREADS) fe_spectral_kernel(FeArgs p) {
   float* s_win = reinterpret_cast<float*>(s_twu + n + 1);
   float* s_fbw = s_win + n_fft;
   int* s_fbs = reinterpret_cast<int*>(s_fbw + d.fb_total);
-  float* s_span = reinterpret_cast<float*>(s_fbs + 3 * n_mels);
+  // 8-byte aligned: the n_fft = 400 path reads sample pairs
+  float* s_span = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_fbs + 3 * n_mels) + 7) & ~uintptr_t(7));
   size_t off = reinterpret_cast<unsigned char*>(s_span + span_len) - fe_smem;
   off = (off + 15) & ~size_t(15);
   const int work_stride = 2 * n + 2;  // float2 elements per warp (two ping-pong buffers)
@@ -223,14 +283,18 @@ __global__ void __launch_bounds__(FE_THREADS) fe_spectral_kernel(FeArgs p) {
       for (int i = lane; i < n_fft; i += 32) s += x[i] * x[i];
       rms = sqrtf(warp_sum(s) / (float)n_fft);
     }
-    for (int j = lane; j < n; j += 32)
-      bufA[j] = make_float2(x[2 * j] * s_win[2 * j], x[2 * j + 1] * s_win[2 * j + 1]);
-    __syncwarp();
-
     float2* src = bufA;
     float2* dst = bufB;
+    const bool fast400 = n_fft == 400 && (hop & 1) == 0 && !p.generic_fft;
+    if (fast400) {
+      fft200_windowed(x, s_win, s_tw, bufA, bufB, lane);
+    } else {
+      for (int j = lane; j < n; j += 32)
+        bufA[j] = make_float2(x[2 * j] * s_win[2 * j], x[2 * j + 1] * s_win[2 * j + 1]);
+      __syncwarp();
+    }
     int Ns = 1;
-    for (int s = 0; s < d.n_fac; ++s) {
+    for (int s = 0; s < (fast400 ? 0 : d.n_fac); ++s) {
       const int R = d.fac[s];
       switch (R) {
         case 2: fft_pass<2>(src, dst, s_tw, n, Ns, lane); break;
@@ -441,7 +505,7 @@ __global__ void fe_librosa_delta_kernel(FeArgs p) {
 static size_t fe_spectral_smem(const plas_frontend_desc& d) {
   const int n = d.n_fft / 2;
   size_t bytes = (size_t)n * 8 + (size_t)(n + 1) * 8 + (size_t)d.n_fft * 4 + (size_t)d.fb_total * 4 +
-                 (size_t)3 * d.n_mels * 4 + (size_t)((FE_FRAMES - 1) * d.hop + d.n_fft) * 4;
+                 (size_t)3 * d.n_mels * 4 + 8 + (size_t)((FE_FRAMES - 1) * d.hop + d.n_fft) * 4;
   bytes = (bytes + 15) & ~size_t(15);
   bytes += (size_t)FE_WARPS * (2 * n + 2) * 8;
   return bytes;
@@ -501,6 +565,7 @@ extern "C" int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave,
   a.wave = wave; a.n_samples = n_samples; a.wave_stride = wave_stride; a.B = B;
   a.feats = feats; a.n_frames = n_frames; a.T_max = T_max; a.C = C;
   a.db = nullptr; a.rms = nullptr; a.umax = nullptr; a.base = nullptr;
+  a.generic_fft = getenv("PLAS_FE_GENERIC") ? 1 : 0;
   size_t o_db, o_rms, o_umax, o_base, total;
   fe_ws_layout(*d, B, T_max, &o_db, &o_rms, &o_umax, &o_base, &total);
   if (d->backend == 1) {
