@@ -2,7 +2,7 @@
 import collections, csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles"); SRC = os.path.join(ROOT, "gpurun_out")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 os.makedirs(OUT, exist_ok=True)
 
 # launch list -> per-kernel totals and shares
@@ -14,7 +14,7 @@ for row in csv.DictReader(lines):
     a = agg.setdefault(row["Kernel Name"], [0, 0.0, row["Grid Size"], row["Block Size"]]); a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(OUT, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none over `python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none over `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sub-records`\n")
     f.write("# (5 passes of the hot path; per-launch times are cold-cache and serialised: compare SHARES)\n")
     f.write(f"{'kernel':80s} {'launches':>8s} {'total_ms':>10s} {'share':>7s}  grid block\n")
     for k, (n, t, g, b) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -29,28 +29,39 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "launch__shared_mem_per_block_dynamic"]
 traffic = {}
-fam = {"rec_tc_kernel": "rec", "decoder_tc_kernel": "decoder", "gemm_bf16_tcgen05_kernel": "inproj_gemm", "fe_spectral_kernel": "frontend"}
+fam = {"rec_tc_kernel": "rec", "decoder_fold_kernel": "decoder", "gemm_bf16_tcgen05_kernel": "inproj_gemm", "fe_spectral_kernel": "frontend"}
+notes = {"rec_tc_kernel": "-s 4 -c 1: the layer-0 launch (T = 1501) of the second pass",
+         "decoder_fold_kernel": "-s 1 -c 1: the whole 188-step decode of the second pass",
+         "gemm_bf16_tcgen05_kernel": "-s 7 -c 4: the FOUR in-projection launches (layers 0..3) of the second pass",
+         "fe_spectral_kernel": "-s 1 -c 1: second pass"}
+def num(vals, key):
+    v, u = vals.get(key, ("nan", ""))
+    try: x = float(v.replace(",", ""))
+    except ValueError: return float("nan")
+    return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 for k, name in fam.items():
     rep = os.path.join(SRC, f"prof_{k}.ncu-rep")
     if not os.path.exists(rep): continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(raw)))
-    hdr, units, row = r[0], r[1], r[2]
-    vals = {h: (v, u) for h, u, v in zip(hdr, units, row)}
+    hdr, units, rows = r[0], r[1], r[2:]
     with open(os.path.join(OUT, f"{tag}_ncu_{k}.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{k} -s 4 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n")
-        f.write(f"# kernel: {vals.get('Kernel Name', ('?',))[0]}\n")
-        for key in KEYS:
-            for h in hdr:
-                if h == key or h.endswith(key):
-                    f.write(f"{h:90s} {vals[h][0]:>16s} {vals[h][1]}\n")
-        stalls = sorted(((float(v[0]), h) for h, v in vals.items() if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and v[0] not in ("", "n/a")), reverse=True)[:8]
-        f.write("# top warp-stall reasons (per issue-active):\n")
-        for v, h in stalls: f.write(f"{h:90s} {v:16.3f}\n")
-    def num(key):
-        v, u = vals.get(key, ("nan", ""))
-        x = float(v.replace(",", ""))
-        return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
-    traffic[name] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{k} ({notes[k]}) python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sub-records\n")
+        tot = 0.0
+        for li, row in enumerate(rows):
+            vals = {h: (v, u) for h, u, v in zip(hdr, units, row)}
+            f.write(f"# ---- launch {li}: {vals.get('Kernel Name', ('?',))[0]}\n")
+            for key in KEYS:
+                for h in hdr:
+                    if h == key or h.endswith(key):
+                        f.write(f"{h:90s} {vals[h][0]:>16s} {vals[h][1]}\n")
+            stalls = sorted(((float(v[0]), h) for h, v in vals.items() if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and v[0] not in ("", "n/a")), reverse=True)[:8]
+            f.write("# top warp-stall reasons (per issue-active):\n")
+            for v, h in stalls: f.write(f"{h:90s} {v:16.3f}\n")
+            tot += num(vals, "dram__bytes_read.sum") + num(vals, "dram__bytes_write.sum")
+        traffic[name] = tot / max(len(rows), 1)
+traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full, r02): rec = the layer-0 launch (algorithmic 983.7 MB), "
+                    "inproj_gemm = mean of the four in-projection launches of one pass, decoder = the whole 188-step decode of decoder_fold_kernel "
+                    "(keys resident in shared memory, VW / PV stay L2-resident: its per-step operand reads are L2->SM traffic), frontend = fe_spectral_kernel")
 json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(OUT, f"{tag}_launches_summary.txt")).read()[:3000]); print(traffic)

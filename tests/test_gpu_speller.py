@@ -110,7 +110,7 @@ def test_teacher_forced_parity(precision, att):
     import torch
     from phones_las_b200.speller import speller
     hp, params, enc, lens, D = _setup(precision, att, 6, 15, 16, 64, 2, 18, seed=3)
-    hp["sampling_probability"] = 0.0
+    hp["sampling_probability"] = hp["dropout"] = 0.0  # deterministic teacher forcing (TRAIN applies both when they are > 0)
     tin, tout, tlen = synth.synth_labels(6, 9, 18, seed=4)
     tlen[2] = 5
     sp = ol.Speller(enc, lens, params, hp, precision)
@@ -230,7 +230,7 @@ def test_bottom_only_and_pass_hidden_state_greedy_and_teacher_forced(att, B, Tm,
         assert_parity(logits, ref_logits, "fp32", "logits")
         assert_parity(align, ref_align, "fp32", "alignment")
     tin, tout, tlen = synth.synth_labels(B, 5, V, seed=4)
-    hp["sampling_probability"] = 0.0
+    hp["sampling_probability"] = hp["dropout"] = 0.0  # deterministic teacher forcing (TRAIN applies both when they are > 0)
     ref_tf, _ = ol.Speller(enc, lens, params, hp, "fp32", encoder_state=state).teacher_forced(tin, tlen)
     out, _, _ = speller(enc_t, state_t, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(),
                         "train", hp, w)
@@ -267,7 +267,7 @@ def test_attention_layer_size_greedy_and_teacher_forced(att, B, Tm, U, Ud, Ld, V
         assert_parity(logits, ref_logits, "fp32", "logits")
         assert_parity(to_np(st.alignment_history), ref_align, "fp32", "alignment")
     tin, tout, tlen = synth.synth_labels(B, 5, V, seed=4)
-    hp["sampling_probability"] = 0.0
+    hp["sampling_probability"] = hp["dropout"] = 0.0  # deterministic teacher forcing (TRAIN applies both when they are > 0)
     ref_tf, _ = ol.Speller(enc, lens, params, hp, "fp32").teacher_forced(tin, tlen)
     out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(), "train", hp, w)
     assert_parity(out.rnn_output, ref_tf, "fp32", "teacher-forced logits")
@@ -304,7 +304,7 @@ def test_target_embedding_greedy_and_teacher_forced(precision, att, B, Tm, U, Ud
         np.testing.assert_array_equal(ids, ref_ids)
         assert_parity(logits, ref_logits, precision, "logits")
     tin, tout, tlen = synth.synth_labels(B, 5, V, seed=4)
-    hp["sampling_probability"] = 0.0
+    hp["sampling_probability"] = hp["dropout"] = 0.0  # deterministic teacher forcing (TRAIN applies both when they are > 0)
     ref_tf, _ = ol.Speller(enc, lens, params, hp, precision).teacher_forced(tin, tlen)
     out, _, _ = speller(enc_t, None, torch.from_numpy(tin).cuda(), torch.from_numpy(lens).cuda(), torch.from_numpy(tlen).cuda(), "train", hp, w)
     assert_parity(out.rnn_output, ref_tf, precision, "teacher-forced logits")
