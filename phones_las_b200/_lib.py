@@ -214,6 +214,28 @@ def torch_dtype(precision):
     return {"fp32": torch.float32, "bf16": torch.bfloat16}[precision]
 
 
+# Kernels whose CTAs spin on each other beyond one thread-block cluster (grid barriers through L2: the fused decoders, the
+# cooperative recurrences) need ALL their CTAs resident at once.  Two of them in flight on different streams could each hold
+# part of the GPU and wait for the rest forever, so every such launch is chained behind the previous one with an event: at most
+# one is ever in flight.  (rec_tc_kernel only synchronises inside its clusters; GEMMs / front-end never wait on other CTAs.)
+_grid_sync_done = None
+
+
+class grid_sync_kernel:
+    """``with _lib.grid_sync_kernel():`` around a launch that needs device-wide co-residency."""
+
+    def __enter__(self):
+        if _grid_sync_done is not None:
+            torch.cuda.current_stream().wait_event(_grid_sync_done)
+        return self
+
+    def __exit__(self, *exc):
+        global _grid_sync_done
+        ev = torch.cuda.Event()
+        ev.record()
+        _grid_sync_done = ev
+
+
 # launch accounting for bench.py's gpu_launches (our kernels only)
 launch_count = 0
 

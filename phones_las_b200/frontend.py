@@ -161,7 +161,7 @@ class FrontendPlan:
         d.stdv = self.t_std.data_ptr() if self.t_std is not None else None
         self.desc = d
         self.fac = fac
-        self._ws = None
+        self._ws = {}  # workspace per CUDA stream: consecutive batches may run on different streams concurrently
 
     def max_frames(self, n_samples):
         if self.backend == 0:
@@ -186,12 +186,14 @@ class FrontendPlan:
         n_frames = torch.empty((B,), dtype=torch.int32, device=wave.device)
         L = _lib.lib()
         need = L.plas_frontend_workspace_bytes(C.byref(self.desc), B, T_max)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty((need,), dtype=torch.uint8, device=wave.device)
+        sid = torch.cuda.current_stream().cuda_stream
+        ws = self._ws.get(sid)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[sid] = torch.empty((max(need, 1),), dtype=torch.uint8, device=wave.device)
         with _lib.stage("frontend"):
             _lib.check(L.plas_frontend_fwd(C.byref(self.desc), _lib.ptr(wave), _lib.ptr(n_samples), B, wave.stride(0),
-                                           _lib.ptr(feats), _lib.ptr(n_frames), T_max, self.C, _lib.ptr(self._ws),
-                                           self._ws.numel(), _lib.stream_ptr()))
+                                           _lib.ptr(feats), _lib.ptr(n_frames), T_max, self.C, _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr()))
         _lib.count_launches(self.launches() * ((B + 32767) // 32768))  # the C side cuts batches above the grid limit into chunks
         return feats, n_frames
 

@@ -133,8 +133,15 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
     d.whh_tc = lw["whh_tc"].data_ptr() if lw.get("whh_tc") is not None else None
     need = L.plas_rec_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
-    with _lib.stage("rec"):
-        _lib.check(L.plas_bilstm_rec_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    # the tensor-core recurrence only synchronises inside its clusters; the cooperative fallbacks exchange h through L2 across
+    # the whole grid and must not share the GPU with another grid-synchronising kernel (_lib.grid_sync_kernel)
+    cluster_only = precision == "bf16" and lw.get("whh_tc") is not None and os.environ.get("PLAS_REC_IMPL", "tc") == "tc"
+    if cluster_only:
+        with _lib.stage("rec"):
+            _lib.check(L.plas_bilstm_rec_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
+    else:
+        with _lib.grid_sync_kernel(), _lib.stage("rec"):
+            _lib.check(L.plas_bilstm_rec_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1)
     return out, (c_fin, h_fin)
 
@@ -165,7 +172,7 @@ def _bilstm_layer_f32(x, lengths, lw, U, ndir, t_alloc_out, per_direction_input)
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
     need = L.plas_rec_train_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
-    with _lib.stage("rec"):
+    with _lib.grid_sync_kernel(), _lib.stage("rec"):  # groups of CTAs exchange h through L2 when they are not one cluster
         _lib.check(L.plas_bilstm_rec_train_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1)
     return out, (c_fin, h_fin)

@@ -176,35 +176,72 @@ class LASModel:
         key, klen = ("sample_ids", "final_sequence_length") if "sample_ids" in pred else ("sample_ids_phones_binf", "final_sequence_length_binf")
         return pred[key].cpu(), pred[klen].cpu()
 
-    def transcribe_stream(self, host_batches):
-        """Serving loop over pinned host waveform batches ([B,N] float32 each), fully pipelined: the host->device copy
-        of batch i+1 runs on a copy stream into one of two preallocated device buffers while the kernels of batch i
-        execute, nothing in a step synchronises the host (the decode step count stays on the device), and the ids of
-        batch i are read back (pinned, asynchronous) while batch i+1 is already enqueued.  Yields
+    def default_streams(self):
+        """Compute streams of the serving loop: 2 on the fused bf16 tensor-core path (its recurrence occupies 64 of the 148 SMs
+        and its decoder is latency-bound, so the next batch's front-end / GEMMs / recurrence fill the idle SMs: measured
+        14.5 -> 11.7 ms per c2 batch), 1 otherwise."""
+        w = self.weights
+        fused = (self.precision == "bf16" and getattr(w.speller, "tc", False)
+                 and all(lw.get("whh_tc") is not None for lw in w.listener.layers))
+        return 2 if fused else 1
+
+    def transcribe_stream(self, host_batches, n_streams=None):
+        """Serving loop over pinned host waveform batches ([B,N] float32 each), fully pipelined: the host->device copy of a batch
+        runs on a copy stream into one of ``n_streams + 1`` preallocated device buffers, consecutive batches run on ``n_streams``
+        compute streams (default: ``default_streams()``), nothing in a step synchronises the host (the decode step count stays
+        on the device), and the ids of a batch are read back (pinned, asynchronous) while the following batches are already
+        enqueued.  Kernels that need the whole GPU co-resident never overlap each other (_lib.grid_sync_kernel).  Yields
         (sample_ids [B,steps], final_sequence_length [B]) host tensors per batch, in order."""
+        from collections import deque
         dev = self.plan.device
-        # staging state lives on the model: cudaMalloc / cudaHostAlloc are slow and synchronise the device, so the
-        # copy stream, the two device input buffers and the pinned result buffers are created once and reused
-        st = self.__dict__.setdefault("_stream_state", {"copy_stream": torch.cuda.Stream(device=dev),
-                                                        "bufs": [None, None], "pinned": [None, None]})
-        copy_stream, bufs, pinned = st["copy_stream"], st["bufs"], st["pinned"]
-        consumed = [None, None]  # "kernels are done with the staging buffer" events of this call
+        ns = int(n_streams or self.default_streams())
+        nb = ns + 1
+        if int(self.hp.get("beam_width", 0) or 0) > 0:
+            raise NotImplementedError("transcribe_stream serves greedy decoding (beam search returns [B, T, W] ids: use transcribe)")
+        # staging state lives on the model: cudaMalloc / cudaHostAlloc are slow and synchronise the device, so the streams,
+        # the device input buffers and the pinned result buffers are created once and reused
+        st = self.__dict__.setdefault("_stream_state", {"copy_stream": torch.cuda.Stream(device=dev), "compute": [], "bufs": [], "pinned": []})
+        while len(st["compute"]) < ns:
+            st["compute"].append(torch.cuda.Stream(device=dev))
+        while len(st["bufs"]) < nb:
+            st["bufs"].append(None)
+            st["pinned"].append(None)
+        copy_stream, compute, bufs, pinned = st["copy_stream"], st["compute"], st["bufs"], st["pinned"]
+        consumed = [None] * nb  # "kernels are done with the staging buffer" events of this call
         main_stream = torch.cuda.current_stream()
         main_stream.synchronize()  # buffers may still be in use by an earlier call
+        for cs in compute[:ns]:
+            cs.wait_stream(main_stream)
 
-        def stage(hw, slot):
+        def launch(hw, i):
+            slot, cs = i % nb, compute[i % ns]
             with torch.cuda.stream(copy_stream):
                 if bufs[slot] is None or bufs[slot].shape != hw.shape:
-                    # allocated under the copy stream: a block the caching allocator hands out here is then ordered after its
-                    # previous owner's work on THIS stream, and main-stream kernels never saw it
-                    copy_stream.wait_stream(main_stream)
+                    # allocated under the copy stream: the block is then ordered after its previous owner's work on this stream
                     bufs[slot] = torch.empty(hw.shape, dtype=torch.float32, device=dev)
                 if consumed[slot] is not None:
                     copy_stream.wait_event(consumed[slot])  # do not overwrite a batch that is still being read
                 bufs[slot].copy_(hw, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return bufs[slot], ev
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev)
+                pred = self.transcribe(bufs[slot], want_alignment=False, trim=False, want_probs=False)
+                done = torch.cuda.Event()
+                done.record(cs)
+                consumed[slot] = done
+                key, klen = (("sample_ids", "final_sequence_length") if "sample_ids" in pred
+                             else ("sample_ids_phones_binf", "final_sequence_length_binf"))  # --binf_projection without --multitask
+                ids_d, len_d, n_d = pred[key], pred[klen], pred["n_steps"]
+                if pinned[slot] is None or pinned[slot][0].shape != ids_d.shape:
+                    pinned[slot] = (torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory(),
+                                    torch.empty(len_d.shape, dtype=len_d.dtype).pin_memory(),
+                                    torch.empty(n_d.shape, dtype=n_d.dtype).pin_memory())
+                for h_t, d_t in zip(pinned[slot], (ids_d, len_d, n_d)):
+                    h_t.copy_(d_t, non_blocking=True)
+                rd = torch.cuda.Event()
+                rd.record(cs)
+            return pinned[slot], rd
 
         def finish(job):
             (ids_h, len_h, n_h), ev = job
@@ -212,39 +249,12 @@ class LASModel:
             n = int(n_h[0])
             return ids_h[:, :n].clone(), len_h.clone()
 
-        it = iter(host_batches)
-        first = next(it, None)
-        if first is None:
-            return
-        slot = 0
-        cur = stage(first, slot)
-        pending = None
-        while cur is not None:
-            nxt = next(it, None)
-            staged = stage(nxt, slot ^ 1) if nxt is not None else None
-            dw, ev = cur
-            main = torch.cuda.current_stream()
-            main.wait_event(ev)
-            pred = self.transcribe(dw, want_alignment=False, trim=False, want_probs=False)
-            done = torch.cuda.Event()
-            done.record(main)
-            consumed[slot] = done
-            if int(self.hp.get("beam_width", 0) or 0) > 0:
-                raise NotImplementedError("transcribe_stream serves greedy decoding (beam search returns [B, T, W] ids: use transcribe)")
-            key, klen = (("sample_ids", "final_sequence_length") if "sample_ids" in pred
-                         else ("sample_ids_phones_binf", "final_sequence_length_binf"))  # --binf_projection without --multitask
-            ids_d, len_d, n_d = pred[key], pred[klen], pred["n_steps"]
-            if pinned[slot] is None or pinned[slot][0].shape != ids_d.shape:
-                pinned[slot] = (torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory(),
-                                torch.empty(len_d.shape, dtype=len_d.dtype).pin_memory(),
-                                torch.empty(n_d.shape, dtype=n_d.dtype).pin_memory())
-            for h_t, d_t in zip(pinned[slot], (ids_d, len_d, n_d)):
-                h_t.copy_(d_t, non_blocking=True)
-            rd = torch.cuda.Event()
-            rd.record(main)
-            if pending is not None:
-                yield finish(pending)  # batch i-1 is read while batch i runs
-            pending = (pinned[slot], rd)
-            cur, slot = staged, slot ^ 1
-        if pending is not None:
-            yield finish(pending)
+        pending = deque()
+        for i, hw in enumerate(host_batches):
+            if len(pending) == ns:  # the slot batch i is about to reuse belongs to batch i - ns - 1: already yielded
+                yield finish(pending.popleft())
+            pending.append(launch(hw, i))
+        while pending:
+            yield finish(pending.popleft())
+        for cs in compute[:ns]:
+            main_stream.wait_stream(cs)

@@ -348,7 +348,7 @@ def decode(encoder_outputs, source_sequence_length, w, hp, forced_ids=None, max_
                     d.w_x_tc[k] = w.w_x_tc[k].data_ptr()
     need = L.plas_decoder_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
-    with _lib.stage("decoder"):
+    with _lib.grid_sync_kernel(), _lib.stage("decoder"):
         _lib.check(L.plas_decoder_fwd(C.byref(d), _lib.ptr(ws), need, _lib.stream_ptr()))
     _lib.count_launches(1)
     if trim:
