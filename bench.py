@@ -433,6 +433,20 @@ def ours(args):
             ent.update(bound="hbm", achieved=w["bytes"] / (t_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
         if "achieved" in ent:
             ent["frac"] = ent["achieved"] / ent["peak"]
+        if name == "rec" and cfg["precision"] == "bf16" and hp["encoder_units"] == 512:
+            # the h exchange inside a 16-CTA cluster is what bounds a step: the SM-to-SM network moves 23 B/clk per SM (in + out)
+            # with one 16-utterance group in flight and 28.5 with two (scripts/micro/dsmem_bench.cu: 0.726 / 1.158 us per step)
+            n_groups = (B + 15) // 16
+            ng = next(g for g in (1, 2, 4) if 2 * ((n_groups + g - 1) // g) <= 7 or g == 4)
+            floor_us = {1: 0.726, 2: 1.158}.get(ng, 0.58 * ng)
+            steps_total, t = 0, cfg["T"]
+            for l in range(hp["encoder_layers"]):
+                steps_total += t
+                if l != 0:
+                    t = (t + 1) // 2
+            ent.update(exchange_floor_ms=steps_total * floor_us * 1e-3, exchange_floor_frac=steps_total * floor_us * 1e-3 / t_ms,
+                       sequential_steps=steps_total, groups_per_cluster=ng,
+                       exchange_note="time the DSMEM all-to-all of h alone would take (measured network rate) / measured kernel time")
         if name == "frontend":  # formally HBM-bound (north_star), in practice FP32-issue-bound: report both
             fl = frontend_flops_per_frame(fa) * B * cfg["T"]
             ent.update(fp32_tflops=fl / (t_ms * 1e-3) / 1e12, fp32_peak_tflops=FP32_PEAK_TFLOPS,
