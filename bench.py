@@ -436,17 +436,29 @@ def ours(args):
         if name == "rec" and cfg["precision"] == "bf16" and hp["encoder_units"] == 512:
             # the h exchange inside a 16-CTA cluster is what bounds a step: the SM-to-SM network moves 23 B/clk per SM (in + out)
             # with one 16-utterance group in flight and 28.5 with two (scripts/micro/dsmem_bench.cu: 0.726 / 1.158 us per step)
-            n_groups = (B + 15) // 16
-            ng = next(g for g in (1, 2, 4) if 2 * ((n_groups + g - 1) // g) <= 7 or g == 4)
-            floor_us = {1: 0.726, 2: 1.158}.get(ng, 0.58 * ng)
+            # plan of rec_tc.cu: clusters of one direction in one wave = 7 // 2; fewest groups per cluster with <= 16 rows per group
+            cpd = 7 // 2
+            ng = next((g for g in (1, 2, 4) if -(-B // (cpd * g)) <= 16), 4)
+            rows = min(16, -(-B // (cpd * ng)))
+            n_groups = -(-B // rows)
+            floor_us = {1: 0.726, 2: 1.158}.get(ng, 0.58 * ng) * rows / 16.0
             steps_total, t = 0, cfg["T"]
             for l in range(hp["encoder_layers"]):
                 steps_total += t
                 if l != 0:
                     t = (t + 1) // 2
+            U = hp["encoder_units"]
+            smem_peak = 148 * 128 * 1.965e9  # shared-memory / tensor-memory operand bandwidth, bytes/s (128 B/clk per SM)
+            alg = steps_total * 2 * U * 4 * U * 2  # W_hh of both directions read once per step
+            streamed = steps_total * 2 * n_groups * U * 4 * U * 2  # what the MMAs read: once per (direction, group) and step
             ent.update(exchange_floor_ms=steps_total * floor_us * 1e-3, exchange_floor_frac=steps_total * floor_us * 1e-3 / t_ms,
-                       sequential_steps=steps_total, groups_per_cluster=ng,
-                       exchange_note="time the DSMEM all-to-all of h alone would take (measured network rate) / measured kernel time")
+                       sequential_steps=steps_total, groups_per_cluster=ng, rows_per_group=rows,
+                       exchange_note="time the DSMEM all-to-all of h alone would take (measured network rate) / measured kernel time",
+                       onchip={"bound": "smem", "unit": "TB/s", "peak": smem_peak / 1e12,
+                               "achieved_algorithmic": alg / (t_ms * 1e-3) / 1e12, "frac_algorithmic": alg / (t_ms * 1e-3) / smem_peak,
+                               "achieved_streamed": streamed / (t_ms * 1e-3) / 1e12, "frac_streamed": streamed / (t_ms * 1e-3) / smem_peak,
+                               "note": "north_star (3) SMEM roofline: resident W_hh operand bytes per step (algorithmic: once per "
+                                       "step and direction; streamed: once per 16-column group MMA chain, from tensor memory)"})
         if name == "frontend":  # formally HBM-bound (north_star), in practice FP32-issue-bound: report both
             fl = frontend_flops_per_frame(fa) * B * cfg["T"]
             ent.update(fp32_tflops=fl / (t_ms * 1e-3) / 1e12, fp32_peak_tflops=FP32_PEAK_TFLOPS,

@@ -44,7 +44,14 @@ __device__ __forceinline__ void lstm_gates(float zi, float zj, float zf, float z
 // Cheaper gate math for the bf16 kernels, still ~2e-7 relative: sigmoid through ex2.approx/rcp.approx
 // (no cancellation: 1 + e^-x >= 1) and tanh as the Cephes odd polynomial below 0.625 (where
 // 1 - 2/(e^2x + 1) would lose relative accuracy to cancellation) and the exponential form above.
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// e^x as ONE MUFU.EX2: __expf without -ftz wraps ex2.approx in a denormal-result path (compare, halve, square: +3 instructions
+// per call); results that small vanish in the 1 + e^x that follows, everything else is bit-identical.
+__device__ __forceinline__ float exp_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + exp_ftz(-x)); }
 __device__ __forceinline__ float tanhf_fast(float x) {
   const float ax = fabsf(x);
   const float x2 = x * x;
@@ -53,7 +60,7 @@ __device__ __forceinline__ float tanhf_fast(float x) {
   p = fmaf(p, x2, 1.33314422036e-1f);
   p = fmaf(p, x2, -3.33332819422e-1f);
   const float small = fmaf(x * x2, p, x);
-  const float big = copysignf(1.0f - __fdividef(2.0f, __expf(2.0f * ax) + 1.0f), x);
+  const float big = copysignf(1.0f - __fdividef(2.0f, exp_ftz(2.0f * ax) + 1.0f), x);
   return ax < 0.625f ? small : big;
 }
 __device__ __forceinline__ void lstm_gates_fast(float zi, float zj, float zf, float zo, float c_prev, float& c,

@@ -33,6 +33,7 @@ struct RecTcArgs {
   plas_rec_desc d;
   const void* whh_tc;  // [ndir][G][128][U] bf16, row (TMEM lane) m = 32*q + 8*gate + u8 for unit 8*q + u8
   int n_groups;
+  int rows;            // utterances per group (<= 16): groups are padded to the N = 16 of the MMA, pad rows are never exchanged
   unsigned long long* tdbg;  // optional [8] ns counters written by CTA 0 (PLAS_DEBUG)
 };
 
@@ -114,10 +115,11 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
   __shared__ __align__(8) unsigned long long s_bar[NG][3];  // h buffers 0/1, MMA completion
   __shared__ uint32_t s_tmem;
 
+  const int R = p.rows;              // real utterances per group
   if (tid < NG * NR) {
     const int gg = tid / NR, r = tid % NR;
-    const int b = (grp0 + gg) * NR + r;
-    s_len[gg][r] = (grp0 + gg < p.n_groups && b < B) ? min(d.lengths[b], T) : 0;
+    const int b = (grp0 + gg) * R + r;
+    s_len[gg][r] = (grp0 + gg < p.n_groups && r < R && b < B) ? min(d.lengths[b], T) : 0;
   }
   __syncthreads();
   if (tid < NG) {
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     hbar[gg][1] = smem_u32(&s_bar[gg][1]);
     mbar[gg] = smem_u32(&s_bar[gg][2]);
   }
-  const uint32_t step_bytes = (uint32_t)(G * NR * 64);  // bytes every CTA receives per group step
+  const uint32_t step_bytes = (uint32_t)(G * R * 64);  // bytes every CTA receives per group step
   if (tid == 0) {
 #pragma unroll
     for (int gg = 0; gg < NG; ++gg) {
@@ -160,6 +162,10 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
       if (Tg[gg] >= 3) mbar_expect_tx(hbar[gg][1], step_bytes);  // h_1
     }
   }
+
+  // pad rows of a group (rows >= R) are never written by the exchange: keep them finite
+  for (int i = tid; i < NG * 2 * HBUF / 16; i += RT_THREADS2) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 
   // ---- resident W slice -> TMEM (lane m = gate column, 8*KS packed-bf16 columns) ---------------
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -237,18 +243,20 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
             if (idx < G * NR * 4) {
               const int rank = idx / (NR * 4), chunk = idx % (NR * 4);
               const int r = chunk >> 2, ch = chunk & 3;
-              const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 32 + ch * 8);
-              const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
-              const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-              rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
+              if (r < R) {  // pad rows of a group are never exchanged (their accumulator columns are ignored)
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 32 + ch * 8);
+                const int c = (ci & 1) * 4 + ch;  // 16-byte chunk inside the 128-byte row of the k block
+                const uint32_t local = dst_buf + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+                rt_st_async_v4(rt_mapa(local, (uint32_t)rank), v, rt_mapa(bar_l, (uint32_t)rank));
+              }
             }
           }
         }
         if (ptid < NR * 4) {
           const int r = ptid >> 2, ch = ptid & 3;
-          const int b = (grp0 + gg) * NR + r;
+          const int b = (grp0 + gg) * R + r;
           const int len = s_len[gg][r];
-          if (b < B) {
+          if (r < R && b < B) {
             // active step: h at its own time index (bw walks len-1-s); past the length: the zero padding of frame s
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             int t = s;
@@ -274,8 +282,8 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
         const int n_t = t_alloc - Tg[gg];
         for (int i = ptid; i < n_t * NR * 4; i += RT_NPUB) {
           const int t = Tg[gg] + i / (NR * 4), r = (i / 4) % NR, ch = i & 3;
-          const int b = (grp0 + gg) * NR + r;
-          if (b < B)
+          const int b = (grp0 + gg) * R + r;
+          if (r < R && b < B)
             *reinterpret_cast<uint4*>(out + (size_t)b * d.out_batch_stride + (size_t)t * (ndir * U) + dir * U + ci * 32 + ch * 8) =
                 make_uint4(0u, 0u, 0u, 0u);
         }
@@ -290,7 +298,8 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     const __nv_bfloat16* xproj = reinterpret_cast<const __nv_bfloat16*>(d.xproj);
     const int NX = ndir * 4 * U;
     int len_p[NG][PP];
-    const __nv_bfloat16* xrow[NG][PP];
+    const __nv_bfloat16* xnext[NG][PP];  // pre-activations of the step after the one held in xp (walks +-NX per step)
+    const long long xstep = dir ? -(long long)NX : (long long)NX;
     float c_state[NG][PP], h_state[NG][PP];
     uint2 xp[NG][PP];
 #pragma unroll
@@ -299,13 +308,15 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
       for (int i = 0; i < PP; ++i) {
         const int r = half0 + 2 * jq + i;
         len_p[gg][i] = s_len[gg][r];
-        xrow[gg][i] = xproj + ((size_t)min((grp0 + gg) * NR + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
+        const __nv_bfloat16* xrow = xproj + ((size_t)min((grp0 + gg) * R + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
         c_state[gg][i] = 0.f;
         h_state[gg][i] = 0.f;
         xp[gg][i] = make_uint2(0u, 0u);
+        const int t0 = dir ? (len_p[gg][i] - 1) : 0;
+        xnext[gg][i] = xrow + (long long)max(t0, 0) * NX;
         if (0 < len_p[gg][i]) {
-          const int t = dir ? (len_p[gg][i] - 1) : 0;
-          xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][i] + (size_t)t * NX));
+          xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xnext[gg][i]));
+          xnext[gg][i] += xstep;
         }
       }
     uint32_t mma_parity[NG];
@@ -349,16 +360,15 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
           float cn, hn;
           lstm_gates_fast(z.x + __low2float(x01), z.y + __high2float(x01), z.z + __low2float(x23), z.w + __high2float(x23),
                           c_state[gg][i], cn, hn);
-          if (s < len_p[gg][i]) {
-            c_state[gg][i] = cn;
-            h_state[gg][i] = bf16_round(hn);
-          }
+          const bool live = s < len_p[gg][i];
+          c_state[gg][i] = live ? cn : c_state[gg][i];
+          h_state[gg][i] = live ? bf16_round(hn) : h_state[gg][i];
           stg[(half0 + rl) * 32 + (warp & 3) * 8 + u8] = __float2bfloat16_rn(h_state[gg][i]);
           // prefetch this group's next gate pre-activations (consumed one full round later)
           xp[gg][i] = make_uint2(0u, 0u);
           if (s + 1 < len_p[gg][i]) {
-            const int t = dir ? (len_p[gg][i] - 2 - s) : (s + 1);
-            xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xrow[gg][i] + (size_t)t * NX));
+            xp[gg][i] = __ldg(reinterpret_cast<const uint2*>(xnext[gg][i]));
+            xnext[gg][i] += xstep;
           }
         }
         __threadfence_block();
@@ -372,8 +382,9 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
       for (int i = 0; i < PP; ++i) {
-        const int b = (grp0 + gg) * NR + half0 + 2 * jq + i;
-        if (grp0 + gg < p.n_groups && b < B) {
+        const int r = half0 + 2 * jq + i;
+        const int b = (grp0 + gg) * R + r;
+        if (grp0 + gg < p.n_groups && r < R && b < B) {
           d.c_final[((size_t)dir * B + b) * U + unit] = c_state[gg][i];
           d.h_final[((size_t)dir * B + b) * U + unit] = h_state[gg][i];
         }
@@ -402,10 +413,8 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   auto fn = rec_tc_kernel<KS, NG>;
   PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (G > 8) PLAS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  a.n_groups = (d.B + NR - 1) / NR;
-  const int clusters = d.ndir * ((a.n_groups + NG - 1) / NG);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * G));
+  cfg.gridDim = dim3((unsigned)G);
   cfg.blockDim = dim3(RT_THREADS2);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -416,16 +425,37 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  int max_clusters = 0;
-  cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg);
-  if (getenv("PLAS_DEBUG"))
-    fprintf(stderr, "[plas] rec tc path: U=%d NG=%d G=%d clusters=%d max_active_clusters=%d (query %s) smem=%zu\n", U, NG, G,
-            clusters, max_clusters, cudaGetErrorString(qe), smem);
+  static int cached_max[1][64];  // the occupancy query costs ~20 us: cache it per (template, device)
+  int dev = 0;
+  PLAS_CUDA(cudaGetDevice(&dev));
+  int max_clusters = dev < 64 ? cached_max[0][dev] : 0;
+  cudaError_t qe = cudaSuccess;
+  if (max_clusters == 0) {
+    qe = cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg);
+    if (qe == cudaSuccess && dev < 64) cached_max[0][dev] = max_clusters;
+  }
   if (qe != cudaSuccess || max_clusters < 1) {
     (void)cudaGetLastError();
     return PLAS_OK;
   }
-  if (must_fit_one_wave && clusters > max_clusters) return PLAS_OK;
+  // The exchange is what bounds a step and its bytes per SM grow with the utterances a cluster carries, so the batch is
+  // spread over as many clusters as the GPU can hold at once (7 of 16 CTAs on a B200): groups of `rows` <= 16
+  // utterances, padded to the MMA's N = 16 (pad rows are neither exchanged nor stored).
+  const int cpd_fit = max_clusters / d.ndir > 0 ? max_clusters / d.ndir : 1;  // clusters per direction in one wave
+  int rows = (d.B + cpd_fit * NG - 1) / (cpd_fit * NG);
+  if (const char* fr = getenv("PLAS_REC_ROWS")) rows = atoi(fr);
+  if (rows < 1) rows = 1;
+  if (rows > NR) {
+    if (must_fit_one_wave) return PLAS_OK;
+    rows = NR;
+  }
+  a.rows = rows;
+  a.n_groups = (d.B + rows - 1) / rows;
+  const int clusters = d.ndir * ((a.n_groups + NG - 1) / NG);
+  cfg.gridDim = dim3((unsigned)(clusters * G));
+  if (getenv("PLAS_DEBUG"))
+    fprintf(stderr, "[plas] rec tc path: U=%d NG=%d G=%d rows=%d groups=%d clusters=%d max_active_clusters=%d smem=%zu\n", U, NG,
+            G, rows, a.n_groups, clusters, max_clusters, smem);
   unsigned long long* dbgbuf = nullptr;
   if (getenv("PLAS_DEBUG")) {
     PLAS_CUDA(cudaMalloc(&dbgbuf, 64));
@@ -445,7 +475,9 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   return PLAS_OK;
 }
 
-// Fewest groups per cluster such that all clusters are co-resident (a B200 schedules 7 clusters of 16 CTAs).
+// Fewest groups per cluster such that the batch fits in one wave of clusters with <= 16 rows per group (measured at
+// U = 512, us per step: B = 16: NG 1 x 6 rows 1.21, NG 2 x 3 rows 1.31; B = 32: NG 1 x 11 rows 1.36, NG 2 x 6 rows 1.41;
+// B = 64: NG 2 x 11 rows 1.56 (NG 2 x 16 rows on 4 clusters: 1.68); B = 128: NG 4 x 11 rows 3.22 (16 rows: 3.54)).
 template <int KS>
 static int rec_tc_launch_ks(const RecTcArgs& a, cudaStream_t stream) {
   bool launched = false;
@@ -474,6 +506,7 @@ int rec_tc_launch(const plas_rec_desc& d, cudaStream_t stream) {
   a.d = d;
   a.whh_tc = d.whh_tc;
   a.n_groups = 0;
+  a.rows = 16;
   a.tdbg = nullptr;
   switch (d.U) {
     case 64: return rec_tc_launch_ks<4>(a, stream);
