@@ -26,7 +26,8 @@
 
 namespace plas {
 
-constexpr int RT_THREADS2 = 416;  // 8 gate-math warps + 1 MMA-issuer warp + 4 publisher warps
+constexpr int RT_GW = 16;                        // gate-math warps: 4 per TMEM lane quadrant, one (unit, utterance) cell per thread and group
+constexpr int RT_THREADS2 = (RT_GW + 5) * 32;    // gate-math warps + 1 MMA-issuer warp + 4 publisher warps
 constexpr int RT_NPUB = 128;      // publisher threads
 
 struct RecTcArgs {
@@ -77,6 +78,44 @@ __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld_16x128b(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+// The gate math is MUFU-bound (16 transcendentals per clock and SM; 512 cells per group step): 7 instead of 10 MUFU
+// instructions per cell by putting the three factors of the cell update, and the two of the output, over one common
+// denominator -- c = (c_prev (1+b)(1+d) + n_j (1+a)) / ((1+a)(1+b)(1+d)) with a = e^-(zf+1), b = e^-zi, d = e^-2|zj| and
+// n_j = tanh(zj) (1+d) (the Cephes polynomial below 0.625, 1-d above, as tanhf_fast) -- one reciprocal each.  The
+// exponents of a, b, e are clamped to 2^40 (sigmoid error < 1e-12) so that the products stay finite.
+__device__ __forceinline__ float rt_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rt_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rt_tanh_num(float x, float d) {  // tanh(x) * (1 + d), d = e^-2|x|
+  const float x2 = x * x;
+  float p = fmaf(x2, -5.70498872745e-3f, 2.06390887954e-2f);
+  p = fmaf(p, x2, -5.37397155531e-2f);
+  p = fmaf(p, x2, 1.33314422036e-1f);
+  p = fmaf(p, x2, -3.33332819422e-1f);
+  const float small = fmaf(x * x2, p, x) * (1.0f + d);
+  return fabsf(x) < 0.625f ? small : copysignf(1.0f - d, x);
+}
+__device__ __forceinline__ void rt_lstm_gates(float zi, float zj, float zf, float zo, float c_prev, float& c, float& h) {
+  constexpr float L2E = 1.4426950408889634f;
+  const float a = rt_ex2(fminf((zf + 1.0f) * -L2E, 40.0f));
+  const float b = rt_ex2(fminf(zi * -L2E, 40.0f));
+  const float e = rt_ex2(fminf(zo * -L2E, 40.0f));
+  const float d = rt_ex2(fabsf(zj) * (-2.0f * L2E));
+  const float A = 1.0f + a, BD = (1.0f + b) * (1.0f + d);
+  c = fmaf(c_prev, BD, rt_tanh_num(zj, d) * A) * rt_rcp(A * BD);
+  const float g = rt_ex2(fabsf(c) * (-2.0f * L2E));
+  h = rt_tanh_num(c, g) * rt_rcp((1.0f + e) * (1.0f + g));
+}
 // NG independent 16-utterance groups of one direction share a cluster (and the TMEM-resident weights) and are
 // software-pipelined against each other: warp 8 waits for a group's h_{s-1} to land and issues its U/16 MMAs
 // (asynchronous, own accumulator columns), while the 8 epilogue warps run the gate math / exchange of the other
@@ -87,8 +126,9 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
   constexpr int G = U / 32;          // CTAs per cluster
   constexpr int KB = U / 64;         // 64-wide k blocks of the h operand
   constexpr int NR = 16;             // utterances per group
-  constexpr int HR = NR / 2;         // utterances per warp half
-  constexpr int PP = NR / 8;         // (unit, utterance) pairs per thread and group
+  constexpr int WQ = RT_GW / 4;      // gate-math warps per TMEM lane quadrant
+  constexpr int HR = NR / WQ;        // utterances per gate-math warp (8: two per thread, 4: one per thread)
+  constexpr int PP = HR / 4;         // (unit, utterance) pairs per thread and group
   constexpr int TILE = NR * 128;     // bytes of one k block of the h operand
   constexpr int HBUF = KB * TILE;    // bytes of one h operand buffer
   constexpr int ACOL0 = 64;          // first TMEM column of the resident W slice; accumulator of group g: 16g..16g+15
@@ -147,6 +187,8 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     hbar[gg][1] = smem_u32(&s_bar[gg][1]);
     mbar[gg] = smem_u32(&s_bar[gg][2]);
   }
+  // gate-math warps whose HR utterances are all padding (rows >= R) sit the sequence out: fewer MUFU instructions in flight, smaller barriers
+  const int nbar = 4 * ((R + HR - 1) / HR) * 32 + RT_NPUB;
   const uint32_t step_bytes = (uint32_t)(G * R * 64);  // bytes every CTA receives per group step
   if (tid == 0) {
 #pragma unroll
@@ -186,7 +228,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
   rt_cluster_sync();
   tc_fence_after();
 
-  if (warp == 8) {
+  if (warp == RT_GW) {
     // ===== MMA issuer: per (step, group) wait for h_{s-1}, re-arm the buffer's barrier, issue, commit =====
     if (elect_one()) {
       unsigned long long t_wait = 0, t_issue = 0, t0 = 0, t1 = 0;
@@ -216,14 +258,14 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
       if (tm) { p.tdbg[0] = t_wait; p.tdbg[1] = t_issue; }
     }
     __syncwarp();
-  } else if (warp >= 9) {
+  } else if (warp > RT_GW) {
     // ===== publisher warps 9..12: push every staged 16 x 32 slice (a) into the swizzled h operand of every CTA of
     // the cluster -- thread = (destination, row, 16-byte chunk), so the four chunks of a row leave as one contiguous
     // 64-byte DSMEM segment (scattered 16-byte remote stores were measured 30% slower) -- and (b) for active rows to
     // the [B,T,ndir*U] layer output in HBM.  An SM sends only ~20 bytes/clk over the SM-to-SM network, so the
     // 16 KB of a group step keep the store unit busy for ~0.4 us: on their own warps these stores overlap the gate
     // math of the next group instead of stalling it. =====
-    const int ptid = tid - 9 * 32;
+    const int ptid = tid - (RT_GW + 1) * 32;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.out);
     int n_item = 0;
     for (int s = 0; s < Tmax; ++s) {
@@ -233,7 +275,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
         const int sb = n_item & 1;
         ++n_item;
         const __nv_bfloat16* stg = s_stage + sb * (NR * 32);
-        rt_bar_sync(2 + sb, 256 + RT_NPUB);  // wait until the gate-math warps have filled the tile
+        rt_bar_sync(2 + sb, nbar);  // wait until the gate-math warps have filled the tile
         if (s + 1 < Tg[gg]) {
           const uint32_t dst_buf = hbuf_u + (uint32_t)((gg * 2 + (s & 1)) * HBUF) + (uint32_t)((ci >> 1) * TILE);
           const uint32_t bar_l = hbar[gg][s & 1];
@@ -270,7 +312,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
             }
           }
         }
-        rt_bar_arrive(4 + sb, 256 + RT_NPUB);  // tile published: the gate-math warps may overwrite it
+        rt_bar_arrive(4 + sb, nbar);  // tile published: the gate-math warps may overwrite it
       }
     }
     if (!d.out_zeroed) {
@@ -306,7 +348,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
       for (int i = 0; i < PP; ++i) {
-        const int r = half0 + 2 * jq + i;
+        const int r = half0 + PP * jq + i;
         len_p[gg][i] = s_len[gg][r];
         const __nv_bfloat16* xrow = xproj + ((size_t)min((grp0 + gg) * R + r, B - 1) * T) * NX + (size_t)dir * 4 * U + 4 * unit;
         c_state[gg][i] = 0.f;
@@ -326,14 +368,14 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     int n_item = 0;
     unsigned long long e_wait = 0, e_gate = 0, e_push = 0, e0 = 0, e1 = 0;
     const bool tme = p.tdbg != nullptr && blockIdx.x == 0 && tid == 0;
-    for (int s = 0; s < Tmax; ++s) {
+    for (int s = 0; s < (half0 < R ? Tmax : 0); ++s) {
 #pragma unroll
       for (int gg = 0; gg < NG; ++gg) {
         if (s >= Tg[gg]) continue;  // uniform over the cluster
         if (tme) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e0));
         const int sb = n_item & 1;
         __nv_bfloat16* stg = s_stage + sb * (NR * 32);
-        if (n_item >= 2) rt_bar_sync(4 + sb, 256 + RT_NPUB);  // the publishers are done with this tile's previous content
+        if (n_item >= 2) rt_bar_sync(4 + sb, nbar);  // the publishers are done with this tile's previous content
         ++n_item;
         uint32_t zr[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // [i,j | gates 0,1 of rows 0,1] then [f,o]: see below
         if (s > 0) {
@@ -344,21 +386,27 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
           // accumulator: TMEM lane = gate column (8*gate + unit inside the warp's 32-lane quadrant), column =
           // utterance.  Two 16x256b loads hand thread t all four gates of unit t/4 for utterances 2*(t%4), +1 of
           // this warp half -- no shared-memory transpose.
-          tmem_ld_16x256b(tmem_base + lane_base + (uint32_t)(gg * NR + half0), zr);
-          tmem_ld_16x256b(tmem_base + lane_base + (16u << 16) + (uint32_t)(gg * NR + half0), zr + 4);
+          if (PP == 2) {
+            tmem_ld_16x256b(tmem_base + lane_base + (uint32_t)(gg * NR + half0), zr);
+            tmem_ld_16x256b(tmem_base + lane_base + (16u << 16) + (uint32_t)(gg * NR + half0), zr + 4);
+          } else {  // 16x128b: thread t gets lane t/4 (r0) and lane t/4 + 8 (r1) of column t%4
+            tmem_ld_16x128b(tmem_base + lane_base + (uint32_t)(gg * NR + half0), zr);
+            tmem_ld_16x128b(tmem_base + lane_base + (16u << 16) + (uint32_t)(gg * NR + half0), zr + 2);
+          }
           tmem_ld_wait();
           tc_fence_before();
         }
 #pragma unroll
         for (int i = 0; i < PP; ++i) {
-          const int rl = 2 * jq + i;  // utterance inside the warp half
-          // zr[0..1] = gate i (lane u8) rows 0,1; zr[2..3] = gate j (lane u8+8); zr[4..5] = gate f; zr[6..7] = gate o
-          const float4 z = make_float4(__uint_as_float(zr[i]), __uint_as_float(zr[2 + i]), __uint_as_float(zr[4 + i]),
-                                       __uint_as_float(zr[6 + i]));
+          const int rl = PP * jq + i;  // utterance inside the warp's HR
+          // PP == 2: zr[0..1] = gate i (lane u8) rows 0,1; zr[2..3] = gate j (lane u8+8); zr[4..5] = gate f; zr[6..7] = gate o
+          // PP == 1: zr[0..3] = gates i, j, f, o
+          const float4 z = make_float4(__uint_as_float(zr[i]), __uint_as_float(zr[PP + i]), __uint_as_float(zr[2 * PP + i]),
+                                       __uint_as_float(zr[3 * PP + i]));
           const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][i].x);
           const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&xp[gg][i].y);
           float cn, hn;
-          lstm_gates_fast(z.x + __low2float(x01), z.y + __high2float(x01), z.z + __low2float(x23), z.w + __high2float(x23),
+          rt_lstm_gates(z.x + __low2float(x01), z.y + __high2float(x01), z.z + __low2float(x23), z.w + __high2float(x23),
                           c_state[gg][i], cn, hn);
           const bool live = s < len_p[gg][i];
           c_state[gg][i] = live ? cn : c_state[gg][i];
@@ -372,7 +420,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
           }
         }
         __threadfence_block();
-        rt_bar_arrive(2 + sb, 256 + RT_NPUB);  // stage tile sb is full: the publisher warps take it from here
+        rt_bar_arrive(2 + sb, nbar);  // stage tile sb is full: the publisher warps take it from here
         if (tme) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e1)); e_gate += e1 - e0; e0 = e1; }
         if (tme) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(e1)); e_push += e1 - e0; }
       }
@@ -382,7 +430,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     for (int gg = 0; gg < NG; ++gg)
 #pragma unroll
       for (int i = 0; i < PP; ++i) {
-        const int r = half0 + 2 * jq + i;
+        const int r = half0 + PP * jq + i;
         const int b = (grp0 + gg) * R + r;
         if (grp0 + gg < p.n_groups && r < R && b < B) {
           d.c_final[((size_t)dir * B + b) * U + unit] = c_state[gg][i];
