@@ -12,7 +12,9 @@ Pure Python + numpy, no TensorFlow.  Written from the published on-disk formats:
   * ``.data-*`` -- the raw little-endian tensor bytes at [offset, offset + size).
 PROVENANCE: TensorFlow is not installable in this environment, so this module has been exercised only
 against files produced by its own writer (round trip, CRC known-answer vectors, hand-built snappy blocks) -- it has NOT
-been run against a TF-written checkpoint.  Partitioned variables (``slices``) are rejected.
+been run against a TF-written checkpoint.  The BundleHeaderProto / BundleEntryProto values are cross-checked in both directions
+against the google.protobuf runtime with TensorFlow's published tensor_bundle.proto schema (tests/test_proto_crosscheck.py); the
+leveldb-style table container stays self-round-trip only.  Partitioned variables (``slices``) are rejected.
 """
 import os
 import re

@@ -4,7 +4,9 @@
 
 Pure Python + numpy (TensorFlow is not installable here): the TFRecord framing (uint64 length, masked CRC-32C of the
 length, payload, masked CRC-32C of the payload) and a minimal protobuf reader/writer for the three message types involved.
-PROVENANCE: exercised against files produced by its own writer only (round trip + CRC known answers), like tf_checkpoint.py.
+PROVENANCE: no TF-written file has been read (TensorFlow is not installable here); the protobuf layer is cross-checked in both
+directions against the google.protobuf runtime with TensorFlow's published feature.proto / example.proto schemas
+(tests/test_proto_crosscheck.py), the framing against CRC-32C known answers.
 
 ``batches(...)`` mirrors ``process_dataset`` for the labelled case without shuffling: vocabulary lookup (unknown -> ``<unk>``
 = 0), per-channel ``(x - mean) / std``, ``targets_inputs = [sos] + ids``, ``targets_outputs = ids + [eos]``,

@@ -31,5 +31,9 @@ def run(n_streams):
     return (time.perf_counter() - t0) / K * 1e3
 
 
-for n in (1, 2, 1, 2, 3):
-    print(f"{n} stream(s): {run(n):.3f} ms per batch", flush=True)
+for ng, rows in ((0, 0), (2, 16), (4, 16), (4, 11)):
+    for k, v in (("PLAS_REC_NG", ng), ("PLAS_REC_ROWS", rows)):
+        if v: os.environ[k] = str(v)
+        else: os.environ.pop(k, None)
+    for n in (1, 2, 3, 4):
+        print(f"rec NG={ng or 'auto'} rows={rows or 'auto'}  {n} stream(s): {run(n):.3f} ms per batch", flush=True)
