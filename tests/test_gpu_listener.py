@@ -17,6 +17,14 @@ CONFIGS = [
     ("bf16", 3, 13, 5, 64, 3, True),
     ("bf16", 16, 37, 80, 128, 4, True),
     ("bf16", 33, 50, 81, 512, 2, True),
+    # group plans of rec_tc.cu (rows per group x groups per cluster x clusters): 1 utterance; 3 x 1 x 6; 9 x 2 x 6; 9 x 4 x 6;
+    # 11 x 4 x 6 with ragged last groups; 8-CTA clusters
+    ("bf16", 1, 20, 80, 512, 1, False),
+    ("bf16", 7, 25, 80, 512, 1, True),
+    ("bf16", 49, 30, 80, 512, 1, True),
+    ("bf16", 100, 24, 80, 512, 1, True),
+    ("bf16", 130, 16, 80, 512, 1, True),
+    ("bf16", 40, 30, 40, 256, 2, True),
 ]
 
 
@@ -77,7 +85,8 @@ def test_listener_batch_independence_full_width():
 
 @gpu
 @pytest.mark.parametrize("precision,B,T,C,U,L,uni", [("fp32", 5, 17, 9, 32, 3, False), ("bf16", 20, 33, 40, 64, 2, False),
-                                                     ("fp32", 3, 12, 6, 32, 2, True), ("bf16", 9, 21, 80, 128, 3, False)])
+                                                     ("fp32", 3, 12, 6, 32, 2, True), ("bf16", 9, 21, 80, 128, 3, False),
+                                                     ("bf16", 50, 19, 80, 512, 2, True)])
 def test_non_pyramidal_listener(precision, B, T, C, U, L, uni):
     """las/model.py:111-142: stacked MultiRNNCell per direction, no time reduction, output depth ndir*U."""
     import torch
