@@ -118,6 +118,11 @@ typedef struct plas_rec_desc {
   const void* whh_tc;       /* bf16, optional: [ndir][U/32][128][U], row (TMEM lane) 32*q + 8*gate + u8 holds
                                W_h[:, gate*U + 32*cta + 8*q + u8]; the TMEM-resident operand of the tcgen05
                                recurrence (NULL: mma.sync kernels)                                         */
+  int32_t max_clusters;     /* tcgen05 recurrence: upper bound on the thread-block clusters (of U/32 CTAs) the call may
+                               occupy; 0 = as many as the GPU holds at once (lowest latency).  A serving loop that overlaps
+                               consecutive batches on several streams passes a smaller budget so that the other batch's
+                               kernels find free SMs                                                            */
+  int32_t reserved0;
 } plas_rec_desc;
 
 /* Layout contract for whh (host side packs once per checkpoint load):

@@ -30,7 +30,7 @@ class RecDesc(C.Structure):
                 ("out_zeroed", C.c_int32),
                 ("xproj", C.c_void_p), ("whh", C.c_void_p), ("lengths", C.c_void_p), ("out", C.c_void_p),
                 ("out_batch_stride", C.c_int64), ("c_final", C.c_void_p), ("h_final", C.c_void_p),
-                ("whh_tc", C.c_void_p)]
+                ("whh_tc", C.c_void_p), ("max_clusters", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class DecDesc(C.Structure):
@@ -234,6 +234,28 @@ class grid_sync_kernel:
         ev = torch.cuda.Event()
         ev.record()
         _grid_sync_done = ev
+
+
+# SM budget of the tcgen05 recurrence (-> plas_rec_desc.max_clusters; 0 = every cluster the GPU holds, the lowest latency): the
+# serving loop lowers it while consecutive batches overlap on several streams, so that the other batch's kernels find free SMs
+# (c2, two streams: 64 SMs = 4 clusters of 16 -> 86 k audio-s/s end to end, all 6 placeable clusters -> 81 k)
+rec_sm_budget = 0
+
+
+class rec_sms:
+    """``with _lib.rec_sms(64):`` -- recurrences launched inside occupy at most that many SMs."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        global rec_sm_budget
+        self.prev, rec_sm_budget = rec_sm_budget, self.n
+        return self
+
+    def __exit__(self, *exc):
+        global rec_sm_budget
+        rec_sm_budget = self.prev
 
 
 # launch accounting for bench.py's gpu_launches (our kernels only)

@@ -489,7 +489,10 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
   // The exchange is what bounds a step and its bytes per SM grow with the utterances a cluster carries, so the batch is
   // spread over as many clusters as the GPU can hold at once (7 of 16 CTAs on a B200): groups of `rows` <= 16
   // utterances, padded to the MMA's N = 16 (pad rows are neither exchanged nor stored).
-  const int cpd_fit = max_clusters / d.ndir > 0 ? max_clusters / d.ndir : 1;  // clusters per direction in one wave
+  int budget = max_clusters;  // the caller may keep SMs free for concurrent work (plas_rec_desc.max_clusters)
+  if (d.max_clusters > 0 && d.max_clusters < budget) budget = d.max_clusters;
+  if (const char* fb = getenv("PLAS_REC_MAX_CLUSTERS")) budget = atoi(fb) > 0 && atoi(fb) < max_clusters ? atoi(fb) : max_clusters;
+  const int cpd_fit = budget / d.ndir > 0 ? budget / d.ndir : 1;  // clusters per direction in one wave
   int rows = (d.B + cpd_fit * NG - 1) / (cpd_fit * NG);
   if (const char* fr = getenv("PLAS_REC_ROWS")) rows = atoi(fr);
   if (rows < 1) rows = 1;

@@ -131,6 +131,7 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
     d.out_batch_stride = out.stride(0)
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
     d.whh_tc = lw["whh_tc"].data_ptr() if lw.get("whh_tc") is not None else None
+    d.max_clusters = max(ndir, _lib.rec_sm_budget // max(1, U // 32)) if _lib.rec_sm_budget else 0
     need = L.plas_rec_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
     # the tensor-core recurrence only synchronises inside its clusters; the cooperative fallbacks exchange h through L2 across

@@ -176,6 +176,9 @@ class LASModel:
         key, klen = ("sample_ids", "final_sequence_length") if "sample_ids" in pred else ("sample_ids_phones_binf", "final_sequence_length_binf")
         return pred[key].cpu(), pred[klen].cpu()
 
+    # SMs the recurrence may hold while batches overlap on several streams (the other batch's front-end / GEMMs need the rest)
+    PIPELINED_REC_SMS = 64
+
     def default_streams(self):
         """Compute streams of the serving loop: 2 on the fused bf16 tensor-core path (its recurrence occupies 64 of the 148 SMs
         and its decoder is latency-bound, so the next batch's front-end / GEMMs / recurrence fill the idle SMs: measured
@@ -224,7 +227,7 @@ class LASModel:
                 bufs[slot].copy_(hw, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            with torch.cuda.stream(cs):
+            with torch.cuda.stream(cs), _lib.rec_sms(self.PIPELINED_REC_SMS if ns > 1 else 0):
                 cs.wait_event(ev)
                 pred = self.transcribe(bufs[slot], want_alignment=False, trim=False, want_probs=False)
                 done = torch.cuda.Event()
