@@ -378,9 +378,19 @@ def ours(args):
     ev0.record()
     for cs in streams or []:
         cs.wait_stream(main_stream)
+    from collections import deque
+    inflight = deque()
     for i in range(args.steps):
-        # trim=False: nothing in the step synchronises the host, the streams stay full across steps
+        # trim=False: nothing inside a step synchronises the host.  Like the serving loop (LASModel.transcribe_stream, which reads
+        # batch i - ns back before it enqueues batch i) the host stays at most `ns` batches ahead: free-running streams drift into
+        # lock step (both batches in their recurrences at once: 8 clusters wanted, 7 placeable) and the value then varies by 8 %
+        if streams is not None and len(inflight) == ns:
+            inflight.popleft().synchronize()
         pred = run_step(i, want_alignment=True, trim=False)
+        if streams is not None:
+            done = torch.cuda.Event()
+            done.record(streams[i % ns])
+            inflight.append(done)
     for cs in streams or []:
         main_stream.wait_stream(cs)
     ev1.record()

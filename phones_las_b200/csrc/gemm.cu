@@ -6,9 +6,13 @@
 //                                 M=128, N=BN, K=16 per instruction; accumulators in TMEM)
 //   warp 2      : TMEM allocator (2 accumulator stages x BN columns)
 //   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> +bias -> bf16 -> 16-byte global stores)
-// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), and a static
-// round-robin tile schedule over a grid of min(#tiles, #SMs) CTAs.  K and M tails rely on TMA
-// out-of-bounds zero fill; N must be a multiple of 128.
+//   warp 3      : work scheduler (cluster launch control: clusterlaunchcontrol.try_cancel)
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), and the work ring (scheduler -> the
+// other roles).  The grid has ONE CTA PER WORK UNIT (up to four n-blocks of one m-block); a running CTA takes over units
+// whose CTAs have not started yet by cancelling their launch, so the kernel is persistent on however many SMs it gets --
+// all 148 when it runs alone, the 52-84 a co-resident recurrence of the other stream's batch leaves otherwise (a static
+// round-robin grid cannot finish before its last CTA has found an SM).  K and M tails rely on TMA out-of-bounds zero
+// fill; N must be a multiple of 128.
 //
 // f32 path (plas_gemm_f32): exact-fp32 SIMT kernel, used only by the reference-precision mode.
 #include <mutex>
@@ -24,6 +28,30 @@ namespace plas {
 // ---------------------------------------------------------------------------------------
 constexpr int G_BM = 128;
 constexpr int G_BK = 64;
+constexpr int G_SCHED = 4;  // depth of the work ring: units a CTA may have claimed ahead of the one it is working on
+
+// ---- cluster launch control: take over the work of a CTA of this grid that has not been launched yet -------------------
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(resp), "r"(bar)
+               : "memory");
+}
+// -> true and the cancelled CTA's blockIdx.x when a launch was cancelled, false when every CTA of the grid has started
+__device__ __forceinline__ bool clc_read(uint32_t resp, int& bx) {
+  uint32_t valid, x = 0, y, z;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %3, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t}"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(valid)
+      : "r"(resp)
+      : "memory");
+  (void)y;
+  (void)z;
+  bx = (int)x;
+  return valid != 0;
+}
 
 template <int BN>
 struct GemmCfg {
@@ -32,7 +60,7 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * G_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, work ring*/;
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                     ((uint32_t)(G_BM >> 4) << 24);
@@ -42,7 +70,7 @@ template <int BN, bool OUT_F32>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const float* __restrict__ bias, void* __restrict__ Cv, long long M, int N,
-                         int K, long long ldc) {
+                         int K, long long ldc, int tpu) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ unsigned char gemm_smem_raw[];
   const uint32_t raw = smem_u32(gemm_smem_raw);
@@ -55,12 +83,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * (2 * Cfg::STAGES + 4));
+  // work ring: slot i = response of the i-th try_cancel (16 bytes) + "response landed" / "every role has read it" barriers
+  auto wfull_bar = [&](int s) { return bar_base + 144u + 8u * s; };
+  auto wempty_bar = [&](int s) { return bar_base + 144u + 8u * (G_SCHED + s); };
+  auto wresp = [&](int s) { return bar_base + 272u + 16u * s; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (int)((M + G_BM - 1) / G_BM);
   const int num_n = N / BN;
-  const int num_tiles = num_m * num_n;
   const int num_k = (K + G_BK - 1) / G_BK;
+  const int upm = num_n / tpu;  // work units per m-block; unit u = n-blocks (u % upm) * tpu ... + tpu - 1 of m-block u / upm
+  (void)num_m;
+  // every role walks the same unit sequence: its own blockIdx.x first, then whatever the scheduler's cancellations return
+  auto next_unit = [&](int it, int& unit, bool leader, bool whole_warp) -> bool {
+    const int slot = it % G_SCHED;
+    mbar_wait(wfull_bar(slot), (uint32_t)((it / G_SCHED) & 1));
+    const bool ok = clc_read(wresp(slot), unit);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this read vs the next asynchronous write of the slot
+    if (whole_warp) __syncwarp();  // every lane has read the response before the leader releases the slot
+    if (leader) mbar_arrive(wempty_bar(slot));
+    return ok;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -74,6 +117,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);
+    }
+    for (int s = 0; s < G_SCHED; ++s) {
+      mbar_init(wfull_bar(s), 1);
+      mbar_init(wempty_bar(s), 6);  // TMA producer, MMA issuer, four epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -92,17 +139,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, kb * G_BK, m_blk * G_BM, full_bar(stage));
-          tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * G_BK, n_blk * BN, full_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+      int unit = blockIdx.x, it = 0;
+      do {
+        const int m_blk = unit / upm, nb0 = (unit % upm) * tpu;
+        for (int sub = 0; sub < tpu; ++sub) {
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+            tma_load_2d(sa, &tmA, kb * G_BK, m_blk * G_BM, full_bar(stage));
+            tma_load_2d(sa + Cfg::A_BYTES, &tmB, kb * G_BK, (nb0 + sub) * BN, full_bar(stage));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
-      }
+      } while (next_unit(it++, unit, true, false));
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -111,26 +161,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+      int unit = blockIdx.x, it = 0;
+      do {
+        for (int sub = 0; sub < tpu; ++sub) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
-          const uint64_t adesc = umma_smem_desc(sa);
-          const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < num_k; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = base + stage * Cfg::STAGE_BYTES;
+            const uint64_t adesc = umma_smem_desc(sa);
+            const uint64_t bdesc = umma_smem_desc(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < G_BK / 16; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::IDESC,
-                      (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+            for (int k = 0; k < G_BK / 16; ++k)
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), Cfg::IDESC,
+                        (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(tfull_bar(acc));
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
         }
-        umma_commit(tfull_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+      } while (next_unit(it++, unit, true, false));
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===== work scheduler: one cancellation request at a time (a request after a failed one is undefined); it runs up to
+    // G_SCHED units ahead of the roles that consume the responses =====
+    if (elect_one()) {
+      int it = 0, dummy;
+      while (true) {
+        const int slot = it % G_SCHED;
+        if (it >= G_SCHED) mbar_wait(wempty_bar(slot), (uint32_t)(((it / G_SCHED) - 1) & 1));
+        mbar_expect_tx(wfull_bar(slot), 16);
+        clc_try_cancel(wresp(slot), wfull_bar(slot));
+        mbar_wait(wfull_bar(slot), (uint32_t)((it / G_SCHED) & 1));
+        const bool ok = clc_read(wresp(slot), dummy);
+        ++it;
+        if (!ok) break;
       }
     }
     __syncwarp();
@@ -138,8 +208,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    int unit = blockIdx.x, it = 0;
+    do {
+     const int m_blk = unit / upm, nb0 = (unit % upm) * tpu;
+     for (int sub = 0; sub < tpu; ++sub) {
+      const int n_blk = nb0 + sub;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const long long row = (long long)m_blk * G_BM + ew * 32 + lane;
@@ -186,7 +259,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-    }
+     }
+     __syncwarp();
+    } while (next_unit(it++, unit, lane == 0, true));
   }
 
   tc_fence_before();
@@ -269,10 +344,13 @@ static int launch_gemm_bf16(const void* A, long long M, int K, long long lda, co
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   PLAS_CUDA(attr_err);
-  const long long tiles = ((M + G_BM - 1) / G_BM) * (N / BN);
-  const int sms = num_sms() > 0 ? num_sms() : 148;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  gemm_bf16_tcgen05_kernel<BN, OUT_F32><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, bias, C, M, N, K, ldc);
+  // one CTA per work unit = up to 4 consecutive n-blocks of one m-block (a unit must outlast a cancellation round trip);
+  // CTAs that find an SM take over the units of those that have not started (cluster launch control)
+  const int num_n = N / BN;
+  const int tpu = num_n % 4 == 0 ? 4 : (num_n % 2 == 0 ? 2 : 1);
+  const long long units = ((M + G_BM - 1) / G_BM) * (num_n / tpu);
+  PLAS_REQUIRE(units <= 0x7fffffffLL, "gemm_bf16: %lld work units exceed the grid limit", units);
+  gemm_bf16_tcgen05_kernel<BN, OUT_F32><<<(unsigned)units, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, bias, C, M, N, K, ldc, tpu);
   PLAS_CUDA(cudaGetLastError());
   return PLAS_OK;
 }
