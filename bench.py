@@ -829,7 +829,7 @@ def reference_arm_train(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cfg = workload("c3")
-    batch = args.ref_batch
+    batch = args.ref_batch or cfg["batch"]  # the GPU arm's own batch (same_config)
     train_cpu_sample(cfg, 1)
     ts = []
     for _ in range(max(args.steps, 1)):

@@ -7,7 +7,7 @@ timeout 600 python bench.py --workload c3 --impl reference --steps 2 --warmup 0 
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/train_launches.csv \
     python scripts/train_probe.py --one > gpurun_out/ncu_train.log 2>&1; echo "ncu launches rc=$?"
 # kernel, launch-skip (a representative launch: layer-1 projection GEMM, layer-0 recurrences, a mid-sequence decoder step)
-for spec in gemm_f32_ex_kernel:2 rec_train_fwd_kernel:0 rec_train_bwd_kernel:2 dec_cell_fwd_kernel:20 dec_gemv_t_kernel:20 dec_att_fwd_kernel:20 dec_att_bwd_kernel:20; do
+for spec in gemm_tf32x3_tcgen05_kernel:2 gemm_f32_ex_kernel:2 rec_train_fwd_kernel:0 rec_train_bwd_kernel:2 dec_cell_fwd_kernel:20 dec_gemv_t_kernel:20 dec_att_fwd_kernel:20 dec_att_bwd_kernel:20; do
   k=${spec%%:*}; s=${spec##*:}
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -f -o gpurun_out/prof_train_$k \
       python scripts/train_probe.py --one > gpurun_out/ncu_train_$k.log 2>&1; echo "ncu $k rc=$?"
