@@ -397,9 +397,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             tc_fence_after();
             const uint64_t adesc = umma_smem_desc(ring + j * STA);
             const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(kb * ncols * 128));
-            // measured (A/B in one run): an SS-mode MMA of this size costs ~60 ns whatever M (64 / 128), N (32 / 128) or the
-            // accumulator it targets (one chain or four interleaved ones) -- the 2 us of a phase's 32 MMAs are a fixed
-            // per-instruction operand-fetch cost; only the A-from-TMEM form (rec_tc.cu: ~6 ns per MMA) avoids it
+            // measured (scripts/micro/mma_cost.cu, unrolled issue): an SS-mode MMA with M = 64 costs 27 + N/2 cycles (43 at N = 32),
+            // i.e. ~0.7 us for the 32 MMAs of a phase; the rest of the ~2 us between the first tile and the last MMA is the arrival
+            // of the other k-block tiles (the issue loop follows the copies), not tensor-core time
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i0 | j | k) != 0 ? 1u : 0u);

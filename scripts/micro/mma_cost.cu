@@ -38,11 +38,16 @@ __global__ void __launch_bounds__(128, 1) cost(long long* out, int M, int N, int
       long long t0 = 0;
       for (int rep = -2; rep < reps; ++rep) {
         if (rep == 0) t0 = clock64();
-        for (int i = 0; i < NM; ++i) {
-          const int kb = (i >> 2) & 7, k = i & 3;
-          const uint64_t bdesc = umma_smem_desc(B0 + kb * N * 128) + (uint64_t)(2 * k);
-          if (ts) umma_ts(tb, tb + 128 + 8 * (i & 31), bdesc, idesc, i != 0);
-          else umma_bf16(tb, umma_smem_desc(A0 + kb * 16384) + (uint64_t)(2 * k), bdesc, idesc, i != 0);
+        const uint64_t a0 = umma_smem_desc(A0), b0 = umma_smem_desc(B0);
+        const uint32_t bstep = (uint32_t)(N * 128) >> 4;
+        for (int pass = 0; pass < NM / 32; ++pass) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {  // descriptors are base + compile-time offsets: nothing but the MMA itself per iteration
+            const int kb = i >> 2, k = i & 3;
+            const uint64_t bdesc = b0 + (uint64_t)(kb * bstep + 2 * k);
+            if (ts) umma_ts(tb, tb + 128 + 8 * i, bdesc, idesc, (pass | i) != 0);
+            else umma_bf16(tb, a0 + (uint64_t)(kb * 1024 + 2 * k), bdesc, idesc, (pass | i) != 0);
+          }
         }
         umma_commit(smem_u32(&s_bar));
         mbar_wait(smem_u32(&s_bar), par);
