@@ -376,10 +376,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             wave_parity ^= 1u;
           }
           const int n = min(NSTA, nkb - i0);
+          int kb = rot + i0;
+          if (kb >= nkb) kb -= nkb;
           for (int j = 0; j < n; ++j) {
-            const int kb = (rot + i0 + j) % nkb;
             mbar_expect_tx(fullA(j), (uint32_t)STA);
             df_bulk_g2s(ring + j * STA, a_tiles + (size_t)kb * STA, (uint32_t)STA, fullA(j));
+            if (++kb == nkb) kb = 0;
           }
         }
       }
@@ -387,22 +389,25 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
     } else if (warp == 0) {
       if (elect_one()) {
         tc_fence_after();
+        // lean issue loop: descriptors are base + a multiple of the tile size (the single issuing thread is the critical path of
+        // the phase: rebuilding them from addresses, or a modulo by the run-time k-block count, costs more than the MMAs)
+        const uint64_t adesc0 = umma_smem_desc(ring), bdesc0 = umma_smem_desc(w_smem);
+        const uint32_t astep = (uint32_t)STA >> 4, bstep = (uint32_t)(ncols * 128) >> 4;
         for (int i0 = 0; i0 < nkb; i0 += NSTA) {
           const int n = min(NSTA, nkb - i0);
+          int kb = rot + i0;
+          if (kb >= nkb) kb -= nkb;
           for (int j = 0; j < n; ++j) {
-            const int kb = (rot + i0 + j) % nkb;
             mbar_wait(fullA(j), (full_bits >> j) & 1u);
             full_bits ^= 1u << j;
             if (detail && i0 + j == 0) fine_stamp(0);
             tc_fence_after();
-            const uint64_t adesc = umma_smem_desc(ring + j * STA);
-            const uint64_t bdesc = umma_smem_desc(w_smem + (uint32_t)(kb * ncols * 128));
-            // measured (scripts/micro/mma_cost.cu, unrolled issue): an SS-mode MMA with M = 64 costs 27 + N/2 cycles (43 at N = 32),
-            // i.e. ~0.7 us for the 32 MMAs of a phase; the rest of the ~2 us between the first tile and the last MMA is the arrival
-            // of the other k-block tiles (the issue loop follows the copies), not tensor-core time
+            const uint64_t adesc = adesc0 + (uint64_t)(j * astep);
+            const uint64_t bdesc = bdesc0 + (uint64_t)(kb * bstep);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i0 | j | k) != 0 ? 1u : 0u);
+            if (++kb == nkb) kb = 0;
           }
           if (i0 + n < nkb) umma_commit(wave_done);
         }
