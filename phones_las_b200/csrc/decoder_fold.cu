@@ -201,6 +201,32 @@ __device__ __forceinline__ void df_scores(const uint4* kb, int kstride, int n_c8
   }
 }
 
+// In-place inclusive prefix sum of a[0..n) by the 256 threads of the CTA (fixed order: each thread sums a contiguous chunk, the
+// chunk totals are scanned with warp shuffles, the eight warp totals through shared memory): three block barriers instead of
+// the log2(n) of a Hillis-Steele scan.  The caller has synchronised after writing a[]; a[] is complete on return.
+__device__ __forceinline__ void df_block_scan(float* a, int n, float* s_tot) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = (n + DF_THREADS - 1) / DF_THREADS;
+  const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+  float tot = 0.f;
+  for (int i = lo; i < hi; ++i) tot += a[i];
+  float inc = tot;  // inclusive scan of the chunk totals inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) s_tot[warp] = inc;
+  __syncthreads();
+  float off = inc - tot;  // exclusive prefix inside the warp
+  for (int w = 0; w < warp; ++w) off += s_tot[w];
+  for (int i = lo; i < hi; ++i) {
+    off += a[i];
+    a[i] = off;
+  }
+  __syncthreads();
+}
+
 }  // namespace
 
 template <int L>
@@ -694,11 +720,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             sa[tm] = logf(fminf(fmaxf(1.f - pc, tiny), 1.f));
           }
           df_sync();
-          for (int off = 1; off < Tm; off <<= 1) {  // inclusive Hillis-Steele scan of the logs
-            for (int tm = tid; tm < Tm; tm += 256) sb[tm] = sa[tm] + (tm >= off ? sa[tm - off] : 0.f);
-            df_sync();
-            float* tmp = sa; sa = sb; sb = tmp;
-          }
+          df_block_scan(sa, Tm, s_red + 32);  // inclusive scan of the logs
           for (int tm = tid; tm < Tm; tm += 256) {
             const float cpv = expf(tm > 0 ? sa[tm - 1] : 0.f);  // exclusive cumulative product of (1 - p)
             const float pv = (t == 0) ? (tm == 0 ? 1.f : 0.f) : __ldcg(prev + tm);
@@ -706,13 +728,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
             s_score[tm] = s_score[tm] * cpv;  // p * cp
           }
           df_sync();
+          df_block_scan(sb, Tm, s_red + 32);
           float* ra = sb;
-          float* rb = sa;
-          for (int off = 1; off < Tm; off <<= 1) {
-            for (int tm = tid; tm < Tm; tm += 256) rb[tm] = ra[tm] + (tm >= off ? ra[tm - off] : 0.f);
-            df_sync();
-            float* tmp = ra; ra = rb; rb = tmp;
-          }
           for (int tm = tid; tm < Tm; tm += 256) s_score[tm] = s_score[tm] * ra[tm];
           df_sync();
         } else {
