@@ -33,6 +33,28 @@ __global__ void k(unsigned* bar, unsigned* flags, int iters, int csize) {
       }
       if (threadIdx.x == 0) { { unsigned sp = 0; while (ld_acq(bar) < (unsigned)(it + 1)) { if (++sp > (1u << 24)) __trap(); } } }
       __syncthreads();
+    } else if (MODE == 4 || MODE == 5) {  // all-gather of per-CTA flags: one store, then every CTA polls all the flags (one hop, no atomics)
+      const int stride = MODE == 4 ? 1 : 32;  // contiguous (4 lines for 128 CTAs) or one line per flag
+      __syncthreads();
+      if (threadIdx.x == 0) { epoch++; asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x * stride), "r"(epoch) : "memory"); }
+      if (threadIdx.x < gridDim.x) { unsigned sp = 0; while (ld_acq(flags + threadIdx.x * stride) < (unsigned)(it + 1)) { if (++sp > (1u << 24)) __trap(); } }
+      __syncthreads();
+    } else if (MODE == 6) {  // as 4, relaxed polling by one warp (4 flags per lane, 16-byte loads), one acquire fence at the end
+      __syncthreads();
+      if (threadIdx.x == 0) { epoch++; asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(epoch) : "memory"); }
+      if (threadIdx.x < 32) {
+        const unsigned want = (unsigned)(it + 1);
+        unsigned sp = 0;
+        while (true) {
+          uint4 v;
+          asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(flags + 4 * threadIdx.x) : "memory");
+          const bool ok = (4 * threadIdx.x >= gridDim.x) || (v.x >= want && v.y >= want && v.z >= want && v.w >= want);
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (++sp > (1u << 24)) __trap();
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      __syncthreads();
     }
   }
 }
@@ -60,5 +82,8 @@ int main() {
   printf("flat relaxed-spin          128 CTAs: %.2f us/barrier\n", run<2>(128, 4, iters));
   printf("flags collected by CTA 0   128 CTAs: %.2f us/barrier\n", run<3>(128, 4, iters));
   printf("flat red+acquire-spin       32 CTAs: %.2f us/barrier\n", run<0>(32, 4, iters));
+  printf("all-gather flags (packed)  128 CTAs: %.2f us/barrier\n", run<4>(128, 4, iters));
+  printf("all-gather flags (padded)  128 CTAs: %.2f us/barrier\n", run<5>(128, 4, iters));
+  printf("all-gather, one warp v4    128 CTAs: %.2f us/barrier\n", run<6>(128, 4, iters));
   return 0;
 }
