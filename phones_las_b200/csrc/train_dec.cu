@@ -231,9 +231,17 @@ __global__ void __launch_bounds__(256) dec_att_fwd_kernel(AttFwdArgs p) {
     const int kq = len * Ud / 4;
     for (int i = tid; i < kq; i += 256) cp_async16(s_keys + 4 * i, kb + 4 * i);
     const int dq = dw / 4;
-    for (int i = tid; i < len * dq; i += 256) {
-      const int t = i / dq, q = i - t * dq;
-      cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+    if ((dq & (dq - 1)) == 0) {  // power-of-two slices: shift / mask instead of a run-time division per element
+      const int lg = 31 - __clz(dq);
+      for (int i = tid; i < len * dq; i += 256) {
+        const int t = i >> lg, q = i & (dq - 1);
+        cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+      }
+    } else {
+      for (int i = tid; i < len * dq; i += 256) {
+        const int t = i / dq, q = i - t * dq;
+        cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -426,13 +434,25 @@ __global__ void __launch_bounds__(256) dec_att_bwd_kernel(AttBwdArgs p) {
   const float* kb = p.keys + (size_t)b * Tm * Ud;
   if (p.staged) {
     const int dq = dper / 4, uq = uper / 4;
-    for (int i = tid; i < len * dq; i += 256) {
-      const int t = i / dq, q = i - t * dq;
-      cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
-    }
-    for (int i = tid; i < len * uq; i += 256) {
-      const int t = i / uq, q = i - t * uq;
-      cp_async16(s_keys + (size_t)t * uper + 4 * q, kb + (size_t)t * Ud + u_lo + 4 * q);
+    if (((dq & (dq - 1)) | (uq & (uq - 1))) == 0) {  // power-of-two slices: shift / mask instead of run-time divisions
+      const int lgd = 31 - __clz(dq), lgu = 31 - __clz(uq);
+      for (int i = tid; i < len * dq; i += 256) {
+        const int t = i >> lgd, q = i & (dq - 1);
+        cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+      }
+      for (int i = tid; i < len * uq; i += 256) {
+        const int t = i >> lgu, q = i & (uq - 1);
+        cp_async16(s_keys + (size_t)t * uper + 4 * q, kb + (size_t)t * Ud + u_lo + 4 * q);
+      }
+    } else {
+      for (int i = tid; i < len * dq; i += 256) {
+        const int t = i / dq, q = i - t * dq;
+        cp_async16(s_vals + (size_t)t * dper + 4 * q, vb + (size_t)t * D + d_lo + 4 * q);
+      }
+      for (int i = tid; i < len * uq; i += 256) {
+        const int t = i / uq, q = i - t * uq;
+        cp_async16(s_keys + (size_t)t * uper + 4 * q, kb + (size_t)t * Ud + u_lo + 4 * q);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }

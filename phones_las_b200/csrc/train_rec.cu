@@ -277,9 +277,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) rec_train_bwd_kernel(RecTrainAr
       if (tid == 0) rt_wait(ctr, (unsigned)(p.G * j));
       __syncthreads();
       const float4* src = reinterpret_cast<const float4*>(dzx + (((size_t)((j - 1) & 1) * ndir + dir) * p.Bpad + row0) * W4);
-      for (int i = tid; i < R * U; i += RT_THREADS) {
-        const int rr = i / U, c4 = i - rr * U;
-        s_dz[rr * ZS + c4] = __ldcg(src + i);
+      if ((U & (U - 1)) == 0) {  // power-of-two widths: shift / mask instead of a run-time division per element
+        const int lg = 31 - __clz(U);
+        for (int i = tid; i < R * U; i += RT_THREADS) s_dz[(i >> lg) * ZS + (i & (U - 1))] = __ldcg(src + i);
+      } else {
+        for (int i = tid; i < R * U; i += RT_THREADS) {
+          const int rr = i / U, c4 = i - rr * U;
+          s_dz[rr * ZS + c4] = __ldcg(src + i);
+        }
       }
       __syncthreads();
       float racc[RB];
