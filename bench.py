@@ -427,7 +427,7 @@ def ours(args):
             model.transcribe(dev_waves[i % nbuf])
         for k, v in _lib.timeline_stop().items():
             stage_ms.setdefault(k, []).append(sum(v))
-    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    stage_ms = {k: float(np.median(v)) for k, v in stage_ms.items()}
 
     model_rec_sms = model.PIPELINED_REC_SMS if ns > 1 else 0
     del model, dev_waves, host_waves
