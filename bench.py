@@ -486,6 +486,12 @@ def ours(args):
                 "peak_source": peaks["_source"] + " (sustained figure: kernel timed inside a long step)",
                 "share_of_step": stage_ms[dom] / sum(stage_ms.values()),
                 "ms_per_launch": stage_ms[dom] / dw["launches_per_step"]}
+    if dom == "rec" and "onchip" in dw:
+        # north_star (3) asks for the recurrence against the HBM / SMEM roofline: the formal HBM fraction above, and next to it the
+        # on-chip operand stream (resident W_hh re-read by every group step's MMA chain) and the latency chain that actually bounds it
+        roofline["onchip"] = dw["onchip"]
+        roofline["note"] = ("the recurrence synchronises 4129 times per batch: a per-step latency chain (MMA 0.22 us, gate math, five "
+                            "synchronisation hops, DESIGN.md K3), not HBM bytes, bounds it; exchange_floor_frac = %.2f" % dw.get("exchange_floor_frac", float("nan")))
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and cfg["name"] == "c2" and B == cfg["batch"]:  # the captures are of this workload
         try:
