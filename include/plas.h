@@ -30,7 +30,7 @@ extern "C" {
 #define PLAS_ATT_BAHDANAU 1
 #define PLAS_ATT_LUONG_MONOTONIC 2
 #define PLAS_ATT_BAHDANAU_MONOTONIC 3 /* fp32 step kernels only (plas_decoder_infer_f32: mode 'hard'; plas_decoder_train_*: sigmoid noise) */
-#define PLAS_ATT_CUSTOM 4             /* fp32 step kernels only: CustomAttention, las/model.py:72-101 */
+#define PLAS_ATT_CUSTOM 4             /* CustomAttention, las/model.py:72-101: fp32 step kernels, and plas_decoder_fwd's folded bf16 tensor-core kernel (keys already relu'd by the caller) */
 
 typedef void* plas_stream_t;
 

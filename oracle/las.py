@@ -51,7 +51,7 @@ def folded_context_decoder(hp, B, D, precision):
     points differ from the other decoders' (VW instead of the fed-back context), so the emulation must know."""
     Ud = hp["decoder_units"]
     return (precision == "bf16" and not hp.get("bottom_only") and not hp.get("attention_layer_size")
-            and not hp.get("binf_projection") and hp["attention_type"] in ("luong", "bahdanau", "luong_monotonic")
+            and not hp.get("binf_projection") and hp["attention_type"] in ("luong", "bahdanau", "luong_monotonic", "custom")
             and D % 64 == 0 and Ud % 64 == 0 and D <= 2048 and Ud // 4 <= 148 and B <= 128)
 
 

@@ -456,7 +456,8 @@ extern "C" int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t 
   PLAS_REQUIRE(d->B > 0 && d->Tm > 0 && d->V > 0 && d->max_steps >= 0, "decoder: bad shape");
   PLAS_REQUIRE(d->n_layers >= 1 && d->n_layers <= 4, "decoder: n_layers=%d (1..4)", d->n_layers);
   PLAS_REQUIRE(d->Ud % 16 == 0 && d->D % 16 == 0, "decoder: Ud=%d and D=%d must be multiples of 16", d->Ud, d->D);
-  PLAS_REQUIRE(d->attention_type >= 0 && d->attention_type <= 2, "decoder: attention_type %d", d->attention_type);
+  PLAS_REQUIRE((d->attention_type >= 0 && d->attention_type <= 2) || d->attention_type == PLAS_ATT_CUSTOM, "decoder: attention_type %d",
+               d->attention_type);
   PLAS_REQUIRE(d->keys && d->values && d->mem_len && d->w_emb && d->w_proj && d->b_proj && d->logits &&
                    d->sample_ids && d->seq_len && d->n_steps, "decoder: null tensor");
   PLAS_REQUIRE(d->attention_type != PLAS_ATT_BAHDANAU || (d->w_query && d->v_att), "decoder: bahdanau needs query_layer/attention_v");
@@ -465,6 +466,9 @@ extern "C" int plas_decoder_fwd(const plas_dec_desc* d, void* workspace, size_t 
   {
     int rc = dec_fold_launch(*d, workspace, workspace_bytes, stream);
     if (rc != 1) return rc;  // 1 = shape not eligible for the folded-context tensor-core kernel
+    if (d->attention_type == PLAS_ATT_CUSTOM)  // only decoder_fold.cu carries it here (any shape: plas_decoder_infer_f32)
+      return set_err(PLAS_EUNSUPPORTED, "decoder: custom attention runs on the folded tensor-core kernel only (bf16, B <= 128, "
+                     "D and Ud multiples of 64, w_query_tc / vw / pv supplied); use plas_decoder_infer_f32 otherwise");
     rc = dec_tc_launch(*d, workspace, workspace_bytes, stream);
     if (rc != 1) return rc;  // 1 = shape not eligible for the tensor-core kernel
   }

@@ -269,8 +269,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
   const int nq = Ud / 16;
   const bool bahdanau = d.attention_type == PLAS_ATT_BAHDANAU;
   const bool monotonic = d.attention_type == PLAS_ATT_LUONG_MONOTONIC;
+  // CustomAttention (las/model.py:72-101): keys = relu(memory_layer(values)) (the caller passes them), query = relu(query_layer(h)),
+  // luong score -- the query-layer machinery of the bahdanau path with the dot-product score of the luong path
+  const bool custom = d.attention_type == PLAS_ATT_CUSTOM;
+  const bool qlayer = bahdanau || custom;         // the top phase also multiplies h with a query layer
   const int slice = blockIdx.x;                   // this CTA owns gate columns 16*slice .. +15 of every layer
-  const bool q_cta = bahdanau && slice < nq;      // ... and query-layer columns 16*slice .. +15
+  const bool q_cta = qlayer && slice < nq;        // ... and query-layer columns 16*slice .. +15
   const int crank = blockIdx.x % DF_CL;           // rank inside the cluster
   const int AS = p.as;
   const int part = crank % AS;                    // which part of its utterances this CTA handles
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
       acc_parity ^= 1u;
       // the barrier after the top phase is only needed when its result is read in this step (query layer) or by the
       // cell 0 that follows the attention (L == 1: ZH0)
-      if (ph < L - 1 || bahdanau || L == 1) {
+      if (ph < L - 1 || qlayer || L == 1) {
         df_grid_barrier(p.bar, epoch);
       } else {
         // the attention phase reuses the ring region, also for what the partner CTAs push into it: every CTA of the
@@ -608,6 +612,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) decoder_fold_kernel(const __gri
         // ---- query ----
         for (int u = tid; u < Ud; u += 256)
           s_q[u] = bahdanau ? __ldcg(p.qbuf + (size_t)b * Ud + u)
+                   : custom ? fmaxf(__ldcg(p.qbuf + (size_t)b * Ud + u), 0.f)
                             : __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short*>(Htop + df_h_off(b, u, STA))) << 16);
         // the id-independent operands of cell 0 (t+1): issued now, consumed after the argmax
         float zb[8];
@@ -925,10 +930,11 @@ struct DecFoldPlan {
 static DecFoldPlan dec_fold_plan(const plas_dec_desc& d) {
   DecFoldPlan pl;
   memset(&pl, 0, sizeof(pl));
-  const bool bahdanau = d.attention_type == PLAS_ATT_BAHDANAU;
+  const bool bahdanau = d.attention_type == PLAS_ATT_BAHDANAU || d.attention_type == PLAS_ATT_CUSTOM;  // a query layer in the top phase
   const bool shape_ok = d.dtype == PLAS_BF16 && d.vw && d.pv && d.w_h_tc[0] && d.B >= 1 && d.B <= 128 && d.Ud % 64 == 0 &&
                         d.Ud >= 64 && (d.Ud / 4) <= num_sms() && d.Tm <= 4096 && d.n_layers >= 1 && d.n_layers <= 4 &&
-                        d.attention_type >= PLAS_ATT_LUONG && d.attention_type <= PLAS_ATT_LUONG_MONOTONIC &&
+                        ((d.attention_type >= PLAS_ATT_LUONG && d.attention_type <= PLAS_ATT_LUONG_MONOTONIC) ||
+                         d.attention_type == PLAS_ATT_CUSTOM) &&
                         (!bahdanau || d.w_query_tc);
   if (!shape_ok) return pl;
   for (int l = 1; l < d.n_layers; ++l)

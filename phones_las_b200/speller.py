@@ -7,9 +7,10 @@ final_state, final_sequence_length)`` (``FinalBeamSearchDecoderOutput`` with ``b
 prepared once per batch (length masking + memory_layer GEMM, las/model.py:168-169).  Two decoder families sit underneath:
 
 * the fused decoders (``plas_decoder_fwd``: the whole decode loop inside one persistent kernel; bf16 tensor-core or SIMT) for the
-  default wiring with luong / bahdanau / luong_monotonic attention -- the BASELINE configurations;
+  default wiring with luong / bahdanau / luong_monotonic attention -- the BASELINE configurations -- and, on the folded bf16
+  tensor-core kernel, custom attention;
 * the fp32 step-kernel decoder (``plas_decoder_infer_f32``, a host loop over the training path's step kernels on the TF weight
-  layout) for reference precision and for every other variant: bahdanau_monotonic (mode 'hard'), custom attention, the
+  layout) for reference precision and for every other variant: bahdanau_monotonic (mode 'hard'), custom attention (fp32), the
   AttentionMultiCell wiring (bottom_only, pass_hidden_state), attention_layer_size, --binf_projection, beam search.
 
 ``embedding_size`` folds into the weights of both (``fold_embedding``).  DESIGN.md section 8 lists what is not built.
@@ -66,7 +67,10 @@ class SpellerWeights:
             return
         if hp["attention_type"] not in _lib.ATT_CODES:
             raise NotImplementedError(f"attention_type={hp['attention_type']}")
-        if hp.get("attention_layer_size") or hp["attention_type"] in ("bahdanau_monotonic", "custom"):
+        # custom attention also runs on the folded bf16 tensor-core decoder (decoder_fold.cu) when that kernel's shape rules hold
+        custom_fused = (hp["attention_type"] == "custom" and not hp.get("attention_layer_size") and precision == "bf16"
+                        and enc_depth % 64 == 0 and hp["decoder_units"] % 64 == 0 and enc_depth <= 2048 and hp["decoder_units"] <= 592)
+        if (hp.get("attention_layer_size") or hp["attention_type"] in ("bahdanau_monotonic", "custom")) and not custom_fused:
             self._init_attention_layer(params, hp, enc_depth, precision, device, scope)  # fp32 step-kernel decoder only
             return
         self.precision = precision
@@ -117,6 +121,9 @@ class SpellerWeights:
             self.v_att = up(params[f"{pre}/bahdanau_attention/attention_v"], torch.float32)
             if self.tc:
                 self.w_query_tc = up(packing.pack_query_tc(params[f"{pre}/bahdanau_attention/query_layer/kernel"], Ud))
+        elif self.att == "custom":  # CustomAttention's own query layer (las/model.py:88-89), scope attention_wrapper/query_layer
+            self.w_query = up(params[f"{pre}/query_layer/kernel"])
+            self.w_query_tc = up(packing.pack_query_tc(params[f"{pre}/query_layer/kernel"], Ud))
         elif self.att == "luong_monotonic":
             self.score_bias = float(params[f"{pre}/luong_monotonic_attention/attention_score_bias"])
             self.score_bias_dev = torch.full((1,), self.score_bias, dtype=torch.float32, device=device)
@@ -265,8 +272,11 @@ def prepare_memory(encoder_outputs, source_sequence_length, w, memory_is_masked=
     if n_pad != w.Ud:
         keys = keys[:, :w.Ud].contiguous()
     if w.att == "custom":  # CustomAttention: keys = relu(memory_layer(values)) (las/model.py:94)
-        _lib.check(L.plas_relu_f32(_lib.ptr(keys), keys.numel(), _lib.stream_ptr()))
-        _lib.count_launches(1)
+        if keys.dtype == torch.float32:
+            _lib.check(L.plas_relu_f32(_lib.ptr(keys), keys.numel(), _lib.stream_ptr()))
+            _lib.count_launches(1)
+        else:
+            keys.relu_()  # bf16: exact, elementwise glue
     pv = vw = None
     if w.tc and B <= 128 and w.w_vw_t is not None and (4 * w.Ud) % 128 == 0:
         # VW = values x W0[V:V+D] (bf16): cell 0's share of the fed-back context, emitted by the attention phase as a . VW

@@ -34,6 +34,10 @@ CONFIGS = [
     # K-split cluster mode of the tensor-core decoder (every K_l a multiple of 256)
     ("bf16", "bahdanau", 40, 30, 64, 256, 2, 40),
     ("bf16", "luong_monotonic", 100, 22, 64, 256, 2, 33),
+    # CustomAttention on the folded tensor-core decoder (relu'd keys, query layer + relu, luong score): 1 and 2 layers, AS = 4 and 2
+    ("bf16", "custom", 9, 21, 32, 64, 1, 24),
+    ("bf16", "custom", 33, 40, 64, 128, 2, 64),
+    ("bf16", "custom", 64, 30, 64, 256, 2, 40),
 ]
 
 
