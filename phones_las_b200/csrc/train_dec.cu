@@ -1521,7 +1521,7 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   const float inv_keep = 1.0f / d->keep_prob;
 
   int rc;
-  if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud))) return rc;
+  if ((rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud, nullptr, 0.f, 1, 0, 0, 0, F(w.splitk), w.splitk_bytes))) return rc;
   if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
   if ((rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]))) return rc;
   PLAS_CUDA(cudaMemset2DAsync(F(w.att_prev), (size_t)S * A * 4, 0, (size_t)A * 4, B, st));
@@ -1602,7 +1602,8 @@ static int dec_train_fwd_bottom(const plas_dec_train_desc* d, void* workspace, c
   }
   PLAS_CUDA(cudaGetLastError());
   if (L > 1) return gemm(st, (long long)B * S, d->n_out, Ud, F(w.h[L - 1]), Ud, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
-  return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+  return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj, 0.f, 1, 0, 0, 0,
+              F(w.splitk), w.splitk_bytes);
 }
 
 static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, cudaStream_t st) {
@@ -1799,7 +1800,7 @@ static int dec_train_bwd_bottom(const plas_dec_train_desc* d, void* workspace, c
     return rc;
   if (mono && (rc = plas_colsum_f32(F(w.dbias), B, 1, 1, d->dscore_bias, 0, st))) return rc;
   if ((rc = gemm(st, (long long)B * Tm, D, Ud, F(w.dkeys), Ud, 1, d->w_mem, 1, Ud, d->dmemory, D, nullptr, 1.f))) return rc;
-  return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud);
+  return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb);
 }
 
 }  // namespace plas
@@ -1826,9 +1827,9 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   const bool custom = d->attention_type == PLAS_ATT_CUSTOM;
   if (bah) PLAS_REQUIRE(d->w_query && d->v_att, "dec_train_fwd: bahdanau needs query_layer / attention_v");
   // keys = memory_layer(values); the memory is already zero past each length (the listener guarantees it)
-  rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud);
+  // (few output tiles, long contraction: deterministic split-K through the workspace's scratch, like the weight gradients)
+  rc = gemm(st, (long long)B * Tm, Ud, D, d->memory, D, 1, d->w_mem, Ud, 1, F(w.keys), Ud, nullptr, 0.f, 1, 0, 0, 0, F(w.splitk), w.splitk_bytes);
   if (rc) return rc;
-  if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
   if (custom) dec_relu_kernel<<<(unsigned)(((size_t)B * Tm * Ud + 255) / 256), 256, 0, st>>>(F(w.keys), (size_t)B * Tm * Ud);
   // Z_0 = x_in W_0[0:E] + b_0 for every step at once
   rc = gemm(st, (long long)B * S, 4 * Ud, E, d->x_in, E, 1, d->kernel[0], 4 * Ud, 1, F(w.z[0]), 4 * Ud, d->bias[0]);
@@ -1922,7 +1923,8 @@ extern "C" int plas_decoder_train_fwd(const plas_dec_train_desc* d, void* worksp
   PLAS_CUDA(cudaGetLastError());
   if (d->att_out) PLAS_CUDA(cudaMemcpyAsync(d->att_out, F(w.att), (size_t)B * S * A * 4, cudaMemcpyDeviceToDevice, st));
   // logits = DenseBinfDecoder(attention)
-  return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj);
+  return gemm(st, (long long)B * S, d->n_out, A, F(w.att), A, 1, d->w_proj, d->n_out, 1, d->logits, d->n_out, d->b_proj, 0.f, 1, 0, 0, 0,
+              F(w.splitk), w.splitk_bytes);
 }
 
 extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* workspace, size_t workspace_bytes,
@@ -1950,7 +1952,7 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   if (d->datt_extra) PLAS_CUDA(cudaMemcpyAsync(datt, d->datt_extra, (size_t)BS * A * 4, cudaMemcpyDeviceToDevice, st));
   if ((rc = gemm(st, BS, A, NO, d->dlogits, NO, 1, d->w_proj, 1, NO, datt, A, nullptr, d->datt_extra ? 1.f : 0.f))) return rc;
   // dw_proj / db_proj NULL: the projection is a constant (transform_binf_to_phones under --binf_projection)
-  if (d->dw_proj && (rc = gemm(st, A, NO, (int)BS, F(w.att), 1, A, d->dlogits, NO, 1, d->dw_proj, NO))) return rc;
+  if (d->dw_proj && (rc = gemm(st, A, NO, (int)BS, F(w.att), 1, A, d->dlogits, NO, 1, d->dw_proj, NO, nullptr, 0.f, 1, 0, 0, 0, F(w.splitk), w.splitk_bytes))) return rc;
   if (d->db_proj && (rc = plas_colsum_f32(d->dlogits, BS, NO, NO, d->db_proj, 0, st))) return rc;
   if (bah) {
     PLAS_REQUIRE(d->dw_query && d->dv_att, "dec_train_bwd: bahdanau needs dw_query / dv_att");
@@ -2099,5 +2101,5 @@ extern "C" int plas_decoder_train_bwd(const plas_dec_train_desc* d, void* worksp
   // memory_layer: dmemory += dkeys W_mem^T, dW_mem = memory^T dkeys
   if (mono && (rc = plas_colsum_f32(F(w.dbias), B, 1, 1, d->dscore_bias, 0, st))) return rc;
   if ((rc = gemm(st, (long long)B * Tm, D, Ud, F(w.dkeys), Ud, 1, d->w_mem, 1, Ud, d->dmemory, D, nullptr, 1.f))) return rc;
-  return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud);
+  return gemm(st, D, Ud, B * Tm, d->memory, 1, D, F(w.dkeys), Ud, 1, d->dw_mem, Ud, nullptr, 0.f, 1, 0, 0, 0, sk, skb);
 }
