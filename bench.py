@@ -453,7 +453,9 @@ def ours(args):
             # plan of rec_tc.cu: clusters of one direction in one wave = min(7, SM budget / 16) // 2; fewest groups per cluster with
             # <= 16 rows per group
             cpd = (min(7, model_rec_sms // 16) if model_rec_sms else 7) // 2
-            ng = next((g for g in (1, 2, 4) if -(-B // (cpd * g)) <= 16), 4)
+            if -(-B // (cpd * 2)) > 16:  # listener.py: the budget is dropped when it would need more than two groups per cluster
+                cpd = 7 // 2
+            ng = next((g for g in (1, 2, 3, 4) if -(-B // (cpd * g)) <= 16), 4)
             rows = min(16, -(-B // (cpd * ng)))
             n_groups = -(-B // rows)
             floor_us = {1: 0.726, 2: 1.158}.get(ng, 0.58 * ng) * rows / 16.0

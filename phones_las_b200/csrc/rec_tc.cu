@@ -527,8 +527,9 @@ static int rec_tc_try(RecTcArgs a, cudaStream_t stream, bool must_fit_one_wave, 
 }
 
 // Fewest groups per cluster such that the batch fits in one wave of clusters with <= 16 rows per group (measured at
-// U = 512, us per step: B = 16: NG 1 x 6 rows 1.21, NG 2 x 3 rows 1.31; B = 32: NG 1 x 11 rows 1.36, NG 2 x 6 rows 1.41;
-// B = 64: NG 2 x 11 rows 1.56 (NG 2 x 16 rows on 4 clusters: 1.68); B = 128: NG 4 x 11 rows 3.22 (16 rows: 3.54)).
+// U = 512, us per step: B = 16: NG 1 x 6 rows 0.95, NG 2 x 3 rows 1.31 (round-2 start); B = 32: NG 1 x 11 rows 1.14; B = 64:
+// NG 2 x 11 rows on 6 clusters 1.34, NG 2 x 16 rows on 4 clusters 1.47, NG 3 x 11 rows on 4 clusters 1.92; B = 128: NG 3 x 15 rows
+// on 6 clusters 2.11, NG 4 x 11 rows 2.61, NG 4 x 16 rows on 4 clusters 2.94).
 template <int KS>
 static int rec_tc_launch_ks(const RecTcArgs& a, cudaStream_t stream) {
   bool launched = false;
@@ -541,6 +542,10 @@ static int rec_tc_launch_ks(const RecTcArgs& a, cudaStream_t stream) {
   }
   if (fng == 0 || fng == 2) {
     rc = rec_tc_try<KS, 2>(a, stream, fng == 0, &launched);
+    if (rc || launched) return rc;
+  }
+  if (fng == 0 || fng == 3) {
+    rc = rec_tc_try<KS, 3>(a, stream, fng == 0, &launched);
     if (rc || launched) return rc;
   }
   rc = rec_tc_try<KS, 4>(a, stream, false, &launched);

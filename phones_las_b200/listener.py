@@ -131,7 +131,13 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
     d.out_batch_stride = out.stride(0)
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
     d.whh_tc = lw["whh_tc"].data_ptr() if lw.get("whh_tc") is not None else None
-    d.max_clusters = max(ndir, _lib.rec_sm_budget // max(1, U // 32)) if _lib.rec_sm_budget else 0
+    d.max_clusters = 0
+    if _lib.rec_sm_budget:
+        # the pipelined loops' SM budget -- unless it would push the plan beyond two groups per cluster: four 16-row groups on
+        # 4 clusters (2.94 us per step at B = 128) lose more than the other batch's GEMMs gain (three 15-row groups on 6: 2.11 us)
+        mc = max(ndir, _lib.rec_sm_budget // max(1, U // 32))
+        if -(-B // (max(1, mc // ndir) * 2)) <= 16:
+            d.max_clusters = mc
     need = L.plas_rec_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
     # the tensor-core recurrence only synchronises inside its clusters; the cooperative fallbacks exchange h through L2 across

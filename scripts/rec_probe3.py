@@ -28,13 +28,8 @@ def probe(B, ng, rows):
     ms = float(np.mean(tl["rec"]))
     print(f"B={B:4d} NG={ng} rows={rows or 'auto':>4} rec {ms:8.3f} ms -> {ms*1e3/T:6.3f} us/step", flush=True)
 
-for B, plans in [(16, [(0, 0)]), (32, [(0, 0)]), (64, [(0, 0), (2, 16)]), (128, [(0, 0)])]:
+for mc, B, plans in [("7", 128, [(4, 11), (3, 15), (0, 0)]), ("4", 128, [(4, 16), (0, 0)]), ("7", 96, [(2, 16), (0, 0)]), ("7", 100, [(3, 12), (4, 9), (0, 0)])]:
+    os.environ["PLAS_REC_MAX_CLUSTERS"] = mc
     for ng, rows in plans:
+        print("max_clusters", mc, end=" ")
         probe(B, ng, rows)
-os.environ["PLAS_DEBUG"] = "1"
-os.environ.pop("PLAS_REC_NG", None); os.environ.pop("PLAS_REC_ROWS", None)
-for B in (8, 16, 64, 128):
-    x = torch.randn(B, T, 64, device="cuda").to(torch.bfloat16)
-    lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
-    bilstm_layer(x, lens, w.layers[0], U, 2, "bf16", T)
-    torch.cuda.synchronize()

@@ -17,13 +17,14 @@ CONFIGS = [
     ("bf16", 3, 13, 5, 64, 3, True),
     ("bf16", 16, 37, 80, 128, 4, True),
     ("bf16", 33, 50, 81, 512, 2, True),
-    # group plans of rec_tc.cu (rows per group x groups per cluster x clusters): 1 utterance; 3 x 1 x 6; 9 x 2 x 6; 9 x 4 x 6;
+    # group plans of rec_tc.cu (rows per group x groups per cluster x clusters): 1 utterance; 3 x 1 x 6; 9 x 2 x 6; 12 x 3 x 6;
     # 11 x 4 x 6 with ragged last groups; 8-CTA clusters
     ("bf16", 1, 20, 80, 512, 1, False),
     ("bf16", 7, 25, 80, 512, 1, True),
     ("bf16", 49, 30, 80, 512, 1, True),
     ("bf16", 100, 24, 80, 512, 1, True),
     ("bf16", 130, 16, 80, 512, 1, True),
+    ("bf16", 128, 18, 80, 512, 1, True),   # 15 x 3 x 6
     ("bf16", 40, 30, 40, 256, 2, True),
 ]
 
