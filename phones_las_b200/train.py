@@ -900,7 +900,7 @@ def train_variable_shapes(hp, num_channels=None, binf_count=0):
     """variable_shapes + the 'speller_binf/' twin of the multitask configuration (model_helper.py:221)."""
     shapes = dict(variable_shapes(hp, num_channels))
     if hp.get("binary_outputs") and hp.get("binf_trainable") and hp.get("binf_projection"):
-        shapes["binf2phone"] = (binf_count, hp["target_vocab_size"])  # model_helper.py:183 (initialised from the constant map)
+        shapes["binf2phone"] = (binf_count, hp["target_vocab_size"])  # model_helper.py:181-184: a variable initialised U(0, 1) (weights.init_params), not from the constant map
     if hp.get("binary_outputs"):
         V = hp["target_vocab_size"]
         for k, s in list(shapes.items()):

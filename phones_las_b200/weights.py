@@ -85,7 +85,7 @@ def variable_shapes(hp, num_channels=None):
 def init_params(hp, num_channels=None, seed=4321, projection_scale=1.0, bias_scale=0.0, shapes=None):
     """Synthetic weights: LSTM kernels and the projection U(-0.075, 0.075)
     (las/ops.py:12, las/model.py:257), LSTM biases 0 (or U(-bias_scale, bias_scale) to exercise the
-    bias path), Dense kernels / attention_v Glorot-uniform, attention_score_bias 0."""
+    bias path), Dense kernels / attention_v Glorot-uniform, attention_score_bias 0, a trainable binf2phone U(0, 1)."""
     rng = np.random.default_rng(seed)
     params = {}
     for name, shape in (shapes or variable_shapes(hp, num_channels)).items():
@@ -97,6 +97,8 @@ def init_params(hp, num_channels=None, seed=4321, projection_scale=1.0, bias_sca
             w = rng.uniform(-bias_scale, bias_scale, size=shape) if bias_scale else np.zeros(shape)
         elif name.endswith("attention_score_bias"):
             w = np.zeros(shape)
+        elif name == "binf2phone":  # --binf_trainable: tf.random_uniform_initializer(0, 1), model_helper.py:181-184
+            w = rng.uniform(0.0, 1.0, size=shape)
         elif name.endswith("attention_v"):
             lim = np.sqrt(6.0 / (shape[0] + 1))
             w = rng.uniform(-lim, lim, size=shape)
