@@ -107,6 +107,16 @@ def _gemm_view(precision, a, a_col0, M, K, lda, wt, w_row0, N, bias, out2d, out_
     _lib.count_launches(1)
 
 
+def rec_cluster_budget(B, U, ndir, sm_budget):
+    """plas_rec_desc.max_clusters for a batch of B utterances under the pipelined loops' SM budget (``_lib.rec_sms``; 0 = none):
+    the budget in clusters of U/32 CTAs -- unless it would push the plan beyond two 16-row groups per cluster: four 16-row groups
+    on 4 clusters (2.94 us per step at B = 128) lose more than the other batch's GEMMs gain (three 15-row groups on 6: 2.11 us)."""
+    if not sm_budget:
+        return 0
+    mc = max(ndir, sm_budget // max(1, U // 32))
+    return mc if -(-B // (max(1, mc // ndir) * 2)) <= 16 else 0
+
+
 def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_input=False):
     """One (bi)LSTM layer: x [B,T,K] (compute dtype, K == lw['k_pad']) -> out [B,t_alloc_out,ndir*U].
     ``per_direction_input``: x is [B,T,ndir*U] and direction d reads only x[..., d*U:(d+1)*U] (stacked MultiRNNCell)."""
@@ -131,13 +141,7 @@ def bilstm_layer(x, lengths, lw, U, ndir, precision, t_alloc_out, per_direction_
     d.out_batch_stride = out.stride(0)
     d.c_final, d.h_final = c_fin.data_ptr(), h_fin.data_ptr()
     d.whh_tc = lw["whh_tc"].data_ptr() if lw.get("whh_tc") is not None else None
-    d.max_clusters = 0
-    if _lib.rec_sm_budget:
-        # the pipelined loops' SM budget -- unless it would push the plan beyond two groups per cluster: four 16-row groups on
-        # 4 clusters (2.94 us per step at B = 128) lose more than the other batch's GEMMs gain (three 15-row groups on 6: 2.11 us)
-        mc = max(ndir, _lib.rec_sm_budget // max(1, U // 32))
-        if -(-B // (max(1, mc // ndir) * 2)) <= 16:
-            d.max_clusters = mc
+    d.max_clusters = rec_cluster_budget(B, U, ndir, _lib.rec_sm_budget)
     need = L.plas_rec_workspace_bytes(C.byref(d))
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
     # the tensor-core recurrence only synchronises inside its clusters; the cooperative fallbacks exchange h through L2 across

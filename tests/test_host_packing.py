@@ -142,3 +142,18 @@ def test_pack_rec_tc_rows():
     assert t.shape == (2, U // 32, 128, U)
     d, ci, ul, gate, k = 1, 1, 13, 2, 33  # unit 13 of the CTA: quadrant 1, u8 = 5
     assert t[d, ci, 32 * (ul // 8) + 8 * gate + ul % 8, k] == kernels[d][din + k, gate * U + ci * 32 + ul]
+
+
+def test_recurrence_cluster_budget_policy():
+    """listener.rec_cluster_budget: the serving loops' 64-SM budget becomes 4 clusters of 16 CTAs at U = 512 (8 of 8 at U = 256) and
+    is dropped when the batch would then need more than two 16-row groups per cluster."""
+    from phones_las_b200.listener import rec_cluster_budget
+    assert rec_cluster_budget(64, 512, 2, 0) == 0          # no budget: every placeable cluster
+    assert rec_cluster_budget(64, 512, 2, 64) == 4         # c2: 2 clusters per direction x 2 groups x 16 rows
+    assert rec_cluster_budget(16, 512, 2, 64) == 4
+    assert rec_cluster_budget(65, 512, 2, 64) == 0         # 17 rows per group: budget dropped
+    assert rec_cluster_budget(128, 512, 2, 64) == 0        # c4 on one GPU: 3 x 15 rows on 6 clusters instead
+    assert rec_cluster_budget(64, 256, 2, 64) == 8
+    assert rec_cluster_budget(64, 512, 1, 64) == 4         # unidirectional: 4 clusters, 1 group of 16 each
+    assert rec_cluster_budget(200, 512, 1, 64) == 0
+    assert rec_cluster_budget(8, 512, 2, 16) == 2          # never fewer clusters than directions
