@@ -12,12 +12,17 @@ shape (default c2 = BASELINE.json configs[1]: 80-mel MFE, 4-layer pBLSTM 512, 2-
 bahdanau, batch 64 x 15 s, bf16).  Utterance batches shard across GPUs by batch (no data-path
 collective; "weak" scaling: every rank runs a full batch).  Rank 0 prints ONE JSON line.
 
-  value     device-resident throughput: waveforms already in HBM when the timed region starts.
+  value     device-resident throughput: waveforms already in HBM when the timed region starts.  Consecutive batches run on
+            the serving loop's compute streams (LASModel.default_streams(): 2 on the fused bf16 path) with the host at most
+            that many batches ahead, the recurrence held to LASModel.PIPELINED_REC_SMS SMs (config.pipelining).
   e2e       same metric through the public host API (LASModel.transcribe_stream): per step pinned host
             waveform -> H2D (overlapping the previous step's kernels) -> kernels -> D2H of the decoded ids,
             all inside the timed region.
   roofline  the dominant kernel of the step (by measured device time), algorithmic bytes/flops per
-            launch / its CUDA-event duration vs MEASURED_PEAKS.json.
+            launch / its CUDA-event duration vs MEASURED_PEAKS.json; for the recurrence also the
+            on-chip operand roofline north_star (3) names (roofline.onchip).  stages.* = every kernel family timed alone on
+            one stream (median of the passes).  sub_records (default c2 run) = the c3 training step with its all-reduce and
+            dp_check, c4 with the global batch of 128 split over the ranks, the c5 front-end sweep.
   cpu_baseline / --impl reference
             the CPU oracle (numpy restatement of the reference path; the reference itself needs
             TF 1.15 + librosa + speechpy, none installable here) timed on the host cores on a
