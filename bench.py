@@ -21,7 +21,7 @@ collective; "weak" scaling: every rank runs a full batch).  Rank 0 prints ONE JS
   roofline  the dominant kernel of the step (by measured device time), algorithmic bytes/flops per
             launch / its CUDA-event duration vs MEASURED_PEAKS.json; for the recurrence also the
             on-chip operand roofline north_star (3) names (roofline.onchip).  stages.* = every kernel family timed alone on
-            one stream (median of the passes).  sub_records (default c2 run) = the c3 training step with its all-reduce and
+            one stream (median of the passes).  sub_records (default c2 run) = c1 (fp32), the c3 training step with its all-reduce and
             dp_check, c4 with the global batch of 128 split over the ranks, the c5 front-end sweep.
   cpu_baseline / --impl reference
             the CPU oracle (numpy restatement of the reference path; the reference itself needs
@@ -991,12 +991,14 @@ def main():
         line = ours(args)
         if args.workload == "c2" and not args.batch and not args.no_sub_records:
             # the other BASELINE configurations, measured in the same run on the same ranks (each with its own barrier + CUDA-event
-            # timing, max over ranks): c3 = the training step with its NCCL all-reduce and the data-parallel check, c4 = long-form
+            # timing, max over ranks): c1 = the reference's own CPU-runnable case in fp32 (batch 8 x 3 s per GPU, the step-kernel
+            # decoder), c3 = the training step with its NCCL all-reduce and the data-parallel check, c4 = long-form
             # inference with the global batch of 128 split over the ranks, c5 = the front-end alone
             sub_args = argparse.Namespace(**vars(args))
             sub_args.steps, sub_args.no_cpu_baseline = max(3, min(args.steps, 5)), True
             subs = {}
-            for name, fn, over in (("train_c3", ours_train, dict(workload="c3")),
+            for name, fn, over in (("c1", ours, dict(workload="c1")),
+                                   ("train_c3", ours_train, dict(workload="c3")),
                                    ("c4", ours, dict(workload="c4", batch=max(1, 128 // world))),
                                    ("c5", ours_frontend, dict(workload="c5", batch=16384))):
                 a = argparse.Namespace(**vars(sub_args))
