@@ -48,7 +48,7 @@ __device__ __forceinline__ void rt_st_async_v4(uint32_t raddr, const uint4& v, u
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
                : "memory");
 }
-// named barriers between the 256 gate-math threads and the 128 publisher threads (double-buffered stage tile):
+// named barriers between the live gate-math warps and the 128 publisher threads (double-buffered stage tile):
 // ids 2,3 = "stage tile b is full", ids 4,5 = "stage tile b has been published"
 __device__ __forceinline__ void rt_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void rt_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -117,8 +117,8 @@ __device__ __forceinline__ void rt_lstm_gates(float zi, float zj, float zf, floa
   h = rt_tanh_num(c, g) * rt_rcp((1.0f + e) * (1.0f + g));
 }
 // NG independent 16-utterance groups of one direction share a cluster (and the TMEM-resident weights) and are
-// software-pipelined against each other: warp 8 waits for a group's h_{s-1} to land and issues its U/16 MMAs
-// (asynchronous, own accumulator columns), while the 8 epilogue warps run the gate math / exchange of the other
+// software-pipelined against each other: warp RT_GW waits for a group's h_{s-1} to land and issues its U/16 MMAs
+// (asynchronous, own accumulator columns), while the gate-math warps run the gate math / exchange of the other
 // group(s).  The exchange latency (~0.5 us) and the MMA time of one group hide behind the epilogue of the others.
 template <int KS, int NG>
 __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
     }
     __syncwarp();
   } else if (warp > RT_GW) {
-    // ===== publisher warps 9..12: push every staged 16 x 32 slice (a) into the swizzled h operand of every CTA of
+    // ===== publisher warps RT_GW+1 .. RT_GW+4: push every staged 16 x 32 slice (a) into the swizzled h operand of every CTA of
     // the cluster -- thread = (destination, row, 16-byte chunk), so the four chunks of a row leave as one contiguous
     // 64-byte DSMEM segment (scattered 16-byte remote stores were measured 30% slower) -- and (b) for active rows to
     // the [B,T,ndir*U] layer output in HBM.  An SM sends only ~20 bytes/clk over the SM-to-SM network, so the
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(RT_THREADS2, 1) rec_tc_kernel(RecTcArgs p) {
       }
     }
   } else {
-    // ===== gate-math warps 0..7 =====
+    // ===== gate-math warps 0 .. RT_GW-1 =====
     // gate-math mapping: lane -> unit u8 = lane/4 of this warp's 8 units, utterances 2*jq, 2*jq+1 of the warp half (w/4)
     const int u8 = lane >> 2, jq = lane & 3;
     const int unit = ci * 32 + (warp & 3) * 8 + u8;
