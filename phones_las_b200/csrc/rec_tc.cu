@@ -6,17 +6,19 @@
 // so that one CTA's slice of W_hh (all four gates of 32 hidden units) is the M = 128 operand of
 // tcgen05.mma and can live in TMEM for the whole sequence (A-from-TMEM "TS" form: 128 lanes x U/2
 // packed-bf16 columns = 128 KB at U = 512), while the small, changing operand h_{s-1} (NR x U bf16,
-// K-major SWIZZLE_128B) sits in shared memory.  A step costs U/16 MMAs of max(M,128)*NR/256 cycles
-// (256 cycles at U = 512, NR = 16) instead of ~1100 cycles of mma.sync.
+// K-major SWIZZLE_128B) sits in shared memory.  A step costs U/16 TS-form MMAs of ~18 cycles each
+// (measured, scripts/micro/mma_cost.cu: 10 + N/2; ~590 cycles at U = 512, NR = 16) instead of ~1100 cycles of mma.sync.
 //
 // The G = U/32 CTAs of one (direction, group of NR utterances) form a thread-block cluster; every
 // CTA pushes its NR x 32 slice of h_s straight into the (swizzled) operand tile of all G CTAs with
 // st.async, completing transaction bytes on each receiver's mbarrier -- h never leaves the chip and
 // there is no cluster barrier, no atomics and no fence on the step path (protocol as in rec.cu).
 //
-// Epilogue: the TMEM lanes of a warp quadrant are ordered 8*gate + unit, so two tcgen05.ld.16x256b hand
-// thread t all four gates of unit t/4 for two utterances -- no transpose --, then the TF gate math
-// (forget_bias 1.0, length masking, bw direction walking len-1-s) runs with the cell state in registers.
+// Epilogue: the TMEM lanes of a warp quadrant are ordered 8*gate + unit, so two tcgen05.ld.16x128b hand
+// thread t all four gates of unit t/4 for one utterance (16 gate-math warps, one cell per thread and group) -- no
+// transpose --, then the TF gate math (forget_bias 1.0, length masking, bw direction walking len-1-s) runs with the
+// cell state in registers.  Groups hold <= 16 utterances (rows); the host spreads the batch over the clusters its
+// budget allows (rec_tc_try) and pad rows are neither exchanged nor stored.
 #include <stdlib.h>
 #include <string.h>
 
