@@ -386,10 +386,12 @@ def ours(args):
     from collections import deque
     inflight = deque()
     for i in range(args.steps):
-        # trim=False: nothing inside a step synchronises the host.  Like the serving loop (LASModel.transcribe_stream, which reads
-        # batch i - ns back before it enqueues batch i) the host stays at most `ns` batches ahead: free-running streams drift into
-        # lock step (both batches in their recurrences at once: 8 clusters wanted, 7 placeable) and the value then varies by 8 %
-        if streams is not None and len(inflight) == ns:
+        # trim=False: nothing inside a step synchronises the host.  The host stays ns + 1 batches ahead: batch i is enqueued behind
+        # batch i - ns on its stream while that one still runs, so WHEN a batch starts on the device is set by stream order, not
+        # by how fast this thread enqueues (with the host only ns ahead a descheduled launch thread showed up as a 10-15 % slower
+        # run, most often under torchrun; the serving loop hides the same enqueue behind its H2D copy).  Free-running streams
+        # (host far ahead) drift into lock step -- both batches in their recurrences at once -- and vary by 8 %
+        if streams is not None and len(inflight) == ns + 1:
             inflight.popleft().synchronize()
         pred = run_step(i, want_alignment=True, trim=False)
         if streams is not None:
