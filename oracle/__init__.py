@@ -12,5 +12,11 @@ un-vendored third-party packages that cannot be installed in this image
 The oracle therefore restates those packages' published algorithms at the
 reference's call sites and is cross-checked against independent implementations
 that ARE available (torch.nn.LSTM, torch ctc_loss, scipy savgol/dct, numpy rfft,
-torchaudio mel filterbanks) in tests/test_oracle_*.py.
+torchaudio mel filterbanks) in tests/test_oracle_*.py.  The librosa branch of the
+front-end is additionally checked END TO END (mel spectrogram, dB with top_db, the
+amplitude_to_db-of-power quirk, MFCC) against torchaudio.transforms and
+transformers.audio_utils, two third-party implementations written to reproduce
+librosa (tests/test_oracle_frontend.py::test_librosa_*_vs_*): agreement to 4e-6 dB /
+5e-5 on MFCCs.  That anchors the librosa rows to something other than this restatement;
+the speechpy rows and the TF seq2seq decoder have no such second implementation here.
 """

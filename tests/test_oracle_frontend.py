@@ -102,3 +102,57 @@ def test_silence_is_finite():
         for b in range(2):
             f = ofe.calculate_acoustic_features(feature_args(backend=be, window=25, **kw), wave[b])
             assert np.isfinite(f).all()
+
+
+# --------------------------------------------------------------------------------------
+# Whole-pipeline pins of the librosa restatement against two independent third-party implementations that are
+# themselves written (and tested upstream) to reproduce librosa: torchaudio.transforms and transformers.audio_utils.
+# librosa==0.7.1 is not installable here; these are the closest available anchors for preprocess_all.py:81-86,93-97.
+# --------------------------------------------------------------------------------------
+def _wave(seconds=3.0):
+    wave, _ = synth.synth_audio(2, seconds)
+    return wave[1].astype(np.float32)
+
+
+@pytest.mark.parametrize("n_fft,n_mels", [(400, 80), (320, 40)])
+def test_librosa_melspectrogram_and_db_vs_torchaudio(n_fft, n_mels):
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    y = _wave()
+    ms = torchaudio.transforms.MelSpectrogram(16000, n_fft=n_fft, hop_length=160, n_mels=n_mels, f_min=0.0, f_max=8000.0, power=2.0,
+                                              center=True, pad_mode="reflect", norm="slaney", mel_scale="slaney")
+    M = ms(torch.from_numpy(y)).numpy()
+    mine = ofe.lr_melspectrogram(y, 16000, n_fft, 160, n_mels)
+    assert M.shape == mine.shape
+    assert np.abs(M - mine).max() <= 1e-5 * np.abs(mine).max()
+    db = torchaudio.transforms.AmplitudeToDB("power", top_db=80.0)(torch.from_numpy(M)).numpy()
+    np.testing.assert_allclose(ofe.lr_power_to_db(mine), db, atol=5e-4)
+    # the reference's MFE quirk (preprocess_all.py:83): amplitude_to_db of a POWER mel spectrogram = power_to_db of its square
+    db2 = torchaudio.transforms.AmplitudeToDB("power", top_db=80.0)(torch.from_numpy(M) ** 2).numpy()
+    np.testing.assert_allclose(ofe.lr_amplitude_to_db(mine), db2, atol=1e-3)
+    fa = feature_args(feature_type="mfe", backend="librosa", n_mels=n_mels, window=n_fft // 16)
+    np.testing.assert_allclose(ofe.calculate_acoustic_features(fa, y), db2.T, atol=1e-3)
+
+
+def test_librosa_mfcc_vs_torchaudio():
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    y = _wave()
+    mf = torchaudio.transforms.MFCC(16000, n_mfcc=13, dct_type=2, norm="ortho", log_mels=False,
+                                    melkwargs=dict(n_fft=400, hop_length=160, n_mels=40, f_min=0.0, f_max=8000.0, center=True,
+                                                   pad_mode="reflect", norm="slaney", mel_scale="slaney"))
+    Q = mf(torch.from_numpy(y)).numpy()
+    mine = ofe.lr_mfcc(y, 16000, 13, 400, 160, 40)
+    np.testing.assert_allclose(mine, Q, atol=1e-3)
+    fa = feature_args(feature_type="mfcc", backend="librosa", n_mfcc=13, n_mels=40, window=25)
+    np.testing.assert_allclose(ofe.calculate_acoustic_features(fa, y), Q.T, atol=1e-3)
+
+
+def test_librosa_log_mel_vs_transformers_audio_utils():
+    au = pytest.importorskip("transformers.audio_utils")
+    y = _wave()
+    fb = au.mel_filter_bank(201, 80, 0.0, 8000.0, 16000, norm="slaney", mel_scale="slaney")
+    np.testing.assert_allclose(ofe.lr_mel_filters(16000, 400, 80), fb.T, atol=1e-7)
+    S = au.spectrogram(y.astype(np.float64), au.window_function(400, "hann", periodic=True), 400, 160, fft_length=400, power=2.0,
+                       center=True, pad_mode="reflect", mel_filters=fb, log_mel="dB", reference=1.0, min_value=1e-10, db_range=80.0)
+    np.testing.assert_allclose(ofe.lr_power_to_db(ofe.lr_melspectrogram(y, 16000, 400, 160, 80)), S, atol=5e-4)
