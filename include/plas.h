@@ -64,7 +64,8 @@ typedef struct plas_frontend_desc {
   const int32_t* fb_start;  /* [n_mels] first FFT bin of each mel filter                       */
   const int32_t* fb_len;    /* [n_mels] number of bins                                         */
   const int32_t* fb_off;    /* [n_mels] offset into fb_w                                       */
-  const float* fb_w;        /* [fb_total] filter weights                                       */
+  const float* fb_w;        /* [fb_total] filter weights; rows whose fb_len and fb_off are
+                               multiples of 4 (zero-padded by the host) take a float4 path     */
   const float* dct;         /* [n_mfcc][n_mels] orthonormal DCT-II rows (mfcc) or NULL         */
   const float* mean;        /* [C] or NULL  (utils/dataset_utils.py:213-220)                   */
   const float* stdv;        /* [C] or NULL                                                     */

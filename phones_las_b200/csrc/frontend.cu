@@ -202,10 +202,13 @@ __device__ __forceinline__ float norm_ch(const FeArgs& p, float v, int c) {
 
 // 4 CTAs per SM (<= 64 registers, ~55 KB of shared memory each at n_fft = 400): the kernel is issue-bound, occupancy hides its
 // shared-memory latencies
+// NFFT = 400: the BASELINE window with every size a compile-time constant (fft200_windowed, unrolled unpack, constant buffer
+// offsets); NFFT = 0: any even n_fft at run time through the generic Stockham passes
+template <int NFFT>
 __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   extern __shared__ __align__(16) unsigned char fe_smem[];
   const plas_frontend_desc& d = p.d;
-  const int n_fft = d.n_fft, hop = d.hop, n = n_fft / 2, n_mels = d.n_mels;
+  const int n_fft = NFFT ? NFFT : d.n_fft, hop = d.hop, n = n_fft / 2, n_mels = d.n_mels;
   const int b = blockIdx.y;
   const int tile0 = blockIdx.x * FE_FRAMES;
   const int N = p.n_samples[b];
@@ -224,18 +227,23 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   }
 
   // ---- shared memory carve-up --------------------------------------------------------
+  // byte offsets from the one shared base, so that every pointer below keeps the shared address space (LDS / STS, not generic
+  // loads); the filterbank weights and the span are 16-byte aligned (float4 rows / float4 staging), see fe_spectral_smem
   const int span_len = (FE_FRAMES - 1) * hop + n_fft;
-  float2* s_tw = reinterpret_cast<float2*>(fe_smem);
-  float2* s_twu = s_tw + n;
-  float* s_win = reinterpret_cast<float*>(s_twu + n + 1);
-  float* s_fbw = s_win + n_fft;
-  int* s_fbs = reinterpret_cast<int*>(s_fbw + d.fb_total);
-  // 8-byte aligned: the n_fft = 400 path reads sample pairs
-  float* s_span = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_fbs + 3 * n_mels) + 7) & ~uintptr_t(7));
-  size_t off = reinterpret_cast<unsigned char*>(s_span + span_len) - fe_smem;
-  off = (off + 15) & ~size_t(15);
+  const int off_twu = 8 * n;
+  const int off_win = off_twu + 8 * (n + 1);
+  const int off_fbw = (off_win + 4 * n_fft + 15) & ~15;
+  const int off_fbs = off_fbw + 4 * d.fb_total;
+  const int off_span = (off_fbs + 12 * n_mels + 15) & ~15;
+  const int off_work = (off_span + 4 * span_len + 15) & ~15;
   const int work_stride = 2 * n + 2;  // float2 elements per warp (two ping-pong buffers)
-  float2* s_work = reinterpret_cast<float2*>(fe_smem + off) + (size_t)warp * work_stride;
+  float2* s_tw = reinterpret_cast<float2*>(fe_smem);
+  float2* s_twu = reinterpret_cast<float2*>(fe_smem + off_twu);
+  float* s_win = reinterpret_cast<float*>(fe_smem + off_win);
+  float* s_fbw = reinterpret_cast<float*>(fe_smem + off_fbw);
+  int* s_fbs = reinterpret_cast<int*>(fe_smem + off_fbs);
+  float* s_span = reinterpret_cast<float*>(fe_smem + off_span);
+  float2* s_work = reinterpret_cast<float2*>(fe_smem + off_work) + warp * work_stride;
 
   for (int i = tid; i < n; i += FE_THREADS) s_tw[i] = reinterpret_cast<const float2*>(d.tw)[i];
   for (int i = tid; i <= n; i += FE_THREADS) s_twu[i] = reinterpret_cast<const float2*>(d.tw_unpack)[i];
@@ -249,6 +257,13 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   {
     const float* w = p.wave + (size_t)b * p.wave_stride;
     const int base = tile0 * hop;
+    const int first = librosa ? base - n : base;
+    if (first >= 0 && first + span_len <= N && (span_len & 3) == 0 && (reinterpret_cast<uintptr_t>(w + first) & 15) == 0) {
+      // interior tile (no reflection, no tail): 16-byte loads
+      const float4* w4 = reinterpret_cast<const float4*>(w + first);
+      float4* s4 = reinterpret_cast<float4*>(s_span);
+      for (int i = tid; i < (span_len >> 2); i += FE_THREADS) s4[i] = __ldg(w4 + i);
+    } else
     for (int i = tid; i < span_len; i += FE_THREADS) {
       int src = base + i;
       if (librosa) {  // centre=True, pad_mode='reflect' by n_fft/2
@@ -285,8 +300,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     }
     float2* src = bufA;
     float2* dst = bufB;
-    const bool fast400 = n_fft == 400 && (hop & 1) == 0 && !p.generic_fft;
-    if (fast400) {
+    if constexpr (NFFT == 400) {
       fft200_windowed(x, s_win, s_tw, bufA, bufB, lane);
     } else {
       for (int j = lane; j < n; j += 32)
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
       __syncwarp();
     }
     int Ns = 1;
-    for (int s = 0; s < (fast400 ? 0 : d.n_fac); ++s) {
+    for (int s = 0; s < (NFFT == 400 ? 0 : d.n_fac); ++s) {
       const int R = d.fac[s];
       switch (R) {
         case 2: fft_pass<2>(src, dst, s_tw, n, Ns, lane); break;
@@ -309,20 +323,25 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     }
     // src = Z (half-size complex spectrum).  Unpack to the real spectrum's power, bins 0..n.
     float* P = reinterpret_cast<float*>(dst);
-    const float pscale = librosa ? 1.0f : 1.0f / (float)n_fft;
+    // the halves of xe / xo are folded into the scale of the power: |X|^2 = |2 xe + w^k 2 xo|^2 / 4
+    const float pscale = librosa ? 0.25f : 0.25f / (float)n_fft;
     float esum = 0.f;
-    for (int k = lane; k <= n; k += 32) {
-      const float2 zk = src[k == n ? 0 : k];
-      const float2 zm0 = src[(k == 0 || k == n) ? 0 : n - k];
-      const float2 zm = make_float2(zm0.x, -zm0.y);
-      const float2 xe = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
-      const float2 dd = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y - zm.y));
-      const float2 xo = mul_mi(dd);
-      const float2 X = cadd(xe, cmul(s_twu[k], xo));
-      const float pw = (X.x * X.x + X.y * X.y) * pscale;
-      P[k] = pw;
-      esum += pw;
+    // bins k and n - k come from the same two points of Z: X[k] = xe + w^k xo, X[n-k] = conj(xe - w^k xo)
+#pragma unroll
+    for (int k = lane; 2 * k <= n; k += 32) {
+      const float2 zk = src[k];
+      const float2 zm = src[k == 0 ? 0 : n - k];
+      const float2 xe = make_float2(zk.x + zm.x, zk.y - zm.y);
+      const float2 xo = make_float2(zk.y + zm.y, zm.x - zk.x);
+      const float2 tx = cmul(s_twu[k], xo);
+      const float2 Xa = cadd(xe, tx), Xb = csub(xe, tx);
+      const float pa = (Xa.x * Xa.x + Xa.y * Xa.y) * pscale;
+      const float pb = (Xb.x * Xb.x + Xb.y * Xb.y) * pscale;
+      P[k] = pa;
+      P[n - k] = pb;
+      esum += (2 * k == n) ? pa : pa + pb;
     }
+    if (lane < 3) P[n + 1 + lane] = 0.f;  // read (times a zero weight) by the four-wide filterbank rows
     __syncwarp();
     const float E = warp_sum(esum);
 
@@ -330,7 +349,20 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     for (int m = lane; m < n_mels; m += 32) {
       const int st = s_fbs[m], len = s_fbs[n_mels + m], o = s_fbs[2 * n_mels + m];
       float acc = 0.f;
-      for (int i = 0; i < len; ++i) acc = fmaf(s_fbw[o + i], P[st + i], acc);
+      if (((len | o) & 3) == 0) {  // rows zero-padded to multiples of four weights by the host (plas.h)
+        const float4* w4 = reinterpret_cast<const float4*>(s_fbw + o);
+        const float* Pm = P + st;
+#pragma unroll 1
+        for (int i = 0; i < len; i += 4) {  // 1 to 4 trips: an unrolled loop's prologue / remainder code costs more than it saves
+          const float4 w = w4[i >> 2];
+          acc = fmaf(w.x, Pm[i], acc);
+          acc = fmaf(w.y, Pm[i + 1], acc);
+          acc = fmaf(w.z, Pm[i + 2], acc);
+          acc = fmaf(w.w, Pm[i + 3], acc);
+        }
+      } else {
+        for (int i = 0; i < len; ++i) acc = fmaf(s_fbw[o + i], P[st + i], acc);
+      }
       mel[m] = acc;
     }
     __syncwarp();
@@ -403,7 +435,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
       for (int m = lane; m < n_mels; m += 32) {
         float v = mel[m];
         if (d.feature_type == 0) v = v * v;  // amplitude_to_db squares its input (preprocess_all.py:83)
-        const float val = 10.0f * log10f(fmaxf(1e-10f, v));
+        const float val = 3.01029995663981195f * __log2f(fmaxf(1e-10f, v));  // 10 log10: lg2.approx (rel. error 2^-22) * 10 log10(2)
         db[m] = val;
         mx = fmaxf(mx, val);
       }
@@ -502,13 +534,15 @@ __global__ void fe_librosa_delta_kernel(FeArgs p) {
   }
 }
 
-static size_t fe_spectral_smem(const plas_frontend_desc& d) {
+static size_t fe_spectral_smem(const plas_frontend_desc& d) {  // the carve-up of fe_spectral_kernel
   const int n = d.n_fft / 2;
-  size_t bytes = (size_t)n * 8 + (size_t)(n + 1) * 8 + (size_t)d.n_fft * 4 + (size_t)d.fb_total * 4 +
-                 (size_t)3 * d.n_mels * 4 + 8 + (size_t)((FE_FRAMES - 1) * d.hop + d.n_fft) * 4;
-  bytes = (bytes + 15) & ~size_t(15);
-  bytes += (size_t)FE_WARPS * (2 * n + 2) * 8;
-  return bytes;
+  size_t off = (size_t)8 * n + (size_t)8 * (n + 1) + (size_t)4 * d.n_fft;
+  off = (off + 15) & ~size_t(15);
+  off += (size_t)4 * d.fb_total + (size_t)12 * d.n_mels;
+  off = (off + 15) & ~size_t(15);
+  off += (size_t)4 * ((FE_FRAMES - 1) * d.hop + d.n_fft);
+  off = (off + 15) & ~size_t(15);
+  return off + (size_t)FE_WARPS * (2 * n + 2) * 8;
 }
 
 static void fe_ws_layout(const plas_frontend_desc& d, int B, int T_max, size_t* o_db, size_t* o_rms,
@@ -579,7 +613,9 @@ extern "C" int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave,
   }
   const size_t smem = fe_spectral_smem(*d);
   PLAS_REQUIRE(smem <= 227 * 1024, "frontend: %zu bytes of shared memory needed", smem);
-  PLAS_CUDA(cudaFuncSetAttribute(fe_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool fast400 = d->n_fft == 400 && (d->hop & 1) == 0 && !a.generic_fft;
+  auto* spectral = fast400 ? fe_spectral_kernel<400> : fe_spectral_kernel<0>;
+  PLAS_CUDA(cudaFuncSetAttribute(spectral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // gridDim.y carries the utterance index (<= 65535): large batches (the 64 k-utterance sweep of BASELINE configs[4]) go in chunks
   const int Dbase = nb + (d->energy ? 1 : 0);
   constexpr int FE_MAX_B = 32768;
@@ -599,7 +635,7 @@ extern "C" int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave,
       if (a0.base) a.base = a0.base + (size_t)b0 * T_max * Dbase;
     }
     dim3 grid((T_max + FE_FRAMES - 1) / FE_FRAMES, nb_here);
-    fe_spectral_kernel<<<grid, FE_THREADS, smem, stream>>>(a);
+    spectral<<<grid, FE_THREADS, smem, stream>>>(a);
     PLAS_CUDA(cudaGetLastError());
     if (d->backend == 1) {
       const size_t smem_b = (size_t)FE_WARPS * d->n_mels * 4;

@@ -108,9 +108,12 @@ def frontend_tables(args):
             starts.append(0)
             lens.append(0)
             continue
+        # rows zero-padded to multiples of four weights: the kernel reads them as float4 (plas.h, fb_w); a padded row may
+        # reach up to three bins past n_fft / 2, which the kernel keeps at zero
+        ln = int(nz[-1] - nz[0] + 1)
         starts.append(int(nz[0]))
-        lens.append(int(nz[-1] - nz[0] + 1))
-        wts.extend(row[nz[0]:nz[-1] + 1].tolist())
+        lens.append((ln + 3) // 4 * 4)
+        wts.extend(row[nz[0]:nz[-1] + 1].tolist() + [0.0] * ((-ln) % 4))
     if not wts:
         wts = [0.0]
     tw = np.exp(-2j * np.pi * np.arange(n) / n)

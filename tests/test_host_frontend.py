@@ -34,10 +34,13 @@ def test_filterbank_tables_match_oracle():
     for backend, n_mels in (("speechpy", 40), ("speechpy", 80), ("librosa", 40), ("librosa", 80)):
         fa = feature_args(feature_type="mfe", backend=backend, n_mels=n_mels, energy=True, window=25)
         tb = frontend_tables(fa)
-        dense = np.zeros((n_mels, 201))
+        dense = np.zeros((n_mels, 201 + 3))  # rows are zero-padded to multiples of four weights (float4 path of the kernel)
         for m in range(n_mels):
             s, l, o = tb["fb_start"][m], tb["fb_len"][m], tb["fb_off"][m]
+            assert l % 4 == 0 and o % 4 == 0 and s + l <= 201 + 3
             dense[m, s:s + l] = tb["fb_w"][o:o + l]
+        assert (dense[:, 201:] == 0).all()
+        dense = dense[:, :201]
         ref = ofe.sp_filterbanks(n_mels, 201, 16000, 0, 8000) if backend == "speechpy" else ofe.lr_mel_filters(16000, 400, n_mels)
         np.testing.assert_allclose(dense, np.nan_to_num(ref), rtol=1e-6, atol=1e-9)
 
