@@ -346,6 +346,9 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     const float E = warp_sum(esum);
 
     float* mel = reinterpret_cast<float*>(src);
+    // librosa: the dB value goes straight from the filterbank accumulator to HBM (top_db is applied in fe_librosa_post_kernel)
+    float* db = librosa ? p.db + ((size_t)b * p.T_max + t) * n_mels : nullptr;
+    float mx = -INFINITY;
     for (int m = lane; m < n_mels; m += 32) {
       const int st = s_fbs[m], len = s_fbs[n_mels + m], o = s_fbs[2 * n_mels + m];
       float acc = 0.f;
@@ -363,7 +366,14 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
       } else {
         for (int i = 0; i < len; ++i) acc = fmaf(s_fbw[o + i], P[st + i], acc);
       }
-      mel[m] = acc;
+      if (librosa) {
+        const float v = d.feature_type == 0 ? acc * acc : acc;  // amplitude_to_db squares its input (preprocess_all.py:83)
+        const float val = 3.01029995663981195f * __log2f(fmaxf(1e-10f, v));  // 10 log10: lg2.approx (rel. error 2^-22) * 10 log10(2)
+        db[m] = val;
+        mx = fmaxf(mx, val);
+      } else {
+        mel[m] = acc;
+      }
     }
     __syncwarp();
 
@@ -429,16 +439,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
         }
       }
     } else {
-      // librosa: dB values + utterance max (top_db is applied in fe_librosa_post_kernel)
-      float* db = p.db + ((size_t)b * p.T_max + t) * n_mels;
-      float mx = -INFINITY;
-      for (int m = lane; m < n_mels; m += 32) {
-        float v = mel[m];
-        if (d.feature_type == 0) v = v * v;  // amplitude_to_db squares its input (preprocess_all.py:83)
-        const float val = 3.01029995663981195f * __log2f(fmaxf(1e-10f, v));  // 10 log10: lg2.approx (rel. error 2^-22) * 10 log10(2)
-        db[m] = val;
-        mx = fmaxf(mx, val);
-      }
+      // librosa: utterance max of the dB values written above
       mx = warp_max(mx);
       if (lane == 0) {
         atomicMax(p.umax + b, float_to_ordered(mx));
