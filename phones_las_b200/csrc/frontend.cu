@@ -450,9 +450,46 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   }
 }
 
+// librosa kernel B for plain MFE (no deltas, no energy column, n_mels a multiple of 4 -- the c2 / c5 mfe80 case): the top_db
+// clip and the normalisation are elementwise over [T_max][n_mels], so this is a streaming kernel of 16-byte accesses with four
+// independent loads in flight per thread (the warp-per-frame kernel below moved 1.7 TB/s on it).
+constexpr int FE_CLIP_VEC = 4;  // float4 per thread
+__global__ void __launch_bounds__(256) fe_librosa_clip_kernel(FeArgs p) {
+  const plas_frontend_desc& d = p.d;
+  const int b = blockIdx.y;
+  const int q4 = d.n_mels >> 2;                  // float4 per frame
+  const int total = p.T_max * q4;                // float4 per utterance
+  const int valid = min(frames_of(d, p.n_samples[b]), p.T_max) * q4;
+  const float floor_db = ordered_to_float(p.umax[b]) - 80.0f;
+  const float4* in = reinterpret_cast<const float4*>(p.db + (size_t)b * p.T_max * d.n_mels);
+  float4* out = reinterpret_cast<float4*>(p.feats + (size_t)b * p.T_max * d.n_mels);
+  const int e0 = blockIdx.x * (256 * FE_CLIP_VEC) + threadIdx.x;
+  float4 v[FE_CLIP_VEC];
+#pragma unroll
+  for (int u = 0; u < FE_CLIP_VEC; ++u) {
+    const int e = e0 + u * 256;
+    v[u] = e < valid ? __ldcs(in + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < FE_CLIP_VEC; ++u) {
+    const int e = e0 + u * 256;
+    if (e >= total) break;
+    float4 r = v[u];
+    if (e < valid) {
+      r = make_float4(fmaxf(r.x, floor_db), fmaxf(r.y, floor_db), fmaxf(r.z, floor_db), fmaxf(r.w, floor_db));
+      if (d.mean) {
+        const int c = (e % q4) * 4;
+        const float4 mu = *reinterpret_cast<const float4*>(d.mean + c), sd = *reinterpret_cast<const float4*>(d.stdv + c);
+        r = make_float4((r.x - mu.x) / sd.x, (r.y - mu.y) / sd.y, (r.z - mu.z) / sd.z, (r.w - mu.w) / sd.w);
+      }
+    }
+    out[e] = r;  // frames past the utterance's end are zero (tf padded_batch)
+  }
+}
+
 // librosa kernel B: top_db clip (+ DCT for mfcc, + rms column); writes final features when
 // there are no deltas, otherwise the base features for kernel C.
-__global__ void __launch_bounds__(FE_THREADS) fe_librosa_post_kernel(FeArgs p) {
+__global__ void __launch_bounds__(FE_THREADS, 4) fe_librosa_post_kernel(FeArgs p) {
   extern __shared__ __align__(16) unsigned char fe_smem[];
   const plas_frontend_desc& d = p.d;
   const int n_mels = d.n_mels;
@@ -463,6 +500,13 @@ __global__ void __launch_bounds__(FE_THREADS) fe_librosa_post_kernel(FeArgs p) {
   const int Dbase = nb + (d.energy ? 1 : 0);
   const bool use_delta = d.deltas && T_b >= 9;
   float* s_db = reinterpret_cast<float*>(fe_smem) + warp * n_mels;
+  float* s_dct = reinterpret_cast<float*>(fe_smem) + FE_WARPS * n_mels;  // [n_mfcc][n_mels | 1] (odd stride: no bank conflicts across q)
+  const int dct_stride = n_mels | 1;
+  const bool dct_split = 2 * nb <= 32;
+  if (d.feature_type != 0) {
+    for (int i = threadIdx.x; i < nb * n_mels; i += FE_THREADS) s_dct[(i / n_mels) * dct_stride + i % n_mels] = d.dct[i];
+    __syncthreads();
+  }
   const float floor_db = ordered_to_float(p.umax[b]) - 80.0f;
   for (int f = warp; f < FE_FRAMES; f += FE_WARPS) {
     const int t = blockIdx.x * FE_FRAMES + f;
@@ -485,10 +529,28 @@ __global__ void __launch_bounds__(FE_THREADS) fe_librosa_post_kernel(FeArgs p) {
     } else {
       for (int m = lane; m < n_mels; m += 32) s_db[m] = fmaxf(db[m], floor_db);
       __syncwarp();
+      if (dct_split) {
+        // 2 nb <= 32: lanes [0, nb) take the first half of the mel axis of coefficient q = lane, lanes [nb, 2 nb) the second
+        // half (13 of 32 lanes walking all 40 mels was 2/3 of this kernel's instructions); DCT rows from shared memory
+        const int part = lane >= nb, q = lane - part * nb, mh = (n_mels + 1) >> 1;
+        float acc = 0.f;
+        if (lane < 2 * nb) {
+          const float* row = s_dct + q * dct_stride;
+          const int m1 = part ? n_mels : mh;
+#pragma unroll 2
+          for (int m = part ? mh : 0; m < m1; ++m) acc = fmaf(row[m], s_db[m], acc);
+        }
+        acc += __shfl_down_sync(0xffffffffu, acc, nb);
+        if (lane < nb) {
+          if (use_delta) base[q] = acc;
+          else if (d.deltas) { out[3 * q] = norm_ch(p, acc, 3 * q); out[3 * q + 1] = norm_ch(p, 0.f, 3 * q + 1); out[3 * q + 2] = norm_ch(p, 0.f, 3 * q + 2); }
+          else out[q] = norm_ch(p, acc, q);
+        }
+      } else
       for (int q = lane; q < nb; q += 32) {
         float acc = 0.f;
-        const float* row = d.dct + (size_t)q * n_mels;
-        for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(row + m), s_db[m], acc);
+        const float* row = s_dct + q * dct_stride;
+        for (int m = 0; m < n_mels; ++m) acc = fmaf(row[m], s_db[m], acc);
         if (use_delta) base[q] = acc;
         else if (d.deltas) { out[3 * q] = norm_ch(p, acc, 3 * q); out[3 * q + 1] = norm_ch(p, 0.f, 3 * q + 1); out[3 * q + 2] = norm_ch(p, 0.f, 3 * q + 2); }
         else out[q] = norm_ch(p, acc, q);
@@ -639,8 +701,16 @@ extern "C" int plas_frontend_fwd(const plas_frontend_desc* d, const float* wave,
     spectral<<<grid, FE_THREADS, smem, stream>>>(a);
     PLAS_CUDA(cudaGetLastError());
     if (d->backend == 1) {
-      const size_t smem_b = (size_t)FE_WARPS * d->n_mels * 4;
-      fe_librosa_post_kernel<<<grid, FE_THREADS, smem_b, stream>>>(a);
+      if (d->feature_type == 0 && !d->deltas && !d->energy && (d->n_mels & 3) == 0 &&
+          (!d->mean || (((uintptr_t)d->mean | (uintptr_t)d->stdv) & 15) == 0) && (((uintptr_t)a.db | (uintptr_t)a.feats) & 15) == 0) {
+        const int per_block = 256 * FE_CLIP_VEC;
+        dim3 grid_c((T_max * (d->n_mels / 4) + per_block - 1) / per_block, nb_here);
+        fe_librosa_clip_kernel<<<grid_c, 256, 0, stream>>>(a);
+      } else {
+        const size_t smem_b = (size_t)FE_WARPS * d->n_mels * 4 + (d->feature_type != 0 ? (size_t)d->n_mfcc * (d->n_mels | 1) * 4 : 0);
+        PLAS_REQUIRE(smem_b <= 48 * 1024, "frontend: %zu bytes of shared memory for the DCT rows", smem_b);
+        fe_librosa_post_kernel<<<grid, FE_THREADS, smem_b, stream>>>(a);
+      }
       PLAS_CUDA(cudaGetLastError());
       if (d->deltas) {
         const size_t total_el = (size_t)nb_here * T_max * Dbase;
