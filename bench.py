@@ -80,7 +80,8 @@ def algorithmic_work(cfg, B, n_dec_steps):
     e = 2 if cfg["precision"] == "bf16" else 4
     U, L, Ud, Ld, V = hp["encoder_units"], hp["encoder_layers"], hp["decoder_units"], hp["decoder_layers"], hp["target_vocab_size"]
     T, C, N = cfg["T"], cfg["C"], cfg["n_samples"]
-    work = {"frontend": {"bytes": B * (4 * N + 4 * T * C), "launches": 1}}
+    fa = cfg["fa"]  # speechpy: one kernel; librosa: spectral + top_db clip / DCT pass (+ the Savitzky-Golay delta kernel)
+    work = {"frontend": {"bytes": B * (4 * N + 4 * T * C), "launches": 1 if fa.backend == "speechpy" else (3 if fa.deltas else 2)}}
     gemm_flops, rec_bytes, rec_flops = 0.0, 0.0, 0.0
     t, din = T, C
     for l in range(L):
@@ -111,7 +112,7 @@ def frontend_flops_per_frame(fa):
     tb = frontend_tables(fa)
     n_fft = tb["n_fft"]
     n = n_fft // 2
-    fl = n_fft + 5.0 * n * np.log2(n) + 13.0 * (n + 1) + 2.0 * len(tb["fb_w"]) + fa.n_mels
+    fl = n_fft + 5.0 * n * np.log2(n) + 13.0 * (n + 1) + 2.0 * np.count_nonzero(tb["fb_w"]) + fa.n_mels  # (rows are zero-padded)
     if fa.feature_type == "mfcc":
         fl += 2.0 * fa.n_mels * fa.n_mfcc
     if fa.deltas:

@@ -140,9 +140,11 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
 // every stride, modulus and twiddle step a compile-time constant (the generic passes above spend most of their instructions on
 // runtime index arithmetic), 16-byte stores out of the radix-8 pass, and the window applied while the first pass loads its
 // samples straight from the staged span.  Result in bufA.
-__device__ __forceinline__ void fft200_windowed(const float* __restrict__ x, const float* __restrict__ win,
-                                                const float2* __restrict__ tw, float2* __restrict__ bufA,
-                                                float2* __restrict__ bufB, int lane) {
+// Returns this lane's share of sum(x^2) over the raw samples when want_sq (librosa's rms energy column), else 0.
+__device__ __forceinline__ float fft200_windowed(const float* __restrict__ x, const float* __restrict__ win,
+                                                 const float2* __restrict__ tw, float2* __restrict__ bufA,
+                                                 float2* __restrict__ bufB, int lane, bool want_sq) {
+  float sq = 0.f;
   if (lane < 25) {  // pass 1: radix 8, Ns = 1: butterfly j reads elements j + 25 t, writes 8 j .. 8 j + 7
     const float2* x2 = reinterpret_cast<const float2*>(x);
     const float2* w2 = reinterpret_cast<const float2*>(win);
@@ -151,6 +153,7 @@ __device__ __forceinline__ void fft200_windowed(const float* __restrict__ x, con
     for (int t = 0; t < 8; ++t) {
       const float2 xv = x2[lane + 25 * t], wv = w2[lane + 25 * t];
       v[t] = make_float2(xv.x * wv.x, xv.y * wv.y);
+      if (want_sq) sq = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, sq));
     }
     Bfly<8>::run(v);
     float4* o = reinterpret_cast<float4*>(bufA + 8 * lane);
@@ -188,6 +191,7 @@ __device__ __forceinline__ void fft200_windowed(const float* __restrict__ x, con
     }
   }
   __syncwarp();
+  return sq;
 }
 
 __device__ __forceinline__ int frames_of(const plas_frontend_desc& d, int N) {
@@ -293,7 +297,8 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     float2* bufB = s_work + n + 1;
 
     float rms = 0.f;
-    if (librosa && d.energy) {
+    const bool want_rms = librosa && d.energy;
+    if (NFFT != 400 && want_rms) {  // (the n_fft = 400 path sums the squares while its first FFT pass loads the samples)
       float s = 0.f;
       for (int i = lane; i < n_fft; i += 32) s += x[i] * x[i];
       rms = sqrtf(warp_sum(s) / (float)n_fft);
@@ -301,7 +306,8 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     float2* src = bufA;
     float2* dst = bufB;
     if constexpr (NFFT == 400) {
-      fft200_windowed(x, s_win, s_tw, bufA, bufB, lane);
+      const float sq = fft200_windowed(x, s_win, s_tw, bufA, bufB, lane, want_rms);
+      if (want_rms) rms = sqrtf(warp_sum(sq) / (float)n_fft);
     } else {
       for (int j = lane; j < n; j += 32)
         bufA[j] = make_float2(x[2 * j] * s_win[2 * j], x[2 * j + 1] * s_win[2 * j + 1]);
