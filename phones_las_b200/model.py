@@ -188,17 +188,19 @@ class LASModel:
                  and all(lw.get("whh_tc") is not None for lw in w.listener.layers))
         return 2 if fused else 1
 
-    def transcribe_stream(self, host_batches, n_streams=None):
+    def transcribe_stream(self, host_batches, n_streams=None, ahead=None):
         """Serving loop over pinned host waveform batches ([B,N] float32 each), fully pipelined: the host->device copy of a batch
         runs on a copy stream into one of ``n_streams + 1`` preallocated device buffers, consecutive batches run on ``n_streams``
         compute streams (default: ``default_streams()``), nothing in a step synchronises the host (the decode step count stays
         on the device), and the ids of a batch are read back (pinned, asynchronous) while the following batches are already
         enqueued.  Kernels that need the whole GPU co-resident never overlap each other (_lib.grid_sync_kernel).  Yields
-        (sample_ids [B,steps], final_sequence_length [B]) host tensors per batch, in order."""
+        (sample_ids [B,steps], final_sequence_length [B]) host tensors per batch, in order.  Batches that are already device
+        tensors skip the staging copy (same streams, pacing and read-back)."""
         from collections import deque
         dev = self.plan.device
         ns = int(n_streams or self.default_streams())
-        nb = ns + 1
+        ahead = int(ahead or ns)  # batches the host may have in flight before it waits for the oldest one's ids
+        nb = ahead + 1
         if int(self.hp.get("beam_width", 0) or 0) > 0:
             raise NotImplementedError("transcribe_stream serves greedy decoding (beam search returns [B, T, W] ids: use transcribe)")
         # staging state lives on the model: cudaMalloc / cudaHostAlloc are slow and synchronise the device, so the streams,
@@ -218,6 +220,9 @@ class LASModel:
 
         def launch(hw, i):
             slot, cs = i % nb, compute[i % ns]
+            if hw.is_cuda:  # already resident (bench.py's device-resident arm): no staging copy, same pacing and read-back
+                with torch.cuda.stream(cs), _lib.rec_sms(self.PIPELINED_REC_SMS if ns > 1 else 0):
+                    return run(hw, slot, cs)
             with torch.cuda.stream(copy_stream):
                 if bufs[slot] is None or bufs[slot].shape != hw.shape:
                     # allocated under the copy stream: the block is then ordered after its previous owner's work on this stream
@@ -229,21 +234,24 @@ class LASModel:
                 ev.record(copy_stream)
             with torch.cuda.stream(cs), _lib.rec_sms(self.PIPELINED_REC_SMS if ns > 1 else 0):
                 cs.wait_event(ev)
-                pred = self.transcribe(bufs[slot], want_alignment=False, trim=False, want_probs=False)
-                done = torch.cuda.Event()
-                done.record(cs)
-                consumed[slot] = done
-                key, klen = (("sample_ids", "final_sequence_length") if "sample_ids" in pred
-                             else ("sample_ids_phones_binf", "final_sequence_length_binf"))  # --binf_projection without --multitask
-                ids_d, len_d, n_d = pred[key], pred[klen], pred["n_steps"]
-                if pinned[slot] is None or pinned[slot][0].shape != ids_d.shape:
-                    pinned[slot] = (torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory(),
-                                    torch.empty(len_d.shape, dtype=len_d.dtype).pin_memory(),
-                                    torch.empty(n_d.shape, dtype=n_d.dtype).pin_memory())
-                for h_t, d_t in zip(pinned[slot], (ids_d, len_d, n_d)):
-                    h_t.copy_(d_t, non_blocking=True)
-                rd = torch.cuda.Event()
-                rd.record(cs)
+                return run(bufs[slot], slot, cs)
+
+        def run(wave, slot, cs):  # under stream cs: transcribe + asynchronous read-back of ids / lengths / step count
+            pred = self.transcribe(wave, want_alignment=False, trim=False, want_probs=False)
+            done = torch.cuda.Event()
+            done.record(cs)
+            consumed[slot] = done
+            key, klen = (("sample_ids", "final_sequence_length") if "sample_ids" in pred
+                         else ("sample_ids_phones_binf", "final_sequence_length_binf"))  # --binf_projection without --multitask
+            ids_d, len_d, n_d = pred[key], pred[klen], pred["n_steps"]
+            if pinned[slot] is None or pinned[slot][0].shape != ids_d.shape:
+                pinned[slot] = (torch.empty(ids_d.shape, dtype=ids_d.dtype).pin_memory(),
+                                torch.empty(len_d.shape, dtype=len_d.dtype).pin_memory(),
+                                torch.empty(n_d.shape, dtype=n_d.dtype).pin_memory())
+            for h_t, d_t in zip(pinned[slot], (ids_d, len_d, n_d)):
+                h_t.copy_(d_t, non_blocking=True)
+            rd = torch.cuda.Event()
+            rd.record(cs)
             return pinned[slot], rd
 
         def finish(job):
@@ -254,7 +262,7 @@ class LASModel:
 
         pending = deque()
         for i, hw in enumerate(host_batches):
-            if len(pending) == ns:  # the slot batch i is about to reuse belongs to batch i - ns - 1: already yielded
+            if len(pending) == ahead:  # the slot batch i is about to reuse belongs to batch i - ahead - 1: already yielded
                 yield finish(pending.popleft())
             pending.append(launch(hw, i))
         while pending:
