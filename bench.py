@@ -402,7 +402,8 @@ def ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count - l0
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    pred = run_step(0, want_alignment=True, trim=False)  # (untimed) the decode step count of this workload
+    pred = model.transcribe(dev_waves[0], want_alignment=True, trim=False)  # (untimed, main stream) the workload's decode step count
+    torch.cuda.synchronize()
     n_dec = int(pred["n_steps"].item())
     audio_s = B * cfg["seconds"]
     value = world * audio_s / (ms * 1e-3)
@@ -481,7 +482,7 @@ def ours(args):
                                "achieved_streamed": streamed / (t_ms * 1e-3) / 1e12, "frac_streamed": streamed / (t_ms * 1e-3) / smem_peak,
                                "note": "north_star (3) SMEM roofline: resident W_hh operand bytes per step (algorithmic: once per "
                                        "step and direction; streamed: once per 16-column group MMA chain, from tensor memory)"})
-        if name == "frontend":  # formally HBM-bound (north_star), in practice FP32-issue-bound: report both
+        if name == "frontend":  # formally HBM-bound (north_star), in practice issue / shared-memory-bound: report both
             fl = frontend_flops_per_frame(fa) * B * cfg["T"]
             ent.update(fp32_tflops=fl / (t_ms * 1e-3) / 1e12, fp32_peak_tflops=FP32_PEAK_TFLOPS,
                        fp32_pipe_frac=fl / (t_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, flops_per_frame=frontend_flops_per_frame(fa))
@@ -922,7 +923,7 @@ def ours_frontend(args):
                 "roofline": {"kernel": "fe_spectral_kernel (+ fe_librosa_post / fe_librosa_delta)", "bound": "hbm", "achieved": head["hbm_gbs"],
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["hbm_gbs"] / peaks["hbm_gbs"], "traffic": None,
                              "peak_source": peaks["_source"],
-                             "note": "FP32-issue-bound mixed-radix FFT (DESIGN.md section 3, K1): the HBM fraction is reported as north_star asks"},
+                             "note": "mixed-radix FFT bound by instruction issue and shared-memory wavefronts (DESIGN.md section 3, K1): the HBM fraction is reported as north_star asks"},
                 "variants": results, "gpu_launches": int(_lib.launch_count - l0)}
         return line
     return None
