@@ -36,3 +36,27 @@ def test_ctc_greedy_decode_known_answer_and_oracle():
     logits = rng.normal(size=(5, 17, 7)).astype(np.float32)
     lens = np.array([17, 3, 9, 1, 12])
     np.testing.assert_array_equal(metrics.ctc_greedy_decode(logits.argmax(-1), lens, 6), olo.ctc_greedy_decoder(logits, lens))
+
+
+def test_levenshtein_core_matches_torchaudio():
+    """The Levenshtein core of metrics.edit_distance (and of the oracle's) against an independent implementation
+    (torchaudio.functional.edit_distance), on random label rows cut at EOS with repeats merged by hand."""
+    import pytest
+    taf = pytest.importorskip("torchaudio.functional")
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        rows = []
+        for _side in range(2):
+            n = int(rng.integers(1, 14))
+            seq = rng.integers(3, 9, n).tolist() + [2] + rng.integers(3, 9, 3).tolist()  # labels, EOS = 2, junk after EOS
+            rows.append(seq)
+        width = max(len(r) for r in rows)
+        hyp, tru = [r + [2] * (width - len(r)) for r in rows]
+        merged = []
+        for r in (hyp, tru):
+            cut = r[:r.index(2)]
+            merged.append([x for i, x in enumerate(cut) if i == 0 or x != cut[i - 1]])
+        want = taf.edit_distance(merged[0], merged[1]) / len(merged[1])
+        got = metrics.edit_distance([hyp], [tru], eos_id=2)[0]
+        assert got == pytest.approx(want, abs=1e-12)
+        assert olo.edit_distance_merge(hyp, tru, eos_id=2) == pytest.approx(want, abs=1e-12)
