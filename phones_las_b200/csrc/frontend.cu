@@ -141,24 +141,33 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
 // runtime index arithmetic), 16-byte stores out of the radix-8 pass, and the window applied while the first pass loads its
 // samples straight from the staged span.  Result in bufA.
 // Returns this lane's share of sum(x^2) over the raw samples when want_sq (librosa's rms energy column), else 0.
-__device__ __forceinline__ float fft200_windowed(const float* __restrict__ x, const float* __restrict__ win,
+// wreg: this lane's eight window pairs win[2 (lane + 25 t)], win[2 (lane + 25 t) + 1], loaded once per CTA (the same for every frame).
+__device__ __forceinline__ float fft200_windowed(const float* __restrict__ x, const float2 (&wreg)[8],
                                                  const float2* __restrict__ tw, float2* __restrict__ bufA,
                                                  float2* __restrict__ bufB, int lane, bool want_sq) {
   float sq = 0.f;
   if (lane < 25) {  // pass 1: radix 8, Ns = 1: butterfly j reads elements j + 25 t, writes 8 j .. 8 j + 7
     const float2* x2 = reinterpret_cast<const float2*>(x);
-    const float2* w2 = reinterpret_cast<const float2*>(win);
     float2 v[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const float2 xv = x2[lane + 25 * t], wv = w2[lane + 25 * t];
+      const float2 xv = x2[lane + 25 * t], wv = wreg[t];
       v[t] = make_float2(xv.x * wv.x, xv.y * wv.y);
       if (want_sq) sq = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, sq));
     }
     Bfly<8>::run(v);
+    // A lane's 8 outputs are one 64-byte block, so the four 16-byte chunks of neighbouring lanes sit 64 bytes apart: stored in
+    // the same order by every lane they hit only two of the eight 16-byte bank groups (13 wavefronts per store instead of 4).
+    // Lane j therefore starts with chunk (j >> 1) & 3: a register rotation, then instruction i stores chunk (i + rot) & 3.
+    float4 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = make_float4(v[2 * u].x, v[2 * u].y, v[2 * u + 1].x, v[2 * u + 1].y);
+    const int rot = (lane >> 1) & 3;
+    if (rot & 1) { const float4 t0 = c[0]; c[0] = c[1]; c[1] = c[2]; c[2] = c[3]; c[3] = t0; }
+    if (rot & 2) { const float4 t0 = c[0], t1 = c[1]; c[0] = c[2]; c[1] = c[3]; c[2] = t0; c[3] = t1; }
     float4* o = reinterpret_cast<float4*>(bufA + 8 * lane);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = make_float4(v[2 * u].x, v[2 * u].y, v[2 * u + 1].x, v[2 * u + 1].y);
+    for (int u = 0; u < 4; ++u) o[(u + rot) & 3] = c[u];
   }
   __syncwarp();
 #pragma unroll
@@ -169,7 +178,7 @@ __device__ __forceinline__ float fft200_windowed(const float* __restrict__ x, co
       float2 v[5];
       v[0] = bufA[j];
 #pragma unroll
-      for (int t = 1; t < 5; ++t) v[t] = cmul(bufA[j + 40 * t], tw[5 * k * t]);
+      for (int t = 1; t < 5; ++t) v[t] = cmul(bufA[j + 40 * t], tw[160 + 8 * (t - 1) + k]);  // w200^(5 k t)
       Bfly<5>::run(v);
       float2* o = bufB + (j - k) * 5 + k;
 #pragma unroll
@@ -184,7 +193,7 @@ __device__ __forceinline__ float fft200_windowed(const float* __restrict__ x, co
       float2 v[5];
       v[0] = bufB[j];
 #pragma unroll
-      for (int t = 1; t < 5; ++t) v[t] = cmul(bufB[j + 40 * t], tw[j * t]);
+      for (int t = 1; t < 5; ++t) v[t] = cmul(bufB[j + 40 * t], tw[40 * (t - 1) + j]);  // w200^(j t): contiguous in j, no bank conflicts
       Bfly<5>::run(v);
 #pragma unroll
       for (int u = 0; u < 5; ++u) bufA[j + 40 * u] = v[u];
@@ -249,7 +258,16 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   float* s_span = reinterpret_cast<float*>(fe_smem + off_span);
   float2* s_work = reinterpret_cast<float2*>(fe_smem + off_work) + warp * work_stride;
 
-  for (int i = tid; i < n; i += FE_THREADS) s_tw[i] = reinterpret_cast<const float2*>(d.tw)[i];
+  if constexpr (NFFT == 400) {
+    // the twiddles of the two radix-5 passes in the order their lanes read them: [0, 160) w^(j t) as [t - 1][j], j < 40 (pass 3);
+    // [160, 192) w^(5 k t) as [t - 1][k], k < 8 (pass 2).  (Read as tw[j t], strides 2 and 4 cost pass 3 a third of its wavefronts.)
+    for (int i = tid; i < 192; i += FE_THREADS) {
+      const int idx = i < 160 ? (i % 40) * (i / 40 + 1) : 5 * ((i - 160) & 7) * (((i - 160) >> 3) + 1);
+      s_tw[i] = reinterpret_cast<const float2*>(d.tw)[idx];
+    }
+  } else {
+    for (int i = tid; i < n; i += FE_THREADS) s_tw[i] = reinterpret_cast<const float2*>(d.tw)[i];
+  }
   for (int i = tid; i <= n; i += FE_THREADS) s_twu[i] = reinterpret_cast<const float2*>(d.tw_unpack)[i];
   for (int i = tid; i < n_fft; i += FE_THREADS) s_win[i] = d.window[i];
   for (int i = tid; i < d.fb_total; i += FE_THREADS) s_fbw[i] = d.fb_w[i];
@@ -282,6 +300,11 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
   __syncthreads();
 
   const float eps64 = 2.220446049250313e-16f;  // np.finfo(float).eps (speechpy zero_handling)
+  float2 wreg[8];  // n_fft = 400: the window pairs of this lane's radix-8 butterfly stay in registers across the CTA's frames
+  if constexpr (NFFT == 400) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) wreg[t] = lane < 25 ? reinterpret_cast<const float2*>(s_win)[lane + 25 * t] : make_float2(0.f, 0.f);
+  }
   for (int f = warp; f < FE_FRAMES; f += FE_WARPS) {
     const int t = tile0 + f;
     if (t >= p.T_max) break;
@@ -306,7 +329,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
     float2* src = bufA;
     float2* dst = bufB;
     if constexpr (NFFT == 400) {
-      const float sq = fft200_windowed(x, s_win, s_tw, bufA, bufB, lane, want_rms);
+      const float sq = fft200_windowed(x, wreg, s_tw, bufA, bufB, lane, want_rms);
       if (want_rms) rms = sqrtf(warp_sum(sq) / (float)n_fft);
     } else {
       for (int j = lane; j < n; j += 32)
