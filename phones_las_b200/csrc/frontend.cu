@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(FE_THREADS, 4) fe_spectral_kernel(FeArgs p) {
 
   if constexpr (NFFT == 400) {
     // the twiddles of the two radix-5 passes in the order their lanes read them: [0, 160) w^(j t) as [t - 1][j], j < 40 (pass 3);
-    // [160, 192) w^(5 k t) as [t - 1][k], k < 8 (pass 2).  (Read as tw[j t], strides 2 and 4 cost pass 3 a third of its wavefronts.)
+    // [160, 192) w^(5 k t) as [t - 1][k], k < 8 (pass 2).  (Read as tw[j t], strides 2 and 4 replayed a quarter of pass 3's wavefronts.)
     for (int i = tid; i < 192; i += FE_THREADS) {
       const int idx = i < 160 ? (i % 40) * (i / 40 + 1) : 5 * ((i - 160) & 7) * (((i - 160) >> 3) + 1);
       s_tw[i] = reinterpret_cast<const float2*>(d.tw)[idx];
