@@ -12,8 +12,11 @@
 // between two per-warp shared buffers and only __syncwarp() separates the passes.
 //   speechpy back end : everything is per-frame -> ONE kernel writes the final features.
 //   librosa back end  : top_db clips against the utterance-global max, so kernel A writes dB
-//                       values + an atomicMax per utterance, kernel B clips/DCTs, kernel C adds
-//                       the Savitzky-Golay deltas along time.
+//                       values + an atomicMax per utterance, kernel B clips (plain MFE: a streaming
+//                       float4 kernel, fe_librosa_clip_kernel) or clips + DCTs, kernel C adds the
+//                       Savitzky-Golay deltas along time.
+// The BASELINE window (n_fft = 400) is a template instance with every size a constant: radix 8-5-5
+// passes, window pairs in registers, conflict-free shared-memory traffic.
 #include <stdlib.h>
 
 #include "common.cuh"
