@@ -18,5 +18,8 @@ amplitude_to_db-of-power quirk, MFCC) against torchaudio.transforms and
 transformers.audio_utils, two third-party implementations written to reproduce
 librosa (tests/test_oracle_frontend.py::test_librosa_*_vs_*): agreement to 4e-6 dB /
 5e-5 on MFCCs.  That anchors the librosa rows to something other than this restatement;
-the speechpy rows and the TF seq2seq decoder have no such second implementation here.
+the speechpy rows and the TF seq2seq decoder have no such second implementation here
+(the monotonic attention's closed forms are checked against the recurrence of Raffel et al. 2017
+they stand for, tests/test_oracle_las.py::test_monotonic_attention_closed_form_matches_the_recurrence;
+the Levenshtein core of the edit-distance metric against torchaudio.functional.edit_distance).
 """

@@ -293,3 +293,46 @@ def test_prediction_embedding_follows_the_reference_state_nesting():
         if has:
             np.testing.assert_array_equal(emb.numpy(), pred["embedding"])
             assert emb.shape == (3, 2, 8 * (1 if (pyr and uni) else 2))
+
+
+@pytest.mark.parametrize("att", ["luong_monotonic", "bahdanau_monotonic"])
+def test_monotonic_attention_closed_form_matches_the_recurrence(att):
+    """The oracle evaluates monotonic attention in the closed ('parallel' / 'hard') forms tf.contrib.seq2seq.monotonic_attention
+    uses.  Both stand for the recurrence of Raffel et al. 2017 (eq. 8-10; TF's mode='recursive'):
+        q_j = (1 - p_{j-1}) q_{j-1} + a^{prev}_j,   a_j = p_j q_j,   q_{-1} = 0, p_{-1} = 0
+    -- checked here over several decode steps, each step feeding its alignments to the next."""
+    rng = np.random.default_rng(3)
+    B, Tm, D = 3, 17, 8
+    memory = rng.standard_normal((B, Tm, D)).astype(np.float32)
+    mem_len = np.array([17, 11, 5])
+    scope, pre = "speller", "speller/decoder/attention_wrapper"
+    params = {f"{scope}/memory_layer/kernel": np.eye(D, dtype=np.float32),
+              f"{pre}/{att}_attention/attention_score_bias": np.float32(-0.3)}
+    if att == "bahdanau_monotonic":
+        params[f"{pre}/{att}_attention/query_layer/kernel"] = (0.5 * rng.standard_normal((D, D))).astype(np.float32)
+        params[f"{pre}/{att}_attention/attention_v"] = rng.standard_normal(D).astype(np.float32)
+    a = ol.Attention(att, memory, mem_len, params, scope)
+    prev = a.initial_alignments()
+    ref_prev = prev.astype(np.float64)
+    mask = np.arange(Tm)[None, :] < mem_len[:, None]
+    for step in range(4):
+        query = rng.standard_normal((B, D)).astype(np.float32)
+        got = a(query, prev)
+        # choose probabilities, restated independently of the class
+        if att == "luong_monotonic":
+            score = np.einsum("btd,bd->bt", memory * mask[:, :, None], query) - 0.3
+            p = np.where(mask, 1.0 / (1.0 + np.exp(-score.astype(np.float64))), 0.0)
+        else:
+            pq = query @ params[f"{pre}/{att}_attention/query_layer/kernel"]
+            score = np.tanh(memory * mask[:, :, None] + pq[:, None, :]) @ params[f"{pre}/{att}_attention/attention_v"] - 0.3
+            p = np.where(mask & (score > 0), 1.0, 0.0)
+        ref = np.zeros((B, Tm))
+        for b in range(B):
+            q_prev, p_prev = 0.0, 0.0
+            for j in range(Tm):
+                q = (1.0 - p_prev) * q_prev + ref_prev[b, j]
+                ref[b, j] = p[b, j] * q
+                q_prev, p_prev = q, p[b, j]
+        np.testing.assert_allclose(got, ref, rtol=2e-4, atol=1e-6)
+        assert (got.sum(axis=1) <= 1.0 + 1e-5).all()  # the mass that attends nowhere is lost, never created
+        prev, ref_prev = got, ref
