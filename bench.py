@@ -18,7 +18,8 @@ collective; "weak" scaling: every rank runs a full batch).  Rank 0 prints ONE JS
             per batch), the recurrence held to LASModel.PIPELINED_REC_SMS SMs (config.pipelining); timed with CUDA events.
   e2e       same metric through the public host API (LASModel.transcribe_stream): per step pinned host
             waveform -> H2D (overlapping the previous step's kernels) -> kernels -> D2H of the decoded ids,
-            all inside the timed region.
+            all inside the timed region.  Both arms ask for the full predictions of the reference's PREDICT mode
+            (want_alignment=True: the decoder also writes the alignment history; it stays on the device).
   roofline  the dominant kernel of the step (by measured device time), algorithmic bytes/flops per
             launch / its CUDA-event duration vs MEASURED_PEAKS.json; for the recurrence also the
             on-chip operand roofline north_star (3) names (roofline.onchip).  stages.* = every kernel family timed alone on
@@ -374,7 +375,7 @@ def ours(args):
     # resident batches have no H2D copy to hide the enqueue behind: the host keeps one more batch in flight than the serving
     # default (A/B on one B200, 3 runs each: 87.4-88.0 k with ns, 88.2-88.7 k with ns + 1; scripts/gpu_ahead.sh)
     ahead = int(os.environ.get("PLAS_BENCH_AHEAD", "0")) or ns + 1
-    for _ in model.transcribe_stream((dev_waves[i % nbuf] for i in range(max(args.warmup, ns + 2))), n_streams=ns, ahead=ahead):
+    for _ in model.transcribe_stream((dev_waves[i % nbuf] for i in range(max(args.warmup, ns + 2))), n_streams=ns, ahead=ahead, want_alignment=True):
         pass
     barrier()
     if rank == 0:
@@ -395,7 +396,7 @@ def ours(args):
     # projection GEMMs squeezed into the 20 SMs left): 70-85 k audio-s/s from run to run; through the serving loop the value
     # repeats to 1.5 % (87.4-88.7 k in six runs).
     ev0.record()
-    for _ in model.transcribe_stream((dev_waves[i % nbuf] for i in range(args.steps)), n_streams=ns, ahead=ahead):
+    for _ in model.transcribe_stream((dev_waves[i % nbuf] for i in range(args.steps)), n_streams=ns, ahead=ahead, want_alignment=True):
         pass
     ev1.record()
     barrier()
@@ -409,13 +410,13 @@ def ours(args):
     value = world * audio_s / (ms * 1e-3)
 
     # ---- end to end through the host API -----------------------------------------------------
-    for _ in model.transcribe_stream((host_waves[i % nbuf] for i in range(max(args.warmup, 3))), n_streams=ns):
+    for _ in model.transcribe_stream((host_waves[i % nbuf] for i in range(max(args.warmup, 3))), n_streams=ns, want_alignment=True):
         pass
     barrier()
     t0 = time.perf_counter()
     # public serving API: every step's waveforms cross PCIe from pinned host memory (the copy of step i+1 overlaps
     # the kernels of step i on a copy stream) and every step's decoded ids + lengths are read back to the host
-    for ids, slen in model.transcribe_stream((host_waves[i % nbuf] for i in range(args.steps)), n_streams=ns):
+    for ids, slen in model.transcribe_stream((host_waves[i % nbuf] for i in range(args.steps)), n_streams=ns, want_alignment=True):
         pass
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps

@@ -188,7 +188,7 @@ class LASModel:
                  and all(lw.get("whh_tc") is not None for lw in w.listener.layers))
         return 2 if fused else 1
 
-    def transcribe_stream(self, host_batches, n_streams=None, ahead=None):
+    def transcribe_stream(self, host_batches, n_streams=None, ahead=None, want_alignment=False):
         """Serving loop over pinned host waveform batches ([B,N] float32 each), fully pipelined: the host->device copy of a batch
         runs on a copy stream into one of ``n_streams + 1`` preallocated device buffers, consecutive batches run on ``n_streams``
         compute streams (default: ``default_streams()``), nothing in a step synchronises the host (the decode step count stays
@@ -237,7 +237,8 @@ class LASModel:
                 return run(bufs[slot], slot, cs)
 
         def run(wave, slot, cs):  # under stream cs: transcribe + asynchronous read-back of ids / lengths / step count
-            pred = self.transcribe(wave, want_alignment=False, trim=False, want_probs=False)
+            # want_alignment: the decoder also writes predictions['alignment'] (it stays on the device; only ids / lengths are read back)
+            pred = self.transcribe(wave, want_alignment=want_alignment, trim=False, want_probs=False)
             done = torch.cuda.Event()
             done.record(cs)
             consumed[slot] = done
