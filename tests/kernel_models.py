@@ -91,9 +91,12 @@ def frame_power(x, tb, librosa):
 
 
 def mel_sparse(P, tb):
+    """Sparse filterbank rows as fe_spectral_kernel walks them: rows are zero-padded to multiples of four weights and may reach up
+    to three bins past n_fft / 2, which the kernel keeps at zero."""
+    Pp = np.concatenate([P, np.zeros(3, np.float32)])
     out = np.zeros(len(tb["fb_start"]), np.float32)
     for m, (st, ln, off) in enumerate(zip(tb["fb_start"], tb["fb_len"], tb["fb_off"])):
-        out[m] = np.dot(tb["fb_w"][off:off + ln], P[st:st + ln])
+        out[m] = np.dot(tb["fb_w"][off:off + ln], Pp[st:st + ln])
     return out
 
 
