@@ -80,14 +80,20 @@ def frame_power(x, tb, librosa):
     tw = (tb["tw"][:, 0] + 1j * tb["tw"][:, 1]).astype(np.complex64)
     twu = (tb["tw_unpack"][:, 0] + 1j * tb["tw_unpack"][:, 1]).astype(np.complex64)
     Z = stockham_fft(z, tb["fac"], tw)
-    k = np.arange(n + 1)
-    zk = Z[np.where(k == n, 0, k)]
-    zm = np.conj(Z[np.where((k == 0) | (k == n), 0, n - k)])
-    xe = 0.5 * (zk + zm)
-    xo = _mi(0.5 * (zk - zm))
-    X = (xe + twu * xo).astype(np.complex64)
-    scale = 1.0 if librosa else 1.0 / n_fft
-    return ((X.real ** 2 + X.imag ** 2) * scale).astype(np.float32)
+    # bins k and n - k from the same two points of Z (k <= n / 2): X[k] = xe + w^k xo, X[n-k] = conj(xe - w^k xo); the kernel keeps
+    # 2 xe and 2 xo and folds the 1/4 into the power scale
+    k = np.arange(n // 2 + 1)
+    zk = Z[k]
+    zm = np.conj(Z[np.where(k == 0, 0, n - k)])
+    xe2 = (zk + zm).astype(np.complex64)
+    xo2 = _mi(zk - zm).astype(np.complex64)
+    t = (twu[k] * xo2).astype(np.complex64)
+    Xa, Xb = xe2 + t, xe2 - t
+    scale = np.float32(0.25 if librosa else 0.25 / n_fft)
+    P = np.zeros(n + 1, np.float32)
+    P[k] = (Xa.real ** 2 + Xa.imag ** 2) * scale
+    P[n - k] = (Xb.real ** 2 + Xb.imag ** 2) * scale
+    return P
 
 
 def mel_sparse(P, tb):
